@@ -1,0 +1,201 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY.  Nothing under cgal_b200/ may include, link or call this.
+// C entry points (ctypes) over the CPU restatement in kernel.hpp / tree.hpp.  Used by tests/, by
+// __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs, never by the product.
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <thread>
+#include <vector>
+#include "tree.hpp"
+
+namespace orc { thread_local Stats g_stats; }
+using namespace orc;
+
+namespace {
+struct Handle { Mesh mesh; std::unique_ptr<Tree> tree; double build_seconds = 0, kd_seconds = 0; };
+
+template <class F> void parallel_for(uint64_t n, int nthreads, F f) {
+    if (nthreads <= 1 || n < 1024) { f(0, n); return; }
+    std::vector<std::thread> th;
+    const uint64_t chunk = (n + nthreads - 1) / nthreads;      // static blocked ranges over queries, standing in for
+    for (int t = 0; t < nthreads; ++t) {                        // tbb::parallel_for (Polygon_mesh_processing/distance.h:163-169)
+        uint64_t b = t * chunk, e = std::min<uint64_t>(n, b + chunk);
+        if (b >= e) break;
+        th.emplace_back([=] { f(b, e); });
+    }
+    for (auto& x : th) x.join();
+}
+inline P3 P(const double* d) { return {d[0], d[1], d[2]}; }
+inline Tri T(const double* d) { return {P(d), P(d + 3), P(d + 6)}; }
+inline Box B(const double* d) { return {{d[0], d[1], d[2]}, {d[3], d[4], d[5]}}; }
+inline void put(double* d, const P3& p) { d[0] = p.x; d[1] = p.y; d[2] = p.z; }
+}  // namespace
+
+extern "C" {
+
+// verts: nv x 3 doubles; faces: nf x 3 uint32 (OFF order).  Builds the median-split tree.
+void* orc_create(const double* verts, uint64_t nv, const uint32_t* faces, uint64_t nf) {
+    (void)nv;
+    Handle* h = new Handle();
+    h->mesh.tris.resize(nf);
+    for (uint64_t i = 0; i < nf; ++i)
+        h->mesh.tris[i] = {P(verts + 3 * (uint64_t)faces[3 * i]), P(verts + 3 * (uint64_t)faces[3 * i + 1]), P(verts + 3 * (uint64_t)faces[3 * i + 2])};
+    auto t0 = std::chrono::steady_clock::now();
+    h->tree.reset(new Tree(h->mesh));
+    h->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return h;
+}
+// triangle soup: tris = n x 9 doubles
+void* orc_create_soup(const double* tris, uint64_t n) {
+    Handle* h = new Handle();
+    h->mesh.tris.resize(n);
+    for (uint64_t i = 0; i < n; ++i) h->mesh.tris[i] = T(tris + 9 * i);
+    auto t0 = std::chrono::steady_clock::now();
+    h->tree.reset(new Tree(h->mesh));
+    h->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return h;
+}
+void orc_destroy(void* hv) { delete (Handle*)hv; }
+double orc_build_seconds(void* hv) { return ((Handle*)hv)->build_seconds; }
+double orc_kd_seconds(void* hv) { return ((Handle*)hv)->kd_seconds; }
+uint64_t orc_size(void* hv) { return ((Handle*)hv)->tree->size(); }
+void orc_accelerate_distance_queries(void* hv) {
+    Handle* h = (Handle*)hv;
+    auto t0 = std::chrono::steady_clock::now();
+    h->tree->accelerate_distance_queries();
+    h->kd_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+void orc_do_not_accelerate_distance_queries(void* hv) { ((Handle*)hv)->tree->do_not_accelerate_distance_queries(); }
+void orc_bbox(void* hv, double* out) { Box b = ((Handle*)hv)->tree->bbox(); for (int i = 0; i < 3; ++i) { out[i] = b.lo[i]; out[3 + i] = b.hi[i]; } }
+
+// kind: 0 = Segment_3 (source,target), 1 = Ray_3 (source, second point); q = n x 6 doubles
+void orc_do_intersect(void* hv, const double* q, uint64_t n, int kind, uint8_t* out, int nthreads) {
+    const Tree& t = *((Handle*)hv)->tree;
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e) {
+        for (uint64_t i = b; i < e; ++i) out[i] = t.do_intersect({P(q + 6 * i), P(q + 6 * i + 3), kind == 1}) ? 1 : 0;
+    });
+}
+void orc_count(void* hv, const double* q, uint64_t n, int kind, uint32_t* out, int nthreads) {
+    const Tree& t = *((Handle*)hv)->tree;
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e) {
+        for (uint64_t i = b; i < e; ++i) out[i] = t.number_of_intersected_primitives({P(q + 6 * i), P(q + 6 * i + 3), kind == 1});
+    });
+}
+// first_intersection(Ray_3).  prim = 0xFFFFFFFF when none.  kind: 0 none, 1 Point_3, 2 Segment_3.
+// pts: n x 6 (point, or the two segment endpoints).  tie[i] = 1 if another primitive produced exactly the same t.
+void orc_first_intersection(void* hv, const double* rays, uint64_t n, uint32_t* prim, double* tpar, double* pts,
+                            uint8_t* kind, uint8_t* tie, int nthreads) {
+    const Tree& t = *((Handle*)hv)->tree;
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e) {
+        for (uint64_t i = b; i < e; ++i) {
+            Tree::FirstHit h = t.first_intersection(P(rays + 6 * i), P(rays + 6 * i + 3));
+            prim[i] = h.hit ? h.prim : 0xFFFFFFFFu;
+            if (tpar) tpar[i] = h.hit ? h.t : 0.0;
+            if (kind) kind[i] = (uint8_t)h.r.kind;
+            if (tie) tie[i] = h.t_tie;
+            if (pts) { std::memset(pts + 6 * i, 0, 48); if (h.hit) { put(pts + 6 * i, h.r.pt[0]); if (h.r.kind == 2) put(pts + 6 * i + 3, h.r.pt[1]); } }
+        }
+    });
+}
+// closest_point_and_primitive(Point_3) (+ squared_distance).  Tree must be non-empty (CGAL_precondition(!empty())).
+int orc_closest_point(void* hv, const double* q, uint64_t n, double* cp, uint32_t* prim, double* sqd, int nthreads) {
+    const Tree& t = *((Handle*)hv)->tree;
+    if (t.size() == 0) return -1;
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e) {
+        for (uint64_t i = b; i < e; ++i) {
+            const P3 p = P(q + 3 * i);
+            auto r = t.closest_point_and_primitive(p);
+            if (cp) put(cp + 3 * i, r.first);
+            if (prim) prim[i] = r.second;
+            if (sqd) sqd[i] = sqdist(p, r.first);
+        }
+    });
+    return 0;
+}
+
+// ---- brute-force counterparts (AABB_tree/test/AABB_tree/AABB_test_util.h:572-676,755-786; aabb_test_ray_intersection.cpp:38-65)
+void orc_naive_count(void* hv, const double* q, uint64_t n, int kind, uint32_t* out, int nthreads) {
+    const Mesh& m = ((Handle*)hv)->mesh;
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e) {
+        for (uint64_t i = b; i < e; ++i) {
+            uint32_t c = 0; const P3 p = P(q + 6 * i), r = P(q + 6 * i + 3);
+            for (const Tri& t : m.tris) c += (kind == 1 ? do_intersect_ray_tri(t, p, r) : do_intersect_seg_tri(t, p, r)) ? 1 : 0;
+            out[i] = c;
+        }
+    });
+}
+// argmin over all primitives of the exact squared distance of the rounded candidate; ntie = #primitives attaining it
+void orc_naive_closest(void* hv, const double* q, uint64_t n, double* cp, uint32_t* prim, uint32_t* ntie, int nthreads) {
+    const Mesh& m = ((Handle*)hv)->mesh;
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e) {
+        for (uint64_t i = b; i < e; ++i) {
+            const P3 p = P(q + 3 * i);
+            P3 best = project_on_triangle(m.tris[0], p); uint32_t arg = 0, ties = 1;
+            for (uint32_t f = 1; f < m.tris.size(); ++f) {
+                const P3 c = project_on_triangle(m.tris[f], p);
+                const int s = compare_distance(p, c, best);
+                if (s < 0) { best = c; arg = f; ties = 1; } else if (s == 0) ++ties;
+            }
+            if (cp) put(cp + 3 * i, best);
+            if (prim) prim[i] = arg;
+            if (ntie) ntie[i] = ties;
+        }
+    });
+}
+// argmin-t over all intersections, first (lowest face id) wins on equal t; ntie = #primitives attaining min t
+void orc_naive_first_intersection(void* hv, const double* rays, uint64_t n, uint32_t* prim, double* tpar, uint32_t* ntie, int nthreads) {
+    const Mesh& m = ((Handle*)hv)->mesh;
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e) {
+        for (uint64_t i = b; i < e; ++i) {
+            const P3 s = P(rays + 6 * i), q = P(rays + 6 * i + 3);
+            const V3 v = vsub(q, s); const int mi = Tree::ray_max_axis(v);
+            double t = std::numeric_limits<double>::max(); uint32_t arg = 0xFFFFFFFFu, ties = 0;
+            for (uint32_t f = 0; f < m.tris.size(); ++f) {
+                RayHit r = ray_tri_intersection(m.tris[f], s, q);
+                if (!r.kind) continue;
+                const double d = Tree::hit_param(s, v, mi, r);
+                if (d < t) { t = d; arg = f; ties = 1; } else if (d == t) ++ties;
+            }
+            prim[i] = arg; if (tpar) tpar[i] = arg == 0xFFFFFFFFu ? 0.0 : t; if (ntie) ntie[i] = ties;
+        }
+    });
+}
+
+// ---- per-primitive candidates, for the parity harness' tie-set checks
+void orc_candidate_closest(void* hv, uint32_t face, const double* q, double* cp) { put(cp, project_on_triangle(((Handle*)hv)->mesh.tris[face], P(q))); }
+int orc_candidate_ray_hit(void* hv, uint32_t face, const double* ray, double* tpar, double* pts) {
+    const P3 s = P(ray), q = P(ray + 3);
+    RayHit r = ray_tri_intersection(((Handle*)hv)->mesh.tris[face], s, q);
+    if (r.kind) { const V3 v = vsub(q, s); *tpar = Tree::hit_param(s, v, Tree::ray_max_axis(v), r); put(pts, r.pt[0]); if (r.kind == 2) put(pts + 3, r.pt[1]); }
+    return r.kind;
+}
+
+// ---- predicate / construction level (KATs and python-fractions checks)
+int orc_orientation(const double* p4) { return orientation(P(p4), P(p4 + 3), P(p4 + 6), P(p4 + 9)); }
+int orc_orientation_exact(const double* p4) { return orientation_exact(P(p4), P(p4 + 3), P(p4 + 6), P(p4 + 9)); }
+int orc_orientation_dir(const double* p5) { return orientation_dir(P(p5), P(p5 + 3), P(p5 + 6), P(p5 + 9), P(p5 + 12)); }
+int orc_coplanar_orientation3(const double* p3) { return coplanar_orientation(P(p3), P(p3 + 3), P(p3 + 6)); }
+int orc_coplanar_orientation4(const double* p4) { return coplanar_orientation(P(p4), P(p4 + 3), P(p4 + 6), P(p4 + 9)); }
+int orc_compare_distance(const double* p3) { return compare_distance(P(p3), P(p3 + 3), P(p3 + 6)); }
+int orc_compare_distance_exact(const double* p3) { return compare_distance_exact(P(p3), P(p3 + 3), P(p3 + 6)); }
+int orc_bbox_do_intersect(const double* box, const double* pq, int is_ray) { return do_intersect_bbox(P(pq), P(pq + 3), B(box), is_ray != 0); }
+int orc_bbox_do_intersect_exact(const double* box, const double* pq, int is_ray) { return bbox_segment_aux<true>(P(pq), P(pq + 3), B(box), true, !is_ray).v; }
+int orc_tri_do_intersect(const double* tri, const double* pq, int is_ray) {
+    return (is_ray ? do_intersect_ray_tri(T(tri), P(pq), P(pq + 3)) : do_intersect_seg_tri(T(tri), P(pq), P(pq + 3))) ? 1 : 0;
+}
+int orc_tri_ray_intersection(const double* tri, const double* ray, double* pts) {
+    RayHit r = ray_tri_intersection(T(tri), P(ray), P(ray + 3));
+    if (r.kind) { put(pts, r.pt[0]); if (r.kind == 2) put(pts + 3, r.pt[1]); }
+    return r.kind;
+}
+void orc_project_on_triangle(const double* tri, const double* q, double* out) { put(out, project_on_triangle(T(tri), P(q))); }
+int orc_ball_reaches_box(const double* q, const double* box, const double* bound) { return ball_reaches_box(P(q), B(box), P(bound)) ? 1 : 0; }
+int orc_intersection_distance(const double* ray, const double* box, double* t) {
+    auto d = intersection_distance(P(ray), vsub(P(ray + 3), P(ray)), B(box));
+    if (d) *t = *d;
+    return d ? 1 : 0;
+}
+void orc_stats(uint64_t* out) { out[0] = g_stats.orient_calls; out[1] = g_stats.orient_exact; out[2] = g_stats.cmpdist_calls; out[3] = g_stats.cmpdist_exact; out[4] = g_stats.bbox_exact; }
+int orc_hardware_concurrency() { return (int)std::thread::hardware_concurrency(); }
+
+}  // extern "C"

@@ -1,0 +1,243 @@
+"""ctypes binding of the CPU oracle (oracle/_build/liboracle.so).  Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = None
+
+_dp = C.POINTER(C.c_double)
+_u32p = C.POINTER(C.c_uint32)
+_u8p = C.POINTER(C.c_uint8)
+
+
+def _ptr(a, ty):
+    return None if a is None else a.ctypes.data_as(ty)
+
+
+def build():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        L = C.CDLL(path)
+        L.orc_create.restype = C.c_void_p
+        L.orc_create.argtypes = [_dp, C.c_uint64, _u32p, C.c_uint64]
+        L.orc_create_soup.restype = C.c_void_p
+        L.orc_create_soup.argtypes = [_dp, C.c_uint64]
+        L.orc_destroy.argtypes = [C.c_void_p]
+        L.orc_build_seconds.restype = C.c_double
+        L.orc_build_seconds.argtypes = [C.c_void_p]
+        L.orc_kd_seconds.restype = C.c_double
+        L.orc_kd_seconds.argtypes = [C.c_void_p]
+        L.orc_size.restype = C.c_uint64
+        L.orc_size.argtypes = [C.c_void_p]
+        L.orc_accelerate_distance_queries.argtypes = [C.c_void_p]
+        L.orc_do_not_accelerate_distance_queries.argtypes = [C.c_void_p]
+        L.orc_bbox.argtypes = [C.c_void_p, _dp]
+        L.orc_do_intersect.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_int, _u8p, C.c_int]
+        L.orc_count.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_int, _u32p, C.c_int]
+        L.orc_first_intersection.argtypes = [C.c_void_p, _dp, C.c_uint64, _u32p, _dp, _dp, _u8p, _u8p, C.c_int]
+        L.orc_closest_point.argtypes = [C.c_void_p, _dp, C.c_uint64, _dp, _u32p, _dp, C.c_int]
+        L.orc_closest_point.restype = C.c_int
+        L.orc_naive_count.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_int, _u32p, C.c_int]
+        L.orc_naive_closest.argtypes = [C.c_void_p, _dp, C.c_uint64, _dp, _u32p, _u32p, C.c_int]
+        L.orc_naive_first_intersection.argtypes = [C.c_void_p, _dp, C.c_uint64, _u32p, _dp, _u32p, C.c_int]
+        L.orc_candidate_closest.argtypes = [C.c_void_p, C.c_uint32, _dp, _dp]
+        L.orc_candidate_ray_hit.argtypes = [C.c_void_p, C.c_uint32, _dp, _dp, _dp]
+        L.orc_candidate_ray_hit.restype = C.c_int
+        for name in ("orc_orientation", "orc_orientation_exact", "orc_orientation_dir", "orc_coplanar_orientation3",
+                     "orc_coplanar_orientation4", "orc_compare_distance", "orc_compare_distance_exact"):
+            getattr(L, name).argtypes = [_dp]
+            getattr(L, name).restype = C.c_int
+        L.orc_bbox_do_intersect.argtypes = [_dp, _dp, C.c_int]
+        L.orc_bbox_do_intersect_exact.argtypes = [_dp, _dp, C.c_int]
+        L.orc_tri_do_intersect.argtypes = [_dp, _dp, C.c_int]
+        L.orc_tri_ray_intersection.argtypes = [_dp, _dp, _dp]
+        L.orc_project_on_triangle.argtypes = [_dp, _dp, _dp]
+        L.orc_ball_reaches_box.argtypes = [_dp, _dp, _dp]
+        L.orc_intersection_distance.argtypes = [_dp, _dp, _dp]
+        L.orc_stats.argtypes = [C.POINTER(C.c_uint64)]
+        _LIB = L
+    return _LIB
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def nthreads():
+    return max(1, os.cpu_count() or 1)
+
+
+class OracleTree:
+    """Mirror of CGAL::AABB_tree<AABB_traits_3<Epick, AABB_face_graph_triangle_primitive<Surface_mesh>>> (CPU)."""
+
+    def __init__(self, verts=None, faces=None, soup=None, accelerate=True):
+        L = lib()
+        if soup is not None:
+            self.soup = _d(soup).reshape(-1, 9)
+            self.h = L.orc_create_soup(_ptr(self.soup, _dp), len(self.soup))
+        else:
+            self.verts = _d(verts).reshape(-1, 3)
+            self.faces = np.ascontiguousarray(faces, dtype=np.uint32).reshape(-1, 3)
+            self.h = L.orc_create(_ptr(self.verts, _dp), len(self.verts), _ptr(self.faces, _u32p), len(self.faces))
+        if accelerate and self.size() > 0:
+            L.orc_accelerate_distance_queries(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_destroy(self.h)
+            self.h = None
+
+    def size(self):
+        return lib().orc_size(self.h)
+
+    def build_seconds(self):
+        return lib().orc_build_seconds(self.h)
+
+    def kd_seconds(self):
+        return lib().orc_kd_seconds(self.h)
+
+    def bbox(self):
+        out = np.zeros(6)
+        lib().orc_bbox(self.h, _ptr(out, _dp))
+        return out
+
+    def do_intersect(self, q, kind, threads=None):
+        q = _d(q).reshape(-1, 6)
+        out = np.zeros(len(q), np.uint8)
+        lib().orc_do_intersect(self.h, _ptr(q, _dp), len(q), kind, _ptr(out, _u8p), threads or nthreads())
+        return out
+
+    def count(self, q, kind, threads=None, naive=False):
+        q = _d(q).reshape(-1, 6)
+        out = np.zeros(len(q), np.uint32)
+        f = lib().orc_naive_count if naive else lib().orc_count
+        f(self.h, _ptr(q, _dp), len(q), kind, _ptr(out, _u32p), threads or nthreads())
+        return out
+
+    def first_intersection(self, rays, threads=None):
+        rays = _d(rays).reshape(-1, 6)
+        n = len(rays)
+        prim = np.zeros(n, np.uint32)
+        t = np.zeros(n)
+        pts = np.zeros((n, 6))
+        kind = np.zeros(n, np.uint8)
+        tie = np.zeros(n, np.uint8)
+        lib().orc_first_intersection(self.h, _ptr(rays, _dp), n, _ptr(prim, _u32p), _ptr(t, _dp), _ptr(pts, _dp),
+                                     _ptr(kind, _u8p), _ptr(tie, _u8p), threads or nthreads())
+        return dict(prim=prim, t=t, pts=pts, kind=kind, tie=tie)
+
+    def naive_first_intersection(self, rays, threads=None):
+        rays = _d(rays).reshape(-1, 6)
+        n = len(rays)
+        prim = np.zeros(n, np.uint32)
+        t = np.zeros(n)
+        ntie = np.zeros(n, np.uint32)
+        lib().orc_naive_first_intersection(self.h, _ptr(rays, _dp), n, _ptr(prim, _u32p), _ptr(t, _dp), _ptr(ntie, _u32p),
+                                           threads or nthreads())
+        return dict(prim=prim, t=t, ntie=ntie)
+
+    def closest_point(self, pts, threads=None):
+        pts = _d(pts).reshape(-1, 3)
+        n = len(pts)
+        cp = np.zeros((n, 3))
+        prim = np.zeros(n, np.uint32)
+        sqd = np.zeros(n)
+        rc = lib().orc_closest_point(self.h, _ptr(pts, _dp), n, _ptr(cp, _dp), _ptr(prim, _u32p), _ptr(sqd, _dp), threads or nthreads())
+        if rc != 0:
+            raise RuntimeError("CGAL_precondition(!empty()) violated")
+        return dict(cp=cp, prim=prim, sqd=sqd)
+
+    def naive_closest(self, pts, threads=None):
+        pts = _d(pts).reshape(-1, 3)
+        n = len(pts)
+        cp = np.zeros((n, 3))
+        prim = np.zeros(n, np.uint32)
+        ntie = np.zeros(n, np.uint32)
+        lib().orc_naive_closest(self.h, _ptr(pts, _dp), n, _ptr(cp, _dp), _ptr(prim, _u32p), _ptr(ntie, _u32p), threads or nthreads())
+        return dict(cp=cp, prim=prim, ntie=ntie)
+
+    def candidate_closest(self, face, q):
+        q = _d(q)
+        out = np.zeros(3)
+        lib().orc_candidate_closest(self.h, int(face), _ptr(q, _dp), _ptr(out, _dp))
+        return out
+
+    def candidate_ray_hit(self, face, ray):
+        ray = _d(ray)
+        t = C.c_double(0)
+        pts = np.zeros(6)
+        k = lib().orc_candidate_ray_hit(self.h, int(face), _ptr(ray, _dp), C.byref(t), _ptr(pts, _dp))
+        return k, t.value, pts
+
+
+# ---- predicate-level helpers
+def _call(name, *arrs):
+    arrs = [_d(a).ravel() for a in arrs]
+    return getattr(lib(), name)(*[_ptr(a, _dp) for a in arrs])
+
+
+def orientation(p, q, r, s, exact=False):
+    return _call("orc_orientation_exact" if exact else "orc_orientation", np.concatenate([p, q, r, s]))
+
+
+def orientation_dir(a, b, c, p, q):
+    return _call("orc_orientation_dir", np.concatenate([a, b, c, p, q]))
+
+
+def coplanar_orientation(*pts):
+    return _call("orc_coplanar_orientation3" if len(pts) == 3 else "orc_coplanar_orientation4", np.concatenate(pts))
+
+
+def compare_distance(p, q, r, exact=False):
+    return _call("orc_compare_distance_exact" if exact else "orc_compare_distance", np.concatenate([p, q, r]))
+
+
+def bbox_do_intersect(box, pq, is_ray, exact=False):
+    box = _d(box).ravel()
+    pq = _d(pq).ravel()
+    f = lib().orc_bbox_do_intersect_exact if exact else lib().orc_bbox_do_intersect
+    return f(_ptr(box, _dp), _ptr(pq, _dp), int(is_ray))
+
+
+def tri_do_intersect(tri, pq, is_ray):
+    tri = _d(tri).ravel()
+    pq = _d(pq).ravel()
+    return lib().orc_tri_do_intersect(_ptr(tri, _dp), _ptr(pq, _dp), int(is_ray))
+
+
+def tri_ray_intersection(tri, ray):
+    tri = _d(tri).ravel()
+    ray = _d(ray).ravel()
+    out = np.zeros(6)
+    k = lib().orc_tri_ray_intersection(_ptr(tri, _dp), _ptr(ray, _dp), _ptr(out, _dp))
+    return k, out.reshape(2, 3)
+
+
+def project_on_triangle(tri, q):
+    tri = _d(tri).ravel()
+    q = _d(q).ravel()
+    out = np.zeros(3)
+    lib().orc_project_on_triangle(_ptr(tri, _dp), _ptr(q, _dp), _ptr(out, _dp))
+    return out
+
+
+def ball_reaches_box(q, box, bound):
+    q, box, bound = _d(q).ravel(), _d(box).ravel(), _d(bound).ravel()
+    return lib().orc_ball_reaches_box(_ptr(q, _dp), _ptr(box, _dp), _ptr(bound, _dp))
+
+
+def intersection_distance(ray, box):
+    ray, box = _d(ray).ravel(), _d(box).ravel()
+    t = C.c_double(0)
+    ok = lib().orc_intersection_distance(_ptr(ray, _dp), _ptr(box, _dp), C.byref(t))
+    return (t.value if ok else None)
