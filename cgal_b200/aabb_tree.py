@@ -1,0 +1,245 @@
+"""Host-side mirror of CGAL::AABB_tree (AABB_tree/include/CGAL/AABB_tree.h:55-677) over the C ABI of libb200aabb.so.
+
+Same member names and meaning as the reference class, with batched arguments: a query argument is an (n, 6) array of
+Segment_3 / Ray_3 records (source, target|second point) or an (n, 3) array of Point_3; results are arrays.
+numpy arrays are HOST buffers (copied inside the call); torch CUDA tensors are used in place (DEVICE pointers).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+SEGMENT, RAY = 0, 1
+FLAG_HIT, FLAG_SEGMENT, FLAG_TIE, FLAG_EXACT = 1, 2, 4, 8
+NO_PRIMITIVE = 0xFFFFFFFF
+_HOST, _DEVICE = 0, 1
+_ERRORS = {-1: "invalid argument", -2: "CUDA error", -3: "out of device memory", -4: "empty tree (CGAL_precondition(!empty()))",
+           -5: "no sm_100 CUDA device (there is no CPU fallback)"}
+_LIB = None
+
+
+class B200AABBError(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        super().__init__("b200aabb: %s (%d)%s" % (_ERRORS.get(code, "error"), code, (": " + detail) if detail else ""))
+
+
+class _Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("exact_fallbacks", C.c_uint64), ("ties", C.c_uint64),
+                ("last_build_ms", C.c_double), ("last_query_ms", C.c_double), ("last_query_total_ms", C.c_double)]
+
+
+SYMBOLS = ["b200aabb_create", "b200aabb_destroy", "b200aabb_set_stream", "b200aabb_last_error", "b200aabb_get_stats",
+           "b200aabb_set_mesh", "b200aabb_set_triangles", "b200aabb_clear", "b200aabb_build",
+           "b200aabb_accelerate_distance_queries", "b200aabb_size", "b200aabb_bbox", "b200aabb_do_intersect",
+           "b200aabb_number_of_intersected_primitives", "b200aabb_first_intersection", "b200aabb_closest_point",
+           "b200aabb_export_layout", "b200aabb_import_alloc", "b200aabb_import_finish", "b200aabb_version"]
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libb200aabb.so")
+
+
+def load_library():
+    """Loads libb200aabb.so.  Raises if it has not been built: the CUDA library IS the implementation."""
+    global _LIB
+    if _LIB is None:
+        path = library_path()
+        if not os.path.exists(path):
+            raise ImportError("libb200aabb.so is missing (%s): run `python -m cgal_b200._build`; there is no fallback path" % path)
+        L = C.CDLL(path)
+        vp, u64, dp = C.c_void_p, C.c_uint64, C.c_void_p
+        L.b200aabb_create.argtypes = [C.c_int, C.POINTER(vp)]
+        L.b200aabb_destroy.argtypes = [vp]
+        L.b200aabb_set_stream.argtypes = [vp, vp]
+        L.b200aabb_last_error.argtypes = [vp]
+        L.b200aabb_last_error.restype = C.c_char_p
+        L.b200aabb_get_stats.argtypes = [vp, C.POINTER(_Stats)]
+        L.b200aabb_set_mesh.argtypes = [vp, dp, u64, dp, dp, u64]
+        L.b200aabb_set_triangles.argtypes = [vp, dp, dp, u64, C.c_int]
+        L.b200aabb_clear.argtypes = [vp]
+        L.b200aabb_build.argtypes = [vp]
+        L.b200aabb_accelerate_distance_queries.argtypes = [vp]
+        L.b200aabb_size.argtypes = [vp, C.POINTER(u64)]
+        L.b200aabb_bbox.argtypes = [vp, C.POINTER(C.c_double)]
+        L.b200aabb_do_intersect.argtypes = [vp, dp, u64, C.c_int, C.c_int, dp]
+        L.b200aabb_number_of_intersected_primitives.argtypes = [vp, dp, u64, C.c_int, C.c_int, dp]
+        L.b200aabb_first_intersection.argtypes = [vp, dp, u64, C.c_int, dp, dp, dp, dp, dp]
+        L.b200aabb_closest_point.argtypes = [vp, dp, u64, C.c_int, dp, dp, dp, dp]
+        L.b200aabb_export_layout.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.c_int, C.POINTER(C.c_int)]
+        L.b200aabb_import_alloc.argtypes = [vp, u64]
+        L.b200aabb_import_finish.argtypes = [vp]
+        L.b200aabb_version.restype = C.c_char_p
+        _LIB = L
+    return _LIB
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+class _Buf:
+    """a query / result buffer: numpy (host) or torch CUDA tensor (device)"""
+
+    def __init__(self, arr, dtype, cols):
+        if _is_torch(arr):
+            import torch
+            want = {np.float64: torch.float64, np.uint32: torch.int32, np.uint8: torch.uint8}[dtype]
+            if not arr.is_cuda:
+                raise ValueError("torch tensors must live on the GPU; pass numpy arrays for host buffers")
+            if arr.dtype != want or not arr.is_contiguous():
+                raise ValueError("expected a contiguous %s CUDA tensor" % want)
+            self.device, self.obj, self.ptr, self.n = True, arr, arr.data_ptr(), (arr.numel() // cols)
+        else:
+            a = np.ascontiguousarray(arr, dtype=dtype)
+            self.device, self.obj, self.ptr, self.n = False, a, a.ctypes.data, (a.size // cols)
+
+
+def _alloc_like(q, n, dtype, cols):
+    if q.device:
+        import torch
+        tdt = {np.float64: torch.float64, np.uint32: torch.int32, np.uint8: torch.uint8}[dtype]
+        shape = (n, cols) if cols > 1 else (n,)
+        return _Buf(torch.empty(shape, dtype=tdt, device=q.obj.device), dtype, cols)
+    shape = (n, cols) if cols > 1 else (n,)
+    return _Buf(np.empty(shape, dtype=dtype), dtype, cols)
+
+
+class AABB_tree:
+    """AABB_tree< AABB_traits_3< Epick, AABB_face_graph_triangle_primitive< Surface_mesh<Point_3> > > > on one B200."""
+
+    def __init__(self, vertices=None, faces=None, triangles=None, ids=None, device=0):
+        self._lib = load_library()
+        h = C.c_void_p()
+        rc = self._lib.b200aabb_create(int(device), C.byref(h))
+        if rc:
+            raise B200AABBError(rc)
+        self._h = h
+        self.device = int(device)
+        if vertices is not None or triangles is not None:
+            self.insert(vertices=vertices, faces=faces, triangles=triangles, ids=ids)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.b200aabb_destroy(self._h)
+            self._h = None
+
+    def _check(self, rc):
+        if rc:
+            raise B200AABBError(rc, self._lib.b200aabb_last_error(self._h).decode())
+
+    # ---- primitives (AABB_tree.h:147-216) ----
+    def insert(self, vertices=None, faces=None, triangles=None, ids=None):
+        """insert(faces(mesh).first, faces(mesh).second, mesh): `vertices` (nv,3) f64 + `faces` (nf,3) u32 in face order;
+        or a triangle soup `triangles` (n,9).  Replaces the current primitives (one face graph per tree)."""
+        idp = None
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.uint32)
+            idp = ids.ctypes.data
+        if triangles is not None:
+            if _is_torch(triangles):
+                b = _Buf(triangles, np.float64, 9)
+                if ids is not None:
+                    raise ValueError("ids with device triangles must be passed as a CUDA tensor via insert_device")
+                self._check(self._lib.b200aabb_set_triangles(self._h, b.ptr, None, b.n, _DEVICE))
+            else:
+                t = np.ascontiguousarray(triangles, dtype=np.float64).reshape(-1, 9)
+                self._check(self._lib.b200aabb_set_triangles(self._h, t.ctypes.data, idp, len(t), _HOST))
+        else:
+            v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+            f = np.ascontiguousarray(faces, dtype=np.uint32).reshape(-1, 3)
+            self._check(self._lib.b200aabb_set_mesh(self._h, v.ctypes.data, len(v), f.ctypes.data, idp, len(f)))
+
+    def clear(self):
+        self._check(self._lib.b200aabb_clear(self._h))
+
+    def build(self):
+        self._check(self._lib.b200aabb_build(self._h))
+
+    rebuild = build
+
+    def accelerate_distance_queries(self):
+        self._check(self._lib.b200aabb_accelerate_distance_queries(self._h))
+        return True
+
+    def do_not_accelerate_distance_queries(self):
+        pass   # the BVH-derived bound needs no auxiliary structure
+
+    def size(self):
+        n = C.c_uint64()
+        self._check(self._lib.b200aabb_size(self._h, C.byref(n)))
+        return n.value
+
+    def empty(self):
+        return self.size() == 0
+
+    def bbox(self):
+        out = (C.c_double * 6)()
+        self._check(self._lib.b200aabb_bbox(self._h, out))
+        return np.array(out[:])
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self._lib.b200aabb_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def stats(self):
+        s = _Stats()
+        self._check(self._lib.b200aabb_get_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in _Stats._fields_}
+
+    # ---- intersection queries (AABB_tree.h:243-354) ----
+    def do_intersect(self, queries, kind=SEGMENT, out=None):
+        q = _Buf(queries, np.float64, 6)
+        o = _Buf(out, np.uint8, 1) if out is not None else _alloc_like(q, q.n, np.uint8, 1)
+        self._check(self._lib.b200aabb_do_intersect(self._h, q.ptr, q.n, kind, int(q.device), o.ptr))
+        return o.obj
+
+    def number_of_intersected_primitives(self, queries, kind=SEGMENT, out=None):
+        q = _Buf(queries, np.float64, 6)
+        o = _Buf(out, np.uint32, 1) if out is not None else _alloc_like(q, q.n, np.uint32, 1)
+        self._check(self._lib.b200aabb_number_of_intersected_primitives(self._h, q.ptr, q.n, kind, int(q.device), o.ptr))
+        return o.obj
+
+    def first_intersection(self, rays, want=("prim", "t", "point", "point2", "flags"), out=None):
+        """first_intersection(Ray_3) for every ray: dict with prim (NO_PRIMITIVE = nullopt), t, point, point2, flags."""
+        q = _Buf(rays, np.float64, 6)
+        spec = {"prim": (np.uint32, 1), "t": (np.float64, 1), "point": (np.float64, 3), "point2": (np.float64, 3), "flags": (np.uint8, 1)}
+        bufs = {}
+        for k in want:
+            bufs[k] = _Buf(out[k], *spec[k]) if out is not None and k in out else _alloc_like(q, q.n, *spec[k])
+        p = lambda k: bufs[k].ptr if k in bufs else None   # noqa: E731
+        self._check(self._lib.b200aabb_first_intersection(self._h, q.ptr, q.n, int(q.device), p("prim"), p("t"), p("point"), p("point2"), p("flags")))
+        return {k: b.obj for k, b in bufs.items()}
+
+    def first_intersected_primitive(self, rays):
+        return self.first_intersection(rays, want=("prim",))["prim"]
+
+    # ---- distance queries (AABB_tree.h:363-377,464-477) ----
+    def closest_point_and_primitive(self, points, want=("point", "prim", "sqdist", "flags"), out=None):
+        q = _Buf(points, np.float64, 3)
+        spec = {"point": (np.float64, 3), "prim": (np.uint32, 1), "sqdist": (np.float64, 1), "flags": (np.uint8, 1)}
+        bufs = {}
+        for k in want:
+            bufs[k] = _Buf(out[k], *spec[k]) if out is not None and k in out else _alloc_like(q, q.n, *spec[k])
+        p = lambda k: bufs[k].ptr if k in bufs else None   # noqa: E731
+        self._check(self._lib.b200aabb_closest_point(self._h, q.ptr, q.n, int(q.device), p("point"), p("prim"), p("sqdist"), p("flags")))
+        return {k: b.obj for k, b in bufs.items()}
+
+    def closest_point(self, points):
+        return self.closest_point_and_primitive(points, want=("point",))["point"]
+
+    def squared_distance(self, points):
+        return self.closest_point_and_primitive(points, want=("sqdist",))["sqdist"]
+
+    # ---- multi-GPU plumbing: the built tree as flat device buffers (for torch.distributed.broadcast) ----
+    def export_layout(self):
+        ptrs = (C.c_void_p * 8)()
+        sizes = (C.c_uint64 * 8)()
+        cnt = C.c_int()
+        self._check(self._lib.b200aabb_export_layout(self._h, ptrs, sizes, 8, C.byref(cnt)))
+        return [(ptrs[i] or 0, sizes[i]) for i in range(cnt.value)]
+
+    def import_alloc(self, n):
+        self._check(self._lib.b200aabb_import_alloc(self._h, int(n)))
+
+    def import_finish(self):
+        self._check(self._lib.b200aabb_import_finish(self._h))

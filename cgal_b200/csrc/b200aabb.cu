@@ -1,0 +1,465 @@
+// b200aabb.cu — libb200aabb.so: traversal kernels + the C ABI declared in include/b200aabb.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+// (-fmad=false: the constructions of geom.cuh must not be contracted into FMAs; explicit fma() calls remain FMAs).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/b200aabb.h"
+#include "build.cuh"
+#include "radix_sort.cuh"
+
+using namespace b2;
+
+// ------------------------------------------------------------------------------------------------------------------
+// Query kernels: one thread per query, iterative stack traversal (bvh.cuh).
+// counters[0] += queries that used the exact stage, counters[1] += ties, counters[2] |= stack overflow
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+__device__ __forceinline__ Vec3 ld3(const double* __restrict__ p) { return {__ldg(p), __ldg(p + 1), __ldg(p + 2)}; }
+
+template <bool IS_RAY, bool COUNT>
+__global__ void __launch_bounds__(128) intersect_kernel(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root,
+                                                        const double* __restrict__ q, uint64_t n, uint8_t* __restrict__ out8,
+                                                        uint32_t* __restrict__ out32, unsigned long long* __restrict__ counters) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int nexact = 0, overflow = 0;
+    const uint32_t r = traverse_intersect<IS_RAY, COUNT>(nodes, tris, root, ld3(q + 6 * i), ld3(q + 6 * i + 3), nexact, overflow);
+    if (COUNT) out32[i] = r; else out8[i] = (uint8_t)(r != 0);
+    if (nexact) atomicAdd(&counters[0], 1ull);
+    if (overflow) atomicOr(&counters[2], 1ull);
+}
+
+__global__ void __launch_bounds__(128) first_intersection_kernel(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root,
+                                                                 const double* __restrict__ rays, uint64_t n, uint32_t* __restrict__ prim,
+                                                                 double* __restrict__ tpar, double* __restrict__ pt, double* __restrict__ pt2,
+                                                                 uint8_t* __restrict__ flags, unsigned long long* __restrict__ counters) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int nexact = 0, overflow = 0;
+    const FirstHit h = traverse_first(nodes, tris, root, ld3(rays + 6 * i), ld3(rays + 6 * i + 3), nexact, overflow);
+    const bool hit = h.prim != kNone;
+    if (prim) prim[i] = h.prim;
+    if (tpar) tpar[i] = hit ? h.t : 0.0;
+    if (pt) { pt[3 * i] = hit ? h.p0.x : 0.0; pt[3 * i + 1] = hit ? h.p0.y : 0.0; pt[3 * i + 2] = hit ? h.p0.z : 0.0; }
+    if (pt2) { const bool seg = hit && h.kind == 2; pt2[3 * i] = seg ? h.p1.x : 0.0; pt2[3 * i + 1] = seg ? h.p1.y : 0.0; pt2[3 * i + 2] = seg ? h.p1.z : 0.0; }
+    if (flags) flags[i] = (uint8_t)((hit ? B200AABB_FLAG_HIT : 0) | (hit && h.kind == 2 ? B200AABB_FLAG_SEGMENT : 0) |
+                                    (h.tie ? B200AABB_FLAG_TIE : 0) | (nexact ? B200AABB_FLAG_EXACT : 0));
+    if (nexact) atomicAdd(&counters[0], 1ull);
+    if (h.tie) atomicAdd(&counters[1], 1ull);
+    if (overflow) atomicOr(&counters[2], 1ull);
+}
+
+__global__ void __launch_bounds__(128) closest_point_kernel(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root,
+                                                            const double* __restrict__ pts, uint64_t n, double* __restrict__ cp,
+                                                            uint32_t* __restrict__ prim, double* __restrict__ sqd, uint8_t* __restrict__ flags,
+                                                            unsigned long long* __restrict__ counters) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int nexact = 0, overflow = 0;
+    const Closest c = traverse_closest(nodes, tris, root, ld3(pts + 3 * i), nexact, overflow);
+    if (cp) { cp[3 * i] = c.p.x; cp[3 * i + 1] = c.p.y; cp[3 * i + 2] = c.p.z; }
+    if (prim) prim[i] = c.prim;
+    if (sqd) sqd[i] = c.sqd;
+    if (flags) flags[i] = (uint8_t)((c.tie ? B200AABB_FLAG_TIE : 0) | (nexact ? B200AABB_FLAG_EXACT : 0));
+    if (nexact) atomicAdd(&counters[0], 1ull);
+    if (c.tie) atomicAdd(&counters[1], 1ull);
+    if (overflow) atomicOr(&counters[2], 1ull);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------------
+// Handle
+// ------------------------------------------------------------------------------------------------------------------
+struct b200aabb_tree {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // primitives as inserted (device): 9 doubles each, optional ids
+    double* d_soup = nullptr;
+    uint32_t* d_ids = nullptr;
+    uint64_t n = 0;
+    // built tree
+    bool built = false;
+    BvhNode* d_nodes = nullptr;
+    TriRec* d_tris = nullptr;
+    double* d_rootbox = nullptr;   // 6 doubles
+    uint32_t root = kNone;
+    double h_bbox[6];
+    unsigned long long* d_counters = nullptr;   // [4]
+    // staging for HOST-pointer batches (two pipeline slots)
+    void* d_stage_in[2] = {nullptr, nullptr};
+    void* d_stage_out[2] = {nullptr, nullptr};
+    size_t stage_in_bytes = 0, stage_out_bytes = 0;
+    cudaStream_t pipe[2] = {nullptr, nullptr};
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_pipe[2] = {nullptr, nullptr};
+    b200aabb_stats stats;
+    bool query_timing_pending = false;
+};
+
+namespace {
+
+#define B2_CUDA(t, call)                                                                                         \
+    do {                                                                                                         \
+        cudaError_t e_ = (call);                                                                                 \
+        if (e_ != cudaSuccess) {                                                                                 \
+            (t)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                       \
+            return e_ == cudaErrorMemoryAllocation ? B200AABB_ERR_OUT_OF_MEMORY : B200AABB_ERR_CUDA;              \
+        }                                                                                                        \
+    } while (0)
+
+constexpr uint64_t kChunk = 1ull << 22;   // queries per pipeline slot for HOST-pointer batches
+
+int fail(b200aabb_tree* t, int code, const char* msg) { if (t) t->err = msg; return code; }
+
+void free_tree_buffers(b200aabb_tree* t) {
+    cudaFree(t->d_nodes); cudaFree(t->d_tris);
+    t->d_nodes = nullptr; t->d_tris = nullptr; t->built = false; t->root = kNone;
+}
+void free_input(b200aabb_tree* t) { cudaFree(t->d_soup); cudaFree(t->d_ids); t->d_soup = nullptr; t->d_ids = nullptr; }
+
+void empty_bbox(double* b) { for (int i = 0; i < 3; ++i) { b[i] = INFINITY; b[3 + i] = -INFINITY; } }
+
+int ensure_stage(b200aabb_tree* t, size_t in_bytes, size_t out_bytes) {
+    if (in_bytes > t->stage_in_bytes) {
+        for (int s = 0; s < 2; ++s) { cudaFree(t->d_stage_in[s]); t->d_stage_in[s] = nullptr; }
+        for (int s = 0; s < 2; ++s) B2_CUDA(t, cudaMalloc(&t->d_stage_in[s], in_bytes));
+        t->stage_in_bytes = in_bytes;
+    }
+    if (out_bytes > t->stage_out_bytes) {
+        for (int s = 0; s < 2; ++s) { cudaFree(t->d_stage_out[s]); t->d_stage_out[s] = nullptr; }
+        for (int s = 0; s < 2; ++s) B2_CUDA(t, cudaMalloc(&t->d_stage_out[s], out_bytes));
+        t->stage_out_bytes = out_bytes;
+    }
+    return B200AABB_OK;
+}
+
+int do_build(b200aabb_tree* t) {
+    B2_CUDA(t, cudaSetDevice(t->device));
+    free_tree_buffers(t);
+    const uint64_t n = t->n;
+    empty_bbox(t->h_bbox);
+    if (n == 0) { t->built = true; t->stats.last_build_ms = 0; return B200AABB_OK; }
+    if (n >= (1ull << 30)) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "at most 2^30 - 1 primitives per tree");
+    cudaStream_t st = t->stream;
+    uint64_t* keys[2] = {nullptr, nullptr};
+    uint32_t* vals[2] = {nullptr, nullptr};
+    void* ws = nullptr; unsigned long long* bounds = nullptr; uint32_t* leaf_parent = nullptr;
+    auto cleanup = [&]() { cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(ws); cudaFree(bounds); cudaFree(leaf_parent); };
+#define B2_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { t->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); free_tree_buffers(t); \
+        return e_ == cudaErrorMemoryAllocation ? B200AABB_ERR_OUT_OF_MEMORY : B200AABB_ERR_CUDA; } } while (0)
+    for (int s = 0; s < 2; ++s) { B2_TRY(cudaMalloc(&keys[s], n * 8)); B2_TRY(cudaMalloc(&vals[s], n * 4)); }
+    B2_TRY(cudaMalloc(&ws, rs_workspace_bytes(n)));
+    B2_TRY(cudaMalloc(&bounds, 6 * 8));
+    B2_TRY(cudaMalloc(&leaf_parent, n * 4));
+    B2_TRY(cudaMalloc(&t->d_nodes, std::max<uint64_t>(n - 1, 1) * sizeof(BvhNode)));
+    B2_TRY(cudaMalloc(&t->d_tris, n * sizeof(TriRec)));
+    B2_TRY(cudaEventRecord(t->ev_a, st));
+    B2_TRY(cudaMemsetAsync(bounds, 0xFF, 3 * 8, st));
+    B2_TRY(cudaMemsetAsync(bounds + 3, 0x00, 3 * 8, st));
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    scene_bounds_kernel<<<std::min<unsigned>(blocks, 148 * 8), 256, 0, st>>>(t->d_soup, n, bounds);
+    morton_kernel<<<blocks, 256, 0, st>>>(t->d_soup, n, bounds, keys[0], vals[0]);
+    t->stats.kernel_launches += 2;
+    const int cur = radix_sort_pairs(keys, vals, n, 8, ws, st, &t->stats.kernel_launches);
+    emit_leaves_kernel<<<blocks, 256, 0, st>>>(t->d_soup, t->d_ids, vals[cur], n, t->d_tris);
+    t->stats.kernel_launches += 1;
+    if (n > 1) {
+        hierarchy_kernel<<<blocks, 256, 0, st>>>(keys[cur], n, t->d_nodes, leaf_parent);
+        t->stats.kernel_launches += 1;
+    }
+    refit_kernel<<<blocks, 256, 0, st>>>(t->d_tris, n, t->d_nodes, leaf_parent, t->d_rootbox);
+    t->stats.kernel_launches += 1;
+    B2_TRY(cudaEventRecord(t->ev_b, st));
+    B2_TRY(cudaMemcpyAsync(t->h_bbox, t->d_rootbox, 48, cudaMemcpyDeviceToHost, st));
+    B2_TRY(cudaStreamSynchronize(st));
+    B2_TRY(cudaGetLastError());
+    float ms = 0; cudaEventElapsedTime(&ms, t->ev_a, t->ev_b);
+    t->stats.last_build_ms = ms;
+    t->root = n == 1 ? (kLeafBit | 0u) : 0u;
+    t->built = true;
+    cleanup();
+#undef B2_TRY
+    return B200AABB_OK;
+}
+
+int ensure_built(b200aabb_tree* t) { return t->built ? B200AABB_OK : do_build(t); }
+
+// Runs `launch(stream, d_in, d_out_base, count)` over the batch.  HOST pointers: chunked, double-buffered
+// H2D -> kernel -> D2H pipeline on two streams; DEVICE pointers: one launch on the handle's stream, no synchronisation.
+struct OutSpec { void* host; size_t elem_bytes; size_t offset; };   // one result array: host pointer, bytes per query, offset in staging
+
+template <class Launch>
+int run_batch(b200aabb_tree* t, const void* in, size_t in_elem_bytes, uint64_t n, b200aabb_memspace space, std::vector<OutSpec> outs, Launch launch) {
+    B2_CUDA(t, cudaSetDevice(t->device));
+    B2_CUDA(t, cudaMemsetAsync(t->d_counters, 0, 4 * sizeof(unsigned long long), t->stream));
+    if (space == B200AABB_DEVICE) {
+        B2_CUDA(t, cudaEventRecord(t->ev_a, t->stream));
+        std::vector<void*> ptrs; for (auto& o : outs) ptrs.push_back(o.host);
+        launch(t->stream, in, ptrs.data(), n);
+        t->stats.kernel_launches += 1;
+        B2_CUDA(t, cudaEventRecord(t->ev_b, t->stream));
+        B2_CUDA(t, cudaGetLastError());
+        t->query_timing_pending = true;
+        return B200AABB_OK;
+    }
+    const uint64_t chunk = std::min<uint64_t>(n, kChunk);
+    size_t out_bytes = 0;
+    for (auto& o : outs) { o.offset = out_bytes; out_bytes += ((o.host ? o.elem_bytes * chunk : 0) + 255) / 256 * 256; }
+    int rc = ensure_stage(t, in_elem_bytes * chunk, std::max<size_t>(out_bytes, 256));
+    if (rc) return rc;
+    B2_CUDA(t, cudaEventRecord(t->ev_a, t->stream));
+    for (int s = 0; s < 2; ++s) B2_CUDA(t, cudaStreamWaitEvent(t->pipe[s], t->ev_a, 0));
+    int slot = 0;
+    for (uint64_t b = 0; b < n; b += chunk, slot ^= 1) {
+        const uint64_t cnt = std::min<uint64_t>(chunk, n - b);
+        cudaStream_t st = t->pipe[slot];
+        B2_CUDA(t, cudaMemcpyAsync(t->d_stage_in[slot], (const char*)in + b * in_elem_bytes, cnt * in_elem_bytes, cudaMemcpyHostToDevice, st));
+        std::vector<void*> ptrs;
+        for (auto& o : outs) ptrs.push_back(o.host ? (char*)t->d_stage_out[slot] + o.offset : nullptr);
+        launch(st, t->d_stage_in[slot], ptrs.data(), cnt);
+        t->stats.kernel_launches += 1;
+        for (auto& o : outs)
+            if (o.host) B2_CUDA(t, cudaMemcpyAsync((char*)o.host + b * o.elem_bytes, (char*)t->d_stage_out[slot] + o.offset, cnt * o.elem_bytes, cudaMemcpyDeviceToHost, st));
+    }
+    for (int s = 0; s < 2; ++s) { B2_CUDA(t, cudaEventRecord(t->ev_pipe[s], t->pipe[s])); B2_CUDA(t, cudaStreamWaitEvent(t->stream, t->ev_pipe[s], 0)); }
+    B2_CUDA(t, cudaEventRecord(t->ev_b, t->stream));
+    B2_CUDA(t, cudaStreamSynchronize(t->stream));
+    B2_CUDA(t, cudaGetLastError());
+    t->query_timing_pending = true;
+    return B200AABB_OK;
+}
+
+unsigned grid_for(uint64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* b200aabb_version(void) { return "b200aabb 0.1 sm_100a"; }
+
+int b200aabb_create(int device, b200aabb_tree** out) {
+    if (!out) return B200AABB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return B200AABB_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) return B200AABB_ERR_NO_DEVICE;
+    if (cudaSetDevice(device) != cudaSuccess) return B200AABB_ERR_CUDA;
+    b200aabb_tree* t = new b200aabb_tree();
+    t->device = device;
+    memset(&t->stats, 0, sizeof(t->stats));
+    empty_bbox(t->h_bbox);
+    bool ok = cudaMalloc(&t->d_rootbox, 48) == cudaSuccess && cudaMalloc(&t->d_counters, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+              cudaEventCreate(&t->ev_a) == cudaSuccess && cudaEventCreate(&t->ev_b) == cudaSuccess;
+    for (int s = 0; s < 2 && ok; ++s)
+        ok = cudaStreamCreateWithFlags(&t->pipe[s], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&t->ev_pipe[s], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { b200aabb_destroy(t); return B200AABB_ERR_CUDA; }
+    t->built = true;   // an empty tree needs no build
+    *out = t;
+    return B200AABB_OK;
+}
+
+int b200aabb_destroy(b200aabb_tree* t) {
+    if (!t) return B200AABB_OK;
+    cudaSetDevice(t->device);
+    cudaDeviceSynchronize();
+    free_tree_buffers(t); free_input(t);
+    cudaFree(t->d_rootbox); cudaFree(t->d_counters);
+    for (int s = 0; s < 2; ++s) { cudaFree(t->d_stage_in[s]); cudaFree(t->d_stage_out[s]); if (t->pipe[s]) cudaStreamDestroy(t->pipe[s]); if (t->ev_pipe[s]) cudaEventDestroy(t->ev_pipe[s]); }
+    if (t->ev_a) cudaEventDestroy(t->ev_a);
+    if (t->ev_b) cudaEventDestroy(t->ev_b);
+    delete t;
+    return B200AABB_OK;
+}
+
+int b200aabb_set_stream(b200aabb_tree* t, void* s) { if (!t) return B200AABB_ERR_INVALID_ARGUMENT; t->stream = (cudaStream_t)s; return B200AABB_OK; }
+const char* b200aabb_last_error(const b200aabb_tree* t) { return t ? t->err.c_str() : "null handle"; }
+
+int b200aabb_get_stats(const b200aabb_tree* tc, b200aabb_stats* out) {
+    b200aabb_tree* t = const_cast<b200aabb_tree*>(tc);
+    if (!t || !out) return B200AABB_ERR_INVALID_ARGUMENT;
+    B2_CUDA(t, cudaSetDevice(t->device));
+    if (t->query_timing_pending) {
+        B2_CUDA(t, cudaEventSynchronize(t->ev_b));
+        float ms = 0; cudaEventElapsedTime(&ms, t->ev_a, t->ev_b);
+        t->stats.last_query_total_ms = ms; t->stats.last_query_ms = ms;
+        unsigned long long c[4];
+        B2_CUDA(t, cudaMemcpy(c, t->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
+        t->stats.exact_fallbacks = c[0]; t->stats.ties = c[1];
+        if (c[2]) t->err = "traversal stack overflow: results incomplete";
+        t->query_timing_pending = false;
+        if (c[2]) { *out = t->stats; return B200AABB_ERR_CUDA; }
+    }
+    *out = t->stats;
+    return B200AABB_OK;
+}
+
+int b200aabb_clear(b200aabb_tree* t) {
+    if (!t) return B200AABB_ERR_INVALID_ARGUMENT;
+    B2_CUDA(t, cudaSetDevice(t->device));
+    B2_CUDA(t, cudaStreamSynchronize(t->stream));
+    free_tree_buffers(t); free_input(t);
+    t->n = 0; t->built = true; empty_bbox(t->h_bbox);
+    return B200AABB_OK;
+}
+
+int b200aabb_set_triangles(b200aabb_tree* t, const double* tris, const uint32_t* ids, uint64_t n, b200aabb_memspace space) {
+    if (!t || (n && !tris)) return B200AABB_ERR_INVALID_ARGUMENT;
+    int rc = b200aabb_clear(t);
+    if (rc) return rc;
+    if (n == 0) return B200AABB_OK;
+    const cudaMemcpyKind kind = space == B200AABB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    B2_CUDA(t, cudaMalloc(&t->d_soup, n * 72));
+    B2_CUDA(t, cudaMemcpyAsync(t->d_soup, tris, n * 72, kind, t->stream));
+    if (ids) { B2_CUDA(t, cudaMalloc(&t->d_ids, n * 4)); B2_CUDA(t, cudaMemcpyAsync(t->d_ids, ids, n * 4, kind, t->stream)); }
+    B2_CUDA(t, cudaStreamSynchronize(t->stream));
+    t->n = n; t->built = false;
+    return B200AABB_OK;
+}
+
+int b200aabb_set_mesh(b200aabb_tree* t, const double* verts, uint64_t nv, const uint32_t* faces, const uint32_t* face_ids, uint64_t nf) {
+    if (!t || (nf && (!verts || !faces))) return B200AABB_ERR_INVALID_ARGUMENT;
+    for (uint64_t i = 0; i < 3 * nf; ++i) if (faces[i] >= nv) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "face references a vertex index >= nv");
+    int rc = b200aabb_clear(t);
+    if (rc) return rc;
+    if (nf == 0) return B200AABB_OK;
+    double* d_v = nullptr; uint32_t* d_f = nullptr;
+    B2_CUDA(t, cudaMalloc(&d_v, nv * 24));
+    cudaError_t e = cudaMalloc(&d_f, nf * 12);
+    if (e != cudaSuccess) { cudaFree(d_v); t->err = "cudaMalloc(faces)"; return B200AABB_ERR_OUT_OF_MEMORY; }
+    e = cudaMalloc(&t->d_soup, nf * 72);
+    if (e != cudaSuccess) { cudaFree(d_v); cudaFree(d_f); t->err = "cudaMalloc(soup)"; return B200AABB_ERR_OUT_OF_MEMORY; }
+    cudaMemcpyAsync(d_v, verts, nv * 24, cudaMemcpyHostToDevice, t->stream);
+    cudaMemcpyAsync(d_f, faces, nf * 12, cudaMemcpyHostToDevice, t->stream);
+    gather_mesh_kernel<<<grid_for(nf, 256), 256, 0, t->stream>>>(d_v, d_f, nf, t->d_soup);
+    t->stats.kernel_launches += 1;
+    if (face_ids) { e = cudaMalloc(&t->d_ids, nf * 4); if (e == cudaSuccess) cudaMemcpyAsync(t->d_ids, face_ids, nf * 4, cudaMemcpyHostToDevice, t->stream); }
+    cudaError_t e2 = cudaStreamSynchronize(t->stream);
+    cudaFree(d_v); cudaFree(d_f);
+    if (e != cudaSuccess || e2 != cudaSuccess) { free_input(t); t->err = "set_mesh: CUDA failure"; return B200AABB_ERR_CUDA; }
+    t->n = nf; t->built = false;
+    return B200AABB_OK;
+}
+
+int b200aabb_build(b200aabb_tree* t) { if (!t) return B200AABB_ERR_INVALID_ARGUMENT; return do_build(t); }
+int b200aabb_accelerate_distance_queries(b200aabb_tree* t) { if (!t) return B200AABB_ERR_INVALID_ARGUMENT; return ensure_built(t); }
+int b200aabb_size(const b200aabb_tree* t, uint64_t* n) { if (!t || !n) return B200AABB_ERR_INVALID_ARGUMENT; *n = t->n; return B200AABB_OK; }
+int b200aabb_bbox(b200aabb_tree* t, double out[6]) {
+    if (!t || !out) return B200AABB_ERR_INVALID_ARGUMENT;
+    int rc = ensure_built(t);
+    if (rc) return rc;
+    memcpy(out, t->h_bbox, 48);
+    return B200AABB_OK;
+}
+
+int b200aabb_do_intersect(b200aabb_tree* t, const double* q, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint8_t* out) {
+    if (!t || (n && (!q || !out))) return B200AABB_ERR_INVALID_ARGUMENT;
+    int rc = ensure_built(t);
+    if (rc || n == 0) return rc;
+    if (t->n == 0) {   // empty tree: false (aabb_test_empty_tree.cpp:44-50)
+        if (space == B200AABB_DEVICE) { B2_CUDA(t, cudaMemsetAsync(out, 0, n, t->stream)); } else memset(out, 0, n);
+        return B200AABB_OK;
+    }
+    const bool ray = kind == B200AABB_RAY;
+    return run_batch(t, q, 48, n, space, {{out, 1, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt) {
+        if (ray) intersect_kernel<true, false><<<grid_for(cnt, 128), 128, 0, st>>>(t->d_nodes, t->d_tris, t->root, (const double*)in, cnt, (uint8_t*)o[0], nullptr, t->d_counters);
+        else intersect_kernel<false, false><<<grid_for(cnt, 128), 128, 0, st>>>(t->d_nodes, t->d_tris, t->root, (const double*)in, cnt, (uint8_t*)o[0], nullptr, t->d_counters);
+    });
+}
+
+int b200aabb_number_of_intersected_primitives(b200aabb_tree* t, const double* q, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint32_t* out) {
+    if (!t || (n && (!q || !out))) return B200AABB_ERR_INVALID_ARGUMENT;
+    int rc = ensure_built(t);
+    if (rc || n == 0) return rc;
+    if (t->n == 0) {
+        if (space == B200AABB_DEVICE) { B2_CUDA(t, cudaMemsetAsync(out, 0, n * 4, t->stream)); } else memset(out, 0, n * 4);
+        return B200AABB_OK;
+    }
+    const bool ray = kind == B200AABB_RAY;
+    return run_batch(t, q, 48, n, space, {{out, 4, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt) {
+        if (ray) intersect_kernel<true, true><<<grid_for(cnt, 128), 128, 0, st>>>(t->d_nodes, t->d_tris, t->root, (const double*)in, cnt, nullptr, (uint32_t*)o[0], t->d_counters);
+        else intersect_kernel<false, true><<<grid_for(cnt, 128), 128, 0, st>>>(t->d_nodes, t->d_tris, t->root, (const double*)in, cnt, nullptr, (uint32_t*)o[0], t->d_counters);
+    });
+}
+
+int b200aabb_first_intersection(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, uint32_t* prim, double* tpar, double* pt,
+                                double* pt2, uint8_t* flags) {
+    if (!t || (n && !rays)) return B200AABB_ERR_INVALID_ARGUMENT;
+    int rc = ensure_built(t);
+    if (rc || n == 0) return rc;
+    if (t->n == 0) {   // nullopt for every ray
+        if (space == B200AABB_DEVICE) {
+            if (prim) B2_CUDA(t, cudaMemsetAsync(prim, 0xFF, n * 4, t->stream));
+            if (tpar) B2_CUDA(t, cudaMemsetAsync(tpar, 0, n * 8, t->stream));
+            if (pt) B2_CUDA(t, cudaMemsetAsync(pt, 0, n * 24, t->stream));
+            if (pt2) B2_CUDA(t, cudaMemsetAsync(pt2, 0, n * 24, t->stream));
+            if (flags) B2_CUDA(t, cudaMemsetAsync(flags, 0, n, t->stream));
+        } else {
+            if (prim) memset(prim, 0xFF, n * 4);
+            if (tpar) memset(tpar, 0, n * 8);
+            if (pt) memset(pt, 0, n * 24);
+            if (pt2) memset(pt2, 0, n * 24);
+            if (flags) memset(flags, 0, n);
+        }
+        return B200AABB_OK;
+    }
+    return run_batch(t, rays, 48, n, space, {{prim, 4, 0}, {tpar, 8, 0}, {pt, 24, 0}, {pt2, 24, 0}, {flags, 1, 0}},
+                     [&](cudaStream_t st, const void* in, void** o, uint64_t cnt) {
+                         first_intersection_kernel<<<grid_for(cnt, 128), 128, 0, st>>>(t->d_nodes, t->d_tris, t->root, (const double*)in, cnt, (uint32_t*)o[0],
+                                                                                        (double*)o[1], (double*)o[2], (double*)o[3], (uint8_t*)o[4], t->d_counters);
+                     });
+}
+
+int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200aabb_memspace space, double* cp, uint32_t* prim, double* sqd, uint8_t* flags) {
+    if (!t || (n && !pts)) return B200AABB_ERR_INVALID_ARGUMENT;
+    int rc = ensure_built(t);
+    if (rc) return rc;
+    if (t->n == 0) return fail(t, B200AABB_ERR_EMPTY_TREE, "distance query on an empty tree (CGAL_precondition(!empty()))");
+    if (n == 0) return B200AABB_OK;
+    return run_batch(t, pts, 24, n, space, {{cp, 24, 0}, {prim, 4, 0}, {sqd, 8, 0}, {flags, 1, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt) {
+        closest_point_kernel<<<grid_for(cnt, 128), 128, 0, st>>>(t->d_nodes, t->d_tris, t->root, (const double*)in, cnt, (double*)o[0], (uint32_t*)o[1], (double*)o[2],
+                                                                  (uint8_t*)o[3], t->d_counters);
+    });
+}
+
+int b200aabb_export_layout(b200aabb_tree* t, void** ptrs, uint64_t* bytes, int cap, int* count) {
+    if (!t || !ptrs || !bytes || !count || cap < 3) return B200AABB_ERR_INVALID_ARGUMENT;
+    int rc = ensure_built(t);
+    if (rc) return rc;
+    ptrs[0] = t->d_nodes; bytes[0] = t->n > 1 ? (t->n - 1) * sizeof(BvhNode) : 0;
+    ptrs[1] = t->d_tris; bytes[1] = t->n * sizeof(TriRec);
+    ptrs[2] = t->d_rootbox; bytes[2] = 48;
+    *count = 3;
+    return B200AABB_OK;
+}
+
+int b200aabb_import_alloc(b200aabb_tree* t, uint64_t n) {
+    if (!t) return B200AABB_ERR_INVALID_ARGUMENT;
+    int rc = b200aabb_clear(t);
+    if (rc) return rc;
+    if (n == 0) return B200AABB_OK;
+    B2_CUDA(t, cudaMalloc(&t->d_nodes, std::max<uint64_t>(n - 1, 1) * sizeof(BvhNode)));
+    B2_CUDA(t, cudaMalloc(&t->d_tris, n * sizeof(TriRec)));
+    t->n = n; t->root = n == 1 ? (kLeafBit | 0u) : 0u; t->built = true;
+    return B200AABB_OK;
+}
+
+int b200aabb_import_finish(b200aabb_tree* t) {
+    if (!t) return B200AABB_ERR_INVALID_ARGUMENT;
+    B2_CUDA(t, cudaSetDevice(t->device));
+    if (t->n) B2_CUDA(t, cudaMemcpy(t->h_bbox, t->d_rootbox, 48, cudaMemcpyDeviceToHost));
+    return B200AABB_OK;
+}
+
+}  // extern "C"

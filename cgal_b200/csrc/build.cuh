@@ -1,0 +1,203 @@
+// build.cuh — LBVH construction kernels (replace AABB_tree::build / expand, AABB_tree/include/CGAL/AABB_tree.h:787-853,
+// and Compute_bbox / Split_primitives, AABB_tree/include/CGAL/AABB_traits_3.h:596-654):
+//   gather_mesh_kernel   indexed Surface_mesh (points + per-face vertex indices) -> 9 doubles per primitive
+//   scene_bounds_kernel  bounding box of all primitives (exact: min/max only), one atomic per block and bound
+//   morton_kernel        63-bit Morton key (21 bits per axis) of each primitive's box centre in the scene box
+//   [radix_sort.cuh]     onesweep sort of (key, primitive index)
+//   emit_leaves_kernel   TriRec records in Morton order
+//   hierarchy_kernel     Karras 2012 radix-tree topology, one thread per internal node
+//   refit_kernel         bottom-up boxes with one atomic arrival counter per node; min/max in binary64 are exact,
+//                        so every node box is bit-equal to the exact union of its primitives' boxes
+#pragma once
+#include "bvh.cuh"
+
+namespace b2 {
+
+// order-preserving map double -> uint64 so that atomicMin/atomicMax on integers order like the doubles
+__device__ __forceinline__ unsigned long long ordered_bits(double v) {
+    const unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double from_ordered_bits(unsigned long long u) {
+    u = (u >> 63) ? (u & 0x7FFFFFFFFFFFFFFFull) : ~u;
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)u);
+#else
+    double d; memcpy(&d, &u, 8); return d;
+#endif
+}
+
+__global__ void __launch_bounds__(256) gather_mesh_kernel(const double* __restrict__ verts, const uint32_t* __restrict__ faces, uint64_t nf, double* __restrict__ tris) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nf) return;
+    double* out = tris + 9 * i;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double* v = verts + 3 * (uint64_t)faces[3 * i + k];
+        out[3 * k] = v[0]; out[3 * k + 1] = v[1]; out[3 * k + 2] = v[2];
+    }
+}
+
+// bounds[0..2] = ordered_bits(min), bounds[3..5] = ordered_bits(max); initialised to ~0 / 0 by the host
+__global__ void __launch_bounds__(256) scene_bounds_kernel(const double* __restrict__ tris, uint64_t n, unsigned long long* __restrict__ bounds) {
+    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double* t = tris + 9 * i;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { const double v = t[k]; lo[k % 3] = fmin(lo[k % 3], v); hi[k % 3] = fmax(hi[k % 3], v); }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        for (int off = 16; off > 0; off >>= 1) {
+            lo[k] = fmin(lo[k], __shfl_xor_sync(0xFFFFFFFFu, lo[k], off));
+            hi[k] = fmax(hi[k], __shfl_xor_sync(0xFFFFFFFFu, hi[k], off));
+        }
+    __shared__ double s[8][6];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) for (int k = 0; k < 3; ++k) { s[warp][k] = lo[k]; s[warp][3 + k] = hi[k]; }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = s[0][threadIdx.x];
+        for (int w = 1; w < 8; ++w) v = threadIdx.x < 3 ? fmin(v, s[w][threadIdx.x]) : fmax(v, s[w][threadIdx.x]);
+        if (threadIdx.x < 3) atomicMin(&bounds[threadIdx.x], ordered_bits(v));
+        else atomicMax(&bounds[threadIdx.x], ordered_bits(v));
+    }
+}
+
+B2_HD uint64_t spread21(uint64_t x) {   // insert two zero bits after each of the low 21 bits
+    x &= 0x1FFFFFull;
+    x = (x | (x << 32)) & 0x1F00000000FFFFull;
+    x = (x | (x << 16)) & 0x1F0000FF0000FFull;
+    x = (x | (x << 8)) & 0x100F00F00F00F00Full;
+    x = (x | (x << 4)) & 0x10C30C30C30C30C3ull;
+    x = (x | (x << 2)) & 0x1249249249249249ull;
+    return x;
+}
+B2_HD uint64_t morton63(double cx, double cy, double cz, const double* lo, const double* scale) {
+    const double fx = (cx - lo[0]) * scale[0], fy = (cy - lo[1]) * scale[1], fz = (cz - lo[2]) * scale[2];
+    const uint64_t qx = (uint64_t)fmin(fmax(fx, 0.0), 2097151.0);
+    const uint64_t qy = (uint64_t)fmin(fmax(fy, 0.0), 2097151.0);
+    const uint64_t qz = (uint64_t)fmin(fmax(fz, 0.0), 2097151.0);
+    return (spread21(qx) << 2) | (spread21(qy) << 1) | spread21(qz);
+}
+
+__global__ void __launch_bounds__(256) morton_kernel(const double* __restrict__ tris, uint64_t n, const unsigned long long* __restrict__ bounds,
+                                                     uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double lo[3], scale[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        lo[k] = from_ordered_bits(bounds[k]);
+        const double ext = from_ordered_bits(bounds[3 + k]) - lo[k];
+        scale[k] = ext > 0.0 ? 2097152.0 / ext : 0.0;
+    }
+    const double* t = tris + 9 * i;
+    double c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double a = t[k], b = t[3 + k], d = t[6 + k];
+        c[k] = 0.5 * (fmin(a, fmin(b, d)) + fmax(a, fmax(b, d)));
+    }
+    keys[i] = morton63(c[0], c[1], c[2], lo, scale);
+    vals[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256) emit_leaves_kernel(const double* __restrict__ tris, const uint32_t* __restrict__ ids, const uint32_t* __restrict__ perm,
+                                                          uint64_t n, TriRec* __restrict__ out) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t src = perm[k];
+    const double* t = tris + 9 * (uint64_t)src;
+    TriRec r;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) r.v[j] = t[j];
+    r.id = ids ? ids[src] : src;
+#pragma unroll
+    for (int j = 0; j < 5; ++j) r.pad[j] = 0;
+    out[k] = r;
+}
+
+// length of the common prefix of the (key, index) pairs i and j; -1 outside [0, n)
+B2_HD int karras_delta(const uint64_t* __restrict__ keys, int64_t n, int64_t i, int64_t j) {
+    if (j < 0 || j >= n) return -1;
+    const uint64_t x = keys[i] ^ keys[j];
+#if defined(__CUDA_ARCH__)
+    if (x) return __clzll((long long)x);
+    return 64 + __clzll((long long)((uint64_t)i ^ (uint64_t)j));
+#else
+    if (x) return __builtin_clzll(x);
+    return 64 + __builtin_clzll((uint64_t)i ^ (uint64_t)j);
+#endif
+}
+
+// topology of internal node i (Karras, "Maximizing Parallelism in the Construction of BVHs, Octrees, and k-d Trees", 2012)
+B2_HD void karras_node(const uint64_t* __restrict__ keys, int64_t n, int64_t i, uint32_t& left, uint32_t& right, uint32_t& first, uint32_t& last) {
+    const int d = karras_delta(keys, n, i, i + 1) - karras_delta(keys, n, i, i - 1) >= 0 ? 1 : -1;
+    const int dmin = karras_delta(keys, n, i, i - d);
+    int64_t lmax = 2;
+    while (karras_delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int64_t l = 0;
+    for (int64_t t = lmax >> 1; t >= 1; t >>= 1)
+        if (karras_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    const int64_t j = i + l * d;
+    const int dnode = karras_delta(keys, n, i, j);
+    int64_t s = 0;
+    for (int64_t t = (l + 1) >> 1;; t = (t + 1) >> 1) {
+        if (karras_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
+        if (t == 1) break;
+    }
+    const int64_t gamma = i + s * d + (d < 0 ? -1 : 0);
+    const int64_t lo = i < j ? i : j, hi = i < j ? j : i;
+    left = lo == gamma ? (kLeafBit | (uint32_t)gamma) : (uint32_t)gamma;
+    right = hi == gamma + 1 ? (kLeafBit | (uint32_t)(gamma + 1)) : (uint32_t)(gamma + 1);
+    first = (uint32_t)lo; last = (uint32_t)hi;
+}
+
+__global__ void __launch_bounds__(256) hierarchy_kernel(const uint64_t* __restrict__ keys, uint64_t n, BvhNode* __restrict__ nodes, uint32_t* __restrict__ leaf_parent) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i + 1 >= n) return;
+    uint32_t l, r, f, e;
+    karras_node(keys, (int64_t)n, (int64_t)i, l, r, f, e);
+    BvhNode* nd = nodes + i;
+    nd->child[0] = l; nd->child[1] = r; nd->visit = 0; nd->first = f; nd->last = e; nd->pad[0] = 0; nd->pad[1] = 0;
+    if (i == 0) nd->parent = kNone;
+    if (l & kLeafBit) leaf_parent[l & ~kLeafBit] = (uint32_t)i; else nodes[l].parent = (uint32_t)i;
+    if (r & kLeafBit) leaf_parent[r & ~kLeafBit] = (uint32_t)i; else nodes[r].parent = (uint32_t)i;
+}
+
+// one thread per leaf; the second thread to arrive at a node continues upwards with the union of both child boxes
+__global__ void __launch_bounds__(256) refit_kernel(const TriRec* __restrict__ tris, uint64_t n, BvhNode* nodes, const uint32_t* __restrict__ leaf_parent,
+                                                    double* __restrict__ root_box) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    double lo[3], hi[3];
+    {
+        const double* v = tris[k].v;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { lo[a] = fmin(v[a], fmin(v[3 + a], v[6 + a])); hi[a] = fmax(v[a], fmax(v[3 + a], v[6 + a])); }
+    }
+    if (n == 1) { for (int a = 0; a < 3; ++a) { root_box[a] = lo[a]; root_box[3 + a] = hi[a]; } return; }
+    uint32_t me = kLeafBit | (uint32_t)k;
+    uint32_t p = leaf_parent[k];
+    while (true) {
+        BvhNode* nd = nodes + p;
+        const int side = (nd->child[0] == me) ? 0 : 1;
+        double* mylo = side ? nd->lo1 : nd->lo0; double* myhi = side ? nd->hi1 : nd->hi0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { mylo[a] = lo[a]; myhi[a] = hi[a]; }
+        __threadfence();
+        if (atomicAdd(&nd->visit, 1u) == 0) return;              // first to arrive: the sibling will carry on
+        __threadfence();
+        // the sibling box was written by another SM: read it through L2 (this SM's L1 may hold the line from the child[] read)
+        const double* olo = side ? nd->lo0 : nd->lo1; const double* ohi = side ? nd->hi0 : nd->hi1;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { lo[a] = fmin(lo[a], __ldcg(olo + a)); hi[a] = fmax(hi[a], __ldcg(ohi + a)); }
+        me = p;
+        p = nd->parent;
+        if (p == kNone) { for (int a = 0; a < 3; ++a) { root_box[a] = lo[a]; root_box[3 + a] = hi[a]; } return; }
+    }
+}
+
+}  // namespace b2

@@ -1,0 +1,280 @@
+// bvh.cuh — HBM layout of the tree and the per-query traversal routines.
+//
+// Layout:
+//   BvhNode  128 B  one INTERNAL node of the binary LBVH; it carries the boxes of BOTH children, so a traversal step
+//                   costs one 128-byte line and leaf boxes never need their own node.  N-1 nodes for N primitives.
+//   TriRec    96 B  one primitive in Morton order: 9 coordinates (v0,v1,v2), the primitive id, padding to 3 sectors.
+// Child reference: bit 31 set = leaf, low bits = slot in the TriRec array; else index of an internal node.
+//
+// Traversal replaces (paths relative to the CGAL source root)
+//   AABB_tree/include/CGAL/AABB_tree/internal/AABB_node.h:129-167              recursive traversal
+//   AABB_tree/include/CGAL/AABB_tree/internal/AABB_traversal_traits.h:150-327  Listing/Do_intersect/Projection traits
+//   AABB_tree/include/CGAL/AABB_tree/internal/AABB_ray_intersection.h:49-150   best-first first_intersection
+// by an iterative stack traversal per query.  Node tests are CONSERVATIVE floating-point tests (never reject a box
+// that contains a qualifying primitive); every decision that reaches the result is taken by the exact leaf routines
+// of geom.cuh, so booleans, counts and winners do not depend on the tree shape (SURVEY.md §3.4, §7 hard part 1).
+#pragma once
+#include <stdint.h>
+#include "geom.cuh"
+
+namespace b2 {
+
+constexpr uint32_t kLeafBit = 0x80000000u;
+constexpr uint32_t kNone = 0xFFFFFFFFu;
+constexpr int kStackCap = 96;
+
+struct __align__(16) BvhNode {
+    double lo0[3], hi0[3];
+    double lo1[3], hi1[3];
+    uint32_t child[2];
+    uint32_t parent;
+    uint32_t visit;       // refit arrival counter (build only)
+    uint32_t first, last; // range of sorted primitive slots below this node
+    uint32_t pad[2];
+};
+static_assert(sizeof(BvhNode) == 128, "node is one 128-byte line");
+
+struct __align__(16) TriRec {
+    double v[9];
+    uint32_t id;
+    uint32_t pad[5];
+};
+static_assert(sizeof(TriRec) == 96, "triangle record is three 32-byte sectors");
+
+struct NodeView { double lo0[3], hi0[3], lo1[3], hi1[3]; uint32_t c0, c1; };
+
+B2_HD NodeView load_node(const BvhNode* __restrict__ nodes, uint32_t i) {
+    NodeView n;
+#if defined(__CUDA_ARCH__)
+    const double2* p = reinterpret_cast<const double2*>(nodes + i);
+    const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4), f = __ldg(p + 5);
+    const uint4 m = __ldg(reinterpret_cast<const uint4*>(p + 6));
+    n.lo0[0] = a.x; n.lo0[1] = a.y; n.lo0[2] = b.x; n.hi0[0] = b.y; n.hi0[1] = c.x; n.hi0[2] = c.y;
+    n.lo1[0] = d.x; n.lo1[1] = d.y; n.lo1[2] = e.x; n.hi1[0] = e.y; n.hi1[1] = f.x; n.hi1[2] = f.y;
+    n.c0 = m.x; n.c1 = m.y;
+#else
+    const BvhNode& s = nodes[i];
+    for (int k = 0; k < 3; ++k) { n.lo0[k] = s.lo0[k]; n.hi0[k] = s.hi0[k]; n.lo1[k] = s.lo1[k]; n.hi1[k] = s.hi1[k]; }
+    n.c0 = s.child[0]; n.c1 = s.child[1];
+#endif
+    return n;
+}
+
+B2_HD Tri3 load_tri(const TriRec* __restrict__ tris, uint32_t slot, uint32_t& id) {
+    Tri3 t;
+#if defined(__CUDA_ARCH__)
+    const double2* p = reinterpret_cast<const double2*>(tris + slot);
+    const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
+    const uint4 m = __ldg(reinterpret_cast<const uint4*>(p + 4));   // v[8] (2 words), id, pad
+    t.a = {a.x, a.y, b.x}; t.b = {b.y, c.x, c.y}; t.c = {d.x, d.y, __hiloint2double((int)m.y, (int)m.x)};
+    id = m.z;
+#else
+    const TriRec& s = tris[slot];
+    t.a = {s.v[0], s.v[1], s.v[2]}; t.b = {s.v[3], s.v[4], s.v[5]}; t.c = {s.v[6], s.v[7], s.v[8]};
+    id = s.id;
+#endif
+    return t;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Conservative node tests
+// ---------------------------------------------------------------------------------------------------------------
+struct LineCtx {              // Segment_3 / Ray_3 query, parametrised x(t) = s + t (q - s)
+    Vec3 s, q, d;             // d = q - s (rounded once)
+    double inv[3];            // 1/d per axis (unused where d == 0)
+    int zero_mask;            // axes with d == 0
+    int major;                // argmax |d| (first max wins), AABB_ray_intersection.h:171-176
+    double t_abs_slack;       // absolute error allowance on computed hit parameters
+};
+B2_HD LineCtx make_line(const Vec3& s, const Vec3& q) {
+    LineCtx c; c.s = s; c.q = q; c.d = q - s;
+    c.zero_mask = (c.d.x == 0.0 ? 1 : 0) | (c.d.y == 0.0 ? 2 : 0) | (c.d.z == 0.0 ? 4 : 0);
+    c.inv[0] = 1.0 / c.d.x; c.inv[1] = 1.0 / c.d.y; c.inv[2] = 1.0 / c.d.z;
+    c.major = ray_major_axis(c.d);
+    const double smax = fmax3(fabs(s.x), fabs(s.y), fabs(s.z));
+    c.t_abs_slack = 1.5e-14 * smax / fabs(comp(c.d, c.major));
+    return c;
+}
+// does x(t), t in [0, tlimit], possibly meet the closed box?  tn = conservative lower bound of the entry parameter.
+// Every computed slab parameter carries <= 4 roundings (d, 1/d, lo - s, product); it is widened by 1e-15 relative.
+B2_HD bool line_box(const double* lo, const double* hi, const LineCtx& c, double tlimit, double& tn) {
+    double tnear = 0.0, tfar = tlimit;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double si = comp(c.s, i);
+        if (c.zero_mask & (1 << i)) {
+            if (si < lo[i] || si > hi[i]) return false;
+        } else {
+            const double t1 = (lo[i] - si) * c.inv[i], t2 = (hi[i] - si) * c.inv[i];
+            double a = fmin(t1, t2), b = fmax(t1, t2);
+            a = a - fabs(a) * 1e-15;
+            b = b + fabs(b) * 1e-15;
+            tnear = fmax(tnear, a);
+            tfar = fmin(tfar, b);
+        }
+    }
+    tn = tnear;
+    return tnear <= tfar;
+}
+// squared distance from p to the closed box, in plain double (relative error a few ulps)
+B2_HD double point_box_sqdist(const double* lo, const double* hi, const Vec3& p) {
+    const double dx = fmax(fmax(lo[0] - p.x, p.x - hi[0]), 0.0);
+    const double dy = fmax(fmax(lo[1] - p.y, p.y - hi[1]), 0.0);
+    const double dz = fmax(fmax(lo[2] - p.z, p.z - hi[2]), 0.0);
+    return (dx * dx + dy * dy) + dz * dz;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// do_intersect / number_of_intersected_primitives   (AABB_tree.h:903-932)
+// ---------------------------------------------------------------------------------------------------------------
+template <bool IS_RAY, bool COUNT>
+B2_HD uint32_t traverse_intersect(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root,
+                                  const Vec3& s, const Vec3& q, int& nexact, int& overflow) {
+    const LineCtx c = make_line(s, q);
+    const double tlimit = IS_RAY ? DBL_MAX : 1.0;
+    uint32_t found = 0;
+    auto leaf = [&](uint32_t ref) {
+        uint32_t id;
+        const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
+        if (IS_RAY ? ray_tri_do_intersect(t, s, q, nexact) : seg_tri_do_intersect(t, s, q, nexact)) ++found;
+    };
+    if (root & kLeafBit) { leaf(root); return found; }   // singleton tree: AABB_tree.h:516-525
+    uint32_t stack[kStackCap];
+    int sp = 0;
+    uint32_t cur = root;
+    while (true) {
+        const NodeView n = load_node(nodes, cur);
+        double tn;
+        const bool h0 = line_box(n.lo0, n.hi0, c, tlimit, tn);
+        const bool h1 = line_box(n.lo1, n.hi1, c, tlimit, tn);
+        uint32_t next = kNone;
+        if (h0) { if (n.c0 & kLeafBit) leaf(n.c0); else next = n.c0; }
+        if (!COUNT && found) return 1;
+        if (h1) {
+            if (n.c1 & kLeafBit) leaf(n.c1);
+            else if (next == kNone) next = n.c1;
+            else if (sp < kStackCap) stack[sp++] = n.c1;
+            else overflow = 1;
+        }
+        if (!COUNT && found) return 1;
+        if (next == kNone) {
+            if (sp == 0) break;
+            next = stack[--sp];
+        }
+        cur = next;
+    }
+    return found;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// first_intersection(Ray_3)   (AABB_ray_intersection.h:49-225)
+// Result = the intersected primitive with the smallest ray parameter t as the reference computes it; on exactly equal
+// t the smallest primitive id wins and `tie` is set (the reference keeps whichever it popped first).
+// ---------------------------------------------------------------------------------------------------------------
+struct FirstHit { uint32_t prim; int kind; double t; Vec3 p0, p1; int tie; };
+
+B2_HD FirstHit traverse_first(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root,
+                              const Vec3& s, const Vec3& q, int& nexact, int& overflow) {
+    const LineCtx c = make_line(s, q);
+    FirstHit best; best.prim = kNone; best.kind = 0; best.t = DBL_MAX; best.p0 = s; best.p1 = s; best.tie = 0;
+    double tlimit = DBL_MAX;   // prune boxes whose entry parameter certainly exceeds the best hit
+    auto leaf = [&](uint32_t ref) {
+        uint32_t id;
+        const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
+        const RayX x = ray_tri_intersection(t, s, q, c.d, c.major, nexact);
+        if (x.kind == 0) return;
+        if (x.t < best.t || (x.t == best.t && id < best.prim)) {
+            if (x.t == best.t) best.tie = 1; else best.tie = 0;
+            best.prim = id; best.kind = x.kind; best.t = x.t; best.p0 = x.p0; best.p1 = x.p1;
+            tlimit = x.t + (fabs(x.t) * 1e-9 + c.t_abs_slack);
+        } else if (x.t == best.t) {
+            best.tie = 1;
+        }
+    };
+    if (root & kLeafBit) { leaf(root); return best; }
+    uint32_t stack[kStackCap];
+    int sp = 0;
+    uint32_t cur = root;
+    while (true) {
+        const NodeView n = load_node(nodes, cur);
+        double t0, t1;
+        bool h0 = line_box(n.lo0, n.hi0, c, tlimit, t0);
+        bool h1 = line_box(n.lo1, n.hi1, c, tlimit, t1);
+        uint32_t c0 = n.c0, c1 = n.c1;
+        if (h0 && h1 && t1 < t0) { const uint32_t tc = c0; c0 = c1; c1 = tc; const double tt = t0; t0 = t1; t1 = tt; }
+        else if (!h0 && h1) { c0 = c1; t0 = t1; h0 = true; h1 = false; }
+        uint32_t next = kNone;
+        if (h0) { if (c0 & kLeafBit) leaf(c0); else next = c0; }
+        if (h1 && t1 <= tlimit) {
+            if (c1 & kLeafBit) leaf(c1);
+            else if (next == kNone) next = c1;
+            else if (sp < kStackCap) stack[sp++] = c1;
+            else overflow = 1;
+        }
+        if (next == kNone) {
+            if (sp == 0) break;
+            next = stack[--sp];
+        }
+        cur = next;
+    }
+    return best;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// closest_point_and_primitive(Point_3)   (AABB_tree.h:987-1055, Projection_traits AABB_traversal_traits.h:277-327)
+// Result = the candidate (per-triangle projected point, rounded exactly as the reference rounds it) with the smallest
+// EXACT squared distance to the query; on exactly equal distance the smallest primitive id wins and `tie` is set.
+// A box is skipped only when it is certainly farther than the incumbent by a 1e-13 relative margin, which is wider
+// than the reference's own semi-static margin (AABB_traits_3.h:318-459): every near-best candidate is examined.
+// ---------------------------------------------------------------------------------------------------------------
+struct Closest { Vec3 p; uint32_t prim; double sqd; int tie; };
+
+B2_HD Closest traverse_closest(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root,
+                               const Vec3& o, int& nexact, int& overflow) {
+    Closest best; best.p = o; best.prim = kNone; best.sqd = DBL_MAX; best.tie = 0;
+    double bound = DBL_MAX;
+    auto leaf = [&](uint32_t ref) {
+        uint32_t id;
+        const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
+        const Vec3 cp = closest_on_triangle(t, o);
+        bool take;
+        if (best.prim == kNone) take = true;
+        else {
+            const int s = cmp_dist(o, cp, best.p, nexact);   // Compare_distance_3(query, candidate, incumbent): AABB_traits_3.h:724-732
+            if (s == 0) { take = id < best.prim; best.tie = 1; }
+            else { take = s < 0; if (take) best.tie = 0; }
+        }
+        if (take) {
+            best.p = cp; best.prim = id;
+            const Vec3 v = cp - o;
+            best.sqd = (v.x * v.x + v.y * v.y) + v.z * v.z;   // Compute_squared_distance_3(query, closest): AABB_tree.h:1024-1032
+            bound = best.sqd + best.sqd * 1e-13;
+        }
+    };
+    if (root & kLeafBit) { leaf(root); return best; }
+    uint32_t stack[kStackCap];
+    int sp = 0;
+    uint32_t cur = root;
+    while (true) {
+        const NodeView n = load_node(nodes, cur);
+        double d0 = point_box_sqdist(n.lo0, n.hi0, o), d1 = point_box_sqdist(n.lo1, n.hi1, o);
+        uint32_t c0 = n.c0, c1 = n.c1;
+        if (d1 < d0) { const uint32_t tc = c0; c0 = c1; c1 = tc; const double td = d0; d0 = d1; d1 = td; }
+        uint32_t next = kNone;
+        if (d0 <= bound) { if (c0 & kLeafBit) leaf(c0); else next = c0; }
+        if (d1 <= bound) {
+            if (c1 & kLeafBit) leaf(c1);
+            else if (next == kNone) next = c1;
+            else if (sp < kStackCap) stack[sp++] = c1;
+            else overflow = 1;
+        }
+        if (next == kNone) {
+            if (sp == 0) break;
+            next = stack[--sp];
+        }
+        cur = next;
+    }
+    return best;
+}
+
+}  // namespace b2

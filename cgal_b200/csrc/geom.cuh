@@ -1,0 +1,289 @@
+// geom.cuh — per-primitive device routines of the traversal kernels: triangle tests (exact) and the plain-double
+// constructions whose operation order must match the reference bit for bit.
+// Compile with -fmad=false: no FMA contraction may happen in the constructions.
+#pragma once
+#include <float.h>
+#include "predicates.cuh"
+
+namespace b2 {
+
+struct Tri3 { Vec3 a, b, c; };
+
+B2_HD Vec3 cross3(const Vec3& v, const Vec3& w) {   // Construct_cross_product_vector_3, Cartesian/function_objects.h:2263-2268
+    return {v.y * w.z - v.z * w.y, v.z * w.x - v.x * w.z, v.x * w.y - v.y * w.x};
+}
+B2_HD double dot3(const Vec3& v, const Vec3& w) { return (v.x * w.x + v.y * w.y) + v.z * w.z; }
+B2_HD double sqlen3(const Vec3& v) { return (v.x * v.x + v.y * v.y) + v.z * v.z; }
+
+// supporting plane a x + b y + c z + d = 0 of (P,Q,R): plane_from_pointsC3, constructions/kernel_ftC3.h:225-241
+struct Plane4 { double a, b, c, d; };
+B2_HD Plane4 plane_of(const Tri3& t) {
+    const Vec3 rp = t.a - t.c, rq = t.b - t.c;
+    Plane4 h;
+    h.a = rp.y * rq.z - rq.y * rp.z;
+    h.b = rp.z * rq.x - rq.z * rp.x;
+    h.c = rp.x * rq.y - rq.x * rp.y;
+    h.d = ((-h.a * t.c.x) - h.b * t.c.y) - h.c * t.c.z;
+    return h;
+}
+
+// "the line (x,y) passes the triangle on the non-positive side of all three edges"
+// = the three Orientation_3 tests shared by all straddling cases of Segment/Ray x Triangle
+B2_HD bool passes_edges(const Vec3& x, const Vec3& y, const Tri3& t, int& nexact) {
+    return orient3(x, y, t.a, t.b, nexact) != 1 && orient3(x, y, t.b, t.c, nexact) != 1 && orient3(x, y, t.c, t.a, nexact) != 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Coplanar configurations (rare).  The 27-way (pqa,pqb,pqc) case analyses of the reference are stored as tables
+// indexed by (pqa+1)*9 + (pqb+1)*3 + (pqc+1); vertices are numbered 0=a 1=b 2=c AFTER the ccw swap.
+// ---------------------------------------------------------------------------------------------------------------
+// Segment x Triangle (Intersections_3/internal/Segment_3_Triangle_3_do_intersect.h:24-152): each entry is two edge
+// tests "coplanar_orientation(edge, endpoint) != NEGATIVE"; edge e: 0=(a,b) 1=(b,c) 2=(c,a); endpoint 0=p 1=q.
+// code = e1 | pt1<<2 | e2<<3 | pt2<<5 ; 0xFF = no intersection
+#define B2_ST(e1, p1, e2, p2) ((e1) | ((p1) << 2) | ((e2) << 3) | ((p2) << 5))
+__constant__ static const unsigned char kSegTriCoplanar[27] = {
+    /* pqa=-1 */ /* pqb=-1 */ 0xFF, B2_ST(1, 0, 2, 1), B2_ST(1, 0, 2, 1),
+                 /* pqb= 0 */ B2_ST(0, 0, 1, 1), B2_ST(0, 0, 2, 1), B2_ST(0, 0, 2, 1),
+                 /* pqb=+1 */ B2_ST(0, 0, 1, 1), B2_ST(0, 0, 1, 1), B2_ST(0, 0, 2, 1),
+    /* pqa= 0 */ /* pqb=-1 */ B2_ST(0, 1, 2, 0), B2_ST(0, 1, 1, 0), B2_ST(0, 1, 1, 0),
+                 /* pqb= 0 */ B2_ST(1, 1, 2, 0), B2_ST(1, 1, 2, 0), B2_ST(1, 0, 2, 1),
+                 /* pqb=+1 */ B2_ST(0, 0, 1, 1), B2_ST(0, 0, 1, 1), B2_ST(0, 0, 2, 1),
+    /* pqa=+1 */ /* pqb=-1 */ B2_ST(0, 1, 2, 0), B2_ST(0, 1, 2, 0), B2_ST(0, 1, 1, 0),
+                 /* pqb= 0 */ B2_ST(0, 1, 2, 0), B2_ST(0, 1, 2, 0), B2_ST(0, 1, 1, 0),
+                 /* pqb=+1 */ B2_ST(1, 1, 2, 0), B2_ST(1, 1, 2, 0), 0xFF};
+// Ray x Triangle do_intersect (Ray_3_Triangle_3_do_intersect.h:75-191): one test "coplanar_orientation(x,y,p) != POSITIVE";
+// code: 0 = (a,c)  1 = (c,b)  2 = (b,a) ; 0xFF = no intersection
+__constant__ static const unsigned char kRayTriCoplanar[27] = {
+    /* pqa=-1 */ 0xFF, 1, 1, /**/ 2, 2, 2, /**/ 2, 2, 2,
+    /* pqa= 0 */ 0, 1, 1, /**/ 0, 0, 1, /**/ 2, 2, 2,
+    /* pqa=+1 */ 0, 0, 1, /**/ 0, 0, 1, /**/ 0, 0, 0xFF};
+// Ray x Triangle intersection (Ray_3_Triangle_3_intersection.h:147-396):
+//   kind 0 none | 1 clip(x,y,z,negative_side) | 2 vertex v | 3 aligned edge (u -> w)
+//   code = kind | arg<<2 ; clip arg = rot | neg<<2 with rot 0=(a,b,c) 1=(b,c,a) 2=(c,a,b); vertex arg = v; edge arg = u | w<<2
+#define B2_CLIP(rot, neg) (1 | (((rot) | ((neg) << 2)) << 2))
+#define B2_VERT(v) (2 | ((v) << 2))
+#define B2_EDGE(u, w) (3 | (((u) | ((w) << 2)) << 2))
+__constant__ static const unsigned char kRayTriIntersectCoplanar[27] = {
+    /* pqa=-1 */ /* pqb=-1 */ 0, B2_VERT(2), B2_CLIP(0, 0),
+                 /* pqb= 0 */ B2_VERT(1), B2_EDGE(2, 1), B2_CLIP(1, 1),
+                 /* pqb=+1 */ B2_CLIP(2, 0), B2_CLIP(2, 0), B2_CLIP(1, 1),
+    /* pqa= 0 */ /* pqb=-1 */ B2_VERT(0), B2_EDGE(0, 2), B2_CLIP(2, 1),
+                 /* pqb= 0 */ B2_EDGE(1, 0), 0, B2_EDGE(0, 1),
+                 /* pqb=+1 */ B2_CLIP(2, 0), B2_EDGE(2, 0), B2_VERT(0),
+    /* pqa=+1 */ /* pqb=-1 */ B2_CLIP(1, 0), B2_CLIP(1, 0), B2_CLIP(2, 1),
+                 /* pqb= 0 */ B2_CLIP(1, 0), B2_EDGE(1, 2), B2_VERT(1),
+                 /* pqb=+1 */ B2_CLIP(0, 1), B2_VERT(2), 0};
+
+#if !defined(__CUDA_ARCH__)
+// host-side copies for the CPU self-check of the device headers (tests/hostcheck); same initialisers
+namespace host_tables {
+static const unsigned char SegTri[27] = {
+    0xFF, B2_ST(1, 0, 2, 1), B2_ST(1, 0, 2, 1), B2_ST(0, 0, 1, 1), B2_ST(0, 0, 2, 1), B2_ST(0, 0, 2, 1), B2_ST(0, 0, 1, 1), B2_ST(0, 0, 1, 1), B2_ST(0, 0, 2, 1),
+    B2_ST(0, 1, 2, 0), B2_ST(0, 1, 1, 0), B2_ST(0, 1, 1, 0), B2_ST(1, 1, 2, 0), B2_ST(1, 1, 2, 0), B2_ST(1, 0, 2, 1), B2_ST(0, 0, 1, 1), B2_ST(0, 0, 1, 1), B2_ST(0, 0, 2, 1),
+    B2_ST(0, 1, 2, 0), B2_ST(0, 1, 2, 0), B2_ST(0, 1, 1, 0), B2_ST(0, 1, 2, 0), B2_ST(0, 1, 2, 0), B2_ST(0, 1, 1, 0), B2_ST(1, 1, 2, 0), B2_ST(1, 1, 2, 0), 0xFF};
+static const unsigned char RayTri[27] = {0xFF, 1, 1, 2, 2, 2, 2, 2, 2, 0, 1, 1, 0, 0, 1, 2, 2, 2, 0, 0, 1, 0, 0, 1, 0, 0, 0xFF};
+static const unsigned char RayTriX[27] = {
+    0, B2_VERT(2), B2_CLIP(0, 0), B2_VERT(1), B2_EDGE(2, 1), B2_CLIP(1, 1), B2_CLIP(2, 0), B2_CLIP(2, 0), B2_CLIP(1, 1),
+    B2_VERT(0), B2_EDGE(0, 2), B2_CLIP(2, 1), B2_EDGE(1, 0), 0, B2_EDGE(0, 1), B2_CLIP(2, 0), B2_EDGE(2, 0), B2_VERT(0),
+    B2_CLIP(1, 0), B2_CLIP(1, 0), B2_CLIP(2, 1), B2_CLIP(1, 0), B2_EDGE(1, 2), B2_VERT(1), B2_CLIP(0, 1), B2_VERT(2), 0};
+}  // namespace host_tables
+#endif
+
+B2_HD unsigned char tbl_segtri(int i) {
+#if defined(__CUDA_ARCH__)
+    return kSegTriCoplanar[i];
+#else
+    return host_tables::SegTri[i];
+#endif
+}
+B2_HD unsigned char tbl_raytri(int i) {
+#if defined(__CUDA_ARCH__)
+    return kRayTriCoplanar[i];
+#else
+    return host_tables::RayTri[i];
+#endif
+}
+B2_HD unsigned char tbl_raytrix(int i) {
+#if defined(__CUDA_ARCH__)
+    return kRayTriIntersectCoplanar[i];
+#else
+    return host_tables::RayTriX[i];
+#endif
+}
+
+struct CoplanarFrame { Vec3 v[3]; int idx; };   // ccw-ordered vertices + table index
+B2_HD CoplanarFrame coplanar_frame(const Tri3& t, const Vec3& p, const Vec3& q, int& nexact) {
+    CoplanarFrame f;
+    const bool ccw = coplanar_orient(t.a, t.b, t.c, nexact) == 1;
+    f.v[0] = t.a; f.v[1] = ccw ? t.b : t.c; f.v[2] = ccw ? t.c : t.b;
+    const int pqa = coplanar_orient(p, q, f.v[0], nexact), pqb = coplanar_orient(p, q, f.v[1], nexact), pqc = coplanar_orient(p, q, f.v[2], nexact);
+    f.idx = (pqa + 1) * 9 + (pqb + 1) * 3 + (pqc + 1);
+    return f;
+}
+
+B2_HD_NOINLINE bool seg_tri_coplanar(const Tri3& t, const Vec3& p, const Vec3& q, int& nexact) {
+    const CoplanarFrame f = coplanar_frame(t, p, q, nexact);
+    const unsigned code = tbl_segtri(f.idx);
+    if (code == 0xFF) return false;
+    const int e1 = code & 3, e2 = (code >> 3) & 3;
+    const Vec3& x1 = ((code >> 2) & 1) ? q : p;
+    const Vec3& x2 = ((code >> 5) & 1) ? q : p;
+    return coplanar_orient(f.v[e1], f.v[(e1 + 1) % 3], x1, nexact) != -1 && coplanar_orient(f.v[e2], f.v[(e2 + 1) % 3], x2, nexact) != -1;
+}
+B2_HD_NOINLINE bool ray_tri_coplanar(const Tri3& t, const Vec3& p, const Vec3& q, int& nexact) {
+    const CoplanarFrame f = coplanar_frame(t, p, q, nexact);
+    const unsigned code = tbl_raytri(f.idx);
+    if (code == 0xFF) return false;
+    const int x = code == 0 ? 0 : (code == 1 ? 2 : 1), y = code == 0 ? 2 : (code == 1 ? 1 : 0);
+    return coplanar_orient(f.v[x], f.v[y], p, nexact) != 1;
+}
+
+// Do_intersect_3(Segment_3, Triangle_3): Segment_3_Triangle_3_do_intersect.h:177-262
+B2_HD bool seg_tri_do_intersect(const Tri3& t, const Vec3& p, const Vec3& q, int& nexact) {
+    const int sp = orient3(t.a, t.b, t.c, p, nexact);
+    const int sq = orient3(t.a, t.b, t.c, q, nexact);
+    if (sp != 0 ? sq == sp : sq == 0) {                 // same open side, or both on the plane
+        if (sp != 0) return false;
+        return seg_tri_coplanar(t, p, q, nexact);
+    }
+    const bool fwd = sp > 0 || (sp == 0 && sq < 0);     // which endpoint sees the triangle counterclockwise
+    return fwd ? passes_edges(p, q, t, nexact) : passes_edges(q, p, t, nexact);
+}
+
+// Do_intersect_3(Ray_3, Triangle_3): Ray_3_Triangle_3_do_intersect.h:193-317 (exact ray direction)
+B2_HD bool ray_tri_do_intersect(const Tri3& t, const Vec3& p, const Vec3& q, int& nexact) {
+    const int dir = orient3_dir(t.a, t.b, t.c, p, q, nexact);
+    const int sp = orient3(t.a, t.b, t.c, p, nexact);
+    if (dir == 0) return sp == 0 ? ray_tri_coplanar(t, p, q, nexact) : false;
+    if (sp == dir) return false;                        // source on one side, heading away
+    const bool fwd = sp > 0 || (sp == 0 && dir < 0);
+    return fwd ? passes_edges(p, q, t, nexact) : passes_edges(q, p, t, nexact);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Intersect_3(Ray_3, Triangle_3) + the ray parameter of AABB_ray_intersection.h:168-198
+// ---------------------------------------------------------------------------------------------------------------
+struct RayX { int kind; Vec3 p0, p1; double t; };   // kind 0 none, 1 point, 2 segment
+
+B2_HD double ray_param(const Vec3& s, const Vec3& d, int ax, const Vec3& x) { return (comp(x, ax) - comp(s, ax)) / comp(d, ax); }
+B2_HD int ray_major_axis(const Vec3& d) {
+    int m = 0;
+    if (fabs(d.y) > fabs(d.x)) m = 1;
+    if (fabs(d.z) > fabs(comp(d, m))) m = 2;
+    return m;
+}
+
+// t3r3_intersection_coplanar_aux (point version), Ray_3_Triangle_3_intersection.h:28-61
+B2_HD Vec3 coplanar_lines_meet(const Vec3& p, const Vec3& v, const Vec3& a, const Vec3& b) {
+    const Vec3 ab = b - a, pa = a - p;
+    const Vec3 pa_ab = cross3(pa, ab), v_ab = cross3(v, ab);
+    const double t = dot3(pa_ab, v_ab) / sqlen3(v_ab);
+    return {p.x + v.x * t, p.y + v.y * t, p.z + v.z * t};
+}
+
+B2_HD_NOINLINE RayX ray_tri_intersection_coplanar(const Tri3& t, const Vec3& p, const Vec3& q, int& nexact) {
+    RayX r; r.kind = 0; r.t = 0; r.p0 = p; r.p1 = p;
+    const CoplanarFrame f = coplanar_frame(t, p, q, nexact);
+    const unsigned code = tbl_raytrix(f.idx);
+    const int kind = code & 3, arg = code >> 2;
+    if (kind == 0) return r;
+    if (kind == 2) {                                    // the line through p,q touches the triangle at one vertex
+        const Vec3& x = f.v[arg];
+        if (collinear_ordered(p, x, q) || collinear_ordered(p, q, x)) { r.kind = 1; r.p0 = x; }
+        return r;
+    }
+    if (kind == 3) {                                    // the ray runs along edge u -> w
+        const Vec3& u = f.v[arg & 3]; const Vec3& w = f.v[arg >> 2];
+        r.kind = 2; r.p0 = collinear_ordered(p, u, w) ? u : p; r.p1 = w;
+        return r;
+    }
+    // clip the ray into the triangle: :63-146, vertices rotated so that `c` is the isolated one
+    const int rot = arg & 3; const bool neg = (arg >> 2) != 0;
+    const Vec3& a = f.v[rot]; const Vec3& b = f.v[(rot + 1) % 3]; const Vec3& c = f.v[(rot + 2) % 3];
+    const int cap = neg ? coplanar_orient(c, a, p, nexact) : coplanar_orient(b, c, p, nexact);
+    if (cap < 0) return r;
+    if (cap == 0) { r.kind = 1; r.p0 = p; return r; }
+    const Vec3 v = q - p;
+    r.kind = 2; r.p0 = p;
+    if (neg) {
+        if (coplanar_orient(b, c, p, nexact) == -1) r.p0 = coplanar_lines_meet(p, v, b, c);
+        r.p1 = coplanar_lines_meet(p, v, c, a);
+    } else {
+        if (coplanar_orient(c, a, p, nexact) == -1) r.p0 = coplanar_lines_meet(p, v, c, a);
+        r.p1 = coplanar_lines_meet(p, v, b, c);
+    }
+    return r;
+}
+
+// Ray_3_Triangle_3_intersection.h:417-539; the hit point is Line_3 x Plane_3 (Line_3_Plane_3_intersection.h:52-85)
+B2_HD RayX ray_tri_intersection(const Tri3& t, const Vec3& s, const Vec3& q, const Vec3& d, int major_axis, int& nexact) {
+    RayX r; r.kind = 0; r.t = 0; r.p0 = s; r.p1 = s;
+    const Vec3 shifted = t.a + d;                         // Ray_3(a, q - s).second_point(): a ROUNDED point (:439)
+    const int dir = orient3(t.a, t.b, t.c, shifted, nexact);
+    const int sp = orient3(t.a, t.b, t.c, s, nexact);
+    if (sp == 0 && dir == 0) {
+        r = ray_tri_intersection_coplanar(t, s, q, nexact);
+        if (r.kind == 1) r.t = ray_param(s, d, major_axis, r.p0);
+        else if (r.kind == 2) r.t = fmin(ray_param(s, d, major_axis, r.p0), ray_param(s, d, major_axis, r.p1));
+        return r;
+    }
+    if (dir == 0 || sp == dir) return r;                  // parallel off-plane, or heading away
+    const bool fwd = sp > 0 || (sp == 0 && dir < 0);
+    if (!(fwd ? passes_edges(s, q, t, nexact) : passes_edges(q, s, t, nexact))) return r;
+    const Plane4 h = plane_of(t);
+    const double num = ((h.a * s.x + h.b * s.y) + h.c * s.z) + h.d;
+    const double den = (h.a * d.x + h.b * d.y) + h.c * d.z;
+    if (den == 0.0) return r;                             // the reference then produces no Point_3
+    Vec3 x = {den * s.x - num * d.x, den * s.y - num * d.y, den * s.z - num * d.z};
+    if (den != 1.0) { x.x = x.x / den; x.y = x.y / den; x.z = x.z / den; }   // Cartesian/Vector_3.h:73-75
+    r.kind = 1; r.p0 = x; r.p1 = x; r.t = ray_param(s, d, major_axis, x);
+    return r;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Construct_projected_point_3(Triangle_3, Point_3): Kernel_23/include/CGAL/Kernel/function_objects.h:3193-3263
+// ---------------------------------------------------------------------------------------------------------------
+B2_HD Vec3 foot_on_line(const Vec3& lp, const Vec3& ld, const Vec3& p) {   // Cartesian/function_objects.h:3200-3217
+    const Vec3 dp = p - lp;
+    const double lambda = ((ld.x * dp.x + ld.y * dp.y) + ld.z * dp.z) / ((ld.x * ld.x + ld.y * ld.y) + ld.z * ld.z);
+    return {lp.x + lambda * ld.x, lp.y + lambda * ld.y, lp.z + lambda * ld.z};
+}
+B2_HD_NOINLINE Vec3 closest_on_segment(const Vec3& s, const Vec3& e, const Vec3& query) {   // function_objects.h:3266-3285
+    if (same_point(s, e)) return s;
+    const Vec3 v = e - s;
+    if (dot3(v, query - s) <= 0) return s;
+    if (dot3(v, query - e) >= 0) return e;
+    return foot_on_line(s, v, query);
+}
+B2_HD_NOINLINE Vec3 closest_on_degenerate_triangle(const Tri3& t, const Vec3& o) {          // :3208-3247
+    const Vec3 ab = t.b - t.a, ac = t.c - t.a, bc = t.c - t.b;
+    const double lab = fmax(fmax(ab.x, ab.y), ab.z), lac = fmax(fmax(ac.x, ac.y), ac.z), lbc = fmax(fmax(bc.x, bc.y), bc.z);
+    if (lab > lac) return lab > lbc ? closest_on_segment(t.a, t.b, o) : closest_on_segment(t.b, t.c, o);
+    return lac > lbc ? closest_on_segment(t.a, t.c, o) : closest_on_segment(t.b, t.c, o);
+}
+B2_HD Vec3 closest_on_triangle(const Tri3& t, const Vec3& o) {
+    const Plane4 h = plane_of(t);
+    if (h.a == 0.0 && h.b == 0.0 && h.c == 0.0) return closest_on_degenerate_triangle(t, o);
+    const double num = ((h.a * o.x + h.b * o.y) + h.c * o.z) + h.d;       // projection_planeC3, kernel_ftC3.h:296-312
+    const double den = (h.a * h.a + h.b * h.b) + h.c * h.c;
+    const double lambda = num / den;
+    const Vec3 foot = {o.x - lambda * h.a, o.y - lambda * h.b, o.z - lambda * h.c};
+    const Vec3 w = {h.a, h.b, h.c};
+    bool outside = false;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {                                         // edges (a,b) (b,c) (c,a): :3130-3132
+        const Vec3& p1 = i == 0 ? t.a : (i == 1 ? t.b : t.c);
+        const Vec3& p2 = i == 0 ? t.b : (i == 1 ? t.c : t.a);
+        const Vec3 e = p2 - p1, u = foot - p1;
+        if (dot3(cross3(e, u), w) < 0) {                                  // foot is outside this edge (:3051-3052)
+            if (dot3(u, e) >= 0 && dot3(foot - p2, p1 - p2) >= 0) return foot_on_line(p1, e, foot);
+            outside = true;
+        }
+    }
+    if (!outside) return foot;
+    const double d1 = sqlen3(t.a - foot), d2 = sqlen3(t.b - foot), d3 = sqlen3(t.c - foot);   // nearest_point_3 :3075-3101
+    if (d2 >= d1 && d3 >= d1) return t.a;
+    return d3 >= d2 ? t.b : t.c;
+}
+
+}  // namespace b2

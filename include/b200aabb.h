@@ -1,0 +1,123 @@
+/* b200aabb.h — C ABI of the B200-native AABB tree (libb200aabb.so).
+ *
+ * This is the drop-in boundary for the hot path of
+ *   CGAL::AABB_tree< AABB_traits_3< Epick, AABB_face_graph_triangle_primitive< Surface_mesh<Epick::Point_3> > > >
+ * Each entry point names the reference interface it replaces (paths relative to the CGAL source root).
+ * Conventions: plain pointers and sizes only; every function returns an int status (0 = ok, < 0 = error, never
+ * throws); batched queries take `n` records and a memory-space flag saying whether the query/result pointers are
+ * host or device pointers.  Geometry is IEEE binary64; primitive ids are uint32 (Surface_mesh face indices,
+ * Surface_mesh/include/CGAL/Surface_mesh/Surface_mesh.h:63,198).  "No result" is id 0xFFFFFFFF.
+ *
+ * The reference-side binding a maintainer would add is include/CGAL_B200/AABB_tree.h.
+ */
+#ifndef B200AABB_H
+#define B200AABB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200aabb_tree b200aabb_tree; /* opaque; owns all device buffers */
+
+enum {
+  B200AABB_OK = 0,
+  B200AABB_ERR_INVALID_ARGUMENT = -1,
+  B200AABB_ERR_CUDA = -2,          /* a CUDA call failed; see b200aabb_last_error() */
+  B200AABB_ERR_OUT_OF_MEMORY = -3,
+  B200AABB_ERR_EMPTY_TREE = -4,    /* CGAL_precondition(!empty()) of the distance queries, AABB_tree.h:993,1008,1039 */
+  B200AABB_ERR_NO_DEVICE = -5      /* no sm_100 device: there is NO CPU fallback */
+};
+
+enum { B200AABB_NO_PRIMITIVE = 0xFFFFFFFFu };
+
+/* where the query / result pointers of a batched call live */
+typedef enum { B200AABB_HOST = 0, B200AABB_DEVICE = 1 } b200aabb_memspace;
+
+/* Query type of the intersection queries: Segment_3(source,target) or Ray_3(source, second point); both are
+ * 6 doubles (Cartesian_kernel/include/CGAL/Cartesian/Ray_3.h:35-47, Segment_3.h). */
+typedef enum { B200AABB_SEGMENT = 0, B200AABB_RAY = 1 } b200aabb_query_kind;
+
+/* per-query result flags (bit set) */
+enum {
+  B200AABB_FLAG_HIT = 1,           /* first_intersection: an intersection exists */
+  B200AABB_FLAG_SEGMENT = 2,       /* first_intersection: the intersection object is a Segment_3 (coplanar ray), not a Point_3 */
+  B200AABB_FLAG_TIE = 4,           /* >= 2 primitives attain the winning value EXACTLY (equal t / equal squared distance):
+                                      the reference's id then depends on its traversal order;
+                                      this library reports the smallest primitive id among them */
+  B200AABB_FLAG_EXACT = 8          /* at least one predicate of this query needed the exact (expansion) stage */
+};
+
+typedef struct b200aabb_stats {
+  uint64_t kernel_launches;        /* kernels of this library launched since the handle was created */
+  uint64_t exact_fallbacks;        /* queries of the last batch that used the exact stage (FLAG_EXACT) */
+  uint64_t ties;                   /* queries of the last batch flagged FLAG_TIE */
+  double last_build_ms;            /* device time of the last b200aabb_build (CUDA events) */
+  double last_query_ms;            /* device time of the traversal kernel(s) of the last batched query */
+  double last_query_total_ms;      /* same, including host<->device copies of the batch when pointers were HOST */
+} b200aabb_stats;
+
+/* ---- lifetime ------------------------------------------------------------------------------------------------ */
+/* AABB_tree(const Traits& = Traits()), AABB_tree/include/CGAL/AABB_tree.h:115-116.  `device` = CUDA ordinal. */
+int b200aabb_create(int device, b200aabb_tree** out);
+/* ~AABB_tree(), AABB_tree.h:186-189 */
+int b200aabb_destroy(b200aabb_tree* t);
+/* all work of this handle is enqueued on `cuda_stream` (a cudaStream_t; NULL = the legacy default stream) */
+int b200aabb_set_stream(b200aabb_tree* t, void* cuda_stream);
+const char* b200aabb_last_error(const b200aabb_tree* t);
+int b200aabb_get_stats(const b200aabb_tree* t, b200aabb_stats* out);
+
+/* ---- primitives ---------------------------------------------------------------------------------------------- */
+/* insert(faces(m).first, faces(m).second, m), AABB_tree.h:730-747, for a triangle Surface_mesh: vertex coordinates
+ * (nv x 3 doubles = mesh.points().data(), Surface_mesh/include/CGAL/Surface_mesh/Properties.h:186) and, per face in
+ * faces(m) order, (target(h), target(next(h)), source(h)) with h = halfedge(f)
+ * (BGL/include/CGAL/boost/graph/property_maps.h:52-63) = the OFF face's (v0,v1,v2).  Primitive id of face i is
+ * `face_ids[i]`, or i when face_ids is NULL.  Replaces the previous content.  Host pointers. */
+int b200aabb_set_mesh(b200aabb_tree* t, const double* vertices, uint64_t nv, const uint32_t* faces, const uint32_t* face_ids, uint64_t nf);
+/* same for a triangle soup: n x 9 doubles (v0,v1,v2); `space` says where `triangles`/`ids` live. */
+int b200aabb_set_triangles(b200aabb_tree* t, const double* triangles, const uint32_t* ids, uint64_t n, b200aabb_memspace space);
+/* clear(), AABB_tree.h:194-201 */
+int b200aabb_clear(b200aabb_tree* t);
+/* build() / custom_build(), AABB_tree.h:820-853: LBVH (63-bit Morton, onesweep radix sort, Karras, atomic refit). */
+int b200aabb_build(b200aabb_tree* t);
+/* accelerate_distance_queries(), AABB_tree.h:896-901.  The kd-tree hint is replaced by a BVH-derived bound (nearest
+ * child first descent), so this only builds the tree if needed and returns OK. */
+int b200aabb_accelerate_distance_queries(b200aabb_tree* t);
+/* size(), AABB_tree.h:213 ; bbox(), AABB_tree.h:204-210 (xmin,ymin,zmin,xmax,ymax,zmax; empty tree: +inf.. -inf..) */
+int b200aabb_size(const b200aabb_tree* t, uint64_t* n);
+int b200aabb_bbox(b200aabb_tree* t, double out[6]);
+
+/* ---- batched queries (each lazily builds, like root_node(), AABB_tree.h:636-652) ------------------------------ */
+/* do_intersect(query), AABB_tree.h:903-913: out[i] = 1 iff query i intersects some primitive.  queries: n x 6. */
+int b200aabb_do_intersect(b200aabb_tree* t, const double* queries, uint64_t n, b200aabb_query_kind kind,
+                          b200aabb_memspace space, uint8_t* out);
+/* number_of_intersected_primitives(query), AABB_tree.h:915-932 */
+int b200aabb_number_of_intersected_primitives(b200aabb_tree* t, const double* queries, uint64_t n, b200aabb_query_kind kind,
+                                              b200aabb_memspace space, uint32_t* out);
+/* first_intersection(Ray_3) / first_intersected_primitive, AABB_tree/internal/AABB_ray_intersection.h:201-240.
+ * rays: n x 6 (source, second point).  Outputs (any may be NULL): prim[n]; t[n] = ray parameter of the hit as the
+ * reference computes it (:168-198); point[n x 3] = the Point_3, or the first endpoint of the Segment_3;
+ * point2[n x 3] = second endpoint when FLAG_SEGMENT; flags[n]. */
+int b200aabb_first_intersection(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space,
+                                uint32_t* prim, double* tparam, double* point, double* point2, uint8_t* flags);
+/* closest_point_and_primitive / closest_point / squared_distance (Point_3), AABB_tree.h:987-1055.
+ * points: n x 3.  Outputs (any may be NULL): closest[n x 3], prim[n], sqdist[n], flags[n]. */
+int b200aabb_closest_point(b200aabb_tree* t, const double* points, uint64_t n, b200aabb_memspace space,
+                           double* closest, uint32_t* prim, double* sqdist, uint8_t* flags);
+
+/* ---- multi-GPU: a built tree is a set of flat device buffers that can be broadcast (NCCL) and adopted ----------
+ * b200aabb_export_layout: fills ptrs/bytes (device pointers, sizes) for up to `cap` buffers, *count = how many.
+ * b200aabb_import_alloc: on a receiving rank, allocates the buffers of a built tree of `n` primitives so that
+ * export_layout returns same-sized buffers to receive into; b200aabb_import_finish marks the tree built. */
+int b200aabb_export_layout(b200aabb_tree* t, void** ptrs, uint64_t* bytes, int cap, int* count);
+int b200aabb_import_alloc(b200aabb_tree* t, uint64_t n);
+int b200aabb_import_finish(b200aabb_tree* t);
+
+/* library / build identification, e.g. "b200aabb 0.1 sm_100a" */
+const char* b200aabb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200AABB_H */

@@ -1,0 +1,133 @@
+"""ctypes binding of tests/hostcheck/libhostcheck.so: the device headers compiled for the host (test infrastructure)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_LIB = None
+_dp = C.POINTER(C.c_double)
+_u32p = C.POINTER(C.c_uint32)
+_u8p = C.POINTER(C.c_uint8)
+
+
+def build():
+    d = os.path.join(ROOT, "tests", "hostcheck")
+    src, out = os.path.join(d, "hostcheck.cu"), os.path.join(d, "libhostcheck.so")
+    deps = [src] + [os.path.join(ROOT, "cgal_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "cgal_b200", "csrc")) if f.endswith(".cuh")]
+    if os.path.exists(out) and all(os.path.getmtime(out) >= os.path.getmtime(p) for p in deps):
+        return out
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-shared",
+                           "-Xcompiler", "-fPIC,-ffp-contract=off", "-o", out, src])
+    return out
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        L = C.CDLL(build())
+        L.hc_build.restype = C.c_void_p
+        L.hc_build.argtypes = [_dp, _u32p, C.c_uint64]
+        L.hc_destroy.argtypes = [C.c_void_p]
+        L.hc_num_nodes.restype = C.c_uint64
+        L.hc_num_nodes.argtypes = [C.c_void_p]
+        L.hc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _dp]
+        L.hc_validate.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.hc_intersect.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_int, C.c_int, _u32p]
+        L.hc_first_intersection.argtypes = [C.c_void_p, _dp, C.c_uint64, _u32p, _dp, _dp, _u8p, _u8p]
+        L.hc_closest_point.argtypes = [C.c_void_p, _dp, C.c_uint64, _dp, _u32p, _dp, _u8p]
+        for n in ("hc_orient3", "hc_orient3_exact", "hc_orient3_dir", "hc_coplanar_orient", "hc_cmp_dist", "hc_cmp_dist_exact"):
+            getattr(L, n).argtypes = [_dp]
+        L.hc_tri_do_intersect.argtypes = [_dp, _dp, C.c_int]
+        L.hc_tri_ray_intersection.argtypes = [_dp, _dp, _dp, _dp]
+        L.hc_closest_on_triangle.argtypes = [_dp, _dp, _dp]
+        L.hc_line_box.argtypes = [_dp, _dp, C.c_int]
+        L.hc_sizeof_node.restype = C.c_uint64
+        L.hc_sizeof_tri.restype = C.c_uint64
+        _LIB = L
+    return _LIB
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a, ty=_dp):
+    return None if a is None else a.ctypes.data_as(ty)
+
+
+class HostTree:
+    def __init__(self, soup, ids=None):
+        self.soup = _d(soup).reshape(-1, 9)
+        self.ids = None if ids is None else np.ascontiguousarray(ids, dtype=np.uint32)
+        self.n = len(self.soup)
+        self.h = lib().hc_build(_p(self.soup), _p(self.ids, _u32p), self.n)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().hc_destroy(self.h)
+            self.h = None
+
+    def export(self):
+        nn = lib().hc_num_nodes(self.h)
+        nodes = np.zeros(nn * 128, np.uint8)
+        tris = np.zeros(self.n * 96, np.uint8)
+        bbox = np.zeros(6)
+        lib().hc_export(self.h, nodes.ctypes.data_as(C.c_void_p), tris.ctypes.data_as(C.c_void_p), _p(bbox))
+        return nodes, tris, bbox
+
+    def intersect(self, q, is_ray, count):
+        q = _d(q).reshape(-1, 6)
+        out = np.zeros(len(q), np.uint32)
+        lib().hc_intersect(self.h, _p(q), len(q), int(is_ray), int(count), _p(out, _u32p))
+        return out
+
+    def first_intersection(self, rays):
+        rays = _d(rays).reshape(-1, 6)
+        n = len(rays)
+        prim, t, pts = np.zeros(n, np.uint32), np.zeros(n), np.zeros((n, 6))
+        kind, tie = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        lib().hc_first_intersection(self.h, _p(rays), n, _p(prim, _u32p), _p(t), _p(pts), _p(kind, _u8p), _p(tie, _u8p))
+        return dict(prim=prim, t=t, pts=pts, kind=kind, tie=tie)
+
+    def closest_point(self, q):
+        q = _d(q).reshape(-1, 3)
+        n = len(q)
+        cp, prim, sqd, tie = np.zeros((n, 3)), np.zeros(n, np.uint32), np.zeros(n), np.zeros(n, np.uint8)
+        lib().hc_closest_point(self.h, _p(q), n, _p(cp), _p(prim, _u32p), _p(sqd), _p(tie, _u8p))
+        return dict(cp=cp, prim=prim, sqd=sqd, tie=tie)
+
+
+def validate(nodes_u8, tris_u8, n):
+    return lib().hc_validate(nodes_u8.ctypes.data_as(C.c_void_p), tris_u8.ctypes.data_as(C.c_void_p), n)
+
+
+def call(name, *arrs):
+    arrs = [_d(a).ravel() for a in arrs]
+    return getattr(lib(), name)(*[_p(a) for a in arrs])
+
+
+def tri_do_intersect(tri, pq, is_ray):
+    tri, pq = _d(tri).ravel(), _d(pq).ravel()
+    return lib().hc_tri_do_intersect(_p(tri), _p(pq), int(is_ray))
+
+
+def tri_ray_intersection(tri, ray):
+    tri, ray = _d(tri).ravel(), _d(ray).ravel()
+    pts = np.zeros(6)
+    t = C.c_double(0)
+    k = lib().hc_tri_ray_intersection(_p(tri), _p(ray), _p(pts), C.byref(t))
+    return k, pts.reshape(2, 3), t.value
+
+
+def closest_on_triangle(tri, q):
+    tri, q = _d(tri).ravel(), _d(q).ravel()
+    out = np.zeros(3)
+    lib().hc_closest_on_triangle(_p(tri), _p(q), _p(out))
+    return out
+
+
+def line_box(box, pq, is_ray):
+    box, pq = _d(box).ravel(), _d(pq).ravel()
+    return lib().hc_line_box(_p(box), _p(pq), int(is_ray))

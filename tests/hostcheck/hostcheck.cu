@@ -1,0 +1,172 @@
+// hostcheck — TEST INFRASTRUCTURE.  Compiles the device headers of cgal_b200/csrc for the HOST so that the
+// per-thread logic of the CUDA kernels (predicates, constructions, Karras topology, Morton keys, traversal) can be
+// checked against the oracle without a GPU (pytest -m "not gpu").  It is not part of libb200aabb.so and is never
+// used as a fallback: the product library has no host execution path.
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "../../cgal_b200/csrc/build.cuh"
+
+using namespace b2;
+
+namespace {
+struct HostTree { std::vector<BvhNode> nodes; std::vector<TriRec> tris; uint32_t root = kNone; uint64_t n = 0; double bbox[6]; std::vector<uint64_t> keys; };
+Vec3 V(const double* p) { return {p[0], p[1], p[2]}; }
+Tri3 T(const double* p) { return {V(p), V(p + 3), V(p + 6)}; }
+
+void refit(HostTree& h, uint32_t ref, double* lo, double* hi) {
+    if (ref & kLeafBit) {
+        const double* v = h.tris[ref & ~kLeafBit].v;
+        for (int a = 0; a < 3; ++a) { lo[a] = std::min(v[a], std::min(v[3 + a], v[6 + a])); hi[a] = std::max(v[a], std::max(v[3 + a], v[6 + a])); }
+        return;
+    }
+    BvhNode& nd = h.nodes[ref];
+    refit(h, nd.child[0], nd.lo0, nd.hi0);
+    refit(h, nd.child[1], nd.lo1, nd.hi1);
+    for (int a = 0; a < 3; ++a) { lo[a] = std::min(nd.lo0[a], nd.lo1[a]); hi[a] = std::max(nd.hi0[a], nd.hi1[a]); }
+}
+}  // namespace
+
+extern "C" {
+
+// emulates b200aabb_build step by step with the same per-element device functions
+void* hc_build(const double* tris, const uint32_t* ids, uint64_t n) {
+    HostTree* h = new HostTree();
+    h->n = n;
+    for (int a = 0; a < 3; ++a) { h->bbox[a] = INFINITY; h->bbox[3 + a] = -INFINITY; }
+    if (n == 0) return h;
+    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    for (uint64_t i = 0; i < n; ++i) for (int k = 0; k < 9; ++k) { lo[k % 3] = std::min(lo[k % 3], tris[9 * i + k]); hi[k % 3] = std::max(hi[k % 3], tris[9 * i + k]); }
+    double scale[3];
+    for (int k = 0; k < 3; ++k) { const double ext = hi[k] - lo[k]; scale[k] = ext > 0.0 ? 2097152.0 / ext : 0.0; }
+    std::vector<uint64_t> keys(n);
+    for (uint64_t i = 0; i < n; ++i) {
+        double c[3];
+        for (int k = 0; k < 3; ++k) { const double a = tris[9 * i + k], b = tris[9 * i + 3 + k], d = tris[9 * i + 6 + k]; c[k] = 0.5 * (fmin(a, fmin(b, d)) + fmax(a, fmax(b, d))); }
+        keys[i] = morton63(c[0], c[1], c[2], lo, scale);
+    }
+    std::vector<uint32_t> perm(n);
+    std::iota(perm.begin(), perm.end(), 0u);
+    std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    h->keys.resize(n);
+    h->tris.resize(n);
+    for (uint64_t k = 0; k < n; ++k) {
+        h->keys[k] = keys[perm[k]];
+        TriRec r; memset(&r, 0, sizeof(r));
+        memcpy(r.v, tris + 9 * (uint64_t)perm[k], 72);
+        r.id = ids ? ids[perm[k]] : perm[k];
+        h->tris[k] = r;
+    }
+    if (n == 1) { h->root = kLeafBit; refit(*h, h->root, h->bbox, h->bbox + 3); return h; }
+    h->nodes.resize(n - 1);
+    memset(h->nodes.data(), 0, (n - 1) * sizeof(BvhNode));
+    h->nodes[0].parent = kNone;
+    for (uint64_t i = 0; i + 1 < n; ++i) {
+        uint32_t l, r, f, e;
+        karras_node(h->keys.data(), (int64_t)n, (int64_t)i, l, r, f, e);
+        h->nodes[i].child[0] = l; h->nodes[i].child[1] = r; h->nodes[i].first = f; h->nodes[i].last = e;
+        if (!(l & kLeafBit)) h->nodes[l].parent = (uint32_t)i;
+        if (!(r & kLeafBit)) h->nodes[r].parent = (uint32_t)i;
+    }
+    h->root = 0;
+    refit(*h, 0, h->bbox, h->bbox + 3);
+    return h;
+}
+void hc_destroy(void* hv) { delete (HostTree*)hv; }
+uint64_t hc_num_nodes(void* hv) { return ((HostTree*)hv)->nodes.size(); }
+void hc_export(void* hv, void* nodes, void* tris, double* bbox) {
+    HostTree* h = (HostTree*)hv;
+    if (nodes) memcpy(nodes, h->nodes.data(), h->nodes.size() * sizeof(BvhNode));
+    if (tris) memcpy(tris, h->tris.data(), h->tris.size() * sizeof(TriRec));
+    if (bbox) memcpy(bbox, h->bbox, 48);
+}
+// structural validation of a node/leaf array (used on the GPU-built tree too): every leaf reachable exactly once,
+// every child box bit-equal to the exact union of the boxes below it.  returns 0 if valid.
+int hc_validate(const void* nodes_v, const void* tris_v, uint64_t n) {
+    if (n < 2) return 0;
+    const BvhNode* nodes = (const BvhNode*)nodes_v; const TriRec* tris = (const TriRec*)tris_v;
+    std::vector<uint8_t> seen(n, 0), nseen(n - 1, 0);
+    struct Item { uint32_t ref; };
+    // iterative post-order computing boxes
+    std::vector<double> blo(3 * (n - 1)), bhi(3 * (n - 1));
+    std::vector<uint32_t> order; order.reserve(n - 1);
+    std::vector<uint32_t> st{0};
+    while (!st.empty()) {
+        uint32_t x = st.back(); st.pop_back();
+        if (x >= n - 1 || nseen[x]) return 1;
+        nseen[x] = 1; order.push_back(x);
+        for (int c = 0; c < 2; ++c) { uint32_t r = nodes[x].child[c]; if (r & kLeafBit) { uint32_t s = r & ~kLeafBit; if (s >= n || seen[s]) return 2; seen[s] = 1; } else { if (nodes[r].parent != x) return 3; st.push_back(r); } }
+    }
+    for (uint64_t i = 0; i < n; ++i) if (!seen[i]) return 4;
+    for (size_t k = order.size(); k-- > 0;) {
+        const uint32_t x = order[k];
+        for (int c = 0; c < 2; ++c) {
+            double lo[3], hi[3];
+            const uint32_t r = nodes[x].child[c];
+            if (r & kLeafBit) { const double* v = tris[r & ~kLeafBit].v; for (int a = 0; a < 3; ++a) { lo[a] = std::min(v[a], std::min(v[3 + a], v[6 + a])); hi[a] = std::max(v[a], std::max(v[3 + a], v[6 + a])); } }
+            else for (int a = 0; a < 3; ++a) { lo[a] = blo[3 * r + a]; hi[a] = bhi[3 * r + a]; }
+            const double* nlo = c ? nodes[x].lo1 : nodes[x].lo0; const double* nhi = c ? nodes[x].hi1 : nodes[x].hi0;
+            for (int a = 0; a < 3; ++a) if (nlo[a] != lo[a] || nhi[a] != hi[a]) return 5;
+            for (int a = 0; a < 3; ++a) { if (c == 0) { blo[3 * x + a] = lo[a]; bhi[3 * x + a] = hi[a]; } else { blo[3 * x + a] = std::min(blo[3 * x + a], lo[a]); bhi[3 * x + a] = std::max(bhi[3 * x + a], hi[a]); } }
+        }
+        if (nodes[x].first > nodes[x].last) return 6;
+    }
+    return 0;
+}
+
+void hc_intersect(void* hv, const double* q, uint64_t n, int is_ray, int count, uint32_t* out) {
+    HostTree* h = (HostTree*)hv;
+    for (uint64_t i = 0; i < n; ++i) {
+        int nex = 0, ovf = 0;
+        if (h->n == 0) { out[i] = 0; continue; }
+        const Vec3 s = V(q + 6 * i), e = V(q + 6 * i + 3);
+        if (is_ray) out[i] = count ? traverse_intersect<true, true>(h->nodes.data(), h->tris.data(), h->root, s, e, nex, ovf) : traverse_intersect<true, false>(h->nodes.data(), h->tris.data(), h->root, s, e, nex, ovf);
+        else out[i] = count ? traverse_intersect<false, true>(h->nodes.data(), h->tris.data(), h->root, s, e, nex, ovf) : traverse_intersect<false, false>(h->nodes.data(), h->tris.data(), h->root, s, e, nex, ovf);
+    }
+}
+void hc_first_intersection(void* hv, const double* rays, uint64_t n, uint32_t* prim, double* t, double* pts, uint8_t* kind, uint8_t* tie) {
+    HostTree* h = (HostTree*)hv;
+    for (uint64_t i = 0; i < n; ++i) {
+        int nex = 0, ovf = 0;
+        if (h->n == 0) { prim[i] = kNone; t[i] = 0; kind[i] = 0; tie[i] = 0; memset(pts + 6 * i, 0, 48); continue; }
+        const FirstHit f = traverse_first(h->nodes.data(), h->tris.data(), h->root, V(rays + 6 * i), V(rays + 6 * i + 3), nex, ovf);
+        prim[i] = f.prim; t[i] = f.prim == kNone ? 0.0 : f.t; kind[i] = (uint8_t)f.kind; tie[i] = (uint8_t)f.tie;
+        memset(pts + 6 * i, 0, 48);
+        if (f.prim != kNone) { pts[6 * i] = f.p0.x; pts[6 * i + 1] = f.p0.y; pts[6 * i + 2] = f.p0.z; if (f.kind == 2) { pts[6 * i + 3] = f.p1.x; pts[6 * i + 4] = f.p1.y; pts[6 * i + 5] = f.p1.z; } }
+    }
+}
+void hc_closest_point(void* hv, const double* q, uint64_t n, double* cp, uint32_t* prim, double* sqd, uint8_t* tie) {
+    HostTree* h = (HostTree*)hv;
+    for (uint64_t i = 0; i < n; ++i) {
+        int nex = 0, ovf = 0;
+        const Closest c = traverse_closest(h->nodes.data(), h->tris.data(), h->root, V(q + 3 * i), nex, ovf);
+        cp[3 * i] = c.p.x; cp[3 * i + 1] = c.p.y; cp[3 * i + 2] = c.p.z; prim[i] = c.prim; sqd[i] = c.sqd; tie[i] = (uint8_t)c.tie;
+    }
+}
+
+// predicate / construction level
+int hc_orient3(const double* p) { int n = 0; return orient3(V(p), V(p + 3), V(p + 6), V(p + 9), n); }
+int hc_orient3_exact(const double* p) {
+    return exact_det3_sign(dd_diff(p[3], p[0]), dd_diff(p[4], p[1]), dd_diff(p[5], p[2]), dd_diff(p[6], p[0]), dd_diff(p[7], p[1]), dd_diff(p[8], p[2]),
+                           dd_diff(p[9], p[0]), dd_diff(p[10], p[1]), dd_diff(p[11], p[2]));
+}
+int hc_orient3_dir(const double* p) { int n = 0; return orient3_dir(V(p), V(p + 3), V(p + 6), V(p + 9), V(p + 12), n); }
+int hc_coplanar_orient(const double* p) { int n = 0; return coplanar_orient(V(p), V(p + 3), V(p + 6), n); }
+int hc_cmp_dist(const double* p) { int n = 0; return cmp_dist(V(p), V(p + 3), V(p + 6), n); }
+int hc_cmp_dist_exact(const double* p) { return exact_cmp_dist_sign(p, p + 3, p + 6); }
+int hc_tri_do_intersect(const double* tri, const double* pq, int is_ray) { int n = 0; return is_ray ? ray_tri_do_intersect(T(tri), V(pq), V(pq + 3), n) : seg_tri_do_intersect(T(tri), V(pq), V(pq + 3), n); }
+int hc_tri_ray_intersection(const double* tri, const double* ray, double* pts, double* t) {
+    int n = 0; const Vec3 s = V(ray), q = V(ray + 3), d = q - s;
+    const RayX x = ray_tri_intersection(T(tri), s, q, d, ray_major_axis(d), n);
+    if (x.kind) { pts[0] = x.p0.x; pts[1] = x.p0.y; pts[2] = x.p0.z; pts[3] = x.p1.x; pts[4] = x.p1.y; pts[5] = x.p1.z; *t = x.t; }
+    return x.kind;
+}
+void hc_closest_on_triangle(const double* tri, const double* q, double* out) { const Vec3 c = closest_on_triangle(T(tri), V(q)); out[0] = c.x; out[1] = c.y; out[2] = c.z; }
+int hc_line_box(const double* box, const double* pq, int is_ray) { const LineCtx c = make_line(V(pq), V(pq + 3)); double tn; return line_box(box, box + 3, c, is_ray ? DBL_MAX : 1.0, tn) ? 1 : 0; }
+uint64_t hc_sizeof_node() { return sizeof(BvhNode); }
+uint64_t hc_sizeof_tri() { return sizeof(TriRec); }
+
+}  // extern "C"

@@ -1,0 +1,181 @@
+"""Checks the per-thread logic of the CUDA kernels (device headers compiled for the host, tests/hostcheck) against the
+oracle on CPU: predicates on random and degenerate inputs, bit-exact constructions, LBVH topology, and whole queries."""
+import numpy as np
+import pytest
+
+import hc
+import orc
+
+SEG, RAY = 0, 1
+
+
+def soup_of(v, f):
+    return v[f.astype(np.int64)].reshape(-1, 9)
+
+
+def lattice(rng, shape, lo=-2, hi=3):
+    return rng.integers(lo, hi, size=shape).astype(float)
+
+
+def test_struct_sizes():
+    assert hc.lib().hc_sizeof_node() == 128 and hc.lib().hc_sizeof_tri() == 96
+
+
+def test_predicates_match_oracle():
+    rng = np.random.default_rng(11)
+    for it in range(4000):
+        mode = it % 4
+        pts = rng.uniform(-10, 10, (5, 3)) if mode == 0 else lattice(rng, (5, 3))
+        if mode == 2:
+            w = rng.uniform(-1, 2, 3); w /= w.sum()
+            pts = rng.uniform(-10, 10, (5, 3)); pts[3] = w @ pts[:3]
+        if mode == 3:
+            pts = lattice(rng, (5, 3)) + 4096.0
+            pts[3] = np.nextafter(pts[3], pts[3] + rng.choice([-1, 1], 3))
+        p4 = pts[:4].ravel()
+        assert hc.call("hc_orient3", p4) == orc.orientation(*pts[:4])
+        assert hc.call("hc_orient3_exact", p4) == orc.orientation(*pts[:4], exact=True)
+        assert hc.call("hc_orient3_dir", pts.ravel()) == orc.orientation_dir(*pts)
+        assert hc.call("hc_coplanar_orient", pts[:3].ravel()) == orc.coplanar_orientation(*pts[:3])
+        p, q = pts[0], pts[1]
+        r = [pts[2], 2 * p - q, np.nextafter(q, q + 1)][it % 3]
+        tri = np.concatenate([p, q, r])
+        assert hc.call("hc_cmp_dist", tri) == orc.compare_distance(p, q, r)
+        assert hc.call("hc_cmp_dist_exact", tri) == orc.compare_distance(p, q, r, exact=True)
+
+
+def test_triangle_tests_and_constructions_match_oracle_bitwise():
+    rng = np.random.default_rng(12)
+    n_hit = n_seg = 0
+    for it in range(10000):
+        if it % 4 == 3:   # everything in one axis-parallel or oblique lattice plane: the coplanar case analyses
+            tri, pq = lattice(rng, 9, -3, 4), lattice(rng, 6, -3, 4)
+            ax = it % 3
+            tri[ax::3] = 1.0; pq[ax::3] = 1.0
+            if it % 8 == 7:   # oblique plane x + y + z = 3
+                tri[2::3] = 3 - tri[0::3] - tri[1::3]; pq[2::3] = 3 - pq[0::3] - pq[1::3]
+        elif it % 3 == 0:
+            tri, pq = rng.uniform(-1, 1, 9), rng.uniform(-1, 1, 6)
+        elif it % 3 == 1:
+            tri, pq = lattice(rng, 9), lattice(rng, 6)
+        else:   # ray aimed at a point of the triangle: exercises the hit construction
+            tri = rng.uniform(-1, 1, 9)
+            w = rng.dirichlet([1, 1, 1])
+            target = w @ tri.reshape(3, 3)
+            s = rng.uniform(-3, 3, 3)
+            pq = np.concatenate([s, s + (target - s) * rng.uniform(0.2, 3)])
+        a, b, c = tri[:3], tri[3:6], tri[6:]
+        if not np.any(np.cross(b - a, c - a)) or np.all(pq[:3] == pq[3:]):
+            continue
+        for is_ray in (0, 1):
+            assert hc.tri_do_intersect(tri, pq, is_ray) == orc.tri_do_intersect(tri, pq, is_ray), (tri, pq, is_ray)
+        k, pts, t = hc.tri_ray_intersection(tri, pq)
+        ko, ptso = orc.tri_ray_intersection(tri, pq)
+        assert k == ko, (tri, pq)
+        if k:
+            n_hit += 1
+            n_seg += k == 2
+            np.testing.assert_array_equal(pts[:k], ptso[:k])     # bit-exact
+        q = rng.uniform(-2, 2, 3) if it % 3 != 1 else lattice(rng, 3)
+        np.testing.assert_array_equal(hc.closest_on_triangle(tri, q), orc.project_on_triangle(tri, q))
+    assert n_hit > 1500 and n_seg > 300, (n_hit, n_seg)
+    # degenerate triangle (documented UB for the tree, still restated): longest-edge segment projection
+    for tri in ([0, 0, 0, 1.0, 1, 1, 2, 2, 2], [0, 0, 0, 0, 0, 0, 1.0, 0, 0], [1.0, 2, 3, 1, 2, 3, 1, 2, 3]):
+        for q in ([0.3, 0.1, 5.0], [-4, 0, 0], [9.0, 9, 9]):
+            np.testing.assert_array_equal(hc.closest_on_triangle(tri, q), orc.project_on_triangle(tri, q))
+
+
+def test_node_test_is_conservative():
+    rng = np.random.default_rng(13)
+    n_true = 0
+    for it in range(6000):
+        if it % 2:
+            lo = lattice(rng, 3, -2, 1); hi = lo + rng.integers(0, 3, 3)
+            pq = lattice(rng, 6, -3, 4)
+        else:
+            lo = rng.uniform(-1, 0, 3); hi = lo + rng.uniform(0.01, 1, 3)
+            corner = np.where(rng.integers(0, 2, 3) == 1, hi, lo)
+            p = rng.uniform(-3, 3, 3)
+            pq = np.concatenate([p, p + (corner - p) * rng.choice([0.5, 1.0, 2.0])])
+        if np.all(pq[:3] == pq[3:]):
+            continue
+        box = np.concatenate([lo, hi])
+        for is_ray in (0, 1):
+            exact = orc.bbox_do_intersect(box, pq, is_ray)
+            n_true += exact
+            if exact:
+                assert hc.line_box(box, pq, is_ray) == 1, (box, pq, is_ray)
+    assert n_true > 1000
+
+
+@pytest.mark.parametrize("name", ["tetrahedron", "cube", "coverrear", "elephant"])
+def test_lbvh_topology_and_boxes(meshes, name):
+    v, f = meshes[name]
+    t = hc.HostTree(soup_of(v, f))
+    nodes, tris, bbox = t.export()
+    assert hc.validate(nodes, tris, t.n) == 0
+    np.testing.assert_array_equal(bbox, np.concatenate([v.min(0), v.max(0)]))
+    ids = tris.view(np.uint32).reshape(-1, 24)[:, 18]
+    assert sorted(ids.tolist()) == list(range(t.n))
+
+
+@pytest.mark.parametrize("name", ["cube", "coverrear", "elephant"])
+def test_queries_match_oracle(meshes, name):
+    v, f = meshes[name]
+    soup = soup_of(v, f)
+    dev, ref = hc.HostTree(soup), orc.OracleTree(v, f)
+    rng = np.random.default_rng(23)
+    bb = ref.bbox()
+    n = 1500
+    q = rng.uniform(bb[:3], bb[3:], size=(n, 2, 3)).reshape(n, 6)
+    for kind in (SEG, RAY):
+        want = ref.count(q, kind)
+        np.testing.assert_array_equal(dev.intersect(q, kind, True), want)
+        np.testing.assert_array_equal(dev.intersect(q, kind, False), (want > 0).astype(np.uint32))
+    # first_intersection: rays between points of the bounding sphere (aabb_test_ray_intersection.cpp:87-125)
+    c, r = 0.5 * (bb[:3] + bb[3:]), 0.5 * (bb[3:] - bb[:3]).max()
+    u = rng.normal(size=(n, 2, 3)); u /= np.linalg.norm(u, axis=2, keepdims=True)
+    rays = (c + r * u).reshape(-1, 6)
+    a, b = dev.first_intersection(rays), ref.first_intersection(rays)
+    assert (b["prim"] != 0xFFFFFFFF).sum() > n // 10
+    ok = a["prim"] == b["prim"]
+    assert np.all(ok | (a["tie"] == 1))
+    np.testing.assert_array_equal(a["t"], b["t"])
+    np.testing.assert_array_equal(a["kind"], b["kind"])
+    np.testing.assert_array_equal(a["pts"][ok], b["pts"][ok])
+    # closest point: same point and id unless an exact-distance tie
+    ext = bb[3:] - bb[:3]
+    pts = rng.uniform(bb[:3] - 0.5 * ext, bb[3:] + 0.5 * ext, size=(n, 3))
+    a, b = dev.closest_point(pts), ref.closest_point(pts)
+    same = a["prim"] == b["prim"]
+    assert np.all(same | (a["tie"] == 1))
+    np.testing.assert_array_equal(a["cp"][same], b["cp"][same])
+    np.testing.assert_array_equal(a["sqd"][same], b["sqd"][same])
+    for i in np.nonzero(~same)[0]:
+        assert orc.compare_distance(pts[i], a["cp"][i], b["cp"][i]) == 0
+        np.testing.assert_array_equal(ref.candidate_closest(a["prim"][i], pts[i]), a["cp"][i])
+    assert same.mean() > 0.2   # far outside points mostly project on vertices / edges: exact ties
+
+
+def test_vertex_and_edge_ties_are_flagged(meshes):
+    v, f = meshes["cube"]
+    dev = hc.HostTree(soup_of(v, f))
+    bb = np.concatenate([v.min(0), v.max(0)])
+    far_corner = bb[3:] + 1.0                        # closest point is a cube vertex shared by several triangles
+    r = dev.closest_point(far_corner[None, :])
+    assert r["tie"][0] == 1 and tuple(r["cp"][0]) == tuple(bb[3:])
+    ray = np.concatenate([bb[3:] + 1.0, bb[3:]])[None, :]   # ray through the same vertex: equal t on several triangles
+    h = dev.first_intersection(ray)
+    assert h["prim"][0] != 0xFFFFFFFF and h["tie"][0] == 1
+
+
+def test_empty_and_singleton():
+    e = hc.HostTree(np.zeros((0, 9)))
+    q = np.array([[0.1, 0.1, -1.0, 0.1, 0.1, 1.0]])
+    assert e.intersect(q, SEG, True)[0] == 0 and e.first_intersection(q)["prim"][0] == 0xFFFFFFFF
+    s = hc.HostTree(np.array([[0, 0, 0, 1.0, 0, 0, 0, 1.0, 0]]), ids=[7])
+    assert s.intersect(q, SEG, True)[0] == 1 and s.intersect(q, RAY, False)[0] == 1
+    fi = s.first_intersection(q)
+    assert fi["prim"][0] == 7 and tuple(fi["pts"][0][:3]) == (0.1, 0.1, 0.0) and fi["t"][0] == 0.5
+    cp = s.closest_point(np.array([[0.25, 0.25, 5.0]]))
+    assert tuple(cp["cp"][0]) == (0.25, 0.25, 0.0) and cp["prim"][0] == 7 and cp["sqd"][0] == 25.0

@@ -1,0 +1,229 @@
+"""-m gpu: parity of the CUDA path (through the C ABI) with the CPU oracle.  Bit-exact for booleans, counts, ids
+(except reported exact ties), ray parameters, hit points, closest points and squared distances."""
+import numpy as np
+import pytest
+
+import hc
+import orc
+from gpu_util import check_closest_point, check_first_intersection, device_to_host
+
+pytestmark = pytest.mark.gpu
+SEG, RAY = 0, 1
+
+
+@pytest.fixture(scope="module")
+def B():
+    import cgal_b200
+    return cgal_b200
+
+
+def soup_of(v, f):
+    return np.ascontiguousarray(v[f.astype(np.int64)].reshape(-1, 9))
+
+
+def test_kats_through_c_abi(B, meshes):
+    # aabb_correctness_triangle_test.cpp:51-108
+    v, f = meshes["tetrahedron"]
+    t = B.AABB_tree(v, f)
+    pq = np.array([[-0.25, 0.251, 0.255, 0.25, 0.253, 0.256]])
+    assert t.do_intersect(pq, SEG)[0] == 1 and t.number_of_intersected_primitives(pq, SEG)[0] == 1
+    assert tuple(t.closest_point(np.array([[0.0, 0.0, 3.0]]))[0]) == (0.0, 0.0, 1.0)
+    # aabb_test_triangle_3.cpp:27-46
+    a, b, c, d = (1.0, 0, 0), (0, 1.0, 0), (0, 0, 1.0), (0, 0, 0)
+    t = B.AABB_tree(triangles=np.array([a + b + c, a + b + d, a + d + c], dtype=np.float64))
+    assert t.number_of_intersected_primitives(np.array([a + b], dtype=np.float64), RAY)[0] == 3
+    r = t.closest_point_and_primitive(np.array([[3.0, 2.0, 2.0]]))
+    assert tuple(r["point"][0]) == a and r["sqdist"][0] == 12.0
+
+
+def test_empty_singleton_and_state_machine(B):
+    # aabb_test_empty_tree.cpp:38-53, aabb_test_singleton_tree.cpp:44-67
+    q = np.array([[0.1, 0.1, -1.0, 0.1, 0.1, 1.0]])
+    e = B.AABB_tree()
+    assert e.size() == 0 and e.empty()
+    assert e.do_intersect(q, SEG)[0] == 0 and e.number_of_intersected_primitives(q, RAY)[0] == 0
+    assert e.first_intersection(q)["prim"][0] == B.NO_PRIMITIVE
+    assert np.all(np.isinf(e.bbox()))
+    with pytest.raises(B.B200AABBError) as ei:
+        e.closest_point(np.zeros((1, 3)))
+    assert ei.value.code == -4
+    s = B.AABB_tree(triangles=np.array([[0, 0, 0, 1.0, 0, 0, 0, 1.0, 0]]), ids=[7])
+    assert s.size() == 1
+    assert s.do_intersect(q, SEG)[0] == 1 and s.number_of_intersected_primitives(q, RAY)[0] == 1
+    fi = s.first_intersection(q)
+    assert fi["prim"][0] == 7 and tuple(fi["point"][0]) == (0.1, 0.1, 0.0) and fi["t"][0] == 0.5 and fi["flags"][0] & B.FLAG_HIT
+    cp = s.closest_point_and_primitive(np.array([[0.25, 0.25, 5.0]]))
+    assert tuple(cp["point"][0]) == (0.25, 0.25, 0.0) and cp["prim"][0] == 7 and cp["sqdist"][0] == 25.0
+    np.testing.assert_array_equal(s.bbox(), [0, 0, 0, 1, 1, 0])
+    s.clear()
+    assert s.empty() and s.do_intersect(q, SEG)[0] == 0
+    s.insert(triangles=np.array([[0, 0, 0, 1.0, 0, 0, 0, 1.0, 0], [0, 0, 1, 1.0, 0, 1, 0, 1.0, 1]]))   # insert after clear, lazy rebuild
+    assert s.size() == 2 and s.number_of_intersected_primitives(q, RAY)[0] == 1
+    assert s.number_of_intersected_primitives(np.array([[0.1, 0.1, -1.0, 0.1, 0.1, 2.0]]), SEG)[0] == 2
+
+
+@pytest.mark.parametrize("name", ["cube", "coverrear", "elephant", "finger"])
+def test_gpu_built_tree_equals_host_emulation(B, meshes, name):
+    """radix sort + Karras + refit on the GPU reproduce the step-by-step host emulation of the same algorithm bit for bit"""
+    v, f = meshes[name]
+    t = B.AABB_tree(v, f)
+    t.build()
+    (pn, bn), (pt, bt), (pb, bb) = t.export_layout()
+    n = len(f)
+    assert bn == (n - 1) * 128 and bt == n * 96 and bb == 48
+    g_nodes, g_tris = device_to_host(pn, bn), device_to_host(pt, bt)
+    assert hc.validate(g_nodes, g_tris, n) == 0
+    h_nodes, h_tris, h_bbox = hc.HostTree(soup_of(v, f)).export()
+    np.testing.assert_array_equal(g_tris, h_tris)
+    gw, hw = g_nodes.view(np.uint32).reshape(-1, 32), h_nodes.view(np.uint32).reshape(-1, 32)
+    cols = list(range(0, 27)) + [28, 29]       # boxes, children, parent, first, last (not the visit counter / padding)
+    np.testing.assert_array_equal(gw[:, cols], hw[:, cols])
+    np.testing.assert_array_equal(t.bbox(), h_bbox)
+    np.testing.assert_array_equal(device_to_host(pb, 48).view(np.float64), h_bbox)
+
+
+def test_large_random_soup_tree_is_valid(B):
+    from cgal_b200 import workloads as W
+    n = 1_000_003           # ragged last sort tile, many Morton prefixes
+    soup = W.triangle_soup(n)
+    t = B.AABB_tree(triangles=soup)
+    t.build()
+    (pn, bn), (pt, bt), _ = t.export_layout()
+    g_nodes, g_tris = device_to_host(pn, bn), device_to_host(pt, bt)
+    assert hc.validate(g_nodes, g_tris, n) == 0
+    ids = g_tris.view(np.uint32).reshape(-1, 24)[:, 18]
+    assert np.array_equal(np.sort(ids), np.arange(n, dtype=np.uint32))
+    np.testing.assert_array_equal(t.bbox(), np.concatenate([soup.reshape(-1, 3).min(0), soup.reshape(-1, 3).max(0)]))
+    # duplicates: 50k copies of 4 triangles -> equal Morton keys resolved by index
+    dup = np.tile(soup[:4], (50_000, 1))
+    t2 = B.AABB_tree(triangles=dup)
+    t2.build()
+    (pn, bn), (pt, bt), _ = t2.export_layout()
+    assert hc.validate(device_to_host(pn, bn), device_to_host(pt, bt), len(dup)) == 0
+
+
+def test_config1_elephant_parity(B, meshes):
+    """BASELINE.json configs[0]: elephant.off, random rays + closest-point queries, CPU oracle on all queries"""
+    from cgal_b200 import workloads as W
+    v, f = meshes["elephant"]
+    g, o = B.AABB_tree(v, f), orc.OracleTree(v, f)
+    bb = g.bbox()
+    np.testing.assert_array_equal(bb, o.bbox())
+    n = 200_000
+    rays = W.sphere_rays(bb, n)
+    gr, rr = g.first_intersection(rays), o.first_intersection(rays)
+    assert (rr["prim"] != B.NO_PRIMITIVE).mean() > 0.05
+    mism, ties = check_first_intersection(gr, rr, o, rays)
+    assert mism <= ties
+    pts = W.bbox_points(bb, n)
+    gc, rc = g.closest_point_and_primitive(pts), o.closest_point(pts)
+    check_closest_point(gc, rc, o, pts)
+    np.testing.assert_array_equal(g.squared_distance(pts[:1000]), gc["sqdist"][:1000])
+    segs = W.bbox_segments(bb, n)
+    for kind, q in ((SEG, segs), (RAY, rays), (RAY, segs)):
+        want = o.count(q, kind)
+        np.testing.assert_array_equal(g.number_of_intersected_primitives(q, kind), want)
+        np.testing.assert_array_equal(g.do_intersect(q, kind), (want > 0).astype(np.uint8))
+
+
+def test_config2_icosphere_distance_field_parity(B):
+    from cgal_b200 import workloads as W
+    v, f = W.icosphere(6)       # 81,920 triangles (config 2 uses level 8; same generator)
+    g, o = B.AABB_tree(v, f), orc.OracleTree(v, f)
+    pts = W.grid_points(64)     # 262,144 grid points over [-1.5,1.5]^3
+    gc, rc = g.closest_point_and_primitive(pts), o.closest_point(pts)
+    mism, ties = check_closest_point(gc, rc, o, pts)
+    r = np.sqrt(gc["sqdist"])
+    assert np.all(np.abs(np.linalg.norm(gc["point"], axis=1) - 1) < 1e-3)      # closest points lie on the unit icosphere
+    assert np.all(np.abs(r - np.abs(np.linalg.norm(pts, axis=1) - 1)) < 2e-3)  # unsigned distance field of a sphere
+
+
+def test_config3_terrain_rays_and_shadow_segments_parity(B):
+    from cgal_b200 import workloads as W
+    v, f = W.terrain(512, 256)  # 262,144 triangles (config 3 uses 4096 x 2048; same generator)
+    g, o = B.AABB_tree(v, f), orc.OracleTree(v, f)
+    rays = W.pinhole_rays(512, 512, 512, 256)
+    gr, rr = g.first_intersection(rays), o.first_intersection(rays)
+    assert (rr["prim"] != B.NO_PRIMITIVE).mean() > 0.2
+    check_first_intersection(gr, rr, o, rays)
+    segs = W.shadow_segments(v, 200_000, length=512.0)
+    want = o.do_intersect(segs, SEG)
+    assert 0.02 < want.mean() < 0.98
+    np.testing.assert_array_equal(g.do_intersect(segs, SEG), want)
+    np.testing.assert_array_equal(g.number_of_intersected_primitives(segs, SEG), o.count(segs, SEG))
+    # axis-parallel and grid-aligned queries: vertical rays through grid vertices / along grid lines (exact stage, ties)
+    xs, ys = np.meshgrid(np.arange(0, 513, 8, dtype=np.float64), np.arange(0, 257, 8, dtype=np.float64))
+    down = np.stack([xs.ravel(), ys.ravel(), np.full(xs.size, 100.0), xs.ravel(), ys.ravel(), np.full(xs.size, 99.0)], 1)
+    gd, rd = g.first_intersection(down), o.first_intersection(down)
+    mism, ties = check_first_intersection(gd, rd, o, down)
+    assert ties > 0 and g.stats()["exact_fallbacks"] > 0
+    np.testing.assert_array_equal(g.number_of_intersected_primitives(down, RAY), o.count(down, RAY))
+
+
+def test_config4_soup_counts_parity(B):
+    from cgal_b200 import workloads as W
+    soup = W.triangle_soup(200_000)
+    g, o = B.AABB_tree(triangles=soup), orc.OracleTree(soup=soup)
+    segs = W.short_segments(100_000)
+    want = o.count(segs, SEG)
+    assert want.max() >= 2
+    np.testing.assert_array_equal(g.number_of_intersected_primitives(segs, SEG), want)
+    np.testing.assert_array_equal(g.do_intersect(segs, SEG), (want > 0).astype(np.uint8))
+
+
+def test_device_pointers_and_host_pointers_agree(B, meshes):
+    import torch
+    from cgal_b200 import workloads as W
+    v, f = meshes["elephant"]
+    g = B.AABB_tree(v, f)
+    rays = W.sphere_rays(g.bbox(), 5_000_000 // 100)
+    h = g.first_intersection(rays)
+    d = g.first_intersection(torch.from_numpy(rays).cuda())
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(d["prim"].cpu().numpy().view(np.uint32), h["prim"])
+    np.testing.assert_array_equal(d["t"].cpu().numpy(), h["t"])
+    np.testing.assert_array_equal(d["flags"].cpu().numpy(), h["flags"])
+    # a HOST batch larger than one pipeline chunk (4 Mi queries) exercises the double-buffered copy pipeline
+    n = (1 << 22) + 12345
+    pts = W.bbox_points(g.bbox(), n)
+    a = g.closest_point_and_primitive(pts)
+    b = g.closest_point_and_primitive(torch.from_numpy(pts).cuda())
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(b["prim"].cpu().numpy().view(np.uint32), a["prim"])
+    np.testing.assert_array_equal(b["point"].cpu().numpy(), a["point"])
+
+
+def test_full_size_properties_16m_terrain(B):
+    """BASELINE.json configs[2] at full size: 16,777,216 triangles.  Size-independent properties instead of the oracle."""
+    import torch
+    from cgal_b200 import workloads as W
+    v, f = W.terrain(4096, 2048)
+    g = B.AABB_tree(v, f)
+    g.build()
+    assert g.size() == 16_777_216
+    np.testing.assert_array_equal(g.bbox(), np.concatenate([v.min(0), v.max(0)]))
+    rays = W.pinhole_rays(8192, 8192, rows=(4096, 4096 + 128))        # 1 Mi primary rays from the image centre rows
+    r = g.first_intersection(rays)
+    hit = r["prim"] != B.NO_PRIMITIVE
+    assert hit.mean() > 0.5
+    np.testing.assert_array_equal(g.do_intersect(rays, RAY), hit.astype(np.uint8))       # any-hit agrees with first-hit
+    assert np.all(r["t"][hit] > 0)
+    tri = v[f[r["prim"][hit]].astype(np.int64)]                                            # hit point lies on the reported triangle
+    nrm = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    off = np.abs(np.einsum("ij,ij->i", r["point"][hit] - tri[:, 0], nrm)) / np.linalg.norm(nrm, axis=1)
+    assert off.max() < 1e-9
+    # a segment cut just short of the hit misses, one extending past it hits (first hit is the FIRST hit)
+    s, d = rays[hit][:, :3], rays[hit][:, 3:] - rays[hit][:, :3]
+    t = r["t"][hit][:, None]
+    short = np.concatenate([s, s + d * t * (1 - 1e-6)], 1)
+    longer = np.concatenate([s, s + d * t * (1 + 1e-6)], 1)
+    assert g.do_intersect(short, SEG).sum() == 0
+    assert g.do_intersect(longer, SEG).all()
+    # closest point: idempotent and never farther than a brute-force scan over a vertex sample
+    pts = W.bbox_points(g.bbox(), 1 << 20)
+    c = g.closest_point_and_primitive(pts)
+    again = g.closest_point_and_primitive(c["point"])
+    assert again["sqdist"].max() < 1e-18 * (4096.0 ** 2)
+    sample = v[:: 4099]
+    dv = ((pts[:2000, None, :] - sample[None, :, :]) ** 2).sum(-1).min(1)
+    assert np.all(c["sqdist"][:2000] <= dv * (1 + 1e-12))
