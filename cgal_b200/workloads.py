@@ -184,8 +184,8 @@ def pinhole_rays(width, height, nx=4096, ny=2048, eye_height=600.0, vfov_deg=60.
     return out
 
 
-def shadow_segments(verts, n, seed=SEED_SEGMENTS, sun=(0.5, 0.3, 0.4), length=4096.0, offset=0):
-    """segments from terrain surface points (lifted by 1e-3 |z|+1e-3) towards a fixed sun direction; (n, 6)"""
+def shadow_segments(verts, n, seed=SEED_SEGMENTS, sun=(0.8, 0.5, 0.2), length=4096.0, offset=0):
+    """segments from terrain surface points (lifted by 1e-3 |z|+1e-3) towards a fixed, low sun (about a quarter of the terrain is in shadow); (n, 6)"""
     sun = np.asarray(sun, dtype=np.float64)
     sun = sun / np.linalg.norm(sun)
     idx = (splitmix64(seed, 2, np.arange(offset, offset + n, dtype=np.uint64)) % np.uint64(len(verts))).astype(np.int64)
