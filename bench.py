@@ -242,13 +242,11 @@ def main():
         bcast = {"bytes": nbytes, "ms": ms, "GB_s": nbytes / ms / 1e6}
     bbox = tree.bbox()
 
-    n_rays = RAYS_PER_RANK if not args.small else RAYS_PER_RANK // 8
-    rays_h = shard_rays(rank)[:n_rays] if not args.small else np.ascontiguousarray(shard_rays(rank)[::8])
-    rays_h[:, 3:] = rays_h[:, 3:] if not args.small else rays_h[:, 3:]
-    if args.small:   # same camera over the smaller terrain
-        rays_h = W.pinhole_rays(IMG // 4, IMG // 4, nx, ny, rows=(0, IMG // 4))[::2][:n_rays]
-        rays_h = np.ascontiguousarray(rays_h)
-        n_rays = len(rays_h)
+    if args.small:   # same camera over the smaller terrain; profiling only
+        rays_h = np.ascontiguousarray(W.pinhole_rays(IMG // 4, IMG // 4, nx, ny)[rank % 4::4])
+    else:
+        rays_h = shard_rays(rank)
+    n_rays = len(rays_h)
     pts_h = shard_points(bbox, rank, n_rays)
     n_pts = len(pts_h)
     rays_d, pts_d = torch.from_numpy(rays_h).cuda(), torch.from_numpy(pts_h).cuda()
@@ -298,7 +296,15 @@ def main():
     ray_ms = sum(m[0].elapsed_time(m[1]) for m in marks) / args.steps
     pt_ms = sum(m[1].elapsed_time(m[2]) for m in marks) / args.steps
     hit_rate = float((out_r["prim"] != -1).float().mean().item())
-    ties, exact = stats["ties"], stats["exact_fallbacks"]
+    # traversal-traffic model: nodes loaded / primitives tested per query, from the kernels' own counters
+    tree.first_intersection(rays_d, want=want_r, out=out_r)
+    sr = tree.stats()
+    tree.closest_point_and_primitive(pts_d, want=want_p, out=out_p)
+    sp = tree.stats()
+    ties, exact, near = sr["ties"] + sp["ties"], sr["exact_fallbacks"] + sp["exact_fallbacks"], sr["near_ties"] + sp["near_ties"]
+    traffic_model = {"ray_nodes_per_query": sr["nodes_visited"] / n_rays, "ray_leaves_per_query": sr["leaves_tested"] / n_rays,
+                     "point_nodes_per_query": sp["nodes_visited"] / n_pts, "point_leaves_per_query": sp["leaves_tested"] / n_pts,
+                     "ray_ms_incl_sort": sr["last_query_ms"], "point_ms_incl_sort": sp["last_query_ms"], "node_bytes": 128, "leaf_bytes": 96}
 
     # e2e: the same step through the C ABI with pinned HOST buffers (copies inside the timed region)
     e2e_ms = None
@@ -332,9 +338,9 @@ def main():
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         total_ms, e2e_max, ray_ms, pt_ms = [float(x) for x in tm.tolist()]
         e2e_ms = e2e_max if e2e_ms is not None else None
-        cnt = torch.tensor([launches, ties, exact], dtype=torch.int64, device="cuda")
+        cnt = torch.tensor([launches, ties, exact, near], dtype=torch.int64, device="cuda")
         dist.all_reduce(cnt)
-        launches, ties, exact = [int(x) for x in cnt.tolist()]
+        launches, ties, exact, near = [int(x) for x in cnt.tolist()]
 
     if rank == 0:
         q_per_step = world * (n_rays + n_pts)
@@ -354,7 +360,8 @@ def main():
                            "parallelism": "tree replicated by NCCL broadcast, queries sharded x%d" % world},
                 "detail": {"first_intersection_Mrays_s": world * n_rays / ray_ms / 1e3, "closest_point_Mqueries_s": world * n_pts / pt_ms / 1e3,
                            "build_ms": build_ms, "build_Mtri_s": n_prims / build_ms / 1e3, "build_GB_s_algorithmic(492B/tri)": 492.0 * n_prims / build_ms / 1e6,
-                           "ray_hit_rate_rank0": hit_rate, "ties": ties, "exact_stage_queries": exact, "tree_broadcast": bcast},
+                           "ray_hit_rate_rank0": hit_rate, "ties": ties, "near_ties": near, "exact_stage_queries": exact, "traversal_rank0": traffic_model,
+                           "tree_broadcast": bcast},
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
                              "note": "traversal is L2-latency / FP64-issue bound, not HBM bound (DESIGN.md §5); ncu counters in profiles/"},
@@ -377,10 +384,11 @@ def main():
             # the sample doubles as a parity check of the benchmarked batch against the oracle
             g_prim = out_r["prim"].cpu().numpy().view(np.uint32)[::stride][:nr]
             g_t = out_r["t"].cpu().numpy()[::stride][:nr]
-            g_tie = (out_r["flags"].cpu().numpy()[::stride][:nr] & B.FLAG_TIE) != 0
+            g_tie = (out_r["flags"].cpu().numpy()[::stride][:nr] & (B.FLAG_TIE | B.FLAG_NEAR_TIE)) != 0
             p_prim = out_p["prim"].cpu().numpy().view(np.uint32)[:npnt]
-            p_tie = (out_p["flags"].cpu().numpy()[:npnt] & B.FLAG_TIE) != 0
-            parity = {"rays_checked": len(cr), "ray_t_bit_equal": bool(np.array_equal(g_t, rr["t"])), "ray_id_mismatch_not_tie": int(((g_prim != rr["prim"]) & ~g_tie).sum()),
+            p_tie = (out_p["flags"].cpu().numpy()[:npnt] & (B.FLAG_TIE | B.FLAG_NEAR_TIE)) != 0
+            parity = {"rays_checked": len(cr), "ray_t_bit_equal_outside_near_ties": bool(np.array_equal(g_t[~g_tie], rr["t"][~g_tie])),
+                      "ray_t_max_rel_diff": float(np.max(np.abs(g_t - rr["t"]) / np.maximum(np.abs(rr["t"]), 1e-300))), "ray_id_mismatch_not_tie": int(((g_prim != rr["prim"]) & ~g_tie).sum()),
                       "points_checked": len(cp), "sqdist_bit_equal": bool(np.array_equal(out_p["sqdist"].cpu().numpy()[:npnt], rc["sqd"])),
                       "point_id_mismatch_not_tie": int(((p_prim != rc["prim"]) & ~p_tie).sum())}
             line["cpu_baseline"] = {"value": 2.0 / (1.0 / rps + 1.0 / pps) / 1e6, "unit": "Mqueries/s", "cores": threads, "kind": "port",

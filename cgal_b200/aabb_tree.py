@@ -10,7 +10,8 @@ import os
 import numpy as np
 
 SEGMENT, RAY = 0, 1
-FLAG_HIT, FLAG_SEGMENT, FLAG_TIE, FLAG_EXACT = 1, 2, 4, 8
+FLAG_HIT, FLAG_SEGMENT, FLAG_TIE, FLAG_EXACT, FLAG_NEAR_TIE = 1, 2, 4, 8, 16
+OPT_SORT_QUERIES = 1
 NO_PRIMITIVE = 0xFFFFFFFF
 _HOST, _DEVICE = 0, 1
 _ERRORS = {-1: "invalid argument", -2: "CUDA error", -3: "out of device memory", -4: "empty tree (CGAL_precondition(!empty()))",
@@ -26,14 +27,15 @@ class B200AABBError(RuntimeError):
 
 class _Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("exact_fallbacks", C.c_uint64), ("ties", C.c_uint64),
+                ("near_ties", C.c_uint64), ("nodes_visited", C.c_uint64), ("leaves_tested", C.c_uint64),
                 ("last_build_ms", C.c_double), ("last_query_ms", C.c_double), ("last_query_total_ms", C.c_double)]
 
 
-SYMBOLS = ["b200aabb_create", "b200aabb_destroy", "b200aabb_set_stream", "b200aabb_last_error", "b200aabb_get_stats",
+SYMBOLS = ["b200aabb_create", "b200aabb_destroy", "b200aabb_set_stream", "b200aabb_set_option", "b200aabb_last_error", "b200aabb_get_stats",
            "b200aabb_set_mesh", "b200aabb_set_triangles", "b200aabb_clear", "b200aabb_build",
            "b200aabb_accelerate_distance_queries", "b200aabb_size", "b200aabb_bbox", "b200aabb_do_intersect",
            "b200aabb_number_of_intersected_primitives", "b200aabb_first_intersection", "b200aabb_closest_point",
-           "b200aabb_export_layout", "b200aabb_import_alloc", "b200aabb_import_finish", "b200aabb_version"]
+           "b200aabb_export_layout", "b200aabb_import_alloc", "b200aabb_import_finish", "b200aabb_debug_predicate", "b200aabb_version"]
 
 
 def library_path():
@@ -52,6 +54,7 @@ def load_library():
         L.b200aabb_create.argtypes = [C.c_int, C.POINTER(vp)]
         L.b200aabb_destroy.argtypes = [vp]
         L.b200aabb_set_stream.argtypes = [vp, vp]
+        L.b200aabb_set_option.argtypes = [vp, C.c_int, C.c_int64]
         L.b200aabb_last_error.argtypes = [vp]
         L.b200aabb_last_error.restype = C.c_char_p
         L.b200aabb_get_stats.argtypes = [vp, C.POINTER(_Stats)]
@@ -69,6 +72,7 @@ def load_library():
         L.b200aabb_export_layout.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.c_int, C.POINTER(C.c_int)]
         L.b200aabb_import_alloc.argtypes = [vp, u64]
         L.b200aabb_import_finish.argtypes = [vp]
+        L.b200aabb_debug_predicate.argtypes = [C.c_int, C.c_int, dp, C.c_int, u64, dp, dp, dp]
         L.b200aabb_version.restype = C.c_char_p
         _LIB = L
     return _LIB
@@ -103,6 +107,19 @@ def _alloc_like(q, n, dtype, cols):
         return _Buf(torch.empty(shape, dtype=tdt, device=q.obj.device), dtype, cols)
     shape = (n, cols) if cols > 1 else (n,)
     return _Buf(np.empty(shape, dtype=dtype), dtype, cols)
+
+
+def debug_predicate(which, records, device=0):
+    """self-test hook: one device predicate per row of `records`; returns (result int32[n], used_exact int32[n], values f64[n,8])"""
+    L = load_library()
+    r = np.ascontiguousarray(records, dtype=np.float64)
+    r = r.reshape(len(r), -1)
+    n = len(r)
+    res, ex, val = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros((n, 8))
+    rc = L.b200aabb_debug_predicate(int(device), int(which), r.ctypes.data, r.shape[1], n, res.ctypes.data, ex.ctypes.data, val.ctypes.data)
+    if rc:
+        raise B200AABBError(rc)
+    return res, ex, val
 
 
 class AABB_tree:
@@ -180,6 +197,9 @@ class AABB_tree:
 
     def set_stream(self, cuda_stream_ptr):
         self._check(self._lib.b200aabb_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_option(self, option, value):
+        self._check(self._lib.b200aabb_set_option(self._h, int(option), int(value)))
 
     def stats(self):
         s = _Stats()

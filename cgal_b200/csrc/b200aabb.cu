@@ -23,54 +23,156 @@ namespace {
 
 __device__ __forceinline__ Vec3 ld3(const double* __restrict__ p) { return {__ldg(p), __ldg(p + 1), __ldg(p + 2)}; }
 
+// what every traversal kernel needs to know about the tree
+struct TreeRef {
+    const BvhNode* nodes;
+    const TriRec* tris;
+    uint32_t root;
+    double mag;                       // largest coordinate magnitude of the root box
+    const uint32_t* perm;             // coherence order of the batch (thread i serves query perm[i]); nullptr = identity
+    unsigned long long* counters;     // [8]: exact-stage queries, ties, stack overflow, nodes visited, leaves tested, near ties
+};
+
+// one atomic per warp and counter instead of one per thread
+__device__ __forceinline__ void flush_stats(const TreeRef& tr, const TravStat& st, int tie, int near) {
+    const unsigned full = 0xFFFFFFFFu;
+    const unsigned nodes = __reduce_add_sync(full, st.nodes), leaves = __reduce_add_sync(full, st.leaves);
+    const unsigned exact = __reduce_add_sync(full, st.nexact ? 1u : 0u), ties = __reduce_add_sync(full, tie ? 1u : 0u);
+    const unsigned nears = __reduce_add_sync(full, near ? 1u : 0u), ovf = __reduce_or_sync(full, st.overflow ? 1u : 0u);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&tr.counters[3], (unsigned long long)nodes);
+        atomicAdd(&tr.counters[4], (unsigned long long)leaves);
+        if (exact) atomicAdd(&tr.counters[0], (unsigned long long)exact);
+        if (ties) atomicAdd(&tr.counters[1], (unsigned long long)ties);
+        if (nears) atomicAdd(&tr.counters[5], (unsigned long long)nears);
+        if (ovf) atomicOr(&tr.counters[2], 1ull);
+    }
+}
+
 template <bool IS_RAY, bool COUNT>
-__global__ void __launch_bounds__(128) intersect_kernel(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root,
-                                                        const double* __restrict__ q, uint64_t n, uint8_t* __restrict__ out8,
-                                                        uint32_t* __restrict__ out32, unsigned long long* __restrict__ counters) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int nexact = 0, overflow = 0;
-    const uint32_t r = traverse_intersect<IS_RAY, COUNT>(nodes, tris, root, ld3(q + 6 * i), ld3(q + 6 * i + 3), nexact, overflow);
-    if (COUNT) out32[i] = r; else out8[i] = (uint8_t)(r != 0);
-    if (nexact) atomicAdd(&counters[0], 1ull);
-    if (overflow) atomicOr(&counters[2], 1ull);
+__global__ void __launch_bounds__(128) intersect_kernel(const TreeRef tr, const double* __restrict__ q, uint64_t n, uint8_t* __restrict__ out8,
+                                                        uint32_t* __restrict__ out32) {
+    const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    TravStat st;
+    if (slot < n) {
+        const uint64_t i = tr.perm ? tr.perm[slot] : slot;
+        const uint32_t r = traverse_intersect<IS_RAY, COUNT>(tr.nodes, tr.tris, tr.root, ld3(q + 6 * i), ld3(q + 6 * i + 3), st);
+        if (COUNT) out32[i] = r; else out8[i] = (uint8_t)(r != 0);
+    }
+    flush_stats(tr, st, 0, 0);
 }
 
-__global__ void __launch_bounds__(128) first_intersection_kernel(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root,
-                                                                 const double* __restrict__ rays, uint64_t n, uint32_t* __restrict__ prim,
+__global__ void __launch_bounds__(128) first_intersection_kernel(const TreeRef tr, const double* __restrict__ rays, uint64_t n, uint32_t* __restrict__ prim,
                                                                  double* __restrict__ tpar, double* __restrict__ pt, double* __restrict__ pt2,
-                                                                 uint8_t* __restrict__ flags, unsigned long long* __restrict__ counters) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int nexact = 0, overflow = 0;
-    const FirstHit h = traverse_first(nodes, tris, root, ld3(rays + 6 * i), ld3(rays + 6 * i + 3), nexact, overflow);
-    const bool hit = h.prim != kNone;
-    if (prim) prim[i] = h.prim;
-    if (tpar) tpar[i] = hit ? h.t : 0.0;
-    if (pt) { pt[3 * i] = hit ? h.p0.x : 0.0; pt[3 * i + 1] = hit ? h.p0.y : 0.0; pt[3 * i + 2] = hit ? h.p0.z : 0.0; }
-    if (pt2) { const bool seg = hit && h.kind == 2; pt2[3 * i] = seg ? h.p1.x : 0.0; pt2[3 * i + 1] = seg ? h.p1.y : 0.0; pt2[3 * i + 2] = seg ? h.p1.z : 0.0; }
-    if (flags) flags[i] = (uint8_t)((hit ? B200AABB_FLAG_HIT : 0) | (hit && h.kind == 2 ? B200AABB_FLAG_SEGMENT : 0) |
-                                    (h.tie ? B200AABB_FLAG_TIE : 0) | (nexact ? B200AABB_FLAG_EXACT : 0));
-    if (nexact) atomicAdd(&counters[0], 1ull);
-    if (h.tie) atomicAdd(&counters[1], 1ull);
-    if (overflow) atomicOr(&counters[2], 1ull);
+                                                                 uint8_t* __restrict__ flags) {
+    const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    TravStat st;
+    int tie = 0, near = 0;
+    if (slot < n) {
+        const uint64_t i = tr.perm ? tr.perm[slot] : slot;
+        const FirstHit h = traverse_first(tr.nodes, tr.tris, tr.root, ld3(rays + 6 * i), ld3(rays + 6 * i + 3), tr.mag, st);
+        const bool hit = h.prim != kNone;
+        tie = h.tie; near = h.near;
+        if (prim) prim[i] = h.prim;
+        if (tpar) tpar[i] = hit ? h.t : 0.0;
+        if (pt) { pt[3 * i] = hit ? h.p0.x : 0.0; pt[3 * i + 1] = hit ? h.p0.y : 0.0; pt[3 * i + 2] = hit ? h.p0.z : 0.0; }
+        if (pt2) { const bool seg = hit && h.kind == 2; pt2[3 * i] = seg ? h.p1.x : 0.0; pt2[3 * i + 1] = seg ? h.p1.y : 0.0; pt2[3 * i + 2] = seg ? h.p1.z : 0.0; }
+        if (flags) flags[i] = (uint8_t)((hit ? B200AABB_FLAG_HIT : 0) | (hit && h.kind == 2 ? B200AABB_FLAG_SEGMENT : 0) | (h.tie ? B200AABB_FLAG_TIE : 0) |
+                                        (st.nexact ? B200AABB_FLAG_EXACT : 0) | (h.near ? B200AABB_FLAG_NEAR_TIE : 0));
+    }
+    flush_stats(tr, st, tie, near);
 }
 
-__global__ void __launch_bounds__(128) closest_point_kernel(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root,
-                                                            const double* __restrict__ pts, uint64_t n, double* __restrict__ cp,
-                                                            uint32_t* __restrict__ prim, double* __restrict__ sqd, uint8_t* __restrict__ flags,
-                                                            unsigned long long* __restrict__ counters) {
+__global__ void __launch_bounds__(128) closest_point_kernel(const TreeRef tr, const double* __restrict__ pts, uint64_t n, double* __restrict__ cp,
+                                                            uint32_t* __restrict__ prim, double* __restrict__ sqd, uint8_t* __restrict__ flags) {
+    const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    TravStat st;
+    int tie = 0, near = 0;
+    if (slot < n) {
+        const uint64_t i = tr.perm ? tr.perm[slot] : slot;
+        const Closest c = traverse_closest(tr.nodes, tr.tris, tr.root, ld3(pts + 3 * i), tr.mag, st);
+        tie = c.tie; near = c.near;
+        if (cp) { cp[3 * i] = c.p.x; cp[3 * i + 1] = c.p.y; cp[3 * i + 2] = c.p.z; }
+        if (prim) prim[i] = c.prim;
+        if (sqd) sqd[i] = c.sqd;
+        if (flags) flags[i] = (uint8_t)((c.tie ? B200AABB_FLAG_TIE : 0) | (st.nexact ? B200AABB_FLAG_EXACT : 0) | (c.near ? B200AABB_FLAG_NEAR_TIE : 0));
+    }
+    flush_stats(tr, st, tie, near);
+}
+
+// ---- predicate self-test hook (b200aabb_debug_predicate): evaluates ONE device predicate per record so that the -m gpu
+// tests can compare the device-compiled filters and exact stage with the oracle on adversarial inputs
+__global__ void __launch_bounds__(128) predicate_kernel(int which, const double* __restrict__ in, int stride, uint64_t n, int* __restrict__ out,
+                                                        int* __restrict__ used_exact, double* __restrict__ dout) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int nexact = 0, overflow = 0;
-    const Closest c = traverse_closest(nodes, tris, root, ld3(pts + 3 * i), nexact, overflow);
-    if (cp) { cp[3 * i] = c.p.x; cp[3 * i + 1] = c.p.y; cp[3 * i + 2] = c.p.z; }
-    if (prim) prim[i] = c.prim;
-    if (sqd) sqd[i] = c.sqd;
-    if (flags) flags[i] = (uint8_t)((c.tie ? B200AABB_FLAG_TIE : 0) | (nexact ? B200AABB_FLAG_EXACT : 0));
-    if (nexact) atomicAdd(&counters[0], 1ull);
-    if (c.tie) atomicAdd(&counters[1], 1ull);
-    if (overflow) atomicOr(&counters[2], 1ull);
+    const double* p = in + (uint64_t)stride * i;
+    int nexact = 0, r = 0;
+    auto V = [&](int k) { return Vec3{p[3 * k], p[3 * k + 1], p[3 * k + 2]}; };
+    switch (which) {
+        case 0: r = orient3(V(0), V(1), V(2), V(3), nexact); break;
+        case 1: r = orient3_dir(V(0), V(1), V(2), V(3), V(4), nexact); break;
+        case 2: r = coplanar_orient(V(0), V(1), V(2), nexact); break;
+        case 3: r = cmp_dist(V(0), V(1), V(2), nexact); break;
+        case 4: r = seg_tri_do_intersect(Tri3{V(0), V(1), V(2)}, V(3), V(4), nexact); break;
+        case 5: r = ray_tri_do_intersect(Tri3{V(0), V(1), V(2)}, V(3), V(4), nexact); break;
+        case 6: {
+            const Vec3 s = V(3), q = V(4), d = q - s;
+            const RayX x = ray_tri_intersection(Tri3{V(0), V(1), V(2)}, s, q, d, ray_major_axis(d), nexact);
+            r = x.kind;
+            if (dout) { double* o = dout + 8 * i; o[0] = x.t; o[1] = x.p0.x; o[2] = x.p0.y; o[3] = x.p0.z; o[4] = x.p1.x; o[5] = x.p1.y; o[6] = x.p1.z; o[7] = x.u; }
+            break;
+        }
+        case 7: {
+            const Vec3 c = closest_on_triangle(Tri3{V(0), V(1), V(2)}, V(3));
+            if (dout) { double* o = dout + 8 * i; o[0] = c.x; o[1] = c.y; o[2] = c.z; }
+            break;
+        }
+        case 8: r = exact_det3_sign(dd_diff(p[3], p[0]), dd_diff(p[4], p[1]), dd_diff(p[5], p[2]), dd_diff(p[6], p[0]), dd_diff(p[7], p[1]), dd_diff(p[8], p[2]),
+                                    dd_diff(p[9], p[0]), dd_diff(p[10], p[1]), dd_diff(p[11], p[2])); break;
+        default: break;
+    }
+    out[i] = r;
+    if (used_exact) used_exact[i] = nexact;
+}
+
+// ---- query coherence keys (sorted with radix_sort.cuh; the traversal kernels then follow the permutation) ------------
+// Point_3: 30-bit Morton code (10 bits per axis) of the point in the isotropic frame of the root box
+__global__ void __launch_bounds__(256) point_keys_kernel(const double* __restrict__ pts, uint64_t n, const double* __restrict__ rootbox,
+                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double lo[3], scale[3];
+    morton_frame(rootbox[0], rootbox[1], rootbox[2], rootbox[3], rootbox[4], rootbox[5], lo, scale);
+    keys[i] = morton63(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], lo, scale) >> 33;
+    vals[i] = (uint32_t)i;
+}
+// Segment_3 / Ray_3: 48-bit key interleaving 8 bits of each origin coordinate (root-box frame) and of each component of
+// the max-norm-normalised direction, most significant bits first
+__global__ void __launch_bounds__(256) line_keys_kernel(const double* __restrict__ q, uint64_t n, const double* __restrict__ rootbox,
+                                                        uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double lo[3], scale[3];
+    morton_frame(rootbox[0], rootbox[1], rootbox[2], rootbox[3], rootbox[4], rootbox[5], lo, scale);
+    const double* r = q + 6 * i;
+    const double d[3] = {r[3] - r[0], r[4] - r[1], r[5] - r[2]};
+    const double dmax = fmax(fabs(d[0]), fmax(fabs(d[1]), fabs(d[2])));
+    uint32_t c[6];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const double f = (r[k] - lo[k]) * scale[k] * (256.0 / 2097152.0);          // root box -> [0, 256)
+        c[k] = (uint32_t)fmin(fmax(f, 0.0), 255.0);
+        const double g = dmax > 0.0 ? (d[k] / dmax + 1.0) * 127.5 : 0.0;             // [-1, 1] -> [0, 255]
+        c[3 + k] = (uint32_t)fmin(fmax(g, 0.0), 255.0);
+    }
+    uint64_t key = 0;
+#pragma unroll
+    for (int b = 7; b >= 0; --b)
+#pragma unroll
+        for (int k = 0; k < 6; ++k) key = (key << 1) | ((c[k] >> b) & 1u);
+    keys[i] = key;
+    vals[i] = (uint32_t)i;
 }
 
 }  // namespace
@@ -93,7 +195,12 @@ struct b200aabb_tree {
     double* d_rootbox = nullptr;   // 6 doubles
     uint32_t root = kNone;
     double h_bbox[6];
-    unsigned long long* d_counters = nullptr;   // [4]
+    double mag = 0.0;              // largest coordinate magnitude of the root box
+    unsigned long long* d_counters = nullptr;   // [8]
+    // options
+    int opt_sort_queries = 1;      // B200AABB_OPT_SORT_QUERIES
+    // query coherence sort scratch, one per pipeline slot (slot 0 also serves DEVICE-pointer batches); grow-only
+    struct SortScratch { uint64_t* keys[2] = {nullptr, nullptr}; uint32_t* vals[2] = {nullptr, nullptr}; void* ws = nullptr; uint64_t cap = 0; } sort[2];
     // staging for HOST-pointer batches (two pipeline slots)
     void* d_stage_in[2] = {nullptr, nullptr};
     void* d_stage_out[2] = {nullptr, nullptr};
@@ -141,6 +248,44 @@ int ensure_stage(b200aabb_tree* t, size_t in_bytes, size_t out_bytes) {
     return B200AABB_OK;
 }
 
+void free_sort(b200aabb_tree* t) {
+    for (auto& sc : t->sort) {
+        cudaFree(sc.keys[0]); cudaFree(sc.keys[1]); cudaFree(sc.vals[0]); cudaFree(sc.vals[1]); cudaFree(sc.ws);
+        sc = b200aabb_tree::SortScratch();
+    }
+}
+int ensure_sort(b200aabb_tree* t, int slot, uint64_t n) {
+    auto& sc = t->sort[slot];
+    if (n <= sc.cap) return B200AABB_OK;
+    cudaFree(sc.keys[0]); cudaFree(sc.keys[1]); cudaFree(sc.vals[0]); cudaFree(sc.vals[1]); cudaFree(sc.ws);
+    sc = b200aabb_tree::SortScratch();
+    for (int k = 0; k < 2; ++k) { B2_CUDA(t, cudaMalloc(&sc.keys[k], n * 8)); B2_CUDA(t, cudaMalloc(&sc.vals[k], n * 4)); }
+    B2_CUDA(t, cudaMalloc(&sc.ws, rs_workspace_bytes(n)));
+    sc.cap = n;
+    return B200AABB_OK;
+}
+
+enum QueryShape { kPointQuery, kLineQuery };
+
+// coherence order of a batch resident on the device: keys -> onesweep sort -> permutation (nullptr when sorting is off)
+int coherence_order(b200aabb_tree* t, int slot, cudaStream_t st, const void* d_in, uint64_t n, QueryShape shape, const uint32_t** perm) {
+    *perm = nullptr;
+    if (!t->opt_sort_queries || n < 4096 || n >= (1ull << 32)) return B200AABB_OK;
+    int rc = ensure_sort(t, slot, n);
+    if (rc) return rc;
+    auto& sc = t->sort[slot];
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    int passes;
+    if (shape == kPointQuery) { point_keys_kernel<<<blocks, 256, 0, st>>>((const double*)d_in, n, t->d_rootbox, sc.keys[0], sc.vals[0]); passes = 4; }
+    else { line_keys_kernel<<<blocks, 256, 0, st>>>((const double*)d_in, n, t->d_rootbox, sc.keys[0], sc.vals[0]); passes = 6; }
+    t->stats.kernel_launches += 1;
+    const int cur = radix_sort_pairs(sc.keys, sc.vals, n, passes, sc.ws, st, &t->stats.kernel_launches);
+    *perm = sc.vals[cur];
+    return B200AABB_OK;
+}
+
+TreeRef tree_ref(const b200aabb_tree* t, const uint32_t* perm) { return TreeRef{t->d_nodes, t->d_tris, t->root, t->mag, perm, t->d_counters}; }
+
 int do_build(b200aabb_tree* t) {
     B2_CUDA(t, cudaSetDevice(t->device));
     free_tree_buffers(t);
@@ -184,6 +329,8 @@ int do_build(b200aabb_tree* t) {
     float ms = 0; cudaEventElapsedTime(&ms, t->ev_a, t->ev_b);
     t->stats.last_build_ms = ms;
     t->root = n == 1 ? (kLeafBit | 0u) : 0u;
+    t->mag = 0.0;
+    for (int a = 0; a < 6; ++a) t->mag = std::max(t->mag, fabs(t->h_bbox[a]));
     t->built = true;
     cleanup();
 #undef B2_TRY
@@ -192,18 +339,21 @@ int do_build(b200aabb_tree* t) {
 
 int ensure_built(b200aabb_tree* t) { return t->built ? B200AABB_OK : do_build(t); }
 
-// Runs `launch(stream, d_in, d_out_base, count)` over the batch.  HOST pointers: chunked, double-buffered
+// Runs `launch(stream, d_in, d_outs, count, perm)` over the batch (perm = coherence order of the chunk, or nullptr).  HOST pointers: chunked, double-buffered
 // H2D -> kernel -> D2H pipeline on two streams; DEVICE pointers: one launch on the handle's stream, no synchronisation.
 struct OutSpec { void* host; size_t elem_bytes; size_t offset; };   // one result array: host pointer, bytes per query, offset in staging
 
 template <class Launch>
-int run_batch(b200aabb_tree* t, const void* in, size_t in_elem_bytes, uint64_t n, b200aabb_memspace space, std::vector<OutSpec> outs, Launch launch) {
+int run_batch(b200aabb_tree* t, const void* in, size_t in_elem_bytes, uint64_t n, b200aabb_memspace space, QueryShape shape, std::vector<OutSpec> outs, Launch launch) {
     B2_CUDA(t, cudaSetDevice(t->device));
-    B2_CUDA(t, cudaMemsetAsync(t->d_counters, 0, 4 * sizeof(unsigned long long), t->stream));
+    B2_CUDA(t, cudaMemsetAsync(t->d_counters, 0, 8 * sizeof(unsigned long long), t->stream));
     if (space == B200AABB_DEVICE) {
         B2_CUDA(t, cudaEventRecord(t->ev_a, t->stream));
         std::vector<void*> ptrs; for (auto& o : outs) ptrs.push_back(o.host);
-        launch(t->stream, in, ptrs.data(), n);
+        const uint32_t* perm = nullptr;
+        int rc = coherence_order(t, 0, t->stream, in, n, shape, &perm);
+        if (rc) return rc;
+        launch(t->stream, in, ptrs.data(), n, perm);
         t->stats.kernel_launches += 1;
         B2_CUDA(t, cudaEventRecord(t->ev_b, t->stream));
         B2_CUDA(t, cudaGetLastError());
@@ -224,7 +374,10 @@ int run_batch(b200aabb_tree* t, const void* in, size_t in_elem_bytes, uint64_t n
         B2_CUDA(t, cudaMemcpyAsync(t->d_stage_in[slot], (const char*)in + b * in_elem_bytes, cnt * in_elem_bytes, cudaMemcpyHostToDevice, st));
         std::vector<void*> ptrs;
         for (auto& o : outs) ptrs.push_back(o.host ? (char*)t->d_stage_out[slot] + o.offset : nullptr);
-        launch(st, t->d_stage_in[slot], ptrs.data(), cnt);
+        const uint32_t* perm = nullptr;
+        rc = coherence_order(t, slot, st, t->d_stage_in[slot], cnt, shape, &perm);
+        if (rc) return rc;
+        launch(st, t->d_stage_in[slot], ptrs.data(), cnt, perm);
         t->stats.kernel_launches += 1;
         for (auto& o : outs)
             if (o.host) B2_CUDA(t, cudaMemcpyAsync((char*)o.host + b * o.elem_bytes, (char*)t->d_stage_out[slot] + o.offset, cnt * o.elem_bytes, cudaMemcpyDeviceToHost, st));
@@ -248,6 +401,25 @@ extern "C" {
 
 const char* b200aabb_version(void) { return "b200aabb 0.1 sm_100a"; }
 
+int b200aabb_debug_predicate(int device, int which, const double* records, int doubles_per_record, uint64_t n, int* result, int* used_exact, double* values) {
+    static const int need[] = {12, 15, 9, 9, 15, 15, 15, 12, 12};
+    if (which < 0 || which > 8 || !records || !result || doubles_per_record < need[which]) return B200AABB_ERR_INVALID_ARGUMENT;
+    if (cudaSetDevice(device) != cudaSuccess) return B200AABB_ERR_NO_DEVICE;
+    if (n == 0) return B200AABB_OK;
+    double* d_in = nullptr; int* d_out = nullptr; int* d_ex = nullptr; double* d_val = nullptr;
+    bool ok = cudaMalloc(&d_in, n * doubles_per_record * 8) == cudaSuccess && cudaMalloc(&d_out, n * 4) == cudaSuccess && cudaMalloc(&d_ex, n * 4) == cudaSuccess &&
+              cudaMalloc(&d_val, n * 64) == cudaSuccess;
+    ok = ok && cudaMemcpy(d_in, records, n * doubles_per_record * 8, cudaMemcpyHostToDevice) == cudaSuccess && cudaMemset(d_val, 0, n * 64) == cudaSuccess;
+    if (ok) {
+        predicate_kernel<<<(unsigned)((n + 127) / 128), 128>>>(which, d_in, doubles_per_record, n, d_out, d_ex, d_val);
+        ok = cudaDeviceSynchronize() == cudaSuccess && cudaMemcpy(result, d_out, n * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+        if (ok && used_exact) ok = cudaMemcpy(used_exact, d_ex, n * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+        if (ok && values) ok = cudaMemcpy(values, d_val, n * 64, cudaMemcpyDeviceToHost) == cudaSuccess;
+    }
+    cudaFree(d_in); cudaFree(d_out); cudaFree(d_ex); cudaFree(d_val);
+    return ok ? B200AABB_OK : B200AABB_ERR_CUDA;
+}
+
 int b200aabb_create(int device, b200aabb_tree** out) {
     if (!out) return B200AABB_ERR_INVALID_ARGUMENT;
     *out = nullptr;
@@ -260,7 +432,7 @@ int b200aabb_create(int device, b200aabb_tree** out) {
     t->device = device;
     memset(&t->stats, 0, sizeof(t->stats));
     empty_bbox(t->h_bbox);
-    bool ok = cudaMalloc(&t->d_rootbox, 48) == cudaSuccess && cudaMalloc(&t->d_counters, 4 * sizeof(unsigned long long)) == cudaSuccess &&
+    bool ok = cudaMalloc(&t->d_rootbox, 48) == cudaSuccess && cudaMalloc(&t->d_counters, 8 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaEventCreate(&t->ev_a) == cudaSuccess && cudaEventCreate(&t->ev_b) == cudaSuccess;
     for (int s = 0; s < 2 && ok; ++s)
         ok = cudaStreamCreateWithFlags(&t->pipe[s], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&t->ev_pipe[s], cudaEventDisableTiming) == cudaSuccess;
@@ -274,7 +446,7 @@ int b200aabb_destroy(b200aabb_tree* t) {
     if (!t) return B200AABB_OK;
     cudaSetDevice(t->device);
     cudaDeviceSynchronize();
-    free_tree_buffers(t); free_input(t);
+    free_tree_buffers(t); free_input(t); free_sort(t);
     cudaFree(t->d_rootbox); cudaFree(t->d_counters);
     for (int s = 0; s < 2; ++s) { cudaFree(t->d_stage_in[s]); cudaFree(t->d_stage_out[s]); if (t->pipe[s]) cudaStreamDestroy(t->pipe[s]); if (t->ev_pipe[s]) cudaEventDestroy(t->ev_pipe[s]); }
     if (t->ev_a) cudaEventDestroy(t->ev_a);
@@ -283,6 +455,13 @@ int b200aabb_destroy(b200aabb_tree* t) {
     return B200AABB_OK;
 }
 
+int b200aabb_set_option(b200aabb_tree* t, int option, int64_t value) {
+    if (!t) return B200AABB_ERR_INVALID_ARGUMENT;
+    switch (option) {
+        case B200AABB_OPT_SORT_QUERIES: t->opt_sort_queries = value != 0; return B200AABB_OK;
+        default: return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "unknown option");
+    }
+}
 int b200aabb_set_stream(b200aabb_tree* t, void* s) { if (!t) return B200AABB_ERR_INVALID_ARGUMENT; t->stream = (cudaStream_t)s; return B200AABB_OK; }
 const char* b200aabb_last_error(const b200aabb_tree* t) { return t ? t->err.c_str() : "null handle"; }
 
@@ -294,9 +473,9 @@ int b200aabb_get_stats(const b200aabb_tree* tc, b200aabb_stats* out) {
         B2_CUDA(t, cudaEventSynchronize(t->ev_b));
         float ms = 0; cudaEventElapsedTime(&ms, t->ev_a, t->ev_b);
         t->stats.last_query_total_ms = ms; t->stats.last_query_ms = ms;
-        unsigned long long c[4];
+        unsigned long long c[8];
         B2_CUDA(t, cudaMemcpy(c, t->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
-        t->stats.exact_fallbacks = c[0]; t->stats.ties = c[1];
+        t->stats.exact_fallbacks = c[0]; t->stats.ties = c[1]; t->stats.nodes_visited = c[3]; t->stats.leaves_tested = c[4]; t->stats.near_ties = c[5];
         if (c[2]) t->err = "traversal stack overflow: results incomplete";
         t->query_timing_pending = false;
         if (c[2]) { *out = t->stats; return B200AABB_ERR_CUDA; }
@@ -372,9 +551,9 @@ int b200aabb_do_intersect(b200aabb_tree* t, const double* q, uint64_t n, b200aab
         return B200AABB_OK;
     }
     const bool ray = kind == B200AABB_RAY;
-    return run_batch(t, q, 48, n, space, {{out, 1, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt) {
-        if (ray) intersect_kernel<true, false><<<grid_for(cnt, 128), 128, 0, st>>>(t->d_nodes, t->d_tris, t->root, (const double*)in, cnt, (uint8_t*)o[0], nullptr, t->d_counters);
-        else intersect_kernel<false, false><<<grid_for(cnt, 128), 128, 0, st>>>(t->d_nodes, t->d_tris, t->root, (const double*)in, cnt, (uint8_t*)o[0], nullptr, t->d_counters);
+    return run_batch(t, q, 48, n, space, kLineQuery, {{out, 1, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
+        if (ray) intersect_kernel<true, false><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint8_t*)o[0], nullptr);
+        else intersect_kernel<false, false><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint8_t*)o[0], nullptr);
     });
 }
 
@@ -387,9 +566,9 @@ int b200aabb_number_of_intersected_primitives(b200aabb_tree* t, const double* q,
         return B200AABB_OK;
     }
     const bool ray = kind == B200AABB_RAY;
-    return run_batch(t, q, 48, n, space, {{out, 4, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt) {
-        if (ray) intersect_kernel<true, true><<<grid_for(cnt, 128), 128, 0, st>>>(t->d_nodes, t->d_tris, t->root, (const double*)in, cnt, nullptr, (uint32_t*)o[0], t->d_counters);
-        else intersect_kernel<false, true><<<grid_for(cnt, 128), 128, 0, st>>>(t->d_nodes, t->d_tris, t->root, (const double*)in, cnt, nullptr, (uint32_t*)o[0], t->d_counters);
+    return run_batch(t, q, 48, n, space, kLineQuery, {{out, 4, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
+        if (ray) intersect_kernel<true, true><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, nullptr, (uint32_t*)o[0]);
+        else intersect_kernel<false, true><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, nullptr, (uint32_t*)o[0]);
     });
 }
 
@@ -414,10 +593,10 @@ int b200aabb_first_intersection(b200aabb_tree* t, const double* rays, uint64_t n
         }
         return B200AABB_OK;
     }
-    return run_batch(t, rays, 48, n, space, {{prim, 4, 0}, {tpar, 8, 0}, {pt, 24, 0}, {pt2, 24, 0}, {flags, 1, 0}},
-                     [&](cudaStream_t st, const void* in, void** o, uint64_t cnt) {
-                         first_intersection_kernel<<<grid_for(cnt, 128), 128, 0, st>>>(t->d_nodes, t->d_tris, t->root, (const double*)in, cnt, (uint32_t*)o[0],
-                                                                                        (double*)o[1], (double*)o[2], (double*)o[3], (uint8_t*)o[4], t->d_counters);
+    return run_batch(t, rays, 48, n, space, kLineQuery, {{prim, 4, 0}, {tpar, 8, 0}, {pt, 24, 0}, {pt2, 24, 0}, {flags, 1, 0}},
+                     [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
+                         first_intersection_kernel<<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint32_t*)o[0], (double*)o[1],
+                                                                                        (double*)o[2], (double*)o[3], (uint8_t*)o[4]);
                      });
 }
 
@@ -427,10 +606,10 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
     if (rc) return rc;
     if (t->n == 0) return fail(t, B200AABB_ERR_EMPTY_TREE, "distance query on an empty tree (CGAL_precondition(!empty()))");
     if (n == 0) return B200AABB_OK;
-    return run_batch(t, pts, 24, n, space, {{cp, 24, 0}, {prim, 4, 0}, {sqd, 8, 0}, {flags, 1, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt) {
-        closest_point_kernel<<<grid_for(cnt, 128), 128, 0, st>>>(t->d_nodes, t->d_tris, t->root, (const double*)in, cnt, (double*)o[0], (uint32_t*)o[1], (double*)o[2],
-                                                                  (uint8_t*)o[3], t->d_counters);
-    });
+    return run_batch(t, pts, 24, n, space, kPointQuery, {{cp, 24, 0}, {prim, 4, 0}, {sqd, 8, 0}, {flags, 1, 0}},
+                     [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
+                         closest_point_kernel<<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (double*)o[0], (uint32_t*)o[1], (double*)o[2], (uint8_t*)o[3]);
+                     });
 }
 
 int b200aabb_export_layout(b200aabb_tree* t, void** ptrs, uint64_t* bytes, int cap, int* count) {
@@ -459,6 +638,8 @@ int b200aabb_import_finish(b200aabb_tree* t) {
     if (!t) return B200AABB_ERR_INVALID_ARGUMENT;
     B2_CUDA(t, cudaSetDevice(t->device));
     if (t->n) B2_CUDA(t, cudaMemcpy(t->h_bbox, t->d_rootbox, 48, cudaMemcpyDeviceToHost));
+    t->mag = 0.0;
+    for (int a = 0; a < 6; ++a) if (t->n) t->mag = std::max(t->mag, fabs(t->h_bbox[a]));
     return B200AABB_OK;
 }
 

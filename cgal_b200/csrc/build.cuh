@@ -82,17 +82,22 @@ B2_HD uint64_t morton63(double cx, double cy, double cz, const double* lo, const
     return (spread21(qx) << 2) | (spread21(qy) << 1) | spread21(qz);
 }
 
+// quantisation frame of the Morton keys: ISOTROPIC cells (one scale, from the longest extent of the scene box), so that
+// a flat scene (terrain) is not split along its thin axis at the top of the tree
+B2_HD void morton_frame(double lx, double ly, double lz, double hx, double hy, double hz, double* lo, double* scale) {
+    lo[0] = lx; lo[1] = ly; lo[2] = lz;
+    const double ext = fmax(hx - lx, fmax(hy - ly, hz - lz));
+    const double sc = ext > 0.0 ? 2097152.0 / ext : 0.0;
+    scale[0] = sc; scale[1] = sc; scale[2] = sc;
+}
+
 __global__ void __launch_bounds__(256) morton_kernel(const double* __restrict__ tris, uint64_t n, const unsigned long long* __restrict__ bounds,
                                                      uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double lo[3], scale[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        lo[k] = from_ordered_bits(bounds[k]);
-        const double ext = from_ordered_bits(bounds[3 + k]) - lo[k];
-        scale[k] = ext > 0.0 ? 2097152.0 / ext : 0.0;
-    }
+    morton_frame(from_ordered_bits(bounds[0]), from_ordered_bits(bounds[1]), from_ordered_bits(bounds[2]),
+                 from_ordered_bits(bounds[3]), from_ordered_bits(bounds[4]), from_ordered_bits(bounds[5]), lo, scale);
     const double* t = tris + 9 * i;
     double c[3];
 #pragma unroll

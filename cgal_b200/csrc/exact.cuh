@@ -15,6 +15,18 @@
 #define B2_HD_NOINLINE
 #endif
 
+// The expansion routines are deliberately NOT inlined on the device.  Measured on B200 (scripts/probe/exact_probe3.cu,
+// CUDA 12.9): with every routine force-inlined into exact_det3_sign / exact_det2_sign, cicc's optimiser merges the stack
+// slots of the per-call scratch arrays incorrectly and the device returns a wrong sign for about half of all inputs
+// (host compilation, -G, and any variant with out-of-line exp_add / exp_scale are bit-identical to the host).  Keeping
+// them out of line also keeps the rarely executed exact stage out of the traversal kernels' instruction stream.
+#if !defined(B2_EXP_LEAF)
+#define B2_EXP_LEAF B2_HD_NOINLINE
+#endif
+#if !defined(B2_EXP_COMP)
+#define B2_EXP_COMP B2_HD_NOINLINE
+#endif
+
 namespace b2 {
 
 B2_HD void two_sum(double a, double b, double& x, double& y) {
@@ -43,7 +55,7 @@ struct DD { double hi, lo; };
 B2_HD DD dd_diff(double a, double b) { DD r; two_diff(a, b, r.hi, r.lo); return r; }
 
 // h = e + f, zero-eliminated; returns length.  h must not alias e or f.
-B2_HD int exp_add(const double* e, int ne, const double* f, int nf, double* h) {
+B2_EXP_LEAF int exp_add(const double* e, int ne, const double* f, int nf, double* h) {
     if (ne == 0) { for (int i = 0; i < nf; ++i) h[i] = f[i]; return nf; }
     if (nf == 0) { for (int i = 0; i < ne; ++i) h[i] = e[i]; return ne; }
     int ei = 0, fi = 0, hi = 0;
@@ -69,7 +81,7 @@ B2_HD int exp_add(const double* e, int ne, const double* f, int nf, double* h) {
 }
 
 // h = e * b, zero-eliminated; returns length (<= 2 ne)
-B2_HD int exp_scale(const double* e, int ne, double b, double* h) {
+B2_EXP_LEAF int exp_scale(const double* e, int ne, double b, double* h) {
     if (ne == 0 || b == 0.0) return 0;
     int hi = 0;
     double Q, sum, hh, p1, p0;
@@ -89,7 +101,7 @@ B2_HD int exp_scale(const double* e, int ne, double b, double* h) {
 B2_HD int exp_sign(const double* e, int n) { return n == 0 ? 0 : (e[n - 1] > 0.0 ? 1 : -1); }
 
 // h = a * b for two exact double-doubles; h has room for 8; returns length
-B2_HD int dd_mul(const DD& a, const DD& b, double* h) {
+B2_EXP_COMP int dd_mul(const DD& a, const DD& b, double* h) {
     double e[2]; int ne = 0;
     if (a.lo != 0.0) e[ne++] = a.lo;
     if (a.hi != 0.0) e[ne++] = a.hi;
@@ -100,7 +112,7 @@ B2_HD int dd_mul(const DD& a, const DD& b, double* h) {
 }
 
 // h = a*b - c*d for exact double-doubles; h has room for 16
-B2_HD int dd_det2(const DD& a, const DD& b, const DD& c, const DD& d, double* h) {
+B2_EXP_COMP int dd_det2(const DD& a, const DD& b, const DD& c, const DD& d, double* h) {
     double p[8], q[8];
     const int np = dd_mul(a, b, p);
     int nq = dd_mul(c, d, q);
@@ -109,7 +121,7 @@ B2_HD int dd_det2(const DD& a, const DD& b, const DD& c, const DD& d, double* h)
 }
 
 // h = e * d for an expansion e (length ne <= 16) and an exact double-double d; h has room for 64; tmp arrays inside
-B2_HD int exp_mul_dd(const double* e, int ne, const DD& d, double* h) {
+B2_EXP_COMP int exp_mul_dd(const double* e, int ne, const DD& d, double* h) {
     double t1[32], t2[32];
     const int n1 = exp_scale(e, ne, d.lo, t1);
     const int n2 = exp_scale(e, ne, d.hi, t2);

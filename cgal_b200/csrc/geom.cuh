@@ -163,7 +163,7 @@ B2_HD bool ray_tri_do_intersect(const Tri3& t, const Vec3& p, const Vec3& q, int
 // ---------------------------------------------------------------------------------------------------------------
 // Intersect_3(Ray_3, Triangle_3) + the ray parameter of AABB_ray_intersection.h:168-198
 // ---------------------------------------------------------------------------------------------------------------
-struct RayX { int kind; Vec3 p0, p1; double t; };   // kind 0 none, 1 point, 2 segment
+struct RayX { int kind; Vec3 p0, p1; double t; double u; };   // kind 0 none, 1 point, 2 segment; u = rounding uncertainty of t
 
 B2_HD double ray_param(const Vec3& s, const Vec3& d, int ax, const Vec3& x) { return (comp(x, ax) - comp(s, ax)) / comp(d, ax); }
 B2_HD int ray_major_axis(const Vec3& d) {
@@ -182,7 +182,7 @@ B2_HD Vec3 coplanar_lines_meet(const Vec3& p, const Vec3& v, const Vec3& a, cons
 }
 
 B2_HD_NOINLINE RayX ray_tri_intersection_coplanar(const Tri3& t, const Vec3& p, const Vec3& q, int& nexact) {
-    RayX r; r.kind = 0; r.t = 0; r.p0 = p; r.p1 = p;
+    RayX r; r.kind = 0; r.t = 0; r.u = 0; r.p0 = p; r.p1 = p;
     const CoplanarFrame f = coplanar_frame(t, p, q, nexact);
     const unsigned code = tbl_raytrix(f.idx);
     const int kind = code & 3, arg = code >> 2;
@@ -217,7 +217,7 @@ B2_HD_NOINLINE RayX ray_tri_intersection_coplanar(const Tri3& t, const Vec3& p, 
 
 // Ray_3_Triangle_3_intersection.h:417-539; the hit point is Line_3 x Plane_3 (Line_3_Plane_3_intersection.h:52-85)
 B2_HD RayX ray_tri_intersection(const Tri3& t, const Vec3& s, const Vec3& q, const Vec3& d, int major_axis, int& nexact) {
-    RayX r; r.kind = 0; r.t = 0; r.p0 = s; r.p1 = s;
+    RayX r; r.kind = 0; r.t = 0; r.u = 0; r.p0 = s; r.p1 = s;
     const Vec3 shifted = t.a + d;                         // Ray_3(a, q - s).second_point(): a ROUNDED point (:439)
     const int dir = orient3(t.a, t.b, t.c, shifted, nexact);
     const int sp = orient3(t.a, t.b, t.c, s, nexact);
@@ -225,6 +225,7 @@ B2_HD RayX ray_tri_intersection(const Tri3& t, const Vec3& s, const Vec3& q, con
         r = ray_tri_intersection_coplanar(t, s, q, nexact);
         if (r.kind == 1) r.t = ray_param(s, d, major_axis, r.p0);
         else if (r.kind == 2) r.t = fmin(ray_param(s, d, major_axis, r.p0), ray_param(s, d, major_axis, r.p1));
+        r.u = 1.8e-15 * fabs(r.t);
         return r;
     }
     if (dir == 0 || sp == dir) return r;                  // parallel off-plane, or heading away
@@ -237,6 +238,9 @@ B2_HD RayX ray_tri_intersection(const Tri3& t, const Vec3& s, const Vec3& q, con
     Vec3 x = {den * s.x - num * d.x, den * s.y - num * d.y, den * s.z - num * d.z};
     if (den != 1.0) { x.x = x.x / den; x.y = x.y / den; x.z = x.z / den; }   // Cartesian/Vector_3.h:73-75
     r.kind = 1; r.p0 = x; r.p1 = x; r.t = ray_param(s, d, major_axis, x);
+    // t = -num/den in exact arithmetic: its rounding error grows like |plane terms| / |den| for a grazing ray.  The
+    // reference compares these rounded values, so inside this band its first hit depends on its traversal order.
+    r.u = 1.8e-15 * (2.0 * (((fabs(h.a * s.x) + fabs(h.b * s.y)) + fabs(h.c * s.z)) + fabs(h.d)) / fabs(den) + fabs(r.t));
     return r;
 }
 

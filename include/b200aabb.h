@@ -46,13 +46,28 @@ enum {
   B200AABB_FLAG_TIE = 4,           /* >= 2 primitives attain the winning value EXACTLY (equal t / equal squared distance):
                                       the reference's id then depends on its traversal order;
                                       this library reports the smallest primitive id among them */
-  B200AABB_FLAG_EXACT = 8          /* at least one predicate of this query needed the exact (expansion) stage */
+  B200AABB_FLAG_EXACT = 8,         /* at least one predicate of this query needed the exact (expansion) stage */
+  B200AABB_FLAG_NEAR_TIE = 16      /* not an exact tie, but the runner-up is within the ROUNDING UNCERTAINTY of the winner:
+                                      first_intersection: |t| uncertainty of the plain-double hit construction (large for a ray
+                                      grazing a triangle); closest_point: 16 ulps of the squared distance.  The reference compares
+                                      the same rounded values while pruning boxes with inexact tests (AABB_traits_3.h:89-125;
+                                      AABB_ray_intersection.h:78), so in this band its own answer depends on the order in which its
+                                      tree presents the candidates; this library reports the smallest rounded value */
+};
+
+/* b200aabb_set_option keys */
+enum {
+  B200AABB_OPT_SORT_QUERIES = 1    /* 1 (default): every batch is traversed in a coherence order (Morton order of the points /
+                                      of ray origin+direction, onesweep radix sort on the device); 0: in the caller's order */
 };
 
 typedef struct b200aabb_stats {
   uint64_t kernel_launches;        /* kernels of this library launched since the handle was created */
   uint64_t exact_fallbacks;        /* queries of the last batch that used the exact stage (FLAG_EXACT) */
   uint64_t ties;                   /* queries of the last batch flagged FLAG_TIE */
+  uint64_t near_ties;              /* queries of the last batch flagged FLAG_NEAR_TIE */
+  uint64_t nodes_visited;          /* BVH nodes loaded by the last batch (traversal-traffic model) */
+  uint64_t leaves_tested;          /* primitives tested by the last batch */
   double last_build_ms;            /* device time of the last b200aabb_build (CUDA events) */
   double last_query_ms;            /* device time of the traversal kernel(s) of the last batched query */
   double last_query_total_ms;      /* same, including host<->device copies of the batch when pointers were HOST */
@@ -65,6 +80,7 @@ int b200aabb_create(int device, b200aabb_tree** out);
 int b200aabb_destroy(b200aabb_tree* t);
 /* all work of this handle is enqueued on `cuda_stream` (a cudaStream_t; NULL = the legacy default stream) */
 int b200aabb_set_stream(b200aabb_tree* t, void* cuda_stream);
+int b200aabb_set_option(b200aabb_tree* t, int option, int64_t value);
 const char* b200aabb_last_error(const b200aabb_tree* t);
 int b200aabb_get_stats(const b200aabb_tree* t, b200aabb_stats* out);
 
@@ -113,6 +129,15 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* points, uint64_t n, b
 int b200aabb_export_layout(b200aabb_tree* t, void** ptrs, uint64_t* bytes, int cap, int* count);
 int b200aabb_import_alloc(b200aabb_tree* t, uint64_t n);
 int b200aabb_import_finish(b200aabb_tree* t);
+
+/* ---- self-test hook (used by tests/, not by the reference-side binding) ---------------------------------------------
+ * Evaluates one DEVICE predicate / construction per record (host pointers).  which: 0 Orientation_3(p,q,r,s) [12 doubles],
+ * 1 ray_direction orientation(a,b,c, a+(q-p)) exact [15], 2 Coplanar_orientation_3(p,q,r) [9], 3 Compare_distance_3(p,q,r) [9],
+ * 4 Do_intersect_3(Triangle_3, Segment_3) [15: triangle, source, target], 5 Do_intersect_3(Triangle_3, Ray_3) [15],
+ * 6 Intersect_3(Triangle_3, Ray_3) [15] -> result = 0 none / 1 Point_3 / 2 Segment_3, values[8i..] = t, point, point2, t uncertainty,
+ * 7 Construct_projected_point_3(Triangle_3, Point_3) [12] -> values[8i..8i+2], 8 the exact stage of Orientation_3 alone [12].
+ * used_exact[i] (optional) = number of predicate evaluations of the record that reached the exact stage. */
+int b200aabb_debug_predicate(int device, int which, const double* records, int doubles_per_record, uint64_t n, int* result, int* used_exact, double* values);
 
 /* library / build identification, e.g. "b200aabb 0.1 sm_100a" */
 const char* b200aabb_version(void);

@@ -89,14 +89,14 @@ class HostTree:
         prim, t, pts = np.zeros(n, np.uint32), np.zeros(n), np.zeros((n, 6))
         kind, tie = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
         lib().hc_first_intersection(self.h, _p(rays), n, _p(prim, _u32p), _p(t), _p(pts), _p(kind, _u8p), _p(tie, _u8p))
-        return dict(prim=prim, t=t, pts=pts, kind=kind, tie=tie)
+        return dict(prim=prim, t=t, pts=pts, kind=kind, tie=tie & 1, near=(tie >> 1) & 1)
 
     def closest_point(self, q):
         q = _d(q).reshape(-1, 3)
         n = len(q)
         cp, prim, sqd, tie = np.zeros((n, 3)), np.zeros(n, np.uint32), np.zeros(n), np.zeros(n, np.uint8)
         lib().hc_closest_point(self.h, _p(q), n, _p(cp), _p(prim, _u32p), _p(sqd), _p(tie, _u8p))
-        return dict(cp=cp, prim=prim, sqd=sqd, tie=tie)
+        return dict(cp=cp, prim=prim, sqd=sqd, tie=tie & 1, near=(tie >> 1) & 1)
 
 
 def validate(nodes_u8, tris_u8, n):

@@ -13,7 +13,8 @@
 using namespace b2;
 
 namespace {
-struct HostTree { std::vector<BvhNode> nodes; std::vector<TriRec> tris; uint32_t root = kNone; uint64_t n = 0; double bbox[6]; std::vector<uint64_t> keys; };
+struct HostTree { std::vector<BvhNode> nodes; std::vector<TriRec> tris; uint32_t root = kNone; uint64_t n = 0; double bbox[6]; std::vector<uint64_t> keys;
+    double mag() const { double m = 0; for (int a = 0; a < 6; ++a) if (std::isfinite(bbox[a])) m = std::max(m, std::fabs(bbox[a])); return m; } };
 Vec3 V(const double* p) { return {p[0], p[1], p[2]}; }
 Tri3 T(const double* p) { return {V(p), V(p + 3), V(p + 6)}; }
 
@@ -40,8 +41,8 @@ void* hc_build(const double* tris, const uint32_t* ids, uint64_t n) {
     if (n == 0) return h;
     double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
     for (uint64_t i = 0; i < n; ++i) for (int k = 0; k < 9; ++k) { lo[k % 3] = std::min(lo[k % 3], tris[9 * i + k]); hi[k % 3] = std::max(hi[k % 3], tris[9 * i + k]); }
-    double scale[3];
-    for (int k = 0; k < 3; ++k) { const double ext = hi[k] - lo[k]; scale[k] = ext > 0.0 ? 2097152.0 / ext : 0.0; }
+    double scale[3], lo_[3];
+    morton_frame(lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], lo_, scale);
     std::vector<uint64_t> keys(n);
     for (uint64_t i = 0; i < n; ++i) {
         double c[3];
@@ -120,20 +121,20 @@ int hc_validate(const void* nodes_v, const void* tris_v, uint64_t n) {
 void hc_intersect(void* hv, const double* q, uint64_t n, int is_ray, int count, uint32_t* out) {
     HostTree* h = (HostTree*)hv;
     for (uint64_t i = 0; i < n; ++i) {
-        int nex = 0, ovf = 0;
+        TravStat st;
         if (h->n == 0) { out[i] = 0; continue; }
         const Vec3 s = V(q + 6 * i), e = V(q + 6 * i + 3);
-        if (is_ray) out[i] = count ? traverse_intersect<true, true>(h->nodes.data(), h->tris.data(), h->root, s, e, nex, ovf) : traverse_intersect<true, false>(h->nodes.data(), h->tris.data(), h->root, s, e, nex, ovf);
-        else out[i] = count ? traverse_intersect<false, true>(h->nodes.data(), h->tris.data(), h->root, s, e, nex, ovf) : traverse_intersect<false, false>(h->nodes.data(), h->tris.data(), h->root, s, e, nex, ovf);
+        if (is_ray) out[i] = count ? traverse_intersect<true, true>(h->nodes.data(), h->tris.data(), h->root, s, e, st) : traverse_intersect<true, false>(h->nodes.data(), h->tris.data(), h->root, s, e, st);
+        else out[i] = count ? traverse_intersect<false, true>(h->nodes.data(), h->tris.data(), h->root, s, e, st) : traverse_intersect<false, false>(h->nodes.data(), h->tris.data(), h->root, s, e, st);
     }
 }
 void hc_first_intersection(void* hv, const double* rays, uint64_t n, uint32_t* prim, double* t, double* pts, uint8_t* kind, uint8_t* tie) {
     HostTree* h = (HostTree*)hv;
     for (uint64_t i = 0; i < n; ++i) {
-        int nex = 0, ovf = 0;
+        TravStat st;
         if (h->n == 0) { prim[i] = kNone; t[i] = 0; kind[i] = 0; tie[i] = 0; memset(pts + 6 * i, 0, 48); continue; }
-        const FirstHit f = traverse_first(h->nodes.data(), h->tris.data(), h->root, V(rays + 6 * i), V(rays + 6 * i + 3), nex, ovf);
-        prim[i] = f.prim; t[i] = f.prim == kNone ? 0.0 : f.t; kind[i] = (uint8_t)f.kind; tie[i] = (uint8_t)f.tie;
+        const FirstHit f = traverse_first(h->nodes.data(), h->tris.data(), h->root, V(rays + 6 * i), V(rays + 6 * i + 3), h->mag(), st);
+        prim[i] = f.prim; t[i] = f.prim == kNone ? 0.0 : f.t; kind[i] = (uint8_t)f.kind; tie[i] = (uint8_t)(f.tie | (f.near << 1));
         memset(pts + 6 * i, 0, 48);
         if (f.prim != kNone) { pts[6 * i] = f.p0.x; pts[6 * i + 1] = f.p0.y; pts[6 * i + 2] = f.p0.z; if (f.kind == 2) { pts[6 * i + 3] = f.p1.x; pts[6 * i + 4] = f.p1.y; pts[6 * i + 5] = f.p1.z; } }
     }
@@ -141,9 +142,9 @@ void hc_first_intersection(void* hv, const double* rays, uint64_t n, uint32_t* p
 void hc_closest_point(void* hv, const double* q, uint64_t n, double* cp, uint32_t* prim, double* sqd, uint8_t* tie) {
     HostTree* h = (HostTree*)hv;
     for (uint64_t i = 0; i < n; ++i) {
-        int nex = 0, ovf = 0;
-        const Closest c = traverse_closest(h->nodes.data(), h->tris.data(), h->root, V(q + 3 * i), nex, ovf);
-        cp[3 * i] = c.p.x; cp[3 * i + 1] = c.p.y; cp[3 * i + 2] = c.p.z; prim[i] = c.prim; sqd[i] = c.sqd; tie[i] = (uint8_t)c.tie;
+        TravStat st;
+        const Closest c = traverse_closest(h->nodes.data(), h->tris.data(), h->root, V(q + 3 * i), h->mag(), st);
+        cp[3 * i] = c.p.x; cp[3 * i + 1] = c.p.y; cp[3 * i + 2] = c.p.z; prim[i] = c.prim; sqd[i] = c.sqd; tie[i] = (uint8_t)(c.tie | (c.near << 1));
     }
 }
 
