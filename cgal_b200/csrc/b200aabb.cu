@@ -320,8 +320,9 @@ int do_build(b200aabb_tree* t) {
         hierarchy_kernel<<<blocks, 256, 0, st>>>(keys[cur], n, t->d_nodes, leaf_parent);
         t->stats.kernel_launches += 1;
     }
-    refit_kernel<<<blocks, 256, 0, st>>>(t->d_tris, n, t->d_nodes, leaf_parent, t->d_rootbox);
-    t->stats.kernel_launches += 1;
+    refit_kernel<<<blocks, 256, 0, st>>>(t->d_tris, n, t->d_nodes, leaf_parent);
+    root_box_kernel<<<1, 32, 0, st>>>(bounds, t->d_rootbox);
+    t->stats.kernel_launches += 2;
     B2_TRY(cudaEventRecord(t->ev_b, st));
     B2_TRY(cudaMemcpyAsync(t->h_bbox, t->d_rootbox, 48, cudaMemcpyDeviceToHost, st));
     B2_TRY(cudaStreamSynchronize(st));

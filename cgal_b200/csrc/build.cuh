@@ -6,8 +6,9 @@
 //   [radix_sort.cuh]     onesweep sort of (key, primitive index)
 //   emit_leaves_kernel   TriRec records in Morton order
 //   hierarchy_kernel     Karras 2012 radix-tree topology, one thread per internal node
-//   refit_kernel         bottom-up boxes with one atomic arrival counter per node; min/max in binary64 are exact,
-//                        so every node box is bit-equal to the exact union of its primitives' boxes
+//   refit_kernel         bottom-up boxes with one atomic arrival counter per node.  A primitive's exact binary64 box is
+//                        rounded OUTWARD to binary32 once; min/max are exact and commute with the monotone rounding, so
+//                        every node box is bit-equal to the outward rounding of the exact union of its primitives' boxes
 #pragma once
 #include "bvh.cuh"
 
@@ -63,6 +64,11 @@ __global__ void __launch_bounds__(256) scene_bounds_kernel(const double* __restr
         if (threadIdx.x < 3) atomicMin(&bounds[threadIdx.x], ordered_bits(v));
         else atomicMax(&bounds[threadIdx.x], ordered_bits(v));
     }
+}
+
+// bbox() of the tree (AABB_tree.h:204-210) = the exact scene bounds, decoded from the ordered-integer atomics
+__global__ void root_box_kernel(const unsigned long long* __restrict__ bounds, double* __restrict__ root_box) {
+    if (threadIdx.x < 6) root_box[threadIdx.x] = from_ordered_bits(bounds[threadIdx.x]);
 }
 
 B2_HD uint64_t spread21(uint64_t x) {   // insert two zero bits after each of the low 21 bits
@@ -138,7 +144,7 @@ B2_HD int karras_delta(const uint64_t* __restrict__ keys, int64_t n, int64_t i, 
 }
 
 // topology of internal node i (Karras, "Maximizing Parallelism in the Construction of BVHs, Octrees, and k-d Trees", 2012)
-B2_HD void karras_node(const uint64_t* __restrict__ keys, int64_t n, int64_t i, uint32_t& left, uint32_t& right, uint32_t& first, uint32_t& last) {
+B2_HD void karras_node(const uint64_t* __restrict__ keys, int64_t n, int64_t i, uint32_t& left, uint32_t& right) {
     const int d = karras_delta(keys, n, i, i + 1) - karras_delta(keys, n, i, i - 1) >= 0 ? 1 : -1;
     const int dmin = karras_delta(keys, n, i, i - d);
     int64_t lmax = 2;
@@ -157,51 +163,48 @@ B2_HD void karras_node(const uint64_t* __restrict__ keys, int64_t n, int64_t i, 
     const int64_t lo = i < j ? i : j, hi = i < j ? j : i;
     left = lo == gamma ? (kLeafBit | (uint32_t)gamma) : (uint32_t)gamma;
     right = hi == gamma + 1 ? (kLeafBit | (uint32_t)(gamma + 1)) : (uint32_t)(gamma + 1);
-    first = (uint32_t)lo; last = (uint32_t)hi;
 }
 
 __global__ void __launch_bounds__(256) hierarchy_kernel(const uint64_t* __restrict__ keys, uint64_t n, BvhNode* __restrict__ nodes, uint32_t* __restrict__ leaf_parent) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i + 1 >= n) return;
-    uint32_t l, r, f, e;
-    karras_node(keys, (int64_t)n, (int64_t)i, l, r, f, e);
+    uint32_t l, r;
+    karras_node(keys, (int64_t)n, (int64_t)i, l, r);
     BvhNode* nd = nodes + i;
-    nd->child[0] = l; nd->child[1] = r; nd->visit = 0; nd->first = f; nd->last = e; nd->pad[0] = 0; nd->pad[1] = 0;
+    nd->child[0] = l; nd->child[1] = r; nd->visit = 0;
     if (i == 0) nd->parent = kNone;
     if (l & kLeafBit) leaf_parent[l & ~kLeafBit] = (uint32_t)i; else nodes[l].parent = (uint32_t)i;
     if (r & kLeafBit) leaf_parent[r & ~kLeafBit] = (uint32_t)i; else nodes[r].parent = (uint32_t)i;
 }
 
 // one thread per leaf; the second thread to arrive at a node continues upwards with the union of both child boxes
-__global__ void __launch_bounds__(256) refit_kernel(const TriRec* __restrict__ tris, uint64_t n, BvhNode* nodes, const uint32_t* __restrict__ leaf_parent,
-                                                    double* __restrict__ root_box) {
+__global__ void __launch_bounds__(256) refit_kernel(const TriRec* __restrict__ tris, uint64_t n, BvhNode* nodes, const uint32_t* __restrict__ leaf_parent) {
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n) return;
-    double lo[3], hi[3];
+    if (k >= n || n == 1) return;
+    float lo[3], hi[3];
     {
         const double* v = tris[k].v;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { lo[a] = fmin(v[a], fmin(v[3 + a], v[6 + a])); hi[a] = fmax(v[a], fmax(v[3 + a], v[6 + a])); }
+        for (int a = 0; a < 3; ++a) { lo[a] = float_below(fmin(v[a], fmin(v[3 + a], v[6 + a]))); hi[a] = float_above(fmax(v[a], fmax(v[3 + a], v[6 + a]))); }
     }
-    if (n == 1) { for (int a = 0; a < 3; ++a) { root_box[a] = lo[a]; root_box[3 + a] = hi[a]; } return; }
     uint32_t me = kLeafBit | (uint32_t)k;
     uint32_t p = leaf_parent[k];
     while (true) {
         BvhNode* nd = nodes + p;
         const int side = (nd->child[0] == me) ? 0 : 1;
-        double* mylo = side ? nd->lo1 : nd->lo0; double* myhi = side ? nd->hi1 : nd->hi0;
+        float* mylo = side ? nd->lo1 : nd->lo0; float* myhi = side ? nd->hi1 : nd->hi0;
 #pragma unroll
         for (int a = 0; a < 3; ++a) { mylo[a] = lo[a]; myhi[a] = hi[a]; }
         __threadfence();
         if (atomicAdd(&nd->visit, 1u) == 0) return;              // first to arrive: the sibling will carry on
         __threadfence();
         // the sibling box was written by another SM: read it through L2 (this SM's L1 may hold the line from the child[] read)
-        const double* olo = side ? nd->lo0 : nd->lo1; const double* ohi = side ? nd->hi0 : nd->hi1;
+        const float* olo = side ? nd->lo0 : nd->lo1; const float* ohi = side ? nd->hi0 : nd->hi1;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { lo[a] = fmin(lo[a], __ldcg(olo + a)); hi[a] = fmax(hi[a], __ldcg(ohi + a)); }
+        for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], __ldcg(olo + a)); hi[a] = fmaxf(hi[a], __ldcg(ohi + a)); }
         me = p;
         p = nd->parent;
-        if (p == kNone) { for (int a = 0; a < 3; ++a) { root_box[a] = lo[a]; root_box[3 + a] = hi[a]; } return; }
+        if (p == kNone) return;
     }
 }
 

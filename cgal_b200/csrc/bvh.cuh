@@ -1,18 +1,20 @@
 // bvh.cuh — HBM layout of the tree and the per-query traversal routines.
 //
 // Layout:
-//   BvhNode  128 B  one INTERNAL node of the binary LBVH; it carries the boxes of BOTH children, so a traversal step
-//                   costs one 128-byte line and leaf boxes never need their own node.  N-1 nodes for N primitives.
-//   TriRec    96 B  one primitive in Morton order: 9 coordinates (v0,v1,v2), the primitive id, padding to 3 sectors.
+//   BvhNode   64 B  one INTERNAL node of the binary LBVH.  It carries the boxes of BOTH children as binary32 intervals
+//                   rounded OUTWARD from the exact binary64 boxes (lo towards -inf, hi towards +inf), so a traversal step
+//                   costs two 32-byte sectors and leaf boxes never need their own node.  N-1 nodes for N primitives.
+//   TriRec    96 B  one primitive in Morton order: 9 binary64 coordinates (v0,v1,v2), the primitive id, padding to 3 sectors.
 // Child reference: bit 31 set = leaf, low bits = slot in the TriRec array; else index of an internal node.
 //
 // Traversal replaces (paths relative to the CGAL source root)
 //   AABB_tree/include/CGAL/AABB_tree/internal/AABB_node.h:129-167              recursive traversal
 //   AABB_tree/include/CGAL/AABB_tree/internal/AABB_traversal_traits.h:150-327  Listing/Do_intersect/Projection traits
 //   AABB_tree/include/CGAL/AABB_tree/internal/AABB_ray_intersection.h:49-150   best-first first_intersection
-// by an iterative stack traversal per query.  Node tests are CONSERVATIVE floating-point tests (never reject a box
-// that contains a qualifying primitive); every decision that reaches the result is taken by the exact leaf routines
-// of geom.cuh, so booleans, counts and winners do not depend on the tree shape (SURVEY.md §3.4, §7 hard part 1).
+// by an iterative stack traversal per query.  Node tests are CONSERVATIVE binary32 tests with explicit error terms
+// (they never reject a box that contains a qualifying primitive) and run on the FP32 pipe; every decision that reaches
+// the result is taken by the exact binary64 leaf routines of geom.cuh, so booleans, counts and winners do not depend on
+// the tree shape or on the box precision (SURVEY.md §3.4, §7 hard part 1).
 #pragma once
 #include <stdint.h>
 #include "geom.cuh"
@@ -24,15 +26,13 @@ constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr int kStackCap = 96;
 
 struct __align__(16) BvhNode {
-    double lo0[3], hi0[3];
-    double lo1[3], hi1[3];
+    float lo0[3], hi0[3];  // child 0
+    float lo1[3], hi1[3];  // child 1
     uint32_t child[2];
-    uint32_t parent;
-    uint32_t visit;       // refit arrival counter (build only)
-    uint32_t first, last; // range of sorted primitive slots below this node
-    uint32_t pad[2];
+    uint32_t parent;       // build / refit only
+    uint32_t visit;        // refit arrival counter (build only)
 };
-static_assert(sizeof(BvhNode) == 128, "node is one 128-byte line");
+static_assert(sizeof(BvhNode) == 64, "node is two 32-byte sectors");
 
 struct __align__(16) TriRec {
     double v[9];
@@ -44,16 +44,58 @@ static_assert(sizeof(TriRec) == 96, "triangle record is three 32-byte sectors");
 // per-query traversal statistics (accumulated into the handle's counters by the kernels)
 struct TravStat { int nexact = 0; int overflow = 0; uint32_t nodes = 0, leaves = 0; };
 
-struct NodeView { double lo0[3], hi0[3], lo1[3], hi1[3]; uint32_t c0, c1; };
+// directed roundings binary64 -> binary32 (any finite input; overflow saturates to +-FLT_MAX / +-inf on the safe side)
+B2_HD float float_below(double v) {
+#if defined(__CUDA_ARCH__)
+    return __double2float_rd(v);
+#else
+    float f = (float)v;
+    if ((double)f > v) f = nextafterf(f, -INFINITY);
+    return f;
+#endif
+}
+B2_HD float float_above(double v) {
+#if defined(__CUDA_ARCH__)
+    return __double2float_ru(v);
+#else
+    float f = (float)v;
+    if ((double)f < v) f = nextafterf(f, INFINITY);
+    return f;
+#endif
+}
+// directed binary32 arithmetic (single instructions with a rounding modifier on the device)
+B2_HD float sub_dn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fsub_rd(a, b);
+#else
+    return float_below((double)a - (double)b);      // the binary64 difference of two floats is exact
+#endif
+}
+B2_HD float mul_dn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fmul_rd(a, b);
+#else
+    return float_below((double)a * (double)b);      // the binary64 product of two floats is exact
+#endif
+}
+B2_HD float add_dn(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return __fadd_rd(a, b);
+#else
+    return float_below((double)a + (double)b);
+#endif
+}
+
+struct NodeView { float lo0[3], hi0[3], lo1[3], hi1[3]; uint32_t c0, c1; };
 
 B2_HD NodeView load_node(const BvhNode* __restrict__ nodes, uint32_t i) {
     NodeView n;
 #if defined(__CUDA_ARCH__)
-    const double2* p = reinterpret_cast<const double2*>(nodes + i);
-    const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3), e = __ldg(p + 4), f = __ldg(p + 5);
-    const uint4 m = __ldg(reinterpret_cast<const uint4*>(p + 6));
-    n.lo0[0] = a.x; n.lo0[1] = a.y; n.lo0[2] = b.x; n.hi0[0] = b.y; n.hi0[1] = c.x; n.hi0[2] = c.y;
-    n.lo1[0] = d.x; n.lo1[1] = d.y; n.lo1[2] = e.x; n.hi1[0] = e.y; n.hi1[1] = f.x; n.hi1[2] = f.y;
+    const float4* p = reinterpret_cast<const float4*>(nodes + i);
+    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
+    const uint4 m = __ldg(reinterpret_cast<const uint4*>(p + 3));
+    n.lo0[0] = a.x; n.lo0[1] = a.y; n.lo0[2] = a.z; n.hi0[0] = a.w; n.hi0[1] = b.x; n.hi0[2] = b.y;
+    n.lo1[0] = b.z; n.lo1[1] = b.w; n.lo1[2] = c.x; n.hi1[0] = c.y; n.hi1[1] = c.z; n.hi1[2] = c.w;
     n.c0 = m.x; n.c1 = m.y;
 #else
     const BvhNode& s = nodes[i];
@@ -80,11 +122,13 @@ B2_HD Tri3 load_tri(const TriRec* __restrict__ tris, uint32_t slot, uint32_t& id
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Conservative node tests
+// Conservative node tests (binary32 with explicit error terms)
 // ---------------------------------------------------------------------------------------------------------------
 struct LineCtx {              // Segment_3 / Ray_3 query, parametrised x(t) = s + t (q - s)
-    Vec3 s, q, d;             // d = q - s (rounded once)
-    double inv[3];            // 1/d per axis (unused where d == 0)
+    Vec3 s, q, d;             // d = q - s (rounded once, binary64)
+    float sf[3];              // s rounded to nearest binary32
+    float inv[3];             // 1/d per axis rounded to binary32 (unused where d == 0)
+    float err[3];             // |s - sf| * |1/d| (rounded up): error of a slab parameter caused by rounding the source
     int zero_mask;            // axes with d == 0
     int major;                // argmax |d| (first max wins), AABB_ray_intersection.h:171-176
     double t_abs_slack;       // absolute error allowance on computed hit parameters
@@ -93,49 +137,56 @@ struct LineCtx {              // Segment_3 / Ray_3 query, parametrised x(t) = s 
 B2_HD LineCtx make_line(const Vec3& s, const Vec3& q, double mag = 0.0) {
     LineCtx c; c.s = s; c.q = q; c.d = q - s;
     c.zero_mask = (c.d.x == 0.0 ? 1 : 0) | (c.d.y == 0.0 ? 2 : 0) | (c.d.z == 0.0 ? 4 : 0);
-    c.inv[0] = 1.0 / c.d.x; c.inv[1] = 1.0 / c.d.y; c.inv[2] = 1.0 / c.d.z;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double si = comp(s, i), inv = 1.0 / comp(c.d, i);
+        c.sf[i] = (float)si;
+        c.inv[i] = (float)inv;
+        c.err[i] = float_above(fabs(si - (double)c.sf[i]) * fabs(inv) * 1.0000001) + 1e-37f;   // + underflow guard
+    }
     c.major = ray_major_axis(c.d);
     const double smax = fmax(mag, fmax3(fabs(s.x), fabs(s.y), fabs(s.z)));
     c.t_abs_slack = 1.5e-14 * smax / fabs(comp(c.d, c.major));
     return c;
 }
-// does x(t), t in [0, tlimit], possibly meet the closed box?  tn = conservative lower bound of the entry parameter.
-// Every computed slab parameter carries <= 4 roundings (d, 1/d, lo - s, product); it is widened by 1e-15 relative.
-B2_HD bool line_box(const double* lo, const double* hi, const LineCtx& c, double tlimit, double& tn) {
-    double tnear = 0.0, tfar = tlimit;
+// Does x(t), t in [0, tlimit], possibly meet the closed box [lo, hi]?  tn = lower bound of the entry parameter.
+// Per axis the computed parameter t_c = (b - sf) * inv differs from the true (b - s) / d by at most
+// |t_c| * 2^-21 (one subtraction, one product, the rounding of 1/d and of d itself: < 4 * 2^-24 relative) + err[i]
+// (rounding of the source).  NaNs (0 * inf, inf - inf) are dropped by fminf/fmaxf, which only loosens the interval.
+B2_HD bool line_box(const float* lo, const float* hi, const LineCtx& c, float tlimit, float& tn) {
+    float tnear = 0.0f, tfar = tlimit;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-        const double si = comp(c.s, i);
         if (c.zero_mask & (1 << i)) {
-            if (si < lo[i] || si > hi[i]) return false;
+            const double si = comp(c.s, i);
+            if (si < (double)lo[i] || si > (double)hi[i]) return false;
         } else {
-            const double t1 = (lo[i] - si) * c.inv[i], t2 = (hi[i] - si) * c.inv[i];
-            double a = fmin(t1, t2), b = fmax(t1, t2);
-            a = a - fabs(a) * 1e-15;
-            b = b + fabs(b) * 1e-15;
-            tnear = fmax(tnear, a);
-            tfar = fmin(tfar, b);
+            const float t1 = (lo[i] - c.sf[i]) * c.inv[i], t2 = (hi[i] - c.sf[i]) * c.inv[i];
+            float a = fminf(t1, t2), b = fmaxf(t1, t2);
+            a = a - (fabsf(a) * 4.76837158e-7f + c.err[i]);
+            b = b + (fabsf(b) * 4.76837158e-7f + c.err[i]);
+            tnear = fmaxf(tnear, a);
+            tfar = fminf(tfar, b);
         }
     }
     tn = tnear;
     return tnear <= tfar;
 }
-// largest float <= v for v >= 0 (a lower bound that survives the narrowing)
-B2_HD float float_below(double v) {
-#if defined(__CUDA_ARCH__)
-    return __double2float_rd(v);
-#else
-    float f = (float)v;
-    if ((double)f > v) f = nextafterf(f, -INFINITY);
-    return f;
-#endif
+
+struct PointCtx { float up[3], dn[3]; };   // the query point rounded up / down to binary32
+B2_HD PointCtx make_point(const Vec3& p) {
+    PointCtx c;
+    c.up[0] = float_above(p.x); c.up[1] = float_above(p.y); c.up[2] = float_above(p.z);
+    c.dn[0] = float_below(p.x); c.dn[1] = float_below(p.y); c.dn[2] = float_below(p.z);
+    return c;
 }
-// squared distance from p to the closed box, in plain double (relative error a few ulps)
-B2_HD double point_box_sqdist(const double* lo, const double* hi, const Vec3& p) {
-    const double dx = fmax(fmax(lo[0] - p.x, p.x - hi[0]), 0.0);
-    const double dy = fmax(fmax(lo[1] - p.y, p.y - hi[1]), 0.0);
-    const double dz = fmax(fmax(lo[2] - p.z, p.z - hi[2]), 0.0);
-    return (dx * dx + dy * dy) + dz * dz;
+// LOWER bound of the squared distance from the query point to the closed box: every operation rounds towards the
+// smaller result (lo - p >= lo - p_up, p - hi >= p_dn - hi; sums and products of non-negative terms rounded down)
+B2_HD float point_box_sqdist(const float* lo, const float* hi, const PointCtx& c) {
+    const float dx = fmaxf(fmaxf(sub_dn(lo[0], c.up[0]), sub_dn(c.dn[0], hi[0])), 0.0f);
+    const float dy = fmaxf(fmaxf(sub_dn(lo[1], c.up[1]), sub_dn(c.dn[1], hi[1])), 0.0f);
+    const float dz = fmaxf(fmaxf(sub_dn(lo[2], c.up[2]), sub_dn(c.dn[2], hi[2])), 0.0f);
+    return add_dn(add_dn(mul_dn(dx, dx), mul_dn(dy, dy)), mul_dn(dz, dz));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -145,7 +196,7 @@ template <bool IS_RAY, bool COUNT>
 B2_HD uint32_t traverse_intersect(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root,
                                   const Vec3& s, const Vec3& q, TravStat& st) {
     const LineCtx c = make_line(s, q);
-    const double tlimit = IS_RAY ? DBL_MAX : 1.0;
+    const float tlimit = IS_RAY ? INFINITY : 1.0f;
     uint32_t found = 0;
     auto leaf = [&](uint32_t ref) {
         uint32_t id;
@@ -160,7 +211,7 @@ B2_HD uint32_t traverse_intersect(const BvhNode* __restrict__ nodes, const TriRe
     while (true) {
         const NodeView n = load_node(nodes, cur);
         ++st.nodes;
-        double tn;
+        float tn;
         const bool h0 = line_box(n.lo0, n.hi0, c, tlimit, tn);
         const bool h1 = line_box(n.lo1, n.hi1, c, tlimit, tn);
         uint32_t next = kNone;
@@ -201,7 +252,7 @@ B2_HD FirstHit traverse_first(const BvhNode* __restrict__ nodes, const TriRec* _
     double best_u = 0.0;
     double runner_up = DBL_MAX;   // smallest t among the intersected primitives that are not the winner
     double runner_lo = DBL_MAX;   // smallest (t - u) among them
-    double tlimit = DBL_MAX;      // prune boxes whose entry parameter certainly exceeds the best hit
+    float tlimit = INFINITY;      // prune boxes whose entry parameter certainly exceeds the best hit (rounded up)
     auto leaf = [&](uint32_t ref) {
         uint32_t id;
         const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
@@ -211,37 +262,37 @@ B2_HD FirstHit traverse_first(const BvhNode* __restrict__ nodes, const TriRec* _
         if (x.t < best.t || (x.t == best.t && id < best.prim)) {
             if (best.prim != kNone) { runner_up = fmin(runner_up, best.t); runner_lo = fmin(runner_lo, best.t - best_u); }
             best.prim = id; best.kind = x.kind; best.t = x.t; best.p0 = x.p0; best.p1 = x.p1; best_u = x.u;
-            tlimit = x.t + ((fabs(x.t) * 2e-6 + x.u) + c.t_abs_slack);
+            tlimit = float_above(x.t + ((fabs(x.t) * 2e-6 + x.u) + c.t_abs_slack));
         } else {
             runner_up = fmin(runner_up, x.t); runner_lo = fmin(runner_lo, x.t - x.u);
         }
     };
     if (root & kLeafBit) { leaf(root); return best; }
     uint32_t stack[kStackCap];
-    float stack_t[kStackCap];     // entry parameter rounded DOWN to float (still a lower bound)
+    float stack_t[kStackCap];     // lower bound of the deferred node's entry parameter
     int sp = 0;
     uint32_t cur = root;
     while (true) {
         const NodeView n = load_node(nodes, cur);
         ++st.nodes;
-        double t0, t1;
+        float t0, t1;
         bool h0 = line_box(n.lo0, n.hi0, c, tlimit, t0);
         bool h1 = line_box(n.lo1, n.hi1, c, tlimit, t1);
         uint32_t c0 = n.c0, c1 = n.c1;
-        if (h0 && h1 && t1 < t0) { const uint32_t tc = c0; c0 = c1; c1 = tc; const double tt = t0; t0 = t1; t1 = tt; }
+        if (h0 && h1 && t1 < t0) { const uint32_t tc = c0; c0 = c1; c1 = tc; const float tt = t0; t0 = t1; t1 = tt; }
         else if (!h0 && h1) { c0 = c1; t0 = t1; h0 = true; h1 = false; }
         uint32_t next = kNone;
         if (h0) { if (c0 & kLeafBit) leaf(c0); else next = c0; }
         if (h1 && t1 <= tlimit) {
             if (c1 & kLeafBit) leaf(c1);
             else if (next == kNone) next = c1;
-            else if (sp < kStackCap) { stack[sp] = c1; stack_t[sp] = float_below(t1); ++sp; }
+            else if (sp < kStackCap) { stack[sp] = c1; stack_t[sp] = t1; ++sp; }
             else st.overflow = 1;
         }
         while (next == kNone) {
             if (sp == 0) goto done;
             --sp;
-            if ((double)stack_t[sp] <= tlimit) next = stack[sp];
+            if (stack_t[sp] <= tlimit) next = stack[sp];
         }
         cur = next;
     }
@@ -270,7 +321,9 @@ B2_HD Closest traverse_closest(const BvhNode* __restrict__ nodes, const TriRec* 
                                const Vec3& o, double mag, TravStat& st) {
     Closest best; best.p = o; best.prim = kNone; best.sqd = DBL_MAX; best.tie = 0; best.near = 0;
     const double delta = 4e-16 * fmax(mag, fmax3(fabs(o.x), fabs(o.y), fabs(o.z)));
-    double bound = DBL_MAX, runner_up = DBL_MAX;
+    const PointCtx pc = make_point(o);
+    float bound = INFINITY;       // prune boxes certainly farther than the incumbent (widened, rounded up)
+    double runner_up = DBL_MAX;
     auto leaf = [&](uint32_t ref) {
         uint32_t id;
         const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
@@ -288,32 +341,32 @@ B2_HD Closest traverse_closest(const BvhNode* __restrict__ nodes, const TriRec* 
         }
         if (take) {
             best.p = cp; best.prim = id; best.sqd = sqd;
-            bound = widen_sqdist(sqd, delta);
+            bound = float_above(widen_sqdist(sqd, delta));
         }
     };
     if (root & kLeafBit) { leaf(root); return best; }
     uint32_t stack[kStackCap];
-    float stack_d[kStackCap];     // box distance rounded DOWN to float (still a lower bound)
+    float stack_d[kStackCap];     // lower bound of the deferred node's squared distance
     int sp = 0;
     uint32_t cur = root;
     while (true) {
         const NodeView n = load_node(nodes, cur);
         ++st.nodes;
-        double d0 = point_box_sqdist(n.lo0, n.hi0, o), d1 = point_box_sqdist(n.lo1, n.hi1, o);
+        float d0 = point_box_sqdist(n.lo0, n.hi0, pc), d1 = point_box_sqdist(n.lo1, n.hi1, pc);
         uint32_t c0 = n.c0, c1 = n.c1;
-        if (d1 < d0) { const uint32_t tc = c0; c0 = c1; c1 = tc; const double td = d0; d0 = d1; d1 = td; }
+        if (d1 < d0) { const uint32_t tc = c0; c0 = c1; c1 = tc; const float td = d0; d0 = d1; d1 = td; }
         uint32_t next = kNone;
         if (d0 <= bound) { if (c0 & kLeafBit) leaf(c0); else next = c0; }
         if (d1 <= bound) {
             if (c1 & kLeafBit) leaf(c1);
             else if (next == kNone) next = c1;
-            else if (sp < kStackCap) { stack[sp] = c1; stack_d[sp] = float_below(d1); ++sp; }
+            else if (sp < kStackCap) { stack[sp] = c1; stack_d[sp] = d1; ++sp; }
             else st.overflow = 1;
         }
         while (next == kNone) {
             if (sp == 0) goto done;
             --sp;
-            if ((double)stack_d[sp] <= bound) next = stack[sp];
+            if (stack_d[sp] <= bound) next = stack[sp];
         }
         cur = next;
     }

@@ -43,6 +43,8 @@ def lib():
         L.hc_tri_ray_intersection.argtypes = [_dp, _dp, _dp, _dp]
         L.hc_closest_on_triangle.argtypes = [_dp, _dp, _dp]
         L.hc_line_box.argtypes = [_dp, _dp, C.c_int]
+        L.hc_point_box_sqdist.argtypes = [_dp, _dp]
+        L.hc_point_box_sqdist.restype = C.c_double
         L.hc_sizeof_node.restype = C.c_uint64
         L.hc_sizeof_tri.restype = C.c_uint64
         _LIB = L
@@ -71,7 +73,7 @@ class HostTree:
 
     def export(self):
         nn = lib().hc_num_nodes(self.h)
-        nodes = np.zeros(nn * 128, np.uint8)
+        nodes = np.zeros(nn * 64, np.uint8)
         tris = np.zeros(self.n * 96, np.uint8)
         bbox = np.zeros(6)
         lib().hc_export(self.h, nodes.ctypes.data_as(C.c_void_p), tris.ctypes.data_as(C.c_void_p), _p(bbox))
@@ -126,6 +128,11 @@ def closest_on_triangle(tri, q):
     out = np.zeros(3)
     lib().hc_closest_on_triangle(_p(tri), _p(q), _p(out))
     return out
+
+
+def point_box_sqdist(box, p):
+    box, p = _d(box).ravel(), _d(p).ravel()
+    return lib().hc_point_box_sqdist(_p(box), _p(p))
 
 
 def line_box(box, pq, is_ray):

@@ -4,6 +4,7 @@
 // used as a fallback: the product library has no host execution path.
 #include <algorithm>
 #include <cstdint>
+#include <cmath>
 #include <cstring>
 #include <numeric>
 #include <vector>
@@ -18,10 +19,10 @@ struct HostTree { std::vector<BvhNode> nodes; std::vector<TriRec> tris; uint32_t
 Vec3 V(const double* p) { return {p[0], p[1], p[2]}; }
 Tri3 T(const double* p) { return {V(p), V(p + 3), V(p + 6)}; }
 
-void refit(HostTree& h, uint32_t ref, double* lo, double* hi) {
+void refit(HostTree& h, uint32_t ref, float* lo, float* hi) {
     if (ref & kLeafBit) {
         const double* v = h.tris[ref & ~kLeafBit].v;
-        for (int a = 0; a < 3; ++a) { lo[a] = std::min(v[a], std::min(v[3 + a], v[6 + a])); hi[a] = std::max(v[a], std::max(v[3 + a], v[6 + a])); }
+        for (int a = 0; a < 3; ++a) { lo[a] = float_below(std::min(v[a], std::min(v[3 + a], v[6 + a]))); hi[a] = float_above(std::max(v[a], std::max(v[3 + a], v[6 + a]))); }
         return;
     }
     BvhNode& nd = h.nodes[ref];
@@ -61,19 +62,21 @@ void* hc_build(const double* tris, const uint32_t* ids, uint64_t n) {
         r.id = ids ? ids[perm[k]] : perm[k];
         h->tris[k] = r;
     }
-    if (n == 1) { h->root = kLeafBit; refit(*h, h->root, h->bbox, h->bbox + 3); return h; }
+    for (int a = 0; a < 3; ++a) { h->bbox[a] = lo[a]; h->bbox[3 + a] = hi[a]; }     // bbox() = the exact scene bounds
+    if (n == 1) { h->root = kLeafBit; return h; }
     h->nodes.resize(n - 1);
     memset(h->nodes.data(), 0, (n - 1) * sizeof(BvhNode));
     h->nodes[0].parent = kNone;
     for (uint64_t i = 0; i + 1 < n; ++i) {
-        uint32_t l, r, f, e;
-        karras_node(h->keys.data(), (int64_t)n, (int64_t)i, l, r, f, e);
-        h->nodes[i].child[0] = l; h->nodes[i].child[1] = r; h->nodes[i].first = f; h->nodes[i].last = e;
+        uint32_t l, r;
+        karras_node(h->keys.data(), (int64_t)n, (int64_t)i, l, r);
+        h->nodes[i].child[0] = l; h->nodes[i].child[1] = r;
         if (!(l & kLeafBit)) h->nodes[l].parent = (uint32_t)i;
         if (!(r & kLeafBit)) h->nodes[r].parent = (uint32_t)i;
     }
     h->root = 0;
-    refit(*h, 0, h->bbox, h->bbox + 3);
+    float rlo[3], rhi[3];
+    refit(*h, 0, rlo, rhi);
     return h;
 }
 void hc_destroy(void* hv) { delete (HostTree*)hv; }
@@ -85,14 +88,14 @@ void hc_export(void* hv, void* nodes, void* tris, double* bbox) {
     if (bbox) memcpy(bbox, h->bbox, 48);
 }
 // structural validation of a node/leaf array (used on the GPU-built tree too): every leaf reachable exactly once,
-// every child box bit-equal to the exact union of the boxes below it.  returns 0 if valid.
+// every child box bit-equal to the outward binary32 rounding of the exact union of the boxes below it.  returns 0 if valid.
 int hc_validate(const void* nodes_v, const void* tris_v, uint64_t n) {
     if (n < 2) return 0;
     const BvhNode* nodes = (const BvhNode*)nodes_v; const TriRec* tris = (const TriRec*)tris_v;
     std::vector<uint8_t> seen(n, 0), nseen(n - 1, 0);
     struct Item { uint32_t ref; };
     // iterative post-order computing boxes
-    std::vector<double> blo(3 * (n - 1)), bhi(3 * (n - 1));
+    std::vector<float> blo(3 * (n - 1)), bhi(3 * (n - 1));
     std::vector<uint32_t> order; order.reserve(n - 1);
     std::vector<uint32_t> st{0};
     while (!st.empty()) {
@@ -105,15 +108,14 @@ int hc_validate(const void* nodes_v, const void* tris_v, uint64_t n) {
     for (size_t k = order.size(); k-- > 0;) {
         const uint32_t x = order[k];
         for (int c = 0; c < 2; ++c) {
-            double lo[3], hi[3];
+            float lo[3], hi[3];
             const uint32_t r = nodes[x].child[c];
-            if (r & kLeafBit) { const double* v = tris[r & ~kLeafBit].v; for (int a = 0; a < 3; ++a) { lo[a] = std::min(v[a], std::min(v[3 + a], v[6 + a])); hi[a] = std::max(v[a], std::max(v[3 + a], v[6 + a])); } }
+            if (r & kLeafBit) { const double* v = tris[r & ~kLeafBit].v; for (int a = 0; a < 3; ++a) { lo[a] = float_below(std::min(v[a], std::min(v[3 + a], v[6 + a]))); hi[a] = float_above(std::max(v[a], std::max(v[3 + a], v[6 + a]))); } }
             else for (int a = 0; a < 3; ++a) { lo[a] = blo[3 * r + a]; hi[a] = bhi[3 * r + a]; }
-            const double* nlo = c ? nodes[x].lo1 : nodes[x].lo0; const double* nhi = c ? nodes[x].hi1 : nodes[x].hi0;
+            const float* nlo = c ? nodes[x].lo1 : nodes[x].lo0; const float* nhi = c ? nodes[x].hi1 : nodes[x].hi0;
             for (int a = 0; a < 3; ++a) if (nlo[a] != lo[a] || nhi[a] != hi[a]) return 5;
             for (int a = 0; a < 3; ++a) { if (c == 0) { blo[3 * x + a] = lo[a]; bhi[3 * x + a] = hi[a]; } else { blo[3 * x + a] = std::min(blo[3 * x + a], lo[a]); bhi[3 * x + a] = std::max(bhi[3 * x + a], hi[a]); } }
         }
-        if (nodes[x].first > nodes[x].last) return 6;
     }
     return 0;
 }
@@ -166,7 +168,19 @@ int hc_tri_ray_intersection(const double* tri, const double* ray, double* pts, d
     return x.kind;
 }
 void hc_closest_on_triangle(const double* tri, const double* q, double* out) { const Vec3 c = closest_on_triangle(T(tri), V(q)); out[0] = c.x; out[1] = c.y; out[2] = c.z; }
-int hc_line_box(const double* box, const double* pq, int is_ray) { const LineCtx c = make_line(V(pq), V(pq + 3)); double tn; return line_box(box, box + 3, c, is_ray ? DBL_MAX : 1.0, tn) ? 1 : 0; }
+// the box is rounded outward to binary32 exactly as the refit does
+int hc_line_box(const double* box, const double* pq, int is_ray) {
+    const LineCtx c = make_line(V(pq), V(pq + 3));
+    float lo[3], hi[3], tn;
+    for (int a = 0; a < 3; ++a) { lo[a] = float_below(box[a]); hi[a] = float_above(box[3 + a]); }
+    return line_box(lo, hi, c, is_ray ? INFINITY : 1.0f, tn) ? 1 : 0;
+}
+// lower bound of the squared distance point - box computed by the traversal (binary32, rounded down)
+double hc_point_box_sqdist(const double* box, const double* p) {
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) { lo[a] = float_below(box[a]); hi[a] = float_above(box[3 + a]); }
+    return (double)point_box_sqdist(lo, hi, make_point(V(p)));
+}
 uint64_t hc_sizeof_node() { return sizeof(BvhNode); }
 uint64_t hc_sizeof_tri() { return sizeof(TriRec); }
 

@@ -18,7 +18,7 @@ def lattice(rng, shape, lo=-2, hi=3):
 
 
 def test_struct_sizes():
-    assert hc.lib().hc_sizeof_node() == 128 and hc.lib().hc_sizeof_tri() == 96
+    assert hc.lib().hc_sizeof_node() == 64 and hc.lib().hc_sizeof_tri() == 96
 
 
 def test_predicates_match_oracle():
@@ -106,6 +106,41 @@ def test_node_test_is_conservative():
             if exact:
                 assert hc.line_box(box, pq, is_ray) == 1, (box, pq, is_ray)
     assert n_true > 1000
+    # terrain-like magnitudes: unit boxes near coordinate 4096 (binary32 spacing 4.9e-4), sources far away, lines aimed
+    # exactly at box corners / edges (grazing contact must never be rejected by the binary32 node test)
+    n_true = 0
+    for it in range(6000):
+        lo = np.concatenate([rng.integers(0, 4096, 2).astype(float), rng.uniform(-40, 40, 1)])
+        hi = lo + np.array([1.0, 1.0, rng.uniform(0.0, 0.5)])
+        corner = np.where(rng.integers(0, 2, 3) == 1, hi, lo)
+        p = np.array([0.0, 0.0, 600.0]) if it % 2 else rng.uniform(-5000, 5000, 3)
+        target = corner if it % 3 else lo + rng.uniform(0, 1, 3) * (hi - lo)
+        pq = np.concatenate([p, p + (target - p) * rng.choice([0.25, 1.0, 3.0])])
+        box = np.concatenate([lo, hi])
+        for is_ray in (0, 1):
+            if orc.bbox_do_intersect(box, pq, is_ray):
+                n_true += 1
+                assert hc.line_box(box, pq, is_ray) == 1, (box, pq, is_ray)
+    assert n_true > 3000
+
+
+def test_point_box_distance_is_a_lower_bound():
+    from fractions import Fraction as Fr
+    rng = np.random.default_rng(14)
+    tight = 0
+    for it in range(4000):
+        scale = [1.0, 64.0, 4096.0][it % 3]
+        lo = rng.uniform(-scale, scale, 3); hi = lo + rng.uniform(0, 1, 3) * (1.0 if it % 2 else scale)
+        p = rng.uniform(-2 * scale, 2 * scale, 3)
+        if it % 5 == 0:
+            p = lo + rng.uniform(0, 1, 3) * (hi - lo)          # inside: distance 0
+        exact = sum(max(Fr(float(l)) - Fr(float(x)), Fr(float(x)) - Fr(float(h)), 0) ** 2 for l, h, x in zip(lo, hi, p))
+        got = hc.point_box_sqdist(np.concatenate([lo, hi]), p)
+        assert Fr(got) <= exact, (lo, hi, p)
+        if exact > 0 and float(exact) > 1e-3 * scale * scale:
+            assert got >= float(exact) * (1 - 1e-3)             # and not uselessly loose
+            tight += 1
+    assert tight > 1000
 
 
 @pytest.mark.parametrize("name", ["tetrahedron", "cube", "coverrear", "elephant"])

@@ -72,13 +72,13 @@ def test_gpu_built_tree_equals_host_emulation(B, meshes, name):
     t.build()
     (pn, bn), (pt, bt), (pb, bb) = t.export_layout()
     n = len(f)
-    assert bn == (n - 1) * 128 and bt == n * 96 and bb == 48
+    assert bn == (n - 1) * 64 and bt == n * 96 and bb == 48
     g_nodes, g_tris = device_to_host(pn, bn), device_to_host(pt, bt)
     assert hc.validate(g_nodes, g_tris, n) == 0
     h_nodes, h_tris, h_bbox = hc.HostTree(soup_of(v, f)).export()
     np.testing.assert_array_equal(g_tris, h_tris)
-    gw, hw = g_nodes.view(np.uint32).reshape(-1, 32), h_nodes.view(np.uint32).reshape(-1, 32)
-    cols = list(range(0, 27)) + [28, 29]       # boxes, children, parent, first, last (not the visit counter / padding)
+    gw, hw = g_nodes.view(np.uint32).reshape(-1, 16), h_nodes.view(np.uint32).reshape(-1, 16)
+    cols = list(range(0, 15))                   # boxes, children, parent (not the refit arrival counter)
     np.testing.assert_array_equal(gw[:, cols], hw[:, cols])
     np.testing.assert_array_equal(t.bbox(), h_bbox)
     np.testing.assert_array_equal(device_to_host(pb, 48).view(np.float64), h_bbox)
