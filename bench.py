@@ -303,7 +303,7 @@ def main():
     sp = tree.stats()
     ties, exact, near = sr["ties"] + sp["ties"], sr["exact_fallbacks"] + sp["exact_fallbacks"], sr["near_ties"] + sp["near_ties"]
     traffic_model = {"ray_nodes_per_query": sr["nodes_visited"] / n_rays, "ray_leaves_per_query": sr["leaves_tested"] / n_rays,
-                     "point_nodes_per_query": sp["nodes_visited"] / n_pts, "point_leaves_per_query": sp["leaves_tested"] / n_pts,
+                     "point_nodes_per_query": sp["nodes_visited"] / n_pts, "point_leaves_per_query": sp["leaves_tested"] / n_pts, "point_leaves_culled_fp32_per_query": sp["leaves_culled"] / n_pts,
                      "ray_ms_incl_sort": sr["last_query_ms"], "point_ms_incl_sort": sp["last_query_ms"], "node_bytes": 64, "leaf_bytes": 96}
 
     # e2e: the same step through the C ABI with pinned HOST buffers (copies inside the timed region)

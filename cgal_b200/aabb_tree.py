@@ -27,7 +27,7 @@ class B200AABBError(RuntimeError):
 
 class _Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("exact_fallbacks", C.c_uint64), ("ties", C.c_uint64),
-                ("near_ties", C.c_uint64), ("nodes_visited", C.c_uint64), ("leaves_tested", C.c_uint64),
+                ("near_ties", C.c_uint64), ("nodes_visited", C.c_uint64), ("leaves_tested", C.c_uint64), ("leaves_culled", C.c_uint64),
                 ("last_build_ms", C.c_double), ("last_query_ms", C.c_double), ("last_query_total_ms", C.c_double)]
 
 

@@ -30,18 +30,19 @@ struct TreeRef {
     uint32_t root;
     double mag;                       // largest coordinate magnitude of the root box
     const uint32_t* perm;             // coherence order of the batch (thread i serves query perm[i]); nullptr = identity
-    unsigned long long* counters;     // [8]: exact-stage queries, ties, stack overflow, nodes visited, leaves tested, near ties
+    unsigned long long* counters;     // [8]: exact-stage queries, ties, stack overflow, nodes visited, leaves visited, near ties, leaves culled by the binary32 pre-test
 };
 
 // one atomic per warp and counter instead of one per thread
 __device__ __forceinline__ void flush_stats(const TreeRef& tr, const TravStat& st, int tie, int near) {
     const unsigned full = 0xFFFFFFFFu;
-    const unsigned nodes = __reduce_add_sync(full, st.nodes), leaves = __reduce_add_sync(full, st.leaves);
+    const unsigned nodes = __reduce_add_sync(full, st.nodes), leaves = __reduce_add_sync(full, st.leaves), culled = __reduce_add_sync(full, st.culled);
     const unsigned exact = __reduce_add_sync(full, st.nexact ? 1u : 0u), ties = __reduce_add_sync(full, tie ? 1u : 0u);
     const unsigned nears = __reduce_add_sync(full, near ? 1u : 0u), ovf = __reduce_or_sync(full, st.overflow ? 1u : 0u);
     if ((threadIdx.x & 31) == 0) {
         atomicAdd(&tr.counters[3], (unsigned long long)nodes);
         atomicAdd(&tr.counters[4], (unsigned long long)leaves);
+        if (culled) atomicAdd(&tr.counters[6], (unsigned long long)culled);
         if (exact) atomicAdd(&tr.counters[0], (unsigned long long)exact);
         if (ties) atomicAdd(&tr.counters[1], (unsigned long long)ties);
         if (nears) atomicAdd(&tr.counters[5], (unsigned long long)nears);
@@ -476,7 +477,7 @@ int b200aabb_get_stats(const b200aabb_tree* tc, b200aabb_stats* out) {
         t->stats.last_query_total_ms = ms; t->stats.last_query_ms = ms;
         unsigned long long c[8];
         B2_CUDA(t, cudaMemcpy(c, t->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
-        t->stats.exact_fallbacks = c[0]; t->stats.ties = c[1]; t->stats.nodes_visited = c[3]; t->stats.leaves_tested = c[4]; t->stats.near_ties = c[5];
+        t->stats.exact_fallbacks = c[0]; t->stats.ties = c[1]; t->stats.nodes_visited = c[3]; t->stats.leaves_tested = c[4]; t->stats.near_ties = c[5]; t->stats.leaves_culled = c[6];
         if (c[2]) t->err = "traversal stack overflow: results incomplete";
         t->query_timing_pending = false;
         if (c[2]) { *out = t->stats; return B200AABB_ERR_CUDA; }

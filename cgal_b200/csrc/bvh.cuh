@@ -42,7 +42,7 @@ struct __align__(16) TriRec {
 static_assert(sizeof(TriRec) == 96, "triangle record is three 32-byte sectors");
 
 // per-query traversal statistics (accumulated into the handle's counters by the kernels)
-struct TravStat { int nexact = 0; int overflow = 0; uint32_t nodes = 0, leaves = 0; };
+struct TravStat { int nexact = 0; int overflow = 0; uint32_t nodes = 0, leaves = 0, culled = 0; };   // culled: leaves rejected by the binary32 pre-test
 
 // directed roundings binary64 -> binary32 (any finite input; overflow saturates to +-FLT_MAX / +-inf on the safe side)
 B2_HD float float_below(double v) {
@@ -317,17 +317,66 @@ struct Closest { Vec3 p; uint32_t prim; double sqd; int tie; int near; };
 
 B2_HD double widen_sqdist(double sqd, double delta) { return sqd + ((2.0 * delta * sqrt(sqd) + delta * delta) + sqd * 1e-13); }
 
+B2_HD float dot3f(const float* u, const float* v) { return (u[0] * v[0] + u[1] * v[1]) + u[2] * v[2]; }
+
+// Approximate closest point of the triangle (a,b,c) to the ORIGIN in binary32 (region walk of Ericson, "Real-Time
+// Collision Detection" 5.1.5, specialised to p = 0).  Only used as a direction for the rigorous bound below, so its own
+// rounding errors (even gross ones on needle triangles) can only weaken that bound, never invalidate it.
+B2_HD void approx_closest_to_origin(const float* a, const float* b, const float* c, float* u) {
+    const float ab[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]}, ac[3] = {c[0] - a[0], c[1] - a[1], c[2] - a[2]};
+    const float d1 = -dot3f(ab, a), d2 = -dot3f(ac, a);
+    const float d3 = -dot3f(ab, b), d4 = -dot3f(ac, b);
+    const float d5 = -dot3f(ab, c), d6 = -dot3f(ac, c);
+    float v = 0.0f, w = 0.0f;                              // result = a + v ab + w ac
+    const float vc = d1 * d4 - d3 * d2, vb = d5 * d2 - d1 * d6, va = d3 * d6 - d5 * d4;
+    if (d1 <= 0.0f && d2 <= 0.0f) { }                                               // vertex a
+    else if (d3 >= 0.0f && d4 <= d3) { v = 1.0f; }                                  // vertex b
+    else if (d6 >= 0.0f && d5 <= d6) { w = 1.0f; }                                  // vertex c
+    else if (vc <= 0.0f && d1 >= 0.0f && d3 <= 0.0f) { v = d1 / (d1 - d3); }        // edge ab
+    else if (vb <= 0.0f && d2 >= 0.0f && d6 <= 0.0f) { w = d2 / (d2 - d6); }        // edge ac
+    else if (va <= 0.0f && (d4 - d3) >= 0.0f && (d5 - d6) >= 0.0f) { w = (d4 - d3) / ((d4 - d3) + (d5 - d6)); v = 1.0f - w; }   // edge bc
+    else { const float den = 1.0f / (va + vb + vc); v = vb * den; w = vc * den; }   // interior
+    u[0] = a[0] + (v * ab[0] + w * ac[0]); u[1] = a[1] + (v * ab[1] + w * ac[1]); u[2] = a[2] + (v * ab[2] + w * ac[2]);
+}
+
+// RIGOROUS lower-bound test: is the triangle certainly farther from the query than `rbound` (>= sqrt of the pruning bound)?
+// ra/rb/rc = triangle vertices relative to the query, rounded to binary32 (each coordinate off by <= m * 2^-23.9,
+// m = largest magnitude among them).  For ANY direction u every point x of the triangle satisfies
+//   |x| >= (u.x)/|u| >= min_i (u.v_i)/|u|     (x is a convex combination of the vertices),
+// so the triangle is rejected when min_i fl(u.r_i) - E > rbound * |u| with E = 5e-7 m |u| covering the coordinate
+// rounding and the three binary32 dot products; `su` = fl(|u|) (2e-7 relative) and the final comparison carry 1e-6.
+B2_HD bool certainly_farther(const float* u, float su, const float* ra, const float* rb, const float* rc, float m, float rbound) {
+    const float md = fminf(dot3f(u, ra), fminf(dot3f(u, rb), dot3f(u, rc)));
+    return su > 1e-18f && md - 5e-7f * m * su > rbound * su * 1.000001f;
+}
+
 B2_HD Closest traverse_closest(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root,
                                const Vec3& o, double mag, TravStat& st) {
     Closest best; best.p = o; best.prim = kNone; best.sqd = DBL_MAX; best.tie = 0; best.near = 0;
     const double delta = 4e-16 * fmax(mag, fmax3(fabs(o.x), fabs(o.y), fabs(o.z)));
     const PointCtx pc = make_point(o);
     float bound = INFINITY;       // prune boxes certainly farther than the incumbent (widened, rounded up)
+    float rbound = INFINITY;      // >= sqrt(bound)
+    float ub[3] = {0.0f, 0.0f, 0.0f}, sub = 0.0f;   // direction query -> incumbent closest point and its length (binary32)
     double runner_up = DBL_MAX;
     auto leaf = [&](uint32_t ref) {
         uint32_t id;
         const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
         ++st.leaves;
+        if (best.prim != kNone) {
+            // binary32 pre-test on coordinates RELATIVE to the query (the subtraction is done in binary64)
+            const float ra[3] = {(float)(t.a.x - o.x), (float)(t.a.y - o.y), (float)(t.a.z - o.z)};
+            const float rb[3] = {(float)(t.b.x - o.x), (float)(t.b.y - o.y), (float)(t.b.z - o.z)};
+            const float rc[3] = {(float)(t.c.x - o.x), (float)(t.c.y - o.y), (float)(t.c.z - o.z)};
+            const float m = fmaxf(fmaxf(fmaxf(fabsf(ra[0]), fabsf(ra[1])), fmaxf(fabsf(ra[2]), fabsf(rb[0]))),
+                                  fmaxf(fmaxf(fabsf(rb[1]), fabsf(rb[2])), fmaxf(fmaxf(fabsf(rc[0]), fabsf(rc[1])), fabsf(rc[2]))));
+            // (1) tangent plane of the incumbent ball: all three vertices beyond it
+            if (certainly_farther(ub, sub, ra, rb, rc, m, rbound)) { ++st.culled; return; }
+            // (2) direction of this triangle's own (approximate) closest point
+            float u[3];
+            approx_closest_to_origin(ra, rb, rc, u);
+            if (certainly_farther(u, sqrtf(dot3f(u, u)), ra, rb, rc, m, rbound)) { ++st.culled; return; }
+        }
         const Vec3 cp = closest_on_triangle(t, o);
         const Vec3 v = cp - o;
         const double sqd = (v.x * v.x + v.y * v.y) + v.z * v.z;   // Compute_squared_distance_3(query, closest): AABB_tree.h:1024-1032
@@ -341,7 +390,11 @@ B2_HD Closest traverse_closest(const BvhNode* __restrict__ nodes, const TriRec* 
         }
         if (take) {
             best.p = cp; best.prim = id; best.sqd = sqd;
-            bound = float_above(widen_sqdist(sqd, delta));
+            const double w = widen_sqdist(sqd, delta);
+            bound = float_above(w);
+            rbound = float_above(sqrt(w));
+            ub[0] = (float)v.x; ub[1] = (float)v.y; ub[2] = (float)v.z;
+            sub = sqrtf(dot3f(ub, ub));
         }
     };
     if (root & kLeafBit) { leaf(root); return best; }

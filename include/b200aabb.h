@@ -67,7 +67,8 @@ typedef struct b200aabb_stats {
   uint64_t ties;                   /* queries of the last batch flagged FLAG_TIE */
   uint64_t near_ties;              /* queries of the last batch flagged FLAG_NEAR_TIE */
   uint64_t nodes_visited;          /* BVH nodes loaded by the last batch (traversal-traffic model) */
-  uint64_t leaves_tested;          /* primitives tested by the last batch */
+  uint64_t leaves_tested;          /* primitives visited by the last batch */
+  uint64_t leaves_culled;          /* of those, rejected by the rigorous binary32 pre-test before any binary64 work (closest_point) */
   double last_build_ms;            /* device time of the last b200aabb_build (CUDA events) */
   double last_query_ms;            /* device time of the traversal kernel(s) of the last batched query */
   double last_query_total_ms;      /* same, including host<->device copies of the batch when pointers were HOST */
