@@ -1,0 +1,384 @@
+// CGAL_B200/AABB_tree.h — header-only C++17 class template with the interface of CGAL::AABB_tree
+// (AABB_tree/include/CGAL/AABB_tree.h:55-677 of the reference) whose work is done by libb200aabb.so (sm_100a CUDA)
+// through the C ABI of b200aabb.h.  This is the reference-side binding of INTEGRATION.md: a user of
+//     CGAL::AABB_tree< CGAL::AABB_traits_3< Epick, CGAL::AABB_face_graph_triangle_primitive< Surface_mesh<Point_3> > > >
+// replaces `CGAL::AABB_tree` by `CGAL_B200::AABB_tree` and keeps the traits, the primitive and the mesh types.
+//
+// What the class needs from its template argument (all provided by CGAL::AABB_traits_3, AABB_traits_3.h:507-560):
+//   AABBTraits::FT, ::Point, ::Primitive (with ::Id, ::Datum, id(), datum([shared_data])), ::Bounding_box (constructible from
+//   six doubles), ::Point_and_primitive_id, ::Geom_traits (with ::Segment_3, ::Ray_3), ::Intersection_and_primitive_id<Q>::Type,
+//   set_shared_data(...) / shared_data() when the primitive has Shared_data (AABBPrimitiveWithSharedData).
+// Geometry objects are read through the kernel-object interface (Point_3::x()/y()/z(), Segment_3::source()/target(),
+// Ray_3::source()/second_point(), Triangle_3::vertex(i)) and results are built with Point(x,y,z) / Segment_3(p,q).
+// The number type must be convertible to/from double without loss (Epick, Simple_cartesian<double>).
+//
+// Primitives are flattened exactly as the reference sees them: the triangle of primitive p is p.datum(shared_data), i.e. for
+// AABB_face_graph_triangle_primitive (P[target(h)], P[target(next(h))], P[source(h)]), h = halfedge(f)
+// (BGL/include/CGAL/boost/graph/property_maps.h:52-63).  The device id of a primitive is its rank in insertion order; the
+// class maps it back to Primitive::id().
+//
+// Besides the reference's one-query-at-a-time members (each is one small GPU batch: correct, but latency-bound) the class
+// has BATCHED overloads taking an iterator range of queries and an output iterator — the way to feed a GPU.
+// There is no CPU fallback: without the library or without an sm_100 device every call throws CGAL_B200::Error.
+#ifndef CGAL_B200_AABB_TREE_H
+#define CGAL_B200_AABB_TREE_H
+
+#include <cstdint>
+#include <iterator>
+#include <mutex>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+#include "../b200aabb.h"
+
+namespace CGAL_B200 {
+
+// thrown for every non-zero status of the C ABI; code() is the B200AABB_ERR_* value
+class Error : public std::runtime_error {
+ public:
+  Error(int code, const std::string& what) : std::runtime_error("b200aabb (" + std::to_string(code) + "): " + what), m_code(code) {}
+  int code() const { return m_code; }
+
+ private:
+  int m_code;
+};
+
+namespace internal {
+template <class P, class = void>
+struct Has_shared_data : std::false_type {};
+template <class P>
+struct Has_shared_data<P, std::void_t<typename P::Shared_data>> : std::true_type {};
+}  // namespace internal
+
+template <typename AABBTraits>
+class AABB_tree {
+  typedef AABB_tree<AABBTraits> Self;
+  typedef std::vector<typename AABBTraits::Primitive> Primitives;
+
+ public:
+  // ---- types, AABB_tree.h:69-104
+  typedef AABBTraits AABB_traits;
+  typedef typename AABBTraits::FT FT;
+  typedef typename AABBTraits::Point Point;
+  typedef typename AABBTraits::Primitive Primitive;
+  typedef typename Primitive::Id Primitive_id;
+  typedef typename Primitives::size_type size_type;
+  typedef typename AABBTraits::Bounding_box Bounding_box;
+  typedef typename AABBTraits::Point_and_primitive_id Point_and_primitive_id;
+  typedef typename AABBTraits::Geom_traits::Segment_3 Segment;
+  typedef typename AABBTraits::Geom_traits::Ray_3 Ray;
+  template <typename Query>
+  struct Intersection_and_primitive_id {
+    typedef typename AABBTraits::template Intersection_and_primitive_id<Query>::Type Type;
+  };
+  typedef std::optional<typename Intersection_and_primitive_id<Ray>::Type> Ray_intersection;   // result of first_intersection
+
+  // ---- creation, AABB_tree.h:115-135.  `device` = CUDA ordinal of the B200 that holds the tree.
+  explicit AABB_tree(const AABBTraits& traits = AABBTraits(), int device = 0) : m_traits(traits) { create(device); }
+  template <typename InputIterator, typename... T>
+  AABB_tree(InputIterator first, InputIterator beyond, T&&... t) {
+    create(0);
+    insert(first, beyond, std::forward<T>(t)...);
+  }
+  AABB_tree(Self&& o) noexcept : m_traits(std::move(o.m_traits)), m_primitives(std::move(o.m_primitives)), m_handle(o.m_handle), m_uploaded(o.m_uploaded) {
+    o.m_handle = nullptr;
+  }
+  Self& operator=(Self&& o) noexcept {
+    if (this != &o) {
+      destroy();
+      m_traits = std::move(o.m_traits); m_primitives = std::move(o.m_primitives); m_handle = o.m_handle; m_uploaded = o.m_uploaded;
+      o.m_handle = nullptr;
+    }
+    return *this;
+  }
+  AABB_tree(const Self&) = delete;
+  Self& operator=(const Self&) = delete;
+  ~AABB_tree() { destroy(); }
+
+  // ---- primitives and build, AABB_tree.h:147-216,730-853
+  template <typename InputIterator, typename... T>
+  void insert(InputIterator first, InputIterator beyond, T&&... t) {
+    set_shared_data(std::forward<T>(t)...);
+    for (; first != beyond; ++first) m_primitives.push_back(Primitive(first, std::forward<T>(t)...));
+    m_uploaded = false;
+  }
+  void insert(const Primitive& p) { m_primitives.push_back(p); m_uploaded = false; }
+  template <typename InputIterator, typename... T>
+  void rebuild(InputIterator first, InputIterator beyond, T&&... t) {
+    clear();
+    insert(first, beyond, std::forward<T>(t)...);
+    build();
+  }
+  template <typename... T>
+  void build(T&&... t) {
+    set_shared_data(std::forward<T>(t)...);
+    build();
+  }
+  // LBVH build on the device (replaces the recursive median split of AABB_tree.h:787-853)
+  void build() {
+    std::lock_guard<std::mutex> lock(m_mutex);
+    m_uploaded = false;
+    upload_and_build();
+  }
+  // the reference lets the caller replace Compute_bbox / Split_primitives; the device builder has a fixed LBVH split
+  template <class ComputeBbox, class SplitPrimitives>
+  void custom_build(const ComputeBbox&, const SplitPrimitives&) { throw Error(B200AABB_ERR_INVALID_ARGUMENT, "custom_build is not supported by the device builder"); }
+  void clear() {
+    std::lock_guard<std::mutex> lock(m_mutex);
+    m_primitives.clear();
+    check(b200aabb_clear(m_handle));
+    m_uploaded = true;   // an empty tree is consistent
+  }
+  const AABBTraits& traits() const { return m_traits; }
+  const Bounding_box bbox() const {
+    ensure_built();
+    double b[6];
+    check(b200aabb_bbox(m_handle, b));
+    return Bounding_box(b[0], b[1], b[2], b[3], b[4], b[5]);
+  }
+  size_type size() const { return m_primitives.size(); }
+  bool empty() const { return m_primitives.empty(); }
+
+  // accelerate_distance_queries, AABB_tree.h:442-459,896-901.  The kd-tree of reference points is replaced by the ordered
+  // BVH descent (nearest child first), so there is nothing extra to build; the call builds the tree and returns true.
+  bool accelerate_distance_queries() {
+    ensure_built();
+    check(b200aabb_accelerate_distance_queries(m_handle));
+    return true;
+  }
+  template <typename ConstPointIterator>
+  bool accelerate_distance_queries(ConstPointIterator, ConstPointIterator) { return accelerate_distance_queries(); }
+  void do_not_accelerate_distance_queries() {}
+
+  // ---- intersection queries, one query per call (AABB_tree.h:243-354,903-932).  Query = Segment or Ray.
+  template <typename Query>
+  bool do_intersect(const Query& query) const {
+    bool r = false;
+    do_intersect(&query, &query + 1, &r);
+    return r;
+  }
+  template <typename Query>
+  size_type number_of_intersected_primitives(const Query& query) const {
+    size_type r = 0;
+    number_of_intersected_primitives(&query, &query + 1, &r);
+    return r;
+  }
+  Ray_intersection first_intersection(const Ray& query) const {
+    Ray_intersection r;
+    first_intersection(&query, &query + 1, &r);
+    return r;
+  }
+  std::optional<Primitive_id> first_intersected_primitive(const Ray& query) const {
+    std::optional<Primitive_id> r;
+    first_intersected_primitive(&query, &query + 1, &r);
+    return r;
+  }
+  // a host functor cannot run inside the traversal kernel: only the trivial skip of the one-argument overload is offloaded
+  template <typename SkipFunctor>
+  Ray_intersection first_intersection(const Ray&, const SkipFunctor&) const { throw Error(B200AABB_ERR_INVALID_ARGUMENT, "first_intersection with a skip functor is not offloaded"); }
+
+  // ---- distance queries, one query per call (AABB_tree.h:363-377,464-477,987-1055)
+  FT squared_distance(const Point& query) const {
+    FT r;
+    squared_distance(&query, &query + 1, &r);
+    return r;
+  }
+  Point closest_point(const Point& query) const { return closest_point_and_primitive(query).first; }
+  Point_and_primitive_id closest_point_and_primitive(const Point& query) const {
+    std::vector<Point_and_primitive_id> r;
+    closest_point_and_primitive(&query, &query + 1, std::back_inserter(r));
+    return r[0];
+  }
+  // A hint only seeds the reference's search ball; the result is the same except on exact-distance ties
+  FT squared_distance(const Point& query, const Point&) const { return squared_distance(query); }
+  Point closest_point(const Point& query, const Point&) const { return closest_point(query); }
+  Point_and_primitive_id closest_point_and_primitive(const Point& query, const Point_and_primitive_id&) const { return closest_point_and_primitive(query); }
+
+  // ---- BATCHED overloads (new): [first, beyond) is a range of queries, results go to `out` in the same order ------------
+  // out receives bool
+  template <typename QueryIterator, typename OutputIterator>
+  OutputIterator do_intersect(QueryIterator first, QueryIterator beyond, OutputIterator out) const {
+    typedef typename std::iterator_traits<QueryIterator>::value_type Query;
+    std::vector<double> q = pack_lines(first, beyond);
+    const uint64_t n = q.size() / 6;
+    std::vector<uint8_t> r(n);
+    ensure_built();
+    check(b200aabb_do_intersect(m_handle, q.data(), n, kind_of<Query>(), B200AABB_HOST, r.data()));
+    for (uint64_t i = 0; i < n; ++i) *out++ = r[i] != 0;
+    return out;
+  }
+  // out receives size_type
+  template <typename QueryIterator, typename OutputIterator>
+  OutputIterator number_of_intersected_primitives(QueryIterator first, QueryIterator beyond, OutputIterator out) const {
+    typedef typename std::iterator_traits<QueryIterator>::value_type Query;
+    std::vector<double> q = pack_lines(first, beyond);
+    const uint64_t n = q.size() / 6;
+    std::vector<uint32_t> r(n);
+    ensure_built();
+    check(b200aabb_number_of_intersected_primitives(m_handle, q.data(), n, kind_of<Query>(), B200AABB_HOST, r.data()));
+    for (uint64_t i = 0; i < n; ++i) *out++ = (size_type)r[i];
+    return out;
+  }
+  // out receives std::optional< Intersection_and_primitive_id<Ray>::Type >; flags (optional) receives the B200AABB_FLAG_* bits
+  template <typename RayIterator, typename OutputIterator>
+  OutputIterator first_intersection(RayIterator first, RayIterator beyond, OutputIterator out, std::vector<uint8_t>* flags = nullptr) const {
+    typedef typename Intersection_and_primitive_id<Ray>::Type Result;
+    typedef typename Result::first_type Intersection;
+    std::vector<double> q = pack_lines(first, beyond);
+    const uint64_t n = q.size() / 6;
+    std::vector<uint32_t> prim(n);
+    std::vector<double> p0(3 * n), p1(3 * n);
+    std::vector<uint8_t> fl(n);
+    ensure_built();
+    check(b200aabb_first_intersection(m_handle, q.data(), n, B200AABB_HOST, prim.data(), nullptr, p0.data(), p1.data(), fl.data()));
+    for (uint64_t i = 0; i < n; ++i) {
+      if (!(fl[i] & B200AABB_FLAG_HIT)) { *out++ = std::nullopt; continue; }
+      const Point a(FT(p0[3 * i]), FT(p0[3 * i + 1]), FT(p0[3 * i + 2]));
+      if (fl[i] & B200AABB_FLAG_SEGMENT) {
+        const Point b(FT(p1[3 * i]), FT(p1[3 * i + 1]), FT(p1[3 * i + 2]));
+        *out++ = Result(Intersection(Segment(a, b)), m_primitives[prim[i]].id());
+      } else {
+        *out++ = Result(Intersection(a), m_primitives[prim[i]].id());
+      }
+    }
+    if (flags) flags->swap(fl);
+    return out;
+  }
+  // out receives std::optional<Primitive_id>
+  template <typename RayIterator, typename OutputIterator>
+  OutputIterator first_intersected_primitive(RayIterator first, RayIterator beyond, OutputIterator out) const {
+    std::vector<double> q = pack_lines(first, beyond);
+    const uint64_t n = q.size() / 6;
+    std::vector<uint32_t> prim(n);
+    ensure_built();
+    check(b200aabb_first_intersection(m_handle, q.data(), n, B200AABB_HOST, prim.data(), nullptr, nullptr, nullptr, nullptr));
+    for (uint64_t i = 0; i < n; ++i) {
+      if (prim[i] == B200AABB_NO_PRIMITIVE) *out++ = std::nullopt;
+      else *out++ = std::optional<Primitive_id>(m_primitives[prim[i]].id());
+    }
+    return out;
+  }
+  // out receives Point_and_primitive_id; flags (optional) receives the B200AABB_FLAG_* bits (exact-distance ties)
+  template <typename PointIterator, typename OutputIterator>
+  OutputIterator closest_point_and_primitive(PointIterator first, PointIterator beyond, OutputIterator out, std::vector<uint8_t>* flags = nullptr) const {
+    std::vector<double> q = pack_points(first, beyond);
+    const uint64_t n = q.size() / 3;
+    std::vector<double> cp(3 * n);
+    std::vector<uint32_t> prim(n);
+    std::vector<uint8_t> fl(n);
+    ensure_built();
+    check(b200aabb_closest_point(m_handle, q.data(), n, B200AABB_HOST, cp.data(), prim.data(), nullptr, fl.data()));
+    for (uint64_t i = 0; i < n; ++i) *out++ = Point_and_primitive_id(Point(FT(cp[3 * i]), FT(cp[3 * i + 1]), FT(cp[3 * i + 2])), m_primitives[prim[i]].id());
+    if (flags) flags->swap(fl);
+    return out;
+  }
+  // out receives Point
+  template <typename PointIterator, typename OutputIterator>
+  OutputIterator closest_point(PointIterator first, PointIterator beyond, OutputIterator out) const {
+    std::vector<double> q = pack_points(first, beyond);
+    const uint64_t n = q.size() / 3;
+    std::vector<double> cp(3 * n);
+    ensure_built();
+    check(b200aabb_closest_point(m_handle, q.data(), n, B200AABB_HOST, cp.data(), nullptr, nullptr, nullptr));
+    for (uint64_t i = 0; i < n; ++i) *out++ = Point(FT(cp[3 * i]), FT(cp[3 * i + 1]), FT(cp[3 * i + 2]));
+    return out;
+  }
+  // out receives FT
+  template <typename PointIterator, typename OutputIterator>
+  OutputIterator squared_distance(PointIterator first, PointIterator beyond, OutputIterator out) const {
+    std::vector<double> q = pack_points(first, beyond);
+    const uint64_t n = q.size() / 3;
+    std::vector<double> d(n);
+    ensure_built();
+    check(b200aabb_closest_point(m_handle, q.data(), n, B200AABB_HOST, nullptr, nullptr, d.data(), nullptr));
+    for (uint64_t i = 0; i < n; ++i) *out++ = FT(d[i]);
+    return out;
+  }
+
+  // ---- access to the C ABI for callers that keep queries and results in device memory (b200aabb.h, B200AABB_DEVICE)
+  b200aabb_tree* handle() const {
+    ensure_built();
+    return m_handle;
+  }
+  b200aabb_stats stats() const {
+    b200aabb_stats s;
+    check(b200aabb_get_stats(m_handle, &s));
+    return s;
+  }
+
+ private:
+  template <typename... T>
+  void set_shared_data(T&&... t) {
+    if constexpr (internal::Has_shared_data<Primitive>::value && sizeof...(T) > 0) m_traits.set_shared_data(std::forward<T>(t)...);
+  }
+  decltype(auto) datum(const Primitive& p) const {   // internal::Primitive_helper::get_datum, AABB_tree/internal/Primitive_helper.h:40-60
+    if constexpr (internal::Has_shared_data<Primitive>::value) return p.datum(m_traits.shared_data());
+    else return p.datum();
+  }
+  void create(int device) {
+    const int rc = b200aabb_create(device, &m_handle);
+    if (rc != B200AABB_OK) { m_handle = nullptr; throw Error(rc, "b200aabb_create failed (no sm_100 device? there is no CPU fallback)"); }
+  }
+  void destroy() {
+    if (m_handle) b200aabb_destroy(m_handle);
+    m_handle = nullptr;
+  }
+  void check(int rc) const {
+    if (rc != B200AABB_OK) throw Error(rc, b200aabb_last_error(m_handle));
+  }
+  // lazy build on the first query, like root_node() (AABB_tree.h:636-652): thread-safe, once
+  void ensure_built() const {
+    if (m_uploaded) return;
+    std::lock_guard<std::mutex> lock(m_mutex);
+    if (!m_uploaded) const_cast<Self*>(this)->upload_and_build();
+  }
+  void upload_and_build() {
+    const uint64_t n = m_primitives.size();
+    std::vector<double> soup(9 * n);
+    for (uint64_t i = 0; i < n; ++i) {
+      decltype(auto) tri = datum(m_primitives[i]);
+      for (int k = 0; k < 3; ++k) {
+        decltype(auto) v = tri.vertex(k);
+        soup[9 * i + 3 * k] = (double)v.x(); soup[9 * i + 3 * k + 1] = (double)v.y(); soup[9 * i + 3 * k + 2] = (double)v.z();
+      }
+    }
+    check(b200aabb_set_triangles(m_handle, soup.data(), nullptr, n, B200AABB_HOST));
+    check(b200aabb_build(m_handle));
+    m_uploaded = true;
+  }
+  template <typename Query>
+  static b200aabb_query_kind kind_of() {
+    static_assert(std::is_same<Query, Segment>::value || std::is_same<Query, Ray>::value, "offloaded intersection queries: Segment_3 and Ray_3");
+    return std::is_same<Query, Ray>::value ? B200AABB_RAY : B200AABB_SEGMENT;
+  }
+  static void put(std::vector<double>& v, const Point& p) { v.push_back((double)p.x()); v.push_back((double)p.y()); v.push_back((double)p.z()); }
+  static void put_line(std::vector<double>& v, const Segment& s) { put(v, s.source()); put(v, s.target()); }
+  template <typename R = Ray, typename = std::enable_if_t<!std::is_same<R, Segment>::value>>
+  static void put_line(std::vector<double>& v, const R& r) { put(v, r.source()); put(v, r.second_point()); }   // Cartesian/Ray_3.h:35-47
+  template <typename It>
+  static std::vector<double> pack_lines(It first, It beyond) {
+    std::vector<double> v;
+    for (; first != beyond; ++first) put_line(v, *first);
+    return v;
+  }
+  template <typename It>
+  static std::vector<double> pack_points(It first, It beyond) {
+    std::vector<double> v;
+    for (; first != beyond; ++first) put(v, *first);
+    return v;
+  }
+
+  AABBTraits m_traits;
+  Primitives m_primitives;
+  b200aabb_tree* m_handle = nullptr;
+  mutable bool m_uploaded = true;   // the device tree reflects m_primitives
+  mutable std::mutex m_mutex;
+};
+
+}  // namespace CGAL_B200
+
+#endif  // CGAL_B200_AABB_TREE_H

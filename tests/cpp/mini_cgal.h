@@ -1,0 +1,161 @@
+// mini_cgal.h — TEST SCAFFOLDING: the smallest set of types with the interfaces of the CGAL classes that
+// CGAL_B200::AABB_tree touches, so that the class template can be compiled and exercised in an image without Boost
+// (CGAL's own headers need Boost from the first include).  Same names, members and conventions as
+//   Epick kernel objects      Cartesian_kernel/include/CGAL/Cartesian/{Point_3,Segment_3,Ray_3,Triangle_3}.h
+//   Bbox_3                    Kernel_23/include/CGAL/Bbox_3.h
+//   Surface_mesh              Surface_mesh/include/CGAL/Surface_mesh/Surface_mesh.h (vertices, faces, halfedge(f), target, next, source)
+//   AABB_face_graph_triangle_primitive  AABB_tree/include/CGAL/AABB_face_graph_triangle_primitive.h:53-196
+//   AABB_traits_3             AABB_tree/include/CGAL/AABB_traits_3.h:507-560
+// Nothing here computes anything: geometry is done by libb200aabb.so.
+#pragma once
+#include <array>
+#include <cstdint>
+#include <utility>
+#include <variant>
+#include <vector>
+
+namespace mini {
+
+struct Point_3 {
+  double c[3] = {0, 0, 0};
+  Point_3() {}
+  Point_3(double x, double y, double z) : c{x, y, z} {}
+  double x() const { return c[0]; }
+  double y() const { return c[1]; }
+  double z() const { return c[2]; }
+  bool operator==(const Point_3& o) const { return c[0] == o.c[0] && c[1] == o.c[1] && c[2] == o.c[2]; }
+  bool operator!=(const Point_3& o) const { return !(*this == o); }
+};
+struct Segment_3 {
+  Point_3 s, t;
+  Segment_3() {}
+  Segment_3(const Point_3& a, const Point_3& b) : s(a), t(b) {}
+  const Point_3& source() const { return s; }
+  const Point_3& target() const { return t; }
+};
+struct Ray_3 {   // stored as (source, second point): Cartesian/Ray_3.h:35-47
+  Point_3 s, q;
+  Ray_3() {}
+  Ray_3(const Point_3& a, const Point_3& b) : s(a), q(b) {}
+  const Point_3& source() const { return s; }
+  const Point_3& second_point() const { return q; }
+};
+struct Triangle_3 {
+  Point_3 v[3];
+  Triangle_3() {}
+  Triangle_3(const Point_3& a, const Point_3& b, const Point_3& c) : v{a, b, c} {}
+  const Point_3& vertex(int i) const { return v[i % 3]; }
+};
+struct Bbox_3 {
+  double b[6];
+  Bbox_3(double x0, double y0, double z0, double x1, double y1, double z1) : b{x0, y0, z0, x1, y1, z1} {}
+  double xmin() const { return b[0]; }
+  double ymin() const { return b[1]; }
+  double zmin() const { return b[2]; }
+  double xmax() const { return b[3]; }
+  double ymax() const { return b[4]; }
+  double zmax() const { return b[5]; }
+};
+
+struct Epick {
+  typedef double FT;
+  typedef mini::Point_3 Point_3;
+  typedef mini::Segment_3 Segment_3;
+  typedef mini::Ray_3 Ray_3;
+  typedef mini::Triangle_3 Triangle_3;
+};
+
+// index types of Surface_mesh (Surface_mesh.h:63-198)
+template <int Tag>
+struct SM_Index {
+  uint32_t i = 0xFFFFFFFFu;
+  SM_Index() {}
+  explicit SM_Index(uint32_t v) : i(v) {}
+  operator uint32_t() const { return i; }
+  bool operator==(const SM_Index& o) const { return i == o.i; }
+  bool operator!=(const SM_Index& o) const { return i != o.i; }
+};
+typedef SM_Index<0> Vertex_index;
+typedef SM_Index<1> Halfedge_index;
+typedef SM_Index<2> Face_index;
+
+// triangle mesh with the halfedge navigation the primitive needs.  Halfedge 3f+k of face f points to vertex k of the
+// face; halfedge(f) is the one pointing to vertex 0, as Euler::add_face leaves it (Euler_operations.h:842-843).
+template <class P>
+class Surface_mesh {
+ public:
+  typedef P Point;
+  typedef mini::Vertex_index Vertex_index;
+  typedef mini::Face_index Face_index;
+  typedef mini::Halfedge_index Halfedge_index;
+  struct Face_iterator {
+    uint32_t i;
+    Face_index operator*() const { return Face_index(i); }
+    Face_iterator& operator++() { ++i; return *this; }
+    bool operator!=(const Face_iterator& o) const { return i != o.i; }
+    bool operator==(const Face_iterator& o) const { return i == o.i; }
+  };
+  Vertex_index add_vertex(const P& p) { m_points.push_back(p); return Vertex_index((uint32_t)m_points.size() - 1); }
+  Face_index add_face(Vertex_index a, Vertex_index b, Vertex_index c) { m_faces.push_back({a, b, c}); return Face_index((uint32_t)m_faces.size() - 1); }
+  const P& point(Vertex_index v) const { return m_points[v]; }
+  Halfedge_index halfedge(Face_index f) const { return Halfedge_index(3 * (uint32_t)f); }
+  Halfedge_index next(Halfedge_index h) const { return Halfedge_index(h / 3 * 3 + (h % 3 + 1) % 3); }
+  Vertex_index target(Halfedge_index h) const { return m_faces[h / 3][h % 3]; }
+  Vertex_index source(Halfedge_index h) const { return m_faces[h / 3][(h % 3 + 2) % 3]; }
+  uint32_t number_of_faces() const { return (uint32_t)m_faces.size(); }
+  uint32_t number_of_vertices() const { return (uint32_t)m_points.size(); }
+  std::pair<Face_iterator, Face_iterator> face_range() const { return {Face_iterator{0}, Face_iterator{number_of_faces()}}; }
+
+ private:
+  std::vector<P> m_points;
+  std::vector<std::array<Vertex_index, 3>> m_faces;
+};
+template <class P>
+std::pair<typename Surface_mesh<P>::Face_iterator, typename Surface_mesh<P>::Face_iterator> faces(const Surface_mesh<P>& m) { return m.face_range(); }
+
+// AABB_face_graph_triangle_primitive<FaceGraph, Default, Tag_true /*one graph per tree*/, Tag_false /*no datum cache*/>
+template <class FaceGraph>
+class AABB_face_graph_triangle_primitive {
+ public:
+  typedef typename FaceGraph::Face_index Id;
+  typedef Triangle_3 Datum;
+  typedef typename FaceGraph::Point Point;
+  typedef const FaceGraph* Shared_data;
+  template <class Iterator>
+  AABB_face_graph_triangle_primitive(Iterator it, const FaceGraph&) : m_id(*it) {}
+  Id id() const { return m_id; }
+  // Triangle_from_face_descriptor_map, BGL/include/CGAL/boost/graph/property_maps.h:52-63
+  Datum datum(Shared_data g) const {
+    const auto h = g->halfedge(m_id);
+    return Datum(g->point(g->target(h)), g->point(g->target(g->next(h))), g->point(g->source(h)));
+  }
+  Point reference_point(Shared_data g) const { return g->point(g->target(g->halfedge(m_id))); }
+  static Shared_data construct_shared_data(const FaceGraph& g) { return &g; }
+
+ private:
+  Id m_id;
+};
+
+template <class GeomTraits, class AABBPrimitive>
+class AABB_traits_3 {
+ public:
+  typedef GeomTraits Geom_traits;
+  typedef typename GeomTraits::FT FT;
+  typedef AABBPrimitive Primitive;
+  typedef typename GeomTraits::Point_3 Point;
+  typedef typename GeomTraits::Point_3 Point_3;
+  typedef Bbox_3 Bounding_box;
+  typedef std::pair<Point, typename Primitive::Id> Point_and_primitive_id;
+  template <typename Query>
+  struct Intersection_and_primitive_id {
+    typedef std::pair<std::variant<typename GeomTraits::Point_3, typename GeomTraits::Segment_3>, typename Primitive::Id> Type;
+  };
+  template <typename... T>
+  void set_shared_data(T&&... t) { m_data = Primitive::construct_shared_data(std::forward<T>(t)...); }
+  const typename Primitive::Shared_data& shared_data() const { return m_data; }
+
+ private:
+  typename Primitive::Shared_data m_data = nullptr;
+};
+
+}  // namespace mini

@@ -1,0 +1,209 @@
+// test_aabb_tree.cpp — exercises CGAL_B200::AABB_tree (include/CGAL_B200/AABB_tree.h) the way the reference's own tests
+// exercise CGAL::AABB_tree.  Needs a B200 (run by tests/test_gpu_cpp_host.py under -m gpu); compiled on CPU as a build check.
+//   no arguments : the reference's known-answer tests
+//                  AABB_tree/test/AABB_tree/aabb_correctness_triangle_test.cpp:51-108, aabb_test_empty_tree.cpp:38-53,
+//                  aabb_test_singleton_tree.cpp:44-67, AABB_tree/examples/AABB_tree/AABB_face_graph_triangle_example.cpp:31-39,
+//                  plus single-query == batched-query consistency, lazy rebuild and move semantics
+//   <in> <out>   : reads a mesh and query sets, answers them through the class, writes the results (compared with the
+//                  CPU oracle by the Python test)
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <variant>
+#include <vector>
+
+#include "../../include/CGAL_B200/AABB_tree.h"
+#include "mini_cgal.h"
+
+typedef mini::Epick K;
+typedef K::Point_3 Point;
+typedef K::Segment_3 Segment;
+typedef K::Ray_3 Ray;
+typedef mini::Surface_mesh<Point> Mesh;
+typedef mini::AABB_face_graph_triangle_primitive<Mesh> Primitive;
+typedef mini::AABB_traits_3<K, Primitive> Traits;
+typedef CGAL_B200::AABB_tree<Traits> Tree;
+
+#define CHECK(cond)                                                              \
+  do {                                                                           \
+    if (!(cond)) {                                                               \
+      std::fprintf(stderr, "%s:%d: CHECK failed: %s\n", __FILE__, __LINE__, #cond); \
+      std::exit(1);                                                              \
+    }                                                                            \
+  } while (0)
+
+static Mesh tetrahedron() {   // Data/data/meshes/tetrahedron.off
+  Mesh m;
+  auto a = m.add_vertex(Point(0, 0, 0)), b = m.add_vertex(Point(1, 0, 0)), c = m.add_vertex(Point(0, 1, 0)), d = m.add_vertex(Point(0, 0, 1));
+  m.add_face(a, b, c); m.add_face(a, d, b); m.add_face(a, c, d); m.add_face(b, d, c);
+  return m;
+}
+
+static Mesh grid(int n) {   // n x n quads, z = a gentle bump, two triangles per quad
+  Mesh m;
+  std::vector<mini::Vertex_index> v;
+  for (int j = 0; j <= n; ++j)
+    for (int i = 0; i <= n; ++i) v.push_back(m.add_vertex(Point(i, j, 0.25 * std::sin(0.7 * i) * std::cos(0.4 * j))));
+  for (int j = 0; j < n; ++j)
+    for (int i = 0; i < n; ++i) {
+      const auto a = v[j * (n + 1) + i], b = v[j * (n + 1) + i + 1], c = v[(j + 1) * (n + 1) + i + 1], d = v[(j + 1) * (n + 1) + i];
+      m.add_face(a, b, c); m.add_face(a, c, d);
+    }
+  return m;
+}
+
+static double u01(uint64_t& s) {   // SplitMix64
+  s += 0x9E3779B97F4A7C15ull;
+  uint64_t z = s;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+}
+
+static int known_answers() {
+  {   // aabb_correctness_triangle_test.cpp:51-108
+    Mesh m = tetrahedron();
+    Tree tree(faces(m).first, faces(m).second, m);
+    const Point p(-0.25, 0.251, 0.255), q(0.25, 0.253, 0.256);
+    const Segment pq(p, q);
+    CHECK(tree.do_intersect(pq));
+    CHECK(tree.number_of_intersected_primitives(pq) == 1);
+    CHECK(tree.closest_point(Point(0.0, 0.0, 3.0)) == Point(0.0, 0.0, 1.0));
+    CHECK(tree.size() == 4 && !tree.empty());
+    const auto bb = tree.bbox();
+    CHECK(bb.xmin() == 0 && bb.ymin() == 0 && bb.zmin() == 0 && bb.xmax() == 1 && bb.ymax() == 1 && bb.zmax() == 1);
+    // AABB_face_graph_triangle_example.cpp:31-39 (there on make_tetrahedron((1,0,0),(0,1,0),(0,0,1),(0,0,0)): same solid)
+    CHECK(tree.number_of_intersected_primitives(Segment(Point(0.2, 0.2, 0.2), Point(1.0, 1.0, 1.0))) == 1);
+    const Point c = tree.closest_point(Point(2.0, 2.0, 2.0));
+    CHECK(std::fabs(c.x() - 1.0 / 3) < 1e-15 && std::fabs(c.y() - 1.0 / 3) < 1e-15 && std::fabs(c.z() - 1.0 / 3) < 1e-15);
+    CHECK(tree.squared_distance(Point(2.0, 2.0, 2.0)) == (c.x() - 2) * (c.x() - 2) + (c.y() - 2) * (c.y() - 2) + (c.z() - 2) * (c.z() - 2));
+    CHECK(tree.accelerate_distance_queries());
+    // first_intersection: a ray along +z from below the base face hits face 0 (z = 0) first, at (0.2,0.2,0)
+    const Ray up(Point(0.2, 0.2, -1.0), Point(0.2, 0.2, 0.0));
+    const auto hit = tree.first_intersection(up);
+    CHECK(hit && hit->second == mini::Face_index(0));
+    CHECK(std::holds_alternative<Point>(hit->first) && std::get<Point>(hit->first) == Point(0.2, 0.2, 0.0));
+    CHECK(tree.first_intersected_primitive(up) && *tree.first_intersected_primitive(up) == mini::Face_index(0));
+    CHECK(tree.number_of_intersected_primitives(up) == 2);
+    CHECK(!tree.first_intersection(Ray(Point(0.2, 0.2, -1.0), Point(0.2, 0.2, -2.0))));
+    const auto cpp = tree.closest_point_and_primitive(Point(0.2, 0.2, -1.0));
+    CHECK(cpp.first == Point(0.2, 0.2, 0.0) && cpp.second == mini::Face_index(0));
+    CHECK(tree.closest_point(Point(0.2, 0.2, -1.0), Point(1, 1, 1)) == cpp.first);   // hinted overload
+  }
+  {   // aabb_test_empty_tree.cpp:38-53
+    Tree tree;
+    const Segment s(Point(0.1, 0.1, -1), Point(0.1, 0.1, 1));
+    CHECK(tree.empty() && tree.size() == 0);
+    CHECK(!tree.do_intersect(s) && tree.number_of_intersected_primitives(s) == 0);
+    CHECK(!tree.first_intersection(Ray(s.source(), s.target())));
+    bool threw = false;
+    try { tree.closest_point(Point(0, 0, 0)); } catch (const CGAL_B200::Error& e) { threw = e.code() == B200AABB_ERR_EMPTY_TREE; }
+    CHECK(threw);   // CGAL_precondition(!empty())
+  }
+  {   // aabb_test_singleton_tree.cpp:44-67 + insert / clear / lazy rebuild / move
+    Mesh one;
+    one.add_face(one.add_vertex(Point(0, 0, 0)), one.add_vertex(Point(1, 0, 0)), one.add_vertex(Point(0, 1, 0)));
+    Tree tree(faces(one).first, faces(one).second, one);
+    const Segment s(Point(0.1, 0.1, -1), Point(0.1, 0.1, 1));
+    CHECK(tree.size() == 1 && tree.do_intersect(s) && tree.number_of_intersected_primitives(s) == 1);
+    CHECK(tree.closest_point(Point(0.25, 0.25, 5)) == Point(0.25, 0.25, 0) && tree.squared_distance(Point(0.25, 0.25, 5)) == 25.0);
+    Mesh m = tetrahedron();
+    tree.rebuild(faces(m).first, faces(m).second, m);
+    CHECK(tree.size() == 4 && tree.number_of_intersected_primitives(Ray(Point(0.2, 0.2, -1), Point(0.2, 0.2, 0))) == 2);
+    Tree moved(std::move(tree));
+    CHECK(moved.size() == 4 && moved.do_intersect(s));
+    moved.clear();
+    CHECK(moved.empty() && !moved.do_intersect(s));
+    moved.insert(faces(one).first, faces(one).second, one);   // no explicit build(): the first query builds
+    CHECK(moved.number_of_intersected_primitives(s) == 1);
+  }
+  {   // batched == one at a time
+    Mesh m = grid(24);
+    Tree tree(faces(m).first, faces(m).second, m);
+    tree.build();
+    uint64_t seed = 23;
+    std::vector<Ray> rays; std::vector<Segment> segs; std::vector<Point> pts;
+    for (int i = 0; i < 600; ++i) {
+      const Point a(24 * u01(seed), 24 * u01(seed), 3 * u01(seed) - 1.5), b(24 * u01(seed), 24 * u01(seed), 3 * u01(seed) - 1.5);
+      rays.push_back(Ray(a, b)); segs.push_back(Segment(a, b)); pts.push_back(a);
+    }
+    std::vector<Tree::Ray_intersection> fi(rays.size());
+    std::vector<uint8_t> flags;
+    tree.first_intersection(rays.begin(), rays.end(), fi.begin(), &flags);
+    std::vector<bool> hit; std::vector<Tree::size_type> cnt; std::vector<Tree::Point_and_primitive_id> cp; std::vector<double> sd;
+    tree.do_intersect(segs.begin(), segs.end(), std::back_inserter(hit));
+    tree.number_of_intersected_primitives(segs.begin(), segs.end(), std::back_inserter(cnt));
+    tree.closest_point_and_primitive(pts.begin(), pts.end(), std::back_inserter(cp));
+    tree.squared_distance(pts.begin(), pts.end(), std::back_inserter(sd));
+    int nhit = 0;
+    for (size_t i = 0; i < rays.size(); ++i) {
+      const auto one = tree.first_intersection(rays[i]);
+      CHECK(one.has_value() == fi[i].has_value());
+      if (one) { CHECK(one->second == fi[i]->second && std::get<Point>(one->first) == std::get<Point>(fi[i]->first)); ++nhit; }
+      CHECK(tree.do_intersect(segs[i]) == hit[i] && tree.number_of_intersected_primitives(segs[i]) == cnt[i] && (cnt[i] > 0) == hit[i]);
+      const auto c1 = tree.closest_point_and_primitive(pts[i]);
+      CHECK(c1.first == cp[i].first && c1.second == cp[i].second && tree.squared_distance(pts[i]) == sd[i]);
+    }
+    CHECK(nhit > 50 && flags.size() == rays.size());
+  }
+  std::printf("test_aabb_tree: all known-answer and consistency checks passed\n");
+  return 0;
+}
+
+// file format (little endian): u64 nv, nf, nrays, nsegs, npts; f64 verts[nv*3]; u32 faces[nf*3]; f64 rays[nrays*6]; f64 segs[nsegs*6]; f64 pts[npts*3]
+// output: per ray u32 id (0xFFFFFFFF none) + f64 point[3]; per segment u32 count + u32 do_intersect; per point u32 id + f64 cp[3] + f64 sqdist
+static int answer_file(const char* in, const char* out) {
+  FILE* f = std::fopen(in, "rb");
+  CHECK(f);
+  uint64_t h[5];
+  CHECK(std::fread(h, 8, 5, f) == 5);
+  std::vector<double> v(3 * h[0]), rays(6 * h[2]), segs(6 * h[3]), pts(3 * h[4]);
+  std::vector<uint32_t> fc(3 * h[1]);
+  CHECK(std::fread(v.data(), 8, v.size(), f) == v.size() && std::fread(fc.data(), 4, fc.size(), f) == fc.size());
+  CHECK(std::fread(rays.data(), 8, rays.size(), f) == rays.size() && std::fread(segs.data(), 8, segs.size(), f) == segs.size() && std::fread(pts.data(), 8, pts.size(), f) == pts.size());
+  std::fclose(f);
+  Mesh m;
+  for (uint64_t i = 0; i < h[0]; ++i) m.add_vertex(Point(v[3 * i], v[3 * i + 1], v[3 * i + 2]));
+  for (uint64_t i = 0; i < h[1]; ++i) m.add_face(mini::Vertex_index(fc[3 * i]), mini::Vertex_index(fc[3 * i + 1]), mini::Vertex_index(fc[3 * i + 2]));
+  Tree tree(faces(m).first, faces(m).second, m);
+  tree.accelerate_distance_queries();
+  std::vector<Ray> R; std::vector<Segment> S; std::vector<Point> P;
+  for (uint64_t i = 0; i < h[2]; ++i) R.push_back(Ray(Point(rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]), Point(rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5])));
+  for (uint64_t i = 0; i < h[3]; ++i) S.push_back(Segment(Point(segs[6 * i], segs[6 * i + 1], segs[6 * i + 2]), Point(segs[6 * i + 3], segs[6 * i + 4], segs[6 * i + 5])));
+  for (uint64_t i = 0; i < h[4]; ++i) P.push_back(Point(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]));
+  std::vector<Tree::Ray_intersection> fi(R.size());
+  tree.first_intersection(R.begin(), R.end(), fi.begin());
+  std::vector<Tree::size_type> cnt; std::vector<bool> hit; std::vector<Tree::Point_and_primitive_id> cp; std::vector<double> sd;
+  tree.number_of_intersected_primitives(S.begin(), S.end(), std::back_inserter(cnt));
+  tree.do_intersect(S.begin(), S.end(), std::back_inserter(hit));
+  tree.closest_point_and_primitive(P.begin(), P.end(), std::back_inserter(cp));
+  tree.squared_distance(P.begin(), P.end(), std::back_inserter(sd));
+  FILE* o = std::fopen(out, "wb");
+  CHECK(o);
+  for (size_t i = 0; i < R.size(); ++i) {
+    uint32_t id = 0xFFFFFFFFu; double p[3] = {0, 0, 0};
+    if (fi[i]) {
+      id = (uint32_t)fi[i]->second;
+      const Point x = std::holds_alternative<Point>(fi[i]->first) ? std::get<Point>(fi[i]->first) : std::get<Segment>(fi[i]->first).source();
+      p[0] = x.x(); p[1] = x.y(); p[2] = x.z();
+    }
+    std::fwrite(&id, 4, 1, o); std::fwrite(p, 8, 3, o);
+  }
+  for (size_t i = 0; i < S.size(); ++i) { const uint32_t c[2] = {(uint32_t)cnt[i], hit[i] ? 1u : 0u}; std::fwrite(c, 4, 2, o); }
+  for (size_t i = 0; i < P.size(); ++i) {
+    const uint32_t id = (uint32_t)cp[i].second; const double p[4] = {cp[i].first.x(), cp[i].first.y(), cp[i].first.z(), sd[i]};
+    std::fwrite(&id, 4, 1, o); std::fwrite(p, 8, 4, o);
+  }
+  std::fclose(o);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  try {
+    if (argc == 3) return answer_file(argv[1], argv[2]);
+    return known_answers();
+  } catch (const std::exception& e) {
+    std::fprintf(stderr, "exception: %s\n", e.what());
+    return 2;
+  }
+}
