@@ -190,6 +190,24 @@ B2_HD float point_box_sqdist(const float* lo, const float* hi, const PointCtx& c
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Traversal scheme shared by the three routines below ("while-while" with deferred leaves).  A thread alternates between
+//   a NODE phase   — pops / descends internal nodes, tests the two child boxes in binary32, and only RECORDS the leaf
+//                    children that pass (a few pending slots per thread), and
+//   a LEAF phase   — runs the binary64 primitive routines of geom.cuh on the recorded leaves.
+// Both phases are loops, so the 32 threads of a warp reconverge at each phase boundary: the long exact leaf routines are
+// executed by all threads that have a pending leaf at once instead of by one thread at a time while the others wait
+// (measured on the one-loop version, profiles/r1_01: 2.9 of 32 threads active per instruction in closest_point).
+// ---------------------------------------------------------------------------------------------------------------
+// warp vote used ONLY as a scheduling hint (when to run a deferred phase); the host emulation sees the thread alone
+B2_HD bool warp_any(bool p) {
+#if defined(__CUDA_ARCH__)
+    return __any_sync(__activemask(), p);
+#else
+    return p;
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // do_intersect / number_of_intersected_primitives   (AABB_tree.h:903-932)
 // ---------------------------------------------------------------------------------------------------------------
 template <bool IS_RAY, bool COUNT>
@@ -207,28 +225,32 @@ B2_HD uint32_t traverse_intersect(const BvhNode* __restrict__ nodes, const TriRe
     if (root & kLeafBit) { leaf(root); return found; }   // singleton tree: AABB_tree.h:516-525
     uint32_t stack[kStackCap];
     int sp = 0;
+    uint32_t pend[2];
+    int np = 0;
     uint32_t cur = root;
     while (true) {
-        const NodeView n = load_node(nodes, cur);
-        ++st.nodes;
-        float tn;
-        const bool h0 = line_box(n.lo0, n.hi0, c, tlimit, tn);
-        const bool h1 = line_box(n.lo1, n.hi1, c, tlimit, tn);
-        uint32_t next = kNone;
-        if (h0) { if (n.c0 & kLeafBit) leaf(n.c0); else next = n.c0; }
-        if (!COUNT && found) return 1;
-        if (h1) {
-            if (n.c1 & kLeafBit) leaf(n.c1);
-            else if (next == kNone) next = n.c1;
-            else if (sp < kStackCap) stack[sp++] = n.c1;
-            else st.overflow = 1;
+        while (cur != kNone && np == 0) {                 // node phase
+            const NodeView n = load_node(nodes, cur);
+            ++st.nodes;
+            float tn;
+            const bool h0 = line_box(n.lo0, n.hi0, c, tlimit, tn);
+            const bool h1 = line_box(n.lo1, n.hi1, c, tlimit, tn);
+            uint32_t next = kNone;
+            if (h0) { if (n.c0 & kLeafBit) pend[np++] = n.c0; else next = n.c0; }
+            if (h1) {
+                if (n.c1 & kLeafBit) pend[np++] = n.c1;
+                else if (next == kNone) next = n.c1;
+                else if (sp < kStackCap) stack[sp++] = n.c1;
+                else st.overflow = 1;
+            }
+            if (next == kNone && sp > 0) next = stack[--sp];
+            cur = next;
         }
-        if (!COUNT && found) return 1;
-        if (next == kNone) {
-            if (sp == 0) break;
-            next = stack[--sp];
+        while (np > 0) {                                  // leaf phase
+            leaf(pend[--np]);
+            if (!COUNT && found) return 1;
         }
-        cur = next;
+        if (cur == kNone) break;
     }
     return found;
 }
@@ -267,36 +289,53 @@ B2_HD FirstHit traverse_first(const BvhNode* __restrict__ nodes, const TriRec* _
             runner_up = fmin(runner_up, x.t); runner_lo = fmin(runner_lo, x.t - x.u);
         }
     };
-    if (root & kLeafBit) { leaf(root); return best; }
-    uint32_t stack[kStackCap];
-    float stack_t[kStackCap];     // lower bound of the deferred node's entry parameter
-    int sp = 0;
-    uint32_t cur = root;
-    while (true) {
-        const NodeView n = load_node(nodes, cur);
-        ++st.nodes;
-        float t0, t1;
-        bool h0 = line_box(n.lo0, n.hi0, c, tlimit, t0);
-        bool h1 = line_box(n.lo1, n.hi1, c, tlimit, t1);
-        uint32_t c0 = n.c0, c1 = n.c1;
-        if (h0 && h1 && t1 < t0) { const uint32_t tc = c0; c0 = c1; c1 = tc; const float tt = t0; t0 = t1; t1 = tt; }
-        else if (!h0 && h1) { c0 = c1; t0 = t1; h0 = true; h1 = false; }
-        uint32_t next = kNone;
-        if (h0) { if (c0 & kLeafBit) leaf(c0); else next = c0; }
-        if (h1 && t1 <= tlimit) {
-            if (c1 & kLeafBit) leaf(c1);
-            else if (next == kNone) next = c1;
-            else if (sp < kStackCap) { stack[sp] = c1; stack_t[sp] = t1; ++sp; }
-            else st.overflow = 1;
+    if (root & kLeafBit) { leaf(root); }
+    else {
+        uint32_t stack[kStackCap];
+        float stack_t[kStackCap];     // lower bound of the deferred node's entry parameter
+        int sp = 0;
+        uint32_t pend[2];             // leaves awaiting the exact test, nearer box first
+        float pend_t[2];
+        int np = 0;
+        uint32_t cur = root;
+        float cur_t = 0.0f;
+        while (true) {
+            while (cur != kNone && np == 0) {             // node phase
+                const NodeView n = load_node(nodes, cur);
+                ++st.nodes;
+                float t0, t1;
+                bool h0 = line_box(n.lo0, n.hi0, c, tlimit, t0);
+                bool h1 = line_box(n.lo1, n.hi1, c, tlimit, t1);
+                uint32_t c0 = n.c0, c1 = n.c1;
+                if (h0 && h1 && t1 < t0) { const uint32_t tc = c0; c0 = c1; c1 = tc; const float tt = t0; t0 = t1; t1 = tt; }
+                else if (!h0 && h1) { c0 = c1; t0 = t1; h0 = true; h1 = false; }
+                uint32_t next = kNone;
+                if (h0) { if (c0 & kLeafBit) { pend[np] = c0; pend_t[np] = t0; ++np; } else { next = c0; cur_t = t0; } }
+                if (h1) {
+                    if (c1 & kLeafBit) { pend[np] = c1; pend_t[np] = t1; ++np; }
+                    else if (next == kNone) { next = c1; cur_t = t1; }
+                    else if (sp < kStackCap) { stack[sp] = c1; stack_t[sp] = t1; ++sp; }
+                    else st.overflow = 1;
+                }
+                while (next == kNone && sp > 0) {
+                    --sp;
+                    if (stack_t[sp] <= tlimit) { next = stack[sp]; cur_t = stack_t[sp]; }
+                }
+                cur = next;
+            }
+            for (int k = 0; k < np; ++k)                   // leaf phase
+                if (pend_t[k] <= tlimit) leaf(pend[k]);
+            np = 0;
+            if (cur != kNone && cur_t > tlimit) {          // the node chosen before the leaf phase may have fallen behind the new hit
+                cur = kNone;
+                while (cur == kNone && sp > 0) {
+                    --sp;
+                    if (stack_t[sp] <= tlimit) { cur = stack[sp]; cur_t = stack_t[sp]; }
+                }
+            }
+            if (cur == kNone) break;
         }
-        while (next == kNone) {
-            if (sp == 0) goto done;
-            --sp;
-            if (stack_t[sp] <= tlimit) next = stack[sp];
-        }
-        cur = next;
     }
-done:
     if (best.prim != kNone) {
         best.tie = runner_up == best.t;
         best.near = !best.tie && runner_lo <= best.t + best_u;
@@ -312,8 +351,17 @@ done:
 // A box is skipped only when it is certainly farther than the incumbent by the margin of `widen` (1e-13 relative plus a
 // few ulps of the coordinate magnitude, since candidates are ROUNDED points), which is wider than the reference's own
 // semi-static margin (AABB_traits_3.h:318-459): every candidate the reference could have preferred is examined.
+//
+// Three phases per round: (A) nodes, recording leaf children whose box reaches into the incumbent ball; (B1) a rigorous
+// division-free binary32 pre-test of the recorded leaves (tangent plane of the incumbent ball, direction of the triangle's
+// centroid); (B2) for the survivors the sharper pre-test and then the binary64 projection of the reference + the exact
+// comparison.  B2 is postponed until a thread has collected kSurvGo survivors (or has no incumbent yet, or is finishing) and
+// then runs for every thread of the warp that has a survivor.
 // ---------------------------------------------------------------------------------------------------------------
 struct Closest { Vec3 p; uint32_t prim; double sqd; int tie; int near; };
+
+constexpr int kPendGo = 3;    // leave the node phase once this many leaves are pending (a node adds at most two)
+constexpr int kSurvGo = 2;    // run the binary64 phase once this many pre-test survivors are waiting
 
 B2_HD double widen_sqdist(double sqd, double delta) { return sqd + ((2.0 * delta * sqrt(sqd) + delta * delta) + sqd * 1e-13); }
 
@@ -358,25 +406,27 @@ B2_HD Closest traverse_closest(const BvhNode* __restrict__ nodes, const TriRec* 
     float bound = INFINITY;       // prune boxes certainly farther than the incumbent (widened, rounded up)
     float rbound = INFINITY;      // >= sqrt(bound)
     float ub[3] = {0.0f, 0.0f, 0.0f}, sub = 0.0f;   // direction query -> incumbent closest point and its length (binary32)
-    double runner_up = DBL_MAX;
-    auto leaf = [&](uint32_t ref) {
-        uint32_t id;
-        const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
-        ++st.leaves;
-        if (best.prim != kNone) {
-            // binary32 pre-test on coordinates RELATIVE to the query (the subtraction is done in binary64)
-            const float ra[3] = {(float)(t.a.x - o.x), (float)(t.a.y - o.y), (float)(t.a.z - o.z)};
-            const float rb[3] = {(float)(t.b.x - o.x), (float)(t.b.y - o.y), (float)(t.b.z - o.z)};
-            const float rc[3] = {(float)(t.c.x - o.x), (float)(t.c.y - o.y), (float)(t.c.z - o.z)};
-            const float m = fmaxf(fmaxf(fmaxf(fabsf(ra[0]), fabsf(ra[1])), fmaxf(fabsf(ra[2]), fabsf(rb[0]))),
-                                  fmaxf(fmaxf(fabsf(rb[1]), fabsf(rb[2])), fmaxf(fmaxf(fabsf(rc[0]), fabsf(rc[1])), fabsf(rc[2]))));
-            // (1) tangent plane of the incumbent ball: all three vertices beyond it
-            if (certainly_farther(ub, sub, ra, rb, rc, m, rbound)) { ++st.culled; return; }
-            // (2) direction of this triangle's own (approximate) closest point
-            float u[3];
-            approx_closest_to_origin(ra, rb, rc, u);
-            if (certainly_farther(u, sqrtf(dot3f(u, u)), ra, rb, rc, m, rbound)) { ++st.culled; return; }
-        }
+    // binary32 pre-test on coordinates RELATIVE to the query (the subtraction is done in binary64): true = the primitive is
+    // certainly farther than the incumbent.  sharp = also try the direction of the triangle's own approximate closest point.
+    auto certainly_outside = [&](const Tri3& t, bool sharp) -> bool {
+        const float ra[3] = {(float)(t.a.x - o.x), (float)(t.a.y - o.y), (float)(t.a.z - o.z)};
+        const float rb[3] = {(float)(t.b.x - o.x), (float)(t.b.y - o.y), (float)(t.b.z - o.z)};
+        const float rc[3] = {(float)(t.c.x - o.x), (float)(t.c.y - o.y), (float)(t.c.z - o.z)};
+        const float m = fmaxf(fmaxf(fmaxf(fabsf(ra[0]), fabsf(ra[1])), fmaxf(fabsf(ra[2]), fabsf(rb[0]))),
+                              fmaxf(fmaxf(fabsf(rb[1]), fabsf(rb[2])), fmaxf(fmaxf(fabsf(rc[0]), fabsf(rc[1])), fabsf(rc[2]))));
+        // (1) tangent plane of the incumbent ball: all three vertices beyond it
+        if (certainly_farther(ub, sub, ra, rb, rc, m, rbound)) return true;
+        // (2) direction of the triangle's centroid: nearly optimal for a triangle that is small compared with its distance
+        const float g[3] = {(ra[0] + rb[0]) + rc[0], (ra[1] + rb[1]) + rc[1], (ra[2] + rb[2]) + rc[2]};
+        if (certainly_farther(g, sqrtf(dot3f(g, g)), ra, rb, rc, m, rbound)) return true;
+        if (!sharp) return false;
+        // (3) direction of this triangle's own (approximate) closest point
+        float u[3];
+        approx_closest_to_origin(ra, rb, rc, u);
+        return certainly_farther(u, sqrtf(dot3f(u, u)), ra, rb, rc, m, rbound);
+    };
+    // the reference's per-primitive step: Construct_projected_point_3 + Compare_distance_3 against the incumbent
+    auto evaluate = [&](const Tri3& t, uint32_t id) {
         const Vec3 cp = closest_on_triangle(t, o);
         const Vec3 v = cp - o;
         const double sqd = (v.x * v.x + v.y * v.y) + v.z * v.z;   // Compute_squared_distance_3(query, closest): AABB_tree.h:1024-1032
@@ -386,7 +436,6 @@ B2_HD Closest traverse_closest(const BvhNode* __restrict__ nodes, const TriRec* 
             const int sg = cmp_dist(o, cp, best.p, st.nexact);     // Compare_distance_3(query, candidate, incumbent): AABB_traits_3.h:724-732
             if (sg == 0) { take = id < best.prim; best.tie = 1; }
             else { take = sg < 0; if (take) best.tie = 0; }
-            runner_up = fmin(runner_up, take ? best.sqd : sqd);
         }
         if (take) {
             best.p = cp; best.prim = id; best.sqd = sqd;
@@ -397,36 +446,77 @@ B2_HD Closest traverse_closest(const BvhNode* __restrict__ nodes, const TriRec* 
             sub = sqrtf(dot3f(ub, ub));
         }
     };
-    if (root & kLeafBit) { leaf(root); return best; }
+    if (root & kLeafBit) {
+        uint32_t id;
+        const Tri3 t = load_tri(tris, root & ~kLeafBit, id);
+        ++st.leaves;
+        evaluate(t, id);
+        return best;
+    }
     uint32_t stack[kStackCap];
     float stack_d[kStackCap];     // lower bound of the deferred node's squared distance
     int sp = 0;
+    uint32_t pend[kPendGo + 1];   // leaves whose box reaches into the ball, awaiting the binary32 pre-test
+    int np = 0;
+    uint32_t surv[kSurvGo + kPendGo + 1];   // pre-test survivors awaiting the binary64 projection
+    int ns = 0;
     uint32_t cur = root;
+    float cur_d = 0.0f;
     while (true) {
-        const NodeView n = load_node(nodes, cur);
-        ++st.nodes;
-        float d0 = point_box_sqdist(n.lo0, n.hi0, pc), d1 = point_box_sqdist(n.lo1, n.hi1, pc);
-        uint32_t c0 = n.c0, c1 = n.c1;
-        if (d1 < d0) { const uint32_t tc = c0; c0 = c1; c1 = tc; const float td = d0; d0 = d1; d1 = td; }
-        uint32_t next = kNone;
-        if (d0 <= bound) { if (c0 & kLeafBit) leaf(c0); else next = c0; }
-        if (d1 <= bound) {
-            if (c1 & kLeafBit) leaf(c1);
-            else if (next == kNone) next = c1;
-            else if (sp < kStackCap) { stack[sp] = c1; stack_d[sp] = d1; ++sp; }
-            else st.overflow = 1;
+        // (A) node phase.  Without an incumbent the first pending leaf ends it: its projection gives the first ball.
+        const int go = best.prim == kNone ? 1 : kPendGo;
+        while (cur != kNone && np < go) {
+            const NodeView n = load_node(nodes, cur);
+            ++st.nodes;
+            float d0 = point_box_sqdist(n.lo0, n.hi0, pc), d1 = point_box_sqdist(n.lo1, n.hi1, pc);
+            uint32_t c0 = n.c0, c1 = n.c1;
+            if (d1 < d0) { const uint32_t tc = c0; c0 = c1; c1 = tc; const float td = d0; d0 = d1; d1 = td; }
+            uint32_t next = kNone;
+            if (d0 <= bound) { if (c0 & kLeafBit) pend[np++] = c0; else { next = c0; cur_d = d0; } }
+            if (d1 <= bound) {
+                if (c1 & kLeafBit) pend[np++] = c1;
+                else if (next == kNone) { next = c1; cur_d = d1; }
+                else if (sp < kStackCap) { stack[sp] = c1; stack_d[sp] = d1; ++sp; }
+                else st.overflow = 1;
+            }
+            while (next == kNone && sp > 0) {
+                --sp;
+                if (stack_d[sp] <= bound) { next = stack[sp]; cur_d = stack_d[sp]; }
+            }
+            cur = next;
         }
-        while (next == kNone) {
-            if (sp == 0) goto done;
-            --sp;
-            if (stack_d[sp] <= bound) next = stack[sp];
+        // (B1) cheap rigorous pre-test of the pending leaves
+        for (int k = 0; k < np; ++k) {
+            uint32_t id;
+            const Tri3 t = load_tri(tris, pend[k] & ~kLeafBit, id);
+            ++st.leaves;
+            if (best.prim != kNone && certainly_outside(t, false)) { ++st.culled; continue; }
+            surv[ns++] = pend[k];
         }
-        cur = next;
+        np = 0;
+        // (B2) binary64 projection of the survivors
+        const bool due = ns > 0 && (best.prim == kNone || ns >= kSurvGo || cur == kNone);
+        if (warp_any(due)) {
+            while (ns > 0) {
+                --ns;
+                uint32_t id;
+                const Tri3 t = load_tri(tris, surv[ns] & ~kLeafBit, id);
+                if (best.prim != kNone && certainly_outside(t, true)) { ++st.culled; continue; }
+                evaluate(t, id);
+            }
+            if (cur != kNone && cur_d > bound) {           // the node chosen before this phase may have fallen outside the new ball
+                cur = kNone;
+                while (cur == kNone && sp > 0) {
+                    --sp;
+                    if (stack_d[sp] <= bound) { cur = stack[sp]; cur_d = stack_d[sp]; }
+                }
+            }
+        }
+        if (cur == kNone && ns == 0) break;
     }
-done:
-    (void)runner_up;   // no near-tie band here: the reference never prunes when unsure and compares candidates exactly, so its
-                       // answer is order-independent except on exact ties (measured: 0 other mismatches in 10^6 queries; candidates
-                       // on a shared edge agree to a few ulps for a third of all queries and are decided identically by both)
+    // no near-tie band here: the reference never prunes when unsure and compares candidates exactly, so its answer is
+    // order-independent except on exact ties (measured: 0 other mismatches in 10^6 queries; candidates on a shared edge agree
+    // to a few ulps for a third of all queries and are decided identically by both)
     return best;
 }
 

@@ -63,8 +63,13 @@ def test_cpp_batched_answers_match_oracle(meshes, tmp_path):
     same = gr["id"] == ref_r["prim"]
     assert same.mean() > 0.999                                        # the rest are reported ties (checked through the C ABI tests)
     np.testing.assert_array_equal(gr["p"][same], ref_r["pts"][same][:, :3])
+    # ids differ from the reference's only on exact-distance ties (a closest point on a shared edge or vertex is the SAME point
+    # for both triangles: the reference keeps the first it visited, this library the smallest id)
     same = gp["id"] == ref_p["prim"]
-    assert same.mean() > 0.99
     np.testing.assert_array_equal(gp["cp"][same], ref_p["cp"][same])
     np.testing.assert_array_equal(gp["sd"][same], ref_p["sqd"][same])
+    same_point = np.all(gp["cp"] == ref_p["cp"], axis=1)
+    assert same_point.mean() > 0.999 and np.all(same | same_point | (gp["sd"] == ref_p["sqd"]))
     assert np.all(np.abs(gp["sd"] - ref_p["sqd"]) <= 1e-12 * ref_p["sqd"])
+    for i in np.nonzero(~same)[0][:100]:        # the reported primitive really attains the reported point
+        np.testing.assert_array_equal(o.candidate_closest(gp["id"][i], pts[i]), gp["cp"][i])

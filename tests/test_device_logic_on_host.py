@@ -44,6 +44,41 @@ def test_predicates_match_oracle():
         assert hc.call("hc_cmp_dist_exact", tri) == orc.compare_distance(p, q, r, exact=True)
 
 
+def test_compare_distance_double_double_stage_is_exact():
+    """the double-double stage of Compare_distance_3 (predicates.cuh: cmp_dist_dd) decides the cases the static filter cannot:
+    candidates a few ulps apart (shared-edge projections), mirrored points (exact ties -> expansion stage), huge offsets, tiny scales"""
+    rng = np.random.default_rng(77)
+    nz = 0
+    for it in range(6000):
+        scale = [1.0, 4096.0, 1e-6, 1e8][it % 4]
+        p = rng.uniform(-1, 1, 3) * scale + (it % 3) * scale
+        q = rng.uniform(-1, 1, 3) * scale + (it % 3) * scale
+        mode = (it // 4) % 5
+        if mode == 0:      # r = q moved by -2..2 ulps per coordinate
+            r = q.copy()
+            for _ in range(2):
+                r = np.nextafter(r, r + rng.choice([-1.0, 0.0, 1.0], 3) * scale)
+        elif mode == 1:    # mirror image of q about p, then a few ulps off
+            r = 2 * p - q
+            if it % 2:
+                r = np.nextafter(r, r + rng.choice([-1.0, 0.0, 1.0], 3) * scale)
+        elif mode == 2:    # same distance by a permutation / sign flip of the offset: exact ties when the arithmetic is exact
+            d = np.round((q - p) / scale * 1024) / 1024 * scale
+            q = p + d
+            r = p + rng.permutation(d) * rng.choice([-1.0, 1.0], 3)
+        elif mode == 3:    # nearly equal distances in unrelated directions
+            d = q - p
+            e = rng.normal(size=3); e *= np.linalg.norm(d) / np.linalg.norm(e)
+            r = p + e
+        else:
+            r = rng.uniform(-1, 1, 3) * scale
+        want = orc.compare_distance(p, q, r, exact=True)
+        assert hc.call("hc_cmp_dist", np.concatenate([p, q, r])) == want
+        assert orc.compare_distance(p, q, r) == want
+        nz += want != 0
+    assert nz > 3000
+
+
 def test_triangle_tests_and_constructions_match_oracle_bitwise():
     rng = np.random.default_rng(12)
     n_hit = n_seg = 0
