@@ -165,33 +165,16 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------------------------- our arm
-class _CudaView:
-    """exposes a raw device buffer of the library to torch (for torch.distributed.broadcast) without copying"""
-
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-
-
 def broadcast_tree(tree, rank, world, dist, torch, n_prims):
     """rank 0 built the tree; the others allocate same-sized buffers and receive them with NCCL (NVLink/NVSwitch)"""
-    if rank != 0:
-        tree.import_alloc(n_prims)
+    from cgal_b200 import sharding
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier()
     e0.record()
-    total = 0
-    for ptr, nbytes in tree.export_layout():
-        if nbytes == 0:
-            continue
-        view = torch.as_tensor(_CudaView(ptr, nbytes), device="cuda")
-        for off in range(0, nbytes, 1 << 30):
-            dist.broadcast(view[off:off + (1 << 30)], src=0)
-        total += nbytes
+    _, total = sharding.broadcast_tree(tree, n_prims, src=0)
     e1.record()
     torch.cuda.synchronize()
-    if rank != 0:
-        tree.import_finish()
     return total, e0.elapsed_time(e1)
 
 
