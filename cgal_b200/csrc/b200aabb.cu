@@ -12,6 +12,7 @@
 #include "../../include/b200aabb.h"
 #include "build.cuh"
 #include "radix_sort.cuh"
+#include "closest_warp.cuh"
 
 using namespace b2;
 
@@ -200,6 +201,12 @@ struct b200aabb_tree {
     unsigned long long* d_counters = nullptr;   // [8]
     // options
     int opt_sort_queries = 1;      // B200AABB_OPT_SORT_QUERIES
+    int opt_closest_kernel = 1;    // B200AABB_OPT_CLOSEST_KERNEL: 1 = warp-cooperative pool (closest_warp.cuh), 0 = one thread per query
+    int opt_warp_refill = 16;      // B200AABB_OPT_WARP_REFILL
+    int opt_warp_surv_go = 24;     // B200AABB_OPT_WARP_SURV_GO
+    // warp-cooperative closest_point: per pipeline slot a batch cursor and the pools' spill area; grid = SMs x resident warps
+    struct WarpScratch { unsigned long long* cursor = nullptr; uint2* spill = nullptr; } warp[2];
+    int warp_grid = 0;
     // query coherence sort scratch, one per pipeline slot (slot 0 also serves DEVICE-pointer batches); grow-only
     struct SortScratch { uint64_t* keys[2] = {nullptr, nullptr}; uint32_t* vals[2] = {nullptr, nullptr}; void* ws = nullptr; uint64_t cap = 0; } sort[2];
     // staging for HOST-pointer batches (two pipeline slots)
@@ -246,6 +253,22 @@ int ensure_stage(b200aabb_tree* t, size_t in_bytes, size_t out_bytes) {
         for (int s = 0; s < 2; ++s) B2_CUDA(t, cudaMalloc(&t->d_stage_out[s], out_bytes));
         t->stage_out_bytes = out_bytes;
     }
+    return B200AABB_OK;
+}
+
+void free_warp(b200aabb_tree* t) {
+    for (auto& w : t->warp) { cudaFree(w.cursor); cudaFree(w.spill); w = b200aabb_tree::WarpScratch(); }
+}
+int ensure_warp(b200aabb_tree* t, int slot) {
+    if (t->warp_grid == 0) {
+        int per_sm = 0, sms = 0;
+        B2_CUDA(t, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, closest_point_warp_kernel, 32, 0));
+        B2_CUDA(t, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device));
+        t->warp_grid = std::max(1, per_sm) * std::max(1, sms);
+    }
+    auto& w = t->warp[slot];
+    if (!w.cursor) B2_CUDA(t, cudaMalloc(&w.cursor, sizeof(unsigned long long)));
+    if (!w.spill) B2_CUDA(t, cudaMalloc(&w.spill, (size_t)t->warp_grid * kWpSpillCap * sizeof(uint2)));
     return B200AABB_OK;
 }
 
@@ -448,7 +471,7 @@ int b200aabb_destroy(b200aabb_tree* t) {
     if (!t) return B200AABB_OK;
     cudaSetDevice(t->device);
     cudaDeviceSynchronize();
-    free_tree_buffers(t); free_input(t); free_sort(t);
+    free_tree_buffers(t); free_input(t); free_sort(t); free_warp(t);
     cudaFree(t->d_rootbox); cudaFree(t->d_counters);
     for (int s = 0; s < 2; ++s) { cudaFree(t->d_stage_in[s]); cudaFree(t->d_stage_out[s]); if (t->pipe[s]) cudaStreamDestroy(t->pipe[s]); if (t->ev_pipe[s]) cudaEventDestroy(t->ev_pipe[s]); }
     if (t->ev_a) cudaEventDestroy(t->ev_a);
@@ -461,6 +484,9 @@ int b200aabb_set_option(b200aabb_tree* t, int option, int64_t value) {
     if (!t) return B200AABB_ERR_INVALID_ARGUMENT;
     switch (option) {
         case B200AABB_OPT_SORT_QUERIES: t->opt_sort_queries = value != 0; return B200AABB_OK;
+        case B200AABB_OPT_CLOSEST_KERNEL: t->opt_closest_kernel = value != 0; return B200AABB_OK;
+        case B200AABB_OPT_WARP_REFILL: t->opt_warp_refill = (int)std::min<int64_t>(32, std::max<int64_t>(1, value)); return B200AABB_OK;
+        case B200AABB_OPT_WARP_SURV_GO: t->opt_warp_surv_go = (int)std::min<int64_t>(64, std::max<int64_t>(1, value)); return B200AABB_OK;
         default: return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "unknown option");
     }
 }
@@ -478,7 +504,7 @@ int b200aabb_get_stats(const b200aabb_tree* tc, b200aabb_stats* out) {
         unsigned long long c[8];
         B2_CUDA(t, cudaMemcpy(c, t->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
         t->stats.exact_fallbacks = c[0]; t->stats.ties = c[1]; t->stats.nodes_visited = c[3]; t->stats.leaves_tested = c[4]; t->stats.near_ties = c[5]; t->stats.leaves_culled = c[6];
-        if (c[2]) t->err = "traversal stack overflow: results incomplete";
+        if (c[2]) t->err = (c[2] & 2) ? "closest_point work pool inconsistency: results incomplete" : "traversal stack overflow: results incomplete";
         t->query_timing_pending = false;
         if (c[2]) { *out = t->stats; return B200AABB_ERR_CUDA; }
     }
@@ -608,9 +634,25 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
     if (rc) return rc;
     if (t->n == 0) return fail(t, B200AABB_ERR_EMPTY_TREE, "distance query on an empty tree (CGAL_precondition(!empty()))");
     if (n == 0) return B200AABB_OK;
+    // the warp-cooperative kernel packs (query slot, node / leaf) in 32 bits and needs an internal root
+    const bool warp_kernel = t->opt_closest_kernel == 1 && t->n >= 2 && t->n <= kWpMaxPrims;
+    if (warp_kernel) { for (int s = 0; s < 2; ++s) { rc = ensure_warp(t, s); if (rc) return rc; } }
     return run_batch(t, pts, 24, n, space, kPointQuery, {{cp, 24, 0}, {prim, 4, 0}, {sqd, 8, 0}, {flags, 1, 0}},
                      [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
-                         closest_point_kernel<<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (double*)o[0], (uint32_t*)o[1], (double*)o[2], (uint8_t*)o[3]);
+                         if (!warp_kernel || cnt >= (1ull << 32)) {
+                             closest_point_kernel<<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (double*)o[0], (uint32_t*)o[1], (double*)o[2], (uint8_t*)o[3]);
+                             return;
+                         }
+                         const int slot = (space == B200AABB_HOST && st == t->pipe[1]) ? 1 : 0;
+                         cudaMemsetAsync(t->warp[slot].cursor, 0, sizeof(unsigned long long), st);
+                         WarpClosestArgs a;
+                         a.nodes = t->d_nodes; a.tris = t->d_tris; a.mag = t->mag; a.perm = perm; a.counters = t->d_counters;
+                         a.pts = (const double*)in; a.n = cnt; a.cp = (double*)o[0]; a.prim = (uint32_t*)o[1]; a.sqd = (double*)o[2]; a.flags = (uint8_t*)o[3];
+                         a.cursor = t->warp[slot].cursor; a.spill = t->warp[slot].spill;
+                         a.refill_min = t->opt_warp_refill; a.surv_go = t->opt_warp_surv_go;
+                         a.flag_tie = B200AABB_FLAG_TIE; a.flag_exact = B200AABB_FLAG_EXACT;
+                         const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)t->warp_grid, (cnt + 31) / 32);
+                         closest_point_warp_kernel<<<grid, 32, 0, st>>>(a);
                      });
 }
 

@@ -398,6 +398,27 @@ B2_HD bool certainly_farther(const float* u, float su, const float* ra, const fl
     return su > 1e-18f && md - 5e-7f * m * su > rbound * su * 1.000001f;
 }
 
+// binary32 pre-test of one primitive on coordinates RELATIVE to the query o (the subtraction is done in binary64): true = the
+// primitive is certainly farther than rbound (>= sqrt of the widened incumbent distance).  ub / sub = direction query ->
+// incumbent closest point and its length.  sharp = also try the direction of the triangle's own approximate closest point.
+B2_HD bool tri_certainly_outside(const Tri3& t, const Vec3& o, const float* ub, float sub, float rbound, bool sharp) {
+    const float ra[3] = {(float)(t.a.x - o.x), (float)(t.a.y - o.y), (float)(t.a.z - o.z)};
+    const float rb[3] = {(float)(t.b.x - o.x), (float)(t.b.y - o.y), (float)(t.b.z - o.z)};
+    const float rc[3] = {(float)(t.c.x - o.x), (float)(t.c.y - o.y), (float)(t.c.z - o.z)};
+    const float m = fmaxf(fmaxf(fmaxf(fabsf(ra[0]), fabsf(ra[1])), fmaxf(fabsf(ra[2]), fabsf(rb[0]))),
+                          fmaxf(fmaxf(fabsf(rb[1]), fabsf(rb[2])), fmaxf(fmaxf(fabsf(rc[0]), fabsf(rc[1])), fabsf(rc[2]))));
+    // (1) tangent plane of the incumbent ball: all three vertices beyond it
+    if (certainly_farther(ub, sub, ra, rb, rc, m, rbound)) return true;
+    // (2) direction of the triangle's centroid: nearly optimal for a triangle that is small compared with its distance
+    const float g[3] = {(ra[0] + rb[0]) + rc[0], (ra[1] + rb[1]) + rc[1], (ra[2] + rb[2]) + rc[2]};
+    if (certainly_farther(g, sqrtf(dot3f(g, g)), ra, rb, rc, m, rbound)) return true;
+    if (!sharp) return false;
+    // (3) direction of this triangle's own (approximate) closest point
+    float u[3];
+    approx_closest_to_origin(ra, rb, rc, u);
+    return certainly_farther(u, sqrtf(dot3f(u, u)), ra, rb, rc, m, rbound);
+}
+
 B2_HD Closest traverse_closest(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root,
                                const Vec3& o, double mag, TravStat& st) {
     Closest best; best.p = o; best.prim = kNone; best.sqd = DBL_MAX; best.tie = 0; best.near = 0;
@@ -406,25 +427,7 @@ B2_HD Closest traverse_closest(const BvhNode* __restrict__ nodes, const TriRec* 
     float bound = INFINITY;       // prune boxes certainly farther than the incumbent (widened, rounded up)
     float rbound = INFINITY;      // >= sqrt(bound)
     float ub[3] = {0.0f, 0.0f, 0.0f}, sub = 0.0f;   // direction query -> incumbent closest point and its length (binary32)
-    // binary32 pre-test on coordinates RELATIVE to the query (the subtraction is done in binary64): true = the primitive is
-    // certainly farther than the incumbent.  sharp = also try the direction of the triangle's own approximate closest point.
-    auto certainly_outside = [&](const Tri3& t, bool sharp) -> bool {
-        const float ra[3] = {(float)(t.a.x - o.x), (float)(t.a.y - o.y), (float)(t.a.z - o.z)};
-        const float rb[3] = {(float)(t.b.x - o.x), (float)(t.b.y - o.y), (float)(t.b.z - o.z)};
-        const float rc[3] = {(float)(t.c.x - o.x), (float)(t.c.y - o.y), (float)(t.c.z - o.z)};
-        const float m = fmaxf(fmaxf(fmaxf(fabsf(ra[0]), fabsf(ra[1])), fmaxf(fabsf(ra[2]), fabsf(rb[0]))),
-                              fmaxf(fmaxf(fabsf(rb[1]), fabsf(rb[2])), fmaxf(fmaxf(fabsf(rc[0]), fabsf(rc[1])), fabsf(rc[2]))));
-        // (1) tangent plane of the incumbent ball: all three vertices beyond it
-        if (certainly_farther(ub, sub, ra, rb, rc, m, rbound)) return true;
-        // (2) direction of the triangle's centroid: nearly optimal for a triangle that is small compared with its distance
-        const float g[3] = {(ra[0] + rb[0]) + rc[0], (ra[1] + rb[1]) + rc[1], (ra[2] + rb[2]) + rc[2]};
-        if (certainly_farther(g, sqrtf(dot3f(g, g)), ra, rb, rc, m, rbound)) return true;
-        if (!sharp) return false;
-        // (3) direction of this triangle's own (approximate) closest point
-        float u[3];
-        approx_closest_to_origin(ra, rb, rc, u);
-        return certainly_farther(u, sqrtf(dot3f(u, u)), ra, rb, rc, m, rbound);
-    };
+    auto certainly_outside = [&](const Tri3& t, bool sharp) -> bool { return tri_certainly_outside(t, o, ub, sub, rbound, sharp); };
     // the reference's per-primitive step: Construct_projected_point_3 + Compare_distance_3 against the incumbent
     auto evaluate = [&](const Tri3& t, uint32_t id) {
         const Vec3 cp = closest_on_triangle(t, o);

@@ -1,0 +1,378 @@
+// closest_warp.cuh — warp-cooperative closest_point_and_primitive(Point_3): one persistent warp serves 32 query SLOTS and
+// keeps ONE shared work pool for all of them in shared memory.
+//
+// Replaces the same reference path as bvh.cuh::traverse_closest (AABB_tree.h:987-1055, Projection_traits
+// AABB_traversal_traits.h:277-327, AABB_traits_3.h:715-733) and produces the same results: the winner is the candidate
+// (reference-rounded projection, geom.cuh::closest_on_triangle) with the smallest EXACT squared distance, ties -> smallest
+// primitive id + FLAG_TIE.  Only the scheduling differs.
+//
+// Why (profiles/r1_03): in the thread-per-query kernel a closest_point query visits ~170 nodes and ~75 leaves, the counts
+// differ a lot between the 32 queries of a warp, and each thread runs its own three-phase loop: 5.2 of 32 threads are active
+// per issued instruction.  Here the unit of work is a (query slot, node) or (query slot, leaf) PAIR, the pairs of the 32 slots
+// are pooled, and every phase takes 32 pairs off the pool whichever slots they belong to:
+//   (A)  node phase     pop 32 (slot,node) entries (LIFO: depth-first per slot); drop entries whose box has fallen outside the
+//                       slot's incumbent ball; load the node, test both child boxes against the slot's point (binary32,
+//                       directed rounding, bvh.cuh::point_box_sqdist); push internal children (far first, near on top) and
+//                       record leaf children as (slot,leaf) pairs
+//   (B1) pre-test phase rigorous binary32 cull of 32 (slot,leaf) pairs (tangent plane of the slot's ball, centroid direction)
+//   (B2) exact phase    sharper pre-test + the reference's Construct_projected_point_3 in binary64 for 32 surviving pairs, then
+//                       the exact Compare_distance_3 against the slot's incumbent, serialised per slot (__match_any_sync)
+// A slot's state (point, incumbent, bounds) lives in shared memory, SoA by slot, so any lane can work for any slot.
+// Every pair counts in its slot's `outst` counter; when it drops to 0 the query is complete, its lane writes the result
+// and the slot is refilled from the batch cursor (queries are taken in coherence order).  A new query first walks down to
+// its nearest leaf on its own lane (nearest child first), pushing the far children, and projects on that leaf: that is its
+// first ball (the kd-tree hint of the reference, AABB_tree.h:591-612, is not needed).
+// The pool is a stack in shared memory whose bottom half is spilled to a per-warp area in global memory when it fills
+// and reloaded when the stack runs empty, so depth is bounded by kWpSpillCap only (overflow is reported, never silent).
+#pragma once
+#include "bvh.cuh"
+
+namespace b2 {
+
+constexpr int kWpNodeCap = 768;                 // (slot,node) entries held in shared memory
+constexpr int kWpSpillChunk = kWpNodeCap / 2;   // entries moved per spill / reload
+constexpr int kWpSpillCap = 8 * kWpSpillChunk;  // entries per warp in the global spill area
+constexpr int kWpLeafCap = 96;                  // < 32 waiting + at most 64 added by one node phase
+constexpr int kWpSurvCap = 160;                 // < surv_go (<= 64) waiting + at most 95 added by one pre-test phase
+constexpr uint32_t kWpRefMask = 0x07FFFFFFu;    // 27 bits of leaf slot next to the 5-bit query slot
+constexpr uint64_t kWpMaxPrims = 1ull << 27;
+
+struct WarpShared {
+    uint2 npool[kWpNodeCap];      // x = child reference (node index, or kLeafBit | leaf slot); y = lower bound of the box's squared distance
+                                  //     (binary32, low 5 mantissa bits cleared = rounded down) | query slot
+    uint32_t lpool[kWpLeafCap];   // query slot << 27 | leaf slot : awaiting the binary32 pre-test
+    uint32_t spool[kWpSurvCap];   // same : pre-test survivors awaiting the binary64 projection
+    double o[3][32];              // query point
+    double bp[3][32];             // incumbent closest point
+    double bsqd[32];              // its squared distance as the reference computes it
+    float up[3][32], dn[3][32];   // query point rounded up / down to binary32
+    float bound[32], rbound[32];  // pruning bound (widened incumbent squared distance, rounded up) and >= its square root
+    float ub[3][32], sub[32];     // direction query -> incumbent and its length
+    uint32_t bprim[32];           // incumbent primitive id
+    uint32_t qidx[32];            // the query's index in the caller's order
+    int outst[32];                // pairs of this slot still in a pool
+    uint32_t flags[32];           // B200AABB_FLAG_TIE / _EXACT
+    uint32_t donemask;            // slots whose outst reached 0
+};
+
+struct WarpClosestArgs {
+    const BvhNode* nodes;
+    const TriRec* tris;
+    double mag;
+    const uint32_t* perm;          // coherence order (slot i of the order serves query perm[i]); nullptr = identity
+    unsigned long long* counters;  // as TreeRef::counters
+    const double* pts;
+    uint64_t n;
+    double* cp;
+    uint32_t* prim;
+    double* sqd;
+    uint8_t* flags;
+    unsigned long long* cursor;    // next position of the batch to hand out (zeroed before the launch)
+    uint2* spill;                  // gridDim.x * kWpSpillCap entries
+    int refill_min;                // refill when at least this many slots are free
+    int surv_go;                   // run the exact phase when at least this many survivors wait
+    uint32_t flag_tie, flag_exact;
+};
+
+#if defined(__CUDACC__)
+
+__device__ __forceinline__ void wp_slot_done(WarpShared& S, unsigned owner, int delta) {
+    if (delta != 0) {
+        const int old = atomicAdd(&S.outst[owner], delta);
+        if (old + delta == 0) atomicOr(&S.donemask, 1u << owner);
+    }
+}
+
+// the reference's per-primitive step for slot `owner`: Compare_distance_3(query, candidate, incumbent) and replacement
+// (AABB_traits_3.h:724-732); same tie rule as bvh.cuh::traverse_closest
+__device__ __forceinline__ void wp_update(WarpShared& S, unsigned owner, const Vec3& cpt, uint32_t id, double mag, uint32_t flag_tie, uint32_t flag_exact) {
+    const Vec3 o = {S.o[0][owner], S.o[1][owner], S.o[2][owner]};
+    const Vec3 bp = {S.bp[0][owner], S.bp[1][owner], S.bp[2][owner]};
+    int nexact = 0;
+    const int sg = cmp_dist(o, cpt, bp, nexact);
+    uint32_t fl = S.flags[owner];
+    if (nexact) fl |= flag_exact;
+    bool take;
+    if (sg == 0) { take = id < S.bprim[owner]; fl |= flag_tie; }
+    else { take = sg < 0; if (take) fl &= ~flag_tie; }
+    S.flags[owner] = fl;
+    if (take) {
+        const Vec3 v = cpt - o;
+        const double sqd = (v.x * v.x + v.y * v.y) + v.z * v.z;   // Compute_squared_distance_3(query, closest): AABB_tree.h:1024-1032
+        const double delta = 4e-16 * fmax(mag, fmax3(fabs(o.x), fabs(o.y), fabs(o.z)));
+        const double w = widen_sqdist(sqd, delta);
+        S.bp[0][owner] = cpt.x; S.bp[1][owner] = cpt.y; S.bp[2][owner] = cpt.z;
+        S.bprim[owner] = id; S.bsqd[owner] = sqd;
+        S.bound[owner] = float_above(w);
+        S.rbound[owner] = float_above(sqrt(w));
+        const float u0 = (float)v.x, u1 = (float)v.y, u2 = (float)v.z;
+        S.ub[0][owner] = u0; S.ub[1][owner] = u1; S.ub[2][owner] = u2;
+        S.sub[owner] = sqrtf((u0 * u0 + u1 * u1) + u2 * u2);
+    }
+}
+
+__global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpClosestArgs a) {
+    __shared__ WarpShared S;
+    const unsigned lane = threadIdx.x;
+    const unsigned full = 0xFFFFFFFFu;
+    const unsigned lt = (1u << lane) - 1u;
+    uint2* const myspill = a.spill + (size_t)blockIdx.x * kWpSpillCap;
+    int ncnt = 0, lcnt = 0, scnt = 0, spilled = 0;   // warp-uniform
+    unsigned free_mask = full;
+    bool more = true;
+    uint32_t st_nodes = 0, st_leaves = 0, st_culled = 0, st_exact = 0, st_ties = 0;
+    if (lane == 0) S.donemask = 0;
+    __syncwarp();
+
+    // moves the bottom kWpSpillChunk entries of the stack to global memory; false = spill area exhausted
+    auto spill_bottom = [&]() -> bool {
+        if (spilled + kWpSpillChunk > kWpSpillCap) return false;
+        for (int i = lane; i < kWpSpillChunk; i += 32) myspill[spilled + i] = S.npool[i];
+        __syncwarp();
+        for (int base = kWpSpillChunk; base < ncnt; base += 32) {
+            const int idx = base + (int)lane;
+            uint2 v = make_uint2(0, 0);
+            if (idx < ncnt) v = S.npool[idx];
+            __syncwarp();
+            if (idx < ncnt) S.npool[idx - kWpSpillChunk] = v;
+            __syncwarp();
+        }
+        spilled += kWpSpillChunk; ncnt -= kWpSpillChunk;
+        return true;
+    };
+
+    while (true) {
+        // ------------------------------------------------------------------------------------------------ refill
+        if (more) {
+            const int nfree = __popc(free_mask);
+            const bool idle = ncnt == 0 && lcnt == 0 && scnt == 0 && spilled == 0;
+            if (nfree >= a.refill_min || (idle && nfree > 0)) {
+                unsigned long long base = 0;
+                if (lane == 0) base = atomicAdd(a.cursor, (unsigned long long)nfree);
+                base = __shfl_sync(full, base, 0);
+                const unsigned long long pos = base + (unsigned long long)__popc(free_mask & lt);
+                const bool valid = ((free_mask >> lane) & 1u) && pos < a.n;
+                if (base + (unsigned long long)nfree >= a.n) more = false;
+                Vec3 o = {0.0, 0.0, 0.0};
+                PointCtx pc;
+                uint32_t qi = 0;
+                if (valid) {
+                    qi = a.perm ? a.perm[pos] : (uint32_t)pos;
+                    const double* p = a.pts + 3 * (uint64_t)qi;
+                    o = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+                    pc = make_point(o);
+                }
+                // walk down to the nearest leaf, nearest child first, pushing every far child
+                uint32_t cur = 0, firstleaf = kNone;
+                int pushed = 0;
+                bool act = valid;
+                while (__any_sync(full, act)) {
+                    if (ncnt + 32 > kWpNodeCap) {
+                        if (!spill_bottom()) { if (lane == 0) atomicOr(&a.counters[2], 1ull); return; }
+                    }
+                    uint32_t farref = 0; float fard = 0.0f; bool stop = false;
+                    if (act) {
+                        const NodeView nd = load_node(a.nodes, cur);
+                        ++st_nodes;
+                        float d0 = point_box_sqdist(nd.lo0, nd.hi0, pc), d1 = point_box_sqdist(nd.lo1, nd.hi1, pc);
+                        uint32_t c0 = nd.c0, c1 = nd.c1;
+                        if (d1 < d0) { const uint32_t tc = c0; c0 = c1; c1 = tc; const float td = d0; d0 = d1; d1 = td; }
+                        farref = c1; fard = d1;
+                        if (c0 & kLeafBit) { firstleaf = c0; stop = true; } else cur = c0;
+                    }
+                    const unsigned pm = __ballot_sync(full, act);
+                    if (act) { S.npool[ncnt + __popc(pm & lt)] = make_uint2(farref, (__float_as_uint(fard) & ~31u) | lane); ++pushed; }
+                    ncnt += __popc(pm);
+                    if (stop) act = false;
+                }
+                if (valid) {
+                    uint32_t id;
+                    const Tri3 t = load_tri(a.tris, firstleaf & ~kLeafBit, id);
+                    ++st_leaves;
+                    const Vec3 cpt = closest_on_triangle(t, o);
+                    const Vec3 v = cpt - o;
+                    const double sqd = (v.x * v.x + v.y * v.y) + v.z * v.z;
+                    const double delta = 4e-16 * fmax(a.mag, fmax3(fabs(o.x), fabs(o.y), fabs(o.z)));
+                    const double w = widen_sqdist(sqd, delta);
+                    S.o[0][lane] = o.x; S.o[1][lane] = o.y; S.o[2][lane] = o.z;
+                    S.up[0][lane] = pc.up[0]; S.up[1][lane] = pc.up[1]; S.up[2][lane] = pc.up[2];
+                    S.dn[0][lane] = pc.dn[0]; S.dn[1][lane] = pc.dn[1]; S.dn[2][lane] = pc.dn[2];
+                    S.bp[0][lane] = cpt.x; S.bp[1][lane] = cpt.y; S.bp[2][lane] = cpt.z;
+                    S.bprim[lane] = id; S.bsqd[lane] = sqd;
+                    S.bound[lane] = float_above(w);
+                    S.rbound[lane] = float_above(sqrt(w));
+                    const float u0 = (float)v.x, u1 = (float)v.y, u2 = (float)v.z;
+                    S.ub[0][lane] = u0; S.ub[1][lane] = u1; S.ub[2][lane] = u2;
+                    S.sub[lane] = sqrtf((u0 * u0 + u1 * u1) + u2 * u2);
+                    S.qidx[lane] = qi;
+                    S.flags[lane] = 0;
+                    S.outst[lane] = pushed;   // >= 1: the root is an internal node
+                }
+                free_mask &= ~__ballot_sync(full, valid);
+                __syncwarp();
+            }
+        }
+        if (free_mask == full && !more) break;
+
+        // ------------------------------------------------------------------------------------------------ phase selection
+        if (ncnt == 0 && spilled > 0) {                       // reload the most recently spilled chunk
+            for (int i = lane; i < kWpSpillChunk; i += 32) S.npool[i] = __ldcg(&myspill[spilled - kWpSpillChunk + i]);
+            spilled -= kWpSpillChunk; ncnt = kWpSpillChunk;
+            __syncwarp();
+        }
+        int phase;                                            // 0 = nodes, 1 = pre-test, 2 = exact
+        if (scnt >= a.surv_go) phase = 2;
+        else if (lcnt >= 32) phase = 1;
+        else if (ncnt > 0) phase = 0;
+        else if (lcnt > 0) phase = 1;
+        else if (scnt > 0) phase = 2;
+        else { if (lane == 0) atomicOr(&a.counters[2], 2ull); return; }   // a busy slot without work: cannot happen; never spin
+
+        if (phase == 0) {
+            // -------------------------------------------------------------------------------------------- (A) node phase
+            if (ncnt + 32 > kWpNodeCap) {
+                if (!spill_bottom()) { if (lane == 0) atomicOr(&a.counters[2], 1ull); return; }
+            }
+            const int take = ncnt < 32 ? ncnt : 32;
+            const bool has = (int)lane < take;
+            ncnt -= take;
+            uint2 e = make_uint2(0, 0);
+            unsigned owner = 0;
+            bool live = false;
+            float bnd = 0.0f;
+            if (has) {
+                e = S.npool[ncnt + lane];
+                owner = e.y & 31u;
+                bnd = S.bound[owner];
+                live = __uint_as_float(e.y & ~31u) <= bnd;
+            }
+            __syncwarp();                                      // all pops read before any push overwrites them
+            int delta = has ? -1 : 0;
+            const bool popped_leaf = live && (e.x & kLeafBit);
+            bool in0 = false, in1 = false;                     // 0 = nearer child, 1 = farther child
+            uint32_t r0 = 0, r1 = 0;
+            float d0 = 0.0f, d1 = 0.0f;
+            if (live && !popped_leaf) {
+                const NodeView nd = load_node(a.nodes, e.x);
+                ++st_nodes;
+                PointCtx pc;
+                pc.up[0] = S.up[0][owner]; pc.up[1] = S.up[1][owner]; pc.up[2] = S.up[2][owner];
+                pc.dn[0] = S.dn[0][owner]; pc.dn[1] = S.dn[1][owner]; pc.dn[2] = S.dn[2][owner];
+                d0 = point_box_sqdist(nd.lo0, nd.hi0, pc); d1 = point_box_sqdist(nd.lo1, nd.hi1, pc);
+                r0 = nd.c0; r1 = nd.c1;
+                if (d1 < d0) { const uint32_t tc = r0; r0 = r1; r1 = tc; const float td = d0; d0 = d1; d1 = td; }
+                in0 = d0 <= bnd; in1 = d1 <= bnd;
+                delta += (in0 ? 1 : 0) + (in1 ? 1 : 0);
+            } else if (popped_leaf) {
+                delta = 0;                                     // the pair moves from the node pool to the leaf pool
+            }
+            // leaf pairs: a popped leaf entry or the nearer child, then the farther child
+            {
+                const bool l0 = popped_leaf || (in0 && (r0 & kLeafBit));
+                const uint32_t ref0 = popped_leaf ? e.x : r0;
+                const unsigned m0 = __ballot_sync(full, l0);
+                if (l0) S.lpool[lcnt + __popc(m0 & lt)] = (owner << 27) | (ref0 & kWpRefMask);
+                lcnt += __popc(m0);
+                const bool l1 = in1 && (r1 & kLeafBit);
+                const unsigned m1 = __ballot_sync(full, l1);
+                if (l1) S.lpool[lcnt + __popc(m1 & lt)] = (owner << 27) | (r1 & kWpRefMask);
+                lcnt += __popc(m1);
+            }
+            // internal children: farther first, nearer on top
+            {
+                const bool p1 = in1 && !(r1 & kLeafBit);
+                const unsigned m1 = __ballot_sync(full, p1);
+                if (p1) S.npool[ncnt + __popc(m1 & lt)] = make_uint2(r1, (__float_as_uint(d1) & ~31u) | owner);
+                ncnt += __popc(m1);
+                const bool p0 = in0 && !(r0 & kLeafBit);
+                const unsigned m0 = __ballot_sync(full, p0);
+                if (p0) S.npool[ncnt + __popc(m0 & lt)] = make_uint2(r0, (__float_as_uint(d0) & ~31u) | owner);
+                ncnt += __popc(m0);
+            }
+            if (has) wp_slot_done(S, owner, delta);
+        } else if (phase == 1) {
+            // -------------------------------------------------------------------------------------------- (B1) binary32 pre-test
+            for (int base = 0; base < lcnt; base += 32) {
+                const int i = base + (int)lane;
+                bool survive = false;
+                uint32_t pair = 0;
+                if (i < lcnt) {
+                    pair = S.lpool[i];
+                    const unsigned owner = pair >> 27;
+                    uint32_t id;
+                    const Tri3 t = load_tri(a.tris, pair & kWpRefMask, id);
+                    ++st_leaves;
+                    const Vec3 o = {S.o[0][owner], S.o[1][owner], S.o[2][owner]};
+                    const float ub[3] = {S.ub[0][owner], S.ub[1][owner], S.ub[2][owner]};
+                    if (tri_certainly_outside(t, o, ub, S.sub[owner], S.rbound[owner], false)) { ++st_culled; wp_slot_done(S, owner, -1); }
+                    else survive = true;
+                }
+                const unsigned sm = __ballot_sync(full, survive);
+                if (survive) S.spool[scnt + __popc(sm & lt)] = pair;
+                scnt += __popc(sm);
+            }
+            lcnt = 0;
+        } else {
+            // -------------------------------------------------------------------------------------------- (B2) binary64 projection + exact comparison
+            for (int base = 0; base < scnt; base += 32) {
+                const int i = base + (int)lane;
+                const bool has = i < scnt;
+                bool pending = false;
+                unsigned owner = 0;
+                uint32_t id = 0;
+                Vec3 cpt = {0.0, 0.0, 0.0};
+                if (has) {
+                    const uint32_t pair = S.spool[i];
+                    owner = pair >> 27;
+                    const Tri3 t = load_tri(a.tris, pair & kWpRefMask, id);
+                    const Vec3 o = {S.o[0][owner], S.o[1][owner], S.o[2][owner]};
+                    const float ub[3] = {S.ub[0][owner], S.ub[1][owner], S.ub[2][owner]};
+                    if (tri_certainly_outside(t, o, ub, S.sub[owner], S.rbound[owner], true)) ++st_culled;
+                    else { cpt = closest_on_triangle(t, o); pending = true; }
+                }
+                unsigned pm = __ballot_sync(full, pending);
+                while (pm) {                                   // one candidate per slot and round
+                    bool lead = false;
+                    if (pending) { const unsigned grp = __match_any_sync(pm, owner); lead = (unsigned)(__ffs(grp) - 1) == lane; }
+                    if (lead) { wp_update(S, owner, cpt, id, a.mag, a.flag_tie, a.flag_exact); pending = false; }
+                    __syncwarp();
+                    pm = __ballot_sync(full, pending);
+                }
+                if (has) wp_slot_done(S, owner, -1);
+            }
+            scnt = 0;
+        }
+        // ------------------------------------------------------------------------------------------------ completed queries
+        __syncwarp();
+        const unsigned done = *(volatile uint32_t*)&S.donemask;
+        if (done) {
+            __syncwarp();
+            if (lane == 0) S.donemask = 0;
+            if ((done >> lane) & 1u) {
+                const uint64_t qi = S.qidx[lane];
+                const uint32_t fl = S.flags[lane];
+                if (a.cp) { a.cp[3 * qi] = S.bp[0][lane]; a.cp[3 * qi + 1] = S.bp[1][lane]; a.cp[3 * qi + 2] = S.bp[2][lane]; }
+                if (a.prim) a.prim[qi] = S.bprim[lane];
+                if (a.sqd) a.sqd[qi] = S.bsqd[lane];
+                if (a.flags) a.flags[qi] = (uint8_t)fl;
+                if (fl & a.flag_tie) ++st_ties;
+                if (fl & a.flag_exact) ++st_exact;
+            }
+            free_mask |= done;
+            __syncwarp();
+        }
+    }
+    const unsigned nodes = __reduce_add_sync(full, st_nodes), leaves = __reduce_add_sync(full, st_leaves), culled = __reduce_add_sync(full, st_culled);
+    const unsigned exact = __reduce_add_sync(full, st_exact), ties = __reduce_add_sync(full, st_ties);
+    if (lane == 0) {
+        atomicAdd(&a.counters[3], (unsigned long long)nodes);
+        atomicAdd(&a.counters[4], (unsigned long long)leaves);
+        if (culled) atomicAdd(&a.counters[6], (unsigned long long)culled);
+        if (exact) atomicAdd(&a.counters[0], (unsigned long long)exact);
+        if (ties) atomicAdd(&a.counters[1], (unsigned long long)ties);
+    }
+}
+
+#endif  // __CUDACC__
+
+}  // namespace b2

@@ -140,6 +140,37 @@ def test_config2_icosphere_distance_field_parity(B):
     assert np.all(np.abs(r - np.abs(np.linalg.norm(pts, axis=1) - 1)) < 2e-3)  # unsigned distance field of a sphere
 
 
+@pytest.mark.parametrize("refill,surv_go,sort", [(16, 24, 1), (1, 1, 1), (32, 64, 0), (8, 16, 1)])
+def test_closest_point_kernels_agree(B, refill, surv_go, sort):
+    """the warp-cooperative work-pool kernel (closest_warp.cuh) and the thread-per-query kernel (bvh.cuh) return identical
+    records, whatever the pool scheduling parameters and the query order; both equal the oracle"""
+    from cgal_b200 import workloads as W
+    v, f = W.terrain(256, 128)      # 65,536 triangles
+    g, o = B.AABB_tree(v, f), orc.OracleTree(v, f)
+    bb = g.bbox()
+    pts = np.concatenate([W.bbox_points(bb, 150_000, margin=0.2), v[::7] + 1e-9, v[5::11],            # near / on vertices: ties
+                          0.5 * (v[f[::13, 0]] + v[f[::13, 1]])])                                     # on edges
+    g.set_option(B.OPT_SORT_QUERIES, sort)
+    g.set_option(B.OPT_CLOSEST_KERNEL, 0)
+    ref = g.closest_point_and_primitive(pts)
+    g.set_option(B.OPT_CLOSEST_KERNEL, 1)
+    g.set_option(B.OPT_WARP_REFILL, refill)
+    g.set_option(B.OPT_WARP_SURV_GO, surv_go)
+    got = g.closest_point_and_primitive(pts)
+    st = g.stats()
+    assert st["nodes_visited"] > 0 and st["leaves_tested"] > 0
+    for k in ("point", "prim", "sqdist"):
+        np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
+    np.testing.assert_array_equal(got["flags"] & B.FLAG_TIE, ref["flags"] & B.FLAG_TIE)   # (FLAG_EXACT depends on which incumbents met)
+    check_closest_point(got, o.closest_point(pts), o, pts)
+    # tiny batches and trees: fewer queries than slots, two-primitive tree
+    few = g.closest_point_and_primitive(pts[:5])
+    np.testing.assert_array_equal(few["prim"], ref["prim"][:5])
+    t2 = B.AABB_tree(triangles=np.array([[0, 0, 0, 1.0, 0, 0, 0, 1.0, 0], [0, 0, 1, 1.0, 0, 1, 0, 1.0, 1]]))
+    r2 = t2.closest_point_and_primitive(np.array([[0.2, 0.2, 0.4], [0.2, 0.2, 0.6], [0.2, 0.2, 0.5]]))
+    assert list(r2["prim"]) == [0, 1, 0] and r2["flags"][2] & B.FLAG_TIE and not (r2["flags"][0] & B.FLAG_TIE)
+
+
 def test_config3_terrain_rays_and_shadow_segments_parity(B):
     from cgal_b200 import workloads as W
     v, f = W.terrain(512, 256)  # 262,144 triangles (config 3 uses 4096 x 2048; same generator)
