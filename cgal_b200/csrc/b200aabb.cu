@@ -204,6 +204,7 @@ struct b200aabb_tree {
     int opt_closest_kernel = 1;    // B200AABB_OPT_CLOSEST_KERNEL: 1 = warp-cooperative pool (closest_warp.cuh), 0 = one thread per query
     int opt_warp_refill = 16;      // B200AABB_OPT_WARP_REFILL
     int opt_warp_surv_go = 24;     // B200AABB_OPT_WARP_SURV_GO
+    int opt_debug_two_pass = 0;    // experiment: run the warp kernel twice, the second time with the first pass's distances as initial bounds
     // warp-cooperative closest_point: per pipeline slot a batch cursor and the pools' spill area; grid = SMs x resident warps
     struct WarpScratch { unsigned long long* cursor = nullptr; uint2* spill = nullptr; } warp[2];
     int warp_grid = 0;
@@ -486,6 +487,7 @@ int b200aabb_set_option(b200aabb_tree* t, int option, int64_t value) {
         case B200AABB_OPT_SORT_QUERIES: t->opt_sort_queries = value != 0; return B200AABB_OK;
         case B200AABB_OPT_CLOSEST_KERNEL: t->opt_closest_kernel = value != 0; return B200AABB_OK;
         case B200AABB_OPT_WARP_REFILL: t->opt_warp_refill = (int)std::min<int64_t>(32, std::max<int64_t>(1, value)); return B200AABB_OK;
+        case 100: t->opt_debug_two_pass = value != 0; return B200AABB_OK;
         case B200AABB_OPT_WARP_SURV_GO: t->opt_warp_surv_go = (int)std::min<int64_t>(64, std::max<int64_t>(1, value)); return B200AABB_OK;
         default: return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "unknown option");
     }
@@ -651,8 +653,19 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
                          a.cursor = t->warp[slot].cursor; a.spill = t->warp[slot].spill;
                          a.refill_min = t->opt_warp_refill; a.surv_go = t->opt_warp_surv_go;
                          a.flag_tie = B200AABB_FLAG_TIE; a.flag_exact = B200AABB_FLAG_EXACT;
+                         a.debug_hint_sqd = nullptr;
                          const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)t->warp_grid, (cnt + 31) / 32);
                          closest_point_warp_kernel<<<grid, 32, 0, st>>>(a);
+                         if (t->opt_debug_two_pass && a.sqd) {
+                             cudaMemsetAsync(t->warp[slot].cursor, 0, sizeof(unsigned long long), st);
+                             cudaMemsetAsync(t->d_counters, 0, 8 * sizeof(unsigned long long), st);
+                             cudaEventRecord(t->ev_a, st);
+                             double* hint = nullptr; cudaMalloc(&hint, cnt * 8);
+                             cudaMemcpyAsync(hint, a.sqd, cnt * 8, cudaMemcpyDeviceToDevice, st);
+                             a.debug_hint_sqd = hint;
+                             closest_point_warp_kernel<<<grid, 32, 0, st>>>(a);
+                             cudaStreamSynchronize(st); cudaFree(hint);
+                         }
                      });
 }
 

@@ -52,6 +52,8 @@ struct WarpShared {
     uint32_t qidx[32];            // the query's index in the caller's order
     int outst[32];                // pairs of this slot still in a pool
     uint32_t flags[32];           // B200AABB_FLAG_TIE / _EXACT
+    float dslack[32];             // >= 2 delta, binary32
+    double delta[32];             // rounding allowance of candidate points: 4e-16 * largest coordinate magnitude (bvh.cuh::traverse_closest)
     uint32_t donemask;            // slots whose outst reached 0
 };
 
@@ -72,6 +74,7 @@ struct WarpClosestArgs {
     int refill_min;                // refill when at least this many slots are free
     int surv_go;                   // run the exact phase when at least this many survivors wait
     uint32_t flag_tie, flag_exact;
+    const double* debug_hint_sqd;  // experiment only: a known upper bound of each query's squared distance (caller order), or nullptr
 };
 
 #if defined(__CUDACC__)
@@ -83,31 +86,61 @@ __device__ __forceinline__ void wp_slot_done(WarpShared& S, unsigned owner, int 
     }
 }
 
-// the reference's per-primitive step for slot `owner`: Compare_distance_3(query, candidate, incumbent) and replacement
-// (AABB_traits_3.h:724-732); same tie rule as bvh.cuh::traverse_closest
-__device__ __forceinline__ void wp_update(WarpShared& S, unsigned owner, const Vec3& cpt, uint32_t id, double mag, uint32_t flag_tie, uint32_t flag_exact) {
-    const Vec3 o = {S.o[0][owner], S.o[1][owner], S.o[2][owner]};
-    const Vec3 bp = {S.bp[0][owner], S.bp[1][owner], S.bp[2][owner]};
-    int nexact = 0;
-    const int sg = cmp_dist(o, cpt, bp, nexact);
+// pruning bounds of a slot from its incumbent's squared distance: bound >= widen_sqdist(sqd, delta) (bvh.cuh) and rbound >= sqrt(bound),
+// with the square roots taken in binary32 rounded up (s >= sqrt(sqd) makes the widened value only larger).  Unless `reset`, the
+// bounds only shrink: the binary32 upper bounds of wp_pretest may already be tighter than this incumbent.
+__device__ __forceinline__ void wp_set_bounds(WarpShared& S, unsigned owner, double sqd, const Vec3& v, bool reset) {
+    const double delta = S.delta[owner];
+    const float s = __fsqrt_ru(float_above(sqd));
+    float bound = float_above(sqd + ((2.0 * delta * (double)s + delta * delta) + sqd * 1e-13));
+    float rbound = __fsqrt_ru(bound);
+    if (!reset) { bound = fminf(bound, S.bound[owner]); rbound = fminf(rbound, S.rbound[owner]); }
+    S.bound[owner] = bound;
+    S.rbound[owner] = rbound;
+    const float u0 = (float)v.x, u1 = (float)v.y, u2 = (float)v.z;
+    S.ub[0][owner] = u0; S.ub[1][owner] = u1; S.ub[2][owner] = u2;
+    S.sub[owner] = sqrtf((u0 * u0 + u1 * u1) + u2 * u2);
+}
+
+// Binary32 pre-test of one (slot, primitive) pair on coordinates relative to the query (bvh.cuh::tri_certainly_outside with all
+// three directions), returning true when the primitive is certainly farther than the slot's pruning bound.  For a primitive that
+// stays, *rb_new is a rigorous UPPER bound of (distance from the query to the primitive) + the slot's rounding allowance, from the
+// approximate closest point P = a + v ab + w ac (v, w >= 0, v + w <= 1 up to an ulp): P's coordinates are within 1.2e-6 m of a point
+// of the true triangle (vertex rounding 2^-24 m each, six binary32 operations on magnitudes <= 2 m), so
+// dist <= |P| + 2.1e-6 m; the formula below allows 8e-6 m + 1e-5 |P| + dslack.  The winner's candidate is no farther than this
+// primitive's candidate, which lies within the rounding allowance of the true distance (the premise of widen_sqdist), so pruning
+// with rb_new (and its square) never discards the winner or a primitive tied with it.
+__device__ __forceinline__ bool wp_pretest(const Tri3& t, const Vec3& o, const float* ub, float sub, float rbound, float dslack, float* rb_new) {
+    const float ra[3] = {(float)(t.a.x - o.x), (float)(t.a.y - o.y), (float)(t.a.z - o.z)};
+    const float rb[3] = {(float)(t.b.x - o.x), (float)(t.b.y - o.y), (float)(t.b.z - o.z)};
+    const float rc[3] = {(float)(t.c.x - o.x), (float)(t.c.y - o.y), (float)(t.c.z - o.z)};
+    const float m = fmaxf(fmaxf(fmaxf(fabsf(ra[0]), fabsf(ra[1])), fmaxf(fabsf(ra[2]), fabsf(rb[0]))),
+                          fmaxf(fmaxf(fabsf(rb[1]), fabsf(rb[2])), fmaxf(fmaxf(fabsf(rc[0]), fabsf(rc[1])), fabsf(rc[2]))));
+    *rb_new = INFINITY;
+    if (certainly_farther(ub, sub, ra, rb, rc, m, rbound)) return true;
+    const float g[3] = {(ra[0] + rb[0]) + rc[0], (ra[1] + rb[1]) + rc[1], (ra[2] + rb[2]) + rc[2]};
+    if (certainly_farther(g, sqrtf(dot3f(g, g)), ra, rb, rc, m, rbound)) return true;
+    float u[3];
+    approx_closest_to_origin(ra, rb, rc, u);
+    const float su = sqrtf(dot3f(u, u));
+    if (certainly_farther(u, su, ra, rb, rc, m, rbound)) return true;
+    const float hi = (su * 1.00001f + 8e-6f * m) + dslack;
+    if (hi == hi) *rb_new = hi;                               // (NaN from a degenerate triangle: no bound)
+    return false;
+}
+
+// the replacement step of the reference (AABB_traits_3.h:724-732) for slot `owner`, given sg = Compare_distance_3(query, candidate,
+// incumbent) <= 0; same tie rule as bvh.cuh::traverse_closest
+__device__ __forceinline__ void wp_apply(WarpShared& S, unsigned owner, int sg, const Vec3& cpt, const Vec3& v, double sqd, uint32_t id, uint32_t flag_tie) {
     uint32_t fl = S.flags[owner];
-    if (nexact) fl |= flag_exact;
     bool take;
     if (sg == 0) { take = id < S.bprim[owner]; fl |= flag_tie; }
-    else { take = sg < 0; if (take) fl &= ~flag_tie; }
+    else { take = true; fl &= ~flag_tie; }
     S.flags[owner] = fl;
     if (take) {
-        const Vec3 v = cpt - o;
-        const double sqd = (v.x * v.x + v.y * v.y) + v.z * v.z;   // Compute_squared_distance_3(query, closest): AABB_tree.h:1024-1032
-        const double delta = 4e-16 * fmax(mag, fmax3(fabs(o.x), fabs(o.y), fabs(o.z)));
-        const double w = widen_sqdist(sqd, delta);
         S.bp[0][owner] = cpt.x; S.bp[1][owner] = cpt.y; S.bp[2][owner] = cpt.z;
         S.bprim[owner] = id; S.bsqd[owner] = sqd;
-        S.bound[owner] = float_above(w);
-        S.rbound[owner] = float_above(sqrt(w));
-        const float u0 = (float)v.x, u1 = (float)v.y, u2 = (float)v.z;
-        S.ub[0][owner] = u0; S.ub[1][owner] = u1; S.ub[2][owner] = u2;
-        S.sub[owner] = sqrtf((u0 * u0 + u1 * u1) + u2 * u2);
+        wp_set_bounds(S, owner, sqd, v, false);
     }
 }
 
@@ -192,18 +225,19 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                     const Vec3 cpt = closest_on_triangle(t, o);
                     const Vec3 v = cpt - o;
                     const double sqd = (v.x * v.x + v.y * v.y) + v.z * v.z;
-                    const double delta = 4e-16 * fmax(a.mag, fmax3(fabs(o.x), fabs(o.y), fabs(o.z)));
-                    const double w = widen_sqdist(sqd, delta);
                     S.o[0][lane] = o.x; S.o[1][lane] = o.y; S.o[2][lane] = o.z;
                     S.up[0][lane] = pc.up[0]; S.up[1][lane] = pc.up[1]; S.up[2][lane] = pc.up[2];
                     S.dn[0][lane] = pc.dn[0]; S.dn[1][lane] = pc.dn[1]; S.dn[2][lane] = pc.dn[2];
                     S.bp[0][lane] = cpt.x; S.bp[1][lane] = cpt.y; S.bp[2][lane] = cpt.z;
                     S.bprim[lane] = id; S.bsqd[lane] = sqd;
-                    S.bound[lane] = float_above(w);
-                    S.rbound[lane] = float_above(sqrt(w));
-                    const float u0 = (float)v.x, u1 = (float)v.y, u2 = (float)v.z;
-                    S.ub[0][lane] = u0; S.ub[1][lane] = u1; S.ub[2][lane] = u2;
-                    S.sub[lane] = sqrtf((u0 * u0 + u1 * u1) + u2 * u2);
+                    S.delta[lane] = 4e-16 * fmax(a.mag, fmax3(fabs(o.x), fabs(o.y), fabs(o.z)));
+                    S.dslack[lane] = float_above(2.0 * S.delta[lane]) + 1e-37f;
+                    wp_set_bounds(S, lane, sqd, v, true);
+                    if (a.debug_hint_sqd) {
+                        const double wh = widen_sqdist(a.debug_hint_sqd[qi], S.delta[lane]);
+                        S.bound[lane] = fminf(S.bound[lane], float_above(wh));
+                        S.rbound[lane] = fminf(S.rbound[lane], float_above(sqrt(wh)));
+                    }
                     S.qidx[lane] = qi;
                     S.flags[lane] = 0;
                     S.outst[lane] = pushed;   // >= 1: the root is an internal node
@@ -304,8 +338,16 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                     ++st_leaves;
                     const Vec3 o = {S.o[0][owner], S.o[1][owner], S.o[2][owner]};
                     const float ub[3] = {S.ub[0][owner], S.ub[1][owner], S.ub[2][owner]};
-                    if (tri_certainly_outside(t, o, ub, S.sub[owner], S.rbound[owner], false)) { ++st_culled; wp_slot_done(S, owner, -1); }
-                    else survive = true;
+                    const float rbound = S.rbound[owner];
+                    float rb_new;
+                    if (wp_pretest(t, o, ub, S.sub[owner], rbound, S.dslack[owner], &rb_new)) { ++st_culled; wp_slot_done(S, owner, -1); }
+                    else {
+                        survive = true;
+                        if (rb_new < rbound) {                 // this primitive is certainly nearer than the slot's ball: shrink it now, in binary32
+                            atomicMin(reinterpret_cast<unsigned*>(&S.rbound[owner]), __float_as_uint(rb_new));
+                            atomicMin(reinterpret_cast<unsigned*>(&S.bound[owner]), __float_as_uint(__fmul_ru(rb_new, rb_new)));
+                        }
+                    }
                 }
                 const unsigned sm = __ballot_sync(full, survive);
                 if (survive) S.spool[scnt + __popc(sm & lt)] = pair;
@@ -319,22 +361,47 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                 const bool has = i < scnt;
                 bool pending = false;
                 unsigned owner = 0;
-                uint32_t id = 0;
-                Vec3 cpt = {0.0, 0.0, 0.0};
+                uint32_t id = 0, key = 0;
+                Vec3 o = {0.0, 0.0, 0.0}, cpt = {0.0, 0.0, 0.0}, v = {0.0, 0.0, 0.0};
+                double sqd = 0.0;
                 if (has) {
                     const uint32_t pair = S.spool[i];
                     owner = pair >> 27;
                     const Tri3 t = load_tri(a.tris, pair & kWpRefMask, id);
-                    const Vec3 o = {S.o[0][owner], S.o[1][owner], S.o[2][owner]};
+                    o = {S.o[0][owner], S.o[1][owner], S.o[2][owner]};
                     const float ub[3] = {S.ub[0][owner], S.ub[1][owner], S.ub[2][owner]};
-                    if (tri_certainly_outside(t, o, ub, S.sub[owner], S.rbound[owner], true)) ++st_culled;
-                    else { cpt = closest_on_triangle(t, o); pending = true; }
+                    float rb_new;
+                    if (wp_pretest(t, o, ub, S.sub[owner], S.rbound[owner], S.dslack[owner], &rb_new)) ++st_culled;
+                    else {
+                        cpt = closest_on_triangle(t, o);
+                        v = cpt - o;
+                        sqd = (v.x * v.x + v.y * v.y) + v.z * v.z;   // Compute_squared_distance_3(query, closest): AABB_tree.h:1024-1032
+                        key = __float_as_uint((float)sqd);
+                        pending = true;
+                    }
                 }
+                // Every waiting candidate is compared (exactly) with its slot's incumbent, all lanes at once; the ones that are farther
+                // retire.  Of the rest, ONE per slot (the apparently nearest) replaces the incumbent, the others meet the new incumbent in
+                // the next round.  Each replacement is a step the sequential reference loop could have taken, and a candidate farther
+                // than an earlier incumbent is farther than every later one, so the outcome is that of the sequential loop.
                 unsigned pm = __ballot_sync(full, pending);
-                while (pm) {                                   // one candidate per slot and round
-                    bool lead = false;
-                    if (pending) { const unsigned grp = __match_any_sync(pm, owner); lead = (unsigned)(__ffs(grp) - 1) == lane; }
-                    if (lead) { wp_update(S, owner, cpt, id, a.mag, a.flag_tie, a.flag_exact); pending = false; }
+                while (pm) {
+                    int sg = 0;
+                    if (pending) {
+                        const Vec3 bp = {S.bp[0][owner], S.bp[1][owner], S.bp[2][owner]};
+                        int nexact = 0;
+                        sg = cmp_dist(o, cpt, bp, nexact);
+                        if (nexact) atomicOr(&S.flags[owner], a.flag_exact);
+                        if (sg > 0) pending = false;
+                    }
+                    __syncwarp();                              // incumbents read before any is replaced
+                    const unsigned cm = __ballot_sync(full, pending);
+                    if (pending) {
+                        const unsigned grp = __match_any_sync(cm, owner);
+                        const unsigned gmin = __reduce_min_sync(grp, key);
+                        const unsigned wm = __ballot_sync(cm, key == gmin) & grp;
+                        if ((unsigned)(__ffs(wm) - 1) == lane) { wp_apply(S, owner, sg, cpt, v, sqd, id, a.flag_tie); pending = false; }
+                    }
                     __syncwarp();
                     pm = __ballot_sync(full, pending);
                 }
