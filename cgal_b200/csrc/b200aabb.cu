@@ -202,8 +202,8 @@ struct b200aabb_tree {
     // options
     int opt_sort_queries = 1;      // B200AABB_OPT_SORT_QUERIES
     int opt_closest_kernel = 1;    // B200AABB_OPT_CLOSEST_KERNEL: 1 = warp-cooperative pool (closest_warp.cuh), 0 = one thread per query
-    int opt_warp_refill = 16;      // B200AABB_OPT_WARP_REFILL
-    int opt_warp_surv_go = 24;     // B200AABB_OPT_WARP_SURV_GO
+    int opt_warp_refill = 32;      // B200AABB_OPT_WARP_REFILL
+    int opt_warp_surv_go = 32;     // B200AABB_OPT_WARP_SURV_GO
     int opt_debug_two_pass = 0;    // experiment: run the warp kernel twice, the second time with the first pass's distances as initial bounds
     // warp-cooperative closest_point: per pipeline slot a batch cursor and the pools' spill area; grid = SMs x resident warps
     struct WarpScratch { unsigned long long* cursor = nullptr; uint2* spill = nullptr; } warp[2];
@@ -651,7 +651,7 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
                          a.nodes = t->d_nodes; a.tris = t->d_tris; a.mag = t->mag; a.perm = perm; a.counters = t->d_counters;
                          a.pts = (const double*)in; a.n = cnt; a.cp = (double*)o[0]; a.prim = (uint32_t*)o[1]; a.sqd = (double*)o[2]; a.flags = (uint8_t*)o[3];
                          a.cursor = t->warp[slot].cursor; a.spill = t->warp[slot].spill;
-                         a.refill_min = t->opt_warp_refill; a.surv_go = t->opt_warp_surv_go;
+                         a.refill_min = t->opt_warp_refill; a.exact_go = t->opt_warp_surv_go;
                          a.flag_tie = B200AABB_FLAG_TIE; a.flag_exact = B200AABB_FLAG_EXACT;
                          a.debug_hint_sqd = nullptr;
                          const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)t->warp_grid, (cnt + 31) / 32);

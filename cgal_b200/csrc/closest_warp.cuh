@@ -14,9 +14,14 @@
 //                       slot's incumbent ball; load the node, test both child boxes against the slot's point (binary32,
 //                       directed rounding, bvh.cuh::point_box_sqdist); push internal children (far first, near on top) and
 //                       record leaf children as (slot,leaf) pairs
-//   (B1) pre-test phase rigorous binary32 cull of 32 (slot,leaf) pairs (tangent plane of the slot's ball, centroid direction)
-//   (B2) exact phase    sharper pre-test + the reference's Construct_projected_point_3 in binary64 for 32 surviving pairs, then
-//                       the exact Compare_distance_3 against the slot's incumbent, serialised per slot (__match_any_sync)
+//   (B1) pre-test 1     rigorous binary32 LOWER bounds of the distance of 32 (slot,leaf) pairs (tangent plane of the slot's ball,
+//                       centroid direction); pairs certainly outside the slot's ball retire, the rest carry their bound on
+//   (B2) pre-test 2     approximate closest point of the triangle in binary32 (divisions, branches): a sharper lower bound, and a
+//                       rigorous UPPER bound of the distance that shrinks the slot's ball at once (atomicMin), before any binary64 work
+//   (B3) exact phase    pairs still inside the ball: the reference's Construct_projected_point_3 in binary64, then the exact
+//                       Compare_distance_3 against the slot's incumbent (all candidates in parallel, one replacement per slot and round)
+// Each stage has its own pool and runs when 32 pairs wait (or when nothing else is left), so every stage runs with (nearly) all
+// lanes busy; a pair's stored lower bound is re-checked against the slot's current ball at every hand-over for free.
 // A slot's state (point, incumbent, bounds) lives in shared memory, SoA by slot, so any lane can work for any slot.
 // Every pair counts in its slot's `outst` counter; when it drops to 0 the query is complete, its lane writes the result
 // and the slot is refilled from the batch cursor (queries are taken in coherence order).  A new query first walks down to
@@ -33,7 +38,8 @@ constexpr int kWpNodeCap = 768;                 // (slot,node) entries held in s
 constexpr int kWpSpillChunk = kWpNodeCap / 2;   // entries moved per spill / reload
 constexpr int kWpSpillCap = 8 * kWpSpillChunk;  // entries per warp in the global spill area
 constexpr int kWpLeafCap = 96;                  // < 32 waiting + at most 64 added by one node phase
-constexpr int kWpSurvCap = 160;                 // < surv_go (<= 64) waiting + at most 95 added by one pre-test phase
+constexpr int kWpMidCap = 128;                  // < 32 waiting + at most 95 added by one pre-test-1 phase
+constexpr int kWpExactCap = 192;                // < exact_go (<= 64) waiting + at most 126 added by one pre-test-2 phase
 constexpr uint32_t kWpRefMask = 0x07FFFFFFu;    // 27 bits of leaf slot next to the 5-bit query slot
 constexpr uint64_t kWpMaxPrims = 1ull << 27;
 
@@ -41,7 +47,8 @@ struct WarpShared {
     uint2 npool[kWpNodeCap];      // x = child reference (node index, or kLeafBit | leaf slot); y = lower bound of the box's squared distance
                                   //     (binary32, low 5 mantissa bits cleared = rounded down) | query slot
     uint32_t lpool[kWpLeafCap];   // query slot << 27 | leaf slot : awaiting the binary32 pre-test
-    uint32_t spool[kWpSurvCap];   // same : pre-test survivors awaiting the binary64 projection
+    uint2 mpool[kWpMidCap];       // x = same, y = lower bound of the distance (binary32) : awaiting pre-test 2
+    uint2 epool[kWpExactCap];     // same : awaiting the binary64 projection
     double o[3][32];              // query point
     double bp[3][32];             // incumbent closest point
     double bsqd[32];              // its squared distance as the reference computes it
@@ -72,7 +79,7 @@ struct WarpClosestArgs {
     unsigned long long* cursor;    // next position of the batch to hand out (zeroed before the launch)
     uint2* spill;                  // gridDim.x * kWpSpillCap entries
     int refill_min;                // refill when at least this many slots are free
-    int surv_go;                   // run the exact phase when at least this many survivors wait
+    int exact_go;                  // run the exact phase when at least this many pairs wait (1..64)
     uint32_t flag_tie, flag_exact;
     const double* debug_hint_sqd;  // experiment only: a known upper bound of each query's squared distance (caller order), or nullptr
 };
@@ -88,7 +95,7 @@ __device__ __forceinline__ void wp_slot_done(WarpShared& S, unsigned owner, int 
 
 // pruning bounds of a slot from its incumbent's squared distance: bound >= widen_sqdist(sqd, delta) (bvh.cuh) and rbound >= sqrt(bound),
 // with the square roots taken in binary32 rounded up (s >= sqrt(sqd) makes the widened value only larger).  Unless `reset`, the
-// bounds only shrink: the binary32 upper bounds of wp_pretest may already be tighter than this incumbent.
+// bounds only shrink: the binary32 upper bounds of wp_sharp may already be tighter than this incumbent.
 __device__ __forceinline__ void wp_set_bounds(WarpShared& S, unsigned owner, double sqd, const Vec3& v, bool reset) {
     const double delta = S.delta[owner];
     const float s = __fsqrt_ru(float_above(sqd));
@@ -102,31 +109,37 @@ __device__ __forceinline__ void wp_set_bounds(WarpShared& S, unsigned owner, dou
     S.sub[owner] = sqrtf((u0 * u0 + u1 * u1) + u2 * u2);
 }
 
-// Binary32 pre-test of one (slot, primitive) pair on coordinates relative to the query (bvh.cuh::tri_certainly_outside with all
-// three directions), returning true when the primitive is certainly farther than the slot's pruning bound.  For a primitive that
-// stays, *rb_new is a rigorous UPPER bound of (distance from the query to the primitive) + the slot's rounding allowance, from the
-// approximate closest point P = a + v ab + w ac (v, w >= 0, v + w <= 1 up to an ulp): P's coordinates are within 1.2e-6 m of a point
-// of the true triangle (vertex rounding 2^-24 m each, six binary32 operations on magnitudes <= 2 m), so
-// dist <= |P| + 2.1e-6 m; the formula below allows 8e-6 m + 1e-5 |P| + dslack.  The winner's candidate is no farther than this
-// primitive's candidate, which lies within the rounding allowance of the true distance (the premise of widen_sqdist), so pruning
-// with rb_new (and its square) never discards the winner or a primitive tied with it.
-__device__ __forceinline__ bool wp_pretest(const Tri3& t, const Vec3& o, const float* ub, float sub, float rbound, float dslack, float* rb_new) {
-    const float ra[3] = {(float)(t.a.x - o.x), (float)(t.a.y - o.y), (float)(t.a.z - o.z)};
-    const float rb[3] = {(float)(t.b.x - o.x), (float)(t.b.y - o.y), (float)(t.b.z - o.z)};
-    const float rc[3] = {(float)(t.c.x - o.x), (float)(t.c.y - o.y), (float)(t.c.z - o.z)};
-    const float m = fmaxf(fmaxf(fmaxf(fabsf(ra[0]), fabsf(ra[1])), fmaxf(fabsf(ra[2]), fabsf(rb[0]))),
-                          fmaxf(fmaxf(fabsf(rb[1]), fabsf(rb[2])), fmaxf(fmaxf(fabsf(rc[0]), fabsf(rc[1])), fabsf(rc[2]))));
-    *rb_new = INFINITY;
-    if (certainly_farther(ub, sub, ra, rb, rc, m, rbound)) return true;
-    const float g[3] = {(ra[0] + rb[0]) + rc[0], (ra[1] + rb[1]) + rc[1], (ra[2] + rb[2]) + rc[2]};
-    if (certainly_farther(g, sqrtf(dot3f(g, g)), ra, rb, rc, m, rbound)) return true;
+// Binary32 bounds of the distance from the query to one primitive, on coordinates RELATIVE to the query (the subtraction is done in
+// binary64; each relative coordinate is then off by <= m 2^-24, m = largest magnitude among them).
+struct RelTri { float ra[3], rb[3], rc[3], m; };
+__device__ __forceinline__ RelTri wp_relative(const Tri3& t, const Vec3& o) {
+    RelTri r;
+    r.ra[0] = (float)(t.a.x - o.x); r.ra[1] = (float)(t.a.y - o.y); r.ra[2] = (float)(t.a.z - o.z);
+    r.rb[0] = (float)(t.b.x - o.x); r.rb[1] = (float)(t.b.y - o.y); r.rb[2] = (float)(t.b.z - o.z);
+    r.rc[0] = (float)(t.c.x - o.x); r.rc[1] = (float)(t.c.y - o.y); r.rc[2] = (float)(t.c.z - o.z);
+    r.m = fmaxf(fmaxf(fmaxf(fabsf(r.ra[0]), fabsf(r.ra[1])), fmaxf(fabsf(r.ra[2]), fabsf(r.rb[0]))),
+                fmaxf(fmaxf(fabsf(r.rb[1]), fabsf(r.rb[2])), fmaxf(fmaxf(fabsf(r.rc[0]), fabsf(r.rc[1])), fabsf(r.rc[2]))));
+    return r;
+}
+// LOWER bound from a direction u (bvh.cuh::certainly_farther solved for the distance): every point x of the triangle has
+// |x| >= min_i (u.r_i)/|u|; E = 5e-7 m |u| covers the coordinate rounding and the dot products, the factor 0.999998 the rounding of
+// |u|, of its reciprocal and of the two products.  -inf when u is (numerically) zero.
+__device__ __forceinline__ float wp_lower(const float* u, float su, const RelTri& r) {
+    const float md = fminf(dot3f(u, r.ra), fminf(dot3f(u, r.rb), dot3f(u, r.rc)));
+    return su > 1e-18f ? (md - 5e-7f * r.m * su) * __frcp_rn(su) * 0.999998f : -INFINITY;
+}
+// Approximate closest point P = a + v ab + w ac (v, w >= 0, v + w <= 1 up to an ulp) -> a sharper lower bound (direction P) and a
+// rigorous UPPER bound of (distance + the slot's rounding allowance): P's coordinates are within 1.2e-6 m of a point of the true
+// triangle (vertex rounding m 2^-24 each, six binary32 operations on magnitudes <= 2 m), so dist <= |P| + 2.1e-6 m; the formula
+// allows 8e-6 m + 1e-5 |P| + dslack.  The winner's candidate is no farther than this primitive's candidate, which lies within the
+// rounding allowance of the true distance (the premise of widen_sqdist), so pruning with `hi` (and its square) never discards the
+// winner or a primitive tied with it.  hi = NaN (degenerate triangle) compares false everywhere: no bound.
+__device__ __forceinline__ void wp_sharp(const RelTri& r, float dslack, float* lower, float* hi) {
     float u[3];
-    approx_closest_to_origin(ra, rb, rc, u);
+    approx_closest_to_origin(r.ra, r.rb, r.rc, u);
     const float su = sqrtf(dot3f(u, u));
-    if (certainly_farther(u, su, ra, rb, rc, m, rbound)) return true;
-    const float hi = (su * 1.00001f + 8e-6f * m) + dslack;
-    if (hi == hi) *rb_new = hi;                               // (NaN from a degenerate triangle: no bound)
-    return false;
+    *lower = wp_lower(u, su, r);
+    *hi = (su * 1.00001f + 8e-6f * r.m) + dslack;
 }
 
 // the replacement step of the reference (AABB_traits_3.h:724-732) for slot `owner`, given sg = Compare_distance_3(query, candidate,
@@ -150,7 +163,7 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
     const unsigned full = 0xFFFFFFFFu;
     const unsigned lt = (1u << lane) - 1u;
     uint2* const myspill = a.spill + (size_t)blockIdx.x * kWpSpillCap;
-    int ncnt = 0, lcnt = 0, scnt = 0, spilled = 0;   // warp-uniform
+    int ncnt = 0, lcnt = 0, mcnt = 0, ecnt = 0, spilled = 0;   // warp-uniform
     unsigned free_mask = full;
     bool more = true;
     uint32_t st_nodes = 0, st_leaves = 0, st_culled = 0, st_exact = 0, st_ties = 0;
@@ -178,7 +191,7 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
         // ------------------------------------------------------------------------------------------------ refill
         if (more) {
             const int nfree = __popc(free_mask);
-            const bool idle = ncnt == 0 && lcnt == 0 && scnt == 0 && spilled == 0;
+            const bool idle = ncnt == 0 && lcnt == 0 && mcnt == 0 && ecnt == 0 && spilled == 0;
             if (nfree >= a.refill_min || (idle && nfree > 0)) {
                 unsigned long long base = 0;
                 if (lane == 0) base = atomicAdd(a.cursor, (unsigned long long)nfree);
@@ -254,12 +267,14 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
             spilled -= kWpSpillChunk; ncnt = kWpSpillChunk;
             __syncwarp();
         }
-        int phase;                                            // 0 = nodes, 1 = pre-test, 2 = exact
-        if (scnt >= a.surv_go) phase = 2;
+        int phase;                                            // 0 = nodes, 1 = pre-test 1, 2 = pre-test 2, 3 = exact
+        if (ecnt >= a.exact_go) phase = 3;
+        else if (mcnt >= 32) phase = 2;
         else if (lcnt >= 32) phase = 1;
         else if (ncnt > 0) phase = 0;
         else if (lcnt > 0) phase = 1;
-        else if (scnt > 0) phase = 2;
+        else if (mcnt > 0) phase = 2;
+        else if (ecnt > 0) phase = 3;
         else { if (lane == 0) atomicOr(&a.counters[2], 2ull); return; }   // a busy slot without work: cannot happen; never spin
 
         if (phase == 0) {
@@ -325,11 +340,12 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
             }
             if (has) wp_slot_done(S, owner, delta);
         } else if (phase == 1) {
-            // -------------------------------------------------------------------------------------------- (B1) binary32 pre-test
+            // -------------------------------------------------------------------------------------------- (B1) pre-test 1: two cheap directions
             for (int base = 0; base < lcnt; base += 32) {
                 const int i = base + (int)lane;
                 bool survive = false;
                 uint32_t pair = 0;
+                float lb = 0.0f;
                 if (i < lcnt) {
                     pair = S.lpool[i];
                     const unsigned owner = pair >> 27;
@@ -337,77 +353,124 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                     const Tri3 t = load_tri(a.tris, pair & kWpRefMask, id);
                     ++st_leaves;
                     const Vec3 o = {S.o[0][owner], S.o[1][owner], S.o[2][owner]};
+                    const RelTri r = wp_relative(t, o);
                     const float ub[3] = {S.ub[0][owner], S.ub[1][owner], S.ub[2][owner]};
+                    const float g[3] = {(r.ra[0] + r.rb[0]) + r.rc[0], (r.ra[1] + r.rb[1]) + r.rc[1], (r.ra[2] + r.rb[2]) + r.rc[2]};
+                    lb = fmaxf(wp_lower(ub, S.sub[owner], r), wp_lower(g, sqrtf(dot3f(g, g)), r));   // tangent plane of the ball; centroid direction
+                    if (lb > S.rbound[owner]) { ++st_culled; wp_slot_done(S, owner, -1); }
+                    else survive = true;
+                }
+                const unsigned sm = __ballot_sync(full, survive);
+                if (survive) S.mpool[mcnt + __popc(sm & lt)] = make_uint2(pair, __float_as_uint(lb));
+                mcnt += __popc(sm);
+            }
+            lcnt = 0;
+        } else if (phase == 2) {
+            // -------------------------------------------------------------------------------------------- (B2) pre-test 2: approximate closest point
+            for (int base = 0; base < mcnt; base += 32) {
+                const int i = base + (int)lane;
+                bool survive = false;
+                uint2 e = make_uint2(0, 0);
+                if (i < mcnt) {
+                    e = S.mpool[i];
+                    const unsigned owner = e.x >> 27;
                     const float rbound = S.rbound[owner];
-                    float rb_new;
-                    if (wp_pretest(t, o, ub, S.sub[owner], rbound, S.dslack[owner], &rb_new)) { ++st_culled; wp_slot_done(S, owner, -1); }
+                    if (__uint_as_float(e.y) > rbound) { ++st_culled; wp_slot_done(S, owner, -1); }   // the ball has shrunk since pre-test 1
                     else {
-                        survive = true;
-                        if (rb_new < rbound) {                 // this primitive is certainly nearer than the slot's ball: shrink it now, in binary32
-                            atomicMin(reinterpret_cast<unsigned*>(&S.rbound[owner]), __float_as_uint(rb_new));
-                            atomicMin(reinterpret_cast<unsigned*>(&S.bound[owner]), __float_as_uint(__fmul_ru(rb_new, rb_new)));
+                        uint32_t id;
+                        const Tri3 t = load_tri(a.tris, e.x & kWpRefMask, id);
+                        const Vec3 o = {S.o[0][owner], S.o[1][owner], S.o[2][owner]};
+                        const RelTri r = wp_relative(t, o);
+                        float lb, hi;
+                        wp_sharp(r, S.dslack[owner], &lb, &hi);
+                        if (hi < rbound) {                     // this primitive is certainly nearer than the slot's ball: shrink it now, in binary32
+                            atomicMin(reinterpret_cast<unsigned*>(&S.rbound[owner]), __float_as_uint(hi));
+                            atomicMin(reinterpret_cast<unsigned*>(&S.bound[owner]), __float_as_uint(__fmul_ru(hi, hi)));
                         }
+                        lb = fmaxf(lb, __uint_as_float(e.y));
+                        if (lb > rbound) { ++st_culled; wp_slot_done(S, owner, -1); }
+                        else { survive = true; e.y = __float_as_uint(lb); }
                     }
                 }
                 const unsigned sm = __ballot_sync(full, survive);
-                if (survive) S.spool[scnt + __popc(sm & lt)] = pair;
-                scnt += __popc(sm);
+                if (survive) S.epool[ecnt + __popc(sm & lt)] = e;
+                ecnt += __popc(sm);
             }
-            lcnt = 0;
+            mcnt = 0;
         } else {
-            // -------------------------------------------------------------------------------------------- (B2) binary64 projection + exact comparison
-            for (int base = 0; base < scnt; base += 32) {
+            // -------------------------------------------------------------------------------------------- (B3) binary64 projection + exact comparison
+            // (i) pairs whose lower bound has fallen outside their slot's ball retire without any binary64 work
+            int kept = 0;
+            for (int base = 0; base < ecnt; base += 32) {
                 const int i = base + (int)lane;
-                const bool has = i < scnt;
-                bool pending = false;
-                unsigned owner = 0;
-                uint32_t id = 0, key = 0;
-                Vec3 o = {0.0, 0.0, 0.0}, cpt = {0.0, 0.0, 0.0}, v = {0.0, 0.0, 0.0};
-                double sqd = 0.0;
-                if (has) {
-                    const uint32_t pair = S.spool[i];
-                    owner = pair >> 27;
-                    const Tri3 t = load_tri(a.tris, pair & kWpRefMask, id);
-                    o = {S.o[0][owner], S.o[1][owner], S.o[2][owner]};
-                    const float ub[3] = {S.ub[0][owner], S.ub[1][owner], S.ub[2][owner]};
-                    float rb_new;
-                    if (wp_pretest(t, o, ub, S.sub[owner], S.rbound[owner], S.dslack[owner], &rb_new)) ++st_culled;
-                    else {
-                        cpt = closest_on_triangle(t, o);
-                        v = cpt - o;
-                        sqd = (v.x * v.x + v.y * v.y) + v.z * v.z;   // Compute_squared_distance_3(query, closest): AABB_tree.h:1024-1032
-                        key = __float_as_uint((float)sqd);
-                        pending = true;
-                    }
+                bool keep = false;
+                uint2 e = make_uint2(0, 0);
+                if (i < ecnt) {
+                    e = S.epool[i];
+                    const unsigned owner = e.x >> 27;
+                    keep = !(__uint_as_float(e.y) > S.rbound[owner]);
+                    if (!keep) { ++st_culled; wp_slot_done(S, owner, -1); }
                 }
-                // Every waiting candidate is compared (exactly) with its slot's incumbent, all lanes at once; the ones that are farther
-                // retire.  Of the rest, ONE per slot (the apparently nearest) replaces the incumbent, the others meet the new incumbent in
-                // the next round.  Each replacement is a step the sequential reference loop could have taken, and a candidate farther
-                // than an earlier incumbent is farther than every later one, so the outcome is that of the sequential loop.
-                unsigned pm = __ballot_sync(full, pending);
-                while (pm) {
-                    int sg = 0;
-                    if (pending) {
-                        const Vec3 bp = {S.bp[0][owner], S.bp[1][owner], S.bp[2][owner]};
-                        int nexact = 0;
-                        sg = cmp_dist(o, cpt, bp, nexact);
-                        if (nexact) atomicOr(&S.flags[owner], a.flag_exact);
-                        if (sg > 0) pending = false;
-                    }
-                    __syncwarp();                              // incumbents read before any is replaced
-                    const unsigned cm = __ballot_sync(full, pending);
-                    if (pending) {
-                        const unsigned grp = __match_any_sync(cm, owner);
-                        const unsigned gmin = __reduce_min_sync(grp, key);
-                        const unsigned wm = __ballot_sync(cm, key == gmin) & grp;
-                        if ((unsigned)(__ffs(wm) - 1) == lane) { wp_apply(S, owner, sg, cpt, v, sqd, id, a.flag_tie); pending = false; }
-                    }
-                    __syncwarp();
-                    pm = __ballot_sync(full, pending);
-                }
-                if (has) wp_slot_done(S, owner, -1);
+                __syncwarp();
+                const unsigned km = __ballot_sync(full, keep);
+                if (keep) S.epool[kept + __popc(km & lt)] = e;
+                kept += __popc(km);
+                __syncwarp();
             }
-            scnt = 0;
+            ecnt = kept;
+            const bool drain = ncnt == 0 && lcnt == 0 && mcnt == 0 && spilled == 0;
+            if (ecnt >= a.exact_go || drain) {
+                for (int base = 0; base < ecnt; base += 32) {
+                    const int i = base + (int)lane;
+                    const bool has = i < ecnt;
+                    bool pending = false;
+                    unsigned owner = 0;
+                    uint32_t id = 0, key = 0;
+                    Vec3 o = {0.0, 0.0, 0.0}, cpt = {0.0, 0.0, 0.0}, v = {0.0, 0.0, 0.0};
+                    double sqd = 0.0;
+                    if (has) {
+                        const uint2 e = S.epool[i];
+                        owner = e.x >> 27;
+                        if (__uint_as_float(e.y) > S.rbound[owner]) ++st_culled;   // (an earlier batch of this very phase may have shrunk the ball)
+                        else {
+                            const Tri3 t = load_tri(a.tris, e.x & kWpRefMask, id);
+                            o = {S.o[0][owner], S.o[1][owner], S.o[2][owner]};
+                            cpt = closest_on_triangle(t, o);
+                            v = cpt - o;
+                            sqd = (v.x * v.x + v.y * v.y) + v.z * v.z;   // Compute_squared_distance_3(query, closest): AABB_tree.h:1024-1032
+                            key = __float_as_uint((float)sqd);
+                            pending = true;
+                        }
+                    }
+                    // Every waiting candidate is compared (exactly) with its slot's incumbent, all lanes at once; the ones that are farther
+                    // retire.  Of the rest, ONE per slot (the apparently nearest) replaces the incumbent, the others meet the new incumbent in
+                    // the next round.  Each replacement is a step the sequential reference loop could have taken, and a candidate farther
+                    // than an earlier incumbent is farther than every later one, so the outcome is that of the sequential loop.
+                    unsigned pm = __ballot_sync(full, pending);
+                    while (pm) {
+                        int sg = 0;
+                        if (pending) {
+                            const Vec3 bp = {S.bp[0][owner], S.bp[1][owner], S.bp[2][owner]};
+                            int nexact = 0;
+                            sg = cmp_dist(o, cpt, bp, nexact);
+                            if (nexact) atomicOr(&S.flags[owner], a.flag_exact);
+                            if (sg > 0) pending = false;
+                        }
+                        __syncwarp();                              // incumbents read before any is replaced
+                        const unsigned cm = __ballot_sync(full, pending);
+                        if (pending) {
+                            const unsigned grp = __match_any_sync(cm, owner);
+                            const unsigned gmin = __reduce_min_sync(grp, key);
+                            const unsigned wm = __ballot_sync(cm, key == gmin) & grp;
+                            if ((unsigned)(__ffs(wm) - 1) == lane) { wp_apply(S, owner, sg, cpt, v, sqd, id, a.flag_tie); pending = false; }
+                        }
+                        __syncwarp();
+                        pm = __ballot_sync(full, pending);
+                    }
+                    if (has) wp_slot_done(S, owner, -1);
+                }
+                ecnt = 0;
+            }
         }
         // ------------------------------------------------------------------------------------------------ completed queries
         __syncwarp();
