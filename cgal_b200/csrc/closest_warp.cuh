@@ -34,9 +34,9 @@
 
 namespace b2 {
 
-constexpr int kWpNodeCap = 768;                 // (slot,node) entries held in shared memory
+constexpr int kWpNodeCap = 512;                 // (slot,node) entries held in shared memory
 constexpr int kWpSpillChunk = kWpNodeCap / 2;   // entries moved per spill / reload
-constexpr int kWpSpillCap = 8 * kWpSpillChunk;  // entries per warp in the global spill area
+constexpr int kWpSpillCap = 16 * kWpSpillChunk; // entries per warp in the global spill area
 constexpr int kWpLeafCap = 96;                  // < 32 waiting + at most 64 added by one node phase
 constexpr int kWpMidCap = 128;                  // < 32 waiting + at most 95 added by one pre-test-1 phase
 constexpr int kWpExactCap = 192;                // < exact_go (<= 64) waiting + at most 126 added by one pre-test-2 phase
@@ -44,23 +44,24 @@ constexpr uint32_t kWpRefMask = 0x07FFFFFFu;    // 27 bits of leaf slot next to 
 constexpr uint64_t kWpMaxPrims = 1ull << 27;
 
 struct WarpShared {
-    uint2 npool[kWpNodeCap];      // x = child reference (node index, or kLeafBit | leaf slot); y = lower bound of the box's squared distance
-                                  //     (binary32, low 5 mantissa bits cleared = rounded down) | query slot
-    uint32_t lpool[kWpLeafCap];   // query slot << 27 | leaf slot : awaiting the binary32 pre-test
+    uint2 npool[kWpNodeCap + 1];  // x = child reference (node index, or kLeafBit | leaf slot); y = lower bound of the box's squared distance from
+                                  //     the binary32 query point (low 5 mantissa bits cleared = rounded down) | query slot.  [+1: sink of masked pushes]
+    uint32_t lpool[kWpLeafCap + 1];   // query slot << 27 | leaf slot : awaiting pre-test 1
     uint2 mpool[kWpMidCap];       // x = same, y = lower bound of the distance (binary32) : awaiting pre-test 2
     uint2 epool[kWpExactCap];     // same : awaiting the binary64 projection
+    float4 qa[32];                // node phase: query point rounded to binary32 (x,y,z); w = (rbound + perr)^2 rounded up
+    float4 qb[32];                // pre-test 1: direction query -> incumbent (x,y,z) and its length (w)
     double o[3][32];              // query point
     double bp[3][32];             // incumbent closest point
     double bsqd[32];              // its squared distance as the reference computes it
-    float up[3][32], dn[3][32];   // query point rounded up / down to binary32
-    float bound[32], rbound[32];  // pruning bound (widened incumbent squared distance, rounded up) and >= its square root
-    float ub[3][32], sub[32];     // direction query -> incumbent and its length
+    double delta[32];             // rounding allowance of candidate points: 4e-16 * largest coordinate magnitude (bvh.cuh::traverse_closest)
+    float rbound[32];             // pruning radius: >= sqrt(widened squared distance of the eventual winner)
+    float perr[32];               // >= |query - its binary32 rounding|
+    float dslack[32];             // >= 2 delta
     uint32_t bprim[32];           // incumbent primitive id
     uint32_t qidx[32];            // the query's index in the caller's order
-    int outst[32];                // pairs of this slot still in a pool
     uint32_t flags[32];           // B200AABB_FLAG_TIE / _EXACT
-    float dslack[32];             // >= 2 delta, binary32
-    double delta[32];             // rounding allowance of candidate points: 4e-16 * largest coordinate magnitude (bvh.cuh::traverse_closest)
+    int outst[32];                // pairs of this slot still in a pool
     uint32_t donemask;            // slots whose outst reached 0
 };
 
@@ -93,20 +94,37 @@ __device__ __forceinline__ void wp_slot_done(WarpShared& S, unsigned owner, int 
     }
 }
 
-// pruning bounds of a slot from its incumbent's squared distance: bound >= widen_sqdist(sqd, delta) (bvh.cuh) and rbound >= sqrt(bound),
-// with the square roots taken in binary32 rounded up (s >= sqrt(sqd) makes the widened value only larger).  Unless `reset`, the
-// bounds only shrink: the binary32 upper bounds of wp_sharp may already be tighter than this incumbent.
+// LOWER bound of the squared distance from the binary32 point q to the closed box (every operation rounds towards the smaller
+// result, as bvh.cuh::point_box_sqdist).  The query itself is within perr of q, so a box can only matter when this value is
+// <= (rbound + perr)^2 = qa.w.
+__device__ __forceinline__ float wp_box_sqdist(const float* lo, const float* hi, const float4& q) {
+    const float dx = fmaxf(fmaxf(__fsub_rd(lo[0], q.x), __fsub_rd(q.x, hi[0])), 0.0f);
+    const float dy = fmaxf(fmaxf(__fsub_rd(lo[1], q.y), __fsub_rd(q.y, hi[1])), 0.0f);
+    const float dz = fmaxf(fmaxf(__fsub_rd(lo[2], q.z), __fsub_rd(q.z, hi[2])), 0.0f);
+    return __fadd_rd(__fadd_rd(__fmul_rd(dx, dx), __fmul_rd(dy, dy)), __fmul_rd(dz, dz));
+}
+
+// shrinks slot `owner`'s ball to radius rb (any lane, any time: both bounds only ever decrease)
+__device__ __forceinline__ void wp_shrink(WarpShared& S, unsigned owner, float rb) {
+    atomicMin(reinterpret_cast<unsigned*>(&S.rbound[owner]), __float_as_uint(rb));
+    const float r = __fadd_ru(rb, S.perr[owner]);
+    atomicMin(reinterpret_cast<unsigned*>(&S.qa[owner].w), __float_as_uint(__fmul_ru(r, r)));
+}
+
+// pruning radius of a slot from its incumbent's squared distance: rbound >= sqrt(widen_sqdist(sqd, delta)) (bvh.cuh), with the
+// square roots taken in binary32 rounded up (s >= sqrt(sqd) makes the widened value only larger).  Unless `reset`, the ball only
+// shrinks: the binary32 upper bounds of wp_sharp may already be tighter than this incumbent.
 __device__ __forceinline__ void wp_set_bounds(WarpShared& S, unsigned owner, double sqd, const Vec3& v, bool reset) {
     const double delta = S.delta[owner];
     const float s = __fsqrt_ru(float_above(sqd));
-    float bound = float_above(sqd + ((2.0 * delta * (double)s + delta * delta) + sqd * 1e-13));
-    float rbound = __fsqrt_ru(bound);
-    if (!reset) { bound = fminf(bound, S.bound[owner]); rbound = fminf(rbound, S.rbound[owner]); }
-    S.bound[owner] = bound;
-    S.rbound[owner] = rbound;
+    const float rb = __fsqrt_ru(float_above(sqd + ((2.0 * delta * (double)s + delta * delta) + sqd * 1e-13)));
+    if (reset) {
+        S.rbound[owner] = rb;
+        const float r = __fadd_ru(rb, S.perr[owner]);
+        S.qa[owner].w = __fmul_ru(r, r);
+    } else wp_shrink(S, owner, rb);
     const float u0 = (float)v.x, u1 = (float)v.y, u2 = (float)v.z;
-    S.ub[0][owner] = u0; S.ub[1][owner] = u1; S.ub[2][owner] = u2;
-    S.sub[owner] = sqrtf((u0 * u0 + u1 * u1) + u2 * u2);
+    S.qb[owner] = make_float4(u0, u1, u2, sqrtf((u0 * u0 + u1 * u1) + u2 * u2));
 }
 
 // Binary32 bounds of the distance from the query to one primitive, on coordinates RELATIVE to the query (the subtraction is done in
@@ -132,8 +150,8 @@ __device__ __forceinline__ float wp_lower(const float* u, float su, const RelTri
 // rigorous UPPER bound of (distance + the slot's rounding allowance): P's coordinates are within 1.2e-6 m of a point of the true
 // triangle (vertex rounding m 2^-24 each, six binary32 operations on magnitudes <= 2 m), so dist <= |P| + 2.1e-6 m; the formula
 // allows 8e-6 m + 1e-5 |P| + dslack.  The winner's candidate is no farther than this primitive's candidate, which lies within the
-// rounding allowance of the true distance (the premise of widen_sqdist), so pruning with `hi` (and its square) never discards the
-// winner or a primitive tied with it.  hi = NaN (degenerate triangle) compares false everywhere: no bound.
+// rounding allowance of the true distance (the premise of widen_sqdist), so pruning with `hi` never discards the winner or a
+// primitive tied with it.  hi = NaN (degenerate triangle) compares false everywhere: no bound.
 __device__ __forceinline__ void wp_sharp(const RelTri& r, float dslack, float* lower, float* hi) {
     float u[3];
     approx_closest_to_origin(r.ra, r.rb, r.rc, u);
@@ -200,13 +218,13 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                 const bool valid = ((free_mask >> lane) & 1u) && pos < a.n;
                 if (base + (unsigned long long)nfree >= a.n) more = false;
                 Vec3 o = {0.0, 0.0, 0.0};
-                PointCtx pc;
+                float4 q = make_float4(0.0f, 0.0f, 0.0f, INFINITY);
                 uint32_t qi = 0;
                 if (valid) {
                     qi = a.perm ? a.perm[pos] : (uint32_t)pos;
                     const double* p = a.pts + 3 * (uint64_t)qi;
                     o = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
-                    pc = make_point(o);
+                    q.x = (float)o.x; q.y = (float)o.y; q.z = (float)o.z;
                 }
                 // walk down to the nearest leaf, nearest child first, pushing every far child
                 uint32_t cur = 0, firstleaf = kNone;
@@ -220,14 +238,15 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                     if (act) {
                         const NodeView nd = load_node(a.nodes, cur);
                         ++st_nodes;
-                        float d0 = point_box_sqdist(nd.lo0, nd.hi0, pc), d1 = point_box_sqdist(nd.lo1, nd.hi1, pc);
+                        float d0 = wp_box_sqdist(nd.lo0, nd.hi0, q), d1 = wp_box_sqdist(nd.lo1, nd.hi1, q);
                         uint32_t c0 = nd.c0, c1 = nd.c1;
                         if (d1 < d0) { const uint32_t tc = c0; c0 = c1; c1 = tc; const float td = d0; d0 = d1; d1 = td; }
                         farref = c1; fard = d1;
                         if (c0 & kLeafBit) { firstleaf = c0; stop = true; } else cur = c0;
                     }
                     const unsigned pm = __ballot_sync(full, act);
-                    if (act) { S.npool[ncnt + __popc(pm & lt)] = make_uint2(farref, (__float_as_uint(fard) & ~31u) | lane); ++pushed; }
+                    S.npool[act ? ncnt + __popc(pm & lt) : kWpNodeCap] = make_uint2(farref, (__float_as_uint(fard) & ~31u) | lane);
+                    if (act) ++pushed;
                     ncnt += __popc(pm);
                     if (stop) act = false;
                 }
@@ -238,19 +257,16 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                     const Vec3 cpt = closest_on_triangle(t, o);
                     const Vec3 v = cpt - o;
                     const double sqd = (v.x * v.x + v.y * v.y) + v.z * v.z;
+                    const double ex = o.x - (double)q.x, ey = o.y - (double)q.y, ez = o.z - (double)q.z;   // exact differences
                     S.o[0][lane] = o.x; S.o[1][lane] = o.y; S.o[2][lane] = o.z;
-                    S.up[0][lane] = pc.up[0]; S.up[1][lane] = pc.up[1]; S.up[2][lane] = pc.up[2];
-                    S.dn[0][lane] = pc.dn[0]; S.dn[1][lane] = pc.dn[1]; S.dn[2][lane] = pc.dn[2];
+                    S.qa[lane] = q;
+                    S.perr[lane] = float_above(sqrt((ex * ex + ey * ey) + ez * ez) * 1.0000001) + 1e-37f;
                     S.bp[0][lane] = cpt.x; S.bp[1][lane] = cpt.y; S.bp[2][lane] = cpt.z;
                     S.bprim[lane] = id; S.bsqd[lane] = sqd;
                     S.delta[lane] = 4e-16 * fmax(a.mag, fmax3(fabs(o.x), fabs(o.y), fabs(o.z)));
                     S.dslack[lane] = float_above(2.0 * S.delta[lane]) + 1e-37f;
                     wp_set_bounds(S, lane, sqd, v, true);
-                    if (a.debug_hint_sqd) {
-                        const double wh = widen_sqdist(a.debug_hint_sqd[qi], S.delta[lane]);
-                        S.bound[lane] = fminf(S.bound[lane], float_above(wh));
-                        S.rbound[lane] = fminf(S.rbound[lane], float_above(sqrt(wh)));
-                    }
+                    if (a.debug_hint_sqd) wp_shrink(S, lane, float_above(sqrt(widen_sqdist(a.debug_hint_sqd[qi], S.delta[lane]))));
                     S.qidx[lane] = qi;
                     S.flags[lane] = 0;
                     S.outst[lane] = pushed;   // >= 1: the root is an internal node
@@ -279,66 +295,59 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
 
         if (phase == 0) {
             // -------------------------------------------------------------------------------------------- (A) node phase
-            if (ncnt + 32 > kWpNodeCap) {
-                if (!spill_bottom()) { if (lane == 0) atomicOr(&a.counters[2], 1ull); return; }
-            }
-            const int take = ncnt < 32 ? ncnt : 32;
-            const bool has = (int)lane < take;
-            ncnt -= take;
-            uint2 e = make_uint2(0, 0);
-            unsigned owner = 0;
-            bool live = false;
-            float bnd = 0.0f;
-            if (has) {
-                e = S.npool[ncnt + lane];
-                owner = e.y & 31u;
-                bnd = S.bound[owner];
-                live = __uint_as_float(e.y & ~31u) <= bnd;
-            }
-            __syncwarp();                                      // all pops read before any push overwrites them
-            int delta = has ? -1 : 0;
-            const bool popped_leaf = live && (e.x & kLeafBit);
-            bool in0 = false, in1 = false;                     // 0 = nearer child, 1 = farther child
-            uint32_t r0 = 0, r1 = 0;
-            float d0 = 0.0f, d1 = 0.0f;
-            if (live && !popped_leaf) {
-                const NodeView nd = load_node(a.nodes, e.x);
-                ++st_nodes;
-                PointCtx pc;
-                pc.up[0] = S.up[0][owner]; pc.up[1] = S.up[1][owner]; pc.up[2] = S.up[2][owner];
-                pc.dn[0] = S.dn[0][owner]; pc.dn[1] = S.dn[1][owner]; pc.dn[2] = S.dn[2][owner];
-                d0 = point_box_sqdist(nd.lo0, nd.hi0, pc); d1 = point_box_sqdist(nd.lo1, nd.hi1, pc);
-                r0 = nd.c0; r1 = nd.c1;
-                if (d1 < d0) { const uint32_t tc = r0; r0 = r1; r1 = tc; const float td = d0; d0 = d1; d1 = td; }
-                in0 = d0 <= bnd; in1 = d1 <= bnd;
-                delta += (in0 ? 1 : 0) + (in1 ? 1 : 0);
-            } else if (popped_leaf) {
-                delta = 0;                                     // the pair moves from the node pool to the leaf pool
-            }
-            // leaf pairs: a popped leaf entry or the nearer child, then the farther child
-            {
-                const bool l0 = popped_leaf || (in0 && (r0 & kLeafBit));
-                const uint32_t ref0 = popped_leaf ? e.x : r0;
-                const unsigned m0 = __ballot_sync(full, l0);
-                if (l0) S.lpool[lcnt + __popc(m0 & lt)] = (owner << 27) | (ref0 & kWpRefMask);
-                lcnt += __popc(m0);
-                const bool l1 = in1 && (r1 & kLeafBit);
-                const unsigned m1 = __ballot_sync(full, l1);
-                if (l1) S.lpool[lcnt + __popc(m1 & lt)] = (owner << 27) | (r1 & kWpRefMask);
-                lcnt += __popc(m1);
-            }
-            // internal children: farther first, nearer on top
-            {
-                const bool p1 = in1 && !(r1 & kLeafBit);
-                const unsigned m1 = __ballot_sync(full, p1);
-                if (p1) S.npool[ncnt + __popc(m1 & lt)] = make_uint2(r1, (__float_as_uint(d1) & ~31u) | owner);
-                ncnt += __popc(m1);
-                const bool p0 = in0 && !(r0 & kLeafBit);
-                const unsigned m0 = __ballot_sync(full, p0);
-                if (p0) S.npool[ncnt + __popc(m0 & lt)] = make_uint2(r0, (__float_as_uint(d0) & ~31u) | owner);
-                ncnt += __popc(m0);
-            }
-            if (has) wp_slot_done(S, owner, delta);
+            do {
+                if (ncnt + 32 > kWpNodeCap) {
+                    if (!spill_bottom()) { if (lane == 0) atomicOr(&a.counters[2], 1ull); return; }
+                }
+                const int take = ncnt < 32 ? ncnt : 32;
+                const bool has = (int)lane < take;
+                ncnt -= take;
+                const uint2 e = S.npool[has ? ncnt + (int)lane : kWpNodeCap];
+                const unsigned owner = e.y & 31u;
+                const float4 q = S.qa[owner];
+                const bool live = has && __uint_as_float(e.y & ~31u) <= q.w;
+                __syncwarp();                                      // all pops read before any push overwrites them
+                const bool popped_leaf = live && (e.x & kLeafBit);
+                const bool expand = live && !(e.x & kLeafBit);
+                int delta = has && !popped_leaf ? -1 : 0;          // (a popped leaf entry just moves from the node pool to the leaf pool)
+                bool in0 = false, in1 = false;                     // 0 = nearer child, 1 = farther child
+                uint32_t r0 = 0, r1 = 0;
+                float d0 = 0.0f, d1 = 0.0f;
+                if (expand) {
+                    const NodeView nd = load_node(a.nodes, e.x);
+                    ++st_nodes;
+                    d0 = wp_box_sqdist(nd.lo0, nd.hi0, q); d1 = wp_box_sqdist(nd.lo1, nd.hi1, q);
+                    r0 = nd.c0; r1 = nd.c1;
+                    if (d1 < d0) { const uint32_t tc = r0; r0 = r1; r1 = tc; const float td = d0; d0 = d1; d1 = td; }
+                    in0 = d0 <= q.w; in1 = d1 <= q.w;
+                    delta += (in0 ? 1 : 0) + (in1 ? 1 : 0);
+                }
+                // leaf pairs: a popped leaf entry or the nearer child, then the farther child (masked lanes write the sink entry)
+                {
+                    const bool l0 = popped_leaf || (in0 && (r0 & kLeafBit));
+                    const uint32_t ref0 = popped_leaf ? e.x : r0;
+                    const unsigned m0 = __ballot_sync(full, l0);
+                    S.lpool[l0 ? lcnt + __popc(m0 & lt) : kWpLeafCap] = (owner << 27) | (ref0 & kWpRefMask);
+                    lcnt += __popc(m0);
+                    const bool l1 = in1 && (r1 & kLeafBit);
+                    const unsigned m1 = __ballot_sync(full, l1);
+                    S.lpool[l1 ? lcnt + __popc(m1 & lt) : kWpLeafCap] = (owner << 27) | (r1 & kWpRefMask);
+                    lcnt += __popc(m1);
+                }
+                // internal children: farther first, nearer on top
+                {
+                    const bool p1 = in1 && !(r1 & kLeafBit);
+                    const unsigned m1 = __ballot_sync(full, p1);
+                    S.npool[p1 ? ncnt + __popc(m1 & lt) : kWpNodeCap] = make_uint2(r1, (__float_as_uint(d1) & ~31u) | owner);
+                    ncnt += __popc(m1);
+                    const bool p0 = in0 && !(r0 & kLeafBit);
+                    const unsigned m0 = __ballot_sync(full, p0);
+                    S.npool[p0 ? ncnt + __popc(m0 & lt) : kWpNodeCap] = make_uint2(r0, (__float_as_uint(d0) & ~31u) | owner);
+                    ncnt += __popc(m0);
+                }
+                wp_slot_done(S, owner, delta);
+                __syncwarp();
+            } while (ncnt > 0 && lcnt < 32 && *(volatile uint32_t*)&S.donemask == 0);
         } else if (phase == 1) {
             // -------------------------------------------------------------------------------------------- (B1) pre-test 1: two cheap directions
             for (int base = 0; base < lcnt; base += 32) {
@@ -354,9 +363,10 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                     ++st_leaves;
                     const Vec3 o = {S.o[0][owner], S.o[1][owner], S.o[2][owner]};
                     const RelTri r = wp_relative(t, o);
-                    const float ub[3] = {S.ub[0][owner], S.ub[1][owner], S.ub[2][owner]};
+                    const float4 qb = S.qb[owner];
+                    const float ub[3] = {qb.x, qb.y, qb.z};
                     const float g[3] = {(r.ra[0] + r.rb[0]) + r.rc[0], (r.ra[1] + r.rb[1]) + r.rc[1], (r.ra[2] + r.rb[2]) + r.rc[2]};
-                    lb = fmaxf(wp_lower(ub, S.sub[owner], r), wp_lower(g, sqrtf(dot3f(g, g)), r));   // tangent plane of the ball; centroid direction
+                    lb = fmaxf(wp_lower(ub, qb.w, r), wp_lower(g, sqrtf(dot3f(g, g)), r));   // tangent plane of the ball; centroid direction
                     if (lb > S.rbound[owner]) { ++st_culled; wp_slot_done(S, owner, -1); }
                     else survive = true;
                 }
@@ -383,10 +393,7 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                         const RelTri r = wp_relative(t, o);
                         float lb, hi;
                         wp_sharp(r, S.dslack[owner], &lb, &hi);
-                        if (hi < rbound) {                     // this primitive is certainly nearer than the slot's ball: shrink it now, in binary32
-                            atomicMin(reinterpret_cast<unsigned*>(&S.rbound[owner]), __float_as_uint(hi));
-                            atomicMin(reinterpret_cast<unsigned*>(&S.bound[owner]), __float_as_uint(__fmul_ru(hi, hi)));
-                        }
+                        if (hi < rbound) wp_shrink(S, owner, hi);   // this primitive is certainly nearer than the slot's ball: shrink it now, in binary32
                         lb = fmaxf(lb, __uint_as_float(e.y));
                         if (lb > rbound) { ++st_culled; wp_slot_done(S, owner, -1); }
                         else { survive = true; e.y = __float_as_uint(lb); }
