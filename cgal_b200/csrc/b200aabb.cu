@@ -194,6 +194,7 @@ struct b200aabb_tree {
     bool built = false;
     BvhNode* d_nodes = nullptr;
     TriRec* d_tris = nullptr;
+    TriF* d_trisf = nullptr;       // binary32 copies (pre-tests of the warp-cooperative closest_point kernel)
     double* d_rootbox = nullptr;   // 6 doubles
     uint32_t root = kNone;
     double h_bbox[6];
@@ -202,8 +203,7 @@ struct b200aabb_tree {
     // options
     int opt_sort_queries = 1;      // B200AABB_OPT_SORT_QUERIES
     int opt_closest_kernel = 1;    // B200AABB_OPT_CLOSEST_KERNEL: 1 = warp-cooperative pool (closest_warp.cuh), 0 = one thread per query
-    int opt_warp_refill = 32;      // B200AABB_OPT_WARP_REFILL
-    int opt_warp_surv_go = 32;     // B200AABB_OPT_WARP_SURV_GO
+    int opt_warp_exact_go = 32;     // B200AABB_OPT_WARP_EXACT_GO
     int opt_debug_two_pass = 0;    // experiment: run the warp kernel twice, the second time with the first pass's distances as initial bounds
     // warp-cooperative closest_point: per pipeline slot a batch cursor and the pools' spill area; grid = SMs x resident warps
     struct WarpScratch { unsigned long long* cursor = nullptr; uint2* spill = nullptr; } warp[2];
@@ -236,8 +236,8 @@ constexpr uint64_t kChunk = 1ull << 22;   // queries per pipeline slot for HOST-
 int fail(b200aabb_tree* t, int code, const char* msg) { if (t) t->err = msg; return code; }
 
 void free_tree_buffers(b200aabb_tree* t) {
-    cudaFree(t->d_nodes); cudaFree(t->d_tris);
-    t->d_nodes = nullptr; t->d_tris = nullptr; t->built = false; t->root = kNone;
+    cudaFree(t->d_nodes); cudaFree(t->d_tris); cudaFree(t->d_trisf);
+    t->d_nodes = nullptr; t->d_tris = nullptr; t->d_trisf = nullptr; t->built = false; t->root = kNone;
 }
 void free_input(b200aabb_tree* t) { cudaFree(t->d_soup); cudaFree(t->d_ids); t->d_soup = nullptr; t->d_ids = nullptr; }
 
@@ -331,6 +331,7 @@ int do_build(b200aabb_tree* t) {
     B2_TRY(cudaMalloc(&leaf_parent, n * 4));
     B2_TRY(cudaMalloc(&t->d_nodes, std::max<uint64_t>(n - 1, 1) * sizeof(BvhNode)));
     B2_TRY(cudaMalloc(&t->d_tris, n * sizeof(TriRec)));
+    B2_TRY(cudaMalloc(&t->d_trisf, n * sizeof(TriF)));
     B2_TRY(cudaEventRecord(t->ev_a, st));
     B2_TRY(cudaMemsetAsync(bounds, 0xFF, 3 * 8, st));
     B2_TRY(cudaMemsetAsync(bounds + 3, 0x00, 3 * 8, st));
@@ -339,7 +340,7 @@ int do_build(b200aabb_tree* t) {
     morton_kernel<<<blocks, 256, 0, st>>>(t->d_soup, n, bounds, keys[0], vals[0]);
     t->stats.kernel_launches += 2;
     const int cur = radix_sort_pairs(keys, vals, n, 8, ws, st, &t->stats.kernel_launches);
-    emit_leaves_kernel<<<blocks, 256, 0, st>>>(t->d_soup, t->d_ids, vals[cur], n, t->d_tris);
+    emit_leaves_kernel<<<blocks, 256, 0, st>>>(t->d_soup, t->d_ids, vals[cur], n, t->d_tris, t->d_trisf);
     t->stats.kernel_launches += 1;
     if (n > 1) {
         hierarchy_kernel<<<blocks, 256, 0, st>>>(keys[cur], n, t->d_nodes, leaf_parent);
@@ -486,9 +487,8 @@ int b200aabb_set_option(b200aabb_tree* t, int option, int64_t value) {
     switch (option) {
         case B200AABB_OPT_SORT_QUERIES: t->opt_sort_queries = value != 0; return B200AABB_OK;
         case B200AABB_OPT_CLOSEST_KERNEL: t->opt_closest_kernel = value != 0; return B200AABB_OK;
-        case B200AABB_OPT_WARP_REFILL: t->opt_warp_refill = (int)std::min<int64_t>(32, std::max<int64_t>(1, value)); return B200AABB_OK;
         case 100: t->opt_debug_two_pass = value != 0; return B200AABB_OK;
-        case B200AABB_OPT_WARP_SURV_GO: t->opt_warp_surv_go = (int)std::min<int64_t>(64, std::max<int64_t>(1, value)); return B200AABB_OK;
+        case B200AABB_OPT_WARP_EXACT_GO: t->opt_warp_exact_go = (int)std::min<int64_t>(64, std::max<int64_t>(1, value)); return B200AABB_OK;
         default: return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "unknown option");
     }
 }
@@ -648,10 +648,10 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
                          const int slot = (space == B200AABB_HOST && st == t->pipe[1]) ? 1 : 0;
                          cudaMemsetAsync(t->warp[slot].cursor, 0, sizeof(unsigned long long), st);
                          WarpClosestArgs a;
-                         a.nodes = t->d_nodes; a.tris = t->d_tris; a.mag = t->mag; a.perm = perm; a.counters = t->d_counters;
+                         a.nodes = t->d_nodes; a.tris = t->d_tris; a.trisf = t->d_trisf; a.mag = t->mag; a.perm = perm; a.counters = t->d_counters;
                          a.pts = (const double*)in; a.n = cnt; a.cp = (double*)o[0]; a.prim = (uint32_t*)o[1]; a.sqd = (double*)o[2]; a.flags = (uint8_t*)o[3];
                          a.cursor = t->warp[slot].cursor; a.spill = t->warp[slot].spill;
-                         a.refill_min = t->opt_warp_refill; a.exact_go = t->opt_warp_surv_go;
+                         a.exact_go = t->opt_warp_exact_go;
                          a.flag_tie = B200AABB_FLAG_TIE; a.flag_exact = B200AABB_FLAG_EXACT;
                          a.debug_hint_sqd = nullptr;
                          const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)t->warp_grid, (cnt + 31) / 32);
@@ -670,13 +670,14 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
 }
 
 int b200aabb_export_layout(b200aabb_tree* t, void** ptrs, uint64_t* bytes, int cap, int* count) {
-    if (!t || !ptrs || !bytes || !count || cap < 3) return B200AABB_ERR_INVALID_ARGUMENT;
+    if (!t || !ptrs || !bytes || !count || cap < 4) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc) return rc;
     ptrs[0] = t->d_nodes; bytes[0] = t->n > 1 ? (t->n - 1) * sizeof(BvhNode) : 0;
     ptrs[1] = t->d_tris; bytes[1] = t->n * sizeof(TriRec);
     ptrs[2] = t->d_rootbox; bytes[2] = 48;
-    *count = 3;
+    ptrs[3] = t->d_trisf; bytes[3] = t->n * sizeof(TriF);
+    *count = 4;
     return B200AABB_OK;
 }
 
@@ -687,6 +688,7 @@ int b200aabb_import_alloc(b200aabb_tree* t, uint64_t n) {
     if (n == 0) return B200AABB_OK;
     B2_CUDA(t, cudaMalloc(&t->d_nodes, std::max<uint64_t>(n - 1, 1) * sizeof(BvhNode)));
     B2_CUDA(t, cudaMalloc(&t->d_tris, n * sizeof(TriRec)));
+    B2_CUDA(t, cudaMalloc(&t->d_trisf, n * sizeof(TriF)));
     t->n = n; t->root = n == 1 ? (kLeafBit | 0u) : 0u; t->built = true;
     return B200AABB_OK;
 }

@@ -4,7 +4,7 @@
 //   scene_bounds_kernel  bounding box of all primitives (exact: min/max only), one atomic per block and bound
 //   morton_kernel        63-bit Morton key (21 bits per axis) of each primitive's box centre in the scene box
 //   [radix_sort.cuh]     onesweep sort of (key, primitive index)
-//   emit_leaves_kernel   TriRec records in Morton order
+//   emit_leaves_kernel   TriRec records (and their binary32 copies, TriF) in Morton order
 //   hierarchy_kernel     Karras 2012 radix-tree topology, one thread per internal node
 //   refit_kernel         bottom-up boxes with one atomic arrival counter per node.  A primitive's exact binary64 box is
 //                        rounded OUTWARD to binary32 once; min/max are exact and commute with the monotone rounding, so
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) morton_kernel(const double* __restrict__ 
 }
 
 __global__ void __launch_bounds__(256) emit_leaves_kernel(const double* __restrict__ tris, const uint32_t* __restrict__ ids, const uint32_t* __restrict__ perm,
-                                                          uint64_t n, TriRec* __restrict__ out) {
+                                                          uint64_t n, TriRec* __restrict__ out, TriF* __restrict__ outf) {
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
     const uint32_t src = perm[k];
@@ -128,6 +128,11 @@ __global__ void __launch_bounds__(256) emit_leaves_kernel(const double* __restri
 #pragma unroll
     for (int j = 0; j < 5; ++j) r.pad[j] = 0;
     out[k] = r;
+    TriF f;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) f.v[j] = (float)t[j];
+    f.pad[0] = f.pad[1] = f.pad[2] = 0;
+    outf[k] = f;
 }
 
 // length of the common prefix of the (key, index) pairs i and j; -1 outside [0, n)

@@ -5,6 +5,7 @@
 //                   rounded OUTWARD from the exact binary64 boxes (lo towards -inf, hi towards +inf), so a traversal step
 //                   costs two 32-byte sectors and leaf boxes never need their own node.  N-1 nodes for N primitives.
 //   TriRec    96 B  one primitive in Morton order: 9 binary64 coordinates (v0,v1,v2), the primitive id, padding to 3 sectors.
+//   TriF      48 B  the same primitive rounded to binary32 (pre-tests of closest_warp.cuh only; never decides a result).
 // Child reference: bit 31 set = leaf, low bits = slot in the TriRec array; else index of an internal node.
 //
 // Traversal replaces (paths relative to the CGAL source root)
@@ -40,6 +41,15 @@ struct __align__(16) TriRec {
     uint32_t pad[5];
 };
 static_assert(sizeof(TriRec) == 96, "triangle record is three 32-byte sectors");
+
+// binary32 copy of a primitive (same order as the TriRec array): each coordinate rounded to nearest.  Read by the rigorous binary32
+// pre-tests of the warp-cooperative closest_point kernel (closest_warp.cuh), which account for the rounding explicitly; 48 bytes
+// = three 128-bit loads instead of six.
+struct __align__(16) TriF {
+    float v[9];
+    uint32_t pad[3];
+};
+static_assert(sizeof(TriF) == 48, "binary32 triangle record is three 16-byte words");
 
 // per-query traversal statistics (accumulated into the handle's counters by the kernels)
 struct TravStat { int nexact = 0; int overflow = 0; uint32_t nodes = 0, leaves = 0, culled = 0; };   // culled: leaves rejected by the binary32 pre-test

@@ -1,5 +1,5 @@
-// closest_warp.cuh — warp-cooperative closest_point_and_primitive(Point_3): one persistent warp serves 32 query SLOTS and
-// keeps ONE shared work pool for all of them in shared memory.
+// closest_warp.cuh — warp-cooperative closest_point_and_primitive(Point_3): one persistent warp serves a BATCH of 32 queries
+// (one per "slot") and keeps ONE shared work pool for all of them in shared memory.
 //
 // Replaces the same reference path as bvh.cuh::traverse_closest (AABB_tree.h:987-1055, Projection_traits
 // AABB_traversal_traits.h:277-327, AABB_traits_3.h:715-733) and produces the same results: the winner is the candidate
@@ -8,27 +8,28 @@
 //
 // Why (profiles/r1_03): in the thread-per-query kernel a closest_point query visits ~170 nodes and ~75 leaves, the counts
 // differ a lot between the 32 queries of a warp, and each thread runs its own three-phase loop: 5.2 of 32 threads are active
-// per issued instruction.  Here the unit of work is a (query slot, node) or (query slot, leaf) PAIR, the pairs of the 32 slots
-// are pooled, and every phase takes 32 pairs off the pool whichever slots they belong to:
+// per issued instruction.  Here the unit of work is a (slot, node) or (slot, leaf) PAIR, the pairs of the 32 slots are pooled,
+// and every phase takes 32 pairs off a pool whichever slots they belong to:
 //   (A)  node phase     pop 32 (slot,node) entries (LIFO: depth-first per slot); drop entries whose box has fallen outside the
-//                       slot's incumbent ball; load the node, test both child boxes against the slot's point (binary32,
-//                       directed rounding, bvh.cuh::point_box_sqdist); push internal children (far first, near on top) and
-//                       record leaf children as (slot,leaf) pairs
+//                       slot's ball; load the node, test both child boxes against the slot's binary32 point (directed rounding);
+//                       push internal children (far first, near on top) and record leaf children as (slot,leaf) pairs
 //   (B1) pre-test 1     rigorous binary32 LOWER bounds of the distance of 32 (slot,leaf) pairs (tangent plane of the slot's ball,
-//                       centroid direction); pairs certainly outside the slot's ball retire, the rest carry their bound on
+//                       centroid direction) on a 48-byte binary32 copy of the triangle; pairs certainly outside the ball retire
 //   (B2) pre-test 2     approximate closest point of the triangle in binary32 (divisions, branches): a sharper lower bound, and a
 //                       rigorous UPPER bound of the distance that shrinks the slot's ball at once (atomicMin), before any binary64 work
 //   (B3) exact phase    pairs still inside the ball: the reference's Construct_projected_point_3 in binary64, then the exact
 //                       Compare_distance_3 against the slot's incumbent (all candidates in parallel, one replacement per slot and round)
 // Each stage has its own pool and runs when 32 pairs wait (or when nothing else is left), so every stage runs with (nearly) all
 // lanes busy; a pair's stored lower bound is re-checked against the slot's current ball at every hand-over for free.
-// A slot's state (point, incumbent, bounds) lives in shared memory, SoA by slot, so any lane can work for any slot.
-// Every pair counts in its slot's `outst` counter; when it drops to 0 the query is complete, its lane writes the result
-// and the slot is refilled from the batch cursor (queries are taken in coherence order).  A new query first walks down to
-// its nearest leaf on its own lane (nearest child first), pushing the far children, and projects on that leaf: that is its
-// first ball (the kd-tree hint of the reference, AABB_tree.h:591-612, is not needed).
-// The pool is a stack in shared memory whose bottom half is spilled to a per-warp area in global memory when it fills
-// and reloaded when the stack runs empty, so depth is bounded by kWpSpillCap only (overflow is reported, never silent).
+// A slot's state (point, incumbent, bounds) lives in shared memory, packed so that a stage reads it with one or two 128-bit loads.
+// When all pools are empty the batch is complete: the lanes write their slots' results and the warp takes the next 32 queries
+// from the batch cursor (queries are handed out in coherence order).  A new query first walks down to its nearest leaf on its
+// own lane (nearest child first), pushing the far children, and projects on that leaf: that is its first ball (the kd-tree hint
+// of the reference, AABB_tree.h:591-612, is not needed).
+// The node pool is a stack in shared memory whose bottom half is spilled to a per-warp area in global memory when it fills and
+// reloaded when the stack runs empty, so depth is bounded by kWpSpillCap only (overflow is reported, never silent).
+// What bounds this kernel (profiles/r1_05): the L1 data stage, one wavefront per cycle, because every lane fetches its own node /
+// triangle: hence the packed slot state, the binary32 triangle copy and no per-slot bookkeeping atomics.
 #pragma once
 #include "bvh.cuh"
 
@@ -49,26 +50,24 @@ struct WarpShared {
     uint32_t lpool[kWpLeafCap + 1];   // query slot << 27 | leaf slot : awaiting pre-test 1
     uint2 mpool[kWpMidCap];       // x = same, y = lower bound of the distance (binary32) : awaiting pre-test 2
     uint2 epool[kWpExactCap];     // same : awaiting the binary64 projection
-    float4 qa[32];                // node phase: query point rounded to binary32 (x,y,z); w = (rbound + perr)^2 rounded up
-    float4 qb[32];                // pre-test 1: direction query -> incumbent (x,y,z) and its length (w)
+    float4 qa[32];                // query point rounded to binary32 (x,y,z); w = (rbound + perr)^2 rounded up (node phase)
+    float4 qb[32];                // direction query -> incumbent (x,y,z) and its length (w)
+    float4 qc[32];                // x = rbound: pruning radius >= sqrt(widened squared distance of the eventual winner);
+                                  // y = e2 >= |error of a binary32 relative vertex| = sqrt(3) ev + perr; z = dslack >= 2 delta; w = perr >= |query - qa.xyz|
     double o[3][32];              // query point
     double bp[3][32];             // incumbent closest point
     double bsqd[32];              // its squared distance as the reference computes it
     double delta[32];             // rounding allowance of candidate points: 4e-16 * largest coordinate magnitude (bvh.cuh::traverse_closest)
-    float rbound[32];             // pruning radius: >= sqrt(widened squared distance of the eventual winner)
-    float perr[32];               // >= |query - its binary32 rounding|
-    float dslack[32];             // >= 2 delta
     uint32_t bprim[32];           // incumbent primitive id
     uint32_t qidx[32];            // the query's index in the caller's order
     uint32_t flags[32];           // B200AABB_FLAG_TIE / _EXACT
-    int outst[32];                // pairs of this slot still in a pool
-    uint32_t donemask;            // slots whose outst reached 0
 };
 
 struct WarpClosestArgs {
     const BvhNode* nodes;
     const TriRec* tris;
-    double mag;
+    const TriF* trisf;             // binary32 copy of the triangles (same order), for the pre-tests
+    double mag;                    // largest coordinate magnitude of the root box
     const uint32_t* perm;          // coherence order (slot i of the order serves query perm[i]); nullptr = identity
     unsigned long long* counters;  // as TreeRef::counters
     const double* pts;
@@ -79,20 +78,12 @@ struct WarpClosestArgs {
     uint8_t* flags;
     unsigned long long* cursor;    // next position of the batch to hand out (zeroed before the launch)
     uint2* spill;                  // gridDim.x * kWpSpillCap entries
-    int refill_min;                // refill when at least this many slots are free
     int exact_go;                  // run the exact phase when at least this many pairs wait (1..64)
     uint32_t flag_tie, flag_exact;
     const double* debug_hint_sqd;  // experiment only: a known upper bound of each query's squared distance (caller order), or nullptr
 };
 
 #if defined(__CUDACC__)
-
-__device__ __forceinline__ void wp_slot_done(WarpShared& S, unsigned owner, int delta) {
-    if (delta != 0) {
-        const int old = atomicAdd(&S.outst[owner], delta);
-        if (old + delta == 0) atomicOr(&S.donemask, 1u << owner);
-    }
-}
 
 // LOWER bound of the squared distance from the binary32 point q to the closed box (every operation rounds towards the smaller
 // result, as bvh.cuh::point_box_sqdist).  The query itself is within perr of q, so a box can only matter when this value is
@@ -106,8 +97,8 @@ __device__ __forceinline__ float wp_box_sqdist(const float* lo, const float* hi,
 
 // shrinks slot `owner`'s ball to radius rb (any lane, any time: both bounds only ever decrease)
 __device__ __forceinline__ void wp_shrink(WarpShared& S, unsigned owner, float rb) {
-    atomicMin(reinterpret_cast<unsigned*>(&S.rbound[owner]), __float_as_uint(rb));
-    const float r = __fadd_ru(rb, S.perr[owner]);
+    atomicMin(reinterpret_cast<unsigned*>(&S.qc[owner].x), __float_as_uint(rb));
+    const float r = __fadd_ru(rb, S.qc[owner].w);
     atomicMin(reinterpret_cast<unsigned*>(&S.qa[owner].w), __float_as_uint(__fmul_ru(r, r)));
 }
 
@@ -119,29 +110,34 @@ __device__ __forceinline__ void wp_set_bounds(WarpShared& S, unsigned owner, dou
     const float s = __fsqrt_ru(float_above(sqd));
     const float rb = __fsqrt_ru(float_above(sqd + ((2.0 * delta * (double)s + delta * delta) + sqd * 1e-13)));
     if (reset) {
-        S.rbound[owner] = rb;
-        const float r = __fadd_ru(rb, S.perr[owner]);
+        S.qc[owner].x = rb;
+        const float r = __fadd_ru(rb, S.qc[owner].w);
         S.qa[owner].w = __fmul_ru(r, r);
     } else wp_shrink(S, owner, rb);
     const float u0 = (float)v.x, u1 = (float)v.y, u2 = (float)v.z;
     S.qb[owner] = make_float4(u0, u1, u2, sqrtf((u0 * u0 + u1 * u1) + u2 * u2));
 }
 
-// Binary32 bounds of the distance from the query to one primitive, on coordinates RELATIVE to the query (the subtraction is done in
-// binary64; each relative coordinate is then off by <= m 2^-24, m = largest magnitude among them).
+// Binary32 bounds of the distance from the query to one primitive, on coordinates RELATIVE to the query computed from the binary32
+// triangle copy and the binary32 query point.  Each relative coordinate is off by <= m 2^-24 (the subtraction; m = largest
+// magnitude among them) + the rounding of the vertex (<= ev = 2^-24 * largest scene coordinate) + that of the query: as vectors,
+// every relative vertex is within e2 = sqrt(3) ev + perr of its true position (plus the m 2^-24 part, which wp_lower / wp_sharp
+// carry themselves), so a distance bound computed from them moves by at most e2.
 struct RelTri { float ra[3], rb[3], rc[3], m; };
-__device__ __forceinline__ RelTri wp_relative(const Tri3& t, const Vec3& o) {
+__device__ __forceinline__ RelTri wp_relative(const TriF* __restrict__ trisf, uint32_t slot, const float4& q) {
+    const float4* p = reinterpret_cast<const float4*>(trisf + slot);
+    const float4 f0 = __ldg(p), f1 = __ldg(p + 1), f2 = __ldg(p + 2);
     RelTri r;
-    r.ra[0] = (float)(t.a.x - o.x); r.ra[1] = (float)(t.a.y - o.y); r.ra[2] = (float)(t.a.z - o.z);
-    r.rb[0] = (float)(t.b.x - o.x); r.rb[1] = (float)(t.b.y - o.y); r.rb[2] = (float)(t.b.z - o.z);
-    r.rc[0] = (float)(t.c.x - o.x); r.rc[1] = (float)(t.c.y - o.y); r.rc[2] = (float)(t.c.z - o.z);
+    r.ra[0] = f0.x - q.x; r.ra[1] = f0.y - q.y; r.ra[2] = f0.z - q.z;
+    r.rb[0] = f0.w - q.x; r.rb[1] = f1.x - q.y; r.rb[2] = f1.y - q.z;
+    r.rc[0] = f1.z - q.x; r.rc[1] = f1.w - q.y; r.rc[2] = f2.x - q.z;
     r.m = fmaxf(fmaxf(fmaxf(fabsf(r.ra[0]), fabsf(r.ra[1])), fmaxf(fabsf(r.ra[2]), fabsf(r.rb[0]))),
                 fmaxf(fmaxf(fabsf(r.rb[1]), fabsf(r.rb[2])), fmaxf(fmaxf(fabsf(r.rc[0]), fabsf(r.rc[1])), fabsf(r.rc[2]))));
     return r;
 }
 // LOWER bound from a direction u (bvh.cuh::certainly_farther solved for the distance): every point x of the triangle has
 // |x| >= min_i (u.r_i)/|u|; E = 5e-7 m |u| covers the coordinate rounding and the dot products, the factor 0.999998 the rounding of
-// |u|, of its reciprocal and of the two products.  -inf when u is (numerically) zero.
+// |u|, of its reciprocal and of the two products.  -inf when u is (numerically) zero.  (Relative to the binary32 data: the caller subtracts e2.)
 __device__ __forceinline__ float wp_lower(const float* u, float su, const RelTri& r) {
     const float md = fminf(dot3f(u, r.ra), fminf(dot3f(u, r.rb), dot3f(u, r.rc)));
     return su > 1e-18f ? (md - 5e-7f * r.m * su) * __frcp_rn(su) * 0.999998f : -INFINITY;
@@ -151,13 +147,13 @@ __device__ __forceinline__ float wp_lower(const float* u, float su, const RelTri
 // triangle (vertex rounding m 2^-24 each, six binary32 operations on magnitudes <= 2 m), so dist <= |P| + 2.1e-6 m; the formula
 // allows 8e-6 m + 1e-5 |P| + dslack.  The winner's candidate is no farther than this primitive's candidate, which lies within the
 // rounding allowance of the true distance (the premise of widen_sqdist), so pruning with `hi` never discards the winner or a
-// primitive tied with it.  hi = NaN (degenerate triangle) compares false everywhere: no bound.
-__device__ __forceinline__ void wp_sharp(const RelTri& r, float dslack, float* lower, float* hi) {
+// primitive tied with it.  hi = NaN (degenerate triangle) compares false everywhere: no bound.  e2: see wp_relative.
+__device__ __forceinline__ void wp_sharp(const RelTri& r, float dslack, float e2, float* lower, float* hi) {
     float u[3];
     approx_closest_to_origin(r.ra, r.rb, r.rc, u);
     const float su = sqrtf(dot3f(u, u));
-    *lower = wp_lower(u, su, r);
-    *hi = (su * 1.00001f + 8e-6f * r.m) + dslack;
+    *lower = wp_lower(u, su, r) - e2;
+    *hi = ((su * 1.00001f + 8e-6f * r.m) + dslack) + e2;
 }
 
 // the replacement step of the reference (AABB_traits_3.h:724-732) for slot `owner`, given sg = Compare_distance_3(query, candidate,
@@ -181,12 +177,10 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
     const unsigned full = 0xFFFFFFFFu;
     const unsigned lt = (1u << lane) - 1u;
     uint2* const myspill = a.spill + (size_t)blockIdx.x * kWpSpillCap;
-    int ncnt = 0, lcnt = 0, mcnt = 0, ecnt = 0, spilled = 0;   // warp-uniform
-    unsigned free_mask = full;
-    bool more = true;
+    const float ev = float_above(a.mag * 5.9604645e-8 * 1.000001);   // >= rounding of a vertex coordinate to binary32
+    int ncnt = 0, lcnt = 0, mcnt = 0, ecnt = 0, spilled = 0;         // warp-uniform
+    unsigned active = 0;                                              // slots holding a query of the current batch
     uint32_t st_nodes = 0, st_leaves = 0, st_culled = 0, st_exact = 0, st_ties = 0;
-    if (lane == 0) S.donemask = 0;
-    __syncwarp();
 
     // moves the bottom kWpSpillChunk entries of the stack to global memory; false = spill area exhausted
     auto spill_bottom = [&]() -> bool {
@@ -206,83 +200,86 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
     };
 
     while (true) {
-        // ------------------------------------------------------------------------------------------------ refill
-        if (more) {
-            const int nfree = __popc(free_mask);
-            const bool idle = ncnt == 0 && lcnt == 0 && mcnt == 0 && ecnt == 0 && spilled == 0;
-            if (nfree >= a.refill_min || (idle && nfree > 0)) {
-                unsigned long long base = 0;
-                if (lane == 0) base = atomicAdd(a.cursor, (unsigned long long)nfree);
-                base = __shfl_sync(full, base, 0);
-                const unsigned long long pos = base + (unsigned long long)__popc(free_mask & lt);
-                const bool valid = ((free_mask >> lane) & 1u) && pos < a.n;
-                if (base + (unsigned long long)nfree >= a.n) more = false;
-                Vec3 o = {0.0, 0.0, 0.0};
-                float4 q = make_float4(0.0f, 0.0f, 0.0f, INFINITY);
-                uint32_t qi = 0;
-                if (valid) {
-                    qi = a.perm ? a.perm[pos] : (uint32_t)pos;
-                    const double* p = a.pts + 3 * (uint64_t)qi;
-                    o = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
-                    q.x = (float)o.x; q.y = (float)o.y; q.z = (float)o.z;
-                }
-                // walk down to the nearest leaf, nearest child first, pushing every far child
-                uint32_t cur = 0, firstleaf = kNone;
-                int pushed = 0;
-                bool act = valid;
-                while (__any_sync(full, act)) {
-                    if (ncnt + 32 > kWpNodeCap) {
-                        if (!spill_bottom()) { if (lane == 0) atomicOr(&a.counters[2], 1ull); return; }
-                    }
-                    uint32_t farref = 0; float fard = 0.0f; bool stop = false;
-                    if (act) {
-                        const NodeView nd = load_node(a.nodes, cur);
-                        ++st_nodes;
-                        float d0 = wp_box_sqdist(nd.lo0, nd.hi0, q), d1 = wp_box_sqdist(nd.lo1, nd.hi1, q);
-                        uint32_t c0 = nd.c0, c1 = nd.c1;
-                        if (d1 < d0) { const uint32_t tc = c0; c0 = c1; c1 = tc; const float td = d0; d0 = d1; d1 = td; }
-                        farref = c1; fard = d1;
-                        if (c0 & kLeafBit) { firstleaf = c0; stop = true; } else cur = c0;
-                    }
-                    const unsigned pm = __ballot_sync(full, act);
-                    S.npool[act ? ncnt + __popc(pm & lt) : kWpNodeCap] = make_uint2(farref, (__float_as_uint(fard) & ~31u) | lane);
-                    if (act) ++pushed;
-                    ncnt += __popc(pm);
-                    if (stop) act = false;
-                }
-                if (valid) {
-                    uint32_t id;
-                    const Tri3 t = load_tri(a.tris, firstleaf & ~kLeafBit, id);
-                    ++st_leaves;
-                    const Vec3 cpt = closest_on_triangle(t, o);
-                    const Vec3 v = cpt - o;
-                    const double sqd = (v.x * v.x + v.y * v.y) + v.z * v.z;
-                    const double ex = o.x - (double)q.x, ey = o.y - (double)q.y, ez = o.z - (double)q.z;   // exact differences
-                    S.o[0][lane] = o.x; S.o[1][lane] = o.y; S.o[2][lane] = o.z;
-                    S.qa[lane] = q;
-                    S.perr[lane] = float_above(sqrt((ex * ex + ey * ey) + ez * ez) * 1.0000001) + 1e-37f;
-                    S.bp[0][lane] = cpt.x; S.bp[1][lane] = cpt.y; S.bp[2][lane] = cpt.z;
-                    S.bprim[lane] = id; S.bsqd[lane] = sqd;
-                    S.delta[lane] = 4e-16 * fmax(a.mag, fmax3(fabs(o.x), fabs(o.y), fabs(o.z)));
-                    S.dslack[lane] = float_above(2.0 * S.delta[lane]) + 1e-37f;
-                    wp_set_bounds(S, lane, sqd, v, true);
-                    if (a.debug_hint_sqd) wp_shrink(S, lane, float_above(sqrt(widen_sqdist(a.debug_hint_sqd[qi], S.delta[lane]))));
-                    S.qidx[lane] = qi;
-                    S.flags[lane] = 0;
-                    S.outst[lane] = pushed;   // >= 1: the root is an internal node
-                }
-                free_mask &= ~__ballot_sync(full, valid);
-                __syncwarp();
-            }
-        }
-        if (free_mask == full && !more) break;
-
-        // ------------------------------------------------------------------------------------------------ phase selection
         if (ncnt == 0 && spilled > 0) {                       // reload the most recently spilled chunk
             for (int i = lane; i < kWpSpillChunk; i += 32) S.npool[i] = __ldcg(&myspill[spilled - kWpSpillChunk + i]);
             spilled -= kWpSpillChunk; ncnt = kWpSpillChunk;
             __syncwarp();
         }
+        if (ncnt == 0 && lcnt == 0 && mcnt == 0 && ecnt == 0) {
+            // -------------------------------------------------------------------------------------------- batch complete: results out, next 32 queries in
+            if ((active >> lane) & 1u) {
+                const uint64_t qi = S.qidx[lane];
+                const uint32_t fl = S.flags[lane];
+                if (a.cp) { a.cp[3 * qi] = S.bp[0][lane]; a.cp[3 * qi + 1] = S.bp[1][lane]; a.cp[3 * qi + 2] = S.bp[2][lane]; }
+                if (a.prim) a.prim[qi] = S.bprim[lane];
+                if (a.sqd) a.sqd[qi] = S.bsqd[lane];
+                if (a.flags) a.flags[qi] = (uint8_t)fl;
+                if (fl & a.flag_tie) ++st_ties;
+                if (fl & a.flag_exact) ++st_exact;
+            }
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(a.cursor, 32ull);
+            base = __shfl_sync(full, base, 0);
+            if (base >= a.n) break;
+            const unsigned long long pos = base + lane;
+            const bool valid = pos < a.n;
+            Vec3 o = {0.0, 0.0, 0.0};
+            float4 q = make_float4(0.0f, 0.0f, 0.0f, INFINITY);
+            uint32_t qi = 0;
+            if (valid) {
+                qi = a.perm ? a.perm[pos] : (uint32_t)pos;
+                const double* p = a.pts + 3 * (uint64_t)qi;
+                o = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+                q.x = (float)o.x; q.y = (float)o.y; q.z = (float)o.z;
+            }
+            // walk down to the nearest leaf, nearest child first, pushing every far child
+            uint32_t cur = 0, firstleaf = kNone;
+            bool act = valid;
+            while (__any_sync(full, act)) {
+                if (ncnt + 32 > kWpNodeCap) {
+                    if (!spill_bottom()) { if (lane == 0) atomicOr(&a.counters[2], 1ull); return; }
+                }
+                uint32_t farref = 0; float fard = 0.0f; bool stop = false;
+                if (act) {
+                    const NodeView nd = load_node(a.nodes, cur);
+                    ++st_nodes;
+                    float d0 = wp_box_sqdist(nd.lo0, nd.hi0, q), d1 = wp_box_sqdist(nd.lo1, nd.hi1, q);
+                    uint32_t c0 = nd.c0, c1 = nd.c1;
+                    if (d1 < d0) { const uint32_t tc = c0; c0 = c1; c1 = tc; const float td = d0; d0 = d1; d1 = td; }
+                    farref = c1; fard = d1;
+                    if (c0 & kLeafBit) { firstleaf = c0; stop = true; } else cur = c0;
+                }
+                const unsigned pm = __ballot_sync(full, act);
+                S.npool[act ? ncnt + __popc(pm & lt) : kWpNodeCap] = make_uint2(farref, (__float_as_uint(fard) & ~31u) | lane);
+                ncnt += __popc(pm);
+                if (stop) act = false;
+            }
+            if (valid) {
+                uint32_t id;
+                const Tri3 t = load_tri(a.tris, firstleaf & ~kLeafBit, id);
+                ++st_leaves;
+                const Vec3 cpt = closest_on_triangle(t, o);
+                const Vec3 v = cpt - o;
+                const double sqd = (v.x * v.x + v.y * v.y) + v.z * v.z;
+                const double ex = o.x - (double)q.x, ey = o.y - (double)q.y, ez = o.z - (double)q.z;   // exact differences
+                const float perr = float_above(sqrt((ex * ex + ey * ey) + ez * ez) * 1.0000001) + 1e-37f;
+                const double delta = 4e-16 * fmax(a.mag, fmax3(fabs(o.x), fabs(o.y), fabs(o.z)));
+                S.o[0][lane] = o.x; S.o[1][lane] = o.y; S.o[2][lane] = o.z;
+                S.qa[lane] = q;
+                S.qc[lane] = make_float4(INFINITY, __fadd_ru(__fmul_ru(1.7320509f, ev), perr), float_above(2.0 * delta) + 1e-37f, perr);
+                S.bp[0][lane] = cpt.x; S.bp[1][lane] = cpt.y; S.bp[2][lane] = cpt.z;
+                S.bprim[lane] = id; S.bsqd[lane] = sqd;
+                S.delta[lane] = delta;
+                wp_set_bounds(S, lane, sqd, v, true);
+                if (a.debug_hint_sqd) wp_shrink(S, lane, float_above(sqrt(widen_sqdist(a.debug_hint_sqd[qi], delta))));
+                S.qidx[lane] = qi;
+                S.flags[lane] = 0;
+            }
+            active = __ballot_sync(full, valid);
+            __syncwarp();
+            continue;
+        }
+        // ------------------------------------------------------------------------------------------------ phase selection
         int phase;                                            // 0 = nodes, 1 = pre-test 1, 2 = pre-test 2, 3 = exact
         if (ecnt >= a.exact_go) phase = 3;
         else if (mcnt >= 32) phase = 2;
@@ -290,8 +287,7 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
         else if (ncnt > 0) phase = 0;
         else if (lcnt > 0) phase = 1;
         else if (mcnt > 0) phase = 2;
-        else if (ecnt > 0) phase = 3;
-        else { if (lane == 0) atomicOr(&a.counters[2], 2ull); return; }   // a busy slot without work: cannot happen; never spin
+        else phase = 3;
 
         if (phase == 0) {
             // -------------------------------------------------------------------------------------------- (A) node phase
@@ -309,7 +305,6 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                 __syncwarp();                                      // all pops read before any push overwrites them
                 const bool popped_leaf = live && (e.x & kLeafBit);
                 const bool expand = live && !(e.x & kLeafBit);
-                int delta = has && !popped_leaf ? -1 : 0;          // (a popped leaf entry just moves from the node pool to the leaf pool)
                 bool in0 = false, in1 = false;                     // 0 = nearer child, 1 = farther child
                 uint32_t r0 = 0, r1 = 0;
                 float d0 = 0.0f, d1 = 0.0f;
@@ -320,7 +315,6 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                     r0 = nd.c0; r1 = nd.c1;
                     if (d1 < d0) { const uint32_t tc = r0; r0 = r1; r1 = tc; const float td = d0; d0 = d1; d1 = td; }
                     in0 = d0 <= q.w; in1 = d1 <= q.w;
-                    delta += (in0 ? 1 : 0) + (in1 ? 1 : 0);
                 }
                 // leaf pairs: a popped leaf entry or the nearer child, then the farther child (masked lanes write the sink entry)
                 {
@@ -345,9 +339,8 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                     S.npool[p0 ? ncnt + __popc(m0 & lt) : kWpNodeCap] = make_uint2(r0, (__float_as_uint(d0) & ~31u) | owner);
                     ncnt += __popc(m0);
                 }
-                wp_slot_done(S, owner, delta);
                 __syncwarp();
-            } while (ncnt > 0 && lcnt < 32 && *(volatile uint32_t*)&S.donemask == 0);
+            } while (ncnt > 0 && lcnt < 32);
         } else if (phase == 1) {
             // -------------------------------------------------------------------------------------------- (B1) pre-test 1: two cheap directions
             for (int base = 0; base < lcnt; base += 32) {
@@ -358,16 +351,14 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                 if (i < lcnt) {
                     pair = S.lpool[i];
                     const unsigned owner = pair >> 27;
-                    uint32_t id;
-                    const Tri3 t = load_tri(a.tris, pair & kWpRefMask, id);
                     ++st_leaves;
-                    const Vec3 o = {S.o[0][owner], S.o[1][owner], S.o[2][owner]};
-                    const RelTri r = wp_relative(t, o);
+                    const RelTri r = wp_relative(a.trisf, pair & kWpRefMask, S.qa[owner]);
                     const float4 qb = S.qb[owner];
+                    const float4 qc = S.qc[owner];
                     const float ub[3] = {qb.x, qb.y, qb.z};
                     const float g[3] = {(r.ra[0] + r.rb[0]) + r.rc[0], (r.ra[1] + r.rb[1]) + r.rc[1], (r.ra[2] + r.rb[2]) + r.rc[2]};
-                    lb = fmaxf(wp_lower(ub, qb.w, r), wp_lower(g, sqrtf(dot3f(g, g)), r));   // tangent plane of the ball; centroid direction
-                    if (lb > S.rbound[owner]) { ++st_culled; wp_slot_done(S, owner, -1); }
+                    lb = fmaxf(wp_lower(ub, qb.w, r), wp_lower(g, sqrtf(dot3f(g, g)), r)) - qc.y;   // tangent plane of the ball; centroid direction
+                    if (lb > qc.x) ++st_culled;
                     else survive = true;
                 }
                 const unsigned sm = __ballot_sync(full, survive);
@@ -384,18 +375,15 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                 if (i < mcnt) {
                     e = S.mpool[i];
                     const unsigned owner = e.x >> 27;
-                    const float rbound = S.rbound[owner];
-                    if (__uint_as_float(e.y) > rbound) { ++st_culled; wp_slot_done(S, owner, -1); }   // the ball has shrunk since pre-test 1
+                    const float4 qc = S.qc[owner];
+                    if (__uint_as_float(e.y) > qc.x) ++st_culled;   // the ball has shrunk since pre-test 1
                     else {
-                        uint32_t id;
-                        const Tri3 t = load_tri(a.tris, e.x & kWpRefMask, id);
-                        const Vec3 o = {S.o[0][owner], S.o[1][owner], S.o[2][owner]};
-                        const RelTri r = wp_relative(t, o);
+                        const RelTri r = wp_relative(a.trisf, e.x & kWpRefMask, S.qa[owner]);
                         float lb, hi;
-                        wp_sharp(r, S.dslack[owner], &lb, &hi);
-                        if (hi < rbound) wp_shrink(S, owner, hi);   // this primitive is certainly nearer than the slot's ball: shrink it now, in binary32
+                        wp_sharp(r, qc.z, qc.y, &lb, &hi);
+                        if (hi < qc.x) wp_shrink(S, owner, hi);   // this primitive is certainly nearer than the slot's ball: shrink it now, in binary32
                         lb = fmaxf(lb, __uint_as_float(e.y));
-                        if (lb > rbound) { ++st_culled; wp_slot_done(S, owner, -1); }
+                        if (lb > qc.x) ++st_culled;
                         else { survive = true; e.y = __float_as_uint(lb); }
                     }
                 }
@@ -415,8 +403,8 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                 if (i < ecnt) {
                     e = S.epool[i];
                     const unsigned owner = e.x >> 27;
-                    keep = !(__uint_as_float(e.y) > S.rbound[owner]);
-                    if (!keep) { ++st_culled; wp_slot_done(S, owner, -1); }
+                    keep = !(__uint_as_float(e.y) > S.qc[owner].x);
+                    if (!keep) ++st_culled;
                 }
                 __syncwarp();
                 const unsigned km = __ballot_sync(full, keep);
@@ -438,7 +426,7 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                     if (has) {
                         const uint2 e = S.epool[i];
                         owner = e.x >> 27;
-                        if (__uint_as_float(e.y) > S.rbound[owner]) ++st_culled;   // (an earlier batch of this very phase may have shrunk the ball)
+                        if (__uint_as_float(e.y) > S.qc[owner].x) ++st_culled;   // (an earlier batch of this very phase may have shrunk the ball)
                         else {
                             const Tri3 t = load_tri(a.tris, e.x & kWpRefMask, id);
                             o = {S.o[0][owner], S.o[1][owner], S.o[2][owner]};
@@ -474,30 +462,11 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                         __syncwarp();
                         pm = __ballot_sync(full, pending);
                     }
-                    if (has) wp_slot_done(S, owner, -1);
                 }
                 ecnt = 0;
             }
         }
-        // ------------------------------------------------------------------------------------------------ completed queries
         __syncwarp();
-        const unsigned done = *(volatile uint32_t*)&S.donemask;
-        if (done) {
-            __syncwarp();
-            if (lane == 0) S.donemask = 0;
-            if ((done >> lane) & 1u) {
-                const uint64_t qi = S.qidx[lane];
-                const uint32_t fl = S.flags[lane];
-                if (a.cp) { a.cp[3 * qi] = S.bp[0][lane]; a.cp[3 * qi + 1] = S.bp[1][lane]; a.cp[3 * qi + 2] = S.bp[2][lane]; }
-                if (a.prim) a.prim[qi] = S.bprim[lane];
-                if (a.sqd) a.sqd[qi] = S.bsqd[lane];
-                if (a.flags) a.flags[qi] = (uint8_t)fl;
-                if (fl & a.flag_tie) ++st_ties;
-                if (fl & a.flag_exact) ++st_exact;
-            }
-            free_mask |= done;
-            __syncwarp();
-        }
     }
     const unsigned nodes = __reduce_add_sync(full, st_nodes), leaves = __reduce_add_sync(full, st_leaves), culled = __reduce_add_sync(full, st_culled);
     const unsigned exact = __reduce_add_sync(full, st_exact), ties = __reduce_add_sync(full, st_ties);

@@ -19,7 +19,7 @@ def main():
     ap.add_argument("--ny", type=int, default=2048)
     ap.add_argument("--points", type=int, default=1 << 23)
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--sweep", default="16:24,8:24,32:24,16:8,16:48,4:16,24:32")
+    ap.add_argument("--sweep", default="32,64,16")
     ap.add_argument("--skip-old", action="store_true")
     ap.add_argument("--two-pass", action="store_true", help="experiment: second pass starts from the first pass's distances (perfect initial bound); ms = last_query_ms of pass 2")
     args = ap.parse_args()
@@ -64,10 +64,8 @@ def main():
     if args.two_pass:
         g.set_option(100, 1)
     for item in args.sweep.split(","):
-        r, s = [int(x) for x in item.split(":")]
-        g.set_option(B.OPT_WARP_REFILL, r)
-        g.set_option(B.OPT_WARP_SURV_GO, s)
-        got, fl = run("warp refill=%d surv_go=%d" % (r, s))
+        g.set_option(B.OPT_WARP_EXACT_GO, int(item))
+        got, fl = run("warp exact_go=%d" % int(item))
         if ref is None:
             ref, ref_fl = got, fl
         else:

@@ -70,13 +70,15 @@ def test_gpu_built_tree_equals_host_emulation(B, meshes, name):
     v, f = meshes[name]
     t = B.AABB_tree(v, f)
     t.build()
-    (pn, bn), (pt, bt), (pb, bb) = t.export_layout()
+    (pn, bn), (pt, bt), (pb, bb), (pf, bf) = t.export_layout()
     n = len(f)
-    assert bn == (n - 1) * 64 and bt == n * 96 and bb == 48
+    assert bn == (n - 1) * 64 and bt == n * 96 and bb == 48 and bf == n * 48
     g_nodes, g_tris = device_to_host(pn, bn), device_to_host(pt, bt)
     assert hc.validate(g_nodes, g_tris, n) == 0
     h_nodes, h_tris, h_bbox = hc.HostTree(soup_of(v, f)).export()
     np.testing.assert_array_equal(g_tris, h_tris)
+    want_f = g_tris.view(np.float64).reshape(-1, 12)[:, :9].astype(np.float32)     # binary32 copies: round to nearest
+    np.testing.assert_array_equal(device_to_host(pf, bf).view(np.float32).reshape(-1, 12)[:, :9], want_f)
     gw, hw = g_nodes.view(np.uint32).reshape(-1, 16), h_nodes.view(np.uint32).reshape(-1, 16)
     cols = list(range(0, 15))                   # boxes, children, parent (not the refit arrival counter)
     np.testing.assert_array_equal(gw[:, cols], hw[:, cols])
@@ -90,7 +92,7 @@ def test_large_random_soup_tree_is_valid(B):
     soup = W.triangle_soup(n)
     t = B.AABB_tree(triangles=soup)
     t.build()
-    (pn, bn), (pt, bt), _ = t.export_layout()
+    (pn, bn), (pt, bt) = t.export_layout()[:2]
     g_nodes, g_tris = device_to_host(pn, bn), device_to_host(pt, bt)
     assert hc.validate(g_nodes, g_tris, n) == 0
     ids = g_tris.view(np.uint32).reshape(-1, 24)[:, 18]
@@ -100,7 +102,7 @@ def test_large_random_soup_tree_is_valid(B):
     dup = np.tile(soup[:4], (50_000, 1))
     t2 = B.AABB_tree(triangles=dup)
     t2.build()
-    (pn, bn), (pt, bt), _ = t2.export_layout()
+    (pn, bn), (pt, bt) = t2.export_layout()[:2]
     assert hc.validate(device_to_host(pn, bn), device_to_host(pt, bt), len(dup)) == 0
 
 
@@ -140,8 +142,8 @@ def test_config2_icosphere_distance_field_parity(B):
     assert np.all(np.abs(r - np.abs(np.linalg.norm(pts, axis=1) - 1)) < 2e-3)  # unsigned distance field of a sphere
 
 
-@pytest.mark.parametrize("refill,surv_go,sort", [(16, 24, 1), (1, 1, 1), (32, 64, 0), (8, 16, 1)])
-def test_closest_point_kernels_agree(B, refill, surv_go, sort):
+@pytest.mark.parametrize("exact_go,sort", [(32, 1), (1, 1), (64, 0), (16, 1)])
+def test_closest_point_kernels_agree(B, exact_go, sort):
     """the warp-cooperative work-pool kernel (closest_warp.cuh) and the thread-per-query kernel (bvh.cuh) return identical
     records, whatever the pool scheduling parameters and the query order; both equal the oracle"""
     from cgal_b200 import workloads as W
@@ -154,8 +156,7 @@ def test_closest_point_kernels_agree(B, refill, surv_go, sort):
     g.set_option(B.OPT_CLOSEST_KERNEL, 0)
     ref = g.closest_point_and_primitive(pts)
     g.set_option(B.OPT_CLOSEST_KERNEL, 1)
-    g.set_option(B.OPT_WARP_REFILL, refill)
-    g.set_option(B.OPT_WARP_SURV_GO, surv_go)
+    g.set_option(B.OPT_WARP_EXACT_GO, exact_go)
     got = g.closest_point_and_primitive(pts)
     st = g.stats()
     assert st["nodes_visited"] > 0 and st["leaves_tested"] > 0
