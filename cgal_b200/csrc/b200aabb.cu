@@ -194,7 +194,6 @@ struct b200aabb_tree {
     bool built = false;
     BvhNode* d_nodes = nullptr;
     TriRec* d_tris = nullptr;
-    WideNode* d_wide = nullptr;    // 4-wide nodes with 8-bit child boxes (node phase of the warp-cooperative closest_point kernel)
     TriF* d_trisf = nullptr;       // binary32 copies (pre-tests of the warp-cooperative closest_point kernel)
     double* d_rootbox = nullptr;   // 6 doubles
     uint32_t root = kNone;
@@ -237,8 +236,8 @@ constexpr uint64_t kChunk = 1ull << 22;   // queries per pipeline slot for HOST-
 int fail(b200aabb_tree* t, int code, const char* msg) { if (t) t->err = msg; return code; }
 
 void free_tree_buffers(b200aabb_tree* t) {
-    cudaFree(t->d_nodes); cudaFree(t->d_tris); cudaFree(t->d_trisf); cudaFree(t->d_wide);
-    t->d_nodes = nullptr; t->d_tris = nullptr; t->d_trisf = nullptr; t->d_wide = nullptr; t->built = false; t->root = kNone;
+    cudaFree(t->d_nodes); cudaFree(t->d_tris); cudaFree(t->d_trisf);
+    t->d_nodes = nullptr; t->d_tris = nullptr; t->d_trisf = nullptr; t->built = false; t->root = kNone;
 }
 void free_input(b200aabb_tree* t) { cudaFree(t->d_soup); cudaFree(t->d_ids); t->d_soup = nullptr; t->d_ids = nullptr; }
 
@@ -333,7 +332,6 @@ int do_build(b200aabb_tree* t) {
     B2_TRY(cudaMalloc(&t->d_nodes, std::max<uint64_t>(n - 1, 1) * sizeof(BvhNode)));
     B2_TRY(cudaMalloc(&t->d_tris, n * sizeof(TriRec)));
     B2_TRY(cudaMalloc(&t->d_trisf, n * sizeof(TriF)));
-    B2_TRY(cudaMalloc(&t->d_wide, std::max<uint64_t>(n - 1, 1) * sizeof(WideNode)));
     B2_TRY(cudaEventRecord(t->ev_a, st));
     B2_TRY(cudaMemsetAsync(bounds, 0xFF, 3 * 8, st));
     B2_TRY(cudaMemsetAsync(bounds + 3, 0x00, 3 * 8, st));
@@ -349,7 +347,6 @@ int do_build(b200aabb_tree* t) {
         t->stats.kernel_launches += 1;
     }
     refit_kernel<<<blocks, 256, 0, st>>>(t->d_tris, n, t->d_nodes, leaf_parent);
-    if (n > 1) { widen_kernel<<<(unsigned)((n - 1 + 255) / 256), 256, 0, st>>>(t->d_nodes, n - 1, t->d_wide); t->stats.kernel_launches += 1; }
     root_box_kernel<<<1, 32, 0, st>>>(bounds, t->d_rootbox);
     t->stats.kernel_launches += 2;
     B2_TRY(cudaEventRecord(t->ev_b, st));
@@ -651,7 +648,7 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
                          const int slot = (space == B200AABB_HOST && st == t->pipe[1]) ? 1 : 0;
                          cudaMemsetAsync(t->warp[slot].cursor, 0, sizeof(unsigned long long), st);
                          WarpClosestArgs a;
-                         a.wide = t->d_wide; a.tris = t->d_tris; a.trisf = t->d_trisf; a.mag = t->mag; a.perm = perm; a.counters = t->d_counters;
+                         a.nodes = t->d_nodes; a.tris = t->d_tris; a.trisf = t->d_trisf; a.mag = t->mag; a.perm = perm; a.counters = t->d_counters;
                          a.pts = (const double*)in; a.n = cnt; a.cp = (double*)o[0]; a.prim = (uint32_t*)o[1]; a.sqd = (double*)o[2]; a.flags = (uint8_t*)o[3];
                          a.cursor = t->warp[slot].cursor; a.spill = t->warp[slot].spill;
                          a.exact_go = t->opt_warp_exact_go;
@@ -673,15 +670,14 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
 }
 
 int b200aabb_export_layout(b200aabb_tree* t, void** ptrs, uint64_t* bytes, int cap, int* count) {
-    if (!t || !ptrs || !bytes || !count || cap < 5) return B200AABB_ERR_INVALID_ARGUMENT;
+    if (!t || !ptrs || !bytes || !count || cap < 4) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc) return rc;
     ptrs[0] = t->d_nodes; bytes[0] = t->n > 1 ? (t->n - 1) * sizeof(BvhNode) : 0;
     ptrs[1] = t->d_tris; bytes[1] = t->n * sizeof(TriRec);
     ptrs[2] = t->d_rootbox; bytes[2] = 48;
     ptrs[3] = t->d_trisf; bytes[3] = t->n * sizeof(TriF);
-    ptrs[4] = t->d_wide; bytes[4] = t->n > 1 ? (t->n - 1) * sizeof(WideNode) : 0;
-    *count = 5;
+    *count = 4;
     return B200AABB_OK;
 }
 
@@ -693,7 +689,6 @@ int b200aabb_import_alloc(b200aabb_tree* t, uint64_t n) {
     B2_CUDA(t, cudaMalloc(&t->d_nodes, std::max<uint64_t>(n - 1, 1) * sizeof(BvhNode)));
     B2_CUDA(t, cudaMalloc(&t->d_tris, n * sizeof(TriRec)));
     B2_CUDA(t, cudaMalloc(&t->d_trisf, n * sizeof(TriF)));
-    B2_CUDA(t, cudaMalloc(&t->d_wide, std::max<uint64_t>(n - 1, 1) * sizeof(WideNode)));
     t->n = n; t->root = n == 1 ? (kLeafBit | 0u) : 0u; t->built = true;
     return B200AABB_OK;
 }

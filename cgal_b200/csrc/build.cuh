@@ -9,7 +9,6 @@
 //   refit_kernel         bottom-up boxes with one atomic arrival counter per node.  A primitive's exact binary64 box is
 //                        rounded OUTWARD to binary32 once; min/max are exact and commute with the monotone rounding, so
 //                        every node box is bit-equal to the outward rounding of the exact union of its primitives' boxes
-//   widen_kernel         4-wide nodes with 8-bit child boxes (WideNode) from the refitted binary nodes, one thread per node
 #pragma once
 #include "bvh.cuh"
 
@@ -212,54 +211,6 @@ __global__ void __launch_bounds__(256) refit_kernel(const TriRec* __restrict__ t
         p = nd->parent;
         if (p == kNone) return;
     }
-}
-
-// WideNode i from binary node i and its internal children (bvh.cuh).  Every binary node gets one; the traversal only follows the
-// ones at even depth below the root (leaf children shorten a branch, so "even" is per path).
-__global__ void __launch_bounds__(256) widen_kernel(const BvhNode* __restrict__ nodes, uint64_t n_internal, WideNode* __restrict__ wide) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_internal) return;
-    const NodeView nd = load_node(nodes, (uint32_t)i);
-    float lo[4][3], hi[4][3];
-    uint32_t ref[4] = {kNone, kNone, kNone, kNone};
-    int ns = 0;
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-        const uint32_t c = side ? nd.c1 : nd.c0;
-        if (c & kLeafBit) {
-            for (int a = 0; a < 3; ++a) { lo[ns][a] = side ? nd.lo1[a] : nd.lo0[a]; hi[ns][a] = side ? nd.hi1[a] : nd.hi0[a]; }
-            ref[ns++] = c;
-        } else {
-            const NodeView ch = load_node(nodes, c);
-            for (int a = 0; a < 3; ++a) { lo[ns][a] = ch.lo0[a]; hi[ns][a] = ch.hi0[a]; lo[ns + 1][a] = ch.lo1[a]; hi[ns + 1][a] = ch.hi1[a]; }
-            ref[ns] = ch.c0; ref[ns + 1] = ch.c1;
-            ns += 2;
-        }
-    }
-    WideNode w;
-    w.nslots = (uint8_t)ns;
-    w.pad[0] = w.pad[1] = 0;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const float o = fminf(nd.lo0[a], nd.lo1[a]);                                   // = min over the slots
-        const float ext = __fsub_ru(fmaxf(nd.hi0[a], nd.hi1[a]), o);
-        const uint32_t bits = __float_as_uint(__fdiv_ru(ext, 255.0f));
-        uint32_t e = (bits >> 23) + ((bits & 0x7FFFFFu) ? 1u : 0u);                   // ceil to a power of two
-        e = e < 1u ? 1u : (e > 255u ? 255u : e);                                        // 255 (infinite / NaN extent): the node is marked unbounded, all slots pass
-        const double step = (double)__uint_as_float(e << 23);
-        w.origin[a] = o; w.exp[a] = (uint8_t)e;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (k < ns) {
-                const double ql = floor(((double)lo[k][a] - (double)o) / step), qh = ceil(((double)hi[k][a] - (double)o) / step);
-                w.qlo[a][k] = (uint8_t)fmin(fmax(ql, 0.0), 255.0);
-                w.qhi[a][k] = (uint8_t)fmin(fmax(qh, 0.0), 255.0);
-            } else { w.qlo[a][k] = 255; w.qhi[a][k] = 0; }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) w.child[k] = ref[k];
-    wide[i] = w;
 }
 
 }  // namespace b2

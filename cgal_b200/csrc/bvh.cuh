@@ -6,7 +6,6 @@
 //                   costs two 32-byte sectors and leaf boxes never need their own node.  N-1 nodes for N primitives.
 //   TriRec    96 B  one primitive in Morton order: 9 binary64 coordinates (v0,v1,v2), the primitive id, padding to 3 sectors.
 //   TriF      48 B  the same primitive rounded to binary32 (pre-tests of closest_warp.cuh only; never decides a result).
-//   WideNode  64 B  4-wide collapse of the binary tree with 8-bit child boxes (node phase of closest_warp.cuh).
 // Child reference: bit 31 set = leaf, low bits = slot in the TriRec array; else index of an internal node.
 //
 // Traversal replaces (paths relative to the CGAL source root)
@@ -51,22 +50,6 @@ struct __align__(16) TriF {
     uint32_t pad[3];
 };
 static_assert(sizeof(TriF) == 48, "binary32 triangle record is three 16-byte words");
-
-// 4-wide node with 8-bit child boxes, 64 B (distance queries, closest_warp.cuh).  WideNode i collapses binary node i with its two
-// children: its slots are the (up to four) grandchildren, a leaf child keeping its own slot.  Child boxes are stored on the node's own
-// grid: origin = low corner of node i's box, per-axis step 2^(e-127) >= extent/255 (e = biased binary32 exponent byte), so that
-//   lo_k = origin + qlo_k * step (rounded down)  <=  true lo_k      and      hi_k = origin + qhi_k * step (rounded up)  >=  true hi_k
-// (q * step is exact; the build takes floor / ceil of exact quotients).  A slot reference is a binary node index (whose WideNode is
-// followed next), kLeafBit | leaf slot, or kNone for an unused slot.
-struct __align__(16) WideNode {
-    float origin[3];
-    uint8_t exp[3], nslots;
-    uint32_t child[4];
-    uint8_t qlo[3][4];             // [axis][slot]
-    uint8_t qhi[3][4];
-    uint32_t pad[2];
-};
-static_assert(sizeof(WideNode) == 64, "wide node is two 32-byte sectors");
 
 // per-query traversal statistics (accumulated into the handle's counters by the kernels)
 struct TravStat { int nexact = 0; int overflow = 0; uint32_t nodes = 0, leaves = 0, culled = 0; };   // culled: leaves rejected by the binary32 pre-test

@@ -11,9 +11,8 @@
 // per issued instruction.  Here the unit of work is a (slot, node) or (slot, leaf) PAIR, the pairs of the 32 slots are pooled,
 // and every phase takes 32 pairs off a pool whichever slots they belong to:
 //   (A)  node phase     pop 32 (slot,node) entries (LIFO: depth-first per slot); drop entries whose box has fallen outside the
-//                       slot's ball; load the 4-wide node (64 B, 8-bit child boxes), test its four child boxes against the slot's
-//                       binary32 point (directed rounding); push internal children (farthest first, nearest on top) and record
-//                       leaf children as (slot,leaf) pairs
+//                       slot's ball; load the node, test both child boxes against the slot's binary32 point (directed rounding);
+//                       push internal children (far first, near on top) and record leaf children as (slot,leaf) pairs
 //   (B1) pre-test 1     rigorous binary32 LOWER bounds of the distance of 32 (slot,leaf) pairs (tangent plane of the slot's ball,
 //                       centroid direction) on a 48-byte binary32 copy of the triangle; pairs certainly outside the ball retire
 //   (B2) pre-test 2     approximate closest point of the triangle in binary32 (divisions, branches): a sharper lower bound, and a
@@ -39,10 +38,9 @@ namespace b2 {
 constexpr int kWpNodeCap = 512;                 // (slot,node) entries held in shared memory
 constexpr int kWpSpillChunk = kWpNodeCap / 2;   // entries moved per spill / reload
 constexpr int kWpSpillCap = 16 * kWpSpillChunk; // entries per warp in the global spill area
-constexpr int kWpLeafCap = 160;                 // < 32 waiting + at most 128 added by one node-phase step
-constexpr int kWpMidCap = 192;                  // < 32 waiting + at most 159 added by one pre-test-1 phase
-constexpr int kWpExactCap = 256;                // < exact_go (<= 64) waiting + at most 190 added by one pre-test-2 phase
-constexpr int kWpNodeRoom = 96;                 // a node-phase step pops t <= 32 entries and pushes at most 4 t
+constexpr int kWpLeafCap = 96;                  // < 32 waiting + at most 64 added by one node phase
+constexpr int kWpMidCap = 128;                  // < 32 waiting + at most 95 added by one pre-test-1 phase
+constexpr int kWpExactCap = 192;                // < exact_go (<= 64) waiting + at most 126 added by one pre-test-2 phase
 constexpr uint32_t kWpRefMask = 0x07FFFFFFu;    // 27 bits of leaf slot next to the 5-bit query slot
 constexpr uint64_t kWpMaxPrims = 1ull << 27;
 
@@ -66,7 +64,7 @@ struct WarpShared {
 };
 
 struct WarpClosestArgs {
-    const WideNode* wide;          // 4-wide nodes (bvh.cuh); the root is wide[0]
+    const BvhNode* nodes;
     const TriRec* tris;
     const TriF* trisf;             // binary32 copy of the triangles (same order), for the pre-tests
     double mag;                    // largest coordinate magnitude of the root box
@@ -95,29 +93,6 @@ __device__ __forceinline__ float wp_box_sqdist(const float* lo, const float* hi,
     const float dy = fmaxf(fmaxf(__fsub_rd(lo[1], q.y), __fsub_rd(q.y, hi[1])), 0.0f);
     const float dz = fmaxf(fmaxf(__fsub_rd(lo[2], q.z), __fsub_rd(q.z, hi[2])), 0.0f);
     return __fadd_rd(__fadd_rd(__fmul_rd(dx, dx), __fmul_rd(dy, dy)), __fmul_rd(dz, dz));
-}
-
-// One step of the node phase for one lane: loads WideNode `idx`, decodes its four child boxes (conservatively, see bvh.cuh) and returns
-// the lower bounds d[k] of their squared distances from the binary32 query point q, and the slot references r[k] (kNone = unused).
-__device__ __forceinline__ void wp_wide_dists(const WideNode* __restrict__ wide, uint32_t idx, const float4& q, float* d, uint32_t* r) {
-    const uint4* p = reinterpret_cast<const uint4*>(wide + idx);
-    const uint4 w0 = __ldg(p), w1 = __ldg(p + 1), w2 = __ldg(p + 2), w3 = __ldg(p + 3);
-    const float ox = __uint_as_float(w0.x), oy = __uint_as_float(w0.y), oz = __uint_as_float(w0.z);
-    const float sx = __uint_as_float((w0.w & 0xFFu) << 23), sy = __uint_as_float((w0.w & 0xFF00u) << 15), sz = __uint_as_float((w0.w & 0xFF0000u) << 7);
-    const bool unbounded = (w0.w & 0xFFu) == 0xFFu || (w0.w & 0xFF00u) == 0xFF00u || (w0.w & 0xFF0000u) == 0xFF0000u;
-    r[0] = w1.x; r[1] = w1.y; r[2] = w1.z; r[3] = w1.w;
-    // byte k of a word as a float: 0x4B000000 | byte = 2^23 + byte exactly
-#define B2_QF(word, k) (__uint_as_float(__byte_perm((word), 0x4B000000u, 0x7540u + (k))) - 8388608.0f)
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float lox = __fmaf_rd(B2_QF(w2.x, k), sx, ox), loy = __fmaf_rd(B2_QF(w2.y, k), sy, oy), loz = __fmaf_rd(B2_QF(w2.z, k), sz, oz);
-        const float hix = __fmaf_ru(B2_QF(w2.w, k), sx, ox), hiy = __fmaf_ru(B2_QF(w3.x, k), sy, oy), hiz = __fmaf_ru(B2_QF(w3.y, k), sz, oz);
-        const float dx = fmaxf(fmaxf(__fsub_rd(lox, q.x), __fsub_rd(q.x, hix)), 0.0f);
-        const float dy = fmaxf(fmaxf(__fsub_rd(loy, q.y), __fsub_rd(q.y, hiy)), 0.0f);
-        const float dz = fmaxf(fmaxf(__fsub_rd(loz, q.z), __fsub_rd(q.z, hiz)), 0.0f);
-        d[k] = unbounded ? 0.0f : __fadd_rd(__fadd_rd(__fmul_rd(dx, dx), __fmul_rd(dy, dy)), __fmul_rd(dz, dz));
-    }
-#undef B2_QF
 }
 
 // shrinks slot `owner`'s ball to radius rb (any lane, any time: both bounds only ever decrease)
@@ -257,34 +232,27 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                 o = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
                 q.x = (float)o.x; q.y = (float)o.y; q.z = (float)o.z;
             }
-            // walk down to the nearest leaf, nearest slot first, pushing the other slots
+            // walk down to the nearest leaf, nearest child first, pushing every far child
             uint32_t cur = 0, firstleaf = kNone;
             bool act = valid;
             while (__any_sync(full, act)) {
-                if (ncnt + kWpNodeRoom > kWpNodeCap) {
+                if (ncnt + 32 > kWpNodeCap) {
                     if (!spill_bottom()) { if (lane == 0) atomicOr(&a.counters[2], 1ull); return; }
                 }
-                float d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                uint32_t r[4] = {kNone, kNone, kNone, kNone};
-                int kmin = -1;
+                uint32_t farref = 0; float fard = 0.0f; bool stop = false;
                 if (act) {
-                    wp_wide_dists(a.wide, cur, q, d, r);
+                    const NodeView nd = load_node(a.nodes, cur);
                     ++st_nodes;
-                    float dmin = INFINITY;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) if (r[k] != kNone && (kmin < 0 || d[k] < dmin)) { kmin = k; dmin = d[k]; }
+                    float d0 = wp_box_sqdist(nd.lo0, nd.hi0, q), d1 = wp_box_sqdist(nd.lo1, nd.hi1, q);
+                    uint32_t c0 = nd.c0, c1 = nd.c1;
+                    if (d1 < d0) { const uint32_t tc = c0; c0 = c1; c1 = tc; const float td = d0; d0 = d1; d1 = td; }
+                    farref = c1; fard = d1;
+                    if (c0 & kLeafBit) { firstleaf = c0; stop = true; } else cur = c0;
                 }
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const bool p = act && r[k] != kNone && k != kmin;
-                    const unsigned pm = __ballot_sync(full, p);
-                    S.npool[p ? ncnt + __popc(pm & lt) : kWpNodeCap] = make_uint2(r[k], (__float_as_uint(d[k]) & ~31u) | lane);
-                    ncnt += __popc(pm);
-                }
-                if (act) {
-                    const uint32_t nx = kmin == 0 ? r[0] : (kmin == 1 ? r[1] : (kmin == 2 ? r[2] : r[3]));
-                    if (nx & kLeafBit) { firstleaf = nx; act = false; } else cur = nx;
-                }
+                const unsigned pm = __ballot_sync(full, act);
+                S.npool[act ? ncnt + __popc(pm & lt) : kWpNodeCap] = make_uint2(farref, (__float_as_uint(fard) & ~31u) | lane);
+                ncnt += __popc(pm);
+                if (stop) act = false;
             }
             if (valid) {
                 uint32_t id;
@@ -324,7 +292,7 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
         if (phase == 0) {
             // -------------------------------------------------------------------------------------------- (A) node phase
             do {
-                if (ncnt + kWpNodeRoom > kWpNodeCap) {
+                if (ncnt + 32 > kWpNodeCap) {
                     if (!spill_bottom()) { if (lane == 0) atomicOr(&a.counters[2], 1ull); return; }
                 }
                 const int take = ncnt < 32 ? ncnt : 32;
@@ -337,35 +305,39 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                 __syncwarp();                                      // all pops read before any push overwrites them
                 const bool popped_leaf = live && (e.x & kLeafBit);
                 const bool expand = live && !(e.x & kLeafBit);
-                float d[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-                uint32_t r[4] = {kNone, kNone, kNone, kNone};
-                if (expand) { wp_wide_dists(a.wide, e.x, q, d, r); ++st_nodes; }
-                bool in[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) in[k] = expand && r[k] != kNone && d[k] <= q.w;
-                // leaf pairs: a popped leaf entry, and the leaf slots inside the ball (masked lanes write the sink entry)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const bool l = (in[k] && (r[k] & kLeafBit)) || (k == 0 && popped_leaf);
-                    const uint32_t ref = (k == 0 && popped_leaf) ? e.x : r[k];
-                    const unsigned m = __ballot_sync(full, l);
-                    S.lpool[l ? lcnt + __popc(m & lt) : kWpLeafCap] = (owner << 27) | (ref & kWpRefMask);
-                    lcnt += __popc(m);
+                bool in0 = false, in1 = false;                     // 0 = nearer child, 1 = farther child
+                uint32_t r0 = 0, r1 = 0;
+                float d0 = 0.0f, d1 = 0.0f;
+                if (expand) {
+                    const NodeView nd = load_node(a.nodes, e.x);
+                    ++st_nodes;
+                    d0 = wp_box_sqdist(nd.lo0, nd.hi0, q); d1 = wp_box_sqdist(nd.lo1, nd.hi1, q);
+                    r0 = nd.c0; r1 = nd.c1;
+                    if (d1 < d0) { const uint32_t tc = r0; r0 = r1; r1 = tc; const float td = d0; d0 = d1; d1 = td; }
+                    in0 = d0 <= q.w; in1 = d1 <= q.w;
                 }
-                // internal slots inside the ball, sorted by distance: the farthest of every lane first, the nearest on top
-                float key[4];
-#pragma unroll
-                for (int k = 0; k < 4; ++k) key[k] = (in[k] && !(r[k] & kLeafBit)) ? d[k] : INFINITY;
-#define B2_CSWAP(i, j) { const bool sw = key[i] < key[j]; const float tk = sw ? key[j] : key[i]; key[j] = sw ? key[i] : key[j]; key[i] = tk; \
-                         const uint32_t tr = sw ? r[j] : r[i]; r[j] = sw ? r[i] : r[j]; r[i] = tr; }
-                B2_CSWAP(0, 1) B2_CSWAP(2, 3) B2_CSWAP(0, 2) B2_CSWAP(1, 3) B2_CSWAP(1, 2)     // descending: key[0] >= key[1] >= key[2] >= key[3]
-#undef B2_CSWAP
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const bool p = key[k] != INFINITY;
-                    const unsigned m = __ballot_sync(full, p);
-                    S.npool[p ? ncnt + __popc(m & lt) : kWpNodeCap] = make_uint2(r[k], (__float_as_uint(key[k]) & ~31u) | owner);
-                    ncnt += __popc(m);
+                // leaf pairs: a popped leaf entry or the nearer child, then the farther child (masked lanes write the sink entry)
+                {
+                    const bool l0 = popped_leaf || (in0 && (r0 & kLeafBit));
+                    const uint32_t ref0 = popped_leaf ? e.x : r0;
+                    const unsigned m0 = __ballot_sync(full, l0);
+                    S.lpool[l0 ? lcnt + __popc(m0 & lt) : kWpLeafCap] = (owner << 27) | (ref0 & kWpRefMask);
+                    lcnt += __popc(m0);
+                    const bool l1 = in1 && (r1 & kLeafBit);
+                    const unsigned m1 = __ballot_sync(full, l1);
+                    S.lpool[l1 ? lcnt + __popc(m1 & lt) : kWpLeafCap] = (owner << 27) | (r1 & kWpRefMask);
+                    lcnt += __popc(m1);
+                }
+                // internal children: farther first, nearer on top
+                {
+                    const bool p1 = in1 && !(r1 & kLeafBit);
+                    const unsigned m1 = __ballot_sync(full, p1);
+                    S.npool[p1 ? ncnt + __popc(m1 & lt) : kWpNodeCap] = make_uint2(r1, (__float_as_uint(d1) & ~31u) | owner);
+                    ncnt += __popc(m1);
+                    const bool p0 = in0 && !(r0 & kLeafBit);
+                    const unsigned m0 = __ballot_sync(full, p0);
+                    S.npool[p0 ? ncnt + __popc(m0 & lt) : kWpNodeCap] = make_uint2(r0, (__float_as_uint(d0) & ~31u) | owner);
+                    ncnt += __popc(m0);
                 }
                 __syncwarp();
             } while (ncnt > 0 && lcnt < 32);

@@ -70,9 +70,9 @@ def test_gpu_built_tree_equals_host_emulation(B, meshes, name):
     v, f = meshes[name]
     t = B.AABB_tree(v, f)
     t.build()
-    (pn, bn), (pt, bt), (pb, bb), (pf, bf), (pw, bw) = t.export_layout()
+    (pn, bn), (pt, bt), (pb, bb), (pf, bf) = t.export_layout()
     n = len(f)
-    assert bn == (n - 1) * 64 and bt == n * 96 and bb == 48 and bf == n * 48 and bw == (n - 1) * 64
+    assert bn == (n - 1) * 64 and bt == n * 96 and bb == 48 and bf == n * 48
     g_nodes, g_tris = device_to_host(pn, bn), device_to_host(pt, bt)
     assert hc.validate(g_nodes, g_tris, n) == 0
     h_nodes, h_tris, h_bbox = hc.HostTree(soup_of(v, f)).export()
