@@ -203,7 +203,7 @@ struct b200aabb_tree {
     // options
     int opt_sort_queries = 1;      // B200AABB_OPT_SORT_QUERIES
     int opt_closest_kernel = 1;    // B200AABB_OPT_CLOSEST_KERNEL: 1 = warp-cooperative pool (closest_warp.cuh), 0 = one thread per query
-    int opt_warp_exact_go = 32;     // B200AABB_OPT_WARP_EXACT_GO
+    int opt_warp_exact_go = 64;     // B200AABB_OPT_WARP_EXACT_GO
     int opt_debug_two_pass = 0;    // experiment: run the warp kernel twice, the second time with the first pass's distances as initial bounds
     // warp-cooperative closest_point: per pipeline slot a batch cursor and the pools' spill area; grid = SMs x resident warps
     struct WarpScratch { unsigned long long* cursor = nullptr; uint2* spill = nullptr; } warp[2];

@@ -131,7 +131,8 @@ __global__ void __launch_bounds__(256) emit_leaves_kernel(const double* __restri
     TriF f;
 #pragma unroll
     for (int j = 0; j < 9; ++j) f.v[j] = (float)t[j];
-    f.pad[0] = f.pad[1] = f.pad[2] = 0;
+#pragma unroll
+    for (int j = 0; j < 7; ++j) f.pad[j] = 0;
     outf[k] = f;
 }
 

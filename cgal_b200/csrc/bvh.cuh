@@ -5,7 +5,7 @@
 //                   rounded OUTWARD from the exact binary64 boxes (lo towards -inf, hi towards +inf), so a traversal step
 //                   costs two 32-byte sectors and leaf boxes never need their own node.  N-1 nodes for N primitives.
 //   TriRec    96 B  one primitive in Morton order: 9 binary64 coordinates (v0,v1,v2), the primitive id, padding to 3 sectors.
-//   TriF      48 B  the same primitive rounded to binary32 (pre-tests of closest_warp.cuh only; never decides a result).
+//   TriF      64 B  the same primitive rounded to binary32 (pre-tests of closest_warp.cuh only; never decides a result).
 // Child reference: bit 31 set = leaf, low bits = slot in the TriRec array; else index of an internal node.
 //
 // Traversal replaces (paths relative to the CGAL source root)
@@ -26,7 +26,7 @@ constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr int kStackCap = 96;
 
-struct __align__(16) BvhNode {
+struct __align__(32) BvhNode {
     float lo0[3], hi0[3];  // child 0
     float lo1[3], hi1[3];  // child 1
     uint32_t child[2];
@@ -35,7 +35,7 @@ struct __align__(16) BvhNode {
 };
 static_assert(sizeof(BvhNode) == 64, "node is two 32-byte sectors");
 
-struct __align__(16) TriRec {
+struct __align__(32) TriRec {
     double v[9];
     uint32_t id;
     uint32_t pad[5];
@@ -43,13 +43,13 @@ struct __align__(16) TriRec {
 static_assert(sizeof(TriRec) == 96, "triangle record is three 32-byte sectors");
 
 // binary32 copy of a primitive (same order as the TriRec array): each coordinate rounded to nearest.  Read by the rigorous binary32
-// pre-tests of the warp-cooperative closest_point kernel (closest_warp.cuh), which account for the rounding explicitly; 48 bytes
-// = three 128-bit loads instead of six.
-struct __align__(16) TriF {
+// pre-tests of the warp-cooperative closest_point kernel (closest_warp.cuh), which account for the rounding explicitly; 64 bytes
+// = two 256-bit loads (two L1 wavefronts per lane) instead of the six 128-bit ones of a TriRec.
+struct __align__(32) TriF {
     float v[9];
-    uint32_t pad[3];
+    uint32_t pad[7];
 };
-static_assert(sizeof(TriF) == 48, "binary32 triangle record is three 16-byte words");
+static_assert(sizeof(TriF) == 64, "binary32 triangle record is two 32-byte sectors");
 
 // per-query traversal statistics (accumulated into the handle's counters by the kernels)
 struct TravStat { int nexact = 0; int overflow = 0; uint32_t nodes = 0, leaves = 0, culled = 0; };   // culled: leaves rejected by the binary32 pre-test
@@ -98,15 +98,26 @@ B2_HD float add_dn(float a, float b) {
 
 struct NodeView { float lo0[3], hi0[3], lo1[3], hi1[3]; uint32_t c0, c1; };
 
+#if defined(__CUDACC__)
+// 256-bit read-only load (sm_100: LDG.E.256): one request per 32-byte sector and lane instead of two 128-bit ones, which halves the
+// L1 wavefronts of the scattered node / triangle fetches that bound the traversal kernels (profiles/r1_05).  p must be 32-byte aligned.
+__device__ __forceinline__ void ldg256(const void* p, uint32_t (&r)[8]) {
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "l"(p));
+}
+#endif
+
 B2_HD NodeView load_node(const BvhNode* __restrict__ nodes, uint32_t i) {
     NodeView n;
 #if defined(__CUDA_ARCH__)
-    const float4* p = reinterpret_cast<const float4*>(nodes + i);
-    const float4 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2);
-    const uint4 m = __ldg(reinterpret_cast<const uint4*>(p + 3));
-    n.lo0[0] = a.x; n.lo0[1] = a.y; n.lo0[2] = a.z; n.hi0[0] = a.w; n.hi0[1] = b.x; n.hi0[2] = b.y;
-    n.lo1[0] = b.z; n.lo1[1] = b.w; n.lo1[2] = c.x; n.hi1[0] = c.y; n.hi1[1] = c.z; n.hi1[2] = c.w;
-    n.c0 = m.x; n.c1 = m.y;
+    uint32_t a[8], b[8];
+    ldg256(nodes + i, a);
+    ldg256(reinterpret_cast<const char*>(nodes + i) + 32, b);
+    n.lo0[0] = __uint_as_float(a[0]); n.lo0[1] = __uint_as_float(a[1]); n.lo0[2] = __uint_as_float(a[2]);
+    n.hi0[0] = __uint_as_float(a[3]); n.hi0[1] = __uint_as_float(a[4]); n.hi0[2] = __uint_as_float(a[5]);
+    n.lo1[0] = __uint_as_float(a[6]); n.lo1[1] = __uint_as_float(a[7]); n.lo1[2] = __uint_as_float(b[0]);
+    n.hi1[0] = __uint_as_float(b[1]); n.hi1[1] = __uint_as_float(b[2]); n.hi1[2] = __uint_as_float(b[3]);
+    n.c0 = b[4]; n.c1 = b[5];
 #else
     const BvhNode& s = nodes[i];
     for (int k = 0; k < 3; ++k) { n.lo0[k] = s.lo0[k]; n.hi0[k] = s.hi0[k]; n.lo1[k] = s.lo1[k]; n.hi1[k] = s.hi1[k]; }
@@ -118,11 +129,14 @@ B2_HD NodeView load_node(const BvhNode* __restrict__ nodes, uint32_t i) {
 B2_HD Tri3 load_tri(const TriRec* __restrict__ tris, uint32_t slot, uint32_t& id) {
     Tri3 t;
 #if defined(__CUDA_ARCH__)
-    const double2* p = reinterpret_cast<const double2*>(tris + slot);
-    const double2 a = __ldg(p), b = __ldg(p + 1), c = __ldg(p + 2), d = __ldg(p + 3);
-    const uint4 m = __ldg(reinterpret_cast<const uint4*>(p + 4));   // v[8] (2 words), id, pad
-    t.a = {a.x, a.y, b.x}; t.b = {b.y, c.x, c.y}; t.c = {d.x, d.y, __hiloint2double((int)m.y, (int)m.x)};
-    id = m.z;
+    uint32_t a[8], b[8], c[8];
+    const char* p = reinterpret_cast<const char*>(tris + slot);
+    ldg256(p, a); ldg256(p + 32, b); ldg256(p + 64, c);
+    auto D = [](uint32_t lo, uint32_t hi) { return __hiloint2double((int)hi, (int)lo); };
+    t.a = {D(a[0], a[1]), D(a[2], a[3]), D(a[4], a[5])};
+    t.b = {D(a[6], a[7]), D(b[0], b[1]), D(b[2], b[3])};
+    t.c = {D(b[4], b[5]), D(b[6], b[7]), D(c[0], c[1])};
+    id = c[2];
 #else
     const TriRec& s = tris[slot];
     t.a = {s.v[0], s.v[1], s.v[2]}; t.b = {s.v[3], s.v[4], s.v[5]}; t.c = {s.v[6], s.v[7], s.v[8]};

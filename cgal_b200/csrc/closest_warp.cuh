@@ -14,7 +14,7 @@
 //                       slot's ball; load the node, test both child boxes against the slot's binary32 point (directed rounding);
 //                       push internal children (far first, near on top) and record leaf children as (slot,leaf) pairs
 //   (B1) pre-test 1     rigorous binary32 LOWER bounds of the distance of 32 (slot,leaf) pairs (tangent plane of the slot's ball,
-//                       centroid direction) on a 48-byte binary32 copy of the triangle; pairs certainly outside the ball retire
+//                       centroid direction) on a 64-byte binary32 copy of the triangle; pairs certainly outside the ball retire
 //   (B2) pre-test 2     approximate closest point of the triangle in binary32 (divisions, branches): a sharper lower bound, and a
 //                       rigorous UPPER bound of the distance that shrinks the slot's ball at once (atomicMin), before any binary64 work
 //   (B3) exact phase    pairs still inside the ball: the reference's Construct_projected_point_3 in binary64, then the exact
@@ -95,6 +95,14 @@ __device__ __forceinline__ float wp_box_sqdist(const float* lo, const float* hi,
     return __fadd_rd(__fadd_rd(__fmul_rd(dx, dx), __fmul_rd(dy, dy)), __fmul_rd(dz, dz));
 }
 
+// UPPER bound of the squared distance from q to the farthest corner of the box (every operation rounds up)
+__device__ __forceinline__ float wp_box_far_sqdist(const float* lo, const float* hi, const float4& q) {
+    const float fx = fmaxf(__fsub_ru(q.x, lo[0]), __fsub_ru(hi[0], q.x));
+    const float fy = fmaxf(__fsub_ru(q.y, lo[1]), __fsub_ru(hi[1], q.y));
+    const float fz = fmaxf(__fsub_ru(q.z, lo[2]), __fsub_ru(hi[2], q.z));
+    return __fadd_ru(__fadd_ru(__fmul_ru(fx, fx), __fmul_ru(fy, fy)), __fmul_ru(fz, fz));
+}
+
 // shrinks slot `owner`'s ball to radius rb (any lane, any time: both bounds only ever decrease)
 __device__ __forceinline__ void wp_shrink(WarpShared& S, unsigned owner, float rb) {
     atomicMin(reinterpret_cast<unsigned*>(&S.qc[owner].x), __float_as_uint(rb));
@@ -125,12 +133,13 @@ __device__ __forceinline__ void wp_set_bounds(WarpShared& S, unsigned owner, dou
 // carry themselves), so a distance bound computed from them moves by at most e2.
 struct RelTri { float ra[3], rb[3], rc[3], m; };
 __device__ __forceinline__ RelTri wp_relative(const TriF* __restrict__ trisf, uint32_t slot, const float4& q) {
-    const float4* p = reinterpret_cast<const float4*>(trisf + slot);
-    const float4 f0 = __ldg(p), f1 = __ldg(p + 1), f2 = __ldg(p + 2);
+    uint32_t f[8];
+    ldg256(trisf + slot, f);
+    const float cz = __ldg(&trisf[slot].v[8]);
     RelTri r;
-    r.ra[0] = f0.x - q.x; r.ra[1] = f0.y - q.y; r.ra[2] = f0.z - q.z;
-    r.rb[0] = f0.w - q.x; r.rb[1] = f1.x - q.y; r.rb[2] = f1.y - q.z;
-    r.rc[0] = f1.z - q.x; r.rc[1] = f1.w - q.y; r.rc[2] = f2.x - q.z;
+    r.ra[0] = __uint_as_float(f[0]) - q.x; r.ra[1] = __uint_as_float(f[1]) - q.y; r.ra[2] = __uint_as_float(f[2]) - q.z;
+    r.rb[0] = __uint_as_float(f[3]) - q.x; r.rb[1] = __uint_as_float(f[4]) - q.y; r.rb[2] = __uint_as_float(f[5]) - q.z;
+    r.rc[0] = __uint_as_float(f[6]) - q.x; r.rc[1] = __uint_as_float(f[7]) - q.y; r.rc[2] = cz - q.z;
     r.m = fmaxf(fmaxf(fmaxf(fabsf(r.ra[0]), fabsf(r.ra[1])), fmaxf(fabsf(r.ra[2]), fabsf(r.rb[0]))),
                 fmaxf(fmaxf(fabsf(r.rb[1]), fabsf(r.rb[2])), fmaxf(fmaxf(fabsf(r.rc[0]), fabsf(r.rc[1])), fabsf(r.rc[2]))));
     return r;
@@ -232,25 +241,36 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                 o = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
                 q.x = (float)o.x; q.y = (float)o.y; q.z = (float)o.z;
             }
-            // walk down to the nearest leaf, nearest child first, pushing every far child
+            const double ex = o.x - (double)q.x, ey = o.y - (double)q.y, ez = o.z - (double)q.z;   // exact differences
+            const float perr = float_above(sqrt((ex * ex + ey * ey) + ez * ez) * 1.0000001) + 1e-37f;
+            const double delta = 4e-16 * fmax(a.mag, fmax3(fabs(o.x), fabs(o.y), fabs(o.z)));
+            const float dslack = float_above(2.0 * delta) + 1e-37f;
+            // Walk down to the nearest leaf, nearest child first, pushing the far children that can still matter: every box holds a
+            // primitive, so the distance to the FARTHEST corner of any box seen so far bounds the winner's distance from above
+            // (far2, rounded up); a far child whose box is certainly beyond that (both sides moved by perr, the winner's side by the
+            // rounding allowance of candidates) is dropped right away instead of being stacked and popped stale later.
             uint32_t cur = 0, firstleaf = kNone;
+            float far2 = INFINITY;
             bool act = valid;
             while (__any_sync(full, act)) {
                 if (ncnt + 32 > kWpNodeCap) {
                     if (!spill_bottom()) { if (lane == 0) atomicOr(&a.counters[2], 1ull); return; }
                 }
-                uint32_t farref = 0; float fard = 0.0f; bool stop = false;
+                uint32_t farref = 0; float fard = 0.0f; bool stop = false, push = false;
                 if (act) {
                     const NodeView nd = load_node(a.nodes, cur);
                     ++st_nodes;
                     float d0 = wp_box_sqdist(nd.lo0, nd.hi0, q), d1 = wp_box_sqdist(nd.lo1, nd.hi1, q);
+                    far2 = fminf(far2, fminf(wp_box_far_sqdist(nd.lo0, nd.hi0, q), wp_box_far_sqdist(nd.lo1, nd.hi1, q)));
                     uint32_t c0 = nd.c0, c1 = nd.c1;
                     if (d1 < d0) { const uint32_t tc = c0; c0 = c1; c1 = tc; const float td = d0; d0 = d1; d1 = td; }
                     farref = c1; fard = d1;
+                    const float reach = __fadd_ru(__fadd_ru(__fsqrt_ru(far2), __fmul_ru(2.0f, perr)), dslack);
+                    push = fard <= __fmul_ru(reach, reach);
                     if (c0 & kLeafBit) { firstleaf = c0; stop = true; } else cur = c0;
                 }
-                const unsigned pm = __ballot_sync(full, act);
-                S.npool[act ? ncnt + __popc(pm & lt) : kWpNodeCap] = make_uint2(farref, (__float_as_uint(fard) & ~31u) | lane);
+                const unsigned pm = __ballot_sync(full, push);
+                S.npool[push ? ncnt + __popc(pm & lt) : kWpNodeCap] = make_uint2(farref, (__float_as_uint(fard) & ~31u) | lane);
                 ncnt += __popc(pm);
                 if (stop) act = false;
             }
@@ -261,12 +281,9 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                 const Vec3 cpt = closest_on_triangle(t, o);
                 const Vec3 v = cpt - o;
                 const double sqd = (v.x * v.x + v.y * v.y) + v.z * v.z;
-                const double ex = o.x - (double)q.x, ey = o.y - (double)q.y, ez = o.z - (double)q.z;   // exact differences
-                const float perr = float_above(sqrt((ex * ex + ey * ey) + ez * ez) * 1.0000001) + 1e-37f;
-                const double delta = 4e-16 * fmax(a.mag, fmax3(fabs(o.x), fabs(o.y), fabs(o.z)));
                 S.o[0][lane] = o.x; S.o[1][lane] = o.y; S.o[2][lane] = o.z;
                 S.qa[lane] = q;
-                S.qc[lane] = make_float4(INFINITY, __fadd_ru(__fmul_ru(1.7320509f, ev), perr), float_above(2.0 * delta) + 1e-37f, perr);
+                S.qc[lane] = make_float4(INFINITY, __fadd_ru(__fmul_ru(1.7320509f, ev), perr), dslack, perr);
                 S.bp[0][lane] = cpt.x; S.bp[1][lane] = cpt.y; S.bp[2][lane] = cpt.z;
                 S.bprim[lane] = id; S.bsqd[lane] = sqd;
                 S.delta[lane] = delta;

@@ -61,7 +61,7 @@ enum {
                                       of ray origin+direction, onesweep radix sort on the device); 0: in the caller's order */
   B200AABB_OPT_CLOSEST_KERNEL = 2, /* closest_point scheduling: 1 (default) = warp-cooperative work pool (32 query slots per persistent
                                       warp, pooled (slot,node)/(slot,leaf) pairs); 0 = one thread per query.  Same results. */
-  B200AABB_OPT_WARP_EXACT_GO = 4   /* warp-cooperative kernel: run the binary64 phase once this many pre-test survivors wait (1..64, default 32) */
+  B200AABB_OPT_WARP_EXACT_GO = 4   /* warp-cooperative kernel: run the binary64 phase once this many pre-test survivors wait (1..64, default 64) */
 };
 
 typedef struct b200aabb_stats {

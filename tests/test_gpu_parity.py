@@ -72,13 +72,13 @@ def test_gpu_built_tree_equals_host_emulation(B, meshes, name):
     t.build()
     (pn, bn), (pt, bt), (pb, bb), (pf, bf) = t.export_layout()
     n = len(f)
-    assert bn == (n - 1) * 64 and bt == n * 96 and bb == 48 and bf == n * 48
+    assert bn == (n - 1) * 64 and bt == n * 96 and bb == 48 and bf == n * 64
     g_nodes, g_tris = device_to_host(pn, bn), device_to_host(pt, bt)
     assert hc.validate(g_nodes, g_tris, n) == 0
     h_nodes, h_tris, h_bbox = hc.HostTree(soup_of(v, f)).export()
     np.testing.assert_array_equal(g_tris, h_tris)
     want_f = g_tris.view(np.float64).reshape(-1, 12)[:, :9].astype(np.float32)     # binary32 copies: round to nearest
-    np.testing.assert_array_equal(device_to_host(pf, bf).view(np.float32).reshape(-1, 12)[:, :9], want_f)
+    np.testing.assert_array_equal(device_to_host(pf, bf).view(np.float32).reshape(-1, 16)[:, :9], want_f)
     gw, hw = g_nodes.view(np.uint32).reshape(-1, 16), h_nodes.view(np.uint32).reshape(-1, 16)
     cols = list(range(0, 15))                   # boxes, children, parent (not the refit arrival counter)
     np.testing.assert_array_equal(gw[:, cols], hw[:, cols])
