@@ -31,6 +31,9 @@ SHARDS = 8                          # a rank's shard = every 8th image row
 RAYS_PER_RANK = IMG * IMG // SHARDS
 POINTS_PER_RANK = RAYS_PER_RANK
 BYTES_PER_RAY, BYTES_PER_POINT = 85, 61      # algorithmic bytes, SURVEY.md §8(d)
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the kernel on this very workload, from the committed ncu --set full
+# captures (profiles/r1_07_warp_pool_ldg256.txt, profiles/r1_03_while_while.txt): the tree itself (nodes + records) is read about once
+NCU_DRAM_BYTES_PER_LAUNCH = {"closest_point_warp_kernel": 9.602370e9 + 4.685018e9, "first_intersection_kernel": 1.074644e9 + 0.303553e9}
 WORKLOAD = "terrain16M(4096x2048 quads, Perlin fBm seed 23) + per GPU 8,388,608 pinhole Ray_3 first_intersection (rows r::8 of 8192^2) + 8,388,608 bbox closest_point_and_primitive"
 
 
@@ -60,7 +63,7 @@ class ClockSampler:
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
@@ -333,7 +336,7 @@ def main():
         if ray_ms >= pt_ms:
             dom, dom_bytes, dom_ms = "first_intersection_kernel", n_rays * BYTES_PER_RAY, ray_ms
         else:
-            dom, dom_bytes, dom_ms = "closest_point_kernel", n_pts * BYTES_PER_POINT, pt_ms
+            dom, dom_bytes, dom_ms = "closest_point_warp_kernel", n_pts * BYTES_PER_POINT, pt_ms
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
         line = {"metric": "Mqueries/s (50% first_intersection Ray_3 + 50% closest_point_and_primitive)", "value": value, "unit": "Mqueries/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -345,9 +348,11 @@ def main():
                            "build_ms": build_ms, "build_Mtri_s": n_prims / build_ms / 1e3, "build_GB_s_algorithmic(492B/tri)": 492.0 * n_prims / build_ms / 1e6,
                            "ray_hit_rate_rank0": hit_rate, "ties": ties, "near_ties": near, "exact_stage_queries": exact, "traversal_rank0": traffic_model,
                            "tree_broadcast": bcast},
-                "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(dom) if not args.small and n_pts == POINTS_PER_RANK else None,
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
-                             "note": "traversal is L2-latency / FP64-issue bound, not HBM bound (DESIGN.md §5); ncu counters in profiles/"},
+                             "note": "traversal is bound by the L1 data stage (one wavefront per scattered node / triangle fetch) and by load latency at 16 warps/SM, not by HBM (DESIGN.md §5); "
+                                     "traffic = dram__bytes_read+write of one launch from the ncu --set full capture named in profiles/README.md"},
                 "clocks": clocks, "gpu_launches": launches}
         if e2e_ms is not None:
             line["e2e"] = {"value": q_per_step * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "Mqueries/s", "h2d_bytes_per_step": world * h2d, "d2h_bytes_per_step": world * d2h}

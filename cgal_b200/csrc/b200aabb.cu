@@ -206,7 +206,7 @@ struct b200aabb_tree {
     int opt_warp_exact_go = 64;     // B200AABB_OPT_WARP_EXACT_GO
     int opt_debug_two_pass = 0;    // experiment: run the warp kernel twice, the second time with the first pass's distances as initial bounds
     // warp-cooperative closest_point: per pipeline slot a batch cursor and the pools' spill area; grid = SMs x resident warps
-    struct WarpScratch { unsigned long long* cursor = nullptr; uint2* spill = nullptr; } warp[2];
+    struct WarpScratch { unsigned long long* cursor = nullptr; uint2* spill = nullptr; WarpSlots64* slots64 = nullptr; } warp[2];
     int warp_grid = 0;
     // query coherence sort scratch, one per pipeline slot (slot 0 also serves DEVICE-pointer batches); grow-only
     struct SortScratch { uint64_t* keys[2] = {nullptr, nullptr}; uint32_t* vals[2] = {nullptr, nullptr}; void* ws = nullptr; uint64_t cap = 0; } sort[2];
@@ -231,7 +231,10 @@ namespace {
         }                                                                                                        \
     } while (0)
 
-constexpr uint64_t kChunk = 1ull << 22;   // queries per pipeline slot for HOST-pointer batches
+constexpr uint64_t kChunkMax = 1ull << 22;   // most queries per pipeline slot for HOST-pointer batches
+constexpr uint64_t kChunkMin = 1ull << 18;
+// a batch is cut into about six chunks so that only the first chunk's upload and the last chunk's download are exposed
+uint64_t chunk_for(uint64_t n) { return std::min<uint64_t>(n, std::min(kChunkMax, std::max(kChunkMin, ((n + 5) / 6 + 32767) / 32768 * 32768))); }
 
 int fail(b200aabb_tree* t, int code, const char* msg) { if (t) t->err = msg; return code; }
 
@@ -258,7 +261,7 @@ int ensure_stage(b200aabb_tree* t, size_t in_bytes, size_t out_bytes) {
 }
 
 void free_warp(b200aabb_tree* t) {
-    for (auto& w : t->warp) { cudaFree(w.cursor); cudaFree(w.spill); w = b200aabb_tree::WarpScratch(); }
+    for (auto& w : t->warp) { cudaFree(w.cursor); cudaFree(w.spill); cudaFree(w.slots64); w = b200aabb_tree::WarpScratch(); }
 }
 int ensure_warp(b200aabb_tree* t, int slot) {
     if (t->warp_grid == 0) {
@@ -270,6 +273,7 @@ int ensure_warp(b200aabb_tree* t, int slot) {
     auto& w = t->warp[slot];
     if (!w.cursor) B2_CUDA(t, cudaMalloc(&w.cursor, sizeof(unsigned long long)));
     if (!w.spill) B2_CUDA(t, cudaMalloc(&w.spill, (size_t)t->warp_grid * kWpSpillCap * sizeof(uint2)));
+    if (!w.slots64) B2_CUDA(t, cudaMalloc(&w.slots64, (size_t)t->warp_grid * sizeof(WarpSlots64)));
     return B200AABB_OK;
 }
 
@@ -387,7 +391,7 @@ int run_batch(b200aabb_tree* t, const void* in, size_t in_elem_bytes, uint64_t n
         t->query_timing_pending = true;
         return B200AABB_OK;
     }
-    const uint64_t chunk = std::min<uint64_t>(n, kChunk);
+    const uint64_t chunk = chunk_for(n);
     size_t out_bytes = 0;
     for (auto& o : outs) { o.offset = out_bytes; out_bytes += ((o.host ? o.elem_bytes * chunk : 0) + 255) / 256 * 256; }
     int rc = ensure_stage(t, in_elem_bytes * chunk, std::max<size_t>(out_bytes, 256));
@@ -650,7 +654,7 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
                          WarpClosestArgs a;
                          a.nodes = t->d_nodes; a.tris = t->d_tris; a.trisf = t->d_trisf; a.mag = t->mag; a.perm = perm; a.counters = t->d_counters;
                          a.pts = (const double*)in; a.n = cnt; a.cp = (double*)o[0]; a.prim = (uint32_t*)o[1]; a.sqd = (double*)o[2]; a.flags = (uint8_t*)o[3];
-                         a.cursor = t->warp[slot].cursor; a.spill = t->warp[slot].spill;
+                         a.cursor = t->warp[slot].cursor; a.spill = t->warp[slot].spill; a.slots64 = t->warp[slot].slots64;
                          a.exact_go = t->opt_warp_exact_go;
                          a.flag_tie = B200AABB_FLAG_TIE; a.flag_exact = B200AABB_FLAG_EXACT;
                          a.debug_hint_sqd = nullptr;

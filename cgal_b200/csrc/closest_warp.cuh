@@ -35,12 +35,13 @@
 
 namespace b2 {
 
-constexpr int kWpNodeCap = 512;                 // (slot,node) entries held in shared memory
+constexpr int kWpNodeCap = 320;                 // (slot,node) entries held in shared memory
 constexpr int kWpSpillChunk = kWpNodeCap / 2;   // entries moved per spill / reload
-constexpr int kWpSpillCap = 16 * kWpSpillChunk; // entries per warp in the global spill area
+constexpr int kWpSpillCap = 24 * kWpSpillChunk; // entries per warp in the global spill area
 constexpr int kWpLeafCap = 96;                  // < 32 waiting + at most 64 added by one node phase
 constexpr int kWpMidCap = 128;                  // < 32 waiting + at most 95 added by one pre-test-1 phase
-constexpr int kWpExactCap = 192;                // < exact_go (<= 64) waiting + at most 126 added by one pre-test-2 phase
+constexpr int kWpExactCap = 128;                // pre-test 2 stops handing over when fewer than 32 places are left
+constexpr int kWpWarpsPerSM = 28;               // resident warps per SM this kernel is sized for (registers <= 72, shared memory <= 7.1 KB)
 constexpr uint32_t kWpRefMask = 0x07FFFFFFu;    // 27 bits of leaf slot next to the 5-bit query slot
 constexpr uint64_t kWpMaxPrims = 1ull << 27;
 
@@ -54,13 +55,17 @@ struct WarpShared {
     float4 qb[32];                // direction query -> incumbent (x,y,z) and its length (w)
     float4 qc[32];                // x = rbound: pruning radius >= sqrt(widened squared distance of the eventual winner);
                                   // y = e2 >= |error of a binary32 relative vertex| = sqrt(3) ev + perr; z = dslack >= 2 delta; w = perr >= |query - qa.xyz|
-    double o[3][32];              // query point
-    double bp[3][32];             // incumbent closest point
-    double bsqd[32];              // its squared distance as the reference computes it
-    double delta[32];             // rounding allowance of candidate points: 4e-16 * largest coordinate magnitude (bvh.cuh::traverse_closest)
     uint32_t bprim[32];           // incumbent primitive id
     uint32_t qidx[32];            // the query's index in the caller's order
     uint32_t flags[32];           // B200AABB_FLAG_TIE / _EXACT
+};
+
+// binary64 state of the 32 slots: only the exact phase, the refill and the result write touch it, so it lives in global memory (L2)
+// and leaves the shared memory to the pools (more resident warps)
+struct WarpSlots64 {
+    double o[3][32];              // query point
+    double bp[3][32];             // incumbent closest point
+    double bsqd[32];              // its squared distance as the reference computes it
 };
 
 struct WarpClosestArgs {
@@ -78,6 +83,7 @@ struct WarpClosestArgs {
     uint8_t* flags;
     unsigned long long* cursor;    // next position of the batch to hand out (zeroed before the launch)
     uint2* spill;                  // gridDim.x * kWpSpillCap entries
+    WarpSlots64* slots64;          // gridDim.x records
     int exact_go;                  // run the exact phase when at least this many pairs wait (1..64)
     uint32_t flag_tie, flag_exact;
     const double* debug_hint_sqd;  // experiment only: a known upper bound of each query's squared distance (caller order), or nullptr
@@ -113,8 +119,7 @@ __device__ __forceinline__ void wp_shrink(WarpShared& S, unsigned owner, float r
 // pruning radius of a slot from its incumbent's squared distance: rbound >= sqrt(widen_sqdist(sqd, delta)) (bvh.cuh), with the
 // square roots taken in binary32 rounded up (s >= sqrt(sqd) makes the widened value only larger).  Unless `reset`, the ball only
 // shrinks: the binary32 upper bounds of wp_sharp may already be tighter than this incumbent.
-__device__ __forceinline__ void wp_set_bounds(WarpShared& S, unsigned owner, double sqd, const Vec3& v, bool reset) {
-    const double delta = S.delta[owner];
+__device__ __forceinline__ void wp_set_bounds(WarpShared& S, unsigned owner, double sqd, const Vec3& v, double delta, bool reset) {
     const float s = __fsqrt_ru(float_above(sqd));
     const float rb = __fsqrt_ru(float_above(sqd + ((2.0 * delta * (double)s + delta * delta) + sqd * 1e-13)));
     if (reset) {
@@ -167,25 +172,28 @@ __device__ __forceinline__ void wp_sharp(const RelTri& r, float dslack, float e2
 
 // the replacement step of the reference (AABB_traits_3.h:724-732) for slot `owner`, given sg = Compare_distance_3(query, candidate,
 // incumbent) <= 0; same tie rule as bvh.cuh::traverse_closest
-__device__ __forceinline__ void wp_apply(WarpShared& S, unsigned owner, int sg, const Vec3& cpt, const Vec3& v, double sqd, uint32_t id, uint32_t flag_tie) {
+__device__ __forceinline__ void wp_apply(WarpShared& S, WarpSlots64& G, unsigned owner, int sg, const Vec3& cpt, const Vec3& v, double sqd, double delta, uint32_t id,
+                                         uint32_t flag_tie) {
     uint32_t fl = S.flags[owner];
     bool take;
     if (sg == 0) { take = id < S.bprim[owner]; fl |= flag_tie; }
     else { take = true; fl &= ~flag_tie; }
     S.flags[owner] = fl;
     if (take) {
-        S.bp[0][owner] = cpt.x; S.bp[1][owner] = cpt.y; S.bp[2][owner] = cpt.z;
-        S.bprim[owner] = id; S.bsqd[owner] = sqd;
-        wp_set_bounds(S, owner, sqd, v, false);
+        __stcg(&G.bp[0][owner], cpt.x); __stcg(&G.bp[1][owner], cpt.y); __stcg(&G.bp[2][owner], cpt.z);
+        __stcg(&G.bsqd[owner], sqd);
+        S.bprim[owner] = id;
+        wp_set_bounds(S, owner, sqd, v, delta, false);
     }
 }
 
-__global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpClosestArgs a) {
+__global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(const WarpClosestArgs a) {
     __shared__ WarpShared S;
     const unsigned lane = threadIdx.x;
     const unsigned full = 0xFFFFFFFFu;
     const unsigned lt = (1u << lane) - 1u;
     uint2* const myspill = a.spill + (size_t)blockIdx.x * kWpSpillCap;
+    WarpSlots64& G = a.slots64[blockIdx.x];
     const float ev = float_above(a.mag * 5.9604645e-8 * 1.000001);   // >= rounding of a vertex coordinate to binary32
     int ncnt = 0, lcnt = 0, mcnt = 0, ecnt = 0, spilled = 0;         // warp-uniform
     unsigned active = 0;                                              // slots holding a query of the current batch
@@ -219,9 +227,9 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
             if ((active >> lane) & 1u) {
                 const uint64_t qi = S.qidx[lane];
                 const uint32_t fl = S.flags[lane];
-                if (a.cp) { a.cp[3 * qi] = S.bp[0][lane]; a.cp[3 * qi + 1] = S.bp[1][lane]; a.cp[3 * qi + 2] = S.bp[2][lane]; }
+                if (a.cp) { a.cp[3 * qi] = __ldcg(&G.bp[0][lane]); a.cp[3 * qi + 1] = __ldcg(&G.bp[1][lane]); a.cp[3 * qi + 2] = __ldcg(&G.bp[2][lane]); }
                 if (a.prim) a.prim[qi] = S.bprim[lane];
-                if (a.sqd) a.sqd[qi] = S.bsqd[lane];
+                if (a.sqd) a.sqd[qi] = __ldcg(&G.bsqd[lane]);
                 if (a.flags) a.flags[qi] = (uint8_t)fl;
                 if (fl & a.flag_tie) ++st_ties;
                 if (fl & a.flag_exact) ++st_exact;
@@ -281,13 +289,13 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                 const Vec3 cpt = closest_on_triangle(t, o);
                 const Vec3 v = cpt - o;
                 const double sqd = (v.x * v.x + v.y * v.y) + v.z * v.z;
-                S.o[0][lane] = o.x; S.o[1][lane] = o.y; S.o[2][lane] = o.z;
+                __stcg(&G.o[0][lane], o.x); __stcg(&G.o[1][lane], o.y); __stcg(&G.o[2][lane], o.z);
                 S.qa[lane] = q;
                 S.qc[lane] = make_float4(INFINITY, __fadd_ru(__fmul_ru(1.7320509f, ev), perr), dslack, perr);
-                S.bp[0][lane] = cpt.x; S.bp[1][lane] = cpt.y; S.bp[2][lane] = cpt.z;
-                S.bprim[lane] = id; S.bsqd[lane] = sqd;
-                S.delta[lane] = delta;
-                wp_set_bounds(S, lane, sqd, v, true);
+                __stcg(&G.bp[0][lane], cpt.x); __stcg(&G.bp[1][lane], cpt.y); __stcg(&G.bp[2][lane], cpt.z);
+                __stcg(&G.bsqd[lane], sqd);
+                S.bprim[lane] = id;
+                wp_set_bounds(S, lane, sqd, v, delta, true);
                 if (a.debug_hint_sqd) wp_shrink(S, lane, float_above(sqrt(widen_sqdist(a.debug_hint_sqd[qi], delta))));
                 S.qidx[lane] = qi;
                 S.flags[lane] = 0;
@@ -385,12 +393,13 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
             lcnt = 0;
         } else if (phase == 2) {
             // -------------------------------------------------------------------------------------------- (B2) pre-test 2: approximate closest point
-            for (int base = 0; base < mcnt; base += 32) {
-                const int i = base + (int)lane;
+            while (mcnt > 0 && ecnt + 32 <= kWpExactCap) {   // (taken from the top; what does not fit waits for the exact phase to make room)
+                const int take = mcnt < 32 ? mcnt : 32;
+                mcnt -= take;
                 bool survive = false;
                 uint2 e = make_uint2(0, 0);
-                if (i < mcnt) {
-                    e = S.mpool[i];
+                if ((int)lane < take) {
+                    e = S.mpool[mcnt + (int)lane];
                     const unsigned owner = e.x >> 27;
                     const float4 qc = S.qc[owner];
                     if (__uint_as_float(e.y) > qc.x) ++st_culled;   // the ball has shrunk since pre-test 1
@@ -408,7 +417,6 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                 if (survive) S.epool[ecnt + __popc(sm & lt)] = e;
                 ecnt += __popc(sm);
             }
-            mcnt = 0;
         } else {
             // -------------------------------------------------------------------------------------------- (B3) binary64 projection + exact comparison
             // (i) pairs whose lower bound has fallen outside their slot's ball retire without any binary64 work
@@ -446,7 +454,7 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                         if (__uint_as_float(e.y) > S.qc[owner].x) ++st_culled;   // (an earlier batch of this very phase may have shrunk the ball)
                         else {
                             const Tri3 t = load_tri(a.tris, e.x & kWpRefMask, id);
-                            o = {S.o[0][owner], S.o[1][owner], S.o[2][owner]};
+                            o = {__ldcg(&G.o[0][owner]), __ldcg(&G.o[1][owner]), __ldcg(&G.o[2][owner])};
                             cpt = closest_on_triangle(t, o);
                             v = cpt - o;
                             sqd = (v.x * v.x + v.y * v.y) + v.z * v.z;   // Compute_squared_distance_3(query, closest): AABB_tree.h:1024-1032
@@ -462,7 +470,7 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                     while (pm) {
                         int sg = 0;
                         if (pending) {
-                            const Vec3 bp = {S.bp[0][owner], S.bp[1][owner], S.bp[2][owner]};
+                            const Vec3 bp = {__ldcg(&G.bp[0][owner]), __ldcg(&G.bp[1][owner]), __ldcg(&G.bp[2][owner])};
                             int nexact = 0;
                             sg = cmp_dist(o, cpt, bp, nexact);
                             if (nexact) atomicOr(&S.flags[owner], a.flag_exact);
@@ -474,7 +482,7 @@ __global__ void __launch_bounds__(32, 16) closest_point_warp_kernel(const WarpCl
                             const unsigned grp = __match_any_sync(cm, owner);
                             const unsigned gmin = __reduce_min_sync(grp, key);
                             const unsigned wm = __ballot_sync(cm, key == gmin) & grp;
-                            if ((unsigned)(__ffs(wm) - 1) == lane) { wp_apply(S, owner, sg, cpt, v, sqd, id, a.flag_tie); pending = false; }
+                            if ((unsigned)(__ffs(wm) - 1) == lane) { wp_apply(S, G, owner, sg, cpt, v, sqd, 4e-16 * fmax(a.mag, fmax3(fabs(o.x), fabs(o.y), fabs(o.z))), id, a.flag_tie); pending = false; }
                         }
                         __syncwarp();
                         pm = __ballot_sync(full, pending);
