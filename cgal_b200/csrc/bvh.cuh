@@ -389,7 +389,8 @@ constexpr int kSurvGo = 2;    // run the binary64 phase once this many pre-test 
 
 B2_HD double widen_sqdist(double sqd, double delta) { return sqd + ((2.0 * delta * sqrt(sqd) + delta * delta) + sqd * 1e-13); }
 
-B2_HD float dot3f(const float* u, const float* v) { return (u[0] * v[0] + u[1] * v[1]) + u[2] * v[2]; }
+// (explicit FMAs: the library is compiled with -fmad=false for the binary64 constructions; the binary32 bounds only gain accuracy)
+B2_HD float dot3f(const float* u, const float* v) { return fmaf(u[2], v[2], fmaf(u[1], v[1], u[0] * v[0])); }
 
 // Approximate closest point of the triangle (a,b,c) to the ORIGIN in binary32 (region walk of Ericson, "Real-Time
 // Collision Detection" 5.1.5, specialised to p = 0).  Only used as a direction for the rigorous bound below, so its own

@@ -98,7 +98,7 @@ __device__ __forceinline__ float wp_box_sqdist(const float* lo, const float* hi,
     const float dx = fmaxf(fmaxf(__fsub_rd(lo[0], q.x), __fsub_rd(q.x, hi[0])), 0.0f);
     const float dy = fmaxf(fmaxf(__fsub_rd(lo[1], q.y), __fsub_rd(q.y, hi[1])), 0.0f);
     const float dz = fmaxf(fmaxf(__fsub_rd(lo[2], q.z), __fsub_rd(q.z, hi[2])), 0.0f);
-    return __fadd_rd(__fadd_rd(__fmul_rd(dx, dx), __fmul_rd(dy, dy)), __fmul_rd(dz, dz));
+    return __fmaf_rd(dz, dz, __fmaf_rd(dy, dy, __fmul_rd(dx, dx)));
 }
 
 // UPPER bound of the squared distance from q to the farthest corner of the box (every operation rounds up)
@@ -106,7 +106,7 @@ __device__ __forceinline__ float wp_box_far_sqdist(const float* lo, const float*
     const float fx = fmaxf(__fsub_ru(q.x, lo[0]), __fsub_ru(hi[0], q.x));
     const float fy = fmaxf(__fsub_ru(q.y, lo[1]), __fsub_ru(hi[1], q.y));
     const float fz = fmaxf(__fsub_ru(q.z, lo[2]), __fsub_ru(hi[2], q.z));
-    return __fadd_ru(__fadd_ru(__fmul_ru(fx, fx), __fmul_ru(fy, fy)), __fmul_ru(fz, fz));
+    return __fmaf_ru(fz, fz, __fmaf_ru(fy, fy, __fmul_ru(fx, fx)));
 }
 
 // shrinks slot `owner`'s ball to radius rb (any lane, any time: both bounds only ever decrease)
@@ -154,7 +154,7 @@ __device__ __forceinline__ RelTri wp_relative(const TriF* __restrict__ trisf, ui
 // |u|, of its reciprocal and of the two products.  -inf when u is (numerically) zero.  (Relative to the binary32 data: the caller subtracts e2.)
 __device__ __forceinline__ float wp_lower(const float* u, float su, const RelTri& r) {
     const float md = fminf(dot3f(u, r.ra), fminf(dot3f(u, r.rb), dot3f(u, r.rc)));
-    return su > 1e-18f ? (md - 5e-7f * r.m * su) * __frcp_rn(su) * 0.999998f : -INFINITY;
+    return su > 1e-18f ? fmaf(-5e-7f * r.m, su, md) * (__frcp_rn(su) * 0.999998f) : -INFINITY;
 }
 // Approximate closest point P = a + v ab + w ac (v, w >= 0, v + w <= 1 up to an ulp) -> a sharper lower bound (direction P) and a
 // rigorous UPPER bound of (distance + the slot's rounding allowance): P's coordinates are within 1.2e-6 m of a point of the true
