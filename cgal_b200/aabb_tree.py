@@ -14,6 +14,7 @@ FLAG_HIT, FLAG_SEGMENT, FLAG_TIE, FLAG_EXACT, FLAG_NEAR_TIE = 1, 2, 4, 8, 16
 OPT_SORT_QUERIES = 1
 OPT_CLOSEST_KERNEL = 2    # 1 = warp-cooperative work pool (default), 0 = one thread per query
 OPT_WARP_EXACT_GO = 4
+OPT_HOST_PARTS = 5
 NO_PRIMITIVE = 0xFFFFFFFF
 _HOST, _DEVICE = 0, 1
 _ERRORS = {-1: "invalid argument", -2: "CUDA error", -3: "out of device memory", -4: "empty tree (CGAL_precondition(!empty()))",

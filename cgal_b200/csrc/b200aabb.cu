@@ -204,6 +204,7 @@ struct b200aabb_tree {
     int opt_sort_queries = 1;      // B200AABB_OPT_SORT_QUERIES
     int opt_closest_kernel = 1;    // B200AABB_OPT_CLOSEST_KERNEL: 1 = warp-cooperative pool (closest_warp.cuh), 0 = one thread per query
     int opt_warp_exact_go = 64;     // B200AABB_OPT_WARP_EXACT_GO
+    int opt_host_parts = 0;        // B200AABB_OPT_HOST_PARTS (0 = automatic)
     int opt_debug_two_pass = 0;    // experiment: run the warp kernel twice, the second time with the first pass's distances as initial bounds
     // warp-cooperative closest_point: per pipeline slot a batch cursor and the pools' spill area; grid = SMs x resident warps
     struct WarpScratch { unsigned long long* cursor = nullptr; uint2* spill = nullptr; WarpSlots64* slots64 = nullptr; } warp[2];
@@ -233,8 +234,8 @@ namespace {
 
 constexpr uint64_t kChunkMax = 1ull << 22;   // most queries per pipeline slot for HOST-pointer batches
 constexpr uint64_t kChunkMin = 1ull << 18;
-// a batch is cut into about six chunks so that only the first chunk's upload and the last chunk's download are exposed
-uint64_t chunk_for(uint64_t n) { return std::min<uint64_t>(n, std::min(kChunkMax, std::max(kChunkMin, ((n + 5) / 6 + 32767) / 32768 * 32768))); }
+// a HOST batch is cut into about `opt_host_parts` chunks so that only the first chunk's upload and the last chunk's download are exposed
+uint64_t chunk_for(uint64_t n, int parts) { const uint64_t p = (uint64_t)std::max(1, parts); return std::min<uint64_t>(n, std::min(kChunkMax, std::max(kChunkMin, ((n + p - 1) / p + 32767) / 32768 * 32768))); }
 
 int fail(b200aabb_tree* t, int code, const char* msg) { if (t) t->err = msg; return code; }
 
@@ -391,7 +392,9 @@ int run_batch(b200aabb_tree* t, const void* in, size_t in_elem_bytes, uint64_t n
         t->query_timing_pending = true;
         return B200AABB_OK;
     }
-    const uint64_t chunk = chunk_for(n);
+    // measured on the benchmark batches (scripts/tune_e2e.py): line queries are copy-bound and gain from six chunks; the
+    // closest_point kernel loses coherence (the chunk is sorted on its own) and pays a drain tail per launch, so two chunks
+    const uint64_t chunk = chunk_for(n, t->opt_host_parts > 0 ? t->opt_host_parts : (shape == kLineQuery ? 6 : 2));
     size_t out_bytes = 0;
     for (auto& o : outs) { o.offset = out_bytes; out_bytes += ((o.host ? o.elem_bytes * chunk : 0) + 255) / 256 * 256; }
     int rc = ensure_stage(t, in_elem_bytes * chunk, std::max<size_t>(out_bytes, 256));
@@ -491,6 +494,7 @@ int b200aabb_set_option(b200aabb_tree* t, int option, int64_t value) {
     switch (option) {
         case B200AABB_OPT_SORT_QUERIES: t->opt_sort_queries = value != 0; return B200AABB_OK;
         case B200AABB_OPT_CLOSEST_KERNEL: t->opt_closest_kernel = value != 0; return B200AABB_OK;
+        case B200AABB_OPT_HOST_PARTS: t->opt_host_parts = (int)std::min<int64_t>(64, std::max<int64_t>(0, value)); return B200AABB_OK;
         case 100: t->opt_debug_two_pass = value != 0; return B200AABB_OK;
         case B200AABB_OPT_WARP_EXACT_GO: t->opt_warp_exact_go = (int)std::min<int64_t>(64, std::max<int64_t>(1, value)); return B200AABB_OK;
         default: return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "unknown option");

@@ -61,6 +61,9 @@ enum {
                                       of ray origin+direction, onesweep radix sort on the device); 0: in the caller's order */
   B200AABB_OPT_CLOSEST_KERNEL = 2, /* closest_point scheduling: 1 (default) = warp-cooperative work pool (32 query slots per persistent
                                       warp, pooled (slot,node)/(slot,leaf) pairs); 0 = one thread per query.  Same results. */
+  B200AABB_OPT_HOST_PARTS = 5,     /* HOST-pointer batches are cut into about this many chunks (each 256 Ki .. 4 Mi queries) that flow through a
+                                      double-buffered upload -> sort -> traverse -> download pipeline (1..64; 0 = default: 6 for ray / segment
+                                      batches, 2 for point batches) */
   B200AABB_OPT_WARP_EXACT_GO = 4   /* warp-cooperative kernel: run the binary64 phase once this many pre-test survivors wait (1..64, default 64) */
 };
 
