@@ -150,7 +150,7 @@ B2_HD int karras_delta(const uint64_t* __restrict__ keys, int64_t n, int64_t i, 
 }
 
 // topology of internal node i (Karras, "Maximizing Parallelism in the Construction of BVHs, Octrees, and k-d Trees", 2012)
-B2_HD void karras_node(const uint64_t* __restrict__ keys, int64_t n, int64_t i, uint32_t& left, uint32_t& right) {
+B2_HD void karras_node(const uint64_t* __restrict__ keys, int64_t n, int64_t i, uint32_t& left, uint32_t& right, uint32_t* other_end = nullptr) {
     const int d = karras_delta(keys, n, i, i + 1) - karras_delta(keys, n, i, i - 1) >= 0 ? 1 : -1;
     const int dmin = karras_delta(keys, n, i, i - d);
     int64_t lmax = 2;
@@ -167,6 +167,7 @@ B2_HD void karras_node(const uint64_t* __restrict__ keys, int64_t n, int64_t i, 
     }
     const int64_t gamma = i + s * d + (d < 0 ? -1 : 0);
     const int64_t lo = i < j ? i : j, hi = i < j ? j : i;
+    if (other_end) *other_end = (uint32_t)j;
     left = lo == gamma ? (kLeafBit | (uint32_t)gamma) : (uint32_t)gamma;
     right = hi == gamma + 1 ? (kLeafBit | (uint32_t)(gamma + 1)) : (uint32_t)(gamma + 1);
 }
@@ -174,18 +175,32 @@ B2_HD void karras_node(const uint64_t* __restrict__ keys, int64_t n, int64_t i, 
 __global__ void __launch_bounds__(256) hierarchy_kernel(const uint64_t* __restrict__ keys, uint64_t n, BvhNode* __restrict__ nodes, uint32_t* __restrict__ leaf_parent) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i + 1 >= n) return;
-    uint32_t l, r;
-    karras_node(keys, (int64_t)n, (int64_t)i, l, r);
+    uint32_t l, r, j;
+    karras_node(keys, (int64_t)n, (int64_t)i, l, r, &j);
     BvhNode* nd = nodes + i;
-    nd->child[0] = l; nd->child[1] = r; nd->visit = 0;
+    nd->child[0] = l; nd->child[1] = r; nd->visit = j;           // the node covers the leaves [min(i,j), max(i,j)]; refit_kernel reads it
     if (i == 0) nd->parent = kNone;
     if (l & kLeafBit) leaf_parent[l & ~kLeafBit] = (uint32_t)i; else nodes[l].parent = (uint32_t)i;
     if (r & kLeafBit) leaf_parent[r & ~kLeafBit] = (uint32_t)i; else nodes[r].parent = (uint32_t)i;
 }
 
-// one thread per leaf; the second thread to arrive at a node continues upwards with the union of both child boxes
-__global__ void __launch_bounds__(256) refit_kernel(const TriRec* __restrict__ tris, uint64_t n, BvhNode* nodes, const uint32_t* __restrict__ leaf_parent) {
-    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// One thread per leaf; the second thread to arrive at a node continues upwards with the union of both child boxes.
+// A block owns kRefitBlock consecutive leaves.  The nodes whose leaf range lies inside the block (node i covers
+// [min(i, visit), max(i, visit)], hierarchy_kernel) are only ever reached by this block's threads and have indices inside the
+// block's range: their links are staged in shared memory and their arrival counters and child boxes live there too, so a level
+// costs shared-memory latency instead of a store + fence + L2 atomic + L2 load.  Only the few nodes that span blocks use the
+// global protocol (arrival flag = atomicExch on `visit`); once a thread is on a spanning node all its ancestors span too.
+constexpr int kRefitBlock = 256;
+__global__ void __launch_bounds__(kRefitBlock) refit_kernel(const TriRec* __restrict__ tris, uint64_t n, BvhNode* nodes, const uint32_t* __restrict__ leaf_parent) {
+    __shared__ uint4 s_link[kRefitBlock];          // child[0], child[1], parent, other end of the range, of node (block base + t)
+    __shared__ unsigned s_cnt[kRefitBlock];
+    __shared__ float s_box[kRefitBlock][2][6];     // child boxes of the block's own nodes
+    const uint64_t base = (uint64_t)blockIdx.x * kRefitBlock;
+    const uint64_t k = base + threadIdx.x;
+    const uint64_t last_leaf = base + kRefitBlock - 1 < n - 1 ? base + kRefitBlock - 1 : n - 1;
+    s_cnt[threadIdx.x] = 0;
+    if (k + 1 < n) s_link[threadIdx.x] = *reinterpret_cast<const uint4*>(&nodes[k].child[0]);
+    __syncthreads();
     if (k >= n || n == 1) return;
     float lo[3], hi[3];
     {
@@ -195,21 +210,50 @@ __global__ void __launch_bounds__(256) refit_kernel(const TriRec* __restrict__ t
     }
     uint32_t me = kLeafBit | (uint32_t)k;
     uint32_t p = leaf_parent[k];
+    bool local = true;                             // still among the block's own nodes
     while (true) {
         BvhNode* nd = nodes + p;
-        const int side = (nd->child[0] == me) ? 0 : 1;
-        float* mylo = side ? nd->lo1 : nd->lo0; float* myhi = side ? nd->hi1 : nd->hi0;
+        uint4 link;
+        if (local && p >= base && p <= last_leaf) {
+            link = s_link[p - base];
+            const uint32_t a = p < link.w ? p : link.w, b = p < link.w ? link.w : p;
+            local = a >= base && b <= last_leaf;
+        } else local = false;
+        if (local) {
+            const unsigned slot = p - (uint32_t)base;
+            const int side = (link.x == me) ? 0 : 1;
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { mylo[a] = lo[a]; myhi[a] = hi[a]; }
-        __threadfence();
-        if (atomicAdd(&nd->visit, 1u) == 0) return;              // first to arrive: the sibling will carry on
-        __threadfence();
-        // the sibling box was written by another SM: read it through L2 (this SM's L1 may hold the line from the child[] read)
-        const float* olo = side ? nd->lo0 : nd->lo1; const float* ohi = side ? nd->hi0 : nd->hi1;
+            for (int a = 0; a < 3; ++a) { s_box[slot][side][a] = lo[a]; s_box[slot][side][3 + a] = hi[a]; }
+            __threadfence_block();
+            if (atomicAdd(&s_cnt[slot], 1u) == 0) return;        // first to arrive: the sibling will carry on
+            __threadfence_block();
+            float olo[3], ohi[3];
 #pragma unroll
-        for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], __ldcg(olo + a)); hi[a] = fmaxf(hi[a], __ldcg(ohi + a)); }
-        me = p;
-        p = nd->parent;
+            for (int a = 0; a < 3; ++a) { olo[a] = ((volatile float*)s_box[slot][1 - side])[a]; ohi[a] = ((volatile float*)s_box[slot][1 - side])[3 + a]; }
+            // the second arrival writes both child boxes of the node at once (48 contiguous bytes)
+            float* o0 = side ? nd->lo0 : nd->lo1; float* o0h = side ? nd->hi0 : nd->hi1;
+            float* m0 = side ? nd->lo1 : nd->lo0; float* m0h = side ? nd->hi1 : nd->hi0;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { o0[a] = olo[a]; o0h[a] = ohi[a]; m0[a] = lo[a]; m0h[a] = hi[a]; }
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], olo[a]); hi[a] = fmaxf(hi[a], ohi[a]); }
+            me = p;
+            p = link.z;
+        } else {
+            const int side = (nd->child[0] == me) ? 0 : 1;
+            float* mylo = side ? nd->lo1 : nd->lo0; float* myhi = side ? nd->hi1 : nd->hi0;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { mylo[a] = lo[a]; myhi[a] = hi[a]; }
+            __threadfence();
+            if (atomicExch(&nd->visit, kNone) != kNone) return;  // first to arrive (the field held the range end until now)
+            __threadfence();
+            // the sibling box was written by another SM: read it through L2 (this SM's L1 may hold the line from the child[] read)
+            const float* olo = side ? nd->lo0 : nd->lo1; const float* ohi = side ? nd->hi0 : nd->hi1;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], __ldcg(olo + a)); hi[a] = fmaxf(hi[a], __ldcg(ohi + a)); }
+            me = p;
+            p = nd->parent;
+        }
         if (p == kNone) return;
     }
 }
