@@ -3,6 +3,7 @@
 // (-fmad=false: the constructions of geom.cuh must not be contracted into FMAs; explicit fma() calls remain FMAs).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -205,6 +206,7 @@ struct b200aabb_tree {
     int opt_closest_kernel = 1;    // B200AABB_OPT_CLOSEST_KERNEL: 1 = warp-cooperative pool (closest_warp.cuh), 0 = one thread per query
     int opt_warp_exact_go = 64;     // B200AABB_OPT_WARP_EXACT_GO
     int opt_host_parts = 0;        // B200AABB_OPT_HOST_PARTS (0 = automatic)
+    int opt_debug_refit_frontier = kRefitFrontierPerBlock;   // test hook (option 101): frontier entries per block of the refit (0: every hand-over overflows)
     int opt_debug_two_pass = 0;    // experiment: run the warp kernel twice, the second time with the first pass's distances as initial bounds
     // warp-cooperative closest_point: per pipeline slot a batch cursor and the pools' spill area; grid = SMs x resident warps
     struct WarpScratch { unsigned long long* cursor = nullptr; uint2* spill = nullptr; WarpSlots64* slots64 = nullptr; } warp[2];
@@ -326,33 +328,51 @@ int do_build(b200aabb_tree* t) {
     cudaStream_t st = t->stream;
     uint64_t* keys[2] = {nullptr, nullptr};
     uint32_t* vals[2] = {nullptr, nullptr};
-    void* ws = nullptr; unsigned long long* bounds = nullptr; uint32_t* leaf_parent = nullptr;
-    auto cleanup = [&]() { cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(ws); cudaFree(bounds); cudaFree(leaf_parent); };
+    void* ws = nullptr; unsigned long long* bounds = nullptr; uint32_t* leaf_parent = nullptr; RefitEntry* frontier = nullptr; unsigned* frontier_count = nullptr;
+    auto cleanup = [&]() { cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(ws); cudaFree(bounds); cudaFree(leaf_parent); cudaFree(frontier); cudaFree(frontier_count); };
 #define B2_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { t->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); free_tree_buffers(t); \
         return e_ == cudaErrorMemoryAllocation ? B200AABB_ERR_OUT_OF_MEMORY : B200AABB_ERR_CUDA; } } while (0)
     for (int s = 0; s < 2; ++s) { B2_TRY(cudaMalloc(&keys[s], n * 8)); B2_TRY(cudaMalloc(&vals[s], n * 4)); }
     B2_TRY(cudaMalloc(&ws, rs_workspace_bytes(n)));
     B2_TRY(cudaMalloc(&bounds, 6 * 8));
     B2_TRY(cudaMalloc(&leaf_parent, n * 4));
+    const uint64_t refit_blocks = (n + kRefitBlock - 1) / kRefitBlock, frontier_cap = refit_blocks * kRefitFrontierPerBlock, frontier_use = refit_blocks * (uint64_t)t->opt_debug_refit_frontier;
+    B2_TRY(cudaMalloc(&frontier, frontier_cap * sizeof(RefitEntry)));
+    B2_TRY(cudaMalloc(&frontier_count, sizeof(unsigned)));
     B2_TRY(cudaMalloc(&t->d_nodes, std::max<uint64_t>(n - 1, 1) * sizeof(BvhNode)));
     B2_TRY(cudaMalloc(&t->d_tris, n * sizeof(TriRec)));
     B2_TRY(cudaMalloc(&t->d_trisf, n * sizeof(TriF)));
+    // B200AABB_BUILD_TIMING=1: per-stage device times on stderr (events between the stages; diagnostic only)
+    const bool stage_timing = getenv("B200AABB_BUILD_TIMING") != nullptr;
+    std::vector<std::pair<const char*, cudaEvent_t>> marks;
+    auto mark = [&](const char* name) { if (stage_timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); marks.push_back({name, e}); } };
     B2_TRY(cudaEventRecord(t->ev_a, st));
+    mark("start");
     B2_TRY(cudaMemsetAsync(bounds, 0xFF, 3 * 8, st));
     B2_TRY(cudaMemsetAsync(bounds + 3, 0x00, 3 * 8, st));
     const unsigned blocks = (unsigned)((n + 255) / 256);
     scene_bounds_kernel<<<std::min<unsigned>(blocks, 148 * 8), 256, 0, st>>>(t->d_soup, n, bounds);
+    mark("scene_bounds");
     morton_kernel<<<blocks, 256, 0, st>>>(t->d_soup, n, bounds, keys[0], vals[0]);
+    mark("morton");
     t->stats.kernel_launches += 2;
     const int cur = radix_sort_pairs(keys, vals, n, 8, ws, st, &t->stats.kernel_launches);
+    mark("sort");
     emit_leaves_kernel<<<blocks, 256, 0, st>>>(t->d_soup, t->d_ids, vals[cur], n, t->d_tris, t->d_trisf);
+    mark("emit_leaves");
     t->stats.kernel_launches += 1;
     if (n > 1) {
         hierarchy_kernel<<<blocks, 256, 0, st>>>(keys[cur], n, t->d_nodes, leaf_parent);
         t->stats.kernel_launches += 1;
     }
-    refit_kernel<<<blocks, 256, 0, st>>>(t->d_tris, n, t->d_nodes, leaf_parent);
+    mark("hierarchy");
+    B2_TRY(cudaMemsetAsync(frontier_count, 0, sizeof(unsigned), st));
+    refit_local_kernel<<<(unsigned)refit_blocks, kRefitBlock, 0, st>>>(t->d_tris, n, t->d_nodes, leaf_parent, frontier, frontier_count, (unsigned)frontier_use);
+    mark("refit_local");
+    if (n > 1) { refit_global_kernel<<<(unsigned)((frontier_cap + 255) / 256), 256, 0, st>>>(t->d_nodes, frontier, frontier_count, (unsigned)frontier_use); t->stats.kernel_launches += 1; }
+    mark("refit_global");
     root_box_kernel<<<1, 32, 0, st>>>(bounds, t->d_rootbox);
+    mark("root_box");
     t->stats.kernel_launches += 2;
     B2_TRY(cudaEventRecord(t->ev_b, st));
     B2_TRY(cudaMemcpyAsync(t->h_bbox, t->d_rootbox, 48, cudaMemcpyDeviceToHost, st));
@@ -360,6 +380,8 @@ int do_build(b200aabb_tree* t) {
     B2_TRY(cudaGetLastError());
     float ms = 0; cudaEventElapsedTime(&ms, t->ev_a, t->ev_b);
     t->stats.last_build_ms = ms;
+    for (size_t i = 1; i < marks.size(); ++i) { float d = 0; cudaEventElapsedTime(&d, marks[i - 1].second, marks[i].second); fprintf(stderr, "[b200aabb build] %-14s %8.3f ms\n", marks[i].first, d); }
+    for (auto& m : marks) cudaEventDestroy(m.second);
     t->root = n == 1 ? (kLeafBit | 0u) : 0u;
     t->mag = 0.0;
     for (int a = 0; a < 6; ++a) t->mag = std::max(t->mag, fabs(t->h_bbox[a]));
@@ -495,6 +517,7 @@ int b200aabb_set_option(b200aabb_tree* t, int option, int64_t value) {
         case B200AABB_OPT_SORT_QUERIES: t->opt_sort_queries = value != 0; return B200AABB_OK;
         case B200AABB_OPT_CLOSEST_KERNEL: t->opt_closest_kernel = value != 0; return B200AABB_OK;
         case B200AABB_OPT_HOST_PARTS: t->opt_host_parts = (int)std::min<int64_t>(64, std::max<int64_t>(0, value)); return B200AABB_OK;
+        case 101: t->opt_debug_refit_frontier = (int)std::min<int64_t>(kRefitFrontierPerBlock, std::max<int64_t>(0, value)); t->built = t->n == 0; return B200AABB_OK;
         case 100: t->opt_debug_two_pass = value != 0; return B200AABB_OK;
         case B200AABB_OPT_WARP_EXACT_GO: t->opt_warp_exact_go = (int)std::min<int64_t>(64, std::max<int64_t>(1, value)); return B200AABB_OK;
         default: return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "unknown option");

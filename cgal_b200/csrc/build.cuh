@@ -6,7 +6,7 @@
 //   [radix_sort.cuh]     onesweep sort of (key, primitive index)
 //   emit_leaves_kernel   TriRec records (and their binary32 copies, TriF) in Morton order
 //   hierarchy_kernel     Karras 2012 radix-tree topology, one thread per internal node
-//   refit_kernel         bottom-up boxes with one atomic arrival counter per node.  A primitive's exact binary64 box is
+//   refit_local/global   bottom-up boxes with one arrival counter per node (shared memory inside a block of 256 leaves, global above).  A primitive's exact binary64 box is
 //                        rounded OUTWARD to binary32 once; min/max are exact and commute with the monotone rounding, so
 //                        every node box is bit-equal to the outward rounding of the exact union of its primitives' boxes
 #pragma once
@@ -184,14 +184,43 @@ __global__ void __launch_bounds__(256) hierarchy_kernel(const uint64_t* __restri
     if (r & kLeafBit) leaf_parent[r & ~kLeafBit] = (uint32_t)i; else nodes[r].parent = (uint32_t)i;
 }
 
-// One thread per leaf; the second thread to arrive at a node continues upwards with the union of both child boxes.
-// A block owns kRefitBlock consecutive leaves.  The nodes whose leaf range lies inside the block (node i covers
+// Refit, bottom-up: one thread per leaf; the second thread to arrive at a node continues upwards with the union of both child boxes.
+// refit_local_kernel: a block owns kRefitBlock consecutive leaves.  The nodes whose leaf range lies inside the block (node i covers
 // [min(i, visit), max(i, visit)], hierarchy_kernel) are only ever reached by this block's threads and have indices inside the
 // block's range: their links are staged in shared memory and their arrival counters and child boxes live there too, so a level
-// costs shared-memory latency instead of a store + fence + L2 atomic + L2 load.  Only the few nodes that span blocks use the
-// global protocol (arrival flag = atomicExch on `visit`); once a thread is on a spanning node all its ancestors span too.
+// costs shared-memory latency instead of a store + fence + L2 atomic + L2 load.  A thread that reaches a node spanning blocks
+// parks its box in the frontier list and ends, so that no block stays resident for the slow levels.
+// refit_global_kernel: one thread per frontier entry finishes the climb with the global protocol (arrival flag = atomicExch on
+// `visit`).  On Morton-ordered input a block hands over a few entries; the list holds 16 per block and a thread that finds it full
+// (a degenerate, caterpillar-like tree) simply finishes its climb in place.
 constexpr int kRefitBlock = 256;
-__global__ void __launch_bounds__(kRefitBlock) refit_kernel(const TriRec* __restrict__ tris, uint64_t n, BvhNode* nodes, const uint32_t* __restrict__ leaf_parent) {
+constexpr int kRefitFrontierPerBlock = 16;
+struct __align__(16) RefitEntry { float lo[3], hi[3]; uint32_t node, from; };
+static_assert(sizeof(RefitEntry) == 32, "frontier entry");
+
+// the climb over nodes that span blocks: global arrival flag (atomicExch on `visit`, which held the range end until then)
+__device__ __forceinline__ void refit_climb_global(BvhNode* nodes, uint32_t p, uint32_t me, float* lo, float* hi) {
+    while (true) {
+        BvhNode* nd = nodes + p;
+        const int side = (nd->child[0] == me) ? 0 : 1;
+        float* mylo = side ? nd->lo1 : nd->lo0; float* myhi = side ? nd->hi1 : nd->hi0;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { mylo[a] = lo[a]; myhi[a] = hi[a]; }
+        __threadfence();
+        if (atomicExch(&nd->visit, kNone) != kNone) return;      // first to arrive: the sibling will carry on
+        __threadfence();
+        // the sibling box was written by another SM: read it through L2 (this SM's L1 may hold the line from the child[] read)
+        const float* olo = side ? nd->lo0 : nd->lo1; const float* ohi = side ? nd->hi0 : nd->hi1;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], __ldcg(olo + a)); hi[a] = fmaxf(hi[a], __ldcg(ohi + a)); }
+        me = p;
+        p = nd->parent;
+        if (p == kNone) return;
+    }
+}
+
+__global__ void __launch_bounds__(kRefitBlock) refit_local_kernel(const TriRec* __restrict__ tris, uint64_t n, BvhNode* nodes, const uint32_t* __restrict__ leaf_parent,
+                                                                  RefitEntry* __restrict__ frontier, unsigned* __restrict__ frontier_count, unsigned frontier_cap) {
     __shared__ uint4 s_link[kRefitBlock];          // child[0], child[1], parent, other end of the range, of node (block base + t)
     __shared__ unsigned s_cnt[kRefitBlock];
     __shared__ float s_box[kRefitBlock][2][6];     // child boxes of the block's own nodes
@@ -210,52 +239,59 @@ __global__ void __launch_bounds__(kRefitBlock) refit_kernel(const TriRec* __rest
     }
     uint32_t me = kLeafBit | (uint32_t)k;
     uint32_t p = leaf_parent[k];
-    bool local = true;                             // still among the block's own nodes
     while (true) {
-        BvhNode* nd = nodes + p;
-        uint4 link;
-        if (local && p >= base && p <= last_leaf) {
+        bool local = p >= base && p <= last_leaf;
+        uint4 link = make_uint4(0, 0, 0, 0);
+        if (local) {
             link = s_link[p - base];
             const uint32_t a = p < link.w ? p : link.w, b = p < link.w ? link.w : p;
             local = a >= base && b <= last_leaf;
-        } else local = false;
-        if (local) {
-            const unsigned slot = p - (uint32_t)base;
-            const int side = (link.x == me) ? 0 : 1;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) { s_box[slot][side][a] = lo[a]; s_box[slot][side][3 + a] = hi[a]; }
-            __threadfence_block();
-            if (atomicAdd(&s_cnt[slot], 1u) == 0) return;        // first to arrive: the sibling will carry on
-            __threadfence_block();
-            float olo[3], ohi[3];
-#pragma unroll
-            for (int a = 0; a < 3; ++a) { olo[a] = ((volatile float*)s_box[slot][1 - side])[a]; ohi[a] = ((volatile float*)s_box[slot][1 - side])[3 + a]; }
-            // the second arrival writes both child boxes of the node at once (48 contiguous bytes)
-            float* o0 = side ? nd->lo0 : nd->lo1; float* o0h = side ? nd->hi0 : nd->hi1;
-            float* m0 = side ? nd->lo1 : nd->lo0; float* m0h = side ? nd->hi1 : nd->hi0;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) { o0[a] = olo[a]; o0h[a] = ohi[a]; m0[a] = lo[a]; m0h[a] = hi[a]; }
-#pragma unroll
-            for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], olo[a]); hi[a] = fmaxf(hi[a], ohi[a]); }
-            me = p;
-            p = link.z;
-        } else {
-            const int side = (nd->child[0] == me) ? 0 : 1;
-            float* mylo = side ? nd->lo1 : nd->lo0; float* myhi = side ? nd->hi1 : nd->hi0;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) { mylo[a] = lo[a]; myhi[a] = hi[a]; }
-            __threadfence();
-            if (atomicExch(&nd->visit, kNone) != kNone) return;  // first to arrive (the field held the range end until now)
-            __threadfence();
-            // the sibling box was written by another SM: read it through L2 (this SM's L1 may hold the line from the child[] read)
-            const float* olo = side ? nd->lo0 : nd->lo1; const float* ohi = side ? nd->hi0 : nd->hi1;
-#pragma unroll
-            for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], __ldcg(olo + a)); hi[a] = fmaxf(hi[a], __ldcg(ohi + a)); }
-            me = p;
-            p = nd->parent;
         }
+        if (!local) {                               // a node that spans blocks: hand over to refit_global_kernel
+            const unsigned slot = atomicAdd(frontier_count, 1u);
+            if (slot >= frontier_cap) { refit_climb_global(nodes, p, me, lo, hi); return; }   // (a degenerate tree: finish here, slowly)
+            RefitEntry e;
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { e.lo[a] = lo[a]; e.hi[a] = hi[a]; }
+            e.node = p; e.from = me;
+            frontier[slot] = e;
+            return;
+        }
+        BvhNode* nd = nodes + p;
+        const unsigned slot = p - (uint32_t)base;
+        const int side = (link.x == me) ? 0 : 1;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { s_box[slot][side][a] = lo[a]; s_box[slot][side][3 + a] = hi[a]; }
+        __threadfence_block();
+        if (atomicAdd(&s_cnt[slot], 1u) == 0) return;            // first to arrive: the sibling will carry on
+        __threadfence_block();
+        float olo[3], ohi[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { olo[a] = ((volatile float*)s_box[slot][1 - side])[a]; ohi[a] = ((volatile float*)s_box[slot][1 - side])[3 + a]; }
+        // the second arrival writes both child boxes of the node at once: 48 contiguous bytes, three 128-bit stores
+        {
+            const float* l0 = side ? olo : lo; const float* h0 = side ? ohi : hi;     // child 0
+            const float* l1 = side ? lo : olo; const float* h1 = side ? hi : ohi;     // child 1
+            float4* dst = reinterpret_cast<float4*>(nd);
+            dst[0] = make_float4(l0[0], l0[1], l0[2], h0[0]);
+            dst[1] = make_float4(h0[1], h0[2], l1[0], l1[1]);
+            dst[2] = make_float4(l1[2], h1[0], h1[1], h1[2]);
+        }
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], olo[a]); hi[a] = fmaxf(hi[a], ohi[a]); }
+        me = p;
+        p = link.z;
         if (p == kNone) return;
     }
+}
+
+__global__ void __launch_bounds__(256) refit_global_kernel(BvhNode* nodes, const RefitEntry* __restrict__ frontier, const unsigned* __restrict__ frontier_count, unsigned cap) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned cnt = *frontier_count;
+    if (i >= (cnt < cap ? cnt : cap)) return;
+    const RefitEntry e = frontier[i];
+    float lo[3] = {e.lo[0], e.lo[1], e.lo[2]}, hi[3] = {e.hi[0], e.hi[1], e.hi[2]};
+    refit_climb_global(nodes, e.node, e.from, lo, hi);
 }
 
 }  // namespace b2

@@ -106,6 +106,28 @@ def test_large_random_soup_tree_is_valid(B):
     assert hc.validate(device_to_host(pn, bn), device_to_host(pt, bt), len(dup)) == 0
 
 
+def test_degenerate_tree_shapes(B):
+    """a deep, unbalanced LBVH (geometrically growing coordinates), built with the refit's frontier list disabled so that every
+    hand-over takes the in-place climb (test hook, option 101) and with the list enabled: same tree; results equal the oracle"""
+    n = 20000
+    s = 1.0005 ** np.arange(n)
+    tri = np.stack([s, s, s, s * 1.0001, s, s, s, s * 1.0001, s], 1)
+    g, o = B.AABB_tree(triangles=tri), orc.OracleTree(soup=tri)
+    g.set_option(101, 0)
+    g.build()
+    (pn, bn), (pt, bt) = g.export_layout()[:2]
+    nodes0 = device_to_host(pn, bn).view(np.uint32).reshape(-1, 16)[:, :15].copy()
+    assert hc.validate(device_to_host(pn, bn), device_to_host(pt, bt), n) == 0
+    g.set_option(101, 16)
+    g.build()
+    (pn, bn), (pt, bt) = g.export_layout()[:2]
+    np.testing.assert_array_equal(device_to_host(pn, bn).view(np.uint32).reshape(-1, 16)[:, :15], nodes0)
+    pts = np.stack([s[::7] * 1.00005, s[::7], s[::7] * 0.9999], 1)
+    check_closest_point(g.closest_point_and_primitive(pts), o.closest_point(pts), o, pts)
+    segs = np.concatenate([pts, pts * 1.01], 1)
+    np.testing.assert_array_equal(g.number_of_intersected_primitives(segs, SEG), o.count(segs, SEG))
+
+
 def test_config1_elephant_parity(B, meshes):
     """BASELINE.json configs[0]: elephant.off, random rays + closest-point queries, CPU oracle on all queries"""
     from cgal_b200 import workloads as W
