@@ -22,7 +22,7 @@ constexpr int kRsWarps = kRsThreads / 32;
 constexpr int kRsItems = 16;
 constexpr int kRsTile = kRsThreads * kRsItems;           // 4096 keys per tile
 constexpr uint32_t kRsFlagAgg = 1u << 30, kRsFlagIncl = 2u << 30, kRsFlagMask = 3u << 30, kRsValMask = ~kRsFlagMask;
-constexpr size_t kRsSmemBytes = kRsTile * 8 + kRsTile * 4 + kRsWarps * kRsBins * 4 + kRsBins * 4 * 2 + 64;
+constexpr size_t kRsSmemBytes = kRsTile * 8 + kRsWarps * kRsBins * 4 + kRsBins * 4 * 2 + 64;   // 42 KB: four blocks per SM (values reuse the key area)
 
 // hist[pass][bin] += number of keys whose digit `pass` is `bin`
 __global__ void __launch_bounds__(256) rs_histogram_kernel(const uint64_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ hist, int npasses) {
@@ -58,14 +58,14 @@ __global__ void __launch_bounds__(kRsBins) rs_scan_kernel(uint32_t* __restrict__
 }
 
 template <bool HAS_VALUES>
-__global__ void __launch_bounds__(kRsThreads) rs_onesweep_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout,
+__global__ void __launch_bounds__(kRsThreads, 4) rs_onesweep_kernel(const uint64_t* __restrict__ kin, uint64_t* __restrict__ kout,
                                                                  const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
                                                                  uint64_t n, int shift, const uint32_t* __restrict__ global_base,
                                                                  volatile uint32_t* lookback, uint32_t* tile_counter) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem_raw);
-    uint32_t* s_vals = reinterpret_cast<uint32_t*>(s_keys + kRsTile);
-    uint32_t* s_whist = s_vals + kRsTile;                 // [warps][bins]: per-warp digit counts, then per-warp exclusive offsets
+    uint32_t* s_vals = reinterpret_cast<uint32_t*>(smem_raw);   // the values pass through the same area once the keys have left it
+    uint32_t* s_whist = reinterpret_cast<uint32_t*>(s_keys + kRsTile);   // [warps][bins]: per-warp digit counts, then per-warp exclusive offsets
     uint32_t* s_dstart = s_whist + kRsWarps * kRsBins;    // exclusive prefix of the tile's digit counts
     uint32_t* s_goff = s_dstart + kRsBins;                // global index of tile-sorted position 0 of each digit run, minus s_dstart
     uint32_t* s_misc = s_goff + kRsBins;
@@ -141,24 +141,32 @@ __global__ void __launch_bounds__(kRsThreads) rs_onesweep_kernel(const uint64_t*
         pos[j] = s_dstart[d] + s_whist[warp * kRsBins + d] + rank[j];
         s_keys[pos[j]] = key[j];
     }
+    __syncthreads();
+    // run-contiguous stores to the final position of this pass
+    uint32_t g[kRsItems];
+#pragma unroll
+    for (int j = 0; j < kRsItems; ++j) {
+        const uint32_t i = tid + j * kRsThreads;
+        g[j] = 0;
+        if (i < valid) {
+            const uint64_t k = s_keys[i];
+            const uint32_t d = (uint32_t)(k >> shift) & (kRsBins - 1);
+            g[j] = s_goff[d] + i;
+            kout[g[j]] = k;
+        }
+    }
     if (HAS_VALUES) {
+        __syncthreads();                                              // every key has left shared memory
 #pragma unroll
         for (int j = 0; j < kRsItems; ++j) {
             const uint64_t idx = wbase + (uint64_t)j * 32;
             s_vals[pos[j]] = idx < n ? vin[idx] : 0u;
         }
-    }
-    __syncthreads();
-    // run-contiguous stores to the final position of this pass
+        __syncthreads();
 #pragma unroll
-    for (int j = 0; j < kRsItems; ++j) {
-        const uint32_t i = tid + j * kRsThreads;
-        if (i < valid) {
-            const uint64_t k = s_keys[i];
-            const uint32_t d = (uint32_t)(k >> shift) & (kRsBins - 1);
-            const uint32_t g = s_goff[d] + i;
-            kout[g] = k;
-            if (HAS_VALUES) vout[g] = s_vals[i];
+        for (int j = 0; j < kRsItems; ++j) {
+            const uint32_t i = tid + j * kRsThreads;
+            if (i < valid) vout[g[j]] = s_vals[i];
         }
     }
 }
