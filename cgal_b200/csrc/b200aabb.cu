@@ -53,7 +53,7 @@ __device__ __forceinline__ void flush_stats(const TreeRef& tr, const TravStat& s
 }
 
 template <bool IS_RAY, bool COUNT>
-__global__ void __launch_bounds__(128) intersect_kernel(const TreeRef tr, const double* __restrict__ q, uint64_t n, uint8_t* __restrict__ out8,
+__global__ void __launch_bounds__(128, 6) intersect_kernel(const TreeRef tr, const double* __restrict__ q, uint64_t n, uint8_t* __restrict__ out8,
                                                         uint32_t* __restrict__ out32) {
     const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     TravStat st;
@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(128) intersect_kernel(const TreeRef tr, const 
     flush_stats(tr, st, 0, 0);
 }
 
-__global__ void __launch_bounds__(128) first_intersection_kernel(const TreeRef tr, const double* __restrict__ rays, uint64_t n, uint32_t* __restrict__ prim,
+__global__ void __launch_bounds__(128, 6) first_intersection_kernel(const TreeRef tr, const double* __restrict__ rays, uint64_t n, uint32_t* __restrict__ prim,
                                                                  double* __restrict__ tpar, double* __restrict__ pt, double* __restrict__ pt2,
                                                                  uint8_t* __restrict__ flags) {
     const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
