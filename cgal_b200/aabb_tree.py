@@ -37,7 +37,8 @@ class _Stats(C.Structure):
 SYMBOLS = ["b200aabb_create", "b200aabb_destroy", "b200aabb_set_stream", "b200aabb_set_option", "b200aabb_last_error", "b200aabb_get_stats",
            "b200aabb_set_mesh", "b200aabb_set_triangles", "b200aabb_clear", "b200aabb_build",
            "b200aabb_accelerate_distance_queries", "b200aabb_size", "b200aabb_bbox", "b200aabb_do_intersect",
-           "b200aabb_number_of_intersected_primitives", "b200aabb_first_intersection", "b200aabb_closest_point",
+           "b200aabb_number_of_intersected_primitives", "b200aabb_any_intersected_primitive", "b200aabb_all_intersected_primitives",
+           "b200aabb_first_intersection", "b200aabb_closest_point",
            "b200aabb_export_layout", "b200aabb_import_alloc", "b200aabb_import_finish", "b200aabb_debug_predicate", "b200aabb_version"]
 
 
@@ -70,6 +71,8 @@ def load_library():
         L.b200aabb_bbox.argtypes = [vp, C.POINTER(C.c_double)]
         L.b200aabb_do_intersect.argtypes = [vp, dp, u64, C.c_int, C.c_int, dp]
         L.b200aabb_number_of_intersected_primitives.argtypes = [vp, dp, u64, C.c_int, C.c_int, dp]
+        L.b200aabb_any_intersected_primitive.argtypes = [vp, dp, u64, C.c_int, C.c_int, dp]
+        L.b200aabb_all_intersected_primitives.argtypes = [vp, dp, u64, C.c_int, C.c_int, dp, dp]
         L.b200aabb_first_intersection.argtypes = [vp, dp, u64, C.c_int, dp, dp, dp, dp, dp]
         L.b200aabb_closest_point.argtypes = [vp, dp, u64, C.c_int, dp, dp, dp, dp]
         L.b200aabb_export_layout.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.c_int, C.POINTER(C.c_int)]
@@ -221,6 +224,24 @@ class AABB_tree:
         o = _Buf(out, np.uint32, 1) if out is not None else _alloc_like(q, q.n, np.uint32, 1)
         self._check(self._lib.b200aabb_number_of_intersected_primitives(self._h, q.ptr, q.n, kind, int(q.device), o.ptr))
         return o.obj
+
+    def any_intersected_primitive(self, queries, kind=SEGMENT, out=None):
+        """any_intersected_primitive(query): id of one intersected primitive per query, NO_PRIMITIVE = nullopt"""
+        q = _Buf(queries, np.float64, 6)
+        o = _Buf(out, np.uint32, 1) if out is not None else _alloc_like(q, q.n, np.uint32, 1)
+        self._check(self._lib.b200aabb_any_intersected_primitive(self._h, q.ptr, q.n, kind, int(q.device), o.ptr))
+        return o.obj
+
+    def all_intersected_primitives(self, queries, kind=SEGMENT):
+        """all_intersected_primitives(query, out) for a HOST batch: (offsets uint64[n+1], ids uint32[total]); the ids of query i are
+        ids[offsets[i]:offsets[i+1]] (count pass -> prefix sums -> fill pass, include/b200aabb.h)"""
+        q = _Buf(np.asarray(queries), np.float64, 6)
+        counts = self.number_of_intersected_primitives(q.obj, kind)
+        offsets = np.zeros(q.n + 1, np.uint64)
+        np.cumsum(counts, out=offsets[1:])
+        ids = np.empty(max(int(offsets[-1]), 1), np.uint32)
+        self._check(self._lib.b200aabb_all_intersected_primitives(self._h, q.ptr, q.n, kind, 0, offsets.ctypes.data, ids.ctypes.data))
+        return offsets, ids[:int(offsets[-1])]
 
     def first_intersection(self, rays, want=("prim", "t", "point", "point2", "flags"), out=None):
         """first_intersection(Ray_3) for every ray: dict with prim (NO_PRIMITIVE = nullopt), t, point, point2, flags."""

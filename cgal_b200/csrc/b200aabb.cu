@@ -52,20 +52,31 @@ __device__ __forceinline__ void flush_stats(const TreeRef& tr, const TravStat& s
     }
 }
 
-template <bool IS_RAY, bool COUNT>
-__global__ void __launch_bounds__(128, 6) intersect_kernel(const TreeRef tr, const double* __restrict__ q, uint64_t n, uint8_t* __restrict__ out8,
-                                                        uint32_t* __restrict__ out32) {
+// out8: kAnyHit; out32: kCount, kAnyId; kList: ids of query i go to list[offsets[i] ..), and a count that disagrees with
+// offsets[i+1] - offsets[i] (the caller's prefix sums of a kCount run over the same batch) raises counters[2] bit 2
+template <bool IS_RAY, int MODE>
+__global__ void __launch_bounds__(128, 5) intersect_kernel(const TreeRef tr, const double* __restrict__ q, uint64_t n, uint8_t* __restrict__ out8,
+                                                           uint32_t* __restrict__ out32, const uint64_t* __restrict__ offsets, uint32_t* __restrict__ list) {
     const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     TravStat st;
     if (slot < n) {
         const uint64_t i = tr.perm ? tr.perm[slot] : slot;
-        const uint32_t r = traverse_intersect<IS_RAY, COUNT>(tr.nodes, tr.tris, tr.root, ld3(q + 6 * i), ld3(q + 6 * i + 3), st);
-        if (COUNT) out32[i] = r; else out8[i] = (uint8_t)(r != 0);
+        if (MODE == kList) {
+            const uint64_t lo = offsets[i], hi = offsets[i + 1];
+            uint32_t r = 0;
+            // (a query with no room for any id still traverses: its count must be 0)
+            if (hi > lo) r = traverse_intersect<IS_RAY, kList>(tr.nodes, tr.tris, tr.root, ld3(q + 6 * i), ld3(q + 6 * i + 3), st, list + lo, (uint32_t)(hi - lo));
+            else r = traverse_intersect<IS_RAY, kAnyHit>(tr.nodes, tr.tris, tr.root, ld3(q + 6 * i), ld3(q + 6 * i + 3), st);
+            if (r != hi - lo) atomicOr(&tr.counters[2], 4ull);
+        } else {
+            const uint32_t r = traverse_intersect<IS_RAY, MODE>(tr.nodes, tr.tris, tr.root, ld3(q + 6 * i), ld3(q + 6 * i + 3), st);
+            if (MODE == kAnyHit) out8[i] = (uint8_t)r; else out32[i] = r;
+        }
     }
     flush_stats(tr, st, 0, 0);
 }
 
-__global__ void __launch_bounds__(128, 6) first_intersection_kernel(const TreeRef tr, const double* __restrict__ rays, uint64_t n, uint32_t* __restrict__ prim,
+__global__ void __launch_bounds__(128, 5) first_intersection_kernel(const TreeRef tr, const double* __restrict__ rays, uint64_t n, uint32_t* __restrict__ prim,
                                                                  double* __restrict__ tpar, double* __restrict__ pt, double* __restrict__ pt2,
                                                                  uint8_t* __restrict__ flags) {
     const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -537,7 +548,7 @@ int b200aabb_get_stats(const b200aabb_tree* tc, b200aabb_stats* out) {
         unsigned long long c[8];
         B2_CUDA(t, cudaMemcpy(c, t->d_counters, sizeof(c), cudaMemcpyDeviceToHost));
         t->stats.exact_fallbacks = c[0]; t->stats.ties = c[1]; t->stats.nodes_visited = c[3]; t->stats.leaves_tested = c[4]; t->stats.near_ties = c[5]; t->stats.leaves_culled = c[6];
-        if (c[2]) t->err = (c[2] & 2) ? "closest_point work pool inconsistency: results incomplete" : "traversal stack overflow: results incomplete";
+        if (c[2]) t->err = (c[2] & 4) ? "offsets disagree with the number of intersected primitives" : (c[2] & 2) ? "closest_point work pool inconsistency: results incomplete" : "traversal stack overflow: results incomplete";
         t->query_timing_pending = false;
         if (c[2]) { *out = t->stats; return B200AABB_ERR_CUDA; }
     }
@@ -613,8 +624,8 @@ int b200aabb_do_intersect(b200aabb_tree* t, const double* q, uint64_t n, b200aab
     }
     const bool ray = kind == B200AABB_RAY;
     return run_batch(t, q, 48, n, space, kLineQuery, {{out, 1, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
-        if (ray) intersect_kernel<true, false><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint8_t*)o[0], nullptr);
-        else intersect_kernel<false, false><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint8_t*)o[0], nullptr);
+        if (ray) intersect_kernel<true, kAnyHit><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint8_t*)o[0], nullptr, nullptr, nullptr);
+        else intersect_kernel<false, kAnyHit><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint8_t*)o[0], nullptr, nullptr, nullptr);
     });
 }
 
@@ -628,9 +639,74 @@ int b200aabb_number_of_intersected_primitives(b200aabb_tree* t, const double* q,
     }
     const bool ray = kind == B200AABB_RAY;
     return run_batch(t, q, 48, n, space, kLineQuery, {{out, 4, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
-        if (ray) intersect_kernel<true, true><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, nullptr, (uint32_t*)o[0]);
-        else intersect_kernel<false, true><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, nullptr, (uint32_t*)o[0]);
+        if (ray) intersect_kernel<true, kCount><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, nullptr, (uint32_t*)o[0], nullptr, nullptr);
+        else intersect_kernel<false, kCount><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, nullptr, (uint32_t*)o[0], nullptr, nullptr);
     });
+}
+
+int b200aabb_any_intersected_primitive(b200aabb_tree* t, const double* q, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint32_t* out) {
+    if (!t || (n && (!q || !out))) return B200AABB_ERR_INVALID_ARGUMENT;
+    int rc = ensure_built(t);
+    if (rc || n == 0) return rc;
+    if (t->n == 0) {   // empty tree: nullopt
+        if (space == B200AABB_DEVICE) { B2_CUDA(t, cudaMemsetAsync(out, 0xFF, n * 4, t->stream)); } else memset(out, 0xFF, n * 4);
+        return B200AABB_OK;
+    }
+    const bool ray = kind == B200AABB_RAY;
+    return run_batch(t, q, 48, n, space, kLineQuery, {{out, 4, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
+        if (ray) intersect_kernel<true, kAnyId><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, nullptr, (uint32_t*)o[0], nullptr, nullptr);
+        else intersect_kernel<false, kAnyId><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, nullptr, (uint32_t*)o[0], nullptr, nullptr);
+    });
+}
+
+int b200aabb_all_intersected_primitives(b200aabb_tree* t, const double* q, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space,
+                                        const uint64_t* offsets, uint32_t* ids) {
+    if (!t || (n && (!q || !offsets))) return B200AABB_ERR_INVALID_ARGUMENT;
+    int rc = ensure_built(t);
+    if (rc || n == 0) return rc;
+    B2_CUDA(t, cudaSetDevice(t->device));
+    const bool ray = kind == B200AABB_RAY;
+    // one launch over the whole batch, in the caller's order (the id lists are variable-length: no chunked staging of the output)
+    const double* d_q = q; const uint64_t* d_off = offsets; uint32_t* d_ids = ids;
+    uint64_t total = 0;
+    void* tmp[3] = {nullptr, nullptr, nullptr};
+    auto release = [&]() { for (void* p : tmp) cudaFree(p); };
+    if (space == B200AABB_HOST) {
+        if (offsets[0] != 0) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "offsets[0] must be 0");
+        for (uint64_t i = 0; i < n; ++i) if (offsets[i + 1] < offsets[i]) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "offsets must be non-decreasing");
+        total = offsets[n];
+        if (total && !ids) return B200AABB_ERR_INVALID_ARGUMENT;
+        if (t->n == 0) return total == 0 ? B200AABB_OK : fail(t, B200AABB_ERR_INVALID_ARGUMENT, "offsets disagree with the number of intersected primitives");
+        cudaError_t e = cudaMalloc(&tmp[0], n * 48);
+        if (e == cudaSuccess) e = cudaMalloc(&tmp[1], (n + 1) * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&tmp[2], std::max<uint64_t>(total, 1) * 4);
+        if (e != cudaSuccess) { release(); t->err = "cudaMalloc(all_intersected_primitives staging)"; return B200AABB_ERR_OUT_OF_MEMORY; }
+        cudaMemcpyAsync(tmp[0], q, n * 48, cudaMemcpyHostToDevice, t->stream);
+        cudaMemcpyAsync(tmp[1], offsets, (n + 1) * 8, cudaMemcpyHostToDevice, t->stream);
+        d_q = (const double*)tmp[0]; d_off = (const uint64_t*)tmp[1]; d_ids = (uint32_t*)tmp[2];
+    } else if (t->n == 0) return B200AABB_OK;
+    cudaMemsetAsync(t->d_counters, 0, 8 * sizeof(unsigned long long), t->stream);
+    cudaEventRecord(t->ev_a, t->stream);
+    const uint32_t* perm = nullptr;
+    rc = coherence_order(t, 0, t->stream, d_q, n, kLineQuery, &perm);
+    if (rc) { release(); return rc; }
+    if (ray) intersect_kernel<true, kList><<<grid_for(n, 128), 128, 0, t->stream>>>(tree_ref(t, perm), d_q, n, nullptr, nullptr, d_off, d_ids);
+    else intersect_kernel<false, kList><<<grid_for(n, 128), 128, 0, t->stream>>>(tree_ref(t, perm), d_q, n, nullptr, nullptr, d_off, d_ids);
+    t->stats.kernel_launches += 1;
+    cudaEventRecord(t->ev_b, t->stream);
+    t->query_timing_pending = true;
+    if (space == B200AABB_HOST) {
+        if (total) cudaMemcpyAsync(ids, d_ids, total * 4, cudaMemcpyDeviceToHost, t->stream);
+        unsigned long long c2 = 0;
+        cudaMemcpyAsync(&c2, t->d_counters + 2, sizeof(c2), cudaMemcpyDeviceToHost, t->stream);
+        const cudaError_t e = cudaStreamSynchronize(t->stream);
+        release();
+        if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) { t->err = "all_intersected_primitives: CUDA failure"; return B200AABB_ERR_CUDA; }
+        if (c2 & 4ull) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "offsets disagree with the number of intersected primitives");
+        if (c2) return fail(t, B200AABB_ERR_CUDA, "traversal stack overflow: results incomplete");
+    }
+    B2_CUDA(t, cudaGetLastError());
+    return B200AABB_OK;
 }
 
 int b200aabb_first_intersection(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, uint32_t* prim, double* tpar, double* pt,

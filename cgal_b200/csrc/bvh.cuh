@@ -234,19 +234,31 @@ B2_HD bool warp_any(bool p) {
 // ---------------------------------------------------------------------------------------------------------------
 // do_intersect / number_of_intersected_primitives   (AABB_tree.h:903-932)
 // ---------------------------------------------------------------------------------------------------------------
-template <bool IS_RAY, bool COUNT>
+// MODE: kAnyHit   do_intersect (AABB_tree.h:903-913): 1 at the first intersected primitive, else 0
+//       kCount    number_of_intersected_primitives (:915-932)
+//       kAnyId    any_intersected_primitive (:947-956, First_primitive_traits): id of the first intersected primitive met, kNone if none
+//       kList     all_intersected_primitives (:934-945, Listing_primitive_traits): ids written to `list`, returns how many
+enum IntersectMode { kAnyHit = 0, kCount = 1, kAnyId = 2, kList = 3 };
+
+template <bool IS_RAY, int MODE>
 B2_HD uint32_t traverse_intersect(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root,
-                                  const Vec3& s, const Vec3& q, TravStat& st) {
+                                  const Vec3& s, const Vec3& q, TravStat& st, uint32_t* list = nullptr, uint32_t list_cap = 0) {
     const LineCtx c = make_line(s, q);
     const float tlimit = IS_RAY ? INFINITY : 1.0f;
-    uint32_t found = 0;
+    uint32_t found = 0, found_id = kNone;
     auto leaf = [&](uint32_t ref) {
         uint32_t id;
         const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
         ++st.leaves;
-        if (IS_RAY ? ray_tri_do_intersect(t, s, q, st.nexact) : seg_tri_do_intersect(t, s, q, st.nexact)) ++found;
+        if (IS_RAY ? ray_tri_do_intersect(t, s, q, st.nexact) : seg_tri_do_intersect(t, s, q, st.nexact)) {
+            if (MODE == kList && found < list_cap) list[found] = id;   // (never writes past the caller's room; the count tells)
+            if (MODE == kAnyId) found_id = id;
+            ++found;
+        }
     };
-    if (root & kLeafBit) { leaf(root); return found; }   // singleton tree: AABB_tree.h:516-525
+    constexpr bool kStopAtFirst = MODE == kAnyHit || MODE == kAnyId;
+    auto result = [&]() -> uint32_t { return MODE == kAnyId ? found_id : (MODE == kAnyHit ? (found ? 1u : 0u) : found); };
+    if (root & kLeafBit) { leaf(root); return result(); }   // singleton tree: AABB_tree.h:516-525
     uint32_t stack[kStackCap];
     int sp = 0;
     uint32_t pend[2];
@@ -272,11 +284,11 @@ B2_HD uint32_t traverse_intersect(const BvhNode* __restrict__ nodes, const TriRe
         }
         while (np > 0) {                                  // leaf phase
             leaf(pend[--np]);
-            if (!COUNT && found) return 1;
+            if (kStopAtFirst && found) return result();
         }
         if (cur == kNone) break;
     }
-    return found;
+    return result();
 }
 
 // ---------------------------------------------------------------------------------------------------------------

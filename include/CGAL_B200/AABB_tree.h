@@ -167,6 +167,21 @@ class AABB_tree {
     number_of_intersected_primitives(&query, &query + 1, &r);
     return r;
   }
+  // all_intersected_primitives(query, out) (AABB_tree.h:253-257,934-945): out receives Primitive_id, in traversal order
+  template <typename Query, typename OutputIterator>
+  OutputIterator all_intersected_primitives(const Query& query, OutputIterator out) const {
+    std::vector<std::vector<Primitive_id>> r;
+    all_intersected_primitives(&query, &query + 1, std::back_inserter(r));
+    for (const Primitive_id& id : r[0]) *out++ = id;
+    return out;
+  }
+  // any_intersected_primitive(query) (AABB_tree.h:265-268,947-956)
+  template <typename Query>
+  std::optional<Primitive_id> any_intersected_primitive(const Query& query) const {
+    std::optional<Primitive_id> r;
+    any_intersected_primitive(&query, &query + 1, &r);
+    return r;
+  }
   Ray_intersection first_intersection(const Ray& query) const {
     Ray_intersection r;
     first_intersection(&query, &query + 1, &r);
@@ -221,6 +236,41 @@ class AABB_tree {
     ensure_built();
     check(b200aabb_number_of_intersected_primitives(m_handle, q.data(), n, kind_of<Query>(), B200AABB_HOST, r.data()));
     for (uint64_t i = 0; i < n; ++i) *out++ = (size_type)r[i];
+    return out;
+  }
+  // out receives std::optional<Primitive_id>
+  template <typename QueryIterator, typename OutputIterator>
+  OutputIterator any_intersected_primitive(QueryIterator first, QueryIterator beyond, OutputIterator out) const {
+    typedef typename std::iterator_traits<QueryIterator>::value_type Query;
+    std::vector<double> q = pack_lines(first, beyond);
+    const uint64_t n = q.size() / 6;
+    std::vector<uint32_t> r(n);
+    ensure_built();
+    check(b200aabb_any_intersected_primitive(m_handle, q.data(), n, kind_of<Query>(), B200AABB_HOST, r.data()));
+    for (uint64_t i = 0; i < n; ++i) {
+      if (r[i] == B200AABB_NO_PRIMITIVE) *out++ = std::nullopt;
+      else *out++ = std::optional<Primitive_id>(m_primitives[r[i]].id());
+    }
+    return out;
+  }
+  // out receives one std::vector<Primitive_id> per query (count pass -> prefix sums -> fill pass, include/b200aabb.h)
+  template <typename QueryIterator, typename OutputIterator>
+  OutputIterator all_intersected_primitives(QueryIterator first, QueryIterator beyond, OutputIterator out) const {
+    typedef typename std::iterator_traits<QueryIterator>::value_type Query;
+    std::vector<double> q = pack_lines(first, beyond);
+    const uint64_t n = q.size() / 6;
+    std::vector<uint32_t> cnt(n);
+    ensure_built();
+    check(b200aabb_number_of_intersected_primitives(m_handle, q.data(), n, kind_of<Query>(), B200AABB_HOST, cnt.data()));
+    std::vector<uint64_t> off(n + 1, 0);
+    for (uint64_t i = 0; i < n; ++i) off[i + 1] = off[i] + cnt[i];
+    std::vector<uint32_t> ids(off[n] ? off[n] : 1);
+    check(b200aabb_all_intersected_primitives(m_handle, q.data(), n, kind_of<Query>(), B200AABB_HOST, off.data(), ids.data()));
+    for (uint64_t i = 0; i < n; ++i) {
+      std::vector<Primitive_id> v;
+      for (uint64_t k = off[i]; k < off[i + 1]; ++k) v.push_back(m_primitives[ids[k]].id());
+      *out++ = v;
+    }
     return out;
   }
   // out receives std::optional< Intersection_and_primitive_id<Ray>::Type >; flags (optional) receives the B200AABB_FLAG_* bits

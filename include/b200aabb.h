@@ -118,6 +118,18 @@ int b200aabb_do_intersect(b200aabb_tree* t, const double* queries, uint64_t n, b
 /* number_of_intersected_primitives(query), AABB_tree.h:915-932 */
 int b200aabb_number_of_intersected_primitives(b200aabb_tree* t, const double* queries, uint64_t n, b200aabb_query_kind kind,
                                               b200aabb_memspace space, uint32_t* out);
+/* any_intersected_primitive(query), AABB_tree.h:947-956 (First_primitive_traits, internal/AABB_traversal_traits.h:188-231):
+ * out[i] = id of ONE intersected primitive (which one depends on the traversal order, in the reference too), or
+ * B200AABB_NO_PRIMITIVE. */
+int b200aabb_any_intersected_primitive(b200aabb_tree* t, const double* queries, uint64_t n, b200aabb_query_kind kind,
+                                       b200aabb_memspace space, uint32_t* out);
+/* all_intersected_primitives(query, out), AABB_tree.h:934-945 (Listing_primitive_traits, :150-184).  Variable-length output in two
+ * steps: the caller runs b200aabb_number_of_intersected_primitives, forms offsets[n+1] = exclusive prefix sums of the counts, and
+ * passes room for offsets[n] ids; the ids of query i are written to ids[offsets[i] .. offsets[i+1]) (in traversal order, which is
+ * unspecified in the reference as well).  A count that disagrees with the offsets is an error (INVALID_ARGUMENT; for DEVICE
+ * pointers it is reported by the next b200aabb_get_stats); nothing is ever written outside a query's own range. */
+int b200aabb_all_intersected_primitives(b200aabb_tree* t, const double* queries, uint64_t n, b200aabb_query_kind kind,
+                                        b200aabb_memspace space, const uint64_t* offsets, uint32_t* ids);
 /* first_intersection(Ray_3) / first_intersected_primitive, AABB_tree/internal/AABB_ray_intersection.h:201-240.
  * rays: n x 6 (source, second point).  Outputs (any may be NULL): prim[n]; t[n] = ray parameter of the hit as the
  * reference computes it (:168-198); point[n x 3] = the Point_3, or the first endpoint of the Segment_3;

@@ -1,6 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY.  Nothing under cgal_b200/ may include, link or call this.
 // C entry points (ctypes) over the CPU restatement in kernel.hpp / tree.hpp.  Used by tests/, by
 // __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs, never by the product.
+#include <atomic>
 #include <chrono>
 #include <cstdint>
 #include <cstring>
@@ -80,6 +81,29 @@ void orc_count(void* hv, const double* q, uint64_t n, int kind, uint32_t* out, i
     parallel_for(n, nthreads, [&](uint64_t b, uint64_t e) {
         for (uint64_t i = b; i < e; ++i) out[i] = t.number_of_intersected_primitives({P(q + 6 * i), P(q + 6 * i + 3), kind == 1});
     });
+}
+// any_intersected_primitive (AABB_tree.h:947-956): 0xFFFFFFFF when none
+void orc_any_intersected_primitive(void* hv, const double* q, uint64_t n, int kind, uint32_t* out, int nthreads) {
+    const Tree& t = *((Handle*)hv)->tree;
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e) {
+        for (uint64_t i = b; i < e; ++i) out[i] = t.any_intersected_primitive({P(q + 6 * i), P(q + 6 * i + 3), kind == 1});
+    });
+}
+// all_intersected_primitives (AABB_tree.h:934-945): ids of query i, in the reference's traversal order, at ids[offsets[i] .. offsets[i+1]);
+// offsets = exclusive prefix sums of orc_count.  Returns -1 if a count disagrees with the offsets.
+int orc_all_intersected_primitives(void* hv, const double* q, uint64_t n, int kind, const uint64_t* offsets, uint32_t* ids, int nthreads) {
+    const Tree& t = *((Handle*)hv)->tree;
+    std::atomic<int> bad{0};
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e) {
+        std::vector<uint32_t> v;
+        for (uint64_t i = b; i < e; ++i) {
+            v.clear();
+            t.all_intersected_primitives({P(q + 6 * i), P(q + 6 * i + 3), kind == 1}, v);
+            if (v.size() != offsets[i + 1] - offsets[i]) { bad = 1; continue; }
+            std::copy(v.begin(), v.end(), ids + offsets[i]);
+        }
+    });
+    return bad ? -1 : 0;
 }
 // first_intersection(Ray_3).  prim = 0xFFFFFFFF when none.  kind: 0 none, 1 Point_3, 2 Segment_3.
 // pts: n x 6 (point, or the two segment endpoints).  tie[i] = 1 if another primitive produced exactly the same t.

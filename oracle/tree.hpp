@@ -218,6 +218,18 @@ struct Tree {
         }
         bool do_intersect(const LineQ& q, const Box& b) const { return do_intersect_bbox(q.p, q.q, b, q.is_ray); }
     };
+    // First_primitive_traits :188-231 (any_intersected_primitive, AABB_tree.h:947-956): the first intersected primitive in traversal order
+    struct FirstPrimitiveTT {
+        const Tree& t; bool found = false; uint32_t id = 0xFFFFFFFFu;
+        bool go_further() const { return !found; }
+        void intersection(const LineQ& q, uint32_t f) {
+            if (q.is_ray ? do_intersect_ray_tri(t.mesh->datum(f), q.p, q.q) : do_intersect_seg_tri(t.mesh->datum(f), q.p, q.q)) { found = true; id = f; }
+        }
+        bool do_intersect(const LineQ& q, const Box& b) const { return do_intersect_bbox(q.p, q.q, b, q.is_ray); }
+    };
+    uint32_t any_intersected_primitive(const LineQ& q) const { FirstPrimitiveTT tt{*this}; traversal(q, tt); return tt.id; }
+    // Listing_primitive_traits :150-184 (all_intersected_primitives, AABB_tree.h:934-945): ids in traversal order
+    void all_intersected_primitives(const LineQ& q, std::vector<uint32_t>& out) const { CountTT tt{*this}; tt.ids = &out; traversal(q, tt); }
     bool do_intersect(const LineQ& q) const { DoIntersectTT tt{*this}; traversal(q, tt); return tt.found; }          // AABB_tree.h:903-913
     uint32_t number_of_intersected_primitives(const LineQ& q) const { CountTT tt{*this}; traversal(q, tt); return tt.count; }  // :915-932
 

@@ -85,6 +85,17 @@ static int known_answers() {
     CHECK(std::holds_alternative<Point>(hit->first) && std::get<Point>(hit->first) == Point(0.2, 0.2, 0.0));
     CHECK(tree.first_intersected_primitive(up) && *tree.first_intersected_primitive(up) == mini::Face_index(0));
     CHECK(tree.number_of_intersected_primitives(up) == 2);
+    {   // all_intersected_primitives / any_intersected_primitive (AABB_tree.h:253-268): the two faces the ray crosses, base face 0 among them
+      std::vector<mini::Face_index> ids;
+      tree.all_intersected_primitives(up, std::back_inserter(ids));
+      CHECK(ids.size() == 2 && (ids[0] == mini::Face_index(0) || ids[1] == mini::Face_index(0)) && !(ids[0] == ids[1]));
+      const auto any = tree.any_intersected_primitive(up);
+      CHECK(any && (*any == ids[0] || *any == ids[1]));
+      CHECK(!tree.any_intersected_primitive(Ray(Point(0.2, 0.2, -1.0), Point(0.2, 0.2, -2.0))));
+      std::vector<mini::Face_index> none;
+      tree.all_intersected_primitives(Segment(Point(5, 5, 5), Point(6, 6, 6)), std::back_inserter(none));
+      CHECK(none.empty());
+    }
     CHECK(!tree.first_intersection(Ray(Point(0.2, 0.2, -1.0), Point(0.2, 0.2, -2.0))));
     const auto cpp = tree.closest_point_and_primitive(Point(0.2, 0.2, -1.0));
     CHECK(cpp.first == Point(0.2, 0.2, 0.0) && cpp.second == mini::Face_index(0));
@@ -95,6 +106,7 @@ static int known_answers() {
     const Segment s(Point(0.1, 0.1, -1), Point(0.1, 0.1, 1));
     CHECK(tree.empty() && tree.size() == 0);
     CHECK(!tree.do_intersect(s) && tree.number_of_intersected_primitives(s) == 0);
+    CHECK(!tree.any_intersected_primitive(s));
     CHECK(!tree.first_intersection(Ray(s.source(), s.target())));
     bool threw = false;
     try { tree.closest_point(Point(0, 0, 0)); } catch (const CGAL_B200::Error& e) { threw = e.code() == B200AABB_ERR_EMPTY_TREE; }

@@ -126,8 +126,8 @@ void hc_intersect(void* hv, const double* q, uint64_t n, int is_ray, int count, 
         TravStat st;
         if (h->n == 0) { out[i] = 0; continue; }
         const Vec3 s = V(q + 6 * i), e = V(q + 6 * i + 3);
-        if (is_ray) out[i] = count ? traverse_intersect<true, true>(h->nodes.data(), h->tris.data(), h->root, s, e, st) : traverse_intersect<true, false>(h->nodes.data(), h->tris.data(), h->root, s, e, st);
-        else out[i] = count ? traverse_intersect<false, true>(h->nodes.data(), h->tris.data(), h->root, s, e, st) : traverse_intersect<false, false>(h->nodes.data(), h->tris.data(), h->root, s, e, st);
+        if (is_ray) out[i] = count ? traverse_intersect<true, kCount>(h->nodes.data(), h->tris.data(), h->root, s, e, st) : traverse_intersect<true, kAnyHit>(h->nodes.data(), h->tris.data(), h->root, s, e, st);
+        else out[i] = count ? traverse_intersect<false, kCount>(h->nodes.data(), h->tris.data(), h->root, s, e, st) : traverse_intersect<false, kAnyHit>(h->nodes.data(), h->tris.data(), h->root, s, e, st);
     }
 }
 void hc_first_intersection(void* hv, const double* rays, uint64_t n, uint32_t* prim, double* t, double* pts, uint8_t* kind, uint8_t* tie) {

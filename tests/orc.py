@@ -44,6 +44,9 @@ def lib():
         L.orc_bbox.argtypes = [C.c_void_p, _dp]
         L.orc_do_intersect.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_int, _u8p, C.c_int]
         L.orc_count.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_int, _u32p, C.c_int]
+        L.orc_any_intersected_primitive.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_int, _u32p, C.c_int]
+        L.orc_all_intersected_primitives.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), _u32p, C.c_int]
+        L.orc_all_intersected_primitives.restype = C.c_int
         L.orc_first_intersection.argtypes = [C.c_void_p, _dp, C.c_uint64, _u32p, _dp, _dp, _u8p, _u8p, C.c_int]
         L.orc_closest_point.argtypes = [C.c_void_p, _dp, C.c_uint64, _dp, _u32p, _dp, C.c_int]
         L.orc_closest_point.restype = C.c_int
@@ -123,6 +126,22 @@ class OracleTree:
         f = lib().orc_naive_count if naive else lib().orc_count
         f(self.h, _ptr(q, _dp), len(q), kind, _ptr(out, _u32p), threads or nthreads())
         return out
+
+    def any_intersected_primitive(self, q, kind, threads=None):
+        q = _d(q).reshape(-1, 6)
+        out = np.zeros(len(q), np.uint32)
+        lib().orc_any_intersected_primitive(self.h, _ptr(q, _dp), len(q), kind, _ptr(out, _u32p), threads or nthreads())
+        return out
+
+    def all_intersected_primitives(self, q, kind, threads=None):
+        """(offsets[n+1], ids): ids of query i, in the reference's traversal order, are ids[offsets[i]:offsets[i+1]]"""
+        q = _d(q).reshape(-1, 6)
+        offsets = np.zeros(len(q) + 1, np.uint64)
+        np.cumsum(self.count(q, kind, threads), out=offsets[1:])
+        ids = np.zeros(max(int(offsets[-1]), 1), np.uint32)
+        rc = lib().orc_all_intersected_primitives(self.h, _ptr(q, _dp), len(q), kind, offsets.ctypes.data_as(C.POINTER(C.c_uint64)), _ptr(ids, _u32p), threads or nthreads())
+        assert rc == 0
+        return offsets, ids[:int(offsets[-1])]
 
     def first_intersection(self, rays, threads=None):
         rays = _d(rays).reshape(-1, 6)

@@ -152,6 +152,44 @@ def test_config1_elephant_parity(B, meshes):
         np.testing.assert_array_equal(g.do_intersect(q, kind), (want > 0).astype(np.uint8))
 
 
+def test_all_and_any_intersected_primitives(B, meshes):
+    """all_intersected_primitives / any_intersected_primitive (AABB_tree.h:934-956): the id SET of every query equals the oracle's
+    (the order within a query is the traversal order, unspecified in the reference too); `any` returns a member of the set"""
+    from cgal_b200 import workloads as W
+    v, f = meshes["elephant"]
+    g, o = B.AABB_tree(v, f), orc.OracleTree(v, f)
+    bb = g.bbox()
+    for kind, q in ((SEG, W.bbox_segments(bb, 60_000)), (RAY, W.sphere_rays(bb, 60_000))):
+        off, ids = g.all_intersected_primitives(q, kind)
+        roff, rids = o.all_intersected_primitives(q, kind)
+        np.testing.assert_array_equal(off, roff)
+        assert off[-1] > 10_000
+        owner = np.repeat(np.arange(len(q)), np.diff(off).astype(np.int64))
+        key = lambda own, i: np.sort(own.astype(np.uint64) << np.uint64(32) | i.astype(np.uint64))   # noqa: E731
+        np.testing.assert_array_equal(key(owner, ids), key(owner, rids))                   # same (query, id) pairs
+        a = g.any_intersected_primitive(q, kind)
+        cnt = np.diff(off)
+        np.testing.assert_array_equal(a == B.NO_PRIMITIVE, cnt == 0)
+        pairs = set(zip(owner.tolist(), ids.tolist()))
+        assert all((i, int(a[i])) in pairs for i in np.nonzero(cnt)[0][:5000])
+    # wrong offsets are refused, and nothing is written outside a query's own range
+    q = W.bbox_segments(bb, 1000)
+    cnt = g.number_of_intersected_primitives(q, SEG)
+    off = np.zeros(len(q) + 1, np.uint64)
+    np.cumsum(cnt, out=off[1:])
+    bad = off.copy()
+    k = int(np.nonzero(cnt)[0][0])
+    bad[k + 1:] -= np.uint64(1)                      # one id short for query k
+    ids = np.full(int(off[-1]) + 8, 0xDEADBEEF, np.uint32)
+    rc = g._lib.b200aabb_all_intersected_primitives(g._h, q.ctypes.data, len(q), SEG, 0, bad.ctypes.data, ids.ctypes.data)
+    assert rc == -1 and np.all(ids[int(bad[-1]):] == 0xDEADBEEF)
+    # empty tree
+    e = B.AABB_tree()
+    assert e.any_intersected_primitive(q[:3], SEG).tolist() == [B.NO_PRIMITIVE] * 3
+    eo, ei = e.all_intersected_primitives(q[:3], SEG)
+    assert eo.tolist() == [0, 0, 0, 0] and len(ei) == 0
+
+
 def test_config2_icosphere_distance_field_parity(B):
     from cgal_b200 import workloads as W
     v, f = W.icosphere(6)       # 81,920 triangles (config 2 uses level 8; same generator)
