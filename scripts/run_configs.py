@@ -48,6 +48,23 @@ def main():
                           "max_abs_err_vs_sphere": float((d - want).abs().max()), "ties": st["ties"]}), flush=True)
         assert float((d - want).abs().max()) < 2e-4          # unsigned distance field of the unit sphere, up to the facet sagitta
         del g, pts, r
+    if "3" in which:
+        v, f = W.terrain(4096, 2048)
+        g = B.AABB_tree(v, f)
+        g.set_stream(torch.cuda.current_stream().cuda_stream)
+        g.build()
+        segs = torch.from_numpy(W.shadow_segments(v, 1 << 24)).cuda()
+        ms, hit = timed(lambda: g.do_intersect(segs, B.SEGMENT))
+        st = g.stats()
+        ms2, cnt = timed(lambda: g.number_of_intersected_primitives(segs, B.SEGMENT))
+        st2 = g.stats()
+        hit, cnt = hit.cpu().numpy(), cnt.cpu().numpy()
+        assert np.array_equal(hit != 0, cnt > 0)
+        print(json.dumps({"config": 3, "triangles": len(f), "shadow_segments": len(segs), "do_intersect_ms": round(ms, 2), "do_intersect_Mq_s": round(len(segs) / ms / 1e3, 1),
+                          "in_shadow": float((hit != 0).mean()), "nodes_q": round(st["nodes_visited"] / len(segs), 1), "leaves_q": round(st["leaves_tested"] / len(segs), 1),
+                          "count_ms": round(ms2, 2), "count_nodes_q": round(st2["nodes_visited"] / len(segs), 1), "count_leaves_q": round(st2["leaves_tested"] / len(segs), 1),
+                          "exact_stage_queries": st2["exact_fallbacks"]}), flush=True)
+        del g, segs
     if "4" in which:
         n = int(os.environ.get("SOUP_N", "100000000"))
         t0 = time.time()
