@@ -26,8 +26,8 @@
 // from the batch cursor (queries are handed out in coherence order).  A new query first walks down to its nearest leaf on its
 // own lane (nearest child first), pushing the far children, and projects on that leaf: that is its first ball (the kd-tree hint
 // of the reference, AABB_tree.h:591-612, is not needed).
-// The node pool is a stack in shared memory whose bottom half is spilled to a per-warp area in global memory when it fills and
-// reloaded when the stack runs empty, so depth is bounded by kWpSpillCap only (overflow is reported, never silent).
+// The node pool is a stack in shared memory (a ring) whose bottom half is spilled to a per-warp area in global memory when it fills
+// and put back when the stack runs low, so depth is bounded by kWpSpillCap only (overflow is reported, never silent).
 // What bounds this kernel (profiles/r1_05): the L1 data stage, one wavefront per cycle, because every lane fetches its own node /
 // triangle: hence the packed slot state, the binary32 triangle copy and no per-slot bookkeeping atomics.
 #pragma once
@@ -35,13 +35,13 @@
 
 namespace b2 {
 
-constexpr int kWpNodeCap = 320;                 // (slot,node) entries held in shared memory
+constexpr int kWpNodeCap = 768;                 // (slot,node) entries held in shared memory
 constexpr int kWpSpillChunk = kWpNodeCap / 2;   // entries moved per spill / reload
-constexpr int kWpSpillCap = 24 * kWpSpillChunk; // entries per warp in the global spill area
+constexpr int kWpSpillCap = 16 * kWpSpillChunk; // entries per warp in the global spill area
 constexpr int kWpLeafCap = 96;                  // < 32 waiting + at most 64 added by one node phase
 constexpr int kWpMidCap = 128;                  // < 32 waiting + at most 95 added by one pre-test-1 phase
 constexpr int kWpExactCap = 128;                // pre-test 2 stops handing over when fewer than 32 places are left
-constexpr int kWpWarpsPerSM = 28;               // resident warps per SM this kernel is sized for (registers <= 72, shared memory <= 7.1 KB)
+constexpr int kWpWarpsPerSM = 20;               // resident warps per SM this kernel is sized for (registers <= 102, shared memory <= 10.4 KB): measured best of 16 / 20 / 24 / 28
 constexpr uint32_t kWpRefMask = 0x07FFFFFFu;    // 27 bits of leaf slot next to the 5-bit query slot
 constexpr uint64_t kWpMaxPrims = 1ull << 27;
 
@@ -200,26 +200,25 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
     uint32_t st_nodes = 0, st_leaves = 0, st_culled = 0, st_exact = 0, st_ties = 0;
 
     // moves the bottom kWpSpillChunk entries of the stack to global memory; false = spill area exhausted
+    // The node pool is a ring: logical entry i (0 = bottom of the stack) sits in npool[ring(i)], so that spilling the bottom or
+    // putting it back moves no other entry.
+    int nbase = 0;                                                    // slot of logical entry 0
+    auto ring = [&](int i) -> int { const int k = nbase + i; return k >= kWpNodeCap ? k - kWpNodeCap : k; };
+    // moves the bottom kWpSpillChunk entries of the stack to global memory; false = spill area exhausted
     auto spill_bottom = [&]() -> bool {
         if (spilled + kWpSpillChunk > kWpSpillCap) return false;
-        for (int i = lane; i < kWpSpillChunk; i += 32) myspill[spilled + i] = S.npool[i];
+        for (int i = lane; i < kWpSpillChunk; i += 32) myspill[spilled + i] = S.npool[ring(i)];
         __syncwarp();
-        for (int base = kWpSpillChunk; base < ncnt; base += 32) {
-            const int idx = base + (int)lane;
-            uint2 v = make_uint2(0, 0);
-            if (idx < ncnt) v = S.npool[idx];
-            __syncwarp();
-            if (idx < ncnt) S.npool[idx - kWpSpillChunk] = v;
-            __syncwarp();
-        }
+        nbase = ring(kWpSpillChunk);
         spilled += kWpSpillChunk; ncnt -= kWpSpillChunk;
         return true;
     };
 
     while (true) {
-        if (ncnt == 0 && spilled > 0) {                       // reload the most recently spilled chunk
-            for (int i = lane; i < kWpSpillChunk; i += 32) S.npool[i] = __ldcg(&myspill[spilled - kWpSpillChunk + i]);
-            spilled -= kWpSpillChunk; ncnt = kWpSpillChunk;
+        if (ncnt < 32 && spilled > 0) {                       // put the most recently spilled chunk back under the stack
+            nbase = nbase >= kWpSpillChunk ? nbase - kWpSpillChunk : nbase - kWpSpillChunk + kWpNodeCap;
+            for (int i = lane; i < kWpSpillChunk; i += 32) S.npool[ring(i)] = __ldcg(&myspill[spilled - kWpSpillChunk + i]);
+            spilled -= kWpSpillChunk; ncnt += kWpSpillChunk;
             __syncwarp();
         }
         if (ncnt == 0 && lcnt == 0 && mcnt == 0 && ecnt == 0) {
@@ -278,7 +277,7 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                     if (c0 & kLeafBit) { firstleaf = c0; stop = true; } else cur = c0;
                 }
                 const unsigned pm = __ballot_sync(full, push);
-                S.npool[push ? ncnt + __popc(pm & lt) : kWpNodeCap] = make_uint2(farref, (__float_as_uint(fard) & ~31u) | lane);
+                S.npool[push ? ring(ncnt + __popc(pm & lt)) : kWpNodeCap] = make_uint2(farref, (__float_as_uint(fard) & ~31u) | lane);
                 ncnt += __popc(pm);
                 if (stop) act = false;
             }
@@ -323,7 +322,7 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                 const int take = ncnt < 32 ? ncnt : 32;
                 const bool has = (int)lane < take;
                 ncnt -= take;
-                const uint2 e = S.npool[has ? ncnt + (int)lane : kWpNodeCap];
+                const uint2 e = S.npool[has ? ring(ncnt + (int)lane) : kWpNodeCap];
                 const unsigned owner = e.y & 31u;
                 const float4 q = S.qa[owner];
                 const bool live = has && __uint_as_float(e.y & ~31u) <= q.w;
@@ -357,11 +356,11 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                 {
                     const bool p1 = in1 && !(r1 & kLeafBit);
                     const unsigned m1 = __ballot_sync(full, p1);
-                    S.npool[p1 ? ncnt + __popc(m1 & lt) : kWpNodeCap] = make_uint2(r1, (__float_as_uint(d1) & ~31u) | owner);
+                    S.npool[p1 ? ring(ncnt + __popc(m1 & lt)) : kWpNodeCap] = make_uint2(r1, (__float_as_uint(d1) & ~31u) | owner);
                     ncnt += __popc(m1);
                     const bool p0 = in0 && !(r0 & kLeafBit);
                     const unsigned m0 = __ballot_sync(full, p0);
-                    S.npool[p0 ? ncnt + __popc(m0 & lt) : kWpNodeCap] = make_uint2(r0, (__float_as_uint(d0) & ~31u) | owner);
+                    S.npool[p0 ? ring(ncnt + __popc(m0 & lt)) : kWpNodeCap] = make_uint2(r0, (__float_as_uint(d0) & ~31u) | owner);
                     ncnt += __popc(m0);
                 }
                 __syncwarp();
