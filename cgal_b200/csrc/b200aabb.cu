@@ -52,10 +52,11 @@ __device__ __forceinline__ void flush_stats(const TreeRef& tr, const TravStat& s
     }
 }
 
+// (8 blocks per SM = 64 registers: measured best of 3 / 4 / 5 / 6 / 8 / 10 on the config 3 and config 4 segment batches)
 // out8: kAnyHit; out32: kCount, kAnyId; kList: ids of query i go to list[offsets[i] ..), and a count that disagrees with
 // offsets[i+1] - offsets[i] (the caller's prefix sums of a kCount run over the same batch) raises counters[2] bit 2
 template <bool IS_RAY, int MODE>
-__global__ void __launch_bounds__(128, 5) intersect_kernel(const TreeRef tr, const double* __restrict__ q, uint64_t n, uint8_t* __restrict__ out8,
+__global__ void __launch_bounds__(128, 8) intersect_kernel(const TreeRef tr, const double* __restrict__ q, uint64_t n, uint8_t* __restrict__ out8,
                                                            uint32_t* __restrict__ out32, const uint64_t* __restrict__ offsets, uint32_t* __restrict__ list) {
     const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     TravStat st;
