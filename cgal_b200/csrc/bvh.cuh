@@ -473,7 +473,7 @@ B2_HD Closest traverse_closest(const BvhNode* __restrict__ nodes, const TriRec* 
     auto certainly_outside = [&](const Tri3& t, bool sharp) -> bool { return tri_certainly_outside(t, o, ub, sub, rbound, sharp); };
     // the reference's per-primitive step: Construct_projected_point_3 + Compare_distance_3 against the incumbent
     auto evaluate = [&](const Tri3& t, uint32_t id) {
-        const Vec3 cp = closest_on_triangle(t, o);
+        const Vec3 cp = closest_candidate(t, o, st.nexact);
         const Vec3 v = cp - o;
         const double sqd = (v.x * v.x + v.y * v.y) + v.z * v.z;   // Compute_squared_distance_3(query, closest): AABB_tree.h:1024-1032
         bool take;

@@ -161,13 +161,31 @@ __device__ __forceinline__ float wp_lower(const float* u, float su, const RelTri
 // triangle (vertex rounding m 2^-24 each, six binary32 operations on magnitudes <= 2 m), so dist <= |P| + 2.1e-6 m; the formula
 // allows 8e-6 m + 1e-5 |P| + dslack.  The winner's candidate is no farther than this primitive's candidate, which lies within the
 // rounding allowance of the true distance (the premise of widen_sqdist), so pruning with `hi` never discards the winner or a
-// primitive tied with it.  hi = NaN (degenerate triangle) compares false everywhere: no bound.  e2: see wp_relative.
+// primitive tied with it.  hi = NaN (no bound) compares false everywhere.  e2: see wp_relative.
 __device__ __forceinline__ void wp_sharp(const RelTri& r, float dslack, float e2, float* lower, float* hi) {
     float u[3];
     approx_closest_to_origin(r.ra, r.rb, r.rc, u);
     const float su = sqrtf(dot3f(u, u));
     *lower = wp_lower(u, su, r) - e2;
-    *hi = ((su * 1.00001f + 8e-6f * r.m) + dslack) + e2;
+    // The upper bound may only be used when the reference's own projection on this primitive is accurate, i.e. when the triangle is
+    // well conditioned: |ab x ac|^2 >= 1e-6 |ab|^2 |ac|^2 (sine of the angle at a >= 1e-3) with both edges well above the noise of
+    // the binary32 coordinates.  For degenerate triangles and slivers Construct_projected_point_3 can return a point far from the
+    // closest one (function_objects.h:3208-3247), so their candidates promise nothing: no bound.
+    const float ab[3] = {r.rb[0] - r.ra[0], r.rb[1] - r.ra[1], r.rb[2] - r.ra[2]}, ac[3] = {r.rc[0] - r.ra[0], r.rc[1] - r.ra[1], r.rc[2] - r.ra[2]};
+    const float n[3] = {ab[1] * ac[2] - ab[2] * ac[1], ab[2] * ac[0] - ab[0] * ac[2], ab[0] * ac[1] - ab[1] * ac[0]};
+    const float lab = dot3f(ab, ab), lac = dot3f(ac, ac), noise = 1e3f * (e2 + r.m * 2.4e-7f);
+    const bool sound = dot3f(n, n) >= 1e-6f * lab * lac && lab > noise * noise && lac > noise * noise;
+    *hi = sound ? ((su * 1.00001f + 8e-6f * r.m) + dslack) + e2 : __int_as_float(0x7fc00000);
+}
+
+// The binary64 projection, out of line and with its arguments in registers: the kernel calls it from the refill and from the exact
+// phase, and keeping this long routine (and its own register needs) out of the body keeps the node loop's allocation tight.
+struct CandOut { double x, y, z; int nexact; };
+__device__ __noinline__ CandOut wp_candidate(double ax, double ay, double az, double bx, double by, double bz, double cx, double cy, double cz,
+                                             double ox, double oy, double oz) {
+    int nexact = 0;
+    const Vec3 p = closest_candidate(Tri3{{ax, ay, az}, {bx, by, bz}, {cx, cy, cz}}, Vec3{ox, oy, oz}, nexact);
+    return CandOut{p.x, p.y, p.z, nexact};
 }
 
 // the replacement step of the reference (AABB_traits_3.h:724-732) for slot `owner`, given sg = Compare_distance_3(query, candidate,
@@ -197,7 +215,8 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
     const float ev = float_above(a.mag * 5.9604645e-8 * 1.000001);   // >= rounding of a vertex coordinate to binary32
     int ncnt = 0, lcnt = 0, mcnt = 0, ecnt = 0, spilled = 0;         // warp-uniform
     unsigned active = 0;                                              // slots holding a query of the current batch
-    uint32_t st_nodes = 0, st_leaves = 0, st_culled = 0, st_exact = 0, st_ties = 0;
+    // statistics as warp-uniform counts taken from ballots (per-lane counters cost five registers that the exact phase needs)
+    uint32_t w_nodes = 0, w_leaves = 0, w_evals = 0, w_exact = 0, w_ties = 0;
 
     // moves the bottom kWpSpillChunk entries of the stack to global memory; false = spill area exhausted
     // The node pool is a ring: logical entry i (0 = bottom of the stack) sits in npool[ring(i)], so that spilling the bottom or
@@ -230,8 +249,12 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                 if (a.prim) a.prim[qi] = S.bprim[lane];
                 if (a.sqd) a.sqd[qi] = __ldcg(&G.bsqd[lane]);
                 if (a.flags) a.flags[qi] = (uint8_t)fl;
-                if (fl & a.flag_tie) ++st_ties;
-                if (fl & a.flag_exact) ++st_exact;
+            }
+            {
+                const bool act = (active >> lane) & 1u;
+                const uint32_t fl = act ? S.flags[lane] : 0u;
+                w_ties += __popc(__ballot_sync(full, (fl & a.flag_tie) != 0));
+                w_exact += __popc(__ballot_sync(full, (fl & a.flag_exact) != 0));
             }
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(a.cursor, 32ull);
@@ -264,9 +287,9 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                     if (!spill_bottom()) { if (lane == 0) atomicOr(&a.counters[2], 1ull); return; }
                 }
                 uint32_t farref = 0; float fard = 0.0f; bool stop = false, push = false;
+                w_nodes += __popc(__ballot_sync(full, act));
                 if (act) {
                     const NodeView nd = load_node(a.nodes, cur);
-                    ++st_nodes;
                     float d0 = wp_box_sqdist(nd.lo0, nd.hi0, q), d1 = wp_box_sqdist(nd.lo1, nd.hi1, q);
                     far2 = fminf(far2, fminf(wp_box_far_sqdist(nd.lo0, nd.hi0, q), wp_box_far_sqdist(nd.lo1, nd.hi1, q)));
                     uint32_t c0 = nd.c0, c1 = nd.c1;
@@ -284,8 +307,9 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
             if (valid) {
                 uint32_t id;
                 const Tri3 t = load_tri(a.tris, firstleaf & ~kLeafBit, id);
-                ++st_leaves;
-                const Vec3 cpt = closest_on_triangle(t, o);
+                const CandOut co = wp_candidate(t.a.x, t.a.y, t.a.z, t.b.x, t.b.y, t.b.z, t.c.x, t.c.y, t.c.z, o.x, o.y, o.z);
+                const int nex0 = co.nexact;
+                const Vec3 cpt = {co.x, co.y, co.z};
                 const Vec3 v = cpt - o;
                 const double sqd = (v.x * v.x + v.y * v.y) + v.z * v.z;
                 __stcg(&G.o[0][lane], o.x); __stcg(&G.o[1][lane], o.y); __stcg(&G.o[2][lane], o.z);
@@ -297,9 +321,10 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                 wp_set_bounds(S, lane, sqd, v, delta, true);
                 if (a.debug_hint_sqd) wp_shrink(S, lane, float_above(sqrt(widen_sqdist(a.debug_hint_sqd[qi], delta))));
                 S.qidx[lane] = qi;
-                S.flags[lane] = 0;
+                S.flags[lane] = nex0 ? a.flag_exact : 0u;
             }
             active = __ballot_sync(full, valid);
+            w_leaves += __popc(active); w_evals += __popc(active);
             __syncwarp();
             continue;
         }
@@ -329,12 +354,12 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                 __syncwarp();                                      // all pops read before any push overwrites them
                 const bool popped_leaf = live && (e.x & kLeafBit);
                 const bool expand = live && !(e.x & kLeafBit);
+                w_nodes += __popc(__ballot_sync(full, expand));
                 bool in0 = false, in1 = false;                     // 0 = nearer child, 1 = farther child
                 uint32_t r0 = 0, r1 = 0;
                 float d0 = 0.0f, d1 = 0.0f;
                 if (expand) {
                     const NodeView nd = load_node(a.nodes, e.x);
-                    ++st_nodes;
                     d0 = wp_box_sqdist(nd.lo0, nd.hi0, q); d1 = wp_box_sqdist(nd.lo1, nd.hi1, q);
                     r0 = nd.c0; r1 = nd.c1;
                     if (d1 < d0) { const uint32_t tc = r0; r0 = r1; r1 = tc; const float td = d0; d0 = d1; d1 = td; }
@@ -375,16 +400,15 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                 if (i < lcnt) {
                     pair = S.lpool[i];
                     const unsigned owner = pair >> 27;
-                    ++st_leaves;
                     const RelTri r = wp_relative(a.trisf, pair & kWpRefMask, S.qa[owner]);
                     const float4 qb = S.qb[owner];
                     const float4 qc = S.qc[owner];
                     const float ub[3] = {qb.x, qb.y, qb.z};
                     const float g[3] = {(r.ra[0] + r.rb[0]) + r.rc[0], (r.ra[1] + r.rb[1]) + r.rc[1], (r.ra[2] + r.rb[2]) + r.rc[2]};
                     lb = fmaxf(wp_lower(ub, qb.w, r), wp_lower(g, sqrtf(dot3f(g, g)), r)) - qc.y;   // tangent plane of the ball; centroid direction
-                    if (lb > qc.x) ++st_culled;
-                    else survive = true;
+                    survive = !(lb > qc.x);
                 }
+                w_leaves += (lcnt - base) < 32 ? (lcnt - base) : 32;
                 const unsigned sm = __ballot_sync(full, survive);
                 if (survive) S.mpool[mcnt + __popc(sm & lt)] = make_uint2(pair, __float_as_uint(lb));
                 mcnt += __popc(sm);
@@ -401,15 +425,13 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                     e = S.mpool[mcnt + (int)lane];
                     const unsigned owner = e.x >> 27;
                     const float4 qc = S.qc[owner];
-                    if (__uint_as_float(e.y) > qc.x) ++st_culled;   // the ball has shrunk since pre-test 1
-                    else {
+                    if (!(__uint_as_float(e.y) > qc.x)) {           // (else: the ball has shrunk since pre-test 1)
                         const RelTri r = wp_relative(a.trisf, e.x & kWpRefMask, S.qa[owner]);
                         float lb, hi;
                         wp_sharp(r, qc.z, qc.y, &lb, &hi);
                         if (hi < qc.x) wp_shrink(S, owner, hi);   // this primitive is certainly nearer than the slot's ball: shrink it now, in binary32
                         lb = fmaxf(lb, __uint_as_float(e.y));
-                        if (lb > qc.x) ++st_culled;
-                        else { survive = true; e.y = __float_as_uint(lb); }
+                        if (!(lb > qc.x)) { survive = true; e.y = __float_as_uint(lb); }
                     }
                 }
                 const unsigned sm = __ballot_sync(full, survive);
@@ -428,7 +450,6 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                     e = S.epool[i];
                     const unsigned owner = e.x >> 27;
                     keep = !(__uint_as_float(e.y) > S.qc[owner].x);
-                    if (!keep) ++st_culled;
                 }
                 __syncwarp();
                 const unsigned km = __ballot_sync(full, keep);
@@ -450,11 +471,12 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                     if (has) {
                         const uint2 e = S.epool[i];
                         owner = e.x >> 27;
-                        if (__uint_as_float(e.y) > S.qc[owner].x) ++st_culled;   // (an earlier batch of this very phase may have shrunk the ball)
-                        else {
+                        if (!(__uint_as_float(e.y) > S.qc[owner].x)) {   // (else: an earlier batch of this very phase has shrunk the ball)
                             const Tri3 t = load_tri(a.tris, e.x & kWpRefMask, id);
                             o = {__ldcg(&G.o[0][owner]), __ldcg(&G.o[1][owner]), __ldcg(&G.o[2][owner])};
-                            cpt = closest_on_triangle(t, o);
+                            const CandOut co = wp_candidate(t.a.x, t.a.y, t.a.z, t.b.x, t.b.y, t.b.z, t.c.x, t.c.y, t.c.z, o.x, o.y, o.z);
+                            cpt = {co.x, co.y, co.z};
+                            if (co.nexact) atomicOr(&S.flags[owner], a.flag_exact);
                             v = cpt - o;
                             sqd = (v.x * v.x + v.y * v.y) + v.z * v.z;   // Compute_squared_distance_3(query, closest): AABB_tree.h:1024-1032
                             key = __float_as_uint((float)sqd);
@@ -466,6 +488,7 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                     // the next round.  Each replacement is a step the sequential reference loop could have taken, and a candidate farther
                     // than an earlier incumbent is farther than every later one, so the outcome is that of the sequential loop.
                     unsigned pm = __ballot_sync(full, pending);
+                    w_evals += __popc(pm);
                     while (pm) {
                         int sg = 0;
                         if (pending) {
@@ -492,14 +515,12 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
         }
         __syncwarp();
     }
-    const unsigned nodes = __reduce_add_sync(full, st_nodes), leaves = __reduce_add_sync(full, st_leaves), culled = __reduce_add_sync(full, st_culled);
-    const unsigned exact = __reduce_add_sync(full, st_exact), ties = __reduce_add_sync(full, st_ties);
     if (lane == 0) {
-        atomicAdd(&a.counters[3], (unsigned long long)nodes);
-        atomicAdd(&a.counters[4], (unsigned long long)leaves);
-        if (culled) atomicAdd(&a.counters[6], (unsigned long long)culled);
-        if (exact) atomicAdd(&a.counters[0], (unsigned long long)exact);
-        if (ties) atomicAdd(&a.counters[1], (unsigned long long)ties);
+        atomicAdd(&a.counters[3], (unsigned long long)w_nodes);
+        atomicAdd(&a.counters[4], (unsigned long long)w_leaves);
+        atomicAdd(&a.counters[6], (unsigned long long)(w_leaves - w_evals));   // leaves that never reached the binary64 projection
+        if (w_exact) atomicAdd(&a.counters[0], (unsigned long long)w_exact);
+        if (w_ties) atomicAdd(&a.counters[1], (unsigned long long)w_ties);
     }
 }
 

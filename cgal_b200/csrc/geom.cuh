@@ -290,4 +290,29 @@ B2_HD Vec3 closest_on_triangle(const Tri3& t, const Vec3& o) {
     return d3 >= d2 ? t.b : t.c;
 }
 
+// The candidate a primitive contributes to closest_point: its projection, or its reference point (first vertex) when that is
+// strictly nearer.  The reference starts every query from best_hint() = the nearest reference point over all primitives
+// (AABB_tree.h:591-612, internal/AABB_search_tree.h) and keeps it unless a projection is not farther (AABB_traits_3.h:724-732);
+// the nearest reference point belongs to a primitive whose box reaches the final ball, so taking the reference point of every
+// visited primitive into account reproduces the hint's effect exactly.  It only ever matters for degenerate (zero-area)
+// triangles, where Construct_projected_point_3 may return a point that is not the closest one (function_objects.h:3208-3247).
+// (arguments by value: a call through references would route the nine coordinates through local memory)
+B2_HD_NOINLINE int cmp_dist_out_of_line(double px, double py, double pz, double qx, double qy, double qz, double rx, double ry, double rz) {
+    int nexact = 0;
+    const int s = cmp_dist(Vec3{px, py, pz}, Vec3{qx, qy, qz}, Vec3{rx, ry, rz}, nexact);
+    return (s + 1) | (nexact ? 4 : 0);
+}
+B2_HD Vec3 closest_candidate(const Tri3& t, const Vec3& o, int& nexact) {
+    const Vec3 cp = closest_on_triangle(t, o);
+    // plain binary64 first: both squared distances are sums of squares (relative error < 1e-15), so a reference point that looks
+    // farther by more than 1e-12 relative IS farther; only the rest (the closest point is at or next to the first vertex, or a
+    // degenerate triangle) takes the exact comparison, kept out of line so that this common path stays short
+    if (same_point(t.a, cp)) return cp;                       // (often: the closest point IS the first vertex)
+    const double da = sqlen3(t.a - o), dc = sqlen3(cp - o);
+    if (da > dc + dc * 1e-12 && dc > 1e-290) return cp;
+    const int r = cmp_dist_out_of_line(o.x, o.y, o.z, t.a.x, t.a.y, t.a.z, cp.x, cp.y, cp.z);
+    if (r & 4) ++nexact;
+    return (r & 3) == 0 ? t.a : cp;
+}
+
 }  // namespace b2

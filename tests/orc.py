@@ -191,6 +191,12 @@ class OracleTree:
         lib().orc_candidate_closest(self.h, int(face), _ptr(q, _dp), _ptr(out, _dp))
         return out
 
+    def reference_point(self, face):
+        """first vertex of the primitive's datum (AABB_face_graph_triangle_primitive reference point)"""
+        if hasattr(self, "soup"):
+            return self.soup[int(face), 0:3].copy()
+        return self.verts[int(self.faces[int(face), 0])].copy()
+
     def candidate_ray_hit(self, face, ray):
         ray = _d(ray)
         t = C.c_double(0)

@@ -232,6 +232,48 @@ def test_closest_point_kernels_agree(B, exact_go, sort):
     assert list(r2["prim"]) == [0, 1, 0] and r2["flags"][2] & B.FLAG_TIE and not (r2["flags"][0] & B.FLAG_TIE)
 
 
+@pytest.mark.parametrize("kernel", [1, 0])
+def test_closest_point_adversarial_inputs(B, kernel):
+    """inputs that stress the binary32 pruning aids of closest_point (they may only ever fail to prune): degenerate and needle
+    triangles, thousands of coincident primitives (exact ties), coordinates far from the origin (binary32 copies useless),
+    a tiny scene; both kernels must return the oracle's records"""
+    from cgal_b200 import workloads as W
+    rng = np.random.default_rng(23)
+
+    def check(tri, pts, min_ties=0):
+        g, o = B.AABB_tree(triangles=tri), orc.OracleTree(soup=tri)
+        g.set_option(B.OPT_CLOSEST_KERNEL, kernel)
+        got = g.closest_point_and_primitive(pts)
+        mism, ties = check_closest_point(got, o.closest_point(pts), o, pts)
+        assert ties >= min_ties
+        return got
+
+    base = W.triangle_soup(3000)
+    # zero-area triangles (a point, a segment), needles, and well-shaped ones mixed
+    deg = base.copy()
+    deg[0::5, 3:6] = deg[0::5, 0:3]; deg[0::5, 6:9] = deg[0::5, 0:3]                   # points
+    deg[1::5, 6:9] = 0.5 * (deg[1::5, 0:3] + deg[1::5, 3:6])                          # collinear
+    deg[2::5, 6:9] = deg[2::5, 0:3] + 1e-13 * rng.standard_normal((len(deg[2::5]), 3))   # needles
+    pts = rng.random((20000, 3))
+    check(deg, pts)
+    check(deg, np.concatenate([deg[0::5, 0:3], deg[1::5, 6:9]]))                      # queries ON the degenerate primitives
+    # 4 triangles, 2500 copies each: every query ties 2500-fold; smallest id wins and the tie is reported
+    dup = np.tile(base[:4], (2500, 1))
+    got = check(dup, pts[:3000], min_ties=3000)
+    assert np.all(got["prim"] < 4) and np.all(got["flags"] & B.FLAG_TIE)
+    # far from the origin: |coordinates| ~ 1e7 with unit-size scene (binary32 ulp = 1) and a micro scene at 1e-6 scale
+    far = base + 1e7
+    check(far, pts[:5000] + 1e7)
+    tiny = base * 1e-6
+    check(tiny, pts[:5000] * 1e-6)
+    # a large flat grid seen from far away: thousands of leaves within the rounding allowance of the same distance
+    v, f = W.terrain(128, 128, amplitude=0.0)
+    g, o = B.AABB_tree(v, f), orc.OracleTree(v, f)
+    g.set_option(B.OPT_CLOSEST_KERNEL, kernel)
+    hi = np.stack([rng.random(2000) * 128, rng.random(2000) * 128, 1e4 + rng.random(2000)], 1)
+    check_closest_point(g.closest_point_and_primitive(hi), o.closest_point(hi), o, hi)
+
+
 def test_config3_terrain_rays_and_shadow_segments_parity(B):
     from cgal_b200 import workloads as W
     v, f = W.terrain(512, 256)  # 262,144 triangles (config 3 uses 4096 x 2048; same generator)
