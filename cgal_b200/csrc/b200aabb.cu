@@ -77,6 +77,36 @@ __global__ void __launch_bounds__(128, 8) intersect_kernel(const TreeRef tr, con
     flush_stats(tr, st, 0, 0);
 }
 
+// all_intersections / any_intersection (Ray_3): bvh.cuh::traverse_ray_objects.  kCount: out32[i]; kList: entries of ray i at offsets[i] ..
+// (a count that disagrees with offsets[i+1] - offsets[i] raises counters[2] bit 2); kAnyId: prim / flags / pt / pt2 like first_intersection
+template <int MODE>
+__global__ void __launch_bounds__(128, 5) ray_objects_kernel(const TreeRef tr, const double* __restrict__ rays, uint64_t n, uint32_t* __restrict__ out32,
+                                                             const uint64_t* __restrict__ offsets, uint32_t* __restrict__ ids, uint8_t* __restrict__ kinds,
+                                                             double* __restrict__ pts, uint32_t* __restrict__ prim, uint8_t* __restrict__ flags,
+                                                             double* __restrict__ pt, double* __restrict__ pt2) {
+    const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    TravStat st;
+    if (slot < n) {
+        const uint64_t i = tr.perm ? tr.perm[slot] : slot;
+        const Vec3 s = ld3(rays + 6 * i), q = ld3(rays + 6 * i + 3);
+        if (MODE == kCount) {
+            out32[i] = traverse_ray_objects<kCount>(tr.nodes, tr.tris, tr.root, s, q, st, nullptr, nullptr, nullptr, 0);
+        } else if (MODE == kList) {
+            const uint64_t lo = offsets[i], hi = offsets[i + 1];
+            const uint32_t r = traverse_ray_objects<kList>(tr.nodes, tr.tris, tr.root, s, q, st, ids + lo, kinds + lo, pts + 6 * lo, (uint32_t)(hi - lo));
+            if (r != hi - lo) atomicOr(&tr.counters[2], 4ull);
+        } else {
+            uint32_t id = kNone; uint8_t kind = 0; double p[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            traverse_ray_objects<kAnyId>(tr.nodes, tr.tris, tr.root, s, q, st, &id, &kind, p, 1);
+            if (prim) prim[i] = id;
+            if (flags) flags[i] = (uint8_t)((kind ? B200AABB_FLAG_HIT : 0) | (kind == 2 ? B200AABB_FLAG_SEGMENT : 0) | (st.nexact ? B200AABB_FLAG_EXACT : 0));
+            if (pt) { pt[3 * i] = p[0]; pt[3 * i + 1] = p[1]; pt[3 * i + 2] = p[2]; }
+            if (pt2) { pt2[3 * i] = p[3]; pt2[3 * i + 1] = p[4]; pt2[3 * i + 2] = p[5]; }
+        }
+    }
+    flush_stats(tr, st, 0, 0);
+}
+
 __global__ void __launch_bounds__(128, 5) first_intersection_kernel(const TreeRef tr, const double* __restrict__ rays, uint64_t n, uint32_t* __restrict__ prim,
                                                                  double* __restrict__ tpar, double* __restrict__ pt, double* __restrict__ pt2,
                                                                  uint8_t* __restrict__ flags) {
@@ -704,6 +734,86 @@ int b200aabb_all_intersected_primitives(b200aabb_tree* t, const double* q, uint6
         release();
         if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) { t->err = "all_intersected_primitives: CUDA failure"; return B200AABB_ERR_CUDA; }
         if (c2 & 4ull) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "offsets disagree with the number of intersected primitives");
+        if (c2) return fail(t, B200AABB_ERR_CUDA, "traversal stack overflow: results incomplete");
+    }
+    B2_CUDA(t, cudaGetLastError());
+    return B200AABB_OK;
+}
+
+int b200aabb_number_of_intersections(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, uint32_t* out) {
+    if (!t || (n && (!rays || !out))) return B200AABB_ERR_INVALID_ARGUMENT;
+    int rc = ensure_built(t);
+    if (rc || n == 0) return rc;
+    if (t->n == 0) {
+        if (space == B200AABB_DEVICE) { B2_CUDA(t, cudaMemsetAsync(out, 0, n * 4, t->stream)); } else memset(out, 0, n * 4);
+        return B200AABB_OK;
+    }
+    return run_batch(t, rays, 48, n, space, kLineQuery, {{out, 4, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
+        ray_objects_kernel<kCount><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint32_t*)o[0], nullptr, nullptr, nullptr, nullptr,
+                                                                       nullptr, nullptr, nullptr, nullptr);
+    });
+}
+
+int b200aabb_any_intersection(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, uint32_t* prim, double* pt, double* pt2, uint8_t* flags) {
+    if (!t || (n && !rays)) return B200AABB_ERR_INVALID_ARGUMENT;
+    int rc = ensure_built(t);
+    if (rc || n == 0) return rc;
+    if (t->n == 0) return b200aabb_first_intersection(t, rays, n, space, prim, nullptr, pt, pt2, flags);   // nullopt for every ray
+    return run_batch(t, rays, 48, n, space, kLineQuery, {{prim, 4, 0}, {pt, 24, 0}, {pt2, 24, 0}, {flags, 1, 0}},
+                     [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
+                         ray_objects_kernel<kAnyId><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                                                        (uint32_t*)o[0], (uint8_t*)o[3], (double*)o[1], (double*)o[2]);
+                     });
+}
+
+int b200aabb_all_intersections(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, const uint64_t* offsets, uint32_t* ids,
+                               uint8_t* kinds, double* points) {
+    if (!t || (n && (!rays || !offsets))) return B200AABB_ERR_INVALID_ARGUMENT;
+    int rc = ensure_built(t);
+    if (rc || n == 0) return rc;
+    B2_CUDA(t, cudaSetDevice(t->device));
+    const double* d_q = rays; const uint64_t* d_off = offsets; uint32_t* d_ids = ids; uint8_t* d_kinds = kinds; double* d_pts = points;
+    uint64_t total = 0;
+    void* tmp[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    auto release = [&]() { for (void* p : tmp) cudaFree(p); };
+    if (space == B200AABB_HOST) {
+        if (offsets[0] != 0) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "offsets[0] must be 0");
+        for (uint64_t i = 0; i < n; ++i) if (offsets[i + 1] < offsets[i]) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "offsets must be non-decreasing");
+        total = offsets[n];
+        if (total && (!ids || !kinds || !points)) return B200AABB_ERR_INVALID_ARGUMENT;
+        if (t->n == 0) return total == 0 ? B200AABB_OK : fail(t, B200AABB_ERR_INVALID_ARGUMENT, "offsets disagree with the number of intersections");
+        const uint64_t room = std::max<uint64_t>(total, 1);
+        cudaError_t e = cudaMalloc(&tmp[0], n * 48);
+        if (e == cudaSuccess) e = cudaMalloc(&tmp[1], (n + 1) * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&tmp[2], room * 4);
+        if (e == cudaSuccess) e = cudaMalloc(&tmp[3], room);
+        if (e == cudaSuccess) e = cudaMalloc(&tmp[4], room * 48);
+        if (e != cudaSuccess) { release(); t->err = "cudaMalloc(all_intersections staging)"; return B200AABB_ERR_OUT_OF_MEMORY; }
+        cudaMemcpyAsync(tmp[0], rays, n * 48, cudaMemcpyHostToDevice, t->stream);
+        cudaMemcpyAsync(tmp[1], offsets, (n + 1) * 8, cudaMemcpyHostToDevice, t->stream);
+        d_q = (const double*)tmp[0]; d_off = (const uint64_t*)tmp[1]; d_ids = (uint32_t*)tmp[2]; d_kinds = (uint8_t*)tmp[3]; d_pts = (double*)tmp[4];
+    } else if (t->n == 0) return B200AABB_OK;
+    cudaMemsetAsync(t->d_counters, 0, 8 * sizeof(unsigned long long), t->stream);
+    cudaEventRecord(t->ev_a, t->stream);
+    const uint32_t* perm = nullptr;
+    rc = coherence_order(t, 0, t->stream, d_q, n, kLineQuery, &perm);
+    if (rc) { release(); return rc; }
+    ray_objects_kernel<kList><<<grid_for(n, 128), 128, 0, t->stream>>>(tree_ref(t, perm), d_q, n, nullptr, d_off, d_ids, d_kinds, d_pts, nullptr, nullptr, nullptr, nullptr);
+    t->stats.kernel_launches += 1;
+    cudaEventRecord(t->ev_b, t->stream);
+    t->query_timing_pending = true;
+    if (space == B200AABB_HOST) {
+        if (total) {
+            cudaMemcpyAsync(ids, d_ids, total * 4, cudaMemcpyDeviceToHost, t->stream);
+            cudaMemcpyAsync(kinds, d_kinds, total, cudaMemcpyDeviceToHost, t->stream);
+            cudaMemcpyAsync(points, d_pts, total * 48, cudaMemcpyDeviceToHost, t->stream);
+        }
+        unsigned long long c2 = 0;
+        cudaMemcpyAsync(&c2, t->d_counters + 2, sizeof(c2), cudaMemcpyDeviceToHost, t->stream);
+        const cudaError_t e = cudaStreamSynchronize(t->stream);
+        release();
+        if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) { t->err = "all_intersections: CUDA failure"; return B200AABB_ERR_CUDA; }
+        if (c2 & 4ull) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "offsets disagree with the number of intersections");
         if (c2) return fail(t, B200AABB_ERR_CUDA, "traversal stack overflow: results incomplete");
     }
     B2_CUDA(t, cudaGetLastError());

@@ -242,25 +242,13 @@ B2_HD bool warp_any(bool p) {
 //       kList     all_intersected_primitives (:934-945, Listing_primitive_traits): ids written to `list`, returns how many
 enum IntersectMode { kAnyHit = 0, kCount = 1, kAnyId = 2, kList = 3 };
 
-template <bool IS_RAY, int MODE>
-B2_HD uint32_t traverse_intersect(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root,
-                                  const Vec3& s, const Vec3& q, TravStat& st, uint32_t* list = nullptr, uint32_t list_cap = 0) {
-    const LineCtx c = make_line(s, q);
+// The traversal shared by all intersection queries: visits every leaf whose box the query line meets and calls leaf(ref) -> bool
+// ("this primitive counts"); returns how many did.  STOP_AT_FIRST ends at the first one.
+template <bool IS_RAY, bool STOP_AT_FIRST, class Leaf>
+B2_HD uint32_t traverse_line(const BvhNode* __restrict__ nodes, uint32_t root, const LineCtx& c, TravStat& st, Leaf&& leaf) {
     const float tlimit = IS_RAY ? INFINITY : 1.0f;
-    uint32_t found = 0, found_id = kNone;
-    auto leaf = [&](uint32_t ref) {
-        uint32_t id;
-        const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
-        ++st.leaves;
-        if (IS_RAY ? ray_tri_do_intersect(t, s, q, st.nexact) : seg_tri_do_intersect(t, s, q, st.nexact)) {
-            if (MODE == kList && found < list_cap) list[found] = id;   // (never writes past the caller's room; the count tells)
-            if (MODE == kAnyId) found_id = id;
-            ++found;
-        }
-    };
-    constexpr bool kStopAtFirst = MODE == kAnyHit || MODE == kAnyId;
-    auto result = [&]() -> uint32_t { return MODE == kAnyId ? found_id : (MODE == kAnyHit ? (found ? 1u : 0u) : found); };
-    if (root & kLeafBit) { leaf(root); return result(); }   // singleton tree: AABB_tree.h:516-525
+    uint32_t found = 0;
+    if (root & kLeafBit) return leaf(root) ? 1u : 0u;       // singleton tree: AABB_tree.h:516-525
     uint32_t stack[kStackCap];
     int sp = 0;
     // Leaves awaiting the exact test: a thread collects up to kPendCount before it leaves the node phase, so that the (long) exact
@@ -289,12 +277,60 @@ B2_HD uint32_t traverse_intersect(const BvhNode* __restrict__ nodes, const TriRe
             cur = next;
         }
         while (np > 0) {                                  // leaf phase
-            leaf(pend[--np]);
-            if (kStopAtFirst && found) return result();
+            if (leaf(pend[--np])) { ++found; if (STOP_AT_FIRST) return found; }
         }
         if (cur == kNone) break;
     }
-    return result();
+    return found;
+}
+
+template <bool IS_RAY, int MODE>
+B2_HD uint32_t traverse_intersect(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root,
+                                  const Vec3& s, const Vec3& q, TravStat& st, uint32_t* list = nullptr, uint32_t list_cap = 0) {
+    const LineCtx c = make_line(s, q);
+    uint32_t nlisted = 0, found_id = kNone;
+    constexpr bool kStopAtFirst = MODE == kAnyHit || MODE == kAnyId;
+    const uint32_t found = traverse_line<IS_RAY, kStopAtFirst>(nodes, root, c, st, [&](uint32_t ref) -> bool {
+        uint32_t id;
+        const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
+        ++st.leaves;
+        if (!(IS_RAY ? ray_tri_do_intersect(t, s, q, st.nexact) : seg_tri_do_intersect(t, s, q, st.nexact))) return false;
+        if (MODE == kList) { if (nlisted < list_cap) list[nlisted] = id; ++nlisted; }   // (never writes past the caller's room; the count tells)
+        if (MODE == kAnyId) found_id = id;
+        return true;
+    });
+    return MODE == kAnyId ? found_id : (MODE == kAnyHit ? (found ? 1u : 0u) : found);
+}
+
+// all_intersections / any_intersection (Ray_3): every primitive whose Intersect_3(Ray_3, Triangle_3) is non-empty, with the
+// intersection object (Listing_intersection_traits / First_intersection_traits, AABB_traversal_traits.h:58-144; AABB_tree.h:958-985).
+// The object is the one first_intersection constructs (geom.cuh::ray_tri_intersection: the reference evaluates the construction-side
+// predicates on the ROUNDED point a + (q - p), so this set can differ from do_intersect's for a ray nearly parallel to a triangle,
+// SURVEY.md §7 hard part 3).  Entry k of the query: ids[k], kinds[k] (1 Point_3, 2 Segment_3), pts[6k..] = point / two endpoints.
+// MODE kCount: count only; kList: fill (at most cap entries); kAnyId: stop at the first, written as entry 0.
+template <int MODE>
+B2_HD uint32_t traverse_ray_objects(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root, const Vec3& s, const Vec3& q,
+                                    TravStat& st, uint32_t* ids, uint8_t* kinds, double* pts, uint32_t cap) {
+    const LineCtx c = make_line(s, q);
+    uint32_t nlisted = 0;
+    return traverse_line<true, MODE == kAnyId>(nodes, root, c, st, [&](uint32_t ref) -> bool {
+        uint32_t id;
+        const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
+        ++st.leaves;
+        const RayX x = ray_tri_intersection(t, s, q, c.d, c.major, st.nexact);
+        if (x.kind == 0) return false;
+        if (MODE != kCount) {
+            if (nlisted < cap) {
+                ids[nlisted] = id; kinds[nlisted] = (uint8_t)x.kind;
+                double* o = pts + 6 * (uint64_t)nlisted;
+                o[0] = x.p0.x; o[1] = x.p0.y; o[2] = x.p0.z;
+                const bool seg = x.kind == 2;
+                o[3] = seg ? x.p1.x : 0.0; o[4] = seg ? x.p1.y : 0.0; o[5] = seg ? x.p1.z : 0.0;
+            }
+            ++nlisted;
+        }
+        return true;
+    });
 }
 
 // ---------------------------------------------------------------------------------------------------------------

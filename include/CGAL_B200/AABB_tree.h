@@ -182,6 +182,19 @@ class AABB_tree {
     any_intersected_primitive(&query, &query + 1, &r);
     return r;
   }
+  // all_intersections(ray, out) / any_intersection(ray) (AABB_tree.h:283-296,958-985): out receives Intersection_and_primitive_id<Ray>::Type
+  template <typename OutputIterator>
+  OutputIterator all_intersections(const Ray& query, OutputIterator out) const {
+    std::vector<std::vector<typename Intersection_and_primitive_id<Ray>::Type>> r;
+    all_intersections(&query, &query + 1, std::back_inserter(r));
+    for (const auto& x : r[0]) *out++ = x;
+    return out;
+  }
+  Ray_intersection any_intersection(const Ray& query) const {
+    Ray_intersection r;
+    any_intersection(&query, &query + 1, &r);
+    return r;
+  }
   Ray_intersection first_intersection(const Ray& query) const {
     Ray_intersection r;
     first_intersection(&query, &query + 1, &r);
@@ -269,6 +282,54 @@ class AABB_tree {
     for (uint64_t i = 0; i < n; ++i) {
       std::vector<Primitive_id> v;
       for (uint64_t k = off[i]; k < off[i + 1]; ++k) v.push_back(m_primitives[ids[k]].id());
+      *out++ = v;
+    }
+    return out;
+  }
+  // out receives std::optional< Intersection_and_primitive_id<Ray>::Type >
+  template <typename RayIterator, typename OutputIterator>
+  OutputIterator any_intersection(RayIterator first, RayIterator beyond, OutputIterator out) const {
+    typedef typename Intersection_and_primitive_id<Ray>::Type Result;
+    typedef typename Result::first_type Intersection;
+    std::vector<double> q = pack_lines(first, beyond);
+    const uint64_t n = q.size() / 6;
+    std::vector<uint32_t> prim(n);
+    std::vector<double> p0(3 * n), p1(3 * n);
+    std::vector<uint8_t> fl(n);
+    ensure_built();
+    check(b200aabb_any_intersection(m_handle, q.data(), n, B200AABB_HOST, prim.data(), p0.data(), p1.data(), fl.data()));
+    for (uint64_t i = 0; i < n; ++i) {
+      if (!(fl[i] & B200AABB_FLAG_HIT)) { *out++ = std::nullopt; continue; }
+      const Point a(FT(p0[3 * i]), FT(p0[3 * i + 1]), FT(p0[3 * i + 2]));
+      if (fl[i] & B200AABB_FLAG_SEGMENT) *out++ = Result(Intersection(Segment(a, Point(FT(p1[3 * i]), FT(p1[3 * i + 1]), FT(p1[3 * i + 2])))), m_primitives[prim[i]].id());
+      else *out++ = Result(Intersection(a), m_primitives[prim[i]].id());
+    }
+    return out;
+  }
+  // out receives one std::vector< Intersection_and_primitive_id<Ray>::Type > per ray (count pass -> prefix sums -> fill pass)
+  template <typename RayIterator, typename OutputIterator>
+  OutputIterator all_intersections(RayIterator first, RayIterator beyond, OutputIterator out) const {
+    typedef typename Intersection_and_primitive_id<Ray>::Type Result;
+    typedef typename Result::first_type Intersection;
+    std::vector<double> q = pack_lines(first, beyond);
+    const uint64_t n = q.size() / 6;
+    std::vector<uint32_t> cnt(n);
+    ensure_built();
+    check(b200aabb_number_of_intersections(m_handle, q.data(), n, B200AABB_HOST, cnt.data()));
+    std::vector<uint64_t> off(n + 1, 0);
+    for (uint64_t i = 0; i < n; ++i) off[i + 1] = off[i] + cnt[i];
+    const uint64_t room = off[n] ? off[n] : 1;
+    std::vector<uint32_t> ids(room);
+    std::vector<uint8_t> kinds(room);
+    std::vector<double> pts(6 * room);
+    check(b200aabb_all_intersections(m_handle, q.data(), n, B200AABB_HOST, off.data(), ids.data(), kinds.data(), pts.data()));
+    for (uint64_t i = 0; i < n; ++i) {
+      std::vector<Result> v;
+      for (uint64_t k = off[i]; k < off[i + 1]; ++k) {
+        const Point a(FT(pts[6 * k]), FT(pts[6 * k + 1]), FT(pts[6 * k + 2]));
+        if (kinds[k] == 2) v.push_back(Result(Intersection(Segment(a, Point(FT(pts[6 * k + 3]), FT(pts[6 * k + 4]), FT(pts[6 * k + 5])))), m_primitives[ids[k]].id()));
+        else v.push_back(Result(Intersection(a), m_primitives[ids[k]].id()));
+      }
       *out++ = v;
     }
     return out;

@@ -130,6 +130,19 @@ int b200aabb_any_intersected_primitive(b200aabb_tree* t, const double* queries, 
  * pointers it is reported by the next b200aabb_get_stats); nothing is ever written outside a query's own range. */
 int b200aabb_all_intersected_primitives(b200aabb_tree* t, const double* queries, uint64_t n, b200aabb_query_kind kind,
                                         b200aabb_memspace space, const uint64_t* offsets, uint32_t* ids);
+/* all_intersections(Ray_3, out), AABB_tree.h:958-970 (Listing_intersection_traits, internal/AABB_traversal_traits.h:105-144): every
+ * primitive whose Intersect_3(Ray_3, Triangle_3) is non-empty, with the intersection object.  Two steps like all_intersected_primitives:
+ * b200aabb_number_of_intersections gives the counts (they can differ from number_of_intersected_primitives for a ray nearly parallel to a
+ * triangle: the reference's construction evaluates its predicates on a rounded point), the caller forms offsets[n+1] and
+ * passes room for offsets[n] entries: ids[k], kinds[k] (1 = Point_3, 2 = Segment_3), points[6k..6k+5] (the point, or the two endpoints). */
+int b200aabb_number_of_intersections(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, uint32_t* out);
+int b200aabb_all_intersections(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, const uint64_t* offsets,
+                               uint32_t* ids, uint8_t* kinds, double* points);
+/* any_intersection(Ray_3), AABB_tree.h:972-985 (First_intersection_traits, :58-101): ONE intersection object per ray (which one depends on
+ * the traversal order, in the reference too).  Outputs as first_intersection: prim (NO_PRIMITIVE = nullopt), point, point2, flags
+ * (FLAG_HIT, FLAG_SEGMENT, FLAG_EXACT); any may be NULL. */
+int b200aabb_any_intersection(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, uint32_t* prim, double* point,
+                              double* point2, uint8_t* flags);
 /* first_intersection(Ray_3) / first_intersected_primitive, AABB_tree/internal/AABB_ray_intersection.h:201-240.
  * rays: n x 6 (source, second point).  Outputs (any may be NULL): prim[n]; t[n] = ray parameter of the hit as the
  * reference computes it (:168-198); point[n x 3] = the Point_3, or the first endpoint of the Segment_3;

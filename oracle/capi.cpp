@@ -105,6 +105,32 @@ int orc_all_intersected_primitives(void* hv, const double* q, uint64_t n, int ki
     });
     return bad ? -1 : 0;
 }
+// all_intersections(Ray_3) (AABB_tree.h:958-970).  Pass 1 (ids == nullptr): counts[i] = number of intersection objects of ray i.
+// Pass 2: offsets = exclusive prefix sums of the counts; entry k of ray i -> ids[offsets[i]+k], kinds[..] (1 Point_3, 2 Segment_3),
+// pts[6 * (..)] (point, or the two segment endpoints), in the reference's traversal order.  first_only: any_intersection (:972-985).
+int orc_ray_intersections(void* hv, const double* rays, uint64_t n, int first_only, uint32_t* counts, const uint64_t* offsets, uint32_t* ids,
+                          uint8_t* kinds, double* pts, int nthreads) {
+    const Tree& t = *((Handle*)hv)->tree;
+    std::atomic<int> bad{0};
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e) {
+        std::vector<std::pair<uint32_t, RayHit>> v;
+        for (uint64_t i = b; i < e; ++i) {
+            v.clear();
+            t.ray_intersections(P(rays + 6 * i), P(rays + 6 * i + 3), first_only != 0, v);
+            if (counts) counts[i] = (uint32_t)v.size();
+            if (!ids) continue;
+            if (v.size() != offsets[i + 1] - offsets[i]) { bad = 1; continue; }
+            for (size_t k = 0; k < v.size(); ++k) {
+                const uint64_t o = offsets[i] + k;
+                ids[o] = v[k].first; kinds[o] = (uint8_t)v[k].second.kind;
+                std::memset(pts + 6 * o, 0, 48);
+                put(pts + 6 * o, v[k].second.pt[0]);
+                if (v[k].second.kind == 2) put(pts + 6 * o + 3, v[k].second.pt[1]);
+            }
+        }
+    });
+    return bad ? -1 : 0;
+}
 // first_intersection(Ray_3).  prim = 0xFFFFFFFF when none.  kind: 0 none, 1 Point_3, 2 Segment_3.
 // pts: n x 6 (point, or the two segment endpoints).  tie[i] = 1 if another primitive produced exactly the same t.
 void orc_first_intersection(void* hv, const double* rays, uint64_t n, uint32_t* prim, double* tpar, double* pts,

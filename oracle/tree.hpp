@@ -230,6 +230,22 @@ struct Tree {
     uint32_t any_intersected_primitive(const LineQ& q) const { FirstPrimitiveTT tt{*this}; traversal(q, tt); return tt.id; }
     // Listing_primitive_traits :150-184 (all_intersected_primitives, AABB_tree.h:934-945): ids in traversal order
     void all_intersected_primitives(const LineQ& q, std::vector<uint32_t>& out) const { CountTT tt{*this}; tt.ids = &out; traversal(q, tt); }
+    // Listing_intersection_traits :105-144 (all_intersections, AABB_tree.h:958-970) and First_intersection_traits :58-101
+    // (any_intersection, :972-985) for Ray_3: every primitive whose Intersect_3(Ray_3, Triangle_3) is non-empty, with the object
+    struct RayObjectsTT {
+        const Tree& t; bool first_only; bool found = false;
+        std::vector<std::pair<uint32_t, RayHit>>* out;
+        bool go_further() const { return !(first_only && found); }
+        void intersection(const LineQ& q, uint32_t f) {
+            RayHit r = ray_tri_intersection(t.mesh->datum(f), q.p, q.q);
+            if (r.kind) { found = true; out->push_back({f, r}); }
+        }
+        bool do_intersect(const LineQ& q, const Box& b) const { return do_intersect_bbox(q.p, q.q, b, true); }
+    };
+    void ray_intersections(const P3& s, const P3& q, bool first_only, std::vector<std::pair<uint32_t, RayHit>>& out) const {
+        RayObjectsTT tt{*this, first_only, false, &out};
+        traversal(LineQ{s, q, true}, tt);
+    }
     bool do_intersect(const LineQ& q) const { DoIntersectTT tt{*this}; traversal(q, tt); return tt.found; }          // AABB_tree.h:903-913
     uint32_t number_of_intersected_primitives(const LineQ& q) const { CountTT tt{*this}; traversal(q, tt); return tt.count; }  // :915-932
 

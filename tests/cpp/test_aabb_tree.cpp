@@ -95,6 +95,22 @@ static int known_answers() {
       std::vector<mini::Face_index> none;
       tree.all_intersected_primitives(Segment(Point(5, 5, 5), Point(6, 6, 6)), std::back_inserter(none));
       CHECK(none.empty());
+      // all_intersections / any_intersection (AABB_tree.h:283-296): the ray enters through the base face at (0.2,0.2,0) and leaves
+      // through the slanted face x + y + z = 1 at (0.2,0.2,0.6); first_intersection is the nearer of the two
+      std::vector<Tree::Intersection_and_primitive_id<Ray>::Type> all;
+      tree.all_intersections(up, std::back_inserter(all));
+      CHECK(all.size() == 2);
+      bool base = false, slant = false;
+      for (const auto& x : all) {
+        CHECK(std::holds_alternative<Point>(x.first));
+        const Point p = std::get<Point>(x.first);
+        if (x.second == mini::Face_index(0)) base = p == Point(0.2, 0.2, 0.0);
+        else slant = std::fabs(p.x() - 0.2) < 1e-15 && std::fabs(p.y() - 0.2) < 1e-15 && std::fabs(p.z() - 0.6) < 1e-15;
+      }
+      CHECK(base && slant);
+      const auto anyx = tree.any_intersection(up);
+      CHECK(anyx && (anyx->second == all[0].second || anyx->second == all[1].second));
+      CHECK(!tree.any_intersection(Ray(Point(0.2, 0.2, -1.0), Point(0.2, 0.2, -2.0))));
     }
     CHECK(!tree.first_intersection(Ray(Point(0.2, 0.2, -1.0), Point(0.2, 0.2, -2.0))));
     const auto cpp = tree.closest_point_and_primitive(Point(0.2, 0.2, -1.0));

@@ -47,6 +47,8 @@ def lib():
         L.orc_any_intersected_primitive.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_int, _u32p, C.c_int]
         L.orc_all_intersected_primitives.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_int, C.POINTER(C.c_uint64), _u32p, C.c_int]
         L.orc_all_intersected_primitives.restype = C.c_int
+        L.orc_ray_intersections.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_int, _u32p, C.POINTER(C.c_uint64), _u32p, _u8p, _dp, C.c_int]
+        L.orc_ray_intersections.restype = C.c_int
         L.orc_first_intersection.argtypes = [C.c_void_p, _dp, C.c_uint64, _u32p, _dp, _dp, _u8p, _u8p, C.c_int]
         L.orc_closest_point.argtypes = [C.c_void_p, _dp, C.c_uint64, _dp, _u32p, _dp, C.c_int]
         L.orc_closest_point.restype = C.c_int
@@ -142,6 +144,22 @@ class OracleTree:
         rc = lib().orc_all_intersected_primitives(self.h, _ptr(q, _dp), len(q), kind, offsets.ctypes.data_as(C.POINTER(C.c_uint64)), _ptr(ids, _u32p), threads or nthreads())
         assert rc == 0
         return offsets, ids[:int(offsets[-1])]
+
+    def all_intersections(self, rays, first_only=False, threads=None):
+        """all_intersections(Ray_3) (first_only: any_intersection): (offsets[n+1], ids, kinds (1 Point_3 / 2 Segment_3), pts[total,6])"""
+        q = _d(rays).reshape(-1, 6)
+        th = threads or nthreads()
+        counts = np.zeros(len(q), np.uint32)
+        lib().orc_ray_intersections(self.h, _ptr(q, _dp), len(q), int(first_only), _ptr(counts, _u32p), None, None, None, None, th)
+        offsets = np.zeros(len(q) + 1, np.uint64)
+        np.cumsum(counts, out=offsets[1:])
+        tot = max(int(offsets[-1]), 1)
+        ids, kinds, pts = np.zeros(tot, np.uint32), np.zeros(tot, np.uint8), np.zeros((tot, 6))
+        rc = lib().orc_ray_intersections(self.h, _ptr(q, _dp), len(q), int(first_only), None, offsets.ctypes.data_as(C.POINTER(C.c_uint64)), _ptr(ids, _u32p),
+                                         _ptr(kinds, _u8p), _ptr(pts, _dp), th)
+        assert rc == 0
+        tot = int(offsets[-1])
+        return offsets, ids[:tot], kinds[:tot], pts[:tot]
 
     def first_intersection(self, rays, threads=None):
         rays = _d(rays).reshape(-1, 6)

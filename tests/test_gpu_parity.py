@@ -190,6 +190,43 @@ def test_all_and_any_intersected_primitives(B, meshes):
     assert eo.tolist() == [0, 0, 0, 0] and len(ei) == 0
 
 
+def test_all_and_any_intersections_of_rays(B, meshes):
+    """all_intersections / any_intersection (Ray_3), AABB_tree.h:958-985: the set of (ray, primitive, object) records equals the oracle's,
+    objects bit for bit; first_intersection is the nearest member of a ray's set (aabb_test_ray_intersection.cpp:38-65)"""
+    from cgal_b200 import workloads as W
+    v, f = meshes["elephant"]
+    g, o = B.AABB_tree(v, f), orc.OracleTree(v, f)
+    rays = W.sphere_rays(g.bbox(), 60_000)
+    # axis-parallel rays through vertices and along edges of a grid mesh: coplanar hits (Segment_3 objects), exact stage
+    gv, gf = W.terrain(24, 24, amplitude=0.0)
+    flat, oflat = B.AABB_tree(gv, gf), orc.OracleTree(gv, gf)
+    xs = np.arange(0.0, 25.0)
+    inplane = np.stack([np.full(25, -1.0), xs, np.zeros(25), np.full(25, 0.0), xs, np.zeros(25)], 1)          # along grid lines, in the plane
+    through = np.stack([xs, xs[::-1], np.full(25, 5.0), xs, xs[::-1], np.full(25, 4.0)], 1)                       # through vertices
+    for tree, orac, q in ((g, o, rays), (flat, oflat, np.concatenate([inplane, through]))):
+        off, ids, kinds, pts = tree.all_intersections(q)
+        roff, rids, rkinds, rpts = orac.all_intersections(q)
+        np.testing.assert_array_equal(off, roff)
+        owner = np.repeat(np.arange(len(q)), np.diff(off).astype(np.int64))
+        order = np.lexsort((ids, owner)); rorder = np.lexsort((rids, owner))
+        np.testing.assert_array_equal(ids[order], rids[rorder])
+        np.testing.assert_array_equal(kinds[order], rkinds[rorder])
+        np.testing.assert_array_equal(pts[order], rpts[rorder])                                # objects bit-equal
+        a = tree.any_intersection(q)
+        cnt = np.diff(off)
+        np.testing.assert_array_equal(a["prim"] == B.NO_PRIMITIVE, cnt == 0)
+        np.testing.assert_array_equal((a["flags"] & B.FLAG_HIT) != 0, cnt > 0)
+        fi = tree.first_intersection(q)
+        lookup = {(int(w), int(i)): k for k, (w, i) in enumerate(zip(owner, ids))}
+        for i in np.nonzero(cnt)[0][:4000]:
+            k = lookup[(int(i), int(a["prim"][i]))]                                              # a member of the ray's set, with its object
+            assert np.array_equal(a["point"][i], pts[k, :3]) and bool(a["flags"][i] & B.FLAG_SEGMENT) == (kinds[k] == 2)
+            assert (int(i), int(fi["prim"][i])) in lookup
+    assert (kinds == 2).any()                                                                    # the grid-line rays produced Segment_3 objects
+    e = B.AABB_tree()
+    assert e.any_intersection(rays[:3])["prim"].tolist() == [B.NO_PRIMITIVE] * 3 and len(e.all_intersections(rays[:3])[1]) == 0
+
+
 def test_config2_icosphere_distance_field_parity(B):
     from cgal_b200 import workloads as W
     v, f = W.icosphere(6)       # 81,920 triangles (config 2 uses level 8; same generator)
