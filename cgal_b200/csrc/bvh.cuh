@@ -317,7 +317,9 @@ B2_HD uint32_t traverse_ray_objects(const BvhNode* __restrict__ nodes, const Tri
         uint32_t id;
         const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
         ++st.leaves;
-        const RayX x = ray_tri_intersection(t, s, q, c.d, c.major, st.nexact);
+        int nex = 0;
+        const RayX x = ray_tri_intersection_call(t.a.x, t.a.y, t.a.z, t.b.x, t.b.y, t.b.z, t.c.x, t.c.y, t.c.z, s.x, s.y, s.z, q.x, q.y, q.z, c.major, &nex);
+        st.nexact += nex;
         if (x.kind == 0) return false;
         if (MODE != kCount) {
             if (nlisted < cap) {
@@ -357,7 +359,9 @@ B2_HD FirstHit traverse_first(const BvhNode* __restrict__ nodes, const TriRec* _
         uint32_t id;
         const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
         ++st.leaves;
-        const RayX x = ray_tri_intersection(t, s, q, c.d, c.major, st.nexact);
+        int nex = 0;
+        const RayX x = ray_tri_intersection_call(t.a.x, t.a.y, t.a.z, t.b.x, t.b.y, t.b.z, t.c.x, t.c.y, t.c.z, s.x, s.y, s.z, q.x, q.y, q.z, c.major, &nex);
+        st.nexact += nex;
         if (x.kind == 0) return;
         if (x.t < best.t || (x.t == best.t && id < best.prim)) {
             if (best.prim != kNone) { runner_up = fmin(runner_up, best.t); runner_lo = fmin(runner_lo, best.t - best_u); }

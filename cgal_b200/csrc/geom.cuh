@@ -244,6 +244,17 @@ B2_HD RayX ray_tri_intersection(const Tri3& t, const Vec3& s, const Vec3& q, con
     return r;
 }
 
+// The same routine OUT OF LINE with its arguments in registers, for the traversal kernels: a ray meets ~1.3 leaves, and keeping this long
+// routine (five orientation predicates, a division chain) out of the traversal loop lets the loop run at 8 blocks per SM without spilling.
+B2_HD_NOINLINE RayX ray_tri_intersection_call(double ax, double ay, double az, double bx, double by, double bz, double cx, double cy, double cz,
+                                              double sx, double sy, double sz, double qx, double qy, double qz, int major_axis, int* nexact_out) {
+    int nexact = 0;
+    const Vec3 s = {sx, sy, sz}, q = {qx, qy, qz};
+    const RayX r = ray_tri_intersection(Tri3{{ax, ay, az}, {bx, by, bz}, {cx, cy, cz}}, s, q, q - s, major_axis, nexact);
+    *nexact_out = nexact;
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Construct_projected_point_3(Triangle_3, Point_3): Kernel_23/include/CGAL/Kernel/function_objects.h:3193-3263
 // ---------------------------------------------------------------------------------------------------------------
