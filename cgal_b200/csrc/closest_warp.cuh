@@ -392,13 +392,15 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
             } while (ncnt > 0 && lcnt < 32);
         } else if (phase == 1) {
             // -------------------------------------------------------------------------------------------- (B1) pre-test 1: two cheap directions
-            for (int base = 0; base < lcnt; base += 32) {
-                const int i = base + (int)lane;
+            // full groups of 32 from the top; what is left (< 32) waits for more unless the node pool has run dry
+            while (lcnt >= 32 || (lcnt > 0 && ncnt == 0)) {
+                const int take = lcnt < 32 ? lcnt : 32;
+                lcnt -= take;
                 bool survive = false;
                 uint32_t pair = 0;
                 float lb = 0.0f;
-                if (i < lcnt) {
-                    pair = S.lpool[i];
+                if ((int)lane < take) {
+                    pair = S.lpool[lcnt + (int)lane];
                     const unsigned owner = pair >> 27;
                     const RelTri r = wp_relative(a.trisf, pair & kWpRefMask, S.qa[owner]);
                     const float4 qb = S.qb[owner];
@@ -408,15 +410,15 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                     lb = fmaxf(wp_lower(ub, qb.w, r), wp_lower(g, sqrtf(dot3f(g, g)), r)) - qc.y;   // tangent plane of the ball; centroid direction
                     survive = !(lb > qc.x);
                 }
-                w_leaves += (lcnt - base) < 32 ? (lcnt - base) : 32;
+                w_leaves += take;
                 const unsigned sm = __ballot_sync(full, survive);
                 if (survive) S.mpool[mcnt + __popc(sm & lt)] = make_uint2(pair, __float_as_uint(lb));
                 mcnt += __popc(sm);
             }
-            lcnt = 0;
         } else if (phase == 2) {
             // -------------------------------------------------------------------------------------------- (B2) pre-test 2: approximate closest point
-            while (mcnt > 0 && ecnt + 32 <= kWpExactCap) {   // (taken from the top; what does not fit waits for the exact phase to make room)
+            // full groups of 32 from the top (the rest waits unless nothing upstream is left); what does not fit waits for the exact phase
+            while ((mcnt >= 32 || (mcnt > 0 && ncnt == 0 && lcnt == 0)) && ecnt + 32 <= kWpExactCap) {
                 const int take = mcnt < 32 ? mcnt : 32;
                 mcnt -= take;
                 bool survive = false;
