@@ -328,21 +328,14 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
             __syncwarp();
             continue;
         }
-        // ------------------------------------------------------------------------------------------------ phase selection
-        // Progress: every branch below either hands over / retires at least one pair or (exact phase below its threshold) leaves the
-        // pools as they are with ecnt < exact_go, so that the next round selects another phase; with all other pools empty the exact
-        // phase drains.  (A per-round watchdog counter was measured at 8 % of the kernel's time - there are ~16 rounds per query - and
+        // ------------------------------------------------------------------------------------------------ one round: every stage that is due, in order
+        // A stage runs when its pool holds a full group (or nothing upstream can add to it) and the pool it feeds has room; the
+        // stages are chained within a round, so a pair can travel from the node pool to the exact pool without the loop's housekeeping
+        // in between (there are ~16 rounds per query).  Progress: if the node phase is held (lcnt >= 32) then pre-test 1 is due unless
+        // mcnt >= 32, then pre-test 2 is due unless the exact pool is full, and a full exact pool (> 96 >= exact_go) is due itself;
+        // with every upstream pool empty each stage drains.  (A per-round watchdog counter was measured at 8 % of the kernel's time and
         // is not kept; the GPU tests run every scheduling setting under a timeout instead.)
-        int phase;                                            // 0 = nodes, 1 = pre-test 1, 2 = pre-test 2, 3 = exact
-        if (ecnt >= a.exact_go) phase = 3;
-        else if (mcnt >= 32) phase = 2;
-        else if (lcnt >= 32) phase = 1;
-        else if (ncnt > 0) phase = 0;
-        else if (lcnt > 0) phase = 1;
-        else if (mcnt > 0) phase = 2;
-        else phase = 3;
-
-        if (phase == 0) {
+        if (ncnt > 0 && lcnt < 32) {
             // -------------------------------------------------------------------------------------------- (A) node phase
             do {
                 if (ncnt + 32 > kWpNodeCap) {
@@ -394,7 +387,8 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                 }
                 __syncwarp();
             } while (ncnt > 0 && lcnt < 32);
-        } else if (phase == 1) {
+        }
+        if (mcnt < 32) {
             // -------------------------------------------------------------------------------------------- (B1) pre-test 1: two cheap directions
             // full groups of 32 from the top; what is left (< 32) waits for more unless the node pool has run dry
             while (lcnt >= 32 || (lcnt > 0 && ncnt == 0)) {
@@ -419,7 +413,8 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                 if (survive) S.mpool[mcnt + __popc(sm & lt)] = make_uint2(pair, __float_as_uint(lb));
                 mcnt += __popc(sm);
             }
-        } else if (phase == 2) {
+        }
+        {
             // -------------------------------------------------------------------------------------------- (B2) pre-test 2: approximate closest point
             // full groups of 32 from the top (the rest waits unless nothing upstream is left); what does not fit waits for the exact phase
             while ((mcnt >= 32 || (mcnt > 0 && ncnt == 0 && lcnt == 0)) && ecnt + 32 <= kWpExactCap) {
@@ -444,7 +439,8 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                 if (survive) S.epool[ecnt + __popc(sm & lt)] = e;
                 ecnt += __popc(sm);
             }
-        } else {
+        }
+        if (ecnt >= a.exact_go || (ecnt > 0 && ncnt == 0 && lcnt == 0 && mcnt == 0 && spilled == 0)) {
             // -------------------------------------------------------------------------------------------- (B3) binary64 projection + exact comparison
             // (i) pairs whose lower bound has fallen outside their slot's ball retire without any binary64 work
             int kept = 0;
