@@ -26,8 +26,8 @@
 // from the batch cursor (queries are handed out in coherence order).  A new query first walks down to its nearest leaf on its
 // own lane (nearest child first), pushing the far children, and projects on that leaf: that is its first ball (the kd-tree hint
 // of the reference, AABB_tree.h:591-612, is not needed).
-// The node pool is a stack in shared memory (a ring) whose bottom half is spilled to a per-warp area in global memory when it fills
-// and put back when the stack runs low, so depth is bounded by kWpSpillCap only (overflow is reported, never silent).
+// The node pool is a stack in shared memory whose bottom half is spilled to a per-warp area in global memory when it fills
+// and reloaded when the stack runs empty, so depth is bounded by kWpSpillCap only (overflow is reported, never silent).
 // What bounds this kernel (profiles/r1_05): the L1 data stage, one wavefront per cycle, because every lane fetches its own node /
 // triangle: hence the packed slot state, the binary32 triangle copy and no per-slot bookkeeping atomics.
 #pragma once
@@ -216,25 +216,28 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
     uint32_t w_nodes = 0, w_leaves = 0, w_evals = 0, w_exact = 0, w_ties = 0;
 
     // moves the bottom kWpSpillChunk entries of the stack to global memory; false = spill area exhausted
-    // The node pool is a ring: logical entry i (0 = bottom of the stack) sits in npool[ring(i)], so that spilling the bottom or
-    // putting it back moves no other entry.
-    int nbase = 0;                                                    // slot of logical entry 0
-    auto ring = [&](int i) -> int { const int k = nbase + i; return k >= kWpNodeCap ? k - kWpNodeCap : k; };
-    // moves the bottom kWpSpillChunk entries of the stack to global memory; false = spill area exhausted
+    // moves the bottom kWpSpillChunk entries of the stack to global memory and the rest down; false = spill area exhausted.
+    // (A ring buffer that avoids the move was measured 2 % slower: its index arithmetic sits in the node loop, the move is rare.)
     auto spill_bottom = [&]() -> bool {
         if (spilled + kWpSpillChunk > kWpSpillCap) return false;
-        for (int i = lane; i < kWpSpillChunk; i += 32) myspill[spilled + i] = S.npool[ring(i)];
+        for (int i = lane; i < kWpSpillChunk; i += 32) myspill[spilled + i] = S.npool[i];
         __syncwarp();
-        nbase = ring(kWpSpillChunk);
+        for (int base = kWpSpillChunk; base < ncnt; base += 32) {
+            const int idx = base + (int)lane;
+            uint2 v = make_uint2(0, 0);
+            if (idx < ncnt) v = S.npool[idx];
+            __syncwarp();
+            if (idx < ncnt) S.npool[idx - kWpSpillChunk] = v;
+            __syncwarp();
+        }
         spilled += kWpSpillChunk; ncnt -= kWpSpillChunk;
         return true;
     };
 
     while (true) {
-        if (ncnt < 32 && spilled > 0) {                       // put the most recently spilled chunk back under the stack
-            nbase = nbase >= kWpSpillChunk ? nbase - kWpSpillChunk : nbase - kWpSpillChunk + kWpNodeCap;
-            for (int i = lane; i < kWpSpillChunk; i += 32) S.npool[ring(i)] = __ldcg(&myspill[spilled - kWpSpillChunk + i]);
-            spilled -= kWpSpillChunk; ncnt += kWpSpillChunk;
+        if (ncnt == 0 && spilled > 0) {                       // reload the most recently spilled chunk
+            for (int i = lane; i < kWpSpillChunk; i += 32) S.npool[i] = __ldcg(&myspill[spilled - kWpSpillChunk + i]);
+            spilled -= kWpSpillChunk; ncnt = kWpSpillChunk;
             __syncwarp();
         }
         if (ncnt == 0 && lcnt == 0 && mcnt == 0 && ecnt == 0) {
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                     if (c0 & kLeafBit) { firstleaf = c0; stop = true; } else cur = c0;
                 }
                 const unsigned pm = __ballot_sync(full, push);
-                S.npool[push ? ring(ncnt + __popc(pm & lt)) : kWpNodeCap] = make_uint2(farref, (__float_as_uint(fard) & ~31u) | lane);
+                S.npool[push ? ncnt + __popc(pm & lt) : kWpNodeCap] = make_uint2(farref, (__float_as_uint(fard) & ~31u) | lane);
                 ncnt += __popc(pm);
                 if (stop) act = false;
             }
@@ -341,7 +344,7 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                 const int take = ncnt < 32 ? ncnt : 32;
                 const bool has = (int)lane < take;
                 ncnt -= take;
-                const uint2 e = S.npool[has ? ring(ncnt + (int)lane) : kWpNodeCap];
+                const uint2 e = S.npool[has ? ncnt + (int)lane : kWpNodeCap];
                 const unsigned owner = e.y & 31u;
                 const float4 q = S.qa[owner];
                 const bool live = has && __uint_as_float(e.y & ~31u) <= q.w;
@@ -375,11 +378,11 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                 {
                     const bool p1 = in1 && !(r1 & kLeafBit);
                     const unsigned m1 = __ballot_sync(full, p1);
-                    S.npool[p1 ? ring(ncnt + __popc(m1 & lt)) : kWpNodeCap] = make_uint2(r1, (__float_as_uint(d1) & ~31u) | owner);
+                    S.npool[p1 ? ncnt + __popc(m1 & lt) : kWpNodeCap] = make_uint2(r1, (__float_as_uint(d1) & ~31u) | owner);
                     ncnt += __popc(m1);
                     const bool p0 = in0 && !(r0 & kLeafBit);
                     const unsigned m0 = __ballot_sync(full, p0);
-                    S.npool[p0 ? ring(ncnt + __popc(m0 & lt)) : kWpNodeCap] = make_uint2(r0, (__float_as_uint(d0) & ~31u) | owner);
+                    S.npool[p0 ? ncnt + __popc(m0 & lt) : kWpNodeCap] = make_uint2(r0, (__float_as_uint(d0) & ~31u) | owner);
                     ncnt += __popc(m0);
                 }
                 __syncwarp();
