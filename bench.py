@@ -32,8 +32,8 @@ RAYS_PER_RANK = IMG * IMG // SHARDS
 POINTS_PER_RANK = RAYS_PER_RANK
 BYTES_PER_RAY, BYTES_PER_POINT = 85, 61      # algorithmic bytes, SURVEY.md §8(d)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the kernel on this very workload, from the committed ncu --set full
-# captures (profiles/r1_13_warp_pool_final.txt, profiles/r1_03_while_while.txt): the tree itself (nodes + records) is read about once
-NCU_DRAM_BYTES_PER_LAUNCH = {"closest_point_warp_kernel": 12.422741e9 + 5.292676e9, "first_intersection_kernel": 1.074644e9 + 0.303553e9}
+# captures (profiles/r1_14_warp_pool_final.txt, profiles/r1_03_while_while.txt): the tree itself (nodes + records) is read about once
+NCU_DRAM_BYTES_PER_LAUNCH = {"closest_point_warp_kernel": 12.337272e9 + 5.284005e9, "first_intersection_kernel": 1.074644e9 + 0.303553e9}
 WORKLOAD = "terrain16M(4096x2048 quads, Perlin fBm seed 23) + per GPU 8,388,608 pinhole Ray_3 first_intersection (rows r::8 of 8192^2) + 8,388,608 bbox closest_point_and_primitive"
 
 
@@ -351,7 +351,7 @@ def main():
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(dom) if not args.small and n_pts == POINTS_PER_RANK else None,
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
-                             "note": "traversal is bound by the L1 data stage (one wavefront per scattered node / triangle fetch) and by instruction issue (52 %) at 20 warps/SM, not by HBM (DESIGN.md §5); "
+                             "note": "traversal is bound by the L1 data stage (one wavefront per scattered node / triangle fetch) and by instruction issue (51 %) at 20 warps/SM, not by HBM (DESIGN.md §5); "
                                      "traffic = dram__bytes_read+write of one launch from the ncu --set full capture named in profiles/README.md"},
                 "clocks": clocks, "gpu_launches": launches}
         if e2e_ms is not None:
