@@ -246,7 +246,7 @@ struct b200aabb_tree {
     // options
     int opt_sort_queries = 1;      // B200AABB_OPT_SORT_QUERIES
     int opt_closest_kernel = 1;    // B200AABB_OPT_CLOSEST_KERNEL: 1 = warp-cooperative pool (closest_warp.cuh), 0 = one thread per query
-    int opt_warp_exact_go = 64;     // B200AABB_OPT_WARP_EXACT_GO
+    int opt_warp_exact_go = 160;     // B200AABB_OPT_WARP_EXACT_GO
     int opt_host_parts = 0;        // B200AABB_OPT_HOST_PARTS (0 = automatic)
     int opt_debug_refit_frontier = kRefitFrontierPerBlock;   // test hook (option 101): frontier entries per block of the refit (0: every hand-over overflows)
     int opt_debug_two_pass = 0;    // experiment: run the warp kernel twice, the second time with the first pass's distances as initial bounds
@@ -561,7 +561,7 @@ int b200aabb_set_option(b200aabb_tree* t, int option, int64_t value) {
         case B200AABB_OPT_HOST_PARTS: t->opt_host_parts = (int)std::min<int64_t>(64, std::max<int64_t>(0, value)); return B200AABB_OK;
         case 101: t->opt_debug_refit_frontier = (int)std::min<int64_t>(kRefitFrontierPerBlock, std::max<int64_t>(0, value)); t->built = t->n == 0; return B200AABB_OK;
         case 100: t->opt_debug_two_pass = value != 0; return B200AABB_OK;
-        case B200AABB_OPT_WARP_EXACT_GO: t->opt_warp_exact_go = (int)std::min<int64_t>(64, std::max<int64_t>(1, value)); return B200AABB_OK;
+        case B200AABB_OPT_WARP_EXACT_GO: t->opt_warp_exact_go = (int)std::min<int64_t>(kWpExactCap - 32, std::max<int64_t>(1, value)); return B200AABB_OK;
         default: return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "unknown option");
     }
 }

@@ -40,7 +40,7 @@ constexpr int kWpSpillChunk = kWpNodeCap / 2;   // entries moved per spill / rel
 constexpr int kWpSpillCap = 16 * kWpSpillChunk; // entries per warp in the global spill area
 constexpr int kWpLeafCap = 96;                  // < 32 waiting + at most 64 added by one node phase
 constexpr int kWpMidCap = 128;                  // < 32 waiting + at most 95 added by one pre-test-1 phase
-constexpr int kWpExactCap = 128;                // pre-test 2 stops handing over when fewer than 32 places are left
+constexpr int kWpExactCap = 192;                // pre-test 2 stops handing over when fewer than 32 places are left
 constexpr int kWpWarpsPerSM = 20;               // resident warps per SM this kernel is sized for (registers <= 102, shared memory <= 10.4 KB): measured best of 16 / 20 / 24 / 28
 constexpr uint32_t kWpRefMask = 0x07FFFFFFu;    // 27 bits of leaf slot next to the 5-bit query slot
 constexpr uint64_t kWpMaxPrims = 1ull << 27;
@@ -83,7 +83,7 @@ struct WarpClosestArgs {
     unsigned long long* cursor;    // next position of the batch to hand out (zeroed before the launch)
     uint2* spill;                  // gridDim.x * kWpSpillCap entries
     WarpSlots64* slots64;          // gridDim.x records
-    int exact_go;                  // run the exact phase when at least this many pairs wait (1..64)
+    int exact_go;                  // run the exact phase when at least this many pairs wait (1 .. kWpExactCap - 32)
     uint32_t flag_tie, flag_exact;
     const double* debug_hint_sqd;  // experiment only: a known upper bound of each query's squared distance (caller order), or nullptr
 };
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
         // A stage runs when its pool holds a full group (or nothing upstream can add to it) and the pool it feeds has room; the
         // stages are chained within a round, so a pair can travel from the node pool to the exact pool without the loop's housekeeping
         // in between (there are ~16 rounds per query).  Progress: if the node phase is held (lcnt >= 32) then pre-test 1 is due unless
-        // mcnt >= 32, then pre-test 2 is due unless the exact pool is full, and a full exact pool (> 96 >= exact_go) is due itself;
+        // mcnt >= 32, then pre-test 2 is due unless the exact pool is full, and a full exact pool (> kWpExactCap - 32 >= exact_go) is due itself;
         // with every upstream pool empty each stage drains.  (A per-round watchdog counter was measured at 8 % of the kernel's time and
         // is not kept; the GPU tests run every scheduling setting under a timeout instead.)
         if (ncnt > 0 && lcnt < 32) {

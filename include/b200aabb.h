@@ -64,7 +64,7 @@ enum {
   B200AABB_OPT_HOST_PARTS = 5,     /* HOST-pointer batches are cut into about this many chunks (each 256 Ki .. 4 Mi queries) that flow through a
                                       double-buffered upload -> sort -> traverse -> download pipeline (1..64; 0 = default: 6 for ray / segment
                                       batches, 2 for point batches) */
-  B200AABB_OPT_WARP_EXACT_GO = 4   /* warp-cooperative kernel: run the binary64 phase once this many pre-test survivors wait (1..64, default 64) */
+  B200AABB_OPT_WARP_EXACT_GO = 4   /* warp-cooperative kernel: run the binary64 phase once this many pre-test survivors wait (1..160, default 160) */
 };
 
 typedef struct b200aabb_stats {

@@ -19,7 +19,7 @@ def main():
     ap.add_argument("--ny", type=int, default=2048)
     ap.add_argument("--points", type=int, default=1 << 23)
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--sweep", default="32,64,16")
+    ap.add_argument("--sweep", default="160,128,64")
     ap.add_argument("--skip-old", action="store_true")
     ap.add_argument("--two-pass", action="store_true", help="experiment: second pass starts from the first pass's distances (perfect initial bound); ms = last_query_ms of pass 2")
     args = ap.parse_args()
