@@ -32,8 +32,8 @@ RAYS_PER_RANK = IMG * IMG // SHARDS
 POINTS_PER_RANK = RAYS_PER_RANK
 BYTES_PER_RAY, BYTES_PER_POINT = 85, 61      # algorithmic bytes, SURVEY.md §8(d)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the kernel on this very workload, from the committed ncu --set full
-# captures (profiles/r1_14_warp_pool_final.txt, profiles/r1_03_while_while.txt): the tree itself (nodes + records) is read about once
-NCU_DRAM_BYTES_PER_LAUNCH = {"closest_point_warp_kernel": 12.337272e9 + 5.284005e9, "first_intersection_kernel": 1.074644e9 + 0.303553e9}
+# captures (profiles/r1_15_warp_pool_final.txt, profiles/r1_03_while_while.txt): the tree itself (nodes + records) is read about once
+NCU_DRAM_BYTES_PER_LAUNCH = {"closest_point_warp_kernel": 10.892577e9 + 4.193736e9, "first_intersection_kernel": 1.074644e9 + 0.303553e9}
 WORKLOAD = "terrain16M(4096x2048 quads, Perlin fBm seed 23) + per GPU 8,388,608 pinhole Ray_3 first_intersection (rows r::8 of 8192^2) + 8,388,608 bbox closest_point_and_primitive"
 
 
