@@ -46,6 +46,8 @@ constexpr uint32_t kWpRefMask = 0x07FFFFFFu;    // 27 bits of leaf slot next to 
 constexpr uint64_t kWpMaxPrims = 1ull << 27;
 
 struct WarpShared {
+    // (npool / lpool end in a SINK entry: lanes with nothing to push store there instead of branching; the sink is never read, so the
+    //  write/write hazards compute-sanitizer's racecheck reports on it are the only ones it reports for this kernel, and are benign)
     uint2 npool[kWpNodeCap + 1];  // x = child reference (node index, or kLeafBit | leaf slot); y = lower bound of the box's squared distance from
                                   //     the binary32 query point (low 5 mantissa bits cleared = rounded down) | query slot.  [+1: sink of masked pushes]
     uint32_t lpool[kWpLeafCap + 1];   // query slot << 27 | leaf slot : awaiting pre-test 1
@@ -388,6 +390,7 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                 __syncwarp();
             } while (ncnt > 0 && lcnt < 32);
         }
+        __syncwarp();                                          // the node phase's pool writes are visible to every lane
         if (mcnt < 32) {
             // -------------------------------------------------------------------------------------------- (B1) pre-test 1: two cheap directions
             // full groups of 32 from the top; what is left (< 32) waits for more unless the node pool has run dry
@@ -414,6 +417,7 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                 mcnt += __popc(sm);
             }
         }
+        __syncwarp();
         {
             // -------------------------------------------------------------------------------------------- (B2) pre-test 2: approximate closest point
             // full groups of 32 from the top (the rest waits unless nothing upstream is left); what does not fit waits for the exact phase
@@ -440,6 +444,7 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                 ecnt += __popc(sm);
             }
         }
+        __syncwarp();
         if (ecnt >= a.exact_go || (ecnt > 0 && ncnt == 0 && lcnt == 0 && mcnt == 0 && spilled == 0)) {
             // -------------------------------------------------------------------------------------------- (B3) binary64 projection + exact comparison
             // (i) pairs whose lower bound has fallen outside their slot's ball retire without any binary64 work
