@@ -28,7 +28,7 @@
 // of the reference, AABB_tree.h:591-612, is not needed).
 // The node pool is a stack in shared memory whose bottom half is spilled to a per-warp area in global memory when it fills
 // and reloaded when the stack runs empty, so depth is bounded by kWpSpillCap only (overflow is reported, never silent).
-// What bounds this kernel (profiles/r1_05): the L1 data stage, one wavefront per cycle, because every lane fetches its own node /
+// What bounds this kernel (profiles/r1_05 .. r1_15): the L1 data stage, one wavefront per cycle, because every lane fetches its own node /
 // triangle: hence the packed slot state, the binary32 triangle copy and no per-slot bookkeeping atomics.
 #pragma once
 #include "bvh.cuh"
