@@ -151,9 +151,14 @@ __device__ __forceinline__ RelTri wp_relative(const TriF* __restrict__ trisf, ui
 // LOWER bound from a direction u (bvh.cuh::certainly_farther solved for the distance): every point x of the triangle has
 // |x| >= min_i (u.r_i)/|u|; E = 5e-7 m |u| covers the coordinate rounding and the dot products, the factor 0.999998 the rounding of
 // |u|, of its reciprocal and of the two products.  -inf when u is (numerically) zero.  (Relative to the binary32 data: the caller subtracts e2.)
-__device__ __forceinline__ float wp_lower(const float* u, float su, const RelTri& r) {
+B2_HD float wp_lower(const float* u, float su, const RelTri& r) {   // (host build: tests/hostcheck checks the bounds against exact distances)
     const float md = fminf(dot3f(u, r.ra), fminf(dot3f(u, r.rb), dot3f(u, r.rc)));
-    return su > 1e-18f ? fmaf(-5e-7f * r.m, su, md) * (__frcp_rn(su) * 0.999998f) : -INFINITY;
+#if defined(__CUDA_ARCH__)
+    const float rcp = __frcp_rn(su);
+#else
+    const float rcp = 1.0f / su;
+#endif
+    return su > 1e-18f ? fmaf(-5e-7f * r.m, su, md) * (rcp * 0.999998f) : -INFINITY;
 }
 // Approximate closest point P = a + v ab + w ac (v, w >= 0, v + w <= 1 up to an ulp) -> a sharper lower bound (direction P) and a
 // rigorous UPPER bound of (distance + the slot's rounding allowance): P's coordinates are within 1.2e-6 m of a point of the true
@@ -161,7 +166,7 @@ __device__ __forceinline__ float wp_lower(const float* u, float su, const RelTri
 // allows 8e-6 m + 1e-5 |P| + dslack.  The winner's candidate is no farther than this primitive's candidate, which lies within the
 // rounding allowance of the true distance (the premise of widen_sqdist), so pruning with `hi` never discards the winner or a
 // primitive tied with it.  hi = NaN (no bound) compares false everywhere.  e2: see wp_relative.
-__device__ __forceinline__ void wp_sharp(const RelTri& r, float dslack, float e2, float* lower, float* hi) {
+B2_HD void wp_sharp(const RelTri& r, float dslack, float e2, float* lower, float* hi) {
     float u[3];
     approx_closest_to_origin(r.ra, r.rb, r.rc, u);
     const float su = sqrtf(dot3f(u, u));
@@ -174,7 +179,12 @@ __device__ __forceinline__ void wp_sharp(const RelTri& r, float dslack, float e2
     const float n[3] = {ab[1] * ac[2] - ab[2] * ac[1], ab[2] * ac[0] - ab[0] * ac[2], ab[0] * ac[1] - ab[1] * ac[0]};
     const float lab = dot3f(ab, ab), lac = dot3f(ac, ac), noise = 1e3f * (e2 + r.m * 2.4e-7f);
     const bool sound = dot3f(n, n) >= 1e-6f * lab * lac && lab > noise * noise && lac > noise * noise;
-    *hi = sound ? ((su * 1.00001f + 8e-6f * r.m) + dslack) + e2 : __int_as_float(0x7fc00000);
+#if defined(__CUDA_ARCH__)
+    const float no_bound = __int_as_float(0x7fc00000);
+#else
+    const float no_bound = NAN;
+#endif
+    *hi = sound ? ((su * 1.00001f + 8e-6f * r.m) + dslack) + e2 : no_bound;
 }
 
 // The binary64 projection, out of line and with its arguments in registers: the kernel calls it from the refill and from the exact

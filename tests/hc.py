@@ -12,6 +12,13 @@ _u32p = C.POINTER(C.c_uint32)
 _u8p = C.POINTER(C.c_uint8)
 
 
+def warp_bounds(tri, q, mag):
+    """(lower1, lower2, upper or nan, e2, dslack) of closest_warp.cuh's pre-tests for one (query, primitive) pair"""
+    t, p, out = np.ascontiguousarray(tri, np.float64), np.ascontiguousarray(q, np.float64), np.zeros(5, np.float32)
+    lib().hc_warp_bounds(t.ctypes.data_as(_dp), p.ctypes.data_as(_dp), float(mag), out.ctypes.data_as(C.POINTER(C.c_float)))
+    return out
+
+
 def build():
     d = os.path.join(ROOT, "tests", "hostcheck")
     src, out = os.path.join(d, "hostcheck.cu"), os.path.join(d, "libhostcheck.so")
@@ -30,6 +37,7 @@ def lib():
         L.hc_build.restype = C.c_void_p
         L.hc_build.argtypes = [_dp, _u32p, C.c_uint64]
         L.hc_destroy.argtypes = [C.c_void_p]
+        L.hc_warp_bounds.argtypes = [_dp, _dp, C.c_double, C.POINTER(C.c_float)]
         L.hc_num_nodes.restype = C.c_uint64
         L.hc_num_nodes.argtypes = [C.c_void_p]
         L.hc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _dp]

@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "../../cgal_b200/csrc/build.cuh"
+#include "../../cgal_b200/csrc/closest_warp.cuh"
 
 using namespace b2;
 
@@ -180,6 +181,30 @@ double hc_point_box_sqdist(const double* box, const double* p) {
     float lo[3], hi[3];
     for (int a = 0; a < 3; ++a) { lo[a] = float_below(box[a]); hi[a] = float_above(box[3 + a]); }
     return (double)point_box_sqdist(lo, hi, make_point(V(p)));
+}
+// The binary32 distance bounds of the warp-cooperative closest_point kernel (closest_warp.cuh), computed exactly as its pre-test
+// stages compute them for one (query, primitive) pair: out = {lower bound of stage 1, lower bound of stage 2, upper bound of stage 2
+// (NaN = none), e2, dslack}.  mag = largest coordinate magnitude of the scene.
+void hc_warp_bounds(const double* tri, const double* q, double mag, float* out) {
+    const float qx = (float)q[0], qy = (float)q[1], qz = (float)q[2];
+    const double ex = q[0] - (double)qx, ey = q[1] - (double)qy, ez = q[2] - (double)qz;
+    const float perr = float_above(std::sqrt((ex * ex + ey * ey) + ez * ez) * 1.0000001) + 1e-37f;
+    const float ev = float_above(mag * 5.9604645e-8 * 1.000001);
+    const float e2 = float_above((double)float_above(1.7320509 * (double)ev) + (double)perr);        // >= fadd_ru(fmul_ru(sqrt3, ev), perr)
+    const double delta = 4e-16 * std::max(mag, std::max(std::fabs(q[0]), std::max(std::fabs(q[1]), std::fabs(q[2]))));
+    const float dslack = float_above(2.0 * delta) + 1e-37f;
+    float f[9];
+    for (int k = 0; k < 9; ++k) f[k] = (float)tri[k];                                                  // the TriF record
+    RelTri r;                                                                                        // as wp_relative
+    r.ra[0] = f[0] - qx; r.ra[1] = f[1] - qy; r.ra[2] = f[2] - qz;
+    r.rb[0] = f[3] - qx; r.rb[1] = f[4] - qy; r.rb[2] = f[5] - qz;
+    r.rc[0] = f[6] - qx; r.rc[1] = f[7] - qy; r.rc[2] = f[8] - qz;
+    r.m = 0.0f;
+    for (int k = 0; k < 3; ++k) r.m = std::max(r.m, std::max(std::fabs(r.ra[k]), std::max(std::fabs(r.rb[k]), std::fabs(r.rc[k]))));
+    const float g[3] = {(r.ra[0] + r.rb[0]) + r.rc[0], (r.ra[1] + r.rb[1]) + r.rc[1], (r.ra[2] + r.rb[2]) + r.rc[2]};
+    out[0] = wp_lower(g, sqrtf(dot3f(g, g)), r) - e2;
+    wp_sharp(r, dslack, e2, &out[1], &out[2]);
+    out[3] = e2; out[4] = dslack;
 }
 uint64_t hc_sizeof_node() { return sizeof(BvhNode); }
 uint64_t hc_sizeof_tri() { return sizeof(TriRec); }

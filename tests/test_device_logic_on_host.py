@@ -251,3 +251,72 @@ def test_empty_and_singleton():
     assert fi["prim"][0] == 7 and tuple(fi["pts"][0][:3]) == (0.1, 0.1, 0.0) and fi["t"][0] == 0.5
     cp = s.closest_point(np.array([[0.25, 0.25, 5.0]]))
     assert tuple(cp["cp"][0]) == (0.25, 0.25, 0.0) and cp["prim"][0] == 7 and cp["sqd"][0] == 25.0
+
+
+def _exact_point_triangle_distance(tri, q):
+    """distance from q to the triangle in extended precision (Ericson, Real-Time Collision Detection 5.1.5)"""
+    L = np.longdouble
+    a, b, c, p = (np.array(x, dtype=L) for x in (tri[0:3], tri[3:6], tri[6:9], q))
+    ab, ac, ap = b - a, c - a, p - a
+    d1, d2 = ab @ ap, ac @ ap
+    if d1 <= 0 and d2 <= 0:
+        return float(np.sqrt((p - a) @ (p - a)))
+    bp = p - b
+    d3, d4 = ab @ bp, ac @ bp
+    if d3 >= 0 and d4 <= d3:
+        return float(np.sqrt(bp @ bp))
+    vc = d1 * d4 - d3 * d2
+    if vc <= 0 and d1 >= 0 and d3 <= 0:
+        x = a + (d1 / (d1 - d3)) * ab
+        return float(np.sqrt((p - x) @ (p - x)))
+    cp = p - c
+    d5, d6 = ab @ cp, ac @ cp
+    if d6 >= 0 and d5 <= d6:
+        return float(np.sqrt(cp @ cp))
+    vb = d5 * d2 - d1 * d6
+    if vb <= 0 and d2 >= 0 and d6 <= 0:
+        x = a + (d2 / (d2 - d6)) * ac
+        return float(np.sqrt((p - x) @ (p - x)))
+    va = d3 * d6 - d5 * d4
+    if va <= 0 and (d4 - d3) >= 0 and (d5 - d6) >= 0:
+        x = b + ((d4 - d3) / ((d4 - d3) + (d5 - d6))) * (c - b)
+        return float(np.sqrt((p - x) @ (p - x)))
+    den = va + vb + vc
+    if den == 0:                                        # degenerate triangle: the nearest of its three segments' end cases above
+        return float(min(np.sqrt((p - v) @ (p - v)) for v in (a, b, c)))
+    x = a + ab * (vb / den) + ac * (vc / den)
+    return float(np.sqrt((p - x) @ (p - x)))
+
+
+def test_warp_kernel_binary32_bounds_are_rigorous():
+    """closest_warp.cuh prunes with binary32 LOWER bounds (stage 1: centroid direction, stage 2: approximate closest point) and shrinks a
+    query's ball with a binary32 UPPER bound; every one must hold against the distance from the true (binary64) query to the true
+    triangle, whatever the scale, the offset from the origin (binary32 copies lose everything) or the shape (needles, degenerate)"""
+    rng = np.random.default_rng(7)
+    n_upper = 0
+    for trial in range(30000):
+        scale = 10.0 ** rng.uniform(-6, 4)
+        offset = rng.choice([0.0, 1.0, 1e3, 1e7]) * rng.standard_normal(3)
+        tri = rng.standard_normal(9) * scale
+        kind = trial % 6
+        if kind == 1:                                    # needle
+            tri[6:9] = tri[0:3] + (tri[3:6] - tri[0:3]) * rng.uniform(0, 1) + 1e-9 * scale * rng.standard_normal(3)
+        elif kind == 2:                                  # exactly degenerate: a segment / a point
+            tri[6:9] = tri[3:6] if trial % 12 == 2 else tri[0:3]
+        tri = tri + np.tile(offset, 3)
+        dist = 10.0 ** rng.uniform(-3, 3) * scale
+        q = tri[0:3] + rng.standard_normal(3) * dist
+        if kind == 3:                                    # query on the triangle
+            w = rng.dirichlet([1, 1, 1])
+            q = w[0] * tri[0:3] + w[1] * tri[3:6] + w[2] * tri[6:9]
+        mag = float(max(np.abs(tri).max(), np.abs(q).max()))
+        lo1, lo2, up, e2, dslack = hc.warp_bounds(tri, q, mag)
+        d = _exact_point_triangle_distance(tri, q)
+        slack = 1e-9 * d + 1e-300
+        assert lo1 <= d + slack and lo2 <= d + slack, (trial, tri, q, lo1, lo2, d)
+        if not np.isnan(up):
+            n_upper += 1
+            assert up >= d - slack, (trial, tri, q, up, d)
+            m_rel = float(np.abs(tri.reshape(3, 3) - q).max())
+            assert up <= 1.001 * d + 4 * float(e2) + 2 * float(dslack) + 1e-3 * m_rel     # and it is useful (any point of the triangle is valid: ill-conditioned barycentrics only loosen it)
+    assert n_upper > 10000                                # well-conditioned triangles do get an upper bound
