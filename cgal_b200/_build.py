@@ -11,8 +11,9 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 
 
 def sources():
+    inc = os.path.join(os.path.dirname(HERE), "include")
     return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + \
-           [os.path.join(os.path.dirname(HERE), "include", "b200aabb.h")]
+           [os.path.join(inc, "b200aabb.h"), os.path.join(inc, "b200work.h")]
 
 
 def up_to_date():
@@ -22,7 +23,8 @@ def up_to_date():
 def build(force=False, verbose=False):
     if not force and up_to_date():
         return LIB
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-o", LIB, os.path.join(CSRC, "b200aabb.cu")]
+    extra = os.environ.get("B200AABB_NVCC_EXTRA", "").split()      # tuning experiments only (scripts/), e.g. -DB2_PP_WARPS_PER_SM=16
+    cmd = ["nvcc"] + NVCC_FLAGS + extra + ["-o", LIB, os.path.join(CSRC, "b200aabb.cu"), os.path.join(CSRC, "workload.cu")]
     if verbose:
         print(" ".join(cmd), file=sys.stderr)
     subprocess.check_call(cmd)

@@ -12,13 +12,13 @@ import numpy as np
 SEGMENT, RAY = 0, 1
 FLAG_HIT, FLAG_SEGMENT, FLAG_TIE, FLAG_EXACT, FLAG_NEAR_TIE = 1, 2, 4, 8, 16
 OPT_SORT_QUERIES = 1
-OPT_CLOSEST_KERNEL = 2    # 1 = warp-cooperative work pool (default), 0 = one thread per query
+OPT_CLOSEST_KERNEL = 2    # 1 = warp-cooperative work pool (default), 2 = lane pairs with private stacks, 0 = one thread per query
 OPT_WARP_EXACT_GO = 4
 OPT_HOST_PARTS = 5
 NO_PRIMITIVE = 0xFFFFFFFF
 _HOST, _DEVICE = 0, 1
 _ERRORS = {-1: "invalid argument", -2: "CUDA error", -3: "out of device memory", -4: "empty tree (CGAL_precondition(!empty()))",
-           -5: "no sm_100 CUDA device (there is no CPU fallback)"}
+           -5: "no sm_100 CUDA device (there is no CPU fallback)", -6: "traversal incomplete", -7: "NCCL unavailable or failed"}
 _LIB = None
 
 
@@ -40,7 +40,9 @@ SYMBOLS = ["b200aabb_create", "b200aabb_destroy", "b200aabb_set_stream", "b200aa
            "b200aabb_number_of_intersected_primitives", "b200aabb_any_intersected_primitive", "b200aabb_all_intersected_primitives",
            "b200aabb_number_of_intersections", "b200aabb_all_intersections", "b200aabb_any_intersection",
            "b200aabb_first_intersection", "b200aabb_closest_point",
-           "b200aabb_export_layout", "b200aabb_import_alloc", "b200aabb_import_finish", "b200aabb_debug_predicate", "b200aabb_version"]
+           "b200aabb_export_layout", "b200aabb_import_alloc", "b200aabb_import_finish", "b200aabb_debug_predicate", "b200aabb_version",
+           "b200aabb_comm_unique_id", "b200aabb_comm_init", "b200aabb_comm_init_all", "b200aabb_comm_destroy", "b200aabb_comm_last_error",
+           "b200aabb_comm_broadcast_tree", "b200aabb_comm_broadcast_tree_all"]
 
 
 def library_path():
@@ -84,6 +86,14 @@ def load_library():
         L.b200aabb_import_finish.argtypes = [vp]
         L.b200aabb_debug_predicate.argtypes = [C.c_int, C.c_int, dp, C.c_int, u64, dp, dp, dp]
         L.b200aabb_version.restype = C.c_char_p
+        L.b200aabb_comm_unique_id.argtypes = [C.c_char_p]
+        L.b200aabb_comm_init.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(vp)]
+        L.b200aabb_comm_init_all.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(vp)]
+        L.b200aabb_comm_destroy.argtypes = [vp]
+        L.b200aabb_comm_last_error.argtypes = [vp]
+        L.b200aabb_comm_last_error.restype = C.c_char_p
+        L.b200aabb_comm_broadcast_tree.argtypes = [vp, vp, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(u64)]
+        L.b200aabb_comm_broadcast_tree_all.argtypes = [C.POINTER(vp), C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(u64)]
         _LIB = L
     return _LIB
 

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -14,6 +15,7 @@
 #include "build.cuh"
 #include "radix_sort.cuh"
 #include "closest_warp.cuh"
+#include "closest_pair.cuh"
 
 using namespace b2;
 
@@ -226,6 +228,10 @@ __global__ void __launch_bounds__(256) line_keys_kernel(const double* __restrict
 // Handle
 // ------------------------------------------------------------------------------------------------------------------
 struct b200aabb_tree {
+    // Every entry point that touches the handle takes this lock: concurrent calls on ONE handle (the reference's callers run
+    // tbb::parallel_for over const queries, AABB_tree.h:593-612) are serialised, never interleaved on the shared staging / scratch buffers.
+    std::recursive_mutex mu;
+    bool imported = false;         // the tree came from b200aabb_import_alloc: there are no primitives to rebuild from
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -245,14 +251,14 @@ struct b200aabb_tree {
     unsigned long long* d_counters = nullptr;   // [8]
     // options
     int opt_sort_queries = 1;      // B200AABB_OPT_SORT_QUERIES
-    int opt_closest_kernel = 1;    // B200AABB_OPT_CLOSEST_KERNEL: 1 = warp-cooperative pool (closest_warp.cuh), 0 = one thread per query
-    int opt_warp_exact_go = 160;     // B200AABB_OPT_WARP_EXACT_GO
+    int opt_closest_kernel = 1;    // B200AABB_OPT_CLOSEST_KERNEL: 1 = warp-cooperative pool (closest_warp.cuh), 2 = lane pairs with private stacks (closest_pair.cuh; measured slower, profiles/r2_02), 0 = one thread per query
+    int opt_warp_exact_go = 0;       // B200AABB_OPT_WARP_EXACT_GO (0 = the kernel's default: 64 pair kernel, 160 pool kernel)
     int opt_host_parts = 0;        // B200AABB_OPT_HOST_PARTS (0 = automatic)
     int opt_debug_refit_frontier = kRefitFrontierPerBlock;   // test hook (option 101): frontier entries per block of the refit (0: every hand-over overflows)
-    int opt_debug_two_pass = 0;    // experiment: run the warp kernel twice, the second time with the first pass's distances as initial bounds
     // warp-cooperative closest_point: per pipeline slot a batch cursor and the pools' spill area; grid = SMs x resident warps
     struct WarpScratch { unsigned long long* cursor = nullptr; uint2* spill = nullptr; WarpSlots64* slots64 = nullptr; } warp[2];
     int warp_grid = 0;
+    int pair_grid = 0;             // grid of closest_point_pair_kernel (closest_pair.cuh); it shares the scratch of the pool kernel
     // query coherence sort scratch, one per pipeline slot (slot 0 also serves DEVICE-pointer batches); grow-only
     struct SortScratch { uint64_t* keys[2] = {nullptr, nullptr}; uint32_t* vals[2] = {nullptr, nullptr}; void* ws = nullptr; uint64_t cap = 0; } sort[2];
     // staging for HOST-pointer batches (two pipeline slots)
@@ -280,6 +286,8 @@ constexpr uint64_t kChunkMax = 1ull << 22;   // most queries per pipeline slot f
 constexpr uint64_t kChunkMin = 1ull << 18;
 // a HOST batch is cut into about `opt_host_parts` chunks so that only the first chunk's upload and the last chunk's download are exposed
 uint64_t chunk_for(uint64_t n, int parts) { const uint64_t p = (uint64_t)std::max(1, parts); return std::min<uint64_t>(n, std::min(kChunkMax, std::max(kChunkMin, ((n + p - 1) / p + 32767) / 32768 * 32768))); }
+
+#define B2_LOCK(t) std::unique_lock<std::recursive_mutex> lock_; if (t) lock_ = std::unique_lock<std::recursive_mutex>(const_cast<b200aabb_tree*>(t)->mu)
 
 int fail(b200aabb_tree* t, int code, const char* msg) { if (t) t->err = msg; return code; }
 
@@ -315,10 +323,18 @@ int ensure_warp(b200aabb_tree* t, int slot) {
         B2_CUDA(t, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device));
         t->warp_grid = std::max(1, per_sm) * std::max(1, sms);
     }
+    if (t->pair_grid == 0) {
+        int per_sm = 0, sms = 0;
+        B2_CUDA(t, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, closest_point_pair_kernel, 32, 0));
+        B2_CUDA(t, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device));
+        t->pair_grid = std::max(1, per_sm) * std::max(1, sms);
+    }
+    static_assert(kPpSpillPerWarp <= kWpSpillCap, "the pair kernel's spill area fits the pool kernel's");
+    const size_t grid = (size_t)std::max(t->warp_grid, t->pair_grid);
     auto& w = t->warp[slot];
     if (!w.cursor) B2_CUDA(t, cudaMalloc(&w.cursor, sizeof(unsigned long long)));
-    if (!w.spill) B2_CUDA(t, cudaMalloc(&w.spill, (size_t)t->warp_grid * kWpSpillCap * sizeof(uint2)));
-    if (!w.slots64) B2_CUDA(t, cudaMalloc(&w.slots64, (size_t)t->warp_grid * sizeof(WarpSlots64)));
+    if (!w.spill) B2_CUDA(t, cudaMalloc(&w.spill, grid * kWpSpillCap * sizeof(uint2)));
+    if (!w.slots64) B2_CUDA(t, cudaMalloc(&w.slots64, grid * sizeof(WarpSlots64)));
     return B200AABB_OK;
 }
 
@@ -344,7 +360,7 @@ enum QueryShape { kPointQuery, kLineQuery };
 // coherence order of a batch resident on the device: keys -> onesweep sort -> permutation (nullptr when sorting is off)
 int coherence_order(b200aabb_tree* t, int slot, cudaStream_t st, const void* d_in, uint64_t n, QueryShape shape, const uint32_t** perm) {
     *perm = nullptr;
-    if (!t->opt_sort_queries || n < 4096 || n >= (1ull << 32)) return B200AABB_OK;
+    if (!t->opt_sort_queries || n < 4096 || n >= (1ull << 30)) return B200AABB_OK;   // (the sort's look-back words carry 30-bit prefixes)
     int rc = ensure_sort(t, slot, n);
     if (rc) return rc;
     auto& sc = t->sort[slot];
@@ -362,6 +378,10 @@ TreeRef tree_ref(const b200aabb_tree* t, const uint32_t* perm) { return TreeRef{
 
 int do_build(b200aabb_tree* t) {
     B2_CUDA(t, cudaSetDevice(t->device));
+    if (t->imported) {   // a replica received from another rank: it IS built, and it has no primitive input to rebuild from
+        if (t->built) return B200AABB_OK;
+        return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "an imported tree can not be rebuilt: insert primitives first");
+    }
     free_tree_buffers(t);
     const uint64_t n = t->n;
     empty_bbox(t->h_bbox);
@@ -482,9 +502,14 @@ int run_batch(b200aabb_tree* t, const void* in, size_t in_elem_bytes, uint64_t n
     }
     for (int s = 0; s < 2; ++s) { B2_CUDA(t, cudaEventRecord(t->ev_pipe[s], t->pipe[s])); B2_CUDA(t, cudaStreamWaitEvent(t->stream, t->ev_pipe[s], 0)); }
     B2_CUDA(t, cudaEventRecord(t->ev_b, t->stream));
+    unsigned long long incomplete = 0;
+    B2_CUDA(t, cudaMemcpyAsync(&incomplete, t->d_counters + 2, sizeof(incomplete), cudaMemcpyDeviceToHost, t->stream));
     B2_CUDA(t, cudaStreamSynchronize(t->stream));
     B2_CUDA(t, cudaGetLastError());
     t->query_timing_pending = true;
+    // a traversal that could not finish (stack / pool overflow: impossible for trees this library builds, see closest_pair.cuh) is an error,
+    // never a silent partial result
+    if (incomplete) return fail(t, B200AABB_ERR_INCOMPLETE, "traversal stack overflow: results incomplete");
     return B200AABB_OK;
 }
 
@@ -553,22 +578,21 @@ int b200aabb_destroy(b200aabb_tree* t) {
     return B200AABB_OK;
 }
 
-int b200aabb_set_option(b200aabb_tree* t, int option, int64_t value) {
+int b200aabb_set_option(b200aabb_tree* t, int option, int64_t value) { B2_LOCK(t);
     if (!t) return B200AABB_ERR_INVALID_ARGUMENT;
     switch (option) {
         case B200AABB_OPT_SORT_QUERIES: t->opt_sort_queries = value != 0; return B200AABB_OK;
-        case B200AABB_OPT_CLOSEST_KERNEL: t->opt_closest_kernel = value != 0; return B200AABB_OK;
+        case B200AABB_OPT_CLOSEST_KERNEL: t->opt_closest_kernel = (int)std::min<int64_t>(2, std::max<int64_t>(0, value)); return B200AABB_OK;
         case B200AABB_OPT_HOST_PARTS: t->opt_host_parts = (int)std::min<int64_t>(64, std::max<int64_t>(0, value)); return B200AABB_OK;
-        case 101: t->opt_debug_refit_frontier = (int)std::min<int64_t>(kRefitFrontierPerBlock, std::max<int64_t>(0, value)); t->built = t->n == 0; return B200AABB_OK;
-        case 100: t->opt_debug_two_pass = value != 0; return B200AABB_OK;
-        case B200AABB_OPT_WARP_EXACT_GO: t->opt_warp_exact_go = (int)std::min<int64_t>(kWpExactCap - 32, std::max<int64_t>(1, value)); return B200AABB_OK;
+        case 101: t->opt_debug_refit_frontier = (int)std::min<int64_t>(kRefitFrontierPerBlock, std::max<int64_t>(0, value)); if (!t->imported) t->built = t->n == 0; return B200AABB_OK;
+        case B200AABB_OPT_WARP_EXACT_GO: t->opt_warp_exact_go = (int)std::min<int64_t>(kWpExactCap - 32, std::max<int64_t>(0, value)); return B200AABB_OK;
         default: return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "unknown option");
     }
 }
-int b200aabb_set_stream(b200aabb_tree* t, void* s) { if (!t) return B200AABB_ERR_INVALID_ARGUMENT; t->stream = (cudaStream_t)s; return B200AABB_OK; }
+int b200aabb_set_stream(b200aabb_tree* t, void* s) { B2_LOCK(t); if (!t) return B200AABB_ERR_INVALID_ARGUMENT; t->stream = (cudaStream_t)s; return B200AABB_OK; }
 const char* b200aabb_last_error(const b200aabb_tree* t) { return t ? t->err.c_str() : "null handle"; }
 
-int b200aabb_get_stats(const b200aabb_tree* tc, b200aabb_stats* out) {
+int b200aabb_get_stats(const b200aabb_tree* tc, b200aabb_stats* out) { B2_LOCK(tc);
     b200aabb_tree* t = const_cast<b200aabb_tree*>(tc);
     if (!t || !out) return B200AABB_ERR_INVALID_ARGUMENT;
     B2_CUDA(t, cudaSetDevice(t->device));
@@ -581,22 +605,22 @@ int b200aabb_get_stats(const b200aabb_tree* tc, b200aabb_stats* out) {
         t->stats.exact_fallbacks = c[0]; t->stats.ties = c[1]; t->stats.nodes_visited = c[3]; t->stats.leaves_tested = c[4]; t->stats.near_ties = c[5]; t->stats.leaves_culled = c[6];
         if (c[2]) t->err = (c[2] & 4) ? "offsets disagree with the number of intersected primitives" : (c[2] & 2) ? "closest_point work pool inconsistency: results incomplete" : "traversal stack overflow: results incomplete";
         t->query_timing_pending = false;
-        if (c[2]) { *out = t->stats; return B200AABB_ERR_CUDA; }
+        if (c[2]) { *out = t->stats; return (c[2] & 4) ? B200AABB_ERR_INVALID_ARGUMENT : B200AABB_ERR_INCOMPLETE; }
     }
     *out = t->stats;
     return B200AABB_OK;
 }
 
-int b200aabb_clear(b200aabb_tree* t) {
+int b200aabb_clear(b200aabb_tree* t) { B2_LOCK(t);
     if (!t) return B200AABB_ERR_INVALID_ARGUMENT;
     B2_CUDA(t, cudaSetDevice(t->device));
     B2_CUDA(t, cudaStreamSynchronize(t->stream));
     free_tree_buffers(t); free_input(t);
-    t->n = 0; t->built = true; empty_bbox(t->h_bbox);
+    t->n = 0; t->built = true; t->imported = false; empty_bbox(t->h_bbox);
     return B200AABB_OK;
 }
 
-int b200aabb_set_triangles(b200aabb_tree* t, const double* tris, const uint32_t* ids, uint64_t n, b200aabb_memspace space) {
+int b200aabb_set_triangles(b200aabb_tree* t, const double* tris, const uint32_t* ids, uint64_t n, b200aabb_memspace space) { B2_LOCK(t);
     if (!t || (n && !tris)) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = b200aabb_clear(t);
     if (rc) return rc;
@@ -610,7 +634,7 @@ int b200aabb_set_triangles(b200aabb_tree* t, const double* tris, const uint32_t*
     return B200AABB_OK;
 }
 
-int b200aabb_set_mesh(b200aabb_tree* t, const double* verts, uint64_t nv, const uint32_t* faces, const uint32_t* face_ids, uint64_t nf) {
+int b200aabb_set_mesh(b200aabb_tree* t, const double* verts, uint64_t nv, const uint32_t* faces, const uint32_t* face_ids, uint64_t nf) { B2_LOCK(t);
     if (!t || (nf && (!verts || !faces))) return B200AABB_ERR_INVALID_ARGUMENT;
     for (uint64_t i = 0; i < 3 * nf; ++i) if (faces[i] >= nv) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "face references a vertex index >= nv");
     int rc = b200aabb_clear(t);
@@ -634,10 +658,10 @@ int b200aabb_set_mesh(b200aabb_tree* t, const double* verts, uint64_t nv, const 
     return B200AABB_OK;
 }
 
-int b200aabb_build(b200aabb_tree* t) { if (!t) return B200AABB_ERR_INVALID_ARGUMENT; return do_build(t); }
-int b200aabb_accelerate_distance_queries(b200aabb_tree* t) { if (!t) return B200AABB_ERR_INVALID_ARGUMENT; return ensure_built(t); }
-int b200aabb_size(const b200aabb_tree* t, uint64_t* n) { if (!t || !n) return B200AABB_ERR_INVALID_ARGUMENT; *n = t->n; return B200AABB_OK; }
-int b200aabb_bbox(b200aabb_tree* t, double out[6]) {
+int b200aabb_build(b200aabb_tree* t) { B2_LOCK(t); if (!t) return B200AABB_ERR_INVALID_ARGUMENT; return do_build(t); }
+int b200aabb_accelerate_distance_queries(b200aabb_tree* t) { B2_LOCK(t); if (!t) return B200AABB_ERR_INVALID_ARGUMENT; return ensure_built(t); }
+int b200aabb_size(const b200aabb_tree* t, uint64_t* n) { B2_LOCK(t); if (!t || !n) return B200AABB_ERR_INVALID_ARGUMENT; *n = t->n; return B200AABB_OK; }
+int b200aabb_bbox(b200aabb_tree* t, double out[6]) { B2_LOCK(t);
     if (!t || !out) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc) return rc;
@@ -645,7 +669,7 @@ int b200aabb_bbox(b200aabb_tree* t, double out[6]) {
     return B200AABB_OK;
 }
 
-int b200aabb_do_intersect(b200aabb_tree* t, const double* q, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint8_t* out) {
+int b200aabb_do_intersect(b200aabb_tree* t, const double* q, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint8_t* out) { B2_LOCK(t);
     if (!t || (n && (!q || !out))) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
@@ -660,7 +684,7 @@ int b200aabb_do_intersect(b200aabb_tree* t, const double* q, uint64_t n, b200aab
     });
 }
 
-int b200aabb_number_of_intersected_primitives(b200aabb_tree* t, const double* q, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint32_t* out) {
+int b200aabb_number_of_intersected_primitives(b200aabb_tree* t, const double* q, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint32_t* out) { B2_LOCK(t);
     if (!t || (n && (!q || !out))) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
@@ -675,7 +699,7 @@ int b200aabb_number_of_intersected_primitives(b200aabb_tree* t, const double* q,
     });
 }
 
-int b200aabb_any_intersected_primitive(b200aabb_tree* t, const double* q, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint32_t* out) {
+int b200aabb_any_intersected_primitive(b200aabb_tree* t, const double* q, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint32_t* out) { B2_LOCK(t);
     if (!t || (n && (!q || !out))) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
@@ -691,7 +715,7 @@ int b200aabb_any_intersected_primitive(b200aabb_tree* t, const double* q, uint64
 }
 
 int b200aabb_all_intersected_primitives(b200aabb_tree* t, const double* q, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space,
-                                        const uint64_t* offsets, uint32_t* ids) {
+                                        const uint64_t* offsets, uint32_t* ids) { B2_LOCK(t);
     if (!t || (n && (!q || !offsets))) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
@@ -734,13 +758,13 @@ int b200aabb_all_intersected_primitives(b200aabb_tree* t, const double* q, uint6
         release();
         if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) { t->err = "all_intersected_primitives: CUDA failure"; return B200AABB_ERR_CUDA; }
         if (c2 & 4ull) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "offsets disagree with the number of intersected primitives");
-        if (c2) return fail(t, B200AABB_ERR_CUDA, "traversal stack overflow: results incomplete");
+        if (c2) return fail(t, B200AABB_ERR_INCOMPLETE, "traversal stack overflow: results incomplete");
     }
     B2_CUDA(t, cudaGetLastError());
     return B200AABB_OK;
 }
 
-int b200aabb_number_of_intersections(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, uint32_t* out) {
+int b200aabb_number_of_intersections(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, uint32_t* out) { B2_LOCK(t);
     if (!t || (n && (!rays || !out))) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
@@ -754,7 +778,7 @@ int b200aabb_number_of_intersections(b200aabb_tree* t, const double* rays, uint6
     });
 }
 
-int b200aabb_any_intersection(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, uint32_t* prim, double* pt, double* pt2, uint8_t* flags) {
+int b200aabb_any_intersection(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, uint32_t* prim, double* pt, double* pt2, uint8_t* flags) { B2_LOCK(t);
     if (!t || (n && !rays)) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
@@ -767,7 +791,7 @@ int b200aabb_any_intersection(b200aabb_tree* t, const double* rays, uint64_t n, 
 }
 
 int b200aabb_all_intersections(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, const uint64_t* offsets, uint32_t* ids,
-                               uint8_t* kinds, double* points) {
+                               uint8_t* kinds, double* points) { B2_LOCK(t);
     if (!t || (n && (!rays || !offsets))) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
@@ -814,14 +838,14 @@ int b200aabb_all_intersections(b200aabb_tree* t, const double* rays, uint64_t n,
         release();
         if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) { t->err = "all_intersections: CUDA failure"; return B200AABB_ERR_CUDA; }
         if (c2 & 4ull) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "offsets disagree with the number of intersections");
-        if (c2) return fail(t, B200AABB_ERR_CUDA, "traversal stack overflow: results incomplete");
+        if (c2) return fail(t, B200AABB_ERR_INCOMPLETE, "traversal stack overflow: results incomplete");
     }
     B2_CUDA(t, cudaGetLastError());
     return B200AABB_OK;
 }
 
 int b200aabb_first_intersection(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, uint32_t* prim, double* tpar, double* pt,
-                                double* pt2, uint8_t* flags) {
+                                double* pt2, uint8_t* flags) { B2_LOCK(t);
     if (!t || (n && !rays)) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
@@ -848,14 +872,14 @@ int b200aabb_first_intersection(b200aabb_tree* t, const double* rays, uint64_t n
                      });
 }
 
-int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200aabb_memspace space, double* cp, uint32_t* prim, double* sqd, uint8_t* flags) {
+int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200aabb_memspace space, double* cp, uint32_t* prim, double* sqd, uint8_t* flags) { B2_LOCK(t);
     if (!t || (n && !pts)) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc) return rc;
     if (t->n == 0) return fail(t, B200AABB_ERR_EMPTY_TREE, "distance query on an empty tree (CGAL_precondition(!empty()))");
     if (n == 0) return B200AABB_OK;
     // the warp-cooperative kernel packs (query slot, node / leaf) in 32 bits and needs an internal root
-    const bool warp_kernel = t->opt_closest_kernel == 1 && t->n >= 2 && t->n <= kWpMaxPrims;
+    const bool warp_kernel = t->opt_closest_kernel >= 1 && t->n >= 2 && t->n <= kWpMaxPrims;
     if (warp_kernel) { for (int s = 0; s < 2; ++s) { rc = ensure_warp(t, s); if (rc) return rc; } }
     return run_batch(t, pts, 24, n, space, kPointQuery, {{cp, 24, 0}, {prim, 4, 0}, {sqd, 8, 0}, {flags, 1, 0}},
                      [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
@@ -865,29 +889,29 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
                          }
                          const int slot = (space == B200AABB_HOST && st == t->pipe[1]) ? 1 : 0;
                          cudaMemsetAsync(t->warp[slot].cursor, 0, sizeof(unsigned long long), st);
+                         if (t->opt_closest_kernel >= 2) {
+                             PairClosestArgs a;
+                             a.nodes = t->d_nodes; a.tris = t->d_tris; a.trisf = t->d_trisf; a.mag = t->mag; a.perm = perm; a.counters = t->d_counters;
+                             a.pts = (const double*)in; a.n = cnt; a.cp = (double*)o[0]; a.prim = (uint32_t*)o[1]; a.sqd = (double*)o[2]; a.flags = (uint8_t*)o[3];
+                             a.cursor = t->warp[slot].cursor; a.spill = t->warp[slot].spill; a.slots64 = t->warp[slot].slots64;
+                             a.exact_go = t->opt_warp_exact_go > 0 ? std::min(t->opt_warp_exact_go, kPpExactCap - 32) : 64;
+                             a.flag_tie = B200AABB_FLAG_TIE; a.flag_exact = B200AABB_FLAG_EXACT;
+                             const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)t->pair_grid, (cnt + kPpChunk - 1) / kPpChunk);
+                             closest_point_pair_kernel<<<grid, 32, 0, st>>>(a);
+                             return;
+                         }
                          WarpClosestArgs a;
                          a.nodes = t->d_nodes; a.tris = t->d_tris; a.trisf = t->d_trisf; a.mag = t->mag; a.perm = perm; a.counters = t->d_counters;
                          a.pts = (const double*)in; a.n = cnt; a.cp = (double*)o[0]; a.prim = (uint32_t*)o[1]; a.sqd = (double*)o[2]; a.flags = (uint8_t*)o[3];
                          a.cursor = t->warp[slot].cursor; a.spill = t->warp[slot].spill; a.slots64 = t->warp[slot].slots64;
-                         a.exact_go = t->opt_warp_exact_go;
+                         a.exact_go = t->opt_warp_exact_go > 0 ? t->opt_warp_exact_go : 160;
                          a.flag_tie = B200AABB_FLAG_TIE; a.flag_exact = B200AABB_FLAG_EXACT;
-                         a.debug_hint_sqd = nullptr;
                          const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)t->warp_grid, (cnt + 31) / 32);
                          closest_point_warp_kernel<<<grid, 32, 0, st>>>(a);
-                         if (t->opt_debug_two_pass && a.sqd) {
-                             cudaMemsetAsync(t->warp[slot].cursor, 0, sizeof(unsigned long long), st);
-                             cudaMemsetAsync(t->d_counters, 0, 8 * sizeof(unsigned long long), st);
-                             cudaEventRecord(t->ev_a, st);
-                             double* hint = nullptr; cudaMalloc(&hint, cnt * 8);
-                             cudaMemcpyAsync(hint, a.sqd, cnt * 8, cudaMemcpyDeviceToDevice, st);
-                             a.debug_hint_sqd = hint;
-                             closest_point_warp_kernel<<<grid, 32, 0, st>>>(a);
-                             cudaStreamSynchronize(st); cudaFree(hint);
-                         }
                      });
 }
 
-int b200aabb_export_layout(b200aabb_tree* t, void** ptrs, uint64_t* bytes, int cap, int* count) {
+int b200aabb_export_layout(b200aabb_tree* t, void** ptrs, uint64_t* bytes, int cap, int* count) { B2_LOCK(t);
     if (!t || !ptrs || !bytes || !count || cap < 4) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc) return rc;
@@ -899,7 +923,7 @@ int b200aabb_export_layout(b200aabb_tree* t, void** ptrs, uint64_t* bytes, int c
     return B200AABB_OK;
 }
 
-int b200aabb_import_alloc(b200aabb_tree* t, uint64_t n) {
+int b200aabb_import_alloc(b200aabb_tree* t, uint64_t n) { B2_LOCK(t);
     if (!t) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = b200aabb_clear(t);
     if (rc) return rc;
@@ -907,16 +931,283 @@ int b200aabb_import_alloc(b200aabb_tree* t, uint64_t n) {
     B2_CUDA(t, cudaMalloc(&t->d_nodes, std::max<uint64_t>(n - 1, 1) * sizeof(BvhNode)));
     B2_CUDA(t, cudaMalloc(&t->d_tris, n * sizeof(TriRec)));
     B2_CUDA(t, cudaMalloc(&t->d_trisf, n * sizeof(TriF)));
-    t->n = n; t->root = n == 1 ? (kLeafBit | 0u) : 0u; t->built = true;
+    t->n = n; t->root = n == 1 ? (kLeafBit | 0u) : 0u; t->built = true; t->imported = true;
     return B200AABB_OK;
 }
 
-int b200aabb_import_finish(b200aabb_tree* t) {
+int b200aabb_import_finish(b200aabb_tree* t) { B2_LOCK(t);
     if (!t) return B200AABB_ERR_INVALID_ARGUMENT;
     B2_CUDA(t, cudaSetDevice(t->device));
     if (t->n) B2_CUDA(t, cudaMemcpy(t->h_bbox, t->d_rootbox, 48, cudaMemcpyDeviceToHost));
     t->mag = 0.0;
     for (int a = 0; a < 6; ++a) if (t->n) t->mag = std::max(t->mag, fabs(t->h_bbox[a]));
+    return B200AABB_OK;
+}
+
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------------------
+// Multi-GPU behind the C ABI: the tree is built on one rank and replicated with NCCL over NVLink / NVSwitch; every rank
+// then answers its own block of the query batch (no collective in the query loop).  NCCL is resolved at run time (dlopen), so the
+// library loads — and every single-GPU entry point works — without it.
+// ------------------------------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+#include <nccl.h>
+
+namespace {
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+
+NcclApi& nccl() {
+    static NcclApi api;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        // the soname first: a process that already carries an NCCL (e.g. PyTorch's) gets that very copy
+        for (const char* name : {"libnccl.so.2", "libnccl.so"}) { api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (api.lib) break; }
+        if (!api.lib) return;
+        auto sym = [&](const char* n) { return dlsym(api.lib, n); };
+        api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+        api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+        api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
+        api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+        api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
+        api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+        api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+        api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+        api.ok = api.GetUniqueId && api.CommInitRank && api.CommInitAll && api.CommDestroy && api.Broadcast && api.GroupStart && api.GroupEnd;
+    });
+    return api;
+}
+
+// binary32 copies of the primitive records (the receiver of a broadcast derives them instead of receiving 64 bytes per primitive)
+__global__ void __launch_bounds__(256) derive_trisf_kernel(const TriRec* __restrict__ tris, uint64_t n, TriF* __restrict__ outf) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    TriF f;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) f.v[j] = (float)tris[k].v[j];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) f.pad[j] = 0;
+    outf[k] = f;
+}
+
+}  // namespace
+
+struct b200aabb_comm {
+    ncclComm_t comm = nullptr;
+    int device = 0, rank = 0, world = 1;
+    unsigned long long* d_header = nullptr;   // [4]: primitives, has ids, mode, reserved
+    std::string err;
+};
+
+namespace {
+
+#define B2_NCCL(c, call)                                                                                        \
+    do {                                                                                                         \
+        ncclResult_t r_ = (call);                                                                                \
+        if (r_ != ncclSuccess) {                                                                                 \
+            (c)->err = std::string(#call) + ": " + (nccl().GetErrorString ? nccl().GetErrorString(r_) : "NCCL error"); \
+            return B200AABB_ERR_NCCL;                                                                            \
+        }                                                                                                        \
+    } while (0)
+
+// the per-rank part of a tree replication; the caller brackets it with ncclGroupStart / End when it drives several ranks from one thread
+// (phase 0: header, phase 1: payload — the payload sizes depend on the header, so the two can not share a group)
+int bcast_header(b200aabb_comm* c, b200aabb_tree* t, int root, int mode, cudaStream_t st) {
+    if (c->rank == root) {
+        const unsigned long long h[4] = {t->n, t->d_ids ? 1ull : 0ull, (unsigned long long)mode, 0ull};
+        if (cudaMemcpyAsync(c->d_header, h, sizeof(h), cudaMemcpyHostToDevice, st) != cudaSuccess) return B200AABB_ERR_CUDA;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return B200AABB_ERR_CUDA;   // (h lives on this stack frame)
+    }
+    B2_NCCL(c, nccl().Broadcast(c->d_header, c->d_header, 32, ncclUint8, root, c->comm, st));
+    return B200AABB_OK;
+}
+
+int bcast_prepare(b200aabb_comm* c, b200aabb_tree* t, int root, int mode, cudaStream_t st) {
+    unsigned long long h[4];
+    if (cudaMemcpyAsync(h, c->d_header, sizeof(h), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return B200AABB_ERR_CUDA;
+    if (c->rank == root) return B200AABB_OK;
+    const uint64_t n = h[0];
+    if (mode == 0) return b200aabb_import_alloc(t, n);
+    int rc = b200aabb_clear(t);
+    if (rc || n == 0) return rc;
+    if (cudaMalloc(&t->d_soup, n * 72) != cudaSuccess) return B200AABB_ERR_OUT_OF_MEMORY;
+    if (h[1] && cudaMalloc(&t->d_ids, n * 4) != cudaSuccess) return B200AABB_ERR_OUT_OF_MEMORY;
+    t->n = n; t->built = false;
+    return B200AABB_OK;
+}
+
+int bcast_payload(b200aabb_comm* c, b200aabb_tree* t, int root, int mode, cudaStream_t st, uint64_t* bytes) {
+    const uint64_t n = t->n;
+    *bytes = 0;
+    if (n == 0) return B200AABB_OK;
+    if (mode == 0) {
+        if (n > 1) { B2_NCCL(c, nccl().Broadcast(t->d_nodes, t->d_nodes, (n - 1) * sizeof(BvhNode), ncclUint8, root, c->comm, st)); *bytes += (n - 1) * sizeof(BvhNode); }
+        B2_NCCL(c, nccl().Broadcast(t->d_tris, t->d_tris, n * sizeof(TriRec), ncclUint8, root, c->comm, st));
+        B2_NCCL(c, nccl().Broadcast(t->d_rootbox, t->d_rootbox, 48, ncclUint8, root, c->comm, st));
+        *bytes += n * sizeof(TriRec) + 48;
+    } else {
+        B2_NCCL(c, nccl().Broadcast(t->d_soup, t->d_soup, n * 72, ncclUint8, root, c->comm, st));
+        *bytes += n * 72;
+        if (t->d_ids) { B2_NCCL(c, nccl().Broadcast(t->d_ids, t->d_ids, n * 4, ncclUint8, root, c->comm, st)); *bytes += n * 4; }
+    }
+    return B200AABB_OK;
+}
+
+int bcast_finish(b200aabb_comm* c, b200aabb_tree* t, int root, int mode, cudaStream_t st) {
+    if (c->rank == root || t->n == 0) return B200AABB_OK;
+    if (mode == 0) {
+        derive_trisf_kernel<<<grid_for(t->n, 256), 256, 0, st>>>(t->d_tris, t->n, t->d_trisf);
+        t->stats.kernel_launches += 1;
+        if (cudaGetLastError() != cudaSuccess) return B200AABB_ERR_CUDA;
+        return B200AABB_OK;   // (b200aabb_import_finish after the stream has drained: it reads the root box)
+    }
+    return do_build(t);
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200aabb_comm_unique_id(char id[128]) {
+    if (!id) return B200AABB_ERR_INVALID_ARGUMENT;
+    if (!nccl().ok) return B200AABB_ERR_NCCL;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    ncclUniqueId u;
+    if (nccl().GetUniqueId(&u) != ncclSuccess) return B200AABB_ERR_NCCL;
+    memcpy(id, &u, 128);
+    return B200AABB_OK;
+}
+
+static int comm_setup(b200aabb_comm* c) {
+    if (cudaSetDevice(c->device) != cudaSuccess) return B200AABB_ERR_NO_DEVICE;
+    if (cudaMalloc(&c->d_header, 32) != cudaSuccess) return B200AABB_ERR_OUT_OF_MEMORY;
+    cudaMemset(c->d_header, 0, 32);
+    return B200AABB_OK;
+}
+
+int b200aabb_comm_init(int device, int rank, int world, const char id[128], b200aabb_comm** out) {
+    if (!out || !id || world < 1 || rank < 0 || rank >= world) return B200AABB_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    if (!nccl().ok) return B200AABB_ERR_NCCL;
+    b200aabb_comm* c = new b200aabb_comm();
+    c->device = device; c->rank = rank; c->world = world;
+    int rc = comm_setup(c);
+    if (rc) { delete c; return rc; }
+    ncclUniqueId u;
+    memcpy(&u, id, 128);
+    if (nccl().CommInitRank(&c->comm, world, u, rank) != ncclSuccess) { cudaFree(c->d_header); delete c; return B200AABB_ERR_NCCL; }
+    // warm-up: the first collective of a communicator sets up its channels (tens of milliseconds); do it here, not in the first tree replication
+    if (nccl().Broadcast(c->d_header, c->d_header, 32, ncclUint8, 0, c->comm, nullptr) != ncclSuccess || cudaStreamSynchronize(nullptr) != cudaSuccess) {
+        b200aabb_comm_destroy(c);
+        return B200AABB_ERR_NCCL;
+    }
+    *out = c;
+    return B200AABB_OK;
+}
+
+int b200aabb_comm_init_all(int ndev, const int* devices, b200aabb_comm** out) {
+    if (!out || ndev < 1 || ndev > 64) return B200AABB_ERR_INVALID_ARGUMENT;
+    for (int i = 0; i < ndev; ++i) out[i] = nullptr;
+    if (!nccl().ok) return B200AABB_ERR_NCCL;
+    std::vector<int> devs(ndev);
+    for (int i = 0; i < ndev; ++i) devs[i] = devices ? devices[i] : i;
+    std::vector<ncclComm_t> comms(ndev);
+    if (nccl().CommInitAll(comms.data(), ndev, devs.data()) != ncclSuccess) return B200AABB_ERR_NCCL;
+    int rc = B200AABB_OK;
+    for (int i = 0; i < ndev; ++i) {
+        out[i] = new b200aabb_comm();
+        out[i]->comm = comms[i]; out[i]->device = devs[i]; out[i]->rank = i; out[i]->world = ndev;
+        if (int r = comm_setup(out[i])) rc = r;
+    }
+    if (rc == B200AABB_OK) {   // warm-up, see b200aabb_comm_init
+        nccl().GroupStart();
+        for (int i = 0; i < ndev; ++i) { cudaSetDevice(devs[i]); nccl().Broadcast(out[i]->d_header, out[i]->d_header, 32, ncclUint8, 0, comms[i], nullptr); }
+        if (nccl().GroupEnd() != ncclSuccess) rc = B200AABB_ERR_NCCL;
+        for (int i = 0; i < ndev; ++i) { cudaSetDevice(devs[i]); if (cudaStreamSynchronize(nullptr) != cudaSuccess) rc = B200AABB_ERR_CUDA; }
+    }
+    if (rc) for (int i = 0; i < ndev; ++i) { b200aabb_comm_destroy(out[i]); out[i] = nullptr; }
+    return rc;
+}
+
+int b200aabb_comm_destroy(b200aabb_comm* c) {
+    if (!c) return B200AABB_OK;
+    cudaSetDevice(c->device);
+    if (c->comm && nccl().ok) nccl().CommDestroy(c->comm);
+    cudaFree(c->d_header);
+    delete c;
+    return B200AABB_OK;
+}
+
+const char* b200aabb_comm_last_error(const b200aabb_comm* c) { return c ? c->err.c_str() : "null communicator"; }
+
+int b200aabb_comm_broadcast_tree(b200aabb_comm* c, b200aabb_tree* t, int root, int mode, double* ms, uint64_t* bytes) {
+    if (!c || !t || root < 0 || root >= c->world || (mode != 0 && mode != 1) || t->device != c->device) return B200AABB_ERR_INVALID_ARGUMENT;
+    B2_LOCK(t);
+    B2_CUDA(t, cudaSetDevice(t->device));
+    cudaStream_t st = t->stream;
+    int rc = B200AABB_OK;
+    if (c->rank == root) {
+        rc = ensure_built(t);
+        if (rc) return rc;
+        if (mode == 1 && t->n && !t->d_soup) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "mode 1 replicates the inserted primitives: the root holds none (imported tree)");
+    }
+    B2_CUDA(t, cudaEventRecord(t->ev_a, st));
+    if ((rc = bcast_header(c, t, root, mode, st))) return rc;
+    if ((rc = bcast_prepare(c, t, root, mode, st))) return rc;
+    uint64_t nbytes = 0;
+    if ((rc = bcast_payload(c, t, root, mode, st, &nbytes))) return rc;
+    if ((rc = bcast_finish(c, t, root, mode, st))) return rc;
+    B2_CUDA(t, cudaEventRecord(t->ev_b, st));
+    B2_CUDA(t, cudaStreamSynchronize(st));
+    if (c->rank != root && mode == 0) { rc = b200aabb_import_finish(t); if (rc) return rc; }
+    float f = 0; cudaEventElapsedTime(&f, t->ev_a, t->ev_b);
+    if (ms) *ms = f;
+    if (bytes) *bytes = nbytes;
+    return B200AABB_OK;
+}
+
+int b200aabb_comm_broadcast_tree_all(b200aabb_comm** cs, b200aabb_tree** ts, int ndev, int root, int mode, double* ms, uint64_t* bytes) {
+    if (!cs || !ts || ndev < 1 || root < 0 || root >= ndev || (mode != 0 && mode != 1)) return B200AABB_ERR_INVALID_ARGUMENT;
+    for (int i = 0; i < ndev; ++i) if (!cs[i] || !ts[i] || ts[i]->device != cs[i]->device || cs[i]->world != ndev) return B200AABB_ERR_INVALID_ARGUMENT;
+    int rc = ensure_built(ts[root]);
+    if (rc) return rc;
+    if (mode == 1 && ts[root]->n && !ts[root]->d_soup) return fail(ts[root], B200AABB_ERR_INVALID_ARGUMENT, "mode 1 replicates the inserted primitives: the root holds none");
+    for (int i = 0; i < ndev; ++i) { cudaSetDevice(ts[i]->device); cudaEventRecord(ts[i]->ev_a, ts[i]->stream); }
+    nccl().GroupStart();
+    for (int i = 0; i < ndev && !rc; ++i) { cudaSetDevice(ts[i]->device); rc = bcast_header(cs[i], ts[i], root, mode, ts[i]->stream); }
+    if (nccl().GroupEnd() != ncclSuccess && !rc) rc = B200AABB_ERR_NCCL;
+    for (int i = 0; i < ndev && !rc; ++i) { cudaSetDevice(ts[i]->device); rc = bcast_prepare(cs[i], ts[i], root, mode, ts[i]->stream); }
+    if (rc) return rc;
+    uint64_t nbytes = 0;
+    nccl().GroupStart();
+    for (int i = 0; i < ndev && !rc; ++i) { cudaSetDevice(ts[i]->device); rc = bcast_payload(cs[i], ts[i], root, mode, ts[i]->stream, &nbytes); }
+    if (nccl().GroupEnd() != ncclSuccess && !rc) rc = B200AABB_ERR_NCCL;
+    for (int i = 0; i < ndev && !rc; ++i) { cudaSetDevice(ts[i]->device); rc = bcast_finish(cs[i], ts[i], root, mode, ts[i]->stream); }
+    if (rc) return rc;
+    double worst = 0;
+    for (int i = 0; i < ndev; ++i) {
+        cudaSetDevice(ts[i]->device);
+        cudaEventRecord(ts[i]->ev_b, ts[i]->stream);
+        if (cudaStreamSynchronize(ts[i]->stream) != cudaSuccess) return B200AABB_ERR_CUDA;
+        if (i != root && mode == 0) { rc = b200aabb_import_finish(ts[i]); if (rc) return rc; }
+        float f = 0; cudaEventElapsedTime(&f, ts[i]->ev_a, ts[i]->ev_b);
+        worst = std::max(worst, (double)f);
+    }
+    if (ms) *ms = worst;
+    if (bytes) *bytes = nbytes;
     return B200AABB_OK;
 }
 

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(256) hierarchy_kernel(const uint64_t* __restri
     uint32_t l, r, j;
     karras_node(keys, (int64_t)n, (int64_t)i, l, r, &j);
     BvhNode* nd = nodes + i;
-    nd->child[0] = l; nd->child[1] = r; nd->visit = j;           // the node covers the leaves [min(i,j), max(i,j)]; refit_kernel reads it
+    nd->child0 = l; nd->child1 = r; nd->visit = j;           // the node covers the leaves [min(i,j), max(i,j)]; refit_kernel reads it
     if (i == 0) nd->parent = kNone;
     if (l & kLeafBit) leaf_parent[l & ~kLeafBit] = (uint32_t)i; else nodes[l].parent = (uint32_t)i;
     if (r & kLeafBit) leaf_parent[r & ~kLeafBit] = (uint32_t)i; else nodes[r].parent = (uint32_t)i;
@@ -202,7 +202,7 @@ static_assert(sizeof(RefitEntry) == 32, "frontier entry");
 __device__ __forceinline__ void refit_climb_global(BvhNode* nodes, uint32_t p, uint32_t me, float* lo, float* hi) {
     while (true) {
         BvhNode* nd = nodes + p;
-        const int side = (nd->child[0] == me) ? 0 : 1;
+        const int side = (nd->child0 == me) ? 0 : 1;
         float* mylo = side ? nd->lo1 : nd->lo0; float* myhi = side ? nd->hi1 : nd->hi0;
 #pragma unroll
         for (int a = 0; a < 3; ++a) { mylo[a] = lo[a]; myhi[a] = hi[a]; }
@@ -228,7 +228,10 @@ __global__ void __launch_bounds__(kRefitBlock) refit_local_kernel(const TriRec* 
     const uint64_t k = base + threadIdx.x;
     const uint64_t last_leaf = base + kRefitBlock - 1 < n - 1 ? base + kRefitBlock - 1 : n - 1;
     s_cnt[threadIdx.x] = 0;
-    if (k + 1 < n) s_link[threadIdx.x] = *reinterpret_cast<const uint4*>(&nodes[k].child[0]);
+    if (k + 1 < n) {
+        const uint2 a = *reinterpret_cast<const uint2*>(&nodes[k].child0), b = *reinterpret_cast<const uint2*>(&nodes[k].child1);   // (child0, parent), (child1, visit)
+        s_link[threadIdx.x] = make_uint4(a.x, b.x, a.y, b.y);
+    }
     __syncthreads();
     if (k >= n || n == 1) return;
     float lo[3], hi[3];
@@ -268,14 +271,15 @@ __global__ void __launch_bounds__(kRefitBlock) refit_local_kernel(const TriRec* 
         float olo[3], ohi[3];
 #pragma unroll
         for (int a = 0; a < 3; ++a) { olo[a] = ((volatile float*)s_box[slot][1 - side])[a]; ohi[a] = ((volatile float*)s_box[slot][1 - side])[3 + a]; }
-        // the second arrival writes both child boxes of the node at once: 48 contiguous bytes, three 128-bit stores
+        // the second arrival writes the node at once: each 32-byte half = a child's box + the links already staged in shared memory, four 128-bit stores
         {
             const float* l0 = side ? olo : lo; const float* h0 = side ? ohi : hi;     // child 0
             const float* l1 = side ? lo : olo; const float* h1 = side ? hi : ohi;     // child 1
             float4* dst = reinterpret_cast<float4*>(nd);
             dst[0] = make_float4(l0[0], l0[1], l0[2], h0[0]);
-            dst[1] = make_float4(h0[1], h0[2], l1[0], l1[1]);
-            dst[2] = make_float4(l1[2], h1[0], h1[1], h1[2]);
+            dst[1] = make_float4(h0[1], h0[2], __uint_as_float(link.x), __uint_as_float(link.z));
+            dst[2] = make_float4(l1[0], l1[1], l1[2], h1[0]);
+            dst[3] = make_float4(h1[1], h1[2], __uint_as_float(link.y), __uint_as_float(link.w));
         }
 #pragma unroll
         for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], olo[a]); hi[a] = fmaxf(hi[a], ohi[a]); }

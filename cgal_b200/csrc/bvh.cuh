@@ -27,12 +27,16 @@ constexpr uint32_t kLeafBit = 0x80000000u;
 constexpr uint32_t kNone = 0xFFFFFFFFu;
 constexpr int kStackCap = 96;
 
+// Each 32-byte half of a node is self-contained (one child's box + its reference): a thread that needs both children reads the two
+// sectors with two 256-bit loads, and the lane PAIRS of closest_pair.cuh read one half each, so a node costs ONE L1 wavefront per pair.
 struct __align__(32) BvhNode {
     float lo0[3], hi0[3];  // child 0
-    float lo1[3], hi1[3];  // child 1
-    uint32_t child[2];
+    uint32_t child0;
     uint32_t parent;       // build / refit only
-    uint32_t visit;        // refit arrival counter (build only)
+    float lo1[3], hi1[3];  // child 1
+    uint32_t child1;
+    uint32_t visit;        // refit: the other end of the node's leaf range, then the arrival flag (build only)
+    B2_HD uint32_t child(int c) const { return c ? child1 : child0; }
 };
 static_assert(sizeof(BvhNode) == 64, "node is two 32-byte sectors");
 
@@ -117,13 +121,13 @@ B2_HD NodeView load_node(const BvhNode* __restrict__ nodes, uint32_t i) {
     ldg256(reinterpret_cast<const char*>(nodes + i) + 32, b);
     n.lo0[0] = __uint_as_float(a[0]); n.lo0[1] = __uint_as_float(a[1]); n.lo0[2] = __uint_as_float(a[2]);
     n.hi0[0] = __uint_as_float(a[3]); n.hi0[1] = __uint_as_float(a[4]); n.hi0[2] = __uint_as_float(a[5]);
-    n.lo1[0] = __uint_as_float(a[6]); n.lo1[1] = __uint_as_float(a[7]); n.lo1[2] = __uint_as_float(b[0]);
-    n.hi1[0] = __uint_as_float(b[1]); n.hi1[1] = __uint_as_float(b[2]); n.hi1[2] = __uint_as_float(b[3]);
-    n.c0 = b[4]; n.c1 = b[5];
+    n.lo1[0] = __uint_as_float(b[0]); n.lo1[1] = __uint_as_float(b[1]); n.lo1[2] = __uint_as_float(b[2]);
+    n.hi1[0] = __uint_as_float(b[3]); n.hi1[1] = __uint_as_float(b[4]); n.hi1[2] = __uint_as_float(b[5]);
+    n.c0 = a[6]; n.c1 = b[6];
 #else
     const BvhNode& s = nodes[i];
     for (int k = 0; k < 3; ++k) { n.lo0[k] = s.lo0[k]; n.hi0[k] = s.hi0[k]; n.lo1[k] = s.lo1[k]; n.hi1[k] = s.hi1[k]; }
-    n.c0 = s.child[0]; n.c1 = s.child[1];
+    n.c0 = s.child0; n.c1 = s.child1;
 #endif
     return n;
 }
@@ -478,7 +482,8 @@ B2_HD void approx_closest_to_origin(const float* a, const float* b, const float*
 // rounding and the three binary32 dot products; `su` = fl(|u|) (2e-7 relative) and the final comparison carry 1e-6.
 B2_HD bool certainly_farther(const float* u, float su, const float* ra, const float* rb, const float* rc, float m, float rbound) {
     const float md = fminf(dot3f(u, ra), fminf(dot3f(u, rb), dot3f(u, rc)));
-    return su > 1e-18f && md - 5e-7f * m * su > rbound * su * 1.000001f;
+    // (range guard as closest_warp.cuh::wp_lower: no binary32 overflow of the dot products, and they and E stay above the denormal range)
+    return su > 1e-18f && su < 1e19f && m < 1e18f && m * su > 1e-30f && md - 5e-7f * m * su > rbound * su * 1.000001f;
 }
 
 // binary32 pre-test of one primitive on coordinates RELATIVE to the query o (the subtraction is done in binary64): true = the

@@ -87,7 +87,6 @@ struct WarpClosestArgs {
     WarpSlots64* slots64;          // gridDim.x records
     int exact_go;                  // run the exact phase when at least this many pairs wait (1 .. kWpExactCap - 32)
     uint32_t flag_tie, flag_exact;
-    const double* debug_hint_sqd;  // experiment only: a known upper bound of each query's squared distance (caller order), or nullptr
 };
 
 #if defined(__CUDACC__)
@@ -158,7 +157,11 @@ B2_HD float wp_lower(const float* u, float su, const RelTri& r) {   // (host bui
 #else
     const float rcp = 1.0f / su;
 #endif
-    return su > 1e-18f ? fmaf(-5e-7f * r.m, su, md) * (rcp * 0.999998f) : -INFINITY;
+    // Range guard (binary32 under/overflow): the bound is only formed when m < 1e18 (no product can overflow: |u.r_i| <= 3 m |u| < 1e37) and
+    // m |u| > 1e-30 (the dot products and the allowance E are far above the denormal range, whose absolute rounding would exceed E).
+    // Outside that range: no bound (the pair goes on to the binary64 stage), never a wrong one.
+    const bool in_range = su > 1e-18f && su < 1e19f && r.m < 1e18f && r.m * su > 1e-30f;   // (su = inf / NaN: the direction itself is the product of an overflow)
+    return in_range ? fmaf(-5e-7f * r.m, su, md) * (rcp * 0.999998f) : -INFINITY;
 }
 // Approximate closest point P = a + v ab + w ac (v, w >= 0, v + w <= 1 up to an ulp) -> a sharper lower bound (direction P) and a
 // rigorous UPPER bound of (distance + the slot's rounding allowance): P's coordinates are within 1.2e-6 m of a point of the true
@@ -178,7 +181,8 @@ B2_HD void wp_sharp(const RelTri& r, float dslack, float e2, float* lower, float
     const float ab[3] = {r.rb[0] - r.ra[0], r.rb[1] - r.ra[1], r.rb[2] - r.ra[2]}, ac[3] = {r.rc[0] - r.ra[0], r.rc[1] - r.ra[1], r.rc[2] - r.ra[2]};
     const float n[3] = {ab[1] * ac[2] - ab[2] * ac[1], ab[2] * ac[0] - ab[0] * ac[2], ab[0] * ac[1] - ab[1] * ac[0]};
     const float lab = dot3f(ab, ab), lac = dot3f(ac, ac), noise = 1e3f * (e2 + r.m * 2.4e-7f);
-    const bool sound = dot3f(n, n) >= 1e-6f * lab * lac && lab > noise * noise && lac > noise * noise;
+    // (m in [1e-9, 1e9]: |n|^2 and |ab|^2 |ac|^2 ~ m^4 stay normal binary32 numbers, so the conditioning test and |u| itself mean what they say)
+    const bool sound = r.m > 1e-9f && r.m < 1e9f && dot3f(n, n) >= 1e-6f * lab * lac && lab > noise * noise && lac > noise * noise;
 #if defined(__CUDA_ARCH__)
     const float no_bound = __int_as_float(0x7fc00000);
 #else
@@ -331,7 +335,6 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                 __stcg(&G.bsqd[lane], sqd);
                 S.bprim[lane] = id;
                 wp_set_bounds(S, lane, sqd, v, delta, true);
-                if (a.debug_hint_sqd) wp_shrink(S, lane, float_above(sqrt(widen_sqdist(a.debug_hint_sqd[qi], delta))));
                 S.qidx[lane] = qi;
                 S.flags[lane] = nex0 ? a.flag_exact : 0u;
             }
@@ -367,6 +370,9 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                 bool in0 = false, in1 = false;                     // 0 = nearer child, 1 = farther child
                 uint32_t r0 = 0, r1 = 0;
                 float d0 = 0.0f, d1 = 0.0f;
+                // (Measured and rejected, profiles/r2_03: lane PAIRS fetching the two halves of one node with one load instruction, each
+                //  lane testing the half it fetched of both nodes and shuffling the partner's results back: L1 wavefronts -5 %, instructions
+                //  +16 % (six shuffles + selects per step), 26.0 ms instead of 24.0.)
                 if (expand) {
                     const NodeView nd = load_node(a.nodes, e.x);
                     d0 = wp_box_sqdist(nd.lo0, nd.hi0, q); d1 = wp_box_sqdist(nd.lo1, nd.hi1, q);

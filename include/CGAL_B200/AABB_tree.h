@@ -25,6 +25,7 @@
 
 #include <cstdint>
 #include <iterator>
+#include <atomic>
 #include <mutex>
 #include <optional>
 #include <stdexcept>
@@ -84,13 +85,13 @@ class AABB_tree {
     create(0);
     insert(first, beyond, std::forward<T>(t)...);
   }
-  AABB_tree(Self&& o) noexcept : m_traits(std::move(o.m_traits)), m_primitives(std::move(o.m_primitives)), m_handle(o.m_handle), m_uploaded(o.m_uploaded) {
+  AABB_tree(Self&& o) noexcept : m_traits(std::move(o.m_traits)), m_primitives(std::move(o.m_primitives)), m_handle(o.m_handle), m_uploaded(o.m_uploaded.load()) {
     o.m_handle = nullptr;
   }
   Self& operator=(Self&& o) noexcept {
     if (this != &o) {
       destroy();
-      m_traits = std::move(o.m_traits); m_primitives = std::move(o.m_primitives); m_handle = o.m_handle; m_uploaded = o.m_uploaded;
+      m_traits = std::move(o.m_traits); m_primitives = std::move(o.m_primitives); m_handle = o.m_handle; m_uploaded = o.m_uploaded.load();
       o.m_handle = nullptr;
     }
     return *this;
@@ -486,7 +487,7 @@ class AABB_tree {
   AABBTraits m_traits;
   Primitives m_primitives;
   b200aabb_tree* m_handle = nullptr;
-  mutable bool m_uploaded = true;   // the device tree reflects m_primitives
+  mutable std::atomic<bool> m_uploaded{true};   // the device tree reflects m_primitives (read without the lock by const queries)
   mutable std::mutex m_mutex;
 };
 

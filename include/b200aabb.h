@@ -27,7 +27,11 @@ enum {
   B200AABB_ERR_CUDA = -2,          /* a CUDA call failed; see b200aabb_last_error() */
   B200AABB_ERR_OUT_OF_MEMORY = -3,
   B200AABB_ERR_EMPTY_TREE = -4,    /* CGAL_precondition(!empty()) of the distance queries, AABB_tree.h:993,1008,1039 */
-  B200AABB_ERR_NO_DEVICE = -5      /* no sm_100 device: there is NO CPU fallback */
+  B200AABB_ERR_NO_DEVICE = -5,     /* no sm_100 device: there is NO CPU fallback */
+  B200AABB_ERR_NCCL = -7,          /* NCCL is not available (libnccl.so.2 could not be loaded) or an NCCL call failed */
+  B200AABB_ERR_INCOMPLETE = -6     /* a traversal could not finish (stack overflow on a tree deeper than this library ever builds): the results of
+                                      the batch are incomplete.  HOST batches report it from the call itself, DEVICE batches (asynchronous) from the
+                                      next b200aabb_get_stats */
 };
 
 enum { B200AABB_NO_PRIMITIVE = 0xFFFFFFFFu };
@@ -47,24 +51,26 @@ enum {
                                       the reference's id then depends on its traversal order;
                                       this library reports the smallest primitive id among them */
   B200AABB_FLAG_EXACT = 8,         /* at least one predicate of this query needed the exact (expansion) stage */
-  B200AABB_FLAG_NEAR_TIE = 16      /* not an exact tie, but the runner-up is within the ROUNDING UNCERTAINTY of the winner:
-                                      first_intersection: |t| uncertainty of the plain-double hit construction (large for a ray
-                                      grazing a triangle); closest_point: 16 ulps of the squared distance.  The reference compares
-                                      the same rounded values while pruning boxes with inexact tests (AABB_traits_3.h:89-125;
-                                      AABB_ray_intersection.h:78), so in this band its own answer depends on the order in which its
-                                      tree presents the candidates; this library reports the smallest rounded value */
+  B200AABB_FLAG_NEAR_TIE = 16      /* first_intersection only: not an exact tie, but the runner-up's t lies within the ROUNDING UNCERTAINTY of the
+                                      winner's (the plain-double hit construction; large for a ray grazing a triangle).  The reference compares
+                                      the same rounded values while pruning boxes with an inexact test (AABB_traits_3.h:89-125;
+                                      AABB_ray_intersection.h:78), so in this band its own answer depends on the order in which its tree presents
+                                      the candidates; this library reports the smallest rounded value.  closest_point never sets it: there the
+                                      reference compares candidates exactly and never prunes when unsure, so only exact ties are order dependent */
 };
 
 /* b200aabb_set_option keys */
 enum {
   B200AABB_OPT_SORT_QUERIES = 1,   /* 1 (default): every batch is traversed in a coherence order (Morton order of the points /
                                       of ray origin+direction, onesweep radix sort on the device); 0: in the caller's order */
-  B200AABB_OPT_CLOSEST_KERNEL = 2, /* closest_point scheduling: 1 (default) = warp-cooperative work pool (32 query slots per persistent
-                                      warp, pooled (slot,node)/(slot,leaf) pairs); 0 = one thread per query.  Same results. */
+  B200AABB_OPT_CLOSEST_KERNEL = 2, /* closest_point scheduling: 1 (default) = warp-cooperative work pool (32 query slots per persistent warp, pooled
+                                      (slot,node)/(slot,leaf) pairs, closest_warp.cuh); 2 = lane pairs walk the tree with private stacks
+                                      (closest_pair.cuh; measured slower on the benchmark, kept as the reference point of that design);
+                                      0 = one thread per query.  Same results. */
   B200AABB_OPT_HOST_PARTS = 5,     /* HOST-pointer batches are cut into about this many chunks (each 256 Ki .. 4 Mi queries) that flow through a
                                       double-buffered upload -> sort -> traverse -> download pipeline (1..64; 0 = default: 6 for ray / segment
                                       batches, 2 for point batches) */
-  B200AABB_OPT_WARP_EXACT_GO = 4   /* warp-cooperative kernel: run the binary64 phase once this many pre-test survivors wait (1..160, default 160) */
+  B200AABB_OPT_WARP_EXACT_GO = 4   /* warp-cooperative kernels: run the binary64 phase once this many pre-test survivors wait (1..160; 0 = the kernel's default) */
 };
 
 typedef struct b200aabb_stats {
@@ -161,6 +167,29 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* points, uint64_t n, b
 int b200aabb_export_layout(b200aabb_tree* t, void** ptrs, uint64_t* bytes, int cap, int* count);
 int b200aabb_import_alloc(b200aabb_tree* t, uint64_t n);
 int b200aabb_import_finish(b200aabb_tree* t);
+
+/* ---- multi-GPU behind the boundary --------------------------------------------------------------------
+ * The reference has no multi-device path: its callers shard queries over threads (tbb::parallel_for,
+ * Polygon_mesh_processing/include/CGAL/Polygon_mesh_processing/distance.h:127-169).  Here the tree is built on ONE GPU and replicated with
+ * NCCL over NVLink / NVSwitch; every GPU then answers its own block of the batch against its replica (no collective in the query loop).
+ * NCCL is loaded at run time (libnccl.so.2); without it these calls return B200AABB_ERR_NCCL and everything else works.
+ *
+ * One process per GPU: rank 0 calls b200aabb_comm_unique_id and hands the 128 bytes to the other ranks by any means (MPI, a file, a
+ * socket); every rank calls b200aabb_comm_init.  One process driving several GPUs: b200aabb_comm_init_all (ncclCommInitAll) and the
+ * *_all variant of the broadcast.  Both warm the communicator up, so the first replication does not pay NCCL's channel set-up. */
+typedef struct b200aabb_comm b200aabb_comm;
+int b200aabb_comm_unique_id(char id[128]);
+int b200aabb_comm_init(int device, int rank, int world, const char id[128], b200aabb_comm** out);
+int b200aabb_comm_init_all(int ndev, const int* devices /* NULL = 0..ndev-1 */, b200aabb_comm** out /* [ndev] */);
+int b200aabb_comm_destroy(b200aabb_comm* c);
+const char* b200aabb_comm_last_error(const b200aabb_comm* c);
+/* Replicates the tree of rank `root` into the handle of every other rank (collective: every rank calls it with its own handle, created
+ * on the communicator's device).  mode 0: broadcast the built tree (64-byte nodes + 96-byte primitive records + root box; the receiver
+ * derives the binary32 record copies itself); mode 1: broadcast the inserted primitives (72 bytes each, + ids) and build on every rank
+ * (the build runs at several G primitives/s: SURVEY.md §8e asks for both to be measured).  ms / bytes (optional): device time of the
+ * replication on this rank and the bytes it moved. */
+int b200aabb_comm_broadcast_tree(b200aabb_comm* c, b200aabb_tree* t, int root, int mode, double* ms, uint64_t* bytes);
+int b200aabb_comm_broadcast_tree_all(b200aabb_comm** comms, b200aabb_tree** trees, int ndev, int root, int mode, double* ms, uint64_t* bytes);
 
 /* ---- self-test hook (used by tests/, not by the reference-side binding) ---------------------------------------------
  * Evaluates one DEVICE predicate / construction per record (host pointers).  which: 0 Orientation_3(p,q,r,s) [12 doubles],

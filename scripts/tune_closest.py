@@ -1,13 +1,12 @@
 #!/usr/bin/env python
-"""GPU-side tuning sweep for closest_point on the benchmark workload (terrain16M + bbox points): compares the
-thread-per-query kernel with the warp-cooperative pool kernel over its scheduling parameters.  Not a bench value."""
+"""GPU-side tuning sweep for closest_point on the benchmark workload (terrain16M + bbox points): compares the closest_point kernels
+(0 thread per query, 1 warp-cooperative pool, 2 lane pairs with private stacks) over their scheduling parameter and checks that they
+return identical records.  Not a bench value."""
 import argparse
 import json
 import os
 import sys
 import time
-
-import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -19,9 +18,8 @@ def main():
     ap.add_argument("--ny", type=int, default=2048)
     ap.add_argument("--points", type=int, default=1 << 23)
     ap.add_argument("--reps", type=int, default=3)
-    ap.add_argument("--sweep", default="160,128,64")
-    ap.add_argument("--skip-old", action="store_true")
-    ap.add_argument("--two-pass", action="store_true", help="experiment: second pass starts from the first pass's distances (perfect initial bound); ms = last_query_ms of pass 2")
+    ap.add_argument("--cfgs", default="1:160,2:64", help="comma separated kernel:exact_go")
+    ap.add_argument("--label", default="")
     args = ap.parse_args()
     import torch
     import cgal_b200 as B
@@ -36,9 +34,11 @@ def main():
     out = {"point": torch.empty((n, 3), dtype=torch.float64, device="cuda"), "prim": torch.empty(n, dtype=torch.int32, device="cuda"),
            "sqdist": torch.empty(n, dtype=torch.float64, device="cuda"), "flags": torch.empty(n, dtype=torch.uint8, device="cuda")}
     want = ("point", "prim", "sqdist", "flags")
-    print("setup %.1fs, %d triangles, %d points" % (time.time() - t0, len(f), n), flush=True)
+    print("setup %.1fs, %d triangles, %d points %s" % (time.time() - t0, len(f), n, args.label), flush=True)
 
     def run(label):
+        for k in out:
+            out[k].zero_()
         best = None
         for _ in range(args.reps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -50,22 +50,16 @@ def main():
             ms = e0.elapsed_time(e1)
             best = ms if best is None else min(best, ms)
         st = g.stats()
-        if args.two_pass:
-            best = st["last_query_ms"]
         print(json.dumps({"cfg": label, "ms": round(best, 3), "Mq_s": round(n / best / 1e3, 1), "nodes_q": round(st["nodes_visited"] / n, 1),
                           "leaves_q": round(st["leaves_tested"] / n, 1), "culled_q": round(st["leaves_culled"] / n, 1), "ties": st["ties"], "exact": st["exact_fallbacks"]}), flush=True)
         return {k: out[k].clone() for k in ("prim", "sqdist", "point")}, out["flags"].clone()
 
     ref = None
-    if not args.skip_old:
-        g.set_option(B.OPT_CLOSEST_KERNEL, 0)
-        ref, ref_fl = run("thread-per-query")
-    g.set_option(B.OPT_CLOSEST_KERNEL, 1)
-    if args.two_pass:
-        g.set_option(100, 1)
-    for item in args.sweep.split(","):
-        g.set_option(B.OPT_WARP_EXACT_GO, int(item))
-        got, fl = run("warp exact_go=%d" % int(item))
+    for item in args.cfgs.split(","):
+        kern, go = [int(x) for x in item.split(":")]
+        g.set_option(B.OPT_CLOSEST_KERNEL, kern)
+        g.set_option(B.OPT_WARP_EXACT_GO, go)
+        got, fl = run("kernel=%d exact_go=%d" % (kern, go))
         if ref is None:
             ref, ref_fl = got, fl
         else:

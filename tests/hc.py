@@ -45,6 +45,7 @@ def lib():
         L.hc_intersect.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_int, C.c_int, _u32p]
         L.hc_first_intersection.argtypes = [C.c_void_p, _dp, C.c_uint64, _u32p, _dp, _dp, _u8p, _u8p]
         L.hc_closest_point.argtypes = [C.c_void_p, _dp, C.c_uint64, _dp, _u32p, _dp, _u8p]
+        L.hc_closest_point_pair.argtypes = [C.c_void_p, _dp, C.c_uint64, _u32p, C.c_int, C.c_int, _dp, _u32p, _dp, _u8p, C.POINTER(C.c_uint64)]
         for n in ("hc_orient3", "hc_orient3_exact", "hc_orient3_dir", "hc_coplanar_orient", "hc_cmp_dist", "hc_cmp_dist_exact"):
             getattr(L, n).argtypes = [_dp]
         L.hc_tri_do_intersect.argtypes = [_dp, _dp, C.c_int]
@@ -107,6 +108,19 @@ class HostTree:
         cp, prim, sqd, tie = np.zeros((n, 3)), np.zeros(n, np.uint32), np.zeros(n), np.zeros(n, np.uint8)
         lib().hc_closest_point(self.h, _p(q), n, _p(cp), _p(prim, _u32p), _p(sqd), _p(tie, _u8p))
         return dict(cp=cp, prim=prim, sqd=sqd, tie=tie & 1, near=(tie >> 1) & 1)
+
+
+    def closest_point_pair(self, q, perm=None, warps=1, exact_go=64):
+        """closest_pair.cuh's kernel body on emulated warps (32 fibers each): the code the GPU runs"""
+        q = _d(q).reshape(-1, 3)
+        n = len(q)
+        cp, prim, sqd, fl = np.zeros((n, 3)), np.full(n, 0xFFFFFFFF, np.uint32), np.zeros(n), np.zeros(n, np.uint8)
+        stats = np.zeros(3, np.uint64)
+        pm = None if perm is None else np.ascontiguousarray(perm, dtype=np.uint32)
+        rc = lib().hc_closest_point_pair(self.h, _p(q), n, _p(pm, _u32p), int(warps), int(exact_go), _p(cp), _p(prim, _u32p), _p(sqd), _p(fl, _u8p),
+                                         stats.ctypes.data_as(C.POINTER(C.c_uint64)))
+        assert rc == 0, "emulated pair kernel: %s" % {1: "dead-lock (non-uniform control flow at a collective)", 2: "overflow reported"}.get(rc, rc)
+        return dict(cp=cp, prim=prim, sqd=sqd, tie=(fl >> 2) & 1, exact=(fl >> 3) & 1, nodes=int(stats[0]), leaves=int(stats[1]), culled=int(stats[2]))
 
 
 def validate(nodes_u8, tris_u8, n):

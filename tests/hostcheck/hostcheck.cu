@@ -11,6 +11,8 @@
 
 #include "../../cgal_b200/csrc/build.cuh"
 #include "../../cgal_b200/csrc/closest_warp.cuh"
+#define B2_WARP_EMU 1
+#include "warp_emu.h"
 
 using namespace b2;
 
@@ -27,8 +29,8 @@ void refit(HostTree& h, uint32_t ref, float* lo, float* hi) {
         return;
     }
     BvhNode& nd = h.nodes[ref];
-    refit(h, nd.child[0], nd.lo0, nd.hi0);
-    refit(h, nd.child[1], nd.lo1, nd.hi1);
+    refit(h, nd.child0, nd.lo0, nd.hi0);
+    refit(h, nd.child1, nd.lo1, nd.hi1);
     for (int a = 0; a < 3; ++a) { lo[a] = std::min(nd.lo0[a], nd.lo1[a]); hi[a] = std::max(nd.hi0[a], nd.hi1[a]); }
 }
 }  // namespace
@@ -71,7 +73,7 @@ void* hc_build(const double* tris, const uint32_t* ids, uint64_t n) {
     for (uint64_t i = 0; i + 1 < n; ++i) {
         uint32_t l, r;
         karras_node(h->keys.data(), (int64_t)n, (int64_t)i, l, r);
-        h->nodes[i].child[0] = l; h->nodes[i].child[1] = r;
+        h->nodes[i].child0 = l; h->nodes[i].child1 = r;
         if (!(l & kLeafBit)) h->nodes[l].parent = (uint32_t)i;
         if (!(r & kLeafBit)) h->nodes[r].parent = (uint32_t)i;
     }
@@ -103,14 +105,14 @@ int hc_validate(const void* nodes_v, const void* tris_v, uint64_t n) {
         uint32_t x = st.back(); st.pop_back();
         if (x >= n - 1 || nseen[x]) return 1;
         nseen[x] = 1; order.push_back(x);
-        for (int c = 0; c < 2; ++c) { uint32_t r = nodes[x].child[c]; if (r & kLeafBit) { uint32_t s = r & ~kLeafBit; if (s >= n || seen[s]) return 2; seen[s] = 1; } else { if (nodes[r].parent != x) return 3; st.push_back(r); } }
+        for (int c = 0; c < 2; ++c) { uint32_t r = nodes[x].child(c); if (r & kLeafBit) { uint32_t s = r & ~kLeafBit; if (s >= n || seen[s]) return 2; seen[s] = 1; } else { if (nodes[r].parent != x) return 3; st.push_back(r); } }
     }
     for (uint64_t i = 0; i < n; ++i) if (!seen[i]) return 4;
     for (size_t k = order.size(); k-- > 0;) {
         const uint32_t x = order[k];
         for (int c = 0; c < 2; ++c) {
             float lo[3], hi[3];
-            const uint32_t r = nodes[x].child[c];
+            const uint32_t r = nodes[x].child(c);
             if (r & kLeafBit) { const double* v = tris[r & ~kLeafBit].v; for (int a = 0; a < 3; ++a) { lo[a] = float_below(std::min(v[a], std::min(v[3 + a], v[6 + a]))); hi[a] = float_above(std::max(v[a], std::max(v[3 + a], v[6 + a]))); } }
             else for (int a = 0; a < 3; ++a) { lo[a] = blo[3 * r + a]; hi[a] = bhi[3 * r + a]; }
             const float* nlo = c ? nodes[x].lo1 : nodes[x].lo0; const float* nhi = c ? nodes[x].hi1 : nodes[x].hi0;
@@ -205,6 +207,48 @@ void hc_warp_bounds(const double* tri, const double* q, double mag, float* out) 
     out[0] = wp_lower(g, sqrtf(dot3f(g, g)), r) - e2;
     wp_sharp(r, dslack, e2, &out[1], &out[2]);
     out[3] = e2; out[4] = dslack;
+}
+// closest_pair.cuh's kernel body run by `warps` emulated warps (32 fibers each, one warp after the other sharing the batch cursor) over
+// the host-built tree: the SAME code the GPU runs.  perm = optional coherence order.  Returns 0, or 1 when a warp dead-locked (non-uniform
+// control flow at a collective), 2 when the kernel reported an overflow.  stats[0..2] = nodes visited, leaves tested, leaves culled.
+int hc_closest_point_pair(void* hv, const double* q, uint64_t n, const uint32_t* perm, int warps, int exact_go, double* cp, uint32_t* prim, double* sqd,
+                          uint8_t* flags, uint64_t* stats) {
+    HostTree* h = (HostTree*)hv;
+    std::vector<TriF> trisf(h->tris.size());
+    for (size_t k = 0; k < h->tris.size(); ++k) { memset(&trisf[k], 0, sizeof(TriF)); for (int j = 0; j < 9; ++j) trisf[k].v[j] = (float)h->tris[k].v[j]; }
+    unsigned long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0}, cursor = 0;
+    std::vector<uint2> spill((size_t)warps * kPpSpillPerWarp);
+    std::vector<WarpSlots64> slots((size_t)warps);
+    PairClosestArgs a;
+    a.nodes = h->nodes.data(); a.tris = h->tris.data(); a.trisf = trisf.data(); a.mag = h->mag(); a.perm = perm; a.counters = counters;
+    a.pts = q; a.n = n; a.cp = cp; a.prim = prim; a.sqd = sqd; a.flags = flags; a.cursor = &cursor; a.spill = spill.data(); a.slots64 = slots.data();
+    a.exact_go = exact_go; a.flag_tie = 4; a.flag_exact = 8;
+    // the warps run one after the other (each to completion): warp 0 would take every chunk, so the cursor is advanced by hand to deal the
+    // chunks round-robin — warp k sees a cursor that skips the other warps' chunks
+    int rc = 0;
+    for (int k = 0; k < warps && rc == 0; ++k) {
+        std::vector<unsigned long long> handed;
+        PairShared S;
+        memset(&S, 0, sizeof(S));
+        b2emu::Warp W;
+        // a private view of the batch: queries whose chunk index % warps == k
+        std::vector<uint32_t> myperm;
+        for (uint64_t c = (uint64_t)k * kPpChunk; c < n; c += (uint64_t)warps * kPpChunk)
+            for (uint64_t i = c; i < std::min<uint64_t>(n, c + kPpChunk); ++i) myperm.push_back(perm ? perm[i] : (uint32_t)i);
+        PairClosestArgs b = a;
+        unsigned long long mycursor = 0;
+        b.perm = myperm.data(); b.n = myperm.size(); b.cursor = &mycursor;
+        b.spill = spill.data() + (size_t)k * kPpSpillPerWarp;
+        if (b.n == 0) continue;
+        const bool ok = b2emu::run_warp(W, [&](unsigned lane) {
+            WarpCtx w; w.lane = lane; w.emu = &W; w.phase = 0;
+            closest_pair_body(b, S, slots[k], b.spill, w);
+        });
+        if (!ok) rc = 1;
+    }
+    if (rc == 0 && counters[2]) rc = 2;
+    if (stats) { stats[0] = counters[3]; stats[1] = counters[4]; stats[2] = counters[6]; }
+    return rc;
 }
 uint64_t hc_sizeof_node() { return sizeof(BvhNode); }
 uint64_t hc_sizeof_tri() { return sizeof(TriRec); }

@@ -229,6 +229,54 @@ def test_queries_match_oracle(meshes, name):
     assert same.mean() > 0.2   # far outside points mostly project on vertices / edges: exact ties
 
 
+@pytest.mark.parametrize("name,warps,exact_go", [("cube", 1, 64), ("coverrear", 2, 32), ("elephant", 3, 64), ("elephant", 1, 128)])
+def test_pair_kernel_body_on_emulated_warps(meshes, name, warps, exact_go):
+    """closest_pair.cuh (the default closest_point kernel) run on the CPU by 32 cooperatively scheduled fibers per warp: same records as the
+    thread-per-query traversal (bit for bit, tie flags included) and as the oracle up to reported exact ties; ragged batch sizes, queries far
+    outside the box (ties on vertices / edges), with and without a coherence order"""
+    v, f = meshes[name]
+    dev, ref = hc.HostTree(soup_of(v, f)), orc.OracleTree(v, f)
+    rng = np.random.default_rng(5)
+    bb = ref.bbox()
+    ext = bb[3:] - bb[:3]
+    for n, order in ((1, False), (31, False), (777, True), (2500, False)):
+        pts = rng.uniform(bb[:3] - 0.5 * ext, bb[3:] + 0.5 * ext, size=(n, 3))
+        perm = rng.permutation(n).astype(np.uint32) if order else None
+        a, t = dev.closest_point_pair(pts, perm=perm, warps=warps, exact_go=exact_go), dev.closest_point(pts)
+        for k in ("cp", "prim", "sqd", "tie"):
+            np.testing.assert_array_equal(a[k], t[k])
+        b = ref.closest_point(pts)
+        same = a["prim"] == b["prim"]
+        assert np.all(same | (a["tie"] == 1))
+        np.testing.assert_array_equal(a["sqd"], b["sqd"])
+        np.testing.assert_array_equal(a["cp"][same], b["cp"][same])
+        assert a["leaves"] >= n and a["nodes"] >= n
+
+
+def test_pair_kernel_body_degenerate_and_deep_trees():
+    """zero-area triangles (the reference's projection may not be the closest point: the first-vertex candidate rule), many duplicates
+    (index tie-break levels of the Karras tree) and a chain-shaped tree (Morton keys 2^k: one level per key bit)"""
+    rng = np.random.default_rng(9)
+    base = rng.uniform(-1, 1, (40, 9))
+    base[::4, 6:9] = base[::4, 3:6]                     # segments
+    base[1::8, 3:6] = base[1::8, 0:3]; base[1::8, 6:9] = base[1::8, 0:3]   # points
+    soup = np.concatenate([base, np.repeat(base[:5], 60, axis=0)])          # 300 duplicates
+    chain = np.zeros((63, 9))
+    for k in range(63):                                 # centres at one cell of a 2^21 grid per key bit: a 63-level chain
+        c = np.zeros(3); c[2 - k % 3] = float(2 ** (k // 3))
+        chain[k] = np.tile(c, 3) + np.array([0, 0, 0, 0.25, 0, 0, 0, 0.25, 0])
+    chain = np.concatenate([chain, np.tile(np.array([2.0 ** 21, 2.0 ** 21, 2.0 ** 21]), 3)[None, :] + np.array([[0, 0, 0, 0.25, 0, 0, 0, 0.25, 0.0]])])
+    for tris, lo, hi in ((soup, -2.0, 2.0), (chain, -10.0, 300.0)):
+        dev = hc.HostTree(tris)
+        pts = rng.uniform(lo, hi, size=(600, 3))
+        a, t = dev.closest_point_pair(pts, warps=2, exact_go=48), dev.closest_point(pts)
+        for k in ("cp", "prim", "sqd", "tie"):
+            np.testing.assert_array_equal(a[k], t[k])
+        # brute force over all candidates (projection, or the first vertex when strictly nearer), exact comparison
+        o = orc.OracleTree(tris.reshape(-1, 3), np.arange(3 * len(tris), dtype=np.uint32).reshape(-1, 3))
+        np.testing.assert_array_equal(a["sqd"], o.closest_point(pts)["sqd"])
+
+
 def test_vertex_and_edge_ties_are_flagged(meshes):
     v, f = meshes["cube"]
     dev = hc.HostTree(soup_of(v, f))
@@ -253,10 +301,23 @@ def test_empty_and_singleton():
     assert tuple(cp["cp"][0]) == (0.25, 0.25, 0.0) and cp["prim"][0] == 7 and cp["sqd"][0] == 25.0
 
 
+def _seg_dist(p, a, b):
+    e = b - a
+    ee = e @ e
+    if ee == 0:
+        return float(np.sqrt((p - a) @ (p - a)))
+    t = min(max(((p - a) @ e) / ee, 0), 1)
+    x = a + t * e
+    return float(np.sqrt((p - x) @ (p - x)))
+
+
 def _exact_point_triangle_distance(tri, q):
-    """distance from q to the triangle in extended precision (Ericson, Real-Time Collision Detection 5.1.5)"""
+    """distance from q to the triangle in extended precision (Ericson, Real-Time Collision Detection 5.1.5); a triangle with a zero-length
+    edge (vertices that coincide after rounding at extreme scale / offset ratios) is the union of its edges"""
     L = np.longdouble
     a, b, c, p = (np.array(x, dtype=L) for x in (tri[0:3], tri[3:6], tri[6:9], q))
+    if not (np.any(a != b) and np.any(a != c) and np.any(b != c)):
+        return min(_seg_dist(p, a, b), _seg_dist(p, a, c), _seg_dist(p, b, c))
     ab, ac, ap = b - a, c - a, p - a
     d1, d2 = ab @ ap, ac @ ap
     if d1 <= 0 and d2 <= 0:
@@ -295,7 +356,7 @@ def test_warp_kernel_binary32_bounds_are_rigorous():
     rng = np.random.default_rng(7)
     n_upper = 0
     for trial in range(30000):
-        scale = 10.0 ** rng.uniform(-6, 4)
+        scale = 10.0 ** (rng.uniform(-30, 30) if trial % 5 == 4 else rng.uniform(-6, 4))   # (every fifth pair: the edges of the binary32 range)
         offset = rng.choice([0.0, 1.0, 1e3, 1e7]) * rng.standard_normal(3)
         tri = rng.standard_normal(9) * scale
         kind = trial % 6
