@@ -4,13 +4,15 @@
   python bench.py [--gpus N] [--steps K] [--warmup W]            the CUDA library (libb200aabb.so) through its C ABI
   python bench.py --impl reference [--steps K] [--warmup W]       the reference's CPU algorithm (the oracle port) on host cores
 
-Workload: Perlin terrain 4096 x 2048 quads = 16,777,216 triangles; the tree is built on
-rank 0 and broadcast over NCCL; every rank then owns a fixed shard of queries ("weak" scaling): image rows
-r, r+8, r+16, ... of the 8192 x 8192 pinhole camera (8192 x 1024 = 8,388,608 Ray_3 first_intersection queries) and
-8,388,608 closest_point_and_primitive queries uniform in the tree's bbox.  One STEP = one first_intersection batch +
-one closest_point batch over the rank's shard.  `value` = M queries/s with the shard resident in HBM; `e2e` = the same
-step through the C ABI with pinned HOST buffers (H2D + kernels + D2H inside the timed region).
-Input sets (403 MB rays + 201 MB points per rank) exceed the 126 MB L2, so no explicit flush is needed between steps.
+Workload: Perlin terrain 4096 x 2048 quads = 16,777,216 triangles; the tree is built on rank 0 and
+replicated with NCCL through the C ABI (b200aabb_comm_*); every rank then owns a fixed shard of queries ("weak" scaling): image rows
+r, r+8, r+16, ... of the 8192 x 8192 pinhole camera (8192 x 1024 = 8,388,608 Ray_3 first_intersection queries) and 8,388,608
+closest_point_and_primitive queries uniform in the tree's bbox.  One STEP = one first_intersection batch + one closest_point batch
+over the rank's shard.  `value` = M queries/s with the shard resident in HBM; `e2e` = the same steps through the C ABI with pinned HOST
+buffers (H2D + kernels + D2H inside the timed region; B200AABB_OPT_ASYNC_HOST lets consecutive batches overlap, one synchronize at the
+end).  Input sets (403 MB rays + 201 MB points per rank) exceed the 126 MB L2, so no explicit flush is needed between steps.
+`detail.config5`: BASELINE.json's config 5 — 2^30 mixed queries GENERATED ON THE DEVICE in 2^26-query batches, results reduced to a
+128-bit checksum per batch, the batches split over the ranks (a fixed total: the strong-scaling line).
 """
 import argparse
 import json
@@ -31,10 +33,12 @@ SHARDS = 8                          # a rank's shard = every 8th image row
 RAYS_PER_RANK = IMG * IMG // SHARDS
 POINTS_PER_RANK = RAYS_PER_RANK
 BYTES_PER_RAY, BYTES_PER_POINT = 85, 61      # algorithmic bytes, SURVEY.md §8(d)
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the kernel on this very workload, from the committed ncu --set full
-# captures (profiles/r1_15_warp_pool_final.txt, profiles/r1_03_while_while.txt): the tree itself (nodes + records) is read about once
-NCU_DRAM_BYTES_PER_LAUNCH = {"closest_point_warp_kernel": 10.892577e9 + 4.193736e9, "first_intersection_kernel": 1.074644e9 + 0.303553e9}
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the kernel on this very workload, from the committed `ncu --set full`
+# capture of the final state of the round (the file is named in the line; the tree itself — nodes + records — is read about once)
+NCU_DRAM = {"closest_point_warp_kernel": (10.903129e9 + 4.189776e9, "profiles/r2_01_pool_kernel_start_of_round.txt"),
+            "first_intersection_kernel": (None, None)}
 WORKLOAD = "terrain16M(4096x2048 quads, Perlin fBm seed 23) + per GPU 8,388,608 pinhole Ray_3 first_intersection (rows r::8 of 8192^2) + 8,388,608 bbox closest_point_and_primitive"
+C5_BATCH, C5_BATCHES = 1 << 26, 8            # config 5: 8 ray batches (one 8192^2 image each) + 8 point batches of 2^26 = 2^30 queries
 
 
 def shard_rays(rank):
@@ -101,26 +105,33 @@ def measured_peak_gbs():
 def oracle_tree(verts, faces):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import orc
-    t0 = time.perf_counter()
     o = orc.OracleTree(verts, faces)       # median-split build + kd-tree hint (accelerate_distance_queries)
-    return o, time.perf_counter() - t0
+    return o
 
 
-def cpu_sample(o, n_rays, n_pts, threads, step=0):
-    """one bounded step of the CPU path: n_rays first_intersection + n_pts closest_point; returns seconds (rays, points)"""
-    rays = shard_rays(0)[step * n_rays % RAYS_PER_RANK:][:n_rays] if n_rays else None
-    t_r = t_p = 0.0
-    if n_rays:
-        t0 = time.perf_counter()
-        o.first_intersection(rays, threads=threads)
-        t_r = time.perf_counter() - t0
-    if n_pts:
-        from cgal_b200 import workloads as W
-        pts = W.bbox_points(o.bbox(), n_pts, offset=step * n_pts)
-        t0 = time.perf_counter()
-        o.closest_point(pts, threads=threads)
-        t_p = time.perf_counter() - t0
-    return t_r, t_p
+def cpu_rates(o, rays, pts, threads, rays_1t=1 << 17, pts_1t=1 << 14):
+    """the oracle on `threads` host threads and on ONE thread (north star: both), plus its traversal work per query"""
+    import orc
+    orc.traversal_totals()
+    t0 = time.perf_counter()
+    rr = o.first_intersection(rays, threads=threads)
+    t1 = time.perf_counter()
+    rb, rp = orc.traversal_totals()
+    rc = o.closest_point(pts, threads=threads)
+    t2 = time.perf_counter()
+    pb, pp = orc.traversal_totals()
+    s0 = time.perf_counter()
+    o.first_intersection(rays[:rays_1t], threads=1)
+    s1 = time.perf_counter()
+    o.closest_point(pts[:pts_1t], threads=1)
+    s2 = time.perf_counter()
+    orc.traversal_totals()
+    rates = {"first_intersection_Mrays_s": len(rays) / (t1 - t0) / 1e6, "closest_point_Mqueries_s": len(pts) / (t2 - t1) / 1e6,
+             "single_thread": {"first_intersection_Mrays_s": min(rays_1t, len(rays)) / (s1 - s0) / 1e6, "closest_point_Mqueries_s": min(pts_1t, len(pts)) / (s2 - s1) / 1e6,
+                               "sample": "%d rays + %d points" % (min(rays_1t, len(rays)), min(pts_1t, len(pts)))},
+             "traversal": {"ray_box_tests_per_query": rb / len(rays), "ray_primitives_per_query": rp / len(rays),
+                           "point_box_tests_per_query": pb / len(pts), "point_primitives_per_query": pp / len(pts)}}
+    return rates, rr, rc
 
 
 def run_reference(args):
@@ -131,7 +142,7 @@ def run_reference(args):
     from cgal_b200 import workloads as W
     threads = os.cpu_count() or 1
     verts, faces = W.terrain(NX, NY)
-    o, build_s = oracle_tree(verts, faces)
+    o = oracle_tree(verts, faces)
     n_rays, n_pts = 1 << 20, 1 << 17
     rays_all = shard_rays(0)
     pts_all = W.bbox_points(o.bbox(), n_pts * (args.steps + args.warmup))
@@ -156,29 +167,136 @@ def run_reference(args):
     rays_ps, pts_ps = n_rays * args.steps / tr, n_pts * args.steps / tp
     # the GPU step is 50 % rays / 50 % points: harmonic combination gives the mixed rate of the same step on the CPU
     mixed = 2.0 / (1.0 / rays_ps + 1.0 / pts_ps) / 1e6
+    one, _, _ = cpu_rates(o, np.ascontiguousarray(rays_all[::stride][:1 << 17]), pts_all[:1 << 14], 1)
     sample = "%d steps x (%d rays + %d points) against the full 16,777,216-triangle tree; mixed rate for the 50/50 step" % (args.steps, n_rays, n_pts)
     line = {"impl": "reference", "metric": "Mqueries/s (50% first_intersection Ray_3 + 50% closest_point_and_primitive)", "value": mixed, "unit": "Mqueries/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (tr + tp) / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOAD, "reference_sample": sample},
             "detail": {"first_intersection_Mrays_s": rays_ps / 1e6, "closest_point_Mqueries_s": pts_ps / 1e6, "build_Mtri_s": len(faces) / o.build_seconds() / 1e6,
-                       "build_s": o.build_seconds(), "kd_hint_build_s": o.kd_seconds()},
+                       "build_s": o.build_seconds(), "kd_hint_build_s": o.kd_seconds(),
+                       "single_thread": {"first_intersection_Mrays_s": one["first_intersection_Mrays_s"], "closest_point_Mqueries_s": one["closest_point_Mqueries_s"]},
+                       "traversal": one["traversal"]},
             "cpu_baseline": {"value": mixed, "unit": "Mqueries/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": mixed, "unit": "Mqueries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------- our arm
-def broadcast_tree(tree, rank, world, dist, torch, n_prims):
-    """rank 0 built the tree; the others allocate same-sized buffers and receive them with NCCL (NVLink/NVSwitch)"""
-    from cgal_b200 import sharding
+def replicate_tree(tree, rank, world, local, dist, torch, B):
+    """rank 0 built the tree; the C ABI replicates it with NCCL (b200aabb_comm_broadcast_tree).  Both variants SURVEY.md §8e names are
+    timed: the built tree (64-byte nodes + 96-byte records; binary32 copies derived by the receiver) and the primitives + a build on every rank."""
+    uid = [B.Comm.unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    comm = B.Comm(local, rank, world, uid[0])        # (warms the communicator up: the first collective sets up NCCL's channels)
+    out = {}
+    for mode, name in ((1, "primitives_then_build_on_every_rank"), (0, "built_tree")):   # (the replica kept is the built tree)
+        times = []
+        for _ in range(3):
+            dist.barrier()
+            ms, nbytes = comm.broadcast_tree(tree, root=0, mode=mode)
+            t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times.append(float(t.item()))
+        out[name] = {"bytes": nbytes, "ms_max_over_ranks": min(times), "ms_all": times, "GB_s": nbytes / min(times) / 1e6}
+    return comm, out
+
+
+def pcie_ceiling(torch, h2d_bytes, d2h_bytes, reps=3):
+    """bare pinned cudaMemcpyAsync of one step's bytes, H2D and D2H concurrently on two streams: what the host link allows"""
+    hin = torch.empty(h2d_bytes, dtype=torch.uint8, pin_memory=True)
+    hout = torch.empty(d2h_bytes, dtype=torch.uint8, pin_memory=True)
+    din = torch.empty(h2d_bytes, dtype=torch.uint8, device="cuda")
+    dout = torch.empty(d2h_bytes, dtype=torch.uint8, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    best = None
+    for _ in range(reps + 1):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            din.copy_(hin, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hout.copy_(dout, non_blocking=True)
+        torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        best = ms if best is None else min(best, ms)
+    return best
+
+
+def config5(tree, rank, world, local, dist, torch, B, bbox, oracle_check=None):
+    """BASELINE.json config 5: 2^30 mixed queries generated on the device (b200work_*) in 2^26 batches, batches split over the ranks;
+    128-bit checksum of every result array; the first 2^20 rays / points of batch 0 are kept for parity with the oracle (rank 0)."""
+    from cgal_b200 import device_workloads as D
+    per = C5_BATCH // world                     # queries of a batch this rank answers (a block of image rows / of point indices)
+    rows = IMG // world
+    rays = torch.empty((per, 6), dtype=torch.float64, device="cuda")
+    pts = torch.empty((per, 3), dtype=torch.float64, device="cuda")
+    o_r = {"prim": torch.empty(per, dtype=torch.int32, device="cuda"), "t": torch.empty(per, dtype=torch.float64, device="cuda"),
+           "point": torch.empty((per, 3), dtype=torch.float64, device="cuda"), "flags": torch.empty(per, dtype=torch.uint8, device="cuda")}
+    o_p = {"point": torch.empty((per, 3), dtype=torch.float64, device="cuda"), "prim": torch.empty(per, dtype=torch.int32, device="cuda"),
+           "sqdist": torch.empty(per, dtype=torch.float64, device="cuda"), "flags": torch.empty(per, dtype=torch.uint8, device="cuda")}
+    want_r, want_p = ("prim", "t", "point", "flags"), ("point", "prim", "sqdist", "flags")
+    cams = [D.pinhole_camera(NX, NY, eye_xy=(256.0 * k, 128.0 * k)) for k in range(C5_BATCHES)]
+    sums = {}
+    kept = {}
+
+    def add(name, t, index0):
+        sums[name] = D.add128(sums.get(name, (0, 0)), D.checksum128(t, index0=index0))
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+    q_ms = {"rays": 0.0, "points": 0.0}
+    if dist is not None:
+        dist.barrier()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    dist.barrier()
+    e0, e1 = ev(), ev()
     e0.record()
-    _, total = sharding.broadcast_tree(tree, n_prims, src=0)
+    for k in range(C5_BATCHES):
+        a, b, c = ev(), ev(), ev()
+        D.pinhole_rays(cams[k], IMG, IMG, rank * rows, rows, rays)
+        a.record()
+        tree.first_intersection(rays, want=want_r, out=o_r)
+        b.record()
+        for name in want_r:                       # word positions are global: the shards' checksums add up to the batch's
+            words_per_q = {"prim": 0.5, "t": 1, "point": 3, "flags": 0.125}[name]
+            add("ray_" + name, o_r[name], int((k * C5_BATCH + rank * per) * words_per_q))
+        if k == 0 and rank == 0:
+            kept["rays"] = rays[:1 << 20].cpu().numpy()
+            kept["ray_out"] = {n: o_r[n][:1 << 20].cpu().numpy() for n in want_r}
+        D.bbox_points(bbox, per, pts, offset=k * C5_BATCH + rank * per)
+        c.record()
+        d = ev()
+        tree.closest_point_and_primitive(pts, want=want_p, out=o_p)
+        d.record()
+        for name in want_p:
+            words_per_q = {"prim": 0.5, "sqdist": 1, "point": 3, "flags": 0.125}[name]
+            add("point_" + name, o_p[name], int((k * C5_BATCH + rank * per) * words_per_q))
+        if k == 0 and rank == 0:
+            kept["pts"] = pts[:1 << 20].cpu().numpy()
+            kept["pt_out"] = {n: o_p[n][:1 << 20].cpu().numpy() for n in want_p}
+        torch.cuda.synchronize()
+        q_ms["rays"] += a.elapsed_time(b)
+        q_ms["points"] += c.elapsed_time(d)
     e1.record()
     torch.cuda.synchronize()
-    return total, e0.elapsed_time(e1)
+    total_ms = e0.elapsed_time(e1)
+    names = sorted(sums)
+    vec = torch.tensor([[sums[n][0] - (1 << 64) if sums[n][0] >= (1 << 63) else sums[n][0], sums[n][1] - (1 << 64) if sums[n][1] >= (1 << 63) else sums[n][1]] for n in names],
+                       dtype=torch.int64, device="cuda")
+    tm = torch.tensor([total_ms, q_ms["rays"], q_ms["points"]], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(vec)                       # (int64 addition wraps: sums modulo 2^64)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    total_ms, ray_ms, pt_ms = [float(x) for x in tm.tolist()]
+    digest = "".join("%016x%016x" % (int(a) & 0xFFFFFFFFFFFFFFFF, int(b) & 0xFFFFFFFFFFFFFFFF) for a, b in vec.tolist())
+    import hashlib
+    nq = 2 * C5_BATCHES * C5_BATCH
+    res = {"queries": nq, "batches": "%d x 2^26 rays (one 8192^2 image each, eye moved per batch) + %d x 2^26 bbox points, generated on the device" % (C5_BATCHES, C5_BATCHES),
+           "ms_total_incl_generation_and_checksums": total_ms, "Mqueries_s_total": nq / total_ms / 1e3,
+           "first_intersection_Mrays_s": C5_BATCHES * C5_BATCH / ray_ms / 1e3, "closest_point_Mqueries_s": C5_BATCHES * C5_BATCH / pt_ms / 1e3,
+           "Mqueries_s_queries_only": nq / (ray_ms + pt_ms) / 1e3, "scaling": "strong (2^30 queries split over %d GPU(s))" % world,
+           "checksum128_per_array": {n: "%016x%016x" % (int(a) & 0xFFFFFFFFFFFFFFFF, int(b) & 0xFFFFFFFFFFFFFFFF) for n, (a, b) in zip(names, vec.tolist())},
+           "checksum_of_checksums": hashlib.sha256(digest.encode()).hexdigest()[:32]}
+    return res, kept
 
 
 def main():
@@ -189,6 +307,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer e2e leg (profiling runs)")
+    ap.add_argument("--no-config5", action="store_true", help="skip the 2^30-query config 5 leg (profiling runs)")
     ap.add_argument("--small", action="store_true", help="1M-triangle terrain, for quick profiling only (not a bench value)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" and not args.small else args.warmup
@@ -197,6 +316,7 @@ def main():
 
     import torch
     import cgal_b200 as B
+    from cgal_b200 import device_workloads as D
     from cgal_b200 import workloads as W
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
@@ -210,7 +330,6 @@ def main():
 
     tree = B.AABB_tree(device=local)
     tree.set_stream(torch.cuda.current_stream().cuda_stream)
-    launches0 = tree.stats()["kernel_launches"]
     n_prims = 2 * nx * ny
     build_ms, bcast = None, None
     verts = faces = None
@@ -219,23 +338,25 @@ def main():
         tree.insert(verts, faces)
         tree.build()                       # warm-up build (allocations, module load)
         times = []
-        for _ in range(3):
+        for _ in range(5):
             tree.build()
             times.append(tree.stats()["last_build_ms"])
         build_ms = min(times)
+    comm = None
     if world > 1:
-        nbytes, ms = broadcast_tree(tree, rank, world, dist, torch, n_prims)
-        bcast = {"bytes": nbytes, "ms": ms, "GB_s": nbytes / ms / 1e6}
+        comm, bcast = replicate_tree(tree, rank, world, local, dist, torch, B)
     bbox = tree.bbox()
 
-    if args.small:   # same camera over the smaller terrain; profiling only
-        rays_h = np.ascontiguousarray(W.pinhole_rays(IMG // 4, IMG // 4, nx, ny)[rank % 4::4])
-    else:
-        rays_h = shard_rays(rank)
-    n_rays = len(rays_h)
-    pts_h = shard_points(bbox, rank, n_rays)
-    n_pts = len(pts_h)
-    rays_d, pts_d = torch.from_numpy(rays_h).cuda(), torch.from_numpy(pts_h).cuda()
+    # the rank's shard, generated on the device (bit-equal to cgal_b200.workloads, tests/test_gpu_workload.py)
+    img = IMG // 4 if args.small else IMG
+    n_rays = img * img // SHARDS
+    n_pts = n_rays
+    rays_d = torch.empty((n_rays, 6), dtype=torch.float64, device="cuda")
+    cam = D.pinhole_camera(nx, ny)
+    for j in range(img // SHARDS):          # rows rank, rank + 8, ...
+        D.pinhole_rays(cam, img, img, (rank % SHARDS) + j * SHARDS, 1, rays_d[j * img:(j + 1) * img])
+    pts_d = torch.empty((n_pts, 3), dtype=torch.float64, device="cuda")
+    D.bbox_points(bbox, n_pts, pts_d, offset=rank * POINTS_PER_RANK)
     out_r = {"prim": torch.empty(n_rays, dtype=torch.int32, device="cuda"), "t": torch.empty(n_rays, dtype=torch.float64, device="cuda"),
              "point": torch.empty((n_rays, 3), dtype=torch.float64, device="cuda"), "flags": torch.empty(n_rays, dtype=torch.uint8, device="cuda")}
     out_p = {"point": torch.empty((n_pts, 3), dtype=torch.float64, device="cuda"), "prim": torch.empty(n_pts, dtype=torch.int32, device="cuda"),
@@ -291,39 +412,69 @@ def main():
     traffic_model = {"ray_nodes_per_query": sr["nodes_visited"] / n_rays, "ray_leaves_per_query": sr["leaves_tested"] / n_rays,
                      "point_nodes_per_query": sp["nodes_visited"] / n_pts, "point_leaves_per_query": sp["leaves_tested"] / n_pts, "point_leaves_culled_fp32_per_query": sp["leaves_culled"] / n_pts,
                      "ray_ms_incl_sort": sr["last_query_ms"], "point_ms_incl_sort": sp["last_query_ms"], "node_bytes": 64, "leaf_bytes": 96}
+    # a camera that fills the frame (every ray hits): looking almost straight down on the terrain's centre
+    allhit = None
+    if not args.small:
+        cam2 = D.pinhole_camera(nx, ny, eye_height=1400.0, eye_xy=(nx / 2.0, ny / 2.0 - 1.0))
+        rays2 = torch.empty_like(rays_d)
+        for j in range(img // SHARDS):
+            D.pinhole_rays(cam2, img, img, (rank % SHARDS) + j * SHARDS, 1, rays2[j * img:(j + 1) * img])
+        prim2 = torch.empty(n_rays, dtype=torch.int32, device="cuda")
+        tree.first_intersection(rays2, want=("prim",), out={"prim": prim2})
+        a, b = ev(), ev()
+        a.record()
+        for _ in range(3):
+            tree.first_intersection(rays2, want=want_r, out=out_r)
+        b.record()
+        torch.cuda.synchronize()
+        allhit = {"Mrays_s": world * n_rays * 3 / a.elapsed_time(b) / 1e3, "hit_rate": float((prim2 != -1).float().mean().item()),
+                  "camera": "eye 1400 above the terrain centre looking down, 60 deg, rows r::8 of 8192^2"}
+        tree.first_intersection(rays_d, want=want_r, out=out_r)    # (restore the benchmark batch's results for the parity sample)
+        del rays2, prim2
 
-    # e2e: the same step through the C ABI with pinned HOST buffers (copies inside the timed region)
-    e2e_ms = None
+    # e2e: the same steps through the C ABI with pinned HOST buffers (copies inside the timed region)
+    e2e_ms, ceiling_ms = None, None
     h2d = n_rays * 48 + n_pts * 24
     d2h = n_rays * (4 + 8 + 24 + 1) + n_pts * (24 + 4 + 8 + 1)
     if not args.no_e2e:
         def pinned(shape, dtype):
             return torch.empty(shape, dtype=dtype, pin_memory=True).numpy()
         rays_p, pts_p = pinned((n_rays, 6), torch.float64), pinned((n_pts, 3), torch.float64)
-        rays_p[:], pts_p[:] = rays_h, pts_h
+        rays_p[:], pts_p[:] = rays_d.cpu().numpy(), pts_d.cpu().numpy()
         hout_r = {"prim": pinned(n_rays, torch.int32).view(np.uint32), "t": pinned(n_rays, torch.float64), "point": pinned((n_rays, 3), torch.float64), "flags": pinned(n_rays, torch.uint8)}
         hout_p = {"point": pinned((n_pts, 3), torch.float64), "prim": pinned(n_pts, torch.int32).view(np.uint32), "sqdist": pinned(n_pts, torch.float64), "flags": pinned(n_pts, torch.uint8)}
 
         def host_step():
             tree.first_intersection(rays_p, want=want_r, out=hout_r)
             tree.closest_point_and_primitive(pts_p, want=want_p, out=hout_p)
+        tree.set_option(B.OPT_ASYNC_HOST, 1)     # batches return once enqueued; one synchronize after the last step
         host_step()
+        tree.synchronize()
         barrier()
         f0, f1 = ev(), ev()
         f0.record()
         for _ in range(args.steps):
             host_step()
+        tree.synchronize()
         f1.record()
         barrier()
         e2e_ms = f0.elapsed_time(f1)
+        tree.set_option(B.OPT_ASYNC_HOST, 0)
         # the HOST-pointer path must return what the DEVICE-pointer path returned
         assert np.array_equal(hout_r["prim"], out_r["prim"].cpu().numpy().view(np.uint32)) and np.array_equal(hout_p["sqdist"], out_p["sqdist"].cpu().numpy())
+        barrier()
+        ceiling_ms = pcie_ceiling(torch, h2d, d2h)
+
+    c5, kept = (None, {})
+    if not args.no_config5 and not args.small:
+        c5, kept = config5(tree, rank, world, local, dist, torch, B, bbox)
 
     if dist is not None:
-        tm = torch.tensor([total_ms, e2e_ms or 0.0, ray_ms, pt_ms], dtype=torch.float64, device="cuda")
+        tm = torch.tensor([total_ms, e2e_ms or 0.0, ray_ms, pt_ms, ceiling_ms or 0.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        total_ms, e2e_max, ray_ms, pt_ms = [float(x) for x in tm.tolist()]
+        total_ms, e2e_max, ray_ms, pt_ms, ceil_max = [float(x) for x in tm.tolist()]
         e2e_ms = e2e_max if e2e_ms is not None else None
+        ceiling_ms = ceil_max if ceiling_ms is not None else None
         cnt = torch.tensor([launches, ties, exact, near], dtype=torch.int64, device="cuda")
         dist.all_reduce(cnt)
         launches, ties, exact, near = [int(x) for x in cnt.tolist()]
@@ -338,54 +489,75 @@ def main():
         else:
             dom, dom_bytes, dom_ms = "closest_point_warp_kernel", n_pts * BYTES_PER_POINT, pt_ms
         achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+        traffic, traffic_src = NCU_DRAM.get(dom, (None, None))
+        try:
+            dfma = D.dfma_tflops(local)
+        except Exception:
+            dfma = None
         line = {"metric": "Mqueries/s (50% first_intersection Ray_3 + 50% closest_point_and_primitive)", "value": value, "unit": "Mqueries/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": WORKLOAD if not args.small else "SMALL profiling variant (1M-triangle terrain): not a bench value", "triangles": n_prims,
                            "rays_per_gpu": n_rays, "points_per_gpu": n_pts, "l2": "inputs (%.0f MB per GPU) larger than L2" % ((n_rays * 48 + n_pts * 24) / 1e6),
-                           "parallelism": "tree replicated by NCCL broadcast, queries sharded x%d" % world},
-                "detail": {"first_intersection_Mrays_s": world * n_rays / ray_ms / 1e3, "closest_point_Mqueries_s": world * n_pts / pt_ms / 1e3,
+                           "parallelism": "tree replicated by NCCL through the C ABI (b200aabb_comm_broadcast_tree), queries sharded x%d" % world},
+                "detail": {"first_intersection_Mrays_s": world * n_rays / ray_ms / 1e3, "first_intersection_hits_Mrays_s": hit_rate * world * n_rays / ray_ms / 1e3,
+                           "first_intersection_all_hit_camera": allhit, "closest_point_Mqueries_s": world * n_pts / pt_ms / 1e3,
                            "build_ms": build_ms, "build_Mtri_s": n_prims / build_ms / 1e3, "build_GB_s_algorithmic(492B/tri)": 492.0 * n_prims / build_ms / 1e6,
+                           "build_frac_of_hbm_roofline(492B/tri)": 492.0 * n_prims / build_ms / 1e6 / peak,
                            "ray_hit_rate_rank0": hit_rate, "ties": ties, "near_ties": near, "exact_stage_queries": exact, "traversal_rank0": traffic_model,
-                           "tree_broadcast": bcast},
+                           "fp64_dfma_peak_TFLOP_s": dfma, "tree_broadcast": bcast, "config5": c5},
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": NCU_DRAM_BYTES_PER_LAUNCH.get(dom) if not args.small and n_pts == POINTS_PER_RANK else None,
+                             "traffic": traffic if not args.small and n_pts == POINTS_PER_RANK else None, "traffic_source": traffic_src,
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
-                             "note": "traversal is bound by the L1 data stage (one wavefront per scattered node / triangle fetch) and by instruction issue (51 %) at 20 warps/SM, not by HBM (DESIGN.md §5); "
-                                     "traffic = dram__bytes_read+write of one launch from the ncu --set full capture named in profiles/README.md"},
+                             "note": "traversal is bound by the L1 data stage (one wavefront per scattered 32-byte sector of a node / triangle fetch) and by instruction issue at 20 warps/SM, "
+                                     "not by HBM (DESIGN.md §5); traffic = dram__bytes_read+write of one launch from the ncu --set full capture named in traffic_source"},
                 "clocks": clocks, "gpu_launches": launches}
         if e2e_ms is not None:
-            line["e2e"] = {"value": q_per_step * args.steps / (e2e_ms * 1e-3) / 1e6, "unit": "Mqueries/s", "h2d_bytes_per_step": world * h2d, "d2h_bytes_per_step": world * d2h}
+            e2e_v = q_per_step * args.steps / (e2e_ms * 1e-3) / 1e6
+            line["e2e"] = {"value": e2e_v, "unit": "Mqueries/s", "h2d_bytes_per_step": world * h2d, "d2h_bytes_per_step": world * d2h,
+                           "frac_of_value": e2e_v / value, "mode": "B200AABB_OPT_ASYNC_HOST: %d steps enqueued, one b200aabb_synchronize" % args.steps,
+                           "bare_memcpy_ms_per_step": ceiling_ms, "frac_of_bare_memcpy_ceiling": (ceiling_ms / (e2e_ms / args.steps)) if ceiling_ms else None}
         if world == 1 and not args.no_cpu_baseline:
-            o, _ = oracle_tree(verts, faces)
+            o = oracle_tree(verts, faces)
             threads = os.cpu_count() or 1
             nr, npnt = 1 << 20, 1 << 17
             stride = max(1, n_rays // nr)
+            rays_h = rays_d.cpu().numpy()
             cr = np.ascontiguousarray(rays_h[::stride][:nr])
-            cp = pts_h[:npnt]
-            t0 = time.perf_counter()
-            rr = o.first_intersection(cr, threads=threads)
-            t1 = time.perf_counter()
-            rc = o.closest_point(cp, threads=threads)
-            t2 = time.perf_counter()
-            rps, pps = len(cr) / (t1 - t0), len(cp) / (t2 - t1)
+            cp = pts_d[:npnt].cpu().numpy()
+            rates, rr, rc = cpu_rates(o, cr, cp, threads)
+            rps, pps = rates["first_intersection_Mrays_s"] * 1e6, rates["closest_point_Mqueries_s"] * 1e6
             # the sample doubles as a parity check of the benchmarked batch against the oracle
             g_prim = out_r["prim"].cpu().numpy().view(np.uint32)[::stride][:nr]
             g_t = out_r["t"].cpu().numpy()[::stride][:nr]
-            g_tie = (out_r["flags"].cpu().numpy()[::stride][:nr] & (B.FLAG_TIE | B.FLAG_NEAR_TIE)) != 0
+            g_fl = out_r["flags"].cpu().numpy()[::stride][:nr]
+            g_tie = (g_fl & (B.FLAG_TIE | B.FLAG_NEAR_TIE)) != 0
             p_prim = out_p["prim"].cpu().numpy().view(np.uint32)[:npnt]
             p_tie = (out_p["flags"].cpu().numpy()[:npnt] & (B.FLAG_TIE | B.FLAG_NEAR_TIE)) != 0
             parity = {"rays_checked": len(cr), "ray_t_bit_equal_outside_near_ties": bool(np.array_equal(g_t[~g_tie], rr["t"][~g_tie])),
                       "ray_t_max_rel_diff": float(np.max(np.abs(g_t - rr["t"]) / np.maximum(np.abs(rr["t"]), 1e-300))), "ray_id_mismatch_not_tie": int(((g_prim != rr["prim"]) & ~g_tie).sum()),
+                      "ray_near_ties_in_sample": int(((g_fl & B.FLAG_NEAR_TIE) != 0).sum()),
                       "points_checked": len(cp), "sqdist_bit_equal": bool(np.array_equal(out_p["sqdist"].cpu().numpy()[:npnt], rc["sqd"])),
                       "point_id_mismatch_not_tie": int(((p_prim != rc["prim"]) & ~p_tie).sum())}
+            if kept:      # config 5: the first 2^20 rays / 2^17 points of batch 0 against the oracle
+                k5r = o.first_intersection(kept["rays"], threads=threads)
+                k5p = o.closest_point(kept["pts"][:npnt], threads=threads)
+                fl = kept["ray_out"]["flags"]
+                tie5 = (fl & (B.FLAG_TIE | B.FLAG_NEAR_TIE)) != 0
+                ptie5 = (kept["pt_out"]["flags"][:npnt] & B.FLAG_TIE) != 0
+                parity["config5_first_batch"] = {"rays_checked": len(kept["rays"]), "ray_t_bit_equal_outside_near_ties": bool(np.array_equal(kept["ray_out"]["t"][~tie5], k5r["t"][~tie5])),
+                                                 "ray_id_mismatch_not_tie": int(((kept["ray_out"]["prim"].view(np.uint32) != k5r["prim"]) & ~tie5).sum()),
+                                                 "points_checked": npnt, "sqdist_bit_equal": bool(np.array_equal(kept["pt_out"]["sqdist"][:npnt], k5p["sqd"])),
+                                                 "point_id_mismatch_not_tie": int(((kept["pt_out"]["prim"][:npnt].view(np.uint32) != k5p["prim"]) & ~ptie5).sum())}
             line["cpu_baseline"] = {"value": 2.0 / (1.0 / rps + 1.0 / pps) / 1e6, "unit": "Mqueries/s", "cores": threads, "kind": "port",
                                     "sample": "%d rays (every %dth of the shard) + %d points against the full tree; 50/50 mixed rate" % (len(cr), stride, len(cp)),
-                                    "first_intersection_Mrays_s": rps / 1e6, "closest_point_Mqueries_s": pps / 1e6, "build_s": o.build_seconds(),
+                                    "first_intersection_Mrays_s": rps / 1e6, "closest_point_Mqueries_s": pps / 1e6, "single_thread": rates["single_thread"],
+                                    "oracle_traversal": rates["traversal"], "build_s": o.build_seconds(),
                                     "build_Mtri_s": n_prims / o.build_seconds() / 1e6, "kd_hint_build_s": o.kd_seconds(), "parity_on_sample": parity}
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()
+        del comm
         dist.destroy_process_group()
 
 

@@ -15,6 +15,7 @@ OPT_SORT_QUERIES = 1
 OPT_CLOSEST_KERNEL = 2    # 1 = warp-cooperative work pool (default), 2 = lane pairs with private stacks, 0 = one thread per query
 OPT_WARP_EXACT_GO = 4
 OPT_HOST_PARTS = 5
+OPT_ASYNC_HOST = 6
 NO_PRIMITIVE = 0xFFFFFFFF
 _HOST, _DEVICE = 0, 1
 _ERRORS = {-1: "invalid argument", -2: "CUDA error", -3: "out of device memory", -4: "empty tree (CGAL_precondition(!empty()))",
@@ -34,12 +35,12 @@ class _Stats(C.Structure):
                 ("last_build_ms", C.c_double), ("last_query_ms", C.c_double), ("last_query_total_ms", C.c_double)]
 
 
-SYMBOLS = ["b200aabb_create", "b200aabb_destroy", "b200aabb_set_stream", "b200aabb_set_option", "b200aabb_last_error", "b200aabb_get_stats",
-           "b200aabb_set_mesh", "b200aabb_set_triangles", "b200aabb_clear", "b200aabb_build",
+SYMBOLS = ["b200aabb_create", "b200aabb_destroy", "b200aabb_set_stream", "b200aabb_set_option", "b200aabb_last_error", "b200aabb_get_stats", "b200aabb_synchronize",
+           "b200aabb_set_mesh", "b200aabb_set_triangles", "b200aabb_clear", "b200aabb_build", "b200aabb_refit", "b200aabb_refit_mesh",
            "b200aabb_accelerate_distance_queries", "b200aabb_size", "b200aabb_bbox", "b200aabb_do_intersect",
            "b200aabb_number_of_intersected_primitives", "b200aabb_any_intersected_primitive", "b200aabb_all_intersected_primitives",
            "b200aabb_number_of_intersections", "b200aabb_all_intersections", "b200aabb_any_intersection",
-           "b200aabb_first_intersection", "b200aabb_closest_point",
+           "b200aabb_first_intersection", "b200aabb_first_intersection_skip", "b200aabb_closest_point", "b200aabb_max_distance_to_mesh",
            "b200aabb_export_layout", "b200aabb_import_alloc", "b200aabb_import_finish", "b200aabb_debug_predicate", "b200aabb_version",
            "b200aabb_comm_unique_id", "b200aabb_comm_init", "b200aabb_comm_init_all", "b200aabb_comm_destroy", "b200aabb_comm_last_error",
            "b200aabb_comm_broadcast_tree", "b200aabb_comm_broadcast_tree_all"]
@@ -65,9 +66,12 @@ def load_library():
         L.b200aabb_last_error.argtypes = [vp]
         L.b200aabb_last_error.restype = C.c_char_p
         L.b200aabb_get_stats.argtypes = [vp, C.POINTER(_Stats)]
+        L.b200aabb_synchronize.argtypes = [vp]
         L.b200aabb_set_mesh.argtypes = [vp, dp, u64, dp, dp, u64]
         L.b200aabb_set_triangles.argtypes = [vp, dp, dp, u64, C.c_int]
         L.b200aabb_clear.argtypes = [vp]
+        L.b200aabb_refit.argtypes = [vp, dp, u64, C.c_int]
+        L.b200aabb_refit_mesh.argtypes = [vp, dp, u64, dp, u64]
         L.b200aabb_build.argtypes = [vp]
         L.b200aabb_accelerate_distance_queries.argtypes = [vp]
         L.b200aabb_size.argtypes = [vp, C.POINTER(u64)]
@@ -80,7 +84,9 @@ def load_library():
         L.b200aabb_all_intersections.argtypes = [vp, dp, u64, C.c_int, dp, dp, dp, dp]
         L.b200aabb_any_intersection.argtypes = [vp, dp, u64, C.c_int, dp, dp, dp, dp]
         L.b200aabb_first_intersection.argtypes = [vp, dp, u64, C.c_int, dp, dp, dp, dp, dp]
+        L.b200aabb_first_intersection_skip.argtypes = [vp, dp, u64, C.c_int, dp, dp, C.c_uint32, dp, dp, dp, dp, dp]
         L.b200aabb_closest_point.argtypes = [vp, dp, u64, C.c_int, dp, dp, dp, dp]
+        L.b200aabb_max_distance_to_mesh.argtypes = [vp, dp, u64, C.c_int, C.POINTER(C.c_double), C.POINTER(u64)]
         L.b200aabb_export_layout.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.c_int, C.POINTER(C.c_int)]
         L.b200aabb_import_alloc.argtypes = [vp, u64]
         L.b200aabb_import_finish.argtypes = [vp]
@@ -195,6 +201,20 @@ class AABB_tree:
 
     rebuild = build
 
+    def refit(self, vertices=None, faces=None, triangles=None):
+        """the primitives have moved (same count and order): new coordinates, boxes recomputed over the existing hierarchy (b200aabb_refit)"""
+        if triangles is not None:
+            if _is_torch(triangles):
+                b = _Buf(triangles, np.float64, 9)
+                self._check(self._lib.b200aabb_refit(self._h, b.ptr, b.n, _DEVICE))
+            else:
+                t = np.ascontiguousarray(triangles, dtype=np.float64).reshape(-1, 9)
+                self._check(self._lib.b200aabb_refit(self._h, t.ctypes.data, len(t), _HOST))
+        else:
+            v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+            f = np.ascontiguousarray(faces, dtype=np.uint32).reshape(-1, 3)
+            self._check(self._lib.b200aabb_refit_mesh(self._h, v.ctypes.data, len(v), f.ctypes.data, len(f)))
+
     def accelerate_distance_queries(self):
         self._check(self._lib.b200aabb_accelerate_distance_queries(self._h))
         return True
@@ -220,6 +240,10 @@ class AABB_tree:
 
     def set_option(self, option, value):
         self._check(self._lib.b200aabb_set_option(self._h, int(option), int(value)))
+
+    def synchronize(self):
+        """waits for the batches in flight (OPT_ASYNC_HOST); raises if one of them could not finish"""
+        self._check(self._lib.b200aabb_synchronize(self._h))
 
     def stats(self):
         s = _Stats()
@@ -293,6 +317,24 @@ class AABB_tree:
         self._check(self._lib.b200aabb_first_intersection(self._h, q.ptr, q.n, int(q.device), p("prim"), p("t"), p("point"), p("point2"), p("flags")))
         return {k: b.obj for k, b in bufs.items()}
 
+    def first_intersection_skip(self, rays, skip_ids=None, skip_mask=None, want=("prim", "t", "point", "point2", "flags")):
+        """first_intersection(Ray_3, skip): skip_ids = one primitive id per ray to ignore (NO_PRIMITIVE: none), skip_mask = bool array indexed
+        by primitive id (True: ignore).  HOST batches."""
+        q = _Buf(np.asarray(rays), np.float64, 6)
+        spec = {"prim": (np.uint32, 1), "t": (np.float64, 1), "point": (np.float64, 3), "point2": (np.float64, 3), "flags": (np.uint8, 1)}
+        bufs = {k: _alloc_like(q, q.n, *spec[k]) for k in want}
+        p = lambda k: bufs[k].ptr if k in bufs else None   # noqa: E731
+        ids = None if skip_ids is None else np.ascontiguousarray(skip_ids, dtype=np.uint32)
+        words, nwords = None, 0
+        if skip_mask is not None:
+            bits = np.packbits(np.asarray(skip_mask, dtype=bool), bitorder="little")
+            bits = np.concatenate([bits, np.zeros((-len(bits)) % 4, np.uint8)])
+            words = np.ascontiguousarray(bits.view(np.uint32))
+            nwords = len(words)
+        self._check(self._lib.b200aabb_first_intersection_skip(self._h, q.ptr, q.n, 0, None if ids is None else ids.ctypes.data, None if words is None else words.ctypes.data,
+                                                               nwords, p("prim"), p("t"), p("point"), p("point2"), p("flags")))
+        return {k: b.obj for k, b in bufs.items()}
+
     def first_intersected_primitive(self, rays):
         return self.first_intersection(rays, want=("prim",))["prim"]
 
@@ -313,6 +355,13 @@ class AABB_tree:
     def squared_distance(self, points):
         return self.closest_point_and_primitive(points, want=("sqdist",))["sqdist"]
 
+    def max_distance_to_mesh(self, points):
+        """PMP::max_distance_to_mesh's inner loop (distance.h:98-190): (largest distance from the sample points to the mesh, index of a farthest sample)"""
+        q = _Buf(points, np.float64, 3)
+        d, i = C.c_double(), C.c_uint64()
+        self._check(self._lib.b200aabb_max_distance_to_mesh(self._h, q.ptr, q.n, int(q.device), C.byref(d), C.byref(i)))
+        return d.value, i.value
+
     # ---- multi-GPU plumbing: the built tree as flat device buffers (for torch.distributed.broadcast) ----
     def export_layout(self):
         ptrs = (C.c_void_p * 8)()
@@ -326,3 +375,66 @@ class AABB_tree:
 
     def import_finish(self):
         self._check(self._lib.b200aabb_import_finish(self._h))
+
+
+class Comm:
+    """b200aabb_comm: one NCCL communicator rank (include/b200aabb.h, multi-GPU section).  One process per GPU: rank 0 makes
+    Comm.unique_id(), hands the 128 bytes to the other ranks, every rank constructs Comm(device, rank, world, uid).  One process driving
+    several GPUs: Comm.init_all(devices) and broadcast_tree_all."""
+
+    def __init__(self, device, rank, world, uid, _handle=None):
+        self._lib = load_library()
+        self.device, self.rank, self.world = int(device), int(rank), int(world)
+        if _handle is not None:
+            self._h = _handle
+            return
+        h = C.c_void_p()
+        rc = self._lib.b200aabb_comm_init(self.device, self.rank, self.world, C.c_char_p(bytes(uid)), C.byref(h))
+        if rc:
+            raise B200AABBError(rc)
+        self._h = h
+
+    @staticmethod
+    def unique_id():
+        buf = C.create_string_buffer(128)
+        rc = load_library().b200aabb_comm_unique_id(buf)
+        if rc:
+            raise B200AABBError(rc)
+        return buf.raw
+
+    @classmethod
+    def init_all(cls, devices):
+        L = load_library()
+        n = len(devices)
+        devs = (C.c_int * n)(*[int(d) for d in devices])
+        hs = (C.c_void_p * n)()
+        rc = L.b200aabb_comm_init_all(n, devs, hs)
+        if rc:
+            raise B200AABBError(rc)
+        return [cls(devices[i], i, n, None, _handle=C.c_void_p(hs[i])) for i in range(n)]
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.b200aabb_comm_destroy(self._h)
+            self._h = None
+
+    def broadcast_tree(self, tree, root=0, mode=0):
+        """replicates rank `root`'s tree into `tree` on every other rank; returns (device ms, bytes moved) of this rank"""
+        ms, nb = C.c_double(), C.c_uint64()
+        rc = self._lib.b200aabb_comm_broadcast_tree(self._h, tree._h, int(root), int(mode), C.byref(ms), C.byref(nb))
+        if rc:
+            raise B200AABBError(rc, (self._lib.b200aabb_comm_last_error(self._h) or b"").decode() or self._lib.b200aabb_last_error(tree._h).decode())
+        return ms.value, nb.value
+
+
+def broadcast_tree_all(comms, trees, root=0, mode=0):
+    """single-process form: comms = Comm.init_all(devices), trees[i] lives on devices[i]; returns (ms of the slowest rank, bytes)"""
+    L = load_library()
+    n = len(comms)
+    cs = (C.c_void_p * n)(*[c._h for c in comms])
+    ts = (C.c_void_p * n)(*[t._h for t in trees])
+    ms, nb = C.c_double(), C.c_uint64()
+    rc = L.b200aabb_comm_broadcast_tree_all(cs, ts, n, int(root), int(mode), C.byref(ms), C.byref(nb))
+    if rc:
+        raise B200AABBError(rc, (L.b200aabb_comm_last_error(comms[0]._h) or b"").decode())
+    return ms.value, nb.value

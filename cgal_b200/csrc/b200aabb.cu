@@ -13,7 +13,6 @@
 
 #include "../../include/b200aabb.h"
 #include "build.cuh"
-#include "radix_sort.cuh"
 #include "closest_warp.cuh"
 #include "closest_pair.cuh"
 
@@ -111,13 +110,14 @@ __global__ void __launch_bounds__(128, 5) ray_objects_kernel(const TreeRef tr, c
 
 __global__ void __launch_bounds__(128, 5) first_intersection_kernel(const TreeRef tr, const double* __restrict__ rays, uint64_t n, uint32_t* __restrict__ prim,
                                                                  double* __restrict__ tpar, double* __restrict__ pt, double* __restrict__ pt2,
-                                                                 uint8_t* __restrict__ flags) {
+                                                                 uint8_t* __restrict__ flags, const uint32_t* __restrict__ skip_ids,
+                                                                 const uint32_t* __restrict__ skip_mask, uint32_t mask_words) {
     const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     TravStat st;
     int tie = 0, near = 0;
     if (slot < n) {
         const uint64_t i = tr.perm ? tr.perm[slot] : slot;
-        const FirstHit h = traverse_first(tr.nodes, tr.tris, tr.root, ld3(rays + 6 * i), ld3(rays + 6 * i + 3), tr.mag, st);
+        const FirstHit h = traverse_first(tr.nodes, tr.tris, tr.root, ld3(rays + 6 * i), ld3(rays + 6 * i + 3), tr.mag, st, skip_ids ? skip_ids[i] : kNone, skip_mask, mask_words);
         const bool hit = h.prim != kNone;
         tie = h.tie; near = h.near;
         if (prim) prim[i] = h.prim;
@@ -183,6 +183,23 @@ __global__ void __launch_bounds__(128) predicate_kernel(int which, const double*
     if (used_exact) used_exact[i] = nexact;
 }
 
+// max and arg max of n non-negative doubles (squared distances): non-negative binary64 values order like their bit patterns, so one 64-bit
+// atomicMax per block does it; the index rides along in a second pass over the (few) maxima — ties -> smallest index
+__global__ void __launch_bounds__(256) max_sqdist_kernel(const double* __restrict__ v, uint64_t n, unsigned long long* __restrict__ best_bits) {
+    unsigned long long m = 0;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) m = max(m, (unsigned long long)__double_as_longlong(v[i]));
+    for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xFFFFFFFFu, m, off));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(best_bits, m);
+}
+__global__ void __launch_bounds__(256) argmax_sqdist_kernel(const double* __restrict__ v, uint64_t n, const unsigned long long* __restrict__ best_bits,
+                                                            unsigned long long* __restrict__ best_index) {
+    const unsigned long long b = *best_bits;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        if ((unsigned long long)__double_as_longlong(v[i]) == b) atomicMin(best_index, (unsigned long long)i);
+}
+
 // ---- query coherence keys (sorted with radix_sort.cuh; the traversal kernels then follow the permutation) ------------
 // Point_3: 30-bit Morton code (10 bits per axis) of the point in the isotropic frame of the root box
 __global__ void __launch_bounds__(256) point_keys_kernel(const double* __restrict__ pts, uint64_t n, const double* __restrict__ rootbox,
@@ -227,6 +244,11 @@ __global__ void __launch_bounds__(256) line_keys_kernel(const double* __restrict
 // ------------------------------------------------------------------------------------------------------------------
 // Handle
 // ------------------------------------------------------------------------------------------------------------------
+constexpr int kLineSlots = 4;                   // chunks of a HOST ray / segment batch in flight (upload / sort + traverse / download on as many streams)
+constexpr int kPointSlots = 2;                  // HOST point batches have their own two streams: a long closest_point launch never holds up the ray chunks behind it
+constexpr int kPipeSlots = kLineSlots + kPointSlots;
+constexpr int kScratchSlots = kPipeSlots + 1;   // + one set of scratch buffers for DEVICE-pointer batches (on the handle's own stream)
+
 struct b200aabb_tree {
     // Every entry point that touches the handle takes this lock: concurrent calls on ONE handle (the reference's callers run
     // tbb::parallel_for over const queries, AABB_tree.h:593-612) are serialised, never interleaved on the shared staging / scratch buffers.
@@ -245,6 +267,11 @@ struct b200aabb_tree {
     TriRec* d_tris = nullptr;
     TriF* d_trisf = nullptr;       // binary32 copies (pre-tests of the warp-cooperative closest_point kernel)
     double* d_rootbox = nullptr;   // 6 doubles
+    uint32_t* d_leaf_parent = nullptr;   // parent node of every leaf (refit)
+    unsigned long long* d_bounds = nullptr;   // scene bounds as ordered integers (build.cuh); valid when bounds_valid
+    bool bounds_valid = false;     // b200aabb_set_mesh computed them while gathering the primitives
+    int opt_exact_keys = 0;        // 1: always sort full 63-bit keys (the build's fallback path; test hook, option 102)
+    int last_build_packed = 0; unsigned long long last_build_dups = 0;
     uint32_t root = kNone;
     double h_bbox[6];
     double mag = 0.0;              // largest coordinate magnitude of the root box
@@ -256,17 +283,24 @@ struct b200aabb_tree {
     int opt_host_parts = 0;        // B200AABB_OPT_HOST_PARTS (0 = automatic)
     int opt_debug_refit_frontier = kRefitFrontierPerBlock;   // test hook (option 101): frontier entries per block of the refit (0: every hand-over overflows)
     // warp-cooperative closest_point: per pipeline slot a batch cursor and the pools' spill area; grid = SMs x resident warps
-    struct WarpScratch { unsigned long long* cursor = nullptr; uint2* spill = nullptr; WarpSlots64* slots64 = nullptr; } warp[2];
+    struct WarpScratch { unsigned long long* cursor = nullptr; uint2* spill = nullptr; WarpSlots64* slots64 = nullptr; } warp[kScratchSlots];
     int warp_grid = 0;
     int pair_grid = 0;             // grid of closest_point_pair_kernel (closest_pair.cuh); it shares the scratch of the pool kernel
     // query coherence sort scratch, one per pipeline slot (slot 0 also serves DEVICE-pointer batches); grow-only
-    struct SortScratch { uint64_t* keys[2] = {nullptr, nullptr}; uint32_t* vals[2] = {nullptr, nullptr}; void* ws = nullptr; uint64_t cap = 0; } sort[2];
+    struct SortScratch { uint64_t* keys[2] = {nullptr, nullptr}; uint32_t* vals[2] = {nullptr, nullptr}; void* ws = nullptr; uint64_t cap = 0; } sort[kScratchSlots];
     // staging for HOST-pointer batches (two pipeline slots)
-    void* d_stage_in[2] = {nullptr, nullptr};
-    void* d_stage_out[2] = {nullptr, nullptr};
-    size_t stage_in_bytes = 0, stage_out_bytes = 0;
-    cudaStream_t pipe[2] = {nullptr, nullptr};
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_pipe[2] = {nullptr, nullptr};
+    void* d_stage_in[kPipeSlots] = {};
+    void* d_stage_out[kPipeSlots] = {};
+    size_t stage_in_bytes[kPipeSlots] = {}, stage_out_bytes[kPipeSlots] = {};
+    cudaStream_t pipe[kPipeSlots] = {};
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_pipe[kPipeSlots] = {};
+    int next_line_slot = 0, next_point_slot = 0, cur_slot = 0;   // pipeline slot of the next chunk / of the chunk being launched
+    uint64_t cur_offset = 0;           // first query of the chunk being launched (HOST batches)
+    uint32_t* d_stage_aux[kPipeSlots] = {}; size_t stage_aux_bytes = 0;   // per-query side input of a HOST batch (skip ids)
+    int opt_async_host = 0;        // B200AABB_OPT_ASYNC_HOST
+    bool async_pending = false;
+    struct TraceRec { cudaEvent_t e[4]; int slot; uint64_t cnt; int shape; };   // B200AABB_PIPE_TRACE=1: per-chunk events of the HOST pipeline (diagnostic)
+    std::vector<TraceRec> trace;
     b200aabb_stats stats;
     bool query_timing_pending = false;
 };
@@ -282,33 +316,34 @@ namespace {
         }                                                                                                        \
     } while (0)
 
-constexpr uint64_t kChunkMax = 1ull << 22;   // most queries per pipeline slot for HOST-pointer batches
+constexpr uint64_t kChunkMax = 1ull << 22;   // most queries per pipeline slot for HOST-pointer batches of rays / segments
+constexpr uint64_t kPointChunkMax = 1ull << 24;   // ... of points
 constexpr uint64_t kChunkMin = 1ull << 18;
 // a HOST batch is cut into about `opt_host_parts` chunks so that only the first chunk's upload and the last chunk's download are exposed
-uint64_t chunk_for(uint64_t n, int parts) { const uint64_t p = (uint64_t)std::max(1, parts); return std::min<uint64_t>(n, std::min(kChunkMax, std::max(kChunkMin, ((n + p - 1) / p + 32767) / 32768 * 32768))); }
+uint64_t chunk_for(uint64_t n, int parts, uint64_t cap) { const uint64_t p = (uint64_t)std::max(1, parts); return std::min<uint64_t>(n, std::min(cap, std::max(kChunkMin, ((n + p - 1) / p + 32767) / 32768 * 32768))); }
 
 #define B2_LOCK(t) std::unique_lock<std::recursive_mutex> lock_; if (t) lock_ = std::unique_lock<std::recursive_mutex>(const_cast<b200aabb_tree*>(t)->mu)
 
 int fail(b200aabb_tree* t, int code, const char* msg) { if (t) t->err = msg; return code; }
 
 void free_tree_buffers(b200aabb_tree* t) {
-    cudaFree(t->d_nodes); cudaFree(t->d_tris); cudaFree(t->d_trisf);
-    t->d_nodes = nullptr; t->d_tris = nullptr; t->d_trisf = nullptr; t->built = false; t->root = kNone;
+    cudaFree(t->d_nodes); cudaFree(t->d_tris); cudaFree(t->d_trisf); cudaFree(t->d_leaf_parent);
+    t->d_nodes = nullptr; t->d_tris = nullptr; t->d_trisf = nullptr; t->d_leaf_parent = nullptr; t->built = false; t->root = kNone;
 }
 void free_input(b200aabb_tree* t) { cudaFree(t->d_soup); cudaFree(t->d_ids); t->d_soup = nullptr; t->d_ids = nullptr; }
 
 void empty_bbox(double* b) { for (int i = 0; i < 3; ++i) { b[i] = INFINITY; b[3 + i] = -INFINITY; } }
 
-int ensure_stage(b200aabb_tree* t, size_t in_bytes, size_t out_bytes) {
-    if (in_bytes > t->stage_in_bytes) {
-        for (int s = 0; s < 2; ++s) { cudaFree(t->d_stage_in[s]); t->d_stage_in[s] = nullptr; }
-        for (int s = 0; s < 2; ++s) B2_CUDA(t, cudaMalloc(&t->d_stage_in[s], in_bytes));
-        t->stage_in_bytes = in_bytes;
+int ensure_stage(b200aabb_tree* t, int slot, size_t in_bytes, size_t out_bytes) {   // (grow only; cudaFree waits for the work in flight)
+    if (in_bytes > t->stage_in_bytes[slot]) {
+        cudaFree(t->d_stage_in[slot]); t->d_stage_in[slot] = nullptr; t->stage_in_bytes[slot] = 0;
+        B2_CUDA(t, cudaMalloc(&t->d_stage_in[slot], in_bytes));
+        t->stage_in_bytes[slot] = in_bytes;
     }
-    if (out_bytes > t->stage_out_bytes) {
-        for (int s = 0; s < 2; ++s) { cudaFree(t->d_stage_out[s]); t->d_stage_out[s] = nullptr; }
-        for (int s = 0; s < 2; ++s) B2_CUDA(t, cudaMalloc(&t->d_stage_out[s], out_bytes));
-        t->stage_out_bytes = out_bytes;
+    if (out_bytes > t->stage_out_bytes[slot]) {
+        cudaFree(t->d_stage_out[slot]); t->d_stage_out[slot] = nullptr; t->stage_out_bytes[slot] = 0;
+        B2_CUDA(t, cudaMalloc(&t->d_stage_out[slot], out_bytes));
+        t->stage_out_bytes[slot] = out_bytes;
     }
     return B200AABB_OK;
 }
@@ -382,6 +417,7 @@ int do_build(b200aabb_tree* t) {
         if (t->built) return B200AABB_OK;
         return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "an imported tree can not be rebuilt: insert primitives first");
     }
+    for (int s = 0; s < kPipeSlots; ++s) B2_CUDA(t, cudaStreamSynchronize(t->pipe[s]));   // (asynchronous HOST batches may still be in flight)
     free_tree_buffers(t);
     const uint64_t n = t->n;
     empty_bbox(t->h_bbox);
@@ -390,14 +426,15 @@ int do_build(b200aabb_tree* t) {
     cudaStream_t st = t->stream;
     uint64_t* keys[2] = {nullptr, nullptr};
     uint32_t* vals[2] = {nullptr, nullptr};
-    void* ws = nullptr; unsigned long long* bounds = nullptr; uint32_t* leaf_parent = nullptr; RefitEntry* frontier = nullptr; unsigned* frontier_count = nullptr;
-    auto cleanup = [&]() { cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(ws); cudaFree(bounds); cudaFree(leaf_parent); cudaFree(frontier); cudaFree(frontier_count); };
+    void* ws = nullptr; RefitEntry* frontier = nullptr; unsigned* frontier_count = nullptr; unsigned long long* d_dups = nullptr;
+    auto cleanup = [&]() { cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(ws); cudaFree(frontier); cudaFree(frontier_count); cudaFree(d_dups); };
 #define B2_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { t->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); free_tree_buffers(t); \
         return e_ == cudaErrorMemoryAllocation ? B200AABB_ERR_OUT_OF_MEMORY : B200AABB_ERR_CUDA; } } while (0)
-    for (int s = 0; s < 2; ++s) { B2_TRY(cudaMalloc(&keys[s], n * 8)); B2_TRY(cudaMalloc(&vals[s], n * 4)); }
+    for (int s = 0; s < 2; ++s) B2_TRY(cudaMalloc(&keys[s], n * 8));
     B2_TRY(cudaMalloc(&ws, rs_workspace_bytes(n)));
-    B2_TRY(cudaMalloc(&bounds, 6 * 8));
-    B2_TRY(cudaMalloc(&leaf_parent, n * 4));
+    B2_TRY(cudaMalloc(&t->d_leaf_parent, n * 4));
+    uint32_t* const leaf_parent = t->d_leaf_parent;
+    B2_TRY(cudaMalloc(&d_dups, 8));
     const uint64_t refit_blocks = (n + kRefitBlock - 1) / kRefitBlock, frontier_cap = refit_blocks * kRefitFrontierPerBlock, frontier_use = refit_blocks * (uint64_t)t->opt_debug_refit_frontier;
     B2_TRY(cudaMalloc(&frontier, frontier_cap * sizeof(RefitEntry)));
     B2_TRY(cudaMalloc(&frontier_count, sizeof(unsigned)));
@@ -408,32 +445,63 @@ int do_build(b200aabb_tree* t) {
     const bool stage_timing = getenv("B200AABB_BUILD_TIMING") != nullptr;
     std::vector<std::pair<const char*, cudaEvent_t>> marks;
     auto mark = [&](const char* name) { if (stage_timing) { cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, st); marks.push_back({name, e}); } };
+    const unsigned blocks = (unsigned)((n + 255) / 256), pblocks = std::min<unsigned>(blocks, 148 * 8);
+    const int ib = index_bits_for(n);                                 // PACKED words: index in the low ib bits, 64 - ib key bits above
+    const int packed_passes = std::min(8, (64 - ib + 7) / 8);
+    unsigned long long dups = 0;
     B2_TRY(cudaEventRecord(t->ev_a, st));
     mark("start");
-    B2_TRY(cudaMemsetAsync(bounds, 0xFF, 3 * 8, st));
-    B2_TRY(cudaMemsetAsync(bounds + 3, 0x00, 3 * 8, st));
-    const unsigned blocks = (unsigned)((n + 255) / 256);
-    scene_bounds_kernel<<<std::min<unsigned>(blocks, 148 * 8), 256, 0, st>>>(t->d_soup, n, bounds);
-    mark("scene_bounds");
-    morton_kernel<<<blocks, 256, 0, st>>>(t->d_soup, n, bounds, keys[0], vals[0]);
-    mark("morton");
-    t->stats.kernel_launches += 2;
-    const int cur = radix_sort_pairs(keys, vals, n, 8, ws, st, &t->stats.kernel_launches);
-    mark("sort");
-    emit_leaves_kernel<<<blocks, 256, 0, st>>>(t->d_soup, t->d_ids, vals[cur], n, t->d_tris, t->d_trisf);
-    mark("emit_leaves");
-    t->stats.kernel_launches += 1;
-    if (n > 1) {
-        hierarchy_kernel<<<blocks, 256, 0, st>>>(keys[cur], n, t->d_nodes, leaf_parent);
+    if (!t->bounds_valid) {
+        B2_TRY(cudaMemsetAsync(t->d_bounds, 0xFF, 3 * 8, st));
+        B2_TRY(cudaMemsetAsync(t->d_bounds + 3, 0x00, 3 * 8, st));
+        scene_bounds_kernel<<<pblocks, 256, 0, st>>>(t->d_soup, n, t->d_bounds);
         t->stats.kernel_launches += 1;
+        t->bounds_valid = true;
     }
-    mark("hierarchy");
+    mark("scene_bounds");
+    // Two attempts at most: PACKED sort words first (build.cuh::pack_sort_word); if more than 1/16 of the primitives start a run of four with equal kept key
+    // bits (a scene whose primitives crowd a tiny part of its box), once more with full 63-bit keys + values.
+    for (int attempt = t->opt_exact_keys ? 1 : 0; attempt < 2; ++attempt) {
+        const bool packed = attempt == 0;
+        int cur;
+        if (packed) {
+            rs_begin(ws, n, st);
+            morton_kernel<true><<<pblocks, 256, 0, st>>>(t->d_soup, n, t->d_bounds, keys[0], nullptr, ib, packed_passes, rs_hist_of(ws));
+            mark("morton");
+            t->stats.kernel_launches += 1;
+            cur = rs_sort_passes(keys, nullptr, n, ib, packed_passes, ws, st, &t->stats.kernel_launches);
+        } else {
+            for (int s = 0; s < 2; ++s) if (!vals[s]) B2_TRY(cudaMalloc(&vals[s], n * 4));
+            morton_kernel<false><<<pblocks, 256, 0, st>>>(t->d_soup, n, t->d_bounds, keys[0], vals[0], 0, 0, nullptr);
+            mark("morton");
+            t->stats.kernel_launches += 1;
+            cur = radix_sort_pairs(keys, vals, n, 8, ws, st, &t->stats.kernel_launches);
+        }
+        mark("sort");
+        emit_leaves_kernel<<<blocks, 256, 0, st>>>(t->d_soup, t->d_ids, packed ? nullptr : vals[cur], keys[cur], ib, n, t->d_tris, t->d_trisf);
+        mark("emit_leaves");
+        t->stats.kernel_launches += 1;
+        B2_TRY(cudaMemsetAsync(d_dups, 0, 8, st));
+        if (n > 1) {
+            hierarchy_kernel<<<blocks, 256, 0, st>>>(keys[cur], n, t->d_nodes, leaf_parent, packed ? ib : 0, d_dups);
+            t->stats.kernel_launches += 1;
+        }
+        mark("hierarchy");
+        if (packed) {
+            B2_TRY(cudaMemcpyAsync(&dups, d_dups, 8, cudaMemcpyDeviceToHost, st));
+            B2_TRY(cudaStreamSynchronize(st));
+            if (dups > n / 16) continue;
+        }
+        t->last_build_packed = packed ? 1 : 0;
+        t->last_build_dups = packed ? dups : 0;
+        break;
+    }
     B2_TRY(cudaMemsetAsync(frontier_count, 0, sizeof(unsigned), st));
     refit_local_kernel<<<(unsigned)refit_blocks, kRefitBlock, 0, st>>>(t->d_tris, n, t->d_nodes, leaf_parent, frontier, frontier_count, (unsigned)frontier_use);
     mark("refit_local");
     if (n > 1) { refit_global_kernel<<<(unsigned)((frontier_cap + 255) / 256), 256, 0, st>>>(t->d_nodes, frontier, frontier_count, (unsigned)frontier_use); t->stats.kernel_launches += 1; }
     mark("refit_global");
-    root_box_kernel<<<1, 32, 0, st>>>(bounds, t->d_rootbox);
+    root_box_kernel<<<1, 32, 0, st>>>(t->d_bounds, t->d_rootbox);
     mark("root_box");
     t->stats.kernel_launches += 2;
     B2_TRY(cudaEventRecord(t->ev_b, st));
@@ -443,6 +511,7 @@ int do_build(b200aabb_tree* t) {
     float ms = 0; cudaEventElapsedTime(&ms, t->ev_a, t->ev_b);
     t->stats.last_build_ms = ms;
     for (size_t i = 1; i < marks.size(); ++i) { float d = 0; cudaEventElapsedTime(&d, marks[i - 1].second, marks[i].second); fprintf(stderr, "[b200aabb build] %-14s %8.3f ms\n", marks[i].first, d); }
+    if (stage_timing) fprintf(stderr, "[b200aabb build] %s sort words, %d passes, %llu runs of >= 4 equal key bits\n", t->last_build_packed ? "packed" : "full (key, index)", t->last_build_packed ? packed_passes : 8, dups);
     for (auto& m : marks) cudaEventDestroy(m.second);
     t->root = n == 1 ? (kLeafBit | 0u) : 0u;
     t->mag = 0.0;
@@ -459,16 +528,53 @@ int ensure_built(b200aabb_tree* t) { return t->built ? B200AABB_OK : do_build(t)
 // H2D -> kernel -> D2H pipeline on two streams; DEVICE pointers: one launch on the handle's stream, no synchronisation.
 struct OutSpec { void* host; size_t elem_bytes; size_t offset; };   // one result array: host pointer, bytes per query, offset in staging
 
+// zeroes the statistics counters of a batch ([2], the incomplete-traversal flags, is sticky while asynchronous batches are in flight)
+int reset_counters(b200aabb_tree* t, cudaStream_t st) {
+    if (!t->async_pending) { B2_CUDA(t, cudaMemsetAsync(t->d_counters, 0, 8 * sizeof(unsigned long long), st)); return B200AABB_OK; }
+    B2_CUDA(t, cudaMemsetAsync(t->d_counters, 0, 2 * sizeof(unsigned long long), st));
+    B2_CUDA(t, cudaMemsetAsync(t->d_counters + 3, 0, 5 * sizeof(unsigned long long), st));
+    return B200AABB_OK;
+}
+
+// waits for every batch in flight on the handle and reports a traversal that could not finish
+int drain(b200aabb_tree* t) {
+    for (int s = 0; s < kPipeSlots; ++s) B2_CUDA(t, cudaStreamSynchronize(t->pipe[s]));
+    B2_CUDA(t, cudaStreamSynchronize(t->stream));
+    B2_CUDA(t, cudaGetLastError());
+    t->async_pending = false;
+    if (!t->trace.empty()) {
+        for (auto& r : t->trace) {
+            float a = 0, b = 0, c = 0, d = 0;
+            cudaEventElapsedTime(&a, t->trace[0].e[0], r.e[0]); cudaEventElapsedTime(&b, t->trace[0].e[0], r.e[1]);
+            cudaEventElapsedTime(&c, t->trace[0].e[0], r.e[2]); cudaEventElapsedTime(&d, t->trace[0].e[0], r.e[3]);
+            fprintf(stderr, "[b200aabb pipe] slot %d %s %8llu  start %8.3f  h2d-done %8.3f  kernels-done %8.3f  d2h-done %8.3f\n", r.slot, r.shape == kPointQuery ? "points" : "lines ",
+                    (unsigned long long)r.cnt, a, b, c, d);
+        }
+        for (auto& r : t->trace) for (auto& e : r.e) cudaEventDestroy(e);
+        t->trace.clear();
+    }
+    unsigned long long incomplete = 0;
+    B2_CUDA(t, cudaMemcpy(&incomplete, t->d_counters + 2, sizeof(incomplete), cudaMemcpyDeviceToHost));
+    if (incomplete) {
+        cudaMemset(t->d_counters + 2, 0, sizeof(incomplete));
+        return fail(t, (incomplete & 4) ? B200AABB_ERR_INVALID_ARGUMENT : B200AABB_ERR_INCOMPLETE,
+                    (incomplete & 4) ? "offsets disagree with the number of intersected primitives" : "traversal stack overflow: results incomplete");
+    }
+    return B200AABB_OK;
+}
+
 template <class Launch>
 int run_batch(b200aabb_tree* t, const void* in, size_t in_elem_bytes, uint64_t n, b200aabb_memspace space, QueryShape shape, std::vector<OutSpec> outs, Launch launch) {
     B2_CUDA(t, cudaSetDevice(t->device));
-    B2_CUDA(t, cudaMemsetAsync(t->d_counters, 0, 8 * sizeof(unsigned long long), t->stream));
     if (space == B200AABB_DEVICE) {
+        int rc = reset_counters(t, t->stream);
+        if (rc) return rc;
         B2_CUDA(t, cudaEventRecord(t->ev_a, t->stream));
         std::vector<void*> ptrs; for (auto& o : outs) ptrs.push_back(o.host);
         const uint32_t* perm = nullptr;
-        int rc = coherence_order(t, 0, t->stream, in, n, shape, &perm);
+        rc = coherence_order(t, kPipeSlots, t->stream, in, n, shape, &perm);
         if (rc) return rc;
+        t->cur_slot = kPipeSlots; t->cur_offset = 0;
         launch(t->stream, in, ptrs.data(), n, perm);
         t->stats.kernel_launches += 1;
         B2_CUDA(t, cudaEventRecord(t->ev_b, t->stream));
@@ -476,41 +582,57 @@ int run_batch(b200aabb_tree* t, const void* in, size_t in_elem_bytes, uint64_t n
         t->query_timing_pending = true;
         return B200AABB_OK;
     }
-    // measured on the benchmark batches (scripts/tune_e2e.py): line queries are copy-bound and gain from six chunks; the
-    // closest_point kernel loses coherence (the chunk is sorted on its own) and pays a drain tail per launch, so two chunks
-    const uint64_t chunk = chunk_for(n, t->opt_host_parts > 0 ? t->opt_host_parts : (shape == kLineQuery ? 6 : 2));
+    // HOST pointers.  Ray / segment batches are cut into chunks that flow through upload -> sort -> traverse -> download on kLineSlots
+    // streams, so that the copies of one chunk hide behind the kernels of the others (such batches are copy bound: ~1 ms of PCIe per Mi rays
+    // each way, 0.6 ms of kernel).  A point batch stays WHOLE: its queries are sorted into one coherence order, and a chunk of an unordered
+    // batch covers the whole scene at a fraction of the density — measured (scripts/tune_e2e.py, profiles/r2_05): four chunks of 2 Mi
+    // points take 4 x 8 ms against 23.8 ms for the batch in one launch.  Its copies hide behind OTHER batches instead (B200AABB_OPT_ASYNC_HOST),
+    // on streams of their own so that the chunks of the next ray batch do not queue behind it.
+    const bool points = shape == kPointQuery;
+    const uint64_t chunk = chunk_for(n, t->opt_host_parts > 0 ? t->opt_host_parts : (points ? 1 : 8), points ? kPointChunkMax : kChunkMax);
     size_t out_bytes = 0;
     for (auto& o : outs) { o.offset = out_bytes; out_bytes += ((o.host ? o.elem_bytes * chunk : 0) + 255) / 256 * 256; }
-    int rc = ensure_stage(t, in_elem_bytes * chunk, std::max<size_t>(out_bytes, 256));
+    int rc = B200AABB_OK;
+    rc = reset_counters(t, t->stream);
     if (rc) return rc;
     B2_CUDA(t, cudaEventRecord(t->ev_a, t->stream));
-    for (int s = 0; s < 2; ++s) B2_CUDA(t, cudaStreamWaitEvent(t->pipe[s], t->ev_a, 0));
-    int slot = 0;
-    for (uint64_t b = 0; b < n; b += chunk, slot ^= 1) {
+    for (int s = 0; s < kPipeSlots; ++s) B2_CUDA(t, cudaStreamWaitEvent(t->pipe[s], t->ev_a, 0));
+    for (uint64_t b = 0; b < n; b += chunk) {
         const uint64_t cnt = std::min<uint64_t>(chunk, n - b);
+        int slot;
+        if (points) { slot = kLineSlots + t->next_point_slot; t->next_point_slot = (t->next_point_slot + 1) % kPointSlots; }
+        else { slot = t->next_line_slot; t->next_line_slot = (t->next_line_slot + 1) % kLineSlots; }
+        rc = ensure_stage(t, slot, in_elem_bytes * chunk, std::max<size_t>(out_bytes, 256));
+        if (rc) return rc;
         cudaStream_t st = t->pipe[slot];
+        static const bool tracing = getenv("B200AABB_PIPE_TRACE") != nullptr;
+        b200aabb_tree::TraceRec tr;
+        if (tracing) { for (auto& e : tr.e) cudaEventCreate(&e); tr.slot = slot; tr.cnt = cnt; tr.shape = (int)shape; cudaEventRecord(tr.e[0], st); }
         B2_CUDA(t, cudaMemcpyAsync(t->d_stage_in[slot], (const char*)in + b * in_elem_bytes, cnt * in_elem_bytes, cudaMemcpyHostToDevice, st));
+        if (tracing) cudaEventRecord(tr.e[1], st);
         std::vector<void*> ptrs;
         for (auto& o : outs) ptrs.push_back(o.host ? (char*)t->d_stage_out[slot] + o.offset : nullptr);
         const uint32_t* perm = nullptr;
         rc = coherence_order(t, slot, st, t->d_stage_in[slot], cnt, shape, &perm);
         if (rc) return rc;
+        t->cur_slot = slot; t->cur_offset = b;
         launch(st, t->d_stage_in[slot], ptrs.data(), cnt, perm);
         t->stats.kernel_launches += 1;
+        if (tracing) cudaEventRecord(tr.e[2], st);
         for (auto& o : outs)
             if (o.host) B2_CUDA(t, cudaMemcpyAsync((char*)o.host + b * o.elem_bytes, (char*)t->d_stage_out[slot] + o.offset, cnt * o.elem_bytes, cudaMemcpyDeviceToHost, st));
+        if (tracing) { cudaEventRecord(tr.e[3], st); t->trace.push_back(tr); }
     }
-    for (int s = 0; s < 2; ++s) { B2_CUDA(t, cudaEventRecord(t->ev_pipe[s], t->pipe[s])); B2_CUDA(t, cudaStreamWaitEvent(t->stream, t->ev_pipe[s], 0)); }
+    if (t->opt_async_host) {   // the caller keeps its buffers alive and calls b200aabb_synchronize before it reads the results
+        t->async_pending = true;
+        t->query_timing_pending = false;
+        return B200AABB_OK;
+    }
+    for (int s = 0; s < kPipeSlots; ++s) { B2_CUDA(t, cudaEventRecord(t->ev_pipe[s], t->pipe[s])); B2_CUDA(t, cudaStreamWaitEvent(t->stream, t->ev_pipe[s], 0)); }
     B2_CUDA(t, cudaEventRecord(t->ev_b, t->stream));
-    unsigned long long incomplete = 0;
-    B2_CUDA(t, cudaMemcpyAsync(&incomplete, t->d_counters + 2, sizeof(incomplete), cudaMemcpyDeviceToHost, t->stream));
-    B2_CUDA(t, cudaStreamSynchronize(t->stream));
-    B2_CUDA(t, cudaGetLastError());
+    rc = drain(t);   // a traversal that could not finish is an error of THIS call, never a silent partial result
     t->query_timing_pending = true;
-    // a traversal that could not finish (stack / pool overflow: impossible for trees this library builds, see closest_pair.cuh) is an error,
-    // never a silent partial result
-    if (incomplete) return fail(t, B200AABB_ERR_INCOMPLETE, "traversal stack overflow: results incomplete");
-    return B200AABB_OK;
+    return rc;
 }
 
 unsigned grid_for(uint64_t n, int block) { return (unsigned)((n + block - 1) / block); }
@@ -555,9 +677,9 @@ int b200aabb_create(int device, b200aabb_tree** out) {
     t->device = device;
     memset(&t->stats, 0, sizeof(t->stats));
     empty_bbox(t->h_bbox);
-    bool ok = cudaMalloc(&t->d_rootbox, 48) == cudaSuccess && cudaMalloc(&t->d_counters, 8 * sizeof(unsigned long long)) == cudaSuccess &&
+    bool ok = cudaMalloc(&t->d_rootbox, 48) == cudaSuccess && cudaMalloc(&t->d_bounds, 48) == cudaSuccess && cudaMalloc(&t->d_counters, 8 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaEventCreate(&t->ev_a) == cudaSuccess && cudaEventCreate(&t->ev_b) == cudaSuccess;
-    for (int s = 0; s < 2 && ok; ++s)
+    for (int s = 0; s < kPipeSlots && ok; ++s)
         ok = cudaStreamCreateWithFlags(&t->pipe[s], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&t->ev_pipe[s], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { b200aabb_destroy(t); return B200AABB_ERR_CUDA; }
     t->built = true;   // an empty tree needs no build
@@ -570,8 +692,8 @@ int b200aabb_destroy(b200aabb_tree* t) {
     cudaSetDevice(t->device);
     cudaDeviceSynchronize();
     free_tree_buffers(t); free_input(t); free_sort(t); free_warp(t);
-    cudaFree(t->d_rootbox); cudaFree(t->d_counters);
-    for (int s = 0; s < 2; ++s) { cudaFree(t->d_stage_in[s]); cudaFree(t->d_stage_out[s]); if (t->pipe[s]) cudaStreamDestroy(t->pipe[s]); if (t->ev_pipe[s]) cudaEventDestroy(t->ev_pipe[s]); }
+    cudaFree(t->d_rootbox); cudaFree(t->d_bounds); cudaFree(t->d_counters);
+    for (int s = 0; s < kPipeSlots; ++s) { cudaFree(t->d_stage_in[s]); cudaFree(t->d_stage_out[s]); cudaFree(t->d_stage_aux[s]); if (t->pipe[s]) cudaStreamDestroy(t->pipe[s]); if (t->ev_pipe[s]) cudaEventDestroy(t->ev_pipe[s]); }
     if (t->ev_a) cudaEventDestroy(t->ev_a);
     if (t->ev_b) cudaEventDestroy(t->ev_b);
     delete t;
@@ -583,7 +705,9 @@ int b200aabb_set_option(b200aabb_tree* t, int option, int64_t value) { B2_LOCK(t
     switch (option) {
         case B200AABB_OPT_SORT_QUERIES: t->opt_sort_queries = value != 0; return B200AABB_OK;
         case B200AABB_OPT_CLOSEST_KERNEL: t->opt_closest_kernel = (int)std::min<int64_t>(2, std::max<int64_t>(0, value)); return B200AABB_OK;
+        case B200AABB_OPT_ASYNC_HOST: t->opt_async_host = value != 0; return B200AABB_OK;
         case B200AABB_OPT_HOST_PARTS: t->opt_host_parts = (int)std::min<int64_t>(64, std::max<int64_t>(0, value)); return B200AABB_OK;
+        case 102: t->opt_exact_keys = value != 0; if (!t->imported) t->built = t->n == 0; return B200AABB_OK;
         case 101: t->opt_debug_refit_frontier = (int)std::min<int64_t>(kRefitFrontierPerBlock, std::max<int64_t>(0, value)); if (!t->imported) t->built = t->n == 0; return B200AABB_OK;
         case B200AABB_OPT_WARP_EXACT_GO: t->opt_warp_exact_go = (int)std::min<int64_t>(kWpExactCap - 32, std::max<int64_t>(0, value)); return B200AABB_OK;
         default: return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "unknown option");
@@ -611,12 +735,20 @@ int b200aabb_get_stats(const b200aabb_tree* tc, b200aabb_stats* out) { B2_LOCK(t
     return B200AABB_OK;
 }
 
+int b200aabb_synchronize(b200aabb_tree* t) {
+    if (!t) return B200AABB_ERR_INVALID_ARGUMENT;
+    B2_LOCK(t);
+    B2_CUDA(t, cudaSetDevice(t->device));
+    return drain(t);
+}
+
 int b200aabb_clear(b200aabb_tree* t) { B2_LOCK(t);
     if (!t) return B200AABB_ERR_INVALID_ARGUMENT;
     B2_CUDA(t, cudaSetDevice(t->device));
+    for (int s = 0; s < kPipeSlots; ++s) B2_CUDA(t, cudaStreamSynchronize(t->pipe[s]));   // (asynchronous HOST batches may still be in flight)
     B2_CUDA(t, cudaStreamSynchronize(t->stream));
     free_tree_buffers(t); free_input(t);
-    t->n = 0; t->built = true; t->imported = false; empty_bbox(t->h_bbox);
+    t->n = 0; t->built = true; t->imported = false; t->bounds_valid = false; empty_bbox(t->h_bbox);
     return B200AABB_OK;
 }
 
@@ -648,14 +780,103 @@ int b200aabb_set_mesh(b200aabb_tree* t, const double* verts, uint64_t nv, const 
     if (e != cudaSuccess) { cudaFree(d_v); cudaFree(d_f); t->err = "cudaMalloc(soup)"; return B200AABB_ERR_OUT_OF_MEMORY; }
     cudaMemcpyAsync(d_v, verts, nv * 24, cudaMemcpyHostToDevice, t->stream);
     cudaMemcpyAsync(d_f, faces, nf * 12, cudaMemcpyHostToDevice, t->stream);
-    gather_mesh_kernel<<<grid_for(nf, 256), 256, 0, t->stream>>>(d_v, d_f, nf, t->d_soup);
+    cudaMemsetAsync(t->d_bounds, 0xFF, 3 * 8, t->stream);
+    cudaMemsetAsync(t->d_bounds + 3, 0x00, 3 * 8, t->stream);
+    gather_mesh_kernel<<<std::min<unsigned>(grid_for(nf, 256), 148 * 8), 256, 0, t->stream>>>(d_v, d_f, nf, t->d_soup, t->d_bounds);
     t->stats.kernel_launches += 1;
     if (face_ids) { e = cudaMalloc(&t->d_ids, nf * 4); if (e == cudaSuccess) cudaMemcpyAsync(t->d_ids, face_ids, nf * 4, cudaMemcpyHostToDevice, t->stream); }
     cudaError_t e2 = cudaStreamSynchronize(t->stream);
     cudaFree(d_v); cudaFree(d_f);
     if (e != cudaSuccess || e2 != cudaSuccess) { free_input(t); t->err = "set_mesh: CUDA failure"; return B200AABB_ERR_CUDA; }
-    t->n = nf; t->built = false;
+    t->n = nf; t->built = false; t->bounds_valid = true;
     return B200AABB_OK;
+}
+
+// bottom-up boxes over the existing topology from the current leaf records (shared by b200aabb_refit)
+static int refit_boxes(b200aabb_tree* t, cudaStream_t st) {
+    const uint64_t n = t->n;
+    if (n < 2) return B200AABB_OK;
+    const uint64_t refit_blocks = (n + kRefitBlock - 1) / kRefitBlock, frontier_cap = refit_blocks * kRefitFrontierPerBlock;
+    RefitEntry* frontier = nullptr; unsigned* frontier_count = nullptr;
+    if (cudaMalloc(&frontier, frontier_cap * sizeof(RefitEntry)) != cudaSuccess || cudaMalloc(&frontier_count, sizeof(unsigned)) != cudaSuccess) {
+        cudaFree(frontier); cudaFree(frontier_count);
+        return fail(t, B200AABB_ERR_OUT_OF_MEMORY, "cudaMalloc(refit frontier)");
+    }
+    cudaMemsetAsync(frontier_count, 0, sizeof(unsigned), st);
+    refit_local_kernel<<<(unsigned)refit_blocks, kRefitBlock, 0, st>>>(t->d_tris, n, t->d_nodes, t->d_leaf_parent, frontier, frontier_count, (unsigned)frontier_cap);
+    refit_global_kernel<<<(unsigned)((frontier_cap + 255) / 256), 256, 0, st>>>(t->d_nodes, frontier, frontier_count, (unsigned)frontier_cap);
+    t->stats.kernel_launches += 2;
+    const cudaError_t e = cudaStreamSynchronize(st);
+    cudaFree(frontier); cudaFree(frontier_count);
+    return e == cudaSuccess && cudaGetLastError() == cudaSuccess ? B200AABB_OK : fail(t, B200AABB_ERR_CUDA, "refit: CUDA failure");
+}
+
+static int refit_from_soup(b200aabb_tree* t) {
+    cudaStream_t st = t->stream;
+    const uint64_t n = t->n;
+    const unsigned blocks = (unsigned)((n + 255) / 256);
+    B2_CUDA(t, cudaEventRecord(t->ev_a, st));
+    if (!t->bounds_valid) {
+        cudaMemsetAsync(t->d_bounds, 0xFF, 3 * 8, st);
+        cudaMemsetAsync(t->d_bounds + 3, 0x00, 3 * 8, st);
+        scene_bounds_kernel<<<std::min<unsigned>(blocks, 148 * 8), 256, 0, st>>>(t->d_soup, n, t->d_bounds);
+        t->bounds_valid = true;
+        t->stats.kernel_launches += 1;
+    }
+    refresh_leaves_kernel<<<blocks, 256, 0, st>>>(t->d_soup, n, t->d_tris, t->d_trisf);
+    t->stats.kernel_launches += 1;
+    int rc = refit_boxes(t, st);
+    if (rc) return rc;
+    root_box_kernel<<<1, 32, 0, st>>>(t->d_bounds, t->d_rootbox);
+    B2_CUDA(t, cudaEventRecord(t->ev_b, st));
+    B2_CUDA(t, cudaMemcpyAsync(t->h_bbox, t->d_rootbox, 48, cudaMemcpyDeviceToHost, st));
+    B2_CUDA(t, cudaStreamSynchronize(st));
+    float ms = 0; cudaEventElapsedTime(&ms, t->ev_a, t->ev_b);
+    t->stats.last_build_ms = ms;
+    t->mag = 0.0;
+    for (int a = 0; a < 6; ++a) t->mag = std::max(t->mag, fabs(t->h_bbox[a]));
+    return B200AABB_OK;
+}
+
+static int refit_precheck(b200aabb_tree* t, uint64_t n) {
+    if (t->imported || !t->d_soup) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "refit needs a tree built from inserted primitives");
+    if (n != t->n) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "refit keeps the topology: the number of primitives must not change (use set_* + build)");
+    int rc = ensure_built(t);
+    if (rc) return rc;
+    for (int s = 0; s < kPipeSlots; ++s) B2_CUDA(t, cudaStreamSynchronize(t->pipe[s]));
+    return B200AABB_OK;
+}
+
+int b200aabb_refit(b200aabb_tree* t, const double* tris, uint64_t n, b200aabb_memspace space) {
+    if (!t || (n && !tris)) return B200AABB_ERR_INVALID_ARGUMENT;
+    B2_LOCK(t);
+    B2_CUDA(t, cudaSetDevice(t->device));
+    int rc = refit_precheck(t, n);
+    if (rc || n == 0) return rc;
+    B2_CUDA(t, cudaMemcpyAsync(t->d_soup, tris, n * 72, space == B200AABB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, t->stream));
+    t->bounds_valid = false;
+    return refit_from_soup(t);
+}
+
+int b200aabb_refit_mesh(b200aabb_tree* t, const double* verts, uint64_t nv, const uint32_t* faces, uint64_t nf) {
+    if (!t || (nf && (!verts || !faces))) return B200AABB_ERR_INVALID_ARGUMENT;
+    B2_LOCK(t);
+    B2_CUDA(t, cudaSetDevice(t->device));
+    for (uint64_t i = 0; i < 3 * nf; ++i) if (faces[i] >= nv) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "face references a vertex index >= nv");
+    int rc = refit_precheck(t, nf);
+    if (rc || nf == 0) return rc;
+    double* d_v = nullptr; uint32_t* d_f = nullptr;
+    if (cudaMalloc(&d_v, nv * 24) != cudaSuccess || cudaMalloc(&d_f, nf * 12) != cudaSuccess) { cudaFree(d_v); cudaFree(d_f); return fail(t, B200AABB_ERR_OUT_OF_MEMORY, "cudaMalloc(refit_mesh)"); }
+    cudaMemcpyAsync(d_v, verts, nv * 24, cudaMemcpyHostToDevice, t->stream);
+    cudaMemcpyAsync(d_f, faces, nf * 12, cudaMemcpyHostToDevice, t->stream);
+    cudaMemsetAsync(t->d_bounds, 0xFF, 3 * 8, t->stream);
+    cudaMemsetAsync(t->d_bounds + 3, 0x00, 3 * 8, t->stream);
+    gather_mesh_kernel<<<std::min<unsigned>(grid_for(nf, 256), 148 * 8), 256, 0, t->stream>>>(d_v, d_f, nf, t->d_soup, t->d_bounds);
+    t->stats.kernel_launches += 1;
+    t->bounds_valid = true;
+    rc = refit_from_soup(t);
+    cudaFree(d_v); cudaFree(d_f);
+    return rc;
 }
 
 int b200aabb_build(b200aabb_tree* t) { B2_LOCK(t); if (!t) return B200AABB_ERR_INVALID_ARGUMENT; return do_build(t); }
@@ -743,7 +964,7 @@ int b200aabb_all_intersected_primitives(b200aabb_tree* t, const double* q, uint6
     cudaMemsetAsync(t->d_counters, 0, 8 * sizeof(unsigned long long), t->stream);
     cudaEventRecord(t->ev_a, t->stream);
     const uint32_t* perm = nullptr;
-    rc = coherence_order(t, 0, t->stream, d_q, n, kLineQuery, &perm);
+    rc = coherence_order(t, kPipeSlots, t->stream, d_q, n, kLineQuery, &perm);
     if (rc) { release(); return rc; }
     if (ray) intersect_kernel<true, kList><<<grid_for(n, 128), 128, 0, t->stream>>>(tree_ref(t, perm), d_q, n, nullptr, nullptr, d_off, d_ids);
     else intersect_kernel<false, kList><<<grid_for(n, 128), 128, 0, t->stream>>>(tree_ref(t, perm), d_q, n, nullptr, nullptr, d_off, d_ids);
@@ -820,7 +1041,7 @@ int b200aabb_all_intersections(b200aabb_tree* t, const double* rays, uint64_t n,
     cudaMemsetAsync(t->d_counters, 0, 8 * sizeof(unsigned long long), t->stream);
     cudaEventRecord(t->ev_a, t->stream);
     const uint32_t* perm = nullptr;
-    rc = coherence_order(t, 0, t->stream, d_q, n, kLineQuery, &perm);
+    rc = coherence_order(t, kPipeSlots, t->stream, d_q, n, kLineQuery, &perm);
     if (rc) { release(); return rc; }
     ray_objects_kernel<kList><<<grid_for(n, 128), 128, 0, t->stream>>>(tree_ref(t, perm), d_q, n, nullptr, d_off, d_ids, d_kinds, d_pts, nullptr, nullptr, nullptr, nullptr);
     t->stats.kernel_launches += 1;
@@ -844,9 +1065,10 @@ int b200aabb_all_intersections(b200aabb_tree* t, const double* rays, uint64_t n,
     return B200AABB_OK;
 }
 
-int b200aabb_first_intersection(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, uint32_t* prim, double* tpar, double* pt,
-                                double* pt2, uint8_t* flags) { B2_LOCK(t);
-    if (!t || (n && !rays)) return B200AABB_ERR_INVALID_ARGUMENT;
+static int first_intersection_impl(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, const uint32_t* skip_ids, const uint32_t* skip_mask,
+                                   uint32_t mask_words, uint32_t* prim, double* tpar, double* pt, double* pt2, uint8_t* flags) {
+    if (!t || (n && !rays) || (skip_mask == nullptr && mask_words != 0)) return B200AABB_ERR_INVALID_ARGUMENT;
+    B2_LOCK(t);
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     if (t->n == 0) {   // nullopt for every ray
@@ -865,11 +1087,46 @@ int b200aabb_first_intersection(b200aabb_tree* t, const double* rays, uint64_t n
         }
         return B200AABB_OK;
     }
-    return run_batch(t, rays, 48, n, space, kLineQuery, {{prim, 4, 0}, {tpar, 8, 0}, {pt, 24, 0}, {pt2, 24, 0}, {flags, 1, 0}},
-                     [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
-                         first_intersection_kernel<<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint32_t*)o[0], (double*)o[1],
-                                                                                        (double*)o[2], (double*)o[3], (uint8_t*)o[4]);
-                     });
+    // HOST batches: the mask travels once (before the chunks), the per-ray skip ids chunk by chunk next to the rays
+    uint32_t* d_mask = nullptr;
+    if (space == B200AABB_HOST) {
+        B2_CUDA(t, cudaSetDevice(t->device));
+        if (skip_mask && mask_words) {
+            if (cudaMalloc(&d_mask, (size_t)mask_words * 4) != cudaSuccess) return fail(t, B200AABB_ERR_OUT_OF_MEMORY, "cudaMalloc(skip mask)");
+            cudaMemcpy(d_mask, skip_mask, (size_t)mask_words * 4, cudaMemcpyHostToDevice);
+        }
+        if (skip_ids) {
+            const size_t need = 4 * (size_t)kChunkMax;
+            if (t->stage_aux_bytes < need) {
+                for (int s = 0; s < kPipeSlots; ++s) { cudaFree(t->d_stage_aux[s]); t->d_stage_aux[s] = nullptr; }
+                for (int s = 0; s < kPipeSlots; ++s) if (cudaMalloc(&t->d_stage_aux[s], need) != cudaSuccess) { cudaFree(d_mask); return fail(t, B200AABB_ERR_OUT_OF_MEMORY, "cudaMalloc(skip ids)"); }
+                t->stage_aux_bytes = need;
+            }
+        }
+    }
+    const uint32_t* mask_dev = space == B200AABB_HOST ? d_mask : skip_mask;
+    rc = run_batch(t, rays, 48, n, space, kLineQuery, {{prim, 4, 0}, {tpar, 8, 0}, {pt, 24, 0}, {pt2, 24, 0}, {flags, 1, 0}},
+                   [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
+                       const uint32_t* sk = skip_ids;
+                       if (skip_ids && space == B200AABB_HOST) {
+                           cudaMemcpyAsync(t->d_stage_aux[t->cur_slot], skip_ids + t->cur_offset, cnt * 4, cudaMemcpyHostToDevice, st);
+                           sk = t->d_stage_aux[t->cur_slot];
+                       }
+                       first_intersection_kernel<<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint32_t*)o[0], (double*)o[1],
+                                                                                      (double*)o[2], (double*)o[3], (uint8_t*)o[4], sk, mask_dev, mask_words);
+                   });
+    if (d_mask) { if (t->async_pending) drain(t); cudaFree(d_mask); }
+    return rc;
+}
+
+int b200aabb_first_intersection(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, uint32_t* prim, double* tpar, double* pt,
+                                double* pt2, uint8_t* flags) {
+    return first_intersection_impl(t, rays, n, space, nullptr, nullptr, 0, prim, tpar, pt, pt2, flags);
+}
+
+int b200aabb_first_intersection_skip(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, const uint32_t* skip_ids, const uint32_t* skip_mask,
+                                     uint32_t mask_words, uint32_t* prim, double* tpar, double* pt, double* pt2, uint8_t* flags) {
+    return first_intersection_impl(t, rays, n, space, skip_ids, skip_mask, mask_words, prim, tpar, pt, pt2, flags);
 }
 
 int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200aabb_memspace space, double* cp, uint32_t* prim, double* sqd, uint8_t* flags) { B2_LOCK(t);
@@ -880,14 +1137,14 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
     if (n == 0) return B200AABB_OK;
     // the warp-cooperative kernel packs (query slot, node / leaf) in 32 bits and needs an internal root
     const bool warp_kernel = t->opt_closest_kernel >= 1 && t->n >= 2 && t->n <= kWpMaxPrims;
-    if (warp_kernel) { for (int s = 0; s < 2; ++s) { rc = ensure_warp(t, s); if (rc) return rc; } }
+    if (warp_kernel) { for (int s = kLineSlots; s < kScratchSlots; ++s) { rc = ensure_warp(t, s); if (rc) return rc; } }   // (the point slots and the DEVICE-batch slot)
     return run_batch(t, pts, 24, n, space, kPointQuery, {{cp, 24, 0}, {prim, 4, 0}, {sqd, 8, 0}, {flags, 1, 0}},
                      [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
                          if (!warp_kernel || cnt >= (1ull << 32)) {
                              closest_point_kernel<<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (double*)o[0], (uint32_t*)o[1], (double*)o[2], (uint8_t*)o[3]);
                              return;
                          }
-                         const int slot = (space == B200AABB_HOST && st == t->pipe[1]) ? 1 : 0;
+                         const int slot = t->cur_slot;
                          cudaMemsetAsync(t->warp[slot].cursor, 0, sizeof(unsigned long long), st);
                          if (t->opt_closest_kernel >= 2) {
                              PairClosestArgs a;
@@ -909,6 +1166,44 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
                          const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)t->warp_grid, (cnt + 31) / 32);
                          closest_point_warp_kernel<<<grid, 32, 0, st>>>(a);
                      });
+}
+
+int b200aabb_max_distance_to_mesh(b200aabb_tree* t, const double* pts, uint64_t n, b200aabb_memspace space, double* max_distance, uint64_t* farthest) {
+    if (!t || (n && !pts) || !max_distance) return B200AABB_ERR_INVALID_ARGUMENT;
+    B2_LOCK(t);
+    int rc = ensure_built(t);
+    if (rc) return rc;
+    if (t->n == 0) return fail(t, B200AABB_ERR_EMPTY_TREE, "distance query on an empty tree (CGAL_precondition(!empty()))");
+    *max_distance = 0.0;
+    if (farthest) *farthest = 0;
+    if (n == 0) return B200AABB_OK;
+    B2_CUDA(t, cudaSetDevice(t->device));
+    double* d_pts = nullptr; double* d_sqd = nullptr; unsigned long long* d_best = nullptr;
+    auto release = [&]() { if (space == B200AABB_HOST) cudaFree(d_pts); cudaFree(d_sqd); cudaFree(d_best); };
+    cudaError_t e = cudaMalloc(&d_sqd, n * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&d_best, 16);
+    if (e == cudaSuccess && space == B200AABB_HOST) e = cudaMalloc(&d_pts, n * 24);
+    if (e != cudaSuccess) { release(); t->err = "cudaMalloc(max_distance_to_mesh)"; return B200AABB_ERR_OUT_OF_MEMORY; }
+    if (space == B200AABB_HOST) cudaMemcpyAsync(d_pts, pts, n * 24, cudaMemcpyHostToDevice, t->stream);
+    else d_pts = const_cast<double*>(pts);
+    rc = b200aabb_closest_point(t, d_pts, n, B200AABB_DEVICE, nullptr, nullptr, d_sqd, nullptr);
+    if (rc) { release(); return rc; }
+    const unsigned long long init[2] = {0ull, ~0ull};
+    cudaMemcpyAsync(d_best, init, 16, cudaMemcpyHostToDevice, t->stream);
+    const unsigned grid = (unsigned)std::min<uint64_t>((n + 255) / 256, 148 * 8);
+    max_sqdist_kernel<<<grid, 256, 0, t->stream>>>(d_sqd, n, d_best);
+    argmax_sqdist_kernel<<<grid, 256, 0, t->stream>>>(d_sqd, n, d_best, d_best + 1);
+    t->stats.kernel_launches += 2;
+    unsigned long long out[2] = {0, 0};
+    cudaMemcpyAsync(out, d_best, 16, cudaMemcpyDeviceToHost, t->stream);
+    e = cudaStreamSynchronize(t->stream);
+    release();
+    if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) { t->err = "max_distance_to_mesh: CUDA failure"; return B200AABB_ERR_CUDA; }
+    double sq; memcpy(&sq, &out[0], 8);
+    *max_distance = sqrt(sq);                 // to_double(approximate_sqrt(sq_hdist)), distance.h:186
+    if (farthest) *farthest = out[1] == ~0ull ? 0 : out[1];
+    b200aabb_stats st;
+    return b200aabb_get_stats(t, &st);        // (surfaces an incomplete traversal of the DEVICE batch)
 }
 
 int b200aabb_export_layout(b200aabb_tree* t, void** ptrs, uint64_t* bytes, int cap, int* count) { B2_LOCK(t);
@@ -1040,7 +1335,10 @@ int bcast_prepare(b200aabb_comm* c, b200aabb_tree* t, int root, int mode, cudaSt
     if (cudaMemcpyAsync(h, c->d_header, sizeof(h), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return B200AABB_ERR_CUDA;
     if (c->rank == root) return B200AABB_OK;
     const uint64_t n = h[0];
-    if (mode == 0) return b200aabb_import_alloc(t, n);
+    if (mode == 0) {
+        if (t->imported && t->n == n && t->d_tris && t->d_trisf && (n < 2 || t->d_nodes)) return B200AABB_OK;   // a replica of the same size: refresh it in place
+        return b200aabb_import_alloc(t, n);
+    }
     int rc = b200aabb_clear(t);
     if (rc || n == 0) return rc;
     if (cudaMalloc(&t->d_soup, n * 72) != cudaSuccess) return B200AABB_ERR_OUT_OF_MEMORY;

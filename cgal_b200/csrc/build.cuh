@@ -11,6 +11,7 @@
 //                        every node box is bit-equal to the outward rounding of the exact union of its primitives' boxes
 #pragma once
 #include "bvh.cuh"
+#include "radix_sort.cuh"
 
 namespace b2 {
 
@@ -28,26 +29,8 @@ __host__ __device__ __forceinline__ double from_ordered_bits(unsigned long long 
 #endif
 }
 
-__global__ void __launch_bounds__(256) gather_mesh_kernel(const double* __restrict__ verts, const uint32_t* __restrict__ faces, uint64_t nf, double* __restrict__ tris) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nf) return;
-    double* out = tris + 9 * i;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const double* v = verts + 3 * (uint64_t)faces[3 * i + k];
-        out[3 * k] = v[0]; out[3 * k + 1] = v[1]; out[3 * k + 2] = v[2];
-    }
-}
-
-// bounds[0..2] = ordered_bits(min), bounds[3..5] = ordered_bits(max); initialised to ~0 / 0 by the host
-__global__ void __launch_bounds__(256) scene_bounds_kernel(const double* __restrict__ tris, uint64_t n, unsigned long long* __restrict__ bounds) {
-    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const double* t = tris + 9 * i;
-#pragma unroll
-        for (int k = 0; k < 9; ++k) { const double v = t[k]; lo[k % 3] = fmin(lo[k % 3], v); hi[k % 3] = fmax(hi[k % 3], v); }
-    }
+// block reduction of per-thread bounds + one atomic per block and bound (shared by scene_bounds_kernel and gather_mesh_kernel)
+__device__ __forceinline__ void bounds_block_reduce(double* lo, double* hi, unsigned long long* __restrict__ bounds) {
 #pragma unroll
     for (int k = 0; k < 3; ++k)
         for (int off = 16; off > 0; off >>= 1) {
@@ -64,6 +47,36 @@ __global__ void __launch_bounds__(256) scene_bounds_kernel(const double* __restr
         if (threadIdx.x < 3) atomicMin(&bounds[threadIdx.x], ordered_bits(v));
         else atomicMax(&bounds[threadIdx.x], ordered_bits(v));
     }
+}
+
+// indexed Surface_mesh -> 9 doubles per primitive; the scene bounds come out of the same pass (the coordinates are in registers anyway),
+// so that a build after b200aabb_set_mesh does not read the primitives a second time for them
+__global__ void __launch_bounds__(256) gather_mesh_kernel(const double* __restrict__ verts, const uint32_t* __restrict__ faces, uint64_t nf, double* __restrict__ tris,
+                                                          unsigned long long* __restrict__ bounds) {
+    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nf; i += stride) {
+        double* out = tris + 9 * i;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double* v = verts + 3 * (uint64_t)faces[3 * i + k];
+#pragma unroll
+            for (int a = 0; a < 3; ++a) { const double c = v[a]; out[3 * k + a] = c; lo[a] = fmin(lo[a], c); hi[a] = fmax(hi[a], c); }
+        }
+    }
+    bounds_block_reduce(lo, hi, bounds);
+}
+
+// bounds[0..2] = ordered_bits(min), bounds[3..5] = ordered_bits(max); initialised to ~0 / 0 by the host
+__global__ void __launch_bounds__(256) scene_bounds_kernel(const double* __restrict__ tris, uint64_t n, unsigned long long* __restrict__ bounds) {
+    double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double* t = tris + 9 * i;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) { const double v = t[k]; lo[k % 3] = fmin(lo[k % 3], v); hi[k % 3] = fmax(hi[k % 3], v); }
+    }
+    bounds_block_reduce(lo, hi, bounds);
 }
 
 // bbox() of the tree (AABB_tree.h:204-210) = the exact scene bounds, decoded from the ordered-integer atomics
@@ -97,36 +110,60 @@ B2_HD void morton_frame(double lx, double ly, double lz, double hx, double hy, d
     scale[0] = sc; scale[1] = sc; scale[2] = sc;
 }
 
+// PACKED sort word of primitive `index` (index < 2^ib): the top 64 - ib bits of its 63-bit Morton key above its index.  Sorting the words by
+// their key bits alone (stable) orders equal keys by index, so one 8-byte word per primitive replaces the (key, index) pair: a third less
+// traffic per pass and — 40 key bits for 16.8 M primitives — five passes instead of eight.  The words are all different, so the radix tree
+// over them needs no tie-break, and it IS the tree of the (63-bit key, index) pairs whenever no two primitives agree in the kept key bits
+// (hierarchy_kernel counts the runs of four or more that do; the build falls back to full keys when they are not rare).
+B2_HD uint64_t pack_sort_word(uint64_t key63, uint64_t index, int ib) { return (((key63 << 1) >> ib) << ib) | index; }
+B2_HD int index_bits_for(uint64_t n) { int b = 1; while (b < 32 && (1ull << b) < n) ++b; return b; }
+
+// PACKED: keys[i] = pack_sort_word (vals unused) and the digit histograms of the sort are accumulated on the way (rs_hist_*);
+// otherwise keys[i] = the 63-bit key, vals[i] = i.
+template <bool PACKED>
 __global__ void __launch_bounds__(256) morton_kernel(const double* __restrict__ tris, uint64_t n, const unsigned long long* __restrict__ bounds,
-                                                     uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+                                                     uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int ib, int npasses, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t sh[PACKED ? 8 * kRsBins : 1];
+    if (PACKED) rs_hist_begin(sh);
     double lo[3], scale[3];
     morton_frame(from_ordered_bits(bounds[0]), from_ordered_bits(bounds[1]), from_ordered_bits(bounds[2]),
                  from_ordered_bits(bounds[3]), from_ordered_bits(bounds[4]), from_ordered_bits(bounds[5]), lo, scale);
-    const double* t = tris + 9 * i;
-    double c[3];
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const double* t = tris + 9 * i;
+        double c[3];
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const double a = t[k], b = t[3 + k], d = t[6 + k];
-        c[k] = 0.5 * (fmin(a, fmin(b, d)) + fmax(a, fmax(b, d)));
+        for (int k = 0; k < 3; ++k) {
+            const double a = t[k], b = t[3 + k], d = t[6 + k];
+            c[k] = 0.5 * (fmin(a, fmin(b, d)) + fmax(a, fmax(b, d)));
+        }
+        const uint64_t key = morton63(c[0], c[1], c[2], lo, scale);
+        if (PACKED) {
+            const uint64_t w = pack_sort_word(key, i, ib);
+            keys[i] = w;
+            rs_hist_add(sh, w, ib, npasses);
+        } else {
+            keys[i] = key;
+            vals[i] = (uint32_t)i;
+        }
     }
-    keys[i] = morton63(c[0], c[1], c[2], lo, scale);
-    vals[i] = (uint32_t)i;
+    if (PACKED) rs_hist_end(sh, hist, npasses);
 }
 
+// (perm == nullptr: the sorted PACKED words carry the primitive index in their low ib bits)
 __global__ void __launch_bounds__(256) emit_leaves_kernel(const double* __restrict__ tris, const uint32_t* __restrict__ ids, const uint32_t* __restrict__ perm,
-                                                          uint64_t n, TriRec* __restrict__ out, TriF* __restrict__ outf) {
+                                                          const uint64_t* __restrict__ words, int ib, uint64_t n, TriRec* __restrict__ out, TriF* __restrict__ outf) {
     const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n) return;
-    const uint32_t src = perm[k];
+    const uint32_t src = perm ? perm[k] : (uint32_t)(words[k] & ((1ull << ib) - 1ull));
     const double* t = tris + 9 * (uint64_t)src;
     TriRec r;
 #pragma unroll
     for (int j = 0; j < 9; ++j) r.v[j] = t[j];
     r.id = ids ? ids[src] : src;
+    r.pad[0] = src;                                              // position of the primitive in the inserted order (b200aabb_refit re-reads it there)
 #pragma unroll
-    for (int j = 0; j < 5; ++j) r.pad[j] = 0;
+    for (int j = 1; j < 5; ++j) r.pad[j] = 0;
     out[k] = r;
     TriF f;
 #pragma unroll
@@ -134,6 +171,15 @@ __global__ void __launch_bounds__(256) emit_leaves_kernel(const double* __restri
 #pragma unroll
     for (int j = 0; j < 7; ++j) f.pad[j] = 0;
     outf[k] = f;
+}
+
+// b200aabb_refit: the primitives have moved (same count, same order): rewrite the coordinates of the leaf records in place, topology kept
+__global__ void __launch_bounds__(256) refresh_leaves_kernel(const double* __restrict__ tris, uint64_t n, TriRec* __restrict__ out, TriF* __restrict__ outf) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const double* t = tris + 9 * (uint64_t)out[k].pad[0];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) { const double c = t[j]; out[k].v[j] = c; outf[k].v[j] = (float)c; }
 }
 
 // length of the common prefix of the (key, index) pairs i and j; -1 outside [0, n)
@@ -172,8 +218,17 @@ B2_HD void karras_node(const uint64_t* __restrict__ keys, int64_t n, int64_t i, 
     right = hi == gamma + 1 ? (kLeafBit | (uint32_t)(gamma + 1)) : (uint32_t)(gamma + 1);
 }
 
-__global__ void __launch_bounds__(256) hierarchy_kernel(const uint64_t* __restrict__ keys, uint64_t n, BvhNode* __restrict__ nodes, uint32_t* __restrict__ leaf_parent) {
+// ib > 0: the keys are PACKED words; *dups += positions that start a run of four words agreeing in all their key bits (see pack_sort_word)
+__global__ void __launch_bounds__(256) hierarchy_kernel(const uint64_t* __restrict__ keys, uint64_t n, BvhNode* __restrict__ nodes, uint32_t* __restrict__ leaf_parent,
+                                                        int ib, unsigned long long* __restrict__ dups) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (ib > 0) {
+        // (runs of FOUR: pairs of primitives with equal key bits — the two triangles of a terrain quad have the same box centre in x and y —
+        //  are siblings in either tree; what would hurt are long runs, which the index bits split without regard to geometry)
+        const bool dup = i + 3 < n && (((keys[i] ^ keys[i + 1]) | (keys[i] ^ keys[i + 2]) | (keys[i] ^ keys[i + 3])) >> ib) == 0;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, dup);
+        if (m && (threadIdx.x & 31) == 0) atomicAdd(dups, (unsigned long long)__popc(m));
+    }
     if (i + 1 >= n) return;
     uint32_t l, r, j;
     karras_node(keys, (int64_t)n, (int64_t)i, l, r, &j);
@@ -207,7 +262,9 @@ __device__ __forceinline__ void refit_climb_global(BvhNode* nodes, uint32_t p, u
 #pragma unroll
         for (int a = 0; a < 3; ++a) { mylo[a] = lo[a]; myhi[a] = hi[a]; }
         __threadfence();
-        if (atomicExch(&nd->visit, kNone) != kNone) return;      // first to arrive: the sibling will carry on
+        // arrival flag = bit 31 of `visit` (the low bits keep the other end of the node's leaf range): each arrival toggles it, the first one
+        // finds it clear, the second one set — and leaves it clear again, so a later refit (b200aabb_refit) finds the node as the build left it
+        if ((atomicXor(&nd->visit, 0x80000000u) & 0x80000000u) == 0) return;      // first to arrive: the sibling will carry on
         __threadfence();
         // the sibling box was written by another SM: read it through L2 (this SM's L1 may hold the line from the child[] read)
         const float* olo = side ? nd->lo0 : nd->lo1; const float* ohi = side ? nd->hi0 : nd->hi1;
@@ -247,6 +304,7 @@ __global__ void __launch_bounds__(kRefitBlock) refit_local_kernel(const TriRec* 
         uint4 link = make_uint4(0, 0, 0, 0);
         if (local) {
             link = s_link[p - base];
+            link.w &= 0x7FFFFFFFu;
             const uint32_t a = p < link.w ? p : link.w, b = p < link.w ? link.w : p;
             local = a >= base && b <= last_leaf;
         }

@@ -351,29 +351,37 @@ B2_HD uint32_t traverse_ray_objects(const BvhNode* __restrict__ nodes, const Tri
 // ---------------------------------------------------------------------------------------------------------------
 struct FirstHit { uint32_t prim; int kind; double t; Vec3 p0, p1; int tie; int near; };
 
+// skip_id / skip_mask: first_intersection(query, skip) (AABB_tree.h:307-328): primitives the caller's functor rejects are ignored — here the
+// one primitive skip_id (kNone: none) and those whose bit is set in skip_mask (bit per primitive id, mask_words 32-bit words; nullptr: none)
 B2_HD FirstHit traverse_first(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root,
-                              const Vec3& s, const Vec3& q, double mag, TravStat& st) {
+                              const Vec3& s, const Vec3& q, double mag, TravStat& st, uint32_t skip_id = kNone,
+                              const uint32_t* __restrict__ skip_mask = nullptr, uint32_t mask_words = 0) {
     const LineCtx c = make_line(s, q, mag);
     FirstHit best; best.prim = kNone; best.kind = 0; best.t = DBL_MAX; best.p0 = s; best.p1 = s; best.tie = 0; best.near = 0;
     double best_u = 0.0;
-    double runner_up = DBL_MAX;   // smallest t among the intersected primitives that are not the winner
-    double runner_lo = DBL_MAX;   // smallest (t - u) among them
+    double strict_lo = DBL_MAX;   // smallest (t - u) among the intersected primitives whose t is LARGER than the winner's
+    double tie_lo = DBL_MAX;      // smallest (t - u) among those whose t EQUALS the winner's
+    bool tie = false;
     float tlimit = INFINITY;      // prune boxes whose entry parameter certainly exceeds the best hit (rounded up)
     auto leaf = [&](uint32_t ref) {
         uint32_t id;
         const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
         ++st.leaves;
+        // skip(primitive.id()): AABB_ray_intersection.h:86,99,113 — NOT consulted for a one-primitive tree, which the reference answers directly (:214)
+        if (!(root & kLeafBit) && (id == skip_id || (skip_mask && (id >> 5) < mask_words && ((skip_mask[id >> 5] >> (id & 31u)) & 1u)))) return;
         int nex = 0;
         const RayX x = ray_tri_intersection_call(t.a.x, t.a.y, t.a.z, t.b.x, t.b.y, t.b.z, t.c.x, t.c.y, t.c.z, s.x, s.y, s.z, q.x, q.y, q.z, c.major, &nex);
         st.nexact += nex;
         if (x.kind == 0) return;
         if (x.t < best.t || (x.t == best.t && id < best.prim)) {
-            if (best.prim != kNone) { runner_up = fmin(runner_up, best.t); runner_lo = fmin(runner_lo, best.t - best_u); }
+            if (best.prim != kNone) {
+                if (x.t < best.t) { strict_lo = fmin(strict_lo, fmin(best.t - best_u, tie_lo)); tie = false; tie_lo = DBL_MAX; }   // the old winner and its ties fall behind
+                else { tie = true; tie_lo = fmin(tie_lo, best.t - best_u); }                                                       // same t, smaller id
+            }
             best.prim = id; best.kind = x.kind; best.t = x.t; best.p0 = x.p0; best.p1 = x.p1; best_u = x.u;
             tlimit = float_above(x.t + ((fabs(x.t) * 2e-6 + x.u) + c.t_abs_slack));
-        } else {
-            runner_up = fmin(runner_up, x.t); runner_lo = fmin(runner_lo, x.t - x.u);
-        }
+        } else if (x.t == best.t) { tie = true; tie_lo = fmin(tie_lo, x.t - x.u); }
+        else strict_lo = fmin(strict_lo, x.t - x.u);
     };
     if (root & kLeafBit) { leaf(root); }
     else {
@@ -423,8 +431,8 @@ B2_HD FirstHit traverse_first(const BvhNode* __restrict__ nodes, const TriRec* _
         }
     }
     if (best.prim != kNone) {
-        best.tie = runner_up == best.t;
-        best.near = !best.tie && runner_lo <= best.t + best_u;
+        best.tie = tie;                                    // another primitive attains exactly the winner's t
+        best.near = strict_lo <= best.t + best_u;          // another one, with a larger rounded t, lies within the rounding uncertainty (both may hold)
     }
     return best;
 }

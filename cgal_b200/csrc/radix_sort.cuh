@@ -24,21 +24,29 @@ constexpr int kRsTile = kRsThreads * kRsItems;           // 4096 keys per tile
 constexpr uint32_t kRsFlagAgg = 1u << 30, kRsFlagIncl = 2u << 30, kRsFlagMask = 3u << 30, kRsValMask = ~kRsFlagMask;
 constexpr size_t kRsSmemBytes = kRsTile * 8 + kRsWarps * kRsBins * 4 + kRsBins * 4 * 2 + 64;   // 42 KB: four blocks per SM (values reuse the key area)
 
-// hist[pass][bin] += number of keys whose digit `pass` is `bin`
-__global__ void __launch_bounds__(256) rs_histogram_kernel(const uint64_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ hist, int npasses) {
-    __shared__ uint32_t sh[8 * kRsBins];
+// Digit histograms of all passes, accumulated by a block in shared memory (sh[8 * kRsBins], zeroed by rs_hist_begin) and flushed once.
+// Kernels that PRODUCE the keys (the Morton kernel of the build) call these themselves, which saves the separate 8 B/key read.
+__device__ __forceinline__ void rs_hist_begin(uint32_t* sh) {
     for (int i = threadIdx.x; i < 8 * kRsBins; i += blockDim.x) sh[i] = 0;
     __syncthreads();
-    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        const uint64_t k = keys[i];
+}
+__device__ __forceinline__ void rs_hist_add(uint32_t* sh, uint64_t k, int first_bit, int npasses) {
 #pragma unroll
-        for (int p = 0; p < 8; ++p)
-            if (p < npasses) atomicAdd(&sh[p * kRsBins + ((k >> (p * kRsBits)) & (kRsBins - 1))], 1u);
-    }
+    for (int p = 0; p < 8; ++p)
+        if (p < npasses) atomicAdd(&sh[p * kRsBins + ((k >> (first_bit + p * kRsBits)) & (kRsBins - 1))], 1u);
+}
+__device__ __forceinline__ void rs_hist_end(const uint32_t* sh, uint32_t* __restrict__ hist, int npasses) {
     __syncthreads();
     for (int i = threadIdx.x; i < npasses * kRsBins; i += blockDim.x)
         if (sh[i]) atomicAdd(&hist[i], sh[i]);
+}
+// hist[pass][bin] += number of keys whose digit `pass` (bits first_bit + 8 pass ..) is `bin`
+__global__ void __launch_bounds__(256) rs_histogram_kernel(const uint64_t* __restrict__ keys, uint64_t n, uint32_t* __restrict__ hist, int first_bit, int npasses) {
+    __shared__ uint32_t sh[8 * kRsBins];
+    rs_hist_begin(sh);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) rs_hist_add(sh, keys[i], first_bit, npasses);
+    rs_hist_end(sh, hist, npasses);
 }
 
 // in place: hist[pass][*] -> exclusive prefix sums
@@ -182,38 +190,57 @@ struct RadixSortWorkspace {
 inline uint64_t rs_num_tiles(uint64_t n) { return (n + kRsTile - 1) / kRsTile; }
 inline size_t rs_workspace_bytes(uint64_t n) { return 8 * kRsBins * 4 + 8 * rs_num_tiles(n) * kRsBins * 4 + 8 * 4; }
 
-// Sorts n (key,value) pairs by the low `npasses`*8 key bits.  keys/vals ping-pong between the two buffers; returns
-// the index (0/1) of the buffer pair holding the sorted result.  ws = rs_workspace_bytes(n) bytes of device memory.
-// launches: number of kernels launched is added to *launches.
-inline int radix_sort_pairs(uint64_t* keys[2], uint32_t* vals[2], uint64_t n, int npasses, void* ws, cudaStream_t stream, uint64_t* launches) {
+inline void rs_set_attributes() {
+    // (per device: a process may drive several GPUs)
+    static bool attr_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        cudaFuncSetAttribute(rs_onesweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsSmemBytes);
+        cudaFuncSetAttribute(rs_onesweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsSmemBytes);
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+}
+
+// Zeroes the workspace (histograms, look-back words, tile counters).  Call before the digit histograms are accumulated.
+inline void rs_begin(void* ws, uint64_t n, cudaStream_t stream) { cudaMemsetAsync(ws, 0, rs_workspace_bytes(n), stream); }
+inline uint32_t* rs_hist_of(void* ws) { return reinterpret_cast<uint32_t*>(ws); }
+
+// The sorting passes over key bits [first_bit, first_bit + 8 npasses), given the digit histograms in the workspace (rs_histogram_kernel, or
+// the kernel that produced the keys).  vals[0] == nullptr: keys only.  Returns the index (0/1) of the buffers holding the result.
+inline int rs_sort_passes(uint64_t* keys[2], uint32_t* vals[2], uint64_t n, int first_bit, int npasses, void* ws, cudaStream_t stream, uint64_t* launches) {
     if (n == 0) return 0;
     const uint64_t ntiles = rs_num_tiles(n);
     uint32_t* hist = reinterpret_cast<uint32_t*>(ws);
     uint32_t* lookback = hist + 8 * kRsBins;
     uint32_t* counters = lookback + 8 * ntiles * kRsBins;
-    cudaMemsetAsync(ws, 0, rs_workspace_bytes(n), stream);
-    const uint64_t hblocks = (n + 255) / 256;
-    const int hgrid = (int)(hblocks < 148 * 8 ? hblocks : 148 * 8);
-    rs_histogram_kernel<<<hgrid, 256, 0, stream>>>(keys[0], n, hist, npasses);
     rs_scan_kernel<<<npasses, kRsBins, 0, stream>>>(hist);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(rs_onesweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsSmemBytes);
-        cudaFuncSetAttribute(rs_onesweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRsSmemBytes);
-        attr_set = true;
-    }
+    rs_set_attributes();
     int cur = 0;
     for (int p = 0; p < npasses; ++p) {
-        if (vals[0])
-            rs_onesweep_kernel<true><<<(unsigned)ntiles, kRsThreads, kRsSmemBytes, stream>>>(keys[cur], keys[cur ^ 1], vals[cur], vals[cur ^ 1], n, p * kRsBits,
+        if (vals && vals[0])
+            rs_onesweep_kernel<true><<<(unsigned)ntiles, kRsThreads, kRsSmemBytes, stream>>>(keys[cur], keys[cur ^ 1], vals[cur], vals[cur ^ 1], n, first_bit + p * kRsBits,
                                                                                          hist + p * kRsBins, lookback + (uint64_t)p * ntiles * kRsBins, counters + p);
         else
-            rs_onesweep_kernel<false><<<(unsigned)ntiles, kRsThreads, kRsSmemBytes, stream>>>(keys[cur], keys[cur ^ 1], nullptr, nullptr, n, p * kRsBits,
+            rs_onesweep_kernel<false><<<(unsigned)ntiles, kRsThreads, kRsSmemBytes, stream>>>(keys[cur], keys[cur ^ 1], nullptr, nullptr, n, first_bit + p * kRsBits,
                                                                                           hist + p * kRsBins, lookback + (uint64_t)p * ntiles * kRsBins, counters + p);
         cur ^= 1;
     }
-    if (launches) *launches += 2 + npasses;
+    if (launches) *launches += 1 + npasses;
     return cur;
+}
+
+// Sorts n (key,value) pairs by the low `npasses`*8 key bits.  keys/vals ping-pong between the two buffers; returns
+// the index (0/1) of the buffer pair holding the sorted result.  ws = rs_workspace_bytes(n) bytes of device memory.
+// launches: number of kernels launched is added to *launches.
+inline int radix_sort_pairs(uint64_t* keys[2], uint32_t* vals[2], uint64_t n, int npasses, void* ws, cudaStream_t stream, uint64_t* launches) {
+    if (n == 0) return 0;
+    rs_begin(ws, n, stream);
+    const uint64_t hblocks = (n + 255) / 256;
+    const int hgrid = (int)(hblocks < 148 * 8 ? hblocks : 148 * 8);
+    rs_histogram_kernel<<<hgrid, 256, 0, stream>>>(keys[0], n, rs_hist_of(ws), 0, npasses);
+    if (launches) *launches += 1;
+    return rs_sort_passes(keys, vals, n, 0, npasses, ws, stream, launches);
 }
 
 }  // namespace b2

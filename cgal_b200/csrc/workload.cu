@@ -69,6 +69,16 @@ __global__ void __launch_bounds__(256) checksum_kernel(const uint64_t* __restric
     if ((threadIdx.x & 31) == 0) { atomicAdd(&sums[0], s0); atomicAdd(&sums[1], s1); }
 }
 
+// FP64 pipe microbenchmark: 8 independent DFMA chains per thread (SURVEY.md §8d asks for the measured FP64 peak next to the traversal's FP64 share)
+__global__ void __launch_bounds__(256) dfma_kernel(double* __restrict__ out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
 unsigned grid_for(uint64_t n) { const uint64_t b = (n + 255) / 256; return (unsigned)(b < 148ull * 16 ? (b ? b : 1) : 148ull * 16); }
 
 }  // namespace
@@ -94,6 +104,28 @@ int b200work_pinhole_rays(int device, void* cuda_stream, const double camera[13]
     const uint64_t n = (uint64_t)nrows * width;
     pinhole_rays_kernel<<<grid_for(n), 256, 0, (cudaStream_t)cuda_stream>>>(c, width, height, row0, n, out);
     return cudaGetLastError() == cudaSuccess ? B200AABB_OK : B200AABB_ERR_CUDA;
+}
+
+int b200work_dfma_tflops(int device, double* tflops) {
+    if (!tflops) return B200AABB_ERR_INVALID_ARGUMENT;
+    if (cudaSetDevice(device) != cudaSuccess) return B200AABB_ERR_NO_DEVICE;
+    const int blocks = 148 * 8, iters = 1 << 14;
+    double* d = nullptr;
+    if (cudaMalloc(&d, (size_t)blocks * 256 * 8) != cudaSuccess) return B200AABB_ERR_OUT_OF_MEMORY;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        dfma_kernel<<<blocks, 256>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return B200AABB_ERR_CUDA; }
+        float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && (best == 0 || ms < best)) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d);
+    *tflops = 2.0 * 8.0 * (double)iters * blocks * 256 / (best * 1e-3) / 1e12;
+    return B200AABB_OK;
 }
 
 int b200work_checksum128(int device, void* cuda_stream, const void* data, uint64_t nbytes, uint64_t index0, uint64_t sum[2]) {

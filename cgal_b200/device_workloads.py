@@ -21,6 +21,7 @@ def _lib():
         L.b200work_bbox_points.argtypes = [C.c_int, vp, C.POINTER(C.c_double), u32, u64, u64, vp]
         L.b200work_pinhole_rays.argtypes = [C.c_int, vp, C.POINTER(C.c_double), u32, u32, u32, u32, vp]
         L.b200work_checksum128.argtypes = [C.c_int, vp, vp, u64, u64, C.POINTER(u64)]
+        L.b200work_dfma_tflops.argtypes = [C.c_int, C.POINTER(C.c_double)]
         _BOUND = True
     return L
 
@@ -85,6 +86,15 @@ def checksum128(t, index0=0):
     if rc:
         raise B200AABBError(rc)
     return int(s[0]), int(s[1])
+
+
+def dfma_tflops(device=0):
+    """measured FP64 FMA peak of the device, TFLOP/s"""
+    v = C.c_double()
+    rc = _lib().b200work_dfma_tflops(int(device), C.byref(v))
+    if rc:
+        raise B200AABBError(rc)
+    return v.value
 
 
 def _mix64(x):

@@ -206,9 +206,21 @@ class AABB_tree {
     first_intersected_primitive(&query, &query + 1, &r);
     return r;
   }
-  // a host functor cannot run inside the traversal kernel: only the trivial skip of the one-argument overload is offloaded
+  // first_intersection(query, skip) / first_intersected_primitive(query, skip), AABB_tree.h:307-354.  A host functor cannot run inside the
+  // traversal kernel, so it is evaluated ONCE PER PRIMITIVE on the host and travels as a bit mask (b200aabb_first_intersection_skip):
+  // O(size()) functor calls per call of this overload — batch the rays (first_intersection_skip below) where that matters.
   template <typename SkipFunctor>
-  Ray_intersection first_intersection(const Ray&, const SkipFunctor&) const { throw Error(B200AABB_ERR_INVALID_ARGUMENT, "first_intersection with a skip functor is not offloaded"); }
+  Ray_intersection first_intersection(const Ray& query, const SkipFunctor& skip) const {
+    Ray_intersection r;
+    first_intersection_skip(&query, &query + 1, &r, skip);
+    return r;
+  }
+  template <typename SkipFunctor>
+  std::optional<Primitive_id> first_intersected_primitive(const Ray& query, const SkipFunctor& skip) const {
+    const Ray_intersection r = first_intersection(query, skip);
+    if (r) return r->second;
+    return std::nullopt;
+  }
 
   // ---- distance queries, one query per call (AABB_tree.h:363-377,464-477,987-1055)
   FT squared_distance(const Point& query) const {
@@ -338,6 +350,29 @@ class AABB_tree {
   // out receives std::optional< Intersection_and_primitive_id<Ray>::Type >; flags (optional) receives the B200AABB_FLAG_* bits
   template <typename RayIterator, typename OutputIterator>
   OutputIterator first_intersection(RayIterator first, RayIterator beyond, OutputIterator out, std::vector<uint8_t>* flags = nullptr) const {
+    return first_intersection_masked(first, beyond, out, std::vector<uint32_t>(), flags);
+  }
+  // the same with the reference's skip functor (AABB_tree.h:307-328), evaluated once per primitive
+  template <typename RayIterator, typename OutputIterator, typename SkipFunctor>
+  OutputIterator first_intersection_skip(RayIterator first, RayIterator beyond, OutputIterator out, const SkipFunctor& skip, std::vector<uint8_t>* flags = nullptr) const {
+    std::vector<uint32_t> mask((m_primitives.size() + 31) / 32 + 1, 0u);
+    for (std::size_t k = 0; k < m_primitives.size(); ++k)
+      if (skip(m_primitives[k].id())) mask[k >> 5] |= 1u << (k & 31);
+    return first_intersection_masked(first, beyond, out, mask, flags);
+  }
+  // PMP::max_distance_to_mesh's inner loop (Polygon_mesh_processing/distance.h:98-190): the largest distance from the points of [first, beyond) to the primitives
+  template <typename PointIterator>
+  double max_distance_to_mesh(PointIterator first, PointIterator beyond) const {
+    std::vector<double> q = pack_points(first, beyond);
+    ensure_built();
+    double d = 0;
+    check(b200aabb_max_distance_to_mesh(m_handle, q.data(), q.size() / 3, B200AABB_HOST, &d, nullptr));
+    return d;
+  }
+
+ private:
+  template <typename RayIterator, typename OutputIterator>
+  OutputIterator first_intersection_masked(RayIterator first, RayIterator beyond, OutputIterator out, const std::vector<uint32_t>& mask, std::vector<uint8_t>* flags) const {
     typedef typename Intersection_and_primitive_id<Ray>::Type Result;
     typedef typename Result::first_type Intersection;
     std::vector<double> q = pack_lines(first, beyond);
@@ -346,7 +381,8 @@ class AABB_tree {
     std::vector<double> p0(3 * n), p1(3 * n);
     std::vector<uint8_t> fl(n);
     ensure_built();
-    check(b200aabb_first_intersection(m_handle, q.data(), n, B200AABB_HOST, prim.data(), nullptr, p0.data(), p1.data(), fl.data()));
+    check(b200aabb_first_intersection_skip(m_handle, q.data(), n, B200AABB_HOST, nullptr, mask.empty() ? nullptr : mask.data(), (uint32_t)mask.size(), prim.data(), nullptr,
+                                           p0.data(), p1.data(), fl.data()));
     for (uint64_t i = 0; i < n; ++i) {
       if (!(fl[i] & B200AABB_FLAG_HIT)) { *out++ = std::nullopt; continue; }
       const Point a(FT(p0[3 * i]), FT(p0[3 * i + 1]), FT(p0[3 * i + 2]));
@@ -360,6 +396,8 @@ class AABB_tree {
     if (flags) flags->swap(fl);
     return out;
   }
+
+ public:
   // out receives std::optional<Primitive_id>
   template <typename RayIterator, typename OutputIterator>
   OutputIterator first_intersected_primitive(RayIterator first, RayIterator beyond, OutputIterator out) const {

@@ -51,8 +51,8 @@ enum {
                                       the reference's id then depends on its traversal order;
                                       this library reports the smallest primitive id among them */
   B200AABB_FLAG_EXACT = 8,         /* at least one predicate of this query needed the exact (expansion) stage */
-  B200AABB_FLAG_NEAR_TIE = 16      /* first_intersection only: not an exact tie, but the runner-up's t lies within the ROUNDING UNCERTAINTY of the
-                                      winner's (the plain-double hit construction; large for a ray grazing a triangle).  The reference compares
+  B200AABB_FLAG_NEAR_TIE = 16      /* first_intersection only: a primitive with a LARGER rounded t lies within the ROUNDING UNCERTAINTY of the
+                                      winner's (the plain-double hit construction; large for a ray grazing a triangle; independent of FLAG_TIE).  The reference compares
                                       the same rounded values while pruning boxes with an inexact test (AABB_traits_3.h:89-125;
                                       AABB_ray_intersection.h:78), so in this band its own answer depends on the order in which its tree presents
                                       the candidates; this library reports the smallest rounded value.  closest_point never sets it: there the
@@ -67,9 +67,12 @@ enum {
                                       (slot,node)/(slot,leaf) pairs, closest_warp.cuh); 2 = lane pairs walk the tree with private stacks
                                       (closest_pair.cuh; measured slower on the benchmark, kept as the reference point of that design);
                                       0 = one thread per query.  Same results. */
-  B200AABB_OPT_HOST_PARTS = 5,     /* HOST-pointer batches are cut into about this many chunks (each 256 Ki .. 4 Mi queries) that flow through a
-                                      double-buffered upload -> sort -> traverse -> download pipeline (1..64; 0 = default: 6 for ray / segment
-                                      batches, 2 for point batches) */
+  B200AABB_OPT_HOST_PARTS = 5,     /* HOST-pointer batches are cut into about this many chunks (each 256 Ki .. 4 Mi rays / segments, .. 16 Mi points) that flow
+                                      through an upload -> sort -> traverse -> download pipeline (1..64; 0 = default: 8 for ray / segment batches on
+                                      four streams; 1 for point batches — a point batch is sorted into ONE coherence order — on two streams of their own) */
+  B200AABB_OPT_ASYNC_HOST = 6,     /* 1: batched queries with HOST pointers return as soon as their chunks are enqueued (uploads, kernels and downloads of
+                                      consecutive calls then overlap across calls); the caller keeps the query / result buffers alive and unread until
+                                      b200aabb_synchronize.  0 (default): every call returns with its results in place. */
   B200AABB_OPT_WARP_EXACT_GO = 4   /* warp-cooperative kernels: run the binary64 phase once this many pre-test survivors wait (1..160; 0 = the kernel's default) */
 };
 
@@ -96,6 +99,9 @@ int b200aabb_set_stream(b200aabb_tree* t, void* cuda_stream);
 int b200aabb_set_option(b200aabb_tree* t, int option, int64_t value);
 const char* b200aabb_last_error(const b200aabb_tree* t);
 int b200aabb_get_stats(const b200aabb_tree* t, b200aabb_stats* out);
+/* waits for every batch in flight on the handle (B200AABB_OPT_ASYNC_HOST, DEVICE-pointer batches) and returns B200AABB_ERR_INCOMPLETE /
+ * INVALID_ARGUMENT if one of them reported it; the per-batch statistics of asynchronous batches are not kept apart */
+int b200aabb_synchronize(b200aabb_tree* t);
 
 /* ---- primitives ---------------------------------------------------------------------------------------------- */
 /* insert(faces(m).first, faces(m).second, m), AABB_tree.h:730-747, for a triangle Surface_mesh: vertex coordinates
@@ -110,6 +116,13 @@ int b200aabb_set_triangles(b200aabb_tree* t, const double* triangles, const uint
 int b200aabb_clear(b200aabb_tree* t);
 /* build() / custom_build(), AABB_tree.h:820-853: LBVH (63-bit Morton, onesweep radix sort, Karras, atomic refit). */
 int b200aabb_build(b200aabb_tree* t);
+/* Deforming meshes: the reference's rebuild(first, beyond) (AABB_tree.h:167,752) is clear + insert + build.  When the
+ * primitives only MOVE (same number, same order, same ids) the hierarchy can be kept: these calls replace the coordinates and recompute every
+ * box bottom-up over the existing topology (no sort, no hierarchy pass).  Query results are those of a fresh build — they never depend on the
+ * tree (exact leaf decisions, smallest-id tie rule) — only the traversal cost grows as the primitives drift from their Morton order.
+ * b200aabb_refit: triangles = n x 9 doubles in the inserted order (HOST or DEVICE); b200aabb_refit_mesh: as b200aabb_set_mesh (host pointers). */
+int b200aabb_refit(b200aabb_tree* t, const double* triangles, uint64_t n, b200aabb_memspace space);
+int b200aabb_refit_mesh(b200aabb_tree* t, const double* vertices, uint64_t nv, const uint32_t* faces, uint64_t nf);
 /* accelerate_distance_queries(), AABB_tree.h:896-901.  The kd-tree hint is replaced by a BVH-derived bound (nearest
  * child first descent), so this only builds the tree if needed and returns OK. */
 int b200aabb_accelerate_distance_queries(b200aabb_tree* t);
@@ -155,6 +168,14 @@ int b200aabb_any_intersection(b200aabb_tree* t, const double* rays, uint64_t n, 
  * point2[n x 3] = second endpoint when FLAG_SEGMENT; flags[n]. */
 int b200aabb_first_intersection(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space,
                                 uint32_t* prim, double* tparam, double* point, double* point2, uint8_t* flags);
+/* first_intersection(query, skip) / first_intersected_primitive(query, skip), AABB_tree.h:307-354 (the skip functor is consulted at every
+ * primitive, internal/AABB_ray_intersection.h:86,99,113): primitives the functor rejects are ignored.  A device kernel can not call the caller's
+ * functor, so it is passed as data: skip_ids[n] = ONE primitive id per ray to ignore (B200AABB_NO_PRIMITIVE = none; the usual "the face
+ * the ray starts on"), and / or skip_mask = one bit per primitive id (bit id & 31 of word id >> 5; mask_words words) for an arbitrary
+ * predicate evaluated once per primitive.  Either may be NULL.  Pointers live in `space` like the rays. */
+int b200aabb_first_intersection_skip(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, const uint32_t* skip_ids,
+                                     const uint32_t* skip_mask, uint32_t mask_words, uint32_t* prim, double* tparam, double* point, double* point2,
+                                     uint8_t* flags);
 /* closest_point_and_primitive / closest_point / squared_distance (Point_3), AABB_tree.h:987-1055.
  * points: n x 3.  Outputs (any may be NULL): closest[n x 3], prim[n], sqdist[n], flags[n]. */
 int b200aabb_closest_point(b200aabb_tree* t, const double* points, uint64_t n, b200aabb_memspace space,
@@ -167,6 +188,14 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* points, uint64_t n, b
 int b200aabb_export_layout(b200aabb_tree* t, void** ptrs, uint64_t* bytes, int cap, int* count);
 int b200aabb_import_alloc(b200aabb_tree* t, uint64_t n);
 int b200aabb_import_finish(b200aabb_tree* t);
+
+/* ---- consumers of the query path ----------------------------------------------------------------
+ * Polygon_mesh_processing::max_distance_to_mesh / approximate_Hausdorff_distance's inner loop
+ * (Polygon_mesh_processing/include/CGAL/Polygon_mesh_processing/distance.h:98-190, max_distance_to_mesh_impl): the largest distance from the
+ * sample points to the tree's primitives = sqrt of the largest squared_distance(closest_point(p), p).  The reference chains each
+ * query's result as the next query's hint (:133,180); a hint only decides exact ties, never the distance, so the value is the same.
+ * *max_distance = that distance; *farthest (optional) = index of the first sample attaining it.  points: n x 3, HOST or DEVICE. */
+int b200aabb_max_distance_to_mesh(b200aabb_tree* t, const double* points, uint64_t n, b200aabb_memspace space, double* max_distance, uint64_t* farthest);
 
 /* ---- multi-GPU behind the boundary --------------------------------------------------------------------
  * The reference has no multi-device path: its callers shard queries over threads (tbb::parallel_for,

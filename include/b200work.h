@@ -28,6 +28,9 @@ int b200work_pinhole_rays(int device, void* cuda_stream, const double camera[13]
  * checksums of the shards of a batch add up to the checksum of the whole batch.  Synchronises the stream; sum is a HOST pointer. */
 int b200work_checksum128(int device, void* cuda_stream, const void* data, uint64_t nbytes, uint64_t index0, uint64_t sum[2]);
 
+/* FP64 pipe microbenchmark (8 independent DFMA chains per thread, 148 x 8 blocks): the measured peak in TFLOP/s (2 flops per DFMA). */
+int b200work_dfma_tflops(int device, double* tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,16 +13,17 @@ namespace orc { thread_local Stats g_stats; }
 using namespace orc;
 
 namespace {
+std::atomic<uint64_t> g_box_tests{0}, g_prim_tests{0};   // traversal work of the batched queries, summed over the worker threads
 struct Handle { Mesh mesh; std::unique_ptr<Tree> tree; double build_seconds = 0, kd_seconds = 0; };
 
 template <class F> void parallel_for(uint64_t n, int nthreads, F f) {
-    if (nthreads <= 1 || n < 1024) { f(0, n); return; }
+    if (nthreads <= 1 || n < 1024) { const Stats s0 = g_stats; f(0, n); g_box_tests += g_stats.box_tests - s0.box_tests; g_prim_tests += g_stats.prim_tests - s0.prim_tests; return; }
     std::vector<std::thread> th;
     const uint64_t chunk = (n + nthreads - 1) / nthreads;      // static blocked ranges over queries, standing in for
     for (int t = 0; t < nthreads; ++t) {                        // tbb::parallel_for (Polygon_mesh_processing/distance.h:163-169)
         uint64_t b = t * chunk, e = std::min<uint64_t>(n, b + chunk);
         if (b >= e) break;
-        th.emplace_back([=] { f(b, e); });
+        th.emplace_back([=] { const Stats s0 = g_stats; f(b, e); g_box_tests += g_stats.box_tests - s0.box_tests; g_prim_tests += g_stats.prim_tests - s0.prim_tests; });
     }
     for (auto& x : th) x.join();
 }
@@ -147,6 +148,20 @@ void orc_first_intersection(void* hv, const double* rays, uint64_t n, uint32_t* 
         }
     });
 }
+// first_intersection(Ray_3, skip): skip = one primitive id per ray (0xFFFFFFFF: none) and / or a bit mask over primitive ids
+void orc_first_intersection_skip(void* hv, const double* rays, uint64_t n, const uint32_t* skip_ids, const uint32_t* mask, uint32_t mask_words, uint32_t* prim, double* tpar,
+                                 int nthreads) {
+    const Tree& t = *((Handle*)hv)->tree;
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e) {
+        for (uint64_t i = b; i < e; ++i) {
+            const uint32_t sid = skip_ids ? skip_ids[i] : 0xFFFFFFFFu;
+            auto h = t.first_intersection(P(rays + 6 * i), P(rays + 6 * i + 3),
+                                          [&](uint32_t f) { return f == sid || (mask && (f >> 5) < mask_words && ((mask[f >> 5] >> (f & 31u)) & 1u)); });
+            prim[i] = h.prim;
+            tpar[i] = h.hit ? h.t : 0.0;
+        }
+    });
+}
 // closest_point_and_primitive(Point_3) (+ squared_distance).  Tree must be non-empty (CGAL_precondition(!empty())).
 int orc_closest_point(void* hv, const double* q, uint64_t n, double* cp, uint32_t* prim, double* sqd, int nthreads) {
     const Tree& t = *((Handle*)hv)->tree;
@@ -246,6 +261,8 @@ int orc_intersection_distance(const double* ray, const double* box, double* t) {
     return d ? 1 : 0;
 }
 void orc_stats(uint64_t* out) { out[0] = g_stats.orient_calls; out[1] = g_stats.orient_exact; out[2] = g_stats.cmpdist_calls; out[3] = g_stats.cmpdist_exact; out[4] = g_stats.bbox_exact; }
+// child boxes / primitives tested by the batched queries since the last call (all threads)
+void orc_traversal_totals(uint64_t* out) { out[0] = g_box_tests.exchange(0); out[1] = g_prim_tests.exchange(0); }
 int orc_hardware_concurrency() { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"

@@ -42,7 +42,8 @@ static inline double sqdist(const P3& p, const P3& q) {
 struct Tri { P3 a, b, c; };      // Triangle_3(v0, v1, v2) in Surface_mesh/OFF order
 struct Box { double lo[3], hi[3]; };  // Bbox_3
 
-struct Stats { uint64_t orient_calls = 0, orient_exact = 0, cmpdist_calls = 0, cmpdist_exact = 0, bbox_exact = 0; };
+struct Stats { uint64_t orient_calls = 0, orient_exact = 0, cmpdist_calls = 0, cmpdist_exact = 0, bbox_exact = 0;
+               uint64_t box_tests = 0, prim_tests = 0; };   // traversal work: child boxes tested, primitives tested (SURVEY.md §8d asks for them next to the GPU's)
 extern thread_local Stats g_stats;
 
 // ------------------------------------------------------------------------------------------------

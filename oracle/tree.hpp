@@ -171,22 +171,24 @@ struct Tree {
     }
 
     // AABB_node::traversal: internal/AABB_node.h:129-167 ; AABB_tree::traversal: AABB_tree.h:513-526
+    template <class Q, class TT> static bool box_test(TT& tt, const Q& q, const Box& b) { ++g_stats.box_tests; return tt.do_intersect(q, b); }
+    template <class Q, class TT> static void prim_test(TT& tt, const Q& q, uint32_t f) { ++g_stats.prim_tests; tt.intersection(q, f); }
     template <class Q, class TT> void traverse_node(int n, const Q& q, TT& tt, size_t nb) const {
         const Node& nd = nodes[n];
         switch (nb) {
         case 2:
-            tt.intersection(q, prims[nd.left]);
-            if (tt.go_further()) tt.intersection(q, prims[nd.right]);
+            prim_test(tt, q, prims[nd.left]);
+            if (tt.go_further()) prim_test(tt, q, prims[nd.right]);
             break;
         case 3:
-            tt.intersection(q, prims[nd.left]);
-            if (tt.go_further() && tt.do_intersect(q, nodes[nd.right].bbox)) traverse_node(nd.right, q, tt, 2);
+            prim_test(tt, q, prims[nd.left]);
+            if (tt.go_further() && box_test(tt, q, nodes[nd.right].bbox)) traverse_node(nd.right, q, tt, 2);
             break;
         default:
-            if (tt.do_intersect(q, nodes[nd.left].bbox)) {
+            if (box_test(tt, q, nodes[nd.left].bbox)) {
                 traverse_node(nd.left, q, tt, nb / 2);
-                if (tt.go_further() && tt.do_intersect(q, nodes[nd.right].bbox)) traverse_node(nd.right, q, tt, nb - nb / 2);
-            } else if (tt.do_intersect(q, nodes[nd.right].bbox)) {
+                if (tt.go_further() && box_test(tt, q, nodes[nd.right].bbox)) traverse_node(nd.right, q, tt, nb - nb / 2);
+            } else if (box_test(tt, q, nodes[nd.right].bbox)) {
                 traverse_node(nd.right, q, tt, nb - nb / 2);
             }
         }
@@ -194,7 +196,7 @@ struct Tree {
     template <class Q, class TT> void traversal(const Q& q, TT& tt) const {
         switch (size()) {
         case 0: break;
-        case 1: tt.intersection(q, prims[0]); break;
+        case 1: prim_test(tt, q, prims[0]); break;
         default: traverse_node(0, q, tt, size());
         }
     }
@@ -280,11 +282,16 @@ struct Tree {
         if (r.kind == 2) return std::min(ray_param(s, v, max_i, r.pt[0]), ray_param(s, v, max_i, r.pt[1]));   // :178-187
         return ray_param(s, v, max_i, r.pt[0]);
     }
-    FirstHit first_intersection(const P3& s, const P3& q) const {
+    FirstHit first_intersection(const P3& s, const P3& q) const { return first_intersection(s, q, [](uint32_t) { return false; }); }
+    // first_intersection(query, skip): AABB_tree.h:307-328, internal/AABB_ray_intersection.h:201-225 (skip is consulted at every primitive
+    // of a tree of two or more, :86,99,113; a one-primitive tree is answered directly, :214)
+    template <class Skip> FirstHit first_intersection(const P3& s, const P3& q, Skip skip) const {
         FirstHit best;
         const V3 v = vsub(q, s);
         const int max_i = ray_max_axis(v);
         auto leaf = [&](uint32_t f, double& t) {
+            if (skip(f)) return;
+            ++g_stats.prim_tests;
             RayHit r = ray_tri_intersection(mesh->datum(f), s, q);
             if (r.kind) {
                 const double d = hit_param(s, v, max_i, r);
@@ -312,11 +319,13 @@ struct Tree {
             case 2: leaf(prims[nd.left], t); leaf(prims[nd.right], t); break;
             case 3: {
                 leaf(prims[nd.left], t);
+                ++g_stats.box_tests;
                 auto d = intersection_distance(s, v, nodes[nd.right].bbox);
                 if (d) pq.push({nd.right, 2, *d});
                 break;
             }
             default: {
+                g_stats.box_tests += 2;
                 auto d = intersection_distance(s, v, nodes[nd.left].bbox);
                 if (d) pq.push({nd.left, cur.nb / 2, *d});
                 d = intersection_distance(s, v, nodes[nd.right].bbox);

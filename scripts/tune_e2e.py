@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""GPU-side sweep of the HOST-pointer pipeline (chunk count) on the benchmark batch + raw pinned-copy bandwidth.  Not a bench value."""
+"""GPU-side look at the HOST-pointer pipeline on the benchmark batch: asynchronous steps (B200AABB_OPT_ASYNC_HOST) over chunk counts, and —
+with B200AABB_PIPE_TRACE=1 — the per-chunk timeline (upload / kernels / download) the library prints at b200aabb_synchronize.
+Not a bench value."""
 import os
 import sys
 import time
@@ -13,47 +15,43 @@ sys.path.insert(0, ROOT)
 def main():
     import torch
     import cgal_b200 as B
+    from cgal_b200 import device_workloads as D
     from cgal_b200 import workloads as W
-    import bench
     v, f = W.terrain(4096, 2048)
     g = B.AABB_tree(v, f)
     g.set_stream(torch.cuda.current_stream().cuda_stream)
     g.build()
     n = 1 << 23
-    rays_h = bench.shard_rays(0)
-    pts_h = W.bbox_points(g.bbox(), n)
+    rays_d = torch.empty((n, 6), dtype=torch.float64, device="cuda")
+    cam = D.pinhole_camera(4096, 2048)
+    for j in range(1024):
+        D.pinhole_rays(cam, 8192, 8192, j * 8, 1, rays_d[j * 8192:(j + 1) * 8192])
+    pts_d = torch.empty((n, 3), dtype=torch.float64, device="cuda")
+    D.bbox_points(g.bbox(), n, pts_d)
 
     def pinned(shape, dtype):
         return torch.empty(shape, dtype=dtype, pin_memory=True).numpy()
     rays_p, pts_p = pinned((n, 6), torch.float64), pinned((n, 3), torch.float64)
-    rays_p[:], pts_p[:] = rays_h, pts_h
+    rays_p[:], pts_p[:] = rays_d.cpu().numpy(), pts_d.cpu().numpy()
     out_r = {"prim": pinned(n, torch.int32).view(np.uint32), "t": pinned(n, torch.float64), "point": pinned((n, 3), torch.float64), "flags": pinned(n, torch.uint8)}
     out_p = {"point": pinned((n, 3), torch.float64), "prim": pinned(n, torch.int32).view(np.uint32), "sqdist": pinned(n, torch.float64), "flags": pinned(n, torch.uint8)}
-    # raw copy bandwidth
-    d = torch.empty(n * 6, dtype=torch.float64, device="cuda")
-    src = torch.from_numpy(rays_p.reshape(-1))
-    for name, fn in (("H2D", lambda: d.copy_(src, non_blocking=True)), ("D2H", lambda: src.copy_(d, non_blocking=True))):
-        fn(); torch.cuda.synchronize()
+    want_r, want_p = ("prim", "t", "point", "flags"), ("point", "prim", "sqdist", "flags")
+    steps = int(os.environ.get("STEPS", "4"))
+    g.set_option(B.OPT_ASYNC_HOST, 1)
+    for rparts, pparts in [(8, 4)] if os.environ.get("B200AABB_PIPE_TRACE") else [(8, 4), (4, 2), (8, 8), (16, 4), (16, 8), (6, 3)]:
+        def step():
+            g.set_option(B.OPT_HOST_PARTS, rparts)
+            g.first_intersection(rays_p, want=want_r, out=out_r)
+            g.set_option(B.OPT_HOST_PARTS, pparts)
+            g.closest_point_and_primitive(pts_p, want=want_p, out=out_p)
+        step()
+        g.synchronize()
         t0 = time.perf_counter()
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        print("%s pinned: %.1f GB/s" % (name, 3 * n * 48 / (time.perf_counter() - t0) / 1e9), flush=True)
-    rays_p[:] = rays_h
-    for parts in (2, 3, 6, 12):
-        g.set_option(B.OPT_HOST_PARTS, parts)
-        for which in ("rays", "points"):
-            def step():
-                if which == "rays":
-                    g.first_intersection(rays_p, want=("prim", "t", "point", "flags"), out=out_r)
-                else:
-                    g.closest_point_and_primitive(pts_p, want=("point", "prim", "sqdist", "flags"), out=out_p)
+        for _ in range(steps):
             step()
-            t0 = time.perf_counter()
-            for _ in range(3):
-                step()
-            ms = (time.perf_counter() - t0) / 3 * 1e3
-            print("parts=%2d %-6s %.2f ms  (%.0f Mq/s)" % (parts, which, ms, n / ms / 1e3), flush=True)
+        g.synchronize()
+        ms = (time.perf_counter() - t0) / steps * 1e3
+        print("ray chunks %2d point chunks %2d: %.2f ms per step (%.0f Mq/s)" % (rparts, pparts, ms, 2 * n / ms / 1e3), flush=True)
 
 
 if __name__ == "__main__":

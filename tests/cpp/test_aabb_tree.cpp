@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <variant>
+#include <thread>
 #include <vector>
 
 #include "../../include/CGAL_B200/AABB_tree.h"
@@ -173,6 +174,39 @@ static int known_answers() {
       CHECK(c1.first == cp[i].first && c1.second == cp[i].second && tree.squared_distance(pts[i]) == sd[i]);
     }
     CHECK(nhit > 50 && flags.size() == rays.size());
+    // first_intersection(ray, skip) (AABB_tree.h:307-328): skipping the first hit's face gives a later (or no) hit; skipping nothing changes nothing
+    int nskip = 0;
+    for (size_t i = 0; i < rays.size() && nskip < 40; ++i) {
+      if (!fi[i]) continue;
+      const auto first_id = fi[i]->second;
+      const auto second = tree.first_intersection(rays[i], [&](const Tree::Primitive_id& id) { return id == first_id; });
+      CHECK(!second || second->second != first_id);
+      const auto same = tree.first_intersection(rays[i], [](const Tree::Primitive_id&) { return false; });
+      CHECK(same && same->second == first_id);
+      const auto prim = tree.first_intersected_primitive(rays[i], [&](const Tree::Primitive_id& id) { return id == first_id; });
+      CHECK(prim.has_value() == second.has_value());
+      ++nskip;
+    }
+    CHECK(nskip > 10);
+    // PMP::max_distance_to_mesh's inner loop: the largest of the per-point distances
+    double worst = 0;
+    for (double d2 : sd) worst = std::max(worst, std::sqrt(d2));
+    CHECK(tree.max_distance_to_mesh(pts.begin(), pts.end()) == worst);
+    // const queries from several host threads at once (the reference's callers run tbb::parallel_for over them): serialised per handle, same answers
+    std::vector<std::thread> th;
+    std::vector<int> ok(4, 0);
+    for (int k = 0; k < 4; ++k)
+      th.emplace_back([&, k] {
+        int good = 1;
+        for (size_t i = k; i < pts.size(); i += 4) {
+          const auto c1 = tree.closest_point_and_primitive(pts[i]);
+          good &= (c1.first == cp[i].first && c1.second == cp[i].second) ? 1 : 0;
+          good &= (tree.number_of_intersected_primitives(segs[i]) == cnt[i]) ? 1 : 0;
+        }
+        ok[k] = good;
+      });
+    for (auto& x : th) x.join();
+    CHECK(ok[0] && ok[1] && ok[2] && ok[3]);
   }
   std::printf("test_aabb_tree: all known-answer and consistency checks passed\n");
   return 0;

@@ -45,10 +45,14 @@ def check_first_intersection(gpu, ref, oracle_tree, rays, max_mismatch_frac=1e-4
     np.testing.assert_array_equal(gpu["t"][same], ref["t"][same])                 # bit-exact ray parameter
     np.testing.assert_array_equal(gpu["point"][same], ref["pts"][same][:, :3])    # bit-exact hit point
     assert np.all(same | tie | near), "id mismatch without a reported tie: %d" % int((~(same | tie | near)).sum())
-    assert (~same & ~tie).sum() <= max(2, max_mismatch_frac * len(same)), "too many near-tie mismatches"
+    # an id that differs on an EXACT tie carries the same t, bit for bit; only rows flagged NEAR_TIE (the runner-up lies inside the rounding
+    # uncertainty of the winner, where the reference's answer depends on its own traversal order) may differ in t, by at most that band
+    exact_rows = ~same & ~near
+    np.testing.assert_array_equal(gpu["t"][exact_rows], ref["t"][exact_rows])
+    assert (~same & near & ~tie).sum() <= max(2, max_mismatch_frac * len(same)), "too many near-tie mismatches"
     for i in np.nonzero(~same)[0][:300]:                                          # the reference id must be in the (near-)tie set
         k, t, _ = oracle_tree.candidate_ray_hit(ref["prim"][i], rays[i])
-        assert k and t == ref["t"][i] and abs(t - gpu["t"][i]) <= 1e-5 * abs(t)
+        assert k and t == ref["t"][i] and (abs(t - gpu["t"][i]) <= 1e-5 * abs(t) if near[i] else t == gpu["t"][i])
     return int((~same).sum()), int((tie | near).sum())
 
 

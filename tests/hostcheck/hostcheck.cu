@@ -53,16 +53,25 @@ void* hc_build(const double* tris, const uint32_t* ids, uint64_t n) {
         for (int k = 0; k < 3; ++k) { const double a = tris[9 * i + k], b = tris[9 * i + 3 + k], d = tris[9 * i + 6 + k]; c[k] = 0.5 * (fmin(a, fmin(b, d)) + fmax(a, fmax(b, d))); }
         keys[i] = morton63(c[0], c[1], c[2], lo, scale);
     }
+    // the build's sort words (build.cuh::pack_sort_word), with its fall-back to full (key, index) pairs when many primitives share their kept key bits
+    const int ib = index_bits_for(n);
+    std::vector<uint64_t> words(n);
+    for (uint64_t i = 0; i < n; ++i) words[i] = pack_sort_word(keys[i], i, ib);
     std::vector<uint32_t> perm(n);
     std::iota(perm.begin(), perm.end(), 0u);
-    std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+    std::sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return words[a] < words[b]; });
+    uint64_t dups = 0;
+    for (uint64_t k = 0; k + 3 < n; ++k) dups += (((words[perm[k]] ^ words[perm[k + 1]]) | (words[perm[k]] ^ words[perm[k + 2]]) | (words[perm[k]] ^ words[perm[k + 3]])) >> ib) == 0 ? 1 : 0;
+    const bool packed = dups <= n / 16;
+    if (!packed) { std::iota(perm.begin(), perm.end(), 0u); std::stable_sort(perm.begin(), perm.end(), [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; }); }
     h->keys.resize(n);
     h->tris.resize(n);
     for (uint64_t k = 0; k < n; ++k) {
-        h->keys[k] = keys[perm[k]];
+        h->keys[k] = packed ? words[perm[k]] : keys[perm[k]];
         TriRec r; memset(&r, 0, sizeof(r));
         memcpy(r.v, tris + 9 * (uint64_t)perm[k], 72);
         r.id = ids ? ids[perm[k]] : perm[k];
+        r.pad[0] = perm[k];
         h->tris[k] = r;
     }
     for (int a = 0; a < 3; ++a) { h->bbox[a] = lo[a]; h->bbox[3 + a] = hi[a]; }     // bbox() = the exact scene bounds

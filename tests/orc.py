@@ -50,6 +50,7 @@ def lib():
         L.orc_ray_intersections.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_int, _u32p, C.POINTER(C.c_uint64), _u32p, _u8p, _dp, C.c_int]
         L.orc_ray_intersections.restype = C.c_int
         L.orc_first_intersection.argtypes = [C.c_void_p, _dp, C.c_uint64, _u32p, _dp, _dp, _u8p, _u8p, C.c_int]
+        L.orc_first_intersection_skip.argtypes = [C.c_void_p, _dp, C.c_uint64, _u32p, _u32p, C.c_uint32, _u32p, _dp, C.c_int]
         L.orc_closest_point.argtypes = [C.c_void_p, _dp, C.c_uint64, _dp, _u32p, _dp, C.c_int]
         L.orc_closest_point.restype = C.c_int
         L.orc_naive_count.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_int, _u32p, C.c_int]
@@ -76,6 +77,13 @@ def lib():
 
 def _d(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def traversal_totals():
+    """(child boxes tested, primitives tested) by the batched oracle queries since the last call"""
+    out = np.zeros(2, np.uint64)
+    lib().orc_traversal_totals(out.ctypes.data_as(C.POINTER(C.c_uint64)))
+    return int(out[0]), int(out[1])
 
 
 def nthreads():
@@ -172,6 +180,21 @@ class OracleTree:
         lib().orc_first_intersection(self.h, _ptr(rays, _dp), n, _ptr(prim, _u32p), _ptr(t, _dp), _ptr(pts, _dp),
                                      _ptr(kind, _u8p), _ptr(tie, _u8p), threads or nthreads())
         return dict(prim=prim, t=t, pts=pts, kind=kind, tie=tie)
+
+    def first_intersection_skip(self, rays, skip_ids=None, skip_mask=None, threads=None):
+        rays = _d(rays).reshape(-1, 6)
+        n = len(rays)
+        prim, t = np.zeros(n, np.uint32), np.zeros(n)
+        ids = None if skip_ids is None else np.ascontiguousarray(skip_ids, dtype=np.uint32)
+        words, nw = None, 0
+        if skip_mask is not None:
+            bits = np.packbits(np.asarray(skip_mask, dtype=bool), bitorder="little")
+            bits = np.concatenate([bits, np.zeros((-len(bits)) % 4, np.uint8)])
+            words = np.ascontiguousarray(bits.view(np.uint32))
+            nw = len(words)
+        lib().orc_first_intersection_skip(self.h, _ptr(rays, _dp), n, None if ids is None else _ptr(ids, _u32p), None if words is None else _ptr(words, _u32p), nw,
+                                          _ptr(prim, _u32p), _ptr(t, _dp), threads or nthreads())
+        return dict(prim=prim, t=t)
 
     def naive_first_intersection(self, rays, threads=None):
         rays = _d(rays).reshape(-1, 6)

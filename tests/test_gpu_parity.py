@@ -128,6 +128,60 @@ def test_degenerate_tree_shapes(B):
     np.testing.assert_array_equal(g.number_of_intersected_primitives(segs, SEG), o.count(segs, SEG))
 
 
+def test_packed_and_full_key_builds(B, meshes):
+    """the build sorts PACKED words (top key bits | primitive index, build.cuh::pack_sort_word) and falls back to full 63-bit keys + values when
+    many primitives share their kept key bits: same tree on a mesh without such pairs; a crowded scene takes the fall-back; both equal
+    the host emulation"""
+    v, f = meshes["elephant"]
+    t = B.AABB_tree(v, f)
+    t.build()
+    (pn, bn) = t.export_layout()[0]
+    packed = device_to_host(pn, bn).view(np.uint32).reshape(-1, 16)[:, :15].copy()
+    t.set_option(102, 1)             # test hook: full keys
+    t.build()
+    (pn, bn) = t.export_layout()[0]
+    np.testing.assert_array_equal(device_to_host(pn, bn).view(np.uint32).reshape(-1, 16)[:, :15], packed)
+    # 60,000 triangles crowded into 1e-9 of the scene's extent + one far away: most neighbours agree in the kept key bits
+    rng = np.random.default_rng(3)
+    tri = rng.random((60000, 9)) * 1e-9
+    tri = np.concatenate([tri, [[1.0, 1.0, 1.0, 1.0, 1.1, 1.0, 1.1, 1.0, 1.0]]])
+    g = B.AABB_tree(triangles=tri)
+    g.build()
+    (pn, bn), (pt, bt) = g.export_layout()[:2]
+    assert hc.validate(device_to_host(pn, bn), device_to_host(pt, bt), len(tri)) == 0
+    h_nodes, h_tris, _ = hc.HostTree(tri).export()
+    np.testing.assert_array_equal(device_to_host(pt, bt), h_tris)
+    np.testing.assert_array_equal(device_to_host(pn, bn).view(np.uint32).reshape(-1, 16)[:, :15], h_nodes.view(np.uint32).reshape(-1, 16)[:, :15])
+    o = orc.OracleTree(soup=tri)
+    pts = rng.random((3000, 3)) * 2e-9
+    check_closest_point(g.closest_point_and_primitive(pts), o.closest_point(pts), o, pts)
+
+
+def test_chain_shaped_tree_depth(B):
+    """the deepest trees the builder can produce: Morton keys 2^k give one level per key bit (a 63-level chain), 4,096 coincident primitives
+    add 12 index levels below it; rays, segments and points equal the oracle and no traversal reports an overflow (closest_pair.cuh: depth
+    <= 94 by construction, stacks hold 96)"""
+    chain = np.zeros((63, 9))
+    for k in range(63):
+        c = np.zeros(3); c[2 - k % 3] = float(2 ** (k // 3))
+        chain[k] = np.tile(c, 3) + np.array([0, 0, 0, 0.25, 0, 0, 0, 0.25, 0])
+    top = np.tile(np.array([2.0 ** 21] * 3), 3) + np.array([0, 0, 0, 0.25, 0, 0, 0, 0.25, 0.0])
+    tri = np.concatenate([chain, top[None, :], np.tile(chain[:1], (4096, 1))])
+    g, o = B.AABB_tree(triangles=tri), orc.OracleTree(soup=tri)
+    rng = np.random.default_rng(4)
+    pts = np.concatenate([rng.uniform(-2, 40, (3000, 3)), rng.uniform(-2, 2.0 ** 21, (1000, 3))])
+    for kernel in (1, 2, 0):
+        g.set_option(B.OPT_CLOSEST_KERNEL, kernel)
+        check_closest_point(g.closest_point_and_primitive(pts), o.closest_point(pts), o, pts)
+        g.stats()                      # raises if the batch reported an incomplete traversal
+    segs = np.concatenate([pts, pts[::-1]], 1)
+    np.testing.assert_array_equal(g.number_of_intersected_primitives(segs, SEG), o.count(segs, SEG))
+    np.testing.assert_array_equal(g.number_of_intersected_primitives(segs, RAY), o.count(segs, RAY))
+    rays = np.concatenate([pts + [0, 0, 5.0], pts - [0, 0, 5.0]], 1)
+    check_first_intersection(g.first_intersection(rays), o.first_intersection(rays), o, rays, max_mismatch_frac=1.0)
+    g.stats()
+
+
 def test_config1_elephant_parity(B, meshes):
     """BASELINE.json configs[0]: elephant.off, random rays + closest-point queries, CPU oracle on all queries"""
     from cgal_b200 import workloads as W
@@ -252,15 +306,18 @@ def test_closest_point_kernels_agree(B, exact_go, sort):
     g.set_option(B.OPT_SORT_QUERIES, sort)
     g.set_option(B.OPT_CLOSEST_KERNEL, 0)
     ref = g.closest_point_and_primitive(pts)
+    for kernel in (1, 2):            # the work-pool kernel and the lane-pair kernel (closest_pair.cuh)
+        g.set_option(B.OPT_CLOSEST_KERNEL, kernel)
+        g.set_option(B.OPT_WARP_EXACT_GO, min(exact_go, 128) if kernel == 2 else exact_go)
+        got = g.closest_point_and_primitive(pts)
+        st = g.stats()
+        assert st["nodes_visited"] > 0 and st["leaves_tested"] > 0
+        for k in ("point", "prim", "sqdist"):
+            np.testing.assert_array_equal(got[k], ref[k], err_msg="%s kernel %d" % (k, kernel))
+        np.testing.assert_array_equal(got["flags"] & B.FLAG_TIE, ref["flags"] & B.FLAG_TIE)   # (FLAG_EXACT depends on which incumbents met)
+        check_closest_point(got, o.closest_point(pts), o, pts)
     g.set_option(B.OPT_CLOSEST_KERNEL, 1)
     g.set_option(B.OPT_WARP_EXACT_GO, exact_go)
-    got = g.closest_point_and_primitive(pts)
-    st = g.stats()
-    assert st["nodes_visited"] > 0 and st["leaves_tested"] > 0
-    for k in ("point", "prim", "sqdist"):
-        np.testing.assert_array_equal(got[k], ref[k], err_msg=k)
-    np.testing.assert_array_equal(got["flags"] & B.FLAG_TIE, ref["flags"] & B.FLAG_TIE)   # (FLAG_EXACT depends on which incumbents met)
-    check_closest_point(got, o.closest_point(pts), o, pts)
     # tiny batches and trees: fewer queries than slots, two-primitive tree
     few = g.closest_point_and_primitive(pts[:5])
     np.testing.assert_array_equal(few["prim"], ref["prim"][:5])
@@ -269,7 +326,7 @@ def test_closest_point_kernels_agree(B, exact_go, sort):
     assert list(r2["prim"]) == [0, 1, 0] and r2["flags"][2] & B.FLAG_TIE and not (r2["flags"][0] & B.FLAG_TIE)
 
 
-@pytest.mark.parametrize("kernel", [1, 0])
+@pytest.mark.parametrize("kernel", [1, 2, 0])
 def test_closest_point_adversarial_inputs(B, kernel):
     """inputs that stress the binary32 pruning aids of closest_point (they may only ever fail to prune): degenerate and needle
     triangles, thousands of coincident primitives (exact ties), coordinates far from the origin (binary32 copies useless),
@@ -303,6 +360,9 @@ def test_closest_point_adversarial_inputs(B, kernel):
     check(far, pts[:5000] + 1e7)
     tiny = base * 1e-6
     check(tiny, pts[:5000] * 1e-6)
+    # the edges of the binary32 range (squares under / overflow in binary32: the pre-tests must go quiet, not wrong)
+    for scale in (1e-21, 1e-13, 1e13, 1e20, 1e30):
+        check(base[:600] * scale, pts[:1500] * scale)
     # a large flat grid seen from far away: thousands of leaves within the rounding allowance of the same distance
     v, f = W.terrain(128, 128, amplitude=0.0)
     g, o = B.AABB_tree(v, f), orc.OracleTree(v, f)
@@ -402,3 +462,46 @@ def test_full_size_properties_16m_terrain(B):
     sample = v[:: 4099]
     dv = ((pts[:2000, None, :] - sample[None, :, :]) ** 2).sum(-1).min(1)
     assert np.all(c["sqdist"][:2000] <= dv * (1 + 1e-12))
+
+
+def test_first_intersection_with_skip(B, meshes):
+    """first_intersection(ray, skip) (AABB_tree.h:307-328): per-ray skipped primitive (the face the ray leaves) and a mask over primitive ids,
+    against the oracle's restatement; a one-primitive tree ignores skip, as the reference does"""
+    from cgal_b200 import workloads as W
+    v, f = meshes["elephant"]
+    g, o = B.AABB_tree(v, f), orc.OracleTree(v, f)
+    rays = W.sphere_rays(g.bbox(), 20000)
+    first = g.first_intersection(rays)
+    hit = first["prim"] != B.NO_PRIMITIVE
+    # second hit along each ray = first hit when the first primitive is skipped
+    got = g.first_intersection_skip(rays, skip_ids=first["prim"])
+    ref = o.first_intersection_skip(rays, skip_ids=first["prim"])
+    tie = (got["flags"] & (B.FLAG_TIE | B.FLAG_NEAR_TIE)) != 0
+    ok = got["prim"] == ref["prim"]
+    assert np.all(ok | tie)
+    np.testing.assert_array_equal(got["t"][ok], ref["t"][ok])
+    assert np.all(got["prim"][hit] != first["prim"][hit]) and np.all(got["t"][hit & (got["prim"] != B.NO_PRIMITIVE)] >= first["t"][hit & (got["prim"] != B.NO_PRIMITIVE)])
+    mask = (np.arange(len(f)) % 3) == 0
+    got = g.first_intersection_skip(rays, skip_mask=mask)
+    ref = o.first_intersection_skip(rays, skip_mask=mask)
+    tie = (got["flags"] & (B.FLAG_TIE | B.FLAG_NEAR_TIE)) != 0
+    ok = got["prim"] == ref["prim"]
+    assert np.all(ok | tie) and not np.any(mask[got["prim"][got["prim"] != B.NO_PRIMITIVE]])
+    np.testing.assert_array_equal(got["t"][ok], ref["t"][ok])
+    one = B.AABB_tree(triangles=np.array([[0, 0, 0, 1.0, 0, 0, 0, 1.0, 0]]), ids=[5])
+    r = one.first_intersection_skip(np.array([[0.1, 0.1, -1.0, 0.1, 0.1, 1.0]]), skip_ids=[5])
+    assert r["prim"][0] == 5
+
+
+def test_max_distance_to_mesh(B, meshes):
+    """PMP::max_distance_to_mesh_impl (distance.h:98-190) = sqrt of the largest squared distance of the samples; host and device pointers"""
+    import torch
+    from cgal_b200 import workloads as W
+    v, f = meshes["elephant"]
+    g, o = B.AABB_tree(v, f), orc.OracleTree(v, f)
+    pts = W.bbox_points(g.bbox(), 50000, margin=0.3)
+    sq = o.closest_point(pts)["sqd"]
+    d, i = g.max_distance_to_mesh(pts)
+    assert d == np.sqrt(sq.max()) and sq[i] == sq.max()
+    d2, i2 = g.max_distance_to_mesh(torch.from_numpy(pts).cuda())
+    assert (d2, i2) == (d, i)
