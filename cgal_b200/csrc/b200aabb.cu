@@ -244,10 +244,15 @@ __global__ void __launch_bounds__(256) line_keys_kernel(const double* __restrict
 // ------------------------------------------------------------------------------------------------------------------
 // Handle
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kLineSlots = 4;                   // chunks of a HOST ray / segment batch in flight (upload / sort + traverse / download on as many streams)
-constexpr int kPointSlots = 2;                  // HOST point batches have their own two streams: a long closest_point launch never holds up the ray chunks behind it
+// HOST-pointer batches flow through THREE streams — uploads, kernels, downloads — each in issue order, tied together per staging slot by
+// events (upload done -> kernels; kernels done -> download; kernels done -> the slot's next upload; download done -> the slot's next
+// kernels).  The kernels of a batch fill the GPU one after the other anyway, and both copy engines work through their queues behind them;
+// with one stream per chunk (round 1) the chunks' kernels queued up behind a long closest_point launch and — streams sharing hardware
+// queues — held back uploads that had nothing to wait for (profiles/r2_05).
+constexpr int kLineSlots = 8;                   // staging slots of ray / segment chunks: a whole batch can be uploaded while a closest_point launch runs
+constexpr int kPointSlots = 2;                  // staging slots of point batches (a point batch stays whole, see run_batch)
 constexpr int kPipeSlots = kLineSlots + kPointSlots;
-constexpr int kScratchSlots = kPipeSlots + 1;   // + one set of scratch buffers for DEVICE-pointer batches (on the handle's own stream)
+constexpr int kHostScratch = 0, kDeviceScratch = 1, kScratchSlots = 2;   // sort / work-pool scratch: HOST batches (their kernels share one stream), DEVICE batches
 
 struct b200aabb_tree {
     // Every entry point that touches the handle takes this lock: concurrent calls on ONE handle (the reference's callers run
@@ -292,8 +297,8 @@ struct b200aabb_tree {
     void* d_stage_in[kPipeSlots] = {};
     void* d_stage_out[kPipeSlots] = {};
     size_t stage_in_bytes[kPipeSlots] = {}, stage_out_bytes[kPipeSlots] = {};
-    cudaStream_t pipe[kPipeSlots] = {};
-    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_pipe[kPipeSlots] = {};
+    cudaStream_t s_up = nullptr, s_run = nullptr, s_down = nullptr;   // uploads, kernels, downloads of HOST batches
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr, ev_up[kPipeSlots] = {}, ev_run[kPipeSlots] = {}, ev_down[kPipeSlots] = {};
     int next_line_slot = 0, next_point_slot = 0, cur_slot = 0;   // pipeline slot of the next chunk / of the chunk being launched
     uint64_t cur_offset = 0;           // first query of the chunk being launched (HOST batches)
     uint32_t* d_stage_aux[kPipeSlots] = {}; size_t stage_aux_bytes = 0;   // per-query side input of a HOST batch (skip ids)
@@ -323,6 +328,9 @@ constexpr uint64_t kChunkMin = 1ull << 18;
 uint64_t chunk_for(uint64_t n, int parts, uint64_t cap) { const uint64_t p = (uint64_t)std::max(1, parts); return std::min<uint64_t>(n, std::min(cap, std::max(kChunkMin, ((n + p - 1) / p + 32767) / 32768 * 32768))); }
 
 #define B2_LOCK(t) std::unique_lock<std::recursive_mutex> lock_; if (t) lock_ = std::unique_lock<std::recursive_mutex>(const_cast<b200aabb_tree*>(t)->mu)
+
+int sync_pipeline(b200aabb_tree* t);
+unsigned grid_for(uint64_t n, int block);
 
 int fail(b200aabb_tree* t, int code, const char* msg) { if (t) t->err = msg; return code; }
 
@@ -417,7 +425,7 @@ int do_build(b200aabb_tree* t) {
         if (t->built) return B200AABB_OK;
         return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "an imported tree can not be rebuilt: insert primitives first");
     }
-    for (int s = 0; s < kPipeSlots; ++s) B2_CUDA(t, cudaStreamSynchronize(t->pipe[s]));   // (asynchronous HOST batches may still be in flight)
+    { const int rc_ = sync_pipeline(t); if (rc_) return rc_; }   // (asynchronous HOST batches may still be in flight)
     free_tree_buffers(t);
     const uint64_t n = t->n;
     empty_bbox(t->h_bbox);
@@ -524,9 +532,17 @@ int do_build(b200aabb_tree* t) {
 
 int ensure_built(b200aabb_tree* t) { return t->built ? B200AABB_OK : do_build(t); }
 
+
 // Runs `launch(stream, d_in, d_outs, count, perm)` over the batch (perm = coherence order of the chunk, or nullptr).  HOST pointers: chunked, double-buffered
 // H2D -> kernel -> D2H pipeline on two streams; DEVICE pointers: one launch on the handle's stream, no synchronisation.
 struct OutSpec { void* host; size_t elem_bytes; size_t offset; };   // one result array: host pointer, bytes per query, offset in staging
+
+int sync_pipeline(b200aabb_tree* t) {
+    B2_CUDA(t, cudaStreamSynchronize(t->s_up));
+    B2_CUDA(t, cudaStreamSynchronize(t->s_run));
+    B2_CUDA(t, cudaStreamSynchronize(t->s_down));
+    return B200AABB_OK;
+}
 
 // zeroes the statistics counters of a batch ([2], the incomplete-traversal flags, is sticky while asynchronous batches are in flight)
 int reset_counters(b200aabb_tree* t, cudaStream_t st) {
@@ -538,7 +554,7 @@ int reset_counters(b200aabb_tree* t, cudaStream_t st) {
 
 // waits for every batch in flight on the handle and reports a traversal that could not finish
 int drain(b200aabb_tree* t) {
-    for (int s = 0; s < kPipeSlots; ++s) B2_CUDA(t, cudaStreamSynchronize(t->pipe[s]));
+    { const int rc_ = sync_pipeline(t); if (rc_) return rc_; }
     B2_CUDA(t, cudaStreamSynchronize(t->stream));
     B2_CUDA(t, cudaGetLastError());
     t->async_pending = false;
@@ -572,9 +588,9 @@ int run_batch(b200aabb_tree* t, const void* in, size_t in_elem_bytes, uint64_t n
         B2_CUDA(t, cudaEventRecord(t->ev_a, t->stream));
         std::vector<void*> ptrs; for (auto& o : outs) ptrs.push_back(o.host);
         const uint32_t* perm = nullptr;
-        rc = coherence_order(t, kPipeSlots, t->stream, in, n, shape, &perm);
+        rc = coherence_order(t, kDeviceScratch, t->stream, in, n, shape, &perm);
         if (rc) return rc;
-        t->cur_slot = kPipeSlots; t->cur_offset = 0;
+        t->cur_slot = kDeviceScratch; t->cur_offset = 0;
         launch(t->stream, in, ptrs.data(), n, perm);
         t->stats.kernel_launches += 1;
         B2_CUDA(t, cudaEventRecord(t->ev_b, t->stream));
@@ -583,20 +599,20 @@ int run_batch(b200aabb_tree* t, const void* in, size_t in_elem_bytes, uint64_t n
         return B200AABB_OK;
     }
     // HOST pointers.  Ray / segment batches are cut into chunks that flow through upload -> sort -> traverse -> download on kLineSlots
-    // streams, so that the copies of one chunk hide behind the kernels of the others (such batches are copy bound: ~1 ms of PCIe per Mi rays
+    // staging slots, so that the copies of one chunk hide behind the kernels of the others (such batches are copy bound: ~1 ms of PCIe per Mi rays
     // each way, 0.6 ms of kernel).  A point batch stays WHOLE: its queries are sorted into one coherence order, and a chunk of an unordered
     // batch covers the whole scene at a fraction of the density — measured (scripts/tune_e2e.py, profiles/r2_05): four chunks of 2 Mi
-    // points take 4 x 8 ms against 23.8 ms for the batch in one launch.  Its copies hide behind OTHER batches instead (B200AABB_OPT_ASYNC_HOST),
-    // on streams of their own so that the chunks of the next ray batch do not queue behind it.
+    // points take 4 x 8 ms against 23.8 ms for the batch in one launch.  Its copies hide behind OTHER batches instead (B200AABB_OPT_ASYNC_HOST).
     const bool points = shape == kPointQuery;
     const uint64_t chunk = chunk_for(n, t->opt_host_parts > 0 ? t->opt_host_parts : (points ? 1 : 8), points ? kPointChunkMax : kChunkMax);
     size_t out_bytes = 0;
     for (auto& o : outs) { o.offset = out_bytes; out_bytes += ((o.host ? o.elem_bytes * chunk : 0) + 255) / 256 * 256; }
     int rc = B200AABB_OK;
-    rc = reset_counters(t, t->stream);
-    if (rc) return rc;
     B2_CUDA(t, cudaEventRecord(t->ev_a, t->stream));
-    for (int s = 0; s < kPipeSlots; ++s) B2_CUDA(t, cudaStreamWaitEvent(t->pipe[s], t->ev_a, 0));
+    B2_CUDA(t, cudaStreamWaitEvent(t->s_run, t->ev_a, 0));               // (whatever the caller enqueued on the handle's stream, e.g. the build)
+    rc = reset_counters(t, t->s_run);
+    if (rc) return rc;
+    static const bool tracing = getenv("B200AABB_PIPE_TRACE") != nullptr;
     for (uint64_t b = 0; b < n; b += chunk) {
         const uint64_t cnt = std::min<uint64_t>(chunk, n - b);
         int slot;
@@ -604,32 +620,40 @@ int run_batch(b200aabb_tree* t, const void* in, size_t in_elem_bytes, uint64_t n
         else { slot = t->next_line_slot; t->next_line_slot = (t->next_line_slot + 1) % kLineSlots; }
         rc = ensure_stage(t, slot, in_elem_bytes * chunk, std::max<size_t>(out_bytes, 256));
         if (rc) return rc;
-        cudaStream_t st = t->pipe[slot];
-        static const bool tracing = getenv("B200AABB_PIPE_TRACE") != nullptr;
         b200aabb_tree::TraceRec tr;
-        if (tracing) { for (auto& e : tr.e) cudaEventCreate(&e); tr.slot = slot; tr.cnt = cnt; tr.shape = (int)shape; cudaEventRecord(tr.e[0], st); }
-        B2_CUDA(t, cudaMemcpyAsync(t->d_stage_in[slot], (const char*)in + b * in_elem_bytes, cnt * in_elem_bytes, cudaMemcpyHostToDevice, st));
-        if (tracing) cudaEventRecord(tr.e[1], st);
+        if (tracing) { for (auto& e : tr.e) cudaEventCreate(&e); tr.slot = slot; tr.cnt = cnt; tr.shape = (int)shape; }
+        // upload: once the kernels that last read this slot's input have finished
+        B2_CUDA(t, cudaStreamWaitEvent(t->s_up, t->ev_run[slot], 0));
+        if (tracing) cudaEventRecord(tr.e[0], t->s_up);
+        B2_CUDA(t, cudaMemcpyAsync(t->d_stage_in[slot], (const char*)in + b * in_elem_bytes, cnt * in_elem_bytes, cudaMemcpyHostToDevice, t->s_up));
+        B2_CUDA(t, cudaEventRecord(t->ev_up[slot], t->s_up));
+        if (tracing) cudaEventRecord(tr.e[1], t->s_up);
+        // kernels: once the chunk is there and the slot's previous results have left
+        B2_CUDA(t, cudaStreamWaitEvent(t->s_run, t->ev_up[slot], 0));
+        B2_CUDA(t, cudaStreamWaitEvent(t->s_run, t->ev_down[slot], 0));
         std::vector<void*> ptrs;
         for (auto& o : outs) ptrs.push_back(o.host ? (char*)t->d_stage_out[slot] + o.offset : nullptr);
         const uint32_t* perm = nullptr;
-        rc = coherence_order(t, slot, st, t->d_stage_in[slot], cnt, shape, &perm);
+        rc = coherence_order(t, kHostScratch, t->s_run, t->d_stage_in[slot], cnt, shape, &perm);
         if (rc) return rc;
         t->cur_slot = slot; t->cur_offset = b;
-        launch(st, t->d_stage_in[slot], ptrs.data(), cnt, perm);
+        launch(t->s_run, t->d_stage_in[slot], ptrs.data(), cnt, perm);
         t->stats.kernel_launches += 1;
-        if (tracing) cudaEventRecord(tr.e[2], st);
+        B2_CUDA(t, cudaEventRecord(t->ev_run[slot], t->s_run));
+        if (tracing) cudaEventRecord(tr.e[2], t->s_run);
+        // download
+        B2_CUDA(t, cudaStreamWaitEvent(t->s_down, t->ev_run[slot], 0));
         for (auto& o : outs)
-            if (o.host) B2_CUDA(t, cudaMemcpyAsync((char*)o.host + b * o.elem_bytes, (char*)t->d_stage_out[slot] + o.offset, cnt * o.elem_bytes, cudaMemcpyDeviceToHost, st));
-        if (tracing) { cudaEventRecord(tr.e[3], st); t->trace.push_back(tr); }
+            if (o.host) B2_CUDA(t, cudaMemcpyAsync((char*)o.host + b * o.elem_bytes, (char*)t->d_stage_out[slot] + o.offset, cnt * o.elem_bytes, cudaMemcpyDeviceToHost, t->s_down));
+        B2_CUDA(t, cudaEventRecord(t->ev_down[slot], t->s_down));
+        if (tracing) { cudaEventRecord(tr.e[3], t->s_down); t->trace.push_back(tr); }
     }
     if (t->opt_async_host) {   // the caller keeps its buffers alive and calls b200aabb_synchronize before it reads the results
         t->async_pending = true;
         t->query_timing_pending = false;
         return B200AABB_OK;
     }
-    for (int s = 0; s < kPipeSlots; ++s) { B2_CUDA(t, cudaEventRecord(t->ev_pipe[s], t->pipe[s])); B2_CUDA(t, cudaStreamWaitEvent(t->stream, t->ev_pipe[s], 0)); }
-    B2_CUDA(t, cudaEventRecord(t->ev_b, t->stream));
+    B2_CUDA(t, cudaEventRecord(t->ev_b, t->s_down));
     rc = drain(t);   // a traversal that could not finish is an error of THIS call, never a silent partial result
     t->query_timing_pending = true;
     return rc;
@@ -679,8 +703,11 @@ int b200aabb_create(int device, b200aabb_tree** out) {
     empty_bbox(t->h_bbox);
     bool ok = cudaMalloc(&t->d_rootbox, 48) == cudaSuccess && cudaMalloc(&t->d_bounds, 48) == cudaSuccess && cudaMalloc(&t->d_counters, 8 * sizeof(unsigned long long)) == cudaSuccess &&
               cudaEventCreate(&t->ev_a) == cudaSuccess && cudaEventCreate(&t->ev_b) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&t->s_up, cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&t->s_run, cudaStreamNonBlocking) == cudaSuccess &&
+         cudaStreamCreateWithFlags(&t->s_down, cudaStreamNonBlocking) == cudaSuccess;
     for (int s = 0; s < kPipeSlots && ok; ++s)
-        ok = cudaStreamCreateWithFlags(&t->pipe[s], cudaStreamNonBlocking) == cudaSuccess && cudaEventCreateWithFlags(&t->ev_pipe[s], cudaEventDisableTiming) == cudaSuccess;
+        ok = cudaEventCreateWithFlags(&t->ev_up[s], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&t->ev_run[s], cudaEventDisableTiming) == cudaSuccess &&
+             cudaEventCreateWithFlags(&t->ev_down[s], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { b200aabb_destroy(t); return B200AABB_ERR_CUDA; }
     t->built = true;   // an empty tree needs no build
     *out = t;
@@ -693,7 +720,13 @@ int b200aabb_destroy(b200aabb_tree* t) {
     cudaDeviceSynchronize();
     free_tree_buffers(t); free_input(t); free_sort(t); free_warp(t);
     cudaFree(t->d_rootbox); cudaFree(t->d_bounds); cudaFree(t->d_counters);
-    for (int s = 0; s < kPipeSlots; ++s) { cudaFree(t->d_stage_in[s]); cudaFree(t->d_stage_out[s]); cudaFree(t->d_stage_aux[s]); if (t->pipe[s]) cudaStreamDestroy(t->pipe[s]); if (t->ev_pipe[s]) cudaEventDestroy(t->ev_pipe[s]); }
+    for (int s = 0; s < kPipeSlots; ++s) {
+        cudaFree(t->d_stage_in[s]); cudaFree(t->d_stage_out[s]); cudaFree(t->d_stage_aux[s]);
+        if (t->ev_up[s]) cudaEventDestroy(t->ev_up[s]);
+        if (t->ev_run[s]) cudaEventDestroy(t->ev_run[s]);
+        if (t->ev_down[s]) cudaEventDestroy(t->ev_down[s]);
+    }
+    for (cudaStream_t st : {t->s_up, t->s_run, t->s_down}) if (st) cudaStreamDestroy(st);
     if (t->ev_a) cudaEventDestroy(t->ev_a);
     if (t->ev_b) cudaEventDestroy(t->ev_b);
     delete t;
@@ -745,7 +778,7 @@ int b200aabb_synchronize(b200aabb_tree* t) {
 int b200aabb_clear(b200aabb_tree* t) { B2_LOCK(t);
     if (!t) return B200AABB_ERR_INVALID_ARGUMENT;
     B2_CUDA(t, cudaSetDevice(t->device));
-    for (int s = 0; s < kPipeSlots; ++s) B2_CUDA(t, cudaStreamSynchronize(t->pipe[s]));   // (asynchronous HOST batches may still be in flight)
+    { const int rc_ = sync_pipeline(t); if (rc_) return rc_; }   // (asynchronous HOST batches may still be in flight)
     B2_CUDA(t, cudaStreamSynchronize(t->stream));
     free_tree_buffers(t); free_input(t);
     t->n = 0; t->built = true; t->imported = false; t->bounds_valid = false; empty_bbox(t->h_bbox);
@@ -843,7 +876,7 @@ static int refit_precheck(b200aabb_tree* t, uint64_t n) {
     if (n != t->n) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "refit keeps the topology: the number of primitives must not change (use set_* + build)");
     int rc = ensure_built(t);
     if (rc) return rc;
-    for (int s = 0; s < kPipeSlots; ++s) B2_CUDA(t, cudaStreamSynchronize(t->pipe[s]));
+    { const int rc_ = sync_pipeline(t); if (rc_) return rc_; }
     return B200AABB_OK;
 }
 
@@ -964,7 +997,7 @@ int b200aabb_all_intersected_primitives(b200aabb_tree* t, const double* q, uint6
     cudaMemsetAsync(t->d_counters, 0, 8 * sizeof(unsigned long long), t->stream);
     cudaEventRecord(t->ev_a, t->stream);
     const uint32_t* perm = nullptr;
-    rc = coherence_order(t, kPipeSlots, t->stream, d_q, n, kLineQuery, &perm);
+    rc = coherence_order(t, kDeviceScratch, t->stream, d_q, n, kLineQuery, &perm);
     if (rc) { release(); return rc; }
     if (ray) intersect_kernel<true, kList><<<grid_for(n, 128), 128, 0, t->stream>>>(tree_ref(t, perm), d_q, n, nullptr, nullptr, d_off, d_ids);
     else intersect_kernel<false, kList><<<grid_for(n, 128), 128, 0, t->stream>>>(tree_ref(t, perm), d_q, n, nullptr, nullptr, d_off, d_ids);
@@ -1041,7 +1074,7 @@ int b200aabb_all_intersections(b200aabb_tree* t, const double* rays, uint64_t n,
     cudaMemsetAsync(t->d_counters, 0, 8 * sizeof(unsigned long long), t->stream);
     cudaEventRecord(t->ev_a, t->stream);
     const uint32_t* perm = nullptr;
-    rc = coherence_order(t, kPipeSlots, t->stream, d_q, n, kLineQuery, &perm);
+    rc = coherence_order(t, kDeviceScratch, t->stream, d_q, n, kLineQuery, &perm);
     if (rc) { release(); return rc; }
     ray_objects_kernel<kList><<<grid_for(n, 128), 128, 0, t->stream>>>(tree_ref(t, perm), d_q, n, nullptr, d_off, d_ids, d_kinds, d_pts, nullptr, nullptr, nullptr, nullptr);
     t->stats.kernel_launches += 1;
@@ -1137,14 +1170,14 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
     if (n == 0) return B200AABB_OK;
     // the warp-cooperative kernel packs (query slot, node / leaf) in 32 bits and needs an internal root
     const bool warp_kernel = t->opt_closest_kernel >= 1 && t->n >= 2 && t->n <= kWpMaxPrims;
-    if (warp_kernel) { for (int s = kLineSlots; s < kScratchSlots; ++s) { rc = ensure_warp(t, s); if (rc) return rc; } }   // (the point slots and the DEVICE-batch slot)
+    if (warp_kernel) { for (int s = 0; s < kScratchSlots; ++s) { rc = ensure_warp(t, s); if (rc) return rc; } }
     return run_batch(t, pts, 24, n, space, kPointQuery, {{cp, 24, 0}, {prim, 4, 0}, {sqd, 8, 0}, {flags, 1, 0}},
                      [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
                          if (!warp_kernel || cnt >= (1ull << 32)) {
                              closest_point_kernel<<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (double*)o[0], (uint32_t*)o[1], (double*)o[2], (uint8_t*)o[3]);
                              return;
                          }
-                         const int slot = t->cur_slot;
+                         const int slot = space == B200AABB_HOST ? kHostScratch : kDeviceScratch;
                          cudaMemsetAsync(t->warp[slot].cursor, 0, sizeof(unsigned long long), st);
                          if (t->opt_closest_kernel >= 2) {
                              PairClosestArgs a;

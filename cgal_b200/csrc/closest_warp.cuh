@@ -370,9 +370,11 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                 bool in0 = false, in1 = false;                     // 0 = nearer child, 1 = farther child
                 uint32_t r0 = 0, r1 = 0;
                 float d0 = 0.0f, d1 = 0.0f;
-                // (Measured and rejected, profiles/r2_03: lane PAIRS fetching the two halves of one node with one load instruction, each
-                //  lane testing the half it fetched of both nodes and shuffling the partner's results back: L1 wavefronts -5 %, instructions
-                //  +16 % (six shuffles + selects per step), 26.0 ms instead of 24.0.)
+                // (Measured and rejected, profiles/r2_03: lane PAIRS fetching the two halves of one node with one load instruction, each lane testing the
+                //  half it fetched of both nodes and shuffling the partner's results back: L1 wavefronts -5 %, instructions +16 %, 26.0 ms instead of
+                //  24.0.  profiles/r2_04: 32-byte nodes with 16-bit grid boxes, one sector per visit: the L1 data stage drops from 74 % to 55 % of its peak,
+                //  but decoding + 4 % more node and 9 % more leaf visits (boxes loosened by up to two cells) cost +17 % instructions: 25.6 ms.  The kernel
+                //  is bound by instruction issue at the 20 warps per SM its registers and shared memory allow, not by the L1 wavefronts alone.)
                 if (expand) {
                     const NodeView nd = load_node(a.nodes, e.x);
                     d0 = wp_box_sqdist(nd.lo0, nd.hi0, q); d1 = wp_box_sqdist(nd.lo1, nd.hi1, q);

@@ -38,7 +38,7 @@ def main():
     want_r, want_p = ("prim", "t", "point", "flags"), ("point", "prim", "sqdist", "flags")
     steps = int(os.environ.get("STEPS", "4"))
     g.set_option(B.OPT_ASYNC_HOST, 1)
-    for rparts, pparts in [(8, 4)] if os.environ.get("B200AABB_PIPE_TRACE") else [(8, 4), (4, 2), (8, 8), (16, 4), (16, 8), (6, 3)]:
+    for rparts, pparts in [(8, 1)] if os.environ.get("B200AABB_PIPE_TRACE") else [(8, 1), (4, 1), (16, 1), (8, 2)]:
         def step():
             g.set_option(B.OPT_HOST_PARTS, rparts)
             g.first_intersection(rays_p, want=want_r, out=out_r)

@@ -505,3 +505,56 @@ def test_max_distance_to_mesh(B, meshes):
     assert d == np.sqrt(sq.max()) and sq[i] == sq.max()
     d2, i2 = g.max_distance_to_mesh(torch.from_numpy(pts).cuda())
     assert (d2, i2) == (d, i)
+
+
+def test_refit_keeps_results_of_a_fresh_build(B, meshes):
+    """b200aabb_refit / _refit_mesh: the primitives move, the hierarchy stays; boxes are recomputed bottom-up (valid tree) and every query
+    answers like a freshly built tree and like the oracle on the deformed mesh; twice in a row (the refit's arrival flags reset themselves)"""
+    from cgal_b200 import workloads as W
+    v, f = meshes["elephant"]
+    g = B.AABB_tree(v, f)
+    g.build()
+    rng = np.random.default_rng(8)
+    for rnd in range(2):
+        v2 = v + 0.02 * (v.max(0) - v.min(0)) * rng.standard_normal(v.shape) * (rnd + 1)
+        if rnd == 0:
+            g.refit(vertices=v2, faces=f)
+        else:
+            g.refit(triangles=soup_of(v2, f))
+        (pn, bn), (pt, bt) = g.export_layout()[:2]
+        assert hc.validate(device_to_host(pn, bn), device_to_host(pt, bt), len(f)) == 0
+        o = orc.OracleTree(v2, f)
+        assert np.array_equal(g.bbox(), o.bbox())
+        bb = g.bbox()
+        rays, pts, segs = W.sphere_rays(bb, 5000), W.bbox_points(bb, 5000), W.bbox_segments(bb, 5000)
+        check_first_intersection(g.first_intersection(rays), o.first_intersection(rays), o, rays)
+        check_closest_point(g.closest_point_and_primitive(pts), o.closest_point(pts), o, pts)
+        np.testing.assert_array_equal(g.number_of_intersected_primitives(segs, SEG), o.count(segs, SEG))
+    with pytest.raises(B.B200AABBError):
+        g.refit(triangles=soup_of(v, f)[:-1])      # the number of primitives must not change
+
+
+def test_async_host_batches(B, meshes):
+    """B200AABB_OPT_ASYNC_HOST: HOST batches return once enqueued and overlap across calls; after b200aabb_synchronize the results equal the
+    synchronous ones"""
+    import torch
+    from cgal_b200 import workloads as W
+    v, f = W.terrain(256, 128)
+    g = B.AABB_tree(v, f)
+    bb = g.bbox()
+    n = 300_000
+    rays = torch.from_numpy(W.pinhole_rays(600, 500, 256, 128)).pin_memory().numpy()
+    pts = torch.from_numpy(W.bbox_points(bb, n)).pin_memory().numpy()
+    want_r = g.first_intersection(rays)
+    want_p = g.closest_point_and_primitive(pts)
+    g.set_option(B.OPT_ASYNC_HOST, 1)
+    outs = []
+    for _ in range(3):
+        outs.append((g.first_intersection(rays), g.closest_point_and_primitive(pts)))
+    g.synchronize()
+    g.set_option(B.OPT_ASYNC_HOST, 0)
+    for r, p in outs:
+        for k in want_r:
+            np.testing.assert_array_equal(r[k], want_r[k])
+        for k in want_p:
+            np.testing.assert_array_equal(p[k], want_p[k])
