@@ -120,15 +120,17 @@ def cpu_rates(o, rays, pts, threads, rays_1t=1 << 17, pts_1t=1 << 14):
     rc = o.closest_point(pts, threads=threads)
     t2 = time.perf_counter()
     pb, pp = orc.traversal_totals()
+    r1 = np.ascontiguousarray(rays[::max(1, len(rays) // rays_1t)][:rays_1t])     # (strided: the same mix of hits and misses as the whole sample)
+    p1 = pts[:pts_1t]
     s0 = time.perf_counter()
-    o.first_intersection(rays[:rays_1t], threads=1)
+    o.first_intersection(r1, threads=1)
     s1 = time.perf_counter()
-    o.closest_point(pts[:pts_1t], threads=1)
+    o.closest_point(p1, threads=1)
     s2 = time.perf_counter()
     orc.traversal_totals()
     rates = {"first_intersection_Mrays_s": len(rays) / (t1 - t0) / 1e6, "closest_point_Mqueries_s": len(pts) / (t2 - t1) / 1e6,
-             "single_thread": {"first_intersection_Mrays_s": min(rays_1t, len(rays)) / (s1 - s0) / 1e6, "closest_point_Mqueries_s": min(pts_1t, len(pts)) / (s2 - s1) / 1e6,
-                               "sample": "%d rays + %d points" % (min(rays_1t, len(rays)), min(pts_1t, len(pts)))},
+             "single_thread": {"first_intersection_Mrays_s": len(r1) / (s1 - s0) / 1e6, "closest_point_Mqueries_s": len(p1) / (s2 - s1) / 1e6,
+                               "sample": "%d rays (strided) + %d points" % (len(r1), len(p1))},
              "traversal": {"ray_box_tests_per_query": rb / len(rays), "ray_primitives_per_query": rp / len(rays),
                            "point_box_tests_per_query": pb / len(pts), "point_primitives_per_query": pp / len(pts)}}
     return rates, rr, rc

@@ -9,7 +9,7 @@ import os
 
 import numpy as np
 
-SEGMENT, RAY = 0, 1
+SEGMENT, RAY, LINE, PLANE = 0, 1, 2, 3      # LINE: (point, direction vector) per query; PLANE: (a, b, c, d)
 FLAG_HIT, FLAG_SEGMENT, FLAG_TIE, FLAG_EXACT, FLAG_NEAR_TIE = 1, 2, 4, 8, 16
 OPT_SORT_QUERIES = 1
 OPT_CLOSEST_KERNEL = 2    # 1 = warp-cooperative work pool (default), 2 = lane pairs with private stacks, 0 = one thread per query
@@ -252,20 +252,20 @@ class AABB_tree:
 
     # ---- intersection queries (AABB_tree.h:243-354) ----
     def do_intersect(self, queries, kind=SEGMENT, out=None):
-        q = _Buf(queries, np.float64, 6)
+        q = _Buf(queries, np.float64, 4 if kind == PLANE else 6)
         o = _Buf(out, np.uint8, 1) if out is not None else _alloc_like(q, q.n, np.uint8, 1)
         self._check(self._lib.b200aabb_do_intersect(self._h, q.ptr, q.n, kind, int(q.device), o.ptr))
         return o.obj
 
     def number_of_intersected_primitives(self, queries, kind=SEGMENT, out=None):
-        q = _Buf(queries, np.float64, 6)
+        q = _Buf(queries, np.float64, 4 if kind == PLANE else 6)
         o = _Buf(out, np.uint32, 1) if out is not None else _alloc_like(q, q.n, np.uint32, 1)
         self._check(self._lib.b200aabb_number_of_intersected_primitives(self._h, q.ptr, q.n, kind, int(q.device), o.ptr))
         return o.obj
 
     def any_intersected_primitive(self, queries, kind=SEGMENT, out=None):
         """any_intersected_primitive(query): id of one intersected primitive per query, NO_PRIMITIVE = nullopt"""
-        q = _Buf(queries, np.float64, 6)
+        q = _Buf(queries, np.float64, 4 if kind == PLANE else 6)
         o = _Buf(out, np.uint32, 1) if out is not None else _alloc_like(q, q.n, np.uint32, 1)
         self._check(self._lib.b200aabb_any_intersected_primitive(self._h, q.ptr, q.n, kind, int(q.device), o.ptr))
         return o.obj
@@ -273,7 +273,7 @@ class AABB_tree:
     def all_intersected_primitives(self, queries, kind=SEGMENT):
         """all_intersected_primitives(query, out) for a HOST batch: (offsets uint64[n+1], ids uint32[total]); the ids of query i are
         ids[offsets[i]:offsets[i+1]] (count pass -> prefix sums -> fill pass, include/b200aabb.h)"""
-        q = _Buf(np.asarray(queries), np.float64, 6)
+        q = _Buf(np.asarray(queries), np.float64, 4 if kind == PLANE else 6)
         counts = self.number_of_intersected_primitives(q.obj, kind)
         offsets = np.zeros(q.n + 1, np.uint64)
         np.cumsum(counts, out=offsets[1:])

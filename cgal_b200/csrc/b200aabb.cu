@@ -56,7 +56,7 @@ __device__ __forceinline__ void flush_stats(const TreeRef& tr, const TravStat& s
 // (8 blocks per SM = 64 registers: measured best of 3 / 4 / 5 / 6 / 8 / 10 on the config 3 and config 4 segment batches)
 // out8: kAnyHit; out32: kCount, kAnyId; kList: ids of query i go to list[offsets[i] ..), and a count that disagrees with
 // offsets[i+1] - offsets[i] (the caller's prefix sums of a kCount run over the same batch) raises counters[2] bit 2
-template <bool IS_RAY, int MODE>
+template <int KIND, int MODE>
 __global__ void __launch_bounds__(128, 8) intersect_kernel(const TreeRef tr, const double* __restrict__ q, uint64_t n, uint8_t* __restrict__ out8,
                                                            uint32_t* __restrict__ out32, const uint64_t* __restrict__ offsets, uint32_t* __restrict__ list) {
     const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -67,11 +67,33 @@ __global__ void __launch_bounds__(128, 8) intersect_kernel(const TreeRef tr, con
             const uint64_t lo = offsets[i], hi = offsets[i + 1];
             uint32_t r = 0;
             // (a query with no room for any id still traverses: its count must be 0)
-            if (hi > lo) r = traverse_intersect<IS_RAY, kList>(tr.nodes, tr.tris, tr.root, ld3(q + 6 * i), ld3(q + 6 * i + 3), st, list + lo, (uint32_t)(hi - lo));
-            else r = traverse_intersect<IS_RAY, kAnyHit>(tr.nodes, tr.tris, tr.root, ld3(q + 6 * i), ld3(q + 6 * i + 3), st);
+            if (hi > lo) r = traverse_intersect<KIND, kList>(tr.nodes, tr.tris, tr.root, ld3(q + 6 * i), ld3(q + 6 * i + 3), st, list + lo, (uint32_t)(hi - lo));
+            else r = traverse_intersect<KIND, kAnyHit>(tr.nodes, tr.tris, tr.root, ld3(q + 6 * i), ld3(q + 6 * i + 3), st);
             if (r != hi - lo) atomicOr(&tr.counters[2], 4ull);
         } else {
-            const uint32_t r = traverse_intersect<IS_RAY, MODE>(tr.nodes, tr.tris, tr.root, ld3(q + 6 * i), ld3(q + 6 * i + 3), st);
+            const uint32_t r = traverse_intersect<KIND, MODE>(tr.nodes, tr.tris, tr.root, ld3(q + 6 * i), ld3(q + 6 * i + 3), st);
+            if (MODE == kAnyHit) out8[i] = (uint8_t)r; else out32[i] = r;
+        }
+    }
+    flush_stats(tr, st, 0, 0);
+}
+
+// the same for Plane_3 queries: q = n x 4 coefficients (a, b, c, d)
+template <int MODE>
+__global__ void __launch_bounds__(128, 8) plane_kernel(const TreeRef tr, const double* __restrict__ q, uint64_t n, uint8_t* __restrict__ out8, uint32_t* __restrict__ out32,
+                                                       const uint64_t* __restrict__ offsets, uint32_t* __restrict__ list) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    TravStat st;
+    if (i < n) {
+        const double a = __ldg(q + 4 * i), b = __ldg(q + 4 * i + 1), c = __ldg(q + 4 * i + 2), d = __ldg(q + 4 * i + 3);
+        if (MODE == kList) {
+            const uint64_t lo = offsets[i], hi = offsets[i + 1];
+            uint32_t r = 0;
+            if (hi > lo) r = traverse_plane<kList>(tr.nodes, tr.tris, tr.root, a, b, c, d, st, list + lo, (uint32_t)(hi - lo));
+            else r = traverse_plane<kAnyHit>(tr.nodes, tr.tris, tr.root, a, b, c, d, st);
+            if (r != hi - lo) atomicOr(&tr.counters[2], 4ull);
+        } else {
+            const uint32_t r = traverse_plane<MODE>(tr.nodes, tr.tris, tr.root, a, b, c, d, st);
             if (MODE == kAnyHit) out8[i] = (uint8_t)r; else out32[i] = r;
         }
     }
@@ -108,6 +130,7 @@ __global__ void __launch_bounds__(128, 5) ray_objects_kernel(const TreeRef tr, c
     flush_stats(tr, st, 0, 0);
 }
 
+template <bool SKIP>
 __global__ void __launch_bounds__(128, 5) first_intersection_kernel(const TreeRef tr, const double* __restrict__ rays, uint64_t n, uint32_t* __restrict__ prim,
                                                                  double* __restrict__ tpar, double* __restrict__ pt, double* __restrict__ pt2,
                                                                  uint8_t* __restrict__ flags, const uint32_t* __restrict__ skip_ids,
@@ -117,7 +140,8 @@ __global__ void __launch_bounds__(128, 5) first_intersection_kernel(const TreeRe
     int tie = 0, near = 0;
     if (slot < n) {
         const uint64_t i = tr.perm ? tr.perm[slot] : slot;
-        const FirstHit h = traverse_first(tr.nodes, tr.tris, tr.root, ld3(rays + 6 * i), ld3(rays + 6 * i + 3), tr.mag, st, skip_ids ? skip_ids[i] : kNone, skip_mask, mask_words);
+        const FirstHit h = SKIP ? traverse_first<true>(tr.nodes, tr.tris, tr.root, ld3(rays + 6 * i), ld3(rays + 6 * i + 3), tr.mag, st, skip_ids ? skip_ids[i] : kNone, skip_mask, mask_words)
+                                : traverse_first<false>(tr.nodes, tr.tris, tr.root, ld3(rays + 6 * i), ld3(rays + 6 * i + 3), tr.mag, st);
         const bool hit = h.prim != kNone;
         tie = h.tie; near = h.near;
         if (prim) prim[i] = h.prim;
@@ -214,13 +238,13 @@ __global__ void __launch_bounds__(256) point_keys_kernel(const double* __restric
 // Segment_3 / Ray_3: 48-bit key interleaving 8 bits of each origin coordinate (root-box frame) and of each component of
 // the max-norm-normalised direction, most significant bits first
 __global__ void __launch_bounds__(256) line_keys_kernel(const double* __restrict__ q, uint64_t n, const double* __restrict__ rootbox,
-                                                        uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+                                                        uint64_t* __restrict__ keys, uint32_t* __restrict__ vals, int second_is_vector) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double lo[3], scale[3];
     morton_frame(rootbox[0], rootbox[1], rootbox[2], rootbox[3], rootbox[4], rootbox[5], lo, scale);
     const double* r = q + 6 * i;
-    const double d[3] = {r[3] - r[0], r[4] - r[1], r[5] - r[2]};
+    const double d[3] = {second_is_vector ? r[3] : r[3] - r[0], second_is_vector ? r[4] : r[4] - r[1], second_is_vector ? r[5] : r[5] - r[2]};
     const double dmax = fmax(fabs(d[0]), fmax(fabs(d[1]), fabs(d[2])));
     uint32_t c[6];
 #pragma unroll
@@ -398,19 +422,19 @@ int ensure_sort(b200aabb_tree* t, int slot, uint64_t n) {
     return B200AABB_OK;
 }
 
-enum QueryShape { kPointQuery, kLineQuery };
+enum QueryShape { kPointQuery, kLineQuery, kLineVecQuery /* Line_3: point + direction vector */, kPlaneQuery /* not sorted */ };
 
 // coherence order of a batch resident on the device: keys -> onesweep sort -> permutation (nullptr when sorting is off)
 int coherence_order(b200aabb_tree* t, int slot, cudaStream_t st, const void* d_in, uint64_t n, QueryShape shape, const uint32_t** perm) {
     *perm = nullptr;
-    if (!t->opt_sort_queries || n < 4096 || n >= (1ull << 30)) return B200AABB_OK;   // (the sort's look-back words carry 30-bit prefixes)
+    if (!t->opt_sort_queries || n < 4096 || n >= (1ull << 30) || shape == kPlaneQuery) return B200AABB_OK;   // (the sort's look-back words carry 30-bit prefixes)
     int rc = ensure_sort(t, slot, n);
     if (rc) return rc;
     auto& sc = t->sort[slot];
     const unsigned blocks = (unsigned)((n + 255) / 256);
     int passes;
     if (shape == kPointQuery) { point_keys_kernel<<<blocks, 256, 0, st>>>((const double*)d_in, n, t->d_rootbox, sc.keys[0], sc.vals[0]); passes = 4; }
-    else { line_keys_kernel<<<blocks, 256, 0, st>>>((const double*)d_in, n, t->d_rootbox, sc.keys[0], sc.vals[0]); passes = 6; }
+    else { line_keys_kernel<<<blocks, 256, 0, st>>>((const double*)d_in, n, t->d_rootbox, sc.keys[0], sc.vals[0], shape == kLineVecQuery ? 1 : 0); passes = 6; }
     t->stats.kernel_launches += 1;
     const int cur = radix_sort_pairs(sc.keys, sc.vals, n, passes, sc.ws, st, &t->stats.kernel_launches);
     *perm = sc.vals[cur];
@@ -457,6 +481,7 @@ int do_build(b200aabb_tree* t) {
     const int ib = index_bits_for(n);                                 // PACKED words: index in the low ib bits, 64 - ib key bits above
     const int packed_passes = std::min(8, (64 - ib + 7) / 8);
     unsigned long long dups = 0;
+    EmitArgs emit{};
     B2_TRY(cudaEventRecord(t->ev_a, st));
     mark("start");
     if (!t->bounds_valid) {
@@ -486,9 +511,7 @@ int do_build(b200aabb_tree* t) {
             cur = radix_sort_pairs(keys, vals, n, 8, ws, st, &t->stats.kernel_launches);
         }
         mark("sort");
-        emit_leaves_kernel<<<blocks, 256, 0, st>>>(t->d_soup, t->d_ids, packed ? nullptr : vals[cur], keys[cur], ib, n, t->d_tris, t->d_trisf);
-        mark("emit_leaves");
-        t->stats.kernel_launches += 1;
+        emit = EmitArgs{t->d_soup, t->d_ids, packed ? nullptr : vals[cur], keys[cur], ib, t->d_trisf};   // (the leaf records are written by the refit kernel)
         B2_TRY(cudaMemsetAsync(d_dups, 0, 8, st));
         if (n > 1) {
             hierarchy_kernel<<<blocks, 256, 0, st>>>(keys[cur], n, t->d_nodes, leaf_parent, packed ? ib : 0, d_dups);
@@ -505,8 +528,8 @@ int do_build(b200aabb_tree* t) {
         break;
     }
     B2_TRY(cudaMemsetAsync(frontier_count, 0, sizeof(unsigned), st));
-    refit_local_kernel<<<(unsigned)refit_blocks, kRefitBlock, 0, st>>>(t->d_tris, n, t->d_nodes, leaf_parent, frontier, frontier_count, (unsigned)frontier_use);
-    mark("refit_local");
+    refit_local_kernel<true><<<(unsigned)refit_blocks, kRefitBlock, 0, st>>>(t->d_tris, n, t->d_nodes, leaf_parent, frontier, frontier_count, (unsigned)frontier_use, emit);
+    mark("leaves+refit");
     if (n > 1) { refit_global_kernel<<<(unsigned)((frontier_cap + 255) / 256), 256, 0, st>>>(t->d_nodes, frontier, frontier_count, (unsigned)frontier_use); t->stats.kernel_launches += 1; }
     mark("refit_global");
     root_box_kernel<<<1, 32, 0, st>>>(t->d_bounds, t->d_rootbox);
@@ -666,6 +689,22 @@ unsigned grid_for(uint64_t n, int block) { return (unsigned)((n + block - 1) / b
 // ------------------------------------------------------------------------------------------------------------------
 // C ABI
 // ------------------------------------------------------------------------------------------------------------------
+// launches the intersection kernel of a query kind (Segment_3 / Ray_3 / Line_3: 6 doubles per query; Plane_3: 4) in one of the modes of bvh.cuh
+template <int MODE>
+static void launch_intersect(b200aabb_tree* t, int kind, cudaStream_t st, const double* in, uint64_t cnt, const uint32_t* perm, uint8_t* out8, uint32_t* out32,
+                             const uint64_t* offsets, uint32_t* list) {
+    const unsigned grid = grid_for(cnt, 128);
+    switch (kind) {
+        case B200AABB_RAY: intersect_kernel<kRayQ, MODE><<<grid, 128, 0, st>>>(tree_ref(t, perm), in, cnt, out8, out32, offsets, list); break;
+        case B200AABB_LINE: intersect_kernel<kLineQ, MODE><<<grid, 128, 0, st>>>(tree_ref(t, perm), in, cnt, out8, out32, offsets, list); break;
+        case B200AABB_PLANE: plane_kernel<MODE><<<grid, 128, 0, st>>>(tree_ref(t, nullptr), in, cnt, out8, out32, offsets, list); break;
+        default: intersect_kernel<kSegmentQ, MODE><<<grid, 128, 0, st>>>(tree_ref(t, perm), in, cnt, out8, out32, offsets, list); break;
+    }
+}
+static bool valid_kind(int kind) { return kind >= B200AABB_SEGMENT && kind <= B200AABB_PLANE; }
+static size_t query_bytes(int kind) { return kind == B200AABB_PLANE ? 32 : 48; }
+static QueryShape query_shape(int kind) { return kind == B200AABB_PLANE ? kPlaneQuery : (kind == B200AABB_LINE ? kLineVecQuery : kLineQuery); }
+
 extern "C" {
 
 const char* b200aabb_version(void) { return "b200aabb 0.1 sm_100a"; }
@@ -836,7 +875,7 @@ static int refit_boxes(b200aabb_tree* t, cudaStream_t st) {
         return fail(t, B200AABB_ERR_OUT_OF_MEMORY, "cudaMalloc(refit frontier)");
     }
     cudaMemsetAsync(frontier_count, 0, sizeof(unsigned), st);
-    refit_local_kernel<<<(unsigned)refit_blocks, kRefitBlock, 0, st>>>(t->d_tris, n, t->d_nodes, t->d_leaf_parent, frontier, frontier_count, (unsigned)frontier_cap);
+    refit_local_kernel<false><<<(unsigned)refit_blocks, kRefitBlock, 0, st>>>(t->d_tris, n, t->d_nodes, t->d_leaf_parent, frontier, frontier_count, (unsigned)frontier_cap, EmitArgs{});
     refit_global_kernel<<<(unsigned)((frontier_cap + 255) / 256), 256, 0, st>>>(t->d_nodes, frontier, frontier_count, (unsigned)frontier_cap);
     t->stats.kernel_launches += 2;
     const cudaError_t e = cudaStreamSynchronize(st);
@@ -924,57 +963,51 @@ int b200aabb_bbox(b200aabb_tree* t, double out[6]) { B2_LOCK(t);
 }
 
 int b200aabb_do_intersect(b200aabb_tree* t, const double* q, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint8_t* out) { B2_LOCK(t);
-    if (!t || (n && (!q || !out))) return B200AABB_ERR_INVALID_ARGUMENT;
+    if (!t || (n && (!q || !out)) || !valid_kind(kind)) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     if (t->n == 0) {   // empty tree: false (aabb_test_empty_tree.cpp:44-50)
         if (space == B200AABB_DEVICE) { B2_CUDA(t, cudaMemsetAsync(out, 0, n, t->stream)); } else memset(out, 0, n);
         return B200AABB_OK;
     }
-    const bool ray = kind == B200AABB_RAY;
-    return run_batch(t, q, 48, n, space, kLineQuery, {{out, 1, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
-        if (ray) intersect_kernel<true, kAnyHit><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint8_t*)o[0], nullptr, nullptr, nullptr);
-        else intersect_kernel<false, kAnyHit><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint8_t*)o[0], nullptr, nullptr, nullptr);
+    return run_batch(t, q, query_bytes(kind), n, space, query_shape(kind), {{out, 1, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
+        launch_intersect<kAnyHit>(t, kind, st, (const double*)in, cnt, perm, (uint8_t*)o[0], nullptr, nullptr, nullptr);
     });
 }
 
 int b200aabb_number_of_intersected_primitives(b200aabb_tree* t, const double* q, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint32_t* out) { B2_LOCK(t);
-    if (!t || (n && (!q || !out))) return B200AABB_ERR_INVALID_ARGUMENT;
+    if (!t || (n && (!q || !out)) || !valid_kind(kind)) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     if (t->n == 0) {
         if (space == B200AABB_DEVICE) { B2_CUDA(t, cudaMemsetAsync(out, 0, n * 4, t->stream)); } else memset(out, 0, n * 4);
         return B200AABB_OK;
     }
-    const bool ray = kind == B200AABB_RAY;
-    return run_batch(t, q, 48, n, space, kLineQuery, {{out, 4, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
-        if (ray) intersect_kernel<true, kCount><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, nullptr, (uint32_t*)o[0], nullptr, nullptr);
-        else intersect_kernel<false, kCount><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, nullptr, (uint32_t*)o[0], nullptr, nullptr);
+    return run_batch(t, q, query_bytes(kind), n, space, query_shape(kind), {{out, 4, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
+        launch_intersect<kCount>(t, kind, st, (const double*)in, cnt, perm, nullptr, (uint32_t*)o[0], nullptr, nullptr);
     });
 }
 
 int b200aabb_any_intersected_primitive(b200aabb_tree* t, const double* q, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint32_t* out) { B2_LOCK(t);
-    if (!t || (n && (!q || !out))) return B200AABB_ERR_INVALID_ARGUMENT;
+    if (!t || (n && (!q || !out)) || !valid_kind(kind)) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     if (t->n == 0) {   // empty tree: nullopt
         if (space == B200AABB_DEVICE) { B2_CUDA(t, cudaMemsetAsync(out, 0xFF, n * 4, t->stream)); } else memset(out, 0xFF, n * 4);
         return B200AABB_OK;
     }
-    const bool ray = kind == B200AABB_RAY;
-    return run_batch(t, q, 48, n, space, kLineQuery, {{out, 4, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
-        if (ray) intersect_kernel<true, kAnyId><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, nullptr, (uint32_t*)o[0], nullptr, nullptr);
-        else intersect_kernel<false, kAnyId><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, nullptr, (uint32_t*)o[0], nullptr, nullptr);
+    return run_batch(t, q, query_bytes(kind), n, space, query_shape(kind), {{out, 4, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
+        launch_intersect<kAnyId>(t, kind, st, (const double*)in, cnt, perm, nullptr, (uint32_t*)o[0], nullptr, nullptr);
     });
 }
 
 int b200aabb_all_intersected_primitives(b200aabb_tree* t, const double* q, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space,
                                         const uint64_t* offsets, uint32_t* ids) { B2_LOCK(t);
-    if (!t || (n && (!q || !offsets))) return B200AABB_ERR_INVALID_ARGUMENT;
+    if (!t || (n && (!q || !offsets)) || !valid_kind(kind)) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     B2_CUDA(t, cudaSetDevice(t->device));
-    const bool ray = kind == B200AABB_RAY;
+    const size_t qbytes = query_bytes(kind);
     // one launch over the whole batch, in the caller's order (the id lists are variable-length: no chunked staging of the output)
     const double* d_q = q; const uint64_t* d_off = offsets; uint32_t* d_ids = ids;
     uint64_t total = 0;
@@ -986,21 +1019,20 @@ int b200aabb_all_intersected_primitives(b200aabb_tree* t, const double* q, uint6
         total = offsets[n];
         if (total && !ids) return B200AABB_ERR_INVALID_ARGUMENT;
         if (t->n == 0) return total == 0 ? B200AABB_OK : fail(t, B200AABB_ERR_INVALID_ARGUMENT, "offsets disagree with the number of intersected primitives");
-        cudaError_t e = cudaMalloc(&tmp[0], n * 48);
+        cudaError_t e = cudaMalloc(&tmp[0], n * qbytes);
         if (e == cudaSuccess) e = cudaMalloc(&tmp[1], (n + 1) * 8);
         if (e == cudaSuccess) e = cudaMalloc(&tmp[2], std::max<uint64_t>(total, 1) * 4);
         if (e != cudaSuccess) { release(); t->err = "cudaMalloc(all_intersected_primitives staging)"; return B200AABB_ERR_OUT_OF_MEMORY; }
-        cudaMemcpyAsync(tmp[0], q, n * 48, cudaMemcpyHostToDevice, t->stream);
+        cudaMemcpyAsync(tmp[0], q, n * qbytes, cudaMemcpyHostToDevice, t->stream);
         cudaMemcpyAsync(tmp[1], offsets, (n + 1) * 8, cudaMemcpyHostToDevice, t->stream);
         d_q = (const double*)tmp[0]; d_off = (const uint64_t*)tmp[1]; d_ids = (uint32_t*)tmp[2];
     } else if (t->n == 0) return B200AABB_OK;
     cudaMemsetAsync(t->d_counters, 0, 8 * sizeof(unsigned long long), t->stream);
     cudaEventRecord(t->ev_a, t->stream);
     const uint32_t* perm = nullptr;
-    rc = coherence_order(t, kDeviceScratch, t->stream, d_q, n, kLineQuery, &perm);
+    rc = coherence_order(t, kDeviceScratch, t->stream, d_q, n, query_shape(kind), &perm);
     if (rc) { release(); return rc; }
-    if (ray) intersect_kernel<true, kList><<<grid_for(n, 128), 128, 0, t->stream>>>(tree_ref(t, perm), d_q, n, nullptr, nullptr, d_off, d_ids);
-    else intersect_kernel<false, kList><<<grid_for(n, 128), 128, 0, t->stream>>>(tree_ref(t, perm), d_q, n, nullptr, nullptr, d_off, d_ids);
+    launch_intersect<kList>(t, kind, t->stream, d_q, n, perm, nullptr, nullptr, d_off, d_ids);
     t->stats.kernel_launches += 1;
     cudaEventRecord(t->ev_b, t->stream);
     t->query_timing_pending = true;
@@ -1145,8 +1177,12 @@ static int first_intersection_impl(b200aabb_tree* t, const double* rays, uint64_
                            cudaMemcpyAsync(t->d_stage_aux[t->cur_slot], skip_ids + t->cur_offset, cnt * 4, cudaMemcpyHostToDevice, st);
                            sk = t->d_stage_aux[t->cur_slot];
                        }
-                       first_intersection_kernel<<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint32_t*)o[0], (double*)o[1],
-                                                                                      (double*)o[2], (double*)o[3], (uint8_t*)o[4], sk, mask_dev, mask_words);
+                       if (sk || mask_dev)
+                           first_intersection_kernel<true><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint32_t*)o[0], (double*)o[1],
+                                                                                                (double*)o[2], (double*)o[3], (uint8_t*)o[4], sk, mask_dev, mask_words);
+                       else
+                           first_intersection_kernel<false><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint32_t*)o[0], (double*)o[1],
+                                                                                                 (double*)o[2], (double*)o[3], (uint8_t*)o[4], nullptr, nullptr, 0);
                    });
     if (d_mask) { if (t->async_pending) drain(t); cudaFree(d_mask); }
     return rc;

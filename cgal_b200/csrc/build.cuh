@@ -276,8 +276,13 @@ __device__ __forceinline__ void refit_climb_global(BvhNode* nodes, uint32_t p, u
     }
 }
 
-__global__ void __launch_bounds__(kRefitBlock) refit_local_kernel(const TriRec* __restrict__ tris, uint64_t n, BvhNode* nodes, const uint32_t* __restrict__ leaf_parent,
-                                                                  RefitEntry* __restrict__ frontier, unsigned* __restrict__ frontier_count, unsigned frontier_cap) {
+// EMIT: the kernel also WRITES the leaf records (the work of emit_leaves_kernel: gather the primitive `src`, store the 96-byte record and its
+// binary32 copy) before it climbs, so that the build reads every primitive once instead of writing the records and reading them back
+// (1.6 GB at 16.8 M primitives); the stores of one thread overlap the climbs of the others.
+struct EmitArgs { const double* soup; const uint32_t* ids; const uint32_t* perm; const uint64_t* words; int ib; TriF* outf; };
+template <bool EMIT>
+__global__ void __launch_bounds__(kRefitBlock) refit_local_kernel(TriRec* __restrict__ tris, uint64_t n, BvhNode* nodes, const uint32_t* __restrict__ leaf_parent,
+                                                                  RefitEntry* __restrict__ frontier, unsigned* __restrict__ frontier_count, unsigned frontier_cap, EmitArgs em) {
     __shared__ uint4 s_link[kRefitBlock];          // child[0], child[1], parent, other end of the range, of node (block base + t)
     __shared__ unsigned s_cnt[kRefitBlock];
     __shared__ float s_box[kRefitBlock][2][6];     // child boxes of the block's own nodes
@@ -290,13 +295,33 @@ __global__ void __launch_bounds__(kRefitBlock) refit_local_kernel(const TriRec* 
         s_link[threadIdx.x] = make_uint4(a.x, b.x, a.y, b.y);
     }
     __syncthreads();
-    if (k >= n || n == 1) return;
+    if (k >= n) return;
     float lo[3], hi[3];
-    {
+    if (EMIT) {
+        const uint32_t src = em.perm ? em.perm[k] : (uint32_t)(em.words[k] & ((1ull << em.ib) - 1ull));
+        const double* t = em.soup + 9 * (uint64_t)src;
+        TriRec r;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) r.v[j] = t[j];
+        r.id = em.ids ? em.ids[src] : src;
+        r.pad[0] = src;                                          // position of the primitive in the inserted order (b200aabb_refit re-reads it there)
+#pragma unroll
+        for (int j = 1; j < 5; ++j) r.pad[j] = 0;
+        tris[k] = r;
+        TriF f;
+#pragma unroll
+        for (int j = 0; j < 9; ++j) f.v[j] = (float)r.v[j];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) f.pad[j] = 0;
+        em.outf[k] = f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { lo[a] = float_below(fmin(r.v[a], fmin(r.v[3 + a], r.v[6 + a]))); hi[a] = float_above(fmax(r.v[a], fmax(r.v[3 + a], r.v[6 + a]))); }
+    } else {
         const double* v = tris[k].v;
 #pragma unroll
         for (int a = 0; a < 3; ++a) { lo[a] = float_below(fmin(v[a], fmin(v[3 + a], v[6 + a]))); hi[a] = float_above(fmax(v[a], fmax(v[3 + a], v[6 + a]))); }
     }
+    if (n == 1) return;
     uint32_t me = kLeafBit | (uint32_t)k;
     uint32_t p = leaf_parent[k];
     while (true) {

@@ -179,12 +179,26 @@ B2_HD LineCtx make_line(const Vec3& s, const Vec3& q, double mag = 0.0) {
     c.t_abs_slack = 1.5e-14 * smax / fabs(comp(c.d, c.major));
     return c;
 }
+// the same for a Line_3 given as point + direction vector (x(t) = p + t v, t unbounded)
+B2_HD LineCtx make_line_pv(const Vec3& p, const Vec3& v) {
+    LineCtx c = make_line(p, p, 0.0);
+    c.q = p + v; c.d = v;
+    c.zero_mask = (v.x == 0.0 ? 1 : 0) | (v.y == 0.0 ? 2 : 0) | (v.z == 0.0 ? 4 : 0);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double si = comp(p, i), inv = 1.0 / comp(v, i);
+        c.inv[i] = (float)inv;
+        c.err[i] = float_above(fabs(si - (double)c.sf[i]) * fabs(inv) * 1.0000001) + 1e-37f;
+    }
+    c.major = ray_major_axis(v);
+    return c;
+}
 // Does x(t), t in [0, tlimit], possibly meet the closed box [lo, hi]?  tn = lower bound of the entry parameter.
 // Per axis the computed parameter t_c = (b - sf) * inv differs from the true (b - s) / d by at most
 // |t_c| * 2^-21 (one subtraction, one product, the rounding of 1/d and of d itself: < 4 * 2^-24 relative) + err[i]
 // (rounding of the source).  NaNs (0 * inf, inf - inf) are dropped by fminf/fmaxf, which only loosens the interval.
-B2_HD bool line_box(const float* lo, const float* hi, const LineCtx& c, float tlimit, float& tn) {
-    float tnear = 0.0f, tfar = tlimit;
+B2_HD bool line_box(const float* lo, const float* hi, const LineCtx& c, float tlimit, float& tn, float tstart = 0.0f) {
+    float tnear = tstart, tfar = tlimit;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         if (c.zero_mask & (1 << i)) {
@@ -248,9 +262,10 @@ enum IntersectMode { kAnyHit = 0, kCount = 1, kAnyId = 2, kList = 3 };
 
 // The traversal shared by all intersection queries: visits every leaf whose box the query line meets and calls leaf(ref) -> bool
 // ("this primitive counts"); returns how many did.  STOP_AT_FIRST ends at the first one.
-template <bool IS_RAY, bool STOP_AT_FIRST, class Leaf>
+enum LineKind { kSegmentQ = 0, kRayQ = 1, kLineQ = 2 };
+template <int KIND, bool STOP_AT_FIRST, class Leaf>
 B2_HD uint32_t traverse_line(const BvhNode* __restrict__ nodes, uint32_t root, const LineCtx& c, TravStat& st, Leaf&& leaf) {
-    const float tlimit = IS_RAY ? INFINITY : 1.0f;
+    const float tlimit = KIND == kSegmentQ ? 1.0f : INFINITY, tstart = KIND == kLineQ ? -INFINITY : 0.0f;
     uint32_t found = 0;
     if (root & kLeafBit) return leaf(root) ? 1u : 0u;       // singleton tree: AABB_tree.h:516-525
     uint32_t stack[kStackCap];
@@ -267,8 +282,8 @@ B2_HD uint32_t traverse_line(const BvhNode* __restrict__ nodes, uint32_t root, c
             const NodeView n = load_node(nodes, cur);
             ++st.nodes;
             float tn;
-            const bool h0 = line_box(n.lo0, n.hi0, c, tlimit, tn);
-            const bool h1 = line_box(n.lo1, n.hi1, c, tlimit, tn);
+            const bool h0 = line_box(n.lo0, n.hi0, c, tlimit, tn, tstart);
+            const bool h1 = line_box(n.lo1, n.hi1, c, tlimit, tn, tstart);
             uint32_t next = kNone;
             if (h0) { if (n.c0 & kLeafBit) pend[np++] = n.c0; else next = n.c0; }
             if (h1) {
@@ -288,21 +303,71 @@ B2_HD uint32_t traverse_line(const BvhNode* __restrict__ nodes, uint32_t root, c
     return found;
 }
 
-template <bool IS_RAY, int MODE>
+// KIND: kSegmentQ (s, q = source, target), kRayQ (source, second point), kLineQ (s = a point of the line, q = its DIRECTION VECTOR)
+template <int KIND, int MODE>
 B2_HD uint32_t traverse_intersect(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root,
                                   const Vec3& s, const Vec3& q, TravStat& st, uint32_t* list = nullptr, uint32_t list_cap = 0) {
-    const LineCtx c = make_line(s, q);
+    const LineCtx c = KIND == kLineQ ? make_line_pv(s, q) : make_line(s, q);
     uint32_t nlisted = 0, found_id = kNone;
     constexpr bool kStopAtFirst = MODE == kAnyHit || MODE == kAnyId;
-    const uint32_t found = traverse_line<IS_RAY, kStopAtFirst>(nodes, root, c, st, [&](uint32_t ref) -> bool {
+    const uint32_t found = traverse_line<KIND, kStopAtFirst>(nodes, root, c, st, [&](uint32_t ref) -> bool {
         uint32_t id;
         const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
         ++st.leaves;
-        if (!(IS_RAY ? ray_tri_do_intersect(t, s, q, st.nexact) : seg_tri_do_intersect(t, s, q, st.nexact))) return false;
+        if (!(KIND == kRayQ ? ray_tri_do_intersect(t, s, q, st.nexact) : KIND == kLineQ ? line_tri_do_intersect(t, s, q, st.nexact) : seg_tri_do_intersect(t, s, q, st.nexact))) return false;
         if (MODE == kList) { if (nlisted < list_cap) list[nlisted] = id; ++nlisted; }   // (never writes past the caller's room; the count tells)
         if (MODE == kAnyId) found_id = id;
         return true;
     });
+    return MODE == kAnyId ? found_id : (MODE == kAnyHit ? (found ? 1u : 0u) : found);
+}
+
+// Plane_3 queries (a x + b y + c z + d = 0): Do_intersect_3(Plane_3, Bbox_3) (Iso_cuboid_3_Plane_3_do_intersect.h:90-125: the signs of the two
+// corners extreme along the normal) is replaced by a conservative binary64 test — the plane can only meet the box if its value at the box
+// centre is within the box's half extent along the normal, plus the rounding of that evaluation — and the leaves decide exactly.
+B2_HD bool plane_box(const float* lo, const float* hi, double a, double b, double c, double d) {
+    const double cx = 0.5 * ((double)lo[0] + (double)hi[0]), cy = 0.5 * ((double)lo[1] + (double)hi[1]), cz = 0.5 * ((double)lo[2] + (double)hi[2]);
+    const double hx = 0.5 * ((double)hi[0] - (double)lo[0]), hy = 0.5 * ((double)hi[1] - (double)lo[1]), hz = 0.5 * ((double)hi[2] - (double)lo[2]);
+    const double s = ((a * cx + b * cy) + c * cz) + d;
+    const double r = (fabs(a) * hx + fabs(b) * hy) + fabs(c) * hz;
+    const double mag = ((fabs(a) * (fabs(cx) + hx) + fabs(b) * (fabs(cy) + hy)) + fabs(c) * (fabs(cz) + hz)) + fabs(d);
+    return !(fabs(s) > r + 1e-14 * mag);      // (NaN / overflow: keep the box)
+}
+template <int MODE>
+B2_HD uint32_t traverse_plane(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root, double a, double b, double c, double d,
+                              TravStat& st, uint32_t* list = nullptr, uint32_t list_cap = 0) {
+    constexpr bool kStopAtFirst = MODE == kAnyHit || MODE == kAnyId;
+    uint32_t nlisted = 0, found_id = kNone, found = 0;
+    auto leaf = [&](uint32_t ref) -> bool {
+        uint32_t id;
+        const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
+        ++st.leaves;
+        if (!plane_tri_do_intersect(t, a, b, c, d, st.nexact)) return false;
+        if (MODE == kList) { if (nlisted < list_cap) list[nlisted] = id; ++nlisted; }
+        if (MODE == kAnyId) found_id = id;
+        return true;
+    };
+    if (root & kLeafBit) found = leaf(root) ? 1u : 0u;
+    else {
+        uint32_t stack[kStackCap];
+        int sp = 0;
+        uint32_t cur = root;
+        while (cur != kNone) {
+            const NodeView n = load_node(nodes, cur);
+            ++st.nodes;
+            const bool h0 = plane_box(n.lo0, n.hi0, a, b, c, d), h1 = plane_box(n.lo1, n.hi1, a, b, c, d);
+            uint32_t next = kNone;
+            if (h0) { if (n.c0 & kLeafBit) { if (leaf(n.c0)) { ++found; if (kStopAtFirst) break; } } else next = n.c0; }
+            if (h1) {
+                if (n.c1 & kLeafBit) { if (leaf(n.c1)) { ++found; if (kStopAtFirst) break; } }
+                else if (next == kNone) next = n.c1;
+                else if (sp < kStackCap) stack[sp++] = n.c1;
+                else st.overflow = 1;
+            }
+            if (next == kNone && sp > 0) next = stack[--sp];
+            cur = next;
+        }
+    }
     return MODE == kAnyId ? found_id : (MODE == kAnyHit ? (found ? 1u : 0u) : found);
 }
 
@@ -317,7 +382,7 @@ B2_HD uint32_t traverse_ray_objects(const BvhNode* __restrict__ nodes, const Tri
                                     TravStat& st, uint32_t* ids, uint8_t* kinds, double* pts, uint32_t cap) {
     const LineCtx c = make_line(s, q);
     uint32_t nlisted = 0;
-    return traverse_line<true, MODE == kAnyId>(nodes, root, c, st, [&](uint32_t ref) -> bool {
+    return traverse_line<kRayQ, MODE == kAnyId>(nodes, root, c, st, [&](uint32_t ref) -> bool {
         uint32_t id;
         const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
         ++st.leaves;
@@ -353,6 +418,7 @@ struct FirstHit { uint32_t prim; int kind; double t; Vec3 p0, p1; int tie; int n
 
 // skip_id / skip_mask: first_intersection(query, skip) (AABB_tree.h:307-328): primitives the caller's functor rejects are ignored — here the
 // one primitive skip_id (kNone: none) and those whose bit is set in skip_mask (bit per primitive id, mask_words 32-bit words; nullptr: none)
+template <bool SKIP = false>
 B2_HD FirstHit traverse_first(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root,
                               const Vec3& s, const Vec3& q, double mag, TravStat& st, uint32_t skip_id = kNone,
                               const uint32_t* __restrict__ skip_mask = nullptr, uint32_t mask_words = 0) {
@@ -368,7 +434,7 @@ B2_HD FirstHit traverse_first(const BvhNode* __restrict__ nodes, const TriRec* _
         const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
         ++st.leaves;
         // skip(primitive.id()): AABB_ray_intersection.h:86,99,113 — NOT consulted for a one-primitive tree, which the reference answers directly (:214)
-        if (!(root & kLeafBit) && (id == skip_id || (skip_mask && (id >> 5) < mask_words && ((skip_mask[id >> 5] >> (id & 31u)) & 1u)))) return;
+        if (SKIP && !(root & kLeafBit) && (id == skip_id || (skip_mask && (id >> 5) < mask_words && ((skip_mask[id >> 5] >> (id & 31u)) & 1u)))) return;
         int nex = 0;
         const RayX x = ray_tri_intersection_call(t.a.x, t.a.y, t.a.z, t.b.x, t.b.y, t.b.z, t.c.x, t.c.y, t.c.z, s.x, s.y, s.z, q.x, q.y, q.z, c.major, &nex);
         st.nexact += nex;

@@ -160,6 +160,29 @@ B2_HD bool ray_tri_do_intersect(const Tri3& t, const Vec3& p, const Vec3& q, int
     return fwd ? passes_edges(p, q, t, nexact) : passes_edges(q, p, t, nexact);
 }
 
+// Do_intersect_3(Line_3, Triangle_3): Line_3_Triangle_3_do_intersect.h:27-79.  The line is (point p, direction vector v) as CGAL stores it;
+// "q" of the reference is p + v, formed exactly (the predicate runs in Filtered_predicate's exact kernel when the filter fails).
+B2_HD bool line_tri_do_intersect(const Tri3& t, const Vec3& p, const Vec3& v, int& nexact) {
+    // orientation(a,b,c,p) != COPLANAR || orientation(a,b,c,q) != COPLANAR; with the first zero, the second is the sign of det[b-a | c-a | v]
+    const Vec3 zero = {0.0, 0.0, 0.0};
+    if (orient3(t.a, t.b, t.c, p, nexact) != 0 || orient3_dir(t.a, t.b, t.c, zero, v, nexact) != 0) {
+        const int pqab = orient3_vec(v, p, t.a, t.b, nexact), pqbc = orient3_vec(v, p, t.b, t.c, nexact);
+        if (pqab > 0) return pqbc != -1 && orient3_vec(v, p, t.c, t.a, nexact) != -1;
+        if (pqab < 0) return pqbc != 1 && orient3_vec(v, p, t.c, t.a, nexact) != 1;
+        if (pqbc > 0) return orient3_vec(v, p, t.c, t.a, nexact) != -1;
+        if (pqbc < 0) return orient3_vec(v, p, t.c, t.a, nexact) != 1;
+        return true;
+    }
+    const int pqa = coplanar_orient_vec(p, v, t.a, nexact);                 // the line lies in the triangle's plane (:76-77)
+    return coplanar_orient_vec(p, v, t.b, nexact) != pqa || coplanar_orient_vec(p, v, t.c, nexact) != pqa;
+}
+// Do_intersect_3(Plane_3, Triangle_3): Plane_3_Triangle_3_do_intersect.h:27-51; the plane is its four coefficients (a, b, c, d)
+B2_HD bool plane_tri_do_intersect(const Tri3& t, double a, double b, double c, double d, int& nexact) {
+    const int s0 = plane_side(a, b, c, d, t.a, nexact);
+    if (s0 == 0) return true;
+    return plane_side(a, b, c, d, t.b, nexact) != s0 || plane_side(a, b, c, d, t.c, nexact) != s0;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Intersect_3(Ray_3, Triangle_3) + the ray parameter of AABB_ray_intersection.h:168-198
 // ---------------------------------------------------------------------------------------------------------------

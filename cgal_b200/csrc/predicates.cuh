@@ -62,6 +62,17 @@ B2_HD int orient3_dir(const Vec3& a, const Vec3& b, const Vec3& c, const Vec3& p
     });
 }
 
+// sign det[v | a-p | b-p] = Orientation_3(p, p + v, a, b) with the point p + v formed EXACTLY: what Filtered_predicate evaluates for the
+// Line_3 queries (a Line_3 is stored as point + direction vector, Cartesian/Line_3.h; Line_3_Triangle_3_do_intersect.h:45-46 takes
+// point(0) and point(1) = p + v inside the exact kernel)
+B2_HD int orient3_vec(const Vec3& v, const Vec3& p, const Vec3& a, const Vec3& b, int& nexact) {
+    return filtered_det3(v, a - p, b - p, nexact, [&]() {
+        return exact_det3_sign(DD{v.x, 0.0}, DD{v.y, 0.0}, DD{v.z, 0.0},
+                               dd_diff(a.x, p.x), dd_diff(a.y, p.y), dd_diff(a.z, p.z),
+                               dd_diff(b.x, p.x), dd_diff(b.y, p.y), dd_diff(b.z, p.z));
+    });
+}
+
 // orientationC2 (kernel_ftC2.h:403-408): sign((qx-px)(ry-py) - (rx-px)(qy-py))
 B2_HD int orient2(double px, double py, double qx, double qy, double rx, double ry, int& nexact) {
     const double a = qx - px, b = qy - py, c = rx - px, d = ry - py;
@@ -83,6 +94,55 @@ B2_HD int coplanar_orient(const Vec3& p, const Vec3& q, const Vec3& r, int& nexa
     if (o != 0) return o;
     return orient2(p.x, p.z, q.x, q.z, r.x, r.z, nexact);
 }
+// the same with q = p + v formed exactly (Line_3 queries): sign(vx (ry - py) - (rx - px) vy), and the coplanar_orientationC3 cascade over it
+B2_HD int orient2_vec(double vx, double vy, double px, double py, double rx, double ry, int& nexact) {
+    const double c = rx - px, d = ry - py;
+    const double l = vx * d, r = c * vy, det = l - r;
+    const double mag = fmax(fmax(fabs(vx), fabs(vy)), fmax(fabs(c), fabs(d)));
+    if (mag > 1e-140 && mag < 1e140) {
+        const double err = 8.8817841970012523e-16 * (fabs(l) + fabs(r));
+        if (det > err) return 1;
+        if (det < -err) return -1;
+    }
+    ++nexact;
+    return exact_det2_sign(DD{vx, 0.0}, dd_diff(ry, py), dd_diff(rx, px), DD{vy, 0.0});
+}
+B2_HD int coplanar_orient_vec(const Vec3& p, const Vec3& v, const Vec3& r, int& nexact) {
+    int o = orient2_vec(v.x, v.y, p.x, p.y, r.x, r.y, nexact);
+    if (o != 0) return o;
+    o = orient2_vec(v.y, v.z, p.y, p.z, r.y, r.z, nexact);
+    if (o != 0) return o;
+    return orient2_vec(v.x, v.z, p.x, p.z, r.x, r.z, nexact);
+}
+// Oriented_side_3(Plane_3, Point_3) = sign(a x + b y + c z + d) (side_of_oriented_planeC3, kernel_ftC3.h), exact: a filter on the rounded sum,
+// then the seven-component expansion of the three products and d
+B2_HD_NOINLINE int plane_side_exact(double a, double b, double c, double d, double x, double y, double z) {
+    double t1[2], t2[2], t3[2], s1[4], s2[6], s3[8];
+    int n1 = 0, n2 = 0, n3 = 0;
+    double hi, lo;
+    two_prod(a, x, hi, lo); if (lo != 0.0) t1[n1++] = lo; if (hi != 0.0) t1[n1++] = hi;
+    two_prod(b, y, hi, lo); if (lo != 0.0) t2[n2++] = lo; if (hi != 0.0) t2[n2++] = hi;
+    two_prod(c, z, hi, lo); if (lo != 0.0) t3[n3++] = lo; if (hi != 0.0) t3[n3++] = hi;
+    const int m1 = exp_add(t1, n1, t2, n2, s1);
+    const int m2 = exp_add(s1, m1, t3, n3, s2);
+    double dd[1] = {d};
+    const int m3 = exp_add(s2, m2, dd, d != 0.0 ? 1 : 0, s3);
+    return exp_sign(s3, m3);
+}
+B2_HD int plane_side(double a, double b, double c, double d, const Vec3& p, int& nexact) {
+    const double ax = a * p.x, by = b * p.y, cz = c * p.z;
+    const double v = ((ax + by) + cz) + d;
+    const double mag = ((fabs(ax) + fabs(by)) + fabs(cz)) + fabs(d);
+    if (mag < 1e290 && (mag > 1e-290 || mag == 0.0)) {
+        const double err = 6.7e-16 * mag;                     // three products + three sums: < 6 * 2^-53 relative to the magnitude sum
+        if (v > err) return 1;
+        if (v < -err) return -1;
+        if (mag == 0.0) return 0;
+    }
+    ++nexact;
+    return plane_side_exact(a, b, c, d, p.x, p.y, p.z);
+}
+
 // collinear_are_ordered_along_lineC3 (kernel_ftC3.h:279-291)
 B2_HD bool collinear_ordered(const Vec3& p, const Vec3& q, const Vec3& r) {
     if (p.x < q.x) return !(r.x < q.x);

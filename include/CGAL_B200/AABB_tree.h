@@ -245,7 +245,7 @@ class AABB_tree {
   OutputIterator do_intersect(QueryIterator first, QueryIterator beyond, OutputIterator out) const {
     typedef typename std::iterator_traits<QueryIterator>::value_type Query;
     std::vector<double> q = pack_lines(first, beyond);
-    const uint64_t n = q.size() / 6;
+    const uint64_t n = q.size() / doubles_per_query<Query>();
     std::vector<uint8_t> r(n);
     ensure_built();
     check(b200aabb_do_intersect(m_handle, q.data(), n, kind_of<Query>(), B200AABB_HOST, r.data()));
@@ -257,7 +257,7 @@ class AABB_tree {
   OutputIterator number_of_intersected_primitives(QueryIterator first, QueryIterator beyond, OutputIterator out) const {
     typedef typename std::iterator_traits<QueryIterator>::value_type Query;
     std::vector<double> q = pack_lines(first, beyond);
-    const uint64_t n = q.size() / 6;
+    const uint64_t n = q.size() / doubles_per_query<Query>();
     std::vector<uint32_t> r(n);
     ensure_built();
     check(b200aabb_number_of_intersected_primitives(m_handle, q.data(), n, kind_of<Query>(), B200AABB_HOST, r.data()));
@@ -269,7 +269,7 @@ class AABB_tree {
   OutputIterator any_intersected_primitive(QueryIterator first, QueryIterator beyond, OutputIterator out) const {
     typedef typename std::iterator_traits<QueryIterator>::value_type Query;
     std::vector<double> q = pack_lines(first, beyond);
-    const uint64_t n = q.size() / 6;
+    const uint64_t n = q.size() / doubles_per_query<Query>();
     std::vector<uint32_t> r(n);
     ensure_built();
     check(b200aabb_any_intersected_primitive(m_handle, q.data(), n, kind_of<Query>(), B200AABB_HOST, r.data()));
@@ -284,7 +284,7 @@ class AABB_tree {
   OutputIterator all_intersected_primitives(QueryIterator first, QueryIterator beyond, OutputIterator out) const {
     typedef typename std::iterator_traits<QueryIterator>::value_type Query;
     std::vector<double> q = pack_lines(first, beyond);
-    const uint64_t n = q.size() / 6;
+    const uint64_t n = q.size() / doubles_per_query<Query>();
     std::vector<uint32_t> cnt(n);
     ensure_built();
     check(b200aabb_number_of_intersected_primitives(m_handle, q.data(), n, kind_of<Query>(), B200AABB_HOST, cnt.data()));
@@ -500,15 +500,36 @@ class AABB_tree {
     check(b200aabb_build(m_handle));
     m_uploaded = true;
   }
+  // Query types are told apart by the kernel-object interface: Segment_3 / Ray_3 are the traits' own types; a Line_3 has point() and
+  // to_vector() (Cartesian/Line_3.h), a Plane_3 has a(), b(), c(), d() (Cartesian/Plane_3.h)
+  template <typename Q, typename = void> struct has_line_interface : std::false_type {};
+  template <typename Q> struct has_line_interface<Q, std::void_t<decltype(std::declval<const Q&>().point()), decltype(std::declval<const Q&>().to_vector())>> : std::true_type {};
+  template <typename Q, typename = void> struct has_plane_interface : std::false_type {};
+  template <typename Q> struct has_plane_interface<Q, std::void_t<decltype(std::declval<const Q&>().a()), decltype(std::declval<const Q&>().d())>> : std::true_type {};
   template <typename Query>
-  static b200aabb_query_kind kind_of() {
-    static_assert(std::is_same<Query, Segment>::value || std::is_same<Query, Ray>::value, "offloaded intersection queries: Segment_3 and Ray_3");
-    return std::is_same<Query, Ray>::value ? B200AABB_RAY : B200AABB_SEGMENT;
+  static constexpr b200aabb_query_kind kind_of() {
+    if constexpr (std::is_same<Query, Segment>::value) return B200AABB_SEGMENT;
+    else if constexpr (std::is_same<Query, Ray>::value) return B200AABB_RAY;
+    else if constexpr (has_plane_interface<Query>::value) return B200AABB_PLANE;
+    else {
+      static_assert(has_line_interface<Query>::value, "offloaded intersection queries: Segment_3, Ray_3, Line_3 and Plane_3");
+      return B200AABB_LINE;
+    }
   }
+  template <typename Query>
+  static constexpr uint64_t doubles_per_query() { return kind_of<Query>() == B200AABB_PLANE ? 4 : 6; }
   static void put(std::vector<double>& v, const Point& p) { v.push_back((double)p.x()); v.push_back((double)p.y()); v.push_back((double)p.z()); }
-  static void put_line(std::vector<double>& v, const Segment& s) { put(v, s.source()); put(v, s.target()); }
-  template <typename R = Ray, typename = std::enable_if_t<!std::is_same<R, Segment>::value>>
-  static void put_line(std::vector<double>& v, const R& r) { put(v, r.source()); put(v, r.second_point()); }   // Cartesian/Ray_3.h:35-47
+  template <typename Query>
+  static void put_line(std::vector<double>& v, const Query& q) {
+    if constexpr (kind_of<Query>() == B200AABB_SEGMENT) { put(v, q.source()); put(v, q.target()); }
+    else if constexpr (kind_of<Query>() == B200AABB_RAY) { put(v, q.source()); put(v, q.second_point()); }   // Cartesian/Ray_3.h:35-47
+    else if constexpr (kind_of<Query>() == B200AABB_PLANE) { v.push_back((double)q.a()); v.push_back((double)q.b()); v.push_back((double)q.c()); v.push_back((double)q.d()); }
+    else {                                                                                                    // the stored members, not two points
+      put(v, q.point());
+      decltype(auto) d = q.to_vector();
+      v.push_back((double)d.x()); v.push_back((double)d.y()); v.push_back((double)d.z());
+    }
+  }
   template <typename It>
   static std::vector<double> pack_lines(It first, It beyond) {
     std::vector<double> v;

@@ -39,9 +39,13 @@ enum { B200AABB_NO_PRIMITIVE = 0xFFFFFFFFu };
 /* where the query / result pointers of a batched call live */
 typedef enum { B200AABB_HOST = 0, B200AABB_DEVICE = 1 } b200aabb_memspace;
 
-/* Query type of the intersection queries: Segment_3(source,target) or Ray_3(source, second point); both are
- * 6 doubles (Cartesian_kernel/include/CGAL/Cartesian/Ray_3.h:35-47, Segment_3.h). */
-typedef enum { B200AABB_SEGMENT = 0, B200AABB_RAY = 1 } b200aabb_query_kind;
+/* Query type of the intersection queries (do_intersect, number_of_intersected_primitives, any_ / all_intersected_primitives):
+ *   Segment_3 (source, target) and Ray_3 (source, second point): 6 doubles (Cartesian_kernel/include/CGAL/Cartesian/Ray_3.h:35-47, Segment_3.h);
+ *   Line_3: 6 doubles = a point of the line + its DIRECTION VECTOR, the two members a Cartesian Line_3 stores (Cartesian/Line_3.h: line.point(),
+ *           line.to_vector()) — Line_3(p, q) keeps the ROUNDED difference q - p, and the reference's exact predicates work on what is stored;
+ *   Plane_3: 4 doubles = the coefficients (a, b, c, d) of a x + b y + c z + d = 0 (Cartesian/Plane_3.h).
+ * first_intersection / all_intersections / any_intersection take Ray_3 only. */
+typedef enum { B200AABB_SEGMENT = 0, B200AABB_RAY = 1, B200AABB_LINE = 2, B200AABB_PLANE = 3 } b200aabb_query_kind;
 
 /* per-query result flags (bit set) */
 enum {

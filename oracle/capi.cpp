@@ -70,24 +70,29 @@ void orc_accelerate_distance_queries(void* hv) {
 void orc_do_not_accelerate_distance_queries(void* hv) { ((Handle*)hv)->tree->do_not_accelerate_distance_queries(); }
 void orc_bbox(void* hv, double* out) { Box b = ((Handle*)hv)->tree->bbox(); for (int i = 0; i < 3; ++i) { out[i] = b.lo[i]; out[3 + i] = b.hi[i]; } }
 
-// kind: 0 = Segment_3 (source,target), 1 = Ray_3 (source, second point); q = n x 6 doubles
+// kind: 0 = Segment_3 (source,target), 1 = Ray_3 (source, second point), 2 = Line_3 (point, direction vector): q = n x 6 doubles;
+//       3 = Plane_3 (a, b, c, d): q = n x 4 doubles
+static inline Tree::LineQ LQ(const double* q, uint64_t i, int kind) {
+    if (kind == 3) return {P(q + 4 * i), P3{q[4 * i + 3], 0, 0}, 3};
+    return {P(q + 6 * i), P(q + 6 * i + 3), kind};
+}
 void orc_do_intersect(void* hv, const double* q, uint64_t n, int kind, uint8_t* out, int nthreads) {
     const Tree& t = *((Handle*)hv)->tree;
     parallel_for(n, nthreads, [&](uint64_t b, uint64_t e) {
-        for (uint64_t i = b; i < e; ++i) out[i] = t.do_intersect({P(q + 6 * i), P(q + 6 * i + 3), kind == 1}) ? 1 : 0;
+        for (uint64_t i = b; i < e; ++i) out[i] = t.do_intersect(LQ(q, i, kind)) ? 1 : 0;
     });
 }
 void orc_count(void* hv, const double* q, uint64_t n, int kind, uint32_t* out, int nthreads) {
     const Tree& t = *((Handle*)hv)->tree;
     parallel_for(n, nthreads, [&](uint64_t b, uint64_t e) {
-        for (uint64_t i = b; i < e; ++i) out[i] = t.number_of_intersected_primitives({P(q + 6 * i), P(q + 6 * i + 3), kind == 1});
+        for (uint64_t i = b; i < e; ++i) out[i] = t.number_of_intersected_primitives(LQ(q, i, kind));
     });
 }
 // any_intersected_primitive (AABB_tree.h:947-956): 0xFFFFFFFF when none
 void orc_any_intersected_primitive(void* hv, const double* q, uint64_t n, int kind, uint32_t* out, int nthreads) {
     const Tree& t = *((Handle*)hv)->tree;
     parallel_for(n, nthreads, [&](uint64_t b, uint64_t e) {
-        for (uint64_t i = b; i < e; ++i) out[i] = t.any_intersected_primitive({P(q + 6 * i), P(q + 6 * i + 3), kind == 1});
+        for (uint64_t i = b; i < e; ++i) out[i] = t.any_intersected_primitive(LQ(q, i, kind));
     });
 }
 // all_intersected_primitives (AABB_tree.h:934-945): ids of query i, in the reference's traversal order, at ids[offsets[i] .. offsets[i+1]);
@@ -99,7 +104,7 @@ int orc_all_intersected_primitives(void* hv, const double* q, uint64_t n, int ki
         std::vector<uint32_t> v;
         for (uint64_t i = b; i < e; ++i) {
             v.clear();
-            t.all_intersected_primitives({P(q + 6 * i), P(q + 6 * i + 3), kind == 1}, v);
+            t.all_intersected_primitives(LQ(q, i, kind), v);
             if (v.size() != offsets[i + 1] - offsets[i]) { bad = 1; continue; }
             std::copy(v.begin(), v.end(), ids + offsets[i]);
         }
@@ -183,8 +188,8 @@ void orc_naive_count(void* hv, const double* q, uint64_t n, int kind, uint32_t* 
     const Mesh& m = ((Handle*)hv)->mesh;
     parallel_for(n, nthreads, [&](uint64_t b, uint64_t e) {
         for (uint64_t i = b; i < e; ++i) {
-            uint32_t c = 0; const P3 p = P(q + 6 * i), r = P(q + 6 * i + 3);
-            for (const Tri& t : m.tris) c += (kind == 1 ? do_intersect_ray_tri(t, p, r) : do_intersect_seg_tri(t, p, r)) ? 1 : 0;
+            uint32_t c = 0; const Tree::LineQ lq = LQ(q, i, kind);
+            for (const Tri& t : m.tris) c += Tree::prim_hit(t, lq) ? 1 : 0;
             out[i] = c;
         }
     });
@@ -245,6 +250,8 @@ int orc_compare_distance(const double* p3) { return compare_distance(P(p3), P(p3
 int orc_compare_distance_exact(const double* p3) { return compare_distance_exact(P(p3), P(p3 + 3), P(p3 + 6)); }
 int orc_bbox_do_intersect(const double* box, const double* pq, int is_ray) { return do_intersect_bbox(P(pq), P(pq + 3), B(box), is_ray != 0); }
 int orc_bbox_do_intersect_exact(const double* box, const double* pq, int is_ray) { return bbox_segment_aux<true>(P(pq), P(pq + 3), B(box), true, !is_ray).v; }
+int orc_tri_do_intersect_kind(const double* tri, const double* q, int kind) { return Tree::prim_hit(T(tri), LQ(q, 0, kind)) ? 1 : 0; }
+int orc_bbox_do_intersect_kind(const double* box, const double* q, int kind) { return Tree::box_hit(LQ(q, 0, kind), B(box)) ? 1 : 0; }
 int orc_tri_do_intersect(const double* tri, const double* pq, int is_ray) {
     return (is_ray ? do_intersect_ray_tri(T(tri), P(pq), P(pq + 3)) : do_intersect_seg_tri(T(tri), P(pq), P(pq + 3))) ? 1 : 0;
 }

@@ -316,6 +316,102 @@ static inline bool do_intersect_bbox(const P3& p, const P3& q, const Box& bb, bo
 }
 
 // ------------------------------------------------------------------------------------------------
+// Line_3 and Plane_3 queries.  Do_intersect_3 on (Line_3 | Plane_3, Triangle_3 | Bbox_3) has no static filter in Epick
+// (Filtered_kernel/include/CGAL/Filtered_kernel/internal/Static_filters/ holds none for these pairs), so the WHOLE function body —
+// including point_on(l, 1) = l.point() + l.to_vector() (Cartesian/Line_3.h) — runs inside Filtered_predicate's interval and then exact
+// kernel: the answer is the exact evaluation of the decision tree on the STORED members (point + direction vector; a, b, c, d).
+// The restatement evaluates every sign with expansion arithmetic and no filter.
+// ------------------------------------------------------------------------------------------------
+static inline Expansion ex_of(double v) { return Expansion(v); }
+// sign det [ u | v | w ] of three exact vectors (columns)
+static inline int exact_det3(const Expansion u[3], const Expansion v[3], const Expansion w[3]) {
+    return exact_det3_of_diffs(u[0], u[1], u[2], v[0], v[1], v[2], w[0], w[1], w[2]);
+}
+static inline void ex_vec(const P3& to, const P3& from, Expansion out[3]) { out[0] = ex_diff(to.x, from.x); out[1] = ex_diff(to.y, from.y); out[2] = ex_diff(to.z, from.z); }
+// orientation(p, p+v, r, s) = sign det [ v | r-p | s-p ]     (kernel_ftC3.h:134-142 with q - p = v exactly)
+static inline int orientation_line(const P3& p, const V3& v, const P3& r, const P3& s) {
+    Expansion a[3] = {ex_of(v.x), ex_of(v.y), ex_of(v.z)}, b[3], c[3];
+    ex_vec(r, p, b); ex_vec(s, p, c);
+    return exact_det3(a, b, c);
+}
+// orientation(a, b, c, p + v) = sign det [ b-a | c-a | (p-a)+v ]
+static inline int orientation_translated(const P3& a, const P3& b, const P3& c, const P3& p, const V3& v) {
+    Expansion u[3], w[3], x[3];
+    ex_vec(b, a, u); ex_vec(c, a, w); ex_vec(p, a, x);
+    x[0] = x[0] + ex_of(v.x); x[1] = x[1] + ex_of(v.y); x[2] = x[2] + ex_of(v.z);
+    return exact_det3(u, w, x);
+}
+// coplanar_orientation(p, p+v, r): coplanar_orientationC3 (kernel_ftC3.h:196-211) with orientationC2(p, q, r) = sign(vx (ry-py) - vy (rx-px))
+static inline int coplanar_orientation_line(const P3& p, const V3& v, const P3& r) {
+    auto o2 = [](double va, double vb, double pa, double pb, double ra, double rb) { return (ex_of(va) * ex_diff(rb, pb) - ex_of(vb) * ex_diff(ra, pa)).sign(); };
+    int oxy = o2(v.x, v.y, p.x, p.y, r.x, r.y);
+    if (oxy != 0) return oxy;
+    int oyz = o2(v.y, v.z, p.y, p.z, r.y, r.z);
+    if (oyz != 0) return oyz;
+    return o2(v.x, v.z, p.x, p.z, r.x, r.z);
+}
+// Do_intersect_3(Triangle_3, Line_3): Intersections_3/include/CGAL/Intersections_3/internal/Line_3_Triangle_3_do_intersect.h:27-79
+static inline bool do_intersect_line_tri(const Tri& t, const P3& p, const V3& v) {
+    const P3 &a = t.a, &b = t.b, &c = t.c;
+    if (orientation(a, b, c, p) != 0 || orientation_translated(a, b, c, p, v) != 0) {
+        const int pqab = orientation_line(p, v, a, b), pqbc = orientation_line(p, v, b, c);
+        switch (pqab) {
+            case 1: return pqbc != -1 && orientation_line(p, v, c, a) != -1;
+            case -1: return pqbc != 1 && orientation_line(p, v, c, a) != 1;
+            default:
+                if (pqbc == 1) return orientation_line(p, v, c, a) != -1;
+                if (pqbc == -1) return orientation_line(p, v, c, a) != 1;
+                return true;
+        }
+    }
+    const int pqa = coplanar_orientation_line(p, v, a);
+    return coplanar_orientation_line(p, v, b) != pqa || coplanar_orientation_line(p, v, c) != pqa;
+}
+// Do_intersect_3(Line_3, Bbox_3): Bbox_3_Line_3_do_intersect.h:28-131, every comparison exact
+static inline bool do_intersect_line_bbox(const P3& p, const V3& v, const Box& bb) {
+    const double pc[3] = {p.x, p.y, p.z}, vc[3] = {v.x, v.y, v.z};
+    if (pc[0] >= bb.lo[0] && pc[0] <= bb.hi[0] && pc[1] >= bb.lo[1] && pc[1] <= bb.hi[1] && pc[2] >= bb.lo[2] && pc[2] <= bb.hi[2]) return true;
+    auto axis = [&](int k, Expansion& tmin, Expansion& tmax, Expansion& d) {
+        if (vc[k] < 0) { tmin = ex_diff(pc[k], bb.hi[k]); tmax = ex_diff(pc[k], bb.lo[k]); d = ex_of(-vc[k]); }
+        else { tmin = ex_diff(bb.lo[k], pc[k]); tmax = ex_diff(bb.hi[k], pc[k]); d = ex_of(vc[k]); }
+    };
+    auto less = [](const Expansion& x, const Expansion& y) { return (x - y).sign() < 0; };
+    Expansion dmin, tmin, tmax, d_, tmin_, tmax_;
+    axis(0, tmin, tmax, dmin);
+    if (dmin.sign() == 0 && (tmin.sign() > 0 || tmax.sign() < 0)) return false;
+    Expansion dmax = dmin;
+    axis(1, tmin_, tmax_, d_);
+    if (d_.sign() == 0) {
+        if (tmin_.sign() > 0 || tmax_.sign() < 0) return false;
+    } else {
+        if (less(dmin * tmax_, d_ * tmin) || less(d_ * tmax, dmax * tmin_)) return false;
+    }
+    if (less(d_ * tmin, dmin * tmin_)) { tmin = tmin_; dmin = d_; }
+    if (less(dmax * tmax_, d_ * tmax)) { tmax = tmax_; dmax = d_; }
+    axis(2, tmin_, tmax_, d_);
+    return !less(dmin * tmax_, d_ * tmin) && !less(d_ * tmax, dmax * tmin_);
+}
+// Oriented_side_3(Plane_3, Point_3) = side_of_oriented_planeC3 (kernel_ftC3.h:402-409): sign(a px + b py + c pz + d)
+static inline int plane_oriented_side(const double h[4], const P3& p) {
+    return (ex_of(h[0]) * ex_of(p.x) + ex_of(h[1]) * ex_of(p.y) + ex_of(h[2]) * ex_of(p.z) + ex_of(h[3])).sign();
+}
+// Do_intersect_3(Triangle_3, Plane_3): Plane_3_Triangle_3_do_intersect.h:27-51
+static inline bool do_intersect_plane_tri(const Tri& t, const double h[4]) {
+    const int s0 = plane_oriented_side(h, t.a);
+    if (s0 == 0) return true;
+    return plane_oriented_side(h, t.b) != s0 || plane_oriented_side(h, t.c) != s0;
+}
+// Do_intersect_3(Plane_3, Bbox_3): Iso_cuboid_3_Plane_3_do_intersect.h:28-125 (get_min_max by the signs of the normal, certain in the
+// exact kernel; the eight-corner fallback of the interval stage decides the same exact fact)
+static inline bool do_intersect_plane_bbox(const double h[4], const Box& bb) {
+    P3 pmin, pmax;
+    pmin.x = h[0] > 0 ? bb.lo[0] : bb.hi[0]; pmax.x = h[0] > 0 ? bb.hi[0] : bb.lo[0];
+    pmin.y = h[1] > 0 ? bb.lo[1] : bb.hi[1]; pmax.y = h[1] > 0 ? bb.hi[1] : bb.lo[1];
+    pmin.z = h[2] > 0 ? bb.lo[2] : bb.hi[2]; pmax.z = h[2] > 0 ? bb.hi[2] : bb.lo[2];
+    return !(plane_oriented_side(h, pmax) < 0 || plane_oriented_side(h, pmin) > 0);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Do_intersect_3(Segment_3, Triangle_3): Intersections_3/internal/Segment_3_Triangle_3_do_intersect.h:24-152,177-262
 // ------------------------------------------------------------------------------------------------
 static inline bool seg_tri_coplanar(const P3& A, const P3& B, const P3& C, const P3& p, const P3& q) {

@@ -201,33 +201,49 @@ struct Tree {
         }
     }
 
-    struct LineQ { P3 p, q; bool is_ray; };   // Segment_3 (source,target) or Ray_3 (source, second point)
+    // kind 0: Segment_3 (source, target); 1: Ray_3 (source, second point); 2: Line_3 (point p, direction vector q); 3: Plane_3 (a, b, c = p; d = q.x)
+    struct LineQ { P3 p, q; int kind; };
+    static bool prim_hit(const Tri& tr, const LineQ& q) {
+        switch (q.kind) {
+            case 1: return do_intersect_ray_tri(tr, q.p, q.q);
+            case 2: return do_intersect_line_tri(tr, q.p, V3{q.q.x, q.q.y, q.q.z});
+            case 3: { const double h[4] = {q.p.x, q.p.y, q.p.z, q.q.x}; return do_intersect_plane_tri(tr, h); }
+            default: return do_intersect_seg_tri(tr, q.p, q.q);
+        }
+    }
+    static bool box_hit(const LineQ& q, const Box& b) {
+        switch (q.kind) {
+            case 2: return do_intersect_line_bbox(q.p, V3{q.q.x, q.q.y, q.q.z}, b);
+            case 3: { const double h[4] = {q.p.x, q.p.y, q.p.z, q.q.x}; return do_intersect_plane_bbox(h, b); }
+            default: return do_intersect_bbox(q.p, q.q, b, q.kind == 1);
+        }
+    }
 
     // Do_intersect_traits :236-271 / Listing_primitive_traits + Counting_output_iterator :26-50,150-184
     struct DoIntersectTT {
         const Tree& t; bool found = false;
         bool go_further() const { return !found; }
         void intersection(const LineQ& q, uint32_t f) {
-            if (q.is_ray ? do_intersect_ray_tri(t.mesh->datum(f), q.p, q.q) : do_intersect_seg_tri(t.mesh->datum(f), q.p, q.q)) found = true;
+            if (prim_hit(t.mesh->datum(f), q)) found = true;
         }
-        bool do_intersect(const LineQ& q, const Box& b) const { return do_intersect_bbox(q.p, q.q, b, q.is_ray); }
+        bool do_intersect(const LineQ& q, const Box& b) const { return box_hit(q, b); }
     };
     struct CountTT {
         const Tree& t; uint32_t count = 0; std::vector<uint32_t>* ids = nullptr;
         bool go_further() const { return true; }
         void intersection(const LineQ& q, uint32_t f) {
-            if (q.is_ray ? do_intersect_ray_tri(t.mesh->datum(f), q.p, q.q) : do_intersect_seg_tri(t.mesh->datum(f), q.p, q.q)) { ++count; if (ids) ids->push_back(f); }
+            if (prim_hit(t.mesh->datum(f), q)) { ++count; if (ids) ids->push_back(f); }
         }
-        bool do_intersect(const LineQ& q, const Box& b) const { return do_intersect_bbox(q.p, q.q, b, q.is_ray); }
+        bool do_intersect(const LineQ& q, const Box& b) const { return box_hit(q, b); }
     };
     // First_primitive_traits :188-231 (any_intersected_primitive, AABB_tree.h:947-956): the first intersected primitive in traversal order
     struct FirstPrimitiveTT {
         const Tree& t; bool found = false; uint32_t id = 0xFFFFFFFFu;
         bool go_further() const { return !found; }
         void intersection(const LineQ& q, uint32_t f) {
-            if (q.is_ray ? do_intersect_ray_tri(t.mesh->datum(f), q.p, q.q) : do_intersect_seg_tri(t.mesh->datum(f), q.p, q.q)) { found = true; id = f; }
+            if (prim_hit(t.mesh->datum(f), q)) { found = true; id = f; }
         }
-        bool do_intersect(const LineQ& q, const Box& b) const { return do_intersect_bbox(q.p, q.q, b, q.is_ray); }
+        bool do_intersect(const LineQ& q, const Box& b) const { return box_hit(q, b); }
     };
     uint32_t any_intersected_primitive(const LineQ& q) const { FirstPrimitiveTT tt{*this}; traversal(q, tt); return tt.id; }
     // Listing_primitive_traits :150-184 (all_intersected_primitives, AABB_tree.h:934-945): ids in traversal order
@@ -246,7 +262,7 @@ struct Tree {
     };
     void ray_intersections(const P3& s, const P3& q, bool first_only, std::vector<std::pair<uint32_t, RayHit>>& out) const {
         RayObjectsTT tt{*this, first_only, false, &out};
-        traversal(LineQ{s, q, true}, tt);
+        traversal(LineQ{s, q, 1}, tt);
     }
     bool do_intersect(const LineQ& q) const { DoIntersectTT tt{*this}; traversal(q, tt); return tt.found; }          // AABB_tree.h:903-913
     uint32_t number_of_intersected_primitives(const LineQ& q) const { CountTT tt{*this}; traversal(q, tt); return tt.count; }  // :915-932

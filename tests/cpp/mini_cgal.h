@@ -40,6 +40,31 @@ struct Ray_3 {   // stored as (source, second point): Cartesian/Ray_3.h:35-47
   const Point_3& source() const { return s; }
   const Point_3& second_point() const { return q; }
 };
+struct Vector_3 {
+  double cx = 0, cy = 0, cz = 0;
+  Vector_3() {}
+  Vector_3(double x, double y, double z) : cx(x), cy(y), cz(z) {}
+  double x() const { return cx; }
+  double y() const { return cy; }
+  double z() const { return cz; }
+};
+struct Line_3 {   // stored as (point, direction vector); Line_3(p, q) keeps the rounded difference q - p: Cartesian/Line_3.h
+  Point_3 p; Vector_3 v;
+  Line_3() {}
+  Line_3(const Point_3& a, const Vector_3& d) : p(a), v(d) {}
+  Line_3(const Point_3& a, const Point_3& b) : p(a), v(b.x() - a.x(), b.y() - a.y(), b.z() - a.z()) {}
+  const Point_3& point() const { return p; }
+  const Vector_3& to_vector() const { return v; }
+};
+struct Plane_3 {  // a x + b y + c z + d = 0: Cartesian/Plane_3.h
+  double ca, cb, cc, cd;
+  Plane_3() : ca(0), cb(0), cc(1), cd(0) {}
+  Plane_3(double a, double b, double c, double d) : ca(a), cb(b), cc(c), cd(d) {}
+  double a() const { return ca; }
+  double b() const { return cb; }
+  double c() const { return cc; }
+  double d() const { return cd; }
+};
 struct Triangle_3 {
   Point_3 v[3];
   Triangle_3() {}
@@ -62,6 +87,9 @@ struct Epick {
   typedef mini::Point_3 Point_3;
   typedef mini::Segment_3 Segment_3;
   typedef mini::Ray_3 Ray_3;
+  typedef mini::Line_3 Line_3;
+  typedef mini::Plane_3 Plane_3;
+  typedef mini::Vector_3 Vector_3;
   typedef mini::Triangle_3 Triangle_3;
 };
 

@@ -86,6 +86,18 @@ static int known_answers() {
     CHECK(std::holds_alternative<Point>(hit->first) && std::get<Point>(hit->first) == Point(0.2, 0.2, 0.0));
     CHECK(tree.first_intersected_primitive(up) && *tree.first_intersected_primitive(up) == mini::Face_index(0));
     CHECK(tree.number_of_intersected_primitives(up) == 2);
+    {   // Line_3 and Plane_3 queries (the AABB_tree concept takes any query type the traits can intersect: AABB_traits_3.h:378-400)
+      const mini::Line_3 zline(Point(0.2, 0.2, 5.0), mini::Vector_3(0.0, 0.0, -1.0));
+      CHECK(tree.do_intersect(zline) && tree.number_of_intersected_primitives(zline) == 2);
+      CHECK(!tree.do_intersect(mini::Line_3(Point(2.0, 2.0, 0.0), Point(2.0, 2.0, 1.0))));
+      CHECK(tree.number_of_intersected_primitives(mini::Plane_3(0.0, 0.0, 1.0, -0.5)) == 3);     // z = 1/2 misses the base face only
+      CHECK(tree.number_of_intersected_primitives(mini::Plane_3(0.0, 0.0, 1.0, 0.0)) == 4);      // the base plane touches every face
+      CHECK(!tree.do_intersect(mini::Plane_3(0.0, 0.0, 1.0, -1.5)) && !tree.any_intersected_primitive(mini::Plane_3(1.0, 1.0, 1.0, -1.5)));
+      std::vector<mini::Plane_3> planes = {mini::Plane_3(0.0, 0.0, 1.0, -0.5), mini::Plane_3(1.0, 0.0, 0.0, 3.0)};
+      std::vector<std::size_t> pc;
+      tree.number_of_intersected_primitives(planes.begin(), planes.end(), std::back_inserter(pc));
+      CHECK(pc.size() == 2 && pc[0] == 3 && pc[1] == 0);
+    }
     {   // all_intersected_primitives / any_intersected_primitive (AABB_tree.h:253-268): the two faces the ray crosses, base face 0 among them
       std::vector<mini::Face_index> ids;
       tree.all_intersected_primitives(up, std::back_inserter(ids));

@@ -94,6 +94,13 @@ class HostTree:
         lib().hc_intersect(self.h, _p(q), len(q), int(is_ray), int(count), _p(out, _u32p))
         return out
 
+    def count_line_plane(self, q, kind):
+        """number_of_intersected_primitives of Line_3 (kind 2: point + vector) / Plane_3 (kind 3: a, b, c, d) queries through bvh.cuh"""
+        q = _d(q).reshape(-1, 4 if kind == 3 else 6)
+        out = np.zeros(len(q), np.uint32)
+        lib().hc_count_line_plane(self.h, _p(q), len(q), int(kind), _p(out, _u32p))
+        return out
+
     def first_intersection(self, rays):
         rays = _d(rays).reshape(-1, 6)
         n = len(rays)
@@ -130,6 +137,11 @@ def validate(nodes_u8, tris_u8, n):
 def call(name, *arrs):
     arrs = [_d(a).ravel() for a in arrs]
     return getattr(lib(), name)(*[_p(a) for a in arrs])
+
+
+def tri_do_intersect_kind(tri, q, kind):
+    tri, q = _d(tri).ravel(), _d(q).ravel()
+    return lib().hc_tri_do_intersect_kind(_p(tri), _p(q), int(kind))
 
 
 def tri_do_intersect(tri, pq, is_ray):

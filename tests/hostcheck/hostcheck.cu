@@ -138,8 +138,18 @@ void hc_intersect(void* hv, const double* q, uint64_t n, int is_ray, int count, 
         TravStat st;
         if (h->n == 0) { out[i] = 0; continue; }
         const Vec3 s = V(q + 6 * i), e = V(q + 6 * i + 3);
-        if (is_ray) out[i] = count ? traverse_intersect<true, kCount>(h->nodes.data(), h->tris.data(), h->root, s, e, st) : traverse_intersect<true, kAnyHit>(h->nodes.data(), h->tris.data(), h->root, s, e, st);
-        else out[i] = count ? traverse_intersect<false, kCount>(h->nodes.data(), h->tris.data(), h->root, s, e, st) : traverse_intersect<false, kAnyHit>(h->nodes.data(), h->tris.data(), h->root, s, e, st);
+        if (is_ray) out[i] = count ? traverse_intersect<kRayQ, kCount>(h->nodes.data(), h->tris.data(), h->root, s, e, st) : traverse_intersect<kRayQ, kAnyHit>(h->nodes.data(), h->tris.data(), h->root, s, e, st);
+        else out[i] = count ? traverse_intersect<kSegmentQ, kCount>(h->nodes.data(), h->tris.data(), h->root, s, e, st) : traverse_intersect<kSegmentQ, kAnyHit>(h->nodes.data(), h->tris.data(), h->root, s, e, st);
+    }
+}
+// Line_3 (kind 2: point + direction vector, 6 doubles) and Plane_3 (kind 3: a, b, c, d) counts through the device traversal routines
+void hc_count_line_plane(void* hv, const double* q, uint64_t n, int kind, uint32_t* out) {
+    HostTree* h = (HostTree*)hv;
+    for (uint64_t i = 0; i < n; ++i) {
+        TravStat st;
+        if (h->n == 0) { out[i] = 0; continue; }
+        if (kind == 2) out[i] = traverse_intersect<kLineQ, kCount>(h->nodes.data(), h->tris.data(), h->root, V(q + 6 * i), V(q + 6 * i + 3), st);
+        else out[i] = traverse_plane<kCount>(h->nodes.data(), h->tris.data(), h->root, q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3], st);
     }
 }
 void hc_first_intersection(void* hv, const double* rays, uint64_t n, uint32_t* prim, double* t, double* pts, uint8_t* kind, uint8_t* tie) {
@@ -172,6 +182,12 @@ int hc_orient3_dir(const double* p) { int n = 0; return orient3_dir(V(p), V(p + 
 int hc_coplanar_orient(const double* p) { int n = 0; return coplanar_orient(V(p), V(p + 3), V(p + 6), n); }
 int hc_cmp_dist(const double* p) { int n = 0; return cmp_dist(V(p), V(p + 3), V(p + 6), n); }
 int hc_cmp_dist_exact(const double* p) { return exact_cmp_dist_sign(p, p + 3, p + 6); }
+int hc_tri_do_intersect_kind(const double* tri, const double* q, int kind) {
+    int n = 0;
+    if (kind == 2) return line_tri_do_intersect(T(tri), V(q), V(q + 3), n);
+    if (kind == 3) return plane_tri_do_intersect(T(tri), q[0], q[1], q[2], q[3], n);
+    return kind == 1 ? ray_tri_do_intersect(T(tri), V(q), V(q + 3), n) : seg_tri_do_intersect(T(tri), V(q), V(q + 3), n);
+}
 int hc_tri_do_intersect(const double* tri, const double* pq, int is_ray) { int n = 0; return is_ray ? ray_tri_do_intersect(T(tri), V(pq), V(pq + 3), n) : seg_tri_do_intersect(T(tri), V(pq), V(pq + 3), n); }
 int hc_tri_ray_intersection(const double* tri, const double* ray, double* pts, double* t) {
     int n = 0; const Vec3 s = V(ray), q = V(ray + 3), d = q - s;

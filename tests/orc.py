@@ -125,27 +125,27 @@ class OracleTree:
         return out
 
     def do_intersect(self, q, kind, threads=None):
-        q = _d(q).reshape(-1, 6)
+        q = _d(q).reshape(-1, 4 if kind == 3 else 6)
         out = np.zeros(len(q), np.uint8)
         lib().orc_do_intersect(self.h, _ptr(q, _dp), len(q), kind, _ptr(out, _u8p), threads or nthreads())
         return out
 
     def count(self, q, kind, threads=None, naive=False):
-        q = _d(q).reshape(-1, 6)
+        q = _d(q).reshape(-1, 4 if kind == 3 else 6)
         out = np.zeros(len(q), np.uint32)
         f = lib().orc_naive_count if naive else lib().orc_count
         f(self.h, _ptr(q, _dp), len(q), kind, _ptr(out, _u32p), threads or nthreads())
         return out
 
     def any_intersected_primitive(self, q, kind, threads=None):
-        q = _d(q).reshape(-1, 6)
+        q = _d(q).reshape(-1, 4 if kind == 3 else 6)
         out = np.zeros(len(q), np.uint32)
         lib().orc_any_intersected_primitive(self.h, _ptr(q, _dp), len(q), kind, _ptr(out, _u32p), threads or nthreads())
         return out
 
     def all_intersected_primitives(self, q, kind, threads=None):
         """(offsets[n+1], ids): ids of query i, in the reference's traversal order, are ids[offsets[i]:offsets[i+1]]"""
-        q = _d(q).reshape(-1, 6)
+        q = _d(q).reshape(-1, 4 if kind == 3 else 6)
         offsets = np.zeros(len(q) + 1, np.uint64)
         np.cumsum(self.count(q, kind, threads), out=offsets[1:])
         ids = np.zeros(max(int(offsets[-1]), 1), np.uint32)
@@ -273,6 +273,17 @@ def bbox_do_intersect(box, pq, is_ray, exact=False):
     pq = _d(pq).ravel()
     f = lib().orc_bbox_do_intersect_exact if exact else lib().orc_bbox_do_intersect
     return f(_ptr(box, _dp), _ptr(pq, _dp), int(is_ray))
+
+
+def tri_do_intersect_kind(tri, q, kind):
+    """kind 0 Segment_3, 1 Ray_3, 2 Line_3 (point, vector), 3 Plane_3 (a, b, c, d)"""
+    tri, q = _d(tri).ravel(), _d(q).ravel()
+    return lib().orc_tri_do_intersect_kind(_ptr(tri, _dp), _ptr(q, _dp), int(kind))
+
+
+def bbox_do_intersect_kind(box, q, kind):
+    box, q = _d(box).ravel(), _d(q).ravel()
+    return lib().orc_bbox_do_intersect_kind(_ptr(box, _dp), _ptr(q, _dp), int(kind))
 
 
 def tri_do_intersect(tri, pq, is_ray):

@@ -558,3 +558,37 @@ def test_async_host_batches(B, meshes):
             np.testing.assert_array_equal(r[k], want_r[k])
         for k in want_p:
             np.testing.assert_array_equal(p[k], want_p[k])
+
+
+@pytest.mark.parametrize("name", ["elephant", "cube"])
+def test_line_and_plane_queries(B, meshes, name):
+    """Line_3 (point + direction vector) and Plane_3 (a, b, c, d) queries — do_intersect, number_of_intersected_primitives,
+    any_ / all_intersected_primitives — against the oracle's exact evaluation of Line_3_Triangle_3_do_intersect.h:27-79 and
+    Plane_3_Triangle_3_do_intersect.h:27-51; random queries plus lines through vertices / along edges / in facet planes and planes
+    through vertices / facets (tests/test_line_plane_queries.py builds them); host and device pointers"""
+    import torch
+    from test_line_plane_queries import _mesh_queries
+    v, f = meshes[name]
+    rng = np.random.default_rng(21)
+    lines, planes = _mesh_queries(rng, v, f, 20_000 if name == "elephant" else 2_000)
+    g, o = B.AABB_tree(v, f), orc.OracleTree(v, f)
+    for kind, q in ((B.LINE, lines), (B.PLANE, planes)):
+        want = o.count(q, kind)
+        cnt = g.number_of_intersected_primitives(q, kind)
+        np.testing.assert_array_equal(cnt, want)
+        np.testing.assert_array_equal(g.do_intersect(q, kind) != 0, want > 0)
+        assert want.max() > 2 and (want == 0).any()
+        off, ids = g.all_intersected_primitives(q, kind)
+        roff, rids = o.all_intersected_primitives(q, kind)
+        np.testing.assert_array_equal(off, roff)
+        owner = np.repeat(np.arange(len(q)), np.diff(off).astype(np.int64))
+        key = lambda own, i: np.sort(own.astype(np.uint64) << np.uint64(32) | i.astype(np.uint64))   # noqa: E731
+        np.testing.assert_array_equal(key(owner, ids), key(owner, rids))
+        a = g.any_intersected_primitive(q, kind)
+        np.testing.assert_array_equal(a == B.NO_PRIMITIVE, want == 0)
+        pairs = set(zip(owner.tolist(), ids.tolist()))
+        assert all((i, int(a[i])) in pairs for i in np.nonzero(want)[0][:3000])
+        qd = torch.from_numpy(q).cuda()
+        np.testing.assert_array_equal(g.number_of_intersected_primitives(qd, kind).cpu().numpy(), want)
+    with pytest.raises(B.B200AABBError):
+        g.do_intersect(lines[:4], 7)
