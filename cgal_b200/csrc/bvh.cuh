@@ -57,6 +57,9 @@ struct __align__(32) TriF {
 static_assert(sizeof(TriF) == 64, "binary32 triangle record is two 32-byte sectors");
 
 // per-query traversal statistics (accumulated into the handle's counters by the kernels)
+#ifndef B2_TRACE_NODE
+#define B2_TRACE_NODE(index)          // tests/hostcheck defines it to record which nodes traverse_closest fetches (depth histogram)
+#endif
 struct TravStat { int nexact = 0; int overflow = 0; uint32_t nodes = 0, leaves = 0, culled = 0; };   // culled: leaves rejected by the binary32 pre-test
 
 // directed roundings binary64 -> binary32 (any finite input; overflow saturates to +-FLT_MAX / +-inf on the safe side)
@@ -633,6 +636,7 @@ B2_HD Closest traverse_closest(const BvhNode* __restrict__ nodes, const TriRec* 
         while (cur != kNone && np < go) {
             const NodeView n = load_node(nodes, cur);
             ++st.nodes;
+            B2_TRACE_NODE(cur);
             float d0 = point_box_sqdist(n.lo0, n.hi0, pc), d1 = point_box_sqdist(n.lo1, n.hi1, pc);
             uint32_t c0 = n.c0, c1 = n.c1;
             if (d1 < d0) { const uint32_t tc = c0; c0 = c1; c1 = tc; const float td = d0; d0 = d1; d1 = td; }

@@ -9,6 +9,13 @@
 #include <numeric>
 #include <vector>
 
+static std::vector<uint32_t>* g_node_trace = nullptr;       // nodes fetched by traverse_closest (hc_closest_depth_histogram)
+static void trace_node(uint32_t index) { if (g_node_trace) g_node_trace->push_back(index); }
+#if defined(__CUDA_ARCH__)
+#define B2_TRACE_NODE(index)
+#else
+#define B2_TRACE_NODE(index) trace_node(index)
+#endif
 #include "../../cgal_b200/csrc/build.cuh"
 #include "../../cgal_b200/csrc/closest_warp.cuh"
 #define B2_WARP_EMU 1
@@ -151,6 +158,28 @@ void hc_count_line_plane(void* hv, const double* q, uint64_t n, int kind, uint32
         if (kind == 2) out[i] = traverse_intersect<kLineQ, kCount>(h->nodes.data(), h->tris.data(), h->root, V(q + 6 * i), V(q + 6 * i + 3), st);
         else out[i] = traverse_plane<kCount>(h->nodes.data(), h->tris.data(), h->root, q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3], st);
     }
+}
+// how many of the nodes a closest_point query fetches lie at each depth of the tree (root = 0): hist[64] summed over the queries; returns the tree depth
+int hc_closest_depth_histogram(void* hv, const double* q, uint64_t n, uint64_t* hist) {
+    HostTree* h = (HostTree*)hv;
+    std::vector<uint8_t> depth(h->nodes.size(), 0);
+    std::vector<uint32_t> order{h->root};
+    int maxd = 0;
+    for (size_t i = 0; i < order.size(); ++i) {
+        const BvhNode& nd = h->nodes[order[i]];
+        for (uint32_t c : {nd.child0, nd.child1})
+            if (!(c & kLeafBit)) { depth[c] = (uint8_t)std::min(63, depth[order[i]] + 1); maxd = std::max<int>(maxd, depth[c]); order.push_back(c); }
+    }
+    std::vector<uint32_t> trace;
+    g_node_trace = &trace;
+    for (uint64_t i = 0; i < n; ++i) {
+        TravStat st;
+        trace.clear();
+        traverse_closest(h->nodes.data(), h->tris.data(), h->root, V(q + 3 * i), h->mag(), st);
+        for (uint32_t nd : trace) ++hist[depth[nd]];
+    }
+    g_node_trace = nullptr;
+    return maxd;
 }
 void hc_first_intersection(void* hv, const double* rays, uint64_t n, uint32_t* prim, double* t, double* pts, uint8_t* kind, uint8_t* tie) {
     HostTree* h = (HostTree*)hv;
