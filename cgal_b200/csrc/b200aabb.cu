@@ -301,6 +301,8 @@ struct b200aabb_tree {
     bool bounds_valid = false;     // b200aabb_set_mesh computed them while gathering the primitives
     int opt_exact_keys = 0;        // 1: always sort full 63-bit keys (the build's fallback path; test hook, option 102)
     int last_build_packed = 0; unsigned long long last_build_dups = 0;
+    int opt_classic_build = 0;     // 1: hierarchy_kernel for every node + refit_local_kernel instead of the fused bottom-up kernel (the fallback of a full frontier; test hook, option 103)
+    int last_build_classic = 0;
     uint32_t root = kNone;
     double h_bbox[6];
     double mag = 0.0;              // largest coordinate magnitude of the root box
@@ -458,18 +460,19 @@ int do_build(b200aabb_tree* t) {
     cudaStream_t st = t->stream;
     uint64_t* keys[2] = {nullptr, nullptr};
     uint32_t* vals[2] = {nullptr, nullptr};
-    void* ws = nullptr; RefitEntry* frontier = nullptr; unsigned* frontier_count = nullptr; unsigned long long* d_dups = nullptr;
-    auto cleanup = [&]() { cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(ws); cudaFree(frontier); cudaFree(frontier_count); cudaFree(d_dups); };
+    void* ws = nullptr; RefitEntry* frontier = nullptr; unsigned* frontier_count = nullptr; unsigned long long* d_flags = nullptr; uint32_t* rest = nullptr;
+    auto cleanup = [&]() { cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(ws); cudaFree(frontier); cudaFree(frontier_count); cudaFree(d_flags); cudaFree(rest); };
 #define B2_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { t->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); free_tree_buffers(t); \
         return e_ == cudaErrorMemoryAllocation ? B200AABB_ERR_OUT_OF_MEMORY : B200AABB_ERR_CUDA; } } while (0)
     for (int s = 0; s < 2; ++s) B2_TRY(cudaMalloc(&keys[s], n * 8));
     B2_TRY(cudaMalloc(&ws, rs_workspace_bytes(n)));
     B2_TRY(cudaMalloc(&t->d_leaf_parent, n * 4));
     uint32_t* const leaf_parent = t->d_leaf_parent;
-    B2_TRY(cudaMalloc(&d_dups, 8));
+    B2_TRY(cudaMalloc(&d_flags, 16));      // [0] runs of equal PACKED key bits, [1] frontier overflow of the fused path
     const uint64_t refit_blocks = (n + kRefitBlock - 1) / kRefitBlock, frontier_cap = refit_blocks * kRefitFrontierPerBlock, frontier_use = refit_blocks * (uint64_t)t->opt_debug_refit_frontier;
     B2_TRY(cudaMalloc(&frontier, frontier_cap * sizeof(RefitEntry)));
-    B2_TRY(cudaMalloc(&frontier_count, sizeof(unsigned)));
+    B2_TRY(cudaMalloc(&frontier_count, 2 * sizeof(unsigned)));      // [1]: length of `rest`
+    B2_TRY(cudaMalloc(&rest, frontier_cap * 4));       // nodes the fused path leaves to the searches (fewer than its frontier entries)
     B2_TRY(cudaMalloc(&t->d_nodes, std::max<uint64_t>(n - 1, 1) * sizeof(BvhNode)));
     B2_TRY(cudaMalloc(&t->d_tris, n * sizeof(TriRec)));
     B2_TRY(cudaMalloc(&t->d_trisf, n * sizeof(TriF)));
@@ -494,6 +497,10 @@ int do_build(b200aabb_tree* t) {
     mark("scene_bounds");
     // Two attempts at most: PACKED sort words first (build.cuh::pack_sort_word); if more than 1/16 of the primitives start a run of four with equal kept key
     // bits (a scene whose primitives crowd a tiny part of its box), once more with full 63-bit keys + values.
+    // After the sort, the FUSED path: build_local_kernel (leaf records, topology and boxes of all nodes inside a block of leaves, bottom-up),
+    // hierarchy_kernel for the few nodes that span blocks, refit_global_kernel for their boxes.  Its frontier list filling up (a degenerate,
+    // chain-like tree) sends the build down the CLASSIC path: hierarchy_kernel for every node, refit_local_kernel, refit_global_kernel.
+    bool classic = t->opt_classic_build != 0;
     for (int attempt = t->opt_exact_keys ? 1 : 0; attempt < 2; ++attempt) {
         const bool packed = attempt == 0;
         int cur;
@@ -511,27 +518,39 @@ int do_build(b200aabb_tree* t) {
             cur = radix_sort_pairs(keys, vals, n, 8, ws, st, &t->stats.kernel_launches);
         }
         mark("sort");
-        emit = EmitArgs{t->d_soup, t->d_ids, packed ? nullptr : vals[cur], keys[cur], ib, t->d_trisf};   // (the leaf records are written by the refit kernel)
-        B2_TRY(cudaMemsetAsync(d_dups, 0, 8, st));
-        if (n > 1) {
-            hierarchy_kernel<<<blocks, 256, 0, st>>>(keys[cur], n, t->d_nodes, leaf_parent, packed ? ib : 0, d_dups);
-            t->stats.kernel_launches += 1;
-        }
-        mark("hierarchy");
-        if (packed) {
-            B2_TRY(cudaMemcpyAsync(&dups, d_dups, 8, cudaMemcpyDeviceToHost, st));
+        emit = EmitArgs{t->d_soup, t->d_ids, packed ? nullptr : vals[cur], keys[cur], packed ? ib : 0, t->d_trisf};
+        unsigned long long flags[2] = {0, 0};
+        while (true) {
+            B2_TRY(cudaMemsetAsync(d_flags, 0, 16, st));
+            B2_TRY(cudaMemsetAsync(frontier_count, 0, 2 * sizeof(unsigned), st));
+            if (!classic) {
+                build_local_kernel<<<(unsigned)refit_blocks, kRefitBlock, 0, st>>>(keys[cur], t->d_tris, n, t->d_nodes, leaf_parent, frontier, frontier_count, (unsigned)frontier_use,
+                                                                                   emit, rest, frontier_count + 1, d_flags);
+                mark("leaves+tree");
+                if (n > 1) hierarchy_kernel<<<(unsigned)((frontier_use + 255) / 256) + 1, 256, 0, st>>>(keys[cur], n, t->d_nodes, leaf_parent, 0, nullptr, rest, frontier_count + 1, (unsigned)frontier_use);
+                mark("hierarchy_rest");
+                t->stats.kernel_launches += n > 1 ? 2 : 1;
+            } else {
+                if (n > 1) hierarchy_kernel<<<blocks, 256, 0, st>>>(keys[cur], n, t->d_nodes, leaf_parent, packed ? ib : 0, d_flags, nullptr, nullptr, 0);
+                mark("hierarchy");
+                refit_local_kernel<true><<<(unsigned)refit_blocks, kRefitBlock, 0, st>>>(t->d_tris, n, t->d_nodes, leaf_parent, frontier, frontier_count, (unsigned)frontier_use, emit);
+                mark("leaves+refit");
+                t->stats.kernel_launches += n > 1 ? 2 : 1;
+            }
+            if (n > 1) { refit_global_kernel<<<(unsigned)((frontier_cap + 255) / 256), 256, 0, st>>>(t->d_nodes, leaf_parent, frontier, frontier_count, (unsigned)frontier_use); t->stats.kernel_launches += 1; }
+            mark("refit_global");
+            B2_TRY(cudaMemcpyAsync(flags, d_flags, 16, cudaMemcpyDeviceToHost, st));
             B2_TRY(cudaStreamSynchronize(st));
-            if (dups > n / 16) continue;
+            if (!classic && flags[1]) { classic = true; continue; }      // frontier overflow: the classic path finishes such climbs in place
+            break;
         }
+        dups = flags[0];
+        if (packed && dups > n / 16) continue;
         t->last_build_packed = packed ? 1 : 0;
         t->last_build_dups = packed ? dups : 0;
+        t->last_build_classic = classic ? 1 : 0;
         break;
     }
-    B2_TRY(cudaMemsetAsync(frontier_count, 0, sizeof(unsigned), st));
-    refit_local_kernel<true><<<(unsigned)refit_blocks, kRefitBlock, 0, st>>>(t->d_tris, n, t->d_nodes, leaf_parent, frontier, frontier_count, (unsigned)frontier_use, emit);
-    mark("leaves+refit");
-    if (n > 1) { refit_global_kernel<<<(unsigned)((frontier_cap + 255) / 256), 256, 0, st>>>(t->d_nodes, frontier, frontier_count, (unsigned)frontier_use); t->stats.kernel_launches += 1; }
-    mark("refit_global");
     root_box_kernel<<<1, 32, 0, st>>>(t->d_bounds, t->d_rootbox);
     mark("root_box");
     t->stats.kernel_launches += 2;
@@ -542,7 +561,7 @@ int do_build(b200aabb_tree* t) {
     float ms = 0; cudaEventElapsedTime(&ms, t->ev_a, t->ev_b);
     t->stats.last_build_ms = ms;
     for (size_t i = 1; i < marks.size(); ++i) { float d = 0; cudaEventElapsedTime(&d, marks[i - 1].second, marks[i].second); fprintf(stderr, "[b200aabb build] %-14s %8.3f ms\n", marks[i].first, d); }
-    if (stage_timing) fprintf(stderr, "[b200aabb build] %s sort words, %d passes, %llu runs of >= 4 equal key bits\n", t->last_build_packed ? "packed" : "full (key, index)", t->last_build_packed ? packed_passes : 8, dups);
+    if (stage_timing) fprintf(stderr, "[b200aabb build] %s sort words, %d passes, %llu runs of >= 4 equal key bits, %s path\n", t->last_build_packed ? "packed" : "full (key, index)", t->last_build_packed ? packed_passes : 8, dups, t->last_build_classic ? "classic" : "fused");
     for (auto& m : marks) cudaEventDestroy(m.second);
     t->root = n == 1 ? (kLeafBit | 0u) : 0u;
     t->mag = 0.0;
@@ -779,6 +798,7 @@ int b200aabb_set_option(b200aabb_tree* t, int option, int64_t value) { B2_LOCK(t
         case B200AABB_OPT_CLOSEST_KERNEL: t->opt_closest_kernel = (int)std::min<int64_t>(2, std::max<int64_t>(0, value)); return B200AABB_OK;
         case B200AABB_OPT_ASYNC_HOST: t->opt_async_host = value != 0; return B200AABB_OK;
         case B200AABB_OPT_HOST_PARTS: t->opt_host_parts = (int)std::min<int64_t>(64, std::max<int64_t>(0, value)); return B200AABB_OK;
+        case 103: t->opt_classic_build = value != 0; if (!t->imported) t->built = t->n == 0; return B200AABB_OK;
         case 102: t->opt_exact_keys = value != 0; if (!t->imported) t->built = t->n == 0; return B200AABB_OK;
         case 101: t->opt_debug_refit_frontier = (int)std::min<int64_t>(kRefitFrontierPerBlock, std::max<int64_t>(0, value)); if (!t->imported) t->built = t->n == 0; return B200AABB_OK;
         case B200AABB_OPT_WARP_EXACT_GO: t->opt_warp_exact_go = (int)std::min<int64_t>(kWpExactCap - 32, std::max<int64_t>(0, value)); return B200AABB_OK;
@@ -830,7 +850,7 @@ int b200aabb_set_triangles(b200aabb_tree* t, const double* tris, const uint32_t*
     if (rc) return rc;
     if (n == 0) return B200AABB_OK;
     const cudaMemcpyKind kind = space == B200AABB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-    B2_CUDA(t, cudaMalloc(&t->d_soup, n * 72));
+    B2_CUDA(t, cudaMalloc(&t->d_soup, n * 72 + kSoupSlack));
     B2_CUDA(t, cudaMemcpyAsync(t->d_soup, tris, n * 72, kind, t->stream));
     if (ids) { B2_CUDA(t, cudaMalloc(&t->d_ids, n * 4)); B2_CUDA(t, cudaMemcpyAsync(t->d_ids, ids, n * 4, kind, t->stream)); }
     B2_CUDA(t, cudaStreamSynchronize(t->stream));
@@ -848,7 +868,7 @@ int b200aabb_set_mesh(b200aabb_tree* t, const double* verts, uint64_t nv, const 
     B2_CUDA(t, cudaMalloc(&d_v, nv * 24));
     cudaError_t e = cudaMalloc(&d_f, nf * 12);
     if (e != cudaSuccess) { cudaFree(d_v); t->err = "cudaMalloc(faces)"; return B200AABB_ERR_OUT_OF_MEMORY; }
-    e = cudaMalloc(&t->d_soup, nf * 72);
+    e = cudaMalloc(&t->d_soup, nf * 72 + kSoupSlack);
     if (e != cudaSuccess) { cudaFree(d_v); cudaFree(d_f); t->err = "cudaMalloc(soup)"; return B200AABB_ERR_OUT_OF_MEMORY; }
     cudaMemcpyAsync(d_v, verts, nv * 24, cudaMemcpyHostToDevice, t->stream);
     cudaMemcpyAsync(d_f, faces, nf * 12, cudaMemcpyHostToDevice, t->stream);
@@ -876,7 +896,7 @@ static int refit_boxes(b200aabb_tree* t, cudaStream_t st) {
     }
     cudaMemsetAsync(frontier_count, 0, sizeof(unsigned), st);
     refit_local_kernel<false><<<(unsigned)refit_blocks, kRefitBlock, 0, st>>>(t->d_tris, n, t->d_nodes, t->d_leaf_parent, frontier, frontier_count, (unsigned)frontier_cap, EmitArgs{});
-    refit_global_kernel<<<(unsigned)((frontier_cap + 255) / 256), 256, 0, st>>>(t->d_nodes, frontier, frontier_count, (unsigned)frontier_cap);
+    refit_global_kernel<<<(unsigned)((frontier_cap + 255) / 256), 256, 0, st>>>(t->d_nodes, t->d_leaf_parent, frontier, frontier_count, (unsigned)frontier_cap);
     t->stats.kernel_launches += 2;
     const cudaError_t e = cudaStreamSynchronize(st);
     cudaFree(frontier); cudaFree(frontier_count);
@@ -1410,7 +1430,7 @@ int bcast_prepare(b200aabb_comm* c, b200aabb_tree* t, int root, int mode, cudaSt
     }
     int rc = b200aabb_clear(t);
     if (rc || n == 0) return rc;
-    if (cudaMalloc(&t->d_soup, n * 72) != cudaSuccess) return B200AABB_ERR_OUT_OF_MEMORY;
+    if (cudaMalloc(&t->d_soup, n * 72 + kSoupSlack) != cudaSuccess) return B200AABB_ERR_OUT_OF_MEMORY;
     if (h[1] && cudaMalloc(&t->d_ids, n * 4) != cudaSuccess) return B200AABB_ERR_OUT_OF_MEMORY;
     t->n = n; t->built = false;
     return B200AABB_OK;

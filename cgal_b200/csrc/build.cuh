@@ -219,9 +219,16 @@ B2_HD void karras_node(const uint64_t* __restrict__ keys, int64_t n, int64_t i, 
 }
 
 // ib > 0: the keys are PACKED words; *dups += positions that start a run of four words agreeing in all their key bits (see pack_sort_word)
+// list != nullptr: only the nodes list[0 .. min(*list_count, list_cap)) (those build_local_kernel left: they span blocks of leaves)
 __global__ void __launch_bounds__(256) hierarchy_kernel(const uint64_t* __restrict__ keys, uint64_t n, BvhNode* __restrict__ nodes, uint32_t* __restrict__ leaf_parent,
-                                                        int ib, unsigned long long* __restrict__ dups) {
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+                                                        int ib, unsigned long long* __restrict__ dups, const uint32_t* __restrict__ list,
+                                                        const unsigned* __restrict__ list_count, unsigned list_cap) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (list) {
+        const unsigned cnt = *list_count;
+        if (i >= (cnt < list_cap ? cnt : list_cap)) return;
+        i = list[i];
+    }
     if (ib > 0) {
         // (runs of FOUR: pairs of primitives with equal key bits — the two triangles of a terrain quad have the same box centre in x and y —
         //  are siblings in either tree; what would hurt are long runs, which the index bits split without regard to geometry)
@@ -372,13 +379,233 @@ __global__ void __launch_bounds__(kRefitBlock) refit_local_kernel(TriRec* __rest
     }
 }
 
-__global__ void __launch_bounds__(256) refit_global_kernel(BvhNode* nodes, const RefitEntry* __restrict__ frontier, const unsigned* __restrict__ frontier_count, unsigned cap) {
+// (an entry of build_local_kernel does not know its parent's index yet: e.node == kNone, and the parent link written since by hierarchy_kernel is read here)
+__global__ void __launch_bounds__(256) refit_global_kernel(BvhNode* nodes, const uint32_t* __restrict__ leaf_parent, const RefitEntry* __restrict__ frontier,
+                                                           const unsigned* __restrict__ frontier_count, unsigned cap) {
     const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned cnt = *frontier_count;
     if (i >= (cnt < cap ? cnt : cap)) return;
     const RefitEntry e = frontier[i];
     float lo[3] = {e.lo[0], e.lo[1], e.lo[2]}, hi[3] = {e.hi[0], e.hi[1], e.hi[2]};
-    refit_climb_global(nodes, e.node, e.from, lo, hi);
+    const uint32_t p = e.node != kNone ? e.node : ((e.from & kLeafBit) ? leaf_parent[e.from & ~kLeafBit] : nodes[e.from].parent);
+    refit_climb_global(nodes, p, e.from, lo, hi);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// build_local_kernel: leaf records + radix-tree TOPOLOGY + boxes of every node whose leaf range lies inside one block of kRefitBlock leaves,
+// in ONE bottom-up pass (no searches: after Apetrei, "Fast and Simple Agglomerative LBVH Construction", 2014, but with Karras' node numbering so
+// that the tree is, bit for bit, the one hierarchy_kernel + refit_local_kernel build).
+//   A thread starts at its leaf with the range [l, r] = [k, k] and repeatedly joins its range with the sibling's: the parent of [l, r] splits
+//   at s = r (we are its left child) when the pairs r, r+1 share a longer prefix than the pairs l-1, l, else at s = l-1 (right child).  The two
+//   children meet at the shared-memory slot of s; the second to arrive knows the parent's range [L, R], and with it
+//     * whether THAT node is a left child itself (same rule), hence its index in Karras' numbering: R if it is a left child, L otherwise
+//       (a left child [l, gamma] is node gamma, a right child [gamma+1, r] node gamma+1, the root node 0);
+//     * both child references and boxes: it writes the node, tells the children their parent, and carries on.
+//   The parent of a range that touches the block's border spans blocks when the border key shares the parent's prefix: decided from s alone
+//   (both children must agree without knowing each other), by comparing the pair s with the pairs just outside the block.  Such a child is
+//   parked in the frontier list; hierarchy_kernel then builds the few spanning nodes (listed in `rest`) with Karras' searches and
+//   refit_global_kernel finishes the boxes.  A full frontier list (a degenerate tree) sets *overflow and the build takes the classic path.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr size_t kSoupSlack = 16;       // bytes allocated past the last inserted primitive: build_local_kernel gathers a primitive with five 128-bit loads
+struct __align__(16) LocalBuildShared {
+    uint64_t key[kRefitBlock + 2];      // sort words / keys of the pairs base-1 .. base+kRefitBlock
+    float4 arr[kRefitBlock][2][2];      // the child that arrived at the slot of split position base + t from the left [0] / right [1]: (lo.xyz, hi.x), (hi.y, hi.z, reference,
+                                        // far end of its range).  16 KB: before the climb, the warps' staging area of the coalesced leaf-record stores
+    unsigned cnt[kRefitBlock];          // arrivals at the slot
+    short len[kRefitBlock + 1];         // len[p - (base-1)] = karras_delta(p, p+1), p = base-1 .. last_leaf; + kSpanFlag when the node splitting at p spans blocks
+    unsigned char done[kRefitBlock];    // node base + t was built here
+};
+constexpr short kSpanFlag = 0x4000;
+static_assert(offsetof(LocalBuildShared, arr) % 16 == 0, "staging area");
+
+// prefix length of the pairs i and j (as karras_delta) read from the block's staged keys; positions outside [0, n) give -1
+B2_HD int local_delta(const LocalBuildShared& S, int64_t base, int64_t n, int64_t i, int64_t j) {
+    if (j < 0 || j >= n) return -1;
+    const uint64_t x = S.key[i - (base - 1)] ^ S.key[j - (base - 1)];
+#if defined(__CUDA_ARCH__)
+    if (x) return __clzll((long long)x);
+    return 64 + __clzll((long long)((uint64_t)i ^ (uint64_t)j));
+#else
+    if (x) return __builtin_clzll(x);
+    return 64 + __builtin_clzll((uint64_t)i ^ (uint64_t)j);
+#endif
+}
+
+#if defined(__CUDA_ARCH__)
+#define B2_ARRIVE(counter) atomicAdd(counter, 1u)
+#define B2_FENCE_BLOCK() __threadfence_block()
+#else
+#define B2_ARRIVE(counter) ((*(counter))++)
+#define B2_FENCE_BLOCK()
+#endif
+
+// len[] entry of split position p, with the flag that the node splitting there spans blocks (decided from p alone: both children must agree without knowing each
+// other): the key just outside the block, on either side, shares the node's prefix
+B2_HD short local_len_entry(const LocalBuildShared& S, int64_t base, int64_t last_leaf, int64_t n, int64_t p) {
+    if (p < 0 || p + 1 >= n) return (short)(-1);
+    const int plen = local_delta(S, base, n, p, p + 1);
+    const bool spans = p < base || p >= last_leaf || local_delta(S, base, n, p, base - 1) >= plen || local_delta(S, base, n, p, last_leaf + 1) >= plen;
+    return (short)(plen | (spans ? kSpanFlag : 0));
+}
+B2_HD int len_of(short entry) { return entry < 0 ? -1 : (entry & (kSpanFlag - 1)); }
+
+// the climb of the thread of leaf k (box lo/hi) through the block's own nodes
+B2_HD void build_local_climb(LocalBuildShared& S, int64_t base, int64_t last_leaf, int64_t n, int64_t k, float* lo, float* hi, BvhNode* nodes,
+                             uint32_t* leaf_parent, RefitEntry* frontier, unsigned* frontier_count, unsigned frontier_cap, unsigned* overflow) {
+    uint32_t me = kLeafBit | (uint32_t)k;
+    int64_t l = k, r = k;
+    bool left = l == 0 || (r != n - 1 && len_of(S.len[r - (base - 1)]) > len_of(S.len[l - 1 - (base - 1)]));
+    while (true) {
+        const int64_t s = left ? r : l - 1;                       // split position of the parent
+        if (S.len[s - (base - 1)] & kSpanFlag) {                  // the parent spans blocks
+#if defined(__CUDA_ARCH__)
+            const unsigned slot = atomicAdd(frontier_count, 1u);
+#else
+            const unsigned slot = (*frontier_count)++;
+#endif
+            if (slot >= frontier_cap) { *overflow = 1u; return; }
+            RefitEntry e;
+            for (int a = 0; a < 3; ++a) { e.lo[a] = lo[a]; e.hi[a] = hi[a]; }
+            e.node = kNone; e.from = me;
+            frontier[slot] = e;
+            return;
+        }
+        const unsigned slot = (unsigned)(s - base);
+        const int side = left ? 0 : 1;
+#if defined(__CUDA_ARCH__)
+        S.arr[slot][side][0] = make_float4(lo[0], lo[1], lo[2], hi[0]);
+        S.arr[slot][side][1] = make_float4(hi[1], hi[2], __uint_as_float(me), __uint_as_float((uint32_t)(left ? l : r)));
+#else
+        { float4 a0, a1; a0.x = lo[0]; a0.y = lo[1]; a0.z = lo[2]; a0.w = hi[0]; a1.x = hi[1]; a1.y = hi[2];
+          const uint32_t end = (uint32_t)(left ? l : r); memcpy(&a1.z, &me, 4); memcpy(&a1.w, &end, 4); S.arr[slot][side][0] = a0; S.arr[slot][side][1] = a1; }
+#endif
+        B2_FENCE_BLOCK();
+        if (B2_ARRIVE(&S.cnt[slot]) == 0) return;                 // first to arrive: the sibling will carry on
+        B2_FENCE_BLOCK();
+        const float4 o0 = S.arr[slot][1 - side][0], o1 = S.arr[slot][1 - side][1];       // (the fence and the atomic order these loads after the sibling's stores)
+        const float olo[3] = {o0.x, o0.y, o0.z}, ohi[3] = {o0.w, o1.x, o1.y};
+        uint32_t sib, sib_end;
+#if defined(__CUDA_ARCH__)
+        sib = __float_as_uint(o1.z); sib_end = __float_as_uint(o1.w);
+#else
+        memcpy(&sib, &o1.z, 4); memcpy(&sib_end, &o1.w, 4);
+#endif
+        const int64_t L = left ? l : (int64_t)sib_end, R = left ? (int64_t)sib_end : r;
+        const uint32_t c0 = left ? me : sib, c1 = left ? sib : me;
+        const bool root = L == 0 && R == n - 1;
+        const bool nleft = !root && (L == 0 || (R != n - 1 && len_of(S.len[R - (base - 1)]) > len_of(S.len[L - 1 - (base - 1)])));
+        const uint32_t idx = root ? 0u : (uint32_t)(nleft ? R : L);
+        BvhNode* nd = nodes + idx;
+        {
+            const float* l0 = side ? olo : lo; const float* h0 = side ? ohi : hi;     // child 0
+            const float* l1 = side ? lo : olo; const float* h1 = side ? hi : ohi;     // child 1
+#if defined(__CUDA_ARCH__)
+            float4* dst = reinterpret_cast<float4*>(nd);
+            dst[0] = make_float4(l0[0], l0[1], l0[2], h0[0]);
+            *reinterpret_cast<float2*>(&nd->hi0[1]) = make_float2(h0[1], h0[2]);      // (the parent link next to child0 is written by whoever builds the parent)
+            nd->child0 = c0;
+            dst[2] = make_float4(l1[0], l1[1], l1[2], h1[0]);
+            dst[3] = make_float4(h1[1], h1[2], __uint_as_float(c1), __uint_as_float(idx == (uint32_t)L ? (uint32_t)R : (uint32_t)L));
+#else
+            for (int a = 0; a < 3; ++a) { nd->lo0[a] = l0[a]; nd->hi0[a] = h0[a]; nd->lo1[a] = l1[a]; nd->hi1[a] = h1[a]; }
+            nd->child0 = c0; nd->child1 = c1; nd->visit = idx == (uint32_t)L ? (uint32_t)R : (uint32_t)L;
+#endif
+            if (root) nd->parent = kNone;
+        }
+        if (c0 & kLeafBit) leaf_parent[c0 & ~kLeafBit] = idx; else nodes[c0].parent = idx;
+        if (c1 & kLeafBit) leaf_parent[c1 & ~kLeafBit] = idx; else nodes[c1].parent = idx;
+        S.done[idx - (uint32_t)base] = 1;
+        if (root) return;
+        for (int a = 0; a < 3; ++a) { lo[a] = fminf(lo[a], olo[a]); hi[a] = fmaxf(hi[a], ohi[a]); }
+        me = idx; l = L; r = R; left = nleft;
+    }
+}
+
+#if defined(__CUDACC__)
+// flags[0] += positions that start a run of four PACKED words with equal key bits (ib > 0; see hierarchy_kernel); flags[1] = frontier overflow
+__global__ void __launch_bounds__(kRefitBlock, 6) build_local_kernel(const uint64_t* __restrict__ keys, TriRec* __restrict__ tris, uint64_t n, BvhNode* nodes, uint32_t* leaf_parent,
+                                                                  RefitEntry* __restrict__ frontier, unsigned* __restrict__ frontier_count, unsigned frontier_cap,
+                                                                  EmitArgs em, uint32_t* __restrict__ rest, unsigned* __restrict__ rest_count, unsigned long long* __restrict__ flags) {
+    __shared__ LocalBuildShared S;
+    const int64_t base = (int64_t)blockIdx.x * kRefitBlock, k = base + threadIdx.x;
+    const int64_t last_leaf = base + kRefitBlock - 1 < (int64_t)n - 1 ? base + kRefitBlock - 1 : (int64_t)n - 1;
+    S.cnt[threadIdx.x] = 0;
+    S.done[threadIdx.x] = 0;
+    if (k < (int64_t)n) S.key[threadIdx.x + 1] = keys[k];
+    if (threadIdx.x == 0) { S.key[0] = base > 0 ? keys[base - 1] : 0; S.key[last_leaf - base + 2] = last_leaf + 1 < (int64_t)n ? keys[last_leaf + 1] : 0; }
+    __syncthreads();
+    if (k <= last_leaf) S.len[threadIdx.x + 1] = local_len_entry(S, base, last_leaf, (int64_t)n, k);
+    if (threadIdx.x == 0) S.len[0] = local_len_entry(S, base, last_leaf, (int64_t)n, base - 1);
+    if (em.ib > 0) {
+        const bool dup = k + 3 < (int64_t)n && (((keys[k] ^ keys[k + 1]) | (keys[k] ^ keys[k + 2]) | (keys[k] ^ keys[k + 3])) >> em.ib) == 0;
+        const unsigned m = __ballot_sync(0xFFFFFFFFu, dup);
+        if (m && (threadIdx.x & 31) == 0) atomicAdd(&flags[0], (unsigned long long)__popc(m));
+    }
+    __syncthreads();
+    // Leaf records.  A thread gathers its primitive (72 bytes at 72 * src: five 128-bit loads from the 16-byte boundary below it) and the warp writes its
+    // 32 records — 3 KB of TriRec, 2 KB of TriF, contiguous in Morton order — through its 2 KB staging area with fully coalesced 128-bit stores: the L1
+    // data stage bounds this kernel (profiles/r2_08), and a thread storing its own 96-byte record costs 32 sectors per instruction.
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t k0 = base + warp * 32;
+    const int valid = (int64_t)n - k0 >= 32 ? 32 : ((int64_t)n - k0 > 0 ? (int)((int64_t)n - k0) : 0);
+    double v[9];
+    uint32_t src = 0, id = 0;
+    if (lane < valid) {
+        src = em.perm ? em.perm[k] : (uint32_t)(S.key[threadIdx.x + 1] & ((1ull << em.ib) - 1ull));
+        const double* t = em.soup + 9 * (uint64_t)src;
+        if ((reinterpret_cast<uintptr_t>(em.soup) & 15) == 0) {
+            const double2* q = reinterpret_cast<const double2*>(t - (src & 1));      // 72 * src is 8 modulo 16 exactly when src is odd
+            const double2 q0 = q[0], q1 = q[1], q2 = q[2], q3 = q[3], q4 = q[4];     // (even src: q4.y lies past the primitive — kSoupSlack)
+            const bool odd = src & 1;
+            v[0] = odd ? q0.y : q0.x; v[1] = odd ? q1.x : q0.y; v[2] = odd ? q1.y : q1.x; v[3] = odd ? q2.x : q1.y; v[4] = odd ? q2.y : q2.x;
+            v[5] = odd ? q3.x : q2.y; v[6] = odd ? q3.y : q3.x; v[7] = odd ? q4.x : q3.y; v[8] = odd ? q4.y : q4.x;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 9; ++j) v[j] = t[j];
+        }
+        id = em.ids ? em.ids[src] : src;
+    }
+    {
+        float4* stage = &S.arr[0][0][0] + warp * 128;
+        double2* stage2 = reinterpret_cast<double2*>(stage);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            if ((lane >> 4) == half && lane < valid) {                                // 16 records of 96 bytes at a stride of 7 x 16 bytes (bank spread)
+                double2* d = stage2 + (lane & 15) * 7;
+                d[0] = make_double2(v[0], v[1]); d[1] = make_double2(v[2], v[3]); d[2] = make_double2(v[4], v[5]); d[3] = make_double2(v[6], v[7]);
+                d[4] = make_double2(v[8], __longlong_as_double((long long)(((unsigned long long)src << 32) | id)));   // id, pad[0] = position in the inserted order
+                d[5] = make_double2(0.0, 0.0);
+            }
+            __syncwarp();
+            const int cnt = valid - 16 * half >= 16 ? 16 : (valid - 16 * half > 0 ? valid - 16 * half : 0);
+            float4* dst = reinterpret_cast<float4*>(tris + k0 + 16 * half);
+            for (int e = lane; e < cnt * 6; e += 32) dst[e] = stage[(e / 6) * 7 + e % 6];
+            __syncwarp();
+        }
+        if (lane < valid) {                                                           // 32 records of 64 bytes, 16-byte parts swizzled over the banks
+            const int sw = (lane >> 1) & 3;
+            stage[4 * lane + (0 ^ sw)] = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+            stage[4 * lane + (1 ^ sw)] = make_float4((float)v[4], (float)v[5], (float)v[6], (float)v[7]);
+            stage[4 * lane + (2 ^ sw)] = make_float4((float)v[8], 0.0f, 0.0f, 0.0f);
+            stage[4 * lane + (3 ^ sw)] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        }
+        __syncwarp();
+        float4* dstf = reinterpret_cast<float4*>(em.outf + k0);
+        for (int e = lane; e < valid * 4; e += 32) { const int i = e >> 2, j = e & 3; dstf[e] = stage[4 * i + (j ^ ((i >> 1) & 3))]; }
+    }
+    __syncthreads();                                                                  // the staging area becomes the arrival records
+    if (lane < valid) {
+        float lo[3], hi[3];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) { lo[a] = float_below(fmin(v[a], fmin(v[3 + a], v[6 + a]))); hi[a] = float_above(fmax(v[a], fmax(v[3 + a], v[6 + a]))); }
+        if (n > 1) build_local_climb(S, base, last_leaf, (int64_t)n, k, lo, hi, nodes, leaf_parent, frontier, frontier_count, frontier_cap, reinterpret_cast<unsigned*>(&flags[1]));
+    }
+    __syncthreads();
+    if (k < (int64_t)n - 1 && !S.done[threadIdx.x]) {            // node k spans blocks: hierarchy_kernel builds it from the list
+        const unsigned slot = atomicAdd(rest_count, 1u);
+        if (slot < frontier_cap) rest[slot] = (uint32_t)k;
+    }
+}
+#endif
 
 }  // namespace b2

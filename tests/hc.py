@@ -88,6 +88,14 @@ class HostTree:
         lib().hc_export(self.h, nodes.ctypes.data_as(C.c_void_p), tris.ctypes.data_as(C.c_void_p), _p(bbox))
         return nodes, tris, bbox
 
+    def fused_build_diff(self, frontier_per_block=-1):
+        """(number of node words in which the fused bottom-up build differs from the classic one, frontier entries, nodes left to the searches, overflow)"""
+        st = np.zeros(3, np.uint64)
+        f = lib().hc_fused_build_diff
+        f.restype = C.c_int64
+        d = f(self.h, int(frontier_per_block), st.ctypes.data_as(C.POINTER(C.c_uint64)))
+        return int(d), int(st[0]), int(st[1]), int(st[2])
+
     def intersect(self, q, is_ray, count):
         q = _d(q).reshape(-1, 6)
         out = np.zeros(len(q), np.uint32)

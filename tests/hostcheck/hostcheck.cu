@@ -98,6 +98,84 @@ void* hc_build(const double* tris, const uint32_t* ids, uint64_t n) {
     refit(*h, 0, rlo, rhi);
     return h;
 }
+// Re-builds the nodes of a tree with the FUSED bottom-up path of b200aabb_build (build.cuh: build_local_climb per block of kRefitBlock leaves with the
+// threads run one after the other, then Karras' searches for the nodes not built there, then the frontier climbs) and returns the number of node words
+// (boxes, children, parent, range end) that differ from the classic emulation of hc_build: 0 = identical.  stats[0] = frontier entries, [1] = nodes left to
+// the searches, [2] = frontier overflow.  frontier_per_block < 0: the build's own capacity.
+int64_t hc_fused_build_diff(void* hv, int frontier_per_block, uint64_t* stats) {
+    HostTree* h = (HostTree*)hv;
+    const int64_t n = (int64_t)h->n;
+    stats[0] = stats[1] = stats[2] = 0;
+    if (n < 2) return 0;
+    std::vector<BvhNode> nodes(n - 1);
+    memset(nodes.data(), 0xCD, (n - 1) * sizeof(BvhNode));
+    std::vector<uint32_t> leaf_parent(n, 0xCDCDCDCDu);
+    const int64_t blocks = (n + kRefitBlock - 1) / kRefitBlock;
+    const unsigned cap = (unsigned)(blocks * (frontier_per_block < 0 ? kRefitFrontierPerBlock : frontier_per_block));
+    std::vector<RefitEntry> frontier(std::max<unsigned>(cap, 1));
+    unsigned count = 0, overflow = 0;
+    std::vector<uint32_t> done(blocks * (kRefitBlock / 32), 0);
+    for (int64_t b = 0; b < blocks; ++b) {
+        LocalBuildShared S;
+        memset(&S, 0, sizeof(S));
+        const int64_t base = b * kRefitBlock, last_leaf = std::min<int64_t>(base + kRefitBlock - 1, n - 1);
+        for (int64_t k = base; k <= last_leaf; ++k) S.key[k - base + 1] = h->keys[k];
+        S.key[0] = base > 0 ? h->keys[base - 1] : 0;
+        S.key[last_leaf - base + 2] = last_leaf + 1 < n ? h->keys[last_leaf + 1] : 0;
+        for (int64_t k = base; k <= last_leaf; ++k) S.len[k - base + 1] = local_len_entry(S, base, last_leaf, n, k);
+        S.len[0] = local_len_entry(S, base, last_leaf, n, base - 1);
+        for (int64_t k = base; k <= last_leaf; ++k) {
+            const double* v = h->tris[k].v;
+            float lo[3], hi[3];
+            for (int a = 0; a < 3; ++a) { lo[a] = float_below(std::min(v[a], std::min(v[3 + a], v[6 + a]))); hi[a] = float_above(std::max(v[a], std::max(v[3 + a], v[6 + a]))); }
+            build_local_climb(S, base, last_leaf, n, k, lo, hi, nodes.data(), leaf_parent.data(), frontier.data(), &count, cap, &overflow);
+        }
+        for (int64_t k = base; k <= last_leaf; ++k) if (S.done[k - base]) done[k >> 5] |= 1u << (k & 31);
+    }
+    stats[0] = count; stats[2] = overflow;
+    if (overflow) return -1;
+    for (int64_t i = 0; i + 1 < n; ++i) {                 // hierarchy_kernel with the `done` bitmap
+        if ((done[i >> 5] >> (i & 31)) & 1u) continue;
+        ++stats[1];
+        uint32_t l, r, j;
+        karras_node(h->keys.data(), n, i, l, r, &j);
+        nodes[i].child0 = l; nodes[i].child1 = r; nodes[i].visit = j;
+        if (i == 0) nodes[i].parent = kNone;
+        if (l & kLeafBit) leaf_parent[l & ~kLeafBit] = (uint32_t)i; else nodes[l].parent = (uint32_t)i;
+        if (r & kLeafBit) leaf_parent[r & ~kLeafBit] = (uint32_t)i; else nodes[r].parent = (uint32_t)i;
+    }
+    for (unsigned e = 0; e < count; ++e) {                // refit_global_kernel, one entry after the other
+        float lo[3] = {frontier[e].lo[0], frontier[e].lo[1], frontier[e].lo[2]}, hi[3] = {frontier[e].hi[0], frontier[e].hi[1], frontier[e].hi[2]};
+        uint32_t me = frontier[e].from;
+        uint32_t p = (me & kLeafBit) ? leaf_parent[me & ~kLeafBit] : nodes[me].parent;
+        while (p != kNone) {
+            BvhNode& nd = nodes[p];
+            const int side = nd.child0 == me ? 0 : 1;
+            float* mylo = side ? nd.lo1 : nd.lo0; float* myhi = side ? nd.hi1 : nd.hi0;
+            for (int a = 0; a < 3; ++a) { mylo[a] = lo[a]; myhi[a] = hi[a]; }
+            const uint32_t old = nd.visit;
+            nd.visit ^= 0x80000000u;
+            if ((old & 0x80000000u) == 0) break;
+            const float* olo = side ? nd.lo0 : nd.lo1; const float* ohi = side ? nd.hi0 : nd.hi1;
+            for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], olo[a]); hi[a] = std::max(hi[a], ohi[a]); }
+            me = p; p = nd.parent;
+        }
+    }
+    // the classic emulation does not fill `visit`: compare it with the range end Karras' search gives
+    int64_t diff = 0;
+    for (int64_t i = 0; i + 1 < n; ++i) {
+        const uint32_t* a = (const uint32_t*)&nodes[i]; const uint32_t* b = (const uint32_t*)&h->nodes[i];
+        for (int w = 0; w < 15; ++w) diff += a[w] != b[w];
+        uint32_t l, r, j;
+        karras_node(h->keys.data(), n, i, l, r, &j);
+        diff += nodes[i].visit != j;
+    }
+    for (int64_t k = 0; k < n; ++k) {
+        const uint32_t p = leaf_parent[k];
+        diff += !(p < (uint32_t)(n - 1) && (h->nodes[p].child0 == (kLeafBit | (uint32_t)k) || h->nodes[p].child1 == (kLeafBit | (uint32_t)k)));
+    }
+    return diff;
+}
 void hc_destroy(void* hv) { delete (HostTree*)hv; }
 uint64_t hc_num_nodes(void* hv) { return ((HostTree*)hv)->nodes.size(); }
 void hc_export(void* hv, void* nodes, void* tris, double* bbox) {

@@ -381,3 +381,33 @@ def test_warp_kernel_binary32_bounds_are_rigorous():
             m_rel = float(np.abs(tri.reshape(3, 3) - q).max())
             assert up <= 1.001 * d + 4 * float(e2) + 2 * float(dslack) + 1e-3 * m_rel     # and it is useful (any point of the triangle is valid: ill-conditioned barycentrics only loosen it)
     assert n_upper > 10000                                # well-conditioned triangles do get an upper bound
+
+
+def test_fused_bottom_up_build_equals_the_classic_build(meshes):
+    """build.cuh::build_local_climb (topology + boxes of a block of 256 leaves in one bottom-up pass, then Karras' searches for the nodes that span
+    blocks and the frontier climbs) produces, word for word, the nodes of hierarchy_kernel + refit: reference meshes, terrain, random soup, equal and
+    duplicated primitives (index tie-break), a chain-shaped tree, and sizes around the block size"""
+    from cgal_b200 import workloads as W
+    rng = np.random.default_rng(5)
+    soup = W.triangle_soup(40_000)
+    cases = {name: meshes[name][0][meshes[name][1].astype(np.int64)].reshape(-1, 9) for name in ("cube", "tetrahedron", "elephant", "finger")}
+    v, f = W.terrain(256, 128)
+    cases["terrain"] = v[f.astype(np.int64)].reshape(-1, 9)
+    cases["soup"] = soup
+    cases["all equal"] = np.repeat(rng.uniform(0, 1, (1, 9)), 3000, 0)
+    cases["duplicates"] = np.concatenate([soup[:5000], np.repeat(soup[:100], 50, 0)])
+    k = np.arange(2000)
+    x = 2.0 ** (-k / 40.0)
+    c = np.stack([x, x, x], 1)
+    cases["chain"] = np.concatenate([c, c + 1e-9 * x[:, None], c + 2e-9 * x[:, None]], 1)
+    for n in (2, 3, 255, 256, 257, 511, 512, 513, 1025):
+        cases["soup[:%d]" % n] = soup[:n]
+    spanning = 0
+    for name, tri in cases.items():
+        diff, entries, rest, overflow = hc.HostTree(tri).fused_build_diff()
+        assert (diff, overflow) == (0, 0), (name, diff, entries, rest, overflow)
+        assert entries == (rest + 1 if rest else 0), (name, entries, rest)      # every spanning node is reached by exactly two parked children, the root included
+        spanning += rest
+    assert spanning > 1000
+    # a frontier list that is too small is reported (the build then takes the classic path), never silently wrong
+    assert hc.HostTree(cases["terrain"]).fused_build_diff(frontier_per_block=1)[3] == 1

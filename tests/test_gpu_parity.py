@@ -592,3 +592,30 @@ def test_line_and_plane_queries(B, meshes, name):
         np.testing.assert_array_equal(g.number_of_intersected_primitives(qd, kind).cpu().numpy(), want)
     with pytest.raises(B.B200AABBError):
         g.do_intersect(lines[:4], 7)
+
+
+def test_fused_and_classic_build_paths_agree(B, meshes):
+    """the fused bottom-up build (build.cuh::build_local_kernel + searches for the spanning nodes) and the classic path (Karras' searches for every
+    node + refit; test hook 103, also taken when the fused path's frontier list fills up: hook 101 = 0) give identical node arrays"""
+    from cgal_b200 import workloads as W
+    v, f = W.terrain(1024, 512)
+    cases = [dict(vertices=v, faces=f), dict(triangles=W.triangle_soup(300_000)),
+             dict(triangles=np.repeat(np.random.default_rng(9).uniform(0, 1, (1, 9)), 5000, 0))]
+    for kw in cases:
+        t = B.AABB_tree(**kw)
+        t.build()
+        n = t.size()
+        (pn, bn), (pt, bt) = t.export_layout()[:2]
+        fused = device_to_host(pn, bn).view(np.uint32).reshape(-1, 16)[:, :15].copy()
+        assert hc.validate(device_to_host(pn, bn), device_to_host(pt, bt), n) == 0
+        for hook, value in ((103, 1), (101, 0)):
+            c = B.AABB_tree(**kw)
+            c.set_option(hook, value)
+            c.build()
+            (qn, _), (qt, _) = c.export_layout()[:2]
+            np.testing.assert_array_equal(device_to_host(qn, bn).view(np.uint32).reshape(-1, 16)[:, :15], fused)
+            np.testing.assert_array_equal(device_to_host(qt, bt), device_to_host(pt, bt))
+        # a refit of the fused tree (b200aabb_refit climbs with the stored links and range ends) leaves it as it is
+        t.refit(**kw)
+        (pn2, _) = t.export_layout()[0]
+        np.testing.assert_array_equal(device_to_host(pn2, bn).view(np.uint32).reshape(-1, 16)[:, :15], fused)
