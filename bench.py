@@ -35,8 +35,8 @@ POINTS_PER_RANK = RAYS_PER_RANK
 BYTES_PER_RAY, BYTES_PER_POINT = 85, 61      # algorithmic bytes, SURVEY.md §8(d)
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the kernel on this very workload, from the committed `ncu --set full`
 # capture of the final state of the round (the file is named in the line; the tree itself — nodes + records — is read about once)
-NCU_DRAM = {"closest_point_warp_kernel": (10.903129e9 + 4.189776e9, "profiles/r2_01_pool_kernel_start_of_round.txt"),
-            "first_intersection_kernel": (None, None)}
+NCU_DRAM = {"closest_point_warp_kernel": (10.899676e9 + 4.182020e9, "profiles/r2_08_closest_point_warp_kernel_final.txt"),
+            "first_intersection_kernel": (1.113175e9 + 0.945382e9, "profiles/r2_08_first_intersection_kernel_final.txt")}
 WORKLOAD = "terrain16M(4096x2048 quads, Perlin fBm seed 23) + per GPU 8,388,608 pinhole Ray_3 first_intersection (rows r::8 of 8192^2) + 8,388,608 bbox closest_point_and_primitive"
 C5_BATCH, C5_BATCHES = 1 << 26, 8            # config 5: 8 ray batches (one 8192^2 image each) + 8 point batches of 2^26 = 2^30 queries
 
