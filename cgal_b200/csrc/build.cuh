@@ -103,11 +103,11 @@ B2_HD uint64_t morton63(double cx, double cy, double cz, const double* lo, const
 
 // quantisation frame of the Morton keys: ISOTROPIC cells (one scale, from the longest extent of the scene box), so that
 // a flat scene (terrain) is not split along its thin axis at the top of the tree
-B2_HD void morton_frame(double lx, double ly, double lz, double hx, double hy, double hz, double* lo, double* scale) {
+B2_HD void morton_frame(double lx, double ly, double lz, double hx, double hy, double hz, double* lo, double* scale, const double* weight = nullptr) {
     lo[0] = lx; lo[1] = ly; lo[2] = lz;
     const double ext = fmax(hx - lx, fmax(hy - ly, hz - lz));
     const double sc = ext > 0.0 ? 2097152.0 / ext : 0.0;
-    scale[0] = sc; scale[1] = sc; scale[2] = sc;
+    scale[0] = sc * (weight ? weight[0] : 1.0); scale[1] = sc * (weight ? weight[1] : 1.0); scale[2] = sc * (weight ? weight[2] : 1.0);
 }
 
 // PACKED sort word of primitive `index` (index < 2^ib): the top 64 - ib bits of its 63-bit Morton key above its index.  Sorting the words by

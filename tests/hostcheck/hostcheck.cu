@@ -4,6 +4,8 @@
 // used as a fallback: the product library has no host execution path.
 #include <algorithm>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <numeric>
@@ -53,7 +55,9 @@ void* hc_build(const double* tris, const uint32_t* ids, uint64_t n) {
     double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
     for (uint64_t i = 0; i < n; ++i) for (int k = 0; k < 9; ++k) { lo[k % 3] = std::min(lo[k % 3], tris[9 * i + k]); hi[k % 3] = std::max(hi[k % 3], tris[9 * i + k]); }
     double scale[3], lo_[3];
-    morton_frame(lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], lo_, scale);
+    double weight[3] = {1.0, 1.0, 1.0};
+    if (const char* e = getenv("HC_KEY_WEIGHTS")) sscanf(e, "%lf,%lf,%lf", &weight[0], &weight[1], &weight[2]);     // experiment hook (scripts/key_weight_experiment.py)
+    morton_frame(lo[0], lo[1], lo[2], hi[0], hi[1], hi[2], lo_, scale, weight);
     std::vector<uint64_t> keys(n);
     for (uint64_t i = 0; i < n; ++i) {
         double c[3];
