@@ -40,7 +40,7 @@ SYMBOLS = ["b200aabb_create", "b200aabb_destroy", "b200aabb_set_stream", "b200aa
            "b200aabb_accelerate_distance_queries", "b200aabb_size", "b200aabb_bbox", "b200aabb_do_intersect",
            "b200aabb_number_of_intersected_primitives", "b200aabb_any_intersected_primitive", "b200aabb_all_intersected_primitives",
            "b200aabb_number_of_intersections", "b200aabb_all_intersections", "b200aabb_any_intersection",
-           "b200aabb_first_intersection", "b200aabb_first_intersection_skip", "b200aabb_closest_point", "b200aabb_max_distance_to_mesh",
+           "b200aabb_first_intersection", "b200aabb_first_intersection_skip", "b200aabb_closest_point", "b200aabb_max_distance_to_mesh", "b200aabb_side_of_mesh",
            "b200aabb_export_layout", "b200aabb_import_alloc", "b200aabb_import_finish", "b200aabb_debug_predicate", "b200aabb_version",
            "b200aabb_comm_unique_id", "b200aabb_comm_init", "b200aabb_comm_init_all", "b200aabb_comm_destroy", "b200aabb_comm_last_error",
            "b200aabb_comm_broadcast_tree", "b200aabb_comm_broadcast_tree_all"]
@@ -114,7 +114,7 @@ class _Buf:
     def __init__(self, arr, dtype, cols):
         if _is_torch(arr):
             import torch
-            want = {np.float64: torch.float64, np.uint32: torch.int32, np.uint8: torch.uint8}[dtype]
+            want = {np.float64: torch.float64, np.uint32: torch.int32, np.uint8: torch.uint8, np.int8: torch.int8}[dtype]
             if not arr.is_cuda:
                 raise ValueError("torch tensors must live on the GPU; pass numpy arrays for host buffers")
             if arr.dtype != want or not arr.is_contiguous():
@@ -128,7 +128,7 @@ class _Buf:
 def _alloc_like(q, n, dtype, cols):
     if q.device:
         import torch
-        tdt = {np.float64: torch.float64, np.uint32: torch.int32, np.uint8: torch.uint8}[dtype]
+        tdt = {np.float64: torch.float64, np.uint32: torch.int32, np.uint8: torch.uint8, np.int8: torch.int8}[dtype]
         shape = (n, cols) if cols > 1 else (n,)
         return _Buf(torch.empty(shape, dtype=tdt, device=q.obj.device), dtype, cols)
     shape = (n, cols) if cols > 1 else (n,)
@@ -361,6 +361,15 @@ class AABB_tree:
         d, i = C.c_double(), C.c_uint64()
         self._check(self._lib.b200aabb_max_distance_to_mesh(self._h, q.ptr, q.n, int(q.device), C.byref(d), C.byref(i)))
         return d.value, i.value
+
+    def side_of_mesh(self, points, want_attempts=False):
+        """Side_of_triangle_mesh::operator() for a CLOSED mesh (Side_of_triangle_mesh.h:265-306): int8 per point, +1 ON_BOUNDED_SIDE, 0 ON_BOUNDARY,
+        -1 ON_UNBOUNDED_SIDE; with want_attempts also the number of rays cast per point"""
+        q = _Buf(points, np.float64, 3)
+        o = _alloc_like(q, q.n, np.int8, 1)
+        a = _alloc_like(q, q.n, np.uint8, 1) if want_attempts else None
+        self._check(self._lib.b200aabb_side_of_mesh(self._h, q.ptr, q.n, int(q.device), o.ptr, a.ptr if a is not None else None))
+        return (o.obj, a.obj) if want_attempts else o.obj
 
     # ---- multi-GPU plumbing: the built tree as flat device buffers (for torch.distributed.broadcast) ----
     def export_layout(self):

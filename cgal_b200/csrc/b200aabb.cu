@@ -78,6 +78,54 @@ __global__ void __launch_bounds__(128, 8) intersect_kernel(const TreeRef tr, con
     flush_stats(tr, st, 0, 0);
 }
 
+// Side_of_triangle_mesh (Side_of_triangle_mesh.h:265-306): -1 ON_UNBOUNDED_SIDE, 0 ON_BOUNDARY, +1 ON_BOUNDED_SIDE of a closed mesh.  A point outside
+// the tree's box is outside; otherwise rays are cast until one is decisive: first the vertical one towards the nearer z face of the box
+// (Point_inside_vertical_ray_cast.h:79-81), then fixed pseudo-random directions — the same for every query, as the reference's re-seeded generator
+// gives (:85-91; its particular sequence does not matter: the answer does not depend on the ray, only the number of attempts does).
+// out_attempts (optional) = rays cast per query.
+__device__ __forceinline__ Vec3 side_direction(int attempt, double pz, const double* box) {
+    if (attempt == 0) return {0.0, 0.0, 2.0 * pz < box[5] + box[2] ? -1.0 : 1.0};
+    unsigned long long z = 0x9E3779B97F4A7C15ull * (unsigned long long)attempt;       // SplitMix64 of the attempt number -> a direction in [-1, 1]^3
+    double c[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        z += 0x9E3779B97F4A7C15ull;
+        unsigned long long x = z;
+        x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull; x = (x ^ (x >> 27)) * 0x94D049BB133111EBull; x ^= x >> 31;
+        c[k] = (double)(x >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+    }
+    if (fabs(c[0]) + fabs(c[1]) + fabs(c[2]) < 0.25) c[attempt % 3] = 1.0;
+    return {c[0], c[1], c[2]};
+}
+constexpr int kSideMaxAttempts = 64;
+__global__ void __launch_bounds__(128, 8) side_of_mesh_kernel(const TreeRef tr, const double* __restrict__ pts, uint64_t n, const double* __restrict__ rootbox,
+                                                              int8_t* __restrict__ out, uint8_t* __restrict__ out_attempts) {
+    const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    TravStat st;
+    if (slot < n) {
+        const uint64_t i = tr.perm ? tr.perm[slot] : slot;
+        const Vec3 p = ld3(pts + 3 * i);
+        double box[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) box[k] = rootbox[k];
+        int side = -1, attempts = 0;
+        if (!(p.x < box[0] || p.x > box[3] || p.y < box[1] || p.y > box[4] || p.z < box[2] || p.z > box[5])) {
+            const double scale = fmax(1.0, tr.mag);          // p + d must differ from p
+            int r = kSideIndeterminate;
+            for (; attempts < kSideMaxAttempts && r == kSideIndeterminate; ++attempts) {
+                const Vec3 d = side_direction(attempts, p.z, box);
+                const Vec3 q = {p.x + d.x * scale, p.y + d.y * scale, p.z + d.z * scale};
+                r = traverse_side(tr.nodes, tr.tris, tr.root, p, q, st);
+            }
+            if (r == kSideIndeterminate) st.overflow = 1;   // (64 degenerate rays in a row: reported, never guessed)
+            side = r == kSideBoundary ? 0 : ((r & 1) ? 1 : -1);
+        }
+        out[i] = (int8_t)side;
+        if (out_attempts) out_attempts[i] = (uint8_t)attempts;
+    }
+    flush_stats(tr, st, 0, 0);
+}
+
 // the same for Plane_3 queries: q = n x 4 coefficients (a, b, c, d)
 template <int MODE>
 __global__ void __launch_bounds__(128, 8) plane_kernel(const TreeRef tr, const double* __restrict__ q, uint64_t n, uint8_t* __restrict__ out8, uint32_t* __restrict__ out32,
@@ -1255,6 +1303,23 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
                          const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)t->warp_grid, (cnt + 31) / 32);
                          closest_point_warp_kernel<<<grid, 32, 0, st>>>(a);
                      });
+}
+
+int b200aabb_side_of_mesh(b200aabb_tree* t, const double* pts, uint64_t n, b200aabb_memspace space, int8_t* side, uint8_t* attempts) { B2_LOCK(t);
+    if (!t || (n && (!pts || !side))) return B200AABB_ERR_INVALID_ARGUMENT;
+    int rc = ensure_built(t);
+    if (rc || n == 0) return rc;
+    if (t->n == 0) {                                                   // no primitives: everything is outside
+        if (space == B200AABB_HOST) { memset(side, 0xFF, n); if (attempts) memset(attempts, 0, n); return B200AABB_OK; }
+        B2_CUDA(t, cudaSetDevice(t->device));
+        B2_CUDA(t, cudaMemsetAsync(side, 0xFF, n, t->stream));
+        if (attempts) B2_CUDA(t, cudaMemsetAsync(attempts, 0, n, t->stream));
+        return B200AABB_OK;
+    }
+    B2_CUDA(t, cudaSetDevice(t->device));
+    return run_batch(t, pts, 24, n, space, kPointQuery, {{side, 1, 0}, {attempts, 1, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
+        side_of_mesh_kernel<<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, t->d_rootbox, (int8_t*)o[0], (uint8_t*)o[1]);
+    });
 }
 
 int b200aabb_max_distance_to_mesh(b200aabb_tree* t, const double* pts, uint64_t n, b200aabb_memspace space, double* max_distance, uint64_t* farthest) {

@@ -325,6 +325,28 @@ B2_HD uint32_t traverse_intersect(const BvhNode* __restrict__ nodes, const TriRe
     return MODE == kAnyId ? found_id : (MODE == kAnyHit ? (found ? 1u : 0u) : found);
 }
 
+// Side_of_triangle_mesh (Polygon_mesh_processing/include/CGAL/Side_of_triangle_mesh.h:265-306, internal/Side_of_triangle_mesh/
+// Point_inside_vertical_ray_cast.h:69-121, Ray_3_Triangle_3_traversal_traits.h:30-76): one ray from the point; every primitive it crosses in the
+// interior of a facet counts, the source lying on a primitive ends the query (ON_BOUNDARY), and a ray that passes through an edge or a vertex or
+// lies in a primitive's plane makes the attempt INDETERMINATE (the caller takes another ray).  Returns the number of crossings, kSideBoundary or
+// kSideIndeterminate.
+constexpr int kSideBoundary = -1, kSideIndeterminate = -2;
+B2_HD int traverse_side(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root, const Vec3& s, const Vec3& q, TravStat& st) {
+    const LineCtx c = make_line(s, q);
+    int crossings = 0, status = 0;
+    traverse_line<kRayQ, true>(nodes, root, c, st, [&](uint32_t ref) -> bool {
+        uint32_t id;
+        const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
+        ++st.leaves;
+        const int k = ray_tri_classify(t, s, q, st.nexact);
+        if (k < 0) return false;
+        if (k == 0) { ++crossings; return false; }
+        status = k == 4 ? kSideBoundary : kSideIndeterminate;
+        return true;                                         // m_stop
+    });
+    return status ? status : crossings;
+}
+
 // Plane_3 queries (a x + b y + c z + d = 0): Do_intersect_3(Plane_3, Bbox_3) (Iso_cuboid_3_Plane_3_do_intersect.h:90-125: the signs of the two
 // corners extreme along the normal) is replaced by a conservative binary64 test — the plane can only meet the box if its value at the box
 // centre is within the box's half extent along the normal, plus the rounding of that evaluation — and the leaves decide exactly.

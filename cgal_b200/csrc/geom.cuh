@@ -160,6 +160,29 @@ B2_HD bool ray_tri_do_intersect(const Tri3& t, const Vec3& p, const Vec3& q, int
     return fwd ? passes_edges(p, q, t, nexact) : passes_edges(q, p, t, nexact);
 }
 
+// The same with r3t3_do_intersect_endpoint_position_visitor (Ray_3_Triangle_3_do_intersect.h:23-62): HOW the ray meets the triangle.
+// -1 no intersection; 0 CROSS_FACET; 1 CROSS_SEGMENT; 2 CROSS_VERTEX (the ray passes through an edge / a vertex: one / two of the three edge
+// orientations vanish); 3 COPLANAR_RAY; 4 ENDPOINT_IN_TRIANGLE (the source lies in the triangle's plane, on the closed triangle).
+B2_HD int ray_tri_classify(const Tri3& t, const Vec3& p, const Vec3& q, int& nexact) {
+    const int dir = orient3_dir(t.a, t.b, t.c, p, q, nexact);
+    const int sp = orient3(t.a, t.b, t.c, p, nexact);
+    if (dir == 0) return sp == 0 && ray_tri_coplanar(t, p, q, nexact) ? 3 : -1;
+    if (sp == dir) return -1;
+    const bool fwd = sp > 0 || (sp == 0 && dir < 0);
+    const Vec3& x = fwd ? p : q; const Vec3& y = fwd ? q : p;
+    int zeros = 0;
+    const int o0 = orient3(x, y, t.a, t.b, nexact);
+    if (o0 == 1) return -1;
+    zeros += o0 == 0;
+    const int o1 = orient3(x, y, t.b, t.c, nexact);
+    if (o1 == 1) return -1;
+    zeros += o1 == 0;
+    const int o2 = orient3(x, y, t.c, t.a, nexact);
+    if (o2 == 1) return -1;
+    zeros += o2 == 0;
+    return sp == 0 ? 4 : zeros;
+}
+
 // Do_intersect_3(Line_3, Triangle_3): Line_3_Triangle_3_do_intersect.h:27-79.  The line is (point p, direction vector v) as CGAL stores it;
 // "q" of the reference is p + v, formed exactly (the predicate runs in Filtered_predicate's exact kernel when the filter fails).
 B2_HD bool line_tri_do_intersect(const Tri3& t, const Vec3& p, const Vec3& v, int& nexact) {

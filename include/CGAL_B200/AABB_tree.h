@@ -543,11 +543,47 @@ class AABB_tree {
     return v;
   }
 
+public:
+  // Side_of_triangle_mesh::operator() on the tree of a CLOSED triangle mesh (Polygon_mesh_processing/include/CGAL/Side_of_triangle_mesh.h:265-306):
+  // +1 ON_BOUNDED_SIDE, 0 ON_BOUNDARY, -1 ON_UNBOUNDED_SIDE — the values of CGAL::Bounded_side; out receives int.  See CGAL_B200::Side_of_triangle_mesh.
+  template <typename PointIterator, typename OutputIterator>
+  OutputIterator bounded_side(PointIterator first, PointIterator beyond, OutputIterator out) const {
+    std::vector<double> q = pack_points(first, beyond);
+    const uint64_t n = q.size() / 3;
+    std::vector<int8_t> r(n);
+    ensure_built();
+    check(b200aabb_side_of_mesh(m_handle, q.data(), n, B200AABB_HOST, r.data(), nullptr));
+    for (uint64_t i = 0; i < n; ++i) *out++ = (int)r[i];
+    return out;
+  }
+  int bounded_side(const Point& p) const { int r = -1; const Point* a = &p; bounded_side(a, a + 1, &r); return r; }
+
+private:
   AABBTraits m_traits;
   Primitives m_primitives;
   b200aabb_tree* m_handle = nullptr;
   mutable std::atomic<bool> m_uploaded{true};   // the device tree reflects m_primitives (read without the lock by const queries)
   mutable std::mutex m_mutex;
+};
+
+// The functor of Polygon_mesh_processing/include/CGAL/Side_of_triangle_mesh.h over a CGAL_B200::AABB_tree (its constructor from an AABB_tree, :226-236):
+//   CGAL_B200::Side_of_triangle_mesh<Tree> inside(tree);   int s = inside(p);   inside(points.begin(), points.end(), out);
+// Values as CGAL::Bounded_side: ON_UNBOUNDED_SIDE = -1, ON_BOUNDARY = 0, ON_BOUNDED_SIDE = 1.  The mesh must be closed.
+enum Bounded_side { ON_UNBOUNDED_SIDE = -1, ON_BOUNDARY = 0, ON_BOUNDED_SIDE = 1 };
+template <typename Tree>
+class Side_of_triangle_mesh {
+public:
+  explicit Side_of_triangle_mesh(const Tree& tree) : m_tree(&tree) {}
+  Bounded_side operator()(const typename Tree::Point& p) const { return (Bounded_side)m_tree->bounded_side(p); }
+  template <typename PointIterator, typename OutputIterator>
+  OutputIterator operator()(PointIterator first, PointIterator beyond, OutputIterator out) const {
+    std::vector<int> r;
+    m_tree->bounded_side(first, beyond, std::back_inserter(r));
+    for (int v : r) *out++ = (Bounded_side)v;
+    return out;
+  }
+private:
+  const Tree* m_tree;
 };
 
 }  // namespace CGAL_B200

@@ -200,6 +200,14 @@ int b200aabb_import_finish(b200aabb_tree* t);
  * query's result as the next query's hint (:133,180); a hint only decides exact ties, never the distance, so the value is the same.
  * *max_distance = that distance; *farthest (optional) = index of the first sample attaining it.  points: n x 3, HOST or DEVICE. */
 int b200aabb_max_distance_to_mesh(b200aabb_tree* t, const double* points, uint64_t n, b200aabb_memspace space, double* max_distance, uint64_t* farthest);
+/* Side_of_triangle_mesh::operator()(Point_3) (Polygon_mesh_processing/include/CGAL/Side_of_triangle_mesh.h:265-306; the ray casts of
+ * internal/Side_of_triangle_mesh/Point_inside_vertical_ray_cast.h:69-121 with Ray_3_Triangle_3_traversal_traits.h:30-76): for a CLOSED triangle mesh,
+ * side[i] = +1 ON_BOUNDED_SIDE, 0 ON_BOUNDARY, -1 ON_UNBOUNDED_SIDE (the values of CGAL::Bounded_side) of point i.  A point outside the tree's bbox is
+ * outside; otherwise one ray from the point counts the facets it crosses, with exact predicates; a ray that passes through an edge or a vertex, or lies
+ * in a facet's plane, is replaced by another (first the vertical ray towards the nearer z face of the box, then a fixed sequence of directions) — the
+ * answer does not depend on the rays, only attempts[i] (optional: rays cast for point i; 0 = decided by the bbox) does.  As in the reference, the
+ * result is unspecified for a mesh that is not closed.  points: n x 3, HOST or DEVICE. */
+int b200aabb_side_of_mesh(b200aabb_tree* t, const double* points, uint64_t n, b200aabb_memspace space, int8_t* side, uint8_t* attempts);
 
 /* ---- multi-GPU behind the boundary --------------------------------------------------------------------
  * The reference has no multi-device path: its callers shard queries over threads (tbb::parallel_for,

@@ -154,6 +154,14 @@ void orc_first_intersection(void* hv, const double* rays, uint64_t n, uint32_t* 
     });
 }
 // first_intersection(Ray_3, skip): skip = one primitive id per ray (0xFFFFFFFF: none) and / or a bit mask over primitive ids
+// Side_of_triangle_mesh: side[i] in {-1 ON_UNBOUNDED_SIDE, 0 ON_BOUNDARY, 1 ON_BOUNDED_SIDE}; attempts (optional) = rays cast
+void orc_side_of_mesh(void* hv, const double* pts, uint64_t n, int8_t* side, uint8_t* attempts, int nthreads) {
+    const Tree& t = *((Handle*)hv)->tree;
+    parallel_for(n, nthreads, [&](uint64_t b, uint64_t e) {
+        for (uint64_t i = b; i < e; ++i) { int a = 0; side[i] = (int8_t)t.side_of_mesh(P(pts + 3 * i), &a); if (attempts) attempts[i] = (uint8_t)std::min(a, 255); }
+    });
+}
+int orc_classify_ray_tri(const double* tri, const double* pq) { return classify_ray_tri(T(tri), P(pq), P(pq + 3)); }
 void orc_first_intersection_skip(void* hv, const double* rays, uint64_t n, const uint32_t* skip_ids, const uint32_t* mask, uint32_t mask_words, uint32_t* prim, double* tpar,
                                  int nthreads) {
     const Tree& t = *((Handle*)hv)->tree;

@@ -540,6 +540,35 @@ static inline bool do_intersect_ray_tri(const Tri& t, const P3& p, const P3& q) 
     }
 }
 
+// The same with r3t3_do_intersect_endpoint_position_visitor (Ray_3_Triangle_3_do_intersect.h:23-62,193-317): -1 = no intersection, else the
+// R3T3_intersection::type: 0 CROSS_FACET, 1 CROSS_SEGMENT, 2 CROSS_VERTEX (visitor.update counts the vanishing edge orientations), 3 COPLANAR_RAY,
+// 4 ENDPOINT_IN_TRIANGLE.  Used by Side_of_triangle_mesh's generic-ray traversal traits.
+static inline int classify_ray_tri(const Tri& t, const P3& p, const P3& q) {
+    const P3 &a = t.a, &b = t.b, &c = t.c;
+    const int dir = orientation_dir(a, b, c, p, q);
+    if (dir == 0) {
+        if (orientation(a, b, c, p) == 0) return ray_tri_coplanar(a, b, c, p, q) ? 3 : -1;      // visitor.ray_coplanar()
+        return -1;
+    }
+    const int abcp = orientation(a, b, c, p);
+    auto straddle = [&](const P3& x, const P3& y) -> int {
+        int zeros = 0, o;
+        o = orientation(x, y, a, b); if (o == 1) return -1; zeros += o == 0;
+        o = orientation(x, y, b, c); if (o == 1) return -1; zeros += o == 0;
+        o = orientation(x, y, c, a); if (o == 1) return -1; zeros += o == 0;
+        return zeros;
+    };
+    switch (abcp) {
+    case 1: return dir == 1 ? -1 : straddle(p, q);
+    case -1: return dir == -1 ? -1 : straddle(q, p);
+    default: {                                                                                     // visitor.end_point_in_triangle()
+        const bool hit = dir == 1 ? (orientation(q, p, a, b) != 1 && orientation(q, p, b, c) != 1 && orientation(q, p, c, a) != 1)
+                                  : (orientation(p, q, a, b) != 1 && orientation(p, q, b, c) != 1 && orientation(p, q, c, a) != 1);
+        return hit ? 4 : -1;
+    }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Intersect_3(Ray_3, Triangle_3): Intersections_3/internal/Ray_3_Triangle_3_intersection.h:28-539
 // Result: kind 0 = none, 1 = Point_3 (pt[0]), 2 = Segment_3 (pt[0], pt[1]).

@@ -264,6 +264,93 @@ struct Tree {
         RayObjectsTT tt{*this, first_only, false, &out};
         traversal(LineQ{s, q, 1}, tt);
     }
+    // ---- Side_of_triangle_mesh (Polygon_mesh_processing/include/CGAL/Side_of_triangle_mesh.h:265-306) ----------------------------------
+    // Ray_3_Triangle_3_traversal_traits<..., Tag_false> (internal/Side_of_triangle_mesh/Ray_3_Triangle_3_traversal_traits.h:30-76): any ray
+    struct SideTT {
+        const Tree& t; int status = 1 /* tribool: 1 true, 0 false, 2 indeterminate */; size_t count = 0; bool stop = false;
+        bool go_further() const { return !stop; }
+        void intersection(const LineQ& q, uint32_t f) {
+            const int k = classify_ray_tri(t.mesh->datum(f), q.p, q.q);
+            if (k < 0) return;
+            if (k == 0) ++count;
+            else if (k == 4) { status = 0; stop = true; }
+            else { status = 2; stop = true; }
+        }
+        bool do_intersect(const LineQ& q, const Box& b) const { return do_intersect_bbox(q.p, q.q, b, true); }
+    };
+    // the Tag_true specialisation (:79-222): a vertical ray, box and primitive tests by comparisons and 2D orientations of the z-projection
+    struct SideVerticalTT {
+        const Tree& t; int status = 1; size_t count = 0; bool stop = false;
+        bool go_further() const { return !stop; }
+        static bool box_test(const LineQ& q, const Box& b) {                                    // :96-110
+            const bool inc_z = q.q.z > q.p.z;
+            if ((inc_z && q.p.z > b.hi[2]) || (!inc_z && q.p.z < b.lo[2])) return false;
+            if (q.p.x > b.hi[0] || q.p.x < b.lo[0]) return false;
+            return q.p.y <= b.hi[1] && q.p.y >= b.lo[1];
+        }
+        bool do_intersect(const LineQ& q, const Box& b) const { return box_test(q, b); }
+        void intersection(const LineQ& q, uint32_t f) {                                          // :129-221
+            const Tri tr = t.mesh->datum(f);
+            Box tb;
+            const P3* v[3] = {&tr.a, &tr.b, &tr.c};
+            for (int k = 0; k < 3; ++k) { tb.lo[k] = std::min((*v[0])[k], std::min((*v[1])[k], (*v[2])[k])); tb.hi[k] = std::max((*v[0])[k], std::max((*v[1])[k], (*v[2])[k])); }
+            if (!box_test(q, tb)) return;
+            int i1 = 1, i2 = 2;
+            const int orient_2 = orientation2(v[0]->x, v[0]->y, v[1]->x, v[1]->y, v[2]->x, v[2]->y);
+            if (orient_2 == 0) {                     // the facet is vertical: its z-projection is a segment
+                const bool same01 = v[0]->x == v[1]->x && v[0]->y == v[1]->y;
+                const P3* other = same01 ? v[2] : v[1];
+                if (orientation2(v[0]->x, v[0]->y, other->x, other->y, q.p.x, q.p.y) != 0) return;
+                status = 2; stop = true;
+                return;
+            }
+            if (orient_2 == -1) std::swap(i1, i2);
+            const P3 &p0 = *v[0], &p1 = *v[i1], &p2 = *v[i2];
+            const int orient_3 = orientation(p0, p1, p2, q.p);
+            const double dz = q.q.z - q.p.z;         // query.to_vector().z()
+            if (orient_3 != 0 && ((dz > 0) == (orient_3 == 1))) return;
+            const int o01 = orientation2(p0.x, p0.y, p1.x, p1.y, q.p.x, q.p.y);
+            if (o01 == 0) { status = 2; stop = true; return; }
+            if (o01 == -1) return;
+            const int o12 = orientation2(p1.x, p1.y, p2.x, p2.y, q.p.x, q.p.y);
+            if (o12 == 0) { status = 2; stop = true; return; }
+            if (o12 == -1) return;
+            const int o20 = orientation2(p2.x, p2.y, p0.x, p0.y, q.p.x, q.p.y);
+            if (o20 == 0) { status = 2; stop = true; return; }
+            if (o20 == -1) return;
+            if (orient_3 == 0) { status = 0; stop = true; }
+            else ++count;
+        }
+    };
+    // Point_inside_vertical_ray_cast::operator() (Point_inside_vertical_ray_cast.h:69-96) behind the bbox test of Side_of_triangle_mesh.h:269-277.
+    // The retry directions: the reference draws them from CGAL::Random(1340818006) through Random_points_on_sphere_3 — an un-vendored generator
+    // stream that is not restated; any sequence gives the same answer for a closed mesh (this one differs from the device's on purpose).
+    // returns -1 ON_UNBOUNDED_SIDE, 0 ON_BOUNDARY, 1 ON_BOUNDED_SIDE; *attempts = rays cast
+    int side_of_mesh(const P3& pt, int* attempts = nullptr) const {
+        const Box bb = bbox();
+        if (attempts) *attempts = 0;
+        if (pt.x < bb.lo[0] || pt.x > bb.hi[0] || pt.y < bb.lo[1] || pt.y > bb.hi[1] || pt.z < bb.lo[2] || pt.z > bb.hi[2]) return -1;
+        auto verdict = [](int status, size_t count) { return status == 0 ? 0 : ((count & 1) ? 1 : -1); };
+        {
+            const double dz = 2 * pt.z < bb.hi[2] + bb.lo[2] ? -1.0 : 1.0;
+            SideVerticalTT tt{*this};
+            traversal(LineQ{pt, P3{pt.x + 0.0, pt.y + 0.0, pt.z + dz}, 1}, tt);
+            if (attempts) ++*attempts;
+            if (tt.status != 2) return verdict(tt.status, tt.count);
+        }
+        uint64_t lcg = 1340818006ull;
+        for (int k = 0; k < 1000; ++k) {
+            double d[3];
+            for (int a = 0; a < 3; ++a) { lcg = lcg * 6364136223846793005ull + 1442695040888963407ull; d[a] = (double)(lcg >> 11) / 9007199254740992.0 * 2.0 - 1.0; }
+            if (d[0] == 0 && d[1] == 0 && d[2] == 0) continue;
+            SideTT tt{*this};
+            traversal(LineQ{pt, P3{pt.x + d[0], pt.y + d[1], pt.z + d[2]}, 1}, tt);
+            if (attempts) ++*attempts;
+            if (tt.status != 2) return verdict(tt.status, tt.count);
+        }
+        return -2;
+    }
+
     bool do_intersect(const LineQ& q) const { DoIntersectTT tt{*this}; traversal(q, tt); return tt.found; }          // AABB_tree.h:903-913
     uint32_t number_of_intersected_primitives(const LineQ& q) const { CountTT tt{*this}; traversal(q, tt); return tt.count; }  // :915-932
 

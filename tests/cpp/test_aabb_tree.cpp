@@ -86,6 +86,19 @@ static int known_answers() {
     CHECK(std::holds_alternative<Point>(hit->first) && std::get<Point>(hit->first) == Point(0.2, 0.2, 0.0));
     CHECK(tree.first_intersected_primitive(up) && *tree.first_intersected_primitive(up) == mini::Face_index(0));
     CHECK(tree.number_of_intersected_primitives(up) == 2);
+    {   // Side_of_triangle_mesh (Side_of_triangle_mesh.h:265-306) on the tetrahedron (0,0,0),(1,0,0),(0,1,0),(0,0,1)
+      CGAL_B200::Side_of_triangle_mesh<Tree> inside(tree);
+      CHECK(inside(Point(0.1, 0.1, 0.1)) == CGAL_B200::ON_BOUNDED_SIDE);
+      CHECK(inside(Point(0.5, 0.5, 0.5)) == CGAL_B200::ON_UNBOUNDED_SIDE);      // inside the bbox, outside the solid
+      CHECK(inside(Point(2.0, 0.1, 0.1)) == CGAL_B200::ON_UNBOUNDED_SIDE);
+      CHECK(inside(Point(0.25, 0.25, 0.0)) == CGAL_B200::ON_BOUNDARY);          // on the base facet
+      CHECK(inside(Point(0.0, 0.0, 0.0)) == CGAL_B200::ON_BOUNDARY);            // a vertex
+      CHECK(inside(Point(0.25, 0.25, 0.25)) == CGAL_B200::ON_BOUNDED_SIDE);
+      std::vector<Point> ps = {Point(0.1, 0.1, 0.1), Point(0.9, 0.9, 0.9), Point(0.5, 0.0, 0.0)};
+      std::vector<CGAL_B200::Bounded_side> rs;
+      inside(ps.begin(), ps.end(), std::back_inserter(rs));
+      CHECK(rs.size() == 3 && rs[0] == CGAL_B200::ON_BOUNDED_SIDE && rs[1] == CGAL_B200::ON_UNBOUNDED_SIDE && rs[2] == CGAL_B200::ON_BOUNDARY);
+    }
     {   // Line_3 and Plane_3 queries (the AABB_tree concept takes any query type the traits can intersect: AABB_traits_3.h:378-400)
       const mini::Line_3 zline(Point(0.2, 0.2, 5.0), mini::Vector_3(0.0, 0.0, -1.0));
       CHECK(tree.do_intersect(zline) && tree.number_of_intersected_primitives(zline) == 2);

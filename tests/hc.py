@@ -109,6 +109,13 @@ class HostTree:
         lib().hc_count_line_plane(self.h, _p(q), len(q), int(kind), _p(out, _u32p))
         return out
 
+    def side_of_mesh(self, pts, dirs):
+        """Side_of_triangle_mesh through bvh.cuh::traverse_side with the given ray directions; (side, rays cast); side -2 = no decisive ray"""
+        pts, dirs = _d(pts).reshape(-1, 3), _d(dirs).reshape(-1, 3)
+        side, att = np.zeros(len(pts), np.int8), np.zeros(len(pts), np.uint8)
+        lib().hc_side_of_mesh(self.h, _p(pts), len(pts), _p(dirs), len(dirs), side.ctypes.data_as(C.POINTER(C.c_int8)), _p(att, _u8p))
+        return side, att
+
     def first_intersection(self, rays):
         rays = _d(rays).reshape(-1, 6)
         n = len(rays)
@@ -145,6 +152,11 @@ def validate(nodes_u8, tris_u8, n):
 def call(name, *arrs):
     arrs = [_d(a).ravel() for a in arrs]
     return getattr(lib(), name)(*[_p(a) for a in arrs])
+
+
+def classify_ray_tri(tri, pq):
+    tri, pq = _d(tri).ravel(), _d(pq).ravel()
+    return lib().hc_classify_ray_tri(_p(tri), _p(pq))
 
 
 def tri_do_intersect_kind(tri, q, kind):

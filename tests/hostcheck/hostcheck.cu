@@ -293,6 +293,24 @@ int hc_orient3_dir(const double* p) { int n = 0; return orient3_dir(V(p), V(p + 
 int hc_coplanar_orient(const double* p) { int n = 0; return coplanar_orient(V(p), V(p + 3), V(p + 6), n); }
 int hc_cmp_dist(const double* p) { int n = 0; return cmp_dist(V(p), V(p + 3), V(p + 6), n); }
 int hc_cmp_dist_exact(const double* p) { return exact_cmp_dist_sign(p, p + 3, p + 6); }
+int hc_classify_ray_tri(const double* tri, const double* pq) { int n = 0; return ray_tri_classify(T(tri), V(pq), V(pq + 3), n); }
+// Side_of_triangle_mesh through bvh.cuh::traverse_side: rays along the given directions (ndir x 3) until one is decisive; -2 = none was
+void hc_side_of_mesh(void* hv, const double* pts, uint64_t n, const double* dirs, int ndir, int8_t* side, uint8_t* attempts) {
+    HostTree* h = (HostTree*)hv;
+    for (uint64_t i = 0; i < n; ++i) {
+        const Vec3 p = V(pts + 3 * i);
+        side[i] = -1; attempts[i] = 0;
+        if (h->n == 0 || p.x < h->bbox[0] || p.x > h->bbox[3] || p.y < h->bbox[1] || p.y > h->bbox[4] || p.z < h->bbox[2] || p.z > h->bbox[5]) continue;
+        int r = kSideIndeterminate;
+        for (int k = 0; k < ndir && r == kSideIndeterminate; ++k) {
+            TravStat st;
+            const Vec3 q = {p.x + dirs[3 * k], p.y + dirs[3 * k + 1], p.z + dirs[3 * k + 2]};
+            r = traverse_side(h->nodes.data(), h->tris.data(), h->root, p, q, st);
+            ++attempts[i];
+        }
+        side[i] = (int8_t)(r == kSideIndeterminate ? -2 : (r == kSideBoundary ? 0 : ((r & 1) ? 1 : -1)));
+    }
+}
 int hc_tri_do_intersect_kind(const double* tri, const double* q, int kind) {
     int n = 0;
     if (kind == 2) return line_tri_do_intersect(T(tri), V(q), V(q + 3), n);

@@ -137,6 +137,13 @@ class OracleTree:
         f(self.h, _ptr(q, _dp), len(q), kind, _ptr(out, _u32p), threads or nthreads())
         return out
 
+    def side_of_mesh(self, pts, threads=None):
+        """Side_of_triangle_mesh: (side[n] in {-1 outside, 0 boundary, 1 inside}, rays cast per point)"""
+        pts = _d(pts).reshape(-1, 3)
+        side, att = np.zeros(len(pts), np.int8), np.zeros(len(pts), np.uint8)
+        lib().orc_side_of_mesh(self.h, _ptr(pts, _dp), len(pts), side.ctypes.data_as(C.POINTER(C.c_int8)), _ptr(att, _u8p), threads or nthreads())
+        return side, att
+
     def any_intersected_primitive(self, q, kind, threads=None):
         q = _d(q).reshape(-1, 4 if kind == 3 else 6)
         out = np.zeros(len(q), np.uint32)
@@ -273,6 +280,12 @@ def bbox_do_intersect(box, pq, is_ray, exact=False):
     pq = _d(pq).ravel()
     f = lib().orc_bbox_do_intersect_exact if exact else lib().orc_bbox_do_intersect
     return f(_ptr(box, _dp), _ptr(pq, _dp), int(is_ray))
+
+
+def classify_ray_tri(tri, pq):
+    """R3T3_intersection::type of Ray_3 x Triangle_3 (-1 none, 0 facet, 1 edge, 2 vertex, 3 coplanar ray, 4 endpoint in triangle)"""
+    tri, pq = _d(tri).ravel(), _d(pq).ravel()
+    return lib().orc_classify_ray_tri(_ptr(tri, _dp), _ptr(pq, _dp))
 
 
 def tri_do_intersect_kind(tri, q, kind):

@@ -619,3 +619,37 @@ def test_fused_and_classic_build_paths_agree(B, meshes):
         t.refit(**kw)
         (pn2, _) = t.export_layout()[0]
         np.testing.assert_array_equal(device_to_host(pn2, bn).view(np.uint32).reshape(-1, 16)[:, :15], fused)
+
+
+def test_side_of_mesh(B, meshes):
+    """Side_of_triangle_mesh (Side_of_triangle_mesh.h:265-306) through the C ABI against the oracle's restatement of the reference's ray casts: random
+    points, points on the mesh (vertices, edge midpoints), points whose vertical ray runs through a vertex or an edge (re-tries), a lattice cube where
+    every lattice point is a degenerate case; host and device pointers; the answer is independent of the rays (the two sides use different ones)"""
+    import torch
+    from test_side_of_mesh import lattice_cube, special_points
+    rng = np.random.default_rng(41)
+    for name in ("elephant", "finger", "cube"):
+        v, f = meshes[name]
+        pts = special_points(rng, v, f, 60_000 if name != "cube" else 2_000)
+        g, o = B.AABB_tree(v, f), orc.OracleTree(v, f)
+        want, _ = o.side_of_mesh(pts)
+        got, attempts = g.side_of_mesh(pts, want_attempts=True)
+        np.testing.assert_array_equal(got, want)
+        assert (want == 1).sum() > 100 and (want == -1).sum() > 100 and attempts.max() >= 2 and attempts.min() == 0
+        np.testing.assert_array_equal(g.side_of_mesh(torch.from_numpy(pts).cuda()).cpu().numpy(), want)
+    soup = lattice_cube()
+    grid = np.arange(-1, 7) * 0.5
+    pts = np.array([[x, y, z] for x in grid for y in grid for z in grid])
+    got = B.AABB_tree(triangles=soup).side_of_mesh(pts)
+    inside = np.all((pts > 0) & (pts < 2), axis=1)
+    outside = np.any((pts < 0) | (pts > 2), axis=1)
+    np.testing.assert_array_equal(got, np.where(inside, 1, np.where(outside, -1, 0)))          # the cube (0,2)^3, exactly
+    # unit sphere (icosphere level 5): inside / outside known analytically away from the surface
+    from cgal_b200 import workloads as W
+    v, f = W.icosphere(5)
+    g = B.AABB_tree(v, f)
+    pts = rng.uniform(-1.1, 1.1, (200_000, 3))
+    r = np.linalg.norm(pts, axis=1)
+    got = g.side_of_mesh(pts)
+    assert np.all(got[r < 0.995] == 1) and np.all(got[r > 1.0] == -1)
+    assert B.AABB_tree().side_of_mesh(pts[:5]).tolist() == [-1] * 5
