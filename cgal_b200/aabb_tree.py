@@ -87,6 +87,7 @@ def load_library():
         L.b200aabb_first_intersection_skip.argtypes = [vp, dp, u64, C.c_int, dp, dp, C.c_uint32, dp, dp, dp, dp, dp]
         L.b200aabb_closest_point.argtypes = [vp, dp, u64, C.c_int, dp, dp, dp, dp]
         L.b200aabb_max_distance_to_mesh.argtypes = [vp, dp, u64, C.c_int, C.POINTER(C.c_double), C.POINTER(u64)]
+        L.b200aabb_side_of_mesh.argtypes = [vp, dp, u64, C.c_int, dp, dp]
         L.b200aabb_export_layout.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.c_int, C.POINTER(C.c_int)]
         L.b200aabb_import_alloc.argtypes = [vp, u64]
         L.b200aabb_import_finish.argtypes = [vp]

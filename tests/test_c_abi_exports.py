@@ -45,3 +45,13 @@ def test_product_does_not_reference_the_oracle():
                 assert "oracle/" not in txt and "liboracle" not in txt and "import orc" not in txt, f
     so = open(os.path.join(ROOT, "cgal_b200", "libb200aabb.so"), "rb").read()
     assert b"liboracle" not in so and b"orc_" not in so
+
+
+def test_every_bound_symbol_declares_its_argument_types():
+    """ctypes passes an undeclared Python int as a 32-bit C int: a pointer handed to such a function is truncated (found on the GPU box with
+    b200aabb_side_of_mesh); every symbol the mirror binds must declare argtypes"""
+    import cgal_b200
+    from cgal_b200 import aabb_tree
+    L = cgal_b200.load_library()
+    missing = [s for s in aabb_tree.SYMBOLS if getattr(L, s).argtypes is None and s not in ("b200aabb_version",)]
+    assert not missing, missing
