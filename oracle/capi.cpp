@@ -114,15 +114,22 @@ int orc_all_intersected_primitives(void* hv, const double* q, uint64_t n, int ki
 // all_intersections(Ray_3) (AABB_tree.h:958-970).  Pass 1 (ids == nullptr): counts[i] = number of intersection objects of ray i.
 // Pass 2: offsets = exclusive prefix sums of the counts; entry k of ray i -> ids[offsets[i]+k], kinds[..] (1 Point_3, 2 Segment_3),
 // pts[6 * (..)] (point, or the two segment endpoints), in the reference's traversal order.  first_only: any_intersection (:972-985).
+int orc_line_intersections(void* hv, const double* rays, uint64_t n, int kind, int first_only, uint32_t* counts, const uint64_t* offsets, uint32_t* ids,
+                           uint8_t* kinds, double* pts, int nthreads);
 int orc_ray_intersections(void* hv, const double* rays, uint64_t n, int first_only, uint32_t* counts, const uint64_t* offsets, uint32_t* ids,
                           uint8_t* kinds, double* pts, int nthreads) {
+    return orc_line_intersections(hv, rays, n, 1, first_only, counts, offsets, ids, kinds, pts, nthreads);
+}
+// the same for kind 0 = Segment_3 (source, target) or 1 = Ray_3
+int orc_line_intersections(void* hv, const double* rays, uint64_t n, int kind, int first_only, uint32_t* counts, const uint64_t* offsets, uint32_t* ids,
+                           uint8_t* kinds, double* pts, int nthreads) {
     const Tree& t = *((Handle*)hv)->tree;
     std::atomic<int> bad{0};
     parallel_for(n, nthreads, [&](uint64_t b, uint64_t e) {
         std::vector<std::pair<uint32_t, RayHit>> v;
         for (uint64_t i = b; i < e; ++i) {
             v.clear();
-            t.ray_intersections(P(rays + 6 * i), P(rays + 6 * i + 3), first_only != 0, v);
+            t.ray_intersections(P(rays + 6 * i), P(rays + 6 * i + 3), first_only != 0, v, kind);
             if (counts) counts[i] = (uint32_t)v.size();
             if (!ids) continue;
             if (v.size() != offsets[i + 1] - offsets[i]) { bad = 1; continue; }
@@ -262,6 +269,11 @@ int orc_tri_do_intersect_kind(const double* tri, const double* q, int kind) { re
 int orc_bbox_do_intersect_kind(const double* box, const double* q, int kind) { return Tree::box_hit(LQ(q, 0, kind), B(box)) ? 1 : 0; }
 int orc_tri_do_intersect(const double* tri, const double* pq, int is_ray) {
     return (is_ray ? do_intersect_ray_tri(T(tri), P(pq), P(pq + 3)) : do_intersect_seg_tri(T(tri), P(pq), P(pq + 3))) ? 1 : 0;
+}
+int orc_tri_seg_intersection(const double* tri, const double* seg, double* pts) {
+    RayHit r = seg_tri_intersection(T(tri), P(seg), P(seg + 3));
+    if (r.kind) { put(pts, r.pt[0]); if (r.kind == 2) put(pts + 3, r.pt[1]); }
+    return r.kind;
 }
 int orc_tri_ray_intersection(const double* tri, const double* ray, double* pts) {
     RayHit r = ray_tri_intersection(T(tri), P(ray), P(ray + 3));

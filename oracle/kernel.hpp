@@ -716,6 +716,119 @@ static inline RayHit ray_tri_intersection(const Tri& t, const P3& p, const P3& q
 }
 
 // ------------------------------------------------------------------------------------------------
+// Intersect_3(Segment_3, Triangle_3): Intersections_3/internal/Segment_3_Triangle_3_intersection.h:28-569.  Same result record as the ray's
+// (kind 0 none, 1 Point_3, 2 Segment_3).  Predicates are the filtered (exact) ones, constructions plain doubles in the reference's order.
+// ------------------------------------------------------------------------------------------------
+// :28-61  intersection point of the coplanar segments [p,q] and [a,b]
+static inline P3 t3s3_point(const P3& p, const P3& q, const P3& a, const P3& b) { return coplanar_line_line(p, vsub(q, p), a, b); }
+// :63-133  clip [p,q] into the triangle; c is isolated on the negative side of (p,q)
+static inline RayHit t3s3_clip(const P3& a, const P3& b, const P3& c, const P3& p, const P3& q, bool negative_side) {
+    RayHit r;
+    const int bcq = coplanar_orientation(b, c, q), cap = coplanar_orientation(c, a, p);
+    if (bcq == -1 || cap == -1) return r;
+    if (bcq == 0) { r.kind = 1; r.pt[0] = q; return r; }
+    if (cap == 0) { r.kind = 1; r.pt[0] = p; return r; }
+    P3 pe = p, qe = q;
+    if (coplanar_orientation(b, c, p) == -1) pe = t3s3_point(p, q, b, c);
+    if (coplanar_orientation(c, a, q) == -1) qe = t3s3_point(p, q, c, a);
+    r.kind = 2;
+    r.pt[0] = negative_side ? pe : qe; r.pt[1] = negative_side ? qe : pe;
+    return r;
+}
+// :135-186  [a,b] and [p,q] collinear with the same direction
+static inline RayHit t3s3_collinear(const P3& a, const P3& b, const P3& p, const P3& q) {
+    RayHit r;
+    auto point = [&](const P3& x) { r.kind = 1; r.pt[0] = x; return r; };
+    auto segment = [&](const P3& x, const P3& y) { r.kind = 2; r.pt[0] = x; r.pt[1] = y; return r; };
+    if (collinear_ordered(p, a, b)) {
+        if (collinear_ordered(a, b, q)) return segment(a, b);
+        if (collinear_ordered(q, a, b)) return a == q ? point(a) : r;
+        return segment(a, q);
+    }
+    if (collinear_ordered(p, b, q)) return p == b ? point(p) : segment(p, b);
+    if (collinear_ordered(a, b, p)) return p == b ? point(p) : r;
+    return segment(p, q);
+}
+// :188-398
+static inline RayHit seg_tri_intersection_coplanar(const Tri& t, const P3& p, const P3& q) {
+    const P3* v[3] = {&t.a, &t.b, &t.c};
+    if (coplanar_orientation(t.a, t.b, t.c) != 1) std::swap(v[1], v[2]);
+    const P3 &a = *v[0], &b = *v[1], &c = *v[2];
+    const int pqa = coplanar_orientation(p, q, a), pqb = coplanar_orientation(p, q, b), pqc = coplanar_orientation(p, q, c);
+    RayHit none;
+    auto vertex_if_inside = [&](const P3& x) { RayHit r; if (collinear_ordered(p, x, q)) { r.kind = 1; r.pt[0] = x; } return r; };
+    switch (pqa) {
+    case 1:
+        switch (pqb) {
+        case 1:
+            if (pqc == 1) return none;
+            if (pqc == -1) return t3s3_clip(a, b, c, p, q, true);
+            return vertex_if_inside(c);
+        case -1:
+            if (pqc == 1) return t3s3_clip(c, a, b, p, q, true);
+            return t3s3_clip(b, c, a, q, p, false);
+        default:
+            if (pqc == 1) return vertex_if_inside(b);
+            if (pqc == -1) return t3s3_clip(b, c, a, q, p, false);
+            return t3s3_collinear(b, c, p, q);
+        }
+    case -1:
+        switch (pqb) {
+        case 1:
+            if (pqc == 1) return t3s3_clip(b, c, a, p, q, true);
+            return t3s3_clip(c, a, b, q, p, false);
+        case -1:
+            if (pqc == 1) return t3s3_clip(a, b, c, q, p, false);
+            if (pqc == -1) return none;
+            return vertex_if_inside(c);
+        default:
+            if (pqc == 1) return t3s3_clip(b, c, a, p, q, true);
+            if (pqc == -1) return vertex_if_inside(b);
+            return t3s3_collinear(c, b, p, q);
+        }
+    default:
+        switch (pqb) {
+        case 1:
+            if (pqc == 1) return vertex_if_inside(a);
+            if (pqc == -1) return t3s3_clip(c, a, b, q, p, false);
+            return t3s3_collinear(c, a, p, q);
+        case -1:
+            if (pqc == 1) return t3s3_clip(c, a, b, p, q, true);
+            if (pqc == -1) return vertex_if_inside(a);
+            return t3s3_collinear(a, c, p, q);
+        default:
+            if (pqc == 1) return t3s3_collinear(a, b, p, q);
+            if (pqc == -1) return t3s3_collinear(b, a, p, q);
+            return none;                                                   // (degenerate triangle: CGAL_error in the reference)
+        }
+    }
+}
+// :400-548
+static inline RayHit seg_tri_intersection(const Tri& t, const P3& p, const P3& q) {
+    const P3 &a = t.a, &b = t.b, &c = t.c;
+    const int abcp = orientation(a, b, c, p), abcq = orientation(a, b, c, q);
+    RayHit r;
+    auto from_p = [&]() { return orientation(p, q, a, b) != 1 && orientation(p, q, b, c) != 1 && orientation(p, q, c, a) != 1; };
+    auto from_q = [&]() { return orientation(q, p, a, b) != 1 && orientation(q, p, b, c) != 1 && orientation(q, p, c, a) != 1; };
+    auto crossing = [&]() { P3 x; if (line_plane_point(t, p, q, x)) { r.kind = 1; r.pt[0] = x; } return r; };
+    auto point = [&](const P3& x) { r.kind = 1; r.pt[0] = x; return r; };
+    switch (abcp) {
+    case 1:
+        if (abcq == 1) return r;
+        if (abcq == -1) return from_p() ? crossing() : r;
+        return from_p() ? point(q) : r;
+    case -1:
+        if (abcq == 1) return from_q() ? crossing() : r;
+        if (abcq == -1) return r;
+        return from_q() ? point(q) : r;
+    default:
+        if (abcq == 1) return from_q() ? point(p) : r;
+        if (abcq == -1) return from_p() ? point(p) : r;
+        return seg_tri_intersection_coplanar(t, p, q);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Construct_projected_point_3(Triangle_3, Point_3): Kernel_23/include/CGAL/Kernel/function_objects.h:3193-3263
 // ------------------------------------------------------------------------------------------------
 // Construct_projected_point_3(Line_3, Point_3): Cartesian/function_objects.h:3200-3217 ; line(p1,p2) = (p1, p2-p1) :2690-2691

@@ -160,18 +160,19 @@ class OracleTree:
         assert rc == 0
         return offsets, ids[:int(offsets[-1])]
 
-    def all_intersections(self, rays, first_only=False, threads=None):
-        """all_intersections(Ray_3) (first_only: any_intersection): (offsets[n+1], ids, kinds (1 Point_3 / 2 Segment_3), pts[total,6])"""
+    def all_intersections(self, rays, first_only=False, threads=None, kind=1):
+        """all_intersections(Ray_3 | kind 0: Segment_3) (first_only: any_intersection): (offsets[n+1], ids, kinds (1 Point_3 / 2 Segment_3), pts[total,6])"""
         q = _d(rays).reshape(-1, 6)
         th = threads or nthreads()
         counts = np.zeros(len(q), np.uint32)
-        lib().orc_ray_intersections(self.h, _ptr(q, _dp), len(q), int(first_only), _ptr(counts, _u32p), None, None, None, None, th)
+        f = lib().orc_line_intersections
+        f(self.h, _ptr(q, _dp), len(q), int(kind), int(first_only), _ptr(counts, _u32p), None, None, None, None, th)
         offsets = np.zeros(len(q) + 1, np.uint64)
         np.cumsum(counts, out=offsets[1:])
         tot = max(int(offsets[-1]), 1)
         ids, kinds, pts = np.zeros(tot, np.uint32), np.zeros(tot, np.uint8), np.zeros((tot, 6))
-        rc = lib().orc_ray_intersections(self.h, _ptr(q, _dp), len(q), int(first_only), None, offsets.ctypes.data_as(C.POINTER(C.c_uint64)), _ptr(ids, _u32p),
-                                         _ptr(kinds, _u8p), _ptr(pts, _dp), th)
+        rc = f(self.h, _ptr(q, _dp), len(q), int(kind), int(first_only), None, offsets.ctypes.data_as(C.POINTER(C.c_uint64)), _ptr(ids, _u32p),
+               _ptr(kinds, _u8p), _ptr(pts, _dp), th)
         assert rc == 0
         tot = int(offsets[-1])
         return offsets, ids[:tot], kinds[:tot], pts[:tot]
@@ -303,6 +304,13 @@ def tri_do_intersect(tri, pq, is_ray):
     tri = _d(tri).ravel()
     pq = _d(pq).ravel()
     return lib().orc_tri_do_intersect(_ptr(tri, _dp), _ptr(pq, _dp), int(is_ray))
+
+
+def tri_seg_intersection(tri, seg):
+    tri, seg = _d(tri).ravel(), _d(seg).ravel()
+    out = np.zeros(6)
+    k = lib().orc_tri_seg_intersection(_ptr(tri, _dp), _ptr(seg, _dp), _ptr(out, _dp))
+    return k, out.reshape(2, 3)
 
 
 def tri_ray_intersection(tri, ray):
