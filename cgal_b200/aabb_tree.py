@@ -40,6 +40,7 @@ SYMBOLS = ["b200aabb_create", "b200aabb_destroy", "b200aabb_set_stream", "b200aa
            "b200aabb_accelerate_distance_queries", "b200aabb_size", "b200aabb_bbox", "b200aabb_do_intersect",
            "b200aabb_number_of_intersected_primitives", "b200aabb_any_intersected_primitive", "b200aabb_all_intersected_primitives",
            "b200aabb_number_of_intersections", "b200aabb_all_intersections", "b200aabb_any_intersection",
+           "b200aabb_number_of_intersections_q", "b200aabb_all_intersections_q", "b200aabb_any_intersection_q",
            "b200aabb_first_intersection", "b200aabb_first_intersection_skip", "b200aabb_closest_point", "b200aabb_max_distance_to_mesh", "b200aabb_side_of_mesh",
            "b200aabb_export_layout", "b200aabb_import_alloc", "b200aabb_import_finish", "b200aabb_debug_predicate", "b200aabb_version",
            "b200aabb_comm_unique_id", "b200aabb_comm_init", "b200aabb_comm_init_all", "b200aabb_comm_destroy", "b200aabb_comm_last_error",
@@ -83,6 +84,9 @@ def load_library():
         L.b200aabb_number_of_intersections.argtypes = [vp, dp, u64, C.c_int, dp]
         L.b200aabb_all_intersections.argtypes = [vp, dp, u64, C.c_int, dp, dp, dp, dp]
         L.b200aabb_any_intersection.argtypes = [vp, dp, u64, C.c_int, dp, dp, dp, dp]
+        L.b200aabb_number_of_intersections_q.argtypes = [vp, dp, u64, C.c_int, C.c_int, dp]
+        L.b200aabb_all_intersections_q.argtypes = [vp, dp, u64, C.c_int, C.c_int, dp, dp, dp, dp]
+        L.b200aabb_any_intersection_q.argtypes = [vp, dp, u64, C.c_int, C.c_int, dp, dp, dp, dp]
         L.b200aabb_first_intersection.argtypes = [vp, dp, u64, C.c_int, dp, dp, dp, dp, dp]
         L.b200aabb_first_intersection_skip.argtypes = [vp, dp, u64, C.c_int, dp, dp, C.c_uint32, dp, dp, dp, dp, dp]
         L.b200aabb_closest_point.argtypes = [vp, dp, u64, C.c_int, dp, dp, dp, dp]
@@ -282,29 +286,29 @@ class AABB_tree:
         self._check(self._lib.b200aabb_all_intersected_primitives(self._h, q.ptr, q.n, kind, 0, offsets.ctypes.data, ids.ctypes.data))
         return offsets, ids[:int(offsets[-1])]
 
-    def all_intersections(self, rays):
-        """all_intersections(Ray_3, out) for a HOST batch: (offsets uint64[n+1], ids uint32[total], kinds uint8[total] (1 Point_3 /
-        2 Segment_3), points f64[total, 6]); the entries of ray i are [offsets[i], offsets[i+1])"""
+    def all_intersections(self, rays, kind=RAY):
+        """all_intersections(Ray_3 | Segment_3, out) for a HOST batch: (offsets uint64[n+1], ids uint32[total], kinds uint8[total] (1 Point_3 /
+        2 Segment_3), points f64[total, 6]); the entries of query i are [offsets[i], offsets[i+1])"""
         q = _Buf(np.asarray(rays), np.float64, 6)
         counts = np.empty(q.n, np.uint32)
-        self._check(self._lib.b200aabb_number_of_intersections(self._h, q.ptr, q.n, 0, counts.ctypes.data))
+        self._check(self._lib.b200aabb_number_of_intersections_q(self._h, q.ptr, q.n, int(kind), 0, counts.ctypes.data))
         offsets = np.zeros(q.n + 1, np.uint64)
         np.cumsum(counts, out=offsets[1:])
         tot = max(int(offsets[-1]), 1)
         ids, kinds, pts = np.empty(tot, np.uint32), np.empty(tot, np.uint8), np.empty((tot, 6))
-        self._check(self._lib.b200aabb_all_intersections(self._h, q.ptr, q.n, 0, offsets.ctypes.data, ids.ctypes.data, kinds.ctypes.data, pts.ctypes.data))
+        self._check(self._lib.b200aabb_all_intersections_q(self._h, q.ptr, q.n, int(kind), 0, offsets.ctypes.data, ids.ctypes.data, kinds.ctypes.data, pts.ctypes.data))
         tot = int(offsets[-1])
         return offsets, ids[:tot], kinds[:tot], pts[:tot]
 
-    def any_intersection(self, rays, want=("prim", "point", "point2", "flags"), out=None):
-        """any_intersection(Ray_3): dict with prim (NO_PRIMITIVE = nullopt), point, point2, flags (FLAG_HIT, FLAG_SEGMENT)"""
+    def any_intersection(self, rays, want=("prim", "point", "point2", "flags"), out=None, kind=RAY):
+        """any_intersection(Ray_3 | Segment_3): dict with prim (NO_PRIMITIVE = nullopt), point, point2, flags (FLAG_HIT, FLAG_SEGMENT)"""
         q = _Buf(rays, np.float64, 6)
         spec = {"prim": (np.uint32, 1), "point": (np.float64, 3), "point2": (np.float64, 3), "flags": (np.uint8, 1)}
         bufs = {}
         for k in want:
             bufs[k] = _Buf(out[k], *spec[k]) if out is not None and k in out else _alloc_like(q, q.n, *spec[k])
         p = lambda k: bufs[k].ptr if k in bufs else None   # noqa: E731
-        self._check(self._lib.b200aabb_any_intersection(self._h, q.ptr, q.n, int(q.device), p("prim"), p("point"), p("point2"), p("flags")))
+        self._check(self._lib.b200aabb_any_intersection_q(self._h, q.ptr, q.n, int(kind), int(q.device), p("prim"), p("point"), p("point2"), p("flags")))
         return {k: b.obj for k, b in bufs.items()}
 
     def first_intersection(self, rays, want=("prim", "t", "point", "point2", "flags"), out=None):

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(128, 8) plane_kernel(const TreeRef tr, const d
 
 // all_intersections / any_intersection (Ray_3): bvh.cuh::traverse_ray_objects.  kCount: out32[i]; kList: entries of ray i at offsets[i] ..
 // (a count that disagrees with offsets[i+1] - offsets[i] raises counters[2] bit 2); kAnyId: prim / flags / pt / pt2 like first_intersection
-template <int MODE>
+template <int MODE, int KIND>
 __global__ void __launch_bounds__(128, 5) ray_objects_kernel(const TreeRef tr, const double* __restrict__ rays, uint64_t n, uint32_t* __restrict__ out32,
                                                              const uint64_t* __restrict__ offsets, uint32_t* __restrict__ ids, uint8_t* __restrict__ kinds,
                                                              double* __restrict__ pts, uint32_t* __restrict__ prim, uint8_t* __restrict__ flags,
@@ -161,14 +161,14 @@ __global__ void __launch_bounds__(128, 5) ray_objects_kernel(const TreeRef tr, c
         const uint64_t i = tr.perm ? tr.perm[slot] : slot;
         const Vec3 s = ld3(rays + 6 * i), q = ld3(rays + 6 * i + 3);
         if (MODE == kCount) {
-            out32[i] = traverse_ray_objects<kCount>(tr.nodes, tr.tris, tr.root, s, q, st, nullptr, nullptr, nullptr, 0);
+            out32[i] = traverse_ray_objects<kCount, KIND>(tr.nodes, tr.tris, tr.root, s, q, st, nullptr, nullptr, nullptr, 0);
         } else if (MODE == kList) {
             const uint64_t lo = offsets[i], hi = offsets[i + 1];
-            const uint32_t r = traverse_ray_objects<kList>(tr.nodes, tr.tris, tr.root, s, q, st, ids + lo, kinds + lo, pts + 6 * lo, (uint32_t)(hi - lo));
+            const uint32_t r = traverse_ray_objects<kList, KIND>(tr.nodes, tr.tris, tr.root, s, q, st, ids + lo, kinds + lo, pts + 6 * lo, (uint32_t)(hi - lo));
             if (r != hi - lo) atomicOr(&tr.counters[2], 4ull);
         } else {
             uint32_t id = kNone; uint8_t kind = 0; double p[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-            traverse_ray_objects<kAnyId>(tr.nodes, tr.tris, tr.root, s, q, st, &id, &kind, p, 1);
+            traverse_ray_objects<kAnyId, KIND>(tr.nodes, tr.tris, tr.root, s, q, st, &id, &kind, p, 1);
             if (prim) prim[i] = id;
             if (flags) flags[i] = (uint8_t)((kind ? B200AABB_FLAG_HIT : 0) | (kind == 2 ? B200AABB_FLAG_SEGMENT : 0) | (st.nexact ? B200AABB_FLAG_EXACT : 0));
             if (pt) { pt[3 * i] = p[0]; pt[3 * i + 1] = p[1]; pt[3 * i + 2] = p[2]; }
@@ -1118,8 +1118,11 @@ int b200aabb_all_intersected_primitives(b200aabb_tree* t, const double* q, uint6
     return B200AABB_OK;
 }
 
-int b200aabb_number_of_intersections(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, uint32_t* out) { B2_LOCK(t);
-    if (!t || (n && (!rays || !out))) return B200AABB_ERR_INVALID_ARGUMENT;
+int b200aabb_number_of_intersections(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, uint32_t* out) {
+    return b200aabb_number_of_intersections_q(t, rays, n, B200AABB_RAY, space, out);
+}
+int b200aabb_number_of_intersections_q(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint32_t* out) { B2_LOCK(t);
+    if (!t || (n && (!rays || !out)) || (kind != B200AABB_RAY && kind != B200AABB_SEGMENT)) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     if (t->n == 0) {
@@ -1127,26 +1130,38 @@ int b200aabb_number_of_intersections(b200aabb_tree* t, const double* rays, uint6
         return B200AABB_OK;
     }
     return run_batch(t, rays, 48, n, space, kLineQuery, {{out, 4, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
-        ray_objects_kernel<kCount><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint32_t*)o[0], nullptr, nullptr, nullptr, nullptr,
-                                                                       nullptr, nullptr, nullptr, nullptr);
+        if (kind == B200AABB_RAY) ray_objects_kernel<kCount, kRayQ><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint32_t*)o[0], nullptr, nullptr, nullptr, nullptr,
+                                                                                                    nullptr, nullptr, nullptr, nullptr);
+        else ray_objects_kernel<kCount, kSegmentQ><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint32_t*)o[0], nullptr, nullptr, nullptr, nullptr,
+                                                                                       nullptr, nullptr, nullptr, nullptr);
     });
 }
 
-int b200aabb_any_intersection(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, uint32_t* prim, double* pt, double* pt2, uint8_t* flags) { B2_LOCK(t);
-    if (!t || (n && !rays)) return B200AABB_ERR_INVALID_ARGUMENT;
+int b200aabb_any_intersection(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, uint32_t* prim, double* pt, double* pt2, uint8_t* flags) {
+    return b200aabb_any_intersection_q(t, rays, n, B200AABB_RAY, space, prim, pt, pt2, flags);
+}
+int b200aabb_any_intersection_q(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint32_t* prim, double* pt, double* pt2,
+                                uint8_t* flags) { B2_LOCK(t);
+    if (!t || (n && !rays) || (kind != B200AABB_RAY && kind != B200AABB_SEGMENT)) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     if (t->n == 0) return b200aabb_first_intersection(t, rays, n, space, prim, nullptr, pt, pt2, flags);   // nullopt for every ray
     return run_batch(t, rays, 48, n, space, kLineQuery, {{prim, 4, 0}, {pt, 24, 0}, {pt2, 24, 0}, {flags, 1, 0}},
                      [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
-                         ray_objects_kernel<kAnyId><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                                                                        (uint32_t*)o[0], (uint8_t*)o[3], (double*)o[1], (double*)o[2]);
+                         if (kind == B200AABB_RAY) ray_objects_kernel<kAnyId, kRayQ><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                                                                                     (uint32_t*)o[0], (uint8_t*)o[3], (double*)o[1], (double*)o[2]);
+                         else ray_objects_kernel<kAnyId, kSegmentQ><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                                                                                        (uint32_t*)o[0], (uint8_t*)o[3], (double*)o[1], (double*)o[2]);
                      });
 }
 
 int b200aabb_all_intersections(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, const uint64_t* offsets, uint32_t* ids,
-                               uint8_t* kinds, double* points) { B2_LOCK(t);
-    if (!t || (n && (!rays || !offsets))) return B200AABB_ERR_INVALID_ARGUMENT;
+                               uint8_t* kinds, double* points) {
+    return b200aabb_all_intersections_q(t, rays, n, B200AABB_RAY, space, offsets, ids, kinds, points);
+}
+int b200aabb_all_intersections_q(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, const uint64_t* offsets, uint32_t* ids,
+                                 uint8_t* kinds, double* points) { B2_LOCK(t);
+    if (!t || (n && (!rays || !offsets)) || (kind != B200AABB_RAY && kind != B200AABB_SEGMENT)) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     B2_CUDA(t, cudaSetDevice(t->device));
@@ -1176,7 +1191,8 @@ int b200aabb_all_intersections(b200aabb_tree* t, const double* rays, uint64_t n,
     const uint32_t* perm = nullptr;
     rc = coherence_order(t, kDeviceScratch, t->stream, d_q, n, kLineQuery, &perm);
     if (rc) { release(); return rc; }
-    ray_objects_kernel<kList><<<grid_for(n, 128), 128, 0, t->stream>>>(tree_ref(t, perm), d_q, n, nullptr, d_off, d_ids, d_kinds, d_pts, nullptr, nullptr, nullptr, nullptr);
+    if (kind == B200AABB_RAY) ray_objects_kernel<kList, kRayQ><<<grid_for(n, 128), 128, 0, t->stream>>>(tree_ref(t, perm), d_q, n, nullptr, d_off, d_ids, d_kinds, d_pts, nullptr, nullptr, nullptr, nullptr);
+    else ray_objects_kernel<kList, kSegmentQ><<<grid_for(n, 128), 128, 0, t->stream>>>(tree_ref(t, perm), d_q, n, nullptr, d_off, d_ids, d_kinds, d_pts, nullptr, nullptr, nullptr, nullptr);
     t->stats.kernel_launches += 1;
     cudaEventRecord(t->ev_b, t->stream);
     t->query_timing_pending = true;

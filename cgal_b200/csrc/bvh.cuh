@@ -402,18 +402,26 @@ B2_HD uint32_t traverse_plane(const BvhNode* __restrict__ nodes, const TriRec* _
 // predicates on the ROUNDED point a + (q - p), so this set can differ from do_intersect's for a ray nearly parallel to a triangle,
 // SURVEY.md §7 hard part 3).  Entry k of the query: ids[k], kinds[k] (1 Point_3, 2 Segment_3), pts[6k..] = point / two endpoints.
 // MODE kCount: count only; kList: fill (at most cap entries); kAnyId: stop at the first, written as entry 0.
-template <int MODE>
+// KIND kSegmentQ: the same for Segment_3 queries with Intersect_3(Segment_3, Triangle_3) (geom.cuh::seg_tri_intersection).
+template <int MODE, int KIND = kRayQ>
 B2_HD uint32_t traverse_ray_objects(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root, const Vec3& s, const Vec3& q,
                                     TravStat& st, uint32_t* ids, uint8_t* kinds, double* pts, uint32_t cap) {
     const LineCtx c = make_line(s, q);
     uint32_t nlisted = 0;
-    return traverse_line<kRayQ, MODE == kAnyId>(nodes, root, c, st, [&](uint32_t ref) -> bool {
+    return traverse_line<KIND, MODE == kAnyId>(nodes, root, c, st, [&](uint32_t ref) -> bool {
         uint32_t id;
         const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
         ++st.leaves;
-        int nex = 0;
-        const RayX x = ray_tri_intersection_call(t.a.x, t.a.y, t.a.z, t.b.x, t.b.y, t.b.z, t.c.x, t.c.y, t.c.z, s.x, s.y, s.z, q.x, q.y, q.z, c.major, &nex);
-        st.nexact += nex;
+        struct { int kind; Vec3 p0, p1; } x;
+        if (KIND == kSegmentQ) {
+            const SegX y = seg_tri_intersection(t, s, q, st.nexact);
+            x.kind = y.kind; x.p0 = y.p0; x.p1 = y.p1;
+        } else {
+            int nex = 0;
+            const RayX y = ray_tri_intersection_call(t.a.x, t.a.y, t.a.z, t.b.x, t.b.y, t.b.z, t.c.x, t.c.y, t.c.z, s.x, s.y, s.z, q.x, q.y, q.z, c.major, &nex);
+            st.nexact += nex;
+            x.kind = y.kind; x.p0 = y.p0; x.p1 = y.p1;
+        }
         if (x.kind == 0) return false;
         if (MODE != kCount) {
             if (nlisted < cap) {

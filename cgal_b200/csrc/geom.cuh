@@ -290,6 +290,97 @@ B2_HD RayX ray_tri_intersection(const Tri3& t, const Vec3& s, const Vec3& q, con
     return r;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Intersect_3(Segment_3, Triangle_3): Intersections_3/internal/Segment_3_Triangle_3_intersection.h:28-569 (kind 0 none, 1 Point_3 p0, 2 Segment_3 p0 p1)
+// ---------------------------------------------------------------------------------------------------------------
+struct SegX { int kind; Vec3 p0, p1; };
+// :63-133  clip [p,q] into the triangle; c is isolated on the negative side of (p,q)
+B2_HD SegX t3s3_clip(const Vec3& a, const Vec3& b, const Vec3& c, const Vec3& p, const Vec3& q, bool negative_side, int& nexact) {
+    SegX r; r.kind = 0; r.p0 = p; r.p1 = p;
+    const int bcq = coplanar_orient(b, c, q, nexact), cap = coplanar_orient(c, a, p, nexact);
+    if (bcq == -1 || cap == -1) return r;
+    if (bcq == 0) { r.kind = 1; r.p0 = q; return r; }
+    if (cap == 0) { r.kind = 1; r.p0 = p; return r; }
+    Vec3 pe = p, qe = q;
+    const Vec3 v = q - p;
+    if (coplanar_orient(b, c, p, nexact) == -1) pe = coplanar_lines_meet(p, v, b, c);     // t3s3_intersection_coplanar_aux (point version), :28-61
+    if (coplanar_orient(c, a, q, nexact) == -1) qe = coplanar_lines_meet(p, v, c, a);
+    r.kind = 2; r.p0 = negative_side ? pe : qe; r.p1 = negative_side ? qe : pe;
+    return r;
+}
+// :135-186  [a,b] and [p,q] collinear, same direction
+B2_HD SegX t3s3_collinear(const Vec3& a, const Vec3& b, const Vec3& p, const Vec3& q) {
+    SegX r; r.kind = 0; r.p0 = p; r.p1 = p;
+    if (collinear_ordered(p, a, b)) {
+        if (collinear_ordered(a, b, q)) { r.kind = 2; r.p0 = a; r.p1 = b; }
+        else if (collinear_ordered(q, a, b)) { if (same_point(a, q)) { r.kind = 1; r.p0 = a; } }
+        else { r.kind = 2; r.p0 = a; r.p1 = q; }
+        return r;
+    }
+    if (collinear_ordered(p, b, q)) {
+        if (same_point(p, b)) { r.kind = 1; r.p0 = p; } else { r.kind = 2; r.p0 = p; r.p1 = b; }
+        return r;
+    }
+    if (collinear_ordered(a, b, p)) { if (same_point(p, b)) { r.kind = 1; r.p0 = p; } return r; }
+    r.kind = 2; r.p0 = p; r.p1 = q;
+    return r;
+}
+// :188-398  the 27 sign patterns of (pqa, pqb, pqc)
+B2_HD_NOINLINE SegX seg_tri_intersection_coplanar(const Tri3& t, const Vec3& p, const Vec3& q, int& nexact) {
+    SegX none; none.kind = 0; none.p0 = p; none.p1 = p;
+    const bool ccw = coplanar_orient(t.a, t.b, t.c, nexact) == 1;
+    const Vec3 a = t.a, b = ccw ? t.b : t.c, c = ccw ? t.c : t.b;
+    const int pqa = coplanar_orient(p, q, a, nexact), pqb = coplanar_orient(p, q, b, nexact), pqc = coplanar_orient(p, q, c, nexact);
+    const int code = (pqa + 1) * 9 + (pqb + 1) * 3 + (pqc + 1);
+    const Vec3* vtx = nullptr;                      // "vertex x if it lies inside [p,q]"
+    switch (code) {
+        case 26: case 0: case 13: return none;                                  // (+,+,+), (-,-,-), degenerate (0,0,0)
+        case 24: return t3s3_clip(a, b, c, p, q, true, nexact);                 // (+,+,-)
+        case 25: case 1: vtx = &c; break;                                       // (+,+,0), (-,-,0)
+        case 20: return t3s3_clip(c, a, b, p, q, true, nexact);                 // (+,-,+)
+        case 18: case 19: return t3s3_clip(b, c, a, q, p, false, nexact);       // (+,-,-), (+,-,0)
+        case 23: case 3: vtx = &b; break;                                       // (+,0,+), (-,0,-)
+        case 21: return t3s3_clip(b, c, a, q, p, false, nexact);                // (+,0,-)
+        case 22: return t3s3_collinear(b, c, p, q);                             // (+,0,0)
+        case 8: return t3s3_clip(b, c, a, p, q, true, nexact);                  // (-,+,+)
+        case 6: case 7: return t3s3_clip(c, a, b, q, p, false, nexact);         // (-,+,-), (-,+,0)
+        case 2: return t3s3_clip(a, b, c, q, p, false, nexact);                 // (-,-,+)
+        case 5: return t3s3_clip(b, c, a, p, q, true, nexact);                  // (-,0,+)
+        case 4: return t3s3_collinear(c, b, p, q);                              // (-,0,0)
+        case 17: case 9: vtx = &a; break;                                       // (0,+,+), (0,-,-)
+        case 15: return t3s3_clip(c, a, b, q, p, false, nexact);                // (0,+,-)
+        case 16: return t3s3_collinear(c, a, p, q);                             // (0,+,0)
+        case 11: return t3s3_clip(c, a, b, p, q, true, nexact);                 // (0,-,+)
+        case 10: return t3s3_collinear(a, c, p, q);                             // (0,-,0)
+        case 14: return t3s3_collinear(a, b, p, q);                             // (0,0,+)
+        case 12: return t3s3_collinear(b, a, p, q);                             // (0,0,-)
+        default: return none;
+    }
+    if (collinear_ordered(p, *vtx, q)) { none.kind = 1; none.p0 = *vtx; }
+    return none;
+}
+// :400-548
+B2_HD SegX seg_tri_intersection(const Tri3& t, const Vec3& p, const Vec3& q, int& nexact) {
+    SegX r; r.kind = 0; r.p0 = p; r.p1 = p;
+    const int sp = orient3(t.a, t.b, t.c, p, nexact), sq = orient3(t.a, t.b, t.c, q, nexact);
+    if (sp == 0 && sq == 0) return seg_tri_intersection_coplanar(t, p, q, nexact);
+    if (sp == sq) return r;
+    // which endpoint sees the triangle counterclockwise: p when it is on the positive side, or in the plane with q on the negative side
+    const bool fwd = sp > 0 || (sp == 0 && sq < 0);
+    if (!(fwd ? passes_edges(p, q, t, nexact) : passes_edges(q, p, t, nexact))) return r;
+    if (sp == 0) { r.kind = 1; r.p0 = p; return r; }
+    if (sq == 0) { r.kind = 1; r.p0 = q; return r; }
+    const Plane4 h = plane_of(t);                          // Line_3 x Plane_3, Line_3_Plane_3_intersection.h:52-85, as for the ray
+    const Vec3 d = q - p;
+    const double num = ((h.a * p.x + h.b * p.y) + h.c * p.z) + h.d;
+    const double den = (h.a * d.x + h.b * d.y) + h.c * d.z;
+    if (den == 0.0) return r;
+    Vec3 x = {den * p.x - num * d.x, den * p.y - num * d.y, den * p.z - num * d.z};
+    if (den != 1.0) { x.x = x.x / den; x.y = x.y / den; x.z = x.z / den; }
+    r.kind = 1; r.p0 = x;
+    return r;
+}
+
 // The same routine OUT OF LINE with its arguments in registers, for the traversal kernels: a ray meets ~1.3 leaves, and keeping this long
 // routine (five orientation predicates, a division chain) out of the traversal loop lets the loop run at 8 blocks per SM without spilling.
 B2_HD_NOINLINE RayX ray_tri_intersection_call(double ax, double ay, double az, double bx, double by, double bz, double cx, double cy, double cz,

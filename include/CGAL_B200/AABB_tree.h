@@ -183,7 +183,8 @@ class AABB_tree {
     any_intersected_primitive(&query, &query + 1, &r);
     return r;
   }
-  // all_intersections(ray, out) / any_intersection(ray) (AABB_tree.h:283-296,958-985): out receives Intersection_and_primitive_id<Ray>::Type
+  // all_intersections(query, out) / any_intersection(query) for Ray_3 and Segment_3 queries (AABB_tree.h:283-296,958-985): out receives
+  // Intersection_and_primitive_id<Query>::Type
   template <typename OutputIterator>
   OutputIterator all_intersections(const Ray& query, OutputIterator out) const {
     std::vector<std::vector<typename Intersection_and_primitive_id<Ray>::Type>> r;
@@ -191,8 +192,20 @@ class AABB_tree {
     for (const auto& x : r[0]) *out++ = x;
     return out;
   }
+  template <typename OutputIterator>
+  OutputIterator all_intersections(const Segment& query, OutputIterator out) const {
+    std::vector<std::vector<typename Intersection_and_primitive_id<Segment>::Type>> r;
+    all_intersections(&query, &query + 1, std::back_inserter(r));
+    for (const auto& x : r[0]) *out++ = x;
+    return out;
+  }
   Ray_intersection any_intersection(const Ray& query) const {
     Ray_intersection r;
+    any_intersection(&query, &query + 1, &r);
+    return r;
+  }
+  std::optional<typename Intersection_and_primitive_id<Segment>::Type> any_intersection(const Segment& query) const {
+    std::optional<typename Intersection_and_primitive_id<Segment>::Type> r;
     any_intersection(&query, &query + 1, &r);
     return r;
   }
@@ -299,10 +312,12 @@ class AABB_tree {
     }
     return out;
   }
-  // out receives std::optional< Intersection_and_primitive_id<Ray>::Type >
+  // out receives std::optional< Intersection_and_primitive_id<Query>::Type >, Query = Ray_3 or Segment_3 (the range's value type)
   template <typename RayIterator, typename OutputIterator>
   OutputIterator any_intersection(RayIterator first, RayIterator beyond, OutputIterator out) const {
-    typedef typename Intersection_and_primitive_id<Ray>::Type Result;
+    typedef typename std::iterator_traits<RayIterator>::value_type Query;
+    static_assert(std::is_same<Query, Ray>::value || std::is_same<Query, Segment>::value, "intersection objects: Ray_3 and Segment_3 queries");
+    typedef typename Intersection_and_primitive_id<Query>::Type Result;
     typedef typename Result::first_type Intersection;
     std::vector<double> q = pack_lines(first, beyond);
     const uint64_t n = q.size() / 6;
@@ -310,7 +325,7 @@ class AABB_tree {
     std::vector<double> p0(3 * n), p1(3 * n);
     std::vector<uint8_t> fl(n);
     ensure_built();
-    check(b200aabb_any_intersection(m_handle, q.data(), n, B200AABB_HOST, prim.data(), p0.data(), p1.data(), fl.data()));
+    check(b200aabb_any_intersection_q(m_handle, q.data(), n, kind_of<Query>(), B200AABB_HOST, prim.data(), p0.data(), p1.data(), fl.data()));
     for (uint64_t i = 0; i < n; ++i) {
       if (!(fl[i] & B200AABB_FLAG_HIT)) { *out++ = std::nullopt; continue; }
       const Point a(FT(p0[3 * i]), FT(p0[3 * i + 1]), FT(p0[3 * i + 2]));
@@ -319,23 +334,25 @@ class AABB_tree {
     }
     return out;
   }
-  // out receives one std::vector< Intersection_and_primitive_id<Ray>::Type > per ray (count pass -> prefix sums -> fill pass)
+  // out receives one std::vector< Intersection_and_primitive_id<Query>::Type > per query (count pass -> prefix sums -> fill pass)
   template <typename RayIterator, typename OutputIterator>
   OutputIterator all_intersections(RayIterator first, RayIterator beyond, OutputIterator out) const {
-    typedef typename Intersection_and_primitive_id<Ray>::Type Result;
+    typedef typename std::iterator_traits<RayIterator>::value_type Query;
+    static_assert(std::is_same<Query, Ray>::value || std::is_same<Query, Segment>::value, "intersection objects: Ray_3 and Segment_3 queries");
+    typedef typename Intersection_and_primitive_id<Query>::Type Result;
     typedef typename Result::first_type Intersection;
     std::vector<double> q = pack_lines(first, beyond);
     const uint64_t n = q.size() / 6;
     std::vector<uint32_t> cnt(n);
     ensure_built();
-    check(b200aabb_number_of_intersections(m_handle, q.data(), n, B200AABB_HOST, cnt.data()));
+    check(b200aabb_number_of_intersections_q(m_handle, q.data(), n, kind_of<Query>(), B200AABB_HOST, cnt.data()));
     std::vector<uint64_t> off(n + 1, 0);
     for (uint64_t i = 0; i < n; ++i) off[i + 1] = off[i] + cnt[i];
     const uint64_t room = off[n] ? off[n] : 1;
     std::vector<uint32_t> ids(room);
     std::vector<uint8_t> kinds(room);
     std::vector<double> pts(6 * room);
-    check(b200aabb_all_intersections(m_handle, q.data(), n, B200AABB_HOST, off.data(), ids.data(), kinds.data(), pts.data()));
+    check(b200aabb_all_intersections_q(m_handle, q.data(), n, kind_of<Query>(), B200AABB_HOST, off.data(), ids.data(), kinds.data(), pts.data()));
     for (uint64_t i = 0; i < n; ++i) {
       std::vector<Result> v;
       for (uint64_t k = off[i]; k < off[i + 1]; ++k) {

@@ -161,6 +161,13 @@ int b200aabb_all_intersected_primitives(b200aabb_tree* t, const double* queries,
 int b200aabb_number_of_intersections(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, uint32_t* out);
 int b200aabb_all_intersections(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, const uint64_t* offsets,
                                uint32_t* ids, uint8_t* kinds, double* points);
+/* The same three calls for Segment_3 queries as well (kind = B200AABB_SEGMENT: (source, target), Intersect_3(Segment_3, Triangle_3),
+ * Intersections_3/include/CGAL/Intersections_3/internal/Segment_3_Triangle_3_intersection.h:400-548; kind = B200AABB_RAY: as above). */
+int b200aabb_number_of_intersections_q(b200aabb_tree* t, const double* queries, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint32_t* out);
+int b200aabb_all_intersections_q(b200aabb_tree* t, const double* queries, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, const uint64_t* offsets,
+                                 uint32_t* ids, uint8_t* kinds, double* points);
+int b200aabb_any_intersection_q(b200aabb_tree* t, const double* queries, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint32_t* prim, double* point,
+                                double* point2, uint8_t* flags);
 /* any_intersection(Ray_3), AABB_tree.h:972-985 (First_intersection_traits, :58-101): ONE intersection object per ray (which one depends on
  * the traversal order, in the reference too).  Outputs as first_intersection: prim (NO_PRIMITIVE = nullopt), point, point2, flags
  * (FLAG_HIT, FLAG_SEGMENT, FLAG_EXACT); any may be NULL. */

@@ -86,6 +86,26 @@ static int known_answers() {
     CHECK(std::holds_alternative<Point>(hit->first) && std::get<Point>(hit->first) == Point(0.2, 0.2, 0.0));
     CHECK(tree.first_intersected_primitive(up) && *tree.first_intersected_primitive(up) == mini::Face_index(0));
     CHECK(tree.number_of_intersected_primitives(up) == 2);
+    {   // intersection objects of Segment_3 queries (AABB_tree.h:958-985 with Intersect_3(Segment_3, Triangle_3))
+      const Segment through(Point(0.2, 0.2, -1.0), Point(0.2, 0.2, 2.0));          // crosses the base facet at z = 0 and the slanted one at z = 0.6
+      std::vector<Tree::Intersection_and_primitive_id<Segment>::Type> objs;
+      tree.all_intersections(through, std::back_inserter(objs));
+      CHECK(objs.size() == 2);
+      bool base = false;
+      for (const auto& o : objs) {          // (the point is Line_3 x Plane_3 in plain doubles: (den * 0.2) / den need not be 0.2 to the last bit)
+        if (!std::holds_alternative<Point>(o.first) || !(o.second == mini::Face_index(0))) continue;
+        const Point x = std::get<Point>(o.first);
+        base |= std::fabs(x.x() - 0.2) < 1e-15 && std::fabs(x.y() - 0.2) < 1e-15 && std::fabs(x.z()) < 1e-15;
+      }
+      CHECK(base);
+      CHECK(tree.any_intersection(through).has_value() && !tree.any_intersection(Segment(Point(0.2, 0.2, -1.0), Point(0.2, 0.2, -0.5))).has_value());
+      const Segment in_base(Point(0.1, 0.1, 0.0), Point(0.3, 0.1, 0.0));            // lies inside the base facet: a Segment_3 object
+      objs.clear();
+      tree.all_intersections(in_base, std::back_inserter(objs));
+      bool seg = false;
+      for (const auto& o : objs) seg |= std::holds_alternative<Segment>(o.first) && o.second == mini::Face_index(0);
+      CHECK(seg);
+    }
     {   // Side_of_triangle_mesh (Side_of_triangle_mesh.h:265-306) on the tetrahedron (0,0,0),(1,0,0),(0,1,0),(0,0,1)
       CGAL_B200::Side_of_triangle_mesh<Tree> inside(tree);
       CHECK(inside(Point(0.1, 0.1, 0.1)) == CGAL_B200::ON_BOUNDED_SIDE);

@@ -169,6 +169,13 @@ def tri_do_intersect(tri, pq, is_ray):
     return lib().hc_tri_do_intersect(_p(tri), _p(pq), int(is_ray))
 
 
+def tri_seg_intersection(tri, seg):
+    tri, seg = _d(tri).ravel(), _d(seg).ravel()
+    pts = np.zeros(6)
+    k = lib().hc_tri_seg_intersection(_p(tri), _p(seg), _p(pts))
+    return k, pts.reshape(2, 3)
+
+
 def tri_ray_intersection(tri, ray):
     tri, ray = _d(tri).ravel(), _d(ray).ravel()
     pts = np.zeros(6)

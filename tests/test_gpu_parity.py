@@ -653,3 +653,39 @@ def test_side_of_mesh(B, meshes):
     got = g.side_of_mesh(pts)
     assert np.all(got[r < 0.995] == 1) and np.all(got[r > 1.0] == -1)
     assert B.AABB_tree().side_of_mesh(pts[:5]).tolist() == [-1] * 5
+
+
+def test_all_and_any_intersections_of_segments(B, meshes):
+    """the intersection OBJECTS of Segment_3 queries (Intersect_3(Segment_3, Triangle_3), Segment_3_Triangle_3_intersection.h:400-548 through
+    all_intersections / any_intersection, AABB_tree.h:958-985): records equal to the oracle's, objects bit for bit; segments in the plane of a flat
+    grid (Segment_3 objects, clipped and collinear cases), through its vertices, ending on it; consistent with number_of_intersected_primitives"""
+    from cgal_b200 import workloads as W
+    v, f = meshes["elephant"]
+    g, o = B.AABB_tree(v, f), orc.OracleTree(v, f)
+    segs = W.bbox_segments(g.bbox(), 60_000)
+    gv, gf = W.terrain(24, 24, amplitude=0.0)
+    flat, oflat = B.AABB_tree(gv, gf), orc.OracleTree(gv, gf)
+    xs = np.arange(0.0, 25.0)
+    rng = np.random.default_rng(61)
+    inplane = np.stack([np.full(25, -1.0), xs, np.zeros(25), np.full(25, 7.5), xs, np.zeros(25)], 1)              # along grid lines, ending inside
+    oblique = np.concatenate([rng.uniform(0, 24, (200, 2)), np.zeros((200, 1)), rng.uniform(0, 24, (200, 2)), np.zeros((200, 1))], 1)   # in the plane
+    through = np.stack([xs, xs[::-1], np.full(25, 5.0), xs, xs[::-1], np.full(25, -4.0)], 1)                      # through vertices
+    ending = np.stack([xs, xs[::-1] * 0.5, np.full(25, 3.0), xs, xs[::-1] * 0.5, np.zeros(25)], 1)                # target on the surface
+    for tree, orac, q in ((g, o, segs), (flat, oflat, np.concatenate([inplane, oblique, through, ending]))):
+        off, ids, kinds, pts = tree.all_intersections(q, kind=SEG)
+        roff, rids, rkinds, rpts = orac.all_intersections(q, kind=SEG)
+        np.testing.assert_array_equal(off, roff)
+        np.testing.assert_array_equal(np.diff(off), tree.number_of_intersected_primitives(q, SEG))
+        owner = np.repeat(np.arange(len(q)), np.diff(off).astype(np.int64))
+        order = np.lexsort((ids, owner)); rorder = np.lexsort((rids, owner))
+        np.testing.assert_array_equal(ids[order], rids[rorder])
+        np.testing.assert_array_equal(kinds[order], rkinds[rorder])
+        np.testing.assert_array_equal(pts[order], rpts[rorder])
+        a = tree.any_intersection(q, kind=SEG)
+        cnt = np.diff(off)
+        np.testing.assert_array_equal(a["prim"] == B.NO_PRIMITIVE, cnt == 0)
+        lookup = {(int(w), int(i)): k for k, (w, i) in enumerate(zip(owner, ids))}
+        for i in np.nonzero(cnt)[0][:4000]:
+            k = lookup[(int(i), int(a["prim"][i]))]
+            assert np.array_equal(a["point"][i], pts[k, :3]) and bool(a["flags"][i] & B.FLAG_SEGMENT) == (kinds[k] == 2)
+    assert (kinds == 2).sum() > 100 and (kinds == 1).sum() > 50

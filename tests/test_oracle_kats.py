@@ -154,3 +154,21 @@ def test_first_intersection_is_argmin_of_all(meshes):
     np.testing.assert_array_equal(a["t"][hit], b["t"][hit])
     same = a["prim"] == b["prim"]
     assert np.all(same | (b["ntie"] > 1))
+
+
+def test_segment_triangle_intersection_kats():
+    # Intersections_3/test/Intersections_3/test_intersections_Segment_3.cpp:152-176: the intersection OBJECTS (Segment_3_Triangle_3_intersection.h)
+    def chk(seg, tri, kind, *pts):
+        k, out = orc.tri_seg_intersection(np.array(tri, float), np.array(seg, float))
+        assert k == kind, (seg, tri, k)
+        got = [tuple(out[i]) for i in range(k)]
+        assert sorted(got) == sorted(pts), (seg, tri, got)
+    chk((1, 4, 7, 2, 3, 9), (-1, 9, 8, -5, 3, 4, -0, 8, 9), 0)
+    chk((4, 2, 7, 1, 3, 7), (1, 3, 7, 3, 9, -1, -7, 6, 3), 1, (1, 3, 7))
+    chk((1, 3, 9, 5, 1, 7), (3, 2, 8, -1, 9, 7, -2, 2, 8), 1, (3, 2, 8))
+    chk((3, 2, 7, 1, -2, -9), (3, 2, 7, 1, -2, -9, 4, 3, 9), 2, (3, 2, 7), (1, -2, -9))
+    chk((3, 2, 7, 1, -2, -9), (5, 6, 23, 1, -2, -9, 4, 3, 9), 2, (3, 2, 7), (1, -2, -9))
+    chk((3, 2, 7, 1, -2, -9), (5, 6, 23, -1, -6, -25, 4, 3, 9), 2, (3, 2, 7), (1, -2, -9))
+    chk((1, 3, 9, 5, 1, 7), (4, 0, 6, 2, 4, 10, -2, 2, 8), 2, (1, 3, 9), (3, 2, 8))
+    for tri in ((4, 0, 7, 2, 4, 7, -2, 2, 7), (4, 0, 7, 2, 4, 7, 1, 2, 7)):                     # :172-173 only ask for a Segment_3
+        assert orc.tri_seg_intersection(np.array(tri, float), np.array((1, 3, 7, 5, 1, 7), float))[0] == 2
