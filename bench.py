@@ -333,17 +333,19 @@ def main():
     tree = B.AABB_tree(device=local)
     tree.set_stream(torch.cuda.current_stream().cuda_stream)
     n_prims = 2 * nx * ny
-    build_ms, bcast = None, None
+    build_ms, build_wall_ms, bcast = None, None, None
     verts = faces = None
     if rank == 0:
         verts, faces = W.terrain(nx, ny)
         tree.insert(verts, faces)
         tree.build()                       # warm-up build (allocations, module load)
-        times = []
+        times, walls = [], []
         for _ in range(5):
+            t0 = time.perf_counter()
             tree.build()
+            walls.append((time.perf_counter() - t0) * 1e3)   # host wall clock of the call: the build's buffers are kept by the handle, so a re-build allocates nothing
             times.append(tree.stats()["last_build_ms"])
-        build_ms = min(times)
+        build_ms, build_wall_ms = min(times), min(walls)
     comm = None
     if world > 1:
         comm, bcast = replicate_tree(tree, rank, world, local, dist, torch, B)
@@ -511,7 +513,7 @@ def main():
                            "parallelism": "tree replicated by NCCL through the C ABI (b200aabb_comm_broadcast_tree), queries sharded x%d" % world},
                 "detail": {"first_intersection_Mrays_s": world * n_rays / ray_ms / 1e3, "first_intersection_hits_Mrays_s": hit_rate * world * n_rays / ray_ms / 1e3,
                            "first_intersection_all_hit_camera": allhit, "closest_point_Mqueries_s": world * n_pts / pt_ms / 1e3,
-                           "build_ms": build_ms, "build_Mtri_s": n_prims / build_ms / 1e3, "build_GB_s_algorithmic(492B/tri)": 492.0 * n_prims / build_ms / 1e6,
+                           "build_ms": build_ms, "build_call_wall_ms": build_wall_ms, "build_Mtri_s": n_prims / build_ms / 1e3, "build_GB_s_algorithmic(492B/tri)": 492.0 * n_prims / build_ms / 1e6,
                            "build_frac_of_hbm_roofline(492B/tri)": 492.0 * n_prims / build_ms / 1e6 / peak,
                            "ray_hit_rate_rank0": hit_rate, "ties": ties, "near_ties": near, "exact_stage_queries": exact, "traversal_rank0": traffic_model,
                            "fp64_dfma_peak_TFLOP_s": dfma, "tree_broadcast": bcast, "config5": c5},

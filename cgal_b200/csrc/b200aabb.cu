@@ -349,6 +349,11 @@ struct b200aabb_tree {
     bool bounds_valid = false;     // b200aabb_set_mesh computed them while gathering the primitives
     int opt_exact_keys = 0;        // 1: always sort full 63-bit keys (the build's fallback path; test hook, option 102)
     int last_build_packed = 0; unsigned long long last_build_dups = 0;
+    // Buffers of the build kept between builds (grow only; released by clear / destroy): cudaMalloc + cudaFree of a few GB cost 10 - 300 ms per
+    // build on this driver, five to a hundred times the kernels (profiles/README.md, r2_12).  tree_cap = primitives the tree buffers have room for.
+    struct BuildScratch { uint64_t* keys[2] = {nullptr, nullptr}; uint32_t* vals[2] = {nullptr, nullptr}; void* ws = nullptr; RefitEntry* frontier = nullptr;
+                          unsigned* frontier_count = nullptr; uint32_t* rest = nullptr; unsigned long long* flags = nullptr; uint64_t cap = 0; uint64_t vals_cap = 0; } bs;
+    uint64_t tree_cap = 0;
     int opt_classic_build = 0;     // 1: hierarchy_kernel for every node + refit_local_kernel instead of the fused bottom-up kernel (the fallback of a full frontier; test hook, option 103)
     int last_build_classic = 0;
     uint32_t root = kNone;
@@ -410,7 +415,13 @@ int fail(b200aabb_tree* t, int code, const char* msg) { if (t) t->err = msg; ret
 
 void free_tree_buffers(b200aabb_tree* t) {
     cudaFree(t->d_nodes); cudaFree(t->d_tris); cudaFree(t->d_trisf); cudaFree(t->d_leaf_parent);
-    t->d_nodes = nullptr; t->d_tris = nullptr; t->d_trisf = nullptr; t->d_leaf_parent = nullptr; t->built = false; t->root = kNone;
+    t->d_nodes = nullptr; t->d_tris = nullptr; t->d_trisf = nullptr; t->d_leaf_parent = nullptr; t->built = false; t->root = kNone; t->tree_cap = 0;
+}
+void free_build_scratch(b200aabb_tree* t) {
+    auto& b = t->bs;
+    cudaFree(b.keys[0]); cudaFree(b.keys[1]); cudaFree(b.vals[0]); cudaFree(b.vals[1]); cudaFree(b.ws); cudaFree(b.frontier); cudaFree(b.frontier_count);
+    cudaFree(b.rest); cudaFree(b.flags);
+    b = b200aabb_tree::BuildScratch();
 }
 void free_input(b200aabb_tree* t) { cudaFree(t->d_soup); cudaFree(t->d_ids); t->d_soup = nullptr; t->d_ids = nullptr; }
 
@@ -493,6 +504,25 @@ int coherence_order(b200aabb_tree* t, int slot, cudaStream_t st, const void* d_i
 
 TreeRef tree_ref(const b200aabb_tree* t, const uint32_t* perm) { return TreeRef{t->d_nodes, t->d_tris, t->root, t->mag, perm, t->d_counters}; }
 
+// scratch of the build and of the refit for n primitives, kept with the handle (grow only, given back when four times too large)
+int ensure_build_scratch(b200aabb_tree* t, uint64_t n) {
+    auto& bs = t->bs;
+    if (n <= bs.cap && n >= bs.cap / 4) return B200AABB_OK;
+    B2_CUDA(t, cudaStreamSynchronize(t->stream));
+    free_build_scratch(t);
+    const uint64_t frontier_cap = (n + kRefitBlock - 1) / kRefitBlock * kRefitFrontierPerBlock;
+    cudaError_t e = cudaSuccess;
+    for (int s_ = 0; s_ < 2 && e == cudaSuccess; ++s_) e = cudaMalloc(&bs.keys[s_], n * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&bs.ws, rs_workspace_bytes(n));
+    if (e == cudaSuccess) e = cudaMalloc(&bs.flags, 16);                             // [0] runs of equal PACKED key bits, [1] frontier overflow of the fused path
+    if (e == cudaSuccess) e = cudaMalloc(&bs.frontier, frontier_cap * sizeof(RefitEntry));
+    if (e == cudaSuccess) e = cudaMalloc(&bs.frontier_count, 2 * sizeof(unsigned));  // [1]: length of `rest`
+    if (e == cudaSuccess) e = cudaMalloc(&bs.rest, frontier_cap * 4);               // nodes the fused path leaves to the searches (fewer than its frontier entries)
+    if (e != cudaSuccess) { free_build_scratch(t); t->err = std::string("cudaMalloc(build scratch): ") + cudaGetErrorString(e); return e == cudaErrorMemoryAllocation ? B200AABB_ERR_OUT_OF_MEMORY : B200AABB_ERR_CUDA; }
+    bs.cap = n;
+    return B200AABB_OK;
+}
+
 int do_build(b200aabb_tree* t) {
     B2_CUDA(t, cudaSetDevice(t->device));
     if (t->imported) {   // a replica received from another rank: it IS built, and it has no primitive input to rebuild from
@@ -500,30 +530,32 @@ int do_build(b200aabb_tree* t) {
         return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "an imported tree can not be rebuilt: insert primitives first");
     }
     { const int rc_ = sync_pipeline(t); if (rc_) return rc_; }   // (asynchronous HOST batches may still be in flight)
-    free_tree_buffers(t);
     const uint64_t n = t->n;
+    t->built = false; t->root = kNone;
     empty_bbox(t->h_bbox);
-    if (n == 0) { t->built = true; t->stats.last_build_ms = 0; return B200AABB_OK; }
+    if (n == 0) { free_tree_buffers(t); t->built = true; t->stats.last_build_ms = 0; return B200AABB_OK; }
     if (n >= (1ull << 30)) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "at most 2^30 - 1 primitives per tree");
     cudaStream_t st = t->stream;
-    uint64_t* keys[2] = {nullptr, nullptr};
-    uint32_t* vals[2] = {nullptr, nullptr};
-    void* ws = nullptr; RefitEntry* frontier = nullptr; unsigned* frontier_count = nullptr; unsigned long long* d_flags = nullptr; uint32_t* rest = nullptr;
-    auto cleanup = [&]() { cudaFree(keys[0]); cudaFree(keys[1]); cudaFree(vals[0]); cudaFree(vals[1]); cudaFree(ws); cudaFree(frontier); cudaFree(frontier_count); cudaFree(d_flags); cudaFree(rest); };
-#define B2_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { t->err = std::string(#call) + ": " + cudaGetErrorString(e_); cleanup(); free_tree_buffers(t); \
+    auto& bs = t->bs;
+    auto cleanup = [&]() {};                                          // (the scratch stays with the handle)
+#define B2_TRY(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { t->err = std::string(#call) + ": " + cudaGetErrorString(e_); free_build_scratch(t); free_tree_buffers(t); \
         return e_ == cudaErrorMemoryAllocation ? B200AABB_ERR_OUT_OF_MEMORY : B200AABB_ERR_CUDA; } } while (0)
-    for (int s = 0; s < 2; ++s) B2_TRY(cudaMalloc(&keys[s], n * 8));
-    B2_TRY(cudaMalloc(&ws, rs_workspace_bytes(n)));
-    B2_TRY(cudaMalloc(&t->d_leaf_parent, n * 4));
-    uint32_t* const leaf_parent = t->d_leaf_parent;
-    B2_TRY(cudaMalloc(&d_flags, 16));      // [0] runs of equal PACKED key bits, [1] frontier overflow of the fused path
     const uint64_t refit_blocks = (n + kRefitBlock - 1) / kRefitBlock, frontier_cap = refit_blocks * kRefitFrontierPerBlock, frontier_use = refit_blocks * (uint64_t)t->opt_debug_refit_frontier;
-    B2_TRY(cudaMalloc(&frontier, frontier_cap * sizeof(RefitEntry)));
-    B2_TRY(cudaMalloc(&frontier_count, 2 * sizeof(unsigned)));      // [1]: length of `rest`
-    B2_TRY(cudaMalloc(&rest, frontier_cap * 4));       // nodes the fused path leaves to the searches (fewer than its frontier entries)
-    B2_TRY(cudaMalloc(&t->d_nodes, std::max<uint64_t>(n - 1, 1) * sizeof(BvhNode)));
-    B2_TRY(cudaMalloc(&t->d_tris, n * sizeof(TriRec)));
-    B2_TRY(cudaMalloc(&t->d_trisf, n * sizeof(TriF)));
+    { const int rc_ = ensure_build_scratch(t, n); if (rc_) { free_tree_buffers(t); return rc_; } }
+    if (n > t->tree_cap || n < t->tree_cap / 4 || !t->d_tris) {
+        B2_TRY(cudaStreamSynchronize(st));
+        free_tree_buffers(t);
+        B2_TRY(cudaMalloc(&t->d_leaf_parent, n * 4));
+        B2_TRY(cudaMalloc(&t->d_nodes, std::max<uint64_t>(n - 1, 1) * sizeof(BvhNode)));
+        B2_TRY(cudaMalloc(&t->d_tris, n * sizeof(TriRec)));
+        B2_TRY(cudaMalloc(&t->d_trisf, n * sizeof(TriF)));
+        t->tree_cap = n;
+    }
+    uint64_t** const keys = bs.keys;
+    uint32_t** const vals = bs.vals;
+    void* const ws = bs.ws; RefitEntry* const frontier = bs.frontier; unsigned* const frontier_count = bs.frontier_count; unsigned long long* const d_flags = bs.flags;
+    uint32_t* const rest = bs.rest;
+    uint32_t* const leaf_parent = t->d_leaf_parent;
     // B200AABB_BUILD_TIMING=1: per-stage device times on stderr (events between the stages; diagnostic only)
     const bool stage_timing = getenv("B200AABB_BUILD_TIMING") != nullptr;
     std::vector<std::pair<const char*, cudaEvent_t>> marks;
@@ -559,7 +591,7 @@ int do_build(b200aabb_tree* t) {
             t->stats.kernel_launches += 1;
             cur = rs_sort_passes(keys, nullptr, n, ib, packed_passes, ws, st, &t->stats.kernel_launches);
         } else {
-            for (int s = 0; s < 2; ++s) if (!vals[s]) B2_TRY(cudaMalloc(&vals[s], n * 4));
+            if (bs.vals_cap < n) { for (int s_ = 0; s_ < 2; ++s_) { cudaFree(vals[s_]); vals[s_] = nullptr; B2_TRY(cudaMalloc(&vals[s_], n * 4)); } bs.vals_cap = n; }
             morton_kernel<false><<<pblocks, 256, 0, st>>>(t->d_soup, n, t->d_bounds, keys[0], vals[0], 0, 0, nullptr);
             mark("morton");
             t->stats.kernel_launches += 1;
@@ -824,7 +856,7 @@ int b200aabb_destroy(b200aabb_tree* t) {
     if (!t) return B200AABB_OK;
     cudaSetDevice(t->device);
     cudaDeviceSynchronize();
-    free_tree_buffers(t); free_input(t); free_sort(t); free_warp(t);
+    free_tree_buffers(t); free_build_scratch(t); free_input(t); free_sort(t); free_warp(t);
     cudaFree(t->d_rootbox); cudaFree(t->d_bounds); cudaFree(t->d_counters);
     for (int s = 0; s < kPipeSlots; ++s) {
         cudaFree(t->d_stage_in[s]); cudaFree(t->d_stage_out[s]); cudaFree(t->d_stage_aux[s]);
@@ -887,7 +919,7 @@ int b200aabb_clear(b200aabb_tree* t) { B2_LOCK(t);
     B2_CUDA(t, cudaSetDevice(t->device));
     { const int rc_ = sync_pipeline(t); if (rc_) return rc_; }   // (asynchronous HOST batches may still be in flight)
     B2_CUDA(t, cudaStreamSynchronize(t->stream));
-    free_tree_buffers(t); free_input(t);
+    free_tree_buffers(t); free_build_scratch(t); free_input(t);
     t->n = 0; t->built = true; t->imported = false; t->bounds_valid = false; empty_bbox(t->h_bbox);
     return B200AABB_OK;
 }
@@ -937,18 +969,13 @@ static int refit_boxes(b200aabb_tree* t, cudaStream_t st) {
     const uint64_t n = t->n;
     if (n < 2) return B200AABB_OK;
     const uint64_t refit_blocks = (n + kRefitBlock - 1) / kRefitBlock, frontier_cap = refit_blocks * kRefitFrontierPerBlock;
-    RefitEntry* frontier = nullptr; unsigned* frontier_count = nullptr;
-    if (cudaMalloc(&frontier, frontier_cap * sizeof(RefitEntry)) != cudaSuccess || cudaMalloc(&frontier_count, sizeof(unsigned)) != cudaSuccess) {
-        cudaFree(frontier); cudaFree(frontier_count);
-        return fail(t, B200AABB_ERR_OUT_OF_MEMORY, "cudaMalloc(refit frontier)");
-    }
+    { const int rc_ = ensure_build_scratch(t, n); if (rc_) return rc_; }
+    RefitEntry* const frontier = t->bs.frontier; unsigned* const frontier_count = t->bs.frontier_count;
     cudaMemsetAsync(frontier_count, 0, sizeof(unsigned), st);
     refit_local_kernel<false><<<(unsigned)refit_blocks, kRefitBlock, 0, st>>>(t->d_tris, n, t->d_nodes, t->d_leaf_parent, frontier, frontier_count, (unsigned)frontier_cap, EmitArgs{});
     refit_global_kernel<<<(unsigned)((frontier_cap + 255) / 256), 256, 0, st>>>(t->d_nodes, t->d_leaf_parent, frontier, frontier_count, (unsigned)frontier_cap);
     t->stats.kernel_launches += 2;
-    const cudaError_t e = cudaStreamSynchronize(st);
-    cudaFree(frontier); cudaFree(frontier_count);
-    return e == cudaSuccess && cudaGetLastError() == cudaSuccess ? B200AABB_OK : fail(t, B200AABB_ERR_CUDA, "refit: CUDA failure");
+    return cudaGetLastError() == cudaSuccess ? B200AABB_OK : fail(t, B200AABB_ERR_CUDA, "refit: CUDA failure");
 }
 
 static int refit_from_soup(b200aabb_tree* t) {
