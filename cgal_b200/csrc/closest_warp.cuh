@@ -35,13 +35,19 @@
 
 namespace b2 {
 
-constexpr int kWpNodeCap = 768;                 // (slot,node) entries held in shared memory
+#ifndef B2_WP_NODE_CAP
+#define B2_WP_NODE_CAP 768
+#endif
+constexpr int kWpNodeCap = B2_WP_NODE_CAP;                 // (slot,node) entries held in shared memory
 constexpr int kWpSpillChunk = kWpNodeCap / 2;   // entries moved per spill / reload
 constexpr int kWpSpillCap = 16 * kWpSpillChunk; // entries per warp in the global spill area
 constexpr int kWpLeafCap = 96;                  // < 32 waiting + at most 64 added by one node phase
 constexpr int kWpMidCap = 128;                  // < 32 waiting + at most 95 added by one pre-test-1 phase
 constexpr int kWpExactCap = 192;                // pre-test 2 stops handing over when fewer than 32 places are left
-constexpr int kWpWarpsPerSM = 20;               // resident warps per SM this kernel is sized for (registers <= 102, shared memory <= 10.4 KB): measured best of 16 / 20 / 24 / 28
+#ifndef B2_WP_WARPS_PER_SM
+#define B2_WP_WARPS_PER_SM 20
+#endif
+constexpr int kWpWarpsPerSM = B2_WP_WARPS_PER_SM;               // resident warps per SM this kernel is sized for (registers <= 102, shared memory <= 10.4 KB): measured best of 16 / 20 / 24 / 28
 constexpr uint32_t kWpRefMask = 0x07FFFFFFu;    // 27 bits of leaf slot next to the 5-bit query slot
 constexpr uint64_t kWpMaxPrims = 1ull << 27;
 
