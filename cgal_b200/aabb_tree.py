@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 SEGMENT, RAY, LINE, PLANE = 0, 1, 2, 3      # LINE: (point, direction vector) per query; PLANE: (a, b, c, d)
-FLAG_HIT, FLAG_SEGMENT, FLAG_TIE, FLAG_EXACT, FLAG_NEAR_TIE = 1, 2, 4, 8, 16
+FLAG_HIT, FLAG_SEGMENT, FLAG_TIE, FLAG_EXACT, FLAG_NEAR_TIE, FLAG_TRIANGLE = 1, 2, 4, 8, 16, 32
 OPT_SORT_QUERIES = 1
 OPT_CLOSEST_KERNEL = 2    # 1 = warp-cooperative work pool (default), 2 = lane pairs with private stacks, 0 = one thread per query
 OPT_WARP_EXACT_GO = 4
@@ -287,9 +287,9 @@ class AABB_tree:
         return offsets, ids[:int(offsets[-1])]
 
     def all_intersections(self, rays, kind=RAY):
-        """all_intersections(Ray_3 | Segment_3, out) for a HOST batch: (offsets uint64[n+1], ids uint32[total], kinds uint8[total] (1 Point_3 /
-        2 Segment_3), points f64[total, 6]); the entries of query i are [offsets[i], offsets[i+1])"""
-        q = _Buf(np.asarray(rays), np.float64, 6)
+        """all_intersections(Ray_3 | Segment_3 | Line_3 | Plane_3, out) for a HOST batch: (offsets uint64[n+1], ids uint32[total], kinds uint8[total] (1 Point_3 /
+        2 Segment_3 / 3 the primitive's Triangle_3), points f64[total, 6]); the entries of query i are [offsets[i], offsets[i+1])"""
+        q = _Buf(np.asarray(rays), np.float64, 4 if kind == PLANE else 6)
         counts = np.empty(q.n, np.uint32)
         self._check(self._lib.b200aabb_number_of_intersections_q(self._h, q.ptr, q.n, int(kind), 0, counts.ctypes.data))
         offsets = np.zeros(q.n + 1, np.uint64)
@@ -301,8 +301,9 @@ class AABB_tree:
         return offsets, ids[:tot], kinds[:tot], pts[:tot]
 
     def any_intersection(self, rays, want=("prim", "point", "point2", "flags"), out=None, kind=RAY):
-        """any_intersection(Ray_3 | Segment_3): dict with prim (NO_PRIMITIVE = nullopt), point, point2, flags (FLAG_HIT, FLAG_SEGMENT)"""
-        q = _Buf(rays, np.float64, 6)
+        """any_intersection(Ray_3 | Segment_3 | Line_3 | Plane_3): dict with prim (NO_PRIMITIVE = nullopt), point, point2, flags (FLAG_HIT, FLAG_SEGMENT,
+        FLAG_TRIANGLE)"""
+        q = _Buf(rays, np.float64, 4 if kind == PLANE else 6)
         spec = {"prim": (np.uint32, 1), "point": (np.float64, 3), "point2": (np.float64, 3), "flags": (np.uint8, 1)}
         bufs = {}
         for k in want:

@@ -150,6 +150,7 @@ __global__ void __launch_bounds__(128, 8) plane_kernel(const TreeRef tr, const d
 
 // all_intersections / any_intersection (Ray_3): bvh.cuh::traverse_ray_objects.  kCount: out32[i]; kList: entries of ray i at offsets[i] ..
 // (a count that disagrees with offsets[i+1] - offsets[i] raises counters[2] bit 2); kAnyId: prim / flags / pt / pt2 like first_intersection
+constexpr int kPlaneObjects = 3;        // KIND of ray_objects_kernel for Plane_3 queries (next to LineKind's 0..2)
 template <int MODE, int KIND>
 __global__ void __launch_bounds__(128, 5) ray_objects_kernel(const TreeRef tr, const double* __restrict__ rays, uint64_t n, uint32_t* __restrict__ out32,
                                                              const uint64_t* __restrict__ offsets, uint32_t* __restrict__ ids, uint8_t* __restrict__ kinds,
@@ -159,18 +160,24 @@ __global__ void __launch_bounds__(128, 5) ray_objects_kernel(const TreeRef tr, c
     TravStat st;
     if (slot < n) {
         const uint64_t i = tr.perm ? tr.perm[slot] : slot;
-        const Vec3 s = ld3(rays + 6 * i), q = ld3(rays + 6 * i + 3);
+        constexpr bool kPlane = KIND == kPlaneObjects;        // Plane_3: four coefficients per query, its own traversal
+        const Vec3 s = kPlane ? ld3(rays + 4 * i) : ld3(rays + 6 * i), q = kPlane ? Vec3{rays[4 * i + 3], 0.0, 0.0} : ld3(rays + 6 * i + 3);
+        auto objects = [&](auto mode, uint32_t* oi, uint8_t* ok, double* op, uint32_t cap) -> uint32_t {
+            constexpr int M = decltype(mode)::value;
+            if constexpr (kPlane) return traverse_plane_objects<M>(tr.nodes, tr.tris, tr.root, s.x, s.y, s.z, q.x, st, oi, ok, op, cap);
+            else return traverse_ray_objects<M, kPlane ? kRayQ : KIND>(tr.nodes, tr.tris, tr.root, s, q, st, oi, ok, op, cap);
+        };
         if (MODE == kCount) {
-            out32[i] = traverse_ray_objects<kCount, KIND>(tr.nodes, tr.tris, tr.root, s, q, st, nullptr, nullptr, nullptr, 0);
+            out32[i] = objects(std::integral_constant<int, kCount>(), nullptr, nullptr, nullptr, 0);
         } else if (MODE == kList) {
             const uint64_t lo = offsets[i], hi = offsets[i + 1];
-            const uint32_t r = traverse_ray_objects<kList, KIND>(tr.nodes, tr.tris, tr.root, s, q, st, ids + lo, kinds + lo, pts + 6 * lo, (uint32_t)(hi - lo));
+            const uint32_t r = objects(std::integral_constant<int, kList>(), ids + lo, kinds + lo, pts + 6 * lo, (uint32_t)(hi - lo));
             if (r != hi - lo) atomicOr(&tr.counters[2], 4ull);
         } else {
             uint32_t id = kNone; uint8_t kind = 0; double p[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-            traverse_ray_objects<kAnyId, KIND>(tr.nodes, tr.tris, tr.root, s, q, st, &id, &kind, p, 1);
+            objects(std::integral_constant<int, kAnyId>(), &id, &kind, p, 1);
             if (prim) prim[i] = id;
-            if (flags) flags[i] = (uint8_t)((kind ? B200AABB_FLAG_HIT : 0) | (kind == 2 ? B200AABB_FLAG_SEGMENT : 0) | (st.nexact ? B200AABB_FLAG_EXACT : 0));
+            if (flags) flags[i] = (uint8_t)((kind ? B200AABB_FLAG_HIT : 0) | (kind == 2 ? B200AABB_FLAG_SEGMENT : 0) | (kind == 3 ? B200AABB_FLAG_TRIANGLE : 0) | (st.nexact ? B200AABB_FLAG_EXACT : 0));
             if (pt) { pt[3 * i] = p[0]; pt[3 * i + 1] = p[1]; pt[3 * i + 2] = p[2]; }
             if (pt2) { pt2[3 * i] = p[3]; pt2[3 * i + 1] = p[4]; pt2[3 * i + 2] = p[5]; }
         }
@@ -803,6 +810,18 @@ static void launch_intersect(b200aabb_tree* t, int kind, cudaStream_t st, const 
 static bool valid_kind(int kind) { return kind >= B200AABB_SEGMENT && kind <= B200AABB_PLANE; }
 static size_t query_bytes(int kind) { return kind == B200AABB_PLANE ? 32 : 48; }
 static QueryShape query_shape(int kind) { return kind == B200AABB_PLANE ? kPlaneQuery : (kind == B200AABB_LINE ? kLineVecQuery : kLineQuery); }
+template <int MODE>
+static void launch_objects(b200aabb_tree* t, int kind, cudaStream_t st, const double* in, uint64_t cnt, const uint32_t* perm, uint32_t* out32, const uint64_t* offsets,
+                           uint32_t* ids, uint8_t* kinds, double* pts, uint32_t* prim, uint8_t* flags, double* pt, double* pt2) {
+    const unsigned grid = grid_for(cnt, 128);
+    switch (kind) {
+        case B200AABB_SEGMENT: ray_objects_kernel<MODE, kSegmentQ><<<grid, 128, 0, st>>>(tree_ref(t, perm), in, cnt, out32, offsets, ids, kinds, pts, prim, flags, pt, pt2); break;
+        case B200AABB_LINE: ray_objects_kernel<MODE, kLineQ><<<grid, 128, 0, st>>>(tree_ref(t, perm), in, cnt, out32, offsets, ids, kinds, pts, prim, flags, pt, pt2); break;
+        case B200AABB_PLANE: ray_objects_kernel<MODE, kPlaneObjects><<<grid, 128, 0, st>>>(tree_ref(t, nullptr), in, cnt, out32, offsets, ids, kinds, pts, prim, flags, pt, pt2); break;
+        default: ray_objects_kernel<MODE, kRayQ><<<grid, 128, 0, st>>>(tree_ref(t, perm), in, cnt, out32, offsets, ids, kinds, pts, prim, flags, pt, pt2); break;
+    }
+}
+
 
 extern "C" {
 
@@ -1149,18 +1168,15 @@ int b200aabb_number_of_intersections(b200aabb_tree* t, const double* rays, uint6
     return b200aabb_number_of_intersections_q(t, rays, n, B200AABB_RAY, space, out);
 }
 int b200aabb_number_of_intersections_q(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint32_t* out) { B2_LOCK(t);
-    if (!t || (n && (!rays || !out)) || (kind != B200AABB_RAY && kind != B200AABB_SEGMENT)) return B200AABB_ERR_INVALID_ARGUMENT;
+    if (!t || (n && (!rays || !out)) || !valid_kind(kind)) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     if (t->n == 0) {
         if (space == B200AABB_DEVICE) { B2_CUDA(t, cudaMemsetAsync(out, 0, n * 4, t->stream)); } else memset(out, 0, n * 4);
         return B200AABB_OK;
     }
-    return run_batch(t, rays, 48, n, space, kLineQuery, {{out, 4, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
-        if (kind == B200AABB_RAY) ray_objects_kernel<kCount, kRayQ><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint32_t*)o[0], nullptr, nullptr, nullptr, nullptr,
-                                                                                                    nullptr, nullptr, nullptr, nullptr);
-        else ray_objects_kernel<kCount, kSegmentQ><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint32_t*)o[0], nullptr, nullptr, nullptr, nullptr,
-                                                                                       nullptr, nullptr, nullptr, nullptr);
+    return run_batch(t, rays, query_bytes(kind), n, space, query_shape(kind), {{out, 4, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
+        launch_objects<kCount>(t, kind, st, (const double*)in, cnt, perm, (uint32_t*)o[0], nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
     });
 }
 
@@ -1169,16 +1185,13 @@ int b200aabb_any_intersection(b200aabb_tree* t, const double* rays, uint64_t n, 
 }
 int b200aabb_any_intersection_q(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint32_t* prim, double* pt, double* pt2,
                                 uint8_t* flags) { B2_LOCK(t);
-    if (!t || (n && !rays) || (kind != B200AABB_RAY && kind != B200AABB_SEGMENT)) return B200AABB_ERR_INVALID_ARGUMENT;
+    if (!t || (n && !rays) || !valid_kind(kind)) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     if (t->n == 0) return b200aabb_first_intersection(t, rays, n, space, prim, nullptr, pt, pt2, flags);   // nullopt for every ray
-    return run_batch(t, rays, 48, n, space, kLineQuery, {{prim, 4, 0}, {pt, 24, 0}, {pt2, 24, 0}, {flags, 1, 0}},
+    return run_batch(t, rays, query_bytes(kind), n, space, query_shape(kind), {{prim, 4, 0}, {pt, 24, 0}, {pt2, 24, 0}, {flags, 1, 0}},
                      [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
-                         if (kind == B200AABB_RAY) ray_objects_kernel<kAnyId, kRayQ><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                                                                                                     (uint32_t*)o[0], (uint8_t*)o[3], (double*)o[1], (double*)o[2]);
-                         else ray_objects_kernel<kAnyId, kSegmentQ><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                                                                                        (uint32_t*)o[0], (uint8_t*)o[3], (double*)o[1], (double*)o[2]);
+                         launch_objects<kAnyId>(t, kind, st, (const double*)in, cnt, perm, nullptr, nullptr, nullptr, nullptr, nullptr, (uint32_t*)o[0], (uint8_t*)o[3], (double*)o[1], (double*)o[2]);
                      });
 }
 
@@ -1188,7 +1201,7 @@ int b200aabb_all_intersections(b200aabb_tree* t, const double* rays, uint64_t n,
 }
 int b200aabb_all_intersections_q(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, const uint64_t* offsets, uint32_t* ids,
                                  uint8_t* kinds, double* points) { B2_LOCK(t);
-    if (!t || (n && (!rays || !offsets)) || (kind != B200AABB_RAY && kind != B200AABB_SEGMENT)) return B200AABB_ERR_INVALID_ARGUMENT;
+    if (!t || (n && (!rays || !offsets)) || !valid_kind(kind)) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     B2_CUDA(t, cudaSetDevice(t->device));
@@ -1203,23 +1216,22 @@ int b200aabb_all_intersections_q(b200aabb_tree* t, const double* rays, uint64_t 
         if (total && (!ids || !kinds || !points)) return B200AABB_ERR_INVALID_ARGUMENT;
         if (t->n == 0) return total == 0 ? B200AABB_OK : fail(t, B200AABB_ERR_INVALID_ARGUMENT, "offsets disagree with the number of intersections");
         const uint64_t room = std::max<uint64_t>(total, 1);
-        cudaError_t e = cudaMalloc(&tmp[0], n * 48);
+        cudaError_t e = cudaMalloc(&tmp[0], n * query_bytes(kind));
         if (e == cudaSuccess) e = cudaMalloc(&tmp[1], (n + 1) * 8);
         if (e == cudaSuccess) e = cudaMalloc(&tmp[2], room * 4);
         if (e == cudaSuccess) e = cudaMalloc(&tmp[3], room);
         if (e == cudaSuccess) e = cudaMalloc(&tmp[4], room * 48);
         if (e != cudaSuccess) { release(); t->err = "cudaMalloc(all_intersections staging)"; return B200AABB_ERR_OUT_OF_MEMORY; }
-        cudaMemcpyAsync(tmp[0], rays, n * 48, cudaMemcpyHostToDevice, t->stream);
+        cudaMemcpyAsync(tmp[0], rays, n * query_bytes(kind), cudaMemcpyHostToDevice, t->stream);
         cudaMemcpyAsync(tmp[1], offsets, (n + 1) * 8, cudaMemcpyHostToDevice, t->stream);
         d_q = (const double*)tmp[0]; d_off = (const uint64_t*)tmp[1]; d_ids = (uint32_t*)tmp[2]; d_kinds = (uint8_t*)tmp[3]; d_pts = (double*)tmp[4];
     } else if (t->n == 0) return B200AABB_OK;
     cudaMemsetAsync(t->d_counters, 0, 8 * sizeof(unsigned long long), t->stream);
     cudaEventRecord(t->ev_a, t->stream);
     const uint32_t* perm = nullptr;
-    rc = coherence_order(t, kDeviceScratch, t->stream, d_q, n, kLineQuery, &perm);
+    rc = coherence_order(t, kDeviceScratch, t->stream, d_q, n, query_shape(kind), &perm);
     if (rc) { release(); return rc; }
-    if (kind == B200AABB_RAY) ray_objects_kernel<kList, kRayQ><<<grid_for(n, 128), 128, 0, t->stream>>>(tree_ref(t, perm), d_q, n, nullptr, d_off, d_ids, d_kinds, d_pts, nullptr, nullptr, nullptr, nullptr);
-    else ray_objects_kernel<kList, kSegmentQ><<<grid_for(n, 128), 128, 0, t->stream>>>(tree_ref(t, perm), d_q, n, nullptr, d_off, d_ids, d_kinds, d_pts, nullptr, nullptr, nullptr, nullptr);
+    launch_objects<kList>(t, kind, t->stream, d_q, n, perm, nullptr, d_off, d_ids, d_kinds, d_pts, nullptr, nullptr, nullptr, nullptr);
     t->stats.kernel_launches += 1;
     cudaEventRecord(t->ev_b, t->stream);
     t->query_timing_pending = true;

@@ -358,20 +358,9 @@ B2_HD bool plane_box(const float* lo, const float* hi, double a, double b, doubl
     const double mag = ((fabs(a) * (fabs(cx) + hx) + fabs(b) * (fabs(cy) + hy)) + fabs(c) * (fabs(cz) + hz)) + fabs(d);
     return !(fabs(s) > r + 1e-14 * mag);      // (NaN / overflow: keep the box)
 }
-template <int MODE>
-B2_HD uint32_t traverse_plane(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root, double a, double b, double c, double d,
-                              TravStat& st, uint32_t* list = nullptr, uint32_t list_cap = 0) {
-    constexpr bool kStopAtFirst = MODE == kAnyHit || MODE == kAnyId;
-    uint32_t nlisted = 0, found_id = kNone, found = 0;
-    auto leaf = [&](uint32_t ref) -> bool {
-        uint32_t id;
-        const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
-        ++st.leaves;
-        if (!plane_tri_do_intersect(t, a, b, c, d, st.nexact)) return false;
-        if (MODE == kList) { if (nlisted < list_cap) list[nlisted] = id; ++nlisted; }
-        if (MODE == kAnyId) found_id = id;
-        return true;
-    };
+template <bool kStopAtFirst, class Leaf>
+B2_HD uint32_t traverse_plane_nodes(const BvhNode* __restrict__ nodes, uint32_t root, double a, double b, double c, double d, TravStat& st, Leaf&& leaf) {
+    uint32_t found = 0;
     if (root & kLeafBit) found = leaf(root) ? 1u : 0u;
     else {
         uint32_t stack[kStackCap];
@@ -393,7 +382,46 @@ B2_HD uint32_t traverse_plane(const BvhNode* __restrict__ nodes, const TriRec* _
             cur = next;
         }
     }
+    return found;
+}
+template <int MODE>
+B2_HD uint32_t traverse_plane(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root, double a, double b, double c, double d,
+                              TravStat& st, uint32_t* list = nullptr, uint32_t list_cap = 0) {
+    uint32_t nlisted = 0, found_id = kNone;
+    const uint32_t found = traverse_plane_nodes<MODE == kAnyHit || MODE == kAnyId>(nodes, root, a, b, c, d, st, [&](uint32_t ref) -> bool {
+        uint32_t id;
+        const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
+        ++st.leaves;
+        if (!plane_tri_do_intersect(t, a, b, c, d, st.nexact)) return false;
+        if (MODE == kList) { if (nlisted < list_cap) list[nlisted] = id; ++nlisted; }
+        if (MODE == kAnyId) found_id = id;
+        return true;
+    });
     return MODE == kAnyId ? found_id : (MODE == kAnyHit ? (found ? 1u : 0u) : found);
+}
+// the intersection OBJECTS of a Plane_3 query (Intersect_3(Plane_3, Triangle_3)): records as traverse_ray_objects; kind 3 = the primitive's triangle itself
+template <int MODE>
+B2_HD uint32_t traverse_plane_objects(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root, double a, double b, double c, double d,
+                                      TravStat& st, uint32_t* ids, uint8_t* kinds, double* pts, uint32_t cap) {
+    uint32_t nlisted = 0;
+    return traverse_plane_nodes<MODE == kAnyId>(nodes, root, a, b, c, d, st, [&](uint32_t ref) -> bool {
+        uint32_t id;
+        const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
+        ++st.leaves;
+        const SegX x = plane_tri_intersection(t, a, b, c, d, st.nexact);
+        if (x.kind == 0) return false;
+        if (MODE != kCount) {
+            if (nlisted < cap) {
+                ids[nlisted] = id; kinds[nlisted] = (uint8_t)x.kind;
+                double* o = pts + 6 * (uint64_t)nlisted;
+                const bool pt = x.kind == 1 || x.kind == 2, seg = x.kind == 2;
+                o[0] = pt ? x.p0.x : 0.0; o[1] = pt ? x.p0.y : 0.0; o[2] = pt ? x.p0.z : 0.0;
+                o[3] = seg ? x.p1.x : 0.0; o[4] = seg ? x.p1.y : 0.0; o[5] = seg ? x.p1.z : 0.0;
+            }
+            ++nlisted;
+        }
+        return true;
+    });
 }
 
 // all_intersections / any_intersection (Ray_3): every primitive whose Intersect_3(Ray_3, Triangle_3) is non-empty, with the
@@ -406,15 +434,19 @@ B2_HD uint32_t traverse_plane(const BvhNode* __restrict__ nodes, const TriRec* _
 template <int MODE, int KIND = kRayQ>
 B2_HD uint32_t traverse_ray_objects(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root, const Vec3& s, const Vec3& q,
                                     TravStat& st, uint32_t* ids, uint8_t* kinds, double* pts, uint32_t cap) {
-    const LineCtx c = make_line(s, q);
+    // Line_3 (s = point, q = direction vector): the reference's Intersect_3(Line_3, Triangle_3) decides with the ROUNDED second point s + q (it is a
+    // construction), while its node test is the exact predicate on (s, q): within rounding of a primitive's border the reference's own answer therefore
+    // depends on its tree.  Here nodes and primitives see the same line, through s and fl(s + q): the result is every primitive whose Intersect_3 is
+    // non-empty, whatever the tree (the reference's result is a subset of it, equal unless the line grazes a primitive within rounding).
+    const LineCtx c = KIND == kLineQ ? make_line(s, s + q) : make_line(s, q);
     uint32_t nlisted = 0;
     return traverse_line<KIND, MODE == kAnyId>(nodes, root, c, st, [&](uint32_t ref) -> bool {
         uint32_t id;
         const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
         ++st.leaves;
         struct { int kind; Vec3 p0, p1; } x;
-        if (KIND == kSegmentQ) {
-            const SegX y = seg_tri_intersection(t, s, q, st.nexact);
+        if (KIND == kSegmentQ || KIND == kLineQ) {
+            const SegX y = KIND == kSegmentQ ? seg_tri_intersection(t, s, q, st.nexact) : line_tri_intersection(t, s, q, st.nexact);   // (Line_3: q is the direction vector)
             x.kind = y.kind; x.p0 = y.p0; x.p1 = y.p1;
         } else {
             int nex = 0;

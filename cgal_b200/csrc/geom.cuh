@@ -381,6 +381,102 @@ B2_HD SegX seg_tri_intersection(const Tri3& t, const Vec3& p, const Vec3& q, int
     return r;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Intersect_3(Line_3, Triangle_3): Line_3_Triangle_3_intersection.h:27-419, and Intersect_3(Plane_3, Triangle_3): Plane_3_Triangle_3_intersection.h:27-146.
+// Constructions: plain doubles with filtered predicates on the points they form — point_on(l, 1) is the ROUNDED p + v here, unlike in the predicate
+// line_tri_do_intersect above.  Object kinds as SegX, plus 3 = the Triangle_3 itself (Plane_3 queries, all three vertices on the plane; no points).
+// ---------------------------------------------------------------------------------------------------------------
+// Intersect_3(Plane_3 (a, b, c, d), Line_3 (point s, direction d)): Line_3_Plane_3_intersection.h:52-85; false: no Point_3
+B2_HD bool plane_line_point(double pa, double pb, double pc, double pd, const Vec3& s, const Vec3& d, Vec3& out) {
+    const double num = ((pa * s.x + pb * s.y) + pc * s.z) + pd;
+    const double den = (pa * d.x + pb * d.y) + pc * d.z;
+    if (den == 0.0) return false;
+    Vec3 x = {den * s.x - num * d.x, den * s.y - num * d.y, den * s.z - num * d.z};
+    if (den != 1.0) { x.x = x.x / den; x.y = x.y / den; x.z = x.z / den; }
+    out = x;
+    return true;
+}
+B2_HD SegX t3l3_clip(const Vec3& a, const Vec3& b, const Vec3& c, const Vec3& p, const Vec3& v, bool negative_side) {      // :66-88
+    const Vec3 l_bc = coplanar_lines_meet(p, v, b, c), l_ca = coplanar_lines_meet(p, v, c, a);
+    SegX r; r.kind = 2; r.p0 = negative_side ? l_bc : l_ca; r.p1 = negative_side ? l_ca : l_bc;
+    return r;
+}
+B2_HD_NOINLINE SegX line_tri_intersection_coplanar(const Tri3& t, const Vec3& p, const Vec3& q, const Vec3& v, int& nexact) {   // :90-277
+    SegX none; none.kind = 0; none.p0 = p; none.p1 = p;
+    const bool ccw = coplanar_orient(t.a, t.b, t.c, nexact) == 1;
+    const Vec3 a = t.a, b = ccw ? t.b : t.c, c = ccw ? t.c : t.b;
+    const int pqa = coplanar_orient(p, q, a, nexact), pqb = coplanar_orient(p, q, b, nexact), pqc = coplanar_orient(p, q, c, nexact);
+    SegX r = none;
+    switch ((pqa + 1) * 9 + (pqb + 1) * 3 + (pqc + 1)) {
+        case 26: case 0: case 13: return none;                                   // (+,+,+), (-,-,-), degenerate
+        case 24: return t3l3_clip(a, b, c, p, v, true);                          // (+,+,-)
+        case 25: case 1: r.kind = 1; r.p0 = c; return r;                         // (+,+,0), (-,-,0)
+        case 20: return t3l3_clip(c, a, b, p, v, true);                          // (+,-,+)
+        case 18: case 19: case 21: return t3l3_clip(b, c, a, p, v, false);       // (+,-,-), (+,-,0), (+,0,-)
+        case 23: case 3: r.kind = 1; r.p0 = b; return r;                         // (+,0,+), (-,0,-)
+        case 22: r.kind = 2; r.p0 = b; r.p1 = c; return r;                       // (+,0,0)
+        case 8: case 5: return t3l3_clip(b, c, a, p, v, true);                   // (-,+,+), (-,0,+)
+        case 6: case 7: case 15: return t3l3_clip(c, a, b, p, v, false);         // (-,+,-), (-,+,0), (0,+,-)
+        case 2: return t3l3_clip(a, b, c, p, v, false);                          // (-,-,+)
+        case 4: r.kind = 2; r.p0 = c; r.p1 = b; return r;                        // (-,0,0)
+        case 17: case 9: r.kind = 1; r.p0 = a; return r;                         // (0,+,+), (0,-,-)
+        case 16: r.kind = 2; r.p0 = c; r.p1 = a; return r;                       // (0,+,0)
+        case 11: return t3l3_clip(c, a, b, p, v, true);                          // (0,-,+)
+        case 10: r.kind = 2; r.p0 = a; r.p1 = c; return r;                       // (0,-,0)
+        case 14: r.kind = 2; r.p0 = a; r.p1 = b; return r;                       // (0,0,+)
+        case 12: r.kind = 2; r.p0 = b; r.p1 = a; return r;                       // (0,0,-)
+        default: return none;
+    }
+}
+B2_HD SegX line_tri_intersection(const Tri3& t, const Vec3& p, const Vec3& v, int& nexact) {                                  // :279-400
+    SegX r; r.kind = 0; r.p0 = p; r.p1 = p;
+    const Vec3 q = p + v;                                   // point_on(l, 1): rounded
+    if (orient3(t.a, t.b, t.c, p, nexact) == 0 && orient3(t.a, t.b, t.c, q, nexact) == 0) return line_tri_intersection_coplanar(t, p, q, v, nexact);
+    const int pqab = orient3(p, q, t.a, t.b, nexact), pqbc = orient3(p, q, t.b, t.c, nexact);
+    bool through;
+    if (pqab > 0) through = pqbc != -1 && orient3(p, q, t.c, t.a, nexact) != -1;
+    else if (pqab < 0) through = pqbc != 1 && orient3(p, q, t.c, t.a, nexact) != 1;
+    else if (pqbc > 0) through = orient3(p, q, t.c, t.a, nexact) != -1;
+    else if (pqbc < 0) through = orient3(p, q, t.c, t.a, nexact) != 1;
+    else through = true;
+    if (!through) return r;
+    const Plane4 h = plane_of(t);
+    Vec3 x;
+    if (plane_line_point(h.a, h.b, h.c, h.d, p, v, x)) { r.kind = 1; r.p0 = x; }
+    return r;
+}
+B2_HD SegX plane_tri_intersection(const Tri3& t, double pa, double pb, double pc, double pd, int& nexact) {
+    SegX r; r.kind = 0; r.p0 = t.a; r.p1 = t.a;
+    const int o0 = plane_side(pa, pb, pc, pd, t.a, nexact), o1 = plane_side(pa, pb, pc, pd, t.b, nexact), o2 = plane_side(pa, pb, pc, pd, t.c, nexact);
+    Vec3 x;
+    if (o0 == 0) {
+        if (o1 == 0) { if (o2 == 0) { r.kind = 3; return r; } r.kind = 2; r.p0 = t.a; r.p1 = t.b; return r; }
+        if (o2 == 0) { r.kind = 2; r.p0 = t.a; r.p1 = t.c; return r; }
+        if (o1 == o2) { r.kind = 1; r.p0 = t.a; return r; }
+        if (plane_line_point(pa, pb, pc, pd, t.b, t.c - t.b, x)) { r.kind = 2; r.p0 = x; r.p1 = t.a; }
+        return r;
+    }
+    if (o1 == 0) {
+        if (o2 == 0) { r.kind = 2; r.p0 = t.b; r.p1 = t.c; return r; }
+        if (o2 == o0) { r.kind = 1; r.p0 = t.b; return r; }
+        if (plane_line_point(pa, pb, pc, pd, t.a, t.c - t.a, x)) { r.kind = 2; r.p0 = x; r.p1 = t.b; }
+        return r;
+    }
+    if (o2 == 0) {
+        if (o1 == o0) { r.kind = 1; r.p0 = t.c; return r; }
+        if (plane_line_point(pa, pb, pc, pd, t.a, t.b - t.a, x)) { r.kind = 2; r.p0 = x; r.p1 = t.c; }
+        return r;
+    }
+    Vec3 first = t.a, last = t.a;
+    int np = 0;
+    if (o0 != o1) { if (!plane_line_point(pa, pb, pc, pd, t.a, t.b - t.a, x)) return r; first = x; last = x; ++np; }
+    if (o0 != o2) { if (!plane_line_point(pa, pb, pc, pd, t.a, t.c - t.a, x)) return r; if (np == 0) first = x; last = x; ++np; }
+    if (o1 != o2) { if (!plane_line_point(pa, pb, pc, pd, t.b, t.c - t.b, x)) return r; if (np == 0) first = x; last = x; ++np; }
+    if (np == 0) return r;
+    r.kind = 2; r.p0 = first; r.p1 = last;
+    return r;
+}
+
 // The same routine OUT OF LINE with its arguments in registers, for the traversal kernels: a ray meets ~1.3 leaves, and keeping this long
 // routine (five orientation predicates, a division chain) out of the traversal loop lets the loop run at 8 blocks per SM without spilling.
 B2_HD_NOINLINE RayX ray_tri_intersection_call(double ax, double ay, double az, double bx, double by, double bz, double cx, double cy, double cz,

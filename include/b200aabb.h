@@ -60,7 +60,8 @@ enum {
                                       the same rounded values while pruning boxes with an inexact test (AABB_traits_3.h:89-125;
                                       AABB_ray_intersection.h:78), so in this band its own answer depends on the order in which its tree presents
                                       the candidates; this library reports the smallest rounded value.  closest_point never sets it: there the
-                                      reference compares candidates exactly and never prunes when unsure, so only exact ties are order dependent */
+                                      reference compares candidates exactly and never prunes when unsure, so only exact ties are order dependent */,
+  B200AABB_FLAG_TRIANGLE = 32      /* any_intersection of a Plane_3 query: the object is the primitive's Triangle_3 itself (it lies in the plane); no point is returned */
 };
 
 /* b200aabb_set_option keys */
@@ -161,8 +162,13 @@ int b200aabb_all_intersected_primitives(b200aabb_tree* t, const double* queries,
 int b200aabb_number_of_intersections(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, uint32_t* out);
 int b200aabb_all_intersections(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, const uint64_t* offsets,
                                uint32_t* ids, uint8_t* kinds, double* points);
-/* The same three calls for Segment_3 queries as well (kind = B200AABB_SEGMENT: (source, target), Intersect_3(Segment_3, Triangle_3),
- * Intersections_3/include/CGAL/Intersections_3/internal/Segment_3_Triangle_3_intersection.h:400-548; kind = B200AABB_RAY: as above). */
+/* The same three calls for every query kind: B200AABB_RAY as above; B200AABB_SEGMENT (source, target): Intersect_3(Segment_3, Triangle_3),
+ * Intersections_3/include/CGAL/Intersections_3/internal/Segment_3_Triangle_3_intersection.h:400-548; B200AABB_LINE (point, direction vector):
+ * Line_3_Triangle_3_intersection.h:279-400 — a construction, so the second point of the line is the ROUNDED point + vector there, unlike in do_intersect
+ *   (and unlike in the reference's own node test, which is the exact predicate: where a line grazes a primitive within rounding the reference's answer
+ *   depends on its tree; this library returns the tree-independent set, every primitive whose Intersect_3 is non-empty, of which the reference's is a subset);
+ * B200AABB_PLANE (a, b, c, d: 4 doubles per query): Plane_3_Triangle_3_intersection.h:27-146, whose object may also be the primitive's Triangle_3 itself
+ * (kinds[k] == 3 / B200AABB_FLAG_TRIANGLE: no points; the caller has the primitive). */
 int b200aabb_number_of_intersections_q(b200aabb_tree* t, const double* queries, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint32_t* out);
 int b200aabb_all_intersections_q(b200aabb_tree* t, const double* queries, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, const uint64_t* offsets,
                                  uint32_t* ids, uint8_t* kinds, double* points);

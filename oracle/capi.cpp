@@ -120,7 +120,8 @@ int orc_ray_intersections(void* hv, const double* rays, uint64_t n, int first_on
                           uint8_t* kinds, double* pts, int nthreads) {
     return orc_line_intersections(hv, rays, n, 1, first_only, counts, offsets, ids, kinds, pts, nthreads);
 }
-// the same for kind 0 = Segment_3 (source, target) or 1 = Ray_3
+// the same for every query kind of LQ(): 0 Segment_3, 1 Ray_3, 2 Line_3 (point, vector), 3 Plane_3 (a, b, c, d: 4 doubles per query); object kind 3 = the
+// primitive's Triangle_3 itself (Plane_3 queries; no points)
 int orc_line_intersections(void* hv, const double* rays, uint64_t n, int kind, int first_only, uint32_t* counts, const uint64_t* offsets, uint32_t* ids,
                            uint8_t* kinds, double* pts, int nthreads) {
     const Tree& t = *((Handle*)hv)->tree;
@@ -129,7 +130,20 @@ int orc_line_intersections(void* hv, const double* rays, uint64_t n, int kind, i
         std::vector<std::pair<uint32_t, RayHit>> v;
         for (uint64_t i = b; i < e; ++i) {
             v.clear();
-            t.ray_intersections(P(rays + 6 * i), P(rays + 6 * i + 3), first_only != 0, v, kind);
+            if (first_only == 2) {                                   // brute force over all primitives, no tree (the tree-independent set)
+                const Mesh& m = ((Handle*)hv)->mesh;
+                const Tree::LineQ lq = LQ(rays, i, kind);
+                for (uint32_t f = 0; f < (uint32_t)m.tris.size(); ++f) {
+                    RayHit r;
+                    switch (kind) {
+                        case 0: r = seg_tri_intersection(m.tris[f], lq.p, lq.q); break;
+                        case 2: r = line_tri_intersection(m.tris[f], lq.p, V3{lq.q.x, lq.q.y, lq.q.z}); break;
+                        case 3: { const double h[4] = {lq.p.x, lq.p.y, lq.p.z, lq.q.x}; r = plane_tri_intersection(m.tris[f], h); break; }
+                        default: r = ray_tri_intersection(m.tris[f], lq.p, lq.q);
+                    }
+                    if (r.kind) v.push_back({f, r});
+                }
+            } else t.query_intersections(LQ(rays, i, kind), first_only != 0, v);
             if (counts) counts[i] = (uint32_t)v.size();
             if (!ids) continue;
             if (v.size() != offsets[i + 1] - offsets[i]) { bad = 1; continue; }
@@ -137,7 +151,7 @@ int orc_line_intersections(void* hv, const double* rays, uint64_t n, int kind, i
                 const uint64_t o = offsets[i] + k;
                 ids[o] = v[k].first; kinds[o] = (uint8_t)v[k].second.kind;
                 std::memset(pts + 6 * o, 0, 48);
-                put(pts + 6 * o, v[k].second.pt[0]);
+                if (v[k].second.kind == 1 || v[k].second.kind == 2) put(pts + 6 * o, v[k].second.pt[0]);
                 if (v[k].second.kind == 2) put(pts + 6 * o + 3, v[k].second.pt[1]);
             }
         }
@@ -269,6 +283,13 @@ int orc_tri_do_intersect_kind(const double* tri, const double* q, int kind) { re
 int orc_bbox_do_intersect_kind(const double* box, const double* q, int kind) { return Tree::box_hit(LQ(q, 0, kind), B(box)) ? 1 : 0; }
 int orc_tri_do_intersect(const double* tri, const double* pq, int is_ray) {
     return (is_ray ? do_intersect_ray_tri(T(tri), P(pq), P(pq + 3)) : do_intersect_seg_tri(T(tri), P(pq), P(pq + 3))) ? 1 : 0;
+}
+int orc_tri_query_intersection(const double* tri, const double* q, int kind, double* pts) {      // kind 2 Line_3, 3 Plane_3
+    RayHit r;
+    if (kind == 2) r = line_tri_intersection(T(tri), P(q), V3{q[3], q[4], q[5]});
+    else r = plane_tri_intersection(T(tri), q);
+    if (r.kind == 1 || r.kind == 2) { put(pts, r.pt[0]); if (r.kind == 2) put(pts + 3, r.pt[1]); }
+    return r.kind;
 }
 int orc_tri_seg_intersection(const double* tri, const double* seg, double* pts) {
     RayHit r = seg_tri_intersection(T(tri), P(seg), P(seg + 3));

@@ -829,6 +829,115 @@ static inline RayHit seg_tri_intersection(const Tri& t, const P3& p, const P3& q
 }
 
 // ------------------------------------------------------------------------------------------------
+// Intersect_3(Line_3, Triangle_3): Intersections_3/internal/Line_3_Triangle_3_intersection.h:27-419, and Intersect_3(Plane_3, Triangle_3):
+// Plane_3_Triangle_3_intersection.h:27-146.  These are CONSTRUCTIONS: unlike Do_intersect_3 they run in plain double arithmetic with filtered
+// predicates on the points they form, so point_on(l, 1) is the ROUNDED point p + v here (Cartesian/Line_3.h).
+// ------------------------------------------------------------------------------------------------
+// Intersect_3(Plane_3, Line_3(point s, direction d)): Line_3_Plane_3_intersection.h:52-85 (den == 0: no Point_3)
+static inline bool plane_line_point(const double h[4], const P3& s, const V3& d, P3& out) {
+    const double num = h[0] * s.x + h[1] * s.y + h[2] * s.z + h[3];
+    const double den = h[0] * d.x + h[1] * d.y + h[2] * d.z;
+    if (den == 0) return false;
+    const double hx = den * s.x - num * d.x, hy = den * s.y - num * d.y, hz = den * s.z - num * d.z;
+    if (den != 1.0) out = {hx / den, hy / den, hz / den};
+    else out = {hx, hy, hz};
+    return true;
+}
+// Line_3_Triangle_3_intersection.h:66-88  the segment cut out of the line by the edges (b,c) and (c,a)
+static inline RayHit t3l3_clip(const P3& a, const P3& b, const P3& c, const P3& p, const V3& v, bool negative_side) {
+    const P3 l_bc = coplanar_line_line(p, v, b, c), l_ca = coplanar_line_line(p, v, c, a);
+    RayHit r; r.kind = 2;
+    r.pt[0] = negative_side ? l_bc : l_ca; r.pt[1] = negative_side ? l_ca : l_bc;
+    return r;
+}
+// :90-277
+static inline RayHit line_tri_intersection_coplanar(const Tri& t, const P3& p, const P3& q, const V3& v) {
+    const P3* w[3] = {&t.a, &t.b, &t.c};
+    if (coplanar_orientation(t.a, t.b, t.c) != 1) std::swap(w[1], w[2]);
+    const P3 &a = *w[0], &b = *w[1], &c = *w[2];
+    const int pqa = coplanar_orientation(p, q, a), pqb = coplanar_orientation(p, q, b), pqc = coplanar_orientation(p, q, c);
+    RayHit none;
+    auto point = [](const P3& x) { RayHit r; r.kind = 1; r.pt[0] = x; return r; };
+    auto segment = [](const P3& x, const P3& y) { RayHit r; r.kind = 2; r.pt[0] = x; r.pt[1] = y; return r; };
+    switch (pqa) {
+    case 1:
+        switch (pqb) {
+        case 1: return pqc == 1 ? none : (pqc == -1 ? t3l3_clip(a, b, c, p, v, true) : point(c));
+        case -1: return pqc == 1 ? t3l3_clip(c, a, b, p, v, true) : t3l3_clip(b, c, a, p, v, false);
+        default: return pqc == 1 ? point(b) : (pqc == -1 ? t3l3_clip(b, c, a, p, v, false) : segment(b, c));
+        }
+    case -1:
+        switch (pqb) {
+        case 1: return pqc == 1 ? t3l3_clip(b, c, a, p, v, true) : t3l3_clip(c, a, b, p, v, false);
+        case -1: return pqc == 1 ? t3l3_clip(a, b, c, p, v, false) : (pqc == -1 ? none : point(c));
+        default: return pqc == 1 ? t3l3_clip(b, c, a, p, v, true) : (pqc == -1 ? point(b) : segment(c, b));
+        }
+    default:
+        switch (pqb) {
+        case 1: return pqc == 1 ? point(a) : (pqc == -1 ? t3l3_clip(c, a, b, p, v, false) : segment(c, a));
+        case -1: return pqc == 1 ? t3l3_clip(c, a, b, p, v, true) : (pqc == -1 ? point(a) : segment(a, c));
+        default: return pqc == 1 ? segment(a, b) : (pqc == -1 ? segment(b, a) : none);
+        }
+    }
+}
+// :279-400  the line is (point p, direction vector v) as stored
+static inline RayHit line_tri_intersection(const Tri& t, const P3& p, const V3& v) {
+    const P3 &a = t.a, &b = t.b, &c = t.c;
+    const P3 q = padd(p, v);                                   // point_on(l, 1): rounded
+    RayHit none;
+    auto crossing = [&]() {
+        const Plane h = plane_from_points(a, b, c);
+        const double hc[4] = {h.a, h.b, h.c, h.d};
+        RayHit r; P3 x;
+        if (plane_line_point(hc, p, v, x)) { r.kind = 1; r.pt[0] = x; }
+        return r;
+    };
+    if (orientation(a, b, c, p) != 0 || orientation(a, b, c, q) != 0) {
+        const int pqab = orientation(p, q, a, b), pqbc = orientation(p, q, b, c);
+        switch (pqab) {
+        case 1: return (pqbc != -1 && orientation(p, q, c, a) != -1) ? crossing() : none;
+        case -1: return (pqbc != 1 && orientation(p, q, c, a) != 1) ? crossing() : none;
+        default:
+            if (pqbc == 1) return orientation(p, q, c, a) != -1 ? crossing() : none;
+            if (pqbc == -1) return orientation(p, q, c, a) != 1 ? crossing() : none;
+            return crossing();
+        }
+    }
+    return line_tri_intersection_coplanar(t, p, q, v);
+}
+// Plane_3_Triangle_3_intersection.h:27-146: kind 0 none, 1 Point_3, 2 Segment_3, 3 = the Triangle_3 itself (all three vertices on the plane; no points stored)
+static inline RayHit plane_tri_intersection(const Tri& t, const double h[4]) {
+    const P3* v[3] = {&t.a, &t.b, &t.c};
+    const int o0 = plane_oriented_side(h, t.a), o1 = plane_oriented_side(h, t.b), o2 = plane_oriented_side(h, t.c);
+    RayHit r;
+    auto point = [&](const P3& x) { r.kind = 1; r.pt[0] = x; return r; };
+    auto segment = [&](const P3& x, const P3& y) { r.kind = 2; r.pt[0] = x; r.pt[1] = y; return r; };
+    auto edge_point = [&](int i, int j, P3& x) { return plane_line_point(h, *v[i], vsub(*v[j], *v[i]), x); };   // Line_3(v_i, v_j): point v_i, direction v_j - v_i
+    P3 x;
+    if (o0 == 0) {
+        if (o1 == 0) { if (o2 == 0) { r.kind = 3; return r; } return segment(t.a, t.b); }
+        if (o2 == 0) return segment(t.a, t.c);
+        if (o1 == o2) return point(t.a);
+        return edge_point(1, 2, x) ? segment(x, t.a) : r;       // (no Point_3: a failed assertion in the reference)
+    }
+    if (o1 == 0) {
+        if (o2 == 0) return segment(t.b, t.c);
+        if (o2 == o0) return point(t.b);
+        return edge_point(0, 2, x) ? segment(x, t.b) : r;
+    }
+    if (o2 == 0) {
+        if (o1 == o0) return point(t.c);
+        return edge_point(0, 1, x) ? segment(x, t.c) : r;
+    }
+    P3 pts[3]; int np = 0;
+    if (o0 != o1) { if (!edge_point(0, 1, x)) return r; pts[np++] = x; }
+    if (o0 != o2) { if (!edge_point(0, 2, x)) return r; pts[np++] = x; }
+    if (o1 != o2) { if (!edge_point(1, 2, x)) return r; pts[np++] = x; }
+    if (np == 0) return r;
+    return segment(pts[0], pts[np - 1]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Construct_projected_point_3(Triangle_3, Point_3): Kernel_23/include/CGAL/Kernel/function_objects.h:3193-3263
 // ------------------------------------------------------------------------------------------------
 // Construct_projected_point_3(Line_3, Point_3): Cartesian/function_objects.h:3200-3217 ; line(p1,p2) = (p1, p2-p1) :2690-2691

@@ -255,15 +255,25 @@ struct Tree {
         std::vector<std::pair<uint32_t, RayHit>>* out;
         bool go_further() const { return !(first_only && found); }
         void intersection(const LineQ& q, uint32_t f) {
-            RayHit r = q.kind == 0 ? seg_tri_intersection(t.mesh->datum(f), q.p, q.q) : ray_tri_intersection(t.mesh->datum(f), q.p, q.q);
+            RayHit r;
+            switch (q.kind) {
+                case 0: r = seg_tri_intersection(t.mesh->datum(f), q.p, q.q); break;
+                case 2: r = line_tri_intersection(t.mesh->datum(f), q.p, V3{q.q.x, q.q.y, q.q.z}); break;
+                case 3: { const double h[4] = {q.p.x, q.p.y, q.p.z, q.q.x}; r = plane_tri_intersection(t.mesh->datum(f), h); break; }
+                default: r = ray_tri_intersection(t.mesh->datum(f), q.p, q.q);
+            }
             if (r.kind) { found = true; out->push_back({f, r}); }
         }
-        bool do_intersect(const LineQ& q, const Box& b) const { return do_intersect_bbox(q.p, q.q, b, q.kind == 1); }
+        bool do_intersect(const LineQ& q, const Box& b) const { return box_hit(q, b); }
     };
     // kind 1: Ray_3 (source, second point); kind 0: Segment_3 (source, target), Intersect_3(Segment_3, Triangle_3)
     void ray_intersections(const P3& s, const P3& q, bool first_only, std::vector<std::pair<uint32_t, RayHit>>& out, int kind = 1) const {
         RayObjectsTT tt{*this, first_only, false, &out};
         traversal(LineQ{s, q, kind}, tt);
+    }
+    void query_intersections(const LineQ& q, bool first_only, std::vector<std::pair<uint32_t, RayHit>>& out) const {   // kinds 0..3 of LineQ
+        RayObjectsTT tt{*this, first_only, false, &out};
+        traversal(q, tt);
     }
     // ---- Side_of_triangle_mesh (Polygon_mesh_processing/include/CGAL/Side_of_triangle_mesh.h:265-306) ----------------------------------
     // Ray_3_Triangle_3_traversal_traits<..., Tag_false> (internal/Side_of_triangle_mesh/Ray_3_Triangle_3_traversal_traits.h:30-76): any ray

@@ -169,6 +169,13 @@ def tri_do_intersect(tri, pq, is_ray):
     return lib().hc_tri_do_intersect(_p(tri), _p(pq), int(is_ray))
 
 
+def tri_query_intersection(tri, q, kind):
+    tri, q = _d(tri).ravel(), _d(q).ravel()
+    pts = np.zeros(6)
+    k = lib().hc_tri_query_intersection(_p(tri), _p(q), int(kind), _p(pts))
+    return k, pts.reshape(2, 3)
+
+
 def tri_seg_intersection(tri, seg):
     tri, seg = _d(tri).ravel(), _d(seg).ravel()
     pts = np.zeros(6)

@@ -318,6 +318,12 @@ int hc_tri_do_intersect_kind(const double* tri, const double* q, int kind) {
     return kind == 1 ? ray_tri_do_intersect(T(tri), V(q), V(q + 3), n) : seg_tri_do_intersect(T(tri), V(q), V(q + 3), n);
 }
 int hc_tri_do_intersect(const double* tri, const double* pq, int is_ray) { int n = 0; return is_ray ? ray_tri_do_intersect(T(tri), V(pq), V(pq + 3), n) : seg_tri_do_intersect(T(tri), V(pq), V(pq + 3), n); }
+int hc_tri_query_intersection(const double* tri, const double* q, int kind, double* pts) {      // kind 2 Line_3 (point, vector), 3 Plane_3 (a, b, c, d)
+    int n = 0;
+    const SegX x = kind == 2 ? line_tri_intersection(T(tri), V(q), V(q + 3), n) : plane_tri_intersection(T(tri), q[0], q[1], q[2], q[3], n);
+    if (x.kind == 1 || x.kind == 2) { pts[0] = x.p0.x; pts[1] = x.p0.y; pts[2] = x.p0.z; if (x.kind == 2) { pts[3] = x.p1.x; pts[4] = x.p1.y; pts[5] = x.p1.z; } }
+    return x.kind;
+}
 int hc_tri_seg_intersection(const double* tri, const double* seg, double* pts) {
     int n = 0;
     const SegX x = seg_tri_intersection(T(tri), V(seg), V(seg + 3), n);

@@ -160,9 +160,12 @@ class OracleTree:
         assert rc == 0
         return offsets, ids[:int(offsets[-1])]
 
-    def all_intersections(self, rays, first_only=False, threads=None, kind=1):
-        """all_intersections(Ray_3 | kind 0: Segment_3) (first_only: any_intersection): (offsets[n+1], ids, kinds (1 Point_3 / 2 Segment_3), pts[total,6])"""
-        q = _d(rays).reshape(-1, 6)
+    def all_intersections(self, rays, first_only=False, threads=None, kind=1, naive=False):
+        """all_intersections(Ray_3 | kind 0 Segment_3 | 2 Line_3 | 3 Plane_3) (first_only: any_intersection; naive: every primitive tested, no tree):
+        (offsets[n+1], ids, kinds (1 Point_3 / 2 Segment_3 / 3 the primitive's Triangle_3), pts[total,6])"""
+        if naive:
+            first_only = 2
+        q = _d(rays).reshape(-1, 4 if kind == 3 else 6)
         th = threads or nthreads()
         counts = np.zeros(len(q), np.uint32)
         f = lib().orc_line_intersections
@@ -304,6 +307,14 @@ def tri_do_intersect(tri, pq, is_ray):
     tri = _d(tri).ravel()
     pq = _d(pq).ravel()
     return lib().orc_tri_do_intersect(_ptr(tri, _dp), _ptr(pq, _dp), int(is_ray))
+
+
+def tri_query_intersection(tri, q, kind):
+    """Intersect_3(Line_3 (kind 2: point, vector) | Plane_3 (kind 3: a, b, c, d), Triangle_3): (object kind 0..3, points[2,3])"""
+    tri, q = _d(tri).ravel(), _d(q).ravel()
+    out = np.zeros(6)
+    k = lib().orc_tri_query_intersection(_ptr(tri, _dp), _ptr(q, _dp), int(kind), _ptr(out, _dp))
+    return k, out.reshape(2, 3)
 
 
 def tri_seg_intersection(tri, seg):

@@ -689,3 +689,52 @@ def test_all_and_any_intersections_of_segments(B, meshes):
             k = lookup[(int(i), int(a["prim"][i]))]
             assert np.array_equal(a["point"][i], pts[k, :3]) and bool(a["flags"][i] & B.FLAG_SEGMENT) == (kinds[k] == 2)
     assert (kinds == 2).sum() > 100 and (kinds == 1).sum() > 50
+
+
+def test_intersection_objects_of_line_and_plane_queries(B, meshes):
+    """all_intersections / any_intersection for Line_3 and Plane_3 queries (Line_3_Triangle_3_intersection.h, Plane_3_Triangle_3_intersection.h) against
+    the oracle: the records (query, primitive, object kind, points) are equal bit for bit; a flat grid gives in-plane lines (Segment_3 objects) and the
+    plane of the grid itself (Triangle_3 objects)"""
+    from cgal_b200 import workloads as W
+    from test_line_plane_queries import _mesh_queries
+    rng = np.random.default_rng(71)
+    v, f = meshes["elephant"]
+    lines, planes = _mesh_queries(rng, v, f, 4_000)
+    gv, gf = W.terrain(12, 12, amplitude=0.0)
+    xs = np.arange(0.0, 13.0)
+    flat_lines = np.concatenate([np.stack([np.full(13, -1.0), xs, np.zeros(13), np.ones(13), np.zeros(13), np.zeros(13)], 1),          # along grid lines
+                                 np.stack([xs, xs, np.full(13, 3.0), np.zeros(13), np.zeros(13), np.full(13, -1.0)], 1),                # through vertices
+                                 np.concatenate([rng.uniform(0, 12, (50, 2)), np.zeros((50, 1)), rng.normal(size=(50, 2)), np.zeros((50, 1))], 1)])
+    flat_planes = np.array([[0, 0, 1.0, 0], [0, 0, 1.0, -1.0], [1.0, 0, 0, -3.0], [1.0, 1.0, 0, -6.0], [1.0, 0, 0, -2.5], [0.3, 0.2, 1.0, -1.0]])
+    seen = set()
+    for tree_in, ql, qp in ((dict(vertices=v, faces=f), lines, planes), (dict(vertices=gv, faces=gf), flat_lines, flat_planes)):
+        g, o = B.AABB_tree(**tree_in), orc.OracleTree(tree_in["vertices"], tree_in["faces"])
+        for kind, q in ((B.LINE, ql), (B.PLANE, qp)):
+            off, ids, kinds, pts = g.all_intersections(q, kind=kind)
+            # Line_3: the reference decides nodes with the exact predicate on (point, vector) and primitives with the ROUNDED second point (a construction), so
+            # where a line grazes a primitive within rounding (lines through mesh vertices) its own answer depends on its tree; this library returns the
+            # tree-independent set — every primitive whose Intersect_3 is non-empty (the oracle's brute-force loop) — and the oracle's tree result is a subset
+            roff, rids, rkinds, rpts = o.all_intersections(q, kind=kind, naive=(kind == B.LINE))
+            if kind == B.LINE:
+                toff, tids, _, _ = o.all_intersections(q, kind=kind)
+                towner = np.repeat(np.arange(len(q)), np.diff(toff).astype(np.int64))
+                mine = set(zip(np.repeat(np.arange(len(q)), np.diff(off).astype(np.int64)).tolist(), ids.tolist()))
+                assert set(zip(towner.tolist(), tids.tolist())) <= mine
+                assert (np.diff(toff) == np.diff(off)).mean() > 0.75                            # they agree except on the grazing lines
+            np.testing.assert_array_equal(off, roff)
+            owner = np.repeat(np.arange(len(q)), np.diff(off).astype(np.int64))
+            order = np.lexsort((ids, owner)); rorder = np.lexsort((rids, owner))
+            np.testing.assert_array_equal(ids[order], rids[rorder])
+            np.testing.assert_array_equal(kinds[order], rkinds[rorder])
+            np.testing.assert_array_equal(pts[order], rpts[rorder])
+            seen |= {(kind, int(k)) for k in np.unique(kinds)}
+            a = g.any_intersection(q, kind=kind)
+            cnt = np.diff(off)
+            np.testing.assert_array_equal(a["prim"] == B.NO_PRIMITIVE, cnt == 0)
+            lookup = {(int(w), int(i)): k for k, (w, i) in enumerate(zip(owner, ids))}
+            for i in np.nonzero(cnt)[0][:2000]:
+                k = lookup[(int(i), int(a["prim"][i]))]
+                assert bool(a["flags"][i] & B.FLAG_SEGMENT) == (kinds[k] == 2) and bool(a["flags"][i] & B.FLAG_TRIANGLE) == (kinds[k] == 3)
+                if kinds[k] in (1, 2):
+                    assert np.array_equal(a["point"][i], pts[k, :3])
+    assert {(B.LINE, 1), (B.LINE, 2), (B.PLANE, 1), (B.PLANE, 2), (B.PLANE, 3)} <= seen, seen

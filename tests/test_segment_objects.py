@@ -117,3 +117,67 @@ def test_device_routine_against_the_oracle():
         np.testing.assert_array_equal(pts[:k], ptso[:k])                          # bit-exact, endpoint order included
         seen[k] += 1
     assert seen.min() > 500, seen
+
+
+# ---- Line_3 and Plane_3 queries: Line_3_Triangle_3_intersection.h:27-419, Plane_3_Triangle_3_intersection.h:27-146 ----------------------------------
+def exact_line_intersection(tri, p, v):
+    """the closed triangle with the line p + t v, in rationals (p + v taken exactly: on lattice input the rounded second point IS exact)"""
+    k, pts = exact_intersection(tri, np.concatenate([p - 1000 * v, p + 1000 * v]))      # lattice triangles live in [-3, 3]^3: a segment long enough
+    return k, pts
+
+
+def exact_plane_intersection(tri, h):
+    """the closed triangle with the plane: vertices on it and the crossing points of the edges that change side"""
+    V = [F(tri[0:3]), F(tri[3:6]), F(tri[6:9])]
+    H = F(h)
+    val = [H[0] * x[0] + H[1] * x[1] + H[2] * x[2] + H[3] for x in V]
+    on = [i for i in range(3) if val[i] == 0]
+    if len(on) == 3:
+        return 3, []
+    pts = [V[i] for i in on]
+    for i, j in ((0, 1), (0, 2), (1, 2)):
+        if val[i] * val[j] < 0:
+            t = val[i] / (val[i] - val[j])
+            pts.append([a + t * (b - a) for a, b in zip(V[i], V[j])])
+    if not pts:
+        return 0, []
+    return (1, pts) if len(pts) == 1 else (2, pts)
+
+
+def test_line_and_plane_objects_against_rationals_and_device_against_oracle():
+    from test_line_plane_queries import line_cases, plane_cases
+    rng = np.random.default_rng(53)
+    seen_l, seen_p = np.zeros(3, int), np.zeros(4, int)
+    for tri, p, v in line_cases(rng, 6000):
+        tri = tri.reshape(9)
+        q = np.concatenate([p, v])
+        k, pts = orc.tri_query_intersection(tri, q, 2)
+        kd, ptsd = hc.tri_query_intersection(tri, q, 2)
+        assert kd == k, (tri, p, v)
+        np.testing.assert_array_equal(ptsd[:k], pts[:k])                                 # device = oracle, bit for bit
+        if np.any(tri != np.round(tri)) or np.any(q != np.round(q)):
+            continue
+        ke, pe = exact_line_intersection(tri, p, v)
+        assert k == ke, (tri, p, v, k, ke)
+        seen_l[k] += 1
+        got = sorted(tuple(x) for x in pts[:k])
+        want = sorted(tuple(float(c) for c in x) for x in pe)
+        np.testing.assert_allclose(np.array(got).reshape(-1), np.array(want).reshape(-1), rtol=0, atol=1e-12)
+    for tri, h in plane_cases(rng, 6000):
+        tri = tri.reshape(9)
+        k, pts = orc.tri_query_intersection(tri, h, 3)
+        kd, ptsd = hc.tri_query_intersection(tri, h, 3)
+        assert kd == k, (tri, h)
+        if k in (1, 2):
+            np.testing.assert_array_equal(ptsd[:k], pts[:k])
+        assert (k > 0) == bool(orc.tri_do_intersect_kind(tri, h, 3)), (tri, h)           # an object exactly when the predicate says so
+        if np.any(tri != np.round(tri)) or np.any(h != np.round(h)):
+            continue
+        ke, pe = exact_plane_intersection(tri, h)
+        assert k == ke, (tri, h, k, ke)
+        seen_p[k] += 1
+        if k in (1, 2):
+            got = sorted(tuple(x) for x in pts[:k])
+            want = sorted(tuple(float(c) for c in x) for x in pe)
+            np.testing.assert_allclose(np.array(got).reshape(-1), np.array(want).reshape(-1), rtol=0, atol=1e-12)
+    assert seen_l.min() > 50 and seen_p[:3].min() > 50, (seen_l, seen_p)
