@@ -22,7 +22,28 @@ def main():
     fi = g.first_intersection(rays)
     c = g.number_of_intersected_primitives(rays, B.RAY)
     off, ids = g.all_intersected_primitives(rays[:1000], B.RAY)
-    print("ok", int(r["prim"].sum() % 1000), int((fi["prim"] != B.NO_PRIMITIVE).sum()), int(c.sum()), len(ids))
+    # round 2: kernel 2, skip mask, segment / line / plane objects, side_of_mesh, max_distance, refit, a 20,000-triangle build (80 blocks of the fused kernel)
+    g.set_option(B.OPT_CLOSEST_KERNEL, 2)
+    r2 = g.closest_point_and_primitive(pts[:2000])
+    g.set_option(B.OPT_CLOSEST_KERNEL, 1)
+    assert np.array_equal(r2["sqdist"], r["sqdist"][:2000])
+    sk = g.first_intersection_skip(rays[:1000], skip_ids=fi["prim"][:1000].copy())
+    segs = W.bbox_segments(bb, 2000)
+    o1 = g.all_intersections(segs, kind=B.SEGMENT)
+    lines = np.concatenate([segs[:, :3], segs[:, 3:] - segs[:, :3]], 1)
+    o2 = g.all_intersections(lines, kind=B.LINE)
+    planes = np.concatenate([np.random.default_rng(1).normal(size=(200, 3)), np.zeros((200, 1))], 1)
+    o3 = g.all_intersections(planes, kind=B.PLANE)
+    side = g.side_of_mesh(pts)
+    md = g.max_distance_to_mesh(pts)
+    g.refit(vertices=v * 1.001, faces=f)
+    soup = W.triangle_soup(20000)
+    t = B.AABB_tree(triangles=soup)
+    t.build()
+    t.set_option(103, 1)
+    t.build()
+    print("ok", int(r["prim"].sum() % 1000), int((fi["prim"] != B.NO_PRIMITIVE).sum()), int(c.sum()), len(ids), int((sk["prim"] != B.NO_PRIMITIVE).sum()), len(o1[1]), len(o2[1]),
+          len(o3[1]), int((side == 1).sum()), round(md[0], 6), t.size())
 
 
 if __name__ == "__main__":

@@ -738,3 +738,40 @@ def test_intersection_objects_of_line_and_plane_queries(B, meshes):
                 if kinds[k] in (1, 2):
                     assert np.array_equal(a["point"][i], pts[k, :3])
     assert {(B.LINE, 1), (B.LINE, 2), (B.PLANE, 1), (B.PLANE, 2), (B.PLANE, 3)} <= seen, seen
+
+
+def test_sdf_shaped_ray_casting(B, meshes):
+    """the ray casts of the shape-diameter function (Surface_mesh_segmentation/.../internal/SDF_calculation.h:272-356,475-515): from every facet's centroid a cone of
+    25 rays about the inward normal, first_intersection with the facet itself SKIPPED (SkipPrimitiveFunctor, :40-60), as ONE batch with per-ray skip ids; the
+    per-facet value (median / MAD outlier removal + weighted mean, :523-580) computed from the GPU's and from the oracle's hits is identical"""
+    v, f = meshes["elephant"]
+    g, o = B.AABB_tree(v, f), orc.OracleTree(v, f)
+    tri = v[f.astype(np.int64)]
+    ctr = tri.mean(1)
+    nrm = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    k = np.arange(25)                                                         # Vogel disk sampling of the cone's base, cone angle 2/3 pi
+    r, th = np.sqrt((k + 0.5) / 25), k * np.pi * (3 - np.sqrt(5))
+    u = np.cross(nrm, np.where(np.abs(nrm[:, :1]) < 0.9, [[1.0, 0, 0]], [[0, 1.0, 0]]))
+    u /= np.linalg.norm(u, axis=1)[:, None]
+    w = np.cross(nrm, u)
+    half = np.pi / 3
+    dirs = (-np.cos(half) * nrm[:, None, :] + np.sin(half) * (r[None, :, None] * np.cos(th)[None, :, None] * u[:, None, :] + r[None, :, None] * np.sin(th)[None, :, None] * w[:, None, :]))
+    rays = np.concatenate([np.repeat(ctr[:, None, :], 25, 1), ctr[:, None, :] + dirs], 2).reshape(-1, 6)
+    skip = np.repeat(np.arange(len(f), dtype=np.uint32), 25)
+    got = g.first_intersection_skip(rays, skip_ids=skip)
+    ref = o.first_intersection_skip(rays, skip_ids=skip)
+    flagged = (got["flags"] & (B.FLAG_TIE | B.FLAG_NEAR_TIE)) != 0
+    same = got["prim"] == ref["prim"]
+    assert np.all(same | flagged) and np.all(got["prim"] != skip)
+    np.testing.assert_array_equal(got["t"][same], ref["t"][same])
+    assert (got["prim"] != B.NO_PRIMITIVE).mean() > 0.9                        # a closed mesh: inward rays hit
+
+    def sdf(t, prim):
+        d = np.where(prim != B.NO_PRIMITIVE, t * np.linalg.norm(dirs.reshape(-1, 3), axis=1), np.nan).reshape(-1, 25)
+        med = np.nanmedian(d, axis=1)
+        mad = np.nanmedian(np.abs(d - med[:, None]), axis=1)
+        keep = np.abs(d - med[:, None]) <= 1.5 * mad[:, None]
+        wgt = np.where(keep & ~np.isnan(d), 1.0, 0.0)
+        return np.nansum(np.where(wgt > 0, d, 0.0) * wgt, axis=1) / np.maximum(wgt.sum(1), 1)
+    np.testing.assert_array_equal(sdf(got["t"], got["prim"])[same.reshape(-1, 25).all(1)], sdf(ref["t"], ref["prim"])[same.reshape(-1, 25).all(1)])
