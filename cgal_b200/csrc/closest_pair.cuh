@@ -607,6 +607,7 @@ B2_HD_NOINLINE uint32_t pp_node_phase(PairShared& S, const BvhNode* __restrict__
             const uint2 e = sp < kPpStackSm ? S.stack[sp][wk] : pp_ld_spill(&myspill[wk * (kPpStackCap - kPpStackSm) + (sp - kPpStackSm)]);
             if (pp_u2f(e.y) <= bound2) cur = e.x;
         }
+        wsync(w);                                                   // both lanes of a pair have read the popped entry before either stacks a new one there
         const bool act = cur != kNone;
         float d = INFINITY;
         uint32_t cref = 0;
