@@ -16,6 +16,7 @@ OPT_CLOSEST_KERNEL = 2    # 1 = warp-cooperative work pool (default), 2 = lane p
 OPT_WARP_EXACT_GO = 4
 OPT_HOST_PARTS = 5
 OPT_ASYNC_HOST = 6
+OPT_RAY_KERNEL = 7
 NO_PRIMITIVE = 0xFFFFFFFF
 _HOST, _DEVICE = 0, 1
 _ERRORS = {-1: "invalid argument", -2: "CUDA error", -3: "out of device memory", -4: "empty tree (CGAL_precondition(!empty()))",

@@ -185,6 +185,130 @@ __global__ void __launch_bounds__(128, 5) ray_objects_kernel(const TreeRef tr, c
     flush_stats(tr, st, 0, 0);
 }
 
+// The same traversal as bvh.cuh::traverse_first (operation for operation: the results are bit-identical) run by PERSISTENT threads that take the next ray of
+// the coherence order from a cursor as soon as their ray is done ("while-while with replacement", Aila & Laine 2009): in the thread-per-ray kernel a warp
+// runs until its slowest ray ends, with 17 of 32 lanes active per instruction on the benchmark batch (profiles/r2_08) — half the pinhole rays miss the terrain.
+// B200AABB_OPT_RAY_KERNEL selects it; rays with a skip list and one-primitive trees use the thread-per-ray kernel.
+__global__ void __launch_bounds__(128, 5) first_intersection_stream_kernel(const TreeRef tr, const double* __restrict__ rays, uint64_t n, unsigned long long* __restrict__ cursor,
+                                                                         uint32_t* __restrict__ prim, double* __restrict__ tpar, double* __restrict__ pt, double* __restrict__ pt2,
+                                                                         uint8_t* __restrict__ flags) {
+    const unsigned full = 0xFFFFFFFFu, lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    TravStat st;
+    unsigned n_exact = 0, n_tie = 0, n_near = 0;
+    bool have = false, more = true;
+    uint64_t qi = 0;
+    Vec3 s = {0.0, 0.0, 0.0}, q = {0.0, 0.0, 0.0};
+    LineCtx c;
+    FirstHit best;
+    double best_u = 0.0, strict_lo = DBL_MAX, tie_lo = DBL_MAX;
+    bool tie = false;
+    float tlimit = INFINITY;
+    uint32_t stack[kStackCap];
+    float stack_t[kStackCap];
+    int sp = 0, np = 0, nex_q = 0;
+    uint32_t pend[2];
+    float pend_t[2];
+    uint32_t cur = kNone;
+    float cur_t = 0.0f;
+    while (true) {
+        const unsigned need = __ballot_sync(full, !have);
+        if (more && need) {                                               // idle lanes take the next rays of the order
+            const int leader = __ffs(need) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(need));
+            base = __shfl_sync(full, base, leader);
+            if (!have) {
+                const unsigned long long pos = base + __popc(need & lt);
+                if (pos < n) {
+                    qi = tr.perm ? tr.perm[pos] : pos;
+                    s = ld3(rays + 6 * qi); q = ld3(rays + 6 * qi + 3);
+                    c = make_line(s, q, tr.mag);
+                    best.prim = kNone; best.kind = 0; best.t = DBL_MAX; best.p0 = s; best.p1 = s; best.tie = 0; best.near = 0;
+                    best_u = 0.0; strict_lo = DBL_MAX; tie_lo = DBL_MAX; tie = false; tlimit = INFINITY;
+                    sp = 0; np = 0; nex_q = 0; cur = tr.root; cur_t = 0.0f;
+                    have = true;
+                }
+            }
+            if (base + __popc(need) >= n) more = false;
+        }
+        if (!__any_sync(full, have)) break;
+        while (have && cur != kNone && np == 0) {                         // node phase (bvh.cuh::traverse_first)
+            const NodeView nd = load_node(tr.nodes, cur);
+            ++st.nodes;
+            float t0, t1;
+            bool h0 = line_box(nd.lo0, nd.hi0, c, tlimit, t0);
+            bool h1 = line_box(nd.lo1, nd.hi1, c, tlimit, t1);
+            uint32_t c0 = nd.c0, c1 = nd.c1;
+            if (h0 && h1 && t1 < t0) { const uint32_t tc = c0; c0 = c1; c1 = tc; const float tt = t0; t0 = t1; t1 = tt; }
+            else if (!h0 && h1) { c0 = c1; t0 = t1; h0 = true; h1 = false; }
+            uint32_t next = kNone;
+            if (h0) { if (c0 & kLeafBit) { pend[np] = c0; pend_t[np] = t0; ++np; } else { next = c0; cur_t = t0; } }
+            if (h1) {
+                if (c1 & kLeafBit) { pend[np] = c1; pend_t[np] = t1; ++np; }
+                else if (next == kNone) { next = c1; cur_t = t1; }
+                else if (sp < kStackCap) { stack[sp] = c1; stack_t[sp] = t1; ++sp; }
+                else st.overflow = 1;
+            }
+            while (next == kNone && sp > 0) {
+                --sp;
+                if (stack_t[sp] <= tlimit) { next = stack[sp]; cur_t = stack_t[sp]; }
+            }
+            cur = next;
+        }
+        if (have) {
+            for (int k = 0; k < np; ++k) {                                // leaf phase
+                if (!(pend_t[k] <= tlimit)) continue;
+                uint32_t id;
+                const Tri3 t = load_tri(tr.tris, pend[k] & ~kLeafBit, id);
+                ++st.leaves;
+                int nex = 0;
+                const RayX x = ray_tri_intersection_call(t.a.x, t.a.y, t.a.z, t.b.x, t.b.y, t.b.z, t.c.x, t.c.y, t.c.z, s.x, s.y, s.z, q.x, q.y, q.z, c.major, &nex);
+                nex_q += nex;
+                if (x.kind == 0) continue;
+                if (x.t < best.t || (x.t == best.t && id < best.prim)) {
+                    if (best.prim != kNone) {
+                        if (x.t < best.t) { strict_lo = fmin(strict_lo, fmin(best.t - best_u, tie_lo)); tie = false; tie_lo = DBL_MAX; }
+                        else { tie = true; tie_lo = fmin(tie_lo, best.t - best_u); }
+                    }
+                    best.prim = id; best.kind = x.kind; best.t = x.t; best.p0 = x.p0; best.p1 = x.p1; best_u = x.u;
+                    tlimit = float_above(x.t + ((fabs(x.t) * 2e-6 + x.u) + c.t_abs_slack));
+                } else if (x.t == best.t) { tie = true; tie_lo = fmin(tie_lo, x.t - x.u); }
+                else strict_lo = fmin(strict_lo, x.t - x.u);
+            }
+            np = 0;
+            if (cur != kNone && cur_t > tlimit) {
+                cur = kNone;
+                while (cur == kNone && sp > 0) {
+                    --sp;
+                    if (stack_t[sp] <= tlimit) { cur = stack[sp]; cur_t = stack_t[sp]; }
+                }
+            }
+            if (cur == kNone) {                                           // this ray is done: results out, the lane is free
+                const bool hit = best.prim != kNone;
+                const bool is_tie = hit && tie, is_near = hit && strict_lo <= best.t + best_u;
+                if (prim) prim[qi] = best.prim;
+                if (tpar) tpar[qi] = hit ? best.t : 0.0;
+                if (pt) { pt[3 * qi] = hit ? best.p0.x : 0.0; pt[3 * qi + 1] = hit ? best.p0.y : 0.0; pt[3 * qi + 2] = hit ? best.p0.z : 0.0; }
+                if (pt2) { const bool seg = hit && best.kind == 2; pt2[3 * qi] = seg ? best.p1.x : 0.0; pt2[3 * qi + 1] = seg ? best.p1.y : 0.0; pt2[3 * qi + 2] = seg ? best.p1.z : 0.0; }
+                if (flags) flags[qi] = (uint8_t)((hit ? B200AABB_FLAG_HIT : 0) | (hit && best.kind == 2 ? B200AABB_FLAG_SEGMENT : 0) | (is_tie ? B200AABB_FLAG_TIE : 0) |
+                                                 (nex_q ? B200AABB_FLAG_EXACT : 0) | (is_near ? B200AABB_FLAG_NEAR_TIE : 0));
+                n_exact += nex_q ? 1u : 0u; n_tie += is_tie ? 1u : 0u; n_near += is_near ? 1u : 0u;
+                have = false;
+            }
+        }
+    }
+    const unsigned nodes = __reduce_add_sync(full, st.nodes), leaves = __reduce_add_sync(full, st.leaves);
+    const unsigned exact = __reduce_add_sync(full, n_exact), ties = __reduce_add_sync(full, n_tie), nears = __reduce_add_sync(full, n_near), ovf = __reduce_or_sync(full, st.overflow ? 1u : 0u);
+    if (lane == 0) {
+        atomicAdd(&tr.counters[3], (unsigned long long)nodes);
+        atomicAdd(&tr.counters[4], (unsigned long long)leaves);
+        if (exact) atomicAdd(&tr.counters[0], (unsigned long long)exact);
+        if (ties) atomicAdd(&tr.counters[1], (unsigned long long)ties);
+        if (nears) atomicAdd(&tr.counters[5], (unsigned long long)nears);
+        if (ovf) atomicOr(&tr.counters[2], 1ull);
+    }
+}
+
 template <bool SKIP>
 __global__ void __launch_bounds__(128, 5) first_intersection_kernel(const TreeRef tr, const double* __restrict__ rays, uint64_t n, uint32_t* __restrict__ prim,
                                                                  double* __restrict__ tpar, double* __restrict__ pt, double* __restrict__ pt2,
@@ -361,6 +485,9 @@ struct b200aabb_tree {
     struct BuildScratch { uint64_t* keys[2] = {nullptr, nullptr}; uint32_t* vals[2] = {nullptr, nullptr}; void* ws = nullptr; RefitEntry* frontier = nullptr;
                           unsigned* frontier_count = nullptr; uint32_t* rest = nullptr; unsigned long long* flags = nullptr; uint64_t cap = 0; uint64_t vals_cap = 0; } bs;
     uint64_t tree_cap = 0;
+    int opt_ray_kernel = 0;        // first_intersection: 0 = one thread per ray, 1 = persistent threads with ray replacement (B200AABB_OPT_RAY_KERNEL)
+    unsigned long long* d_ray_cursor = nullptr;   // [kScratchSlots]
+    int ray_grid = 0;
     int opt_classic_build = 0;     // 1: hierarchy_kernel for every node + refit_local_kernel instead of the fused bottom-up kernel (the fallback of a full frontier; test hook, option 103)
     int last_build_classic = 0;
     uint32_t root = kNone;
@@ -865,6 +992,12 @@ int b200aabb_create(int device, b200aabb_tree** out) {
     for (int s = 0; s < kPipeSlots && ok; ++s)
         ok = cudaEventCreateWithFlags(&t->ev_up[s], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&t->ev_run[s], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&t->ev_down[s], cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaMalloc(&t->d_ray_cursor, kScratchSlots * sizeof(unsigned long long)) == cudaSuccess;
+    if (ok) {
+        int per_sm = 0;
+        ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, first_intersection_stream_kernel, 128, 0) == cudaSuccess;
+        t->ray_grid = std::max(1, per_sm) * prop.multiProcessorCount;
+    }
     if (!ok) { b200aabb_destroy(t); return B200AABB_ERR_CUDA; }
     t->built = true;   // an empty tree needs no build
     *out = t;
@@ -876,7 +1009,7 @@ int b200aabb_destroy(b200aabb_tree* t) {
     cudaSetDevice(t->device);
     cudaDeviceSynchronize();
     free_tree_buffers(t); free_build_scratch(t); free_input(t); free_sort(t); free_warp(t);
-    cudaFree(t->d_rootbox); cudaFree(t->d_bounds); cudaFree(t->d_counters);
+    cudaFree(t->d_rootbox); cudaFree(t->d_bounds); cudaFree(t->d_counters); cudaFree(t->d_ray_cursor);
     for (int s = 0; s < kPipeSlots; ++s) {
         cudaFree(t->d_stage_in[s]); cudaFree(t->d_stage_out[s]); cudaFree(t->d_stage_aux[s]);
         if (t->ev_up[s]) cudaEventDestroy(t->ev_up[s]);
@@ -896,6 +1029,7 @@ int b200aabb_set_option(b200aabb_tree* t, int option, int64_t value) { B2_LOCK(t
         case B200AABB_OPT_SORT_QUERIES: t->opt_sort_queries = value != 0; return B200AABB_OK;
         case B200AABB_OPT_CLOSEST_KERNEL: t->opt_closest_kernel = (int)std::min<int64_t>(2, std::max<int64_t>(0, value)); return B200AABB_OK;
         case B200AABB_OPT_ASYNC_HOST: t->opt_async_host = value != 0; return B200AABB_OK;
+        case B200AABB_OPT_RAY_KERNEL: t->opt_ray_kernel = value != 0; return B200AABB_OK;
         case B200AABB_OPT_HOST_PARTS: t->opt_host_parts = (int)std::min<int64_t>(64, std::max<int64_t>(0, value)); return B200AABB_OK;
         case 103: t->opt_classic_build = value != 0; if (!t->imported) t->built = t->n == 0; return B200AABB_OK;
         case 102: t->opt_exact_keys = value != 0; if (!t->imported) t->built = t->n == 0; return B200AABB_OK;
@@ -1303,7 +1437,13 @@ static int first_intersection_impl(b200aabb_tree* t, const double* rays, uint64_
                        if (sk || mask_dev)
                            first_intersection_kernel<true><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint32_t*)o[0], (double*)o[1],
                                                                                                 (double*)o[2], (double*)o[3], (uint8_t*)o[4], sk, mask_dev, mask_words);
-                       else
+                       else if (t->opt_ray_kernel == 1 && t->n >= 2 && t->d_ray_cursor) {
+                           unsigned long long* cursor = t->d_ray_cursor + (space == B200AABB_HOST ? kHostScratch : kDeviceScratch);
+                           cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st);
+                           const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)t->ray_grid, (cnt + 127) / 128);
+                           first_intersection_stream_kernel<<<grid, 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, cursor, (uint32_t*)o[0], (double*)o[1], (double*)o[2],
+                                                                                  (double*)o[3], (uint8_t*)o[4]);
+                       } else
                            first_intersection_kernel<false><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (uint32_t*)o[0], (double*)o[1],
                                                                                                  (double*)o[2], (double*)o[3], (uint8_t*)o[4], nullptr, nullptr, 0);
                    });

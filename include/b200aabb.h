@@ -78,6 +78,8 @@ enum {
   B200AABB_OPT_ASYNC_HOST = 6,     /* 1: batched queries with HOST pointers return as soon as their chunks are enqueued (uploads, kernels and downloads of
                                       consecutive calls then overlap across calls); the caller keeps the query / result buffers alive and unread until
                                       b200aabb_synchronize.  0 (default): every call returns with its results in place. */
+  B200AABB_OPT_RAY_KERNEL = 7,     /* first_intersection scheduling: 0 = one thread per ray; 1 = persistent threads that take the next ray of the coherence order as soon as
+                                      theirs is done (same traversal, identical results) */
   B200AABB_OPT_WARP_EXACT_GO = 4   /* warp-cooperative kernels: run the binary64 phase once this many pre-test survivors wait (1..160; 0 = the kernel's default) */
 };
 

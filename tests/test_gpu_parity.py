@@ -775,3 +775,30 @@ def test_sdf_shaped_ray_casting(B, meshes):
         wgt = np.where(keep & ~np.isnan(d), 1.0, 0.0)
         return np.nansum(np.where(wgt > 0, d, 0.0) * wgt, axis=1) / np.maximum(wgt.sum(1), 1)
     np.testing.assert_array_equal(sdf(got["t"], got["prim"])[same.reshape(-1, 25).all(1)], sdf(ref["t"], ref["prim"])[same.reshape(-1, 25).all(1)])
+
+
+def test_ray_kernels_agree(B, meshes):
+    """first_intersection with persistent threads and ray replacement (B200AABB_OPT_RAY_KERNEL = 1) returns the records of the thread-per-ray kernel, bit for bit,
+    flags and traversal counters included"""
+    import torch
+    from cgal_b200 import workloads as W
+    from cgal_b200.aabb_tree import OPT_RAY_KERNEL
+    v, f = meshes["elephant"]
+    g = B.AABB_tree(v, f)
+    gv, gf = W.terrain(24, 24, amplitude=0.0)
+    flat = B.AABB_tree(gv, gf)
+    xs = np.arange(0.0, 25.0)
+    grid_rays = np.concatenate([np.stack([np.full(25, -1.0), xs, np.zeros(25), np.zeros(25), xs, np.zeros(25)], 1), np.stack([xs, xs[::-1], np.full(25, 5.0), xs, xs[::-1], np.full(25, 4.0)], 1)])
+    for tree, rays in ((g, W.sphere_rays(g.bbox(), 100_000)), (g, W.sphere_rays(g.bbox(), 37)), (flat, grid_rays)):
+        tree.set_option(OPT_RAY_KERNEL, 0)
+        a = tree.first_intersection(rays)
+        sa = tree.stats()
+        tree.set_option(OPT_RAY_KERNEL, 1)
+        b = tree.first_intersection(rays)
+        sb = tree.stats()
+        d = tree.first_intersection(torch.from_numpy(rays).cuda())
+        for k in a:
+            np.testing.assert_array_equal(a[k], b[k])
+            np.testing.assert_array_equal(a[k], d[k].cpu().numpy())
+        assert (sa["nodes_visited"], sa["leaves_tested"], sa["ties"]) == (sb["nodes_visited"], sb["leaves_tested"], sb["ties"])
+        tree.set_option(OPT_RAY_KERNEL, 0)
