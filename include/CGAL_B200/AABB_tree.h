@@ -34,6 +34,7 @@
 #include <utility>
 #include <vector>
 
+#include <memory>
 #include "../b200aabb.h"
 
 namespace CGAL_B200 {
@@ -46,6 +47,35 @@ class Error : public std::runtime_error {
 
  private:
   int m_code;
+};
+
+// One NCCL communicator per GPU, for replicating a built tree (b200aabb_comm_*: the reference has no multi-device path, its callers shard queries over
+// threads; here a tree is built on one GPU, replicated, and every GPU answers its own block of the batch against its replica).
+//   several processes, one GPU each:  char id[128]; if (rank == 0) Communicator::unique_id(id);  /* ship id to the other ranks */
+//                                     Communicator comm(device, rank, world, id);   tree.replicate(comm, 0);
+//   one process, several GPUs:        auto comms = Communicator::all({0, 1, 2, 3});  AABB_tree<Traits>::replicate_all(trees, comms, 0);
+class Communicator {
+ public:
+  static void unique_id(char id[128]) { check(b200aabb_comm_unique_id(id), nullptr); }
+  Communicator(int device, int rank, int world, const char id[128]) { check(b200aabb_comm_init(device, rank, world, id, &m_comm), nullptr); }
+  ~Communicator() { if (m_comm) b200aabb_comm_destroy(m_comm); }
+  Communicator(const Communicator&) = delete;
+  Communicator& operator=(const Communicator&) = delete;
+  static std::vector<std::unique_ptr<Communicator>> all(const std::vector<int>& devices) {
+    std::vector<b200aabb_comm*> raw(devices.size(), nullptr);
+    check(b200aabb_comm_init_all((int)devices.size(), devices.data(), raw.data()), nullptr);
+    std::vector<std::unique_ptr<Communicator>> out;
+    for (b200aabb_comm* c : raw) out.emplace_back(new Communicator(c));
+    return out;
+  }
+  b200aabb_comm* handle() const { return m_comm; }
+  static void check(int rc, const b200aabb_comm* c) {
+    if (rc != B200AABB_OK) throw Error(rc, c ? b200aabb_comm_last_error(c) : "b200aabb_comm: NCCL not available or the call failed");
+  }
+
+ private:
+  explicit Communicator(b200aabb_comm* c) : m_comm(c) {}
+  b200aabb_comm* m_comm = nullptr;
 };
 
 namespace internal {
@@ -464,6 +494,29 @@ class AABB_tree {
     check(b200aabb_closest_point(m_handle, q.data(), n, B200AABB_HOST, nullptr, nullptr, d.data(), nullptr));
     for (uint64_t i = 0; i < n; ++i) *out++ = FT(d[i]);
     return out;
+  }
+
+  // ---- multi-GPU: COLLECTIVE, every rank calls it with its own tree (created on the communicator's device).  On `root` the tree is built if needed and
+  // sent; on the other ranks the device tree becomes a replica.  Every rank must have inserted the same primitives in the same order (they map the
+  // primitive indices of the results to ids on the host; only the root's are uploaded).  mode 0: the built tree travels; 1: the primitives travel and every
+  // rank builds.  Returns the device time of the replication on this rank in milliseconds.
+  double replicate(Communicator& comm, int root, int rank, int mode = 0) {
+    if (rank == root) ensure_built();
+    double ms = 0;
+    Communicator::check(b200aabb_comm_broadcast_tree(comm.handle(), m_handle, root, mode, &ms, nullptr), comm.handle());
+    m_uploaded = true;
+    return ms;
+  }
+  // the same for one process that drives several GPUs: trees[i] lives on the device of comms[i]
+  static double replicate_all(const std::vector<Self*>& trees, const std::vector<std::unique_ptr<Communicator>>& comms, int root, int mode = 0) {
+    trees[root]->ensure_built();
+    std::vector<b200aabb_comm*> c;
+    std::vector<b200aabb_tree*> t;
+    for (size_t i = 0; i < trees.size(); ++i) { c.push_back(comms[i]->handle()); t.push_back(trees[i]->m_handle); }
+    double ms = 0;
+    Communicator::check(b200aabb_comm_broadcast_tree_all(c.data(), t.data(), (int)trees.size(), root, mode, &ms, nullptr), c[root]);
+    for (Self* x : trees) x->m_uploaded = true;
+    return ms;
   }
 
   // ---- access to the C ABI for callers that keep queries and results in device memory (b200aabb.h, B200AABB_DEVICE)

@@ -86,6 +86,27 @@ static int known_answers() {
     CHECK(std::holds_alternative<Point>(hit->first) && std::get<Point>(hit->first) == Point(0.2, 0.2, 0.0));
     CHECK(tree.first_intersected_primitive(up) && *tree.first_intersected_primitive(up) == mini::Face_index(0));
     CHECK(tree.number_of_intersected_primitives(up) == 2);
+    {   // multi-GPU through the C++ class: replicate the tree with the library's NCCL communicator (two GPUs when there are two, else a world of one)
+      b200aabb_tree* probe = nullptr;
+      const bool two = b200aabb_create(1, &probe) == B200AABB_OK;
+      if (probe) b200aabb_destroy(probe);
+      try {
+        std::vector<int> devices = two ? std::vector<int>{0, 1} : std::vector<int>{0};
+        auto comms = CGAL_B200::Communicator::all(devices);
+        Tree replica(Traits(), two ? 1 : 0);
+        if (two) replica.insert(faces(m).first, faces(m).second, m);               // the same primitives in the same order: they map indices to ids on the host
+        std::vector<Tree*> trees = two ? std::vector<Tree*>{&tree, &replica} : std::vector<Tree*>{&tree};
+        const double ms = Tree::replicate_all(trees, comms, 0);
+        CHECK(ms >= 0.0);
+        Tree& r = two ? replica : tree;
+        CHECK(r.size() == 4 && r.do_intersect(pq) && r.number_of_intersected_primitives(pq) == 1);
+        CHECK(r.closest_point(Point(0.0, 0.0, 3.0)) == Point(0.0, 0.0, 1.0));
+        const auto h2 = r.first_intersection(Ray(Point(0.2, 0.2, -1.0), Point(0.2, 0.2, 0.0)));
+        CHECK(h2 && h2->second == mini::Face_index(0));
+      } catch (const CGAL_B200::Error& e) {
+        CHECK(e.code() == B200AABB_ERR_NCCL);                                        // libnccl.so.2 not loadable on this box: the only acceptable failure
+      }
+    }
     {   // intersection objects of Segment_3 queries (AABB_tree.h:958-985 with Intersect_3(Segment_3, Triangle_3))
       const Segment through(Point(0.2, 0.2, -1.0), Point(0.2, 0.2, 2.0));          // crosses the base facet at z = 0 and the slanted one at z = 0.6
       std::vector<Tree::Intersection_and_primitive_id<Segment>::Type> objs;
