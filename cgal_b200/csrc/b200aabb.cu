@@ -78,6 +78,94 @@ __global__ void __launch_bounds__(128, 8) intersect_kernel(const TreeRef tr, con
     flush_stats(tr, st, 0, 0);
 }
 
+// do_intersect / number_of_intersected_primitives / any_intersected_primitive by PERSISTENT threads with query replacement: the traversal of
+// bvh.cuh::traverse_line (same node tests, same leaf routines, same results) where a lane takes the next query of the coherence order as soon as its own is
+// answered.  On the config 3 shadow segments the thread-per-query kernel runs with 11 of 32 lanes active per instruction (profiles/r2_18): any-hit queries end
+// at their first hit, long segments cross many nodes.  B200AABB_OPT_RAY_KERNEL selects it (modes any hit, count, any id; the list mode keeps the other kernel).
+#ifndef B2_IS_BLOCKS
+#define B2_IS_BLOCKS 8
+#endif
+template <int KIND, int MODE>
+__global__ void __launch_bounds__(128, B2_IS_BLOCKS) intersect_stream_kernel(const TreeRef tr, const double* __restrict__ q, uint64_t n, unsigned long long* __restrict__ cursor,
+                                                                  uint8_t* __restrict__ out8, uint32_t* __restrict__ out32) {
+    const unsigned full = 0xFFFFFFFFu, lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+    constexpr bool kStop = MODE == kAnyHit || MODE == kAnyId;
+    constexpr int kPendCount = 6, kPendGoAt = kPendCount - 1;
+    const float tlimit = KIND == kSegmentQ ? 1.0f : INFINITY, tstart = KIND == kLineQ ? -INFINITY : 0.0f;
+    TravStat st;
+    unsigned n_exact = 0;
+    bool have = false, more = true;
+    uint64_t qi = 0;
+    Vec3 s = {0.0, 0.0, 0.0}, e = {0.0, 0.0, 0.0};
+    LineCtx c;
+    uint32_t stack[kStackCap];
+    uint32_t pend[kPendCount + 1];
+    int sp = 0, np = 0, nex_q = 0;
+    uint32_t cur = kNone, found = 0, found_id = kNone;
+    while (true) {
+        const unsigned need = __ballot_sync(full, !have);
+        if (more && need) {
+            const int leader = __ffs(need) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(need));
+            base = __shfl_sync(full, base, leader);
+            if (!have) {
+                const unsigned long long pos = base + __popc(need & lt);
+                if (pos < n) {
+                    qi = tr.perm ? tr.perm[pos] : pos;
+                    s = ld3(q + 6 * qi); e = ld3(q + 6 * qi + 3);
+                    c = KIND == kLineQ ? make_line_pv(s, e) : make_line(s, e);
+                    sp = 0; np = 0; nex_q = 0; cur = tr.root; found = 0; found_id = kNone;
+                    have = true;
+                }
+            }
+            if (base + __popc(need) >= n) more = false;
+        }
+        if (!__any_sync(full, have)) break;
+        while (have && cur != kNone && np < kPendGoAt) {                  // node phase (bvh.cuh::traverse_line)
+            const NodeView nd = load_node(tr.nodes, cur);
+            ++st.nodes;
+            float tn;
+            const bool h0 = line_box(nd.lo0, nd.hi0, c, tlimit, tn, tstart);
+            const bool h1 = line_box(nd.lo1, nd.hi1, c, tlimit, tn, tstart);
+            uint32_t next = kNone;
+            if (h0) { if (nd.c0 & kLeafBit) pend[np++] = nd.c0; else next = nd.c0; }
+            if (h1) {
+                if (nd.c1 & kLeafBit) pend[np++] = nd.c1;
+                else if (next == kNone) next = nd.c1;
+                else if (sp < kStackCap) stack[sp++] = nd.c1;
+                else st.overflow = 1;
+            }
+            if (next == kNone && sp > 0) next = stack[--sp];
+            cur = next;
+        }
+        if (have) {
+            bool done = false;
+            while (np > 0) {                                              // leaf phase
+                uint32_t id;
+                const Tri3 t = load_tri(tr.tris, pend[--np] & ~kLeafBit, id);
+                ++st.leaves;
+                const bool hit = KIND == kRayQ ? ray_tri_do_intersect(t, s, e, nex_q) : KIND == kLineQ ? line_tri_do_intersect(t, s, e, nex_q) : seg_tri_do_intersect(t, s, e, nex_q);
+                if (hit) { ++found; found_id = id; if (kStop) { done = true; break; } }
+            }
+            if (done || cur == kNone) {
+                if (MODE == kAnyHit) out8[qi] = (uint8_t)(found ? 1u : 0u);
+                else out32[qi] = MODE == kAnyId ? found_id : found;
+                n_exact += nex_q ? 1u : 0u;
+                have = false;
+            }
+        }
+    }
+    const unsigned nodes = __reduce_add_sync(full, st.nodes), leaves = __reduce_add_sync(full, st.leaves);
+    const unsigned exact = __reduce_add_sync(full, n_exact), ovf = __reduce_or_sync(full, st.overflow ? 1u : 0u);
+    if (lane == 0) {
+        atomicAdd(&tr.counters[3], (unsigned long long)nodes);
+        atomicAdd(&tr.counters[4], (unsigned long long)leaves);
+        if (exact) atomicAdd(&tr.counters[0], (unsigned long long)exact);
+        if (ovf) atomicOr(&tr.counters[2], 1ull);
+    }
+}
+
 // Side_of_triangle_mesh (Side_of_triangle_mesh.h:265-306): -1 ON_UNBOUNDED_SIDE, 0 ON_BOUNDARY, +1 ON_BOUNDED_SIDE of a closed mesh.  A point outside
 // the tree's box is outside; otherwise rays are cast until one is decisive: first the vertical one towards the nearer z face of the box
 // (Point_inside_vertical_ray_cast.h:79-81), then fixed pseudo-random directions — the same for every query, as the reference's re-seeded generator
@@ -487,7 +575,7 @@ struct b200aabb_tree {
     uint64_t tree_cap = 0;
     int opt_ray_kernel = 0;        // first_intersection: 0 = one thread per ray, 1 = persistent threads with ray replacement (B200AABB_OPT_RAY_KERNEL)
     unsigned long long* d_ray_cursor = nullptr;   // [kScratchSlots]
-    int ray_grid = 0;
+    int ray_grid = 0, seg_grid = 0;
     int opt_classic_build = 0;     // 1: hierarchy_kernel for every node + refit_local_kernel instead of the fused bottom-up kernel (the fallback of a full frontier; test hook, option 103)
     int last_build_classic = 0;
     uint32_t root = kNone;
@@ -926,6 +1014,19 @@ unsigned grid_for(uint64_t n, int block) { return (unsigned)((n + block - 1) / b
 template <int MODE>
 static void launch_intersect(b200aabb_tree* t, int kind, cudaStream_t st, const double* in, uint64_t cnt, const uint32_t* perm, uint8_t* out8, uint32_t* out32,
                              const uint64_t* offsets, uint32_t* list) {
+    if constexpr (MODE != kList) {
+        if (t->opt_ray_kernel == 1 && t->n >= 2 && kind != B200AABB_PLANE && t->d_ray_cursor) {
+            unsigned long long* cursor = t->d_ray_cursor + (st == t->s_run ? kHostScratch : kDeviceScratch);   // (HOST batches run on s_run, DEVICE batches on the caller's stream)
+            cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st);
+            const unsigned sgrid = (unsigned)std::min<uint64_t>((uint64_t)t->seg_grid, (cnt + 127) / 128);
+            switch (kind) {
+                case B200AABB_RAY: intersect_stream_kernel<kRayQ, MODE><<<sgrid, 128, 0, st>>>(tree_ref(t, perm), in, cnt, cursor, out8, out32); break;
+                case B200AABB_LINE: intersect_stream_kernel<kLineQ, MODE><<<sgrid, 128, 0, st>>>(tree_ref(t, perm), in, cnt, cursor, out8, out32); break;
+                default: intersect_stream_kernel<kSegmentQ, MODE><<<sgrid, 128, 0, st>>>(tree_ref(t, perm), in, cnt, cursor, out8, out32); break;
+            }
+            return;
+        }
+    }
     const unsigned grid = grid_for(cnt, 128);
     switch (kind) {
         case B200AABB_RAY: intersect_kernel<kRayQ, MODE><<<grid, 128, 0, st>>>(tree_ref(t, perm), in, cnt, out8, out32, offsets, list); break;
@@ -997,6 +1098,8 @@ int b200aabb_create(int device, b200aabb_tree** out) {
         int per_sm = 0;
         ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, first_intersection_stream_kernel, 128, 0) == cudaSuccess;
         t->ray_grid = std::max(1, per_sm) * prop.multiProcessorCount;
+        ok = ok && cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, intersect_stream_kernel<kSegmentQ, kAnyHit>, 128, 0) == cudaSuccess;
+        t->seg_grid = std::max(1, per_sm) * prop.multiProcessorCount;
     }
     if (!ok) { b200aabb_destroy(t); return B200AABB_ERR_CUDA; }
     t->built = true;   // an empty tree needs no build

@@ -802,3 +802,16 @@ def test_ray_kernels_agree(B, meshes):
             np.testing.assert_array_equal(a[k], d[k].cpu().numpy().view(a[k].dtype))          # (torch has no uint32: the device ids come back as int32)
         assert (sa["nodes_visited"], sa["leaves_tested"], sa["ties"]) == (sb["nodes_visited"], sb["leaves_tested"], sb["ties"])
         tree.set_option(OPT_RAY_KERNEL, 0)
+    # the same scheduling for do_intersect / counts / any_intersected_primitive (intersect_stream_kernel): Segment_3, Ray_3 and Line_3 queries
+    segs = W.bbox_segments(g.bbox(), 50_000)
+    lines = np.concatenate([segs[:, :3], segs[:, 3:] - segs[:, :3]], 1)
+    for kind, q in ((B.SEGMENT, segs), (B.RAY, segs), (B.LINE, lines)):
+        g.set_option(OPT_RAY_KERNEL, 0)
+        want = (g.do_intersect(q, kind), g.number_of_intersected_primitives(q, kind))
+        g.set_option(OPT_RAY_KERNEL, 1)
+        np.testing.assert_array_equal(g.do_intersect(q, kind), want[0])
+        np.testing.assert_array_equal(g.number_of_intersected_primitives(q, kind), want[1])
+        np.testing.assert_array_equal(g.number_of_intersected_primitives(torch.from_numpy(q).cuda(), kind).cpu().numpy().view(np.uint32), want[1])
+        a = g.any_intersected_primitive(q, kind)
+        np.testing.assert_array_equal(a == B.NO_PRIMITIVE, want[1] == 0)
+        g.set_option(OPT_RAY_KERNEL, 0)
