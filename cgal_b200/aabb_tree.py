@@ -12,7 +12,7 @@ import numpy as np
 SEGMENT, RAY, LINE, PLANE = 0, 1, 2, 3      # LINE: (point, direction vector) per query; PLANE: (a, b, c, d)
 FLAG_HIT, FLAG_SEGMENT, FLAG_TIE, FLAG_EXACT, FLAG_NEAR_TIE, FLAG_TRIANGLE = 1, 2, 4, 8, 16, 32
 OPT_SORT_QUERIES = 1
-OPT_CLOSEST_KERNEL = 2    # 1 = warp-cooperative work pool (default), 2 = lane pairs with private stacks, 0 = one thread per query
+OPT_CLOSEST_KERNEL = 2    # 1 = warp-cooperative work pool (default), 2 = lane pairs with private stacks, 3 = two passes (binary32 filter + exact resolve), 0 = one thread per query
 OPT_WARP_EXACT_GO = 4
 OPT_HOST_PARTS = 5
 OPT_ASYNC_HOST = 6

@@ -589,7 +589,8 @@ struct b200aabb_tree {
     int opt_host_parts = 0;        // B200AABB_OPT_HOST_PARTS (0 = automatic)
     int opt_debug_refit_frontier = kRefitFrontierPerBlock;   // test hook (option 101): frontier entries per block of the refit (0: every hand-over overflows)
     // warp-cooperative closest_point: per pipeline slot a batch cursor and the pools' spill area; grid = SMs x resident warps
-    struct WarpScratch { unsigned long long* cursor = nullptr; uint2* spill = nullptr; WarpSlots64* slots64 = nullptr; } warp[kScratchSlots];
+    struct WarpScratch { unsigned long long* cursor = nullptr; uint2* spill = nullptr; WarpSlots64* slots64 = nullptr;
+                         uint32_t* fc_cand = nullptr; uint8_t* fc_ncand = nullptr; uint32_t* fc_overflow = nullptr; unsigned long long* fc_count = nullptr; uint64_t fc_cap = 0; } warp[kScratchSlots];   // fc_*: the two-pass kernels (closest_filter_kernel)
     int warp_grid = 0;
     int pair_grid = 0;             // grid of closest_point_pair_kernel (closest_pair.cuh); it shares the scratch of the pool kernel
     // query coherence sort scratch, one per pipeline slot (slot 0 also serves DEVICE-pointer batches); grow-only
@@ -664,7 +665,8 @@ int ensure_stage(b200aabb_tree* t, int slot, size_t in_bytes, size_t out_bytes) 
 }
 
 void free_warp(b200aabb_tree* t) {
-    for (auto& w : t->warp) { cudaFree(w.cursor); cudaFree(w.spill); cudaFree(w.slots64); w = b200aabb_tree::WarpScratch(); }
+    for (auto& w : t->warp) { cudaFree(w.cursor); cudaFree(w.spill); cudaFree(w.slots64); cudaFree(w.fc_cand); cudaFree(w.fc_ncand); cudaFree(w.fc_overflow); cudaFree(w.fc_count);
+                              w = b200aabb_tree::WarpScratch(); }
 }
 int ensure_warp(b200aabb_tree* t, int slot) {
     if (t->warp_grid == 0) {
@@ -685,6 +687,19 @@ int ensure_warp(b200aabb_tree* t, int slot) {
     if (!w.cursor) B2_CUDA(t, cudaMalloc(&w.cursor, sizeof(unsigned long long)));
     if (!w.spill) B2_CUDA(t, cudaMalloc(&w.spill, grid * kWpSpillCap * sizeof(uint2)));
     if (!w.slots64) B2_CUDA(t, cudaMalloc(&w.slots64, grid * sizeof(WarpSlots64)));
+    return B200AABB_OK;
+}
+
+int ensure_filter(b200aabb_tree* t, int slot, uint64_t n) {      // candidate lists of the two-pass closest_point kernels (grow only)
+    auto& w = t->warp[slot];
+    if (n <= w.fc_cap) return B200AABB_OK;
+    cudaFree(w.fc_cand); cudaFree(w.fc_ncand); cudaFree(w.fc_overflow); cudaFree(w.fc_count);
+    w.fc_cand = nullptr; w.fc_ncand = nullptr; w.fc_overflow = nullptr; w.fc_count = nullptr; w.fc_cap = 0;
+    B2_CUDA(t, cudaMalloc(&w.fc_cand, n * kFcCand * 4));
+    B2_CUDA(t, cudaMalloc(&w.fc_ncand, n));
+    B2_CUDA(t, cudaMalloc(&w.fc_overflow, n * 4));
+    B2_CUDA(t, cudaMalloc(&w.fc_count, sizeof(unsigned long long)));
+    w.fc_cap = n;
     return B200AABB_OK;
 }
 
@@ -1130,7 +1145,7 @@ int b200aabb_set_option(b200aabb_tree* t, int option, int64_t value) { B2_LOCK(t
     if (!t) return B200AABB_ERR_INVALID_ARGUMENT;
     switch (option) {
         case B200AABB_OPT_SORT_QUERIES: t->opt_sort_queries = value != 0; return B200AABB_OK;
-        case B200AABB_OPT_CLOSEST_KERNEL: t->opt_closest_kernel = (int)std::min<int64_t>(2, std::max<int64_t>(0, value)); return B200AABB_OK;
+        case B200AABB_OPT_CLOSEST_KERNEL: t->opt_closest_kernel = (int)std::min<int64_t>(3, std::max<int64_t>(0, value)); return B200AABB_OK;
         case B200AABB_OPT_ASYNC_HOST: t->opt_async_host = value != 0; return B200AABB_OK;
         case B200AABB_OPT_RAY_KERNEL: t->opt_ray_kernel = value != 0; return B200AABB_OK;
         case B200AABB_OPT_HOST_PARTS: t->opt_host_parts = (int)std::min<int64_t>(64, std::max<int64_t>(0, value)); return B200AABB_OK;
@@ -1573,6 +1588,8 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
     // the warp-cooperative kernel packs (query slot, node / leaf) in 32 bits and needs an internal root
     const bool warp_kernel = t->opt_closest_kernel >= 1 && t->n >= 2 && t->n <= kWpMaxPrims;
     if (warp_kernel) { for (int s = 0; s < kScratchSlots; ++s) { rc = ensure_warp(t, s); if (rc) return rc; } }
+    const bool two_pass = warp_kernel && t->opt_closest_kernel == 3 && n < (1ull << 32);
+    if (two_pass) { rc = ensure_filter(t, space == B200AABB_HOST ? kHostScratch : kDeviceScratch, space == B200AABB_HOST ? std::min<uint64_t>(n, kPointChunkMax) : n); if (rc) return rc; }
     return run_batch(t, pts, 24, n, space, kPointQuery, {{cp, 24, 0}, {prim, 4, 0}, {sqd, 8, 0}, {flags, 1, 0}},
                      [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
                          if (!warp_kernel || cnt >= (1ull << 32)) {
@@ -1581,7 +1598,28 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
                          }
                          const int slot = space == B200AABB_HOST ? kHostScratch : kDeviceScratch;
                          cudaMemsetAsync(t->warp[slot].cursor, 0, sizeof(unsigned long long), st);
-                         if (t->opt_closest_kernel >= 2) {
+                         if (two_pass && cnt <= t->warp[slot].fc_cap) {
+                             // pass 1 (binary32 filter) -> pass 2 (exact resolve) -> the pool kernel for the queries whose candidate list overflowed
+                             auto& w = t->warp[slot];
+                             FilterClosestArgs f;
+                             f.nodes = t->d_nodes; f.tris = t->d_tris; f.trisf = t->d_trisf; f.root = t->root; f.mag = t->mag; f.perm = perm; f.counters = t->d_counters;
+                             f.pts = (const double*)in; f.n = cnt; f.cand = w.fc_cand; f.ncand = w.fc_ncand; f.overflow = w.fc_overflow; f.overflow_count = w.fc_count;
+                             f.cp = (double*)o[0]; f.prim = (uint32_t*)o[1]; f.sqd = (double*)o[2]; f.flags = (uint8_t*)o[3];
+                             f.flag_tie = B200AABB_FLAG_TIE; f.flag_exact = B200AABB_FLAG_EXACT;
+                             cudaMemsetAsync(w.fc_count, 0, sizeof(unsigned long long), st);
+                             closest_filter_kernel<<<grid_for(cnt, 128), 128, 0, st>>>(f);
+                             closest_resolve_kernel<<<grid_for(cnt, 128), 128, 0, st>>>(f);
+                             WarpClosestArgs a;
+                             a.nodes = t->d_nodes; a.tris = t->d_tris; a.trisf = t->d_trisf; a.mag = t->mag; a.perm = w.fc_overflow; a.counters = t->d_counters;
+                             a.pts = (const double*)in; a.n = cnt; a.n_dev = w.fc_count; a.cp = f.cp; a.prim = f.prim; a.sqd = f.sqd; a.flags = f.flags;
+                             a.cursor = w.cursor; a.spill = w.spill; a.slots64 = w.slots64;
+                             a.exact_go = t->opt_warp_exact_go > 0 ? t->opt_warp_exact_go : 160;
+                             a.flag_tie = B200AABB_FLAG_TIE; a.flag_exact = B200AABB_FLAG_EXACT;
+                             closest_point_warp_kernel<<<(unsigned)std::min<uint64_t>((uint64_t)t->warp_grid, (cnt + 31) / 32), 32, 0, st>>>(a);
+                             t->stats.kernel_launches += 2;
+                             return;
+                         }
+                         if (t->opt_closest_kernel == 2) {
                              PairClosestArgs a;
                              a.nodes = t->d_nodes; a.tris = t->d_tris; a.trisf = t->d_trisf; a.mag = t->mag; a.perm = perm; a.counters = t->d_counters;
                              a.pts = (const double*)in; a.n = cnt; a.cp = (double*)o[0]; a.prim = (uint32_t*)o[1]; a.sqd = (double*)o[2]; a.flags = (uint8_t*)o[3];
@@ -1595,7 +1633,7 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
                          WarpClosestArgs a;
                          a.nodes = t->d_nodes; a.tris = t->d_tris; a.trisf = t->d_trisf; a.mag = t->mag; a.perm = perm; a.counters = t->d_counters;
                          a.pts = (const double*)in; a.n = cnt; a.cp = (double*)o[0]; a.prim = (uint32_t*)o[1]; a.sqd = (double*)o[2]; a.flags = (uint8_t*)o[3];
-                         a.cursor = t->warp[slot].cursor; a.spill = t->warp[slot].spill; a.slots64 = t->warp[slot].slots64;
+                         a.cursor = t->warp[slot].cursor; a.spill = t->warp[slot].spill; a.slots64 = t->warp[slot].slots64; a.n_dev = nullptr;
                          a.exact_go = t->opt_warp_exact_go > 0 ? t->opt_warp_exact_go : 160;
                          a.flag_tie = B200AABB_FLAG_TIE; a.flag_exact = B200AABB_FLAG_EXACT;
                          const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)t->warp_grid, (cnt + 31) / 32);

@@ -91,6 +91,7 @@ struct WarpClosestArgs {
     unsigned long long* cursor;    // next position of the batch to hand out (zeroed before the launch)
     uint2* spill;                  // gridDim.x * kWpSpillCap entries
     WarpSlots64* slots64;          // gridDim.x records
+    const unsigned long long* n_dev; // when not null: the number of queries is read from here (the overflow list of closest_filter_kernel)
     int exact_go;                  // run the exact phase when at least this many pairs wait (1 .. kWpExactCap - 32)
     uint32_t flag_tie, flag_exact;
 };
@@ -229,6 +230,7 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
     const unsigned lane = threadIdx.x;
     const unsigned full = 0xFFFFFFFFu;
     const unsigned lt = (1u << lane) - 1u;
+    const unsigned long long total = a.n_dev ? *a.n_dev : a.n;
     uint2* const myspill = a.spill + (size_t)blockIdx.x * kWpSpillCap;
     WarpSlots64& G = a.slots64[blockIdx.x];
     const float ev = float_above(a.mag * 5.9604645e-8 * 1.000001);   // >= rounding of a vertex coordinate to binary32
@@ -281,9 +283,9 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
             unsigned long long base = 0;
             if (lane == 0) base = atomicAdd(a.cursor, 32ull);
             base = __shfl_sync(full, base, 0);
-            if (base >= a.n) break;
+            if (base >= total) break;
             const unsigned long long pos = base + lane;
-            const bool valid = pos < a.n;
+            const bool valid = pos < total;
             Vec3 o = {0.0, 0.0, 0.0};
             float4 q = make_float4(0.0f, 0.0f, 0.0f, INFINITY);
             uint32_t qi = 0;
@@ -552,6 +554,169 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
         atomicAdd(&a.counters[6], (unsigned long long)(w_leaves - w_evals));   // leaves that never reached the binary64 projection
         if (w_exact) atomicAdd(&a.counters[0], (unsigned long long)w_exact);
         if (w_ties) atomicAdd(&a.counters[1], (unsigned long long)w_ties);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// closest_point in TWO PASSES (B200AABB_OPT_CLOSEST_KERNEL = 3).
+//   closest_filter_kernel   one thread per query, binary32 only: the traversal of the pool kernel's stages (A), (B1), (B2) — same rigorous bounds, wp_box_sqdist /
+//                           wp_lower / wp_sharp — with a private stack and NO binary64 work: the ball shrinks with the rigorous upper bounds alone, and every
+//                           primitive whose lower bound stays inside the final ball is a CANDIDATE (at most kFcCand kept; more = the query is handed to the pool kernel)
+//   closest_resolve_kernel  one thread per query: the reference's projection on each candidate (binary64) and the exact comparison; winner = smallest exact distance,
+//                           ties -> smallest primitive id + FLAG_TIE, as everywhere
+// Every primitive that attains the minimum has a true distance <= the final radius, so its lower bound is inside the ball at every moment: it is a candidate.
+// Why: the pool kernel spends ~180 thread instructions per (query, node / leaf) pair, most of them warp-wide bookkeeping of its pools (profiles/r2_17); a private
+// traversal in binary32 needs ~50, and without the binary64 stage in the loop its warps no longer diverge between cheap and expensive phases (what made the
+// thread-per-query kernel of round 1 run with 5 of 32 lanes, profiles/r1_03).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kFcCand = 8;
+constexpr uint8_t kFcOverflow = 255;
+struct FilterClosestArgs {
+    const BvhNode* nodes; const TriRec* tris; const TriF* trisf; uint32_t root; double mag;
+    const uint32_t* perm; unsigned long long* counters; const double* pts; uint64_t n;
+    uint32_t* cand;                // n x kFcCand leaf slots
+    uint8_t* ncand;                // per query: candidates kept, or kFcOverflow
+    uint32_t* overflow;            // queries handed to the pool kernel
+    unsigned long long* overflow_count;
+    double* cp; uint32_t* prim; double* sqd; uint8_t* flags;
+    uint32_t flag_tie, flag_exact;
+};
+
+__global__ void __launch_bounds__(128, 6) closest_filter_kernel(const FilterClosestArgs a) {
+    const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned v_nodes = 0, v_leaves = 0, v_culled = 0;
+    if (slot < a.n) {
+        const uint64_t qi = a.perm ? a.perm[slot] : slot;
+        const double* p = a.pts + 3 * qi;
+        const Vec3 o = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+        float4 q = make_float4((float)o.x, (float)o.y, (float)o.z, INFINITY);
+        const double ex = o.x - (double)q.x, ey = o.y - (double)q.y, ez = o.z - (double)q.z;
+        const float perr = float_above(sqrt((ex * ex + ey * ey) + ez * ez) * 1.0000001) + 1e-37f;
+        const double delta = 4e-16 * fmax(a.mag, fmax3(fabs(o.x), fabs(o.y), fabs(o.z)));
+        const float dslack = float_above(2.0 * delta) + 1e-37f;
+        const float ev = float_above(a.mag * 5.9604645e-8 * 1.000001);
+        const float e2 = __fadd_ru(__fmul_ru(1.7320509f, ev), perr);
+        float rbound = INFINITY;
+        uint32_t cl[kFcCand];
+        float clb[kFcCand];
+        int nc = 0;
+        bool ovf = false;
+        uint32_t sref[kStackCap];
+        float sd[kStackCap];
+        int sp = 0, np = 0;
+        uint32_t pend[4];
+        uint32_t cur = a.root;
+        if (cur & kLeafBit) { pend[np++] = cur; cur = kNone; }
+        while (true) {
+            while (cur != kNone && np < 3) {                             // node phase: stage (A) of the pool kernel
+                const NodeView nd = load_node(a.nodes, cur);
+                ++v_nodes;
+                float d0 = wp_box_sqdist(nd.lo0, nd.hi0, q), d1 = wp_box_sqdist(nd.lo1, nd.hi1, q);
+                uint32_t c0 = nd.c0, c1 = nd.c1;
+                if (d1 < d0) { const uint32_t tc = c0; c0 = c1; c1 = tc; const float td = d0; d0 = d1; d1 = td; }
+                uint32_t next = kNone;
+                if (d0 <= q.w) { if (c0 & kLeafBit) pend[np++] = c0; else next = c0; }
+                if (d1 <= q.w) {
+                    if (c1 & kLeafBit) pend[np++] = c1;
+                    else if (next == kNone) next = c1;
+                    else if (sp < kStackCap) { sref[sp] = c1; sd[sp] = d1; ++sp; }
+                    else ovf = true;                                     // (deeper than any tree this library builds: the pool kernel answers the query)
+                }
+                while (next == kNone && sp > 0) {
+                    --sp;
+                    if (sd[sp] <= q.w) next = sref[sp];
+                }
+                cur = next;
+            }
+            for (int k = 0; k < np; ++k) {                               // leaf phase: stages (B1) and (B2)
+                const uint32_t leaf = pend[k] & ~kLeafBit;
+                ++v_leaves;
+                const RelTri r = wp_relative(a.trisf, leaf, q);
+                const float g[3] = {(r.ra[0] + r.rb[0]) + r.rc[0], (r.ra[1] + r.rb[1]) + r.rc[1], (r.ra[2] + r.rb[2]) + r.rc[2]};
+                const float lb1 = wp_lower(g, sqrtf(dot3f(g, g)), r) - e2;
+                if (lb1 > rbound) { ++v_culled; continue; }
+                float lb, hi;
+                wp_sharp(r, dslack, e2, &lb, &hi);
+                if (hi < rbound) { rbound = hi; const float rr = __fadd_ru(rbound, perr); q.w = __fmul_ru(rr, rr); }
+                lb = fmaxf(lb, lb1);
+                if (lb > rbound) { ++v_culled; continue; }
+                if (nc == kFcCand) {                                     // full: drop the candidates the ball has left behind
+                    int m = 0;
+                    for (int j = 0; j < kFcCand; ++j) if (!(clb[j] > rbound)) { cl[m] = cl[j]; clb[m] = clb[j]; ++m; }
+                    nc = m;
+                }
+                if (nc == kFcCand) ovf = true; else { cl[nc] = leaf; clb[nc] = lb; ++nc; }
+            }
+            np = 0;
+            if (ovf) break;
+            if (cur == kNone) {
+                while (cur == kNone && sp > 0) {
+                    --sp;
+                    if (sd[sp] <= q.w) cur = sref[sp];
+                }
+                if (cur == kNone) break;
+            }
+        }
+        if (ovf) {
+            a.ncand[qi] = kFcOverflow;
+            a.overflow[atomicAdd(a.overflow_count, 1ull)] = (uint32_t)qi;
+        } else {
+            int m = 0;
+            for (int j = 0; j < nc; ++j) if (!(clb[j] > rbound)) a.cand[qi * kFcCand + m++] = cl[j];
+            a.ncand[qi] = (uint8_t)m;
+        }
+    }
+    const unsigned full = 0xFFFFFFFFu;
+    const unsigned nodes = __reduce_add_sync(full, v_nodes), leaves = __reduce_add_sync(full, v_leaves), culled = __reduce_add_sync(full, v_culled);
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&a.counters[3], (unsigned long long)nodes);
+        atomicAdd(&a.counters[4], (unsigned long long)leaves);
+        atomicAdd(&a.counters[6], (unsigned long long)culled);
+    }
+}
+
+__global__ void __launch_bounds__(128) closest_resolve_kernel(const FilterClosestArgs a) {
+    const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool tie = false, exact = false;
+    if (slot < a.n) {
+        const uint64_t qi = a.perm ? a.perm[slot] : slot;
+        const int nc = a.ncand[qi];
+        if (nc != kFcOverflow) {
+            const double* p = a.pts + 3 * qi;
+            const Vec3 o = {__ldg(p), __ldg(p + 1), __ldg(p + 2)};
+            Vec3 bp = o;
+            double bsqd = 0.0;
+            uint32_t bid = kNone;
+            for (int j = 0; j < nc; ++j) {
+                uint32_t id;
+                const Tri3 t = load_tri(a.tris, a.cand[qi * kFcCand + j], id);
+                const CandOut co = wp_candidate(t.a.x, t.a.y, t.a.z, t.b.x, t.b.y, t.b.z, t.c.x, t.c.y, t.c.z, o.x, o.y, o.z);
+                exact |= co.nexact != 0;
+                const Vec3 cpt = {co.x, co.y, co.z};
+                bool take = bid == kNone;
+                if (!take) {
+                    int nexact = 0;
+                    const int sg = cmp_dist(o, cpt, bp, nexact);
+                    exact |= nexact != 0;
+                    if (sg == 0) { tie = true; take = id < bid; }
+                    else if (sg < 0) { tie = false; take = true; }
+                }
+                if (take) {
+                    const Vec3 v = cpt - o;
+                    bp = cpt; bid = id; bsqd = (v.x * v.x + v.y * v.y) + v.z * v.z;   // Compute_squared_distance_3(query, closest): AABB_tree.h:1024-1032
+                }
+            }
+            if (a.cp) { a.cp[3 * qi] = bp.x; a.cp[3 * qi + 1] = bp.y; a.cp[3 * qi + 2] = bp.z; }
+            if (a.prim) a.prim[qi] = bid;
+            if (a.sqd) a.sqd[qi] = bsqd;
+            if (a.flags) a.flags[qi] = (uint8_t)((tie ? a.flag_tie : 0u) | (exact ? a.flag_exact : 0u));
+        } else { tie = false; exact = false; }
+    }
+    const unsigned full = 0xFFFFFFFFu;
+    const unsigned ties = __reduce_add_sync(full, tie ? 1u : 0u), exacts = __reduce_add_sync(full, exact ? 1u : 0u);
+    if ((threadIdx.x & 31) == 0) {
+        if (ties) atomicAdd(&a.counters[1], (unsigned long long)ties);
+        if (exacts) atomicAdd(&a.counters[0], (unsigned long long)exacts);
     }
 }
 

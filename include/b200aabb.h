@@ -71,6 +71,8 @@ enum {
   B200AABB_OPT_CLOSEST_KERNEL = 2, /* closest_point scheduling: 1 (default) = warp-cooperative work pool (32 query slots per persistent warp, pooled
                                       (slot,node)/(slot,leaf) pairs, closest_warp.cuh); 2 = lane pairs walk the tree with private stacks
                                       (closest_pair.cuh; measured slower on the benchmark, kept as the reference point of that design);
+                                      3 = two passes: a binary32-only traversal per thread that keeps the candidates inside the final ball, then the
+                                      exact projection and comparison of the candidates (2.7x slower: its warps diverge; kept for the same reason);
                                       0 = one thread per query.  Same results. */
   B200AABB_OPT_HOST_PARTS = 5,     /* HOST-pointer batches are cut into about this many chunks (each 256 Ki .. 4 Mi rays / segments, .. 16 Mi points) that flow
                                       through an upload -> sort -> traverse -> download pipeline (1..64; 0 = default: 8 for ray / segment batches on

@@ -170,7 +170,7 @@ def test_chain_shaped_tree_depth(B):
     g, o = B.AABB_tree(triangles=tri), orc.OracleTree(soup=tri)
     rng = np.random.default_rng(4)
     pts = np.concatenate([rng.uniform(-2, 40, (3000, 3)), rng.uniform(-2, 2.0 ** 21, (1000, 3))])
-    for kernel in (1, 2, 0):
+    for kernel in (1, 2, 3, 0):
         g.set_option(B.OPT_CLOSEST_KERNEL, kernel)
         check_closest_point(g.closest_point_and_primitive(pts), o.closest_point(pts), o, pts)
         g.stats()                      # raises if the batch reported an incomplete traversal
@@ -306,7 +306,7 @@ def test_closest_point_kernels_agree(B, exact_go, sort):
     g.set_option(B.OPT_SORT_QUERIES, sort)
     g.set_option(B.OPT_CLOSEST_KERNEL, 0)
     ref = g.closest_point_and_primitive(pts)
-    for kernel in (1, 2):            # the work-pool kernel and the lane-pair kernel (closest_pair.cuh)
+    for kernel in (1, 2, 3):         # the work-pool kernel, the lane-pair kernel (closest_pair.cuh) and the two-pass kernels (binary32 filter + exact resolve)
         g.set_option(B.OPT_CLOSEST_KERNEL, kernel)
         g.set_option(B.OPT_WARP_EXACT_GO, min(exact_go, 128) if kernel == 2 else exact_go)
         got = g.closest_point_and_primitive(pts)
@@ -326,7 +326,7 @@ def test_closest_point_kernels_agree(B, exact_go, sort):
     assert list(r2["prim"]) == [0, 1, 0] and r2["flags"][2] & B.FLAG_TIE and not (r2["flags"][0] & B.FLAG_TIE)
 
 
-@pytest.mark.parametrize("kernel", [1, 2, 0])
+@pytest.mark.parametrize("kernel", [1, 2, 3, 0])
 def test_closest_point_adversarial_inputs(B, kernel):
     """inputs that stress the binary32 pruning aids of closest_point (they may only ever fail to prune): degenerate and needle
     triangles, thousands of coincident primitives (exact ties), coordinates far from the origin (binary32 copies useless),
