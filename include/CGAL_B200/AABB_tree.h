@@ -229,6 +229,13 @@ class AABB_tree {
     for (const auto& x : r[0]) *out++ = x;
     return out;
   }
+  template <typename Query, typename OutputIterator, typename = std::enable_if_t<!std::is_same<Query, Ray>::value && !std::is_same<Query, Segment>::value>>
+  OutputIterator all_intersections(const Query& query, OutputIterator out) const {            // Line_3 and Plane_3 queries
+    std::vector<std::vector<typename Intersection_and_primitive_id<Query>::Type>> r;
+    all_intersections(&query, &query + 1, std::back_inserter(r));
+    for (const auto& x : r[0]) *out++ = x;
+    return out;
+  }
   Ray_intersection any_intersection(const Ray& query) const {
     Ray_intersection r;
     any_intersection(&query, &query + 1, &r);
@@ -345,12 +352,11 @@ class AABB_tree {
   // out receives std::optional< Intersection_and_primitive_id<Query>::Type >, Query = Ray_3 or Segment_3 (the range's value type)
   template <typename RayIterator, typename OutputIterator>
   OutputIterator any_intersection(RayIterator first, RayIterator beyond, OutputIterator out) const {
-    typedef typename std::iterator_traits<RayIterator>::value_type Query;
-    static_assert(std::is_same<Query, Ray>::value || std::is_same<Query, Segment>::value, "intersection objects: Ray_3 and Segment_3 queries");
+    typedef typename std::iterator_traits<RayIterator>::value_type Query;     // Ray_3, Segment_3, Line_3 or Plane_3 (kind_of)
     typedef typename Intersection_and_primitive_id<Query>::Type Result;
     typedef typename Result::first_type Intersection;
     std::vector<double> q = pack_lines(first, beyond);
-    const uint64_t n = q.size() / 6;
+    const uint64_t n = q.size() / doubles_per_query<Query>();
     std::vector<uint32_t> prim(n);
     std::vector<double> p0(3 * n), p1(3 * n);
     std::vector<uint8_t> fl(n);
@@ -359,7 +365,8 @@ class AABB_tree {
     for (uint64_t i = 0; i < n; ++i) {
       if (!(fl[i] & B200AABB_FLAG_HIT)) { *out++ = std::nullopt; continue; }
       const Point a(FT(p0[3 * i]), FT(p0[3 * i + 1]), FT(p0[3 * i + 2]));
-      if (fl[i] & B200AABB_FLAG_SEGMENT) *out++ = Result(Intersection(Segment(a, Point(FT(p1[3 * i]), FT(p1[3 * i + 1]), FT(p1[3 * i + 2])))), m_primitives[prim[i]].id());
+      if (fl[i] & B200AABB_FLAG_TRIANGLE) *out++ = Result(triangle_object<Intersection>(prim[i]), m_primitives[prim[i]].id());
+      else if (fl[i] & B200AABB_FLAG_SEGMENT) *out++ = Result(Intersection(Segment(a, Point(FT(p1[3 * i]), FT(p1[3 * i + 1]), FT(p1[3 * i + 2])))), m_primitives[prim[i]].id());
       else *out++ = Result(Intersection(a), m_primitives[prim[i]].id());
     }
     return out;
@@ -367,12 +374,11 @@ class AABB_tree {
   // out receives one std::vector< Intersection_and_primitive_id<Query>::Type > per query (count pass -> prefix sums -> fill pass)
   template <typename RayIterator, typename OutputIterator>
   OutputIterator all_intersections(RayIterator first, RayIterator beyond, OutputIterator out) const {
-    typedef typename std::iterator_traits<RayIterator>::value_type Query;
-    static_assert(std::is_same<Query, Ray>::value || std::is_same<Query, Segment>::value, "intersection objects: Ray_3 and Segment_3 queries");
+    typedef typename std::iterator_traits<RayIterator>::value_type Query;     // Ray_3, Segment_3, Line_3 or Plane_3 (kind_of)
     typedef typename Intersection_and_primitive_id<Query>::Type Result;
     typedef typename Result::first_type Intersection;
     std::vector<double> q = pack_lines(first, beyond);
-    const uint64_t n = q.size() / 6;
+    const uint64_t n = q.size() / doubles_per_query<Query>();
     std::vector<uint32_t> cnt(n);
     ensure_built();
     check(b200aabb_number_of_intersections_q(m_handle, q.data(), n, kind_of<Query>(), B200AABB_HOST, cnt.data()));
@@ -387,7 +393,8 @@ class AABB_tree {
       std::vector<Result> v;
       for (uint64_t k = off[i]; k < off[i + 1]; ++k) {
         const Point a(FT(pts[6 * k]), FT(pts[6 * k + 1]), FT(pts[6 * k + 2]));
-        if (kinds[k] == 2) v.push_back(Result(Intersection(Segment(a, Point(FT(pts[6 * k + 3]), FT(pts[6 * k + 4]), FT(pts[6 * k + 5])))), m_primitives[ids[k]].id()));
+        if (kinds[k] == 3) v.push_back(Result(triangle_object<Intersection>(ids[k]), m_primitives[ids[k]].id()));
+        else if (kinds[k] == 2) v.push_back(Result(Intersection(Segment(a, Point(FT(pts[6 * k + 3]), FT(pts[6 * k + 4]), FT(pts[6 * k + 5])))), m_primitives[ids[k]].id()));
         else v.push_back(Result(Intersection(a), m_primitives[ids[k]].id()));
       }
       *out++ = v;
@@ -585,6 +592,13 @@ class AABB_tree {
       static_assert(has_line_interface<Query>::value, "offloaded intersection queries: Segment_3, Ray_3, Line_3 and Plane_3");
       return B200AABB_LINE;
     }
+  }
+  // the object of a Plane_3 query that contains the whole primitive: the primitive's Triangle_3, when the traits' intersection type can hold one
+  template <typename Intersection>
+  Intersection triangle_object(uint32_t index) const {
+    typedef std::decay_t<decltype(datum(m_primitives[index]))> Triangle;
+    if constexpr (std::is_constructible<Intersection, Triangle>::value) return Intersection(datum(m_primitives[index]));
+    else throw Error(B200AABB_ERR_INVALID_ARGUMENT, "the intersection is the primitive's Triangle_3, which this traits' Intersection_and_primitive_id type cannot hold");
   }
   template <typename Query>
   static constexpr uint64_t doubles_per_query() { return kind_of<Query>() == B200AABB_PLANE ? 4 : 6; }

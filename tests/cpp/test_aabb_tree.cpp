@@ -86,6 +86,18 @@ static int known_answers() {
     CHECK(std::holds_alternative<Point>(hit->first) && std::get<Point>(hit->first) == Point(0.2, 0.2, 0.0));
     CHECK(tree.first_intersected_primitive(up) && *tree.first_intersected_primitive(up) == mini::Face_index(0));
     CHECK(tree.number_of_intersected_primitives(up) == 2);
+    {   // intersection objects of Line_3 and Plane_3 queries
+      std::vector<Tree::Intersection_and_primitive_id<mini::Line_3>::Type> lo;
+      tree.all_intersections(mini::Line_3(Point(0.2, 0.2, 5.0), mini::Vector_3(0.0, 0.0, -1.0)), std::back_inserter(lo));
+      CHECK(lo.size() == 2 && std::holds_alternative<Point>(lo[0].first) && std::holds_alternative<Point>(lo[1].first));
+      std::vector<Tree::Intersection_and_primitive_id<mini::Plane_3>::Type> po;
+      tree.all_intersections(mini::Plane_3(0.0, 0.0, 1.0, -0.5), std::back_inserter(po));          // z = 1/2 cuts the three slanted faces in a segment each
+      CHECK(po.size() == 3 && std::holds_alternative<Segment>(po[0].first) && std::holds_alternative<Segment>(po[1].first) && std::holds_alternative<Segment>(po[2].first));
+      bool threw = false;                                                                           // the base plane contains face 0: a Triangle_3 object, which the stand-in
+      try { po.clear(); tree.all_intersections(mini::Plane_3(0.0, 0.0, 1.0, 0.0), std::back_inserter(po)); }   // traits' variant<Point_3, Segment_3> cannot hold
+      catch (const CGAL_B200::Error& e) { threw = e.code() == B200AABB_ERR_INVALID_ARGUMENT; }
+      CHECK(threw);
+    }
     {   // multi-GPU through the C++ class: replicate the tree with the library's NCCL communicator (two GPUs when there are two, else a world of one)
       b200aabb_tree* probe = nullptr;
       const bool two = b200aabb_create(1, &probe) == B200AABB_OK;
