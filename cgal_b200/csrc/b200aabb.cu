@@ -1829,11 +1829,13 @@ int bcast_prepare(b200aabb_comm* c, b200aabb_tree* t, int root, int mode, cudaSt
         if (t->imported && t->n == n && t->d_tris && t->d_trisf && (n < 2 || t->d_nodes)) return B200AABB_OK;   // a replica of the same size: refresh it in place
         return b200aabb_import_alloc(t, n);
     }
+    // (a handle that already holds inserted primitives of the same size — an earlier mode-1 replica — receives into its buffers: a re-build then allocates nothing)
+    if (!t->imported && t->n == n && n && t->d_soup && (h[1] != 0) == (t->d_ids != nullptr)) { t->built = false; t->bounds_valid = false; return B200AABB_OK; }
     int rc = b200aabb_clear(t);
     if (rc || n == 0) return rc;
     if (cudaMalloc(&t->d_soup, n * 72 + kSoupSlack) != cudaSuccess) return B200AABB_ERR_OUT_OF_MEMORY;
     if (h[1] && cudaMalloc(&t->d_ids, n * 4) != cudaSuccess) return B200AABB_ERR_OUT_OF_MEMORY;
-    t->n = n; t->built = false;
+    t->n = n; t->built = false; t->bounds_valid = false;
     return B200AABB_OK;
 }
 
@@ -1952,16 +1954,21 @@ int b200aabb_comm_broadcast_tree(b200aabb_comm* c, b200aabb_tree* t, int root, i
         if (rc) return rc;
         if (mode == 1 && t->n && !t->d_soup) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "mode 1 replicates the inserted primitives: the root holds none (imported tree)");
     }
-    B2_CUDA(t, cudaEventRecord(t->ev_a, st));
-    if ((rc = bcast_header(c, t, root, mode, st))) return rc;
-    if ((rc = bcast_prepare(c, t, root, mode, st))) return rc;
+    // (events of its own: the build that mode 1 runs on the receivers records the handle's ev_a / ev_b itself)
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    B2_CUDA(t, cudaEventCreate(&e0));
+    B2_CUDA(t, cudaEventCreate(&e1));
+    auto done = [&](int code) { cudaEventDestroy(e0); cudaEventDestroy(e1); return code; };
+    if (cudaEventRecord(e0, st) != cudaSuccess) return done(B200AABB_ERR_CUDA);
+    if ((rc = bcast_header(c, t, root, mode, st))) return done(rc);
+    if ((rc = bcast_prepare(c, t, root, mode, st))) return done(rc);
     uint64_t nbytes = 0;
-    if ((rc = bcast_payload(c, t, root, mode, st, &nbytes))) return rc;
-    if ((rc = bcast_finish(c, t, root, mode, st))) return rc;
-    B2_CUDA(t, cudaEventRecord(t->ev_b, st));
-    B2_CUDA(t, cudaStreamSynchronize(st));
-    if (c->rank != root && mode == 0) { rc = b200aabb_import_finish(t); if (rc) return rc; }
-    float f = 0; cudaEventElapsedTime(&f, t->ev_a, t->ev_b);
+    if ((rc = bcast_payload(c, t, root, mode, st, &nbytes))) return done(rc);
+    if ((rc = bcast_finish(c, t, root, mode, st))) return done(rc);
+    if (cudaEventRecord(e1, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return done(B200AABB_ERR_CUDA);
+    if (c->rank != root && mode == 0) { rc = b200aabb_import_finish(t); if (rc) return done(rc); }
+    float f = 0; cudaEventElapsedTime(&f, e0, e1);
+    done(0);
     if (ms) *ms = f;
     if (bytes) *bytes = nbytes;
     return B200AABB_OK;
@@ -1973,7 +1980,9 @@ int b200aabb_comm_broadcast_tree_all(b200aabb_comm** cs, b200aabb_tree** ts, int
     int rc = ensure_built(ts[root]);
     if (rc) return rc;
     if (mode == 1 && ts[root]->n && !ts[root]->d_soup) return fail(ts[root], B200AABB_ERR_INVALID_ARGUMENT, "mode 1 replicates the inserted primitives: the root holds none");
-    for (int i = 0; i < ndev; ++i) { cudaSetDevice(ts[i]->device); cudaEventRecord(ts[i]->ev_a, ts[i]->stream); }
+    std::vector<cudaEvent_t> e0(ndev, nullptr), e1(ndev, nullptr);     // (events of their own: mode 1's build records the handles' ev_a / ev_b)
+    struct Cleanup { std::vector<cudaEvent_t>&a, &b; b200aabb_tree** ts; ~Cleanup() { for (size_t i = 0; i < a.size(); ++i) { cudaSetDevice(ts[i]->device); if (a[i]) cudaEventDestroy(a[i]); if (b[i]) cudaEventDestroy(b[i]); } } } cleanup{e0, e1, ts};
+    for (int i = 0; i < ndev; ++i) { cudaSetDevice(ts[i]->device); if (cudaEventCreate(&e0[i]) != cudaSuccess || cudaEventCreate(&e1[i]) != cudaSuccess) return B200AABB_ERR_CUDA; cudaEventRecord(e0[i], ts[i]->stream); }
     nccl().GroupStart();
     for (int i = 0; i < ndev && !rc; ++i) { cudaSetDevice(ts[i]->device); rc = bcast_header(cs[i], ts[i], root, mode, ts[i]->stream); }
     if (nccl().GroupEnd() != ncclSuccess && !rc) rc = B200AABB_ERR_NCCL;
@@ -1988,10 +1997,10 @@ int b200aabb_comm_broadcast_tree_all(b200aabb_comm** cs, b200aabb_tree** ts, int
     double worst = 0;
     for (int i = 0; i < ndev; ++i) {
         cudaSetDevice(ts[i]->device);
-        cudaEventRecord(ts[i]->ev_b, ts[i]->stream);
+        cudaEventRecord(e1[i], ts[i]->stream);
         if (cudaStreamSynchronize(ts[i]->stream) != cudaSuccess) return B200AABB_ERR_CUDA;
         if (i != root && mode == 0) { rc = b200aabb_import_finish(ts[i]); if (rc) return rc; }
-        float f = 0; cudaEventElapsedTime(&f, ts[i]->ev_a, ts[i]->ev_b);
+        float f = 0; cudaEventElapsedTime(&f, e0[i], e1[i]);
         worst = std::max(worst, (double)f);
     }
     if (ms) *ms = worst;
