@@ -1,14 +1,17 @@
 // build.cuh — LBVH construction kernels (replace AABB_tree::build / expand, AABB_tree/include/CGAL/AABB_tree.h:787-853,
 // and Compute_bbox / Split_primitives, AABB_tree/include/CGAL/AABB_traits_3.h:596-654):
-//   gather_mesh_kernel   indexed Surface_mesh (points + per-face vertex indices) -> 9 doubles per primitive
-//   scene_bounds_kernel  bounding box of all primitives (exact: min/max only), one atomic per block and bound
-//   morton_kernel        63-bit Morton key (21 bits per axis) of each primitive's box centre in the scene box
-//   [radix_sort.cuh]     onesweep sort of (key, primitive index)
-//   emit_leaves_kernel   TriRec records (and their binary32 copies, TriF) in Morton order
-//   hierarchy_kernel     Karras 2012 radix-tree topology, one thread per internal node
-//   refit_local/global   bottom-up boxes with one arrival counter per node (shared memory inside a block of 256 leaves, global above).  A primitive's exact binary64 box is
-//                        rounded OUTWARD to binary32 once; min/max are exact and commute with the monotone rounding, so
-//                        every node box is bit-equal to the outward rounding of the exact union of its primitives' boxes
+//   gather_mesh_kernel   indexed Surface_mesh (points + per-face vertex indices) -> 9 doubles per primitive, + the scene bounds
+//   scene_bounds_kernel  bounding box of all primitives (exact: min/max only), one atomic per block and bound (after set_triangles)
+//   morton_kernel        63-bit Morton key (21 bits per axis) of each primitive's box centre in the scene box, packed with the primitive index
+//                        into one sort word; the digit histograms of the sort are accumulated on the way
+//   [radix_sort.cuh]     onesweep sort of the words (keys only), or of (key, index) pairs on the fall-back path
+//   build_local_kernel   FUSED: leaf records (TriRec + binary32 copies) in Morton order, and topology + boxes of every node whose leaf range lies
+//                        inside a block of 256 leaves, in one bottom-up pass without searches (Karras' numbering: the same tree as the classic path)
+//   hierarchy_kernel     Karras 2012 radix-tree topology by searches: for the nodes that span blocks (fused path) or for all nodes (classic path)
+//   refit_global         boxes of the spanning nodes, one arrival flag per node
+//   refit_local          the classic path's block-local refit (fall-back of a full frontier list; b200aabb_refit)
+// A primitive's exact binary64 box is rounded OUTWARD to binary32 once; min/max are exact and commute with the monotone rounding, so every
+// node box is bit-equal to the outward rounding of the exact union of its primitives' boxes.
 #pragma once
 #include "bvh.cuh"
 #include "radix_sort.cuh"
