@@ -75,13 +75,13 @@ enum {
                                       exact projection and comparison of the candidates (2.7x slower: its warps diverge; kept for the same reason);
                                       0 = one thread per query.  Same results. */
   B200AABB_OPT_HOST_PARTS = 5,     /* HOST-pointer batches are cut into about this many chunks (each 256 Ki .. 4 Mi rays / segments, .. 16 Mi points) that flow
-                                      through an upload -> sort -> traverse -> download pipeline (1..64; 0 = default: 8 for ray / segment batches on
-                                      four streams; 1 for point batches — a point batch is sorted into ONE coherence order — on two streams of their own) */
+                                      through an upload -> sort -> traverse -> download pipeline of three streams (1..64; 0 = default: 8 for ray / segment batches;
+                                      1 for point batches — a point batch is sorted into ONE coherence order) */
   B200AABB_OPT_ASYNC_HOST = 6,     /* 1: batched queries with HOST pointers return as soon as their chunks are enqueued (uploads, kernels and downloads of
                                       consecutive calls then overlap across calls); the caller keeps the query / result buffers alive and unread until
                                       b200aabb_synchronize.  0 (default): every call returns with its results in place. */
-  B200AABB_OPT_RAY_KERNEL = 7,     /* first_intersection scheduling: 0 = one thread per ray; 1 = persistent threads that take the next ray of the coherence order as soon as
-                                      theirs is done (same traversal, identical results) */
+  B200AABB_OPT_RAY_KERNEL = 7,     /* first_intersection, do_intersect, counts, any_intersected_primitive: 0 (default) = one thread per query; 1 = persistent threads that
+                                      take the next query of the coherence order as soon as theirs is answered (same traversal, identical results; measured equal or slower) */
   B200AABB_OPT_WARP_EXACT_GO = 4   /* warp-cooperative kernels: run the binary64 phase once this many pre-test survivors wait (1..160; 0 = the kernel's default) */
 };
 
