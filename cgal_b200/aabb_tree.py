@@ -9,7 +9,8 @@ import os
 
 import numpy as np
 
-SEGMENT, RAY, LINE, PLANE = 0, 1, 2, 3      # LINE: (point, direction vector) per query; PLANE: (a, b, c, d)
+SEGMENT, RAY, LINE, PLANE, TRIANGLE = 0, 1, 2, 3, 4      # LINE: (point, direction vector) per query; PLANE: (a, b, c, d); TRIANGLE: three vertices (id queries only)
+_QUERY_DOUBLES = {PLANE: 4, TRIANGLE: 9}                  # doubles per query of a kind (every other kind: 6)
 FLAG_HIT, FLAG_SEGMENT, FLAG_TIE, FLAG_EXACT, FLAG_NEAR_TIE, FLAG_TRIANGLE = 1, 2, 4, 8, 16, 32
 OPT_SORT_QUERIES = 1
 OPT_CLOSEST_KERNEL = 2    # 1 = warp-cooperative work pool (default), 2 = lane pairs with private stacks, 3 = two passes (binary32 filter + exact resolve), 0 = one thread per query
@@ -39,7 +40,7 @@ class _Stats(C.Structure):
 SYMBOLS = ["b200aabb_create", "b200aabb_destroy", "b200aabb_set_stream", "b200aabb_set_option", "b200aabb_last_error", "b200aabb_get_stats", "b200aabb_synchronize",
            "b200aabb_set_mesh", "b200aabb_set_triangles", "b200aabb_clear", "b200aabb_build", "b200aabb_refit", "b200aabb_refit_mesh",
            "b200aabb_accelerate_distance_queries", "b200aabb_size", "b200aabb_bbox", "b200aabb_do_intersect",
-           "b200aabb_number_of_intersected_primitives", "b200aabb_any_intersected_primitive", "b200aabb_all_intersected_primitives",
+           "b200aabb_number_of_intersected_primitives", "b200aabb_any_intersected_primitive", "b200aabb_all_intersected_primitives", "b200aabb_do_intersect_tree",
            "b200aabb_number_of_intersections", "b200aabb_all_intersections", "b200aabb_any_intersection",
            "b200aabb_number_of_intersections_q", "b200aabb_all_intersections_q", "b200aabb_any_intersection_q",
            "b200aabb_first_intersection", "b200aabb_first_intersection_skip", "b200aabb_closest_point", "b200aabb_max_distance_to_mesh", "b200aabb_side_of_mesh",
@@ -82,6 +83,7 @@ def load_library():
         L.b200aabb_number_of_intersected_primitives.argtypes = [vp, dp, u64, C.c_int, C.c_int, dp]
         L.b200aabb_any_intersected_primitive.argtypes = [vp, dp, u64, C.c_int, C.c_int, dp]
         L.b200aabb_all_intersected_primitives.argtypes = [vp, dp, u64, C.c_int, C.c_int, dp, dp]
+        L.b200aabb_do_intersect_tree.argtypes = [vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.b200aabb_number_of_intersections.argtypes = [vp, dp, u64, C.c_int, dp]
         L.b200aabb_all_intersections.argtypes = [vp, dp, u64, C.c_int, dp, dp, dp, dp]
         L.b200aabb_any_intersection.argtypes = [vp, dp, u64, C.c_int, dp, dp, dp, dp]
@@ -258,20 +260,20 @@ class AABB_tree:
 
     # ---- intersection queries (AABB_tree.h:243-354) ----
     def do_intersect(self, queries, kind=SEGMENT, out=None):
-        q = _Buf(queries, np.float64, 4 if kind == PLANE else 6)
+        q = _Buf(queries, np.float64, _QUERY_DOUBLES.get(kind, 6))
         o = _Buf(out, np.uint8, 1) if out is not None else _alloc_like(q, q.n, np.uint8, 1)
         self._check(self._lib.b200aabb_do_intersect(self._h, q.ptr, q.n, kind, int(q.device), o.ptr))
         return o.obj
 
     def number_of_intersected_primitives(self, queries, kind=SEGMENT, out=None):
-        q = _Buf(queries, np.float64, 4 if kind == PLANE else 6)
+        q = _Buf(queries, np.float64, _QUERY_DOUBLES.get(kind, 6))
         o = _Buf(out, np.uint32, 1) if out is not None else _alloc_like(q, q.n, np.uint32, 1)
         self._check(self._lib.b200aabb_number_of_intersected_primitives(self._h, q.ptr, q.n, kind, int(q.device), o.ptr))
         return o.obj
 
     def any_intersected_primitive(self, queries, kind=SEGMENT, out=None):
         """any_intersected_primitive(query): id of one intersected primitive per query, NO_PRIMITIVE = nullopt"""
-        q = _Buf(queries, np.float64, 4 if kind == PLANE else 6)
+        q = _Buf(queries, np.float64, _QUERY_DOUBLES.get(kind, 6))
         o = _Buf(out, np.uint32, 1) if out is not None else _alloc_like(q, q.n, np.uint32, 1)
         self._check(self._lib.b200aabb_any_intersected_primitive(self._h, q.ptr, q.n, kind, int(q.device), o.ptr))
         return o.obj
@@ -279,7 +281,7 @@ class AABB_tree:
     def all_intersected_primitives(self, queries, kind=SEGMENT):
         """all_intersected_primitives(query, out) for a HOST batch: (offsets uint64[n+1], ids uint32[total]); the ids of query i are
         ids[offsets[i]:offsets[i+1]] (count pass -> prefix sums -> fill pass, include/b200aabb.h)"""
-        q = _Buf(np.asarray(queries), np.float64, 4 if kind == PLANE else 6)
+        q = _Buf(np.asarray(queries), np.float64, _QUERY_DOUBLES.get(kind, 6))
         counts = self.number_of_intersected_primitives(q.obj, kind)
         offsets = np.zeros(q.n + 1, np.uint64)
         np.cumsum(counts, out=offsets[1:])
@@ -287,10 +289,17 @@ class AABB_tree:
         self._check(self._lib.b200aabb_all_intersected_primitives(self._h, q.ptr, q.n, kind, 0, offsets.ctypes.data, ids.ctypes.data))
         return offsets, ids[:int(offsets[-1])]
 
+    def do_intersect_tree(self, other, witness=False):
+        """tree.do_intersect(other_tree) (AABB_traits_3.h:679-690): True iff a primitive of this tree intersects a primitive of `other` (same device);
+        witness=True -> (bool, id in this tree, id in other) of one intersecting pair (NO_PRIMITIVE twice when there is none)"""
+        r, a, b = C.c_int(0), C.c_uint32(NO_PRIMITIVE), C.c_uint32(NO_PRIMITIVE)
+        self._check(self._lib.b200aabb_do_intersect_tree(self._h, other._h, C.byref(r), C.byref(a), C.byref(b)))
+        return (bool(r.value), a.value, b.value) if witness else bool(r.value)
+
     def all_intersections(self, rays, kind=RAY):
         """all_intersections(Ray_3 | Segment_3 | Line_3 | Plane_3, out) for a HOST batch: (offsets uint64[n+1], ids uint32[total], kinds uint8[total] (1 Point_3 /
         2 Segment_3 / 3 the primitive's Triangle_3), points f64[total, 6]); the entries of query i are [offsets[i], offsets[i+1])"""
-        q = _Buf(np.asarray(rays), np.float64, 4 if kind == PLANE else 6)
+        q = _Buf(np.asarray(rays), np.float64, _QUERY_DOUBLES.get(kind, 6))
         counts = np.empty(q.n, np.uint32)
         self._check(self._lib.b200aabb_number_of_intersections_q(self._h, q.ptr, q.n, int(kind), 0, counts.ctypes.data))
         offsets = np.zeros(q.n + 1, np.uint64)
@@ -304,7 +313,7 @@ class AABB_tree:
     def any_intersection(self, rays, want=("prim", "point", "point2", "flags"), out=None, kind=RAY):
         """any_intersection(Ray_3 | Segment_3 | Line_3 | Plane_3): dict with prim (NO_PRIMITIVE = nullopt), point, point2, flags (FLAG_HIT, FLAG_SEGMENT,
         FLAG_TRIANGLE)"""
-        q = _Buf(rays, np.float64, 4 if kind == PLANE else 6)
+        q = _Buf(rays, np.float64, _QUERY_DOUBLES.get(kind, 6))
         spec = {"prim": (np.uint32, 1), "point": (np.float64, 3), "point2": (np.float64, 3), "flags": (np.uint8, 1)}
         bufs = {}
         for k in want:

@@ -236,6 +236,46 @@ __global__ void __launch_bounds__(128, 8) plane_kernel(const TreeRef tr, const d
     flush_stats(tr, st, 0, 0);
 }
 
+// the same for Triangle_3 queries: query i = the 9 doubles at q + stride * i (stride 9: the caller's batch; 12: the TriRec array of another tree)
+template <int MODE>
+__global__ void __launch_bounds__(128, 6) triangle_kernel(const TreeRef tr, const double* __restrict__ q, uint32_t stride, uint64_t n, uint8_t* __restrict__ out8,
+                                                          uint32_t* __restrict__ out32, const uint64_t* __restrict__ offsets, uint32_t* __restrict__ list) {
+    const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    TravStat st;
+    if (slot < n) {
+        const uint64_t i = tr.perm ? tr.perm[slot] : slot;
+        const double* p = q + (uint64_t)stride * i;
+        const Tri3 t = {ld3(p), ld3(p + 3), ld3(p + 6)};
+        if (MODE == kList) {
+            const uint64_t lo = offsets[i], hi = offsets[i + 1];
+            uint32_t r = 0;
+            if (hi > lo) r = traverse_triangle<kList>(tr.nodes, tr.tris, tr.root, t, st, list + lo, (uint32_t)(hi - lo));
+            else r = traverse_triangle<kAnyHit>(tr.nodes, tr.tris, tr.root, t, st);
+            if (r != hi - lo) atomicOr(&tr.counters[2], 4ull);
+        } else {
+            const uint32_t r = traverse_triangle<MODE>(tr.nodes, tr.tris, tr.root, t, st);
+            if (MODE == kAnyHit) out8[i] = (uint8_t)r; else out32[i] = r;
+        }
+    }
+    flush_stats(tr, st, 0, 0);
+}
+
+// tree.do_intersect(other_tree) (AABB_traits_3.h:679-690: every primitive of the traversed tree is a Triangle_3 query against the other tree, the
+// traversal stops at the first pair): one thread per primitive of `a` (its Morton order is the coherence order), traversing `tr` = the other tree;
+// witness[0] = 1 at the first intersecting pair found, witness[1] / [2] = ids of one such pair (which one is unspecified).  Threads that start after a
+// pair has been found return at once.
+__global__ void __launch_bounds__(128, 6) tree_tree_kernel(const TreeRef tr, const TriRec* __restrict__ a, uint64_t na, unsigned* __restrict__ witness) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    TravStat st;
+    if (i < na && *(volatile unsigned*)witness == 0u) {
+        uint32_t ida;
+        const Tri3 t = load_tri(a, (uint32_t)i, ida);
+        const uint32_t idb = traverse_triangle<kAnyId>(tr.nodes, tr.tris, tr.root, t, st);
+        if (idb != kNone && atomicExch(&witness[0], 1u) == 0u) { witness[1] = ida; witness[2] = idb; }
+    }
+    flush_stats(tr, st, 0, 0);
+}
+
 // all_intersections / any_intersection (Ray_3): bvh.cuh::traverse_ray_objects.  kCount: out32[i]; kList: entries of ray i at offsets[i] ..
 // (a count that disagrees with offsets[i+1] - offsets[i] raises counters[2] bit 2); kAnyId: prim / flags / pt / pt2 like first_intersection
 constexpr int kPlaneObjects = 3;        // KIND of ray_objects_kernel for Plane_3 queries (next to LineKind's 0..2)
@@ -493,13 +533,14 @@ __global__ void __launch_bounds__(256) argmax_sqdist_kernel(const double* __rest
 
 // ---- query coherence keys (sorted with radix_sort.cuh; the traversal kernels then follow the permutation) ------------
 // Point_3: 30-bit Morton code (10 bits per axis) of the point in the isotropic frame of the root box
-__global__ void __launch_bounds__(256) point_keys_kernel(const double* __restrict__ pts, uint64_t n, const double* __restrict__ rootbox,
+__global__ void __launch_bounds__(256) point_keys_kernel(const double* __restrict__ pts, uint32_t stride, uint64_t n, const double* __restrict__ rootbox,
                                                          uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double lo[3], scale[3];
     morton_frame(rootbox[0], rootbox[1], rootbox[2], rootbox[3], rootbox[4], rootbox[5], lo, scale);
-    keys[i] = morton63(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2], lo, scale) >> 33;
+    const double* p = pts + (uint64_t)stride * i;                      // (stride 9: Triangle_3 queries, keyed by their first vertex)
+    keys[i] = morton63(p[0], p[1], p[2], lo, scale) >> 33;
     vals[i] = (uint32_t)i;
 }
 // Segment_3 / Ray_3: 48-bit key interleaving 8 bits of each origin coordinate (root-box frame) and of each component of
@@ -720,7 +761,7 @@ int ensure_sort(b200aabb_tree* t, int slot, uint64_t n) {
     return B200AABB_OK;
 }
 
-enum QueryShape { kPointQuery, kLineQuery, kLineVecQuery /* Line_3: point + direction vector */, kPlaneQuery /* not sorted */ };
+enum QueryShape { kPointQuery, kLineQuery, kLineVecQuery /* Line_3: point + direction vector */, kPlaneQuery /* not sorted */, kTriangleQuery /* sorted by the first vertex */ };
 
 // coherence order of a batch resident on the device: keys -> onesweep sort -> permutation (nullptr when sorting is off)
 int coherence_order(b200aabb_tree* t, int slot, cudaStream_t st, const void* d_in, uint64_t n, QueryShape shape, const uint32_t** perm) {
@@ -731,7 +772,7 @@ int coherence_order(b200aabb_tree* t, int slot, cudaStream_t st, const void* d_i
     auto& sc = t->sort[slot];
     const unsigned blocks = (unsigned)((n + 255) / 256);
     int passes;
-    if (shape == kPointQuery) { point_keys_kernel<<<blocks, 256, 0, st>>>((const double*)d_in, n, t->d_rootbox, sc.keys[0], sc.vals[0]); passes = 4; }
+    if (shape == kPointQuery || shape == kTriangleQuery) { point_keys_kernel<<<blocks, 256, 0, st>>>((const double*)d_in, shape == kTriangleQuery ? 9u : 3u, n, t->d_rootbox, sc.keys[0], sc.vals[0]); passes = 4; }
     else { line_keys_kernel<<<blocks, 256, 0, st>>>((const double*)d_in, n, t->d_rootbox, sc.keys[0], sc.vals[0], shape == kLineVecQuery ? 1 : 0); passes = 6; }
     t->stats.kernel_launches += 1;
     const int cur = radix_sort_pairs(sc.keys, sc.vals, n, passes, sc.ws, st, &t->stats.kernel_launches);
@@ -1030,7 +1071,7 @@ template <int MODE>
 static void launch_intersect(b200aabb_tree* t, int kind, cudaStream_t st, const double* in, uint64_t cnt, const uint32_t* perm, uint8_t* out8, uint32_t* out32,
                              const uint64_t* offsets, uint32_t* list) {
     if constexpr (MODE != kList) {
-        if (t->opt_ray_kernel == 1 && t->n >= 2 && kind != B200AABB_PLANE && t->d_ray_cursor) {
+        if (t->opt_ray_kernel == 1 && t->n >= 2 && kind != B200AABB_PLANE && kind != B200AABB_TRIANGLE && t->d_ray_cursor) {
             unsigned long long* cursor = t->d_ray_cursor + (st == t->s_run ? kHostScratch : kDeviceScratch);   // (HOST batches run on s_run, DEVICE batches on the caller's stream)
             cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), st);
             const unsigned sgrid = (unsigned)std::min<uint64_t>((uint64_t)t->seg_grid, (cnt + 127) / 128);
@@ -1047,12 +1088,16 @@ static void launch_intersect(b200aabb_tree* t, int kind, cudaStream_t st, const 
         case B200AABB_RAY: intersect_kernel<kRayQ, MODE><<<grid, 128, 0, st>>>(tree_ref(t, perm), in, cnt, out8, out32, offsets, list); break;
         case B200AABB_LINE: intersect_kernel<kLineQ, MODE><<<grid, 128, 0, st>>>(tree_ref(t, perm), in, cnt, out8, out32, offsets, list); break;
         case B200AABB_PLANE: plane_kernel<MODE><<<grid, 128, 0, st>>>(tree_ref(t, nullptr), in, cnt, out8, out32, offsets, list); break;
+        case B200AABB_TRIANGLE: triangle_kernel<MODE><<<grid, 128, 0, st>>>(tree_ref(t, perm), in, 9u, cnt, out8, out32, offsets, list); break;
         default: intersect_kernel<kSegmentQ, MODE><<<grid, 128, 0, st>>>(tree_ref(t, perm), in, cnt, out8, out32, offsets, list); break;
     }
 }
-static bool valid_kind(int kind) { return kind >= B200AABB_SEGMENT && kind <= B200AABB_PLANE; }
-static size_t query_bytes(int kind) { return kind == B200AABB_PLANE ? 32 : 48; }
-static QueryShape query_shape(int kind) { return kind == B200AABB_PLANE ? kPlaneQuery : (kind == B200AABB_LINE ? kLineVecQuery : kLineQuery); }
+static bool valid_kind(int kind) { return kind >= B200AABB_SEGMENT && kind <= B200AABB_TRIANGLE; }          // the id queries
+static bool valid_object_kind(int kind) { return kind >= B200AABB_SEGMENT && kind <= B200AABB_PLANE; }    // the intersection OBJECTS (no Triangle_3 queries)
+static size_t query_bytes(int kind) { return kind == B200AABB_PLANE ? 32 : (kind == B200AABB_TRIANGLE ? 72 : 48); }
+static QueryShape query_shape(int kind) {
+    return kind == B200AABB_PLANE ? kPlaneQuery : (kind == B200AABB_LINE ? kLineVecQuery : (kind == B200AABB_TRIANGLE ? kTriangleQuery : kLineQuery));
+}
 template <int MODE>
 static void launch_objects(b200aabb_tree* t, int kind, cudaStream_t st, const double* in, uint64_t cnt, const uint32_t* perm, uint32_t* out32, const uint64_t* offsets,
                            uint32_t* ids, uint8_t* kinds, double* pts, uint32_t* prim, uint8_t* flags, double* pt, double* pt2) {
@@ -1416,11 +1461,59 @@ int b200aabb_all_intersected_primitives(b200aabb_tree* t, const double* q, uint6
     return B200AABB_OK;
 }
 
+int b200aabb_do_intersect_tree(b200aabb_tree* t, b200aabb_tree* other, int* result, uint32_t* prim, uint32_t* other_prim) {
+    if (!t || !other || !result) return B200AABB_ERR_INVALID_ARGUMENT;
+    // both handles are locked, in address order (two threads testing (a, b) and (b, a) must not dead-lock)
+    std::unique_lock<std::recursive_mutex> l1((t < other ? t : other)->mu), l2;
+    if (t != other) l2 = std::unique_lock<std::recursive_mutex>((t < other ? other : t)->mu);
+    *result = 0;
+    if (prim) *prim = kNone;
+    if (other_prim) *other_prim = kNone;
+    if (t->device != other->device) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "do_intersect(tree): both trees must live on the same device");
+    int rc = ensure_built(t);
+    if (rc) return rc;
+    rc = ensure_built(other);
+    if (rc) { t->err = other->err; return rc; }
+    if (t->n == 0 || other->n == 0) return B200AABB_OK;                 // an empty tree intersects nothing (AABB_tree.h:516-525)
+    B2_CUDA(t, cudaSetDevice(t->device));
+    rc = drain(other);                                                   // (its build, or batches still in flight, run on other streams)
+    if (rc) { t->err = other->err; return rc; }
+    // the queries are the primitives of the SMALLER tree, the traversed tree is the larger one: the answer is symmetric
+    // (Do_intersect_3(Triangle_3, Triangle_3) decides exactly), the work is (number of queries) x log(size of the traversed tree)
+    b200aabb_tree* big = t->n >= other->n ? t : other;
+    b200aabb_tree* small = big == t ? other : t;
+    unsigned* d_w = nullptr;
+    if (cudaMalloc(&d_w, 3 * sizeof(unsigned)) != cudaSuccess) { t->err = "cudaMalloc(do_intersect(tree))"; return B200AABB_ERR_OUT_OF_MEMORY; }
+    const unsigned init[3] = {0u, kNone, kNone};
+    cudaMemcpyAsync(d_w, init, sizeof(init), cudaMemcpyHostToDevice, t->stream);
+    rc = reset_counters(big, t->stream);
+    if (rc) { cudaFree(d_w); return rc; }
+    cudaEventRecord(t->ev_a, t->stream);
+    tree_tree_kernel<<<grid_for(small->n, 128), 128, 0, t->stream>>>(tree_ref(big, nullptr), small->d_tris, small->n, d_w);
+    t->stats.kernel_launches += 1;
+    cudaEventRecord(t->ev_b, t->stream);
+    t->query_timing_pending = true;
+    unsigned w[3] = {0, 0, 0};
+    unsigned long long c2 = 0;
+    cudaMemcpyAsync(w, d_w, sizeof(w), cudaMemcpyDeviceToHost, t->stream);
+    cudaMemcpyAsync(&c2, big->d_counters + 2, sizeof(c2), cudaMemcpyDeviceToHost, t->stream);
+    const cudaError_t e = cudaStreamSynchronize(t->stream);
+    cudaFree(d_w);
+    if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) { t->err = "do_intersect(tree): CUDA failure"; return B200AABB_ERR_CUDA; }
+    if (c2 && !w[0]) return fail(t, B200AABB_ERR_INCOMPLETE, "traversal stack overflow: results incomplete");
+    *result = w[0] ? 1 : 0;
+    if (w[0]) {                                                          // w[1]: id in `small`, w[2]: id in `big`
+        if (prim) *prim = small == t ? w[1] : w[2];
+        if (other_prim) *other_prim = small == t ? w[2] : w[1];
+    }
+    return B200AABB_OK;
+}
+
 int b200aabb_number_of_intersections(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_memspace space, uint32_t* out) {
     return b200aabb_number_of_intersections_q(t, rays, n, B200AABB_RAY, space, out);
 }
 int b200aabb_number_of_intersections_q(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint32_t* out) { B2_LOCK(t);
-    if (!t || (n && (!rays || !out)) || !valid_kind(kind)) return B200AABB_ERR_INVALID_ARGUMENT;
+    if (!t || (n && (!rays || !out)) || !valid_object_kind(kind)) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     if (t->n == 0) {
@@ -1437,7 +1530,7 @@ int b200aabb_any_intersection(b200aabb_tree* t, const double* rays, uint64_t n, 
 }
 int b200aabb_any_intersection_q(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint32_t* prim, double* pt, double* pt2,
                                 uint8_t* flags) { B2_LOCK(t);
-    if (!t || (n && !rays) || !valid_kind(kind)) return B200AABB_ERR_INVALID_ARGUMENT;
+    if (!t || (n && !rays) || !valid_object_kind(kind)) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     if (t->n == 0) return b200aabb_first_intersection(t, rays, n, space, prim, nullptr, pt, pt2, flags);   // nullopt for every ray
@@ -1453,7 +1546,7 @@ int b200aabb_all_intersections(b200aabb_tree* t, const double* rays, uint64_t n,
 }
 int b200aabb_all_intersections_q(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, const uint64_t* offsets, uint32_t* ids,
                                  uint8_t* kinds, double* points) { B2_LOCK(t);
-    if (!t || (n && (!rays || !offsets)) || !valid_kind(kind)) return B200AABB_ERR_INVALID_ARGUMENT;
+    if (!t || (n && (!rays || !offsets)) || !valid_object_kind(kind)) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     B2_CUDA(t, cudaSetDevice(t->device));

@@ -325,6 +325,68 @@ B2_HD uint32_t traverse_intersect(const BvhNode* __restrict__ nodes, const TriRe
     return MODE == kAnyId ? found_id : (MODE == kAnyHit ? (found ? 1u : 0u) : found);
 }
 
+// Triangle_3 queries (do_intersect / number_of_intersected_primitives / any_intersected_primitive / all_intersected_primitives with a Triangle_3,
+// AABB_tree.h:903-956; the query a tree-vs-tree do_intersect issues per primitive, AABB_traits_3.h:679-690).  Do_intersect_3(Bbox_3, Triangle_3)
+// (Bbox_3_Triangle_3_do_intersect.h: separating axes) is replaced by a conservative test — the binary32 box of the query, rounded outward, must overlap the
+// child's box — and the leaves decide exactly (geom.cuh::tri_tri_do_intersect), so results do not depend on the tree.  Same while-while scheme as traverse_line.
+struct BoxCtx { float lo[3], hi[3]; };
+B2_HD BoxCtx make_box_of(const Tri3& t) {
+    BoxCtx c;
+    c.lo[0] = float_below(fmin3(t.a.x, t.b.x, t.c.x)); c.lo[1] = float_below(fmin3(t.a.y, t.b.y, t.c.y)); c.lo[2] = float_below(fmin3(t.a.z, t.b.z, t.c.z));
+    c.hi[0] = float_above(fmax3(t.a.x, t.b.x, t.c.x)); c.hi[1] = float_above(fmax3(t.a.y, t.b.y, t.c.y)); c.hi[2] = float_above(fmax3(t.a.z, t.b.z, t.c.z));
+    return c;
+}
+B2_HD bool box_box(const float* lo, const float* hi, const BoxCtx& c) {
+    return lo[0] <= c.hi[0] && c.lo[0] <= hi[0] && lo[1] <= c.hi[1] && c.lo[1] <= hi[1] && lo[2] <= c.hi[2] && c.lo[2] <= hi[2];
+}
+template <int MODE>
+B2_HD uint32_t traverse_triangle(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root, const Tri3& query, TravStat& st,
+                                 uint32_t* list = nullptr, uint32_t list_cap = 0) {
+    constexpr bool kStopAtFirst = MODE == kAnyHit || MODE == kAnyId;
+    const BoxCtx c = make_box_of(query);
+    uint32_t found = 0, nlisted = 0, found_id = kNone;
+    auto leaf = [&](uint32_t ref) -> bool {
+        uint32_t id;
+        const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
+        ++st.leaves;
+        if (!tri_tri_do_intersect(query, t, st.nexact)) return false;
+        if (MODE == kList) { if (nlisted < list_cap) list[nlisted] = id; ++nlisted; }
+        if (MODE == kAnyId) found_id = id;
+        return true;
+    };
+    if (root & kLeafBit) found = leaf(root) ? 1u : 0u;
+    else {
+        uint32_t stack[kStackCap];
+        constexpr int kPendCount = 4, kPendGoAt = kPendCount - 1;
+        uint32_t pend[kPendCount + 1];
+        int sp = 0, np = 0;
+        uint32_t cur = root;
+        bool done = false;
+        while (!done) {
+            while (cur != kNone && np < kPendGoAt) {          // node phase
+                const NodeView n = load_node(nodes, cur);
+                ++st.nodes;
+                const bool h0 = box_box(n.lo0, n.hi0, c), h1 = box_box(n.lo1, n.hi1, c);
+                uint32_t next = kNone;
+                if (h0) { if (n.c0 & kLeafBit) pend[np++] = n.c0; else next = n.c0; }
+                if (h1) {
+                    if (n.c1 & kLeafBit) pend[np++] = n.c1;
+                    else if (next == kNone) next = n.c1;
+                    else if (sp < kStackCap) stack[sp++] = n.c1;
+                    else st.overflow = 1;
+                }
+                if (next == kNone && sp > 0) next = stack[--sp];
+                cur = next;
+            }
+            while (np > 0) {                                  // leaf phase
+                if (leaf(pend[--np])) { ++found; if (kStopAtFirst) { done = true; break; } }
+            }
+            if (cur == kNone) break;
+        }
+    }
+    return MODE == kAnyId ? found_id : (MODE == kAnyHit ? (found ? 1u : 0u) : found);
+}
+
 // Side_of_triangle_mesh (Polygon_mesh_processing/include/CGAL/Side_of_triangle_mesh.h:265-306, internal/Side_of_triangle_mesh/
 // Point_inside_vertical_ray_cast.h:69-121, Ray_3_Triangle_3_traversal_traits.h:30-76): one ray from the point; every primitive it crosses in the
 // interior of a facet counts, the source lying on a primitive ends the query (ON_BOUNDARY), and a ray that passes through an edge or a vertex or

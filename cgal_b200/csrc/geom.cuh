@@ -207,6 +207,64 @@ B2_HD bool plane_tri_do_intersect(const Tri3& t, double a, double b, double c, d
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Do_intersect_3(Triangle_3, Triangle_3): Triangle_3_Triangle_3_do_intersect.h:154-450 (Guigue & Devillers).  The reference's nested switches over the
+// signs of one triangle's vertices against the other's plane select, for each triangle, the two edges that cross the other plane ("min" and "max" edge);
+// here the 27 sign combinations index one table, the same for both triangles.  Entry = s_min | t_min << 2 | s_max << 4 | t_max << 6 (vertex numbers of
+// the triangle), 0xFF = all vertices strictly on one side (no intersection), 0xFE = all three on the plane (coplanar triangles).
+// ---------------------------------------------------------------------------------------------------------------
+#define B2_TT(smin, tmin, smax, tmax) ((smin) | ((tmin) << 2) | ((smax) << 4) | ((tmax) << 6))
+#define B2_TT_TABLE { \
+    /* d0=-1 */ 0xFF, B2_TT(2, 0, 1, 2), B2_TT(2, 0, 1, 2), B2_TT(1, 2, 0, 1), B2_TT(2, 0, 0, 1), B2_TT(2, 0, 0, 1), B2_TT(1, 2, 0, 1), B2_TT(2, 0, 0, 1), B2_TT(2, 0, 0, 1), \
+    /* d0= 0 */ B2_TT(0, 1, 2, 0), B2_TT(0, 1, 1, 2), B2_TT(0, 1, 1, 2), B2_TT(1, 2, 2, 0), 0xFE, B2_TT(2, 0, 1, 2), B2_TT(1, 2, 0, 1), B2_TT(1, 2, 0, 1), B2_TT(2, 0, 0, 1), \
+    /* d0=+1 */ B2_TT(0, 1, 2, 0), B2_TT(0, 1, 2, 0), B2_TT(0, 1, 1, 2), B2_TT(0, 1, 2, 0), B2_TT(0, 1, 2, 0), B2_TT(0, 1, 1, 2), B2_TT(1, 2, 2, 0), B2_TT(1, 2, 2, 0), 0xFF}
+__constant__ static const unsigned char kTriTriEdges[27] = B2_TT_TABLE;
+#if !defined(__CUDA_ARCH__)
+namespace host_tables { static const unsigned char TriTri[27] = B2_TT_TABLE; }
+#endif
+B2_HD unsigned char tbl_tritri(int i) {
+#if defined(__CUDA_ARCH__)
+    return kTriTriEdges[i];
+#else
+    return host_tables::TriTri[i];
+#endif
+}
+B2_HD const Vec3& tri_vertex(const Tri3& t, int i) { return i == 0 ? t.a : (i == 1 ? t.b : t.c); }
+
+// Coplanar triangles (do_intersect_coplanar, :100-152, decides by locating one vertex among the other triangle's edge lines; this is the separating-axis
+// form of the same exact decision): two closed, non-flat triangles of one plane are disjoint exactly when the supporting line of an edge of one of them
+// has the other triangle strictly on its outer side.  Both are first made counterclockwise as the reference does (:120-130).  Flat triangles are outside
+// the reference's precondition (:108-109) and unspecified here too.
+B2_HD_NOINLINE bool tri_tri_coplanar(const Tri3& t1, const Tri3& t2, int& nexact) {
+    Vec3 u[3] = {t1.a, t1.b, t1.c}, w[3] = {t2.a, t2.b, t2.c};
+    if (coplanar_orient(u[0], u[1], u[2], nexact) == -1) { const Vec3 x = u[1]; u[1] = u[2]; u[2] = x; }
+    if (coplanar_orient(w[0], w[1], w[2], nexact) == -1) { const Vec3 x = w[1]; w[1] = w[2]; w[2] = x; }
+    for (int e = 0; e < 3; ++e) {
+        const Vec3 &a = u[e], &b = u[(e + 1) % 3];
+        if (coplanar_orient(a, b, w[0], nexact) == -1 && coplanar_orient(a, b, w[1], nexact) == -1 && coplanar_orient(a, b, w[2], nexact) == -1) return false;
+    }
+    for (int e = 0; e < 3; ++e) {
+        const Vec3 &a = w[e], &b = w[(e + 1) % 3];
+        if (coplanar_orient(a, b, u[0], nexact) == -1 && coplanar_orient(a, b, u[1], nexact) == -1 && coplanar_orient(a, b, u[2], nexact) == -1) return false;
+    }
+    return true;
+}
+
+// t1 = the query (p, q, r), t2 = the primitive (a, b, c): the order of the reference's call do_intersect(query, datum)
+B2_HD_NOINLINE bool tri_tri_do_intersect(const Tri3& t1, const Tri3& t2, int& nexact) {
+    const int dp = orient3(t2.a, t2.b, t2.c, t1.a, nexact), dq = orient3(t2.a, t2.b, t2.c, t1.b, nexact), dr = orient3(t2.a, t2.b, t2.c, t1.c, nexact);   // :176-178
+    const unsigned e1 = tbl_tritri((dp + 1) * 9 + (dq + 1) * 3 + (dr + 1));
+    if (e1 == 0xFF) return false;
+    if (e1 == 0xFE) return tri_tri_coplanar(t1, t2, nexact);
+    const int da = orient3(t1.a, t1.b, t1.c, t2.a, nexact), db = orient3(t1.a, t1.b, t1.c, t2.b, nexact), dc = orient3(t1.a, t1.b, t1.c, t2.c, nexact);   // :312-314
+    const unsigned e2 = tbl_tritri((da + 1) * 9 + (db + 1) * 3 + (dc + 1));
+    if (e2 == 0xFF) return false;
+    if (e2 == 0xFE) return tri_tri_coplanar(t1, t2, nexact);       // (only reachable with a flat t1, :424-428)
+    // the two triangles cut the common line of their planes in two intervals; they overlap iff (:446-447)
+    return orient3(tri_vertex(t1, e1 & 3), tri_vertex(t1, (e1 >> 2) & 3), tri_vertex(t2, e2 & 3), tri_vertex(t2, (e2 >> 2) & 3), nexact) != 1 &&
+           orient3(tri_vertex(t1, (e1 >> 4) & 3), tri_vertex(t1, (e1 >> 6) & 3), tri_vertex(t2, (e2 >> 6) & 3), tri_vertex(t2, (e2 >> 4) & 3), nexact) != 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // Intersect_3(Ray_3, Triangle_3) + the ray parameter of AABB_ray_intersection.h:168-198
 // ---------------------------------------------------------------------------------------------------------------
 struct RayX { int kind; Vec3 p0, p1; double t; double u; };   // kind 0 none, 1 point, 2 segment; u = rounding uncertainty of t

@@ -192,6 +192,15 @@ class AABB_tree {
     do_intersect(&query, &query + 1, &r);
     return r;
   }
+  // do_intersect(other_tree): the AABB_tree-as-query overloads of AABB_traits_3::Do_intersect (AABB_traits_3.h:679-690), one kernel on the device that
+  // holds both trees; true iff a primitive of this tree intersects a primitive of `other`
+  template <typename OtherTraits>
+  bool do_intersect(const AABB_tree<OtherTraits>& other) const {
+    ensure_built();
+    int r = 0;
+    check(b200aabb_do_intersect_tree(m_handle, other.handle(), &r, nullptr, nullptr));
+    return r != 0;
+  }
   template <typename Query>
   size_type number_of_intersected_primitives(const Query& query) const {
     size_type r = 0;
@@ -583,14 +592,19 @@ class AABB_tree {
   template <typename Q> struct has_line_interface<Q, std::void_t<decltype(std::declval<const Q&>().point()), decltype(std::declval<const Q&>().to_vector())>> : std::true_type {};
   template <typename Q, typename = void> struct has_plane_interface : std::false_type {};
   template <typename Q> struct has_plane_interface<Q, std::void_t<decltype(std::declval<const Q&>().a()), decltype(std::declval<const Q&>().d())>> : std::true_type {};
+  // a Triangle_3 has vertex(int) and is none of the above (Cartesian/Triangle_3.h): do_intersect / number_of_intersected_primitives / any_ and
+  // all_intersected_primitives only (the id queries)
+  template <typename Q, typename = void> struct has_triangle_interface : std::false_type {};
+  template <typename Q> struct has_triangle_interface<Q, std::void_t<decltype(std::declval<const Q&>().vertex(0))>> : std::true_type {};
   template <typename Query>
   static constexpr b200aabb_query_kind kind_of() {
     if constexpr (std::is_same<Query, Segment>::value) return B200AABB_SEGMENT;
     else if constexpr (std::is_same<Query, Ray>::value) return B200AABB_RAY;
     else if constexpr (has_plane_interface<Query>::value) return B200AABB_PLANE;
+    else if constexpr (has_line_interface<Query>::value) return B200AABB_LINE;
     else {
-      static_assert(has_line_interface<Query>::value, "offloaded intersection queries: Segment_3, Ray_3, Line_3 and Plane_3");
-      return B200AABB_LINE;
+      static_assert(has_triangle_interface<Query>::value, "offloaded intersection queries: Segment_3, Ray_3, Line_3, Plane_3 and Triangle_3");
+      return B200AABB_TRIANGLE;
     }
   }
   // the object of a Plane_3 query that contains the whole primitive: the primitive's Triangle_3, when the traits' intersection type can hold one
@@ -601,13 +615,14 @@ class AABB_tree {
     else throw Error(B200AABB_ERR_INVALID_ARGUMENT, "the intersection is the primitive's Triangle_3, which this traits' Intersection_and_primitive_id type cannot hold");
   }
   template <typename Query>
-  static constexpr uint64_t doubles_per_query() { return kind_of<Query>() == B200AABB_PLANE ? 4 : 6; }
+  static constexpr uint64_t doubles_per_query() { return kind_of<Query>() == B200AABB_PLANE ? 4 : (kind_of<Query>() == B200AABB_TRIANGLE ? 9 : 6); }
   static void put(std::vector<double>& v, const Point& p) { v.push_back((double)p.x()); v.push_back((double)p.y()); v.push_back((double)p.z()); }
   template <typename Query>
   static void put_line(std::vector<double>& v, const Query& q) {
     if constexpr (kind_of<Query>() == B200AABB_SEGMENT) { put(v, q.source()); put(v, q.target()); }
     else if constexpr (kind_of<Query>() == B200AABB_RAY) { put(v, q.source()); put(v, q.second_point()); }   // Cartesian/Ray_3.h:35-47
     else if constexpr (kind_of<Query>() == B200AABB_PLANE) { v.push_back((double)q.a()); v.push_back((double)q.b()); v.push_back((double)q.c()); v.push_back((double)q.d()); }
+    else if constexpr (kind_of<Query>() == B200AABB_TRIANGLE) { put(v, q.vertex(0)); put(v, q.vertex(1)); put(v, q.vertex(2)); }
     else {                                                                                                    // the stored members, not two points
       put(v, q.point());
       decltype(auto) d = q.to_vector();

@@ -43,9 +43,11 @@ typedef enum { B200AABB_HOST = 0, B200AABB_DEVICE = 1 } b200aabb_memspace;
  *   Segment_3 (source, target) and Ray_3 (source, second point): 6 doubles (Cartesian_kernel/include/CGAL/Cartesian/Ray_3.h:35-47, Segment_3.h);
  *   Line_3: 6 doubles = a point of the line + its DIRECTION VECTOR, the two members a Cartesian Line_3 stores (Cartesian/Line_3.h: line.point(),
  *           line.to_vector()) — Line_3(p, q) keeps the ROUNDED difference q - p, and the reference's exact predicates work on what is stored;
- *   Plane_3: 4 doubles = the coefficients (a, b, c, d) of a x + b y + c z + d = 0 (Cartesian/Plane_3.h).
- * first_intersection / all_intersections / any_intersection take Ray_3 only. */
-typedef enum { B200AABB_SEGMENT = 0, B200AABB_RAY = 1, B200AABB_LINE = 2, B200AABB_PLANE = 3 } b200aabb_query_kind;
+ *   Plane_3: 4 doubles = the coefficients (a, b, c, d) of a x + b y + c z + d = 0 (Cartesian/Plane_3.h);
+ *   Triangle_3: 9 doubles = the three vertices (Do_intersect_3(Triangle_3, Triangle_3), Intersections_3/internal/Triangle_3_Triangle_3_do_intersect.h:154-450;
+ *           the id queries only — the intersection OBJECTS of the *_q calls take kinds 0..3; flat triangles are outside the reference's precondition).
+ * first_intersection takes Ray_3 only. */
+typedef enum { B200AABB_SEGMENT = 0, B200AABB_RAY = 1, B200AABB_LINE = 2, B200AABB_PLANE = 3, B200AABB_TRIANGLE = 4 } b200aabb_query_kind;
 
 /* per-query result flags (bit set) */
 enum {
@@ -140,7 +142,7 @@ int b200aabb_size(const b200aabb_tree* t, uint64_t* n);
 int b200aabb_bbox(b200aabb_tree* t, double out[6]);
 
 /* ---- batched queries (each lazily builds, like root_node(), AABB_tree.h:636-652) ------------------------------ */
-/* do_intersect(query), AABB_tree.h:903-913: out[i] = 1 iff query i intersects some primitive.  queries: n x 6. */
+/* do_intersect(query), AABB_tree.h:903-913: out[i] = 1 iff query i intersects some primitive.  queries: n x 6 doubles (Plane_3: n x 4, Triangle_3: n x 9). */
 int b200aabb_do_intersect(b200aabb_tree* t, const double* queries, uint64_t n, b200aabb_query_kind kind,
                           b200aabb_memspace space, uint8_t* out);
 /* number_of_intersected_primitives(query), AABB_tree.h:915-932 */
@@ -158,6 +160,12 @@ int b200aabb_any_intersected_primitive(b200aabb_tree* t, const double* queries, 
  * pointers it is reported by the next b200aabb_get_stats); nothing is ever written outside a query's own range. */
 int b200aabb_all_intersected_primitives(b200aabb_tree* t, const double* queries, uint64_t n, b200aabb_query_kind kind,
                                         b200aabb_memspace space, const uint64_t* offsets, uint32_t* ids);
+/* tree.do_intersect(other_tree): the AABB_tree-as-query overloads of AABB_traits_3::Do_intersect (AABB_traits_3.h:679-690: other_tree.do_intersect(bbox)
+ * per node, other_tree.do_intersect(datum) per primitive; used by Polygon_mesh_processing/Rigid_triangle_mesh_collision_detection.h).  *result = 1 iff some
+ * primitive of `t` intersects some primitive of `other` (exact, symmetric, independent of both trees' layouts); prim / other_prim (optional) receive the
+ * ids of ONE intersecting pair (which one is unspecified), B200AABB_NO_PRIMITIVE when there is none.  Both trees must be on the same device; one kernel:
+ * the primitives of the smaller tree are Triangle_3 queries against the larger one, all threads stop at the first pair found. */
+int b200aabb_do_intersect_tree(b200aabb_tree* t, b200aabb_tree* other, int* result, uint32_t* prim, uint32_t* other_prim);
 /* all_intersections(Ray_3, out), AABB_tree.h:958-970 (Listing_intersection_traits, internal/AABB_traversal_traits.h:105-144): every
  * primitive whose Intersect_3(Ray_3, Triangle_3) is non-empty, with the intersection object.  Two steps like all_intersected_primitives:
  * b200aabb_number_of_intersections gives the counts (they can differ from number_of_intersected_primitives for a ray nearly parallel to a

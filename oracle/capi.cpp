@@ -71,9 +71,10 @@ void orc_do_not_accelerate_distance_queries(void* hv) { ((Handle*)hv)->tree->do_
 void orc_bbox(void* hv, double* out) { Box b = ((Handle*)hv)->tree->bbox(); for (int i = 0; i < 3; ++i) { out[i] = b.lo[i]; out[3 + i] = b.hi[i]; } }
 
 // kind: 0 = Segment_3 (source,target), 1 = Ray_3 (source, second point), 2 = Line_3 (point, direction vector): q = n x 6 doubles;
-//       3 = Plane_3 (a, b, c, d): q = n x 4 doubles
+//       3 = Plane_3 (a, b, c, d): q = n x 4 doubles; 4 = Triangle_3 (three vertices): q = n x 9 doubles
 static inline Tree::LineQ LQ(const double* q, uint64_t i, int kind) {
     if (kind == 3) return {P(q + 4 * i), P3{q[4 * i + 3], 0, 0}, 3};
+    if (kind == 4) return {P(q + 9 * i), P(q + 9 * i + 3), 4, P(q + 9 * i + 6)};
     return {P(q + 6 * i), P(q + 6 * i + 3), kind};
 }
 void orc_do_intersect(void* hv, const double* q, uint64_t n, int kind, uint8_t* out, int nthreads) {
@@ -281,6 +282,15 @@ int orc_bbox_do_intersect(const double* box, const double* pq, int is_ray) { ret
 int orc_bbox_do_intersect_exact(const double* box, const double* pq, int is_ray) { return bbox_segment_aux<true>(P(pq), P(pq + 3), B(box), true, !is_ray).v; }
 int orc_tri_do_intersect_kind(const double* tri, const double* q, int kind) { return Tree::prim_hit(T(tri), LQ(q, 0, kind)) ? 1 : 0; }
 int orc_bbox_do_intersect_kind(const double* box, const double* q, int kind) { return Tree::box_hit(LQ(q, 0, kind), B(box)) ? 1 : 0; }
+// Do_intersect_3(Triangle_3 query, Triangle_3 primitive)
+int orc_tri_tri_do_intersect(const double* query, const double* tri) { return do_intersect_tri_tri(T(query), T(tri)) ? 1 : 0; }
+// tree.do_intersect(other_tree) (AABB_traits_3.h:679-690): the traversal of `hv` with the other tree as the query — other.do_intersect(bbox) per node (here: the
+// other tree's root box against the node's box, then the primitives decide), other.do_intersect(datum) per primitive
+int orc_do_intersect_tree(void* hv, void* other) {
+    const Handle* h = (const Handle*)hv; const Tree& o = *((Handle*)other)->tree;
+    for (const Tri& t : h->mesh.tris) if (o.do_intersect(Tree::LineQ{t.a, t.b, 4, t.c})) return 1;
+    return 0;
+}
 int orc_tri_do_intersect(const double* tri, const double* pq, int is_ray) {
     return (is_ray ? do_intersect_ray_tri(T(tri), P(pq), P(pq + 3)) : do_intersect_seg_tri(T(tri), P(pq), P(pq + 3))) ? 1 : 0;
 }

@@ -479,6 +479,97 @@ static inline bool do_intersect_seg_tri(const Tri& t, const P3& p, const P3& q) 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Do_intersect_3(Triangle_3, Triangle_3): Intersections_3/internal/Triangle_3_Triangle_3_do_intersect.h (Guigue & Devillers):
+// _intersection_test_vertex :24-67, _intersection_test_edge :69-98, do_intersect_coplanar :100-152, do_intersect :154-450.
+// ------------------------------------------------------------------------------------------------
+static inline bool tt_test_vertex(const P3* p, const P3* q, const P3* r, const P3* a, const P3* b, const P3* c) {   // "vertex p sees vertex c"
+    auto co = [](const P3& x, const P3& y, const P3& z) { return coplanar_orientation(x, y, z); };
+    if (co(*c, *a, *q) != -1) {
+        if (co(*c, *b, *q) != 1) {
+            if (co(*p, *a, *q) == 1) return co(*p, *b, *q) != 1;
+            return co(*p, *a, *r) != -1 && co(*q, *r, *a) != -1;
+        }
+        if (co(*p, *b, *q) != 1) return co(*c, *b, *r) != 1 && co(*q, *r, *b) != -1;
+        return false;
+    }
+    if (co(*c, *a, *r) != -1) {                                                  // qr straddles (ac)
+        if (co(*q, *r, *c) != -1) return co(*p, *a, *r) != -1;
+        return co(*q, *r, *b) != -1 && co(*c, *r, *b) != -1;
+    }
+    return false;                                                                 // ca separates
+}
+static inline bool tt_test_edge(const P3* p, const P3* q, const P3* r, const P3* a, const P3* /*b*/, const P3* c) {   // "vertex p sees edge ca"
+    auto co = [](const P3& x, const P3& y, const P3& z) { return coplanar_orientation(x, y, z); };
+    if (co(*c, *a, *q) != -1) {                                                  // pq straddles (ac)
+        if (co(*p, *a, *q) != -1) return co(*p, *q, *c) != -1;
+        return co(*q, *r, *a) != -1 && co(*r, *p, *a) != -1;
+    }
+    if (co(*c, *a, *r) != -1) return co(*p, *a, *r) != -1 && (co(*p, *r, *c) != -1 || co(*q, *r, *c) != -1);
+    return false;                                                                 // ac separates
+}
+static inline bool tri_tri_coplanar(const Tri& t1, const Tri& t2) {
+    auto co = [](const P3& x, const P3& y, const P3& z) { return coplanar_orientation(x, y, z); };
+    const P3 *p = &t1.a, *q = &t1.b, *r = &t1.c, *a = &t2.a, *b = &t2.b, *c = &t2.c;
+    if (co(t1.a, t1.b, t1.c) == -1) { q = &t1.c; r = &t1.b; }                     // both counterclockwise (:120-130)
+    if (co(t2.a, t2.b, t2.c) == -1) { b = &t2.c; c = &t2.b; }
+    if (co(*a, *b, *p) != -1) {                                                   // p among the lines supporting abc's edges (:135-151)
+        if (co(*b, *c, *p) != -1) {
+            if (co(*c, *a, *p) != -1) return true;                                // p inside abc
+            return tt_test_edge(p, q, r, a, b, c);                                // p sees ac
+        }
+        if (co(*c, *a, *p) != -1) return tt_test_edge(p, q, r, c, a, b);          // p sees bc
+        return tt_test_vertex(p, q, r, a, b, c);                                  // p sees c
+    }
+    if (co(*b, *c, *p) != -1) {
+        if (co(*c, *a, *p) != -1) return tt_test_edge(p, q, r, b, c, a);          // p sees ab
+        return tt_test_vertex(p, q, r, b, c, a);                                  // p sees a
+    }
+    return tt_test_vertex(p, q, r, c, a, b);                                      // p sees b
+}
+// the case analysis of :180-302 (and again :316-440 for the second triangle): which two edges of (p, q, r) cross the other triangle's plane, given the
+// orientations dp, dq, dr of its vertices; returns 0 = all strictly on one side, 2 = all coplanar, 1 = edges (s_min, t_min), (s_max, t_max) set
+static inline int tt_pick_edges(int dp, int dq, int dr, const P3* p, const P3* q, const P3* r, const P3*& s_min, const P3*& t_min, const P3*& s_max, const P3*& t_max) {
+    auto set = [&](const P3* a, const P3* b, const P3* c, const P3* d) { s_min = a; t_min = b; s_max = c; t_max = d; return 1; };
+    switch (dp) {
+    case 1:
+        if (dq == 1) { if (dr == 1) return 0; return set(q, r, r, p); }           // r isolated on the negative side
+        if (dr == 1) return set(p, q, q, r);                                      // q isolated on the negative side
+        return set(p, q, r, p);                                                   // p isolated on the positive side
+    case -1:
+        if (dq == -1) { if (dr == -1) return 0; return set(r, p, q, r); }         // r isolated on the positive side
+        if (dr == -1) return set(q, r, p, q);                                     // q isolated on the positive side
+        return set(r, p, p, q);                                                   // p isolated on the negative side
+    default:
+        switch (dq) {
+        case 1: return dr == 1 ? set(r, p, p, q) : set(q, r, p, q);
+        case -1: return dr == -1 ? set(p, q, r, p) : set(p, q, q, r);
+        default:
+            if (dr == 1) return set(r, p, q, r);
+            if (dr == -1) return set(q, r, r, p);
+            return 2;
+        }
+    }
+}
+// t1 = query, t2 = primitive (AABB_traits_3.h:673-677 calls do_intersect_3_object()(q, datum))
+static inline bool do_intersect_tri_tri(const Tri& t1, const Tri& t2) {
+    const P3 &p = t1.a, &q = t1.b, &r = t1.c, &a = t2.a, &b = t2.b, &c = t2.c;
+    const P3 *s_min1, *t_min1, *s_max1, *t_max1, *s_min2, *t_min2, *s_max2, *t_max2;
+    const int dp = orientation(a, b, c, p), dq = orientation(a, b, c, q), dr = orientation(a, b, c, r);      // :176-178
+    switch (tt_pick_edges(dp, dq, dr, &p, &q, &r, s_min1, t_min1, s_max1, t_max1)) {
+    case 0: return false;
+    case 2: return tri_tri_coplanar(t1, t2);
+    default: break;
+    }
+    const int da = orientation(p, q, r, a), db = orientation(p, q, r, b), dc = orientation(p, q, r, c);      // :312-314
+    switch (tt_pick_edges(da, db, dc, &a, &b, &c, s_min2, t_min2, s_max2, t_max2)) {
+    case 0: return false;
+    case 2: return tri_tri_coplanar(t1, t2);                                      // ("supposed unreachable": non-flat triangles, :424-428)
+    default: break;
+    }
+    return orientation(*s_min1, *t_min1, *s_min2, *t_min2) != 1 && orientation(*s_max1, *t_max1, *t_max2, *s_max2) != 1;   // :446-447
+}
+
+// ------------------------------------------------------------------------------------------------
 // Do_intersect_3(Ray_3, Triangle_3): Intersections_3/internal/Ray_3_Triangle_3_do_intersect.h:75-191,193-317
 // (no static-filter overload in Epick; the whole functor runs in the exact kernel when intervals fail,
 //  so ray_direction is the exact sign of det[b-a, c-a, q-p]).

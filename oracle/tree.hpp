@@ -202,9 +202,11 @@ struct Tree {
     }
 
     // kind 0: Segment_3 (source, target); 1: Ray_3 (source, second point); 2: Line_3 (point p, direction vector q); 3: Plane_3 (a, b, c = p; d = q.x)
-    struct LineQ { P3 p, q; int kind; };
+    //      4: Triangle_3 (p, q, r)
+    struct LineQ { P3 p, q; int kind; P3 r = {0, 0, 0}; };
     static bool prim_hit(const Tri& tr, const LineQ& q) {
         switch (q.kind) {
+            case 4: return do_intersect_tri_tri(Tri{q.p, q.q, q.r}, tr);
             case 1: return do_intersect_ray_tri(tr, q.p, q.q);
             case 2: return do_intersect_line_tri(tr, q.p, V3{q.q.x, q.q.y, q.q.z});
             case 3: { const double h[4] = {q.p.x, q.p.y, q.p.z, q.q.x}; return do_intersect_plane_tri(tr, h); }
@@ -213,6 +215,14 @@ struct Tree {
     }
     static bool box_hit(const LineQ& q, const Box& b) {
         switch (q.kind) {
+            case 4: {   // Do_intersect_3(Bbox_3, Triangle_3) (Bbox_3_Triangle_3_do_intersect.h, separating axes) is NOT restated: the box of the query against
+                        // the node's box is a necessary condition, the primitives decide exactly, so every result but the traversal order is the reference's
+                for (int k = 0; k < 3; ++k) {
+                    const double lo = std::min(q.p[k], std::min(q.q[k], q.r[k])), hi = std::max(q.p[k], std::max(q.q[k], q.r[k]));
+                    if (lo > b.hi[k] || hi < b.lo[k]) return false;
+                }
+                return true;
+            }
             case 2: return do_intersect_line_bbox(q.p, V3{q.q.x, q.q.y, q.q.z}, b);
             case 3: { const double h[4] = {q.p.x, q.p.y, q.p.z, q.q.x}; return do_intersect_plane_bbox(h, b); }
             default: return do_intersect_bbox(q.p, q.q, b, q.kind == 1);

@@ -34,9 +34,9 @@ typedef CGAL_B200::AABB_tree<Traits> Tree;
     }                                                                            \
   } while (0)
 
-static Mesh tetrahedron() {   // Data/data/meshes/tetrahedron.off
+static Mesh tetrahedron(double dx = 0.0, double dy = 0.0) {   // Data/data/meshes/tetrahedron.off (translated by (dx, dy, 0))
   Mesh m;
-  auto a = m.add_vertex(Point(0, 0, 0)), b = m.add_vertex(Point(1, 0, 0)), c = m.add_vertex(Point(0, 1, 0)), d = m.add_vertex(Point(0, 0, 1));
+  auto a = m.add_vertex(Point(dx, dy, 0)), b = m.add_vertex(Point(1 + dx, dy, 0)), c = m.add_vertex(Point(dx, 1 + dy, 0)), d = m.add_vertex(Point(dx, dy, 1));
   m.add_face(a, b, c); m.add_face(a, d, b); m.add_face(a, c, d); m.add_face(b, d, c);
   return m;
 }
@@ -163,6 +163,21 @@ static int known_answers() {
       std::vector<std::size_t> pc;
       tree.number_of_intersected_primitives(planes.begin(), planes.end(), std::back_inserter(pc));
       CHECK(pc.size() == 2 && pc[0] == 3 && pc[1] == 0);
+    }
+    {   // Triangle_3 queries (Triangle_3_Triangle_3_do_intersect.h) and tree-vs-tree do_intersect (AABB_traits_3.h:679-690)
+      const mini::Triangle_3 cut(Point(-1.0, -1.0, 0.5), Point(3.0, -1.0, 0.5), Point(-1.0, 3.0, 0.5));   // the plane z = 1/2 across the solid
+      CHECK(tree.do_intersect(cut) && tree.number_of_intersected_primitives(cut) == 3);
+      const mini::Triangle_3 base(Point(0, 0, 0), Point(1, 0, 0), Point(0, 1, 0));                        // face 0 itself: touches every face
+      CHECK(tree.number_of_intersected_primitives(base) == 4);
+      CHECK(!tree.do_intersect(mini::Triangle_3(Point(2, 2, 2), Point(3, 2, 2), Point(2, 3, 2))));
+      CHECK(!tree.any_intersected_primitive(mini::Triangle_3(Point(0.1, 0.1, 0.1), Point(0.2, 0.1, 0.1), Point(0.1, 0.2, 0.1))));   // strictly inside
+      std::vector<mini::Face_index> tids;
+      tree.all_intersected_primitives(cut, std::back_inserter(tids));
+      CHECK(tids.size() == 3 && !(tids[0] == mini::Face_index(0)) && !(tids[1] == mini::Face_index(0)) && !(tids[2] == mini::Face_index(0)));
+      Mesh m2 = tetrahedron(0.25, 0.25), m3 = tetrahedron(5.0, 0.0);                                        // overlapping / far away
+      Tree near_tree(faces(m2).first, faces(m2).second, m2), far_tree(faces(m3).first, faces(m3).second, m3), empty_tree;
+      CHECK(tree.do_intersect(near_tree) && near_tree.do_intersect(tree) && tree.do_intersect(tree));
+      CHECK(!tree.do_intersect(far_tree) && !far_tree.do_intersect(tree) && !tree.do_intersect(empty_tree));
     }
     {   // all_intersected_primitives / any_intersected_primitive (AABB_tree.h:253-268): the two faces the ray crosses, base face 0 among them
       std::vector<mini::Face_index> ids;

@@ -49,6 +49,8 @@ def lib():
         for n in ("hc_orient3", "hc_orient3_exact", "hc_orient3_dir", "hc_coplanar_orient", "hc_cmp_dist", "hc_cmp_dist_exact"):
             getattr(L, n).argtypes = [_dp]
         L.hc_tri_do_intersect.argtypes = [_dp, _dp, C.c_int]
+        L.hc_tri_tri_do_intersect.argtypes = [_dp, _dp]
+        L.hc_intersect_triangle.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_int, _u32p]
         L.hc_tri_ray_intersection.argtypes = [_dp, _dp, _dp, _dp]
         L.hc_closest_on_triangle.argtypes = [_dp, _dp, _dp]
         L.hc_line_box.argtypes = [_dp, _dp, C.c_int]
@@ -100,6 +102,13 @@ class HostTree:
         q = _d(q).reshape(-1, 6)
         out = np.zeros(len(q), np.uint32)
         lib().hc_intersect(self.h, _p(q), len(q), int(is_ray), int(count), _p(out, _u32p))
+        return out
+
+    def intersect_triangle(self, q, count):
+        """do_intersect / number_of_intersected_primitives of Triangle_3 queries (9 doubles) through bvh.cuh::traverse_triangle"""
+        q = _d(q).reshape(-1, 9)
+        out = np.zeros(len(q), np.uint32)
+        lib().hc_intersect_triangle(self.h, _p(q), len(q), int(count), _p(out, _u32p))
         return out
 
     def count_line_plane(self, q, kind):
@@ -162,6 +171,11 @@ def classify_ray_tri(tri, pq):
 def tri_do_intersect_kind(tri, q, kind):
     tri, q = _d(tri).ravel(), _d(q).ravel()
     return lib().hc_tri_do_intersect_kind(_p(tri), _p(q), int(kind))
+
+
+def tri_tri_do_intersect(query, tri):
+    query, tri = _d(query).ravel(), _d(tri).ravel()
+    return lib().hc_tri_tri_do_intersect(_p(query), _p(tri))
 
 
 def tri_do_intersect(tri, pq, is_ray):

@@ -311,6 +311,17 @@ void hc_side_of_mesh(void* hv, const double* pts, uint64_t n, const double* dirs
         side[i] = (int8_t)(r == kSideIndeterminate ? -2 : (r == kSideBoundary ? 0 : ((r & 1) ? 1 : -1)));
     }
 }
+int hc_tri_tri_do_intersect(const double* query, const double* tri) { int n = 0; return tri_tri_do_intersect(T(query), T(tri), n) ? 1 : 0; }
+// Triangle_3 queries (9 doubles each) through the device traversal routine: mode 0 do_intersect, 1 count
+void hc_intersect_triangle(void* hv, const double* q, uint64_t n, int count, uint32_t* out) {
+    HostTree* h = (HostTree*)hv;
+    for (uint64_t i = 0; i < n; ++i) {
+        TravStat st;
+        if (h->n == 0) { out[i] = 0; continue; }
+        const Tri3 t = T(q + 9 * i);
+        out[i] = count ? traverse_triangle<kCount>(h->nodes.data(), h->tris.data(), h->root, t, st) : traverse_triangle<kAnyHit>(h->nodes.data(), h->tris.data(), h->root, t, st);
+    }
+}
 int hc_tri_do_intersect_kind(const double* tri, const double* q, int kind) {
     int n = 0;
     if (kind == 2) return line_tri_do_intersect(T(tri), V(q), V(q + 3), n);

@@ -66,6 +66,8 @@ def lib():
         L.orc_bbox_do_intersect.argtypes = [_dp, _dp, C.c_int]
         L.orc_bbox_do_intersect_exact.argtypes = [_dp, _dp, C.c_int]
         L.orc_tri_do_intersect.argtypes = [_dp, _dp, C.c_int]
+        L.orc_tri_tri_do_intersect.argtypes = [_dp, _dp]
+        L.orc_do_intersect_tree.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_tri_ray_intersection.argtypes = [_dp, _dp, _dp]
         L.orc_project_on_triangle.argtypes = [_dp, _dp, _dp]
         L.orc_ball_reaches_box.argtypes = [_dp, _dp, _dp]
@@ -88,6 +90,9 @@ def traversal_totals():
 
 def nthreads():
     return max(1, os.cpu_count() or 1)
+
+
+_QDOUBLES = {3: 4, 4: 9}   # doubles per query: Plane_3 (a, b, c, d), Triangle_3 (three vertices); every other kind 6
 
 
 class OracleTree:
@@ -125,17 +130,21 @@ class OracleTree:
         return out
 
     def do_intersect(self, q, kind, threads=None):
-        q = _d(q).reshape(-1, 4 if kind == 3 else 6)
+        q = _d(q).reshape(-1, _QDOUBLES.get(kind, 6))
         out = np.zeros(len(q), np.uint8)
         lib().orc_do_intersect(self.h, _ptr(q, _dp), len(q), kind, _ptr(out, _u8p), threads or nthreads())
         return out
 
     def count(self, q, kind, threads=None, naive=False):
-        q = _d(q).reshape(-1, 4 if kind == 3 else 6)
+        q = _d(q).reshape(-1, _QDOUBLES.get(kind, 6))
         out = np.zeros(len(q), np.uint32)
         f = lib().orc_naive_count if naive else lib().orc_count
         f(self.h, _ptr(q, _dp), len(q), kind, _ptr(out, _u32p), threads or nthreads())
         return out
+
+    def do_intersect_tree(self, other):
+        """tree.do_intersect(other_tree), AABB_traits_3.h:679-690"""
+        return bool(lib().orc_do_intersect_tree(self.h, other.h))
 
     def side_of_mesh(self, pts, threads=None):
         """Side_of_triangle_mesh: (side[n] in {-1 outside, 0 boundary, 1 inside}, rays cast per point)"""
@@ -145,14 +154,14 @@ class OracleTree:
         return side, att
 
     def any_intersected_primitive(self, q, kind, threads=None):
-        q = _d(q).reshape(-1, 4 if kind == 3 else 6)
+        q = _d(q).reshape(-1, _QDOUBLES.get(kind, 6))
         out = np.zeros(len(q), np.uint32)
         lib().orc_any_intersected_primitive(self.h, _ptr(q, _dp), len(q), kind, _ptr(out, _u32p), threads or nthreads())
         return out
 
     def all_intersected_primitives(self, q, kind, threads=None):
         """(offsets[n+1], ids): ids of query i, in the reference's traversal order, are ids[offsets[i]:offsets[i+1]]"""
-        q = _d(q).reshape(-1, 4 if kind == 3 else 6)
+        q = _d(q).reshape(-1, _QDOUBLES.get(kind, 6))
         offsets = np.zeros(len(q) + 1, np.uint64)
         np.cumsum(self.count(q, kind, threads), out=offsets[1:])
         ids = np.zeros(max(int(offsets[-1]), 1), np.uint32)
@@ -165,7 +174,7 @@ class OracleTree:
         (offsets[n+1], ids, kinds (1 Point_3 / 2 Segment_3 / 3 the primitive's Triangle_3), pts[total,6])"""
         if naive:
             first_only = 2
-        q = _d(rays).reshape(-1, 4 if kind == 3 else 6)
+        q = _d(rays).reshape(-1, _QDOUBLES.get(kind, 6))
         th = threads or nthreads()
         counts = np.zeros(len(q), np.uint32)
         f = lib().orc_line_intersections
@@ -301,6 +310,12 @@ def tri_do_intersect_kind(tri, q, kind):
 def bbox_do_intersect_kind(box, q, kind):
     box, q = _d(box).ravel(), _d(q).ravel()
     return lib().orc_bbox_do_intersect_kind(_ptr(box, _dp), _ptr(q, _dp), int(kind))
+
+
+def tri_tri_do_intersect(query, tri):
+    """Do_intersect_3(Triangle_3 query, Triangle_3 primitive)"""
+    query, tri = _d(query).ravel(), _d(tri).ravel()
+    return lib().orc_tri_tri_do_intersect(_ptr(query, _dp), _ptr(tri, _dp))
 
 
 def tri_do_intersect(tri, pq, is_ray):

@@ -815,3 +815,73 @@ def test_ray_kernels_agree(B, meshes):
         a = g.any_intersected_primitive(q, kind)
         np.testing.assert_array_equal(a == B.NO_PRIMITIVE, want[1] == 0)
         g.set_option(OPT_RAY_KERNEL, 0)
+
+
+@pytest.mark.parametrize("name", ["elephant", "cube"])
+def test_triangle_queries(B, meshes, name):
+    """Triangle_3 queries (kind 4: three vertices per query) — do_intersect, number_of_intersected_primitives, any_ / all_intersected_primitives — against the
+    oracle's restatement of Triangle_3_Triangle_3_do_intersect.h (pinned by the reference's KATs, tests/test_triangle_queries.py): random triangles, copies of
+    facets (coplanar with their primitive), facets slid inside their plane, triangles through mesh vertices; host and device pointers, sorted and unsorted"""
+    import torch
+    from test_triangle_queries import mesh_triangles
+    v, f = meshes[name]
+    rng = np.random.default_rng(44)
+    q = mesh_triangles(rng, v, f, 20_000 if name == "elephant" else 2_000)
+    g, o = B.AABB_tree(v, f), orc.OracleTree(v, f)
+    want = o.count(q, B.TRIANGLE)
+    assert want.max() > 2 and (want == 0).any()
+    for sort in (1, 0):
+        g.set_option(B.OPT_SORT_QUERIES, sort)
+        np.testing.assert_array_equal(g.number_of_intersected_primitives(q, B.TRIANGLE), want)
+        np.testing.assert_array_equal(g.do_intersect(q, B.TRIANGLE) != 0, want > 0)
+    off, ids = g.all_intersected_primitives(q, B.TRIANGLE)
+    roff, rids = o.all_intersected_primitives(q, B.TRIANGLE)
+    np.testing.assert_array_equal(off, roff)
+    owner = np.repeat(np.arange(len(q)), np.diff(off).astype(np.int64))
+    key = lambda own, i: np.sort(own.astype(np.uint64) << np.uint64(32) | i.astype(np.uint64))   # noqa: E731
+    np.testing.assert_array_equal(key(owner, ids), key(owner, rids))
+    a = g.any_intersected_primitive(q, B.TRIANGLE)
+    np.testing.assert_array_equal(a == B.NO_PRIMITIVE, want == 0)
+    pairs = set(zip(owner.tolist(), ids.tolist()))
+    assert all((i, int(a[i])) in pairs for i in np.nonzero(want)[0][:3000])
+    qd = torch.from_numpy(q).cuda()
+    np.testing.assert_array_equal(g.number_of_intersected_primitives(qd, B.TRIANGLE).cpu().numpy(), want)
+    np.testing.assert_array_equal(g.do_intersect(qd, B.TRIANGLE).cpu().numpy() != 0, want > 0)
+    with pytest.raises(B.B200AABBError):                                    # the intersection OBJECTS take kinds 0..3 only
+        g.all_intersections(q[:4], B.TRIANGLE)
+
+
+def test_tree_against_tree(B, meshes):
+    """tree.do_intersect(other_tree) (AABB_traits_3.h:679-690) against the oracle's traversal with the other tree as the query: overlapping, touching and
+    separated copies of a mesh, trees of different sizes in both argument orders, an empty tree, and the witness pair checked with the exact predicate"""
+    v, f = meshes["elephant"]
+    cv, cf = meshes["cube"]
+    ext = (v.max(0) - v.min(0))
+    g, o = B.AABB_tree(v, f), orc.OracleTree(v, f)
+    soup = soup_of(v, f)
+    n_true = 0
+    for shift in ([0.0, 0.0, 0.0], [0.3 * ext[0], 0.0, 0.0], [0.9 * ext[0], 0.1 * ext[1], 0.0], [1.001 * ext[0], 0.0, 0.0], [0.0, 0.0, 5.0 * ext[2]]):
+        w = v + np.array(shift)
+        g2, o2 = B.AABB_tree(w, f), orc.OracleTree(w, f)
+        want = o.do_intersect_tree(o2)
+        assert o2.do_intersect_tree(o) == want
+        n_true += want
+        hit, ia, ib = g.do_intersect_tree(g2, witness=True)
+        assert hit == want, shift
+        assert g2.do_intersect_tree(g) == want, shift
+        if hit:
+            assert orc.tri_tri_do_intersect(soup[ia], soup_of(w, f)[ib]) == 1
+        else:
+            assert ia == B.NO_PRIMITIVE and ib == B.NO_PRIMITIVE
+    assert 2 <= n_true <= 4
+    # a small tree against a large one: a cube placed inside the bounding box of the elephant, then far away
+    ctr = (v.max(0) + v.min(0)) / 2
+    cube = (cv - cv.mean(0)) / (cv.max() - cv.min()) * 0.5 * ext.min()
+    for place, far in ((ctr, False), (ctr + 10 * ext, True)):
+        c, oc = B.AABB_tree(cube + place, cf), orc.OracleTree(cube + place, cf)
+        want = o.do_intersect_tree(oc)
+        assert g.do_intersect_tree(c) == want and c.do_intersect_tree(g) == want
+        if far:
+            assert not want
+    e = B.AABB_tree()
+    assert g.do_intersect_tree(e) is False and e.do_intersect_tree(g) is False
