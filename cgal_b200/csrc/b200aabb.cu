@@ -1154,6 +1154,7 @@ int b200aabb_create(int device, b200aabb_tree** out) {
         ok = cudaEventCreateWithFlags(&t->ev_up[s], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&t->ev_run[s], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&t->ev_down[s], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMalloc(&t->d_ray_cursor, kScratchSlots * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMemset(t->d_counters, 0, 8 * sizeof(unsigned long long)) == cudaSuccess;   // (drain() may read them before the first query has reset them)
     if (ok) {
         int per_sm = 0;
         ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, first_intersection_stream_kernel, 128, 0) == cudaSuccess;
