@@ -40,7 +40,7 @@ class _Stats(C.Structure):
 SYMBOLS = ["b200aabb_create", "b200aabb_destroy", "b200aabb_set_stream", "b200aabb_set_option", "b200aabb_last_error", "b200aabb_get_stats", "b200aabb_synchronize",
            "b200aabb_set_mesh", "b200aabb_set_triangles", "b200aabb_clear", "b200aabb_build", "b200aabb_refit", "b200aabb_refit_mesh",
            "b200aabb_accelerate_distance_queries", "b200aabb_size", "b200aabb_bbox", "b200aabb_do_intersect",
-           "b200aabb_number_of_intersected_primitives", "b200aabb_any_intersected_primitive", "b200aabb_all_intersected_primitives", "b200aabb_do_intersect_tree",
+           "b200aabb_number_of_intersected_primitives", "b200aabb_any_intersected_primitive", "b200aabb_all_intersected_primitives", "b200aabb_do_intersect_tree", "b200aabb_do_intersect_tree_transformed",
            "b200aabb_number_of_intersections", "b200aabb_all_intersections", "b200aabb_any_intersection",
            "b200aabb_number_of_intersections_q", "b200aabb_all_intersections_q", "b200aabb_any_intersection_q",
            "b200aabb_first_intersection", "b200aabb_first_intersection_skip", "b200aabb_closest_point", "b200aabb_max_distance_to_mesh", "b200aabb_side_of_mesh",
@@ -84,6 +84,7 @@ def load_library():
         L.b200aabb_any_intersected_primitive.argtypes = [vp, dp, u64, C.c_int, C.c_int, dp]
         L.b200aabb_all_intersected_primitives.argtypes = [vp, dp, u64, C.c_int, C.c_int, dp, dp]
         L.b200aabb_do_intersect_tree.argtypes = [vp, vp, C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.b200aabb_do_intersect_tree_transformed.argtypes = [vp, dp, vp, dp, C.POINTER(C.c_int), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.b200aabb_number_of_intersections.argtypes = [vp, dp, u64, C.c_int, dp]
         L.b200aabb_all_intersections.argtypes = [vp, dp, u64, C.c_int, dp, dp, dp, dp]
         L.b200aabb_any_intersection.argtypes = [vp, dp, u64, C.c_int, dp, dp, dp, dp]
@@ -289,10 +290,18 @@ class AABB_tree:
         self._check(self._lib.b200aabb_all_intersected_primitives(self._h, q.ptr, q.n, kind, 0, offsets.ctypes.data, ids.ctypes.data))
         return offsets, ids[:int(offsets[-1])]
 
-    def do_intersect_tree(self, other, witness=False):
+    def do_intersect_tree(self, other, witness=False, xf=None, other_xf=None):
         """tree.do_intersect(other_tree) (AABB_traits_3.h:679-690): True iff a primitive of this tree intersects a primitive of `other` (same device);
-        witness=True -> (bool, id in this tree, id in other) of one intersecting pair (NO_PRIMITIVE twice when there is none)"""
+        witness=True -> (bool, id in this tree, id in other) of one intersecting pair (NO_PRIMITIVE twice when there is none).
+        xf / other_xf: 3 x 4 affine maps (Aff_transformation_3::m(i, j), row major) the two meshes stand under, as in
+        Rigid_triangle_mesh_collision_detection::does_A_intersect_B; None = identity"""
         r, a, b = C.c_int(0), C.c_uint32(NO_PRIMITIVE), C.c_uint32(NO_PRIMITIVE)
+        if xf is not None or other_xf is not None:
+            m1 = None if xf is None else np.ascontiguousarray(xf, np.float64).reshape(12)
+            m2 = None if other_xf is None else np.ascontiguousarray(other_xf, np.float64).reshape(12)
+            self._check(self._lib.b200aabb_do_intersect_tree_transformed(self._h, None if m1 is None else m1.ctypes.data, other._h, None if m2 is None else m2.ctypes.data,
+                                                                         C.byref(r), C.byref(a), C.byref(b)))
+            return (bool(r.value), a.value, b.value) if witness else bool(r.value)
         self._check(self._lib.b200aabb_do_intersect_tree(self._h, other._h, C.byref(r), C.byref(a), C.byref(b)))
         return (bool(r.value), a.value, b.value) if witness else bool(r.value)
 

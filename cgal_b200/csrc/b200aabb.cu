@@ -264,13 +264,19 @@ __global__ void __launch_bounds__(128, 6) triangle_kernel(const TreeRef tr, cons
 // traversal stops at the first pair): one thread per primitive of `a` (its Morton order is the coherence order), traversing `tr` = the other tree;
 // witness[0] = 1 at the first intersecting pair found, witness[1] / [2] = ids of one such pair (which one is unspecified).  Threads that start after a
 // pair has been found return at once.
-__global__ void __launch_bounds__(128, 6) tree_tree_kernel(const TreeRef tr, const TriRec* __restrict__ a, uint64_t na, unsigned* __restrict__ witness) {
+// XF: both trees stand under affine transformations (Rigid_triangle_mesh_collision_detection::does_A_intersect_B, :149-161): x.q transforms the primitives
+// that serve as queries, x.b the traversed tree (its primitives at the leaves, its boxes at the nodes, bvh.cuh::AffXf).
+struct XfPair { AffXf q, b; };
+template <bool XF>
+__global__ void __launch_bounds__(128, 6) tree_tree_kernel(const TreeRef tr, const TriRec* __restrict__ a, uint64_t na, unsigned* __restrict__ witness, const XfPair x) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     TravStat st;
     if (i < na && *(volatile unsigned*)witness == 0u) {
         uint32_t ida;
-        const Tri3 t = load_tri(a, (uint32_t)i, ida);
-        const uint32_t idb = traverse_triangle<kAnyId>(tr.nodes, tr.tris, tr.root, t, st);
+        Tri3 t = load_tri(a, (uint32_t)i, ida);
+        uint32_t idb;
+        if (XF) { t = x.q.apply(t); idb = traverse_triangle<kAnyId, AffXf>(tr.nodes, tr.tris, tr.root, t, st, nullptr, 0, x.b); }
+        else idb = traverse_triangle<kAnyId>(tr.nodes, tr.tris, tr.root, t, st);
         if (idb != kNone && atomicExch(&witness[0], 1u) == 0u) { witness[1] = ida; witness[2] = idb; }
     }
     flush_stats(tr, st, 0, 0);
@@ -1463,6 +1469,10 @@ int b200aabb_all_intersected_primitives(b200aabb_tree* t, const double* q, uint6
 }
 
 int b200aabb_do_intersect_tree(b200aabb_tree* t, b200aabb_tree* other, int* result, uint32_t* prim, uint32_t* other_prim) {
+    return b200aabb_do_intersect_tree_transformed(t, nullptr, other, nullptr, result, prim, other_prim);
+}
+int b200aabb_do_intersect_tree_transformed(b200aabb_tree* t, const double* xf, b200aabb_tree* other, const double* other_xf, int* result, uint32_t* prim,
+                                           uint32_t* other_prim) {
     if (!t || !other || !result) return B200AABB_ERR_INVALID_ARGUMENT;
     // both handles are locked, in address order (two threads testing (a, b) and (b, a) must not dead-lock)
     std::unique_lock<std::recursive_mutex> l1((t < other ? t : other)->mu), l2;
@@ -1490,7 +1500,14 @@ int b200aabb_do_intersect_tree(b200aabb_tree* t, b200aabb_tree* other, int* resu
     rc = reset_counters(big, t->stream);
     if (rc) { cudaFree(d_w); return rc; }
     cudaEventRecord(t->ev_a, t->stream);
-    tree_tree_kernel<<<grid_for(small->n, 128), 128, 0, t->stream>>>(tree_ref(big, nullptr), small->d_tris, small->n, d_w);
+    XfPair x;
+    static const double kIdentity[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
+    const double* xf_small = small == t ? xf : other_xf;
+    const double* xf_big = big == t ? xf : other_xf;
+    memcpy(x.q.m, xf_small ? xf_small : kIdentity, sizeof(x.q.m));
+    memcpy(x.b.m, xf_big ? xf_big : kIdentity, sizeof(x.b.m));
+    if (xf || other_xf) tree_tree_kernel<true><<<grid_for(small->n, 128), 128, 0, t->stream>>>(tree_ref(big, nullptr), small->d_tris, small->n, d_w, x);
+    else tree_tree_kernel<false><<<grid_for(small->n, 128), 128, 0, t->stream>>>(tree_ref(big, nullptr), small->d_tris, small->n, d_w, x);
     t->stats.kernel_launches += 1;
     cudaEventRecord(t->ev_b, t->stream);
     t->query_timing_pending = true;

@@ -339,15 +339,47 @@ B2_HD BoxCtx make_box_of(const Tri3& t) {
 B2_HD bool box_box(const float* lo, const float* hi, const BoxCtx& c) {
     return lo[0] <= c.hi[0] && c.lo[0] <= hi[0] && lo[1] <= c.hi[1] && c.lo[1] <= hi[1] && lo[2] <= c.hi[2] && c.lo[2] <= hi[2];
 }
-template <int MODE>
+// The traversed tree may stand under an affine transformation (Rigid_triangle_mesh_collision_detection.h: each mesh keeps its tree, built once, and an
+// Aff_transformation_3; Polygon_mesh_processing/internal/AABB_traversal_traits_with_transformation.h:141-156 transforms the DATUM of each primitive and the box of
+// each node on the fly).  m = the 3 x 4 matrix (m(i, j) of Aff_transformation_3, row major).  A point is transformed as Aff_transformation_repC3::transform
+// does (Cartesian/Aff_transformation_rep_3.h:111-117: t11 x + t12 y + t13 z + t14, left to right, no fused operations) — for the translation and scaling
+// representations the same expression gives their results (1 x + 0 y + 0 z + t = x + t; s x + 0 + 0 + 0 = s x) — and the exact predicates see the rounded image.
+struct NoXf {
+    B2_HD Tri3 apply(const Tri3& t) const { return t; }
+    B2_HD bool box_meets(const float* lo, const float* hi, const BoxCtx& c) const { return box_box(lo, hi, c); }
+};
+struct AffXf {
+    double m[12];
+    B2_HD Vec3 point(const Vec3& p) const {
+        return {((m[0] * p.x + m[1] * p.y) + m[2] * p.z) + m[3], ((m[4] * p.x + m[5] * p.y) + m[6] * p.z) + m[7], ((m[8] * p.x + m[9] * p.y) + m[10] * p.z) + m[11]};
+    }
+    B2_HD Tri3 apply(const Tri3& t) const { return {point(t.a), point(t.b), point(t.c)}; }
+    // image of the box as centre +- |M| half-extent (the reference takes the box of the 8 transformed corners in interval arithmetic, :36-68: the same box
+    // up to rounding); widened by a bound of its own rounding and of the rounding of the transformed primitives it has to contain
+    B2_HD bool box_meets(const float* lo, const float* hi, const BoxCtx& c) const {
+        const double cx = 0.5 * ((double)lo[0] + (double)hi[0]), cy = 0.5 * ((double)lo[1] + (double)hi[1]), cz = 0.5 * ((double)lo[2] + (double)hi[2]);
+        const double hx = 0.5 * ((double)hi[0] - (double)lo[0]), hy = 0.5 * ((double)hi[1] - (double)lo[1]), hz = 0.5 * ((double)hi[2] - (double)lo[2]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double* r = m + 4 * k;
+            const double ctr = ((r[0] * cx + r[1] * cy) + r[2] * cz) + r[3];
+            const double ext = (fabs(r[0]) * hx + fabs(r[1]) * hy) + fabs(r[2]) * hz;
+            const double mag = ((fabs(r[0]) * (fabs(cx) + hx) + fabs(r[1]) * (fabs(cy) + hy)) + fabs(r[2]) * (fabs(cz) + hz)) + fabs(r[3]);
+            const double wide = ext + 1e-14 * mag;
+            if (!(ctr - wide <= (double)c.hi[k] && (double)c.lo[k] <= ctr + wide)) return !(ctr == ctr && wide == wide);   // (NaN / overflow: keep the box)
+        }
+        return true;
+    }
+};
+template <int MODE, class XF = NoXf>
 B2_HD uint32_t traverse_triangle(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root, const Tri3& query, TravStat& st,
-                                 uint32_t* list = nullptr, uint32_t list_cap = 0) {
+                                 uint32_t* list = nullptr, uint32_t list_cap = 0, const XF& xf = XF()) {
     constexpr bool kStopAtFirst = MODE == kAnyHit || MODE == kAnyId;
     const BoxCtx c = make_box_of(query);
     uint32_t found = 0, nlisted = 0, found_id = kNone;
     auto leaf = [&](uint32_t ref) -> bool {
         uint32_t id;
-        const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
+        const Tri3 t = xf.apply(load_tri(tris, ref & ~kLeafBit, id));
         ++st.leaves;
         if (!tri_tri_do_intersect(query, t, st.nexact)) return false;
         if (MODE == kList) { if (nlisted < list_cap) list[nlisted] = id; ++nlisted; }
@@ -366,7 +398,7 @@ B2_HD uint32_t traverse_triangle(const BvhNode* __restrict__ nodes, const TriRec
             while (cur != kNone && np < kPendGoAt) {          // node phase
                 const NodeView n = load_node(nodes, cur);
                 ++st.nodes;
-                const bool h0 = box_box(n.lo0, n.hi0, c), h1 = box_box(n.lo1, n.hi1, c);
+                const bool h0 = xf.box_meets(n.lo0, n.hi0, c), h1 = xf.box_meets(n.lo1, n.hi1, c);
                 uint32_t next = kNone;
                 if (h0) { if (n.c0 & kLeafBit) pend[np++] = n.c0; else next = n.c0; }
                 if (h1) {

@@ -201,6 +201,18 @@ class AABB_tree {
     check(b200aabb_do_intersect_tree(m_handle, other.handle(), &r, nullptr, nullptr));
     return r != 0;
   }
+  // the same with both trees under affine transformations: Rigid_triangle_mesh_collision_detection::does_A_intersect_B
+  // (Rigid_triangle_mesh_collision_detection.h:149-161) — trees built once on the untransformed meshes, Aff = CGAL::Aff_transformation_3<K> (m(i, j))
+  template <typename OtherTraits, typename Aff>
+  bool do_intersect(const AABB_tree<OtherTraits>& other, const Aff& transformation, const Aff& other_transformation) const {
+    ensure_built();
+    double a[12], b[12];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 4; ++j) { a[4 * i + j] = (double)transformation.m(i, j); b[4 * i + j] = (double)other_transformation.m(i, j); }
+    int r = 0;
+    check(b200aabb_do_intersect_tree_transformed(m_handle, a, other.handle(), b, &r, nullptr, nullptr));
+    return r != 0;
+  }
   template <typename Query>
   size_type number_of_intersected_primitives(const Query& query) const {
     size_type r = 0;
@@ -683,6 +695,48 @@ public:
   }
 private:
   const Tree* m_tree;
+};
+
+// The face-intersection part of Polygon_mesh_processing/include/CGAL/Rigid_triangle_mesh_collision_detection.h over device trees: meshes are added once
+// (one tree each, built once), moved by set_transformation, and get_all_intersections(id) lists the meshes with at least one face intersecting a face of
+// mesh `id` under the current transformations (:349-388; one tree-vs-tree kernel per candidate, exact on the rounded images of the faces as the reference
+// documents, :45-47).  Tree = a CGAL_B200::AABB_tree over the mesh type's faces; Aff = CGAL::Aff_transformation_3<K>.
+// Not offered: get_all_intersections_and_inclusions (needs Side_of_triangle_mesh under a transformation).
+template <typename Tree, typename Aff>
+class Rigid_triangle_mesh_collision_detection {
+public:
+  // add_mesh(tm) :231-262 — the caller passes what the Tree's range constructor takes (first, beyond, mesh); returns the id of the mesh
+  template <typename... T>
+  std::size_t add_mesh(T&&... t) {
+    std::size_t id = 0;
+    while (id < m_trees.size() && m_trees[id]) ++id;                      // the smallest free id, as the reference's id pool gives (:113-123)
+    if (id == m_trees.size()) { m_trees.emplace_back(); m_transformations.emplace_back(); }
+    m_trees[id].reset(new Tree(std::forward<T>(t)...));
+    m_trees[id]->build();
+    m_transformations[id] = Aff();
+    return id;
+  }
+  void remove_mesh(std::size_t id) { m_trees.at(id).reset(); }                                   // :481-497
+  void set_transformation(std::size_t id, const Aff& transformation) { m_transformations.at(id) = transformation; }   // :320-330
+  bool is_valid_index(std::size_t id) const { return id < m_trees.size() && m_trees[id]; }       // :513-517
+  std::size_t size() const { std::size_t n = 0; for (const auto& t : m_trees) n += t ? 1 : 0; return n; }
+  template <typename MeshIdRange>
+  std::vector<std::size_t> get_all_intersections(std::size_t mesh_id, const MeshIdRange& ids) const {   // :354-377
+    std::vector<std::size_t> res;
+    for (std::size_t k : ids) {
+      if (k == mesh_id || !is_valid_index(k)) continue;
+      if (m_trees.at(mesh_id)->do_intersect(*m_trees[k], m_transformations[mesh_id], m_transformations[k])) res.push_back(k);
+    }
+    return res;
+  }
+  std::vector<std::size_t> get_all_intersections(std::size_t mesh_id) const {                      // :381-388
+    std::vector<std::size_t> all;
+    for (std::size_t k = 0; k < m_trees.size(); ++k) all.push_back(k);
+    return get_all_intersections(mesh_id, all);
+  }
+private:
+  std::vector<std::unique_ptr<Tree>> m_trees;
+  std::vector<Aff> m_transformations;
 };
 
 }  // namespace CGAL_B200

@@ -166,6 +166,15 @@ int b200aabb_all_intersected_primitives(b200aabb_tree* t, const double* queries,
  * ids of ONE intersecting pair (which one is unspecified), B200AABB_NO_PRIMITIVE when there is none.  Both trees must be on the same device; one kernel:
  * the primitives of the smaller tree are Triangle_3 queries against the larger one, all threads stop at the first pair found. */
 int b200aabb_do_intersect_tree(b200aabb_tree* t, b200aabb_tree* other, int* result, uint32_t* prim, uint32_t* other_prim);
+/* The same with each tree standing under an affine transformation — Rigid_triangle_mesh_collision_detection::does_A_intersect_B
+ * (Polygon_mesh_processing/include/CGAL/Rigid_triangle_mesh_collision_detection.h:149-161) with
+ * Do_intersect_traversal_traits_with_transformation / _for_two_trees (Polygon_mesh_processing/internal/AABB_traversal_traits_with_transformation.h:113-306):
+ * the trees are built once on the untransformed meshes; per call every primitive is transformed as Aff_transformation_3::transform(Point_3) does
+ * (Cartesian/Aff_transformation_rep_3.h:111-117, in binary64, left to right) and the exact Do_intersect_3(Triangle_3, Triangle_3) is evaluated on the
+ * rounded images, as the reference states (:45-47); node boxes are transformed conservatively.  xf / other_xf: 12 doubles = m(i, j) of the
+ * Aff_transformation_3, row major (t11 t12 t13 t14  t21 ... t34); NULL = identity. */
+int b200aabb_do_intersect_tree_transformed(b200aabb_tree* t, const double* xf, b200aabb_tree* other, const double* other_xf, int* result, uint32_t* prim,
+                                           uint32_t* other_prim);
 /* all_intersections(Ray_3, out), AABB_tree.h:958-970 (Listing_intersection_traits, internal/AABB_traversal_traits.h:105-144): every
  * primitive whose Intersect_3(Ray_3, Triangle_3) is non-empty, with the intersection object.  Two steps like all_intersected_primitives:
  * b200aabb_number_of_intersections gives the counts (they can differ from number_of_intersected_primitives for a ray nearly parallel to a

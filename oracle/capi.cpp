@@ -3,6 +3,7 @@
 // __graft_entry__.smoke() and by bench.py's cpu_baseline / --impl reference legs, never by the product.
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <thread>
@@ -289,6 +290,56 @@ int orc_tri_tri_do_intersect(const double* query, const double* tri) { return do
 int orc_do_intersect_tree(void* hv, void* other) {
     const Handle* h = (const Handle*)hv; const Tree& o = *((Handle*)other)->tree;
     for (const Tri& t : h->mesh.tris) if (o.do_intersect(Tree::LineQ{t.a, t.b, 4, t.c})) return 1;
+    return 0;
+}
+// Rigid_triangle_mesh_collision_detection::does_A_intersect_B (Rigid_triangle_mesh_collision_detection.h:149-161) with the traversal traits of
+// Polygon_mesh_processing/internal/AABB_traversal_traits_with_transformation.h: tree B is traversed with tree A as the query (:262-306); every primitive of B,
+// transformed by B's Aff_transformation_3, traverses A under A's transformation (:141-156): do_intersect(query, datum.transform(transfo)) at the primitives,
+// the transformed node box at the nodes (:36-68: the box of the 8 transformed corners in interval arithmetic; here the corners in binary64, widened by a few
+// ulps, against the box of the query — a necessary condition, the primitives decide).  xf: 12 doubles, m(i, j) row major; transform(Point_3) as
+// Cartesian/Aff_transformation_rep_3.h:111-117.
+static inline P3 xf_point(const double* m, const P3& p) {
+    return {m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7], m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]};
+}
+static inline Tri xf_tri(const double* m, const Tri& t) { return {xf_point(m, t.a), xf_point(m, t.b), xf_point(m, t.c)}; }
+namespace {
+struct XfTT {
+    const Tree& t; const double* m; bool found = false;
+    bool go_further() const { return !found; }
+    void intersection(const Tree::LineQ& q, uint32_t f) { if (do_intersect_tri_tri(Tri{q.p, q.q, q.r}, xf_tri(m, t.mesh->datum(f)))) found = true; }
+    bool do_intersect(const Tree::LineQ& q, const Box& b) const {
+        double lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}, mag = 0;
+        for (int c = 0; c < 8; ++c) {
+            const P3 w = xf_point(m, P3{c & 1 ? b.hi[0] : b.lo[0], c & 2 ? b.hi[1] : b.lo[1], c & 4 ? b.hi[2] : b.lo[2]});
+            for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], w[k]); hi[k] = std::max(hi[k], w[k]); }
+        }
+        for (int k = 0; k < 3; ++k)
+            mag = std::max(mag, (std::fabs(m[4 * k]) * std::max(std::fabs(b.lo[0]), std::fabs(b.hi[0])) + std::fabs(m[4 * k + 1]) * std::max(std::fabs(b.lo[1]), std::fabs(b.hi[1])) +
+                                 std::fabs(m[4 * k + 2]) * std::max(std::fabs(b.lo[2]), std::fabs(b.hi[2]))) + std::fabs(m[4 * k + 3]));
+        for (int k = 0; k < 3; ++k) {
+            const double qlo = std::min(q.p[k], std::min(q.q[k], q.r[k])), qhi = std::max(q.p[k], std::max(q.q[k], q.r[k]));
+            if (qlo > hi[k] + 1e-14 * mag || qhi < lo[k] - 1e-14 * mag) return false;
+        }
+        return true;
+    }
+};
+}  // namespace
+int orc_do_intersect_tree_transformed(void* hv, const double* xf, void* other, const double* other_xf) {
+    const Handle* a = (const Handle*)hv; const Handle* b = (const Handle*)other;
+    for (const Tri& t : b->mesh.tris) {
+        const Tri q = xf_tri(other_xf, t);
+        XfTT tt{*a->tree, xf};
+        a->tree->traversal(Tree::LineQ{q.a, q.b, 4, q.c}, tt);
+        if (tt.found) return 1;
+    }
+    return 0;
+}
+// the same decided by brute force over all pairs of transformed primitives
+int orc_naive_do_intersect_transformed(void* hv, const double* xf, void* other, const double* other_xf) {
+    const Handle* a = (const Handle*)hv; const Handle* b = (const Handle*)other;
+    std::vector<Tri> ta; ta.reserve(a->mesh.tris.size());
+    for (const Tri& t : a->mesh.tris) ta.push_back(xf_tri(xf, t));
+    for (const Tri& t : b->mesh.tris) { const Tri q = xf_tri(other_xf, t); for (const Tri& u : ta) if (do_intersect_tri_tri(q, u)) return 1; }
     return 0;
 }
 int orc_tri_do_intersect(const double* tri, const double* pq, int is_ray) {

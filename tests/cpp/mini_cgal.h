@@ -65,6 +65,13 @@ struct Plane_3 {  // a x + b y + c z + d = 0: Cartesian/Plane_3.h
   double c() const { return cc; }
   double d() const { return cd; }
 };
+struct Aff_transformation_3 {  // the 3 x 4 matrix of Cartesian/Aff_transformation_rep_3.h (general representation)
+  double t[3][4];
+  Aff_transformation_3() : t{{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}} {}
+  Aff_transformation_3(double m00, double m01, double m02, double m03, double m10, double m11, double m12, double m13, double m20, double m21, double m22, double m23)
+      : t{{m00, m01, m02, m03}, {m10, m11, m12, m13}, {m20, m21, m22, m23}} {}
+  double m(int i, int j) const { return t[i][j]; }
+};
 struct Triangle_3 {
   Point_3 v[3];
   Triangle_3() {}

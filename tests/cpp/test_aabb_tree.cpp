@@ -178,6 +178,28 @@ static int known_answers() {
       Tree near_tree(faces(m2).first, faces(m2).second, m2), far_tree(faces(m3).first, faces(m3).second, m3), empty_tree;
       CHECK(tree.do_intersect(near_tree) && near_tree.do_intersect(tree) && tree.do_intersect(tree));
       CHECK(!tree.do_intersect(far_tree) && !far_tree.do_intersect(tree) && !tree.do_intersect(empty_tree));
+      // both meshes under transformations (Rigid_triangle_mesh_collision_detection): the far copy moved back onto the solid, the solid moved away, a quarter turn
+      const mini::Aff_transformation_3 identity, back(1, 0, 0, -4.75, 0, 1, 0, 0.25, 0, 0, 1, 0), away(1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 7.0),
+          turn(0, -1, 0, 0, 1, 0, 0, 0, 0, 0, 1, 0);                                               // (x, y, z) -> (-y, x, z)
+      CHECK(tree.do_intersect(far_tree, identity, back) && far_tree.do_intersect(tree, back, identity));
+      CHECK(!tree.do_intersect(near_tree, away, identity) && tree.do_intersect(near_tree, away, away));
+      CHECK(tree.do_intersect(tree, identity, turn));                                              // the turned copy shares the z axis edge
+      CHECK(!tree.do_intersect(far_tree, turn, identity));
+      // the collision-detection consumer: three solids, moved by transformations only
+      CGAL_B200::Rigid_triangle_mesh_collision_detection<Tree, mini::Aff_transformation_3> cd;
+      Mesh s0 = tetrahedron(), s1 = tetrahedron(0.25, 0.25), s2 = tetrahedron(5.0, 0.0);
+      const std::size_t i0 = cd.add_mesh(faces(s0).first, faces(s0).second, s0), i1 = cd.add_mesh(faces(s1).first, faces(s1).second, s1),
+                        i2 = cd.add_mesh(faces(s2).first, faces(s2).second, s2);
+      CHECK(i0 == 0 && i1 == 1 && i2 == 2 && cd.size() == 3);
+      CHECK(cd.get_all_intersections(i0) == std::vector<std::size_t>{i1} && cd.get_all_intersections(i2).empty());
+      cd.set_transformation(i2, back);                                                             // onto the other two
+      CHECK((cd.get_all_intersections(i0) == std::vector<std::size_t>{i1, i2}) && (cd.get_all_intersections(i2) == std::vector<std::size_t>{i0, i1}));
+      cd.set_transformation(i0, away);
+      CHECK(cd.get_all_intersections(i0).empty() && cd.get_all_intersections(i1) == std::vector<std::size_t>{i2});
+      cd.remove_mesh(i1);
+      CHECK(cd.size() == 2 && !cd.is_valid_index(i1) && cd.get_all_intersections(i2).empty());
+      Mesh s3 = tetrahedron(0.25, 0.25);
+      CHECK(cd.add_mesh(faces(s3).first, faces(s3).second, s3) == i1 && cd.get_all_intersections(i2) == std::vector<std::size_t>{i1});
     }
     {   // all_intersected_primitives / any_intersected_primitive (AABB_tree.h:253-268): the two faces the ray crosses, base face 0 among them
       std::vector<mini::Face_index> ids;

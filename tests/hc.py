@@ -50,6 +50,8 @@ def lib():
             getattr(L, n).argtypes = [_dp]
         L.hc_tri_do_intersect.argtypes = [_dp, _dp, C.c_int]
         L.hc_tri_tri_do_intersect.argtypes = [_dp, _dp]
+        L.hc_xf_apply.argtypes = [_dp, _dp, _dp]
+        L.hc_xf_box_meets.argtypes = [_dp, C.POINTER(C.c_float), _dp]
         L.hc_intersect_triangle.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_int, _u32p]
         L.hc_tri_ray_intersection.argtypes = [_dp, _dp, _dp, _dp]
         L.hc_closest_on_triangle.argtypes = [_dp, _dp, _dp]
@@ -176,6 +178,20 @@ def tri_do_intersect_kind(tri, q, kind):
 def tri_tri_do_intersect(query, tri):
     query, tri = _d(query).ravel(), _d(tri).ravel()
     return lib().hc_tri_tri_do_intersect(_p(query), _p(tri))
+
+
+def xf_apply(m, tri):
+    """bvh.cuh::AffXf::apply: the triangle's image under the 3 x 4 matrix m (12 doubles, row major)"""
+    m, tri, out = _d(m).ravel(), _d(tri).ravel(), np.zeros(9)
+    lib().hc_xf_apply(_p(m), _p(tri), _p(out))
+    return out
+
+
+def xf_box_meets(m, box_lo, box_hi, query):
+    """bvh.cuh::AffXf::box_meets: may the image of the binary32 box [lo, hi] meet the (binary32, outward) box of the query triangle?"""
+    m, query = _d(m).ravel(), _d(query).ravel()
+    b = np.concatenate([np.asarray(box_lo, np.float32), np.asarray(box_hi, np.float32)])
+    return bool(lib().hc_xf_box_meets(_p(m), b.ctypes.data_as(C.POINTER(C.c_float)), _p(query)))
 
 
 def tri_do_intersect(tri, pq, is_ray):

@@ -322,6 +322,16 @@ void hc_intersect_triangle(void* hv, const double* q, uint64_t n, int count, uin
         out[i] = count ? traverse_triangle<kCount>(h->nodes.data(), h->tris.data(), h->root, t, st) : traverse_triangle<kAnyHit>(h->nodes.data(), h->tris.data(), h->root, t, st);
     }
 }
+// bvh.cuh::AffXf: the image of a triangle under a 3 x 4 affine map, and the conservative node test "transformed box [box] (binary32 bounds) meets the box of query"
+void hc_xf_apply(const double* m, const double* tri, double* out) {
+    AffXf x; for (int i = 0; i < 12; ++i) x.m[i] = m[i];
+    const Tri3 t = x.apply(T(tri));
+    out[0] = t.a.x; out[1] = t.a.y; out[2] = t.a.z; out[3] = t.b.x; out[4] = t.b.y; out[5] = t.b.z; out[6] = t.c.x; out[7] = t.c.y; out[8] = t.c.z;
+}
+int hc_xf_box_meets(const double* m, const float* box, const double* query) {
+    AffXf x; for (int i = 0; i < 12; ++i) x.m[i] = m[i];
+    return x.box_meets(box, box + 3, make_box_of(T(query))) ? 1 : 0;
+}
 int hc_tri_do_intersect_kind(const double* tri, const double* q, int kind) {
     int n = 0;
     if (kind == 2) return line_tri_do_intersect(T(tri), V(q), V(q + 3), n);

@@ -68,6 +68,8 @@ def lib():
         L.orc_tri_do_intersect.argtypes = [_dp, _dp, C.c_int]
         L.orc_tri_tri_do_intersect.argtypes = [_dp, _dp]
         L.orc_do_intersect_tree.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_do_intersect_tree_transformed.argtypes = [C.c_void_p, _dp, C.c_void_p, _dp]
+        L.orc_naive_do_intersect_transformed.argtypes = [C.c_void_p, _dp, C.c_void_p, _dp]
         L.orc_tri_ray_intersection.argtypes = [_dp, _dp, _dp]
         L.orc_project_on_triangle.argtypes = [_dp, _dp, _dp]
         L.orc_ball_reaches_box.argtypes = [_dp, _dp, _dp]
@@ -145,6 +147,14 @@ class OracleTree:
     def do_intersect_tree(self, other):
         """tree.do_intersect(other_tree), AABB_traits_3.h:679-690"""
         return bool(lib().orc_do_intersect_tree(self.h, other.h))
+
+    def do_intersect_tree_transformed(self, xf, other, other_xf, naive=False):
+        """Rigid_triangle_mesh_collision_detection::does_A_intersect_B: both trees under 3 x 4 affine maps (12 doubles, row major; None = identity)"""
+        ident = np.array([1.0, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0])
+        a = _d(ident if xf is None else xf).ravel()
+        b = _d(ident if other_xf is None else other_xf).ravel()
+        f = lib().orc_naive_do_intersect_transformed if naive else lib().orc_do_intersect_tree_transformed
+        return bool(f(self.h, _ptr(a, _dp), other.h, _ptr(b, _dp)))
 
     def side_of_mesh(self, pts, threads=None):
         """Side_of_triangle_mesh: (side[n] in {-1 outside, 0 boundary, 1 inside}, rays cast per point)"""

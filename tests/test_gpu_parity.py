@@ -885,3 +885,29 @@ def test_tree_against_tree(B, meshes):
             assert not want
     e = B.AABB_tree()
     assert g.do_intersect_tree(e) is False and e.do_intersect_tree(g) is False
+
+
+def test_tree_against_tree_under_transformations(B, meshes):
+    """Rigid_triangle_mesh_collision_detection::does_A_intersect_B: both trees built once, each mesh under a rotation + scaling + translation given per call;
+    against the oracle's traversal with transformed datums and boxes (AABB_traversal_traits_with_transformation.h) and, on the cube, against brute force over
+    all pairs of transformed primitives; the witness pair is re-checked with the exact predicate on the transformed triangles"""
+    from test_triangle_queries import rigid
+    rng = np.random.default_rng(47)
+    for name, trials in (("cube", 40), ("elephant", 24)):
+        v, f = meshes[name]
+        ext = (v.max(0) - v.min(0)).max()
+        g, g2, o, o2 = B.AABB_tree(v, f), B.AABB_tree(v, f), orc.OracleTree(v, f), orc.OracleTree(v, f)
+        soup = soup_of(v, f)
+        n_true = 0
+        for it in range(trials):
+            xa = rigid(rng, shift=rng.uniform(-1, 1, 3) * ext) if it % 2 else None
+            xb = rigid(rng, scale=rng.uniform(0.5, 1.5), shift=rng.uniform(-1.2, 1.2, 3) * ext * (0.3 if it % 3 == 0 else 1.0))
+            want = o.do_intersect_tree_transformed(xa, o2, xb, naive=(name == "cube"))
+            n_true += want
+            hit, ia, ib = g.do_intersect_tree(g2, witness=True, xf=xa, other_xf=xb)
+            assert hit == want, (name, it)
+            assert g2.do_intersect_tree(g, xf=xb, other_xf=xa) == want, (name, it)
+            if hit:
+                ta = soup[ia] if xa is None else hc.xf_apply(xa, soup[ia])
+                assert orc.tri_tri_do_intersect(ta, hc.xf_apply(xb, soup[ib])) == 1
+        assert 3 < n_true < trials - 3, (name, n_true)

@@ -168,3 +168,53 @@ def test_oracle_tree_against_tree(meshes):
         b = orc.OracleTree(v + np.array([shift, 0.0, 0.0]), f)
         assert a.do_intersect_tree(b) == want, shift
         assert b.do_intersect_tree(a) == want, shift
+
+
+def rigid(rng, scale=1.0, shift=(0.0, 0.0, 0.0)):
+    """3 x 4 matrix of a rotation about a random axis, a uniform scaling and a translation"""
+    ax = rng.normal(size=3); ax /= np.linalg.norm(ax)
+    ang = rng.uniform(0, 2 * np.pi)
+    K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    R = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * (K @ K)
+    return np.hstack([scale * R, np.asarray(shift, float).reshape(3, 1)])
+
+
+def test_transformed_primitives_and_boxes():
+    """bvh.cuh::AffXf: the image of a primitive is the reference's Aff_transformation_3::transform (oracle, evaluated left to right in binary64), and the
+    conservative image of a node box contains the rounded images of everything inside the box"""
+    rng = np.random.default_rng(45)
+    for it in range(300):
+        m = rigid(rng, scale=rng.uniform(0.5, 2.0), shift=rng.uniform(-5, 5, 3)) if it % 3 else np.hstack([rng.uniform(-2, 2, (3, 3)), rng.uniform(-5, 5, (3, 1))])
+        lo = rng.uniform(-3, 3, 3).astype(np.float32)
+        hi = (lo + rng.uniform(0, 2, 3).astype(np.float32)).astype(np.float32)
+        for _ in range(20):
+            w = rng.uniform(0, 1, (3, 3))
+            if rng.integers(0, 2):
+                w = np.round(w)                                             # vertices at the corners of the box
+            tri = (lo + w * (hi.astype(np.float64) - lo)).ravel()
+            img = hc.xf_apply(m, tri)
+            p = tri.reshape(3, 3)
+            want = np.array([[m[k, 0] * p[i, 0] + m[k, 1] * p[i, 1] + m[k, 2] * p[i, 2] + m[k, 3] for k in range(3)] for i in range(3)]).ravel()
+            assert np.array_equal(img, want)
+            assert hc.xf_box_meets(m, lo, hi, img)                          # the image of a triangle inside the box meets the image of the box
+        far = hc.xf_apply(m, (hi + np.array([50.0, 50.0, 50.0])).repeat(3).reshape(3, 3).T.ravel() + rng.uniform(0, 1, 9))
+        if it % 3:                                                          # (a rigid map keeps distances: something 50 away stays away)
+            assert not hc.xf_box_meets(m, lo, hi, far)
+
+
+def test_oracle_transformed_tree_against_tree(meshes):
+    v, f = meshes["cube"]
+    a, b = orc.OracleTree(v, f), orc.OracleTree(v, f)
+    rng = np.random.default_rng(46)
+    ext = (v.max(0) - v.min(0)).max()
+    n_true = 0
+    for it in range(60):
+        xa = rigid(rng, shift=rng.uniform(-1, 1, 3) * ext) if it % 2 else None
+        xb = rigid(rng, scale=rng.uniform(0.3, 1.5), shift=rng.uniform(-1.5, 1.5, 3) * ext)
+        want = a.do_intersect_tree_transformed(xa, b, xb, naive=True)
+        n_true += want
+        assert a.do_intersect_tree_transformed(xa, b, xb) == want, it
+        assert b.do_intersect_tree_transformed(xb, a, xa) == want, it
+    assert 10 < n_true < 55
+    ident = np.hstack([np.eye(3), np.zeros((3, 1))])
+    assert a.do_intersect_tree_transformed(ident, b, None) == a.do_intersect_tree(b)
