@@ -43,7 +43,7 @@ SYMBOLS = ["b200aabb_create", "b200aabb_destroy", "b200aabb_set_stream", "b200aa
            "b200aabb_number_of_intersected_primitives", "b200aabb_any_intersected_primitive", "b200aabb_all_intersected_primitives", "b200aabb_do_intersect_tree", "b200aabb_do_intersect_tree_transformed",
            "b200aabb_number_of_intersections", "b200aabb_all_intersections", "b200aabb_any_intersection",
            "b200aabb_number_of_intersections_q", "b200aabb_all_intersections_q", "b200aabb_any_intersection_q",
-           "b200aabb_first_intersection", "b200aabb_first_intersection_skip", "b200aabb_closest_point", "b200aabb_max_distance_to_mesh", "b200aabb_side_of_mesh",
+           "b200aabb_first_intersection", "b200aabb_first_intersection_skip", "b200aabb_closest_point", "b200aabb_max_distance_to_mesh", "b200aabb_side_of_mesh", "b200aabb_side_of_mesh_transformed",
            "b200aabb_export_layout", "b200aabb_import_alloc", "b200aabb_import_finish", "b200aabb_debug_predicate", "b200aabb_version",
            "b200aabb_comm_unique_id", "b200aabb_comm_init", "b200aabb_comm_init_all", "b200aabb_comm_destroy", "b200aabb_comm_last_error",
            "b200aabb_comm_broadcast_tree", "b200aabb_comm_broadcast_tree_all"]
@@ -96,6 +96,7 @@ def load_library():
         L.b200aabb_closest_point.argtypes = [vp, dp, u64, C.c_int, dp, dp, dp, dp]
         L.b200aabb_max_distance_to_mesh.argtypes = [vp, dp, u64, C.c_int, C.POINTER(C.c_double), C.POINTER(u64)]
         L.b200aabb_side_of_mesh.argtypes = [vp, dp, u64, C.c_int, dp, dp]
+        L.b200aabb_side_of_mesh_transformed.argtypes = [vp, dp, dp, u64, C.c_int, dp, dp]
         L.b200aabb_export_layout.argtypes = [vp, C.POINTER(vp), C.POINTER(u64), C.c_int, C.POINTER(C.c_int)]
         L.b200aabb_import_alloc.argtypes = [vp, u64]
         L.b200aabb_import_finish.argtypes = [vp]
@@ -387,12 +388,17 @@ class AABB_tree:
         self._check(self._lib.b200aabb_max_distance_to_mesh(self._h, q.ptr, q.n, int(q.device), C.byref(d), C.byref(i)))
         return d.value, i.value
 
-    def side_of_mesh(self, points, want_attempts=False):
+    def side_of_mesh(self, points, want_attempts=False, xf=None):
         """Side_of_triangle_mesh::operator() for a CLOSED mesh (Side_of_triangle_mesh.h:265-306): int8 per point, +1 ON_BOUNDED_SIDE, 0 ON_BOUNDARY,
-        -1 ON_UNBOUNDED_SIDE; with want_attempts also the number of rays cast per point"""
+        -1 ON_UNBOUNDED_SIDE; with want_attempts also the number of rays cast per point.  xf: the 3 x 4 affine map the mesh stands under (the points are in the
+        frame of the transformed mesh), as in Rigid_triangle_mesh_collision_detection::does_A_contains_a_CC_of_B"""
         q = _Buf(points, np.float64, 3)
         o = _alloc_like(q, q.n, np.int8, 1)
         a = _alloc_like(q, q.n, np.uint8, 1) if want_attempts else None
+        if xf is not None:
+            m = np.ascontiguousarray(xf, np.float64).reshape(12)
+            self._check(self._lib.b200aabb_side_of_mesh_transformed(self._h, m.ctypes.data, q.ptr, q.n, int(q.device), o.ptr, a.ptr if a is not None else None))
+            return (o.obj, a.obj) if want_attempts else o.obj
         self._check(self._lib.b200aabb_side_of_mesh(self._h, q.ptr, q.n, int(q.device), o.ptr, a.ptr if a is not None else None))
         return (o.obj, a.obj) if want_attempts else o.obj
 

@@ -186,8 +186,12 @@ __device__ __forceinline__ Vec3 side_direction(int attempt, double pz, const dou
     return {c[0], c[1], c[2]};
 }
 constexpr int kSideMaxAttempts = 64;
+// XF = AffXf: the mesh stands under the affine transformation x.xf (the points are given in the frame of the transformed mesh); x.box = a box that contains
+// the image of the mesh, x.mag = the largest coordinate magnitude of that box
+struct SideXf { AffXf xf; double box[6]; double mag; };
+template <class XF>
 __global__ void __launch_bounds__(128, 8) side_of_mesh_kernel(const TreeRef tr, const double* __restrict__ pts, uint64_t n, const double* __restrict__ rootbox,
-                                                              int8_t* __restrict__ out, uint8_t* __restrict__ out_attempts) {
+                                                              int8_t* __restrict__ out, uint8_t* __restrict__ out_attempts, const SideXf x) {
     const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     TravStat st;
     if (slot < n) {
@@ -195,15 +199,16 @@ __global__ void __launch_bounds__(128, 8) side_of_mesh_kernel(const TreeRef tr, 
         const Vec3 p = ld3(pts + 3 * i);
         double box[6];
 #pragma unroll
-        for (int k = 0; k < 6; ++k) box[k] = rootbox[k];
+        for (int k = 0; k < 6; ++k) box[k] = XF::kIdentity ? rootbox[k] : x.box[k];
         int side = -1, attempts = 0;
         if (!(p.x < box[0] || p.x > box[3] || p.y < box[1] || p.y > box[4] || p.z < box[2] || p.z > box[5])) {
-            const double scale = fmax(1.0, tr.mag);          // p + d must differ from p
+            const double scale = fmax(1.0, XF::kIdentity ? tr.mag : x.mag);          // p + d must differ from p
             int r = kSideIndeterminate;
             for (; attempts < kSideMaxAttempts && r == kSideIndeterminate; ++attempts) {
                 const Vec3 d = side_direction(attempts, p.z, box);
                 const Vec3 q = {p.x + d.x * scale, p.y + d.y * scale, p.z + d.z * scale};
-                r = traverse_side(tr.nodes, tr.tris, tr.root, p, q, st);
+                if constexpr (XF::kIdentity) r = traverse_side(tr.nodes, tr.tris, tr.root, p, q, st);
+                else r = traverse_side<AffXf>(tr.nodes, tr.tris, tr.root, p, q, st, x.xf);
             }
             if (r == kSideIndeterminate) st.overflow = 1;   // (64 degenerate rays in a row: reported, never guessed)
             side = r == kSideBoundary ? 0 : ((r & 1) ? 1 : -1);
@@ -1752,7 +1757,10 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
                      });
 }
 
-int b200aabb_side_of_mesh(b200aabb_tree* t, const double* pts, uint64_t n, b200aabb_memspace space, int8_t* side, uint8_t* attempts) { B2_LOCK(t);
+int b200aabb_side_of_mesh(b200aabb_tree* t, const double* pts, uint64_t n, b200aabb_memspace space, int8_t* side, uint8_t* attempts) {
+    return b200aabb_side_of_mesh_transformed(t, nullptr, pts, n, space, side, attempts);
+}
+int b200aabb_side_of_mesh_transformed(b200aabb_tree* t, const double* xf, const double* pts, uint64_t n, b200aabb_memspace space, int8_t* side, uint8_t* attempts) { B2_LOCK(t);
     if (!t || (n && (!pts || !side))) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
@@ -1764,8 +1772,25 @@ int b200aabb_side_of_mesh(b200aabb_tree* t, const double* pts, uint64_t n, b200a
         return B200AABB_OK;
     }
     B2_CUDA(t, cudaSetDevice(t->device));
+    SideXf x;
+    memset(&x, 0, sizeof(x));
+    if (xf) {   // the image of the root box, conservatively (bvh.cuh::AffXf::box_meets does the same per node)
+        memcpy(x.xf.m, xf, sizeof(x.xf.m));
+        const double* b = t->h_bbox;
+        for (int k = 0; k < 3; ++k) {
+            const double* r = xf + 4 * k;
+            const double c[3] = {0.5 * (b[0] + b[3]), 0.5 * (b[1] + b[4]), 0.5 * (b[2] + b[5])}, h[3] = {0.5 * (b[3] - b[0]), 0.5 * (b[4] - b[1]), 0.5 * (b[5] - b[2])};
+            const double ctr = ((r[0] * c[0] + r[1] * c[1]) + r[2] * c[2]) + r[3];
+            const double ext = (fabs(r[0]) * h[0] + fabs(r[1]) * h[1]) + fabs(r[2]) * h[2];
+            const double mag = ((fabs(r[0]) * (fabs(c[0]) + h[0]) + fabs(r[1]) * (fabs(c[1]) + h[1])) + fabs(r[2]) * (fabs(c[2]) + h[2])) + fabs(r[3]);
+            if (!(ctr == ctr) || !(ext == ext)) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "side_of_mesh: the transformation is not finite");
+            x.box[k] = ctr - (ext + 1e-14 * mag); x.box[3 + k] = ctr + (ext + 1e-14 * mag);
+            x.mag = std::max(x.mag, std::max(fabs(x.box[k]), fabs(x.box[3 + k])));
+        }
+    }
     return run_batch(t, pts, 24, n, space, kPointQuery, {{side, 1, 0}, {attempts, 1, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
-        side_of_mesh_kernel<<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, t->d_rootbox, (int8_t*)o[0], (uint8_t*)o[1]);
+        if (xf) side_of_mesh_kernel<AffXf><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, t->d_rootbox, (int8_t*)o[0], (uint8_t*)o[1], x);
+        else side_of_mesh_kernel<NoXf><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, t->d_rootbox, (int8_t*)o[0], (uint8_t*)o[1], x);
     });
 }
 

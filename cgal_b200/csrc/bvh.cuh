@@ -245,6 +245,66 @@ B2_HD float point_box_sqdist(const float* lo, const float* hi, const PointCtx& c
 // executed by all threads that have a pending leaf at once instead of by one thread at a time while the others wait
 // (measured on the one-loop version, profiles/r1_01: 2.9 of 32 threads active per instruction in closest_point).
 // ---------------------------------------------------------------------------------------------------------------
+// ---- boxes of Triangle_3 queries and trees under an affine transformation (used by traverse_line / traverse_triangle below)
+struct BoxCtx { float lo[3], hi[3]; };
+B2_HD BoxCtx make_box_of(const Tri3& t) {
+    BoxCtx c;
+    c.lo[0] = float_below(fmin3(t.a.x, t.b.x, t.c.x)); c.lo[1] = float_below(fmin3(t.a.y, t.b.y, t.c.y)); c.lo[2] = float_below(fmin3(t.a.z, t.b.z, t.c.z));
+    c.hi[0] = float_above(fmax3(t.a.x, t.b.x, t.c.x)); c.hi[1] = float_above(fmax3(t.a.y, t.b.y, t.c.y)); c.hi[2] = float_above(fmax3(t.a.z, t.b.z, t.c.z));
+    return c;
+}
+B2_HD bool box_box(const float* lo, const float* hi, const BoxCtx& c) {
+    return lo[0] <= c.hi[0] && c.lo[0] <= hi[0] && lo[1] <= c.hi[1] && c.lo[1] <= hi[1] && lo[2] <= c.hi[2] && c.lo[2] <= hi[2];
+}
+// The traversed tree may stand under an affine transformation (Rigid_triangle_mesh_collision_detection.h: each mesh keeps its tree, built once, and an
+// Aff_transformation_3; Polygon_mesh_processing/internal/AABB_traversal_traits_with_transformation.h:141-156 transforms the DATUM of each primitive and the box of
+// each node on the fly).  m = the 3 x 4 matrix (m(i, j) of Aff_transformation_3, row major).  A point is transformed as Aff_transformation_repC3::transform
+// does (Cartesian/Aff_transformation_rep_3.h:111-117: t11 x + t12 y + t13 z + t14, left to right, no fused operations) — for the translation and scaling
+// representations the same expression gives their results (1 x + 0 y + 0 z + t = x + t; s x + 0 + 0 + 0 = s x) — and the exact predicates see the rounded image.
+struct NoXf {
+    static constexpr bool kIdentity = true;
+    B2_HD Tri3 apply(const Tri3& t) const { return t; }
+    B2_HD bool box_meets(const float* lo, const float* hi, const BoxCtx& c) const { return box_box(lo, hi, c); }
+};
+struct AffXf {
+    static constexpr bool kIdentity = false;
+    double m[12];
+    B2_HD Vec3 point(const Vec3& p) const {
+        return {((m[0] * p.x + m[1] * p.y) + m[2] * p.z) + m[3], ((m[4] * p.x + m[5] * p.y) + m[6] * p.z) + m[7], ((m[8] * p.x + m[9] * p.y) + m[10] * p.z) + m[11]};
+    }
+    B2_HD Tri3 apply(const Tri3& t) const { return {point(t.a), point(t.b), point(t.c)}; }
+    // image of the box as centre +- |M| half-extent (the reference takes the box of the 8 transformed corners in interval arithmetic, :36-68: the same box
+    // up to rounding); widened by a bound of its own rounding and of the rounding of the transformed primitives it has to contain
+    // the same image as a binary32 box rounded outward (for the line / box tests of the ray traversals)
+    B2_HD void image_box(const float* lo, const float* hi, float* olo, float* ohi) const {
+        const double cx = 0.5 * ((double)lo[0] + (double)hi[0]), cy = 0.5 * ((double)lo[1] + (double)hi[1]), cz = 0.5 * ((double)lo[2] + (double)hi[2]);
+        const double hx = 0.5 * ((double)hi[0] - (double)lo[0]), hy = 0.5 * ((double)hi[1] - (double)lo[1]), hz = 0.5 * ((double)hi[2] - (double)lo[2]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double* r = m + 4 * k;
+            const double ctr = ((r[0] * cx + r[1] * cy) + r[2] * cz) + r[3];
+            const double ext = (fabs(r[0]) * hx + fabs(r[1]) * hy) + fabs(r[2]) * hz;
+            const double mag = ((fabs(r[0]) * (fabs(cx) + hx) + fabs(r[1]) * (fabs(cy) + hy)) + fabs(r[2]) * (fabs(cz) + hz)) + fabs(r[3]);
+            const double wide = ext + 1e-14 * mag;
+            const bool ok = ctr == ctr && wide == wide;                       // (NaN: the whole axis)
+            olo[k] = ok ? float_below(ctr - wide) : -INFINITY; ohi[k] = ok ? float_above(ctr + wide) : INFINITY;
+        }
+    }
+    B2_HD bool box_meets(const float* lo, const float* hi, const BoxCtx& c) const {
+        const double cx = 0.5 * ((double)lo[0] + (double)hi[0]), cy = 0.5 * ((double)lo[1] + (double)hi[1]), cz = 0.5 * ((double)lo[2] + (double)hi[2]);
+        const double hx = 0.5 * ((double)hi[0] - (double)lo[0]), hy = 0.5 * ((double)hi[1] - (double)lo[1]), hz = 0.5 * ((double)hi[2] - (double)lo[2]);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const double* r = m + 4 * k;
+            const double ctr = ((r[0] * cx + r[1] * cy) + r[2] * cz) + r[3];
+            const double ext = (fabs(r[0]) * hx + fabs(r[1]) * hy) + fabs(r[2]) * hz;
+            const double mag = ((fabs(r[0]) * (fabs(cx) + hx) + fabs(r[1]) * (fabs(cy) + hy)) + fabs(r[2]) * (fabs(cz) + hz)) + fabs(r[3]);
+            const double wide = ext + 1e-14 * mag;
+            if (!(ctr - wide <= (double)c.hi[k] && (double)c.lo[k] <= ctr + wide)) return !(ctr == ctr && wide == wide);   // (NaN / overflow: keep the box)
+        }
+        return true;
+    }
+};
 // warp vote used ONLY as a scheduling hint (when to run a deferred phase); the host emulation sees the thread alone
 B2_HD bool warp_any(bool p) {
 #if defined(__CUDA_ARCH__)
@@ -266,8 +326,13 @@ enum IntersectMode { kAnyHit = 0, kCount = 1, kAnyId = 2, kList = 3 };
 // The traversal shared by all intersection queries: visits every leaf whose box the query line meets and calls leaf(ref) -> bool
 // ("this primitive counts"); returns how many did.  STOP_AT_FIRST ends at the first one.
 enum LineKind { kSegmentQ = 0, kRayQ = 1, kLineQ = 2 };
-template <int KIND, bool STOP_AT_FIRST, class Leaf>
-B2_HD uint32_t traverse_line(const BvhNode* __restrict__ nodes, uint32_t root, const LineCtx& c, TravStat& st, Leaf&& leaf) {
+template <class XF>
+B2_HD bool line_box_under(const XF& xf, const float* lo, const float* hi, const LineCtx& c, float tlimit, float& tn, float tstart) {
+    if constexpr (XF::kIdentity) return line_box(lo, hi, c, tlimit, tn, tstart);
+    else { float l[3], h[3]; xf.image_box(lo, hi, l, h); return line_box(l, h, c, tlimit, tn, tstart); }
+}
+template <int KIND, bool STOP_AT_FIRST, class Leaf, class XF = NoXf>
+B2_HD uint32_t traverse_line(const BvhNode* __restrict__ nodes, uint32_t root, const LineCtx& c, TravStat& st, Leaf&& leaf, const XF& xf = XF()) {
     const float tlimit = KIND == kSegmentQ ? 1.0f : INFINITY, tstart = KIND == kLineQ ? -INFINITY : 0.0f;
     uint32_t found = 0;
     if (root & kLeafBit) return leaf(root) ? 1u : 0u;       // singleton tree: AABB_tree.h:516-525
@@ -285,8 +350,8 @@ B2_HD uint32_t traverse_line(const BvhNode* __restrict__ nodes, uint32_t root, c
             const NodeView n = load_node(nodes, cur);
             ++st.nodes;
             float tn;
-            const bool h0 = line_box(n.lo0, n.hi0, c, tlimit, tn, tstart);
-            const bool h1 = line_box(n.lo1, n.hi1, c, tlimit, tn, tstart);
+            const bool h0 = line_box_under(xf, n.lo0, n.hi0, c, tlimit, tn, tstart);
+            const bool h1 = line_box_under(xf, n.lo1, n.hi1, c, tlimit, tn, tstart);
             uint32_t next = kNone;
             if (h0) { if (n.c0 & kLeafBit) pend[np++] = n.c0; else next = n.c0; }
             if (h1) {
@@ -329,48 +394,6 @@ B2_HD uint32_t traverse_intersect(const BvhNode* __restrict__ nodes, const TriRe
 // AABB_tree.h:903-956; the query a tree-vs-tree do_intersect issues per primitive, AABB_traits_3.h:679-690).  Do_intersect_3(Bbox_3, Triangle_3)
 // (Bbox_3_Triangle_3_do_intersect.h: separating axes) is replaced by a conservative test — the binary32 box of the query, rounded outward, must overlap the
 // child's box — and the leaves decide exactly (geom.cuh::tri_tri_do_intersect), so results do not depend on the tree.  Same while-while scheme as traverse_line.
-struct BoxCtx { float lo[3], hi[3]; };
-B2_HD BoxCtx make_box_of(const Tri3& t) {
-    BoxCtx c;
-    c.lo[0] = float_below(fmin3(t.a.x, t.b.x, t.c.x)); c.lo[1] = float_below(fmin3(t.a.y, t.b.y, t.c.y)); c.lo[2] = float_below(fmin3(t.a.z, t.b.z, t.c.z));
-    c.hi[0] = float_above(fmax3(t.a.x, t.b.x, t.c.x)); c.hi[1] = float_above(fmax3(t.a.y, t.b.y, t.c.y)); c.hi[2] = float_above(fmax3(t.a.z, t.b.z, t.c.z));
-    return c;
-}
-B2_HD bool box_box(const float* lo, const float* hi, const BoxCtx& c) {
-    return lo[0] <= c.hi[0] && c.lo[0] <= hi[0] && lo[1] <= c.hi[1] && c.lo[1] <= hi[1] && lo[2] <= c.hi[2] && c.lo[2] <= hi[2];
-}
-// The traversed tree may stand under an affine transformation (Rigid_triangle_mesh_collision_detection.h: each mesh keeps its tree, built once, and an
-// Aff_transformation_3; Polygon_mesh_processing/internal/AABB_traversal_traits_with_transformation.h:141-156 transforms the DATUM of each primitive and the box of
-// each node on the fly).  m = the 3 x 4 matrix (m(i, j) of Aff_transformation_3, row major).  A point is transformed as Aff_transformation_repC3::transform
-// does (Cartesian/Aff_transformation_rep_3.h:111-117: t11 x + t12 y + t13 z + t14, left to right, no fused operations) — for the translation and scaling
-// representations the same expression gives their results (1 x + 0 y + 0 z + t = x + t; s x + 0 + 0 + 0 = s x) — and the exact predicates see the rounded image.
-struct NoXf {
-    B2_HD Tri3 apply(const Tri3& t) const { return t; }
-    B2_HD bool box_meets(const float* lo, const float* hi, const BoxCtx& c) const { return box_box(lo, hi, c); }
-};
-struct AffXf {
-    double m[12];
-    B2_HD Vec3 point(const Vec3& p) const {
-        return {((m[0] * p.x + m[1] * p.y) + m[2] * p.z) + m[3], ((m[4] * p.x + m[5] * p.y) + m[6] * p.z) + m[7], ((m[8] * p.x + m[9] * p.y) + m[10] * p.z) + m[11]};
-    }
-    B2_HD Tri3 apply(const Tri3& t) const { return {point(t.a), point(t.b), point(t.c)}; }
-    // image of the box as centre +- |M| half-extent (the reference takes the box of the 8 transformed corners in interval arithmetic, :36-68: the same box
-    // up to rounding); widened by a bound of its own rounding and of the rounding of the transformed primitives it has to contain
-    B2_HD bool box_meets(const float* lo, const float* hi, const BoxCtx& c) const {
-        const double cx = 0.5 * ((double)lo[0] + (double)hi[0]), cy = 0.5 * ((double)lo[1] + (double)hi[1]), cz = 0.5 * ((double)lo[2] + (double)hi[2]);
-        const double hx = 0.5 * ((double)hi[0] - (double)lo[0]), hy = 0.5 * ((double)hi[1] - (double)lo[1]), hz = 0.5 * ((double)hi[2] - (double)lo[2]);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const double* r = m + 4 * k;
-            const double ctr = ((r[0] * cx + r[1] * cy) + r[2] * cz) + r[3];
-            const double ext = (fabs(r[0]) * hx + fabs(r[1]) * hy) + fabs(r[2]) * hz;
-            const double mag = ((fabs(r[0]) * (fabs(cx) + hx) + fabs(r[1]) * (fabs(cy) + hy)) + fabs(r[2]) * (fabs(cz) + hz)) + fabs(r[3]);
-            const double wide = ext + 1e-14 * mag;
-            if (!(ctr - wide <= (double)c.hi[k] && (double)c.lo[k] <= ctr + wide)) return !(ctr == ctr && wide == wide);   // (NaN / overflow: keep the box)
-        }
-        return true;
-    }
-};
 template <int MODE, class XF = NoXf>
 B2_HD uint32_t traverse_triangle(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root, const Tri3& query, TravStat& st,
                                  uint32_t* list = nullptr, uint32_t list_cap = 0, const XF& xf = XF()) {
@@ -425,19 +448,22 @@ B2_HD uint32_t traverse_triangle(const BvhNode* __restrict__ nodes, const TriRec
 // lies in a primitive's plane makes the attempt INDETERMINATE (the caller takes another ray).  Returns the number of crossings, kSideBoundary or
 // kSideIndeterminate.
 constexpr int kSideBoundary = -1, kSideIndeterminate = -2;
-B2_HD int traverse_side(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root, const Vec3& s, const Vec3& q, TravStat& st) {
+// XF: the mesh stands under an affine transformation (does_A_contains_a_CC_of_B, Rigid_triangle_mesh_collision_detection.h:131-147, with the
+// Transformed_tree_helper of AABB_traversal_traits_with_transformation.h:190-224): the primitives' images are classified, node boxes are mapped conservatively
+template <class XF = NoXf>
+B2_HD int traverse_side(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root, const Vec3& s, const Vec3& q, TravStat& st, const XF& xf = XF()) {
     const LineCtx c = make_line(s, q);
     int crossings = 0, status = 0;
     traverse_line<kRayQ, true>(nodes, root, c, st, [&](uint32_t ref) -> bool {
         uint32_t id;
-        const Tri3 t = load_tri(tris, ref & ~kLeafBit, id);
+        const Tri3 t = xf.apply(load_tri(tris, ref & ~kLeafBit, id));
         ++st.leaves;
         const int k = ray_tri_classify(t, s, q, st.nexact);
         if (k < 0) return false;
         if (k == 0) { ++crossings; return false; }
         status = k == 4 ? kSideBoundary : kSideIndeterminate;
         return true;                                         // m_stop
-    });
+    }, xf);
     return status ? status : crossings;
 }
 

@@ -668,6 +668,21 @@ public:
     return out;
   }
   int bounded_side(const Point& p) const { int r = -1; const Point* a = &p; bounded_side(a, a + 1, &r); return r; }
+  // the same with the mesh under an affine transformation and the points given in the frame of the transformed mesh (does_A_contains_a_CC_of_B,
+  // Rigid_triangle_mesh_collision_detection.h:131-147)
+  template <typename PointIterator, typename OutputIterator, typename Aff>
+  OutputIterator bounded_side(PointIterator first, PointIterator beyond, OutputIterator out, const Aff& transformation) const {
+    std::vector<double> q = pack_points(first, beyond);
+    const uint64_t n = q.size() / 3;
+    std::vector<int8_t> r(n);
+    double m[12];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 4; ++j) m[4 * i + j] = (double)transformation.m(i, j);
+    ensure_built();
+    check(b200aabb_side_of_mesh_transformed(m_handle, m, q.data(), n, B200AABB_HOST, r.data(), nullptr));
+    for (uint64_t i = 0; i < n; ++i) *out++ = (int)r[i];
+    return out;
+  }
 
 private:
   AABBTraits m_traits;
@@ -701,19 +716,46 @@ private:
 // (one tree each, built once), moved by set_transformation, and get_all_intersections(id) lists the meshes with at least one face intersecting a face of
 // mesh `id` under the current transformations (:349-388; one tree-vs-tree kernel per candidate, exact on the rounded images of the faces as the reference
 // documents, :45-47).  Tree = a CGAL_B200::AABB_tree over the mesh type's faces; Aff = CGAL::Aff_transformation_3<K>.
-// Not offered: get_all_intersections_and_inclusions (needs Side_of_triangle_mesh under a transformation).
+// get_all_intersections_and_inclusions (:391-464) adds the volume inclusions of closed meshes: the caller states whether a mesh is closed and gives one point per
+// connected component (the reference computes both from the mesh, :125-129, 259-260, with BGL algorithms that are host code outside this path).
 template <typename Tree, typename Aff>
 class Rigid_triangle_mesh_collision_detection {
 public:
+  typedef typename Tree::Point Point_3;
+  // add_mesh with what the inclusion test needs: is the mesh closed, one point per connected component (:264-316, the overload that takes them precomputed)
+  template <typename... T>
+  std::size_t add_mesh_with_points(bool is_closed, const std::vector<Point_3>& points_per_cc, T&&... t) {
+    const std::size_t id = add_mesh(std::forward<T>(t)...);
+    m_is_closed[id] = is_closed;
+    m_points_per_cc[id] = points_per_cc;
+    return id;
+  }
+  template <typename MeshIdRange>
+  std::vector<std::pair<std::size_t, bool>> get_all_intersections_and_inclusions(std::size_t mesh_id, const MeshIdRange& ids) const {   // :408-446
+    std::vector<std::pair<std::size_t, bool>> res;
+    for (std::size_t k : ids) {
+      if (k == mesh_id || !is_valid_index(k)) continue;
+      if (m_trees.at(mesh_id)->do_intersect(*m_trees[k], m_transformations[mesh_id], m_transformations[k])) res.push_back(std::make_pair(k, false));
+      else if ((m_is_closed[mesh_id] && contains_a_cc_of(mesh_id, k)) || (m_is_closed[k] && contains_a_cc_of(k, mesh_id))) res.push_back(std::make_pair(k, true));
+    }
+    return res;
+  }
+  std::vector<std::pair<std::size_t, bool>> get_all_intersections_and_inclusions(std::size_t mesh_id) const {   // :454-461
+    std::vector<std::size_t> all;
+    for (std::size_t k = 0; k < m_trees.size(); ++k) all.push_back(k);
+    return get_all_intersections_and_inclusions(mesh_id, all);
+  }
   // add_mesh(tm) :231-262 — the caller passes what the Tree's range constructor takes (first, beyond, mesh); returns the id of the mesh
   template <typename... T>
   std::size_t add_mesh(T&&... t) {
     std::size_t id = 0;
     while (id < m_trees.size() && m_trees[id]) ++id;                      // the smallest free id, as the reference's id pool gives (:113-123)
-    if (id == m_trees.size()) { m_trees.emplace_back(); m_transformations.emplace_back(); }
+    if (id == m_trees.size()) { m_trees.emplace_back(); m_transformations.emplace_back(); m_is_closed.push_back(false); m_points_per_cc.emplace_back(); }
     m_trees[id].reset(new Tree(std::forward<T>(t)...));
     m_trees[id]->build();
     m_transformations[id] = Aff();
+    m_is_closed[id] = false;
+    m_points_per_cc[id].clear();
     return id;
   }
   void remove_mesh(std::size_t id) { m_trees.at(id).reset(); }                                   // :481-497
@@ -735,8 +777,24 @@ public:
     return get_all_intersections(mesh_id, all);
   }
 private:
+  // does_A_contains_a_CC_of_B (:131-147; precondition: A and B do not intersect): one point per connected component of B, moved by B's transformation as
+  // Aff_transformation_3::transform(Point_3) does, classified against A under A's transformation
+  bool contains_a_cc_of(std::size_t a, std::size_t b) const {
+    if (m_points_per_cc[b].empty()) return false;
+    const Aff& tb = m_transformations[b];
+    std::vector<Point_3> moved;
+    for (const Point_3& q : m_points_per_cc[b])
+      moved.push_back(Point_3(tb.m(0, 0) * q.x() + tb.m(0, 1) * q.y() + tb.m(0, 2) * q.z() + tb.m(0, 3), tb.m(1, 0) * q.x() + tb.m(1, 1) * q.y() + tb.m(1, 2) * q.z() + tb.m(1, 3),
+                              tb.m(2, 0) * q.x() + tb.m(2, 1) * q.y() + tb.m(2, 2) * q.z() + tb.m(2, 3)));
+    std::vector<int> side;
+    m_trees[a]->bounded_side(moved.begin(), moved.end(), std::back_inserter(side), m_transformations[a]);
+    for (int s : side) if (s == ON_BOUNDED_SIDE) return true;
+    return false;
+  }
   std::vector<std::unique_ptr<Tree>> m_trees;
   std::vector<Aff> m_transformations;
+  std::vector<bool> m_is_closed;
+  std::vector<std::vector<Point_3>> m_points_per_cc;
 };
 
 }  // namespace CGAL_B200

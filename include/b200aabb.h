@@ -242,6 +242,10 @@ int b200aabb_max_distance_to_mesh(b200aabb_tree* t, const double* points, uint64
  * answer does not depend on the rays, only attempts[i] (optional: rays cast for point i; 0 = decided by the bbox) does.  As in the reference, the
  * result is unspecified for a mesh that is not closed.  points: n x 3, HOST or DEVICE. */
 int b200aabb_side_of_mesh(b200aabb_tree* t, const double* points, uint64_t n, b200aabb_memspace space, int8_t* side, uint8_t* attempts);
+/* The same with the mesh under an affine transformation (xf: 12 doubles as for b200aabb_do_intersect_tree_transformed; NULL = identity) and the points given
+ * in the frame of the transformed mesh: does_A_contains_a_CC_of_B of Rigid_triangle_mesh_collision_detection.h:131-147 (Point_inside_vertical_ray_cast over the
+ * Transformed_tree_helper, AABB_traversal_traits_with_transformation.h:190-224).  The rounded images of the primitives are classified exactly. */
+int b200aabb_side_of_mesh_transformed(b200aabb_tree* t, const double* xf, const double* points, uint64_t n, b200aabb_memspace space, int8_t* side, uint8_t* attempts);
 
 /* ---- multi-GPU behind the boundary --------------------------------------------------------------------
  * The reference has no multi-device path: its callers shard queries over threads (tbb::parallel_for,

@@ -42,6 +42,13 @@ def main():
     t.build()
     t.set_option(103, 1)
     t.build()
+    # Triangle_3 queries and tree-vs-tree (plain and under transformations)
+    tq = np.concatenate([pts[:3000], pts[:3000] + 0.05, pts[:3000] + np.array([0.05, -0.03, 0.02])], 1)
+    ct = g.number_of_intersected_primitives(tq, B.TRIANGLE)
+    offt, idst = g.all_intersected_primitives(tq, B.TRIANGLE)
+    g2 = B.AABB_tree(v + np.array([0.1, 0.0, 0.0]), f)
+    tt = g.do_intersect_tree(g2), g.do_intersect_tree(g2, xf=np.array([[0, -1, 0, 0.2], [1, 0, 0, 0], [0, 0, 1, 0]], float)), g.do_intersect_tree(g2, other_xf=np.array([[1, 0, 0, 9.0], [0, 1, 0, 0], [0, 0, 1, 0]], float))
+    print("triangle queries", int(ct.sum()), len(idst), tt)
     print("ok", int(r["prim"].sum() % 1000), int((fi["prim"] != B.NO_PRIMITIVE).sum()), int(c.sum()), len(ids), int((sk["prim"] != B.NO_PRIMITIVE).sum()), len(o1[1]), len(o2[1]),
           len(o3[1]), int((side == 1).sum()), round(md[0], 6), t.size())
 

@@ -171,8 +171,59 @@ class AABB_face_graph_triangle_primitive {
   Id m_id;
 };
 
+// AABB_face_graph_triangle_primitive<FaceGraph, Default, Tag_false /*SEVERAL graphs per tree*/, Tag_false>: the id carries the graph
+// (AABB_tree/include/CGAL/AABB_face_graph_triangle_primitive.h:73-88: Id = std::pair<face_descriptor, const FaceGraph*>), no shared data
+template <class FaceGraph>
+class AABB_face_graph_triangle_primitive_many {
+ public:
+  typedef std::pair<typename FaceGraph::Face_index, const FaceGraph*> Id;
+  typedef Triangle_3 Datum;
+  typedef typename FaceGraph::Point Point;
+  template <class Iterator>
+  AABB_face_graph_triangle_primitive_many(Iterator it, const FaceGraph& g) : m_id(*it, &g) {}
+  Id id() const { return m_id; }
+  Datum datum() const {
+    const FaceGraph* g = m_id.second;
+    const auto h = g->halfedge(m_id.first);
+    return Datum(g->point(g->target(h)), g->point(g->target(g->next(h))), g->point(g->source(h)));
+  }
+  Point reference_point() const { return m_id.second->point(m_id.second->target(m_id.second->halfedge(m_id.first))); }
+
+ private:
+  Id m_id;
+};
+
+// AABB_triangle_primitive_3<GeomTraits, Iterator> over a range of Triangle_3 (AABB_tree/include/CGAL/AABB_triangle_primitive_3.h:27-95): Id = the iterator
+template <class Iterator>
+class AABB_triangle_primitive_3 {
+ public:
+  typedef Iterator Id;
+  typedef Triangle_3 Datum;
+  typedef Point_3 Point;
+  explicit AABB_triangle_primitive_3(Iterator it) : m_it(it) {}
+  Id id() const { return m_it; }
+  const Datum& datum() const { return *m_it; }
+  Point reference_point() const { return m_it->vertex(0); }
+
+ private:
+  Iterator m_it;
+};
+
+// AABB_traits_base (AABB_traits_3.h:46-76): the shared data exists only for primitives that declare it
+template <class Primitive, class = void>
+struct AABB_traits_base {};
+template <class Primitive>
+struct AABB_traits_base<Primitive, std::void_t<typename Primitive::Shared_data>> {
+  template <typename... T>
+  void set_shared_data(T&&... t) { m_data = Primitive::construct_shared_data(std::forward<T>(t)...); }
+  const typename Primitive::Shared_data& shared_data() const { return m_data; }
+
+ private:
+  typename Primitive::Shared_data m_data = nullptr;
+};
+
 template <class GeomTraits, class AABBPrimitive>
-class AABB_traits_3 {
+class AABB_traits_3 : public AABB_traits_base<AABBPrimitive> {
  public:
   typedef GeomTraits Geom_traits;
   typedef typename GeomTraits::FT FT;
@@ -185,12 +236,6 @@ class AABB_traits_3 {
   struct Intersection_and_primitive_id {
     typedef std::pair<std::variant<typename GeomTraits::Point_3, typename GeomTraits::Segment_3>, typename Primitive::Id> Type;
   };
-  template <typename... T>
-  void set_shared_data(T&&... t) { m_data = Primitive::construct_shared_data(std::forward<T>(t)...); }
-  const typename Primitive::Shared_data& shared_data() const { return m_data; }
-
- private:
-  typename Primitive::Shared_data m_data = nullptr;
 };
 
 }  // namespace mini

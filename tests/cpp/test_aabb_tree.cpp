@@ -200,6 +200,21 @@ static int known_answers() {
       CHECK(cd.size() == 2 && !cd.is_valid_index(i1) && cd.get_all_intersections(i2).empty());
       Mesh s3 = tetrahedron(0.25, 0.25);
       CHECK(cd.add_mesh(faces(s3).first, faces(s3).second, s3) == i1 && cd.get_all_intersections(i2) == std::vector<std::size_t>{i1});
+      // inclusions: a solid scaled down to a tenth and placed inside another one touches no face of it, but lies in its volume
+      CGAL_B200::Rigid_triangle_mesh_collision_detection<Tree, mini::Aff_transformation_3> in;
+      Mesh big = tetrahedron(), small = tetrahedron();
+      const std::size_t ib = in.add_mesh_with_points(true, std::vector<Point>{Point(0, 0, 0)}, faces(big).first, faces(big).second, big),
+                        is = in.add_mesh_with_points(true, std::vector<Point>{Point(0, 0, 0)}, faces(small).first, faces(small).second, small);
+      in.set_transformation(is, mini::Aff_transformation_3(0.1, 0, 0, 0.2, 0, 0.1, 0, 0.2, 0, 0, 0.1, 0.2));     // a tenth of the size, moved to (0.2, 0.2, 0.2)
+      typedef std::vector<std::pair<std::size_t, bool>> Pairs;
+      CHECK(in.get_all_intersections(ib).empty());
+      CHECK((in.get_all_intersections_and_inclusions(ib) == Pairs{{is, true}}) && (in.get_all_intersections_and_inclusions(is) == Pairs{{ib, true}}));
+      in.set_transformation(is, mini::Aff_transformation_3(0.1, 0, 0, 0.95, 0, 0.1, 0, 0.0, 0, 0, 0.1, 0.0));    // across the vertex (1, 0, 0)
+      CHECK((in.get_all_intersections_and_inclusions(ib) == Pairs{{is, false}}));
+      in.set_transformation(is, mini::Aff_transformation_3(0.1, 0, 0, 3.0, 0, 0.1, 0, 3.0, 0, 0, 0.1, 3.0));     // outside
+      CHECK(in.get_all_intersections_and_inclusions(ib).empty());
+      in.set_transformation(ib, mini::Aff_transformation_3(1, 0, 0, 2.9, 0, 1, 0, 2.9, 0, 0, 1, 2.9));           // the large one follows: inside again
+      CHECK((in.get_all_intersections_and_inclusions(ib) == Pairs{{is, true}}));
     }
     {   // all_intersected_primitives / any_intersected_primitive (AABB_tree.h:253-268): the two faces the ray crosses, base face 0 among them
       std::vector<mini::Face_index> ids;
@@ -329,6 +344,50 @@ static int known_answers() {
 
 // file format (little endian): u64 nv, nf, nrays, nsegs, npts; f64 verts[nv*3]; u32 faces[nf*3]; f64 rays[nrays*6]; f64 segs[nsegs*6]; f64 pts[npts*3]
 // output: per ray u32 id (0xFFFFFFFF none) + f64 point[3]; per segment u32 count + u32 do_intersect; per point u32 id + f64 cp[3] + f64 sqdist
+// other primitive types of the reference over the same class: several face graphs in one tree (ids carry the graph), and a range
+// of Triangle_3 (ids are iterators)
+static int other_primitives() {
+  {   // AABB_face_graph_triangle_primitive<..., OneFaceGraphPerTree = Tag_false>: two meshes inserted into one tree
+    typedef mini::AABB_face_graph_triangle_primitive_many<Mesh> Many;
+    typedef CGAL_B200::AABB_tree<mini::AABB_traits_3<K, Many>> Tree2;
+    Mesh a = tetrahedron(), b = tetrahedron(5.0, 0.0);
+    Tree2 tree;
+    tree.insert(faces(a).first, faces(a).second, a);
+    tree.insert(faces(b).first, faces(b).second, b);
+    CHECK(tree.size() == 8);
+    const auto bb = tree.bbox();
+    CHECK(bb.xmin() == 0 && bb.xmax() == 6);
+    const Ray up_a(Point(0.2, 0.2, -1.0), Point(0.2, 0.2, 0.0)), up_b(Point(5.2, 0.2, -1.0), Point(5.2, 0.2, 0.0));
+    const auto ha = tree.first_intersection(up_a), hb = tree.first_intersection(up_b);
+    CHECK(ha && ha->second.second == &a && ha->second.first == mini::Face_index(0));
+    CHECK(hb && hb->second.second == &b && hb->second.first == mini::Face_index(0));
+    const auto cp = tree.closest_point_and_primitive(Point(5.0, 0.0, 3.0));
+    CHECK(cp.first == Point(5.0, 0.0, 1.0) && cp.second.second == &b);
+    CHECK(tree.number_of_intersected_primitives(Segment(Point(-1.0, 0.1, 0.1), Point(7.0, 0.1, 0.1))) == 4);   // through both solids
+    std::vector<Many::Id> ids;
+    tree.all_intersected_primitives(up_b, std::back_inserter(ids));
+    CHECK(ids.size() == 2 && ids[0].second == &b && ids[1].second == &b);
+  }
+  {   // AABB_triangle_primitive_3 over a std::vector<Triangle_3>
+    typedef std::vector<mini::Triangle_3>::const_iterator It;
+    typedef mini::AABB_triangle_primitive_3<It> Prim;
+    typedef CGAL_B200::AABB_tree<mini::AABB_traits_3<K, Prim>> Tree3;
+    std::vector<mini::Triangle_3> soup;
+    for (int i = 0; i < 10; ++i) soup.push_back(mini::Triangle_3(Point(0, 0, i), Point(1, 0, i), Point(0, 1, i)));   // ten parallel triangles
+    Tree3 tree(soup.cbegin(), soup.cend());
+    CHECK(tree.size() == 10);
+    const Ray down(Point(0.2, 0.2, 20.0), Point(0.2, 0.2, 19.0));
+    const auto h = tree.first_intersection(down);
+    CHECK(h && h->second == soup.cbegin() + 9);
+    CHECK(tree.number_of_intersected_primitives(down) == 10);
+    CHECK(tree.number_of_intersected_primitives(Segment(Point(0.2, 0.2, 2.5), Point(0.2, 0.2, 6.5))) == 4);
+    const auto cp = tree.closest_point_and_primitive(Point(0.2, 0.2, 3.4));
+    CHECK(cp.first == Point(0.2, 0.2, 3.0) && cp.second == soup.cbegin() + 3);
+    CHECK(tree.do_intersect(mini::Triangle_3(Point(0.1, 0.1, 4.5), Point(0.3, 0.1, 5.5), Point(0.1, 0.3, 5.5))));      // crosses z = 5
+  }
+  return 0;
+}
+
 static int answer_file(const char* in, const char* out) {
   FILE* f = std::fopen(in, "rb");
   CHECK(f);
@@ -378,7 +437,7 @@ static int answer_file(const char* in, const char* out) {
 int main(int argc, char** argv) {
   try {
     if (argc == 3) return answer_file(argv[1], argv[2]);
-    return known_answers();
+    return known_answers() || other_primitives();
   } catch (const std::exception& e) {
     std::fprintf(stderr, "exception: %s\n", e.what());
     return 2;

@@ -50,6 +50,7 @@ def lib():
             getattr(L, n).argtypes = [_dp]
         L.hc_tri_do_intersect.argtypes = [_dp, _dp, C.c_int]
         L.hc_tri_tri_do_intersect.argtypes = [_dp, _dp]
+        L.hc_side_of_mesh_xf.argtypes = [C.c_void_p, _dp, _dp, C.c_uint64, _dp, C.c_int, C.POINTER(C.c_int8)]
         L.hc_xf_apply.argtypes = [_dp, _dp, _dp]
         L.hc_xf_box_meets.argtypes = [_dp, C.POINTER(C.c_float), _dp]
         L.hc_intersect_triangle.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_int, _u32p]
@@ -126,6 +127,13 @@ class HostTree:
         side, att = np.zeros(len(pts), np.int8), np.zeros(len(pts), np.uint8)
         lib().hc_side_of_mesh(self.h, _p(pts), len(pts), _p(dirs), len(dirs), side.ctypes.data_as(C.POINTER(C.c_int8)), _p(att, _u8p))
         return side, att
+
+    def side_of_mesh_xf(self, m, pts, dirs):
+        """the same with the mesh under the 3 x 4 affine map m (bvh.cuh::traverse_side<AffXf>): side per point, -2 = no decisive ray"""
+        m, pts, dirs = _d(m).ravel(), _d(pts).reshape(-1, 3), _d(dirs).reshape(-1, 3)
+        side = np.zeros(len(pts), np.int8)
+        lib().hc_side_of_mesh_xf(self.h, _p(m), _p(pts), len(pts), _p(dirs), len(dirs), side.ctypes.data_as(C.POINTER(C.c_int8)))
+        return side
 
     def first_intersection(self, rays):
         rays = _d(rays).reshape(-1, 6)

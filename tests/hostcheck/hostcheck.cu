@@ -311,6 +311,23 @@ void hc_side_of_mesh(void* hv, const double* pts, uint64_t n, const double* dirs
         side[i] = (int8_t)(r == kSideIndeterminate ? -2 : (r == kSideBoundary ? 0 : ((r & 1) ? 1 : -1)));
     }
 }
+// the same with the mesh under the affine map m (12 doubles): no root-box shortcut, the traversal decides (a point far outside crosses nothing)
+void hc_side_of_mesh_xf(void* hv, const double* m, const double* pts, uint64_t n, const double* dirs, int ndir, int8_t* side) {
+    HostTree* h = (HostTree*)hv;
+    AffXf x; for (int i = 0; i < 12; ++i) x.m[i] = m[i];
+    for (uint64_t i = 0; i < n; ++i) {
+        const Vec3 p = V(pts + 3 * i);
+        side[i] = -1;
+        if (h->n == 0) continue;
+        int r = kSideIndeterminate;
+        for (int k = 0; k < ndir && r == kSideIndeterminate; ++k) {
+            TravStat st;
+            const Vec3 q = {p.x + dirs[3 * k], p.y + dirs[3 * k + 1], p.z + dirs[3 * k + 2]};
+            r = traverse_side<AffXf>(h->nodes.data(), h->tris.data(), h->root, p, q, st, x);
+        }
+        side[i] = (int8_t)(r == kSideIndeterminate ? -2 : (r == kSideBoundary ? 0 : ((r & 1) ? 1 : -1)));
+    }
+}
 int hc_tri_tri_do_intersect(const double* query, const double* tri) { int n = 0; return tri_tri_do_intersect(T(query), T(tri), n) ? 1 : 0; }
 // Triangle_3 queries (9 doubles each) through the device traversal routine: mode 0 do_intersect, 1 count
 void hc_intersect_triangle(void* hv, const double* q, uint64_t n, int count, uint32_t* out) {

@@ -911,3 +911,29 @@ def test_tree_against_tree_under_transformations(B, meshes):
                 ta = soup[ia] if xa is None else hc.xf_apply(xa, soup[ia])
                 assert orc.tri_tri_do_intersect(ta, hc.xf_apply(xb, soup[ib])) == 1
         assert 3 < n_true < trials - 3, (name, n_true)
+
+
+def test_side_of_mesh_under_a_transformation(B, meshes):
+    """b200aabb_side_of_mesh_transformed (does_A_contains_a_CC_of_B of Rigid_triangle_mesh_collision_detection.h): the tree built once on the mesh, the affine
+    map given per call, against the oracle on a tree built over the rounded images of the primitives; host and device pointers"""
+    import torch
+    from test_side_of_mesh import transformed_soup
+    from test_triangle_queries import rigid
+    rng = np.random.default_rng(48)
+    for name in ("cube", "elephant"):
+        v, f = meshes[name]
+        soup = soup_of(v, f)
+        g = B.AABB_tree(v, f)
+        for trial in range(3):
+            m = rigid(rng, scale=rng.uniform(0.5, 2.0), shift=rng.uniform(-3, 3, 3)) if trial else np.array([[0, -1, 0, 0.5], [1, 0, 0, -0.25], [0, 0, 1, 2.0]], float)
+            img = transformed_soup(m, soup)
+            w = img.reshape(-1, 3)
+            lo, hi = w.min(0), w.max(0)
+            pts = np.concatenate([lo + rng.uniform(-0.1, 1.1, (20_000, 3)) * (hi - lo), w[rng.integers(0, len(w), 500)],
+                                  (w[rng.integers(0, len(w), 500)] + w[rng.integers(0, len(w), 500)]) / 2])
+            want, _ = orc.OracleTree(soup=img).side_of_mesh(pts)
+            np.testing.assert_array_equal(g.side_of_mesh(pts, xf=m), want)
+            np.testing.assert_array_equal(g.side_of_mesh(torch.from_numpy(pts).cuda(), xf=m).cpu().numpy(), want)
+            assert (want == 1).any() and (want == -1).any() and (want == 0).any()
+        ident = np.hstack([np.eye(3), np.zeros((3, 1))])
+        np.testing.assert_array_equal(g.side_of_mesh(pts, xf=ident), g.side_of_mesh(pts))

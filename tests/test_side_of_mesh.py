@@ -194,3 +194,33 @@ def test_device_traversal_against_the_oracle(name, meshes):
     assert (want == 1).any() and (want == -1).any()
     if name in ("lattice", "cube"):
         assert (want == 0).any() and attempts.max() > 1
+
+
+def transformed_soup(m, soup):
+    """images of the primitives as Aff_transformation_3::transform gives them (Cartesian/Aff_transformation_rep_3.h:111-117): left to right in binary64"""
+    p = soup.reshape(-1, 3)
+    m = np.asarray(m, float).reshape(3, 4)
+    out = np.stack([((m[k, 0] * p[:, 0] + m[k, 1] * p[:, 1]) + m[k, 2] * p[:, 2]) + m[k, 3] for k in range(3)], axis=1)
+    return out.reshape(-1, 9)
+
+
+@pytest.mark.parametrize("name", ["cube", "elephant"])
+def test_device_traversal_under_a_transformation(name, meshes):
+    """the mesh under an affine map (does_A_contains_a_CC_of_B, Rigid_triangle_mesh_collision_detection.h:131-147): the device traversal with transformed
+    datums and conservatively mapped node boxes (bvh.cuh::traverse_side<AffXf>) against the oracle on a tree BUILT over the rounded images"""
+    from test_triangle_queries import rigid
+    rng = np.random.default_rng(34)
+    v, f = meshes[name]
+    soup = v[f.astype(np.int64)].reshape(-1, 9)
+    h = hc.HostTree(soup)
+    for trial in range(3):
+        m = rigid(rng, scale=rng.uniform(0.5, 2.0), shift=rng.uniform(-3, 3, 3)) if trial else np.array([[0, -1, 0, 0.5], [1, 0, 0, -0.25], [0, 0, 1, 2.0]], float)
+        img = transformed_soup(m, soup)
+        w = img.reshape(-1, 3)
+        lo, hi = w.min(0), w.max(0)
+        pts = np.concatenate([lo + rng.uniform(-0.1, 1.1, (600, 3)) * (hi - lo), w[rng.integers(0, len(w), 100)],
+                              (w[rng.integers(0, len(w), 100)] + w[rng.integers(0, len(w), 100)]) / 2])
+        want, _ = orc.OracleTree(soup=img).side_of_mesh(pts)
+        got = h.side_of_mesh_xf(m, pts, DIRS)
+        assert np.array_equal(got, want), (name, trial, np.flatnonzero(got != want)[:5])
+        assert (want == 1).any() and (want == -1).any() and (want == 0).any()
