@@ -38,7 +38,7 @@ class _Stats(C.Structure):
 
 
 SYMBOLS = ["b200aabb_create", "b200aabb_destroy", "b200aabb_set_stream", "b200aabb_set_option", "b200aabb_last_error", "b200aabb_get_stats", "b200aabb_synchronize",
-           "b200aabb_set_mesh", "b200aabb_set_triangles", "b200aabb_clear", "b200aabb_build", "b200aabb_refit", "b200aabb_refit_mesh",
+           "b200aabb_set_mesh", "b200aabb_set_triangles", "b200aabb_set_segments", "b200aabb_clear", "b200aabb_build", "b200aabb_refit", "b200aabb_refit_mesh",
            "b200aabb_accelerate_distance_queries", "b200aabb_size", "b200aabb_bbox", "b200aabb_do_intersect",
            "b200aabb_number_of_intersected_primitives", "b200aabb_any_intersected_primitive", "b200aabb_all_intersected_primitives", "b200aabb_do_intersect_tree", "b200aabb_do_intersect_tree_transformed",
            "b200aabb_number_of_intersections", "b200aabb_all_intersections", "b200aabb_any_intersection",
@@ -72,6 +72,7 @@ def load_library():
         L.b200aabb_synchronize.argtypes = [vp]
         L.b200aabb_set_mesh.argtypes = [vp, dp, u64, dp, dp, u64]
         L.b200aabb_set_triangles.argtypes = [vp, dp, dp, u64, C.c_int]
+        L.b200aabb_set_segments.argtypes = [vp, dp, dp, u64, C.c_int]
         L.b200aabb_clear.argtypes = [vp]
         L.b200aabb_refit.argtypes = [vp, dp, u64, C.c_int]
         L.b200aabb_refit_mesh.argtypes = [vp, dp, u64, dp, u64]
@@ -161,7 +162,7 @@ def debug_predicate(which, records, device=0):
 class AABB_tree:
     """AABB_tree< AABB_traits_3< Epick, AABB_face_graph_triangle_primitive< Surface_mesh<Point_3> > > > on one B200."""
 
-    def __init__(self, vertices=None, faces=None, triangles=None, ids=None, device=0):
+    def __init__(self, vertices=None, faces=None, triangles=None, ids=None, device=0, segments=None):
         self._lib = load_library()
         h = C.c_void_p()
         rc = self._lib.b200aabb_create(int(device), C.byref(h))
@@ -169,8 +170,8 @@ class AABB_tree:
             raise B200AABBError(rc)
         self._h = h
         self.device = int(device)
-        if vertices is not None or triangles is not None:
-            self.insert(vertices=vertices, faces=faces, triangles=triangles, ids=ids)
+        if vertices is not None or triangles is not None or segments is not None:
+            self.insert(vertices=vertices, faces=faces, triangles=triangles, ids=ids, segments=segments)
 
     def __del__(self):
         if getattr(self, "_h", None):
@@ -182,13 +183,24 @@ class AABB_tree:
             raise B200AABBError(rc, self._lib.b200aabb_last_error(self._h).decode())
 
     # ---- primitives (AABB_tree.h:147-216) ----
-    def insert(self, vertices=None, faces=None, triangles=None, ids=None):
+    def insert(self, vertices=None, faces=None, triangles=None, ids=None, segments=None):
         """insert(faces(mesh).first, faces(mesh).second, mesh): `vertices` (nv,3) f64 + `faces` (nf,3) u32 in face order;
-        or a triangle soup `triangles` (n,9).  Replaces the current primitives (one face graph per tree)."""
+        or a triangle soup `triangles` (n,9); or Segment_3 primitives `segments` (n,6) = (source, target) (AABB_segment_primitive_3 /
+        AABB_halfedge_graph_segment_primitive: closest_point and Plane_3 / Triangle_3 id queries).  Replaces the current primitives."""
         idp = None
         if ids is not None:
             ids = np.ascontiguousarray(ids, dtype=np.uint32)
             idp = ids.ctypes.data
+        if segments is not None:
+            if _is_torch(segments):
+                b = _Buf(segments, np.float64, 6)
+                if ids is not None:
+                    raise ValueError("ids with device segments are not supported")
+                self._check(self._lib.b200aabb_set_segments(self._h, b.ptr, None, b.n, _DEVICE))
+            else:
+                sg = np.ascontiguousarray(segments, dtype=np.float64).reshape(-1, 6)
+                self._check(self._lib.b200aabb_set_segments(self._h, sg.ctypes.data, idp, len(sg), _HOST))
+            return
         if triangles is not None:
             if _is_torch(triangles):
                 b = _Buf(triangles, np.float64, 9)

@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(128, 8) plane_kernel(const TreeRef tr, const d
 }
 
 // the same for Triangle_3 queries: query i = the 9 doubles at q + stride * i (stride 9: the caller's batch; 12: the TriRec array of another tree)
-template <int MODE>
+template <int MODE, bool SEG>
 __global__ void __launch_bounds__(128, 6) triangle_kernel(const TreeRef tr, const double* __restrict__ q, uint32_t stride, uint64_t n, uint8_t* __restrict__ out8,
                                                           uint32_t* __restrict__ out32, const uint64_t* __restrict__ offsets, uint32_t* __restrict__ list) {
     const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -254,11 +254,11 @@ __global__ void __launch_bounds__(128, 6) triangle_kernel(const TreeRef tr, cons
         if (MODE == kList) {
             const uint64_t lo = offsets[i], hi = offsets[i + 1];
             uint32_t r = 0;
-            if (hi > lo) r = traverse_triangle<kList>(tr.nodes, tr.tris, tr.root, t, st, list + lo, (uint32_t)(hi - lo));
-            else r = traverse_triangle<kAnyHit>(tr.nodes, tr.tris, tr.root, t, st);
+            if (hi > lo) r = traverse_triangle<kList, NoXf, SEG>(tr.nodes, tr.tris, tr.root, t, st, list + lo, (uint32_t)(hi - lo));
+            else r = traverse_triangle<kAnyHit, NoXf, SEG>(tr.nodes, tr.tris, tr.root, t, st);
             if (r != hi - lo) atomicOr(&tr.counters[2], 4ull);
         } else {
-            const uint32_t r = traverse_triangle<MODE>(tr.nodes, tr.tris, tr.root, t, st);
+            const uint32_t r = traverse_triangle<MODE, NoXf, SEG>(tr.nodes, tr.tris, tr.root, t, st);
             if (MODE == kAnyHit) out8[i] = (uint8_t)r; else out32[i] = r;
         }
     }
@@ -472,6 +472,7 @@ __global__ void __launch_bounds__(128, 5) first_intersection_kernel(const TreeRe
     flush_stats(tr, st, tie, near);
 }
 
+template <bool SEG>
 __global__ void __launch_bounds__(128) closest_point_kernel(const TreeRef tr, const double* __restrict__ pts, uint64_t n, double* __restrict__ cp,
                                                             uint32_t* __restrict__ prim, double* __restrict__ sqd, uint8_t* __restrict__ flags) {
     const uint64_t slot = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -479,7 +480,7 @@ __global__ void __launch_bounds__(128) closest_point_kernel(const TreeRef tr, co
     int tie = 0, near = 0;
     if (slot < n) {
         const uint64_t i = tr.perm ? tr.perm[slot] : slot;
-        const Closest c = traverse_closest(tr.nodes, tr.tris, tr.root, ld3(pts + 3 * i), tr.mag, st);
+        const Closest c = traverse_closest<SEG>(tr.nodes, tr.tris, tr.root, ld3(pts + 3 * i), tr.mag, st);
         tie = c.tie; near = c.near;
         if (cp) { cp[3 * i] = c.p.x; cp[3 * i + 1] = c.p.y; cp[3 * i + 2] = c.p.z; }
         if (prim) prim[i] = c.prim;
@@ -602,6 +603,7 @@ struct b200aabb_tree {
     // tbb::parallel_for over const queries, AABB_tree.h:593-612) are serialised, never interleaved on the shared staging / scratch buffers.
     std::recursive_mutex mu;
     bool imported = false;         // the tree came from b200aabb_import_alloc: there are no primitives to rebuild from
+    bool segments = false;         // the primitives are Segment_3 (b200aabb_set_segments), stored as the records (source, target, target)
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
@@ -1099,10 +1101,21 @@ static void launch_intersect(b200aabb_tree* t, int kind, cudaStream_t st, const 
         case B200AABB_RAY: intersect_kernel<kRayQ, MODE><<<grid, 128, 0, st>>>(tree_ref(t, perm), in, cnt, out8, out32, offsets, list); break;
         case B200AABB_LINE: intersect_kernel<kLineQ, MODE><<<grid, 128, 0, st>>>(tree_ref(t, perm), in, cnt, out8, out32, offsets, list); break;
         case B200AABB_PLANE: plane_kernel<MODE><<<grid, 128, 0, st>>>(tree_ref(t, nullptr), in, cnt, out8, out32, offsets, list); break;
-        case B200AABB_TRIANGLE: triangle_kernel<MODE><<<grid, 128, 0, st>>>(tree_ref(t, perm), in, 9u, cnt, out8, out32, offsets, list); break;
+        case B200AABB_TRIANGLE:
+            if (t->segments) triangle_kernel<MODE, true><<<grid, 128, 0, st>>>(tree_ref(t, perm), in, 9u, cnt, out8, out32, offsets, list);
+            else triangle_kernel<MODE, false><<<grid, 128, 0, st>>>(tree_ref(t, perm), in, 9u, cnt, out8, out32, offsets, list);
+            break;
         default: intersect_kernel<kSegmentQ, MODE><<<grid, 128, 0, st>>>(tree_ref(t, perm), in, cnt, out8, out32, offsets, list); break;
     }
 }
+// a tree of Segment_3 primitives answers closest_point / squared_distance and the id queries with Plane_3 and Triangle_3 (what the reference's kernel can
+// intersect with a Segment_3 datum robustly in 3D); every other entry point needs triangles
+static int need_triangles(b200aabb_tree* t, const char* what) {
+    if (!t->segments) return B200AABB_OK;
+    t->err = std::string(what) + ": not offered on a tree of Segment_3 primitives";
+    return B200AABB_ERR_INVALID_ARGUMENT;
+}
+static bool kind_fits_primitives(const b200aabb_tree* t, int kind) { return !t->segments || kind == B200AABB_PLANE || kind == B200AABB_TRIANGLE; }
 static bool valid_kind(int kind) { return kind >= B200AABB_SEGMENT && kind <= B200AABB_TRIANGLE; }          // the id queries
 static bool valid_object_kind(int kind) { return kind >= B200AABB_SEGMENT && kind <= B200AABB_PLANE; }    // the intersection OBJECTS (no Triangle_3 queries)
 static size_t query_bytes(int kind) { return kind == B200AABB_PLANE ? 32 : (kind == B200AABB_TRIANGLE ? 72 : 48); }
@@ -1248,7 +1261,7 @@ int b200aabb_clear(b200aabb_tree* t) { B2_LOCK(t);
     { const int rc_ = sync_pipeline(t); if (rc_) return rc_; }   // (asynchronous HOST batches may still be in flight)
     B2_CUDA(t, cudaStreamSynchronize(t->stream));
     free_tree_buffers(t); free_build_scratch(t); free_input(t);
-    t->n = 0; t->built = true; t->imported = false; t->bounds_valid = false; empty_bbox(t->h_bbox);
+    t->n = 0; t->built = true; t->imported = false; t->segments = false; t->bounds_valid = false; empty_bbox(t->h_bbox);
     return B200AABB_OK;
 }
 
@@ -1262,6 +1275,40 @@ int b200aabb_set_triangles(b200aabb_tree* t, const double* tris, const uint32_t*
     B2_CUDA(t, cudaMemcpyAsync(t->d_soup, tris, n * 72, kind, t->stream));
     if (ids) { B2_CUDA(t, cudaMalloc(&t->d_ids, n * 4)); B2_CUDA(t, cudaMemcpyAsync(t->d_ids, ids, n * 4, kind, t->stream)); }
     B2_CUDA(t, cudaStreamSynchronize(t->stream));
+    t->n = n; t->built = false;
+    return B200AABB_OK;
+}
+
+// Segment_3 primitives (AABB_segment_primitive_3 over a range of segments, AABB_halfedge_graph_segment_primitive over the edges of a graph): each is kept as
+// the record (source, target, target), so the build, the boxes and the binary32 pre-tests see the segment as a flat triangle; the leaf routines that must differ
+// (projection, Triangle_3 queries) are selected by t->segments.
+__global__ void __launch_bounds__(256) expand_segments_kernel(const double* __restrict__ segs, uint64_t n, double* __restrict__ soup) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double* s = segs + 6 * i;
+    double* o = soup + 9 * i;
+    o[0] = s[0]; o[1] = s[1]; o[2] = s[2]; o[3] = s[3]; o[4] = s[4]; o[5] = s[5]; o[6] = s[3]; o[7] = s[4]; o[8] = s[5];
+}
+int b200aabb_set_segments(b200aabb_tree* t, const double* segs, const uint32_t* ids, uint64_t n, b200aabb_memspace space) { B2_LOCK(t);
+    if (!t || (n && !segs)) return B200AABB_ERR_INVALID_ARGUMENT;
+    int rc = b200aabb_clear(t);
+    if (rc) return rc;
+    t->segments = true;
+    if (n == 0) return B200AABB_OK;
+    const cudaMemcpyKind kind = space == B200AABB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    double* d_in = nullptr;
+    B2_CUDA(t, cudaMalloc(&t->d_soup, n * 72 + kSoupSlack));
+    if (space == B200AABB_HOST) {
+        if (cudaMalloc(&d_in, n * 48) != cudaSuccess) { free_input(t); t->err = "cudaMalloc(segments)"; return B200AABB_ERR_OUT_OF_MEMORY; }
+        cudaMemcpyAsync(d_in, segs, n * 48, cudaMemcpyHostToDevice, t->stream);
+    }
+    expand_segments_kernel<<<grid_for(n, 256), 256, 0, t->stream>>>(d_in ? d_in : segs, n, t->d_soup);
+    t->stats.kernel_launches += 1;
+    cudaError_t e = cudaSuccess;
+    if (ids) { e = cudaMalloc(&t->d_ids, n * 4); if (e == cudaSuccess) cudaMemcpyAsync(t->d_ids, ids, n * 4, kind, t->stream); }
+    const cudaError_t e2 = cudaStreamSynchronize(t->stream);
+    cudaFree(d_in);
+    if (e != cudaSuccess || e2 != cudaSuccess || cudaGetLastError() != cudaSuccess) { free_input(t); t->err = "set_segments: CUDA failure"; return B200AABB_ERR_CUDA; }
     t->n = n; t->built = false;
     return B200AABB_OK;
 }
@@ -1346,6 +1393,7 @@ int b200aabb_refit(b200aabb_tree* t, const double* tris, uint64_t n, b200aabb_me
     if (!t || (n && !tris)) return B200AABB_ERR_INVALID_ARGUMENT;
     B2_LOCK(t);
     B2_CUDA(t, cudaSetDevice(t->device));
+    { const int rc_ = need_triangles(t, "refit"); if (rc_) return rc_; }
     int rc = refit_precheck(t, n);
     if (rc || n == 0) return rc;
     B2_CUDA(t, cudaMemcpyAsync(t->d_soup, tris, n * 72, space == B200AABB_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, t->stream));
@@ -1358,6 +1406,7 @@ int b200aabb_refit_mesh(b200aabb_tree* t, const double* verts, uint64_t nv, cons
     B2_LOCK(t);
     B2_CUDA(t, cudaSetDevice(t->device));
     for (uint64_t i = 0; i < 3 * nf; ++i) if (faces[i] >= nv) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "face references a vertex index >= nv");
+    { const int rc_ = need_triangles(t, "refit_mesh"); if (rc_) return rc_; }
     int rc = refit_precheck(t, nf);
     if (rc || nf == 0) return rc;
     double* d_v = nullptr; uint32_t* d_f = nullptr;
@@ -1387,6 +1436,7 @@ int b200aabb_bbox(b200aabb_tree* t, double out[6]) { B2_LOCK(t);
 
 int b200aabb_do_intersect(b200aabb_tree* t, const double* q, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint8_t* out) { B2_LOCK(t);
     if (!t || (n && (!q || !out)) || !valid_kind(kind)) return B200AABB_ERR_INVALID_ARGUMENT;
+    if (!kind_fits_primitives(t, kind)) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "a tree of Segment_3 primitives takes Plane_3 and Triangle_3 queries");
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     if (t->n == 0) {   // empty tree: false (aabb_test_empty_tree.cpp:44-50)
@@ -1400,6 +1450,7 @@ int b200aabb_do_intersect(b200aabb_tree* t, const double* q, uint64_t n, b200aab
 
 int b200aabb_number_of_intersected_primitives(b200aabb_tree* t, const double* q, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint32_t* out) { B2_LOCK(t);
     if (!t || (n && (!q || !out)) || !valid_kind(kind)) return B200AABB_ERR_INVALID_ARGUMENT;
+    if (!kind_fits_primitives(t, kind)) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "a tree of Segment_3 primitives takes Plane_3 and Triangle_3 queries");
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     if (t->n == 0) {
@@ -1413,6 +1464,7 @@ int b200aabb_number_of_intersected_primitives(b200aabb_tree* t, const double* q,
 
 int b200aabb_any_intersected_primitive(b200aabb_tree* t, const double* q, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint32_t* out) { B2_LOCK(t);
     if (!t || (n && (!q || !out)) || !valid_kind(kind)) return B200AABB_ERR_INVALID_ARGUMENT;
+    if (!kind_fits_primitives(t, kind)) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "a tree of Segment_3 primitives takes Plane_3 and Triangle_3 queries");
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     if (t->n == 0) {   // empty tree: nullopt
@@ -1427,6 +1479,7 @@ int b200aabb_any_intersected_primitive(b200aabb_tree* t, const double* q, uint64
 int b200aabb_all_intersected_primitives(b200aabb_tree* t, const double* q, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space,
                                         const uint64_t* offsets, uint32_t* ids) { B2_LOCK(t);
     if (!t || (n && (!q || !offsets)) || !valid_kind(kind)) return B200AABB_ERR_INVALID_ARGUMENT;
+    if (!kind_fits_primitives(t, kind)) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "a tree of Segment_3 primitives takes Plane_3 and Triangle_3 queries");
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     B2_CUDA(t, cudaSetDevice(t->device));
@@ -1486,6 +1539,7 @@ int b200aabb_do_intersect_tree_transformed(b200aabb_tree* t, const double* xf, b
     if (prim) *prim = kNone;
     if (other_prim) *other_prim = kNone;
     if (t->device != other->device) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "do_intersect(tree): both trees must live on the same device");
+    if (t->segments || other->segments) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "do_intersect(tree): not offered on a tree of Segment_3 primitives");
     int rc = ensure_built(t);
     if (rc) return rc;
     rc = ensure_built(other);
@@ -1537,6 +1591,7 @@ int b200aabb_number_of_intersections(b200aabb_tree* t, const double* rays, uint6
 }
 int b200aabb_number_of_intersections_q(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint32_t* out) { B2_LOCK(t);
     if (!t || (n && (!rays || !out)) || !valid_object_kind(kind)) return B200AABB_ERR_INVALID_ARGUMENT;
+    { const int rc_ = need_triangles(t, "intersection objects"); if (rc_) return rc_; }
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     if (t->n == 0) {
@@ -1554,6 +1609,7 @@ int b200aabb_any_intersection(b200aabb_tree* t, const double* rays, uint64_t n, 
 int b200aabb_any_intersection_q(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, uint32_t* prim, double* pt, double* pt2,
                                 uint8_t* flags) { B2_LOCK(t);
     if (!t || (n && !rays) || !valid_object_kind(kind)) return B200AABB_ERR_INVALID_ARGUMENT;
+    { const int rc_ = need_triangles(t, "intersection objects"); if (rc_) return rc_; }
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     if (t->n == 0) return b200aabb_first_intersection(t, rays, n, space, prim, nullptr, pt, pt2, flags);   // nullopt for every ray
@@ -1570,6 +1626,7 @@ int b200aabb_all_intersections(b200aabb_tree* t, const double* rays, uint64_t n,
 int b200aabb_all_intersections_q(b200aabb_tree* t, const double* rays, uint64_t n, b200aabb_query_kind kind, b200aabb_memspace space, const uint64_t* offsets, uint32_t* ids,
                                  uint8_t* kinds, double* points) { B2_LOCK(t);
     if (!t || (n && (!rays || !offsets)) || !valid_object_kind(kind)) return B200AABB_ERR_INVALID_ARGUMENT;
+    { const int rc_ = need_triangles(t, "intersection objects"); if (rc_) return rc_; }
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     B2_CUDA(t, cudaSetDevice(t->device));
@@ -1625,6 +1682,7 @@ static int first_intersection_impl(b200aabb_tree* t, const double* rays, uint64_
                                    uint32_t mask_words, uint32_t* prim, double* tpar, double* pt, double* pt2, uint8_t* flags) {
     if (!t || (n && !rays) || (skip_mask == nullptr && mask_words != 0)) return B200AABB_ERR_INVALID_ARGUMENT;
     B2_LOCK(t);
+    { const int rc_ = need_triangles(t, "first_intersection"); if (rc_) return rc_; }
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     if (t->n == 0) {   // nullopt for every ray
@@ -1702,14 +1760,15 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
     if (t->n == 0) return fail(t, B200AABB_ERR_EMPTY_TREE, "distance query on an empty tree (CGAL_precondition(!empty()))");
     if (n == 0) return B200AABB_OK;
     // the warp-cooperative kernel packs (query slot, node / leaf) in 32 bits and needs an internal root
-    const bool warp_kernel = t->opt_closest_kernel >= 1 && t->n >= 2 && t->n <= kWpMaxPrims;
+    const bool warp_kernel = t->opt_closest_kernel >= 1 && t->n >= 2 && t->n <= kWpMaxPrims && !t->segments;   // (Segment_3 primitives: one thread per query)
     if (warp_kernel) { for (int s = 0; s < kScratchSlots; ++s) { rc = ensure_warp(t, s); if (rc) return rc; } }
     const bool two_pass = warp_kernel && t->opt_closest_kernel == 3 && n < (1ull << 32);
     if (two_pass) { rc = ensure_filter(t, space == B200AABB_HOST ? kHostScratch : kDeviceScratch, space == B200AABB_HOST ? std::min<uint64_t>(n, kPointChunkMax) : n); if (rc) return rc; }
     return run_batch(t, pts, 24, n, space, kPointQuery, {{cp, 24, 0}, {prim, 4, 0}, {sqd, 8, 0}, {flags, 1, 0}},
                      [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
                          if (!warp_kernel || cnt >= (1ull << 32)) {
-                             closest_point_kernel<<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (double*)o[0], (uint32_t*)o[1], (double*)o[2], (uint8_t*)o[3]);
+                             if (t->segments) closest_point_kernel<true><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (double*)o[0], (uint32_t*)o[1], (double*)o[2], (uint8_t*)o[3]);
+                             else closest_point_kernel<false><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, (double*)o[0], (uint32_t*)o[1], (double*)o[2], (uint8_t*)o[3]);
                              return;
                          }
                          const int slot = space == B200AABB_HOST ? kHostScratch : kDeviceScratch;
@@ -1762,6 +1821,7 @@ int b200aabb_side_of_mesh(b200aabb_tree* t, const double* pts, uint64_t n, b200a
 }
 int b200aabb_side_of_mesh_transformed(b200aabb_tree* t, const double* xf, const double* pts, uint64_t n, b200aabb_memspace space, int8_t* side, uint8_t* attempts) { B2_LOCK(t);
     if (!t || (n && (!pts || !side))) return B200AABB_ERR_INVALID_ARGUMENT;
+    { const int rc_ = need_triangles(t, "side_of_mesh"); if (rc_) return rc_; }
     int rc = ensure_built(t);
     if (rc || n == 0) return rc;
     if (t->n == 0) {                                                   // no primitives: everything is outside
@@ -1834,6 +1894,7 @@ int b200aabb_max_distance_to_mesh(b200aabb_tree* t, const double* pts, uint64_t 
 
 int b200aabb_export_layout(b200aabb_tree* t, void** ptrs, uint64_t* bytes, int cap, int* count) { B2_LOCK(t);
     if (!t || !ptrs || !bytes || !count || cap < 4) return B200AABB_ERR_INVALID_ARGUMENT;
+    { const int rc_ = need_triangles(t, "export_layout"); if (rc_) return rc_; }
     int rc = ensure_built(t);
     if (rc) return rc;
     ptrs[0] = t->d_nodes; bytes[0] = t->n > 1 ? (t->n - 1) * sizeof(BvhNode) : 0;

@@ -394,7 +394,9 @@ B2_HD uint32_t traverse_intersect(const BvhNode* __restrict__ nodes, const TriRe
 // AABB_tree.h:903-956; the query a tree-vs-tree do_intersect issues per primitive, AABB_traits_3.h:679-690).  Do_intersect_3(Bbox_3, Triangle_3)
 // (Bbox_3_Triangle_3_do_intersect.h: separating axes) is replaced by a conservative test — the binary32 box of the query, rounded outward, must overlap the
 // child's box — and the leaves decide exactly (geom.cuh::tri_tri_do_intersect), so results do not depend on the tree.  Same while-while scheme as traverse_line.
-template <int MODE, class XF = NoXf>
+// SEG: the primitives are Segment_3 (stored as the records (source, target, target), b200aabb_set_segments): the leaf test is
+// Do_intersect_3(Triangle_3 query, Segment_3 datum) (Segment_3_Triangle_3_do_intersect.h:177-262)
+template <int MODE, class XF = NoXf, bool SEG = false>
 B2_HD uint32_t traverse_triangle(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root, const Tri3& query, TravStat& st,
                                  uint32_t* list = nullptr, uint32_t list_cap = 0, const XF& xf = XF()) {
     constexpr bool kStopAtFirst = MODE == kAnyHit || MODE == kAnyId;
@@ -404,7 +406,7 @@ B2_HD uint32_t traverse_triangle(const BvhNode* __restrict__ nodes, const TriRec
         uint32_t id;
         const Tri3 t = xf.apply(load_tri(tris, ref & ~kLeafBit, id));
         ++st.leaves;
-        if (!tri_tri_do_intersect(query, t, st.nexact)) return false;
+        if (!(SEG ? seg_tri_do_intersect(query, t.a, t.b, st.nexact) : tri_tri_do_intersect(query, t, st.nexact))) return false;
         if (MODE == kList) { if (nlisted < list_cap) list[nlisted] = id; ++nlisted; }
         if (MODE == kAnyId) found_id = id;
         return true;
@@ -766,6 +768,9 @@ B2_HD bool tri_certainly_outside(const Tri3& t, const Vec3& o, const float* ub, 
     return certainly_farther(u, sqrtf(dot3f(u, u)), ra, rb, rc, m, rbound);
 }
 
+// SEG: Segment_3 primitives stored as (source, target, target): the binary32 pre-tests bound the distance to that flat triangle = the segment, the candidate is
+// the reference's projection on the SEGMENT
+template <bool SEG = false>
 B2_HD Closest traverse_closest(const BvhNode* __restrict__ nodes, const TriRec* __restrict__ tris, uint32_t root,
                                const Vec3& o, double mag, TravStat& st) {
     Closest best; best.p = o; best.prim = kNone; best.sqd = DBL_MAX; best.tie = 0; best.near = 0;
@@ -777,7 +782,7 @@ B2_HD Closest traverse_closest(const BvhNode* __restrict__ nodes, const TriRec* 
     auto certainly_outside = [&](const Tri3& t, bool sharp) -> bool { return tri_certainly_outside(t, o, ub, sub, rbound, sharp); };
     // the reference's per-primitive step: Construct_projected_point_3 + Compare_distance_3 against the incumbent
     auto evaluate = [&](const Tri3& t, uint32_t id) {
-        const Vec3 cp = closest_candidate(t, o, st.nexact);
+        const Vec3 cp = SEG ? closest_candidate_segment(t.a, t.b, o, st.nexact) : closest_candidate(t, o, st.nexact);
         const Vec3 v = cp - o;
         const double sqd = (v.x * v.x + v.y * v.y) + v.z * v.z;   // Compute_squared_distance_3(query, closest): AABB_tree.h:1024-1032
         bool take;

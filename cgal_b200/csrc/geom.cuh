@@ -617,4 +617,16 @@ B2_HD Vec3 closest_candidate(const Tri3& t, const Vec3& o, int& nexact) {
     return (r & 3) == 0 ? t.a : cp;
 }
 
+// The same for a Segment_3 primitive (AABB_segment_primitive_3 / AABB_halfedge_graph_segment_primitive; reference point = the source, AABB_segment_primitive_3.h:40-58):
+// Construct_projected_point_3(Segment_3, Point_3) (function_objects.h:3266-3285), or the source when that is strictly nearer than the rounded projection.
+B2_HD Vec3 closest_candidate_segment(const Vec3& a, const Vec3& b, const Vec3& o, int& nexact) {
+    const Vec3 cp = closest_on_segment(a, b, o);
+    if (same_point(a, cp)) return cp;
+    const double da = sqlen3(a - o), dc = sqlen3(cp - o);
+    if (da > dc + dc * 1e-12 && dc > 1e-290) return cp;
+    const int r = cmp_dist_out_of_line(o.x, o.y, o.z, a.x, a.y, a.z, cp.x, cp.y, cp.z);
+    if (r & 4) ++nexact;
+    return (r & 3) == 0 ? a : cp;
+}
+
 }  // namespace b2

@@ -584,17 +584,33 @@ class AABB_tree {
     std::lock_guard<std::mutex> lock(m_mutex);
     if (!m_uploaded) const_cast<Self*>(this)->upload_and_build();
   }
+  // a Segment_3 datum (AABB_segment_primitive_3, AABB_halfedge_graph_segment_primitive) has source() and target(); a Triangle_3 datum has vertex(i)
+  template <typename D, typename = void> struct is_segment_datum : std::false_type {};
+  template <typename D> struct is_segment_datum<D, std::void_t<decltype(std::declval<const D&>().source()), decltype(std::declval<const D&>().target())>> : std::true_type {};
   void upload_and_build() {
     const uint64_t n = m_primitives.size();
-    std::vector<double> soup(9 * n);
-    for (uint64_t i = 0; i < n; ++i) {
-      decltype(auto) tri = datum(m_primitives[i]);
-      for (int k = 0; k < 3; ++k) {
-        decltype(auto) v = tri.vertex(k);
-        soup[9 * i + 3 * k] = (double)v.x(); soup[9 * i + 3 * k + 1] = (double)v.y(); soup[9 * i + 3 * k + 2] = (double)v.z();
+    typedef std::decay_t<decltype(datum(std::declval<const Primitive&>()))> Datum;
+    if constexpr (is_segment_datum<Datum>::value) {
+      std::vector<double> segs(6 * n);
+      for (uint64_t i = 0; i < n; ++i) {
+        decltype(auto) sg = datum(m_primitives[i]);
+        decltype(auto) a = sg.source();
+        decltype(auto) b = sg.target();
+        segs[6 * i] = (double)a.x(); segs[6 * i + 1] = (double)a.y(); segs[6 * i + 2] = (double)a.z();
+        segs[6 * i + 3] = (double)b.x(); segs[6 * i + 4] = (double)b.y(); segs[6 * i + 5] = (double)b.z();
       }
+      check(b200aabb_set_segments(m_handle, segs.data(), nullptr, n, B200AABB_HOST));
+    } else {
+      std::vector<double> soup(9 * n);
+      for (uint64_t i = 0; i < n; ++i) {
+        decltype(auto) tri = datum(m_primitives[i]);
+        for (int k = 0; k < 3; ++k) {
+          decltype(auto) v = tri.vertex(k);
+          soup[9 * i + 3 * k] = (double)v.x(); soup[9 * i + 3 * k + 1] = (double)v.y(); soup[9 * i + 3 * k + 2] = (double)v.z();
+        }
+      }
+      check(b200aabb_set_triangles(m_handle, soup.data(), nullptr, n, B200AABB_HOST));
     }
-    check(b200aabb_set_triangles(m_handle, soup.data(), nullptr, n, B200AABB_HOST));
     check(b200aabb_build(m_handle));
     m_uploaded = true;
   }

@@ -115,6 +115,13 @@ int b200aabb_get_stats(const b200aabb_tree* t, b200aabb_stats* out);
 int b200aabb_synchronize(b200aabb_tree* t);
 
 /* ---- primitives ---------------------------------------------------------------------------------------------- */
+/* Segment_3 primitives: AABB_segment_primitive_3 over a range of segments (AABB_tree/include/CGAL/AABB_segment_primitive_3.h) and
+ * AABB_halfedge_graph_segment_primitive over the edges of a graph (AABB_halfedge_graph_segment_primitive.h); segs = n x 6 doubles (source, target), the
+ * reference point of a primitive is its source, ids as for b200aabb_set_triangles.  Such a tree answers b200aabb_closest_point (the reference's
+ * Construct_projected_point_3(Segment_3, Point_3), Cartesian/function_objects.h:3266-3285, exact comparisons, ties reported), b200aabb_max_distance_to_mesh, and
+ * the id queries (do_intersect / number_of_intersected_primitives / any_ / all_intersected_primitives) with Plane_3 and Triangle_3 queries — what
+ * AABB_tree/examples/AABB_tree/AABB_segment_3_example.cpp asks of it; every other entry point returns INVALID_ARGUMENT on it. */
+int b200aabb_set_segments(b200aabb_tree* t, const double* segs, const uint32_t* ids, uint64_t n, b200aabb_memspace space);
 /* insert(faces(m).first, faces(m).second, m), AABB_tree.h:730-747, for a triangle Surface_mesh: vertex coordinates
  * (nv x 3 doubles = mesh.points().data(), Surface_mesh/include/CGAL/Surface_mesh/Properties.h:186) and, per face in
  * faces(m) order, (target(h), target(next(h)), source(h)) with h = halfedge(f)

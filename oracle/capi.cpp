@@ -58,6 +58,17 @@ void* orc_create_soup(const double* tris, uint64_t n) {
     h->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     return h;
 }
+// Segment_3 primitives: segs = n x 6 doubles (source, target)
+void* orc_create_segments(const double* segs, uint64_t n) {
+    Handle* h = new Handle();
+    h->mesh.segments = true;
+    h->mesh.tris.resize(n);
+    for (uint64_t i = 0; i < n; ++i) h->mesh.tris[i] = {P(segs + 6 * i), P(segs + 6 * i + 3), P(segs + 6 * i + 3)};
+    auto t0 = std::chrono::steady_clock::now();
+    h->tree.reset(new Tree(h->mesh));
+    h->build_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    return h;
+}
 void orc_destroy(void* hv) { delete (Handle*)hv; }
 double orc_build_seconds(void* hv) { return ((Handle*)hv)->build_seconds; }
 double orc_kd_seconds(void* hv) { return ((Handle*)hv)->kd_seconds; }
@@ -220,7 +231,7 @@ void orc_naive_count(void* hv, const double* q, uint64_t n, int kind, uint32_t* 
     parallel_for(n, nthreads, [&](uint64_t b, uint64_t e) {
         for (uint64_t i = b; i < e; ++i) {
             uint32_t c = 0; const Tree::LineQ lq = LQ(q, i, kind);
-            for (const Tri& t : m.tris) c += Tree::prim_hit(t, lq) ? 1 : 0;
+            for (const Tri& t : m.tris) c += (m.segments ? Tree::segment_hit(t, lq) : Tree::prim_hit(t, lq)) ? 1 : 0;
             out[i] = c;
         }
     });
@@ -231,9 +242,10 @@ void orc_naive_closest(void* hv, const double* q, uint64_t n, double* cp, uint32
     parallel_for(n, nthreads, [&](uint64_t b, uint64_t e) {
         for (uint64_t i = b; i < e; ++i) {
             const P3 p = P(q + 3 * i);
-            P3 best = project_on_triangle(m.tris[0], p); uint32_t arg = 0, ties = 1;
+            auto proj = [&](uint32_t f) { return m.segments ? project_on_segment(m.tris[f].a, m.tris[f].b, p) : project_on_triangle(m.tris[f], p); };
+            P3 best = proj(0); uint32_t arg = 0, ties = 1;
             for (uint32_t f = 1; f < m.tris.size(); ++f) {
-                const P3 c = project_on_triangle(m.tris[f], p);
+                const P3 c = proj(f);
                 const int s = compare_distance(p, c, best);
                 if (s < 0) { best = c; arg = f; ties = 1; } else if (s == 0) ++ties;
             }

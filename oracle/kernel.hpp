@@ -1089,6 +1089,12 @@ static inline P3 closest_point_step(const P3& q, const Tri& t, const P3& bound) 
     return compare_distance(q, cp, bound) == 1 ? bound : cp;
 }
 
+// the same for a Segment_3 datum: Construct_projected_point_3(Segment_3, Point_3), function_objects.h:3266-3285
+static inline P3 closest_point_step_segment(const P3& q, const P3& a, const P3& b, const P3& bound) {
+    const P3 cp = project_on_segment(a, b, q);
+    return compare_distance(q, cp, bound) == 1 ? bound : cp;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Intersection_distance (INEXACT ray/box entry distance): AABB_traits_3.h:89-125
 // ------------------------------------------------------------------------------------------------

@@ -25,6 +25,9 @@ struct Mesh {
     // BGL/include/CGAL/boost/graph/IO/Generic_facegraph_builder.h:130-148, Euler_operations.h:842-843,
     // BGL/include/CGAL/boost/graph/property_maps.h:52-63,158-163
     std::vector<Tri> tris;
+    // segments = true: the primitives are Segment_3 (AABB_segment_primitive_3.h:40-95 / AABB_halfedge_graph_segment_primitive.h), kept as (source, target,
+    // target): the box of that record is the segment's (Construct_bbox_3(Segment_3)), the reference point is the source
+    bool segments = false;
     const Tri& datum(uint32_t f) const { return tris[f]; }
     const P3& reference_point(uint32_t f) const { return tris[f].a; }
 };
@@ -204,6 +207,14 @@ struct Tree {
     // kind 0: Segment_3 (source, target); 1: Ray_3 (source, second point); 2: Line_3 (point p, direction vector q); 3: Plane_3 (a, b, c = p; d = q.x)
     //      4: Triangle_3 (p, q, r)
     struct LineQ { P3 p, q; int kind; P3 r = {0, 0, 0}; };
+    // Segment_3 datum (tr = (source, target, target)): Do_intersect_3(Plane_3, Segment_3) (Plane_3_Segment_3_do_intersect.h:22-40: the two oriented sides) and
+    // Do_intersect_3(Triangle_3, Segment_3) (Segment_3_Triangle_3_do_intersect.h:177-262 with the QUERY as the triangle)
+    static bool segment_hit(const Tri& tr, const LineQ& q) {
+        if (q.kind == 4) return do_intersect_seg_tri(Tri{q.p, q.q, q.r}, tr.a, tr.b);
+        const double h[4] = {q.p.x, q.p.y, q.p.z, q.q.x};
+        const int s = plane_oriented_side(h, tr.a), t = plane_oriented_side(h, tr.b);
+        return !(s == t && t != 0);
+    }
     static bool prim_hit(const Tri& tr, const LineQ& q) {
         switch (q.kind) {
             case 4: return do_intersect_tri_tri(Tri{q.p, q.q, q.r}, tr);
@@ -229,12 +240,13 @@ struct Tree {
         }
     }
 
+    bool hit(uint32_t f, const LineQ& q) const { return mesh->segments ? segment_hit(mesh->datum(f), q) : prim_hit(mesh->datum(f), q); }
     // Do_intersect_traits :236-271 / Listing_primitive_traits + Counting_output_iterator :26-50,150-184
     struct DoIntersectTT {
         const Tree& t; bool found = false;
         bool go_further() const { return !found; }
         void intersection(const LineQ& q, uint32_t f) {
-            if (prim_hit(t.mesh->datum(f), q)) found = true;
+            if (t.hit(f, q)) found = true;
         }
         bool do_intersect(const LineQ& q, const Box& b) const { return box_hit(q, b); }
     };
@@ -242,7 +254,7 @@ struct Tree {
         const Tree& t; uint32_t count = 0; std::vector<uint32_t>* ids = nullptr;
         bool go_further() const { return true; }
         void intersection(const LineQ& q, uint32_t f) {
-            if (prim_hit(t.mesh->datum(f), q)) { ++count; if (ids) ids->push_back(f); }
+            if (t.hit(f, q)) { ++count; if (ids) ids->push_back(f); }
         }
         bool do_intersect(const LineQ& q, const Box& b) const { return box_hit(q, b); }
     };
@@ -251,7 +263,7 @@ struct Tree {
         const Tree& t; bool found = false; uint32_t id = 0xFFFFFFFFu;
         bool go_further() const { return !found; }
         void intersection(const LineQ& q, uint32_t f) {
-            if (prim_hit(t.mesh->datum(f), q)) { found = true; id = f; }
+            if (t.hit(f, q)) { found = true; id = f; }
         }
         bool do_intersect(const LineQ& q, const Box& b) const { return box_hit(q, b); }
     };
@@ -380,7 +392,7 @@ struct Tree {
         const Tree& t; P3 closest; uint32_t prim;
         bool go_further() const { return true; }
         void intersection(const P3& q, uint32_t f) {
-            const P3 n = closest_point_step(q, t.mesh->datum(f), closest);
+            const P3 n = t.mesh->segments ? closest_point_step_segment(q, t.mesh->datum(f).a, t.mesh->datum(f).b, closest) : closest_point_step(q, t.mesh->datum(f), closest);
             if (n != closest) { prim = f; closest = n; }
         }
         bool do_intersect(const P3& q, const Box& b) const { return ball_reaches_box(q, b, closest); }

@@ -49,6 +49,12 @@ def main():
     g2 = B.AABB_tree(v + np.array([0.1, 0.0, 0.0]), f)
     tt = g.do_intersect_tree(g2), g.do_intersect_tree(g2, xf=np.array([[0, -1, 0, 0.2], [1, 0, 0, 0], [0, 0, 1, 0]], float)), g.do_intersect_tree(g2, other_xf=np.array([[1, 0, 0, 9.0], [0, 1, 0, 0], [0, 0, 1, 0]], float))
     print("triangle queries", int(ct.sum()), len(idst), tt)
+    # Segment_3 primitives: the edges of the mesh
+    e = np.unique(np.sort(np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]).astype(np.int64), axis=1), axis=0)
+    gs = B.AABB_tree(segments=np.concatenate([v[e[:, 0]], v[e[:, 1]]], axis=1))
+    rs = gs.closest_point_and_primitive(pts[:3000])
+    cs = gs.number_of_intersected_primitives(tq, B.TRIANGLE), gs.number_of_intersected_primitives(planes, B.PLANE)
+    print("segment primitives", gs.size(), float(rs["sqdist"].sum()), int(cs[0].sum()), int(cs[1].sum()))
     print("ok", int(r["prim"].sum() % 1000), int((fi["prim"] != B.NO_PRIMITIVE).sum()), int(c.sum()), len(ids), int((sk["prim"] != B.NO_PRIMITIVE).sum()), len(o1[1]), len(o2[1]),
           len(o3[1]), int((side == 1).sum()), round(md[0], 6), t.size())
 

@@ -209,6 +209,23 @@ class AABB_triangle_primitive_3 {
   Iterator m_it;
 };
 
+// AABB_segment_primitive_3<GeomTraits, Iterator> over a range of Segment_3 (AABB_tree/include/CGAL/AABB_segment_primitive_3.h:27-95): Id = the iterator,
+// reference point = the source
+template <class Iterator>
+class AABB_segment_primitive_3 {
+ public:
+  typedef Iterator Id;
+  typedef Segment_3 Datum;
+  typedef Point_3 Point;
+  explicit AABB_segment_primitive_3(Iterator it) : m_it(it) {}
+  Id id() const { return m_it; }
+  const Datum& datum() const { return *m_it; }
+  Point reference_point() const { return m_it->source(); }
+
+ private:
+  Iterator m_it;
+};
+
 // AABB_traits_base (AABB_traits_3.h:46-76): the shared data exists only for primitives that declare it
 template <class Primitive, class = void>
 struct AABB_traits_base {};

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <variant>
 #include <thread>
+#include <list>
 #include <vector>
 
 #include "../../include/CGAL_B200/AABB_tree.h"
@@ -384,6 +385,27 @@ static int other_primitives() {
     const auto cp = tree.closest_point_and_primitive(Point(0.2, 0.2, 3.4));
     CHECK(cp.first == Point(0.2, 0.2, 3.0) && cp.second == soup.cbegin() + 3);
     CHECK(tree.do_intersect(mini::Triangle_3(Point(0.1, 0.1, 4.5), Point(0.3, 0.1, 5.5), Point(0.1, 0.3, 5.5))));      // crosses z = 5
+  }
+  {   // AABB_segment_primitive_3: AABB_tree/examples/AABB_tree/AABB_segment_3_example.cpp:26-58
+    typedef std::list<Segment>::const_iterator It;
+    typedef mini::AABB_segment_primitive_3<It> Prim;
+    typedef CGAL_B200::AABB_tree<mini::AABB_traits_3<K, Prim>> Tree4;
+    const Point a(1.0, 0.0, 0.0), b(0.0, 1.0, 0.0), c(0.0, 0.0, 1.0), d(0.0, 0.0, 0.0);
+    std::list<Segment> segments;
+    segments.push_back(Segment(a, b)); segments.push_back(Segment(a, c)); segments.push_back(Segment(c, d));
+    Tree4 tree(segments.cbegin(), segments.cend());
+    CHECK(tree.size() == 3);
+    CHECK(tree.number_of_intersected_primitives(mini::Plane_3(0.0, 0.0, 1.0, 0.0)) == 3);         // the plane through a, b, d
+    CHECK(tree.number_of_intersected_primitives(mini::Triangle_3(a, b, c)) == 3);
+    CHECK(tree.number_of_intersected_primitives(mini::Plane_3(0.0, 0.0, 1.0, -0.5)) == 2);        // z = 1/2 cuts (a, c) and (c, d)
+    const Point closest = tree.closest_point(Point(2.0, 2.0, 2.0));
+    CHECK(closest == Point(0.5, 0.5, 0.0) || closest == Point(0.5, 0.0, 0.5));
+    CHECK(tree.squared_distance(Point(2.0, 2.0, 2.0)) == 8.5);
+    const auto cp = tree.closest_point_and_primitive(Point(-1.0, -1.0, 0.25));
+    CHECK(cp.first == Point(0.0, 0.0, 0.25) && cp.second == std::next(segments.cbegin(), 2));
+    bool refused = false;
+    try { tree.do_intersect(Segment(a, c)); } catch (const CGAL_B200::Error&) { refused = true; }   // Segment_3 x Segment_3 is not offered
+    CHECK(refused);
   }
   return 0;
 }

@@ -45,6 +45,8 @@ def lib():
         L.hc_intersect.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_int, C.c_int, _u32p]
         L.hc_first_intersection.argtypes = [C.c_void_p, _dp, C.c_uint64, _u32p, _dp, _dp, _u8p, _u8p]
         L.hc_closest_point.argtypes = [C.c_void_p, _dp, C.c_uint64, _dp, _u32p, _dp, _u8p]
+        L.hc_closest_point_segments.argtypes = [C.c_void_p, _dp, C.c_uint64, _dp, _u32p, _dp, _u8p]
+        L.hc_count_triangle_segments.argtypes = [C.c_void_p, _dp, C.c_uint64, _u32p]
         L.hc_closest_point_pair.argtypes = [C.c_void_p, _dp, C.c_uint64, _u32p, C.c_int, C.c_int, _dp, _u32p, _dp, _u8p, C.POINTER(C.c_uint64)]
         for n in ("hc_orient3", "hc_orient3_exact", "hc_orient3_dir", "hc_coplanar_orient", "hc_cmp_dist", "hc_cmp_dist_exact"):
             getattr(L, n).argtypes = [_dp]
@@ -150,6 +152,21 @@ class HostTree:
         lib().hc_closest_point(self.h, _p(q), n, _p(cp), _p(prim, _u32p), _p(sqd), _p(tie, _u8p))
         return dict(cp=cp, prim=prim, sqd=sqd, tie=tie & 1, near=(tie >> 1) & 1)
 
+
+    def closest_point_segments(self, q):
+        """closest_point on a tree of Segment_3 primitives stored as (source, target, target) records (bvh.cuh::traverse_closest<true>)"""
+        q = _d(q).reshape(-1, 3)
+        n = len(q)
+        cp, prim, sqd, tie = np.zeros((n, 3)), np.zeros(n, np.uint32), np.zeros(n), np.zeros(n, np.uint8)
+        lib().hc_closest_point_segments(self.h, _p(q), n, _p(cp), _p(prim, _u32p), _p(sqd), _p(tie, _u8p))
+        return dict(cp=cp, prim=prim, sqd=sqd, tie=tie & 1, near=(tie >> 1) & 1)
+
+    def count_triangle_segments(self, q):
+        """number_of_intersected_primitives(Triangle_3) on such a tree (bvh.cuh::traverse_triangle<kCount, NoXf, true>)"""
+        q = _d(q).reshape(-1, 9)
+        out = np.zeros(len(q), np.uint32)
+        lib().hc_count_triangle_segments(self.h, _p(q), len(q), _p(out, _u32p))
+        return out
 
     def closest_point_pair(self, q, perm=None, warps=1, exact_go=64):
         """closest_pair.cuh's kernel body on emulated warps (32 fibers each): the code the GPU runs"""

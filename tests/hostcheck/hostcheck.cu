@@ -283,6 +283,23 @@ void hc_closest_point(void* hv, const double* q, uint64_t n, double* cp, uint32_
     }
 }
 
+// a tree over Segment_3 primitives stored as (source, target, target) records: bvh.cuh::traverse_closest<true> and traverse_triangle<.., true>
+void hc_closest_point_segments(void* hv, const double* q, uint64_t n, double* cp, uint32_t* prim, double* sqd, uint8_t* tie) {
+    HostTree* h = (HostTree*)hv;
+    for (uint64_t i = 0; i < n; ++i) {
+        TravStat st;
+        const Closest c = traverse_closest<true>(h->nodes.data(), h->tris.data(), h->root, V(q + 3 * i), h->mag(), st);
+        cp[3 * i] = c.p.x; cp[3 * i + 1] = c.p.y; cp[3 * i + 2] = c.p.z; prim[i] = c.prim; sqd[i] = c.sqd; tie[i] = (uint8_t)(c.tie | (c.near << 1));
+    }
+}
+void hc_count_triangle_segments(void* hv, const double* q, uint64_t n, uint32_t* out) {
+    HostTree* h = (HostTree*)hv;
+    for (uint64_t i = 0; i < n; ++i) {
+        TravStat st;
+        out[i] = h->n == 0 ? 0 : traverse_triangle<kCount, NoXf, true>(h->nodes.data(), h->tris.data(), h->root, T(q + 9 * i), st);
+    }
+}
+
 // predicate / construction level
 int hc_orient3(const double* p) { int n = 0; return orient3(V(p), V(p + 3), V(p + 6), V(p + 9), n); }
 int hc_orient3_exact(const double* p) {

@@ -32,6 +32,8 @@ def lib():
         L.orc_create.argtypes = [_dp, C.c_uint64, _u32p, C.c_uint64]
         L.orc_create_soup.restype = C.c_void_p
         L.orc_create_soup.argtypes = [_dp, C.c_uint64]
+        L.orc_create_segments.restype = C.c_void_p
+        L.orc_create_segments.argtypes = [_dp, C.c_uint64]
         L.orc_destroy.argtypes = [C.c_void_p]
         L.orc_build_seconds.restype = C.c_double
         L.orc_build_seconds.argtypes = [C.c_void_p]
@@ -100,9 +102,12 @@ _QDOUBLES = {3: 4, 4: 9}   # doubles per query: Plane_3 (a, b, c, d), Triangle_3
 class OracleTree:
     """Mirror of CGAL::AABB_tree<AABB_traits_3<Epick, AABB_face_graph_triangle_primitive<Surface_mesh>>> (CPU)."""
 
-    def __init__(self, verts=None, faces=None, soup=None, accelerate=True):
+    def __init__(self, verts=None, faces=None, soup=None, accelerate=True, segments=None):
         L = lib()
-        if soup is not None:
+        if segments is not None:                                            # Segment_3 primitives: (n, 6) = (source, target)
+            self.segments = _d(segments).reshape(-1, 6)
+            self.h = L.orc_create_segments(_ptr(self.segments, _dp), len(self.segments))
+        elif soup is not None:
             self.soup = _d(soup).reshape(-1, 9)
             self.h = L.orc_create_soup(_ptr(self.soup, _dp), len(self.soup))
         else:

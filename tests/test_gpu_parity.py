@@ -937,3 +937,51 @@ def test_side_of_mesh_under_a_transformation(B, meshes):
             assert (want == 1).any() and (want == -1).any() and (want == 0).any()
         ident = np.hstack([np.eye(3), np.zeros((3, 1))])
         np.testing.assert_array_equal(g.side_of_mesh(pts, xf=ident), g.side_of_mesh(pts))
+
+
+def test_segment_primitives(B, meshes):
+    """a tree over Segment_3 primitives (the edges of the elephant, b200aabb_set_segments): closest_point / squared_distance bit-equal to the oracle's traversal with
+    the reference's Construct_projected_point_3(Segment_3, Point_3), Plane_3 and Triangle_3 id queries, max_distance_to_mesh; other entry points are refused"""
+    import torch
+    from test_segment_primitives import mesh_edges
+    rng = np.random.default_rng(53)
+    v, f = meshes["elephant"]
+    segs = mesh_edges(v, f)
+    g, o = B.AABB_tree(segments=segs), orc.OracleTree(segments=segs)
+    assert g.size() == len(segs)
+    np.testing.assert_array_equal(g.bbox(), o.bbox())
+    lo, hi = v.min(0), v.max(0)
+    pts = np.concatenate([lo + rng.uniform(-0.2, 1.2, (30_000, 3)) * (hi - lo), segs[rng.integers(0, len(segs), 500), :3],
+                          (segs[rng.integers(0, len(segs), 500), :3] + segs[rng.integers(0, len(segs), 500), 3:]) / 2])
+    got, want = g.closest_point_and_primitive(pts), o.closest_point(pts)
+    np.testing.assert_array_equal(got["sqdist"], want["sqd"])
+    same = got["prim"] == want["prim"]
+    np.testing.assert_array_equal(got["point"][same], want["cp"][same])
+    assert ((got["flags"][~same] & B.FLAG_TIE) != 0).all() and same.mean() > 0.8
+    gd = g.closest_point_and_primitive(torch.from_numpy(pts).cuda())
+    np.testing.assert_array_equal(gd["sqdist"].cpu().numpy(), want["sqd"])
+    md, far = g.max_distance_to_mesh(pts)
+    assert md == np.sqrt(want["sqd"].max()) and want["sqd"][far] == want["sqd"].max()
+    nrm = rng.normal(size=(5000, 3)); x = lo + rng.uniform(0, 1, (5000, 3)) * (hi - lo)
+    planes = np.concatenate([nrm, -np.sum(nrm * x, axis=1, keepdims=True)], axis=1)
+    planes[::4, :3] = np.eye(3)[rng.integers(0, 3, 1250)]; planes[::4, 3] = -segs[rng.integers(0, len(segs), 1250), 0]
+    ctr = lo + rng.uniform(0, 1, (5000, 3)) * (hi - lo)
+    tris = np.concatenate([ctr, ctr + rng.uniform(-0.2, 0.2, (5000, 3)) * (hi - lo), ctr + rng.uniform(-0.2, 0.2, (5000, 3)) * (hi - lo)], axis=1)
+    tris[::5] = v[f[rng.integers(0, len(f), 1000)]].reshape(-1, 9)
+    for kind, q in ((B.PLANE, planes), (B.TRIANGLE, tris)):
+        wantc = o.count(q, kind)
+        np.testing.assert_array_equal(g.number_of_intersected_primitives(q, kind), wantc)
+        np.testing.assert_array_equal(g.do_intersect(q, kind) != 0, wantc > 0)
+        off, ids = g.all_intersected_primitives(q, kind)
+        roff, rids = o.all_intersected_primitives(q, kind)
+        np.testing.assert_array_equal(off, roff)
+        owner = np.repeat(np.arange(len(q)), np.diff(off).astype(np.int64))
+        key = lambda own, i: np.sort(own.astype(np.uint64) << np.uint64(32) | i.astype(np.uint64))   # noqa: E731
+        np.testing.assert_array_equal(key(owner, ids), key(owner, rids))
+        assert wantc.max() > 2 and (wantc == 0).any()
+    for refused in (lambda: g.do_intersect(segs[:4], B.SEGMENT), lambda: g.first_intersection(segs[:4]), lambda: g.side_of_mesh(pts[:4]),
+                    lambda: g.do_intersect_tree(g), lambda: g.all_intersections(planes[:4], B.PLANE)):
+        with pytest.raises(B.B200AABBError):
+            refused()
+    g.insert(vertices=v, faces=f)                                           # back to triangles: the flag goes with the primitives
+    assert g.do_intersect(segs[:4], B.SEGMENT).shape == (4,)
