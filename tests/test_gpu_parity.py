@@ -957,7 +957,8 @@ def test_segment_primitives(B, meshes):
     np.testing.assert_array_equal(got["sqdist"], want["sqd"])
     same = got["prim"] == want["prim"]
     np.testing.assert_array_equal(got["point"][same], want["cp"][same])
-    assert ((got["flags"][~same] & B.FLAG_TIE) != 0).all() and same.mean() > 0.8
+    # (on the edges of a mesh the closest point is a vertex for about half of the queries: an exact tie between the edges that share it, which is reported)
+    assert ((got["flags"][~same] & B.FLAG_TIE) != 0).all() and same.mean() > 0.3
     gd = g.closest_point_and_primitive(torch.from_numpy(pts).cuda())
     np.testing.assert_array_equal(gd["sqdist"].cpu().numpy(), want["sqd"])
     md, far = g.max_distance_to_mesh(pts)
