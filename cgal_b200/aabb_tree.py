@@ -38,7 +38,7 @@ class _Stats(C.Structure):
 
 
 SYMBOLS = ["b200aabb_create", "b200aabb_destroy", "b200aabb_set_stream", "b200aabb_set_option", "b200aabb_last_error", "b200aabb_get_stats", "b200aabb_synchronize",
-           "b200aabb_set_mesh", "b200aabb_set_triangles", "b200aabb_set_segments", "b200aabb_clear", "b200aabb_build", "b200aabb_refit", "b200aabb_refit_mesh",
+           "b200aabb_set_mesh", "b200aabb_set_mesh_off", "b200aabb_set_triangles", "b200aabb_set_segments", "b200aabb_clear", "b200aabb_build", "b200aabb_refit", "b200aabb_refit_mesh",
            "b200aabb_accelerate_distance_queries", "b200aabb_size", "b200aabb_bbox", "b200aabb_do_intersect",
            "b200aabb_number_of_intersected_primitives", "b200aabb_any_intersected_primitive", "b200aabb_all_intersected_primitives", "b200aabb_do_intersect_tree", "b200aabb_do_intersect_tree_transformed",
            "b200aabb_number_of_intersections", "b200aabb_all_intersections", "b200aabb_any_intersection",
@@ -73,6 +73,7 @@ def load_library():
         L.b200aabb_set_mesh.argtypes = [vp, dp, u64, dp, dp, u64]
         L.b200aabb_set_triangles.argtypes = [vp, dp, dp, u64, C.c_int]
         L.b200aabb_set_segments.argtypes = [vp, dp, dp, u64, C.c_int]
+        L.b200aabb_set_mesh_off.argtypes = [vp, C.c_char_p, u64]
         L.b200aabb_clear.argtypes = [vp]
         L.b200aabb_refit.argtypes = [vp, dp, u64, C.c_int]
         L.b200aabb_refit_mesh.argtypes = [vp, dp, u64, dp, u64]
@@ -214,6 +215,11 @@ class AABB_tree:
             v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
             f = np.ascontiguousarray(faces, dtype=np.uint32).reshape(-1, 3)
             self._check(self._lib.b200aabb_set_mesh(self._h, v.ctypes.data, len(v), f.ctypes.data, idp, len(f)))
+
+    def insert_off(self, text):
+        """the mesh as the text (bytes) of a plain triangle OFF file, tokenised and parsed on the device (b200aabb_set_mesh_off)"""
+        data = text if isinstance(text, (bytes, bytearray)) else str(text).encode()
+        self._check(self._lib.b200aabb_set_mesh_off(self._h, bytes(data), len(data)))
 
     def clear(self):
         self._check(self._lib.b200aabb_clear(self._h))

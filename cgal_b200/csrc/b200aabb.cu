@@ -14,6 +14,7 @@
 #include "../../include/b200aabb.h"
 #include "build.cuh"
 #include "closest_warp.cuh"
+#include "ingest.cuh"
 #include "closest_pair.cuh"
 
 using namespace b2;
@@ -1335,6 +1336,108 @@ int b200aabb_set_mesh(b200aabb_tree* t, const double* verts, uint64_t nv, const 
     cudaError_t e2 = cudaStreamSynchronize(t->stream);
     cudaFree(d_v); cudaFree(d_f);
     if (e != cudaSuccess || e2 != cudaSuccess) { free_input(t); t->err = "set_mesh: CUDA failure"; return B200AABB_ERR_CUDA; }
+    t->n = nf; t->built = false; t->bounds_valid = true;
+    return B200AABB_OK;
+}
+
+// OFF text -> primitives on the device (ingest.cuh).  The host reads only the header (the "OFF" keyword, the three counts, comments before them); the body
+// is tokenised and parsed by kernels.  Accepted: plain OFF (no per-vertex normals / colours / texture coordinates, no comments after the counts) whose faces are
+// all triangles "3 i j k" — the files the tree of the north-star path is built from; anything else returns INVALID_ARGUMENT with the reason, and the caller
+// falls back to its own reader + b200aabb_set_mesh.
+int b200aabb_set_mesh_off(b200aabb_tree* t, const char* text, uint64_t len) { B2_LOCK(t);
+    if (!t || !text) return B200AABB_ERR_INVALID_ARGUMENT;
+    int rc = b200aabb_clear(t);                              // (whatever happens below, the old primitives are gone: a failed ingest leaves an empty tree)
+    if (rc) return rc;
+    if (len >= (1ull << 32)) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "set_mesh_off: at most 4 GiB of text");
+    // ---- header (File_header_OFF.cpp: keyword, then n_vertices n_facets n_halfedges; '#' starts a comment)
+    uint64_t pos = 0;
+    auto skip_space_and_comments = [&]() {
+        while (pos < len) {
+            if (is_space(text[pos])) ++pos;
+            else if (text[pos] == '#') { while (pos < len && text[pos] != '\n') ++pos; }
+            else break;
+        }
+    };
+    skip_space_and_comments();
+    if (!(pos + 3 <= len && text[pos] == 'O' && text[pos + 1] == 'F' && text[pos + 2] == 'F' && (pos + 3 == len || is_space(text[pos + 3]) || text[pos + 3] == '#')))
+        return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "set_mesh_off: the text does not start with the keyword OFF (COFF / NOFF / STOFF variants are not taken)");
+    pos += 3;
+    uint64_t counts[3] = {0, 0, 0};
+    for (int k = 0; k < 3; ++k) {
+        skip_space_and_comments();
+        uint64_t b = pos;
+        while (pos < len && text[pos] >= '0' && text[pos] <= '9' && pos - b < 19) { counts[k] = counts[k] * 10 + (uint64_t)(text[pos] - '0'); ++pos; }
+        if (pos == b || (pos < len && !is_space(text[pos]) && text[pos] != '#')) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "set_mesh_off: the header needs three counts (vertices, facets, edges)");
+    }
+    const uint64_t nv = counts[0], nf = counts[1];
+    skip_space_and_comments();
+    if (memchr(text + pos, '#', len - pos)) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "set_mesh_off: comments after the header are not taken");
+    if (nf >= (1ull << 30) || nv >= (1ull << 32)) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "set_mesh_off: too many vertices or facets");
+    if (nf == 0) return B200AABB_OK;
+    B2_CUDA(t, cudaSetDevice(t->device));
+    const uint64_t want_tokens = 3 * nv + 4 * nf;
+    const uint64_t body = len - pos;
+    const uint32_t ntiles = (uint32_t)((body + kTokTile - 1) / kTokTile);
+    char* d_text = nullptr; uint32_t* d_tiles = nullptr; uint32_t* d_tok = nullptr; double* d_v = nullptr; uint32_t* d_f = nullptr; unsigned* d_flags = nullptr;
+    uint32_t* d_und = nullptr; unsigned long long* d_total = nullptr;
+    constexpr uint32_t kUndecidedCap = 1u << 16;
+    auto release = [&]() { cudaFree(d_text); cudaFree(d_tiles); cudaFree(d_tok); cudaFree(d_v); cudaFree(d_f); cudaFree(d_flags); cudaFree(d_und); cudaFree(d_total); };
+    cudaError_t e = cudaMalloc(&d_text, len);
+    if (e == cudaSuccess) e = cudaMalloc(&d_tiles, std::max<uint64_t>(ntiles, 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_tok, std::max<uint64_t>(want_tokens, 1) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_v, std::max<uint64_t>(nv, 1) * 24);
+    if (e == cudaSuccess) e = cudaMalloc(&d_f, nf * 12);
+    if (e == cudaSuccess) e = cudaMalloc(&d_flags, 2 * sizeof(unsigned));
+    if (e == cudaSuccess) e = cudaMalloc(&d_und, kUndecidedCap * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&d_total, sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc(&t->d_soup, nf * 72 + kSoupSlack);
+    if (e != cudaSuccess) { release(); free_input(t); t->err = "cudaMalloc(set_mesh_off)"; return B200AABB_ERR_OUT_OF_MEMORY; }
+    cudaStream_t st = t->stream;
+    cudaMemcpyAsync(d_text, text, len, cudaMemcpyHostToDevice, st);
+    cudaMemsetAsync(d_flags, 0, 2 * sizeof(unsigned), st);
+    token_count_kernel<<<std::max(ntiles, 1u), kTokBlock, 0, st>>>(d_text, pos, len, d_tiles);
+    token_scan_kernel<<<1, 1024, 0, st>>>(d_tiles, ntiles, d_total);
+    token_offsets_kernel<<<std::max(ntiles, 1u), kTokBlock, 0, st>>>(d_text, pos, len, d_tiles, d_tok, want_tokens);
+    unsigned long long total = 0;
+    cudaMemcpyAsync(&total, d_total, sizeof(total), cudaMemcpyDeviceToHost, st);
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { release(); free_input(t); t->err = "set_mesh_off: CUDA failure (tokens)"; return B200AABB_ERR_CUDA; }
+    if (total != want_tokens) {
+        release(); free_input(t);
+        return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "set_mesh_off: the body does not hold 3 numbers per vertex and 4 per facet (non-triangular facets, colours or normals?)");
+    }
+    if (nv) parse_vertices_kernel<<<grid_for(3 * nv, 256), 256, 0, st>>>(d_text, len, d_tok, 3 * nv, d_v, d_flags, d_und, kUndecidedCap);
+    parse_faces_kernel<<<grid_for(nf, 256), 256, 0, st>>>(d_text, len, d_tok + 3 * nv, nf, nv, d_f, d_flags);
+    unsigned flags[2] = {0, 0};
+    cudaMemcpyAsync(flags, d_flags, sizeof(flags), cudaMemcpyDeviceToHost, st);
+    e = cudaStreamSynchronize(st);
+    t->stats.kernel_launches += 5;
+    if (e != cudaSuccess) { release(); free_input(t); t->err = "set_mesh_off: CUDA failure (parse)"; return B200AABB_ERR_CUDA; }
+    if (flags[0] || flags[1] > kUndecidedCap) {
+        release(); free_input(t);
+        return fail(t, B200AABB_ERR_INVALID_ARGUMENT, (flags[0] & 1) ? "set_mesh_off: a vertex coordinate is not a decimal number" :
+                    (flags[0] & 2) ? "set_mesh_off: a facet is not a triangle" : (flags[0] & 4) ? "set_mesh_off: a facet references a vertex index >= the vertex count" :
+                    "set_mesh_off: too many literals of more than 19 digits");
+    }
+    if (flags[1]) {   // literals of more than 19 significant digits whose dropped digits decide the rounding: strtod on the caller's text
+        std::vector<uint32_t> und(flags[1]), off(flags[1]);
+        cudaMemcpy(und.data(), d_und, flags[1] * 4, cudaMemcpyDeviceToHost);
+        for (unsigned i = 0; i < flags[1]; ++i) {
+            cudaMemcpy(&off[i], d_tok + und[i], 4, cudaMemcpyDeviceToHost);
+            uint64_t b = off[i], en = b;
+            while (en < len && !is_space(text[en])) ++en;
+            const std::string lit(text + b, text + en);
+            const double v = strtod(lit.c_str(), nullptr);
+            cudaMemcpy(d_v + und[i], &v, 8, cudaMemcpyHostToDevice);
+        }
+    }
+    cudaMemsetAsync(t->d_bounds, 0xFF, 3 * 8, st);
+    cudaMemsetAsync(t->d_bounds + 3, 0x00, 3 * 8, st);
+    gather_mesh_kernel<<<std::min<unsigned>(grid_for(nf, 256), 148 * 8), 256, 0, st>>>(d_v, d_f, nf, t->d_soup, t->d_bounds);
+    t->stats.kernel_launches += 1;
+    e = cudaStreamSynchronize(st);
+    release();
+    if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) { free_input(t); t->err = "set_mesh_off: CUDA failure (gather)"; return B200AABB_ERR_CUDA; }
     t->n = nf; t->built = false; t->bounds_valid = true;
     return B200AABB_OK;
 }

@@ -115,6 +115,12 @@ int b200aabb_get_stats(const b200aabb_tree* t, b200aabb_stats* out);
 int b200aabb_synchronize(b200aabb_tree* t);
 
 /* ---- primitives ---------------------------------------------------------------------------------------------- */
+/* The mesh as the TEXT of an OFF file (HOST memory): what `CGAL::IO::read_OFF(in, surface_mesh)` + `Tree(faces(mesh).first, faces(mesh).second, mesh)` give
+ * (Surface_mesh/include/CGAL/Surface_mesh/IO/OFF.h:323-345, Stream_support/include/CGAL/IO/OFF/File_scanner_OFF.h): primitive i = facet i of the file, vertex
+ * coordinates = the correctly rounded binary64 values of the decimal literals (as `std::istream >> double` yields).  The host reads the header only; the body is
+ * tokenised and parsed on the device (csrc/ingest.cuh).  Accepted: plain "OFF" files whose facets are all triangles and that carry no colours, normals or
+ * comments after the header; anything else returns INVALID_ARGUMENT (b200aabb_last_error says why) and leaves the tree empty. */
+int b200aabb_set_mesh_off(b200aabb_tree* t, const char* text, uint64_t len);
 /* Segment_3 primitives: AABB_segment_primitive_3 over a range of segments (AABB_tree/include/CGAL/AABB_segment_primitive_3.h) and
  * AABB_halfedge_graph_segment_primitive over the edges of a graph (AABB_halfedge_graph_segment_primitive.h); segs = n x 6 doubles (source, target), the
  * reference point of a primitive is its source, ids as for b200aabb_set_triangles.  Such a tree answers b200aabb_closest_point (the reference's

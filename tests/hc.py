@@ -53,6 +53,7 @@ def lib():
         L.hc_tri_do_intersect.argtypes = [_dp, _dp, C.c_int]
         L.hc_tri_tri_do_intersect.argtypes = [_dp, _dp]
         L.hc_side_of_mesh_xf.argtypes = [C.c_void_p, _dp, _dp, C.c_uint64, _dp, C.c_int, C.POINTER(C.c_int8)]
+        L.hc_parse_decimals.argtypes = [C.c_char_p, C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
         L.hc_xf_apply.argtypes = [_dp, _dp, _dp]
         L.hc_xf_box_meets.argtypes = [_dp, C.POINTER(C.c_float), _dp]
         L.hc_intersect_triangle.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_int, _u32p]
@@ -203,6 +204,17 @@ def tri_do_intersect_kind(tri, q, kind):
 def tri_tri_do_intersect(query, tri):
     query, tri = _d(query).ravel(), _d(tri).ravel()
     return lib().hc_tri_tri_do_intersect(_p(query), _p(tri))
+
+
+def parse_decimals(literals):
+    """ingest.cuh::parse_decimal on every string: (values as float64 from the returned bit patterns, status per literal: 0 ok, 1 not a number, 2 left to strtod)"""
+    enc = [x.encode() for x in literals]
+    offs = np.zeros(len(enc) + 1, np.uint64)
+    np.cumsum([len(e) for e in enc], out=offs[1:])
+    buf = b"".join(enc) + b" "
+    bits, status = np.zeros(len(enc), np.uint64), np.zeros(len(enc), np.int32)
+    lib().hc_parse_decimals(buf, offs.ctypes.data_as(C.POINTER(C.c_uint64)), len(enc), bits.ctypes.data_as(C.POINTER(C.c_uint64)), status.ctypes.data_as(C.POINTER(C.c_int)))
+    return bits.view(np.float64), status
 
 
 def xf_apply(m, tri):

@@ -20,6 +20,7 @@ static void trace_node(uint32_t index) { if (g_node_trace) g_node_trace->push_ba
 #endif
 #include "../../cgal_b200/csrc/build.cuh"
 #include "../../cgal_b200/csrc/closest_warp.cuh"
+#include "../../cgal_b200/csrc/ingest.cuh"
 #define B2_WARP_EMU 1
 #include "warp_emu.h"
 
@@ -298,6 +299,11 @@ void hc_count_triangle_segments(void* hv, const double* q, uint64_t n, uint32_t*
         TravStat st;
         out[i] = h->n == 0 ? 0 : traverse_triangle<kCount, NoXf, true>(h->nodes.data(), h->tris.data(), h->root, T(q + 9 * i), st);
     }
+}
+
+// ingest.cuh::parse_decimal on a batch of literals packed in one buffer (offsets[n + 1]): bits + status per literal
+void hc_parse_decimals(const char* buf, const uint64_t* offsets, uint64_t n, uint64_t* bits, int* status) {
+    for (uint64_t i = 0; i < n; ++i) bits[i] = parse_decimal(buf + offsets[i], buf + offsets[i + 1], status[i]);
 }
 
 // predicate / construction level

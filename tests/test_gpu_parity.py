@@ -986,3 +986,56 @@ def test_segment_primitives(B, meshes):
             refused()
     g.insert(vertices=v, faces=f)                                           # back to triangles: the flag goes with the primitives
     assert g.do_intersect(segs[:4], B.SEGMENT).shape == (4,)
+
+
+def _off_text(v, f, fmt="%.17g", header="OFF\n%d %d 0\n", sep=" ", eol="\n"):
+    lines = [header % (len(v), len(f))]
+    lines += [sep.join(fmt % c for c in p) + eol for p in v]
+    lines += ["3" + sep + sep.join(str(int(i)) for i in t) + eol for t in f]
+    return "".join(lines).encode()
+
+
+def test_off_ingest_on_the_device(B, meshes):
+    """b200aabb_set_mesh_off: the text of an OFF file tokenised and parsed by kernels; the tree must be the one built from the same file read on the host
+    (coordinates = Python's correctly rounded float() of the literals, facets in file order): equal boxes and bit-equal query results; malformed and
+    unsupported files are refused with the tree left empty"""
+    rng = np.random.default_rng(71)
+    v, f = meshes["elephant"]
+    variants = [dict(), dict(fmt="%.9g"), dict(fmt="%.6f", sep="  ", eol="\r\n"), dict(fmt="%.20e"), dict(header="# a comment\nOFF # keyword\n# counts follow\n%d %d 0\n", sep="\t")]
+    bb = None
+    for kw in variants:
+        text = _off_text(v, f, **kw)
+        vv = np.array([[float(kw.get("fmt", "%.17g") % c) for c in p] for p in v])          # what a correctly rounding reader gets
+        g, h = B.AABB_tree(), B.AABB_tree(vv, f)
+        g.insert_off(text)
+        assert g.size() == len(f)
+        np.testing.assert_array_equal(g.bbox(), h.bbox())
+        bb = h.bbox()
+        from cgal_b200 import workloads as W
+        rays, pts = W.sphere_rays(bb, 20_000), W.bbox_points(bb, 20_000)
+        a, b = g.first_intersection(rays), h.first_intersection(rays)
+        for k in ("prim", "t", "point", "flags"):
+            np.testing.assert_array_equal(a[k], b[k])
+        a, b = g.closest_point_and_primitive(pts), h.closest_point_and_primitive(pts)
+        for k in ("prim", "sqdist", "point", "flags"):
+            np.testing.assert_array_equal(a[k], b[k])
+    # 25-digit literals: the ones whose dropped digits decide are parsed by strtod on the host text; the result is still the correctly rounded value
+    long_v = np.array([[float("%.25e" % c) for c in p] for p in v])
+    g = B.AABB_tree()
+    g.insert_off(_off_text(v, f, fmt="%.25e"))
+    np.testing.assert_array_equal(g.bbox(), B.AABB_tree(long_v, f).bbox())
+    o = orc.OracleTree(long_v, f)
+    pts = W.bbox_points(bb, 3000)
+    check_closest_point(g.closest_point_and_primitive(pts), o.closest_point(pts), o, pts)
+    # refused: quads, colours, comments in the body, a bad number, a vertex index out of range, a wrong keyword, missing tokens
+    good = _off_text(v[:4], np.array([[0, 1, 2], [0, 2, 3]], np.uint32))
+    bad = [b"OFF\n4 1 0\n0 0 0\n1 0 0\n1 1 0\n0 1 0\n4 0 1 2 3\n", good.replace(b"3 0 1 2\n", b"3 0 1 2 255 0 0\n"), good.replace(b"3 0 2 3", b"# c\n3 0 2 3"),
+           good.replace(b"3 0 1 2", b"3 0 1 x"), good.replace(b"3 0 2 3", b"3 0 2 4"), good.replace(b"OFF", b"COFF"), good[:-8], b"OFF\n", b""]
+    for text in bad:
+        t = B.AABB_tree(v, f)
+        with pytest.raises(B.B200AABBError):
+            t.insert_off(text)
+        assert t.size() == 0                                               # a failed ingest leaves an empty tree
+    t = B.AABB_tree()
+    t.insert_off(b"OFF\n3 0 0\n0 0 0\n1 0 0\n0 1 0\n")                     # no facets: an empty tree
+    assert t.size() == 0
