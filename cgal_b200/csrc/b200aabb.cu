@@ -1393,7 +1393,11 @@ int b200aabb_set_mesh_off(b200aabb_tree* t, const char* text, uint64_t len) { B2
     if (e == cudaSuccess) e = cudaMalloc(&t->d_soup, nf * 72 + kSoupSlack);
     if (e != cudaSuccess) { release(); free_input(t); t->err = "cudaMalloc(set_mesh_off)"; return B200AABB_ERR_OUT_OF_MEMORY; }
     cudaStream_t st = t->stream;
+    static const bool timing = getenv("B200AABB_INGEST_TIMING") != nullptr;    // diagnostic: upload / kernels split on stderr
+    cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+    if (timing) { for (auto& x : ev) cudaEventCreate(&x); cudaEventRecord(ev[0], st); }
     cudaMemcpyAsync(d_text, text, len, cudaMemcpyHostToDevice, st);
+    if (timing) cudaEventRecord(ev[1], st);
     cudaMemsetAsync(d_flags, 0, 2 * sizeof(unsigned), st);
     token_count_kernel<<<std::max(ntiles, 1u), kTokBlock, 0, st>>>(d_text, pos, len, d_tiles);
     token_scan_kernel<<<1, 1024, 0, st>>>(d_tiles, ntiles, d_total);
@@ -1435,7 +1439,14 @@ int b200aabb_set_mesh_off(b200aabb_tree* t, const char* text, uint64_t len) { B2
     cudaMemsetAsync(t->d_bounds + 3, 0x00, 3 * 8, st);
     gather_mesh_kernel<<<std::min<unsigned>(grid_for(nf, 256), 148 * 8), 256, 0, st>>>(d_v, d_f, nf, t->d_soup, t->d_bounds);
     t->stats.kernel_launches += 1;
+    if (timing) cudaEventRecord(ev[2], st);
     e = cudaStreamSynchronize(st);
+    if (timing) {
+        float up = 0, run = 0;
+        cudaEventElapsedTime(&up, ev[0], ev[1]); cudaEventElapsedTime(&run, ev[1], ev[2]);
+        fprintf(stderr, "[b200aabb ingest] %.1f MB of text: upload %.2f ms, tokenise + parse + gather %.2f ms (%llu tokens)\n", len / 1e6, up, run, (unsigned long long)want_tokens);
+        for (auto& x : ev) cudaEventDestroy(x);
+    }
     release();
     if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) { free_input(t); t->err = "set_mesh_off: CUDA failure (gather)"; return B200AABB_ERR_CUDA; }
     t->n = nf; t->built = false; t->bounds_valid = true;
