@@ -726,7 +726,7 @@ void free_warp(b200aabb_tree* t) {
 int ensure_warp(b200aabb_tree* t, int slot) {
     if (t->warp_grid == 0) {
         int per_sm = 0, sms = 0;
-        B2_CUDA(t, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, closest_point_warp_kernel, 32, 0));
+        B2_CUDA(t, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, closest_point_warp_kernel<false>, 32, 0));
         B2_CUDA(t, cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, t->device));
         t->warp_grid = std::max(1, per_sm) * std::max(1, sms);
     }
@@ -1664,8 +1664,9 @@ int b200aabb_do_intersect_tree_transformed(b200aabb_tree* t, const double* xf, b
     if (rc) { t->err = other->err; return rc; }
     // the queries are the primitives of the SMALLER tree, the traversed tree is the larger one: the answer is symmetric
     // (Do_intersect_3(Triangle_3, Triangle_3) decides exactly), the work is (number of queries) x log(size of the traversed tree)
-    b200aabb_tree* big = t->n >= other->n ? t : other;
-    b200aabb_tree* small = big == t ? other : t;
+    const bool t_is_big = t->n >= other->n;                               // (not decided by comparing handles: a tree may be tested against itself under another transformation)
+    b200aabb_tree* big = t_is_big ? t : other;
+    b200aabb_tree* small = t_is_big ? other : t;
     unsigned* d_w = nullptr;
     if (cudaMalloc(&d_w, 3 * sizeof(unsigned)) != cudaSuccess) { t->err = "cudaMalloc(do_intersect(tree))"; return B200AABB_ERR_OUT_OF_MEMORY; }
     const unsigned init[3] = {0u, kNone, kNone};
@@ -1675,8 +1676,8 @@ int b200aabb_do_intersect_tree_transformed(b200aabb_tree* t, const double* xf, b
     cudaEventRecord(t->ev_a, t->stream);
     XfPair x;
     static const double kIdentity[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
-    const double* xf_small = small == t ? xf : other_xf;
-    const double* xf_big = big == t ? xf : other_xf;
+    const double* xf_small = t_is_big ? other_xf : xf;
+    const double* xf_big = t_is_big ? xf : other_xf;
     memcpy(x.q.m, xf_small ? xf_small : kIdentity, sizeof(x.q.m));
     memcpy(x.b.m, xf_big ? xf_big : kIdentity, sizeof(x.b.m));
     if (xf || other_xf) tree_tree_kernel<true><<<grid_for(small->n, 128), 128, 0, t->stream>>>(tree_ref(big, nullptr), small->d_tris, small->n, d_w, x);
@@ -1694,8 +1695,8 @@ int b200aabb_do_intersect_tree_transformed(b200aabb_tree* t, const double* xf, b
     if (c2 && !w[0]) return fail(t, B200AABB_ERR_INCOMPLETE, "traversal stack overflow: results incomplete");
     *result = w[0] ? 1 : 0;
     if (w[0]) {                                                          // w[1]: id in `small`, w[2]: id in `big`
-        if (prim) *prim = small == t ? w[1] : w[2];
-        if (other_prim) *other_prim = small == t ? w[2] : w[1];
+        if (prim) *prim = t_is_big ? w[2] : w[1];
+        if (other_prim) *other_prim = t_is_big ? w[1] : w[2];
     }
     return B200AABB_OK;
 }
@@ -1874,7 +1875,8 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
     if (t->n == 0) return fail(t, B200AABB_ERR_EMPTY_TREE, "distance query on an empty tree (CGAL_precondition(!empty()))");
     if (n == 0) return B200AABB_OK;
     // the warp-cooperative kernel packs (query slot, node / leaf) in 32 bits and needs an internal root
-    const bool warp_kernel = t->opt_closest_kernel >= 1 && t->n >= 2 && t->n <= kWpMaxPrims && !t->segments;   // (Segment_3 primitives: one thread per query)
+    // (Segment_3 primitives: the pool kernel, which takes them by a flag, or one thread per query; kernels 2 and 3 are specialised on triangles)
+    const bool warp_kernel = t->opt_closest_kernel >= 1 && t->n >= 2 && t->n <= kWpMaxPrims && !(t->segments && t->opt_closest_kernel != 1);
     if (warp_kernel) { for (int s = 0; s < kScratchSlots; ++s) { rc = ensure_warp(t, s); if (rc) return rc; } }
     const bool two_pass = warp_kernel && t->opt_closest_kernel == 3 && n < (1ull << 32);
     if (two_pass) { rc = ensure_filter(t, space == B200AABB_HOST ? kHostScratch : kDeviceScratch, space == B200AABB_HOST ? std::min<uint64_t>(n, kPointChunkMax) : n); if (rc) return rc; }
@@ -1904,7 +1906,7 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
                              a.cursor = w.cursor; a.spill = w.spill; a.slots64 = w.slots64;
                              a.exact_go = t->opt_warp_exact_go > 0 ? t->opt_warp_exact_go : 160;
                              a.flag_tie = B200AABB_FLAG_TIE; a.flag_exact = B200AABB_FLAG_EXACT;
-                             closest_point_warp_kernel<<<(unsigned)std::min<uint64_t>((uint64_t)t->warp_grid, (cnt + 31) / 32), 32, 0, st>>>(a);
+                             closest_point_warp_kernel<false><<<(unsigned)std::min<uint64_t>((uint64_t)t->warp_grid, (cnt + 31) / 32), 32, 0, st>>>(a);
                              t->stats.kernel_launches += 2;
                              return;
                          }
@@ -1926,7 +1928,8 @@ int b200aabb_closest_point(b200aabb_tree* t, const double* pts, uint64_t n, b200
                          a.exact_go = t->opt_warp_exact_go > 0 ? t->opt_warp_exact_go : 160;
                          a.flag_tie = B200AABB_FLAG_TIE; a.flag_exact = B200AABB_FLAG_EXACT;
                          const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)t->warp_grid, (cnt + 31) / 32);
-                         closest_point_warp_kernel<<<grid, 32, 0, st>>>(a);
+                         if (t->segments) closest_point_warp_kernel<true><<<grid, 32, 0, st>>>(a);
+                         else closest_point_warp_kernel<false><<<grid, 32, 0, st>>>(a);
                      });
 }
 

@@ -201,10 +201,15 @@ B2_HD void wp_sharp(const RelTri& r, float dslack, float e2, float* lower, float
 // The binary64 projection, out of line and with its arguments in registers: the kernel calls it from the refill and from the exact
 // phase, and keeping this long routine (and its own register needs) out of the body keeps the node loop's allocation tight.
 struct CandOut { double x, y, z; int nexact; };
+// seg: the primitives are Segment_3 kept as (source, target, target) records (b200aabb_set_segments): the candidate is the reference's projection on the SEGMENT;
+// the binary32 stages need no change (their bounds hold for the flat triangle = the segment; it yields no upper bound, so only exact candidates shrink the ball)
+// (a template parameter, not an argument: one more live value across the call cost the triangle kernel 4.5 % — 88 -> 112 bytes of spills, measured)
+template <bool SEG = false>
 __device__ __noinline__ CandOut wp_candidate(double ax, double ay, double az, double bx, double by, double bz, double cx, double cy, double cz,
                                              double ox, double oy, double oz) {
     int nexact = 0;
-    const Vec3 p = closest_candidate(Tri3{{ax, ay, az}, {bx, by, bz}, {cx, cy, cz}}, Vec3{ox, oy, oz}, nexact);
+    const Vec3 p = SEG ? closest_candidate_segment(Vec3{ax, ay, az}, Vec3{bx, by, bz}, Vec3{ox, oy, oz}, nexact)
+                       : closest_candidate(Tri3{{ax, ay, az}, {bx, by, bz}, {cx, cy, cz}}, Vec3{ox, oy, oz}, nexact);
     return CandOut{p.x, p.y, p.z, nexact};
 }
 
@@ -225,6 +230,7 @@ __device__ __forceinline__ void wp_apply(WarpShared& S, WarpSlots64& G, unsigned
     }
 }
 
+template <bool SEG>
 __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(const WarpClosestArgs a) {
     __shared__ WarpShared S;
     const unsigned lane = threadIdx.x;
@@ -331,7 +337,7 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
             if (valid) {
                 uint32_t id;
                 const Tri3 t = load_tri(a.tris, firstleaf & ~kLeafBit, id);
-                const CandOut co = wp_candidate(t.a.x, t.a.y, t.a.z, t.b.x, t.b.y, t.b.z, t.c.x, t.c.y, t.c.z, o.x, o.y, o.z);
+                const CandOut co = wp_candidate<SEG>(t.a.x, t.a.y, t.a.z, t.b.x, t.b.y, t.b.z, t.c.x, t.c.y, t.c.z, o.x, o.y, o.z);
                 const int nex0 = co.nexact;
                 const Vec3 cpt = {co.x, co.y, co.z};
                 const Vec3 v = cpt - o;
@@ -507,7 +513,7 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                         if (!(__uint_as_float(e.y) > S.qc[owner].x)) {   // (else: an earlier batch of this very phase has shrunk the ball)
                             const Tri3 t = load_tri(a.tris, e.x & kWpRefMask, id);
                             o = {__ldcg(&G.o[0][owner]), __ldcg(&G.o[1][owner]), __ldcg(&G.o[2][owner])};
-                            const CandOut co = wp_candidate(t.a.x, t.a.y, t.a.z, t.b.x, t.b.y, t.b.z, t.c.x, t.c.y, t.c.z, o.x, o.y, o.z);
+                            const CandOut co = wp_candidate<SEG>(t.a.x, t.a.y, t.a.z, t.b.x, t.b.y, t.b.z, t.c.x, t.c.y, t.c.z, o.x, o.y, o.z);
                             cpt = {co.x, co.y, co.z};
                             if (co.nexact) atomicOr(&S.flags[owner], a.flag_exact);
                             v = cpt - o;

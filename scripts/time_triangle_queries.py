@@ -83,7 +83,35 @@ def main():
     tt["level6_nested_result"] = bool(want6)
     out["tree_vs_tree_icosphere8"] = tt
     print(json.dumps(tt), flush=True)
-    del g
+    # both meshes under transformations (Rigid_triangle_mesh_collision_detection): the same tree twice, the copy turned by 0.3 rad about z and scaled by 1.0001
+    # (nested, nothing intersects) / moved by half a radius (intersects); inclusion test of 1 Mi points against the turned mesh
+    c, s_ = np.cos(0.3), np.sin(0.3)
+    turn = np.array([[c, -s_, 0, 0], [s_, c, 0, 0], [0, 0, 1, 0]], float)
+    xt = {}
+    for name, m in (("turned_and_scaled_1.0001", np.hstack([turn[:, :3] * 1.0001, np.zeros((3, 1))])), ("turned_and_shifted", np.hstack([turn[:, :3], np.array([[0.5], [0.0], [0.0]])]))):
+        ms, r = timed(lambda: g.do_intersect_tree(g, other_xf=m))
+        xt[name] = {"ms": ms, "result": bool(r)}
+    pts1m = torch.from_numpy(rng.uniform(-1.1, 1.1, (1 << 20, 3))).cuda()
+    ms, side = timed(lambda: g.side_of_mesh(pts1m, xf=turn))
+    ms0, side0 = timed(lambda: g.side_of_mesh(pts1m))
+    xt["side_of_mesh_1Mi_points"] = {"ms_under_a_rotation": ms, "ms_plain": ms0, "inside_fraction": float((side == 1).float().mean()), "inside_fraction_plain": float((side0 == 1).float().mean())}
+    out["under_transformations_icosphere8"] = xt
+    print(json.dumps(xt), flush=True)
+    # Segment_3 primitives: the 1,966,080 edges of the sphere; closest_point of 1 Mi points (one thread per query), Plane_3 counts
+    e = np.unique(np.sort(np.concatenate([f[:, [0, 1]], f[:, [1, 2]], f[:, [2, 0]]]).astype(np.int64), axis=1), axis=0)
+    gs = B.AABB_tree(segments=np.concatenate([v[e[:, 0]], v[e[:, 1]]], axis=1))
+    gs.build()
+    ms, r = timed(lambda: gs.closest_point_and_primitive(pts1m))
+    nrm = rng.normal(size=(1 << 16, 3))
+    planes = torch.from_numpy(np.concatenate([nrm, rng.uniform(-1, 1, (1 << 16, 1)) * np.linalg.norm(nrm, axis=1, keepdims=True)], axis=1)).cuda()
+    msp, cnt = timed(lambda: gs.number_of_intersected_primitives(planes, B.PLANE))
+    o_s = orc.OracleTree(segments=np.concatenate([v[e[:, 0]], v[e[:, 1]]], axis=1))
+    smp = pts1m[:20000].cpu().numpy()
+    want = o_s.closest_point(smp)
+    out["segment_primitives_icosphere8_edges"] = {"segments": len(e), "closest_point_ms_1Mi": ms, "Mqueries_s": (1 << 20) / ms / 1e3, "plane_count_ms_64Ki": msp,
+                                                  "mean_edges_per_plane": float(cnt.float().mean()), "sample_sqdist_equal_to_oracle": bool(np.array_equal(r["sqdist"][:20000].cpu().numpy(), want["sqd"]))}
+    print(json.dumps(out["segment_primitives_icosphere8_edges"]), flush=True)
+    del g, gs
     tv, tf = W.terrain()
     gt = B.AABB_tree(tv, tf)
     gt.build()

@@ -911,6 +911,9 @@ def test_tree_against_tree_under_transformations(B, meshes):
                 ta = soup[ia] if xa is None else hc.xf_apply(xa, soup[ia])
                 assert orc.tri_tri_do_intersect(ta, hc.xf_apply(xb, soup[ib])) == 1
         assert 3 < n_true < trials - 3, (name, n_true)
+        # a tree against ITSELF under another transformation (one handle for both arguments)
+        far = np.hstack([np.eye(3), np.array([[10.0 * ext], [0.0], [0.0]])])
+        assert g.do_intersect_tree(g) and not g.do_intersect_tree(g, other_xf=far) and not g.do_intersect_tree(g, xf=far) and g.do_intersect_tree(g, xf=far, other_xf=far)
 
 
 def test_side_of_mesh_under_a_transformation(B, meshes):
