@@ -38,6 +38,11 @@ namespace b2 {
 #ifndef B2_WP_NODE_CAP
 #define B2_WP_NODE_CAP 768
 #endif
+#ifdef B2_WP_NO_STATS               // experiment (profiles/r2_29): the per-round traversal counters compiled out
+#define B2_WP_STAT(x)
+#else
+#define B2_WP_STAT(x) x
+#endif
 constexpr int kWpNodeCap = B2_WP_NODE_CAP;                 // (slot,node) entries held in shared memory
 constexpr int kWpSpillChunk = kWpNodeCap / 2;   // entries moved per spill / reload
 constexpr int kWpSpillCap = 16 * kWpSpillChunk; // entries per warp in the global spill area
@@ -317,7 +322,7 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                     if (!spill_bottom()) { if (lane == 0) atomicOr(&a.counters[2], 1ull); return; }
                 }
                 uint32_t farref = 0; float fard = 0.0f; bool stop = false, push = false;
-                w_nodes += __popc(__ballot_sync(full, act));
+                B2_WP_STAT(w_nodes += __popc(__ballot_sync(full, act)));
                 if (act) {
                     const NodeView nd = load_node(a.nodes, cur);
                     float d0 = wp_box_sqdist(nd.lo0, nd.hi0, q), d1 = wp_box_sqdist(nd.lo1, nd.hi1, q);
@@ -353,7 +358,7 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                 S.flags[lane] = nex0 ? a.flag_exact : 0u;
             }
             active = __ballot_sync(full, valid);
-            w_leaves += __popc(active); w_evals += __popc(active);
+            B2_WP_STAT(w_leaves += __popc(active); w_evals += __popc(active));
             __syncwarp();
             continue;
         }
@@ -380,7 +385,7 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                 __syncwarp();                                      // all pops read before any push overwrites them
                 const bool popped_leaf = live && (e.x & kLeafBit);
                 const bool expand = live && !(e.x & kLeafBit);
-                w_nodes += __popc(__ballot_sync(full, expand));
+                B2_WP_STAT(w_nodes += __popc(__ballot_sync(full, expand)));
                 bool in0 = false, in1 = false;                     // 0 = nearer child, 1 = farther child
                 uint32_t r0 = 0, r1 = 0;
                 float d0 = 0.0f, d1 = 0.0f;
@@ -443,7 +448,7 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                     lb = wp_lower(g, sqrtf(dot3f(g, g)), r) - qc.y;
                     survive = !(lb > qc.x);
                 }
-                w_leaves += take;
+                B2_WP_STAT(w_leaves += take);
                 const unsigned sm = __ballot_sync(full, survive);
                 if (survive) S.mpool[mcnt + __popc(sm & lt)] = make_uint2(pair, __float_as_uint(lb));
                 mcnt += __popc(sm);
@@ -527,7 +532,7 @@ __global__ void __launch_bounds__(32, kWpWarpsPerSM) closest_point_warp_kernel(c
                     // the next round.  Each replacement is a step the sequential reference loop could have taken, and a candidate farther
                     // than an earlier incumbent is farther than every later one, so the outcome is that of the sequential loop.
                     unsigned pm = __ballot_sync(full, pending);
-                    w_evals += __popc(pm);
+                    B2_WP_STAT(w_evals += __popc(pm));
                     while (pm) {
                         int sg = 0;
                         if (pending) {
