@@ -637,6 +637,7 @@ struct b200aabb_tree {
     double h_bbox[6];
     double mag = 0.0;              // largest coordinate magnitude of the root box
     unsigned long long* d_counters = nullptr;   // [8]
+    unsigned* d_witness = nullptr;              // [3]: flag + ids of one intersecting pair of a tree-vs-tree test
     // options
     int opt_sort_queries = 1;      // B200AABB_OPT_SORT_QUERIES
     int opt_closest_kernel = 1;    // B200AABB_OPT_CLOSEST_KERNEL: 1 = warp-cooperative pool (closest_warp.cuh), 2 = lane pairs with private stacks (closest_pair.cuh; measured slower, profiles/r2_02), 0 = one thread per query
@@ -1179,7 +1180,8 @@ int b200aabb_create(int device, b200aabb_tree** out) {
         ok = cudaEventCreateWithFlags(&t->ev_up[s], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&t->ev_run[s], cudaEventDisableTiming) == cudaSuccess &&
              cudaEventCreateWithFlags(&t->ev_down[s], cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaMalloc(&t->d_ray_cursor, kScratchSlots * sizeof(unsigned long long)) == cudaSuccess;
-    ok = ok && cudaMemset(t->d_counters, 0, 8 * sizeof(unsigned long long)) == cudaSuccess;   // (drain() may read them before the first query has reset them)
+    ok = ok && cudaMemset(t->d_counters, 0, 8 * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMalloc(&t->d_witness, 3 * sizeof(unsigned)) == cudaSuccess;   // (drain() may read them before the first query has reset them)
     if (ok) {
         int per_sm = 0;
         ok = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, first_intersection_stream_kernel, 128, 0) == cudaSuccess;
@@ -1198,7 +1200,7 @@ int b200aabb_destroy(b200aabb_tree* t) {
     cudaSetDevice(t->device);
     cudaDeviceSynchronize();
     free_tree_buffers(t); free_build_scratch(t); free_input(t); free_sort(t); free_warp(t);
-    cudaFree(t->d_rootbox); cudaFree(t->d_bounds); cudaFree(t->d_counters); cudaFree(t->d_ray_cursor);
+    cudaFree(t->d_rootbox); cudaFree(t->d_bounds); cudaFree(t->d_counters); cudaFree(t->d_ray_cursor); cudaFree(t->d_witness);
     for (int s = 0; s < kPipeSlots; ++s) {
         cudaFree(t->d_stage_in[s]); cudaFree(t->d_stage_out[s]); cudaFree(t->d_stage_aux[s]);
         if (t->ev_up[s]) cudaEventDestroy(t->ev_up[s]);
@@ -1344,6 +1346,14 @@ int b200aabb_set_mesh(b200aabb_tree* t, const double* verts, uint64_t nv, const 
 // is tokenised and parsed by kernels.  Accepted: plain OFF (no per-vertex normals / colours / texture coordinates, no comments after the counts) whose faces are
 // all triangles "3 i j k" — the files the tree of the north-star path is built from; anything else returns INVALID_ARGUMENT with the reason, and the caller
 // falls back to its own reader + b200aabb_set_mesh.
+__global__ void __launch_bounds__(256) gather_u32_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ idx, uint32_t n, uint32_t* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = src[idx[i]];
+}
+__global__ void __launch_bounds__(256) scatter_f64_kernel(const double* __restrict__ val, const uint32_t* __restrict__ idx, uint32_t n, double* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[idx[i]] = val[i];
+}
 int b200aabb_set_mesh_off(b200aabb_tree* t, const char* text, uint64_t len) { B2_LOCK(t);
     if (!t || !text) return B200AABB_ERR_INVALID_ARGUMENT;
     int rc = b200aabb_clear(t);                              // (whatever happens below, the old primitives are gone: a failed ingest leaves an empty tree)
@@ -1425,15 +1435,24 @@ int b200aabb_set_mesh_off(b200aabb_tree* t, const char* text, uint64_t len) { B2
     }
     if (flags[1]) {   // literals of more than 19 significant digits whose dropped digits decide the rounding: strtod on the caller's text
         std::vector<uint32_t> und(flags[1]), off(flags[1]);
-        cudaMemcpy(und.data(), d_und, flags[1] * 4, cudaMemcpyDeviceToHost);
+        std::vector<double> val(flags[1]);
+        uint32_t* d_off = nullptr; double* d_val = nullptr;
+        if (cudaMalloc(&d_off, flags[1] * 4) != cudaSuccess || cudaMalloc(&d_val, flags[1] * 8) != cudaSuccess) {
+            cudaFree(d_off); release(); free_input(t); t->err = "cudaMalloc(set_mesh_off)"; return B200AABB_ERR_OUT_OF_MEMORY;
+        }
+        gather_u32_kernel<<<grid_for(flags[1], 256), 256, 0, st>>>(d_tok, d_und, flags[1], d_off);
+        cudaMemcpyAsync(und.data(), d_und, flags[1] * 4, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(off.data(), d_off, flags[1] * 4, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
         for (unsigned i = 0; i < flags[1]; ++i) {
-            cudaMemcpy(&off[i], d_tok + und[i], 4, cudaMemcpyDeviceToHost);
             uint64_t b = off[i], en = b;
             while (en < len && !is_space(text[en])) ++en;
-            const std::string lit(text + b, text + en);
-            const double v = strtod(lit.c_str(), nullptr);
-            cudaMemcpy(d_v + und[i], &v, 8, cudaMemcpyHostToDevice);
+            val[i] = strtod(std::string(text + b, text + en).c_str(), nullptr);
         }
+        cudaMemcpyAsync(d_val, val.data(), flags[1] * 8, cudaMemcpyHostToDevice, st);
+        scatter_f64_kernel<<<grid_for(flags[1], 256), 256, 0, st>>>(d_val, d_und, flags[1], d_v);
+        cudaStreamSynchronize(st);
+        cudaFree(d_off); cudaFree(d_val);
     }
     cudaMemsetAsync(t->d_bounds, 0xFF, 3 * 8, st);
     cudaMemsetAsync(t->d_bounds + 3, 0x00, 3 * 8, st);
@@ -1667,12 +1686,11 @@ int b200aabb_do_intersect_tree_transformed(b200aabb_tree* t, const double* xf, b
     const bool t_is_big = t->n >= other->n;                               // (not decided by comparing handles: a tree may be tested against itself under another transformation)
     b200aabb_tree* big = t_is_big ? t : other;
     b200aabb_tree* small = t_is_big ? other : t;
-    unsigned* d_w = nullptr;
-    if (cudaMalloc(&d_w, 3 * sizeof(unsigned)) != cudaSuccess) { t->err = "cudaMalloc(do_intersect(tree))"; return B200AABB_ERR_OUT_OF_MEMORY; }
+    unsigned* const d_w = t->d_witness;                                  // (kept with the handle: no allocation per test)
     const unsigned init[3] = {0u, kNone, kNone};
     cudaMemcpyAsync(d_w, init, sizeof(init), cudaMemcpyHostToDevice, t->stream);
     rc = reset_counters(big, t->stream);
-    if (rc) { cudaFree(d_w); return rc; }
+    if (rc) return rc;
     cudaEventRecord(t->ev_a, t->stream);
     XfPair x;
     static const double kIdentity[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
@@ -1690,7 +1708,6 @@ int b200aabb_do_intersect_tree_transformed(b200aabb_tree* t, const double* xf, b
     cudaMemcpyAsync(w, d_w, sizeof(w), cudaMemcpyDeviceToHost, t->stream);
     cudaMemcpyAsync(&c2, big->d_counters + 2, sizeof(c2), cudaMemcpyDeviceToHost, t->stream);
     const cudaError_t e = cudaStreamSynchronize(t->stream);
-    cudaFree(d_w);
     if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) { t->err = "do_intersect(tree): CUDA failure"; return B200AABB_ERR_CUDA; }
     if (c2 && !w[0]) return fail(t, B200AABB_ERR_INCOMPLETE, "traversal stack overflow: results incomplete");
     *result = w[0] ? 1 : 0;
@@ -2126,7 +2143,7 @@ namespace {
 // (phase 0: header, phase 1: payload — the payload sizes depend on the header, so the two can not share a group)
 int bcast_header(b200aabb_comm* c, b200aabb_tree* t, int root, int mode, cudaStream_t st) {
     if (c->rank == root) {
-        const unsigned long long h[4] = {t->n, t->d_ids ? 1ull : 0ull, (unsigned long long)mode, 0ull};
+        const unsigned long long h[4] = {t->n, t->d_ids ? 1ull : 0ull, (unsigned long long)mode, t->segments ? 1ull : 0ull};
         if (cudaMemcpyAsync(c->d_header, h, sizeof(h), cudaMemcpyHostToDevice, st) != cudaSuccess) return B200AABB_ERR_CUDA;
         if (cudaStreamSynchronize(st) != cudaSuccess) return B200AABB_ERR_CUDA;   // (h lives on this stack frame)
     }
@@ -2139,13 +2156,17 @@ int bcast_prepare(b200aabb_comm* c, b200aabb_tree* t, int root, int mode, cudaSt
     if (cudaMemcpyAsync(h, c->d_header, sizeof(h), cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess) return B200AABB_ERR_CUDA;
     if (c->rank == root) return B200AABB_OK;
     const uint64_t n = h[0];
+    const bool segments = h[3] != 0;                 // the kind of primitive travels with the header (the receiving calls below reset it)
     if (mode == 0) {
-        if (t->imported && t->n == n && t->d_tris && t->d_trisf && (n < 2 || t->d_nodes)) return B200AABB_OK;   // a replica of the same size: refresh it in place
-        return b200aabb_import_alloc(t, n);
+        if (t->imported && t->n == n && t->d_tris && t->d_trisf && (n < 2 || t->d_nodes)) { t->segments = segments; return B200AABB_OK; }   // a replica of the same size: refresh it in place
+        const int rc = b200aabb_import_alloc(t, n);
+        t->segments = segments;
+        return rc;
     }
     // (a handle that already holds inserted primitives of the same size — an earlier mode-1 replica — receives into its buffers: a re-build then allocates nothing)
-    if (!t->imported && t->n == n && n && t->d_soup && (h[1] != 0) == (t->d_ids != nullptr)) { t->built = false; t->bounds_valid = false; return B200AABB_OK; }
+    if (!t->imported && t->n == n && n && t->d_soup && (h[1] != 0) == (t->d_ids != nullptr)) { t->built = false; t->bounds_valid = false; t->segments = segments; return B200AABB_OK; }
     int rc = b200aabb_clear(t);
+    t->segments = segments;
     if (rc || n == 0) return rc;
     if (cudaMalloc(&t->d_soup, n * 72 + kSoupSlack) != cudaSuccess) return B200AABB_ERR_OUT_OF_MEMORY;
     if (h[1] && cudaMalloc(&t->d_ids, n * 4) != cudaSuccess) return B200AABB_ERR_OUT_OF_MEMORY;
