@@ -224,6 +224,37 @@ def pcie_ceiling(torch, h2d_bytes, d2h_bytes, reps=3):
     return best
 
 
+def other_queries(tree, torch, B, pts_d):
+    """NOT part of `value`: the other batched queries of the same tree, timed once each for the line's `detail` (SURVEY.md §8f rows built in round 2):
+    Triangle_3 id queries (2^22 half-unit triangles at the benchmark's points) and tree-vs-tree do_intersect of the terrain against itself under a translation."""
+    import time
+
+    def timed(fn, reps=3):
+        best, out = None, None
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            out = fn()
+            torch.cuda.synchronize()
+            ms = (time.perf_counter() - t0) * 1e3
+            best = ms if best is None else min(best, ms)
+        return best, out
+    n = min(1 << 22, pts_d.shape[0])
+    p = pts_d[:n]
+    e1 = torch.tensor([0.5, 0.0, 0.25], dtype=torch.float64, device="cuda")
+    e2 = torch.tensor([0.0, 0.5, 0.25], dtype=torch.float64, device="cuda")
+    tri = torch.cat([p, p + e1, p + e2], dim=1).contiguous()
+    ms_any, hit = timed(lambda: tree.do_intersect(tri, B.TRIANGLE))
+    ms_cnt, cnt = timed(lambda: tree.number_of_intersected_primitives(tri, B.TRIANGLE))
+    shift = lambda x, y, z: [[1.0, 0, 0, x], [0, 1.0, 0, y], [0, 0, 1.0, z]]      # noqa: E731
+    tt = {}
+    for name, m in (("moved_by_(0.5, 0.5, 0)", shift(0.5, 0.5, 0.0)), ("lifted_by_200", shift(0.0, 0.0, 200.0))):
+        ms, r = timed(lambda: tree.do_intersect_tree(tree, other_xf=np.array(m)))
+        tt[name] = {"ms": ms, "intersect": bool(r)}
+    return {"triangle_queries": n, "triangle_do_intersect_Mq_s": n / ms_any / 1e3, "triangle_count_Mq_s": n / ms_cnt / 1e3, "triangle_hit_fraction": float((hit != 0).float().mean()),
+            "triangle_count_total": int(cnt.sum()), "terrain_against_itself_do_intersect_tree": tt, "timing": "wall clock around the call, best of 3, not in the timed region of `value`"}
+
+
 def config5(tree, rank, world, local, dist, torch, B, bbox, oracle_check=None):
     """BASELINE.json config 5: 2^30 mixed queries generated on the device (b200work_*) in 2^26 batches, batches split over the ranks;
     128-bit checksum of every result array; the first 2^20 rays / points of batch 0 are kept for parity with the oracle (rank 0)."""
@@ -476,6 +507,12 @@ def main():
     c5, kept = (None, {})
     if not args.no_config5 and not args.small:
         c5, kept = config5(tree, rank, world, local, dist, torch, B, bbox)
+    extras = None
+    if rank == 0 and world == 1 and not args.small:
+        try:
+            extras = other_queries(tree, torch, B, pts_d)
+        except Exception as exc:          # (informational leg: never takes the line down)
+            extras = {"error": repr(exc)}
 
     if dist is not None:
         legs = e2e_legs if e2e_ms is not None else [0.0, 0.0]
@@ -516,7 +553,7 @@ def main():
                            "build_ms": build_ms, "build_call_wall_ms": build_wall_ms, "build_Mtri_s": n_prims / build_ms / 1e3, "build_GB_s_algorithmic(492B/tri)": 492.0 * n_prims / build_ms / 1e6,
                            "build_frac_of_hbm_roofline(492B/tri)": 492.0 * n_prims / build_ms / 1e6 / peak,
                            "ray_hit_rate_rank0": hit_rate, "ties": ties, "near_ties": near, "exact_stage_queries": exact, "traversal_rank0": traffic_model,
-                           "fp64_dfma_peak_TFLOP_s": dfma, "tree_broadcast": bcast, "config5": c5},
+                           "fp64_dfma_peak_TFLOP_s": dfma, "tree_broadcast": bcast, "config5": c5, "other_queries": extras},
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic if not args.small and n_pts == POINTS_PER_RANK else None, "traffic_source": traffic_src,
                              "peak_source": peak_src, "algorithmic_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,

@@ -1110,6 +1110,21 @@ static void launch_intersect(b200aabb_tree* t, int kind, cudaStream_t st, const 
         default: intersect_kernel<kSegmentQ, MODE><<<grid, 128, 0, st>>>(tree_ref(t, perm), in, cnt, out8, out32, offsets, list); break;
     }
 }
+// a box that contains the image of the box b (xmin ymin zmin xmax ymax zmax) under the affine map xf (12 doubles; nullptr = identity), widened by the rounding
+// of the images of the primitives inside (as bvh.cuh::AffXf does per node); false = the map is not finite
+static bool image_of_box(const double* xf, const double* b, double* out) {
+    if (!xf) { for (int k = 0; k < 6; ++k) out[k] = b[k]; return true; }
+    for (int k = 0; k < 3; ++k) {
+        const double* r = xf + 4 * k;
+        const double c[3] = {0.5 * (b[0] + b[3]), 0.5 * (b[1] + b[4]), 0.5 * (b[2] + b[5])}, h[3] = {0.5 * (b[3] - b[0]), 0.5 * (b[4] - b[1]), 0.5 * (b[5] - b[2])};
+        const double ctr = ((r[0] * c[0] + r[1] * c[1]) + r[2] * c[2]) + r[3];
+        const double ext = (fabs(r[0]) * h[0] + fabs(r[1]) * h[1]) + fabs(r[2]) * h[2];
+        const double mag = ((fabs(r[0]) * (fabs(c[0]) + h[0]) + fabs(r[1]) * (fabs(c[1]) + h[1])) + fabs(r[2]) * (fabs(c[2]) + h[2])) + fabs(r[3]);
+        if (!(ctr == ctr) || !(ext == ext)) return false;
+        out[k] = ctr - (ext + 1e-14 * mag); out[3 + k] = ctr + (ext + 1e-14 * mag);
+    }
+    return true;
+}
 // a tree of Segment_3 primitives answers closest_point / squared_distance and the id queries with Plane_3 and Triangle_3 (what the reference's kernel can
 // intersect with a Segment_3 datum robustly in 3D); every other entry point needs triangles
 static int need_triangles(b200aabb_tree* t, const char* what) {
@@ -1678,6 +1693,11 @@ int b200aabb_do_intersect_tree_transformed(b200aabb_tree* t, const double* xf, b
     rc = ensure_built(other);
     if (rc) { t->err = other->err; return rc; }
     if (t->n == 0 || other->n == 0) return B200AABB_OK;                 // an empty tree intersects nothing (AABB_tree.h:516-525)
+    {   // the first node test of the reference's traversal: when the (images of the) root boxes are disjoint nothing can intersect
+        double ba[6], bb[6];
+        if (!image_of_box(xf, t->h_bbox, ba) || !image_of_box(other_xf, other->h_bbox, bb)) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "do_intersect(tree): a transformation is not finite");
+        if (ba[0] > bb[3] || bb[0] > ba[3] || ba[1] > bb[4] || bb[1] > ba[4] || ba[2] > bb[5] || bb[2] > ba[5]) return B200AABB_OK;
+    }
     B2_CUDA(t, cudaSetDevice(t->device));
     rc = drain(other);                                                   // (its build, or batches still in flight, run on other streams)
     if (rc) { t->err = other->err; return rc; }
@@ -1970,17 +1990,8 @@ int b200aabb_side_of_mesh_transformed(b200aabb_tree* t, const double* xf, const 
     memset(&x, 0, sizeof(x));
     if (xf) {   // the image of the root box, conservatively (bvh.cuh::AffXf::box_meets does the same per node)
         memcpy(x.xf.m, xf, sizeof(x.xf.m));
-        const double* b = t->h_bbox;
-        for (int k = 0; k < 3; ++k) {
-            const double* r = xf + 4 * k;
-            const double c[3] = {0.5 * (b[0] + b[3]), 0.5 * (b[1] + b[4]), 0.5 * (b[2] + b[5])}, h[3] = {0.5 * (b[3] - b[0]), 0.5 * (b[4] - b[1]), 0.5 * (b[5] - b[2])};
-            const double ctr = ((r[0] * c[0] + r[1] * c[1]) + r[2] * c[2]) + r[3];
-            const double ext = (fabs(r[0]) * h[0] + fabs(r[1]) * h[1]) + fabs(r[2]) * h[2];
-            const double mag = ((fabs(r[0]) * (fabs(c[0]) + h[0]) + fabs(r[1]) * (fabs(c[1]) + h[1])) + fabs(r[2]) * (fabs(c[2]) + h[2])) + fabs(r[3]);
-            if (!(ctr == ctr) || !(ext == ext)) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "side_of_mesh: the transformation is not finite");
-            x.box[k] = ctr - (ext + 1e-14 * mag); x.box[3 + k] = ctr + (ext + 1e-14 * mag);
-            x.mag = std::max(x.mag, std::max(fabs(x.box[k]), fabs(x.box[3 + k])));
-        }
+        if (!image_of_box(xf, t->h_bbox, x.box)) return fail(t, B200AABB_ERR_INVALID_ARGUMENT, "side_of_mesh: the transformation is not finite");
+        for (int k = 0; k < 6; ++k) x.mag = std::max(x.mag, fabs(x.box[k]));
     }
     return run_batch(t, pts, 24, n, space, kPointQuery, {{side, 1, 0}, {attempts, 1, 0}}, [&](cudaStream_t st, const void* in, void** o, uint64_t cnt, const uint32_t* perm) {
         if (xf) side_of_mesh_kernel<AffXf><<<grid_for(cnt, 128), 128, 0, st>>>(tree_ref(t, perm), (const double*)in, cnt, t->d_rootbox, (int8_t*)o[0], (uint8_t*)o[1], x);
