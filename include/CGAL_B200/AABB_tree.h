@@ -310,6 +310,26 @@ class AABB_tree {
   Point closest_point(const Point& query, const Point&) const { return closest_point(query); }
   Point_and_primitive_id closest_point_and_primitive(const Point& query, const Point_and_primitive_id&) const { return closest_point_and_primitive(query); }
 
+  // any_reference_point_and_id() (AABB_tree.h:582-588): the reference point of the first primitive; best_hint(query) (:591-612): the reference point nearest to the
+  // query — what the reference's internal kd-tree returns.  Neither is needed by the queries above (the device traversal finds its own first ball); they are kept
+  // for callers of the public members and run on the host, best_hint in O(size()).
+  Point_and_primitive_id any_reference_point_and_id() const {
+    if (m_primitives.empty()) throw Error(B200AABB_ERR_EMPTY_TREE, "any_reference_point_and_id on an empty tree (CGAL_assertion(!empty()))");
+    return Point_and_primitive_id(reference_point(m_primitives[0]), m_primitives[0].id());
+  }
+  Point_and_primitive_id best_hint(const Point& query) const {
+    if (m_primitives.empty()) throw Error(B200AABB_ERR_EMPTY_TREE, "best_hint on an empty tree");
+    size_type arg = 0;
+    double best = -1.0;
+    for (size_type i = 0; i < m_primitives.size(); ++i) {
+      decltype(auto) r = reference_point(m_primitives[i]);
+      const double dx = (double)r.x() - (double)query.x(), dy = (double)r.y() - (double)query.y(), dz = (double)r.z() - (double)query.z();
+      const double d = dx * dx + dy * dy + dz * dz;
+      if (best < 0.0 || d < best) { best = d; arg = i; }
+    }
+    return Point_and_primitive_id(reference_point(m_primitives[arg]), m_primitives[arg].id());
+  }
+
   // ---- BATCHED overloads (new): [first, beyond) is a range of queries, results go to `out` in the same order ------------
   // out receives bool
   template <typename QueryIterator, typename OutputIterator>
@@ -566,6 +586,10 @@ class AABB_tree {
   decltype(auto) datum(const Primitive& p) const {   // internal::Primitive_helper::get_datum, AABB_tree/internal/Primitive_helper.h:40-60
     if constexpr (internal::Has_shared_data<Primitive>::value) return p.datum(m_traits.shared_data());
     else return p.datum();
+  }
+  decltype(auto) reference_point(const Primitive& p) const {   // internal::Primitive_helper::get_reference_point, AABB_tree/internal/Primitive_helper.h:62-82
+    if constexpr (internal::Has_shared_data<Primitive>::value) return p.reference_point(m_traits.shared_data());
+    else return p.reference_point();
   }
   void create(int device) {
     const int rc = b200aabb_create(device, &m_handle);

@@ -80,6 +80,9 @@ static int known_answers() {
     CHECK(std::fabs(c.x() - 1.0 / 3) < 1e-15 && std::fabs(c.y() - 1.0 / 3) < 1e-15 && std::fabs(c.z() - 1.0 / 3) < 1e-15);
     CHECK(tree.squared_distance(Point(2.0, 2.0, 2.0)) == (c.x() - 2) * (c.x() - 2) + (c.y() - 2) * (c.y() - 2) + (c.z() - 2) * (c.z() - 2));
     CHECK(tree.accelerate_distance_queries());
+    CHECK(tree.any_reference_point_and_id().first == Point(0, 0, 0) && tree.any_reference_point_and_id().second == mini::Face_index(0));   // AABB_tree.h:582-588
+    CHECK(tree.best_hint(Point(0.9, 0.1, 0.0)).first == Point(1, 0, 0) && tree.best_hint(Point(0.9, 0.1, 0.0)).second == mini::Face_index(3));  // face 3 = (b, d, c) starts at b
+    CHECK(tree.closest_point(Point(2.0, 2.0, 2.0), tree.best_hint(Point(2.0, 2.0, 2.0)).first) == tree.closest_point(Point(2.0, 2.0, 2.0)));
     // first_intersection: a ray along +z from below the base face hits face 0 (z = 0) first, at (0.2,0.2,0)
     const Ray up(Point(0.2, 0.2, -1.0), Point(0.2, 0.2, 0.0));
     const auto hit = tree.first_intersection(up);
