@@ -54,6 +54,7 @@ def lib():
         L.hc_tri_tri_do_intersect.argtypes = [_dp, _dp]
         L.hc_side_of_mesh_xf.argtypes = [C.c_void_p, _dp, _dp, C.c_uint64, _dp, C.c_int, C.POINTER(C.c_int8)]
         L.hc_parse_decimals.argtypes = [C.c_char_p, C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint64), C.POINTER(C.c_int)]
+        L.hc_tree_tree_xf.argtypes = [C.c_void_p, _dp, C.c_void_p, _dp, _u32p]
         L.hc_xf_apply.argtypes = [_dp, _dp, _dp]
         L.hc_xf_box_meets.argtypes = [_dp, C.POINTER(C.c_float), _dp]
         L.hc_intersect_triangle.argtypes = [C.c_void_p, _dp, C.c_uint64, C.c_int, _u32p]
@@ -137,6 +138,12 @@ class HostTree:
         side = np.zeros(len(pts), np.int8)
         lib().hc_side_of_mesh_xf(self.h, _p(m), _p(pts), len(pts), _p(dirs), len(dirs), side.ctypes.data_as(C.POINTER(C.c_int8)))
         return side
+
+    def do_intersect_tree_xf(self, m, other, other_m):
+        """tree-vs-tree under affine maps as the device kernel runs it (this tree is traversed, `other`'s primitives are the queries): (bool, id here, id there)"""
+        pair = np.full(2, 0xFFFFFFFF, np.uint32)
+        r = lib().hc_tree_tree_xf(self.h, _p(_d(m).ravel()), other.h, _p(_d(other_m).ravel()), _p(pair, _u32p))
+        return bool(r), int(pair[1]), int(pair[0])
 
     def first_intersection(self, rays):
         rays = _d(rays).reshape(-1, 6)

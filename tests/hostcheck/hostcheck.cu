@@ -351,6 +351,22 @@ void hc_side_of_mesh_xf(void* hv, const double* m, const double* pts, uint64_t n
         side[i] = (int8_t)(r == kSideIndeterminate ? -2 : (r == kSideBoundary ? 0 : ((r & 1) ? 1 : -1)));
     }
 }
+// tree.do_intersect(other_tree) with both trees under affine maps, as b200aabb.cu::tree_tree_kernel<true> runs it: every primitive of `small`, moved by mq,
+// traverses `big` under mb (bvh.cuh::traverse_triangle<kAnyId, AffXf>); returns 1 + the ids of the first pair found, 0 if none
+int hc_tree_tree_xf(void* big, const double* mb, void* small, const double* mq, uint32_t* pair) {
+    HostTree* hb = (HostTree*)big; HostTree* hs = (HostTree*)small;
+    AffXf xq, xb;
+    for (int i = 0; i < 12; ++i) { xq.m[i] = mq[i]; xb.m[i] = mb[i]; }
+    if (hb->n == 0) return 0;
+    for (uint64_t i = 0; i < hs->n; ++i) {
+        TravStat st;
+        uint32_t ida;
+        const Tri3 t = xq.apply(load_tri(hs->tris.data(), (uint32_t)i, ida));
+        const uint32_t idb = traverse_triangle<kAnyId, AffXf>(hb->nodes.data(), hb->tris.data(), hb->root, t, st, nullptr, 0, xb);
+        if (idb != kNone) { pair[0] = ida; pair[1] = idb; return 1; }
+    }
+    return 0;
+}
 int hc_tri_tri_do_intersect(const double* query, const double* tri) { int n = 0; return tri_tri_do_intersect(T(query), T(tri), n) ? 1 : 0; }
 // Triangle_3 queries (9 doubles each) through the device traversal routine: mode 0 do_intersect, 1 count
 void hc_intersect_triangle(void* hv, const double* q, uint64_t n, int count, uint32_t* out) {

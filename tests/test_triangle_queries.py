@@ -218,3 +218,28 @@ def test_oracle_transformed_tree_against_tree(meshes):
     assert 10 < n_true < 55
     ident = np.hstack([np.eye(3), np.zeros((3, 1))])
     assert a.do_intersect_tree_transformed(ident, b, None) == a.do_intersect_tree(b)
+
+
+def test_device_tree_against_tree_under_transformations(meshes):
+    """the traversal the device kernel runs (traverse_triangle<kAnyId, AffXf> per primitive of the other tree, compiled for the host) against the oracle's
+    brute force over all pairs of transformed primitives; the witness pair is re-checked on the transformed triangles"""
+    v, f = meshes["cube"]
+    pv, pf = meshes["pinion_small"]
+    rng = np.random.default_rng(49)
+    ident = np.hstack([np.eye(3), np.zeros((3, 1))])
+    for (va, fa), (vb, fb), trials in (((v, f), (v, f), 30), ((pv, pf), (v * (0.3 * (pv.max() - pv.min()) / (v.max() - v.min())) + pv.mean(0), f), 12)):
+        sa, sb = va[fa].reshape(-1, 9), vb[fb].reshape(-1, 9)
+        ha, hb = hc.HostTree(sa), hc.HostTree(sb)
+        oa, ob = orc.OracleTree(va, fa), orc.OracleTree(vb, fb)
+        ext = (va.max(0) - va.min(0)).max()
+        n_true = 0
+        for it in range(trials):
+            xa = rigid(rng, shift=rng.uniform(-0.5, 0.5, 3) * ext) if it % 2 else ident
+            xb = rigid(rng, scale=rng.uniform(0.5, 1.5), shift=rng.uniform(-1.0, 1.0, 3) * ext)
+            want = oa.do_intersect_tree_transformed(xa, ob, xb, naive=True)
+            n_true += want
+            hit, ia, ib = ha.do_intersect_tree_xf(xa, hb, xb)
+            assert hit == want, it
+            if hit:
+                assert orc.tri_tri_do_intersect(hc.xf_apply(xb, sb[ib]), hc.xf_apply(xa, sa[ia])) == 1
+        assert 0 < n_true < trials
