@@ -34,7 +34,7 @@ enum {
                                       next b200aabb_get_stats */
 };
 
-enum { B200AABB_NO_PRIMITIVE = 0xFFFFFFFFu };
+#define B200AABB_NO_PRIMITIVE 0xFFFFFFFFu   /* (a macro: the value does not fit the int of a C enumerator) */
 
 /* where the query / result pointers of a batched call live */
 typedef enum { B200AABB_HOST = 0, B200AABB_DEVICE = 1 } b200aabb_memspace;
